@@ -1,0 +1,208 @@
+/*
+ * yq_b200.h -- C ABI of libyq_b200.so: the B200-native (sm_100a) INT8 inference hot path of the
+ * quantized darknet fork ArtyZe/yolo_quantization.
+ *
+ * This is the drop-in boundary.  Plain pointers, sizes and opaque handles only; no torch, no C++.
+ * Every entry point names the reference interface it replaces (paths relative to the reference
+ * repository).  INTEGRATION.md shows the stubs a maintainer adds to the reference
+ * (make_*_layer / forward_*_gpu / forward_network_gpu) to bind these.
+ *
+ * Conventions
+ *  - Device activations are uint8 NHWC with a channel stride `cs` >= c (yq_channel_stride(c));
+ *    pad channels are ZERO.  The reference's host-visible layout is CHW (src/im2col.c:13); the
+ *    yq_nchw_to_nhwc_* / yq_nhwc_to_nchw_* kernels convert at the two places data crosses the
+ *    boundary (net->input_uint8 in, l.output / debug pulls out).
+ *  - All functions return 0 on success, non-zero on failure; yq_last_error() returns the message.
+ *    The reference has no return codes: check_error() prints, assert(0)s and exit(-1)s
+ *    (src/cuda.c:27-49).  yq_set_abort_on_error(1) reproduces that convention.
+ *  - `stream` arguments are cudaStream_t passed as void* (NULL = the legacy default stream, which is
+ *    what the reference uses everywhere, src/cuda.c).
+ *  - There is NO CPU fallback: without a CUDA device every compute entry point fails loudly.
+ */
+#ifndef YQ_B200_H
+#define YQ_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define YQ_API __attribute__((visibility("default")))
+
+/* Same numeric values as the reference's ACTIVATION enum (include/darknet.h:87-89) so a binding can
+ * pass l.activation straight through. */
+typedef enum {
+    YQ_LOGISTIC = 0,
+    YQ_RELU = 1,
+    YQ_LINEAR = 3,
+    YQ_RELU6 = 8,
+    YQ_LEAKY = 9
+} yq_activation;
+
+/* ------------------------------------------------------------------------------------------------
+ * errors / device  (replaces check_error, cuda_set_device, cuda_get_device: src/cuda.c:11-49)
+ * ---------------------------------------------------------------------------------------------- */
+YQ_API const char *yq_last_error(void);
+YQ_API void yq_set_abort_on_error(int enable);
+YQ_API int yq_device_count(void);
+YQ_API int yq_set_device(int device);
+YQ_API const char *yq_version(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * device memory  (replaces cuda_make_array / cuda_free / cuda_push_array_int8 /
+ * cuda_pull_array_int8: src/cuda.c:90-104,145-179 -- without the sizeof(float) over-read of
+ * cuda_make_array on uint8 buffers)
+ * ---------------------------------------------------------------------------------------------- */
+YQ_API void *yq_cuda_malloc(size_t bytes);
+YQ_API int yq_cuda_free(void *dev);
+YQ_API int yq_cuda_push(void *dev, const void *host, size_t bytes, void *stream);
+YQ_API int yq_cuda_pull(void *host, const void *dev, size_t bytes, void *stream);
+YQ_API int yq_cuda_memset(void *dev, int value, size_t bytes, void *stream);
+YQ_API int yq_stream_synchronize(void *stream);
+
+/* channel stride used for a c-channel NHWC activation tensor: 4 for c <= 4, else c rounded up to 16 */
+YQ_API int yq_channel_stride(int c);
+
+/* ------------------------------------------------------------------------------------------------
+ * quantized convolution
+ *   replaces forward_convolutional_layer_quant_inputi_outputi (src/convolutional_layer.c:694-761)
+ *            = im2col_cpu_uint8 (src/im2col.c:26-50) + 2x gemm_nn_uint8_int32_te (src/gemm.c:279-299)
+ *              + requantize/activation loop (:726-751) + quant_stop dequant (:752-760)
+ *   binds as  l.forward_gpu of a CONVOLUTIONAL layer (slot assigned at src/convolutional_layer.c:320-340;
+ *             prototype forward_convolutional_layer_quant_gpu, src/convolutional_layer.h:15)
+ * ---------------------------------------------------------------------------------------------- */
+
+/* Host-side description of one prepared layer; field names follow `struct layer`
+ * (include/darknet.h:172-226) after quantization_weights_and_activations (src/blas.c:259-346). */
+typedef struct yq_conv_desc {
+    int h, w, c;                 /* l.h l.w l.c                                                          */
+    int n, size, stride, pad;    /* l.n l.size l.stride l.pad (pad already = size/2 when cfg pad=1)      */
+    int activation;              /* l.activation (yq_activation values)                                   */
+    int quant_stop_flag;         /* l.quant_stop_flag: also emit float (u8 - zp_out) * s_out              */
+    int zp_in;                   /* l.input_data_uint8_zero_point[0]  (pad value of im2col, im2col.c:5-14) */
+    int zp_out;                  /* l.activ_data_uint8_zero_point[0]                                      */
+    float s_out;                 /* l.activ_data_uint8_scales[0]                                          */
+    const uint8_t *weights_uint8;          /* l.weights_uint8, OIHW [n][c][size][size]  (host)            */
+    const uint8_t *weight_zero_point;      /* l.weight_data_uint8_zero_point [n]        (host)            */
+    const int32_t *biases_int32;           /* l.biases_int32 [n]                        (host)            */
+    const double *M_value;                 /* l.M_value [n]  = M0 * 2^-31               (host)            */
+    const double *M0_right_shift_value;    /* l.M0_right_shift_value [n] = 2^-shift     (host)            */
+    int saturate;                /* 0 = reference semantics: uint8 store WRAPS (convolutional_layer.c:737-749);
+                                    1 = clamp to [0,255] (what the MKL variant does at :594)              */
+} yq_conv_desc;
+
+typedef struct yq_conv_layer yq_conv_layer;   /* opaque: packed device weights + per-channel params */
+
+/* replaces the GPU block of make_convolutional_layer (src/convolutional_layer.c:320-340) and
+ * push_convolutional_layer (src/convolutional_kernels.cu:339-350): packs weights into the kernel layout
+ * once and uploads the per-channel parameters.  Returns NULL on failure. */
+YQ_API yq_conv_layer *yq_make_convolutional_layer_quant(const yq_conv_desc *desc);
+YQ_API void yq_free_convolutional_layer_quant(yq_conv_layer *l);
+YQ_API int yq_conv_out_h(const yq_conv_layer *l);
+YQ_API int yq_conv_out_w(const yq_conv_layer *l);
+/* 0 = SIMT dp4a implicit GEMM, 1 = tcgen05 kind::i8 implicit GEMM; -1 (default) = choose per layer */
+YQ_API int yq_conv_set_kernel(yq_conv_layer *l, int kind);
+YQ_API int yq_conv_get_kernel(const yq_conv_layer *l);
+
+/* in_u8   : device, NHWC [batch][h][w][yq_channel_stride(c)]
+ * out_u8  : device, NHWC [batch][out_h][out_w][yq_channel_stride(n)]           (l.output_uint8_final)
+ * out_f32 : device, NCHW [batch][n][out_h][out_w] or NULL; written when quant_stop_flag   (l.output)
+ * out_acc : device, NHWC [batch][out_h][out_w][yq_channel_stride(n)] int32 or NULL -- the exact-integer
+ *           accumulator (l.output_int32) for parity checks                                         */
+YQ_API int yq_forward_convolutional_layer_quant_gpu(yq_conv_layer *l, const uint8_t *in_u8, uint8_t *out_u8,
+                                                    float *out_f32, int32_t *out_acc, int batch, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * memory-bound layers (all device pointers, uint8 NHWC, channel stride yq_channel_stride(c))
+ * ---------------------------------------------------------------------------------------------- */
+/* replaces forward_maxpool_layer_quant (src/maxpool_layer.c:109-153); `pad` is l.pad (size-1 by default) */
+YQ_API int yq_forward_maxpool_layer_quant_gpu(const uint8_t *in, uint8_t *out, int batch, int h, int w, int c,
+                                              int size, int stride, int pad, void *stream);
+/* replaces forward_upsample_layer_quant + upsample_quant_cpu (src/upsample_layer.c:96-113, src/blas.c:781-803) */
+YQ_API int yq_forward_upsample_layer_quant_gpu(const uint8_t *in, uint8_t *out, int batch, int h, int w, int c,
+                                               int stride, void *stream);
+/* replaces forward_route_layer_quant + copy_cpu_uint8 (src/route_layer.c:107-130, src/blas.c:656-660):
+ * channel concat of n_inputs tensors of identical h, w; in_c[i] real channels each. */
+YQ_API int yq_forward_route_layer_quant_gpu(const uint8_t *const *inputs, const int *in_c, int n_inputs,
+                                            uint8_t *out, int batch, int h, int w, void *stream);
+/* replaces forward_yolo_layer's inference part (src/yolo_layer.c:132-146): float NCHW in/out,
+ * logistic on channels {0,1} and {4..4+classes} of each anchor. */
+YQ_API int yq_forward_yolo_layer_gpu(const float *in, float *out, int batch, int n_anchors, int classes, int h,
+                                     int w, void *stream);
+
+/* layout conversion at the boundary (reference tensors are CHW per image) */
+YQ_API int yq_nchw_to_nhwc_u8(const uint8_t *in_nchw, uint8_t *out_nhwc, int batch, int c, int h, int w,
+                              void *stream);
+YQ_API int yq_nhwc_to_nchw_u8(const uint8_t *in_nhwc, uint8_t *out_nchw, int batch, int c, int h, int w,
+                              void *stream);
+YQ_API int yq_nhwc_to_nchw_i32(const int32_t *in_nhwc, int32_t *out_nchw, int batch, int c, int h, int w,
+                               void *stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * network level -- host-side mirror of the reference's public API for this path
+ *   load_network / parse_network_cfg / load_weights   (src/network.c:49-57, src/parser.c:682-815,1201-1305)
+ *   quantization_weights_and_activations              (src/blas.c:259-346; done once inside yq_load_network)
+ *   set_batch_network                                 (src/network.c:415-432; batch is fixed at load here
+ *                                                      because buffers are sized at parse time, Appendix E.6)
+ *   network_predict / forward_network                 (src/network.c:229-261,570-581)
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct yq_network yq_network;
+
+typedef struct yq_layer_info {
+    int type;                 /* 0 conv, 1 maxpool, 2 route, 3 upsample, 4 yolo */
+    int c, h, w;              /* input  */
+    int out_c, out_h, out_w;  /* output */
+    int n, size, stride, pad, activation, batch_normalize, quant_stop_flag;
+    float s_in, s_out;
+    int zp_in, zp_out;
+    int kernel;               /* conv only: 0 SIMT, 1 tcgen05 */
+    int classes, n_anchors;   /* yolo only */
+} yq_layer_info;
+
+/* batch <= 0 keeps the cfg's [net] batch.  Returns NULL on failure (see yq_last_error). */
+YQ_API yq_network *yq_load_network(const char *cfg, const char *weights, int batch, int device);
+YQ_API void yq_free_network(yq_network *net);
+YQ_API int yq_network_num_layers(const yq_network *net);
+YQ_API int yq_network_batch(const yq_network *net);
+YQ_API int yq_network_input_dims(const yq_network *net, int *c, int *h, int *w);
+YQ_API int yq_network_layer_info(const yq_network *net, int i, yq_layer_info *info);
+/* Layer-0 input quantisation (s_in, zp_in).  The reference derives it per image on the host
+ * (quant_weights_with_min_max_channel, src/blas.c:108-168 via :279) and then overwrites the values
+ * loaded from the file; here it is set explicitly (default: the file's values). Re-runs the layer-0 prep. */
+YQ_API int yq_network_set_input_quant(yq_network *net, float s_in, int zp_in);
+/* keep per-layer int32 accumulators / uint8 outputs for yq_network_pull_layer (parity checks) */
+YQ_API int yq_network_set_debug(yq_network *net, int keep_acc);
+/* force one conv kernel flavour for every conv layer (-1 auto, 0 SIMT, 1 tcgen05) */
+YQ_API int yq_network_set_conv_kernel(yq_network *net, int kind);
+
+/* forward_network on device-resident input: in_u8_nchw is [batch][c][h][w] uint8 on the device
+ * (the reference's net->input_uint8 layout).  Asynchronous on the network's stream. */
+YQ_API int yq_forward_network_device(yq_network *net, const uint8_t *in_u8_nchw);
+/* network_predict with HOST buffers: H2D of the uint8 input, forward, D2H of every yolo head into
+ * out_f32 (heads concatenated in layer order, each [batch][out_c][out_h][out_w]); synchronous. */
+YQ_API int yq_network_predict_u8(yq_network *net, const uint8_t *in_u8_nchw_host, float *out_f32_host);
+YQ_API size_t yq_network_output_floats(const yq_network *net);
+YQ_API int yq_network_synchronize(yq_network *net);
+YQ_API void *yq_network_stream(yq_network *net);
+/* capture the forward into a CUDA graph and replay it on later calls (0 disables) */
+YQ_API int yq_network_use_graph(yq_network *net, int enable);
+/* number of kernel launches one forward issues (for bench.py's gpu_launches) */
+YQ_API int yq_network_launches_per_forward(const yq_network *net);
+
+/* pull one layer's output to the host in the REFERENCE's layout (CHW per image):
+ * what = 0: output_uint8_final [batch][out_c][out_h][out_w] u8
+ *        1: output_int32       [batch][out_c][out_h][out_w] i32  (conv, needs yq_network_set_debug(net,1))
+ *        2: output (float)     [batch][out_c][out_h][out_w] f32  (quant_stop convs and yolo layers)   */
+YQ_API int yq_network_pull_layer(yq_network *net, int layer, int what, void *host_out, size_t bytes);
+/* device pointer of a yolo head's float output (NCHW), for device-resident consumers */
+YQ_API const float *yq_network_layer_output_f32_device(const yq_network *net, int layer);
+/* prepared per-channel parameters of conv layer `layer` (host copies, n entries each; any pointer may be NULL) */
+YQ_API int yq_network_conv_params(const yq_network *net, int layer, int32_t *M0, int *M0_right_shift,
+                                  double *M_value, double *M0_right_shift_value, int32_t *biases_int32);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* YQ_B200_H */

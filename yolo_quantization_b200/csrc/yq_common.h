@@ -1,0 +1,63 @@
+// yq_common.h -- shared host-side declarations of libyq_b200.so (error convention, layer object).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string>
+#include <vector>
+
+#include "../../include/yq_b200.h"
+
+namespace yq {
+
+// The reference's convention is check_error(): print + assert(0) + exit(-1) (src/cuda.c:27-49).
+// Here: record the message, return non-zero; yq_set_abort_on_error(1) restores print-and-abort.
+int fail(const char *fmt, ...) __attribute__((format(printf, 1, 2)));
+void clear_error();
+
+#define YQ_CUDA(call)                                                                                       \
+    do {                                                                                                    \
+        cudaError_t e__ = (call);                                                                           \
+        if (e__ != cudaSuccess)                                                                             \
+            return yq::fail("CUDA error %s at %s:%d: %s", cudaGetErrorName(e__), __FILE__, __LINE__,        \
+                            cudaGetErrorString(e__));                                                       \
+    } while (0)
+
+#define YQ_CHECK_LAUNCH() YQ_CUDA(cudaPeekAtLastError())
+
+static inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
+static inline int channel_stride(int c) { return c <= 4 ? 4 : round_up(c, 16); }
+
+}  // namespace yq
+
+// One prepared quantized conv layer on the device.
+struct yq_conv_layer {
+    int h, w, c, cs_in;
+    int n, cs_out, size, stride, pad, out_h, out_w;
+    int activation, quant_stop_flag, zp_in, zp_out, saturate;
+    float s_out;
+    int fused_mult;          // 1: rshift values are exact powers of two -> q = trunc(RN(x * (M_value*rshift)))
+    int kernel;              // resolved flavour: 0 SIMT, 1 tcgen05
+    int kernel_req;          // requested: -1 auto
+    // SIMT packing: [n_pad][k_pad] bytes, K order (ky, kx, ci < cs_in), zero padded
+    int n_pad, k_pad;
+    uint8_t *w_simt = nullptr;
+    // per-channel parameters, n_pad entries (pad rows: zero weights, bias 0, multiplier 0)
+    int32_t *bias = nullptr;
+    int32_t *zw = nullptr;
+    double *mcomb = nullptr;  // M_value * rshift
+    double *mval = nullptr;
+    double *rsh = nullptr;
+    // tcgen05 packing lives behind this pointer (yq_conv_tc.cu)
+    void *tc = nullptr;
+    std::vector<uint8_t> host_w;  // OIHW copy kept for repacking
+    std::vector<uint8_t> host_zw;
+};
+
+// implemented in yq_conv_tc.cu
+int yq_tc_supported(const yq_conv_layer *l);
+int yq_tc_prepare(yq_conv_layer *l);
+void yq_tc_free(yq_conv_layer *l);
+int yq_tc_forward(yq_conv_layer *l, const uint8_t *in_u8, uint8_t *out_u8, float *out_f32, int32_t *out_acc,
+                  int batch, cudaStream_t stream);

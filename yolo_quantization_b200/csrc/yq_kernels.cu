@@ -1,0 +1,685 @@
+// yq_kernels.cu -- sm_100a kernels of the quantized inference hot path + the layer-level C ABI.
+//
+//   conv_u8_simt_kernel   implicit-GEMM uint8 x uint8 -> int32 convolution on the dp4a pipe with the
+//                         requantize / bias / activation / zero-point / uint8-wrap epilogue fused in.
+//                         It is the generic flavour (any c, n, size, stride, pad, zp_in); the tcgen05
+//                         flavour for tensor-core-shaped layers lives in yq_conv_tc.cu.
+//   maxpool / upsample / route / yolo / layout kernels: coalesced, vectorised, HBM-bound.
+//
+// Arithmetic contract (reference src/convolutional_layer.c:694-761):
+//   acc = sum (w - zp_w[oc]) * A,  A = input or zp_in out of bounds   -- EXACT int32
+//   x = acc + bias_i32[oc];  t = trunc((double)x * M_value[oc]);  q = trunc((double)t * rshift[oc])
+//   activation; + zp_out; store to uint8 WRAPS (no saturation) unless desc.saturate.
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <string.h>
+
+#include <cmath>
+
+#include "yq_common.h"
+#include "yq_epilogue.cuh"
+
+// ------------------------------------------------------------------------------------------------
+// error state
+// ------------------------------------------------------------------------------------------------
+namespace yq {
+static thread_local char g_err[1024] = "";
+static int g_abort = 0;
+
+int fail(const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof g_err, fmt, ap);
+    va_end(ap);
+    if (g_abort) {
+        fprintf(stderr, "yq_b200: %s\n", g_err);
+        abort();
+    }
+    return -1;
+}
+void clear_error() { g_err[0] = 0; }
+}  // namespace yq
+
+extern "C" {
+const char *yq_last_error(void) { return yq::g_err; }
+void yq_set_abort_on_error(int enable) { yq::g_abort = enable; }
+const char *yq_version(void) { return "yq_b200 0.1 (sm_100a)"; }
+int yq_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+int yq_set_device(int device)
+{
+    YQ_CUDA(cudaSetDevice(device));
+    return 0;
+}
+void *yq_cuda_malloc(size_t bytes)
+{
+    void *p = nullptr;
+    cudaError_t e = cudaMalloc(&p, bytes ? bytes : 1);
+    if (e != cudaSuccess) {
+        yq::fail("cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(e));
+        return nullptr;
+    }
+    return p;
+}
+int yq_cuda_free(void *dev)
+{
+    YQ_CUDA(cudaFree(dev));
+    return 0;
+}
+int yq_cuda_push(void *dev, const void *host, size_t bytes, void *stream)
+{
+    YQ_CUDA(cudaMemcpyAsync(dev, host, bytes, cudaMemcpyHostToDevice, (cudaStream_t)stream));
+    return 0;
+}
+int yq_cuda_pull(void *host, const void *dev, size_t bytes, void *stream)
+{
+    YQ_CUDA(cudaMemcpyAsync(host, dev, bytes, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    YQ_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+    return 0;
+}
+int yq_cuda_memset(void *dev, int value, size_t bytes, void *stream)
+{
+    YQ_CUDA(cudaMemsetAsync(dev, value, bytes, (cudaStream_t)stream));
+    return 0;
+}
+int yq_stream_synchronize(void *stream)
+{
+    YQ_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+    return 0;
+}
+int yq_channel_stride(int c) { return yq::channel_stride(c); }
+}
+
+// ------------------------------------------------------------------------------------------------
+// SIMT implicit-GEMM convolution (dp4a)
+// ------------------------------------------------------------------------------------------------
+struct ConvArgs {
+    const uint8_t *in;
+    uint8_t *out;
+    float *out_f32;
+    int32_t *out_acc;
+    const uint8_t *wpk;
+    yq::EpiParams ep;
+    int B, H, W, C, CS, OH, OW, N, CSO, size, stride, pad, k_pad, k_bytes, zp_in, M_total;
+};
+
+constexpr int SIMT_BM = 64;        // output pixels per block
+constexpr int SIMT_KC = 64;        // K bytes per stage
+constexpr int SIMT_PITCH = 80;     // smem row pitch (64 + 16): conflict-free 128-bit reads
+constexpr int SIMT_THREADS = 256;
+
+// VEC = gather granularity in bytes (16 when the channel stride is a multiple of 16, else 4).
+// OCT = output channels per thread; block covers BN = 16*OCT output channels.
+template <int VEC, int OCT>
+__global__ void __launch_bounds__(SIMT_THREADS) conv_u8_simt_kernel(const ConvArgs a)
+{
+    constexpr int BN = 16 * OCT;
+    __shared__ __align__(16) uint8_t As[SIMT_BM * SIMT_PITCH];
+    __shared__ __align__(16) uint8_t Bs[BN * SIMT_PITCH];
+    __shared__ __align__(16) uint8_t Os[SIMT_BM * BN];
+
+    const int t = threadIdx.x;
+    const int m0 = blockIdx.x * SIMT_BM;
+    const int oc0 = blockIdx.y * BN;
+
+    // ---- loader role: pixel lp, 16-byte slot ls of the 64-byte stage row
+    const int lp = t >> 2, ls = t & 3;
+    const int lm = m0 + lp;
+    const bool lvalid = lm < a.M_total;
+    int ln = 0, loy = 0, lox = 0;
+    if (lvalid) {
+        ln = lm / (a.OH * a.OW);
+        int r = lm - ln * a.OH * a.OW;
+        loy = r / a.OW;
+        lox = r - loy * a.OW;
+    }
+    const int units_per_tap = a.CS / VEC;
+    const int total_units = a.size * a.size * units_per_tap;
+    const uint32_t zp4 = (uint32_t)a.zp_in * 0x01010101u;
+
+    auto fill_word = [&](int ch0) -> uint32_t {   // zp_in in real channels, 0 in pad channels
+        if (ch0 + 4 <= a.C) return zp4;
+        uint32_t v = 0;
+        for (int b = 0; b < 4; ++b)
+            if (ch0 + b < a.C) v |= (uint32_t)a.zp_in << (8 * b);
+        return v;
+    };
+
+    auto load_a = [&](int stage) -> uint4 {
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (!lvalid) return v;
+        if (VEC == 16) {
+            int gu = stage * 4 + ls;
+            if (gu >= total_units) return v;
+            int tap = gu / units_per_tap, cv = gu - tap * units_per_tap;
+            int ky = tap / a.size, kx = tap - ky * a.size;
+            int iy = loy * a.stride + ky - a.pad, ix = lox * a.stride + kx - a.pad;
+            if (iy < 0 || iy >= a.H || ix < 0 || ix >= a.W) {
+                v.x = fill_word(cv * 16);
+                v.y = fill_word(cv * 16 + 4);
+                v.z = fill_word(cv * 16 + 8);
+                v.w = fill_word(cv * 16 + 12);
+            } else {
+                v = __ldg(reinterpret_cast<const uint4 *>(a.in + ((size_t)(ln * a.H + iy) * a.W + ix) * a.CS + cv * 16));
+            }
+        } else {
+            uint32_t wv[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                int gu = stage * 16 + ls * 4 + j;
+                uint32_t x = 0;
+                if (gu < total_units) {
+                    int tap = gu / units_per_tap, cv = gu - tap * units_per_tap;
+                    int ky = tap / a.size, kx = tap - ky * a.size;
+                    int iy = loy * a.stride + ky - a.pad, ix = lox * a.stride + kx - a.pad;
+                    if (iy < 0 || iy >= a.H || ix < 0 || ix >= a.W)
+                        x = fill_word(cv * 4);
+                    else
+                        x = __ldg(reinterpret_cast<const uint32_t *>(a.in + ((size_t)(ln * a.H + iy) * a.W + ix) * a.CS + cv * 4));
+                }
+                wv[j] = x;
+            }
+            v = make_uint4(wv[0], wv[1], wv[2], wv[3]);
+        }
+        return v;
+    };
+    auto load_b = [&](int stage) -> uint4 {
+        if (lp < BN)
+            return __ldg(reinterpret_cast<const uint4 *>(a.wpk + (size_t)(oc0 + lp) * a.k_pad + stage * SIMT_KC + ls * 16));
+        return make_uint4(0, 0, 0, 0);
+    };
+
+    // ---- compute role
+    const int tx = t & 15, ty = t >> 4;   // oc = oc0 + tx + 16*jj ; px = ty*4 + j
+    uint32_t acc[4][OCT];
+    uint32_t sa[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        sa[j] = 0;
+#pragma unroll
+        for (int jj = 0; jj < OCT; ++jj) acc[j][jj] = 0;
+    }
+
+    const int nstages = a.k_pad / SIMT_KC;
+    uint4 ra = load_a(0), rb = load_b(0);
+    for (int s = 0; s < nstages; ++s) {
+        __syncthreads();
+        *reinterpret_cast<uint4 *>(&As[lp * SIMT_PITCH + ls * 16]) = ra;
+        if (lp < BN) *reinterpret_cast<uint4 *>(&Bs[lp * SIMT_PITCH + ls * 16]) = rb;
+        __syncthreads();
+        if (s + 1 < nstages) {
+            ra = load_a(s + 1);
+            rb = load_b(s + 1);
+        }
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+            uint4 av[4], bv[OCT];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) av[j] = *reinterpret_cast<const uint4 *>(&As[(ty * 4 + j) * SIMT_PITCH + kk * 16]);
+#pragma unroll
+            for (int jj = 0; jj < OCT; ++jj) bv[jj] = *reinterpret_cast<const uint4 *>(&Bs[(tx + 16 * jj) * SIMT_PITCH + kk * 16]);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                sa[j] = __dp4a(av[j].x, 0x01010101u, sa[j]);
+                sa[j] = __dp4a(av[j].y, 0x01010101u, sa[j]);
+                sa[j] = __dp4a(av[j].z, 0x01010101u, sa[j]);
+                sa[j] = __dp4a(av[j].w, 0x01010101u, sa[j]);
+#pragma unroll
+                for (int jj = 0; jj < OCT; ++jj) {
+                    acc[j][jj] = __dp4a(av[j].x, bv[jj].x, acc[j][jj]);
+                    acc[j][jj] = __dp4a(av[j].y, bv[jj].y, acc[j][jj]);
+                    acc[j][jj] = __dp4a(av[j].z, bv[jj].z, acc[j][jj]);
+                    acc[j][jj] = __dp4a(av[j].w, bv[jj].w, acc[j][jj]);
+                }
+            }
+        }
+    }
+
+    // ---- epilogue: zero-point correction, requantize, activation, wrap; stage uint8 tile in smem
+#pragma unroll
+    for (int jj = 0; jj < OCT; ++jj) {
+        const int oc = oc0 + tx + 16 * jj;
+        const yq::ChanParams cp = yq::load_chan(a.ep, oc);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int p = ty * 4 + j;
+            const int m = m0 + p;
+            int accv = (int)acc[j][jj] - cp.zw * (int)sa[j];
+            uint8_t r = 0;
+            if (oc < a.N) r = yq::requant_u8(a.ep, cp, accv);
+            Os[p * BN + tx + 16 * jj] = r;
+            if (m < a.M_total && oc < a.N) {
+                if (a.out_acc) a.out_acc[(size_t)m * a.CSO + oc] = accv;
+                if (a.out_f32) {
+                    int n = m / (a.OH * a.OW);
+                    int rr = m - n * a.OH * a.OW;
+                    a.out_f32[((size_t)n * a.N + oc) * a.OH * a.OW + rr] = yq::dequant_f32(a.ep, r);
+                }
+            }
+        }
+    }
+    __syncthreads();
+    // coalesced store: BN bytes per pixel, 16-byte vectors (BN and CSO are multiples of 16)
+    constexpr int VPP = BN / 16;
+    for (int i = t; i < SIMT_BM * VPP; i += SIMT_THREADS) {
+        int p = i / VPP, v = i - p * VPP;
+        int m = m0 + p;
+        if (m < a.M_total && oc0 + v * 16 < a.CSO)
+            *reinterpret_cast<uint4 *>(a.out + (size_t)m * a.CSO + oc0 + v * 16) = *reinterpret_cast<const uint4 *>(&Os[p * BN + v * 16]);
+    }
+}
+
+static int launch_simt(yq_conv_layer *l, const uint8_t *in, uint8_t *out, float *out_f32, int32_t *out_acc, int batch,
+                       cudaStream_t stream)
+{
+    ConvArgs a;
+    memset(&a, 0, sizeof a);
+    a.in = in;
+    a.out = out;
+    a.out_f32 = l->quant_stop_flag ? out_f32 : nullptr;
+    a.out_acc = out_acc;
+    a.wpk = l->w_simt;
+    a.ep = yq::make_epi(l);
+    a.B = batch; a.H = l->h; a.W = l->w; a.C = l->c; a.CS = l->cs_in;
+    a.OH = l->out_h; a.OW = l->out_w; a.N = l->n; a.CSO = l->cs_out;
+    a.size = l->size; a.stride = l->stride; a.pad = l->pad;
+    a.k_pad = l->k_pad; a.k_bytes = l->size * l->size * l->cs_in;
+    a.zp_in = l->zp_in;
+    a.M_total = batch * l->out_h * l->out_w;
+    if (l->cs_out < 16) return yq::fail("conv: output channel stride %d < 16 unsupported", l->cs_out);
+    const int oct = l->n > 32 ? 4 : (l->n > 16 ? 2 : 1);
+    const int bn = 16 * oct;
+    dim3 grid((a.M_total + SIMT_BM - 1) / SIMT_BM, l->n_pad / bn);
+    const bool v16 = (l->cs_in % 16) == 0;
+#define YQ_LAUNCH(V, O) conv_u8_simt_kernel<V, O><<<grid, SIMT_THREADS, 0, stream>>>(a)
+    if (v16) {
+        if (oct == 4) YQ_LAUNCH(16, 4); else if (oct == 2) YQ_LAUNCH(16, 2); else YQ_LAUNCH(16, 1);
+    } else {
+        if (oct == 4) YQ_LAUNCH(4, 4); else if (oct == 2) YQ_LAUNCH(4, 2); else YQ_LAUNCH(4, 1);
+    }
+#undef YQ_LAUNCH
+    YQ_CHECK_LAUNCH();
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// layer object
+// ------------------------------------------------------------------------------------------------
+static bool is_pow2_le1(double v)
+{
+    if (!(v > 0.0) || v > 1.0) return false;
+    int e;
+    return std::frexp(v, &e) == 0.5;
+}
+
+template <typename T>
+static int upload(T **dst, const std::vector<T> &src)
+{
+    YQ_CUDA(cudaMalloc((void **)dst, src.size() * sizeof(T)));
+    YQ_CUDA(cudaMemcpy(*dst, src.data(), src.size() * sizeof(T), cudaMemcpyHostToDevice));
+    return 0;
+}
+
+extern "C" yq_conv_layer *yq_make_convolutional_layer_quant(const yq_conv_desc *d)
+{
+    yq::clear_error();
+    if (!d || !d->weights_uint8 || !d->weight_zero_point || !d->biases_int32 || !d->M_value || !d->M0_right_shift_value) {
+        yq::fail("yq_make_convolutional_layer_quant: null descriptor field");
+        return nullptr;
+    }
+    if (d->c <= 0 || d->n <= 0 || d->size <= 0 || d->stride <= 0 || d->h <= 0 || d->w <= 0 || d->pad < 0) {
+        yq::fail("yq_make_convolutional_layer_quant: bad geometry");
+        return nullptr;
+    }
+    if (d->activation != YQ_LINEAR && d->activation != YQ_RELU && d->activation != YQ_RELU6 && d->activation != YQ_LEAKY) {
+        // the reference's switch has no other case (convolutional_layer.c:734-748: default: break)
+        yq::fail("yq_make_convolutional_layer_quant: activation %d has no quantized form in the reference", d->activation);
+        return nullptr;
+    }
+    if ((long long)d->c * d->size * d->size > 33025) {
+        yq::fail("yq_make_convolutional_layer_quant: K=%lld exceeds the exact-int32 bound 33025", (long long)d->c * d->size * d->size);
+        return nullptr;
+    }
+    if (yq_device_count() <= 0) {
+        yq::fail("yq_make_convolutional_layer_quant: no CUDA device (there is no CPU fallback)");
+        return nullptr;
+    }
+    yq_conv_layer *l = new yq_conv_layer();
+    l->h = d->h; l->w = d->w; l->c = d->c; l->cs_in = yq::channel_stride(d->c);
+    l->n = d->n; l->cs_out = yq::channel_stride(d->n);
+    l->size = d->size; l->stride = d->stride; l->pad = d->pad;
+    l->out_h = (d->h + 2 * d->pad - d->size) / d->stride + 1;   // convolutional_out_height, convolutional_layer.c:55-63
+    l->out_w = (d->w + 2 * d->pad - d->size) / d->stride + 1;
+    l->activation = d->activation; l->quant_stop_flag = d->quant_stop_flag;
+    l->zp_in = d->zp_in & 0xff; l->zp_out = d->zp_out & 0xff; l->saturate = d->saturate; l->s_out = d->s_out;
+    l->kernel_req = -1;
+
+    const int oct = l->n > 32 ? 4 : (l->n > 16 ? 2 : 1);
+    l->n_pad = yq::round_up(l->n, 16 * oct);
+    if (l->n_pad < l->cs_out) l->n_pad = l->cs_out;
+    const int kb = l->size * l->size * l->cs_in;
+    l->k_pad = yq::round_up(kb, SIMT_KC);
+
+    const size_t K = (size_t)d->c * d->size * d->size;
+    l->host_w.assign(d->weights_uint8, d->weights_uint8 + K * d->n);
+    l->host_zw.assign(d->weight_zero_point, d->weight_zero_point + d->n);
+
+    // pack OIHW -> [oc][ky][kx][ci (stride cs_in)], zero padded (push_convolutional_layer's role)
+    std::vector<uint8_t> wp((size_t)l->n_pad * l->k_pad, 0);
+    for (int oc = 0; oc < l->n; ++oc)
+        for (int ci = 0; ci < l->c; ++ci)
+            for (int ky = 0; ky < l->size; ++ky)
+                for (int kx = 0; kx < l->size; ++kx)
+                    wp[(size_t)oc * l->k_pad + (size_t)(ky * l->size + kx) * l->cs_in + ci] =
+                        d->weights_uint8[((size_t)oc * l->c + ci) * l->size * l->size + ky * l->size + kx];
+    std::vector<int32_t> bias(l->n_pad, 0), zw(l->n_pad, 0);
+    std::vector<double> mcomb(l->n_pad, 0.0), mval(l->n_pad, 0.0), rsh(l->n_pad, 0.0);
+    l->fused_mult = 1;
+    for (int oc = 0; oc < l->n; ++oc) {
+        bias[oc] = d->biases_int32[oc];
+        zw[oc] = d->weight_zero_point[oc];
+        mval[oc] = d->M_value[oc];
+        rsh[oc] = d->M0_right_shift_value[oc];
+        mcomb[oc] = mval[oc] * rsh[oc];   // exact: rsh is a power of two
+        if (!is_pow2_le1(rsh[oc])) l->fused_mult = 0;
+    }
+    if (upload(&l->w_simt, wp) || upload(&l->bias, bias) || upload(&l->zw, zw) || upload(&l->mcomb, mcomb) ||
+        upload(&l->mval, mval) || upload(&l->rsh, rsh)) {
+        yq_free_convolutional_layer_quant(l);
+        return nullptr;
+    }
+    l->kernel = 0;
+    if (yq_tc_supported(l)) {
+        if (yq_tc_prepare(l) == 0) l->kernel = 1;
+    }
+    return l;
+}
+
+extern "C" void yq_free_convolutional_layer_quant(yq_conv_layer *l)
+{
+    if (!l) return;
+    yq_tc_free(l);
+    cudaFree(l->w_simt); cudaFree(l->bias); cudaFree(l->zw); cudaFree(l->mcomb); cudaFree(l->mval); cudaFree(l->rsh);
+    delete l;
+}
+
+extern "C" int yq_conv_out_h(const yq_conv_layer *l) { return l->out_h; }
+extern "C" int yq_conv_out_w(const yq_conv_layer *l) { return l->out_w; }
+extern "C" int yq_conv_get_kernel(const yq_conv_layer *l) { return l->kernel; }
+extern "C" int yq_conv_set_kernel(yq_conv_layer *l, int kind)
+{
+    if (kind == 1 && !(yq_tc_supported(l) && l->tc)) return yq::fail("tcgen05 flavour not available for this layer shape");
+    l->kernel_req = kind;
+    if (kind == 0) l->kernel = 0;
+    else if (kind == 1) l->kernel = 1;
+    else l->kernel = (yq_tc_supported(l) && l->tc) ? 1 : 0;
+    return 0;
+}
+
+extern "C" int yq_forward_convolutional_layer_quant_gpu(yq_conv_layer *l, const uint8_t *in_u8, uint8_t *out_u8,
+                                                        float *out_f32, int32_t *out_acc, int batch, void *stream)
+{
+    if (!l || !in_u8 || !out_u8 || batch <= 0) return yq::fail("yq_forward_convolutional_layer_quant_gpu: bad argument");
+    if (l->quant_stop_flag && !out_f32) return yq::fail("quant_stop layer needs out_f32");
+    if (l->kernel == 1) return yq_tc_forward(l, in_u8, out_u8, out_f32, out_acc, batch, (cudaStream_t)stream);
+    return launch_simt(l, in_u8, out_u8, out_f32, out_acc, batch, (cudaStream_t)stream);
+}
+
+// ------------------------------------------------------------------------------------------------
+// maxpool (src/maxpool_layer.c:109-153): out = max(0, in-bounds taps); window origin i*stride - pad/2
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint4 vmax16(uint4 a, uint4 b)
+{
+    return make_uint4(__vmaxu4(a.x, b.x), __vmaxu4(a.y, b.y), __vmaxu4(a.z, b.z), __vmaxu4(a.w, b.w));
+}
+
+template <typename V>
+__global__ void maxpool_u8_kernel(const V *__restrict__ in, V *__restrict__ out, int B, int H, int W, int OH, int OW,
+                                  int vpp /* vectors per pixel */, int size, int stride, int off, long long total)
+{
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        int v = (int)(i % vpp);
+        long long p = i / vpp;
+        int ox = (int)(p % OW);
+        p /= OW;
+        int oy = (int)(p % OH);
+        int n = (int)(p / OH);
+        V m;
+        memset(&m, 0, sizeof(V));
+        for (int a = 0; a < size; ++a) {
+            int y = off + oy * stride + a;
+            if (y < 0 || y >= H) continue;
+            for (int b = 0; b < size; ++b) {
+                int x = off + ox * stride + b;
+                if (x < 0 || x >= W) continue;
+                V t = __ldg(in + ((size_t)(n * H + y) * W + x) * vpp + v);
+                if constexpr (sizeof(V) == 16) m = vmax16(m, t);
+                else m = __vmaxu4(m, t);
+            }
+        }
+        out[i] = m;
+    }
+}
+
+static inline int grid_for(long long total, int threads)
+{
+    long long b = (total + threads - 1) / threads;
+    long long cap = 148LL * 16;   // a few waves of the 148 SMs; kernels are grid-stride
+    return (int)(b < cap ? (b > 0 ? b : 1) : cap);
+}
+
+extern "C" int yq_forward_maxpool_layer_quant_gpu(const uint8_t *in, uint8_t *out, int batch, int h, int w, int c,
+                                                  int size, int stride, int pad, void *stream)
+{
+    if (!in || !out || batch <= 0) return yq::fail("maxpool: bad argument");
+    const int cs = yq::channel_stride(c);
+    const int oh = (h + pad - size) / stride + 1, ow = (w + pad - size) / stride + 1;   // maxpool_layer.c:31-32
+    const int off = -pad / 2;
+    if (cs % 16 == 0) {
+        long long total = (long long)batch * oh * ow * (cs / 16);
+        maxpool_u8_kernel<uint4><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
+            (const uint4 *)in, (uint4 *)out, batch, h, w, oh, ow, cs / 16, size, stride, off, total);
+    } else {
+        long long total = (long long)batch * oh * ow * (cs / 4);
+        maxpool_u8_kernel<uint32_t><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
+            (const uint32_t *)in, (uint32_t *)out, batch, h, w, oh, ow, cs / 4, size, stride, off, total);
+    }
+    YQ_CHECK_LAUNCH();
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// upsample (src/blas.c:781-803): out[y][x] = in[y/stride][x/stride]
+// ------------------------------------------------------------------------------------------------
+template <typename V>
+__global__ void upsample_u8_kernel(const V *__restrict__ in, V *__restrict__ out, int H, int W, int vpp, int stride,
+                                   long long total)
+{
+    const int OW = W * stride, OH = H * stride;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        int v = (int)(i % vpp);
+        long long p = i / vpp;
+        int ox = (int)(p % OW);
+        p /= OW;
+        int oy = (int)(p % OH);
+        int n = (int)(p / OH);
+        out[i] = __ldg(in + ((size_t)(n * H + oy / stride) * W + ox / stride) * vpp + v);
+    }
+}
+
+extern "C" int yq_forward_upsample_layer_quant_gpu(const uint8_t *in, uint8_t *out, int batch, int h, int w, int c,
+                                                   int stride, void *stream)
+{
+    if (!in || !out || batch <= 0 || stride <= 0) return yq::fail("upsample: bad argument");
+    const int cs = yq::channel_stride(c);
+    if (cs % 16 == 0) {
+        long long total = (long long)batch * h * stride * w * stride * (cs / 16);
+        upsample_u8_kernel<uint4><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>((const uint4 *)in, (uint4 *)out, h, w, cs / 16, stride, total);
+    } else {
+        long long total = (long long)batch * h * stride * w * stride * (cs / 4);
+        upsample_u8_kernel<uint32_t><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>((const uint32_t *)in, (uint32_t *)out, h, w, cs / 4, stride, total);
+    }
+    YQ_CHECK_LAUNCH();
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// route (src/route_layer.c:107-117): channel concat, no rescale
+// ------------------------------------------------------------------------------------------------
+constexpr int ROUTE_MAX_INPUTS = 8;
+struct RouteArgs {
+    const uint8_t *in[ROUTE_MAX_INPUTS];
+    int c[ROUTE_MAX_INPUTS];     // real channels
+    int cs[ROUTE_MAX_INPUTS];    // channel strides
+    int off[ROUTE_MAX_INPUTS];   // channel offset in the output
+    int n, cs_out, c_out;
+    long long pixels;
+};
+
+__global__ void route_u8_kernel(const RouteArgs a, uint8_t *__restrict__ out, int vec)
+{
+    if (vec) {
+        const int vpp = a.cs_out / 16;
+        const long long total = a.pixels * vpp;
+        for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+            int v = (int)(i % vpp);
+            long long p = i / vpp;
+            int ch = v * 16;
+            uint4 val = make_uint4(0, 0, 0, 0);
+            for (int k = 0; k < a.n; ++k)
+                if (ch >= a.off[k] && ch < a.off[k] + a.c[k])
+                    val = __ldg(reinterpret_cast<const uint4 *>(a.in[k] + (size_t)p * a.cs[k] + (ch - a.off[k])));
+            *reinterpret_cast<uint4 *>(out + (size_t)p * a.cs_out + ch) = val;
+        }
+    } else {
+        const long long total = a.pixels * a.cs_out;
+        for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+            int ch = (int)(i % a.cs_out);
+            long long p = i / a.cs_out;
+            uint8_t val = 0;
+            for (int k = 0; k < a.n; ++k)
+                if (ch >= a.off[k] && ch < a.off[k] + a.c[k]) val = a.in[k][(size_t)p * a.cs[k] + (ch - a.off[k])];
+            out[i] = val;
+        }
+    }
+}
+
+extern "C" int yq_forward_route_layer_quant_gpu(const uint8_t *const *inputs, const int *in_c, int n_inputs,
+                                                uint8_t *out, int batch, int h, int w, void *stream)
+{
+    if (!inputs || !in_c || !out || n_inputs <= 0 || n_inputs > ROUTE_MAX_INPUTS) return yq::fail("route: bad argument");
+    RouteArgs a;
+    memset(&a, 0, sizeof a);
+    int off = 0, vec = 1;
+    for (int i = 0; i < n_inputs; ++i) {
+        a.in[i] = inputs[i];
+        a.c[i] = in_c[i];
+        a.cs[i] = yq::channel_stride(in_c[i]);
+        a.off[i] = off;
+        off += in_c[i];
+        if (in_c[i] % 16) vec = 0;
+    }
+    a.n = n_inputs;
+    a.c_out = off;
+    a.cs_out = yq::channel_stride(off);
+    a.pixels = (long long)batch * h * w;
+    if (a.cs_out % 16) vec = 0;
+    long long total = vec ? a.pixels * (a.cs_out / 16) : a.pixels * a.cs_out;
+    route_u8_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(a, out, vec);
+    YQ_CHECK_LAUNCH();
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// yolo head (src/yolo_layer.c:125-146): logistic on x,y and obj+classes, double exp like
+// logistic_activate (src/activations.h:32)
+// ------------------------------------------------------------------------------------------------
+__global__ void yolo_kernel(const float *__restrict__ in, float *__restrict__ out, int per, int hw, long long total)
+{
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        int e = (int)((i / hw) % per);
+        float x = in[i];
+        if (e != 2 && e != 3) x = (float)(1. / (1. + exp(-(double)x)));
+        out[i] = x;
+    }
+}
+
+extern "C" int yq_forward_yolo_layer_gpu(const float *in, float *out, int batch, int n_anchors, int classes, int h,
+                                         int w, void *stream)
+{
+    if (!in || !out || batch <= 0) return yq::fail("yolo: bad argument");
+    const int per = 4 + classes + 1;
+    long long total = (long long)batch * n_anchors * per * h * w;
+    yolo_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(in, out, per, h * w, total);
+    YQ_CHECK_LAUNCH();
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// layout conversion at the boundary
+// ------------------------------------------------------------------------------------------------
+__global__ void nchw_to_nhwc_u8_kernel(const uint8_t *__restrict__ in, uint8_t *__restrict__ out, int C, int HW, int CS,
+                                       long long total /* B*HW*(CS/4) */)
+{
+    const int wpp = CS / 4;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        // pixel-fastest thread order: reads of each channel plane are coalesced across the warp
+        long long g = i / HW;            // (n, word)
+        int p = (int)(i - g * HW);
+        int wd = (int)(g % wpp);
+        long long n = g / wpp;
+        uint32_t v = 0;
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            int ch = wd * 4 + b;
+            if (ch < C) v |= (uint32_t)in[((size_t)n * C + ch) * HW + p] << (8 * b);
+        }
+        *reinterpret_cast<uint32_t *>(out + ((size_t)n * HW + p) * CS + wd * 4) = v;
+    }
+}
+
+template <typename T>
+__global__ void nhwc_to_nchw_kernel(const T *__restrict__ in, T *__restrict__ out, int C, int HW, int CS, long long total)
+{
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        int p = (int)(i % HW);
+        long long g = i / HW;
+        int ch = (int)(g % C);
+        long long n = g / C;
+        out[i] = in[((size_t)n * HW + p) * CS + ch];
+    }
+}
+
+extern "C" int yq_nchw_to_nhwc_u8(const uint8_t *in, uint8_t *out, int batch, int c, int h, int w, void *stream)
+{
+    if (!in || !out) return yq::fail("nchw_to_nhwc: null pointer");
+    const int cs = yq::channel_stride(c);
+    long long total = (long long)batch * h * w * (cs / 4);
+    nchw_to_nhwc_u8_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(in, out, c, h * w, cs, total);
+    YQ_CHECK_LAUNCH();
+    return 0;
+}
+extern "C" int yq_nhwc_to_nchw_u8(const uint8_t *in, uint8_t *out, int batch, int c, int h, int w, void *stream)
+{
+    if (!in || !out) return yq::fail("nhwc_to_nchw: null pointer");
+    long long total = (long long)batch * c * h * w;
+    nhwc_to_nchw_kernel<uint8_t><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(in, out, c, h * w, yq::channel_stride(c), total);
+    YQ_CHECK_LAUNCH();
+    return 0;
+}
+extern "C" int yq_nhwc_to_nchw_i32(const int32_t *in, int32_t *out, int batch, int c, int h, int w, void *stream)
+{
+    if (!in || !out) return yq::fail("nhwc_to_nchw: null pointer");
+    long long total = (long long)batch * c * h * w;
+    nhwc_to_nchw_kernel<int32_t><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(in, out, c, h * w, yq::channel_stride(c), total);
+    YQ_CHECK_LAUNCH();
+    return 0;
+}

@@ -1,0 +1,745 @@
+// yq_network.cu -- host-side network runtime behind the network-level C ABI (include/yq_b200.h).
+//
+// Mirrors, for the QUANTIZATION=1 inference path only, the reference's
+//   parse_network_cfg            src/parser.c:682-815   (INI dialect: read_cfg :817-870)
+//   load_weights_upto            src/parser.c:1201-1305 (per-layer readers :1124-1199)
+//   quantization_weights_and_activations  src/blas.c:259-346  (one-time host prep)
+//   forward_network              src/network.c:229-261  (uint8 hand-off between quantized layers)
+// and drives the sm_100a kernels of yq_kernels.cu / yq_conv_tc.cu.  Written from scratch in C++;
+// device tensors are uint8 NHWC, one buffer per layer, optional CUDA-graph replay.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <string.h>
+
+#include <algorithm>
+#include <cctype>
+#include <fstream>
+#include <map>
+#include <memory>
+#include <sstream>
+#include <string>
+#include <vector>
+
+#include "yq_common.h"
+
+namespace {
+
+enum LType { L_CONV = 0, L_MAXPOOL = 1, L_ROUTE = 2, L_UPSAMPLE = 3, L_YOLO = 4 };
+
+struct Section {
+    std::string type;
+    std::vector<std::pair<std::string, std::string>> kv;
+    const std::string *find(const char *key) const
+    {
+        for (auto &p : kv)
+            if (p.first == key) return &p.second;
+        return nullptr;
+    }
+    int geti(const char *key, int def) const
+    {
+        const std::string *v = find(key);
+        return v ? atoi(v->c_str()) : def;
+    }
+    std::string gets(const char *key, const char *def) const
+    {
+        const std::string *v = find(key);
+        return v ? *v : std::string(def);
+    }
+};
+
+// read_cfg (parser.c:817-870): every line is stripped of ALL blanks (utils.c strip()), '[' opens a
+// section, '#', ';' and empty lines are skipped, everything else is key=value.
+bool read_cfg(const char *path, std::vector<Section> &out, std::string &err)
+{
+    std::ifstream f(path);
+    if (!f) {
+        err = std::string("cannot open cfg file ") + path;
+        return false;
+    }
+    std::string line;
+    int ln = 0;
+    while (std::getline(f, line)) {
+        ++ln;
+        std::string s;
+        for (char ch : line)
+            if (ch != ' ' && ch != '\t' && ch != '\n' && ch != '\r') s.push_back(ch);
+        if (s.empty() || s[0] == '#' || s[0] == ';') continue;
+        if (s[0] == '[') {
+            Section sec;
+            sec.type = s;
+            out.push_back(sec);
+            continue;
+        }
+        size_t eq = s.find('=');
+        if (eq == std::string::npos || out.empty()) {
+            err = "config file error line " + std::to_string(ln) + ", could not parse: " + s;
+            return false;
+        }
+        out.back().kv.emplace_back(s.substr(0, eq), s.substr(eq + 1));
+    }
+    return true;
+}
+
+int activation_from_string(const std::string &s)
+{
+    // get_activation (src/activations.c:44-64); only the four with a quantized form are accepted
+    if (s == "linear") return YQ_LINEAR;
+    if (s == "relu") return YQ_RELU;
+    if (s == "relu6") return YQ_RELU6;
+    if (s == "leaky") return YQ_LEAKY;
+    if (s == "logistic") return YQ_LOGISTIC;
+    return -1;
+}
+
+struct Layer {
+    LType type;
+    int c = 0, h = 0, w = 0, out_c = 0, out_h = 0, out_w = 0;
+    int n = 0, size = 0, stride = 1, pad = 0, activation = YQ_LINEAR, bn = 0;
+    int quantized = 0, quant_stop = 0, first_time = 0;
+    std::vector<int> inputs;   // route
+    int classes = 0, n_anchors = 0;
+    // quantisation state as in `struct layer`
+    float s_in = 0, s_out = 0;
+    int zp_in = 0, zp_out = 0;
+    std::vector<float> biases, bn_scales, bn_mean, bn_var, s_w;
+    std::vector<uint8_t> zp_w, w_u8;
+    std::vector<int32_t> M0, biases_int32;
+    std::vector<int> M0_right_shift;
+    std::vector<double> M_value, rshift_value;
+    // device
+    yq_conv_layer *conv = nullptr;
+    uint8_t *out_u8 = nullptr;     // NHWC; may alias another layer's buffer (single-input route)
+    bool owns_u8 = false;
+    float *out_f32 = nullptr;      // NCHW (quant_stop convs, yolo)
+    int32_t *out_acc = nullptr;    // NHWC, debug
+    size_t u8_bytes = 0, f32_count = 0;
+};
+
+}  // namespace
+
+struct yq_network {
+    int device = 0;
+    int batch = 1, c = 0, h = 0, w = 0;
+    std::vector<Layer> layers;
+    cudaStream_t stream = nullptr;
+    uint8_t *in_stage_nchw = nullptr;   // staging for host-input predict
+    uint8_t *in_nhwc = nullptr;
+    uint8_t *scratch = nullptr;         // pull_layer conversions
+    size_t scratch_bytes = 0;
+    int keep_acc = 0;
+    int conv_kernel = -1;
+    int use_graph = 0;
+    cudaGraphExec_t graph_exec = nullptr;
+    const uint8_t *graph_input = nullptr;
+    int launches = 0;
+    float *out_host_pinned = nullptr;
+    size_t out_floats = 0;
+};
+
+namespace {
+
+// quant_multi_smaller_than_one_to_scale_and_shift (src/blas.c:387-418)
+bool mult_to_m0_shift(float m, int32_t *m0, int *shift)
+{
+    if (!(m > 0.f) || !(m < 1.f)) return false;   // the reference assert()s here
+    int s = 0;
+    while (m < 0.5f) {
+        m *= 2.0f;
+        s++;
+    }
+    long long q = (long long)round((double)m * (double)(1ll << 31));
+    if (q == (1ll << 31)) {
+        q /= 2;
+        s--;
+    }
+    if (s < 0) return false;
+    *m0 = (int32_t)q;
+    *shift = s;
+    return true;
+}
+
+// One conv layer's share of quantization_weights_and_activations (src/blas.c:282-334).
+int prepare_conv(Layer &l, int index)
+{
+    const int n = l.n, K = l.c * l.size * l.size;
+    l.M0.assign(n, 0); l.M0_right_shift.assign(n, 0); l.M_value.assign(n, 0.0); l.rshift_value.assign(n, 0.0);
+    l.biases_int32.assign(n, 0);
+    if (l.s_out == 0.f) return yq::fail("layer %d: activation scale is 0 (blas.c:312 asserts)", index);
+    for (int oc = 0; oc < n; ++oc) {
+        float b = l.biases[oc];
+        // batch_normalize_bias (blas.c:594-601): sqrt() is the double overload, .000001f promotes
+        if (l.bn) b = (float)((double)b - (double)(l.bn_scales[oc] * l.bn_mean[oc]) / (sqrt((double)l.bn_var[oc]) + (double).000001f));
+        if (l.s_w[oc] == 0.f) return yq::fail("layer %d: weight scale of channel %d is 0 (blas.c:293 asserts)", index, oc);
+        uint32_t mult_zero_point = (uint32_t)(K * l.zp_in * (int)l.zp_w[oc]);                 // blas.c:307
+        int32_t wsum = 0;
+        for (int k = 0; k < K; ++k) wsum += l.w_u8[(size_t)oc * K + k];                       // :308-310
+        int32_t weights_sum_int = (int32_t)(mult_zero_point - (uint32_t)(wsum * l.zp_in));    // :311
+        float M = l.s_in * l.s_w[oc] / l.s_out;                                               // :313
+        if (!mult_to_m0_shift(M, &l.M0[oc], &l.M0_right_shift[oc]))
+            return yq::fail("layer %d channel %d: multiplier %g outside (0,1) (blas.c:391-392 asserts)", index, oc, (double)M);
+        l.rshift_value[oc] = pow(2, -l.M0_right_shift[oc]);                                   // :315
+        l.M_value[oc] = pow(2, -31) * l.M0[oc];                                               // :316
+        l.biases_int32[oc] = (int32_t)(b / (l.s_in * l.s_w[oc]) + (float)weights_sum_int);    // :333
+    }
+    return 0;
+}
+
+// kind 0: SIMT everywhere; 1: tcgen05 wherever the layer shape has one (SIMT elsewhere); -1: per-layer default
+void apply_kernel_choice(yq_conv_layer *cl, int kind)
+{
+    if (kind == 1 && yq_conv_set_kernel(cl, 1) != 0) yq_conv_set_kernel(cl, 0);
+    else if (kind != 1) yq_conv_set_kernel(cl, kind);
+    yq::clear_error();
+}
+
+int build_conv_device(yq_network *net, Layer &l)
+{
+    if (l.conv) {
+        yq_free_convolutional_layer_quant(l.conv);
+        l.conv = nullptr;
+    }
+    yq_conv_desc d;
+    memset(&d, 0, sizeof d);
+    d.h = l.h; d.w = l.w; d.c = l.c; d.n = l.n; d.size = l.size; d.stride = l.stride; d.pad = l.pad;
+    d.activation = l.activation; d.quant_stop_flag = l.quant_stop; d.zp_in = l.zp_in; d.zp_out = l.zp_out; d.s_out = l.s_out;
+    d.weights_uint8 = l.w_u8.data(); d.weight_zero_point = l.zp_w.data(); d.biases_int32 = l.biases_int32.data();
+    d.M_value = l.M_value.data(); d.M0_right_shift_value = l.rshift_value.data(); d.saturate = 0;
+    l.conv = yq_make_convolutional_layer_quant(&d);
+    if (!l.conv) return -1;
+    apply_kernel_choice(l.conv, net->conv_kernel);
+    return 0;
+}
+
+template <typename T>
+bool read_vec(FILE *fp, std::vector<T> &v, size_t n)
+{
+    v.resize(n);
+    return fread(v.data(), sizeof(T), n, fp) == n;
+}
+
+void drop_graph(yq_network *net)
+{
+    if (net->graph_exec) {
+        cudaGraphExecDestroy(net->graph_exec);
+        net->graph_exec = nullptr;
+    }
+    net->graph_input = nullptr;
+}
+
+// the kernel sequence of one forward_network pass (network.c:229-261)
+int forward_body(yq_network *net, const uint8_t *in_u8_nchw, int *launches)
+{
+    cudaStream_t st = net->stream;
+    int nl = 0;
+    if (yq_nchw_to_nhwc_u8(in_u8_nchw, net->in_nhwc, net->batch, net->c, net->h, net->w, st)) return -1;
+    ++nl;
+    const uint8_t *cur = net->in_nhwc;
+    const float *cur_f32 = nullptr;
+    for (size_t i = 0; i < net->layers.size(); ++i) {
+        Layer &l = net->layers[i];
+        switch (l.type) {
+        case L_CONV:
+            if (yq_forward_convolutional_layer_quant_gpu(l.conv, cur, l.out_u8, l.out_f32, net->keep_acc ? l.out_acc : nullptr,
+                                                         net->batch, st))
+                return -1;
+            ++nl;
+            cur = l.out_u8;
+            cur_f32 = l.out_f32;
+            break;
+        case L_MAXPOOL:
+            if (yq_forward_maxpool_layer_quant_gpu(cur, l.out_u8, net->batch, l.h, l.w, l.c, l.size, l.stride, l.pad, st)) return -1;
+            ++nl;
+            cur = l.out_u8;
+            break;
+        case L_UPSAMPLE:
+            if (yq_forward_upsample_layer_quant_gpu(cur, l.out_u8, net->batch, l.h, l.w, l.c, l.stride, st)) return -1;
+            ++nl;
+            cur = l.out_u8;
+            break;
+        case L_ROUTE:
+            if (l.inputs.size() > 1) {
+                const uint8_t *ins[8];
+                int cs[8];
+                for (size_t k = 0; k < l.inputs.size(); ++k) {
+                    ins[k] = net->layers[l.inputs[k]].out_u8;
+                    cs[k] = net->layers[l.inputs[k]].out_c;
+                }
+                if (yq_forward_route_layer_quant_gpu(ins, cs, (int)l.inputs.size(), l.out_u8, net->batch, l.out_h, l.out_w, st)) return -1;
+                ++nl;
+            }   // a single-input route is an alias of its input (no copy)
+            cur = l.out_u8;
+            break;
+        case L_YOLO:
+            if (!cur_f32) return yq::fail("layer %zu: yolo layer needs a float input (previous layer must be a quant_stop conv)", i);
+            if (yq_forward_yolo_layer_gpu(cur_f32, l.out_f32, net->batch, l.n_anchors, l.classes, l.h, l.w, st)) return -1;
+            ++nl;
+            break;
+        }
+    }
+    if (launches) *launches = nl;
+    return 0;
+}
+
+}  // namespace
+
+extern "C" yq_network *yq_load_network(const char *cfg, const char *weights, int batch, int device)
+{
+    yq::clear_error();
+    if (!cfg) {
+        yq::fail("yq_load_network: cfg path is NULL");
+        return nullptr;
+    }
+    if (yq_device_count() <= 0) {
+        yq::fail("yq_load_network: no CUDA device visible (this library has no CPU fallback)");
+        return nullptr;
+    }
+    std::vector<Section> secs;
+    std::string err;
+    if (!read_cfg(cfg, secs, err)) {
+        yq::fail("%s", err.c_str());
+        return nullptr;
+    }
+    if (secs.empty() || (secs[0].type != "[net]" && secs[0].type != "[network]")) {
+        yq::fail("First section must be [net] or [network]");   // parser.c:692
+        return nullptr;
+    }
+    std::unique_ptr<yq_network> net(new yq_network());
+    net->device = device;
+    if (cudaSetDevice(device) != cudaSuccess) {
+        yq::fail("cudaSetDevice(%d) failed", device);
+        return nullptr;
+    }
+    const Section &ns = secs[0];
+    net->batch = batch > 0 ? batch : ns.geti("batch", 1);
+    net->h = ns.geti("height", 0);
+    net->w = ns.geti("width", 0);
+    net->c = ns.geti("channels", 0);
+    if (!net->h || !net->w || !net->c) {
+        yq::fail("No input parameters supplied");   // parser.c:624
+        return nullptr;
+    }
+    int c = net->c, h = net->h, w = net->w;
+    for (size_t si = 1; si < secs.size(); ++si) {
+        const Section &s = secs[si];
+        const int index = (int)si - 1;
+        Layer l;
+        l.quantized = s.geti("quantized", 0);
+        l.quant_stop = s.geti("quant_stop", 0);
+        l.first_time = s.geti("first_time", 0);
+        if (s.type == "[convolutional]" || s.type == "[conv]") {
+            l.type = L_CONV;
+            l.n = s.geti("filters", 1);
+            l.size = s.geti("size", 1);
+            l.stride = s.geti("stride", 1);
+            int pad = s.geti("pad", 0), padding = s.geti("padding", 0);
+            if (pad) padding = l.size / 2;                                  // parser.c:178
+            l.pad = padding;
+            if (s.geti("groups", 1) != 1) {
+                yq::fail("layer %d: grouped convolution is outside the quantized path", index);
+                return nullptr;
+            }
+            l.activation = activation_from_string(s.gets("activation", "logistic"));
+            l.bn = s.geti("batch_normalize", 0);
+            if (!l.quantized) {
+                yq::fail("layer %d: convolutional layer without quantized=1 is outside the INT8 path", index);
+                return nullptr;
+            }
+            if (l.activation != YQ_LINEAR && l.activation != YQ_RELU && l.activation != YQ_RELU6 && l.activation != YQ_LEAKY) {
+                yq::fail("layer %d: activation '%s' has no quantized form (convolutional_layer.c:734-748)", index,
+                         s.gets("activation", "logistic").c_str());
+                return nullptr;
+            }
+            l.c = c; l.h = h; l.w = w;
+            l.out_c = l.n;
+            l.out_h = (h + 2 * l.pad - l.size) / l.stride + 1;
+            l.out_w = (w + 2 * l.pad - l.size) / l.stride + 1;
+        } else if (s.type == "[maxpool]" || s.type == "[max]") {
+            l.type = L_MAXPOOL;
+            l.stride = s.geti("stride", 1);
+            l.size = s.geti("size", l.stride);
+            l.pad = s.geti("padding", l.size - 1);                          // parser.c:415
+            l.c = c; l.h = h; l.w = w;
+            l.out_c = c;
+            l.out_h = (h + l.pad - l.size) / l.stride + 1;                  // maxpool_layer.c:31-32
+            l.out_w = (w + l.pad - l.size) / l.stride + 1;
+        } else if (s.type == "[upsample]") {
+            l.type = L_UPSAMPLE;
+            l.stride = s.geti("stride", 2);
+            if (atof(s.gets("scale", "1").c_str()) != 1.0) {
+                yq::fail("layer %d: upsample scale must be 1 on the quantized path (blas.c:785 asserts)", index);
+                return nullptr;
+            }
+            l.c = c; l.h = h; l.w = w;
+            l.out_c = c; l.out_h = h * l.stride; l.out_w = w * l.stride;
+        } else if (s.type == "[route]") {
+            l.type = L_ROUTE;
+            std::string ls = s.gets("layers", "");
+            if (ls.empty()) {
+                yq::fail("Route Layer must specify input layers");          // parser.c:527
+                return nullptr;
+            }
+            std::stringstream ss(ls);
+            std::string tok;
+            while (std::getline(ss, tok, ',')) {
+                int idx = atoi(tok.c_str());
+                if (idx < 0) idx = index + idx;                             // parser.c:538
+                if (idx < 0 || idx >= index) {
+                    yq::fail("layer %d: route input %d out of range", index, idx);
+                    return nullptr;
+                }
+                l.inputs.push_back(idx);
+            }
+            const Layer &first = net->layers[l.inputs[0]];
+            l.out_h = first.out_h; l.out_w = first.out_w; l.out_c = 0;
+            for (int idx : l.inputs) {
+                const Layer &in = net->layers[idx];
+                if (in.out_h != first.out_h || in.out_w != first.out_w) {
+                    yq::fail("layer %d: route inputs differ in spatial size", index);
+                    return nullptr;
+                }
+                if (in.type == L_YOLO) {
+                    yq::fail("layer %d: route from a yolo layer has no uint8 tensor", index);
+                    return nullptr;
+                }
+                l.out_c += in.out_c;
+            }
+            l.c = l.out_c; l.h = l.out_h; l.w = l.out_w;
+        } else if (s.type == "[yolo]") {
+            l.type = L_YOLO;
+            l.classes = s.geti("classes", 20);
+            int total = s.geti("num", 1);
+            std::string mask = s.gets("mask", "");
+            l.n_anchors = mask.empty() ? total : (int)std::count(mask.begin(), mask.end(), ',') + 1;   // parse_yolo_mask
+            l.c = c; l.h = h; l.w = w; l.out_c = c; l.out_h = h; l.out_w = w;
+            if (c != l.n_anchors * (l.classes + 5)) {
+                yq::fail("layer %d: yolo expects %d channels, previous layer has %d", index, l.n_anchors * (l.classes + 5), c);
+                return nullptr;
+            }
+            if (index == 0 || net->layers[index - 1].type != L_CONV || !net->layers[index - 1].quant_stop) {
+                yq::fail("layer %d: yolo must follow a quant_stop=1 convolution", index);
+                return nullptr;
+            }
+        } else {
+            yq::fail("layer %d: type %s is outside the quantized inference path", index, s.type.c_str());
+            return nullptr;
+        }
+        if (l.type != L_YOLO && l.type != L_CONV && !l.quantized) {
+            yq::fail("layer %d: %s without quantized=1 is outside the INT8 path", index, s.type.c_str());
+            return nullptr;
+        }
+        if (l.out_h <= 0 || l.out_w <= 0) {
+            yq::fail("layer %d: empty output", index);
+            return nullptr;
+        }
+        net->layers.push_back(l);
+        c = l.out_c; h = l.out_h; w = l.out_w;
+    }
+    if (net->layers.empty()) {
+        yq::fail("cfg has no layers");
+        return nullptr;
+    }
+
+    // ---- weights: load_weights_upto (parser.c:1201-1305), QUANTIZATION field order
+    if (!weights || !weights[0]) {
+        yq::fail("yq_load_network: a quantized .weights file is required");
+        return nullptr;
+    }
+    FILE *fp = fopen(weights, "rb");
+    if (!fp) {
+        yq::fail("Couldn't open file: %s", weights);   // file_error, utils.c
+        return nullptr;
+    }
+    struct Closer { FILE *f; ~Closer() { fclose(f); } } closer{fp};
+    int major = 0, minor = 0, revision = 0;
+    bool ok = fread(&major, 4, 1, fp) == 1 && fread(&minor, 4, 1, fp) == 1 && fread(&revision, 4, 1, fp) == 1;
+    if (ok) {
+        if ((major * 10 + minor) >= 2 && major < 1000 && minor < 1000) {
+            uint64_t seen;
+            ok = fread(&seen, 8, 1, fp) == 1;
+        } else {
+            int iseen;
+            ok = fread(&iseen, 4, 1, fp) == 1;
+        }
+    }
+    for (size_t i = 0; ok && i < net->layers.size(); ++i) {
+        Layer &l = net->layers[i];
+        uint8_t z;
+        if (l.type == L_CONV) {
+            const size_t K = (size_t)l.c * l.size * l.size;
+            ok = read_vec(fp, l.biases, l.n);
+            if (ok && l.bn) ok = read_vec(fp, l.bn_scales, l.n) && read_vec(fp, l.bn_mean, l.n) && read_vec(fp, l.bn_var, l.n);
+            ok = ok && fread(&l.s_in, 4, 1, fp) == 1 && fread(&z, 1, 1, fp) == 1;
+            l.zp_in = z;
+            ok = ok && fread(&l.s_out, 4, 1, fp) == 1 && fread(&z, 1, 1, fp) == 1;
+            l.zp_out = z;
+            ok = ok && read_vec(fp, l.s_w, l.n) && read_vec(fp, l.zp_w, l.n) && read_vec(fp, l.w_u8, K * l.n);
+            if (ok) ok = fseek(fp, (long)(K * l.n * sizeof(float)), SEEK_CUR) == 0;   // float weights: unused at inference
+        } else if (l.type == L_MAXPOOL || (l.type == L_UPSAMPLE && l.quantized && !l.first_time)) {
+            ok = fread(&l.s_out, 4, 1, fp) == 1 && fread(&z, 1, 1, fp) == 1;
+            l.zp_out = z;
+        } else if (l.type == L_ROUTE && l.quantized) {
+            if (l.inputs.size() > 1 && !l.first_time) {                     // parser.c:1176-1182
+                ok = fread(&l.s_out, 4, 1, fp) == 1 && fread(&z, 1, 1, fp) == 1;
+                l.zp_out = z;
+            } else {
+                l.s_out = net->layers[l.inputs[0]].s_out;
+                l.zp_out = net->layers[l.inputs[0]].zp_out;
+            }
+        }
+    }
+    if (!ok) {
+        yq::fail("weights file %s is truncated for this cfg", weights);
+        return nullptr;
+    }
+
+    // ---- one-time host prep (blas.c:259-346) and device objects
+    if (cudaStreamCreateWithFlags(&net->stream, cudaStreamNonBlocking) != cudaSuccess) {
+        yq::fail("cudaStreamCreate failed");
+        return nullptr;
+    }
+    yq_network *raw = net.release();
+    auto bail = [&]() -> yq_network * {
+        std::string keep = yq_last_error();
+        yq_free_network(raw);
+        yq::fail("%s", keep.c_str());
+        return nullptr;
+    };
+    for (size_t i = 0; i < raw->layers.size(); ++i) {
+        Layer &l = raw->layers[i];
+        if (l.type == L_CONV) {
+            if (i > 0) {   // blas.c:301-305: input params come from the previous layer's activation params
+                const Layer &p = raw->layers[i - 1];
+                if (p.type == L_YOLO) {
+                    yq::fail("layer %zu: convolution directly after a yolo layer has no quantized input", i);
+                    return bail();
+                }
+                l.s_in = p.s_out;
+                l.zp_in = p.zp_out;
+            }
+            if (prepare_conv(l, (int)i) || build_conv_device(raw, l)) return bail();
+        }
+        const int cs = yq::channel_stride(l.out_c);
+        l.u8_bytes = (size_t)raw->batch * l.out_h * l.out_w * cs;
+        if (l.type == L_ROUTE && l.inputs.size() == 1) {
+            l.out_u8 = raw->layers[l.inputs[0]].out_u8;   // alias
+        } else if (l.type != L_YOLO) {
+            if (cudaMalloc((void **)&l.out_u8, l.u8_bytes) != cudaSuccess) {
+                yq::fail("cudaMalloc of layer %zu output (%zu bytes) failed", i, l.u8_bytes);
+                return bail();
+            }
+            l.owns_u8 = true;
+            cudaMemset(l.out_u8, 0, l.u8_bytes);
+        }
+        if ((l.type == L_CONV && l.quant_stop) || l.type == L_YOLO) {
+            l.f32_count = (size_t)raw->batch * l.out_c * l.out_h * l.out_w;
+            if (cudaMalloc((void **)&l.out_f32, l.f32_count * sizeof(float)) != cudaSuccess) {
+                yq::fail("cudaMalloc of layer %zu float output failed", i);
+                return bail();
+            }
+            if (l.type == L_YOLO) raw->out_floats += l.f32_count;
+        }
+    }
+    const size_t in_bytes = (size_t)raw->batch * raw->c * raw->h * raw->w;
+    if (cudaMalloc((void **)&raw->in_stage_nchw, in_bytes) != cudaSuccess ||
+        cudaMalloc((void **)&raw->in_nhwc, (size_t)raw->batch * raw->h * raw->w * yq::channel_stride(raw->c)) != cudaSuccess) {
+        yq::fail("cudaMalloc of network input failed");
+        return bail();
+    }
+    raw->launches = 1;
+    for (auto &l : raw->layers)
+        if (!(l.type == L_ROUTE && l.inputs.size() == 1)) raw->launches++;
+    return raw;
+}
+
+extern "C" void yq_free_network(yq_network *net)
+{
+    if (!net) return;
+    cudaSetDevice(net->device);
+    drop_graph(net);
+    for (auto &l : net->layers) {
+        if (l.conv) yq_free_convolutional_layer_quant(l.conv);
+        if (l.owns_u8) cudaFree(l.out_u8);
+        cudaFree(l.out_f32);
+        cudaFree(l.out_acc);
+    }
+    cudaFree(net->in_stage_nchw);
+    cudaFree(net->in_nhwc);
+    cudaFree(net->scratch);
+    if (net->out_host_pinned) cudaFreeHost(net->out_host_pinned);
+    if (net->stream) cudaStreamDestroy(net->stream);
+    delete net;
+}
+
+extern "C" int yq_network_num_layers(const yq_network *net) { return (int)net->layers.size(); }
+extern "C" int yq_network_batch(const yq_network *net) { return net->batch; }
+extern "C" int yq_network_input_dims(const yq_network *net, int *c, int *h, int *w)
+{
+    if (c) *c = net->c;
+    if (h) *h = net->h;
+    if (w) *w = net->w;
+    return 0;
+}
+extern "C" size_t yq_network_output_floats(const yq_network *net) { return net->out_floats; }
+extern "C" void *yq_network_stream(yq_network *net) { return (void *)net->stream; }
+extern "C" int yq_network_launches_per_forward(const yq_network *net) { return net->launches; }
+
+extern "C" int yq_network_layer_info(const yq_network *net, int i, yq_layer_info *o)
+{
+    if (!net || !o || i < 0 || i >= (int)net->layers.size()) return yq::fail("yq_network_layer_info: bad index");
+    const Layer &l = net->layers[i];
+    memset(o, 0, sizeof *o);
+    o->type = l.type; o->c = l.c; o->h = l.h; o->w = l.w; o->out_c = l.out_c; o->out_h = l.out_h; o->out_w = l.out_w;
+    o->n = l.n; o->size = l.size; o->stride = l.stride; o->pad = l.pad; o->activation = l.activation;
+    o->batch_normalize = l.bn; o->quant_stop_flag = l.quant_stop; o->s_in = l.s_in; o->s_out = l.s_out;
+    o->zp_in = l.zp_in; o->zp_out = l.zp_out; o->kernel = l.conv ? yq_conv_get_kernel(l.conv) : 0;
+    o->classes = l.classes; o->n_anchors = l.n_anchors;
+    return 0;
+}
+
+extern "C" int yq_network_set_input_quant(yq_network *net, float s_in, int zp_in)
+{
+    if (!net || net->layers.empty() || net->layers[0].type != L_CONV) return yq::fail("set_input_quant: layer 0 is not a convolution");
+    YQ_CUDA(cudaSetDevice(net->device));
+    YQ_CUDA(cudaStreamSynchronize(net->stream));
+    drop_graph(net);
+    Layer &l = net->layers[0];
+    l.s_in = s_in;
+    l.zp_in = zp_in & 0xff;
+    if (prepare_conv(l, 0) || build_conv_device(net, l)) return -1;
+    return 0;
+}
+
+extern "C" int yq_network_set_debug(yq_network *net, int keep_acc)
+{
+    YQ_CUDA(cudaSetDevice(net->device));
+    drop_graph(net);
+    net->keep_acc = keep_acc;
+    if (keep_acc)
+        for (auto &l : net->layers)
+            if (l.type == L_CONV && !l.out_acc) {
+                size_t bytes = (size_t)net->batch * l.out_h * l.out_w * yq::channel_stride(l.out_c) * sizeof(int32_t);
+                YQ_CUDA(cudaMalloc((void **)&l.out_acc, bytes));
+            }
+    return 0;
+}
+
+extern "C" int yq_network_set_conv_kernel(yq_network *net, int kind)
+{
+    drop_graph(net);
+    net->conv_kernel = kind;
+    for (auto &l : net->layers)
+        if (l.conv) apply_kernel_choice(l.conv, kind);
+    return 0;
+}
+
+extern "C" int yq_network_use_graph(yq_network *net, int enable)
+{
+    if (!enable) drop_graph(net);
+    net->use_graph = enable;
+    return 0;
+}
+
+extern "C" int yq_forward_network_device(yq_network *net, const uint8_t *in_u8_nchw)
+{
+    if (!net || !in_u8_nchw) return yq::fail("yq_forward_network_device: null argument");
+    YQ_CUDA(cudaSetDevice(net->device));
+    if (!net->use_graph) return forward_body(net, in_u8_nchw, nullptr);
+    if (!net->graph_exec || net->graph_input != in_u8_nchw) {
+        drop_graph(net);
+        cudaGraph_t g = nullptr;
+        YQ_CUDA(cudaStreamBeginCapture(net->stream, cudaStreamCaptureModeThreadLocal));
+        int rc = forward_body(net, in_u8_nchw, nullptr);
+        cudaError_t e = cudaStreamEndCapture(net->stream, &g);
+        if (rc) {
+            if (g) cudaGraphDestroy(g);
+            return rc;
+        }
+        if (e != cudaSuccess) return yq::fail("cudaStreamEndCapture: %s", cudaGetErrorString(e));
+        e = cudaGraphInstantiate(&net->graph_exec, g, 0);
+        cudaGraphDestroy(g);
+        if (e != cudaSuccess) return yq::fail("cudaGraphInstantiate: %s", cudaGetErrorString(e));
+        net->graph_input = in_u8_nchw;
+    }
+    YQ_CUDA(cudaGraphLaunch(net->graph_exec, net->stream));
+    return 0;
+}
+
+extern "C" int yq_network_synchronize(yq_network *net)
+{
+    YQ_CUDA(cudaStreamSynchronize(net->stream));
+    return 0;
+}
+
+extern "C" int yq_network_predict_u8(yq_network *net, const uint8_t *in_host, float *out_host)
+{
+    if (!net || !in_host) return yq::fail("yq_network_predict_u8: null argument");
+    YQ_CUDA(cudaSetDevice(net->device));
+    const size_t in_bytes = (size_t)net->batch * net->c * net->h * net->w;
+    YQ_CUDA(cudaMemcpyAsync(net->in_stage_nchw, in_host, in_bytes, cudaMemcpyHostToDevice, net->stream));
+    if (yq_forward_network_device(net, net->in_stage_nchw)) return -1;
+    if (out_host) {
+        size_t off = 0;
+        for (auto &l : net->layers)
+            if (l.type == L_YOLO) {
+                YQ_CUDA(cudaMemcpyAsync(out_host + off, l.out_f32, l.f32_count * sizeof(float), cudaMemcpyDeviceToHost, net->stream));
+                off += l.f32_count;
+            }
+    }
+    YQ_CUDA(cudaStreamSynchronize(net->stream));
+    return 0;
+}
+
+extern "C" const float *yq_network_layer_output_f32_device(const yq_network *net, int layer)
+{
+    if (!net || layer < 0 || layer >= (int)net->layers.size()) return nullptr;
+    return net->layers[layer].out_f32;
+}
+
+extern "C" int yq_network_pull_layer(yq_network *net, int layer, int what, void *host_out, size_t bytes)
+{
+    if (!net || !host_out || layer < 0 || layer >= (int)net->layers.size()) return yq::fail("yq_network_pull_layer: bad argument");
+    YQ_CUDA(cudaSetDevice(net->device));
+    Layer &l = net->layers[layer];
+    const size_t elems = (size_t)net->batch * l.out_c * l.out_h * l.out_w;
+    const size_t esz = what == 0 ? 1 : 4;
+    if (bytes != elems * esz) return yq::fail("yq_network_pull_layer: expected %zu bytes, got %zu", elems * esz, bytes);
+    if (what == 2) {
+        if (!l.out_f32) return yq::fail("layer %d has no float output", layer);
+        YQ_CUDA(cudaMemcpyAsync(host_out, l.out_f32, bytes, cudaMemcpyDeviceToHost, net->stream));
+        YQ_CUDA(cudaStreamSynchronize(net->stream));
+        return 0;
+    }
+    if (net->scratch_bytes < bytes) {
+        cudaFree(net->scratch);
+        net->scratch = nullptr;
+        net->scratch_bytes = 0;
+        YQ_CUDA(cudaMalloc((void **)&net->scratch, bytes));
+        net->scratch_bytes = bytes;
+    }
+    if (what == 0) {
+        if (!l.out_u8) return yq::fail("layer %d has no uint8 output", layer);
+        if (yq_nhwc_to_nchw_u8(l.out_u8, net->scratch, net->batch, l.out_c, l.out_h, l.out_w, net->stream)) return -1;
+    } else if (what == 1) {
+        if (!l.out_acc) return yq::fail("layer %d has no int32 accumulator (conv layers only, after yq_network_set_debug(net,1))", layer);
+        if (yq_nhwc_to_nchw_i32(l.out_acc, (int32_t *)net->scratch, net->batch, l.out_c, l.out_h, l.out_w, net->stream)) return -1;
+    } else {
+        return yq::fail("yq_network_pull_layer: what=%d", what);
+    }
+    YQ_CUDA(cudaMemcpyAsync(host_out, net->scratch, bytes, cudaMemcpyDeviceToHost, net->stream));
+    YQ_CUDA(cudaStreamSynchronize(net->stream));
+    return 0;
+}
+
+extern "C" int yq_network_conv_params(const yq_network *net, int layer, int32_t *M0, int *M0_right_shift, double *M_value,
+                                      double *M0_right_shift_value, int32_t *biases_int32)
+{
+    if (!net || layer < 0 || layer >= (int)net->layers.size() || net->layers[layer].type != L_CONV)
+        return yq::fail("yq_network_conv_params: layer %d is not a convolution", layer);
+    const Layer &l = net->layers[layer];
+    if (M0) memcpy(M0, l.M0.data(), l.n * sizeof(int32_t));
+    if (M0_right_shift) memcpy(M0_right_shift, l.M0_right_shift.data(), l.n * sizeof(int));
+    if (M_value) memcpy(M_value, l.M_value.data(), l.n * sizeof(double));
+    if (M0_right_shift_value) memcpy(M0_right_shift_value, l.rshift_value.data(), l.n * sizeof(double));
+    if (biases_int32) memcpy(biases_int32, l.biases_int32.data(), l.n * sizeof(int32_t));
+    return 0;
+}

@@ -1,0 +1,343 @@
+"""Thin Python mirror of the reference's public C API for the quantized inference path, over the
+C ABI of libyq_b200.so (include/yq_b200.h).  Python is glue only: every byte of compute happens in
+the sm_100a kernels; nothing here touches the oracle or has a CPU fallback.
+
+Reference names kept (include/darknet.h): ``load_network`` (:730), ``network_predict`` (:904),
+``forward_network`` (:856), ``free_network`` (:907), ``set_batch_network`` (batch is fixed at load,
+see ``load_network``), and per-layer ``forward_*_layer_quant_gpu`` forms.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, List, Optional, Sequence
+
+import numpy as np
+
+from . import _lib
+from ._lib import ConvDesc, LayerInfo, YqError, check
+
+LAYER_TYPES = {0: "conv", 1: "maxpool", 2: "route", 3: "upsample", 4: "yolo"}
+ACTIVATIONS = {"logistic": 0, "relu": 1, "linear": 3, "relu6": 8, "leaky": 9}
+
+
+def channel_stride(c: int) -> int:
+    return _lib.load().yq_channel_stride(int(c))
+
+
+class DeviceBuffer:
+    """cuda_make_array / cuda_free (src/cuda.c:90-104,145-151) for raw bytes."""
+
+    def __init__(self, nbytes: int, zero: bool = True):
+        lib = _lib.load()
+        _lib.require_gpu()
+        self.nbytes = int(nbytes)
+        self.ptr = lib.yq_cuda_malloc(self.nbytes)
+        if not self.ptr:
+            raise YqError(_lib.last_error())
+        if zero:
+            check(lib.yq_cuda_memset(self.ptr, 0, self.nbytes, None))
+
+    @classmethod
+    def from_numpy(cls, a: np.ndarray) -> "DeviceBuffer":
+        a = np.ascontiguousarray(a)
+        b = cls(a.nbytes, zero=False)
+        b.push(a)
+        return b
+
+    def push(self, a: np.ndarray) -> None:
+        a = np.ascontiguousarray(a)
+        assert a.nbytes <= self.nbytes
+        check(_lib.load().yq_cuda_push(self.ptr, a.ctypes.data, a.nbytes, None))
+        check(_lib.load().yq_stream_synchronize(None))
+
+    def pull(self, shape, dtype) -> np.ndarray:
+        out = np.empty(shape, dtype)
+        assert out.nbytes <= self.nbytes
+        check(_lib.load().yq_cuda_pull(out.ctypes.data, self.ptr, out.nbytes, None))
+        return out
+
+    def free(self) -> None:
+        if self.ptr:
+            _lib.load().yq_cuda_free(self.ptr)
+            self.ptr = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+# ----------------------------------------------------------------------------------------------
+# layout helpers at the boundary (the reference's tensors are CHW per image)
+# ----------------------------------------------------------------------------------------------
+
+def push_nchw_u8(x: np.ndarray) -> DeviceBuffer:
+    """Host uint8 [b,c,h,w] -> device NHWC with the library's channel stride."""
+    x = np.ascontiguousarray(x, np.uint8)
+    b, c, h, w = x.shape
+    src = DeviceBuffer.from_numpy(x)
+    dst = DeviceBuffer(b * h * w * channel_stride(c))
+    check(_lib.load().yq_nchw_to_nhwc_u8(src.ptr, dst.ptr, b, c, h, w, None))
+    check(_lib.load().yq_stream_synchronize(None))
+    src.free()
+    return dst
+
+
+def pull_nhwc_u8(buf: DeviceBuffer, b: int, c: int, h: int, w: int) -> np.ndarray:
+    tmp = DeviceBuffer(b * c * h * w)
+    check(_lib.load().yq_nhwc_to_nchw_u8(buf.ptr, tmp.ptr, b, c, h, w, None))
+    out = tmp.pull((b, c, h, w), np.uint8)
+    tmp.free()
+    return out
+
+
+def pull_nhwc_i32(buf: DeviceBuffer, b: int, c: int, h: int, w: int) -> np.ndarray:
+    tmp = DeviceBuffer(b * c * h * w * 4)
+    check(_lib.load().yq_nhwc_to_nchw_i32(buf.ptr, tmp.ptr, b, c, h, w, None))
+    out = tmp.pull((b, c, h, w), np.int32)
+    tmp.free()
+    return out
+
+
+# ----------------------------------------------------------------------------------------------
+# layer level
+# ----------------------------------------------------------------------------------------------
+
+class ConvolutionalLayerQuant:
+    """make_convolutional_layer's quantized GPU state + forward_convolutional_layer_quant_gpu.
+
+    Arguments follow ``struct layer`` after quantization_weights_and_activations (src/blas.c:259-346):
+    weights_uint8 OIHW, per-channel weight zero points, biases_int32, M_value, M0_right_shift_value.
+    """
+
+    def __init__(self, h: int, w: int, c: int, n: int, size: int, stride: int, pad: int, activation: int,
+                 weights_uint8: np.ndarray, weight_zero_point: np.ndarray, biases_int32: np.ndarray,
+                 M_value: np.ndarray, M0_right_shift_value: np.ndarray, zp_in: int, zp_out: int, s_out: float,
+                 quant_stop_flag: int = 0, saturate: int = 0, kernel: int = -1):
+        lib = _lib.load()
+        _lib.require_gpu()
+        self._keep = [np.ascontiguousarray(weights_uint8, np.uint8), np.ascontiguousarray(weight_zero_point, np.uint8),
+                      np.ascontiguousarray(biases_int32, np.int32), np.ascontiguousarray(M_value, np.float64),
+                      np.ascontiguousarray(M0_right_shift_value, np.float64)]
+        assert self._keep[0].size == n * c * size * size
+        d = ConvDesc(h, w, c, n, size, stride, pad, int(activation), int(quant_stop_flag), int(zp_in), int(zp_out),
+                     float(s_out), *(a.ctypes.data for a in self._keep), int(saturate))
+        self.handle = lib.yq_make_convolutional_layer_quant(C.byref(d))
+        if not self.handle:
+            raise YqError(_lib.last_error())
+        self.h, self.w, self.c, self.n = h, w, c, n
+        self.out_h, self.out_w = lib.yq_conv_out_h(self.handle), lib.yq_conv_out_w(self.handle)
+        self.quant_stop_flag = quant_stop_flag
+        if kernel >= 0:
+            check(lib.yq_conv_set_kernel(self.handle, kernel), "yq_conv_set_kernel")
+
+    @property
+    def kernel(self) -> int:
+        return _lib.load().yq_conv_get_kernel(self.handle)
+
+    def forward(self, x_nchw: np.ndarray, want_acc: bool = True) -> Dict[str, np.ndarray]:
+        """x: uint8 [b,c,h,w] (reference layout). Returns dict(u8=[b,n,oh,ow], acc=int32 ..., f32=...)."""
+        lib = _lib.load()
+        b = x_nchw.shape[0]
+        din = push_nchw_u8(x_nchw)
+        cs = channel_stride(self.n)
+        dout = DeviceBuffer(b * self.out_h * self.out_w * cs)
+        dacc = DeviceBuffer(b * self.out_h * self.out_w * cs * 4) if want_acc else None
+        df32 = DeviceBuffer(b * self.n * self.out_h * self.out_w * 4) if self.quant_stop_flag else None
+        check(lib.yq_forward_convolutional_layer_quant_gpu(self.handle, din.ptr, dout.ptr, df32.ptr if df32 else None,
+                                                           dacc.ptr if dacc else None, b, None),
+              "yq_forward_convolutional_layer_quant_gpu")
+        check(lib.yq_stream_synchronize(None))
+        res = {"u8": pull_nhwc_u8(dout, b, self.n, self.out_h, self.out_w)}
+        if dacc:
+            res["acc"] = pull_nhwc_i32(dacc, b, self.n, self.out_h, self.out_w)
+        if df32:
+            res["f32"] = df32.pull((b, self.n, self.out_h, self.out_w), np.float32)
+        for d in (din, dout, dacc, df32):
+            if d:
+                d.free()
+        return res
+
+    def free(self) -> None:
+        if self.handle:
+            _lib.load().yq_free_convolutional_layer_quant(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+def forward_maxpool_layer_quant_gpu(x: np.ndarray, size: int, stride: int, pad: Optional[int] = None) -> np.ndarray:
+    b, c, h, w = x.shape
+    pad = size - 1 if pad is None else pad
+    oh, ow = (h + pad - size) // stride + 1, (w + pad - size) // stride + 1
+    din = push_nchw_u8(x)
+    dout = DeviceBuffer(b * oh * ow * channel_stride(c))
+    check(_lib.load().yq_forward_maxpool_layer_quant_gpu(din.ptr, dout.ptr, b, h, w, c, size, stride, pad, None))
+    out = pull_nhwc_u8(dout, b, c, oh, ow)
+    din.free(); dout.free()
+    return out
+
+
+def forward_upsample_layer_quant_gpu(x: np.ndarray, stride: int) -> np.ndarray:
+    b, c, h, w = x.shape
+    din = push_nchw_u8(x)
+    dout = DeviceBuffer(b * h * stride * w * stride * channel_stride(c))
+    check(_lib.load().yq_forward_upsample_layer_quant_gpu(din.ptr, dout.ptr, b, h, w, c, stride, None))
+    out = pull_nhwc_u8(dout, b, c, h * stride, w * stride)
+    din.free(); dout.free()
+    return out
+
+
+def forward_route_layer_quant_gpu(xs: Sequence[np.ndarray]) -> np.ndarray:
+    b, _, h, w = xs[0].shape
+    dins = [push_nchw_u8(x) for x in xs]
+    cs = [int(x.shape[1]) for x in xs]
+    ctot = sum(cs)
+    dout = DeviceBuffer(b * h * w * channel_stride(ctot))
+    ptrs = (C.c_void_p * len(xs))(*[d.ptr for d in dins])
+    carr = (C.c_int * len(xs))(*cs)
+    check(_lib.load().yq_forward_route_layer_quant_gpu(ptrs, carr, len(xs), dout.ptr, b, h, w, None))
+    out = pull_nhwc_u8(dout, b, ctot, h, w)
+    for d in dins:
+        d.free()
+    dout.free()
+    return out
+
+
+def forward_yolo_layer_gpu(x: np.ndarray, n_anchors: int, classes: int) -> np.ndarray:
+    x = np.ascontiguousarray(x, np.float32)
+    b, c, h, w = x.shape
+    din = DeviceBuffer.from_numpy(x)
+    dout = DeviceBuffer(x.nbytes)
+    check(_lib.load().yq_forward_yolo_layer_gpu(din.ptr, dout.ptr, b, n_anchors, classes, h, w, None))
+    out = dout.pull(x.shape, np.float32)
+    din.free(); dout.free()
+    return out
+
+
+# ----------------------------------------------------------------------------------------------
+# network level
+# ----------------------------------------------------------------------------------------------
+
+class Network:
+    """``network *`` of the reference for the quantized inference path."""
+
+    def __init__(self, handle):
+        self._h = handle
+        lib = _lib.load()
+        self.batch = lib.yq_network_batch(handle)
+        c, h, w = C.c_int(), C.c_int(), C.c_int()
+        lib.yq_network_input_dims(handle, C.byref(c), C.byref(h), C.byref(w))
+        self.c, self.h, self.w = c.value, h.value, w.value
+        self.n = lib.yq_network_num_layers(handle)
+        self.output_floats = lib.yq_network_output_floats(handle)
+
+    @property
+    def handle(self):
+        return self._h
+
+    @property
+    def stream(self) -> int:
+        return _lib.load().yq_network_stream(self._h) or 0
+
+    @property
+    def launches_per_forward(self) -> int:
+        return _lib.load().yq_network_launches_per_forward(self._h)
+
+    def layer_info(self, i: int) -> LayerInfo:
+        info = LayerInfo()
+        check(_lib.load().yq_network_layer_info(self._h, i, C.byref(info)))
+        return info
+
+    def layers(self) -> List[LayerInfo]:
+        return [self.layer_info(i) for i in range(self.n)]
+
+    def set_input_quant(self, s_in: float, zp_in: int) -> None:
+        check(_lib.load().yq_network_set_input_quant(self._h, float(s_in), int(zp_in)))
+
+    def set_debug(self, keep_acc: bool = True) -> None:
+        check(_lib.load().yq_network_set_debug(self._h, int(keep_acc)))
+
+    def set_conv_kernel(self, kind: int) -> None:
+        check(_lib.load().yq_network_set_conv_kernel(self._h, int(kind)))
+
+    def use_graph(self, enable: bool = True) -> None:
+        check(_lib.load().yq_network_use_graph(self._h, int(enable)))
+
+    def forward_device(self, dev_ptr: int) -> None:
+        """forward_network on a device-resident uint8 NCHW batch (asynchronous on self.stream)."""
+        check(_lib.load().yq_forward_network_device(self._h, dev_ptr), "yq_forward_network_device")
+
+    def synchronize(self) -> None:
+        check(_lib.load().yq_network_synchronize(self._h))
+
+    def predict_u8(self, x: np.ndarray, out: Optional[np.ndarray] = None) -> np.ndarray:
+        """network_predict with host buffers: x uint8 [batch,c,h,w]; returns the yolo heads, flat float32."""
+        x = np.ascontiguousarray(x, np.uint8)
+        assert x.shape == (self.batch, self.c, self.h, self.w), x.shape
+        if out is None:
+            out = np.empty(self.output_floats, np.float32)
+        check(_lib.load().yq_network_predict_u8(self._h, x.ctypes.data, out.ctypes.data), "yq_network_predict_u8")
+        return out
+
+    def predict_raw(self, in_ptr: int, out_ptr: int) -> None:
+        """Same as predict_u8 on raw host addresses (e.g. pinned torch tensors)."""
+        check(_lib.load().yq_network_predict_u8(self._h, in_ptr, out_ptr), "yq_network_predict_u8")
+
+    def split_heads(self, flat: np.ndarray) -> List[np.ndarray]:
+        outs, off = [], 0
+        for li in self.layers():
+            if li.type == 4:
+                cnt = self.batch * li.out_c * li.out_h * li.out_w
+                outs.append(flat[off:off + cnt].reshape(self.batch, li.out_c, li.out_h, li.out_w))
+                off += cnt
+        return outs
+
+    def pull_layer(self, i: int, what: str = "u8") -> np.ndarray:
+        li = self.layer_info(i)
+        code, dt = {"u8": (0, np.uint8), "acc": (1, np.int32), "f32": (2, np.float32)}[what]
+        out = np.empty((self.batch, li.out_c, li.out_h, li.out_w), dt)
+        check(_lib.load().yq_network_pull_layer(self._h, i, code, out.ctypes.data, out.nbytes), "yq_network_pull_layer")
+        return out
+
+    def conv_params(self, i: int) -> Dict[str, np.ndarray]:
+        n = self.layer_info(i).n
+        r = {"M0": np.empty(n, np.int32), "M0_right_shift": np.empty(n, np.int32), "M_value": np.empty(n, np.float64),
+             "M0_right_shift_value": np.empty(n, np.float64), "biases_int32": np.empty(n, np.int32)}
+        check(_lib.load().yq_network_conv_params(self._h, i, *(a.ctypes.data for a in r.values())))
+        return r
+
+    def free(self) -> None:
+        if self._h:
+            _lib.load().yq_free_network(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+def load_network(cfg: str, weights: str, batch: int = 0, device: int = 0) -> Network:
+    """load_network(cfg, weights, clear) (src/network.c:49-57) + the one-time
+    quantization_weights_and_activations host prep (src/blas.c:259-346).  ``batch`` overrides the
+    cfg's ``[net] batch`` (the reference sizes its buffers from the cfg at parse time)."""
+    lib = _lib.load()
+    h = lib.yq_load_network(cfg.encode(), weights.encode(), int(batch), int(device))
+    if not h:
+        raise YqError(_lib.last_error())
+    return Network(h)
+
+
+def network_predict(net: Network, x_u8: np.ndarray) -> np.ndarray:
+    return net.predict_u8(x_u8)
+
+
+def free_network(net: Network) -> None:
+    net.free()
