@@ -188,6 +188,9 @@ YQ_API int yq_network_synchronize(yq_network *net);
 YQ_API void *yq_network_stream(yq_network *net);
 /* capture the forward into a CUDA graph and replay it on later calls (0 disables) */
 YQ_API int yq_network_use_graph(yq_network *net, int enable);
+/* one un-graphed forward with a CUDA event after every layer on the network's stream; layer_ms has
+ * num_layers+1 entries: [0] = input layout transform, [1+i] = layer i (0 for aliased routes). Synchronous. */
+YQ_API int yq_network_profile_forward(yq_network *net, const uint8_t *in_u8_nchw, float *layer_ms);
 /* number of kernel launches one forward issues (for bench.py's gpu_launches) */
 YQ_API int yq_network_launches_per_forward(const yq_network *net);
 

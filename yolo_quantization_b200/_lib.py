@@ -86,6 +86,7 @@ SIGNATURES = {
     "yq_network_stream": (_vp, [_vp]),
     "yq_network_use_graph": (_i, [_vp, _i]),
     "yq_network_launches_per_forward": (_i, [_vp]),
+    "yq_network_profile_forward": (_i, [_vp, _vp, _vp]),
     "yq_network_pull_layer": (_i, [_vp, _i, _i, _vp, _sz]),
     "yq_network_layer_output_f32_device": (_vp, [_vp, _i]),
     "yq_network_conv_params": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _vp]),

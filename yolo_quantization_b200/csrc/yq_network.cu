@@ -129,8 +129,8 @@ struct yq_network {
     int keep_acc = 0;
     int conv_kernel = -1;
     int use_graph = 0;
-    cudaGraphExec_t graph_exec = nullptr;
-    const uint8_t *graph_input = nullptr;
+    std::vector<std::pair<const uint8_t *, cudaGraphExec_t>> graphs;   // one captured forward per input pointer
+    std::vector<cudaEvent_t> prof_events;                               // per-layer profiling (yq_network_profile_forward)
     int launches = 0;
     float *out_host_pinned = nullptr;
     size_t out_floats = 0;
@@ -219,19 +219,18 @@ bool read_vec(FILE *fp, std::vector<T> &v, size_t n)
 
 void drop_graph(yq_network *net)
 {
-    if (net->graph_exec) {
-        cudaGraphExecDestroy(net->graph_exec);
-        net->graph_exec = nullptr;
-    }
-    net->graph_input = nullptr;
+    for (auto &g : net->graphs) cudaGraphExecDestroy(g.second);
+    net->graphs.clear();
 }
 
 // the kernel sequence of one forward_network pass (network.c:229-261)
-int forward_body(yq_network *net, const uint8_t *in_u8_nchw, int *launches)
+int forward_body(yq_network *net, const uint8_t *in_u8_nchw, int *launches, bool profile = false)
 {
     cudaStream_t st = net->stream;
     int nl = 0;
+    if (profile) cudaEventRecord(net->prof_events[0], st);
     if (yq_nchw_to_nhwc_u8(in_u8_nchw, net->in_nhwc, net->batch, net->c, net->h, net->w, st)) return -1;
+    if (profile) cudaEventRecord(net->prof_events[1], st);
     ++nl;
     const uint8_t *cur = net->in_nhwc;
     const float *cur_f32 = nullptr;
@@ -275,6 +274,7 @@ int forward_body(yq_network *net, const uint8_t *in_u8_nchw, int *launches)
             ++nl;
             break;
         }
+        if (profile) cudaEventRecord(net->prof_events[i + 2], st);
     }
     if (launches) *launches = nl;
     return 0;
@@ -556,6 +556,7 @@ extern "C" void yq_free_network(yq_network *net)
     if (!net) return;
     cudaSetDevice(net->device);
     drop_graph(net);
+    for (auto e : net->prof_events) cudaEventDestroy(e);
     for (auto &l : net->layers) {
         if (l.conv) yq_free_convolutional_layer_quant(l.conv);
         if (l.owns_u8) cudaFree(l.out_u8);
@@ -644,8 +645,11 @@ extern "C" int yq_forward_network_device(yq_network *net, const uint8_t *in_u8_n
     if (!net || !in_u8_nchw) return yq::fail("yq_forward_network_device: null argument");
     YQ_CUDA(cudaSetDevice(net->device));
     if (!net->use_graph) return forward_body(net, in_u8_nchw, nullptr);
-    if (!net->graph_exec || net->graph_input != in_u8_nchw) {
-        drop_graph(net);
+    cudaGraphExec_t exec = nullptr;
+    for (auto &g : net->graphs)
+        if (g.first == in_u8_nchw) exec = g.second;
+    if (!exec) {
+        if (net->graphs.size() >= 16) drop_graph(net);
         cudaGraph_t g = nullptr;
         YQ_CUDA(cudaStreamBeginCapture(net->stream, cudaStreamCaptureModeThreadLocal));
         int rc = forward_body(net, in_u8_nchw, nullptr);
@@ -655,12 +659,28 @@ extern "C" int yq_forward_network_device(yq_network *net, const uint8_t *in_u8_n
             return rc;
         }
         if (e != cudaSuccess) return yq::fail("cudaStreamEndCapture: %s", cudaGetErrorString(e));
-        e = cudaGraphInstantiate(&net->graph_exec, g, 0);
+        e = cudaGraphInstantiate(&exec, g, 0);
         cudaGraphDestroy(g);
         if (e != cudaSuccess) return yq::fail("cudaGraphInstantiate: %s", cudaGetErrorString(e));
-        net->graph_input = in_u8_nchw;
+        net->graphs.emplace_back(in_u8_nchw, exec);
     }
-    YQ_CUDA(cudaGraphLaunch(net->graph_exec, net->stream));
+    YQ_CUDA(cudaGraphLaunch(exec, net->stream));
+    return 0;
+}
+
+extern "C" int yq_network_profile_forward(yq_network *net, const uint8_t *in_u8_nchw, float *layer_ms)
+{
+    if (!net || !in_u8_nchw || !layer_ms) return yq::fail("yq_network_profile_forward: null argument");
+    YQ_CUDA(cudaSetDevice(net->device));
+    const size_t ne = net->layers.size() + 2;
+    while (net->prof_events.size() < ne) {
+        cudaEvent_t e;
+        YQ_CUDA(cudaEventCreate(&e));
+        net->prof_events.push_back(e);
+    }
+    if (forward_body(net, in_u8_nchw, nullptr, true)) return -1;
+    YQ_CUDA(cudaStreamSynchronize(net->stream));
+    for (size_t i = 0; i + 1 < ne; ++i) YQ_CUDA(cudaEventElapsedTime(&layer_ms[i], net->prof_events[i], net->prof_events[i + 1]));
     return 0;
 }
 

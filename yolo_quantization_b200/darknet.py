@@ -273,6 +273,12 @@ class Network:
         """forward_network on a device-resident uint8 NCHW batch (asynchronous on self.stream)."""
         check(_lib.load().yq_forward_network_device(self._h, dev_ptr), "yq_forward_network_device")
 
+    def profile_forward(self, dev_ptr: int) -> np.ndarray:
+        """Per-layer milliseconds of one forward (CUDA events on the network's stream); [0] = input transform."""
+        ms = np.zeros(self.n + 1, np.float32)
+        check(_lib.load().yq_network_profile_forward(self._h, dev_ptr, ms.ctypes.data), "yq_network_profile_forward")
+        return ms
+
     def synchronize(self) -> None:
         check(_lib.load().yq_network_synchronize(self._h))
 
