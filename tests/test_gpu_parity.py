@@ -82,6 +82,29 @@ def test_conv_simt_vs_oracle(built, case):
     run_conv_case(case, kernel=0)
 
 
+TC_CASES = [
+    # c, h, w, n, k, stride, act, zp_in, zp_out, batch      (tcgen05 flavour: stride 1, k in {1,3}, c % 64 == 0)
+    (64, 52, 52, 128, 3, 1, "relu6", 0, 0, 2),     # layer 6 shape: KC = 64 (SWIZZLE_64B), BN = 128
+    (128, 26, 26, 256, 3, 1, "relu6", 0, 0, 3),    # layer 8: KC = 128, two N tiles
+    (256, 13, 13, 512, 3, 1, "relu6", 0, 0, 9),    # layer 10/14: 13-wide rows, 9 images stacked per tile
+    (512, 13, 13, 64, 3, 1, "relu6", 0, 0, 2),     # K = 4608 (layer 12's K), BN = 64
+    (1024, 13, 13, 256, 1, 1, "relu6", 0, 0, 2),   # layer 13: 1x1, K = 1024
+    (512, 13, 13, 30, 1, 1, "linear", 0, 128, 2),  # layer 15 head: n = 30 -> BN 32, float side output
+    (256, 26, 26, 30, 1, 1, "linear", 0, 128, 1),  # layer 22 head
+    (384, 26, 26, 256, 3, 1, "relu6", 0, 0, 1),    # layer 21: c = 384 = 3 chunks of 128
+    (256, 13, 13, 128, 1, 1, "relu6", 0, 0, 10),   # layer 18, batch not a multiple of the 9-image tile
+    (128, 9, 7, 80, 3, 1, "leaky", 40, 33, 3),     # zp_in != 0: border correction; n = 80 -> partial N tile
+    (64, 5, 130, 48, 3, 1, "leaky", 17, 5, 1),     # wide rows (TW = 128 + remainder), n = 48
+    (64, 1, 1, 32, 3, 1, "relu", 9, 3, 5),         # 1x1 image: 8 of 9 taps are padding
+    (192, 6, 6, 17, 1, 1, "linear", 0, 7, 2),      # c = 192 -> KC = 64, n = 17
+]
+
+
+@pytest.mark.parametrize("case", TC_CASES, ids=lambda c: "c%d_%dx%d_n%d_k%d_s%d_%s_zi%d" % c[:8])
+def test_conv_tcgen05_vs_oracle(built, case):
+    run_conv_case(case, kernel=1)
+
+
 def test_conv_wrap_semantics(built):
     """tiny s_out forces q + zp_out far outside [0,255]: the store must WRAP like the reference (A.3)."""
     case = (16, 8, 8, 32, 3, 1, "linear", 0, 100, 1)

@@ -1,10 +1,557 @@
-// yq_conv_tc.cu -- tcgen05 (kind::i8) implicit-GEMM convolution flavour.  (placeholder: not yet enabled)
-#include "yq_common.h"
+// yq_conv_tc.cu -- tcgen05 (kind::i8, u8 x u8 -> s32 in TMEM) implicit-GEMM convolution for sm_100a.
+//
+// GEMM view:  D[M = 128 output pixels][N = BN output channels] += A[M][K] * B[N][K]^T,  K = (ky, kx, ci)
+//
+//   A  activations, uint8 NHWC.  One pipeline stage = one filter tap (ky,kx) x one KC-byte channel chunk of a
+//      TW x TH x TN patch of output pixels (TW*TH*TN <= 128 rows): a single 4-D *tiled* TMA load whose start
+//      coordinate is shifted by (kx-pad, ky-pad).  Out-of-image taps are ZERO-filled by the TMA unit; the
+//      reference pads with zp_in (im2col.c:5-14), which the epilogue restores exactly with a per-tap
+//      correction  zp_in * sum_ci (w - zp_w)  on border pixels.
+//   B  weights packed once at load as [oc][ky][kx][ci] (K-major), 2-D TMA load of a BN x KC tile.
+//   D  int32 accumulator in TMEM, columns [0,BN).  Columns [BN,BN+16) accumulate A x ONES (one extra N=16 MMA
+//      per K step against a constant all-ones tile) = sum of activations per pixel, which the epilogue needs
+//      because weights are uint8 with a per-channel uint8 zero point (9-bit w - zp_w does not fit s8):
+//          acc = sum w*a - zp_w[oc] * sum a                      (convolutional_layer.c:718-721 restated)
+//   epilogue (4 warps, one TMEM lane = one pixel per thread): tcgen05.ld -> zero-point correction ->
+//      FP64 requantize -> activation -> +zp_out -> uint8 wrap -> swizzled smem tile -> TMA store (clips
+//      partial tiles).  Optional int32 / float (quant_stop) side outputs go straight to global memory.
+//
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer, warps 2-5 = epilogue.
+// One output tile per CTA, up to two CTAs per SM so one CTA's epilogue overlaps the other's main loop.
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <string.h>
 
-int yq_tc_supported(const yq_conv_layer *) { return 0; }
-int yq_tc_prepare(yq_conv_layer *) { return -1; }
-void yq_tc_free(yq_conv_layer *) {}
-int yq_tc_forward(yq_conv_layer *, const uint8_t *, uint8_t *, float *, int32_t *, int, cudaStream_t)
+#include <map>
+#include <vector>
+
+#include "yq_common.h"
+#include "yq_epilogue.cuh"
+
+namespace {
+
+constexpr int TC_THREADS = 192;
+constexpr int TC_STAGES = 3;
+constexpr int ONES_ROWS = 16;
+
+struct TcArgs {
+    yq::EpiParams ep;
+    float *out_f32;
+    int32_t *out_acc;
+    const int32_t *corr;      // [size*size][n_pad] border correction, or nullptr when zp_in == 0
+    int B, OH, OW, N, CSO, n_pad;
+    int TW, TH, TN, tiles_x, tiles_y;
+    int size, pad, cpt /* KC-chunks per tap */, CS;
+    int H, W;
+};
+
+// ---------------------------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
 {
-    return yq::fail("tcgen05 flavour not built");
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity)
+{
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+// Bounded wait: a protocol bug must trap, never hang the GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    if (mbar_try_wait(bar, parity)) return;
+    const long long t0 = clock64();
+    while (!mbar_try_wait(bar, parity)) {
+        if (clock64() - t0 > 4000000000LL) __trap();
+    }
+}
+__device__ __forceinline__ void tma_load_4d(void *smem, const CUtensorMap *map, uint64_t *bar, int c0, int c1, int c2, int c3)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(smem_u32(smem)),
+        "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void *smem, const CUtensorMap *map, uint64_t *bar, int c0, int c1)
+{
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(smem_u32(smem)),
+                 "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap *map, const void *smem, int c0, int c1, int c2, int c3)
+{
+    asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(map), "r"(smem_u32(smem)),
+                 "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_store_commit_wait()
+{
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+template <int COLS>
+__device__ __forceinline__ void tmem_alloc(uint32_t *slot)
+{
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "n"(COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+template <int COLS>
+__device__ __forceinline__ void tmem_dealloc(uint32_t addr)
+{
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "n"(COLS) : "memory");
+}
+__device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t}" ::"r"(tmem_d),
+        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate), "r"(0u)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t *bar)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32])
+{
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n\t"
+        "tcgen05.wait::ld.sync.aligned;"   // same asm block: the registers are only defined after the wait
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+          "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
+          "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
+          "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr));
+}
+__device__ __forceinline__ uint32_t tmem_ld1(uint32_t taddr)
+{
+    uint32_t v;
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];\n\ttcgen05.wait::ld.sync.aligned;" : "=r"(v) : "r"(taddr));
+    return v;
+}
+
+// K-major shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start>>4 [0,14), LBO>>4 [16,30),
+// SBO>>4 [32,46), version=1 [46,48), layout type [61,64): 2 = SWIZZLE_128B, 4 = SWIZZLE_64B.
+template <int KC>
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr)
+{
+    constexpr uint64_t layout = KC == 128 ? 2 : 4;
+    constexpr uint64_t sbo = (8 * KC) >> 4;   // 8 rows of KC bytes
+    return (uint64_t)((saddr & 0x3FFFF) >> 4) | (1ull << 16) | (sbo << 32) | (1ull << 46) | (layout << 61);
+}
+// kind::i8 instruction descriptor: c_format S32 (2) [4,6), a/b format 0 = UINT8 [7,10)/[10,13), K-major,
+// N>>3 [17,23), M>>4 [24,29)
+__host__ __device__ constexpr uint32_t make_idesc(int n) { return (2u << 4) | ((uint32_t)(n >> 3) << 17) | ((128u >> 4) << 24); }
+
+template <int BN>
+__host__ __device__ constexpr int tmem_cols()
+{
+    return BN + ONES_ROWS <= 32 ? 32 : BN + ONES_ROWS <= 64 ? 64 : BN + ONES_ROWS <= 128 ? 128 : BN + ONES_ROWS <= 256 ? 256 : 512;
+}
+
+template <int BN, int KC>
+struct SmemLayout {
+    static constexpr int A_BYTES = 128 * KC;
+    static constexpr int B_BYTES = BN * KC;
+    static constexpr int STAGE = A_BYTES + B_BYTES;          // multiple of 1024
+    static constexpr int ONES_OFF = TC_STAGES * STAGE;
+    static constexpr int ONES_BYTES = 1024 * ((ONES_ROWS * KC + 1023) / 1024);
+    static constexpr int PARAM_OFF = ONES_OFF + ONES_BYTES;  // bias[BN] zw[BN] m0[BN] m1[BN]
+    static constexpr int PARAM_BYTES = BN * (4 + 4 + 8 + 8);
+    static constexpr int BAR_OFF = PARAM_OFF + PARAM_BYTES;
+    static constexpr int TOTAL = BAR_OFF + 128;
+    static_assert(128 * BN <= STAGE, "output staging aliases stage 0");
+};
+
+template <int BN, int KC>
+__global__ void __launch_bounds__(TC_THREADS) conv_u8_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                                                               const __grid_constant__ CUtensorMap tmO, const TcArgs a)
+{
+    using L = SmemLayout<BN, KC>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint64_t *full = (uint64_t *)(smem + L::BAR_OFF);
+    uint64_t *empty = full + TC_STAGES;
+    uint64_t *accum_full = empty + TC_STAGES;
+    uint32_t *tmem_slot = (uint32_t *)(accum_full + 1);
+    int32_t *s_bias = (int32_t *)(smem + L::PARAM_OFF);
+    int32_t *s_zw = s_bias + BN;
+    double *s_m0 = (double *)(s_zw + BN);
+    double *s_m1 = s_m0 + BN;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int oc0 = blockIdx.y * BN;
+    const int tx = blockIdx.x % a.tiles_x;
+    const int ty = (blockIdx.x / a.tiles_x) % a.tiles_y;
+    const int tb = blockIdx.x / (a.tiles_x * a.tiles_y);
+    const int x0 = tx * a.TW, y0 = ty * a.TH, n0 = tb * a.TN;
+    const int rows = a.TW * a.TH * a.TN;
+    const int kiters = a.size * a.size * a.cpt;
+
+    // ---- one-time setup
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < TC_STAGES; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], 1);
+        }
+        mbar_init(accum_full, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) tmem_alloc<tmem_cols<BN>()>(tmem_slot);
+    if (warp >= 2) {
+        const int t = threadIdx.x - 64;
+        for (int i = t; i < BN; i += 128) {
+            const yq::ChanParams cp = yq::load_chan(a.ep, oc0 + i);
+            s_bias[i] = cp.bias;
+            s_zw[i] = cp.zw;
+            s_m0[i] = cp.m0;
+            s_m1[i] = cp.m1;
+        }
+        uint32_t *ones = (uint32_t *)(smem + L::ONES_OFF);
+        for (int i = t; i < ONES_ROWS * KC / 4; i += 128) ones[i] = 0x01010101u;
+        fence_proxy_async();   // generic-proxy writes of the ones tile must be visible to the tensor core (async proxy)
+    }
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmO) : "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            const uint32_t bytes = (uint32_t)(rows * KC + BN * KC);
+            for (int it = 0; it < kiters; ++it) {
+                const int s = it % TC_STAGES;
+                const uint32_t ph = (it / TC_STAGES) & 1;
+                mbar_wait(&empty[s], ph ^ 1);
+                mbar_expect_tx(&full[s], bytes);
+                const int tap = it / a.cpt, chunk = it - tap * a.cpt;
+                const int ky = tap / a.size, kx = tap - ky * a.size;
+                uint8_t *sa = smem + s * L::STAGE;
+                tma_load_4d(sa, &tmA, &full[s], chunk * KC, x0 + kx - a.pad, y0 + ky - a.pad, n0);
+                tma_load_2d(sa + L::A_BYTES, &tmB, &full[s], tap * a.CS + chunk * KC, oc0);
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            constexpr uint32_t idesc_main = make_idesc(BN);
+            constexpr uint32_t idesc_ones = make_idesc(ONES_ROWS);
+            const uint64_t desc_ones = make_desc<KC>(smem_u32(smem + L::ONES_OFF));
+            for (int it = 0; it < kiters; ++it) {
+                const int s = it % TC_STAGES;
+                const uint32_t ph = (it / TC_STAGES) & 1;
+                mbar_wait(&full[s], ph);
+                tc_fence_after();
+                const uint32_t sa = smem_u32(smem + s * L::STAGE);
+                const uint64_t da = make_desc<KC>(sa), db = make_desc<KC>(sa + L::A_BYTES);
+#pragma unroll
+                for (int k = 0; k < KC / 32; ++k) {
+                    const uint32_t accum = (it | k) ? 1u : 0u;
+                    umma_i8(tmem_base, da + 2 * k, db + 2 * k, idesc_main, accum);       // +32 bytes = +2 in 16-byte units
+                    umma_i8(tmem_base + BN, da + 2 * k, desc_ones, idesc_ones, accum);   // sum of activations
+                }
+                umma_commit(&empty[s]);
+            }
+            umma_commit(accum_full);
+        }
+    } else {
+        // ===================== epilogue =====================
+        const int q = warp & 3;                 // TMEM lane quarter this warp may access
+        const int r = q * 32 + lane;            // tile row = TMEM lane = output pixel of the patch
+        const int wi = r % a.TW, hi = (r / a.TW) % a.TH, ni = r / (a.TW * a.TH);
+        const int ox = x0 + wi, oy = y0 + hi, n = n0 + ni;
+        const bool valid = r < rows && ox < a.OW && oy < a.OH && n < a.B;
+        // taps that fall outside the image for this pixel (zero-filled by TMA, zp_in in the reference)
+        uint32_t oob = 0;
+        if (a.corr && valid) {
+            for (int ky = 0; ky < a.size; ++ky)
+                for (int kx = 0; kx < a.size; ++kx) {
+                    const int iy = oy + ky - a.pad, ix = ox + kx - a.pad;
+                    if (iy < 0 || iy >= a.H || ix < 0 || ix >= a.W) oob |= 1u << (ky * a.size + kx);
+                }
+        }
+        mbar_wait(accum_full, 0);
+        tc_fence_after();
+        const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
+        const int sum_a = (int)tmem_ld1(trow + BN);
+        uint8_t *stage_out = smem;              // aliases pipeline stage 0 (all MMAs have completed)
+        const size_t pix = ((size_t)n * a.OH + oy) * a.OW + ox;
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+            uint32_t v[32];
+            tmem_ld32(trow + c0, v);
+            uint32_t packed[8];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                const int oc = c0 + j;
+                yq::ChanParams cp;
+                cp.bias = s_bias[oc]; cp.zw = s_zw[oc]; cp.m0 = s_m0[oc]; cp.m1 = s_m1[oc];
+                int acc = (int)v[j] - cp.zw * sum_a;
+                if (oob) {
+                    for (uint32_t m = oob; m; m &= m - 1) acc += __ldg(a.corr + (size_t)(__ffs(m) - 1) * a.n_pad + oc0 + oc);
+                }
+                const bool real = oc0 + oc < a.N;
+                const uint8_t u = real ? yq::requant_u8(a.ep, cp, acc) : (uint8_t)0;
+                if (j % 4 == 0) packed[j / 4] = 0;
+                packed[j / 4] |= (uint32_t)u << (8 * (j % 4));
+                if (valid && real) {
+                    if (a.out_acc) a.out_acc[pix * a.CSO + oc0 + oc] = acc;
+                    if (a.out_f32) a.out_f32[((size_t)n * a.N + oc0 + oc) * a.OH * a.OW + (size_t)oy * a.OW + ox] = yq::dequant_f32(a.ep, u);
+                }
+            }
+            // swizzled staging (matches the TMA-store tensor map): 16-byte chunk index XOR row bits
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int chunk = c0 / 16 + h;
+                int sw;
+                if (BN >= 128) sw = chunk ^ (r & 7);
+                else if (BN == 64) sw = chunk ^ ((r >> 1) & 3);
+                else sw = chunk ^ ((r >> 2) & 1);
+                *reinterpret_cast<uint4 *>(stage_out + (size_t)r * BN + sw * 16) =
+                    make_uint4(packed[4 * h], packed[4 * h + 1], packed[4 * h + 2], packed[4 * h + 3]);
+            }
+        }
+        tc_fence_before();
+        fence_proxy_async();
+        asm volatile("bar.sync 1, 128;" ::: "memory");   // the four epilogue warps only
+        if (threadIdx.x == 64) {
+            tma_store_4d(&tmO, stage_out, oc0, x0, y0, n0);
+            tma_store_commit_wait();
+        }
+    }
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc<tmem_cols<BN>()>(tmem_base);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode()
+{
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)p;
+    }
+    return fn;
+}
+
+CUtensorMapSwizzle swizzle_for(int inner_bytes)
+{
+    return inner_bytes >= 128 ? CU_TENSOR_MAP_SWIZZLE_128B : inner_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B;
+}
+
+struct TcState {
+    int BN, KC, TW, TH, TN, n_pad;
+    uint8_t *w = nullptr;       // [n_pad][size*size*cs_in]
+    int32_t *corr = nullptr;    // [size*size][n_pad]
+    CUtensorMap tmB;
+    // tensor maps for the activations depend on the pointers handed to forward(); cache the last few
+    struct Key {
+        const void *in;
+        void *out;
+        int batch;
+        bool operator<(const Key &o) const { return in != o.in ? in < o.in : out != o.out ? out < o.out : batch < o.batch; }
+    };
+    std::map<Key, std::pair<CUtensorMap, CUtensorMap>> maps;
+};
+
+int encode_nhwc(CUtensorMap *m, const void *ptr, int B, int H, int W, int CS, int box_c, int TW, int TH, int TN)
+{
+    EncodeTiledFn enc = get_encode();
+    if (!enc) return yq::fail("cuTensorMapEncodeTiled is not available from this driver");
+    cuuint64_t dims[4] = {(cuuint64_t)CS, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+    cuuint64_t strides[3] = {(cuuint64_t)CS, (cuuint64_t)W * CS, (cuuint64_t)H * W * CS};
+    cuuint32_t box[4] = {(cuuint32_t)box_c, (cuuint32_t)TW, (cuuint32_t)TH, (cuuint32_t)TN};
+    cuuint32_t es[4] = {1, 1, 1, 1};
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 4, const_cast<void *>(ptr), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     swizzle_for(box_c), CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return yq::fail("cuTensorMapEncodeTiled(NHWC %dx%dx%dx%d box %d,%d,%d,%d) failed: %d", B, H, W, CS, box_c, TW, TH, TN, (int)r);
+    return 0;
+}
+
+// choose the output-pixel patch TW x TH x TN (<= 128 rows) that wastes the fewest MMA rows
+void choose_tile(int B, int OH, int OW, int *tw, int *th, int *tn)
+{
+    double best = -1;
+    for (int w = 1; w <= OW && w <= 128; ++w) {
+        const int txs = (OW + w - 1) / w;
+        for (int h = 1; h <= OH && w * h <= 128; ++h) {
+            const int tys = (OH + h - 1) / h;
+            int n = 128 / (w * h);
+            if (n > B) n = B;
+            if (n < 1) n = 1;
+            const int tbs = (B + n - 1) / n;
+            const double eff = (double)B * OH * OW / ((double)txs * tys * tbs * 128.0);
+            // prefer fewer, wider boxes on ties (longer contiguous TMA rows)
+            const double score = eff + 1e-6 * w;
+            if (score > best) {
+                best = score;
+                *tw = w; *th = h; *tn = n;
+            }
+        }
+    }
+}
+
+template <int BN, int KC>
+int launch(yq_conv_layer *l, TcState *st, const CUtensorMap &tmA, const CUtensorMap &tmO, const TcArgs &a, dim3 grid, cudaStream_t stream)
+{
+    using L = SmemLayout<BN, KC>;
+    static bool attr_done = false;
+    const int smem = L::TOTAL + 1024;
+    if (!attr_done) {
+        YQ_CUDA(cudaFuncSetAttribute(conv_u8_tc_kernel<BN, KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        attr_done = true;
+    }
+    conv_u8_tc_kernel<BN, KC><<<grid, TC_THREADS, smem, stream>>>(tmA, st->tmB, tmO, a);
+    YQ_CHECK_LAUNCH();
+    return 0;
+}
+
+}  // namespace
+
+int yq_tc_supported(const yq_conv_layer *l)
+{
+    if (l->stride != 1) return 0;
+    if (!(l->size == 1 || l->size == 3) || l->pad != l->size / 2) return 0;
+    if (l->cs_in % 64) return 0;
+    if (l->cs_out < 32) return 0;
+    return get_encode() != nullptr;
+}
+
+int yq_tc_prepare(yq_conv_layer *l)
+{
+    TcState *st = new TcState();
+    st->BN = l->cs_out >= 128 ? 128 : (l->cs_out >= 64 ? 64 : 32);   // TMA-store box inner extent == BN <= cs_out
+    st->KC = (l->cs_in % 128) ? 64 : 128;
+    st->n_pad = yq::round_up(l->n, st->BN);
+    const int taps = l->size * l->size;
+    const size_t ktot = (size_t)taps * l->cs_in;
+    std::vector<uint8_t> wp((size_t)st->n_pad * ktot, 0);
+    std::vector<int32_t> corr((size_t)taps * st->n_pad, 0);
+    for (int oc = 0; oc < l->n; ++oc)
+        for (int t = 0; t < taps; ++t) {
+            int tsum = 0;
+            for (int ci = 0; ci < l->c; ++ci) {
+                const uint8_t w = l->host_w[((size_t)oc * l->c + ci) * taps + t];
+                wp[(size_t)oc * ktot + (size_t)t * l->cs_in + ci] = w;
+                tsum += w;
+            }
+            corr[(size_t)t * st->n_pad + oc] = l->zp_in * (tsum - (int)l->host_zw[oc] * l->c);
+        }
+    auto cleanup = [&]() {
+        cudaFree(st->w);
+        cudaFree(st->corr);
+        delete st;
+        return -1;
+    };
+    if (cudaMalloc((void **)&st->w, wp.size()) != cudaSuccess) return cleanup();
+    if (cudaMemcpy(st->w, wp.data(), wp.size(), cudaMemcpyHostToDevice) != cudaSuccess) return cleanup();
+    if (l->zp_in != 0 && l->size > 1) {
+        if (cudaMalloc((void **)&st->corr, corr.size() * 4) != cudaSuccess) return cleanup();
+        if (cudaMemcpy(st->corr, corr.data(), corr.size() * 4, cudaMemcpyHostToDevice) != cudaSuccess) return cleanup();
+    }
+    // weights: 2-D [n_pad][ktot], box KC x BN
+    EncodeTiledFn enc = get_encode();
+    cuuint64_t dims[2] = {(cuuint64_t)ktot, (cuuint64_t)st->n_pad};
+    cuuint64_t strides[1] = {(cuuint64_t)ktot};
+    cuuint32_t box[2] = {(cuuint32_t)st->KC, (cuuint32_t)st->BN};
+    cuuint32_t es[2] = {1, 1};
+    CUresult r = enc(&st->tmB, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, st->w, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     swizzle_for(st->KC), CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        yq::fail("cuTensorMapEncodeTiled(weights) failed: %d", (int)r);
+        return cleanup();
+    }
+    l->tc = st;
+    return 0;
+}
+
+void yq_tc_free(yq_conv_layer *l)
+{
+    TcState *st = (TcState *)l->tc;
+    if (!st) return;
+    cudaFree(st->w);
+    cudaFree(st->corr);
+    delete st;
+    l->tc = nullptr;
+}
+
+int yq_tc_forward(yq_conv_layer *l, const uint8_t *in_u8, uint8_t *out_u8, float *out_f32, int32_t *out_acc, int batch, cudaStream_t stream)
+{
+    TcState *st = (TcState *)l->tc;
+    if (!st) return yq::fail("tcgen05 flavour was not prepared for this layer");
+    int TW = 0, TH = 0, TN = 0;
+    choose_tile(batch, l->out_h, l->out_w, &TW, &TH, &TN);
+    TcState::Key key{in_u8, out_u8, batch};
+    auto it = st->maps.find(key);
+    if (it == st->maps.end()) {
+        if (st->maps.size() > 64) st->maps.clear();
+        CUtensorMap tmA, tmO;
+        if (encode_nhwc(&tmA, in_u8, batch, l->h, l->w, l->cs_in, st->KC, TW, TH, TN)) return -1;
+        if (encode_nhwc(&tmO, out_u8, batch, l->out_h, l->out_w, l->cs_out, st->BN, TW, TH, TN)) return -1;
+        it = st->maps.emplace(key, std::make_pair(tmA, tmO)).first;
+    }
+    TcArgs a;
+    memset(&a, 0, sizeof a);
+    a.ep = yq::make_epi(l);
+    a.out_f32 = l->quant_stop_flag ? out_f32 : nullptr;
+    a.out_acc = out_acc;
+    a.corr = st->corr;
+    a.B = batch; a.OH = l->out_h; a.OW = l->out_w; a.N = l->n; a.CSO = l->cs_out; a.n_pad = st->n_pad;
+    a.TW = TW; a.TH = TH; a.TN = TN;
+    a.tiles_x = (l->out_w + TW - 1) / TW;
+    a.tiles_y = (l->out_h + TH - 1) / TH;
+    const int tiles_b = (batch + TN - 1) / TN;
+    a.size = l->size; a.pad = l->pad; a.cpt = l->cs_in / st->KC; a.CS = l->cs_in;
+    a.H = l->h; a.W = l->w;
+    dim3 grid(a.tiles_x * a.tiles_y * tiles_b, st->n_pad / st->BN);
+    const CUtensorMap &tmA = it->second.first, &tmO = it->second.second;
+#define YQ_TC(BN_, KC_) return launch<BN_, KC_>(l, st, tmA, tmO, a, grid, stream)
+    if (st->KC == 128) {
+        if (st->BN == 128) YQ_TC(128, 128);
+        if (st->BN == 64) YQ_TC(64, 128);
+        YQ_TC(32, 128);
+    } else {
+        if (st->BN == 128) YQ_TC(128, 64);
+        if (st->BN == 64) YQ_TC(64, 64);
+        YQ_TC(32, 64);
+    }
+#undef YQ_TC
 }

@@ -380,8 +380,10 @@ extern "C" yq_conv_layer *yq_make_convolutional_layer_quant(const yq_conv_desc *
                 for (int kx = 0; kx < l->size; ++kx)
                     wp[(size_t)oc * l->k_pad + (size_t)(ky * l->size + kx) * l->cs_in + ci] =
                         d->weights_uint8[((size_t)oc * l->c + ci) * l->size * l->size + ky * l->size + kx];
-    std::vector<int32_t> bias(l->n_pad, 0), zw(l->n_pad, 0);
-    std::vector<double> mcomb(l->n_pad, 0.0), mval(l->n_pad, 0.0), rsh(l->n_pad, 0.0);
+    // per-channel parameter arrays are padded to a multiple of 128 so either flavour can read whole tiles
+    const int p_pad = yq::round_up(l->n_pad, 128);
+    std::vector<int32_t> bias(p_pad, 0), zw(p_pad, 0);
+    std::vector<double> mcomb(p_pad, 0.0), mval(p_pad, 0.0), rsh(p_pad, 0.0);
     l->fused_mult = 1;
     for (int oc = 0; oc < l->n; ++oc) {
         bias[oc] = d->biases_int32[oc];
