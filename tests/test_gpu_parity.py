@@ -105,6 +105,25 @@ def test_conv_tcgen05_vs_oracle(built, case):
     run_conv_case(case, kernel=1)
 
 
+TC_SMALL_CASES = [
+    # small-c tcgen05 flavour (threads build the im2col rows): c <= 32, 3x3, n in {16, 32, 64}
+    (3, 40, 40, 16, 3, 1, "relu6", 0, 0, 2),       # layer 0 shape class
+    (3, 33, 17, 16, 3, 1, "leaky", 77, 40, 3),     # zp_in != 0 written straight into the padded taps
+    (16, 24, 24, 32, 3, 1, "relu6", 0, 0, 2),      # layer 2
+    (32, 20, 20, 64, 3, 1, "relu6", 0, 0, 2),      # layer 4
+    (32, 13, 11, 64, 3, 2, "leaky", 40, 40, 3),    # stride 2
+    (16, 7, 9, 16, 3, 1, "linear", 5, 100, 1),     # float side output (quant_stop)
+    (12, 9, 9, 20, 3, 1, "relu", 9, 3, 2),         # c = 12 -> stride 16 (pad lanes), n = 20 -> stride 32
+    (3, 416, 416, 16, 3, 1, "relu6", 0, 0, 1),     # the real layer 0
+    (4, 1, 1, 64, 3, 1, "relu6", 200, 0, 130),     # 1x1 images, more than one tile of them
+]
+
+
+@pytest.mark.parametrize("case", TC_SMALL_CASES, ids=lambda c: "c%d_%dx%d_n%d_k%d_s%d_%s_zi%d" % c[:8])
+def test_conv_tcgen05_small_c_vs_oracle(built, case):
+    run_conv_case(case, kernel=1)
+
+
 def test_conv_wrap_semantics(built):
     """tiny s_out forces q + zp_out far outside [0,255]: the store must WRAP like the reference (A.3)."""
     case = (16, 8, 8, 32, 3, 1, "linear", 0, 100, 1)

@@ -49,13 +49,23 @@ struct yq_conv_layer {
     double *mcomb = nullptr;  // M_value * rshift
     double *mval = nullptr;
     double *rsh = nullptr;
+    void *chanq = nullptr;    // int4 {bias, zw, 2*M0, shift} per channel: integer-form epilogue (tcgen05 flavours)
+    int int_form = 0;         // 1 when every (M_value, rshift) pair is M0*2^-31, 2^-s with integer M0 < 2^31, 0 <= s <= 31
     // tcgen05 packing lives behind this pointer (yq_conv_tc.cu)
     void *tc = nullptr;
+    void *tc_small = nullptr;   // small-c tcgen05 flavour state (yq_conv_tc_small.cu)
     std::vector<uint8_t> host_w;  // OIHW copy kept for repacking
     std::vector<uint8_t> host_zw;
 };
 
-// implemented in yq_conv_tc.cu
+// implemented in yq_conv_tc_small.cu (threads build the im2col rows; c <= 32)
+int yq_tc_small_supported(const yq_conv_layer *l);
+int yq_tc_small_prepare(yq_conv_layer *l, void **state);
+void yq_tc_small_free(void *state);
+int yq_tc_small_forward(yq_conv_layer *l, void *state, const uint8_t *in_u8, uint8_t *out_u8, float *out_f32, int32_t *out_acc,
+                        int batch, cudaStream_t stream);
+
+// implemented in yq_conv_tc.cu (TMA-fed; c % 64 == 0)
 int yq_tc_supported(const yq_conv_layer *l);
 int yq_tc_prepare(yq_conv_layer *l);
 void yq_tc_free(yq_conv_layer *l);

@@ -27,6 +27,9 @@
 
 #include "yq_common.h"
 #include "yq_epilogue.cuh"
+#include "yq_tc_ptx.cuh"
+
+using namespace yqtc;
 
 namespace {
 
@@ -44,125 +47,6 @@ struct TcArgs {
     int size, pad, cpt /* KC-chunks per tap */, CS;
     int H, W;
 };
-
-// ---------------------------------------------------------------------------------------------
-// PTX wrappers
-// ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
-{
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
-{
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity)
-{
-    uint32_t ok;
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok)
-        : "r"(smem_u32(bar)), "r"(parity)
-        : "memory");
-    return ok != 0;
-}
-// Bounded wait: a protocol bug must trap, never hang the GPU.
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
-{
-    if (mbar_try_wait(bar, parity)) return;
-    const long long t0 = clock64();
-    while (!mbar_try_wait(bar, parity)) {
-        if (clock64() - t0 > 4000000000LL) __trap();
-    }
-}
-__device__ __forceinline__ void tma_load_4d(void *smem, const CUtensorMap *map, uint64_t *bar, int c0, int c1, int c2, int c3)
-{
-    asm volatile(
-        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(smem_u32(smem)),
-        "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
-        : "memory");
-}
-__device__ __forceinline__ void tma_load_2d(void *smem, const CUtensorMap *map, uint64_t *bar, int c0, int c1)
-{
-    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(smem_u32(smem)),
-                 "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
-                 : "memory");
-}
-__device__ __forceinline__ void tma_store_4d(const CUtensorMap *map, const void *smem, int c0, int c1, int c2, int c3)
-{
-    asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(map), "r"(smem_u32(smem)),
-                 "r"(c0), "r"(c1), "r"(c2), "r"(c3)
-                 : "memory");
-}
-__device__ __forceinline__ void tma_store_commit_wait()
-{
-    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-}
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-template <int COLS>
-__device__ __forceinline__ void tmem_alloc(uint32_t *slot)
-{
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "n"(COLS) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-}
-template <int COLS>
-__device__ __forceinline__ void tmem_dealloc(uint32_t addr)
-{
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "n"(COLS) : "memory");
-}
-__device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate)
-{
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t}" ::"r"(tmem_d),
-        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate), "r"(0u)
-        : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint64_t *bar)
-{
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32])
-{
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n\t"
-        "tcgen05.wait::ld.sync.aligned;"   // same asm block: the registers are only defined after the wait
-        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
-          "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
-          "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
-          "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-        : "r"(taddr));
-}
-__device__ __forceinline__ uint32_t tmem_ld1(uint32_t taddr)
-{
-    uint32_t v;
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];\n\ttcgen05.wait::ld.sync.aligned;" : "=r"(v) : "r"(taddr));
-    return v;
-}
-
-// K-major shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start>>4 [0,14), LBO>>4 [16,30),
-// SBO>>4 [32,46), version=1 [46,48), layout type [61,64): 2 = SWIZZLE_128B, 4 = SWIZZLE_64B.
-template <int KC>
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr)
-{
-    constexpr uint64_t layout = KC == 128 ? 2 : 4;
-    constexpr uint64_t sbo = (8 * KC) >> 4;   // 8 rows of KC bytes
-    return (uint64_t)((saddr & 0x3FFFF) >> 4) | (1ull << 16) | (sbo << 32) | (1ull << 46) | (layout << 61);
-}
-// kind::i8 instruction descriptor: c_format S32 (2) [4,6), a/b format 0 = UINT8 [7,10)/[10,13), K-major,
-// N>>3 [17,23), M>>4 [24,29)
-__host__ __device__ constexpr uint32_t make_idesc(int n) { return (2u << 4) | ((uint32_t)(n >> 3) << 17) | ((128u >> 4) << 24); }
 
 template <int BN>
 __host__ __device__ constexpr int tmem_cols()
@@ -184,21 +68,35 @@ struct SmemLayout {
     static_assert(128 * BN <= STAGE, "output staging aliases stage 0");
 };
 
+// activation / saturation are uniform per launch: dispatch once per 32-output chunk, not per output
+template <bool HAS_EXTRA>
+__device__ __forceinline__ void epi_chunk(int actm, int sat, const uint32_t (&v)[16], int nsa, const int (&extra)[16], const int4 *cq,
+                                          const double *mc, int zo, uint32_t (&packed)[4])
+{
+    if (sat) {
+        if (actm == 0) yq::requant_chunk<0, true, 16, HAS_EXTRA>(v, nsa, extra, cq, mc, zo, packed);
+        else if (actm == 1) yq::requant_chunk<1, true, 16, HAS_EXTRA>(v, nsa, extra, cq, mc, zo, packed);
+        else yq::requant_chunk<2, true, 16, HAS_EXTRA>(v, nsa, extra, cq, mc, zo, packed);
+    } else {
+        if (actm == 0) yq::requant_chunk<0, false, 16, HAS_EXTRA>(v, nsa, extra, cq, mc, zo, packed);
+        else if (actm == 1) yq::requant_chunk<1, false, 16, HAS_EXTRA>(v, nsa, extra, cq, mc, zo, packed);
+        else yq::requant_chunk<2, false, 16, HAS_EXTRA>(v, nsa, extra, cq, mc, zo, packed);
+    }
+}
+
 template <int BN, int KC>
-__global__ void __launch_bounds__(TC_THREADS) conv_u8_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+__global__ void __launch_bounds__(TC_THREADS, 2) conv_u8_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                                                                const __grid_constant__ CUtensorMap tmO, const TcArgs a)
 {
     using L = SmemLayout<BN, KC>;
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // keeps the shared address space
     uint64_t *full = (uint64_t *)(smem + L::BAR_OFF);
     uint64_t *empty = full + TC_STAGES;
     uint64_t *accum_full = empty + TC_STAGES;
     uint32_t *tmem_slot = (uint32_t *)(accum_full + 1);
-    int32_t *s_bias = (int32_t *)(smem + L::PARAM_OFF);
-    int32_t *s_zw = s_bias + BN;
-    double *s_m0 = (double *)(s_zw + BN);
-    double *s_m1 = s_m0 + BN;
+    int4 *s_q = (int4 *)(smem + L::PARAM_OFF);          // {bias, zw, 2*M0, shift}
+    double *s_mc = (double *)(s_q + BN);                // M_value * 2^-s (FP64 slow path)
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int oc0 = blockIdx.y * BN;
@@ -222,11 +120,8 @@ __global__ void __launch_bounds__(TC_THREADS) conv_u8_tc_kernel(const __grid_con
     if (warp >= 2) {
         const int t = threadIdx.x - 64;
         for (int i = t; i < BN; i += 128) {
-            const yq::ChanParams cp = yq::load_chan(a.ep, oc0 + i);
-            s_bias[i] = cp.bias;
-            s_zw[i] = cp.zw;
-            s_m0[i] = cp.m0;
-            s_m1[i] = cp.m1;
+            s_q[i] = __ldg(a.ep.chanq + oc0 + i);
+            s_mc[i] = __ldg(a.ep.mcomb + oc0 + i);
         }
         uint32_t *ones = (uint32_t *)(smem + L::ONES_OFF);
         for (int i = t; i < ONES_ROWS * KC / 4; i += 128) ones[i] = 0x01010101u;
@@ -300,42 +195,51 @@ __global__ void __launch_bounds__(TC_THREADS) conv_u8_tc_kernel(const __grid_con
         mbar_wait(accum_full, 0);
         tc_fence_after();
         const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
-        const int sum_a = (int)tmem_ld1(trow + BN);
+        const int nsa = -(int)tmem_ld1(trow + BN);   // minus the pixel's activation sum (ones-tile columns)
         uint8_t *stage_out = smem;              // aliases pipeline stage 0 (all MMAs have completed)
         const size_t pix = ((size_t)n * a.OH + oy) * a.OW + ox;
+        const int actm = yq::act_mode(a.ep.act);
+        const bool side = (a.out_acc != nullptr) || (a.out_f32 != nullptr);
 #pragma unroll 1
-        for (int c0 = 0; c0 < BN; c0 += 32) {
-            uint32_t v[32];
-            tmem_ld32(trow + c0, v);
-            uint32_t packed[8];
+        for (int c0 = 0; c0 < BN; c0 += 16) {
+            uint32_t v[16];
+            tmem_ld16(trow + c0, v);
+            uint32_t packed[4];
+            int extra[16];
+            if (oob) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-                const int oc = c0 + j;
-                yq::ChanParams cp;
-                cp.bias = s_bias[oc]; cp.zw = s_zw[oc]; cp.m0 = s_m0[oc]; cp.m1 = s_m1[oc];
-                int acc = (int)v[j] - cp.zw * sum_a;
-                if (oob) {
-                    for (uint32_t m = oob; m; m &= m - 1) acc += __ldg(a.corr + (size_t)(__ffs(m) - 1) * a.n_pad + oc0 + oc);
+                for (int j = 0; j < 16; ++j) extra[j] = 0;
+                for (uint32_t m = oob; m; m &= m - 1) {
+                    const int32_t *cr = a.corr + (size_t)(__ffs(m) - 1) * a.n_pad + oc0 + c0;
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) extra[j] += __ldg(cr + j);
                 }
-                const bool real = oc0 + oc < a.N;
-                const uint8_t u = real ? yq::requant_u8(a.ep, cp, acc) : (uint8_t)0;
-                if (j % 4 == 0) packed[j / 4] = 0;
-                packed[j / 4] |= (uint32_t)u << (8 * (j % 4));
-                if (valid && real) {
-                    if (a.out_acc) a.out_acc[pix * a.CSO + oc0 + oc] = acc;
-                    if (a.out_f32) a.out_f32[((size_t)n * a.N + oc0 + oc) * a.OH * a.OW + (size_t)oy * a.OW + ox] = yq::dequant_f32(a.ep, u);
+                epi_chunk<true>(actm, a.ep.saturate, v, nsa, extra, s_q + c0, s_mc + c0, a.ep.zp_out, packed);
+            } else {
+                epi_chunk<false>(actm, a.ep.saturate, v, nsa, extra, s_q + c0, s_mc + c0, a.ep.zp_out, packed);
+            }
+            yq::mask_pad_channels<16>(packed, a.N - (oc0 + c0));
+            if (side && valid) {   // parity / quant_stop side outputs (not on the throughput path)
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const int oc = oc0 + c0 + j;
+                    if (oc < a.N) {
+                        if (a.out_acc) a.out_acc[pix * a.CSO + oc] = (int)v[j] + s_q[c0 + j].y * nsa + (oob ? extra[j] : 0);
+                        if (a.out_f32) {
+                            const uint8_t u = (uint8_t)(packed[j / 4] >> (8 * (j % 4)));
+                            a.out_f32[((size_t)n * a.N + oc) * a.OH * a.OW + (size_t)oy * a.OW + ox] = yq::dequant_f32(a.ep, u);
+                        }
+                    }
                 }
             }
             // swizzled staging (matches the TMA-store tensor map): 16-byte chunk index XOR row bits
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const int chunk = c0 / 16 + h;
+            {
+                const int chunk = c0 / 16;
                 int sw;
                 if (BN >= 128) sw = chunk ^ (r & 7);
                 else if (BN == 64) sw = chunk ^ ((r >> 1) & 3);
                 else sw = chunk ^ ((r >> 2) & 1);
-                *reinterpret_cast<uint4 *>(stage_out + (size_t)r * BN + sw * 16) =
-                    make_uint4(packed[4 * h], packed[4 * h + 1], packed[4 * h + 2], packed[4 * h + 3]);
+                *reinterpret_cast<uint4 *>(stage_out + (size_t)r * BN + sw * 16) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
             }
         }
         tc_fence_before();
@@ -446,8 +350,13 @@ int launch(yq_conv_layer *l, TcState *st, const CUtensorMap &tmA, const CUtensor
 
 }  // namespace
 
-int yq_tc_supported(const yq_conv_layer *l)
+static int tc_big_supported(const yq_conv_layer *l);
+
+int yq_tc_supported(const yq_conv_layer *l) { return tc_big_supported(l) || yq_tc_small_supported(l); }
+
+static int tc_big_supported(const yq_conv_layer *l)
 {
+    if (!l->int_form || !l->fused_mult) return 0;   // the integer-form epilogue needs M0 * 2^-31 / 2^-s parameters
     if (l->stride != 1) return 0;
     if (!(l->size == 1 || l->size == 3) || l->pad != l->size / 2) return 0;
     if (l->cs_in % 64) return 0;
@@ -457,6 +366,11 @@ int yq_tc_supported(const yq_conv_layer *l)
 
 int yq_tc_prepare(yq_conv_layer *l)
 {
+    if (!tc_big_supported(l)) {
+        if (yq_tc_small_prepare(l, &l->tc_small)) return -1;
+        l->tc = l->tc_small;   // non-null marks "a tcgen05 flavour is ready"
+        return 0;
+    }
     TcState *st = new TcState();
     st->BN = l->cs_out >= 128 ? 128 : (l->cs_out >= 64 ? 64 : 32);   // TMA-store box inner extent == BN <= cs_out
     st->KC = (l->cs_in % 128) ? 64 : 128;
@@ -505,6 +419,12 @@ int yq_tc_prepare(yq_conv_layer *l)
 
 void yq_tc_free(yq_conv_layer *l)
 {
+    if (l->tc_small) {
+        yq_tc_small_free(l->tc_small);
+        l->tc_small = nullptr;
+        l->tc = nullptr;
+        return;
+    }
     TcState *st = (TcState *)l->tc;
     if (!st) return;
     cudaFree(st->w);
@@ -515,6 +435,7 @@ void yq_tc_free(yq_conv_layer *l)
 
 int yq_tc_forward(yq_conv_layer *l, const uint8_t *in_u8, uint8_t *out_u8, float *out_f32, int32_t *out_acc, int batch, cudaStream_t stream)
 {
+    if (l->tc_small) return yq_tc_small_forward(l, l->tc_small, in_u8, out_u8, out_f32, out_acc, batch, stream);
     TcState *st = (TcState *)l->tc;
     if (!st) return yq::fail("tcgen05 flavour was not prepared for this layer");
     int TW = 0, TH = 0, TN = 0;

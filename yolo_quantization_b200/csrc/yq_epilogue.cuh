@@ -1,5 +1,5 @@
-// yq_epilogue.cuh -- the fused requantize / bias / activation / zero-point / uint8 epilogue shared by
-// both convolution flavours.  Restates src/convolutional_layer.c:726-760 of the reference:
+// yq_epilogue.cuh -- the fused requantize / bias / activation / zero-point / uint8 epilogue shared by the
+// convolution flavours.  Restates src/convolutional_layer.c:726-760 of the reference:
 //
 //   x = acc + biases_int32[oc]                                  (int32 add)
 //   t = (int64) trunc( (double)x * M_value[oc] )                (ONE IEEE double multiply, RN, then trunc)
@@ -10,9 +10,22 @@
 //   uint8 store WRAPS mod 256 (the clamp on :749 acts on a uint8_t and is a no-op)
 //   quant_stop : f32 = (float)((int)u8 - zp_out) * s_out
 //
-// Fused multiplier: M0_right_shift_value is 2^-s, so trunc(trunc(y) * 2^-s) == trunc(y * 2^-s) and
-// RN(x*Mv) * 2^-s == RN(x * (Mv*2^-s)) exactly; when the host verified that every rshift is a power of
-// two (always true for the reference's prep, blas.c:315) the epilogue does one multiply + one convert.
+// Two exact forms are used on the device:
+//
+//  (A) FP64 form.  M0_right_shift_value is 2^-s, so trunc(trunc(y) * 2^-s) == trunc(y * 2^-s) and
+//      RN(x*Mv) * 2^-s == RN(x * (Mv*2^-s)); with every rshift a power of two (always true for the reference's
+//      prep, blas.c:315) one DMUL + one truncating convert reproduces the reference bit for bit.  The SIMT
+//      flavour uses it for every output (and keeps the literal two-step form when a binding hands in
+//      something that is not a power of two).
+//
+//  (B) Integer form (tcgen05 flavours' hot path).  M_value = M0 * 2^-31 with integer M0 in [2^30, 2^31).
+//      While |x| < 2^22 the product x*M0 is below 2^53, the double multiply is exact, and
+//          q = sign(x) * ( umulhi(|x|, 2*M0) >> s )       ( = trunc(x * M0 / 2^(31+s)) )
+//      is the same number with two integer instructions and no conversion-unit traffic.  Each thread tracks
+//      max|x| over a chunk of outputs and re-does the chunk with form (A) in the (rare) case the bound is
+//      exceeded, so the result is bit-identical for every input.
+//      LEAKY's round(q*0.1) for q < 0 equals -((|q|+5)/10) exactly (the double product is q/10 + O(2^-22)
+//      and ties round away from zero either way), i.e. umulhi(|q|+5, 0xCCCCCCCD) >> 3.
 #pragma once
 #include <stdint.h>
 
@@ -26,6 +39,7 @@ struct EpiParams {
     const double *mcomb;
     const double *mval;
     const double *rsh;
+    const int4 *chanq;       // {bias, zw, 2*M0, shift} per channel (integer form), or nullptr
     int fused, act, zp_out, saturate;
     float s_out;
 };
@@ -38,12 +52,15 @@ struct ChanParams {
 static inline EpiParams make_epi(const yq_conv_layer *l)
 {
     EpiParams e;
-    e.bias = l->bias; e.zw = l->zw; e.mcomb = l->mcomb; e.mval = l->mval; e.rsh = l->rsh;
+    e.bias = l->bias; e.zw = l->zw; e.mcomb = l->mcomb; e.mval = l->mval; e.rsh = l->rsh; e.chanq = (const int4 *)l->chanq;
     e.fused = l->fused_mult; e.act = l->activation; e.zp_out = l->zp_out; e.saturate = l->saturate; e.s_out = l->s_out;
     return e;
 }
 
 #ifdef __CUDACC__
+// ---------------------------------------------------------------------------------------------
+// form (A): per-output FP64 (SIMT flavour, slow path of the tcgen05 flavours)
+// ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ ChanParams load_chan(const EpiParams &e, int oc)
 {
     ChanParams c;
@@ -86,6 +103,91 @@ __device__ __forceinline__ float dequant_f32(const EpiParams &e, uint8_t u8)
 {
     return __fmul_rn((float)((int)u8 - e.zp_out), e.s_out);
 }
+
+// ---------------------------------------------------------------------------------------------
+// form (B): chunked integer epilogue for the tcgen05 flavours
+// ---------------------------------------------------------------------------------------------
+// ACTM: 0 = RELU6, 1 = LINEAR / RELU, 2 = LEAKY.  SAT: clamp instead of wrap.
+template <int ACTM, bool SAT>
+__device__ __forceinline__ uint32_t act_store_byte(int q, int zo)
+{
+    int r;
+    if (ACTM == 0) {
+        r = q + zo;                                    // callers pass q >= 0 with q == 0 for every x <= 0
+    } else if (ACTM == 2) {
+        if (q < 0) r = zo - (int)(__umulhi((uint32_t)(-q) + 5u, 0xCCCCCCCDu) >> 3);
+        else r = q + zo;
+    } else {
+        r = q + zo;
+    }
+    if (SAT) r = max(0, min(255, r));
+    return (uint32_t)r & 0xffu;
+}
+
+// One chunk of NV consecutive output channels of ONE pixel.
+//   v[j]   raw tensor-core accumulator  sum_k w*a   (uint8 x uint8, zero-filled padding)
+//   nsa    minus the pixel's activation sum          (so  acc = v + zw * nsa)
+//   extra  per-output additive correction (border taps) or nullptr
+//   cq     shared-memory {bias, zw, 2*M0, shift} of the chunk's first channel; mc = matching M_value*2^-s doubles
+// Writes NV/4 packed little-endian words.  Returns nothing; bit-exact for all inputs (see header).
+template <int ACTM, bool SAT, int NV, bool HAS_EXTRA>
+__device__ __forceinline__ void requant_chunk(const uint32_t (&v)[NV], int nsa, const int (&extra)[NV], const int4 *cq, const double *mc,
+                                              int zo, uint32_t (&packed)[NV / 4])
+{
+    uint32_t mx = 0;
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+        const int4 c = cq[j];
+        int x = c.y * nsa + (int)v[j];
+        if (HAS_EXTRA) x += extra[j];
+        x += c.x;
+        int q;
+        if (ACTM == 0) {
+            const uint32_t xp = (uint32_t)max(x, 0);
+            mx = max(mx, xp);
+            q = (int)(__umulhi(xp, (uint32_t)c.z) >> c.w);
+        } else {
+            const uint32_t ax = (uint32_t)abs(x);
+            mx = max(mx, ax);
+            const int h = (int)(__umulhi(ax, (uint32_t)c.z) >> c.w);
+            q = x < 0 ? -h : h;
+        }
+        const uint32_t b = act_store_byte<ACTM, SAT>(q, zo);
+        if (j % 4 == 0) packed[j / 4] = b;
+        else packed[j / 4] |= b << (8 * (j % 4));
+    }
+    if (mx >= (1u << 22)) {
+        // |x*M0| may reach 2^53: the reference's double multiply rounds -> redo this chunk in FP64 form (A)
+#pragma unroll
+        for (int j = 0; j < NV; ++j) {
+            const int4 c = cq[j];
+            int x = c.y * nsa + (int)v[j];
+            if (HAS_EXTRA) x += extra[j];
+            x += c.x;
+            int q = __double2int_rz(__dmul_rn((double)x, mc[j]));
+            if (ACTM == 0) q = max(q, 0);
+            const uint32_t b = act_store_byte<ACTM, SAT>(q, zo);
+            if (j % 4 == 0) packed[j / 4] = b;
+            else packed[j / 4] |= b << (8 * (j % 4));
+        }
+    }
+}
+
+// zero the bytes of pad channels (channel index >= n_real within this chunk): pad lanes of an activation
+// tensor must be 0 because consumers sum every byte of a pixel
+template <int NV>
+__device__ __forceinline__ void mask_pad_channels(uint32_t (&packed)[NV / 4], int n_real)
+{
+    if (n_real >= NV) return;
+#pragma unroll
+    for (int k = 0; k < NV / 4; ++k) {
+        const int left = n_real - 4 * k;
+        const uint32_t m = left >= 4 ? 0xffffffffu : (left <= 0 ? 0u : (0xffffffffu >> (8 * (4 - left))));
+        packed[k] &= m;
+    }
+}
+
+__host__ __device__ constexpr int act_mode(int act) { return act == YQ_RELU6 ? 0 : (act == YQ_LEAKY ? 2 : 1); }
 #endif
 
 }  // namespace yq

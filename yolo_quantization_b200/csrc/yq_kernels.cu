@@ -385,6 +385,8 @@ extern "C" yq_conv_layer *yq_make_convolutional_layer_quant(const yq_conv_desc *
     std::vector<int32_t> bias(p_pad, 0), zw(p_pad, 0);
     std::vector<double> mcomb(p_pad, 0.0), mval(p_pad, 0.0), rsh(p_pad, 0.0);
     l->fused_mult = 1;
+    l->int_form = 1;
+    std::vector<int4> chanq(p_pad, make_int4(0, 0, 0, 0));
     for (int oc = 0; oc < l->n; ++oc) {
         bias[oc] = d->biases_int32[oc];
         zw[oc] = d->weight_zero_point[oc];
@@ -392,9 +394,16 @@ extern "C" yq_conv_layer *yq_make_convolutional_layer_quant(const yq_conv_desc *
         rsh[oc] = d->M0_right_shift_value[oc];
         mcomb[oc] = mval[oc] * rsh[oc];   // exact: rsh is a power of two
         if (!is_pow2_le1(rsh[oc])) l->fused_mult = 0;
+        // integer form: M_value = M0 * 2^-31 (blas.c:316), rshift = 2^-s (blas.c:315)
+        const double m0d = std::ldexp(mval[oc], 31);
+        int e = 0;
+        const double mant = std::frexp(rsh[oc], &e);
+        const int sh = 1 - e;
+        if (!(m0d > 0.0 && m0d < 2147483648.0 && m0d == std::floor(m0d) && mant == 0.5 && sh >= 0 && sh <= 31)) l->int_form = 0;
+        else chanq[oc] = make_int4(bias[oc], zw[oc], (int)(uint32_t)((uint64_t)m0d * 2ull), sh);
     }
     if (upload(&l->w_simt, wp) || upload(&l->bias, bias) || upload(&l->zw, zw) || upload(&l->mcomb, mcomb) ||
-        upload(&l->mval, mval) || upload(&l->rsh, rsh)) {
+        upload(&l->mval, mval) || upload(&l->rsh, rsh) || upload((int4 **)&l->chanq, chanq)) {
         yq_free_convolutional_layer_quant(l);
         return nullptr;
     }
@@ -409,7 +418,7 @@ extern "C" void yq_free_convolutional_layer_quant(yq_conv_layer *l)
 {
     if (!l) return;
     yq_tc_free(l);
-    cudaFree(l->w_simt); cudaFree(l->bias); cudaFree(l->zw); cudaFree(l->mcomb); cudaFree(l->mval); cudaFree(l->rsh);
+    cudaFree(l->w_simt); cudaFree(l->bias); cudaFree(l->zw); cudaFree(l->mcomb); cudaFree(l->mval); cudaFree(l->rsh); cudaFree(l->chanq);
     delete l;
 }
 
