@@ -183,6 +183,11 @@ YQ_API int yq_forward_network_device(yq_network *net, const uint8_t *in_u8_nchw)
 /* network_predict with HOST buffers: H2D of the uint8 input, forward, D2H of every yolo head into
  * out_f32 (heads concatenated in layer order, each [batch][out_c][out_h][out_w]); synchronous. */
 YQ_API int yq_network_predict_u8(yq_network *net, const uint8_t *in_u8_nchw_host, float *out_f32_host);
+/* the same, pipelined two deep so H2D / forward / D2H of neighbouring batches overlap (serving loop):
+ * submit enqueues the H2D of one batch and its forward and returns a slot (>= 0; < 0 on error);
+ * collect waits for that slot and copies the yolo heads to out_f32.  Use pinned host memory. */
+YQ_API int yq_network_submit_u8(yq_network *net, const uint8_t *in_u8_nchw_host);
+YQ_API int yq_network_collect(yq_network *net, int slot, float *out_f32_host);
 YQ_API size_t yq_network_output_floats(const yq_network *net);
 YQ_API int yq_network_synchronize(yq_network *net);
 YQ_API void *yq_network_stream(yq_network *net);

@@ -277,6 +277,49 @@ def test_graph_replay_equals_eager_and_is_deterministic(built, tiny_net_files):
     net.free()
 
 
+def test_pipelined_submit_collect_equals_predict(built, tiny_net_files):
+    """yq_network_submit_u8 / yq_network_collect (2-deep pipeline) == yq_network_predict_u8, batch by batch."""
+    cfg, wts, info, _ = tiny_net_files
+    net = darknet.load_network(cfg, wts, batch=2)
+    net.use_graph(True)
+    batches = [np.stack([synth.synthetic_image(10 * k + s) for s in (1, 2)]) for k in range(4)]
+    want = [net.predict_u8(b).copy() for b in batches]
+    outs = [np.empty(net.output_floats, np.float32) for _ in batches]
+    inflight = []
+    for k, b in enumerate(batches):
+        b = np.ascontiguousarray(b)
+        inflight.append((net.submit_raw(b.ctypes.data), k, b))
+        if len(inflight) == 2:
+            sl, j, _keep = inflight.pop(0)
+            net.collect_raw(sl, outs[j].ctypes.data)
+    for sl, j, _keep in inflight:
+        net.collect_raw(sl, outs[j].ctypes.data)
+    for w, o in zip(want, outs):
+        assert np.array_equal(w, o)
+    from yolo_quantization_b200._lib import YqError
+    s0 = net.submit_raw(batches[0].ctypes.data)
+    s1 = net.submit_raw(batches[1].ctypes.data)
+    with pytest.raises(YqError, match="in flight"):
+        net.submit_raw(batches[2].ctypes.data)
+    net.collect_raw(s0, outs[0].ctypes.data)
+    net.collect_raw(s1, outs[1].ctypes.data)
+    net.free()
+
+
+def test_layout_transform_roundtrip(built):
+    """NCHW -> NHWC (both the c<=4 fast path and the generic one) and back."""
+    rng = np.random.default_rng(4)
+    for c, h, w in ((3, 8, 12), (3, 5, 7), (4, 4, 4), (16, 6, 6), (30, 5, 3), (1, 2, 2)):
+        x = rng.integers(0, 256, size=(2, c, h, w), dtype=np.uint8)
+        d = darknet.push_nchw_u8(x)
+        cs = darknet.channel_stride(c)
+        raw = d.pull((2, h, w, cs), np.uint8)
+        assert np.array_equal(raw[..., :c], x.transpose(0, 2, 3, 1))
+        assert not raw[..., c:].any()                      # pad channels are zero
+        assert np.array_equal(darknet.pull_nhwc_u8(d, 2, c, h, w), x)
+        d.free()
+
+
 def test_full_size_batch128_properties(built, tiny_net_files):
     """BASELINE configs[2] size (batch 128 @ 416x416) through size-independent properties:
     batch-independence (image i of the batch == the same image alone), permutation equivariance and

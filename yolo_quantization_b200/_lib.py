@@ -81,6 +81,8 @@ SIGNATURES = {
     "yq_network_set_conv_kernel": (_i, [_vp, _i]),
     "yq_forward_network_device": (_i, [_vp, _vp]),
     "yq_network_predict_u8": (_i, [_vp, _vp, _vp]),
+    "yq_network_submit_u8": (_i, [_vp, _vp]),
+    "yq_network_collect": (_i, [_vp, _i, _vp]),
     "yq_network_output_floats": (_sz, [_vp]),
     "yq_network_synchronize": (_i, [_vp]),
     "yq_network_stream": (_vp, [_vp]),

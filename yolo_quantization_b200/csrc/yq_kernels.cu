@@ -657,6 +657,26 @@ __global__ void nchw_to_nhwc_u8_kernel(const uint8_t *__restrict__ in, uint8_t *
     }
 }
 
+// c <= 4, HW % 4 == 0: one thread = 4 consecutive pixels: one 4-byte load per channel plane, one 16-byte store
+__global__ void nchw_to_nhwc4_u8_kernel(const uint8_t *__restrict__ in, uint8_t *__restrict__ out, int C, int HW, long long total /* B*HW/4 */)
+{
+    const int q = HW / 4;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long n = i / q;
+        const int p4 = (int)(i - n * q);
+        uint32_t pl[4] = {0, 0, 0, 0};
+#pragma unroll
+        for (int ch = 0; ch < 4; ++ch)
+            if (ch < C) pl[ch] = __ldg(reinterpret_cast<const uint32_t *>(in + ((size_t)n * C + ch) * HW) + p4);
+        uint4 o;   // pixel k = byte k of every plane word
+        o.x = __byte_perm(__byte_perm(pl[0], pl[1], 0x0040), __byte_perm(pl[2], pl[3], 0x0040), 0x5410);
+        o.y = __byte_perm(__byte_perm(pl[0], pl[1], 0x0051), __byte_perm(pl[2], pl[3], 0x0051), 0x5410);
+        o.z = __byte_perm(__byte_perm(pl[0], pl[1], 0x0062), __byte_perm(pl[2], pl[3], 0x0062), 0x5410);
+        o.w = __byte_perm(__byte_perm(pl[0], pl[1], 0x0073), __byte_perm(pl[2], pl[3], 0x0073), 0x5410);
+        reinterpret_cast<uint4 *>(out)[i] = o;
+    }
+}
+
 template <typename T>
 __global__ void nhwc_to_nchw_kernel(const T *__restrict__ in, T *__restrict__ out, int C, int HW, int CS, long long total)
 {
@@ -673,6 +693,12 @@ extern "C" int yq_nchw_to_nhwc_u8(const uint8_t *in, uint8_t *out, int batch, in
 {
     if (!in || !out) return yq::fail("nchw_to_nhwc: null pointer");
     const int cs = yq::channel_stride(c);
+    if (cs == 4 && (h * w) % 4 == 0 && ((uintptr_t)in % 4) == 0) {
+        long long total4 = (long long)batch * h * w / 4;
+        nchw_to_nhwc4_u8_kernel<<<grid_for(total4, 256), 256, 0, (cudaStream_t)stream>>>(in, out, c, h * w, total4);
+        YQ_CHECK_LAUNCH();
+        return 0;
+    }
     long long total = (long long)batch * h * w * (cs / 4);
     nchw_to_nhwc_u8_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(in, out, c, h * w, cs, total);
     YQ_CHECK_LAUNCH();

@@ -134,6 +134,15 @@ struct yq_network {
     int launches = 0;
     float *out_host_pinned = nullptr;
     size_t out_floats = 0;
+    // 2-deep host pipeline (yq_network_submit_u8 / yq_network_collect): H2D, forward and D2H of
+    // neighbouring batches overlap on three streams
+    static const int PIPE = 2;
+    cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;
+    uint8_t *pipe_in[PIPE] = {nullptr, nullptr};
+    float *pipe_out[PIPE] = {nullptr, nullptr};
+    cudaEvent_t ev_in_ready[PIPE] = {nullptr, nullptr}, ev_fwd_done[PIPE] = {nullptr, nullptr};
+    int pipe_next = 0;
+    bool pipe_busy[PIPE] = {false, false};
 };
 
 namespace {
@@ -563,6 +572,14 @@ extern "C" void yq_free_network(yq_network *net)
         cudaFree(l.out_f32);
         cudaFree(l.out_acc);
     }
+    for (int k = 0; k < yq_network::PIPE; ++k) {
+        cudaFree(net->pipe_in[k]);
+        cudaFree(net->pipe_out[k]);
+        if (net->ev_in_ready[k]) cudaEventDestroy(net->ev_in_ready[k]);
+        if (net->ev_fwd_done[k]) cudaEventDestroy(net->ev_fwd_done[k]);
+    }
+    if (net->h2d_stream) cudaStreamDestroy(net->h2d_stream);
+    if (net->d2h_stream) cudaStreamDestroy(net->d2h_stream);
     cudaFree(net->in_stage_nchw);
     cudaFree(net->in_nhwc);
     cudaFree(net->scratch);
@@ -706,6 +723,60 @@ extern "C" int yq_network_predict_u8(yq_network *net, const uint8_t *in_host, fl
             }
     }
     YQ_CUDA(cudaStreamSynchronize(net->stream));
+    return 0;
+}
+
+static int pipe_init(yq_network *net)
+{
+    if (net->h2d_stream) return 0;
+    YQ_CUDA(cudaStreamCreateWithFlags(&net->h2d_stream, cudaStreamNonBlocking));
+    YQ_CUDA(cudaStreamCreateWithFlags(&net->d2h_stream, cudaStreamNonBlocking));
+    const size_t in_bytes = (size_t)net->batch * net->c * net->h * net->w;
+    for (int k = 0; k < yq_network::PIPE; ++k) {
+        YQ_CUDA(cudaMalloc((void **)&net->pipe_in[k], in_bytes));
+        YQ_CUDA(cudaMalloc((void **)&net->pipe_out[k], net->out_floats * sizeof(float) + 16));
+        YQ_CUDA(cudaEventCreateWithFlags(&net->ev_in_ready[k], cudaEventDisableTiming));
+        YQ_CUDA(cudaEventCreateWithFlags(&net->ev_fwd_done[k], cudaEventDisableTiming));
+    }
+    return 0;
+}
+
+// network_predict, pipelined: enqueue H2D of one uint8 CHW batch (pinned host memory for true overlap) and its
+// forward; returns the slot to pass to yq_network_collect.  At most PIPE batches may be in flight.
+extern "C" int yq_network_submit_u8(yq_network *net, const uint8_t *in_host)
+{
+    if (!net || !in_host) return yq::fail("yq_network_submit_u8: null argument");
+    YQ_CUDA(cudaSetDevice(net->device));
+    if (pipe_init(net)) return -1;
+    const int k = net->pipe_next;
+    if (net->pipe_busy[k]) return yq::fail("yq_network_submit_u8: %d batches already in flight; collect one first", yq_network::PIPE);
+    const size_t in_bytes = (size_t)net->batch * net->c * net->h * net->w;
+    // pipe_in[k] was last read by the forward whose completion is ev_fwd_done[k] (already collected => complete)
+    YQ_CUDA(cudaMemcpyAsync(net->pipe_in[k], in_host, in_bytes, cudaMemcpyHostToDevice, net->h2d_stream));
+    YQ_CUDA(cudaEventRecord(net->ev_in_ready[k], net->h2d_stream));
+    YQ_CUDA(cudaStreamWaitEvent(net->stream, net->ev_in_ready[k], 0));
+    if (yq_forward_network_device(net, net->pipe_in[k])) return -1;
+    size_t off = 0;
+    for (auto &l : net->layers)
+        if (l.type == L_YOLO) {   // heads -> per-slot device copy so the next forward may overwrite the layer buffers
+            YQ_CUDA(cudaMemcpyAsync(net->pipe_out[k] + off, l.out_f32, l.f32_count * sizeof(float), cudaMemcpyDeviceToDevice, net->stream));
+            off += l.f32_count;
+        }
+    YQ_CUDA(cudaEventRecord(net->ev_fwd_done[k], net->stream));
+    net->pipe_busy[k] = true;
+    net->pipe_next = (k + 1) % yq_network::PIPE;
+    return k;
+}
+
+// wait for slot's forward, copy every yolo head (layer order, each [batch][out_c][out_h][out_w]) to out_host
+extern "C" int yq_network_collect(yq_network *net, int slot, float *out_host)
+{
+    if (!net || slot < 0 || slot >= yq_network::PIPE || !net->pipe_busy[slot]) return yq::fail("yq_network_collect: slot %d is not in flight", slot);
+    YQ_CUDA(cudaSetDevice(net->device));
+    YQ_CUDA(cudaStreamWaitEvent(net->d2h_stream, net->ev_fwd_done[slot], 0));
+    if (out_host) YQ_CUDA(cudaMemcpyAsync(out_host, net->pipe_out[slot], net->out_floats * sizeof(float), cudaMemcpyDeviceToHost, net->d2h_stream));
+    YQ_CUDA(cudaStreamSynchronize(net->d2h_stream));
+    net->pipe_busy[slot] = false;
     return 0;
 }
 

@@ -295,6 +295,16 @@ class Network:
         """Same as predict_u8 on raw host addresses (e.g. pinned torch tensors)."""
         check(_lib.load().yq_network_predict_u8(self._h, in_ptr, out_ptr), "yq_network_predict_u8")
 
+    def submit_raw(self, in_ptr: int) -> int:
+        """Pipelined network_predict: enqueue H2D + forward of one batch; returns the slot for collect_raw."""
+        slot = _lib.load().yq_network_submit_u8(self._h, in_ptr)
+        if slot < 0:
+            raise YqError(_lib.last_error())
+        return slot
+
+    def collect_raw(self, slot: int, out_ptr: int) -> None:
+        check(_lib.load().yq_network_collect(self._h, slot, out_ptr), "yq_network_collect")
+
     def split_heads(self, flat: np.ndarray) -> List[np.ndarray]:
         outs, off = [], 0
         for li in self.layers():
