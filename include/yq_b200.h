@@ -114,6 +114,14 @@ YQ_API int yq_conv_get_kernel(const yq_conv_layer *l);
 YQ_API int yq_forward_convolutional_layer_quant_gpu(yq_conv_layer *l, const uint8_t *in_u8, uint8_t *out_u8,
                                                     float *out_f32, int32_t *out_acc, int batch, void *stream);
 
+/* The same with the FOLLOWING max-pool layer (size 2, stride 2, default padding: maxpool_layer.c:109-153 with
+ * l.pad = 1) fused into the epilogue: out_pool is NHWC [batch][(out_h+1)/2][(out_w+1)/2][yq_channel_stride(n)].
+ * Either of out_u8 / out_pool may be NULL (not both).  Only flavours for which yq_conv_can_fuse_maxpool() is 1. */
+YQ_API int yq_forward_convolutional_layer_quant_pool_gpu(yq_conv_layer *l, const uint8_t *in_u8, uint8_t *out_u8,
+                                                         uint8_t *out_pool, float *out_f32, int32_t *out_acc, int batch,
+                                                         void *stream);
+YQ_API int yq_conv_can_fuse_maxpool(const yq_conv_layer *l);
+
 /* ------------------------------------------------------------------------------------------------
  * memory-bound layers (all device pointers, uint8 NHWC, channel stride yq_channel_stride(c))
  * ---------------------------------------------------------------------------------------------- */
@@ -174,6 +182,8 @@ YQ_API int yq_network_layer_info(const yq_network *net, int i, yq_layer_info *in
 YQ_API int yq_network_set_input_quant(yq_network *net, float s_in, int zp_in);
 /* keep per-layer int32 accumulators / uint8 outputs for yq_network_pull_layer (parity checks) */
 YQ_API int yq_network_set_debug(yq_network *net, int keep_acc);
+/* fuse conv -> maxpool(2,2) pairs into one launch where the conv flavour supports it (default 1) */
+YQ_API int yq_network_set_fusion(yq_network *net, int enable);
 /* force one conv kernel flavour for every conv layer (-1 auto, 0 SIMT, 1 tcgen05) */
 YQ_API int yq_network_set_conv_kernel(yq_network *net, int kind);
 

@@ -124,6 +124,36 @@ def test_conv_tcgen05_small_c_vs_oracle(built, case):
     run_conv_case(case, kernel=1)
 
 
+@pytest.mark.parametrize("case", [
+    (3, 40, 40, 16, 3, 1, "relu6", 0, 0, 2),
+    (3, 33, 17, 16, 3, 1, "leaky", 77, 40, 3),     # odd sizes: the last pooled row/column sees out-of-image taps (count as 0)
+    (16, 24, 24, 32, 3, 1, "relu6", 0, 0, 2),
+    (32, 21, 19, 64, 3, 1, "relu6", 0, 0, 2),
+    (16, 9, 9, 20, 3, 1, "relu", 9, 3, 2),
+], ids=lambda c: "c%d_%dx%d_n%d" % c[:4])
+def test_conv_fused_maxpool_vs_oracle(built, case):
+    """conv + maxpool(2,2) in one launch == oracle conv followed by oracle maxpool (maxpool_layer.c:109-153)."""
+    c, h, w, n, k, stride, act, zp_in, zp_out, batch = case
+    rng = np.random.default_rng(zlib.crc32(repr(case).encode()) + 1)
+    wq, zp_w, s_w, bias = make_params(rng, n, c * k * k, zp_in)
+    spec = synth.LayerSpec("conv", n, k, stride, 1, 0, act)
+    sl = synth.SynthLayer("conv", c, h, w, n, 0, 0, spec, s_out=0.05, biases=bias, s_w=s_w, zp_w=zp_w, w_u8=wq.reshape(n, c, k, k))
+    p = O.prepare_conv(sl, 0.02, zp_in)
+    x = rng.integers(0, 256, size=(batch, c, h, w), dtype=np.uint8)
+    layer = darknet.ConvolutionalLayerQuant(h, w, c, n, k, stride, 1, synth.ACT_CODES[act], wq, zp_w, p["biases_int32"], p["M_value"],
+                                            p["M0_right_shift_value"], zp_in, zp_out, 0.05, kernel=1)
+    assert layer.can_fuse_maxpool
+    for want_conv in (True, False):
+        got = layer.forward_pooled(x, want_conv=want_conv)
+        for b in range(batch):
+            acc = O.conv_acc(x[b], wq.reshape(n, c, k, k), zp_w, stride, 1, zp_in)
+            u8 = O.requant(acc, p["biases_int32"], p["M_value"], p["M0_right_shift_value"], synth.ACT_CODES[act], zp_out)
+            assert np.array_equal(got["pool"][b], O.maxpool(u8, 2, 2)), f"pooled mismatch image {b}"
+            if want_conv:
+                assert np.array_equal(got["u8"][b], u8)
+    layer.free()
+
+
 def test_conv_wrap_semantics(built):
     """tiny s_out forces q + zp_out far outside [0,255]: the store must WRAP like the reference (A.3)."""
     case = (16, 8, 8, 32, 3, 1, "linear", 0, 100, 1)
@@ -224,6 +254,25 @@ def test_tiny416_batch1_vs_oracle_and_reference_golden(built, tiny_net_files):
             p = net.conv_params(i)
             assert sha(p["M0"]) == e["M0"] and sha(p["biases_int32"]) == e["biases_int32"], f"layer {i} host prep"
             assert sha(p["M0_right_shift"]) == e["M0_right_shift"]
+    net.free()
+
+
+def test_fused_network_equals_unfused_and_oracle(built, tiny_net_files):
+    """production configuration (fusion on, no debug buffers): every tensor that is still materialised and the
+    yolo heads equal the oracle; heads equal the unfused run bit for bit."""
+    cfg, wts, info, _ = tiny_net_files
+    im = synth.synthetic_image(31)[None]
+    net = darknet.load_network(cfg, wts, batch=1)
+    fused_flat = net.predict_u8(im).copy()
+    assert net.launches_per_forward < 1 + 24 - 1          # pools folded into conv launches
+    ref = O.forward_network(info, im[0])
+    for i, (sl, r) in enumerate(zip(info, ref)):
+        if sl.kind == "maxpool" or (sl.kind == "conv" and i >= 6) or sl.kind in ("route", "upsample"):
+            assert np.array_equal(net.pull_layer(i, "u8")[0], r["u8"]), f"layer {i}"
+    for h, i in zip(net.split_heads(fused_flat), (16, 23)):
+        assert np.allclose(h[0], ref[i]["f32"], atol=YOLO_ATOL, rtol=0)
+    net.set_fusion(False)
+    assert np.array_equal(net.predict_u8(im), fused_flat)
     net.free()
 
 

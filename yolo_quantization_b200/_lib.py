@@ -63,6 +63,8 @@ SIGNATURES = {
     "yq_conv_set_kernel": (_i, [_vp, _i]),
     "yq_conv_get_kernel": (_i, [_vp]),
     "yq_forward_convolutional_layer_quant_gpu": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _vp]),
+    "yq_forward_convolutional_layer_quant_pool_gpu": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _vp]),
+    "yq_conv_can_fuse_maxpool": (_i, [_vp]),
     "yq_forward_maxpool_layer_quant_gpu": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "yq_forward_upsample_layer_quant_gpu": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "yq_forward_route_layer_quant_gpu": (_i, [C.POINTER(_vp), C.POINTER(_i), _i, _vp, _i, _i, _i, _vp]),
@@ -79,6 +81,7 @@ SIGNATURES = {
     "yq_network_set_input_quant": (_i, [_vp, C.c_float, _i]),
     "yq_network_set_debug": (_i, [_vp, _i]),
     "yq_network_set_conv_kernel": (_i, [_vp, _i]),
+    "yq_network_set_fusion": (_i, [_vp, _i]),
     "yq_forward_network_device": (_i, [_vp, _vp]),
     "yq_network_predict_u8": (_i, [_vp, _vp, _vp]),
     "yq_network_submit_u8": (_i, [_vp, _vp]),

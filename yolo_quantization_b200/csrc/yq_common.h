@@ -56,18 +56,22 @@ struct yq_conv_layer {
     void *tc_small = nullptr;   // small-c tcgen05 flavour state (yq_conv_tc_small.cu)
     std::vector<uint8_t> host_w;  // OIHW copy kept for repacking
     std::vector<uint8_t> host_zw;
+    std::vector<int32_t> host_chanq;   // 4 ints per channel {bias, zw, 2*M0, shift} (copy of chanq)
+    std::vector<double> host_mcomb;
 };
 
 // implemented in yq_conv_tc_small.cu (threads build the im2col rows; c <= 32)
 int yq_tc_small_supported(const yq_conv_layer *l);
 int yq_tc_small_prepare(yq_conv_layer *l, void **state);
 void yq_tc_small_free(void *state);
-int yq_tc_small_forward(yq_conv_layer *l, void *state, const uint8_t *in_u8, uint8_t *out_u8, float *out_f32, int32_t *out_acc,
-                        int batch, cudaStream_t stream);
+int yq_tc_small_forward(yq_conv_layer *l, void *state, const uint8_t *in_u8, uint8_t *out_u8, uint8_t *out_pool, float *out_f32,
+                        int32_t *out_acc, int batch, cudaStream_t stream);
 
 // implemented in yq_conv_tc.cu (TMA-fed; c % 64 == 0)
 int yq_tc_supported(const yq_conv_layer *l);
 int yq_tc_prepare(yq_conv_layer *l);
 void yq_tc_free(yq_conv_layer *l);
-int yq_tc_forward(yq_conv_layer *l, const uint8_t *in_u8, uint8_t *out_u8, float *out_f32, int32_t *out_acc,
+int yq_tc_forward(yq_conv_layer *l, const uint8_t *in_u8, uint8_t *out_u8, uint8_t *out_pool, float *out_f32, int32_t *out_acc,
                   int batch, cudaStream_t stream);
+// 1 when this layer's current flavour can also emit the 2x2/stride-2 max-pooled tensor from its epilogue
+int yq_tc_can_fuse_pool(const yq_conv_layer *l);

@@ -433,9 +433,13 @@ void yq_tc_free(yq_conv_layer *l)
     l->tc = nullptr;
 }
 
-int yq_tc_forward(yq_conv_layer *l, const uint8_t *in_u8, uint8_t *out_u8, float *out_f32, int32_t *out_acc, int batch, cudaStream_t stream)
+int yq_tc_can_fuse_pool(const yq_conv_layer *l) { return l->kernel == 1 && l->tc_small != nullptr; }
+
+int yq_tc_forward(yq_conv_layer *l, const uint8_t *in_u8, uint8_t *out_u8, uint8_t *out_pool, float *out_f32, int32_t *out_acc, int batch,
+                  cudaStream_t stream)
 {
-    if (l->tc_small) return yq_tc_small_forward(l, l->tc_small, in_u8, out_u8, out_f32, out_acc, batch, stream);
+    if (l->tc_small) return yq_tc_small_forward(l, l->tc_small, in_u8, out_u8, out_pool, out_f32, out_acc, batch, stream);
+    if (out_pool || !out_u8) return yq::fail("the TMA tcgen05 flavour has no fused max-pool output");
     TcState *st = (TcState *)l->tc;
     if (!st) return yq::fail("tcgen05 flavour was not prepared for this layer");
     int TW = 0, TH = 0, TN = 0;

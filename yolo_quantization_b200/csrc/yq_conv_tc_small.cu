@@ -27,17 +27,24 @@ using namespace yqtc;
 
 namespace {
 
-constexpr int SM_THREADS = 128;
+constexpr int SM_THREADS = 128;            // thread = im2col row = TMEM lane = output pixel of the tile
 constexpr int TAPS = 9;
+constexpr int TILE_W = 16, TILE_H = 8;     // 128 output pixels per tile; power-of-two so row -> (x,y) is shifts/masks
 
 struct SmallArgs {
     const uint8_t *in;
-    uint8_t *out;
+    uint8_t *out;          // NHWC conv output, or nullptr when only the pooled output is wanted
+    uint8_t *out_pool;     // NHWC 2x2/stride-2 max-pooled output (fused maxpool_layer.c:109-153), or nullptr
     float *out_f32;
     int32_t *out_acc;
     const uint8_t *wimg;   // pre-swizzled shared-memory image of the filter bank
     yq::EpiParams ep;
-    int B, H, W, C, OH, OW, N, CSO, stride, pad, zp_in, M_total, num_tiles;
+    int B, H, W, C, OH, OW, N, CSO, stride, pad, zp_in;
+    int tiles_x, tiles_y, num_tiles, PH, PW;
+    // per-channel parameters live in kernel-parameter (constant-bank) space: with the channel loop fully unrolled
+    // they become immediate constant operands of the epilogue's IMAD / SHF instructions (no loads, no registers)
+    int4 cq[64];       // {bias, zw, 2*M0, shift}
+    double mc[64];     // M_value * 2^-s (FP64 slow path)
 };
 
 template <int CS>
@@ -46,66 +53,83 @@ struct SmallGeom {
     static constexpr int KPAD = (K + 31) / 32 * 32;
     static constexpr int P = KPAD / 32;          // 32-byte K panels = MMA K steps
     static constexpr int A_BYTES = P * 128 * 32;
+    static constexpr int NCHUNK = 2 * P;         // 16-byte chunks per im2col row
+    static constexpr int NREAL = CS == 4 ? 3 : TAPS * (CS / 16);   // chunks that carry data (the rest are zero)
 };
 
 template <int CS, int BN>
 struct SmallSmem {
     using G = SmallGeom<CS>;
-    static constexpr int A_OFF = 0;
-    static constexpr int B_OFF = G::A_BYTES;
+    static constexpr int A_OFF = 0;                       // two A buffers
+    static constexpr int B_OFF = 2 * G::A_BYTES;
     static constexpr int B_BYTES = G::P * BN * 32;
     static constexpr int ONES_OFF = B_OFF + B_BYTES;
-    static constexpr int PARAM_OFF = ONES_OFF + 512;
-    static constexpr int BAR_OFF = PARAM_OFF + BN * 24;
+    static constexpr int BAR_OFF = ONES_OFF + 512;
     static constexpr int TOTAL = BAR_OFF + 64;
 };
 
+// two accumulators of BN + 16 columns each
 template <int BN>
-__host__ __device__ constexpr int small_tmem_cols() { return BN + 16 <= 32 ? 32 : (BN + 16 <= 64 ? 64 : 128); }
+__host__ __device__ constexpr int small_tmem_cols() { return 2 * (BN + 16) <= 64 ? 64 : (2 * (BN + 16) <= 128 ? 128 : 256); }
 
-template <int NV>
-__device__ __forceinline__ void epi_chunk_small(int actm, int sat, const uint32_t (&v)[NV], int nsa, const int4 *cq, const double *mc, int zo,
+template <int ACTM, int NV>
+__device__ __forceinline__ void epi_chunk_small(int sat, const uint32_t (&v)[NV], int nsa, const int4 *cq, const double *mc, int zo,
                                                 uint32_t (&packed)[NV / 4])
 {
     int extra[NV];   // unused (HAS_EXTRA = false): padded taps already carry zp_in
-    if (sat) {
-        if (actm == 0) yq::requant_chunk<0, true, NV, false>(v, nsa, extra, cq, mc, zo, packed);
-        else if (actm == 1) yq::requant_chunk<1, true, NV, false>(v, nsa, extra, cq, mc, zo, packed);
-        else yq::requant_chunk<2, true, NV, false>(v, nsa, extra, cq, mc, zo, packed);
-    } else {
-        if (actm == 0) yq::requant_chunk<0, false, NV, false>(v, nsa, extra, cq, mc, zo, packed);
-        else if (actm == 1) yq::requant_chunk<1, false, NV, false>(v, nsa, extra, cq, mc, zo, packed);
-        else yq::requant_chunk<2, false, NV, false>(v, nsa, extra, cq, mc, zo, packed);
-    }
+    if (sat) yq::requant_chunk<ACTM, true, NV, false>(v, nsa, extra, cq, mc, zo, packed);
+    else yq::requant_chunk<ACTM, false, NV, false>(v, nsa, extra, cq, mc, zo, packed);
 }
 
-template <int CS, int BN>
-__global__ void __launch_bounds__(SM_THREADS, 4) conv_u8_tc_small_kernel(const SmallArgs a)
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+struct TilePos { int n, ty, tx; };
+
+// Tiles are visited with stride gridDim.x; (n, ty, tx) advance incrementally (no divisions in the loops).
+struct TileWalker {
+    int tiles_x, tiles_y, step_n, step_y, step_x;
+    __device__ __forceinline__ void init(const SmallArgs &a, int step, int first, TilePos &t)
+    {
+        const int per_img = a.tiles_x * a.tiles_y;
+        tiles_x = a.tiles_x; tiles_y = a.tiles_y;
+        step_n = step / per_img; step_y = (step % per_img) / a.tiles_x; step_x = step % a.tiles_x;
+        t.n = first / per_img; t.ty = (first % per_img) / a.tiles_x; t.tx = first % a.tiles_x;
+    }
+    __device__ __forceinline__ void advance(TilePos &t) const
+    {
+        t.tx += step_x;
+        if (t.tx >= tiles_x) { t.tx -= tiles_x; ++t.ty; }
+        t.ty += step_y;
+        if (t.ty >= tiles_y) { t.ty -= tiles_y; ++t.n; }
+        t.n += step_n;
+    }
+};
+
+template <int CS, int BN, int ACTM>
+__global__ void __launch_bounds__(SM_THREADS, (CS == 32 ? 2 : (CS == 16 ? 4 : 6))) conv_u8_tc_small_kernel(const __grid_constant__ SmallArgs a)
 {
     using G = SmallGeom<CS>;
     using L = SmallSmem<CS, BN>;
     extern __shared__ __align__(16) uint8_t smem_raw[];
     uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // keeps the shared address space
-    uint8_t *sA = smem + L::A_OFF;
     uint8_t *sB = smem + L::B_OFF;
-    int4 *s_q = (int4 *)(smem + L::PARAM_OFF);          // {bias, zw, 2*M0, shift}
-    double *s_mc = (double *)(s_q + BN);                // M_value * 2^-s (FP64 slow path)
-    uint64_t *mma_done = (uint64_t *)(smem + L::BAR_OFF);
-    uint32_t *tmem_slot = (uint32_t *)(mma_done + 1);
+    uint64_t *mma_done = (uint64_t *)(smem + L::BAR_OFF);   // [2]
+    uint32_t *tmem_slot = (uint32_t *)(mma_done + 2);
 
     const int r = threadIdx.x;            // A-tile row == TMEM lane == pixel within the tile
-    const int warp = r >> 5;
+    const int warp = r >> 5, lane = r & 31;
+    const int wi = r & (TILE_W - 1), hi = r >> 4;
 
-    // ---- one-time setup: resident filter bank, ones tile, per-channel parameters, barrier, TMEM
+    // ---- one-time setup: resident filter bank, ones tile, barriers, TMEM
     for (int i = r; i < L::B_BYTES / 16; i += SM_THREADS)
         reinterpret_cast<uint4 *>(sB)[i] = __ldg(reinterpret_cast<const uint4 *>(a.wimg) + i);
     for (int i = r; i < 512 / 4; i += SM_THREADS) reinterpret_cast<uint32_t *>(smem + L::ONES_OFF)[i] = 0x01010101u;
-    for (int i = r; i < BN; i += SM_THREADS) {
-        s_q[i] = __ldg(a.ep.chanq + i);
-        s_mc[i] = __ldg(a.ep.mcomb + i);
-    }
     if (r == 0) {
-        mbar_init(mma_done, 1);
+        mbar_init(&mma_done[0], 1);
+        mbar_init(&mma_done[1], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) tmem_alloc<small_tmem_cols<BN>()>(tmem_slot);
@@ -125,111 +149,200 @@ __global__ void __launch_bounds__(SM_THREADS, 4) conv_u8_tc_small_kernel(const S
             if (ch0 + b < a.C) v |= (uint32_t)a.zp_in << (8 * b);
         return v;
     };
-    const int actm = yq::act_mode(a.ep.act);
     const int swz = (r >> 2) & 1;          // SWIZZLE_32B: 16-byte chunk index ^= address bit 7 = (row >> 2) & 1
-    uint32_t phase = 0;
+    // index arithmetic = per-thread constant part (computed once) + per-tile uniform part
+    const int thr_in_off = (hi * a.stride * a.W + wi * a.stride) * CS;
+    const int row_pitch = a.W * CS;
+    const int thr_out_off = (hi * a.OW + wi) * a.CSO;
+    const int thr_pool_off = ((hi >> 1) * a.PW + (wi >> 1)) * a.CSO;
+    uint8_t *const sA_thr = smem + L::A_OFF + r * 32;
 
-    for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
-        const int m = tile * 128 + r;
-        const bool valid = m < a.M_total;
-        int n = 0, oy = 0, ox = 0;
-        if (valid) {
-            n = m / (a.OH * a.OW);
-            const int rem = m - n * a.OH * a.OW;
-            oy = rem / a.OW;
-            ox = rem - oy * a.OW;
-        }
-        const int iy0 = oy * a.stride - a.pad, ix0 = ox * a.stride - a.pad;
-        const uint8_t *img = a.in + (size_t)n * a.H * a.W * CS;
+    const int first = blockIdx.x, step = gridDim.x;
+    const int cnt = first < a.num_tiles ? (a.num_tiles - first + step - 1) / step : 0;
+    TileWalker walk;
+    TilePos lp;                          // position of the next tile to LOAD
+    walk.init(a, step, first, lp);
+    auto pack_pos = [](const TilePos &t) -> uint32_t { return ((uint32_t)t.n << 16) | ((uint32_t)t.ty << 8) | (uint32_t)t.tx; };
 
-        // ---- build this pixel's im2col row: chunk g (16 bytes) of the K axis -> panel g/2, half g%2
+    // ---- gather this thread's im2col row for the tile at `t` into registers (the loads stay in flight while the
+    //      previous tile's MMA and epilogue run)
+    auto load_row = [&](const TilePos &t, uint4 (&pre)[G::NREAL]) {
+        const int y0 = t.ty * TILE_H * a.stride - a.pad, x0 = t.tx * TILE_W * a.stride - a.pad;   // first tap of the tile
+        const uint8_t *row0 = a.in + ((long long)(t.n * a.H + y0) * a.W + x0) * CS + thr_in_off;
+        const uint8_t *rows[3] = {row0, row0 + row_pitch, row0 + 2 * row_pitch};
+        // interior tile: every tap of every pixel is inside the image and every pixel inside the output
+        const bool interior = y0 >= 0 && x0 >= 0 && y0 + (TILE_H - 1) * a.stride + 2 < a.H && x0 + (TILE_W - 1) * a.stride + 2 < a.W &&
+                              t.ty * TILE_H + TILE_H <= a.OH && t.tx * TILE_W + TILE_W <= a.OW;
+        if (interior) {
+            if (CS == 4) {
+                uint32_t wv[12];
 #pragma unroll
-        for (int g = 0; g < 2 * G::P; ++g) {
-            uint4 v = make_uint4(0, 0, 0, 0);
-            if (valid) {
-                if (CS == 4) {
-                    uint32_t wv[4] = {0, 0, 0, 0};
+                for (int tap = 0; tap < 12; ++tap)
+                    wv[tap] = tap < TAPS ? __ldg(reinterpret_cast<const uint32_t *>(rows[tap < TAPS ? tap / 3 : 0] + (tap % 3) * 4)) : 0u;
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const int tap = 4 * g + j;
-                        if (tap < TAPS) {
-                            const int iy = iy0 + tap / 3, ix = ix0 + tap % 3;
-                            wv[j] = (iy < 0 || iy >= a.H || ix < 0 || ix >= a.W)
-                                        ? fill_word(0)
-                                        : __ldg(reinterpret_cast<const uint32_t *>(img + ((size_t)iy * a.W + ix) * 4));
-                        }
-                    }
-                    v = make_uint4(wv[0], wv[1], wv[2], wv[3]);
-                } else {
-                    constexpr int CPT = CS / 16;   // 16-byte chunks per tap
-                    const int tap = g / CPT, sub = g % CPT;
-                    if (tap < TAPS) {
-                        const int iy = iy0 + tap / 3, ix = ix0 + tap % 3;
-                        if (iy < 0 || iy >= a.H || ix < 0 || ix >= a.W)
-                            v = make_uint4(fill_word(sub * 16), fill_word(sub * 16 + 4), fill_word(sub * 16 + 8), fill_word(sub * 16 + 12));
-                        else
-                            v = __ldg(reinterpret_cast<const uint4 *>(img + ((size_t)iy * a.W + ix) * CS + sub * 16));
-                    }
+                for (int g = 0; g < 3; ++g) pre[g] = make_uint4(wv[4 * g], wv[4 * g + 1], wv[4 * g + 2], wv[4 * g + 3]);
+            } else {
+                constexpr int CPT = CS / 16;
+#pragma unroll
+                for (int g = 0; g < G::NREAL; ++g) {
+                    const int tap = g / CPT;
+                    pre[g] = __ldg(reinterpret_cast<const uint4 *>(rows[tap / 3] + (tap % 3) * CS + (g % CPT) * 16));
                 }
             }
-            *reinterpret_cast<uint4 *>(sA + (g >> 1) * 4096 + r * 32 + (((g & 1) ^ swz) << 4)) = v;
+            return;
         }
-        fence_proxy_async();     // generic-proxy smem writes -> visible to the tensor core (async proxy)
-        __syncthreads();
+        const int oy = t.ty * TILE_H + hi, ox = t.tx * TILE_W + wi;
+        const bool valid = ox < a.OW && oy < a.OH;
+        const int iy0 = y0 + hi * a.stride, ix0 = x0 + wi * a.stride;
+        bool vy[3], vx[3];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            vy[k] = valid && (unsigned)(iy0 + k) < (unsigned)a.H;
+            vx[k] = (unsigned)(ix0 + k) < (unsigned)a.W;
+        }
+        if (CS == 4) {
+            uint32_t wv[12];
+            const uint32_t fw = valid ? fill_word(0) : 0u;
+#pragma unroll
+            for (int tap = 0; tap < 12; ++tap) {
+                wv[tap] = 0;
+                if (tap < TAPS)
+                    wv[tap] = (vy[tap / 3] && vx[tap % 3]) ? __ldg(reinterpret_cast<const uint32_t *>(rows[tap < TAPS ? tap / 3 : 0] + (tap % 3) * 4)) : fw;
+            }
+#pragma unroll
+            for (int g = 0; g < 3; ++g) pre[g] = make_uint4(wv[4 * g], wv[4 * g + 1], wv[4 * g + 2], wv[4 * g + 3]);
+        } else {
+            constexpr int CPT = CS / 16;   // 16-byte chunks per tap
+#pragma unroll
+            for (int g = 0; g < G::NREAL; ++g) {
+                const int tap = g / CPT, sub = g % CPT;
+                if (vy[tap / 3] && vx[tap % 3])
+                    pre[g] = __ldg(reinterpret_cast<const uint4 *>(rows[tap / 3] + (tap % 3) * CS + sub * 16));
+                else if (valid)
+                    pre[g] = make_uint4(fill_word(sub * 16), fill_word(sub * 16 + 4), fill_word(sub * 16 + 8), fill_word(sub * 16 + 12));
+                else
+                    pre[g] = make_uint4(0, 0, 0, 0);
+            }
+        }
+    };
+    // chunk g (16 bytes) of the K axis -> panel g/2, half g%2, SWIZZLE_32B
+    auto store_row = [&](const uint4 (&pre)[G::NREAL], int buf) {
+        uint8_t *sA = sA_thr + buf * G::A_BYTES;
+#pragma unroll
+        for (int g = 0; g < G::NCHUNK; ++g) {
+            const uint4 v = g < G::NREAL ? pre[g < G::NREAL ? g : 0] : make_uint4(0, 0, 0, 0);
+            *reinterpret_cast<uint4 *>(sA + (g >> 1) * 4096 + (((g & 1) ^ swz) << 4)) = v;
+        }
+    };
+    auto issue_mma = [&](int buf) {   // one thread issues the MMAs of a whole tile
+        constexpr uint32_t idesc_main = make_idesc(BN);
+        constexpr uint32_t idesc_ones = make_idesc(16);
+        const uint64_t d_ones = make_desc<32>(smem_u32(smem + L::ONES_OFF));
+        const uint32_t a0 = smem_u32(smem + L::A_OFF + buf * G::A_BYTES), b0 = smem_u32(sB);
+        const uint32_t acc = tmem_base + buf * (BN + 16);
+#pragma unroll
+        for (int p = 0; p < G::P; ++p) {
+            const uint64_t da = make_desc<32>(a0 + p * 4096);
+            umma_i8(acc, da, make_desc<32>(b0 + p * BN * 32), idesc_main, p ? 1u : 0u);
+            umma_i8(acc + BN, da, d_ones, idesc_ones, p ? 1u : 0u);   // sum of activations
+        }
+        umma_commit(&mma_done[buf]);
+    };
 
-        // ---- one thread issues the MMAs for the whole tile
+    uint32_t q0 = 0, q1 = 0;             // packed positions of the tiles whose epilogues are pending (q0 = oldest)
+    uint32_t phase_bits = 0;
+    uint4 pre[G::NREAL];
+    if (cnt > 0) {
+        load_row(lp, pre);
+        q0 = pack_pos(lp);
+        walk.advance(lp);
+        store_row(pre, 0);
+        fence_proxy_async();     // generic-proxy smem writes -> visible to the tensor core (async proxy)
+        tc_fence_before();
+        __syncthreads();
         if (r == 0) {
             tc_fence_after();
-            constexpr uint32_t idesc_main = make_idesc(BN);
-            constexpr uint32_t idesc_ones = make_idesc(16);
-            const uint64_t d_ones = make_desc<32>(smem_u32(smem + L::ONES_OFF));
-            const uint32_t a0 = smem_u32(sA), b0 = smem_u32(sB);
-#pragma unroll
-            for (int p = 0; p < G::P; ++p) {
-                const uint64_t da = make_desc<32>(a0 + p * 4096);
-                umma_i8(tmem_base, da, make_desc<32>(b0 + p * BN * 32), idesc_main, p ? 1u : 0u);
-                umma_i8(tmem_base + BN, da, d_ones, idesc_ones, p ? 1u : 0u);
-            }
-            umma_commit(mma_done);
+            issue_mma(0);
         }
-        mbar_wait(mma_done, phase);
-        phase ^= 1;
+        if (cnt > 1) {
+            load_row(lp, pre);
+            q1 = pack_pos(lp);
+            walk.advance(lp);
+        }
+    }
+    const bool side = (a.out_acc != nullptr) || (a.out_f32 != nullptr);
+    for (int i = 0; i < cnt; ++i) {
+        const int b = i & 1;
+        const uint32_t qe = q0;          // tile whose epilogue runs in this iteration
+        q0 = q1;
+        if (i + 1 < cnt) {
+            // A[b^1] is free (MMA(i-1) was waited for in the previous iteration); acc[b^1] was drained by every
+            // thread before it reaches this barrier
+            store_row(pre, b ^ 1);
+            fence_proxy_async();
+            tc_fence_before();
+            __syncthreads();
+            if (r == 0) {
+                tc_fence_after();
+                issue_mma(b ^ 1);
+            }
+            if (i + 2 < cnt) {
+                load_row(lp, pre);
+                q1 = pack_pos(lp);
+                walk.advance(lp);
+            }
+        }
+        mbar_wait(&mma_done[b], (phase_bits >> b) & 1u);
+        phase_bits ^= 1u << b;
         tc_fence_after();
 
-        // ---- epilogue: this thread owns TMEM lane r = its pixel
-        const int nsa = -(int)tmem_ld1(trow + BN);   // minus the pixel's activation sum (ones-tile columns)
-        uint8_t *orow = a.out + (size_t)m * a.CSO;
-        constexpr int STEP = 16;
-        const bool side = (a.out_acc != nullptr) || (a.out_f32 != nullptr);
-#pragma unroll 1
-        for (int c0 = 0; c0 < BN; c0 += STEP) {
-            uint32_t v[STEP];
-            tmem_ld16(trow + c0, v);
-            uint32_t packed[STEP / 4];
-            epi_chunk_small<STEP>(actm, a.ep.saturate, v, nsa, s_q + c0, s_mc + c0, a.ep.zp_out, packed);
-            yq::mask_pad_channels<STEP>(packed, a.N - c0);
-            if (side && valid) {   // parity / quant_stop side outputs (not on the throughput path)
+        // ---- epilogue of tile i: this thread owns TMEM lane r = its pixel
+        const int tn = (int)(qe >> 16), tty = (int)((qe >> 8) & 255u), ttx = (int)(qe & 255u);
+        const int ox = ttx * TILE_W + wi, oy = tty * TILE_H + hi;
+        const bool valid = ox < a.OW && oy < a.OH;
+        const uint32_t tacc = trow + b * (BN + 16);
+        const int nsa = -(int)tmem_ld1(tacc + BN);   // minus the pixel's activation sum (ones-tile columns)
+        uint8_t *const orow = a.out + ((size_t)(tn * a.OH + tty * TILE_H) * a.OW + ttx * TILE_W) * a.CSO + thr_out_off;
+        // fused 2x2 stride-2 max-pool: partners are lane^1 (x neighbour) and lane^16 (next row); out-of-image pixels count as 0
+        uint8_t *const prow = a.out_pool + ((size_t)(tn * a.PH + tty * (TILE_H / 2)) * a.PW + ttx * (TILE_W / 2)) * a.CSO + thr_pool_off;
+        const bool pool_writer = a.out_pool && ((lane & 17) == 0) && (ox >> 1) < a.PW && (oy >> 1) < a.PH;
 #pragma unroll
-                for (int j = 0; j < STEP; ++j) {
-                    const int oc = c0 + j;
+        for (int c0 = 0; c0 < BN; c0 += 16) {
+            uint32_t v[16];
+            tmem_ld16(tacc + c0, v);
+            uint32_t packed[4];
+            epi_chunk_small<ACTM, 16>(a.ep.saturate, v, nsa, a.cq + c0, a.mc + c0, a.ep.zp_out, packed);
+            yq::mask_pad_channels<16>(packed, a.N - c0);
+            if (side && valid) {   // parity / quant_stop side outputs (not on the throughput path)
+                const size_t pix = ((size_t)tn * a.OH + oy) * a.OW + ox;
+#pragma unroll
+                for (int jj = 0; jj < 16; ++jj) {
+                    const int oc = c0 + jj;
                     if (oc < a.N) {
-                        if (a.out_acc) a.out_acc[(size_t)m * a.CSO + oc] = (int)v[j] + s_q[oc].y * nsa;
+                        if (a.out_acc) a.out_acc[pix * a.CSO + oc] = (int)v[jj] + a.cq[oc].y * nsa;
                         if (a.out_f32) {
-                            const uint8_t u = (uint8_t)(packed[j / 4] >> (8 * (j % 4)));
-                            a.out_f32[((size_t)n * a.N + oc) * a.OH * a.OW + (size_t)oy * a.OW + ox] = yq::dequant_f32(a.ep, u);
+                            const uint8_t u = (uint8_t)(packed[jj / 4] >> (8 * (jj % 4)));
+                            a.out_f32[((size_t)tn * a.N + oc) * a.OH * a.OW + (size_t)oy * a.OW + ox] = yq::dequant_f32(a.ep, u);
                         }
                     }
                 }
             }
-            if (valid) {
+            if (a.out && valid) *reinterpret_cast<uint4 *>(orow + c0) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+            if (a.out_pool) {
+                uint32_t pm[4];
 #pragma unroll
-                for (int h = 0; h < STEP / 16; ++h)
-                    *reinterpret_cast<uint4 *>(orow + c0 + h * 16) = make_uint4(packed[4 * h], packed[4 * h + 1], packed[4 * h + 2], packed[4 * h + 3]);
+                for (int k = 0; k < 4; ++k) {
+                    uint32_t m = valid ? packed[k] : 0u;
+                    m = __vmaxu4(m, __shfl_xor_sync(0xffffffffu, m, 1));
+                    m = __vmaxu4(m, __shfl_xor_sync(0xffffffffu, m, 16));
+                    pm[k] = m;
+                }
+                if (pool_writer) *reinterpret_cast<uint4 *>(prow + c0) = make_uint4(pm[0], pm[1], pm[2], pm[3]);
             }
         }
         tc_fence_before();
-        __syncthreads();         // every lane drained before the next tile's MMAs overwrite TMEM / rows are rebuilt
     }
+    __syncthreads();
     if (warp == 0) {
         tc_fence_after();
         tmem_dealloc<small_tmem_cols<BN>()>(tmem_base);
@@ -241,19 +354,19 @@ struct SmallState {
     uint8_t *wimg = nullptr;
 };
 
-template <int CS, int BN>
+template <int CS, int BN, int ACTM>
 int launch_small(SmallState *st, const SmallArgs &a, cudaStream_t stream)
 {
     using L = SmallSmem<CS, BN>;
     static int ctas_per_sm = 0, n_sm = 0;
     const int smem = L::TOTAL + 1024;
     if (!ctas_per_sm) {
-        YQ_CUDA(cudaFuncSetAttribute(conv_u8_tc_small_kernel<CS, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        YQ_CUDA(cudaFuncSetAttribute(conv_u8_tc_small_kernel<CS, BN, ACTM>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         // cudaOccupancyMaxActiveBlocksPerMultiprocessor answers 1 for kernels that allocate tensor memory (measured on
         // B200), although the hardware co-schedules as many CTAs as smem / registers / TMEM columns allow: count by hand.
         int dev = 0, smem_sm = 0;
         cudaFuncAttributes fa;
-        YQ_CUDA(cudaFuncGetAttributes(&fa, conv_u8_tc_small_kernel<CS, BN>));
+        YQ_CUDA(cudaFuncGetAttributes(&fa, conv_u8_tc_small_kernel<CS, BN, ACTM>));
         YQ_CUDA(cudaGetDevice(&dev));
         YQ_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
         YQ_CUDA(cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev));
@@ -265,14 +378,22 @@ int launch_small(SmallState *st, const SmallArgs &a, cudaStream_t stream)
         if (by_threads < occ) occ = by_threads;
         const int tmem_limit = 512 / small_tmem_cols<BN>();   // every resident CTA must own its TMEM columns
         ctas_per_sm = occ < tmem_limit ? occ : tmem_limit;
-        if (getenv("YQ_DEBUG")) fprintf(stderr, "yq: small<%d,%d> occ=%d tmem_limit=%d n_sm=%d smem=%d\n", CS, BN, occ, tmem_limit, n_sm, smem);
+        if (getenv("YQ_DEBUG")) fprintf(stderr, "yq: small<%d,%d,%d> regs=%d occ=%d tmem_limit=%d n_sm=%d smem=%d\n", CS, BN, ACTM, fa.numRegs, occ, tmem_limit, n_sm, smem);
         if (ctas_per_sm < 1) return yq::fail("conv_u8_tc_small_kernel<%d,%d> does not fit on an SM", CS, BN);
     }
     int grid = n_sm * ctas_per_sm;
     if (grid > a.num_tiles) grid = a.num_tiles;
-    conv_u8_tc_small_kernel<CS, BN><<<grid, SM_THREADS, smem, stream>>>(a);
+    conv_u8_tc_small_kernel<CS, BN, ACTM><<<grid, SM_THREADS, smem, stream>>>(a);
     YQ_CHECK_LAUNCH();
     return 0;
+}
+
+template <int CS, int BN>
+int launch_small_act(SmallState *st, const SmallArgs &a, int actm, cudaStream_t stream)
+{
+    if (actm == 0) return launch_small<CS, BN, 0>(st, a, stream);
+    if (actm == 1) return launch_small<CS, BN, 1>(st, a, stream);
+    return launch_small<CS, BN, 2>(st, a, stream);
 }
 
 }  // namespace
@@ -282,8 +403,9 @@ int yq_tc_small_supported(const yq_conv_layer *l)
     if (!l->int_form || !l->fused_mult) return 0;   // the integer-form epilogue needs M0 * 2^-31 / 2^-s parameters
     if (l->size != 3 || l->pad != 1 || (l->stride != 1 && l->stride != 2)) return 0;
     if (!(l->cs_in == 4 || l->cs_in == 16 || l->cs_in == 32)) return 0;
-    if (l->cs_out < 16 || l->cs_out > 64 || (l->cs_out != 16 && l->cs_out != 32 && l->cs_out != 64)) return 0;
-    return 1;
+    // instantiated (cs_in, cs_out) pairs -- see yq_tc_small_forward
+    const int ci = l->cs_in, co = l->cs_out;
+    return (ci == 4 && (co == 16 || co == 64)) || (ci == 16 && (co == 16 || co == 32)) || (ci == 32 && co == 64);
 }
 
 int yq_tc_small_prepare(yq_conv_layer *l, void **state)
@@ -318,22 +440,30 @@ void yq_tc_small_free(void *state)
     delete st;
 }
 
-int yq_tc_small_forward(yq_conv_layer *l, void *state, const uint8_t *in_u8, uint8_t *out_u8, float *out_f32, int32_t *out_acc, int batch,
-                        cudaStream_t stream)
+int yq_tc_small_forward(yq_conv_layer *l, void *state, const uint8_t *in_u8, uint8_t *out_u8, uint8_t *out_pool, float *out_f32,
+                        int32_t *out_acc, int batch, cudaStream_t stream)
 {
     SmallState *st = (SmallState *)state;
     SmallArgs a;
     memset(&a, 0, sizeof a);
-    a.in = in_u8; a.out = out_u8; a.out_f32 = l->quant_stop_flag ? out_f32 : nullptr; a.out_acc = out_acc; a.wimg = st->wimg;
+    a.in = in_u8; a.out = out_u8; a.out_pool = out_pool; a.out_f32 = l->quant_stop_flag ? out_f32 : nullptr; a.out_acc = out_acc; a.wimg = st->wimg;
     a.ep = yq::make_epi(l);
     a.B = batch; a.H = l->h; a.W = l->w; a.C = l->c; a.OH = l->out_h; a.OW = l->out_w; a.N = l->n; a.CSO = l->cs_out;
     a.stride = l->stride; a.pad = l->pad; a.zp_in = l->zp_in;
-    a.M_total = batch * l->out_h * l->out_w;
-    a.num_tiles = (a.M_total + 127) / 128;
-#define YQ_SM(CS_, BN_) if (st->CS == CS_ && st->BN == BN_) return launch_small<CS_, BN_>(st, a, stream)
-    YQ_SM(4, 16); YQ_SM(4, 32); YQ_SM(4, 64);
-    YQ_SM(16, 16); YQ_SM(16, 32); YQ_SM(16, 64);
-    YQ_SM(32, 16); YQ_SM(32, 32); YQ_SM(32, 64);
+    a.tiles_x = (l->out_w + TILE_W - 1) / TILE_W;
+    a.tiles_y = (l->out_h + TILE_H - 1) / TILE_H;
+    a.num_tiles = a.tiles_x * a.tiles_y * batch;
+    a.PH = (l->out_h + 1) / 2;   // maxpool 2/2 with the default padding size-1: (h + 1 - 2)/2 + 1 (maxpool_layer.c:31-32)
+    a.PW = (l->out_w + 1) / 2;
+    if (!out_u8 && !out_pool) return yq::fail("conv: neither the conv output nor the pooled output was requested");
+    const int p = l->n < 64 ? l->n : 64;
+    memcpy(a.cq, l->host_chanq.data(), (size_t)p * 16);
+    memcpy(a.mc, l->host_mcomb.data(), (size_t)p * 8);
+    const int actm = yq::act_mode(l->activation);
+#define YQ_SM(CS_, BN_) if (st->CS == CS_ && st->BN == BN_) return launch_small_act<CS_, BN_>(st, a, actm, stream)
+    YQ_SM(4, 16); YQ_SM(4, 64);
+    YQ_SM(16, 16); YQ_SM(16, 32);
+    YQ_SM(32, 64);
 #undef YQ_SM
     return yq::fail("tcgen05 small-c flavour: no instantiation for cs_in=%d cs_out=%d", st->CS, st->BN);
 }

@@ -402,6 +402,9 @@ extern "C" yq_conv_layer *yq_make_convolutional_layer_quant(const yq_conv_desc *
         if (!(m0d > 0.0 && m0d < 2147483648.0 && m0d == std::floor(m0d) && mant == 0.5 && sh >= 0 && sh <= 31)) l->int_form = 0;
         else chanq[oc] = make_int4(bias[oc], zw[oc], (int)(uint32_t)((uint64_t)m0d * 2ull), sh);
     }
+    l->host_chanq.resize((size_t)p_pad * 4);
+    memcpy(l->host_chanq.data(), chanq.data(), (size_t)p_pad * 16);
+    l->host_mcomb = mcomb;
     if (upload(&l->w_simt, wp) || upload(&l->bias, bias) || upload(&l->zw, zw) || upload(&l->mcomb, mcomb) ||
         upload(&l->mval, mval) || upload(&l->rsh, rsh) || upload((int4 **)&l->chanq, chanq)) {
         yq_free_convolutional_layer_quant(l);
@@ -435,14 +438,24 @@ extern "C" int yq_conv_set_kernel(yq_conv_layer *l, int kind)
     return 0;
 }
 
+extern "C" int yq_forward_convolutional_layer_quant_pool_gpu(yq_conv_layer *l, const uint8_t *in_u8, uint8_t *out_u8, uint8_t *out_pool,
+                                                             float *out_f32, int32_t *out_acc, int batch, void *stream)
+{
+    if (!l || !in_u8 || (!out_u8 && !out_pool) || batch <= 0) return yq::fail("yq_forward_convolutional_layer_quant_gpu: bad argument");
+    if (l->quant_stop_flag && !out_f32) return yq::fail("quant_stop layer needs out_f32");
+    if (out_pool && !yq_tc_can_fuse_pool(l)) return yq::fail("this layer's kernel flavour cannot fuse the max-pool (see yq_conv_can_fuse_maxpool)");
+    if (l->kernel == 1) return yq_tc_forward(l, in_u8, out_u8, out_pool, out_f32, out_acc, batch, (cudaStream_t)stream);
+    return launch_simt(l, in_u8, out_u8, out_f32, out_acc, batch, (cudaStream_t)stream);
+}
+
 extern "C" int yq_forward_convolutional_layer_quant_gpu(yq_conv_layer *l, const uint8_t *in_u8, uint8_t *out_u8,
                                                         float *out_f32, int32_t *out_acc, int batch, void *stream)
 {
-    if (!l || !in_u8 || !out_u8 || batch <= 0) return yq::fail("yq_forward_convolutional_layer_quant_gpu: bad argument");
-    if (l->quant_stop_flag && !out_f32) return yq::fail("quant_stop layer needs out_f32");
-    if (l->kernel == 1) return yq_tc_forward(l, in_u8, out_u8, out_f32, out_acc, batch, (cudaStream_t)stream);
-    return launch_simt(l, in_u8, out_u8, out_f32, out_acc, batch, (cudaStream_t)stream);
+    if (!out_u8) return yq::fail("yq_forward_convolutional_layer_quant_gpu: bad argument");
+    return yq_forward_convolutional_layer_quant_pool_gpu(l, in_u8, out_u8, nullptr, out_f32, out_acc, batch, stream);
 }
+
+extern "C" int yq_conv_can_fuse_maxpool(const yq_conv_layer *l) { return l ? yq_tc_can_fuse_pool(l) : 0; }
 
 // ------------------------------------------------------------------------------------------------
 // maxpool (src/maxpool_layer.c:109-153): out = max(0, in-bounds taps); window origin i*stride - pad/2

@@ -113,6 +113,8 @@ struct Layer {
     float *out_f32 = nullptr;      // NCHW (quant_stop convs, yolo)
     int32_t *out_acc = nullptr;    // NHWC, debug
     size_t u8_bytes = 0, f32_count = 0;
+    bool fuse_pool = false;        // conv: the next layer (maxpool 2/2) is produced by this layer's epilogue
+    bool fused_away = false;       // maxpool: produced by the previous conv, no launch
 };
 
 }  // namespace
@@ -128,6 +130,7 @@ struct yq_network {
     size_t scratch_bytes = 0;
     int keep_acc = 0;
     int conv_kernel = -1;
+    int fusion = 1;
     int use_graph = 0;
     std::vector<std::pair<const uint8_t *, cudaGraphExec_t>> graphs;   // one captured forward per input pointer
     std::vector<cudaEvent_t> prof_events;                               // per-layer profiling (yq_network_profile_forward)
@@ -232,6 +235,39 @@ void drop_graph(yq_network *net)
     net->graphs.clear();
 }
 
+// Decide which conv -> maxpool(2,2) pairs run as one launch, and count launches.  A pair fuses when the conv's
+// flavour can pool in its epilogue and the pool is the 2x2 / stride-2 / default-padding kind.  The conv's own
+// (unpooled) tensor is still written when another layer routes from it or when debug pulls are enabled.
+void plan(yq_network *net)
+{
+    const int n = (int)net->layers.size();
+    for (auto &l : net->layers) l.fuse_pool = l.fused_away = false;
+    int launches = 1;
+    for (int i = 0; i < n; ++i) {
+        Layer &l = net->layers[i];
+        if (l.type == L_CONV && net->fusion && i + 1 < n && l.conv && yq_conv_can_fuse_maxpool(l.conv)) {
+            Layer &p = net->layers[i + 1];
+            if (p.type == L_MAXPOOL && p.size == 2 && p.stride == 2 && p.pad == 1) {
+                l.fuse_pool = true;
+                p.fused_away = true;
+            }
+        }
+        if (l.fused_away || (l.type == L_ROUTE && l.inputs.size() == 1)) continue;
+        ++launches;
+    }
+    net->launches = launches;
+}
+
+bool conv_output_needed(const yq_network *net, int i)
+{
+    if (net->keep_acc) return true;   // debug: every layer stays pullable
+    for (const auto &l : net->layers)
+        if (l.type == L_ROUTE)
+            for (int idx : l.inputs)
+                if (idx == i) return true;
+    return false;
+}
+
 // the kernel sequence of one forward_network pass (network.c:229-261)
 int forward_body(yq_network *net, const uint8_t *in_u8_nchw, int *launches, bool profile = false)
 {
@@ -247,16 +283,24 @@ int forward_body(yq_network *net, const uint8_t *in_u8_nchw, int *launches, bool
         Layer &l = net->layers[i];
         switch (l.type) {
         case L_CONV:
-            if (yq_forward_convolutional_layer_quant_gpu(l.conv, cur, l.out_u8, l.out_f32, net->keep_acc ? l.out_acc : nullptr,
-                                                         net->batch, st))
+            if (l.fuse_pool) {
+                uint8_t *conv_out = conv_output_needed(net, (int)i) ? l.out_u8 : nullptr;
+                if (yq_forward_convolutional_layer_quant_pool_gpu(l.conv, cur, conv_out, net->layers[i + 1].out_u8, l.out_f32,
+                                                                  net->keep_acc ? l.out_acc : nullptr, net->batch, st))
+                    return -1;
+            } else if (yq_forward_convolutional_layer_quant_gpu(l.conv, cur, l.out_u8, l.out_f32, net->keep_acc ? l.out_acc : nullptr,
+                                                                net->batch, st)) {
                 return -1;
+            }
             ++nl;
             cur = l.out_u8;
             cur_f32 = l.out_f32;
             break;
         case L_MAXPOOL:
-            if (yq_forward_maxpool_layer_quant_gpu(cur, l.out_u8, net->batch, l.h, l.w, l.c, l.size, l.stride, l.pad, st)) return -1;
-            ++nl;
+            if (!l.fused_away) {
+                if (yq_forward_maxpool_layer_quant_gpu(cur, l.out_u8, net->batch, l.h, l.w, l.c, l.size, l.stride, l.pad, st)) return -1;
+                ++nl;
+            }
             cur = l.out_u8;
             break;
         case L_UPSAMPLE:
@@ -554,9 +598,7 @@ extern "C" yq_network *yq_load_network(const char *cfg, const char *weights, int
         yq::fail("cudaMalloc of network input failed");
         return bail();
     }
-    raw->launches = 1;
-    for (auto &l : raw->layers)
-        if (!(l.type == L_ROUTE && l.inputs.size() == 1)) raw->launches++;
+    plan(raw);
     return raw;
 }
 
@@ -624,6 +666,7 @@ extern "C" int yq_network_set_input_quant(yq_network *net, float s_in, int zp_in
     l.s_in = s_in;
     l.zp_in = zp_in & 0xff;
     if (prepare_conv(l, 0) || build_conv_device(net, l)) return -1;
+    plan(net);
     return 0;
 }
 
@@ -647,6 +690,15 @@ extern "C" int yq_network_set_conv_kernel(yq_network *net, int kind)
     net->conv_kernel = kind;
     for (auto &l : net->layers)
         if (l.conv) apply_kernel_choice(l.conv, kind);
+    plan(net);
+    return 0;
+}
+
+extern "C" int yq_network_set_fusion(yq_network *net, int enable)
+{
+    drop_graph(net);
+    net->fusion = enable;
+    plan(net);
     return 0;
 }
 

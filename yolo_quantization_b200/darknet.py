@@ -159,6 +159,32 @@ class ConvolutionalLayerQuant:
                 d.free()
         return res
 
+    @property
+    def can_fuse_maxpool(self) -> bool:
+        return bool(_lib.load().yq_conv_can_fuse_maxpool(self.handle))
+
+    def forward_pooled(self, x_nchw: np.ndarray, want_conv: bool = True) -> Dict[str, np.ndarray]:
+        """conv + fused maxpool(2,2): returns dict(pool=[b,n,ceil(oh/2),ceil(ow/2)], u8=... when want_conv)."""
+        lib = _lib.load()
+        b = x_nchw.shape[0]
+        din = push_nchw_u8(x_nchw)
+        cs = channel_stride(self.n)
+        ph, pw = (self.out_h + 1) // 2, (self.out_w + 1) // 2
+        dout = DeviceBuffer(b * self.out_h * self.out_w * cs) if want_conv else None
+        dpool = DeviceBuffer(b * ph * pw * cs)
+        df32 = DeviceBuffer(b * self.n * self.out_h * self.out_w * 4) if self.quant_stop_flag else None
+        check(lib.yq_forward_convolutional_layer_quant_pool_gpu(self.handle, din.ptr, dout.ptr if dout else None, dpool.ptr,
+                                                                df32.ptr if df32 else None, None, b, None),
+              "yq_forward_convolutional_layer_quant_pool_gpu")
+        check(lib.yq_stream_synchronize(None))
+        res = {"pool": pull_nhwc_u8(dpool, b, self.n, ph, pw)}
+        if dout:
+            res["u8"] = pull_nhwc_u8(dout, b, self.n, self.out_h, self.out_w)
+        for d in (din, dout, dpool, df32):
+            if d:
+                d.free()
+        return res
+
     def free(self) -> None:
         if self.handle:
             _lib.load().yq_free_convolutional_layer_quant(self.handle)
@@ -262,6 +288,9 @@ class Network:
 
     def set_debug(self, keep_acc: bool = True) -> None:
         check(_lib.load().yq_network_set_debug(self._h, int(keep_acc)))
+
+    def set_fusion(self, enable: bool) -> None:
+        check(_lib.load().yq_network_set_fusion(self._h, int(enable)))
 
     def set_conv_kernel(self, kind: int) -> None:
         check(_lib.load().yq_network_set_conv_kernel(self._h, int(kind)))
