@@ -108,7 +108,9 @@ struct TileWalker {
     }
 };
 
-template <int CS, int BN, int ACTM>
+// SLOW = the variant that also serves the int32 / float side outputs and the saturate switch (parity checks,
+// quant_stop heads); the production variant (SLOW = false) carries none of that code.
+template <int CS, int BN, int ACTM, bool SLOW>
 __global__ void __launch_bounds__(SM_THREADS, (CS == 32 ? 2 : (CS == 16 ? 4 : 6))) conv_u8_tc_small_kernel(const __grid_constant__ SmallArgs a)
 {
     using G = SmallGeom<CS>;
@@ -164,9 +166,13 @@ __global__ void __launch_bounds__(SM_THREADS, (CS == 32 ? 2 : (CS == 16 ? 4 : 6)
     walk.init(a, step, first, lp);
     auto pack_pos = [](const TilePos &t) -> uint32_t { return ((uint32_t)t.n << 16) | ((uint32_t)t.ty << 8) | (uint32_t)t.tx; };
 
-    // ---- gather this thread's im2col row for the tile at `t` into registers (the loads stay in flight while the
-    //      previous tile's MMA and epilogue run)
-    auto load_row = [&](const TilePos &t, uint4 (&pre)[G::NREAL]) {
+    // ---- gather this thread's im2col row for the tile at `t` straight into the swizzled A buffer with cp.async
+    //      (no staging registers; the copies stay in flight while the previous tile's MMA and epilogue run).
+    //      chunk g (16 bytes) of the K axis -> panel g/2, half g%2, SWIZZLE_32B.  Zero K-padding was written once.
+    auto chunk_addr = [&](int buf, int g) -> uint32_t {
+        return smem_u32(sA_thr + buf * G::A_BYTES + (g >> 1) * 4096 + (((g & 1) ^ swz) << 4));
+    };
+    auto issue_row = [&](const TilePos &t, int buf) {
         const int y0 = t.ty * TILE_H * a.stride - a.pad, x0 = t.tx * TILE_W * a.stride - a.pad;   // first tap of the tile
         const uint8_t *row0 = a.in + ((long long)(t.n * a.H + y0) * a.W + x0) * CS + thr_in_off;
         const uint8_t *rows[3] = {row0, row0 + row_pitch, row0 + 2 * row_pitch};
@@ -175,18 +181,14 @@ __global__ void __launch_bounds__(SM_THREADS, (CS == 32 ? 2 : (CS == 16 ? 4 : 6)
                               t.ty * TILE_H + TILE_H <= a.OH && t.tx * TILE_W + TILE_W <= a.OW;
         if (interior) {
             if (CS == 4) {
-                uint32_t wv[12];
 #pragma unroll
-                for (int tap = 0; tap < 12; ++tap)
-                    wv[tap] = tap < TAPS ? __ldg(reinterpret_cast<const uint32_t *>(rows[tap < TAPS ? tap / 3 : 0] + (tap % 3) * 4)) : 0u;
-#pragma unroll
-                for (int g = 0; g < 3; ++g) pre[g] = make_uint4(wv[4 * g], wv[4 * g + 1], wv[4 * g + 2], wv[4 * g + 3]);
+                for (int tap = 0; tap < TAPS; ++tap) cp_async4(chunk_addr(buf, tap / 4) + (tap % 4) * 4, rows[tap / 3] + (tap % 3) * 4);
             } else {
                 constexpr int CPT = CS / 16;
 #pragma unroll
                 for (int g = 0; g < G::NREAL; ++g) {
                     const int tap = g / CPT;
-                    pre[g] = __ldg(reinterpret_cast<const uint4 *>(rows[tap / 3] + (tap % 3) * CS + (g % CPT) * 16));
+                    cp_async16(chunk_addr(buf, g), rows[tap / 3] + (tap % 3) * CS + (g % CPT) * 16);
                 }
             }
             return;
@@ -201,37 +203,23 @@ __global__ void __launch_bounds__(SM_THREADS, (CS == 32 ? 2 : (CS == 16 ? 4 : 6)
             vx[k] = (unsigned)(ix0 + k) < (unsigned)a.W;
         }
         if (CS == 4) {
-            uint32_t wv[12];
             const uint32_t fw = valid ? fill_word(0) : 0u;
 #pragma unroll
-            for (int tap = 0; tap < 12; ++tap) {
-                wv[tap] = 0;
-                if (tap < TAPS)
-                    wv[tap] = (vy[tap / 3] && vx[tap % 3]) ? __ldg(reinterpret_cast<const uint32_t *>(rows[tap < TAPS ? tap / 3 : 0] + (tap % 3) * 4)) : fw;
+            for (int tap = 0; tap < TAPS; ++tap) {
+                const uint32_t dst = chunk_addr(buf, tap / 4) + (tap % 4) * 4;
+                if (vy[tap / 3] && vx[tap % 3]) cp_async4(dst, rows[tap / 3] + (tap % 3) * 4);
+                else st_shared32(dst, fw);
             }
-#pragma unroll
-            for (int g = 0; g < 3; ++g) pre[g] = make_uint4(wv[4 * g], wv[4 * g + 1], wv[4 * g + 2], wv[4 * g + 3]);
         } else {
             constexpr int CPT = CS / 16;   // 16-byte chunks per tap
 #pragma unroll
             for (int g = 0; g < G::NREAL; ++g) {
                 const int tap = g / CPT, sub = g % CPT;
-                if (vy[tap / 3] && vx[tap % 3])
-                    pre[g] = __ldg(reinterpret_cast<const uint4 *>(rows[tap / 3] + (tap % 3) * CS + sub * 16));
-                else if (valid)
-                    pre[g] = make_uint4(fill_word(sub * 16), fill_word(sub * 16 + 4), fill_word(sub * 16 + 8), fill_word(sub * 16 + 12));
-                else
-                    pre[g] = make_uint4(0, 0, 0, 0);
+                const uint32_t dst = chunk_addr(buf, g);
+                if (vy[tap / 3] && vx[tap % 3]) cp_async16(dst, rows[tap / 3] + (tap % 3) * CS + sub * 16);
+                else if (valid) st_shared128(dst, make_uint4(fill_word(sub * 16), fill_word(sub * 16 + 4), fill_word(sub * 16 + 8), fill_word(sub * 16 + 12)));
+                else st_shared128(dst, make_uint4(0, 0, 0, 0));
             }
-        }
-    };
-    // chunk g (16 bytes) of the K axis -> panel g/2, half g%2, SWIZZLE_32B
-    auto store_row = [&](const uint4 (&pre)[G::NREAL], int buf) {
-        uint8_t *sA = sA_thr + buf * G::A_BYTES;
-#pragma unroll
-        for (int g = 0; g < G::NCHUNK; ++g) {
-            const uint4 v = g < G::NREAL ? pre[g < G::NREAL ? g : 0] : make_uint4(0, 0, 0, 0);
-            *reinterpret_cast<uint4 *>(sA + (g >> 1) * 4096 + (((g & 1) ^ swz) << 4)) = v;
         }
     };
     auto issue_mma = [&](int buf) {   // one thread issues the MMAs of a whole tile
@@ -249,14 +237,24 @@ __global__ void __launch_bounds__(SM_THREADS, (CS == 32 ? 2 : (CS == 16 ? 4 : 6)
         umma_commit(&mma_done[buf]);
     };
 
+    // zero the K padding of both A buffers once (cp.async only ever writes the data chunks)
+    for (int buf = 0; buf < 2; ++buf) {
+        if (CS == 4) {
+#pragma unroll
+            for (int g = 2; g < G::NCHUNK; ++g) st_shared128(chunk_addr(buf, g), make_uint4(0, 0, 0, 0));   // taps 8..15: tap 8 is rewritten per tile
+        } else {
+#pragma unroll
+            for (int g = G::NREAL; g < G::NCHUNK; ++g) st_shared128(chunk_addr(buf, g), make_uint4(0, 0, 0, 0));
+        }
+    }
+
     uint32_t q0 = 0, q1 = 0;             // packed positions of the tiles whose epilogues are pending (q0 = oldest)
     uint32_t phase_bits = 0;
-    uint4 pre[G::NREAL];
     if (cnt > 0) {
-        load_row(lp, pre);
+        issue_row(lp, 0);
         q0 = pack_pos(lp);
         walk.advance(lp);
-        store_row(pre, 0);
+        cp_async_wait_all();
         fence_proxy_async();     // generic-proxy smem writes -> visible to the tensor core (async proxy)
         tc_fence_before();
         __syncthreads();
@@ -265,20 +263,20 @@ __global__ void __launch_bounds__(SM_THREADS, (CS == 32 ? 2 : (CS == 16 ? 4 : 6)
             issue_mma(0);
         }
         if (cnt > 1) {
-            load_row(lp, pre);
+            issue_row(lp, 1);
             q1 = pack_pos(lp);
             walk.advance(lp);
         }
     }
-    const bool side = (a.out_acc != nullptr) || (a.out_f32 != nullptr);
+    const bool side = SLOW && ((a.out_acc != nullptr) || (a.out_f32 != nullptr));
     for (int i = 0; i < cnt; ++i) {
         const int b = i & 1;
         const uint32_t qe = q0;          // tile whose epilogue runs in this iteration
         q0 = q1;
         if (i + 1 < cnt) {
-            // A[b^1] is free (MMA(i-1) was waited for in the previous iteration); acc[b^1] was drained by every
+            // tile i+1's row has been landing in A[b^1] since the previous iteration; acc[b^1] was drained by every
             // thread before it reaches this barrier
-            store_row(pre, b ^ 1);
+            cp_async_wait_all();
             fence_proxy_async();
             tc_fence_before();
             __syncthreads();
@@ -286,15 +284,15 @@ __global__ void __launch_bounds__(SM_THREADS, (CS == 32 ? 2 : (CS == 16 ? 4 : 6)
                 tc_fence_after();
                 issue_mma(b ^ 1);
             }
-            if (i + 2 < cnt) {
-                load_row(lp, pre);
-                q1 = pack_pos(lp);
-                walk.advance(lp);
-            }
         }
-        mbar_wait(&mma_done[b], (phase_bits >> b) & 1u);
+        mbar_wait(&mma_done[b], (phase_bits >> b) & 1u);   // MMA(i) complete: acc[b] ready, A[b] free
         phase_bits ^= 1u << b;
         tc_fence_after();
+        if (i + 2 < cnt) {
+            issue_row(lp, b);
+            q1 = pack_pos(lp);
+            walk.advance(lp);
+        }
 
         // ---- epilogue of tile i: this thread owns TMEM lane r = its pixel
         const int tn = (int)(qe >> 16), tty = (int)((qe >> 8) & 255u), ttx = (int)(qe & 255u);
@@ -311,9 +309,9 @@ __global__ void __launch_bounds__(SM_THREADS, (CS == 32 ? 2 : (CS == 16 ? 4 : 6)
             uint32_t v[16];
             tmem_ld16(tacc + c0, v);
             uint32_t packed[4];
-            epi_chunk_small<ACTM, 16>(a.ep.saturate, v, nsa, a.cq + c0, a.mc + c0, a.ep.zp_out, packed);
+            epi_chunk_small<ACTM, 16>(SLOW ? a.ep.saturate : 0, v, nsa, a.cq + c0, a.mc + c0, a.ep.zp_out, packed);
             yq::mask_pad_channels<16>(packed, a.N - c0);
-            if (side && valid) {   // parity / quant_stop side outputs (not on the throughput path)
+            if (SLOW && side && valid) {   // parity / quant_stop side outputs (not on the throughput path)
                 const size_t pix = ((size_t)tn * a.OH + oy) * a.OW + ox;
 #pragma unroll
                 for (int jj = 0; jj < 16; ++jj) {
@@ -354,19 +352,19 @@ struct SmallState {
     uint8_t *wimg = nullptr;
 };
 
-template <int CS, int BN, int ACTM>
+template <int CS, int BN, int ACTM, bool SLOW>
 int launch_small(SmallState *st, const SmallArgs &a, cudaStream_t stream)
 {
     using L = SmallSmem<CS, BN>;
     static int ctas_per_sm = 0, n_sm = 0;
     const int smem = L::TOTAL + 1024;
     if (!ctas_per_sm) {
-        YQ_CUDA(cudaFuncSetAttribute(conv_u8_tc_small_kernel<CS, BN, ACTM>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        YQ_CUDA(cudaFuncSetAttribute(conv_u8_tc_small_kernel<CS, BN, ACTM, SLOW>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         // cudaOccupancyMaxActiveBlocksPerMultiprocessor answers 1 for kernels that allocate tensor memory (measured on
         // B200), although the hardware co-schedules as many CTAs as smem / registers / TMEM columns allow: count by hand.
         int dev = 0, smem_sm = 0;
         cudaFuncAttributes fa;
-        YQ_CUDA(cudaFuncGetAttributes(&fa, conv_u8_tc_small_kernel<CS, BN, ACTM>));
+        YQ_CUDA(cudaFuncGetAttributes(&fa, conv_u8_tc_small_kernel<CS, BN, ACTM, SLOW>));
         YQ_CUDA(cudaGetDevice(&dev));
         YQ_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
         YQ_CUDA(cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev));
@@ -378,12 +376,12 @@ int launch_small(SmallState *st, const SmallArgs &a, cudaStream_t stream)
         if (by_threads < occ) occ = by_threads;
         const int tmem_limit = 512 / small_tmem_cols<BN>();   // every resident CTA must own its TMEM columns
         ctas_per_sm = occ < tmem_limit ? occ : tmem_limit;
-        if (getenv("YQ_DEBUG")) fprintf(stderr, "yq: small<%d,%d,%d> regs=%d occ=%d tmem_limit=%d n_sm=%d smem=%d\n", CS, BN, ACTM, fa.numRegs, occ, tmem_limit, n_sm, smem);
+        if (getenv("YQ_DEBUG")) fprintf(stderr, "yq: small<%d,%d,%d,%d> regs=%d occ=%d tmem_limit=%d n_sm=%d smem=%d\n", CS, BN, ACTM, (int)SLOW, fa.numRegs, occ, tmem_limit, n_sm, smem);
         if (ctas_per_sm < 1) return yq::fail("conv_u8_tc_small_kernel<%d,%d> does not fit on an SM", CS, BN);
     }
     int grid = n_sm * ctas_per_sm;
     if (grid > a.num_tiles) grid = a.num_tiles;
-    conv_u8_tc_small_kernel<CS, BN, ACTM><<<grid, SM_THREADS, smem, stream>>>(a);
+    conv_u8_tc_small_kernel<CS, BN, ACTM, SLOW><<<grid, SM_THREADS, smem, stream>>>(a);
     YQ_CHECK_LAUNCH();
     return 0;
 }
@@ -391,9 +389,15 @@ int launch_small(SmallState *st, const SmallArgs &a, cudaStream_t stream)
 template <int CS, int BN>
 int launch_small_act(SmallState *st, const SmallArgs &a, int actm, cudaStream_t stream)
 {
-    if (actm == 0) return launch_small<CS, BN, 0>(st, a, stream);
-    if (actm == 1) return launch_small<CS, BN, 1>(st, a, stream);
-    return launch_small<CS, BN, 2>(st, a, stream);
+    const bool slow = a.out_acc || a.out_f32 || a.ep.saturate;
+    if (slow) {
+        if (actm == 0) return launch_small<CS, BN, 0, true>(st, a, stream);
+        if (actm == 1) return launch_small<CS, BN, 1, true>(st, a, stream);
+        return launch_small<CS, BN, 2, true>(st, a, stream);
+    }
+    if (actm == 0) return launch_small<CS, BN, 0, false>(st, a, stream);
+    if (actm == 1) return launch_small<CS, BN, 1, false>(st, a, stream);
+    return launch_small<CS, BN, 2, false>(st, a, stream);
 }
 
 }  // namespace
