@@ -8,8 +8,9 @@
 //      reference pads with zp_in (im2col.c:5-14), which the epilogue restores exactly with a per-tap
 //      correction  zp_in * sum_ci (w - zp_w)  on border pixels.
 //   B  weights packed once at load as [oc][ky][kx][ci] (K-major), 2-D TMA load of a BN x KC tile.
-//   D  int32 accumulator in TMEM, columns [0,BN).  Columns [BN,BN+16) accumulate A x ONES (one extra N=16 MMA
-//      per K step against a constant all-ones tile) = sum of activations per pixel, which the epilogue needs
+//   D  int32 accumulator in TMEM, columns [0,BN).  Columns [BN,BN+16) accumulate A x ONES (16 constant all-ones
+//      rows appended to every stage's B tile, so one N = BN+16 MMA per K step reads A from shared memory once)
+//      = sum of activations per pixel, which the epilogue needs
 //      because weights are uint8 with a per-channel uint8 zero point (9-bit w - zp_w does not fit s8):
 //          acc = sum w*a - zp_w[oc] * sum a                      (convolutional_layer.c:718-721 restated)
 //   epilogue (4 warps, one TMEM lane = one pixel per thread): tcgen05.ld -> zero-point correction ->
@@ -57,12 +58,12 @@ __host__ __device__ constexpr int tmem_cols()
 template <int BN, int KC>
 struct SmemLayout {
     static constexpr int A_BYTES = 128 * KC;
-    static constexpr int B_BYTES = BN * KC;
-    static constexpr int STAGE = A_BYTES + B_BYTES;          // multiple of 1024
-    static constexpr int ONES_OFF = TC_STAGES * STAGE;
-    static constexpr int ONES_BYTES = 1024 * ((ONES_ROWS * KC + 1023) / 1024);
-    static constexpr int PARAM_OFF = ONES_OFF + ONES_BYTES;  // bias[BN] zw[BN] m0[BN] m1[BN]
-    static constexpr int PARAM_BYTES = BN * (4 + 4 + 8 + 8);
+    static constexpr int B_BYTES = BN * KC;                  // written by TMA every stage
+    static constexpr int ONES_BYTES = ONES_ROWS * KC;        // rows BN..BN+15 of the B tile: constant 0x01, written once
+    static constexpr int STAGE = A_BYTES + B_BYTES + ONES_BYTES;   // multiple of 1024
+    static constexpr int PARAM_OFF = TC_STAGES * STAGE;      // int4 {bias, zw, 2*M0, shift}[BN], double mcomb[BN]
+    static constexpr int PARAM_BYTES = BN * 24;
+    static_assert(STAGE % 1024 == 0, "stage buffers must keep the 1024-byte swizzle alignment");
     static constexpr int BAR_OFF = PARAM_OFF + PARAM_BYTES;
     static constexpr int TOTAL = BAR_OFF + 128;
     static_assert(128 * BN <= STAGE, "output staging aliases stage 0");
@@ -84,7 +85,8 @@ __device__ __forceinline__ void epi_chunk(int actm, int sat, const uint32_t (&v)
     }
 }
 
-template <int BN, int KC>
+// SLOW = the variant that also serves the int32 / float side outputs and the saturate switch
+template <int BN, int KC, bool SLOW>
 __global__ void __launch_bounds__(TC_THREADS, 2) conv_u8_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                                                                const __grid_constant__ CUtensorMap tmO, const TcArgs a)
 {
@@ -123,9 +125,12 @@ __global__ void __launch_bounds__(TC_THREADS, 2) conv_u8_tc_kernel(const __grid_
             s_q[i] = __ldg(a.ep.chanq + oc0 + i);
             s_mc[i] = __ldg(a.ep.mcomb + oc0 + i);
         }
-        uint32_t *ones = (uint32_t *)(smem + L::ONES_OFF);
-        for (int i = t; i < ONES_ROWS * KC / 4; i += 128) ones[i] = 0x01010101u;
-        fence_proxy_async();   // generic-proxy writes of the ones tile must be visible to the tensor core (async proxy)
+        // the 16 all-ones filter rows that follow the TMA-written BN rows of every stage's B tile (never overwritten)
+        for (int s = 0; s < TC_STAGES; ++s) {
+            uint32_t *ones = (uint32_t *)(smem + s * L::STAGE + L::A_BYTES + L::B_BYTES);
+            for (int i = t; i < L::ONES_BYTES / 4; i += 128) ones[i] = 0x01010101u;
+        }
+        fence_proxy_async();   // generic-proxy writes of the ones rows must be visible to the tensor core (async proxy)
     }
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
@@ -156,9 +161,9 @@ __global__ void __launch_bounds__(TC_THREADS, 2) conv_u8_tc_kernel(const __grid_
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
         if (lane == 0) {
-            constexpr uint32_t idesc_main = make_idesc(BN);
-            constexpr uint32_t idesc_ones = make_idesc(ONES_ROWS);
-            const uint64_t desc_ones = make_desc<KC>(smem_u32(smem + L::ONES_OFF));
+            // ONE instruction per K step: N = BN filter rows + 16 all-ones rows, so A is read from smem once and
+            // TMEM columns [BN, BN+16) receive the per-pixel activation sum
+            constexpr uint32_t idesc_main = make_idesc(BN + ONES_ROWS);
             for (int it = 0; it < kiters; ++it) {
                 const int s = it % TC_STAGES;
                 const uint32_t ph = (it / TC_STAGES) & 1;
@@ -170,7 +175,6 @@ __global__ void __launch_bounds__(TC_THREADS, 2) conv_u8_tc_kernel(const __grid_
                 for (int k = 0; k < KC / 32; ++k) {
                     const uint32_t accum = (it | k) ? 1u : 0u;
                     umma_i8(tmem_base, da + 2 * k, db + 2 * k, idesc_main, accum);       // +32 bytes = +2 in 16-byte units
-                    umma_i8(tmem_base + BN, da + 2 * k, desc_ones, idesc_ones, accum);   // sum of activations
                 }
                 umma_commit(&empty[s]);
             }
@@ -199,7 +203,8 @@ __global__ void __launch_bounds__(TC_THREADS, 2) conv_u8_tc_kernel(const __grid_
         uint8_t *stage_out = smem;              // aliases pipeline stage 0 (all MMAs have completed)
         const size_t pix = ((size_t)n * a.OH + oy) * a.OW + ox;
         const int actm = yq::act_mode(a.ep.act);
-        const bool side = (a.out_acc != nullptr) || (a.out_f32 != nullptr);
+        const bool side = SLOW && ((a.out_acc != nullptr) || (a.out_f32 != nullptr));
+        const int sat = SLOW ? a.ep.saturate : 0;
 #pragma unroll 1
         for (int c0 = 0; c0 < BN; c0 += 16) {
             uint32_t v[16];
@@ -214,12 +219,12 @@ __global__ void __launch_bounds__(TC_THREADS, 2) conv_u8_tc_kernel(const __grid_
 #pragma unroll
                     for (int j = 0; j < 16; ++j) extra[j] += __ldg(cr + j);
                 }
-                epi_chunk<true>(actm, a.ep.saturate, v, nsa, extra, s_q + c0, s_mc + c0, a.ep.zp_out, packed);
+                epi_chunk<true>(actm, sat, v, nsa, extra, s_q + c0, s_mc + c0, a.ep.zp_out, packed);
             } else {
-                epi_chunk<false>(actm, a.ep.saturate, v, nsa, extra, s_q + c0, s_mc + c0, a.ep.zp_out, packed);
+                epi_chunk<false>(actm, sat, v, nsa, extra, s_q + c0, s_mc + c0, a.ep.zp_out, packed);
             }
             yq::mask_pad_channels<16>(packed, a.N - (oc0 + c0));
-            if (side && valid) {   // parity / quant_stop side outputs (not on the throughput path)
+            if (SLOW && side && valid) {   // parity / quant_stop side outputs (not on the throughput path)
 #pragma unroll
                 for (int j = 0; j < 16; ++j) {
                     const int oc = oc0 + c0 + j;
@@ -333,19 +338,26 @@ void choose_tile(int B, int OH, int OW, int *tw, int *th, int *tn)
     }
 }
 
-template <int BN, int KC>
-int launch(yq_conv_layer *l, TcState *st, const CUtensorMap &tmA, const CUtensorMap &tmO, const TcArgs &a, dim3 grid, cudaStream_t stream)
+template <int BN, int KC, bool SLOW>
+int launch_v(TcState *st, const CUtensorMap &tmA, const CUtensorMap &tmO, const TcArgs &a, dim3 grid, cudaStream_t stream)
 {
     using L = SmemLayout<BN, KC>;
     static bool attr_done = false;
     const int smem = L::TOTAL + 1024;
     if (!attr_done) {
-        YQ_CUDA(cudaFuncSetAttribute(conv_u8_tc_kernel<BN, KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        YQ_CUDA(cudaFuncSetAttribute(conv_u8_tc_kernel<BN, KC, SLOW>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         attr_done = true;
     }
-    conv_u8_tc_kernel<BN, KC><<<grid, TC_THREADS, smem, stream>>>(tmA, st->tmB, tmO, a);
+    conv_u8_tc_kernel<BN, KC, SLOW><<<grid, TC_THREADS, smem, stream>>>(tmA, st->tmB, tmO, a);
     YQ_CHECK_LAUNCH();
     return 0;
+}
+
+template <int BN, int KC>
+int launch(yq_conv_layer *l, TcState *st, const CUtensorMap &tmA, const CUtensorMap &tmO, const TcArgs &a, dim3 grid, cudaStream_t stream)
+{
+    if (a.out_acc || a.out_f32 || a.ep.saturate) return launch_v<BN, KC, true>(st, tmA, tmO, a, grid, stream);
+    return launch_v<BN, KC, false>(st, tmA, tmO, a, grid, stream);
 }
 
 }  // namespace
