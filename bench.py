@@ -53,7 +53,7 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks/throttle reasons sampled every 200 ms while the timed regions run."""
+    """nvidia-smi clocks/throttle reasons sampled every 50 ms while the timed regions run."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
@@ -62,7 +62,7 @@ class ClockSampler:
         self.proc = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.th = threading.Thread(target=self._read, daemon=True)
             self.th.start()
@@ -314,7 +314,13 @@ def main():
         else:
             ach = top["bytes"] / (top["ms"] * 1e-3) / 1e9
             roof = {"bound": "hbm", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ach / pk["hbm_gbs"]}
-        roof.update(traffic=None, kernel=f"layer {top['layer']} ({top['type']}, flavour {top['kernel']})",
+        traffic = None
+        try:
+            with open(os.path.join(ROOT, "profiles", "r1_traffic.json")) as f:
+                traffic = json.load(f).get(str(top["layer"])) if B == 128 else None
+        except Exception:
+            pass
+        roof.update(traffic=traffic, kernel=f"layer {top['layer']} ({top['type']}, flavour {top['kernel']})",
                     share_of_step=top["ms"] / float(lm.sum()),
                     peak_source=(f"{pk['source']} MEASURED_PEAKS.json: int8 tensor peak taken as 2 x sustained bf16 "
                                  f"({pk['bf16_tflops_sustained']} TF/s; nominal dense int8 {NOMINAL_INT8_TOPS} TOP/s), "
@@ -329,8 +335,8 @@ def main():
             "config": {"workload": f"yolov3-tiny INT8 per-channel (24 layers, relu6, 5 classes), 416x416, batch {B} per GPU "
                                    f"(BASELINE configs[2]; x{world} GPUs = configs[3] sharding)",
                        "global_batch": B * world, "parallelism": f"dp{world}", "cuda_graph": not args.no_graph,
-                       "l2": f"{R} rotating input batches ({R * in_bytes >> 20} MiB) and ~{sum(r['bytes'] for r in rows) >> 20} MiB "
-                             f"of per-step activations, both > 126 MB L2; no explicit flush"},
+                       "l2": f"{R} rotating input batches ({R * in_bytes >> 20} MiB) > 126 MB L2 and several hundred MiB of "
+                             f"activations written per step; no explicit flush"},
             "e2e": {"value": ips_e2e, "unit": UNIT, "h2d_bytes_per_step": in_bytes * world,
                     "d2h_bytes_per_step": int(net.output_floats) * 4 * world, "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": net.launches_per_forward * args.steps * world,
