@@ -34,8 +34,8 @@ using namespace yqtc;
 
 namespace {
 
-constexpr int TC_EPI_WARPS = 8;                                  // two per TMEM lane quarter, each owns half of the BN columns
-constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS;               // warp 0 TMA, warp 1 MMA + TMEM owner, warps 2..9 epilogue
+constexpr int TC_THREADS = 192;
+constexpr int TC_STAGES = 3;
 constexpr int ONES_ROWS = 16;
 
 struct TcArgs {
@@ -44,16 +44,15 @@ struct TcArgs {
     int32_t *out_acc;
     const int32_t *corr;      // [size*size][n_pad] border correction, or nullptr when zp_in == 0
     int B, OH, OW, N, CSO, n_pad;
-    int TW, TH, TN, tiles_x, tiles_y, m_tiles, n_tiles, total_tiles;
+    int TW, TH, TN, tiles_x, tiles_y;
     int size, pad, cpt /* KC-chunks per tap */, CS;
     int H, W;
 };
 
-// two accumulators of BN + 16 columns
 template <int BN>
 __host__ __device__ constexpr int tmem_cols()
 {
-    return 2 * (BN + ONES_ROWS) <= 128 ? 128 : (2 * (BN + ONES_ROWS) <= 256 ? 256 : 512);
+    return BN + ONES_ROWS <= 32 ? 32 : BN + ONES_ROWS <= 64 ? 64 : BN + ONES_ROWS <= 128 ? 128 : BN + ONES_ROWS <= 256 ? 256 : 512;
 }
 
 template <int BN, int KC>
@@ -62,21 +61,15 @@ struct SmemLayout {
     static constexpr int B_BYTES = BN * KC;                  // written by TMA every stage
     static constexpr int ONES_BYTES = ONES_ROWS * KC;        // rows BN..BN+15 of the B tile: constant 0x01, written once
     static constexpr int STAGE = A_BYTES + B_BYTES + ONES_BYTES;   // multiple of 1024
-    static constexpr int BUDGET = 222 * 1024;                // one persistent CTA per SM
-    static constexpr int OUT_BYTES = 128 * BN;               // uint8 output tile staging (x2)
-    static constexpr int PARAM_BYTES = BN * 24;              // int4 {bias, zw, 2*M0, shift}[BN] + double mcomb[BN] (x2)
-    static constexpr int FIXED = 2 * OUT_BYTES + 2 * PARAM_BYTES + 256;
-    static constexpr int STAGES_RAW = (BUDGET - FIXED) / STAGE;
-    static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
-    static constexpr int OUT_OFF = STAGES * STAGE;           // 1024-aligned
-    static constexpr int PARAM_OFF = OUT_OFF + 2 * OUT_BYTES;
-    static constexpr int BAR_OFF = PARAM_OFF + 2 * PARAM_BYTES;
-    static constexpr int TOTAL = BAR_OFF + 256;
+    static constexpr int PARAM_OFF = TC_STAGES * STAGE;      // int4 {bias, zw, 2*M0, shift}[BN], double mcomb[BN]
+    static constexpr int PARAM_BYTES = BN * 24;
     static_assert(STAGE % 1024 == 0, "stage buffers must keep the 1024-byte swizzle alignment");
-    static_assert(STAGES >= 3, "pipeline too shallow");
+    static constexpr int BAR_OFF = PARAM_OFF + PARAM_BYTES;
+    static constexpr int TOTAL = BAR_OFF + 128;
+    static_assert(128 * BN <= STAGE, "output staging aliases stage 0");
 };
 
-// activation / saturation are uniform per launch: dispatch once per 16-output chunk, not per output
+// activation / saturation are uniform per launch: dispatch once per 32-output chunk, not per output
 template <bool HAS_EXTRA>
 __device__ __forceinline__ void epi_chunk(int actm, int sat, const uint32_t (&v)[16], int nsa, const int (&extra)[16], const int4 *cq,
                                           const double *mc, int zo, uint32_t (&packed)[4])
@@ -92,70 +85,59 @@ __device__ __forceinline__ void epi_chunk(int actm, int sat, const uint32_t (&v)
     }
 }
 
-__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
-{
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(32 * TC_EPI_WARPS) : "memory"); }
-
-struct TileCoord {
-    int oc0, x0, y0, n0;
-};
-__device__ __forceinline__ TileCoord decode_tile(const TcArgs &a, int t, int bn)
-{
-    // m-tile fastest: CTAs that run concurrently stream the SAME weight tile (their requests merge in L2) and
-    // neighbouring activation patches
-    const int mt = t % a.m_tiles, nt = t / a.m_tiles;
-    TileCoord c;
-    c.oc0 = nt * bn;
-    const int tx = mt % a.tiles_x;
-    const int ty = (mt / a.tiles_x) % a.tiles_y;
-    const int tb = mt / (a.tiles_x * a.tiles_y);
-    c.x0 = tx * a.TW; c.y0 = ty * a.TH; c.n0 = tb * a.TN;
-    return c;
-}
-
-// SLOW = the variant that also serves the int32 / float side outputs and the saturate switch
-template <int BN, int KC, bool SLOW>
-__global__ void __launch_bounds__(TC_THREADS, 1) conv_u8_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+// SLOW = the variant that also serves the int32 / float side outputs and the saturate switch.
+// CM x CN = thread-block cluster shape over (m-tile, n-tile).  CTAs of a cluster that share the m-tile take turns
+// loading the activation stage and MULTICAST it to each other (same for the weight stage across CTAs sharing the
+// n-tile), which divides the L2 -> shared-memory operand traffic (the measured bound of this kernel) by up to 2.
+template <int BN, int KC, bool SLOW, int CM, int CN>
+__global__ void __launch_bounds__(TC_THREADS, 2) conv_u8_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                                                                const __grid_constant__ CUtensorMap tmO, const TcArgs a)
 {
     using L = SmemLayout<BN, KC>;
-    constexpr int S = L::STAGES;
-    constexpr int ACC = BN + ONES_ROWS;       // TMEM columns per accumulator
     extern __shared__ __align__(16) uint8_t smem_raw[];
     uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // keeps the shared address space
     uint64_t *full = (uint64_t *)(smem + L::BAR_OFF);
-    uint64_t *empty = full + S;
-    uint64_t *acc_full = empty + S;           // [2] MMA -> epilogue
-    uint64_t *acc_empty = acc_full + 2;       // [2] epilogue -> MMA (one arrival per epilogue warp)
-    uint32_t *tmem_slot = (uint32_t *)(acc_empty + 2);
+    uint64_t *empty = full + TC_STAGES;
+    uint64_t *accum_full = empty + TC_STAGES;
+    uint32_t *tmem_slot = (uint32_t *)(accum_full + 1);
+    int4 *s_q = (int4 *)(smem + L::PARAM_OFF);          // {bias, zw, 2*M0, shift}
+    double *s_mc = (double *)(s_q + BN);                // M_value * 2^-s (FP64 slow path)
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    constexpr bool CLUSTER = CM * CN > 1;
+    const int cx = CLUSTER ? (int)blockIdx.x % CM : 0, cy = CLUSTER ? (int)blockIdx.y % CN : 0;   // position in the cluster
+    uint16_t mask_a = 0, mask_b = 0;      // cluster ranks (x fastest) sharing my activation tile / my weight tile
+    for (int j = 0; j < CN; ++j) mask_a |= (uint16_t)(1u << (cx + CM * j));
+    for (int i = 0; i < CM; ++i) mask_b |= (uint16_t)(1u << (i + CM * cy));
+    const int oc0 = blockIdx.y * BN;
+    const int tx = blockIdx.x % a.tiles_x;
+    const int ty = (blockIdx.x / a.tiles_x) % a.tiles_y;
+    const int tb = blockIdx.x / (a.tiles_x * a.tiles_y);
+    const int x0 = tx * a.TW, y0 = ty * a.TH, n0 = tb * a.TN;
     const int rows = a.TW * a.TH * a.TN;
     const int kiters = a.size * a.size * a.cpt;
-    const int first = blockIdx.x, step = gridDim.x;
-    const int cnt = first < a.total_tiles ? (a.total_tiles - first + step - 1) / step : 0;
 
     // ---- one-time setup
     if (threadIdx.x == 0) {
-        for (int s = 0; s < S; ++s) {
+        for (int s = 0; s < TC_STAGES; ++s) {
             mbar_init(&full[s], 1);
-            mbar_init(&empty[s], 1);
+            mbar_init(&empty[s], CM + CN - 1);   // every CTA that my multicasts write into must have released the slot
         }
-        for (int b = 0; b < 2; ++b) {
-            mbar_init(&acc_full[b], 1);
-            mbar_init(&acc_empty[b], TC_EPI_WARPS);
-        }
+        mbar_init(accum_full, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) tmem_alloc<tmem_cols<BN>()>(tmem_slot);
     if (warp >= 2) {
-        // the 16 all-ones filter rows that follow the TMA-written BN rows of every stage's B tile (never overwritten)
         const int t = threadIdx.x - 64;
-        for (int s = 0; s < S; ++s) {
+        for (int i = t; i < BN; i += 128) {
+            const bool in = oc0 + i < a.n_pad;       // cluster padding may add CTAs past the last n-tile
+            s_q[i] = in ? __ldg(a.ep.chanq + oc0 + i) : make_int4(0, 0, 0, 0);
+            s_mc[i] = in ? __ldg(a.ep.mcomb + oc0 + i) : 0.0;
+        }
+        // the 16 all-ones filter rows that follow the TMA-written BN rows of every stage's B tile (never overwritten)
+        for (int s = 0; s < TC_STAGES; ++s) {
             uint32_t *ones = (uint32_t *)(smem + s * L::STAGE + L::A_BYTES + L::B_BYTES);
-            for (int i = t; i < L::ONES_BYTES / 4; i += 32 * TC_EPI_WARPS) ones[i] = 0x01010101u;
+            for (int i = t; i < L::ONES_BYTES / 4; i += 128) ones[i] = 0x01010101u;
         }
         fence_proxy_async();   // generic-proxy writes of the ones rows must be visible to the tensor core (async proxy)
     }
@@ -165,27 +147,32 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_u8_tc_kernel(const __grid_
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmO) : "memory");
     }
     tc_fence_before();
-    __syncthreads();
+    if (CLUSTER) cluster_sync_all();      // barrier inits of every CTA visible before any multicast / remote arrive
+    else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
-        // ===================== TMA producer: streams K stages of tile after tile =====================
+        // ===================== TMA producer =====================
         if (lane == 0) {
             const uint32_t bytes = (uint32_t)(rows * KC + BN * KC);
-            uint32_t it = 0;                                 // global stage counter across tiles
-            for (int j = 0; j < cnt; ++j) {
-                const TileCoord c = decode_tile(a, first + j * step, BN);
-                for (int k = 0; k < kiters; ++k, ++it) {
-                    const int s = it % S;
-                    const uint32_t ph = (it / S) & 1;
-                    mbar_wait(&empty[s], ph ^ 1);
-                    mbar_expect_tx(&full[s], bytes);
-                    const int tap = k / a.cpt, chunk = k - tap * a.cpt;
-                    const int ky = tap / a.size, kx = tap - ky * a.size;
-                    uint8_t *sa = smem + s * L::STAGE;
-                    tma_load_4d(sa, &tmA, &full[s], chunk * KC, c.x0 + kx - a.pad, c.y0 + ky - a.pad, c.n0);
-                    tma_load_2d(sa + L::A_BYTES, &tmB, &full[s], tap * a.CS + chunk * KC, c.oc0);
+            for (int it = 0; it < kiters; ++it) {
+                const int s = it % TC_STAGES;
+                const uint32_t ph = (it / TC_STAGES) & 1;
+                mbar_wait(&empty[s], ph ^ 1);
+                mbar_expect_tx(&full[s], bytes);
+                const int tap = it / a.cpt, chunk = it - tap * a.cpt;
+                const int ky = tap / a.size, kx = tap - ky * a.size;
+                uint8_t *sa = smem + s * L::STAGE;
+                if (!CLUSTER) {
+                    tma_load_4d(sa, &tmA, &full[s], chunk * KC, x0 + kx - a.pad, y0 + ky - a.pad, n0);
+                    tma_load_2d(sa + L::A_BYTES, &tmB, &full[s], tap * a.CS + chunk * KC, oc0);
+                } else {
+                    // take turns: the CTA whose turn it is loads the stage for everyone sharing that operand
+                    if (CN == 1) tma_load_4d(sa, &tmA, &full[s], chunk * KC, x0 + kx - a.pad, y0 + ky - a.pad, n0);
+                    else if (it % CN == cy) tma_load_4d_mc(sa, &tmA, &full[s], chunk * KC, x0 + kx - a.pad, y0 + ky - a.pad, n0, mask_a);
+                    if (CM == 1) tma_load_2d(sa + L::A_BYTES, &tmB, &full[s], tap * a.CS + chunk * KC, oc0);
+                    else if (it % CM == cx) tma_load_2d_mc(sa + L::A_BYTES, &tmB, &full[s], tap * a.CS + chunk * KC, oc0, mask_b);
                 }
             }
         }
@@ -195,126 +182,101 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_u8_tc_kernel(const __grid_
             // ONE instruction per K step: N = BN filter rows + 16 all-ones rows, so A is read from smem once and
             // TMEM columns [BN, BN+16) receive the per-pixel activation sum
             constexpr uint32_t idesc_main = make_idesc(BN + ONES_ROWS);
-            uint32_t it = 0;
-            for (int j = 0; j < cnt; ++j) {
-                const int b = j & 1;
-                if (j >= 2) mbar_wait(&acc_empty[b], ((j >> 1) - 1) & 1);     // epilogue(j-2) drained accumulator b
+            for (int it = 0; it < kiters; ++it) {
+                const int s = it % TC_STAGES;
+                const uint32_t ph = (it / TC_STAGES) & 1;
+                mbar_wait(&full[s], ph);
                 tc_fence_after();
-                const uint32_t acc = tmem_base + b * ACC;
-                for (int k = 0; k < kiters; ++k, ++it) {
-                    const int s = it % S;
-                    const uint32_t ph = (it / S) & 1;
-                    mbar_wait(&full[s], ph);
-                    tc_fence_after();
-                    const uint32_t sa = smem_u32(smem + s * L::STAGE);
-                    const uint64_t da = make_desc<KC>(sa), db = make_desc<KC>(sa + L::A_BYTES);
+                const uint32_t sa = smem_u32(smem + s * L::STAGE);
+                const uint64_t da = make_desc<KC>(sa), db = make_desc<KC>(sa + L::A_BYTES);
 #pragma unroll
-                    for (int kk = 0; kk < KC / 32; ++kk)
-                        umma_i8(acc, da + 2 * kk, db + 2 * kk, idesc_main, (k | kk) ? 1u : 0u);   // +32 bytes = +2 in 16-byte units
-                    umma_commit(&empty[s]);
+                for (int k = 0; k < KC / 32; ++k) {
+                    const uint32_t accum = (it | k) ? 1u : 0u;
+                    umma_i8(tmem_base, da + 2 * k, db + 2 * k, idesc_main, accum);       // +32 bytes = +2 in 16-byte units
                 }
-                umma_commit(&acc_full[b]);
+                if (CLUSTER) umma_commit_mc(&empty[s], (uint16_t)(mask_a | mask_b));   // release the slot towards every CTA that fills it
+                else umma_commit(&empty[s]);
             }
+            umma_commit(accum_full);
         }
     } else {
-        // ===================== epilogue: 8 warps, thread = TMEM lane = pixel, warp pair splits the columns =====================
-        const int et = threadIdx.x - 64;          // 0..255
-        const int q = warp & 3;                   // TMEM lane quarter this warp may access
-        const int half = (warp - 2) >> 2;         // which half of the BN columns
-        const int r = q * 32 + lane;              // tile row = TMEM lane = output pixel of the patch
+        // ===================== epilogue =====================
+        const int q = warp & 3;                 // TMEM lane quarter this warp may access
+        const int r = q * 32 + lane;            // tile row = TMEM lane = output pixel of the patch
         const int wi = r % a.TW, hi = (r / a.TW) % a.TH, ni = r / (a.TW * a.TH);
+        const int ox = x0 + wi, oy = y0 + hi, n = n0 + ni;
+        const bool valid = r < rows && ox < a.OW && oy < a.OH && n < a.B;
+        // taps that fall outside the image for this pixel (zero-filled by TMA, zp_in in the reference)
+        uint32_t oob = 0;
+        if (a.corr && valid) {
+            for (int ky = 0; ky < a.size; ++ky)
+                for (int kx = 0; kx < a.size; ++kx) {
+                    const int iy = oy + ky - a.pad, ix = ox + kx - a.pad;
+                    if (iy < 0 || iy >= a.H || ix < 0 || ix >= a.W) oob |= 1u << (ky * a.size + kx);
+                }
+        }
+        mbar_wait(accum_full, 0);
+        tc_fence_after();
+        const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
+        const int nsa = -(int)tmem_ld1(trow + BN);   // minus the pixel's activation sum (ones-tile columns)
+        uint8_t *stage_out = smem;              // aliases pipeline stage 0 (all MMAs have completed)
+        const size_t pix = ((size_t)n * a.OH + oy) * a.OW + ox;
         const int actm = yq::act_mode(a.ep.act);
         const bool side = SLOW && ((a.out_acc != nullptr) || (a.out_f32 != nullptr));
         const int sat = SLOW ? a.ep.saturate : 0;
-        constexpr int HALF_COLS = BN / 2;
-        for (int j = 0; j < cnt; ++j) {
-            const int b = j & 1;
-            const TileCoord c = decode_tile(a, first + j * step, BN);
-            int4 *s_q = (int4 *)(smem + L::PARAM_OFF + b * L::PARAM_BYTES);     // {bias, zw, 2*M0, shift}
-            double *s_mc = (double *)(s_q + BN);                                // M_value * 2^-s (FP64 slow path)
-            uint8_t *stage_out = smem + L::OUT_OFF + b * L::OUT_BYTES;
-            // staging[b] was last read by the TMA store of tile j-2: at most one newer store group may be pending
-            if (et == 0 && j >= 2) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-            if (et < BN) s_q[et] = __ldg(a.ep.chanq + c.oc0 + et);
-            else if (et >= 128 && et - 128 < BN) s_mc[et - 128] = __ldg(a.ep.mcomb + c.oc0 + et - 128);
-            epi_bar_sync();
-
-            const int ox = c.x0 + wi, oy = c.y0 + hi, n = c.n0 + ni;
-            const bool valid = r < rows && ox < a.OW && oy < a.OH && n < a.B;
-            // taps that fall outside the image for this pixel (zero-filled by TMA, zp_in in the reference)
-            uint32_t oob = 0;
-            if (a.corr && valid) {
-                for (int ky = 0; ky < a.size; ++ky)
-                    for (int kx = 0; kx < a.size; ++kx) {
-                        const int iy = oy + ky - a.pad, ix = ox + kx - a.pad;
-                        if (iy < 0 || iy >= a.H || ix < 0 || ix >= a.W) oob |= 1u << (ky * a.size + kx);
-                    }
-            }
-            mbar_wait(&acc_full[b], (j >> 1) & 1);
-            tc_fence_after();
-            const uint32_t trow = tmem_base + b * ACC + ((uint32_t)(q * 32) << 16);
-            const int nsa = -(int)tmem_ld1(trow + BN);   // minus the pixel's activation sum (ones-row columns)
-            const size_t pix = ((size_t)n * a.OH + oy) * a.OW + ox;
 #pragma unroll 1
-            for (int cc = 0; cc < HALF_COLS; cc += 16) {
-                const int c0 = half * HALF_COLS + cc;
-                uint32_t v[16];
-                tmem_ld16(trow + c0, v);
-                if (cc + 16 >= HALF_COLS) {
-                    // last TMEM read of this warp for this tile: hand the accumulator back to the MMA warp early
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&acc_empty[b]);
+        for (int c0 = 0; c0 < BN; c0 += 16) {
+            uint32_t v[16];
+            tmem_ld16(trow + c0, v);
+            uint32_t packed[4];
+            int extra[16];
+            if (oob) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) extra[j] = 0;
+                for (uint32_t m = oob; m; m &= m - 1) {
+                    const int32_t *cr = a.corr + (size_t)(__ffs(m) - 1) * a.n_pad + oc0 + c0;
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) extra[j] += __ldg(cr + j);
                 }
-                uint32_t packed[4];
-                int extra[16];
-                if (oob) {
+                epi_chunk<true>(actm, sat, v, nsa, extra, s_q + c0, s_mc + c0, a.ep.zp_out, packed);
+            } else {
+                epi_chunk<false>(actm, sat, v, nsa, extra, s_q + c0, s_mc + c0, a.ep.zp_out, packed);
+            }
+            yq::mask_pad_channels<16>(packed, a.N - (oc0 + c0));
+            if (SLOW && side && valid) {   // parity / quant_stop side outputs (not on the throughput path)
 #pragma unroll
-                    for (int jj = 0; jj < 16; ++jj) extra[jj] = 0;
-                    for (uint32_t m = oob; m; m &= m - 1) {
-                        const int32_t *cr = a.corr + (size_t)(__ffs(m) - 1) * a.n_pad + c.oc0 + c0;
-#pragma unroll
-                        for (int jj = 0; jj < 16; ++jj) extra[jj] += __ldg(cr + jj);
-                    }
-                    epi_chunk<true>(actm, sat, v, nsa, extra, s_q + c0, s_mc + c0, a.ep.zp_out, packed);
-                } else {
-                    epi_chunk<false>(actm, sat, v, nsa, extra, s_q + c0, s_mc + c0, a.ep.zp_out, packed);
-                }
-                yq::mask_pad_channels<16>(packed, a.N - (c.oc0 + c0));
-                if (SLOW && side && valid) {   // parity / quant_stop side outputs (not on the throughput path)
-#pragma unroll
-                    for (int jj = 0; jj < 16; ++jj) {
-                        const int oc = c.oc0 + c0 + jj;
-                        if (oc < a.N) {
-                            if (a.out_acc) a.out_acc[pix * a.CSO + oc] = (int)v[jj] + s_q[c0 + jj].y * nsa + (oob ? extra[jj] : 0);
-                            if (a.out_f32) {
-                                const uint8_t u = (uint8_t)(packed[jj / 4] >> (8 * (jj % 4)));
-                                a.out_f32[((size_t)n * a.N + oc) * a.OH * a.OW + (size_t)oy * a.OW + ox] = yq::dequant_f32(a.ep, u);
-                            }
+                for (int j = 0; j < 16; ++j) {
+                    const int oc = oc0 + c0 + j;
+                    if (oc < a.N) {
+                        if (a.out_acc) a.out_acc[pix * a.CSO + oc] = (int)v[j] + s_q[c0 + j].y * nsa + (oob ? extra[j] : 0);
+                        if (a.out_f32) {
+                            const uint8_t u = (uint8_t)(packed[j / 4] >> (8 * (j % 4)));
+                            a.out_f32[((size_t)n * a.N + oc) * a.OH * a.OW + (size_t)oy * a.OW + ox] = yq::dequant_f32(a.ep, u);
                         }
                     }
                 }
-                // swizzled staging (matches the TMA-store tensor map): 16-byte chunk index XOR row bits
-                {
-                    const int chunk = c0 / 16;
-                    int sw;
-                    if (BN >= 128) sw = chunk ^ (r & 7);
-                    else if (BN == 64) sw = chunk ^ ((r >> 1) & 3);
-                    else sw = chunk ^ ((r >> 2) & 1);
-                    *reinterpret_cast<uint4 *>(stage_out + (size_t)r * BN + sw * 16) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
-                }
             }
-            fence_proxy_async();
-            epi_bar_sync();
-            if (et == 0) {
-                tma_store_4d(&tmO, stage_out, c.oc0, c.x0, c.y0, c.n0);
-                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            // swizzled staging (matches the TMA-store tensor map): 16-byte chunk index XOR row bits
+            {
+                const int chunk = c0 / 16;
+                int sw;
+                if (BN >= 128) sw = chunk ^ (r & 7);
+                else if (BN == 64) sw = chunk ^ ((r >> 1) & 3);
+                else sw = chunk ^ ((r >> 2) & 1);
+                *reinterpret_cast<uint4 *>(stage_out + (size_t)r * BN + sw * 16) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
             }
         }
-        if (et == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        tc_fence_before();
+        fence_proxy_async();
+        asm volatile("bar.sync 1, 128;" ::: "memory");   // the four epilogue warps only
+        if (threadIdx.x == 64) {
+            tma_store_4d(&tmO, stage_out, oc0, x0, y0, n0);
+            tma_store_commit_wait();
+        }
     }
     tc_fence_before();
-    __syncthreads();
+    if (CLUSTER) cluster_sync_all();      // nobody exits while a peer may still multicast into it or arrive on its barriers
+    else __syncthreads();
     if (warp == 1) {
         tc_fence_after();
         tmem_dealloc<tmem_cols<BN>()>(tmem_base);
@@ -397,26 +359,66 @@ void choose_tile(int B, int OH, int OW, int *tw, int *th, int *tn)
     }
 }
 
-template <int BN, int KC, bool SLOW>
+template <int BN, int KC, bool SLOW, int CM, int CN>
 int launch_v(TcState *st, const CUtensorMap &tmA, const CUtensorMap &tmO, const TcArgs &a, dim3 grid, cudaStream_t stream)
 {
     using L = SmemLayout<BN, KC>;
     static bool attr_done = false;
     const int smem = L::TOTAL + 1024;
+    auto kern = conv_u8_tc_kernel<BN, KC, SLOW, CM, CN>;
     if (!attr_done) {
-        YQ_CUDA(cudaFuncSetAttribute(conv_u8_tc_kernel<BN, KC, SLOW>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        YQ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         attr_done = true;
     }
-    conv_u8_tc_kernel<BN, KC, SLOW><<<grid, TC_THREADS, smem, stream>>>(tmA, st->tmB, tmO, a);
+    if (CM * CN == 1) {
+        kern<<<grid, TC_THREADS, smem, stream>>>(tmA, st->tmB, tmO, a);
+    } else {
+        grid.x = (grid.x + CM - 1) / CM * CM;   // pad to whole clusters: the extra CTAs see only out-of-range tiles
+        grid.y = (grid.y + CN - 1) / CN * CN;
+        cudaLaunchConfig_t cfg;
+        memset(&cfg, 0, sizeof cfg);
+        cfg.gridDim = grid;
+        cfg.blockDim = dim3(TC_THREADS);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = CM;
+        attr[0].val.clusterDim.y = CN;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        YQ_CUDA(cudaLaunchKernelEx(&cfg, kern, tmA, st->tmB, tmO, a));
+    }
     YQ_CHECK_LAUNCH();
     return 0;
+}
+
+template <int BN, int KC, int CM, int CN>
+int launch_c(TcState *st, const CUtensorMap &tmA, const CUtensorMap &tmO, const TcArgs &a, dim3 grid, cudaStream_t stream)
+{
+    if (a.out_acc || a.out_f32 || a.ep.saturate) return launch_v<BN, KC, true, CM, CN>(st, tmA, tmO, a, grid, stream);
+    return launch_v<BN, KC, false, CM, CN>(st, tmA, tmO, a, grid, stream);
 }
 
 template <int BN, int KC>
 int launch(yq_conv_layer *l, TcState *st, const CUtensorMap &tmA, const CUtensorMap &tmO, const TcArgs &a, dim3 grid, cudaStream_t stream)
 {
-    if (a.out_acc || a.out_f32 || a.ep.saturate) return launch_v<BN, KC, true>(st, tmA, tmO, a, grid, stream);
-    return launch_v<BN, KC, false>(st, tmA, tmO, a, grid, stream);
+    // Cluster multicast is OFF by default: measured on B200 (profiles/README.md) it is 10-15 % SLOWER than independent
+    // CTAs -- the bound is the per-SM shared-memory ingest rate, which multicast does not reduce (every SM still
+    // receives every byte); it only saves L2 reads.  YQ_TC_CLUSTER=1 enables it for A/B measurements.
+    static int want = -1;
+    if (want < 0) {
+        const char *e = getenv("YQ_TC_CLUSTER");
+        want = e ? atoi(e) : 0;
+    }
+    if constexpr (BN == 128) {
+        if (want && grid.x >= 2) {
+            if (grid.y % 2 == 0) return launch_c<BN, KC, 2, 2>(st, tmA, tmO, a, grid, stream);
+            return launch_c<BN, KC, 2, 1>(st, tmA, tmO, a, grid, stream);
+        }
+    }
+    return launch_c<BN, KC, 1, 1>(st, tmA, tmO, a, grid, stream);
 }
 
 }  // namespace
@@ -535,18 +537,9 @@ int yq_tc_forward(yq_conv_layer *l, const uint8_t *in_u8, uint8_t *out_u8, uint8
     a.tiles_x = (l->out_w + TW - 1) / TW;
     a.tiles_y = (l->out_h + TH - 1) / TH;
     const int tiles_b = (batch + TN - 1) / TN;
-    a.m_tiles = a.tiles_x * a.tiles_y * tiles_b;
-    a.n_tiles = st->n_pad / st->BN;
-    a.total_tiles = a.m_tiles * a.n_tiles;
     a.size = l->size; a.pad = l->pad; a.cpt = l->cs_in / st->KC; a.CS = l->cs_in;
     a.H = l->h; a.W = l->w;
-    static int n_sm = 0;
-    if (!n_sm) {
-        int dev = 0;
-        YQ_CUDA(cudaGetDevice(&dev));
-        YQ_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
-    }
-    dim3 grid(a.total_tiles < n_sm ? a.total_tiles : n_sm);   // persistent: one CTA per SM strides over the tiles
+    dim3 grid(a.tiles_x * a.tiles_y * tiles_b, st->n_pad / st->BN);
     const CUtensorMap &tmA = it->second.first, &tmO = it->second.second;
 #define YQ_TC(BN_, KC_) return launch<BN_, KC_>(l, st, tmA, tmO, a, grid, stream)
     if (st->KC == 128) {

@@ -56,6 +56,40 @@ __device__ __forceinline__ void tma_load_2d(void *smem, const CUtensorMap *map, 
                  "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
                  : "memory");
 }
+// multicast forms: the box lands at the same shared-memory offset of every CTA in `mask` (cluster ranks) and
+// completes transaction bytes on the same-offset mbarrier of each of them
+__device__ __forceinline__ void tma_load_4d_mc(void *smem, const CUtensorMap *map, uint64_t *bar, int c0, int c1, int c2, int c3, uint16_t mask)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%4, %5, %6, %7}], [%2], %3;" ::"r"(
+            smem_u32(smem)),
+        "l"(map), "r"(smem_u32(bar)), "h"(mask), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_mc(void *smem, const CUtensorMap *map, uint64_t *bar, int c0, int c1, uint16_t mask)
+{
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%4, %5}], [%2], %3;" ::"r"(
+                     smem_u32(smem)),
+                 "l"(map), "r"(smem_u32(bar)), "h"(mask), "r"(c0), "r"(c1)
+                 : "memory");
+}
+// tcgen05.commit that arrives on the same-offset mbarrier of every CTA in `mask`
+__device__ __forceinline__ void umma_commit_mc(uint64_t *bar, uint16_t mask)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)), "h"(mask)
+                 : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank()
+{
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all()
+{
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void tma_store_4d(const CUtensorMap *map, const void *smem, int c0, int c1, int c2, int c3)
 {
     asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(map), "r"(smem_u32(smem)),
