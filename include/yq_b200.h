@@ -209,6 +209,16 @@ YQ_API int yq_network_profile_forward(yq_network *net, const uint8_t *in_u8_nchw
 /* number of kernel launches one forward issues (for bench.py's gpu_launches) */
 YQ_API int yq_network_launches_per_forward(const yq_network *net);
 
+/* ---- "next" row 8f-2: box decode + NMS on the device -------------------------------------------------------
+ * get_network_boxes (src/network.c:635-640: get_yolo_detections + correct_yolo_boxes, src/yolo_layer.c:247-343) followed by
+ * do_nms_sort (src/box.c:58-89) when nms_thresh > 0, for every image of the last forward.
+ * counts_host[batch]; dets_host[batch][yq_network_box_capacity][5 + classes] = x, y, w, h, objectness, prob[classes],
+ * candidates in the reference's pre-NMS order (yolo layers in network order, cell, anchor); NMS zeroes suppressed probs. */
+YQ_API int yq_network_box_capacity(const yq_network *net);
+YQ_API int yq_network_classes(const yq_network *net);
+YQ_API int yq_network_get_boxes(yq_network *net, int w, int h, float thresh, float nms_thresh, int relative,
+                                int *counts_host, float *dets_host);
+
 /* pull one layer's output to the host in the REFERENCE's layout (CHW per image):
  * what = 0: output_uint8_final [batch][out_c][out_h][out_w] u8
  *        1: output_int32       [batch][out_c][out_h][out_w] i32  (conv, needs yq_network_set_debug(net,1))

@@ -137,6 +137,28 @@ int main(int argc, char **argv)
     } else {
         die("unknown mode");
     }
+    if (!strcmp(mode, "net")) {
+        /* get_network_boxes + do_nms_sort exactly as test_detector calls them (examples/detector.c:926-930, nms = .45);
+           relative = 1, image size = network size (the synthetic image is already 416x416, no letterbox offset) */
+        int nboxes = 0;
+        layer last = net->layers[net->n - 1];
+        detection *dets = get_network_boxes(net, net->w, net->h, 0.5f, 0.5f, 0, 1, &nboxes);
+        size_t per = 5 + last.classes;
+        float *flat = calloc((size_t)nboxes * per + 1, sizeof(float));
+        for (int pass = 0; pass < 2; ++pass) {
+            if (pass == 1) do_nms_sort(dets, nboxes, last.classes, 0.45f);
+            for (int i = 0; i < nboxes; ++i) {
+                float *d = flat + (size_t)i * per;
+                d[0] = dets[i].bbox.x; d[1] = dets[i].bbox.y; d[2] = dets[i].bbox.w; d[3] = dets[i].bbox.h;
+                d[4] = dets[i].objectness;
+                for (int j = 0; j < last.classes; ++j) d[5 + j] = dets[i].prob[j];
+            }
+            dump(dir, 99, pass ? "boxes_post_nms" : "boxes_pre_nms", flat, (size_t)nboxes * per * sizeof(float));
+        }
+        fprintf(man, "boxes n %d classes %d\n", nboxes, last.classes);
+        free(flat);
+        free_detections(dets, nboxes);
+    }
     dump(dir, 0, "input_uint8", net->input_uint8, nin);
     int nl = !strcmp(mode, "layer") ? 1 : net->n;
     for (int i = 0; i < nl; ++i) dump_layer(dir, man, i, &net->layers[i]);

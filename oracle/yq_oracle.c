@@ -284,3 +284,96 @@ void yq_oracle_prepare_conv(int n, int K, const uint8_t *weights, const uint8_t 
         bias_i32[oc] = (int32_t)(b / (s_in * s_w[oc]) + (float)weights_sum_int);
     }
 }
+
+/* ------------------------------------------------------------------------------------------------
+ * "next" row 8f-2: box decode + NMS
+ * ---------------------------------------------------------------------------------------------- */
+/*
+ * get_yolo_detections + get_yolo_box + correct_yolo_boxes for ONE yolo layer (src/yolo_layer.c:83-91,247-273,
+ * 316-343).  pred: the yolo layer's output, CHW [n_anchors*(5+classes)][lh][lw]; anchor_w/h: l.biases[2*mask[n]] and
+ * [2*mask[n]+1].  Appends 5+classes floats per kept candidate (x, y, w, h, objectness, prob[classes]); returns the count.
+ */
+int yq_oracle_yolo_detections(const float *pred, int lw, int lh, int n_anchors, int classes, const float *anchor_w,
+                              const float *anchor_h, int netw, int neth, int w, int h, int relative, float thresh,
+                              float *dets)
+{
+    int cells = lw * lh, per = 5 + classes, count = 0;
+    int new_w = 0, new_h = 0;
+    if (((float)netw / w) < ((float)neth / h)) { new_w = netw; new_h = (h * netw) / w; }
+    else { new_h = neth; new_w = (w * neth) / h; }
+    for (int i = 0; i < cells; ++i) {
+        int row = i / lw, col = i % lw;
+        for (int n = 0; n < n_anchors; ++n) {
+            const float *x = pred + (size_t)(n * per) * cells + i;
+            float objectness = x[(size_t)4 * cells];
+            if (objectness <= thresh) continue;
+            float *d = dets + (size_t)count * per;
+            float bx = (col + x[0]) / lw;
+            float by = (row + x[(size_t)cells]) / lh;
+            float bw = exp(x[(size_t)2 * cells]) * anchor_w[n] / netw;
+            float bh = exp(x[(size_t)3 * cells]) * anchor_h[n] / neth;
+            bx = (bx - (netw - new_w) / 2. / netw) / ((float)new_w / netw);
+            by = (by - (neth - new_h) / 2. / neth) / ((float)new_h / neth);
+            bw *= (float)netw / new_w;
+            bh *= (float)neth / new_h;
+            if (!relative) { bx *= w; bw *= w; by *= h; bh *= h; }
+            d[0] = bx; d[1] = by; d[2] = bw; d[3] = bh; d[4] = objectness;
+            for (int j = 0; j < classes; ++j) {
+                float prob = objectness * x[(size_t)(5 + j) * cells];
+                d[5 + j] = (prob > thresh) ? prob : 0;
+            }
+            ++count;
+        }
+    }
+    return count;
+}
+
+static float ov1(float x1, float w1, float x2, float w2)          /* overlap, src/box.c:152-161 */
+{
+    float l1 = x1 - w1 / 2, l2 = x2 - w2 / 2;
+    float left = l1 > l2 ? l1 : l2;
+    float r1 = x1 + w1 / 2, r2 = x2 + w2 / 2;
+    float right = r1 < r2 ? r1 : r2;
+    return right - left;
+}
+static float iou(const float *a, const float *b)                  /* box_iou, src/box.c:163-182 */
+{
+    float w = ov1(a[0], a[2], b[0], b[2]), h = ov1(a[1], a[3], b[1], b[3]);
+    float inter = (w < 0 || h < 0) ? 0 : w * h;
+    float uni = a[2] * a[3] + b[2] * b[3] - inter;
+    return inter / uni;
+}
+
+/*
+ * do_nms_sort (src/box.c:58-89) on the flat detection array: per class, order by prob[k] descending, then every box
+ * suppresses later boxes with IoU > thresh (prob[k] = 0).  Ties keep the order left by the previous class's sort
+ * (stable), starting from detection order for class 0 -- see the comment in the loop.
+ * The array itself is NOT reordered (only probabilities are zeroed), so it stays comparable element by element.
+ */
+void yq_oracle_nms_sort(float *dets, int total, int classes, float thresh)
+{
+    int per = 5 + classes;
+    int *order = malloc(sizeof(int) * (size_t)(total > 0 ? total : 1));
+    for (int i = 0; i < total; ++i) order[i] = i;
+    for (int k = 0; k < classes; ++k) {
+        /* the reference qsort()s the SAME array once per class, so each class starts from the previous class's order;
+           glibc's qsort is a stable merge sort for arrays of this size, and uint8-quantised heads make exact probability
+           ties common, so the carried-over order decides which of two tied boxes suppresses the other.  A stable
+           insertion sort on the carried permutation reproduces it. */
+        for (int i = 1; i < total; ++i) {
+            int v = order[i], j = i - 1;
+            float pv = dets[(size_t)v * per + 5 + k];
+            while (j >= 0 && dets[(size_t)order[j] * per + 5 + k] < pv) { order[j + 1] = order[j]; --j; }
+            order[j + 1] = v;
+        }
+        for (int i = 0; i < total; ++i) {
+            float *a = dets + (size_t)order[i] * per;
+            if (a[5 + k] == 0) continue;
+            for (int j = i + 1; j < total; ++j) {
+                float *b = dets + (size_t)order[j] * per;
+                if (iou(a, b) > thresh) b[5 + k] = 0;
+            }
+        }
+    }
+    free(order);
+}

@@ -141,6 +141,29 @@ def prepare_conv(sl, s_in: float, zp_in: int) -> Dict[str, np.ndarray]:
     return {"M0": M0, "M0_right_shift": sh, "M_value": Mv, "M0_right_shift_value": rs, "biases_int32": bi}
 
 
+ANCHORS = [float(v) for v in "25,39, 29,88, 405,102, 407,109,408,113,420,129".split(",")]
+
+
+def yolo_boxes(heads, masks, classes: int, netw: int, neth: int, w: int, h: int, thresh: float = 0.5, nms: float = 0.45,
+               relative: int = 1, anchors=ANCHORS) -> np.ndarray:
+    """get_network_boxes (+ do_nms_sort when nms > 0) for ONE image. heads: list of f32 CHW yolo outputs in network order."""
+    per = 5 + classes
+    cap = sum(int(hd.shape[1] * hd.shape[2] * len(m)) for hd, m in zip(heads, masks))
+    dets = np.zeros((cap, per), np.float32)
+    n = 0
+    for hd, m in zip(heads, masks):
+        hd = np.ascontiguousarray(hd, np.float32)
+        aw = np.array([anchors[2 * q] for q in m], np.float32)
+        ah = np.array([anchors[2 * q + 1] for q in m], np.float32)
+        sub = dets[n:]
+        n += lib().yq_oracle_yolo_detections(_p(hd, C.c_float), hd.shape[2], hd.shape[1], len(m), classes, _p(aw, C.c_float),
+                                             _p(ah, C.c_float), netw, neth, w, h, relative, C.c_float(thresh), _p(sub, C.c_float))
+    dets = np.ascontiguousarray(dets[:n])
+    if nms > 0 and n:
+        lib().yq_oracle_nms_sort(_p(dets, C.c_float), n, classes, C.c_float(nms))
+    return dets
+
+
 def forward_network(info: Sequence, img_u8: np.ndarray, input_quant=(1.0 / 255.0, 0),
                     params_override: Optional[Dict[int, Dict[str, np.ndarray]]] = None,
                     reffloat: bool = False) -> List[Dict[str, np.ndarray]]:
@@ -217,7 +240,7 @@ def ref_times(stderr: str) -> List[float]:
 _DT = {"output_int32": np.int32, "output_uint8": np.uint8, "M0": np.int32, "M0_right_shift": np.int32,
        "M_value": np.float64, "M0_right_shift_value": np.float64, "biases_int32": np.int32,
        "weight_zero_point": np.uint8, "weight_scales": np.float32, "biases_folded": np.float32,
-       "output_f32": np.float32, "input_uint8": np.uint8}
+       "output_f32": np.float32, "input_uint8": np.uint8, "boxes_pre_nms": np.float32, "boxes_post_nms": np.float32}
 
 
 def read_dump(dirname: str) -> List[Dict]:

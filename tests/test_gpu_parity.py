@@ -402,6 +402,29 @@ def test_full_size_batch128_properties(built, tiny_net_files):
     net1.free()
 
 
+def test_device_box_decode_and_nms_vs_oracle(built, tiny_net_files):
+    """row 8f-2: get_network_boxes + do_nms_sort on the device == the oracle restatement (which equals the compiled
+    reference incl. its stable-sort tie behaviour, tests/test_oracle_golden.py).  Coordinates within 1e-5, the set of
+    surviving (box, class) pairs identical."""
+    cfg, wts, info, _ = tiny_net_files
+    imgs = np.stack([synth.synthetic_image(s) for s in (1, 41, 42)])
+    net = darknet.load_network(cfg, wts, batch=3)
+    heads = net.split_heads(net.predict_u8(imgs))
+    for nms in (0.0, 0.45):
+        got = net.get_boxes(416, 416, 0.5, nms, 1)
+        for b in range(3):
+            want = O.yolo_boxes([heads[0][b], heads[1][b]], [(3, 4, 5), (0, 1, 2)], 5, 416, 416, 416, 416, 0.5, nms)
+            assert got[b].shape == want.shape, (nms, b, got[b].shape, want.shape)
+            assert np.allclose(got[b][:, :5], want[:, :5], rtol=1e-5, atol=1e-6)
+            assert np.array_equal(got[b][:, 5:] > 0, want[:, 5:] > 0), f"NMS survivors differ (image {b}, nms {nms})"
+            assert np.allclose(got[b][:, 5:], want[:, 5:], rtol=1e-6, atol=0)
+    # non-square "original image" exercises correct_yolo_boxes' letterbox arithmetic, absolute coordinates
+    got = net.get_boxes(640, 480, 0.6, 0.0, 0)
+    want = O.yolo_boxes([heads[0][1], heads[1][1]], [(3, 4, 5), (0, 1, 2)], 5, 416, 416, 640, 480, 0.6, 0.0, relative=0)
+    assert got[1].shape == want.shape and np.allclose(got[1], want, rtol=1e-5, atol=1e-4)
+    net.free()
+
+
 def test_accumulator_linearity(built):
     """int32 accumulators are linear in the input when zp_in = 0: acc(2x) == 2 acc(x) for x <= 127."""
     rng = np.random.default_rng(9)

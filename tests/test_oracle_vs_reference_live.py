@@ -81,3 +81,27 @@ def test_input_quantiser_live(built, tmp_path):
     # -Ofast may turn x/s into x*(1/s): allow 1 LSB at exact rounding ties
     d = np.abs(u8.astype(int) - ref_u8.astype(int))
     assert d.max() <= 1 and (d > 0).mean() < 1e-3
+
+
+def test_box_decode_and_nms_live(built, tmp_path):
+    """row 8f-2 oracle: get_network_boxes + do_nms_sort restated vs the compiled reference (416x416 net).
+    Decode within 1e-6 (the reference is -Ofast); NMS applied to the reference's own candidates must reproduce its
+    survivors exactly, including the stable-sort tie order carried from class to class."""
+    import ctypes as C
+    layers = synth.yolov3_tiny_quant()
+    cfg, wts, img = (str(tmp_path / n) for n in ("n.cfg", "n.weights", "img.f32"))
+    synth.write_cfg(cfg, layers)
+    info = synth.write_weights(wts, layers)
+    im = synth.synthetic_image(9)
+    synth.image_to_float(im).tofile(img)
+    O.run_reference("net", cfg, wts, img, str(tmp_path / "dump"))
+    pre = np.fromfile(str(tmp_path / "dump" / "L99_boxes_pre_nms.bin"), dtype=np.float32).reshape(-1, 10)
+    post = np.fromfile(str(tmp_path / "dump" / "L99_boxes_post_nms.bin"), dtype=np.float32).reshape(-1, 10)
+    outs = O.forward_network(info, im)
+    mine = O.yolo_boxes([outs[16]["f32"], outs[23]["f32"]], [(3, 4, 5), (0, 1, 2)], 5, 416, 416, 416, 416, 0.5, 0.0)
+    assert mine.shape == pre.shape and np.allclose(mine, pre, rtol=0, atol=2e-6)
+    d = np.ascontiguousarray(pre.copy())
+    O.lib().yq_oracle_nms_sort(O._p(d, C.c_float), d.shape[0], 5, C.c_float(0.45))
+    key = lambda a: sorted(map(tuple, a.tolist()))
+    assert key(d) == key(post)
+    assert (post[:, 5:] > 0).sum() < (pre[:, 5:] > 0).sum()        # NMS really suppressed something

@@ -92,6 +92,9 @@ SIGNATURES = {
     "yq_network_use_graph": (_i, [_vp, _i]),
     "yq_network_launches_per_forward": (_i, [_vp]),
     "yq_network_profile_forward": (_i, [_vp, _vp, _vp]),
+    "yq_network_box_capacity": (_i, [_vp]),
+    "yq_network_classes": (_i, [_vp]),
+    "yq_network_get_boxes": (_i, [_vp, _i, _i, C.c_float, C.c_float, _i, _vp, _vp]),
     "yq_network_pull_layer": (_i, [_vp, _i, _i, _vp, _sz]),
     "yq_network_layer_output_f32_device": (_vp, [_vp, _i]),
     "yq_network_conv_params": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _vp]),

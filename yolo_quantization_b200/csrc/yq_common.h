@@ -60,6 +60,11 @@ struct yq_conv_layer {
     std::vector<double> host_mcomb;
 };
 
+// implemented in yq_detect.cu: yolo box decode (+ NMS when nms_thresh > 0) for a whole batch
+int yq_detect_run(const float *const *head_pred, const int *lw, const int *lh, const int *n_anchors, const float *const *bias_w,
+                  const float *const *bias_h, int n_heads, int classes, int batch, int cap, int netw, int neth, int w, int h, int relative,
+                  float thresh, float nms_thresh, float *dets_dev, int *counts_dev, cudaStream_t stream);
+
 // implemented in yq_conv_tc_small.cu (threads build the im2col rows; c <= 32)
 int yq_tc_small_supported(const yq_conv_layer *l);
 int yq_tc_small_prepare(yq_conv_layer *l, void **state);

@@ -98,6 +98,7 @@ struct Layer {
     int quantized = 0, quant_stop = 0, first_time = 0;
     std::vector<int> inputs;   // route
     int classes = 0, n_anchors = 0;
+    std::vector<float> anchor_w, anchor_h;   // yolo: anchors selected by mask (l.biases[2*mask[n]], [2*mask[n]+1])
     // quantisation state as in `struct layer`
     float s_in = 0, s_out = 0;
     int zp_in = 0, zp_out = 0;
@@ -146,6 +147,10 @@ struct yq_network {
     cudaEvent_t ev_in_ready[PIPE] = {nullptr, nullptr}, ev_fwd_done[PIPE] = {nullptr, nullptr};
     int pipe_next = 0;
     bool pipe_busy[PIPE] = {false, false};
+    // detections (yq_network_get_boxes)
+    float *dets_dev = nullptr;
+    int *counts_dev = nullptr;
+    int det_cap = 0, det_classes = 0;
 };
 
 namespace {
@@ -463,6 +468,28 @@ extern "C" yq_network *yq_load_network(const char *cfg, const char *weights, int
             int total = s.geti("num", 1);
             std::string mask = s.gets("mask", "");
             l.n_anchors = mask.empty() ? total : (int)std::count(mask.begin(), mask.end(), ',') + 1;   // parse_yolo_mask
+            {   // parse_yolo (parser.c:306-340): biases default .5, anchors= overrides, mask= selects
+                std::vector<float> biases((size_t)2 * total, .5f);
+                std::string an = s.gets("anchors", "");
+                std::stringstream as(an);
+                std::string tk;
+                size_t bi = 0;
+                while (std::getline(as, tk, ',') && bi < biases.size()) biases[bi++] = (float)atof(tk.c_str());
+                std::vector<int> mk;
+                if (mask.empty()) for (int q = 0; q < total; ++q) mk.push_back(q);
+                else {
+                    std::stringstream ms(mask);
+                    while (std::getline(ms, tk, ',')) mk.push_back(atoi(tk.c_str()));
+                }
+                for (int q : mk) {
+                    if (q < 0 || q >= total) {
+                        yq::fail("layer %d: yolo mask index %d out of range (num=%d)", index, q, total);
+                        return nullptr;
+                    }
+                    l.anchor_w.push_back(biases[2 * q]);
+                    l.anchor_h.push_back(biases[2 * q + 1]);
+                }
+            }
             l.c = c; l.h = h; l.w = w; l.out_c = c; l.out_h = h; l.out_w = w;
             if (c != l.n_anchors * (l.classes + 5)) {
                 yq::fail("layer %d: yolo expects %d channels, previous layer has %d", index, l.n_anchors * (l.classes + 5), c);
@@ -622,6 +649,8 @@ extern "C" void yq_free_network(yq_network *net)
     }
     if (net->h2d_stream) cudaStreamDestroy(net->h2d_stream);
     if (net->d2h_stream) cudaStreamDestroy(net->d2h_stream);
+    cudaFree(net->dets_dev);
+    cudaFree(net->counts_dev);
     cudaFree(net->in_stage_nchw);
     cudaFree(net->in_nhwc);
     cudaFree(net->scratch);
@@ -829,6 +858,64 @@ extern "C" int yq_network_collect(yq_network *net, int slot, float *out_host)
     if (out_host) YQ_CUDA(cudaMemcpyAsync(out_host, net->pipe_out[slot], net->out_floats * sizeof(float), cudaMemcpyDeviceToHost, net->d2h_stream));
     YQ_CUDA(cudaStreamSynchronize(net->d2h_stream));
     net->pipe_busy[slot] = false;
+    return 0;
+}
+
+extern "C" int yq_network_box_capacity(const yq_network *net)
+{
+    int cap = 0;
+    for (auto &l : net->layers)
+        if (l.type == L_YOLO) cap += l.out_h * l.out_w * l.n_anchors;
+    return cap;
+}
+
+extern "C" int yq_network_classes(const yq_network *net)
+{
+    for (auto &l : net->layers)
+        if (l.type == L_YOLO) return l.classes;
+    return 0;
+}
+
+// get_network_boxes (src/network.c:635-640) + do_nms_sort (src/box.c:58-89) for every image of the last forward,
+// on the device.  counts_host[batch]; dets_host[batch][capacity][5+classes] = x, y, w, h, objectness, prob[classes]
+// in the reference's order before NMS (yolo layers in network order, cell, anchor); NMS zeroes suppressed probs.
+extern "C" int yq_network_get_boxes(yq_network *net, int w, int h, float thresh, float nms_thresh, int relative, int *counts_host,
+                                    float *dets_host)
+{
+    if (!net || !counts_host || !dets_host) return yq::fail("yq_network_get_boxes: null argument");
+    YQ_CUDA(cudaSetDevice(net->device));
+    const float *pred[8];
+    int lw[8], lh[8], na[8];
+    const float *bw[8], *bh[8];
+    int nh = 0, classes = 0;
+    for (auto &l : net->layers)
+        if (l.type == L_YOLO) {
+            if (nh == 8) return yq::fail("too many yolo layers");
+            if (nh && l.classes != classes) return yq::fail("yolo layers disagree on the number of classes");
+            classes = l.classes;
+            pred[nh] = l.out_f32; lw[nh] = l.out_w; lh[nh] = l.out_h; na[nh] = l.n_anchors;
+            bw[nh] = l.anchor_w.data(); bh[nh] = l.anchor_h.data();
+            ++nh;
+        }
+    if (!nh) return yq::fail("network has no yolo layer");
+    const int cap = yq_network_box_capacity(net);
+    const size_t det_floats = (size_t)net->batch * cap * (5 + classes);
+    if (!net->dets_dev || net->det_cap != cap || net->det_classes != classes) {
+        cudaFree(net->dets_dev);
+        cudaFree(net->counts_dev);
+        net->dets_dev = nullptr;
+        net->counts_dev = nullptr;
+        YQ_CUDA(cudaMalloc((void **)&net->dets_dev, det_floats * sizeof(float)));
+        YQ_CUDA(cudaMalloc((void **)&net->counts_dev, net->batch * sizeof(int)));
+        net->det_cap = cap;
+        net->det_classes = classes;
+    }
+    if (yq_detect_run(pred, lw, lh, na, bw, bh, nh, classes, net->batch, cap, net->w, net->h, w, h, relative, thresh, nms_thresh,
+                      net->dets_dev, net->counts_dev, net->stream))
+        return -1;
+    YQ_CUDA(cudaMemcpyAsync(counts_host, net->counts_dev, net->batch * sizeof(int), cudaMemcpyDeviceToHost, net->stream));
+    YQ_CUDA(cudaMemcpyAsync(dets_host, net->dets_dev, det_floats * sizeof(float), cudaMemcpyDeviceToHost, net->stream));
+    YQ_CUDA(cudaStreamSynchronize(net->stream));
     return 0;
 }
 

@@ -343,6 +343,17 @@ class Network:
                 off += cnt
         return outs
 
+    def get_boxes(self, w: int, h: int, thresh: float = 0.5, nms: float = 0.45, relative: int = 1) -> List[np.ndarray]:
+        """get_network_boxes + do_nms_sort for every image of the last forward, on the device.
+        Returns one [count, 5 + classes] array per image: x, y, w, h, objectness, prob[classes]."""
+        lib = _lib.load()
+        cap, classes = lib.yq_network_box_capacity(self._h), lib.yq_network_classes(self._h)
+        counts = np.zeros(self.batch, np.int32)
+        dets = np.empty((self.batch, cap, 5 + classes), np.float32)
+        check(lib.yq_network_get_boxes(self._h, int(w), int(h), float(thresh), float(nms), int(relative), counts.ctypes.data,
+                                       dets.ctypes.data), "yq_network_get_boxes")
+        return [dets[b, :counts[b]].copy() for b in range(self.batch)]
+
     def pull_layer(self, i: int, what: str = "u8") -> np.ndarray:
         li = self.layer_info(i)
         code, dt = {"u8": (0, np.uint8), "acc": (1, np.int32), "f32": (2, np.float32)}[what]
