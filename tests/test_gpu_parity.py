@@ -130,18 +130,23 @@ def test_conv_tcgen05_small_c_vs_oracle(built, case):
     (16, 24, 24, 32, 3, 1, "relu6", 0, 0, 2),
     (32, 21, 19, 64, 3, 1, "relu6", 0, 0, 2),
     (16, 9, 9, 20, 3, 1, "relu", 9, 3, 2),
+    (3, 70, 52, 16, 3, 1, "relu6", 0, 7, 2),       # several 16x8 tiles, partial tiles on both borders, zp_out != 0
+    (16, 37, 50, 32, 3, 1, "relu6", 11, 0, 1),
 ], ids=lambda c: "c%d_%dx%d_n%d" % c[:4])
-def test_conv_fused_maxpool_vs_oracle(built, case):
-    """conv + maxpool(2,2) in one launch == oracle conv followed by oracle maxpool (maxpool_layer.c:109-153)."""
+@pytest.mark.parametrize("s_out", [0.05, 6.0], ids=["wrapping", "in_range"])
+def test_conv_fused_maxpool_vs_oracle(built, case, s_out):
+    """conv + maxpool(2,2) in one launch == oracle conv followed by oracle maxpool (maxpool_layer.c:109-153).
+    s_out = 0.05 drives most bytes through the uint8 wrap (the pool-first kernel's per-pixel FP64 path);
+    s_out = 6.0 keeps them in range (its max-then-requantize path)."""
     c, h, w, n, k, stride, act, zp_in, zp_out, batch = case
     rng = np.random.default_rng(zlib.crc32(repr(case).encode()) + 1)
     wq, zp_w, s_w, bias = make_params(rng, n, c * k * k, zp_in)
     spec = synth.LayerSpec("conv", n, k, stride, 1, 0, act)
-    sl = synth.SynthLayer("conv", c, h, w, n, 0, 0, spec, s_out=0.05, biases=bias, s_w=s_w, zp_w=zp_w, w_u8=wq.reshape(n, c, k, k))
+    sl = synth.SynthLayer("conv", c, h, w, n, 0, 0, spec, s_out=s_out, biases=bias, s_w=s_w, zp_w=zp_w, w_u8=wq.reshape(n, c, k, k))
     p = O.prepare_conv(sl, 0.02, zp_in)
     x = rng.integers(0, 256, size=(batch, c, h, w), dtype=np.uint8)
     layer = darknet.ConvolutionalLayerQuant(h, w, c, n, k, stride, 1, synth.ACT_CODES[act], wq, zp_w, p["biases_int32"], p["M_value"],
-                                            p["M0_right_shift_value"], zp_in, zp_out, 0.05, kernel=1)
+                                            p["M0_right_shift_value"], zp_in, zp_out, s_out, kernel=1)
     assert layer.can_fuse_maxpool
     for want_conv in (True, False):
         got = layer.forward_pooled(x, want_conv=want_conv)
@@ -151,6 +156,31 @@ def test_conv_fused_maxpool_vs_oracle(built, case):
             assert np.array_equal(got["pool"][b], O.maxpool(u8, 2, 2)), f"pooled mismatch image {b}"
             if want_conv:
                 assert np.array_equal(got["u8"][b], u8)
+    layer.free()
+
+
+def test_conv_fused_maxpool_large_accumulators(built):
+    """accumulators beyond 2^22 with in-range bytes: the integer-form requantize is no longer guaranteed to equal
+    the reference's double multiply, so the pool-first kernel must take its FP64 path and still match bit for bit."""
+    c, h, w, n, k = 32, 20, 24, 64, 3
+    rng = np.random.default_rng(77)
+    wq = rng.integers(180, 256, size=(n, c * k * k), dtype=np.uint8)
+    zp_w = rng.integers(0, 20, size=n, dtype=np.uint8)
+    s_w = (rng.random(n).astype(np.float32) * 0.01 + 0.001).astype(np.float32)
+    bias = (rng.standard_normal(n) * 0.5).astype(np.float32)
+    s_out = 25.0
+    spec = synth.LayerSpec("conv", n, k, 1, 1, 0, "relu6")
+    sl = synth.SynthLayer("conv", c, h, w, n, 0, 0, spec, s_out=s_out, biases=bias, s_w=s_w, zp_w=zp_w, w_u8=wq.reshape(n, c, k, k))
+    p = O.prepare_conv(sl, 0.02, 0)
+    x = rng.integers(150, 256, size=(2, c, h, w), dtype=np.uint8)
+    layer = darknet.ConvolutionalLayerQuant(h, w, c, n, k, 1, 1, synth.ACT_CODES["relu6"], wq, zp_w, p["biases_int32"], p["M_value"],
+                                            p["M0_right_shift_value"], 0, 0, s_out, kernel=1)
+    got = layer.forward_pooled(x, want_conv=False)
+    for b in range(2):
+        acc = O.conv_acc(x[b], wq.reshape(n, c, k, k), zp_w, 1, 1, 0)
+        assert acc.max() > (1 << 22)
+        u8 = O.requant(acc, p["biases_int32"], p["M_value"], p["M0_right_shift_value"], synth.ACT_CODES["relu6"], 0)
+        assert np.array_equal(got["pool"][b], O.maxpool(u8, 2, 2))
     layer.free()
 
 

@@ -17,6 +17,7 @@
 #include <cuda_runtime.h>
 #include <string.h>
 
+#include <type_traits>
 #include <vector>
 
 #include "yq_common.h"
@@ -110,9 +111,19 @@ struct TileWalker {
 
 // SLOW = the variant that also serves the int32 / float side outputs and the saturate switch (parity checks,
 // quant_stop heads); the production variant (SLOW = false) carries none of that code.
-template <int CS, int BN, int ACTM, bool SLOW>
+//
+// PQ = "pool-first quad" production variant (RELU6, pooled output only).  Tile rows are ordered so that the four pixels
+// of a 2x2 pooling window sit at TMEM lanes {i, i+8, i+16, i+24} of one warp's lane quarter; the 16x256b tcgen05.ld
+// shape then hands ONE thread all four pixels of a window for BN/4 channels (no shuffles).  The thread max-reduces the
+// raw accumulators first and requantizes the winner only: requantize + RELU6 is monotone in the accumulator, so
+//     max_p u8(f(x_p)) == u8(f(max_p x_p))   as long as f(max) <= 255 (no uint8 wrap) and max < 2^22 (integer form exact);
+// otherwise (rare) the window is redone pixel by pixel in FP64 form with the reference's wrap.  Filter rows are
+// permuted on the host so that thread q = lane & 3 owns channels [q*BN/4, (q+1)*BN/4): its packed bytes are one
+// contiguous BN/4-byte store and a warp writes 8 pooled pixels = 8*BN contiguous bytes.
+template <int CS, int BN, int ACTM, bool SLOW, bool PQ>
 __global__ void __launch_bounds__(SM_THREADS, (CS == 32 ? 2 : (CS == 16 ? 4 : 6))) conv_u8_tc_small_kernel(const __grid_constant__ SmallArgs a)
 {
+    static_assert(!PQ || (ACTM == 0 && !SLOW), "the pool-first variant exists for RELU6 production launches only");
     using G = SmallGeom<CS>;
     using L = SmallSmem<CS, BN>;
     extern __shared__ __align__(16) uint8_t smem_raw[];
@@ -123,7 +134,9 @@ __global__ void __launch_bounds__(SM_THREADS, (CS == 32 ? 2 : (CS == 16 ? 4 : 6)
 
     const int r = threadIdx.x;            // A-tile row == TMEM lane == pixel within the tile
     const int warp = r >> 5, lane = r & 31;
-    const int wi = r & (TILE_W - 1), hi = r >> 4;
+    // pixel of the 16x8 tile this thread's im2col row / TMEM lane stands for
+    const int wi = PQ ? 2 * (lane & 7) + ((lane >> 3) & 1) : (r & (TILE_W - 1));
+    const int hi = PQ ? 2 * warp + (lane >> 4) : (r >> 4);
 
     // ---- one-time setup: resident filter bank, ones tile, barriers, TMEM
     for (int i = r; i < L::B_BYTES / 16; i += SM_THREADS)
@@ -269,6 +282,18 @@ __global__ void __launch_bounds__(SM_THREADS, (CS == 32 ? 2 : (CS == 16 ? 4 : 6)
         }
     }
     const bool side = SLOW && ((a.out_acc != nullptr) || (a.out_f32 != nullptr));
+    // PQ: this thread's BN/4 channels (slot 4j+cc <-> channel qq*BN/4 + 4j + cc), held in registers for the whole launch
+    constexpr int NPQ = PQ ? BN / 4 : 1;
+    const int qi = lane >> 2, qq = lane & 3;
+    int pq_bias[NPQ], pq_zw[NPQ], pq_sh[NPQ];
+    uint32_t pq_m2[NPQ];
+    if constexpr (PQ) {
+#pragma unroll
+        for (int k = 0; k < NPQ; ++k) {
+            const int4 c = a.cq[qq * NPQ + k];
+            pq_bias[k] = c.x; pq_zw[k] = c.y; pq_m2[k] = (uint32_t)c.z; pq_sh[k] = c.w;
+        }
+    }
     for (int i = 0; i < cnt; ++i) {
         const int b = i & 1;
         const uint32_t qe = q0;          // tile whose epilogue runs in this iteration
@@ -294,8 +319,82 @@ __global__ void __launch_bounds__(SM_THREADS, (CS == 32 ? 2 : (CS == 16 ? 4 : 6)
             walk.advance(lp);
         }
 
-        // ---- epilogue of tile i: this thread owns TMEM lane r = its pixel
         const int tn = (int)(qe >> 16), tty = (int)((qe >> 8) & 255u), ttx = (int)(qe & 255u);
+        if constexpr (PQ) {
+            // ---- pool-first epilogue of tile i: this thread owns the 2x2 window (qi, warp) of the tile for channels qq*BN/4 ..
+            const int ppx = ttx * (TILE_W / 2) + qi, ppy = tty * (TILE_H / 2) + warp;
+            const bool is_edge = ttx * TILE_W + TILE_W > a.OW || tty * TILE_H + TILE_H > a.OH;   // uniform per tile
+            const uint32_t tq = trow + b * (BN + 16);
+            // EDGE tiles hang over the right / bottom border: pixels outside the conv output take no part in the max
+            auto pq_epilogue = [&](auto edge_tag) {
+                constexpr bool edge = decltype(edge_tag)::value;
+                bool pv[4] = {true, true, true, true};      // window pixel p = 2*dy + dx inside the conv output?
+                if (edge) {
+#pragma unroll
+                    for (int p = 0; p < 4; ++p) pv[p] = 2 * ppx + (p & 1) < a.OW && 2 * ppy + (p >> 1) < a.OH;
+                }
+                int nsa[4];
+                uint32_t words[BN / 16];
+#pragma unroll
+                for (int j = 0; j < BN / 16; ++j) {
+                    uint32_t v0[8], v1[8];                  // lanes {qi, qi+8} and {qi+16, qi+24}
+                    if (j == 0) {
+                        uint32_t s0[4], s1[4];
+                        tmem_ldq_first(tq + BN, tq, s0, s1, v0, v1);
+                        nsa[0] = -(int)s0[0]; nsa[1] = -(int)s0[2]; nsa[2] = -(int)s1[0]; nsa[3] = -(int)s1[2];
+                    } else {
+                        tmem_ldq(tq + 16 * j, v0, v1);
+                    }
+                    int rr[4];
+                    uint32_t orx = 0, orr = 0;
+#pragma unroll
+                    for (int cc = 0; cc < 4; ++cc) {
+                        const int k = 4 * j + cc, ri = 4 * (cc >> 1) + (cc & 1);   // register of (dx = 0, this channel)
+                        int x0 = pq_zw[k] * nsa[0] + (int)v0[ri], x1 = pq_zw[k] * nsa[1] + (int)v0[ri + 2];
+                        int x2 = pq_zw[k] * nsa[2] + (int)v1[ri], x3 = pq_zw[k] * nsa[3] + (int)v1[ri + 2];
+                        if (edge) {
+                            x0 = pv[0] ? x0 : INT_MIN; x1 = pv[1] ? x1 : INT_MIN; x2 = pv[2] ? x2 : INT_MIN; x3 = pv[3] ? x3 : INT_MIN;
+                        }
+                        const int m = max(max(x0, x1), max(x2, x3));
+                        const uint32_t xq = (uint32_t)max(m + pq_bias[k], 0);   // (a window with no valid pixel is never stored)
+                        rr[cc] = (int)(__umulhi(xq, pq_m2[k]) >> pq_sh[k]) + a.ep.zp_out;
+                        orx |= xq; orr |= (uint32_t)rr[cc];
+                    }
+                    if (orx >= (1u << 22) || orr > 255u) {
+                        // rare: the integer form may round differently from the reference's double multiply, or a byte wraps:
+                        // redo the window pixel by pixel in FP64 form (convolutional_layer.c:732-749), then pool the bytes
+#pragma unroll
+                        for (int cc = 0; cc < 4; ++cc) {
+                            const int k = 4 * j + cc, ri = 4 * (cc >> 1) + (cc & 1);
+                            const int4 c = a.cq[qq * NPQ + k];
+                            const double mcd = a.mc[qq * NPQ + k];
+                            const int xs[4] = {(int)v0[ri], (int)v0[ri + 2], (int)v1[ri], (int)v1[ri + 2]};
+                            int best = 0;
+#pragma unroll
+                            for (int p = 0; p < 4; ++p) {
+                                const int x = c.y * nsa[p] + xs[p] + c.x;
+                                const int q = max(__double2int_rz(__dmul_rn((double)x, mcd)), 0);
+                                const int u8 = (q + a.ep.zp_out) & 255;
+                                if (pv[p]) best = max(best, u8);
+                            }
+                            rr[cc] = best;
+                        }
+                    }
+                    words[j] = __byte_perm(__byte_perm((uint32_t)rr[0], (uint32_t)rr[1], 0x0040), __byte_perm((uint32_t)rr[2], (uint32_t)rr[3], 0x0040), 0x5410);
+                }
+                if (!edge || (ppx < a.PW && ppy < a.PH)) {
+                    uint8_t *dst = a.out_pool + ((size_t)(tn * a.PH + ppy) * a.PW + ppx) * a.CSO + qq * (BN / 4);
+                    if constexpr (BN == 16) *reinterpret_cast<uint32_t *>(dst) = words[0];
+                    else if constexpr (BN == 32) *reinterpret_cast<uint2 *>(dst) = make_uint2(words[0], words[1]);
+                    else *reinterpret_cast<uint4 *>(dst) = make_uint4(words[0], words[1], words[2], words[3]);
+                }
+            };
+            if (is_edge) pq_epilogue(std::true_type{});
+            else pq_epilogue(std::false_type{});
+            tc_fence_before();
+            continue;
+        }
+        // ---- epilogue of tile i: this thread owns TMEM lane r = its pixel
         const int ox = ttx * TILE_W + wi, oy = tty * TILE_H + hi;
         const bool valid = ox < a.OW && oy < a.OH;
         const uint32_t tacc = trow + b * (BN + 16);
@@ -350,21 +449,25 @@ __global__ void __launch_bounds__(SM_THREADS, (CS == 32 ? 2 : (CS == 16 ? 4 : 6)
 struct SmallState {
     int CS, BN, ctas_per_sm;
     uint8_t *wimg = nullptr;
+    uint8_t *wimg_pq = nullptr;   // filter rows in the pool-first variant's TMEM-column order, or nullptr
 };
 
-template <int CS, int BN, int ACTM, bool SLOW>
+// pool-first variant: TMEM column c = 16j + 8k + 2q + e  holds channel  q*BN/4 + 4j + 2k + e
+int pq_channel_of_column(int c, int BN) { return ((c % 8) / 2) * (BN / 4) + 4 * (c / 16) + 2 * ((c % 16) / 8) + (c % 2); }
+
+template <int CS, int BN, int ACTM, bool SLOW, bool PQ = false>
 int launch_small(SmallState *st, const SmallArgs &a, cudaStream_t stream)
 {
     using L = SmallSmem<CS, BN>;
     static int ctas_per_sm = 0, n_sm = 0;
     const int smem = L::TOTAL + 1024;
     if (!ctas_per_sm) {
-        YQ_CUDA(cudaFuncSetAttribute(conv_u8_tc_small_kernel<CS, BN, ACTM, SLOW>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        YQ_CUDA(cudaFuncSetAttribute(conv_u8_tc_small_kernel<CS, BN, ACTM, SLOW, PQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         // cudaOccupancyMaxActiveBlocksPerMultiprocessor answers 1 for kernels that allocate tensor memory (measured on
         // B200), although the hardware co-schedules as many CTAs as smem / registers / TMEM columns allow: count by hand.
         int dev = 0, smem_sm = 0;
         cudaFuncAttributes fa;
-        YQ_CUDA(cudaFuncGetAttributes(&fa, conv_u8_tc_small_kernel<CS, BN, ACTM, SLOW>));
+        YQ_CUDA(cudaFuncGetAttributes(&fa, conv_u8_tc_small_kernel<CS, BN, ACTM, SLOW, PQ>));
         YQ_CUDA(cudaGetDevice(&dev));
         YQ_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
         YQ_CUDA(cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev));
@@ -381,7 +484,7 @@ int launch_small(SmallState *st, const SmallArgs &a, cudaStream_t stream)
     }
     int grid = n_sm * ctas_per_sm;
     if (grid > a.num_tiles) grid = a.num_tiles;
-    conv_u8_tc_small_kernel<CS, BN, ACTM, SLOW><<<grid, SM_THREADS, smem, stream>>>(a);
+    conv_u8_tc_small_kernel<CS, BN, ACTM, SLOW, PQ><<<grid, SM_THREADS, smem, stream>>>(a);
     YQ_CHECK_LAUNCH();
     return 0;
 }
@@ -390,6 +493,11 @@ template <int CS, int BN>
 int launch_small_act(SmallState *st, const SmallArgs &a, int actm, cudaStream_t stream)
 {
     const bool slow = a.out_acc || a.out_f32 || a.ep.saturate;
+    if (!slow && actm == 0 && a.out_pool && !a.out && st->wimg_pq && a.N == BN && a.CSO == BN) {
+        SmallArgs b = a;
+        b.wimg = st->wimg_pq;
+        return launch_small<CS, BN, 0, false, true>(st, b, stream);
+    }
     if (slow) {
         if (actm == 0) return launch_small<CS, BN, 0, true>(st, a, stream);
         if (actm == 1) return launch_small<CS, BN, 1, true>(st, a, stream);
@@ -432,6 +540,24 @@ int yq_tc_small_prepare(yq_conv_layer *l, void **state)
         delete st;
         return yq::fail("tcgen05 small-c flavour: weight upload failed");
     }
+    if (l->n == st->BN) {   // the pool-first variant needs every TMEM column to be a real channel
+        std::vector<uint8_t> pq(img.size(), 0);
+        for (int p = 0; p < P; ++p)
+            for (int col = 0; col < st->BN; ++col) {
+                const int oc = pq_channel_of_column(col, st->BN);
+                // row `col` of the panel keeps its own SWIZZLE_32B phase: move the two 16-byte chunks accordingly
+                for (int c = 0; c < 2; ++c)
+                    memcpy(&pq[(size_t)p * st->BN * 32 + col * 32 + ((c ^ ((col >> 2) & 1)) << 4)],
+                           &img[(size_t)p * st->BN * 32 + oc * 32 + ((c ^ ((oc >> 2) & 1)) << 4)], 16);
+            }
+        if (cudaMalloc((void **)&st->wimg_pq, pq.size()) != cudaSuccess ||
+            cudaMemcpy(st->wimg_pq, pq.data(), pq.size(), cudaMemcpyHostToDevice) != cudaSuccess) {
+            cudaFree(st->wimg);
+            cudaFree(st->wimg_pq);
+            delete st;
+            return yq::fail("tcgen05 small-c flavour: weight upload failed");
+        }
+    }
     *state = st;
     return 0;
 }
@@ -441,6 +567,7 @@ void yq_tc_small_free(void *state)
     SmallState *st = (SmallState *)state;
     if (!st) return;
     cudaFree(st->wimg);
+    cudaFree(st->wimg_pq);
     delete st;
 }
 

@@ -174,6 +174,35 @@ __device__ __forceinline__ uint32_t tmem_ld1(uint32_t taddr)
     return v;
 }
 
+// 16x256b shape (cute Copy_Traits<SM100_TMEM_LOAD_16dp256b{1,2}x>): a warp reads 16 TMEM lanes starting at the lane in
+// taddr (its own quarter, +0 or +16); thread t gets lane t/4 in {r0, r1} = columns 2(t%4), 2(t%4)+1 and lane t/4 + 8 in
+// {r2, r3}; .x2 repeats the pattern 8 columns further in {r4..r7}.  These helpers read BOTH 16-lane halves of the
+// quarter, so thread t ends up with lanes {t/4, t/4+8} (v0) and {t/4+16, t/4+24} (v1).
+__device__ __forceinline__ void tmem_ldq(uint32_t taddr, uint32_t (&v0)[8], uint32_t (&v1)[8])
+{
+    asm volatile(
+        "tcgen05.ld.sync.aligned.16x256b.x2.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%16];\n\t"
+        "tcgen05.ld.sync.aligned.16x256b.x2.b32 {%8, %9, %10, %11, %12, %13, %14, %15}, [%17];\n\t"
+        "tcgen05.wait::ld.sync.aligned;"
+        : "=r"(v0[0]), "=r"(v0[1]), "=r"(v0[2]), "=r"(v0[3]), "=r"(v0[4]), "=r"(v0[5]), "=r"(v0[6]), "=r"(v0[7]), "=r"(v1[0]), "=r"(v1[1]),
+          "=r"(v1[2]), "=r"(v1[3]), "=r"(v1[4]), "=r"(v1[5]), "=r"(v1[6]), "=r"(v1[7])
+        : "r"(taddr), "r"(taddr + (16u << 16)));
+}
+// the same plus 8 columns at tsum (.x1) into s0 / s1 (the activation-sum columns), one wait for all four loads
+__device__ __forceinline__ void tmem_ldq_first(uint32_t tsum, uint32_t taddr, uint32_t (&s0)[4], uint32_t (&s1)[4], uint32_t (&v0)[8],
+                                               uint32_t (&v1)[8])
+{
+    asm volatile(
+        "tcgen05.ld.sync.aligned.16x256b.x1.b32 {%0, %1, %2, %3}, [%24];\n\t"
+        "tcgen05.ld.sync.aligned.16x256b.x1.b32 {%4, %5, %6, %7}, [%25];\n\t"
+        "tcgen05.ld.sync.aligned.16x256b.x2.b32 {%8, %9, %10, %11, %12, %13, %14, %15}, [%26];\n\t"
+        "tcgen05.ld.sync.aligned.16x256b.x2.b32 {%16, %17, %18, %19, %20, %21, %22, %23}, [%27];\n\t"
+        "tcgen05.wait::ld.sync.aligned;"
+        : "=r"(s0[0]), "=r"(s0[1]), "=r"(s0[2]), "=r"(s0[3]), "=r"(s1[0]), "=r"(s1[1]), "=r"(s1[2]), "=r"(s1[3]), "=r"(v0[0]), "=r"(v0[1]),
+          "=r"(v0[2]), "=r"(v0[3]), "=r"(v0[4]), "=r"(v0[5]), "=r"(v0[6]), "=r"(v0[7]), "=r"(v1[0]), "=r"(v1[1]), "=r"(v1[2]), "=r"(v1[3]),
+          "=r"(v1[4]), "=r"(v1[5]), "=r"(v1[6]), "=r"(v1[7])
+        : "r"(tsum), "r"(tsum + (16u << 16)), "r"(taddr), "r"(taddr + (16u << 16)));
+}
 
 // kind::i8 instruction descriptor (cute::UMMA::InstrDescriptor): c_format S32 (2) [4,6), a/b format 0 = UINT8
 // [7,10)/[10,13), a/b K-major (0) [15]/[16], N>>3 [17,23), M>>4 [24,29); M is always 128 here.
