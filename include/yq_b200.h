@@ -122,6 +122,24 @@ YQ_API int yq_forward_convolutional_layer_quant_pool_gpu(yq_conv_layer *l, const
                                                          void *stream);
 YQ_API int yq_conv_can_fuse_maxpool(const yq_conv_layer *l);
 
+/* A halo-padded NHWC activation tensor: pixel (n, y, x) lives at
+ *     base + (((size_t)n * rows_h + y + pad) * pitch_w + x + pad) * yq_channel_stride(c)
+ * The halo (and any slack right / below the image) holds the CONSUMER's input zero point, which is what
+ * im2col_cpu_uint8 pads with (src/im2col.c:5-14).  pad = 0, pitch_w = w, rows_h = h is the plain tensor. */
+typedef struct yq_act_geom {
+    int pad, pitch_w, rows_h;
+} yq_act_geom;
+
+/* The "rows" flavour: 3x3 / stride 1 / pad 1 convolution + RELU6 + the following 2x2/2 max-pool in ONE launch
+ * (convolutional_layer.c:694-751 + maxpool_layer.c:109-153 fused), for c <= 32.  It reads a halo-padded input
+ * (geometry from yq_conv_rows_input_geom) with no im2col gather and writes only the pooled tensor, into any
+ * geometry.  yq_conv_rows_supported() is 1 when the layer has it. */
+YQ_API int yq_conv_rows_supported(const yq_conv_layer *l);
+YQ_API int yq_conv_rows_input_geom(const yq_conv_layer *l, yq_act_geom *geom);
+YQ_API size_t yq_act_geom_bytes(const yq_act_geom *geom, int batch, int c);
+YQ_API int yq_forward_convolutional_layer_quant_rows_pool_gpu(yq_conv_layer *l, const uint8_t *in_padded, uint8_t *out_pool,
+                                                              const yq_act_geom *out_geom, int batch, void *stream);
+
 /* ------------------------------------------------------------------------------------------------
  * memory-bound layers (all device pointers, uint8 NHWC, channel stride yq_channel_stride(c))
  * ---------------------------------------------------------------------------------------------- */
@@ -147,6 +165,11 @@ YQ_API int yq_nhwc_to_nchw_u8(const uint8_t *in_nhwc, uint8_t *out_nchw, int bat
                               void *stream);
 YQ_API int yq_nhwc_to_nchw_i32(const int32_t *in_nhwc, int32_t *out_nchw, int batch, int c, int h, int w,
                                void *stream);
+/* the same conversions from / to a halo-padded tensor (only the h x w interior is read / written) */
+YQ_API int yq_nchw_to_nhwc_u8_geom(const uint8_t *in_nchw, uint8_t *out_nhwc, int batch, int c, int h, int w,
+                                   const yq_act_geom *geom, void *stream);
+YQ_API int yq_nhwc_to_nchw_u8_geom(const uint8_t *in_nhwc, uint8_t *out_nchw, int batch, int c, int h, int w,
+                                   const yq_act_geom *geom, void *stream);
 
 /* ------------------------------------------------------------------------------------------------
  * network level -- host-side mirror of the reference's public API for this path

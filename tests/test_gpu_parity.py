@@ -159,6 +159,53 @@ def test_conv_fused_maxpool_vs_oracle(built, case, s_out):
     layer.free()
 
 
+ROWS_CASES = [
+    # c, h, w, n, zp_in, zp_out, batch
+    (3, 48, 64, 16, 0, 0, 2),
+    (3, 34, 70, 16, 9, 5, 1),        # partial tiles in x and y, w % 4 != 0
+    (3, 16, 32, 32, 0, 0, 1),
+    (16, 32, 48, 32, 0, 0, 2),
+    (16, 18, 22, 32, 40, 0, 1),      # partial tiles, halo = zp_in = 40
+    (16, 16, 16, 16, 0, 3, 1),
+    (16, 20, 36, 64, 0, 0, 1),
+    (32, 16, 16, 64, 0, 0, 2),
+    (32, 26, 40, 64, 17, 0, 1),
+    (32, 14, 18, 32, 0, 0, 1),
+    (20, 12, 20, 32, 0, 0, 1),       # c = 20 -> channel stride 32 with 12 pad lanes
+]
+
+
+@pytest.mark.parametrize("case", ROWS_CASES, ids=lambda c: "c%d_%dx%d_n%d" % c[:4])
+@pytest.mark.parametrize("s_out", [0.05, 6.0], ids=["wrapping", "in_range"])
+@pytest.mark.parametrize("out_pad", [0, 1])
+def test_conv_rows_flavour_vs_oracle(built, case, s_out, out_pad):
+    """halo-input conv + RELU6 + maxpool(2,2) (no im2col; Toeplitz / even-odd MMA groups) == oracle conv + oracle maxpool;
+    with out_pad = 1 the halo of the output tensor must stay untouched."""
+    c, h, w, n, zp_in, zp_out, batch = case
+    k = 3
+    rng = np.random.default_rng(zlib.crc32(repr(case).encode()) + 5)
+    wq, zp_w, s_w, bias = make_params(rng, n, c * k * k, zp_in)
+    spec = synth.LayerSpec("conv", n, k, 1, 1, 0, "relu6")
+    sl = synth.SynthLayer("conv", c, h, w, n, 0, 0, spec, s_out=s_out, biases=bias, s_w=s_w, zp_w=zp_w, w_u8=wq.reshape(n, c, k, k))
+    p = O.prepare_conv(sl, 0.02, zp_in)
+    x = rng.integers(0, 256, size=(batch, c, h, w), dtype=np.uint8)
+    layer = darknet.ConvolutionalLayerQuant(h, w, c, n, k, 1, 1, synth.ACT_CODES["relu6"], wq, zp_w, p["biases_int32"], p["M_value"],
+                                            p["M0_right_shift_value"], zp_in, zp_out, s_out)
+    assert layer.rows_supported
+    got = layer.forward_rows_pooled(x, out_pad=out_pad)
+    for b in range(batch):
+        acc = O.conv_acc(x[b], wq.reshape(n, c, k, k), zp_w, 1, 1, zp_in)
+        u8 = O.requant(acc, p["biases_int32"], p["M_value"], p["M0_right_shift_value"], synth.ACT_CODES["relu6"], zp_out)
+        assert np.array_equal(got[b], O.maxpool(u8, 2, 2)), f"pooled mismatch image {b}"
+    if out_pad:
+        raw, pad, pitch, rows = layer.last_rows_raw
+        cs = darknet.channel_stride(n)
+        t = raw.reshape(batch, rows, pitch, cs).copy()
+        t[:, pad:pad + h // 2, pad:pad + w // 2, :] = 0xEE
+        assert (t == 0xEE).all(), "the rows kernel wrote outside the pooled interior"
+    layer.free()
+
+
 def test_conv_fused_maxpool_large_accumulators(built):
     """accumulators beyond 2^22 with in-range bytes: the integer-form requantize is no longer guaranteed to equal
     the reference's double multiply, so the pool-first kernel must take its FP64 path and still match bit for bit."""

@@ -29,6 +29,10 @@ class ConvDesc(C.Structure):
     ]
 
 
+class ActGeom(C.Structure):
+    _fields_ = [("pad", C.c_int), ("pitch_w", C.c_int), ("rows_h", C.c_int)]
+
+
 class LayerInfo(C.Structure):
     _fields_ = [
         ("type", C.c_int), ("c", C.c_int), ("h", C.c_int), ("w", C.c_int),
@@ -65,6 +69,12 @@ SIGNATURES = {
     "yq_forward_convolutional_layer_quant_gpu": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _vp]),
     "yq_forward_convolutional_layer_quant_pool_gpu": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _vp]),
     "yq_conv_can_fuse_maxpool": (_i, [_vp]),
+    "yq_conv_rows_supported": (_i, [_vp]),
+    "yq_conv_rows_input_geom": (_i, [_vp, C.POINTER(ActGeom)]),
+    "yq_act_geom_bytes": (_sz, [C.POINTER(ActGeom), _i, _i]),
+    "yq_forward_convolutional_layer_quant_rows_pool_gpu": (_i, [_vp, _vp, _vp, C.POINTER(ActGeom), _i, _vp]),
+    "yq_nchw_to_nhwc_u8_geom": (_i, [_vp, _vp, _i, _i, _i, _i, C.POINTER(ActGeom), _vp]),
+    "yq_nhwc_to_nchw_u8_geom": (_i, [_vp, _vp, _i, _i, _i, _i, C.POINTER(ActGeom), _vp]),
     "yq_forward_maxpool_layer_quant_gpu": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "yq_forward_upsample_layer_quant_gpu": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "yq_forward_route_layer_quant_gpu": (_i, [C.POINTER(_vp), C.POINTER(_i), _i, _vp, _i, _i, _i, _vp]),

@@ -1,0 +1,560 @@
+// yq_conv_tc_rows.cu -- tcgen05 (kind::i8) 3x3 / stride 1 / pad 1 convolution + RELU6 + fused 2x2/2 max-pool for
+// SMALL input-channel counts (c <= 32: layers 0, 2, 4 of yolov3-tiny) with NO im2col gather at all.
+//
+// These layers are HBM-bound on paper (45..384 op/B) but were issue-bound in practice: every thread built one im2col
+// row per pixel.  Here the activation tile is copied ONCE, row by row, from a halo-padded NHWC tensor into shared
+// memory (16-byte cp.async chunks, ~2..6 per thread per tile) and the tensor core reads overlapping windows of it
+// through a NO-SWIZZLE K-major descriptor whose leading-byte-offset makes consecutive K chunks overlap:
+//
+//   c = 4  (layer 0): one MMA row = 4 output pixels.  Row i's K = 32 bytes = input pixels 4i-1 .. 4i+6 of one image
+//          row = two 16-byte chunks at 16i and 16i+16 (LBO = 16: chunk 1 of row i IS chunk 0 of row i+1).  The filter
+//          bank is a Toeplitz matrix [4 pixels x n channels][8 input pixels x 4 channels]; the tensor core multiplies
+//          by its zeros for free.  3 MMAs per tile (one per filter row ky, A start shifted by one tile row).
+//   c = 16, 32: pixels are de-interleaved into EVEN / ODD planes while they are copied, and two MMA groups compute
+//          the even and the odd output pixels of a row into different TMEM column ranges:
+//              even pixel 2i  : K chunks (E[i], O[i-1]) (O[i], -)       odd pixel 2i+1 : (E[i], O[i]) (E[i+1], -)
+//          (12 MMAs per tile and 16-channel block).
+//
+// Either way one TMEM lane then holds BOTH x-neighbours of a pooling window in its columns, tile rows are ordered so
+// that lanes {i, i+8} / {i+16, i+24} are y-neighbours, and the 16x256b tcgen05.ld shape hands one thread complete 2x2
+// windows: max in the accumulator domain, requantize the winner only (exact, see yq_conv_tc_small.cu), FP64 per-pixel
+// fallback when a byte would wrap or |x| >= 2^22.  Restates convolutional_layer.c:694-751 + maxpool_layer.c:109-153.
+//
+// Zero point of the weights: 16 extra all-ones filter rows per MMA group give sum(a) per output pixel
+// (acc = sum w*a - zp_w * sum a, convolutional_layer.c:718-721).  Padding: the input tensor carries a halo filled
+// with zp_in (im2col.c:5-14), written once by the host runtime; pad channels never count (their weights are 0).
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <limits.h>
+#include <string.h>
+
+#include <type_traits>
+#include <vector>
+
+#include "yq_common.h"
+#include "yq_epilogue.cuh"
+#include "yq_tc_ptx.cuh"
+
+using namespace yqtc;
+
+namespace {
+
+constexpr int RW_THREADS = 128;
+constexpr int TILE_ROWS = 16;           // conv output rows per tile
+constexpr int PLANE = 144;              // bytes of one shared-memory plane row: 9 x 16
+
+template <int CS>
+struct RowsGeom {
+    static constexpr int TWPX = CS == 4 ? 32 : 16;                  // conv output pixels per tile row
+    static constexpr int NBLK = CS == 32 ? 2 : 1;                   // 16-channel blocks
+    static constexpr int ROWP = CS == 4 ? PLANE : 2 * PLANE * NBLK; // shared-memory bytes per tile row
+    static constexpr int A_ROWS = TILE_ROWS + 2;
+    static constexpr int A_BYTES = A_ROWS * ROWP;
+    static constexpr int CHUNKS = A_BYTES / 16;                     // 162 / 324 / 648
+    static constexpr int CPT = (CHUNKS + RW_THREADS - 1) / RW_THREADS;
+    static constexpr int NMMA = CS == 4 ? 3 : 12 * NBLK;
+};
+
+template <int CS, int NCH>
+struct RowsCfg {
+    using G = RowsGeom<CS>;
+    static constexpr int NB = CS == 4 ? 4 * NCH + 16 : NCH + 16;    // filter rows (TMEM columns) per MMA group
+    static constexpr int NACC = CS == 4 ? NB : 2 * NB;              // TMEM columns of one accumulator
+    static constexpr int TMEM_COLS = NACC <= 32 ? 32 : NACC <= 64 ? 64 : NACC <= 128 ? 128 : NACC <= 256 ? 256 : 512;
+    static constexpr int BSUB = NB * 32;                            // one MMA's filter tile
+    static constexpr int B_BYTES = G::NMMA * BSUB;
+    static constexpr int A_STRIDE = (G::A_BYTES + 32 + 127) / 128 * 128;   // +32: the last window's (zero-weight) overhang
+    static constexpr int A_OFF = 0;
+    static constexpr int B_OFF = 2 * A_STRIDE;
+    static constexpr int BAR_OFF = B_OFF + B_BYTES;
+    static constexpr int TOTAL = BAR_OFF + 64;
+    static_assert(NB % 16 == 0 && NB <= 256, "kind::i8 N");
+};
+
+struct RowsArgs {
+    const uint8_t *in;      // halo-padded NHWC input: pixel (n, y, x) at in + ((n*HP + y + 1)*WP + x + 1)*CS
+    uint8_t *out_pool;      // pooled output:          pixel (n, y, x) at out + ((n*OHP + y + opad)*OWP + x + opad)*NCH
+    const uint8_t *wimg;    // shared-memory image of the filter tiles, one per MMA in issue order
+    int HP, WP, OH, OW, PH, PW, OHP, OWP, opad;
+    int tiles_x, tiles_y, num_tiles, zp_out;
+    int4 cq[64];            // {bias, zw, 2*M0, shift} per channel
+    double mc[64];          // M_value * 2^-s (FP64 fallback)
+};
+
+// K-major, no swizzle: 8 rows x 16 bytes contiguous per core matrix; LBO = byte step between the two K chunks of one
+// MMA, SBO = byte step between 8-row groups (cute::UMMA canonical layout ((8,n),2):((1,SBO),LBO) in 16-byte units)
+__device__ __forceinline__ uint64_t make_desc_ns(uint32_t saddr, uint32_t lbo, uint32_t sbo)
+{
+    return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)(lbo >> 4) << 16) | ((uint64_t)(sbo >> 4) << 32) | (1ull << 46);
+}
+
+__device__ __forceinline__ void tmem_ldq4(uint32_t taddr, uint32_t (&v0)[16], uint32_t (&v1)[16])
+{
+    asm volatile(
+        "tcgen05.ld.sync.aligned.16x256b.x4.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%32];\n\t"
+        "tcgen05.ld.sync.aligned.16x256b.x4.b32 {%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%33];\n\t"
+        "tcgen05.wait::ld.sync.aligned;"
+        : "=r"(v0[0]), "=r"(v0[1]), "=r"(v0[2]), "=r"(v0[3]), "=r"(v0[4]), "=r"(v0[5]), "=r"(v0[6]), "=r"(v0[7]), "=r"(v0[8]), "=r"(v0[9]),
+          "=r"(v0[10]), "=r"(v0[11]), "=r"(v0[12]), "=r"(v0[13]), "=r"(v0[14]), "=r"(v0[15]), "=r"(v1[0]), "=r"(v1[1]), "=r"(v1[2]),
+          "=r"(v1[3]), "=r"(v1[4]), "=r"(v1[5]), "=r"(v1[6]), "=r"(v1[7]), "=r"(v1[8]), "=r"(v1[9]), "=r"(v1[10]), "=r"(v1[11]),
+          "=r"(v1[12]), "=r"(v1[13]), "=r"(v1[14]), "=r"(v1[15])
+        : "r"(taddr), "r"(taddr + (16u << 16)));
+}
+// even / odd column groups, both 16-lane halves: 4 x (.x2)
+__device__ __forceinline__ void tmem_ldq_eo(uint32_t te, uint32_t to, uint32_t (&e0)[8], uint32_t (&e1)[8], uint32_t (&o0)[8], uint32_t (&o1)[8])
+{
+    asm volatile(
+        "tcgen05.ld.sync.aligned.16x256b.x2.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%32];\n\t"
+        "tcgen05.ld.sync.aligned.16x256b.x2.b32 {%8, %9, %10, %11, %12, %13, %14, %15}, [%33];\n\t"
+        "tcgen05.ld.sync.aligned.16x256b.x2.b32 {%16, %17, %18, %19, %20, %21, %22, %23}, [%34];\n\t"
+        "tcgen05.ld.sync.aligned.16x256b.x2.b32 {%24, %25, %26, %27, %28, %29, %30, %31}, [%35];\n\t"
+        "tcgen05.wait::ld.sync.aligned;"
+        : "=r"(e0[0]), "=r"(e0[1]), "=r"(e0[2]), "=r"(e0[3]), "=r"(e0[4]), "=r"(e0[5]), "=r"(e0[6]), "=r"(e0[7]), "=r"(e1[0]), "=r"(e1[1]),
+          "=r"(e1[2]), "=r"(e1[3]), "=r"(e1[4]), "=r"(e1[5]), "=r"(e1[6]), "=r"(e1[7]), "=r"(o0[0]), "=r"(o0[1]), "=r"(o0[2]), "=r"(o0[3]),
+          "=r"(o0[4]), "=r"(o0[5]), "=r"(o0[6]), "=r"(o0[7]), "=r"(o1[0]), "=r"(o1[1]), "=r"(o1[2]), "=r"(o1[3]), "=r"(o1[4]), "=r"(o1[5]),
+          "=r"(o1[6]), "=r"(o1[7])
+        : "r"(te), "r"(te + (16u << 16)), "r"(to), "r"(to + (16u << 16)));
+}
+// activation-sum columns of the even / odd groups, both halves: 4 x (.x1)
+__device__ __forceinline__ void tmem_ldq_sums(uint32_t te, uint32_t to, uint32_t (&e0)[4], uint32_t (&e1)[4], uint32_t (&o0)[4], uint32_t (&o1)[4])
+{
+    asm volatile(
+        "tcgen05.ld.sync.aligned.16x256b.x1.b32 {%0, %1, %2, %3}, [%16];\n\t"
+        "tcgen05.ld.sync.aligned.16x256b.x1.b32 {%4, %5, %6, %7}, [%17];\n\t"
+        "tcgen05.ld.sync.aligned.16x256b.x1.b32 {%8, %9, %10, %11}, [%18];\n\t"
+        "tcgen05.ld.sync.aligned.16x256b.x1.b32 {%12, %13, %14, %15}, [%19];\n\t"
+        "tcgen05.wait::ld.sync.aligned;"
+        : "=r"(e0[0]), "=r"(e0[1]), "=r"(e0[2]), "=r"(e0[3]), "=r"(e1[0]), "=r"(e1[1]), "=r"(e1[2]), "=r"(e1[3]), "=r"(o0[0]), "=r"(o0[1]),
+          "=r"(o0[2]), "=r"(o0[3]), "=r"(o1[0]), "=r"(o1[1]), "=r"(o1[2]), "=r"(o1[3])
+        : "r"(te), "r"(te + (16u << 16)), "r"(to), "r"(to + (16u << 16)));
+}
+
+// Per-launch channel parameters of ONE thread (its NCH/4 channels), kept in registers.
+template <int NPQ>
+struct ThreadChan {
+    int bias[NPQ], zw[NPQ], sh[NPQ];
+    uint32_t m2[NPQ];
+};
+
+// One pooled output: the window's four raw accumulators v0..v3 with their activation sums -> exact zero-point
+// correction, max, bias, RELU6 requantize of the winner.  Returns q + zp_out; *xq is the requantizer's input.
+__device__ __forceinline__ int pool_requant(int zw, int bias, uint32_t m2, int sh, int zo, int v0, int v1, int v2, int v3, int n0, int n1, int n2,
+                                            int n3, uint32_t *xq)
+{
+    const int m = max(max(zw * n0 + v0, zw * n1 + v1), max(zw * n2 + v2, zw * n3 + v3));
+    *xq = (uint32_t)max(m + bias, 0);
+    return (int)(__umulhi(*xq, m2) >> sh) + zo;
+}
+// the reference's per-pixel arithmetic for one window (FP64 multiply, uint8 wrap, then the pool)
+__device__ __forceinline__ int pool_requant_slow(int zw, int bias, double mcd, int zo, int v0, int v1, int v2, int v3, int n0, int n1, int n2, int n3)
+{
+    const int xs[4] = {zw * n0 + v0 + bias, zw * n1 + v1 + bias, zw * n2 + v2 + bias, zw * n3 + v3 + bias};
+    int best = 0;
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+        const int q = max(__double2int_rz(__dmul_rn((double)xs[p], mcd)), 0);
+        best = max(best, (q + zo) & 255);
+    }
+    return best;
+}
+__device__ __forceinline__ uint32_t pack4(const int (&r)[4])
+{
+    return __byte_perm(__byte_perm((uint32_t)r[0], (uint32_t)r[1], 0x0040), __byte_perm((uint32_t)r[2], (uint32_t)r[3], 0x0040), 0x5410);
+}
+
+template <int CS, int NCH>
+__global__ void __launch_bounds__(RW_THREADS, (CS == 32 ? 2 : 4)) conv_u8_tc_rows_kernel(const __grid_constant__ RowsArgs a)
+{
+    using G = RowsGeom<CS>;
+    using L = RowsCfg<CS, NCH>;
+    constexpr int NPQ = NCH / 4;
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    uint8_t *smem = smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u);
+    uint64_t *mma_done = (uint64_t *)(smem + L::BAR_OFF);
+    uint32_t *tmem_slot = (uint32_t *)(mma_done + 1);
+
+    const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+    const int qi = lane >> 2, qq = lane & 3;
+
+    // ---- one-time setup: resident filter tiles, barrier, TMEM
+    for (int i = t; i < L::B_BYTES / 16; i += RW_THREADS)
+        reinterpret_cast<uint4 *>(smem + L::B_OFF)[i] = __ldg(reinterpret_cast<const uint4 *>(a.wimg) + i);
+    for (int i = t; i < 2 * L::A_STRIDE / 16; i += RW_THREADS) reinterpret_cast<uint4 *>(smem + L::A_OFF)[i] = make_uint4(0, 0, 0, 0);
+    if (t == 0) {
+        mbar_init(mma_done, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) tmem_alloc<L::TMEM_COLS>(tmem_slot);
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tq = tmem_base + ((uint32_t)(warp * 32) << 16);
+
+    // ---- this thread's share of a tile copy: CPT 16-byte chunks, (source offset, destination offset) fixed for the launch
+    int src_off[G::CPT];
+    uint32_t dst_off[G::CPT];
+#pragma unroll
+    for (int k = 0; k < G::CPT; ++k) {
+        const int c = t + k * RW_THREADS;
+        int so = 0, d = 0;
+        if (CS == 4) {
+            const int yy = c / 9, cx = c - yy * 9;
+            so = yy * a.WP * 4 + cx * 16;
+            d = yy * G::ROWP + cx * 16;
+        } else {
+            constexpr int PER_ROW = 18 * G::NBLK;
+            const int yy = c / PER_ROW, rem = c - yy * PER_ROW;
+            const int j = rem / G::NBLK, blk = rem - j * G::NBLK;      // j: pixel of the 18-pixel window x0-1 .. x0+16
+            so = (yy * a.WP + j) * CS + blk * 16;
+            // odd j = even output-pixel column x0 + (j-1): plane E; even j: plane O (shifted by one: O[m] = pixel x0-1+2m)
+            d = yy * G::ROWP + blk * 2 * PLANE + ((j & 1) ? ((j - 1) >> 1) * 16 : PLANE + (j >> 1) * 16);
+        }
+        src_off[k] = so;
+        dst_off[k] = (uint32_t)d;
+    }
+    const uint32_t sA = smem_u32(smem + L::A_OFF);
+    auto issue_tile = [&](int tile, int buf) {
+        const int tx = tile % a.tiles_x, r1 = tile / a.tiles_x;
+        const int ty = r1 % a.tiles_y, n = r1 / a.tiles_y;
+        const uint8_t *src = a.in + ((size_t)(n * a.HP + ty * TILE_ROWS) * a.WP + tx * G::TWPX) * CS;
+        const uint32_t dst = sA + buf * L::A_STRIDE;
+#pragma unroll
+        for (int k = 0; k < G::CPT; ++k)
+            if ((k + 1) * RW_THREADS <= G::CHUNKS || t + k * RW_THREADS < G::CHUNKS) cp_async16(dst + dst_off[k], src + src_off[k]);
+    };
+    auto issue_mma = [&](int buf) {   // one thread issues the MMAs of a whole tile
+        constexpr uint32_t idesc = make_idesc(L::NB);
+        const uint32_t a0 = sA + buf * L::A_STRIDE, b0 = smem_u32(smem + L::B_OFF);
+        if (CS == 4) {
+#pragma unroll
+            for (int ky = 0; ky < 3; ++ky)
+                umma_i8(tmem_base, make_desc_ns(a0 + ky * G::ROWP, 16, G::ROWP), make_desc_ns(b0 + ky * L::BSUB, 128, 256), idesc, ky ? 1u : 0u);
+        } else {
+            int m = 0;
+#pragma unroll
+            for (int par = 0; par < 2; ++par)
+#pragma unroll
+                for (int blk = 0; blk < G::NBLK; ++blk)
+#pragma unroll
+                    for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+                        for (int step = 0; step < 2; ++step, ++m) {
+                            const uint32_t row = a0 + blk * 2 * PLANE + ky * G::ROWP;
+                            // even: (E[i], O[i]) then (O[i+1], -);   odd: (E[i], O[i+1]) then (E[i+1], -)    [O[] is the shifted plane]
+                            const uint32_t start = step == 0 ? row : (par == 0 ? row + PLANE + 16 : row + 16);
+                            const uint32_t lbo = step == 0 ? (par == 0 ? PLANE : PLANE + 16) : 16;
+                            umma_i8(tmem_base + par * L::NB, make_desc_ns(start, lbo, G::ROWP), make_desc_ns(b0 + m * L::BSUB, 128, 256), idesc,
+                                    (blk | ky | step) ? 1u : 0u);
+                        }
+        }
+        umma_commit(mma_done);
+    };
+
+    ThreadChan<NPQ> ch;
+#pragma unroll
+    for (int k = 0; k < NPQ; ++k) {
+        const int4 c = a.cq[qq * NPQ + k];
+        ch.bias[k] = c.x; ch.zw[k] = c.y; ch.m2[k] = (uint32_t)c.z; ch.sh[k] = c.w;
+    }
+    const int zo = a.zp_out;
+
+    const int first = blockIdx.x, step = gridDim.x;
+    uint32_t phase = 0;
+    if (first < a.num_tiles) issue_tile(first, 0);
+    int buf = 0;
+    for (int tile = first; tile < a.num_tiles; tile += step, buf ^= 1) {
+        // tile's copy has been in flight since the previous iteration
+        cp_async_wait_all();
+        fence_proxy_async();          // generic-proxy smem writes -> visible to the tensor core (async proxy)
+        tc_fence_before();            // (also orders the previous epilogue's TMEM reads before the next MMA)
+        __syncthreads();
+        if (t == 0) {
+            tc_fence_after();
+            issue_mma(buf);
+        }
+        if (tile + step < a.num_tiles) issue_tile(tile + step, buf ^ 1);   // overlaps this tile's MMA + epilogue
+        mbar_wait(mma_done, phase);
+        phase ^= 1u;
+        tc_fence_after();
+
+        // ---- epilogue: warp = TMEM lane quarter = 4 conv rows = 2 pooled rows; thread (qi, qq) = pooled column(s) qi, channels qq*NPQ ..
+        const int tx = tile % a.tiles_x, r1 = tile / a.tiles_x;
+        const int ty = r1 % a.tiles_y, n = r1 / a.tiles_y;
+        const int py0 = ty * (TILE_ROWS / 2) + 2 * warp;
+        if (CS == 4) {
+            uint32_t s0[8], s1[8];
+            tmem_ldq(tq + 4 * NCH, s0, s1);
+            int nsa0[8], nsa1[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                nsa0[k] = -(int)s0[k];
+                nsa1[k] = -(int)s1[k];
+            }
+#pragma unroll
+            for (int pair = 0; pair < 2; ++pair) {
+                uint32_t w0[NCH / 16], w1[NCH / 16];
+#pragma unroll
+                for (int jj = 0; jj < NCH / 16; ++jj) {
+                    uint32_t v0[16], v1[16];
+                    tmem_ldq4(tq + (pair * NPQ + 4 * jj) * 8, v0, v1);
+                    int r0[4], r1w[4];
+                    uint32_t orx = 0, orr = 0, xq;
+#pragma unroll
+                    for (int gg = 0; gg < 4; ++gg) {
+                        const int k = 4 * jj + gg;
+                        r0[gg] = pool_requant(ch.zw[k], ch.bias[k], ch.m2[k], ch.sh[k], zo, (int)v0[4 * gg], (int)v0[4 * gg + 1], (int)v0[4 * gg + 2],
+                                              (int)v0[4 * gg + 3], nsa0[4 * pair], nsa0[4 * pair + 1], nsa0[4 * pair + 2], nsa0[4 * pair + 3], &xq);
+                        orx |= xq; orr |= (uint32_t)r0[gg];
+                        r1w[gg] = pool_requant(ch.zw[k], ch.bias[k], ch.m2[k], ch.sh[k], zo, (int)v1[4 * gg], (int)v1[4 * gg + 1], (int)v1[4 * gg + 2],
+                                               (int)v1[4 * gg + 3], nsa1[4 * pair], nsa1[4 * pair + 1], nsa1[4 * pair + 2], nsa1[4 * pair + 3], &xq);
+                        orx |= xq; orr |= (uint32_t)r1w[gg];
+                    }
+                    if (orx >= (1u << 22) || orr > 255u) {
+#pragma unroll
+                        for (int gg = 0; gg < 4; ++gg) {
+                            const int k = 4 * jj + gg;
+                            const double mcd = a.mc[qq * NPQ + k];
+                            r0[gg] = pool_requant_slow(ch.zw[k], ch.bias[k], mcd, zo, (int)v0[4 * gg], (int)v0[4 * gg + 1], (int)v0[4 * gg + 2],
+                                                       (int)v0[4 * gg + 3], nsa0[4 * pair], nsa0[4 * pair + 1], nsa0[4 * pair + 2], nsa0[4 * pair + 3]);
+                            r1w[gg] = pool_requant_slow(ch.zw[k], ch.bias[k], mcd, zo, (int)v1[4 * gg], (int)v1[4 * gg + 1], (int)v1[4 * gg + 2],
+                                                        (int)v1[4 * gg + 3], nsa1[4 * pair], nsa1[4 * pair + 1], nsa1[4 * pair + 2], nsa1[4 * pair + 3]);
+                        }
+                    }
+                    w0[jj] = pack4(r0);
+                    w1[jj] = pack4(r1w);
+                }
+                const int px = tx * (G::TWPX / 2) + 2 * qi + pair;
+                if (px < a.PW) {
+                    uint8_t *dst = a.out_pool + ((size_t)(n * a.OHP + py0 + a.opad) * a.OWP + px + a.opad) * NCH + qq * NPQ;
+                    const size_t rowb = (size_t)a.OWP * NCH;
+                    if (py0 < a.PH) {
+                        if constexpr (NCH == 16) *reinterpret_cast<uint32_t *>(dst) = w0[0];
+                        else *reinterpret_cast<uint2 *>(dst) = make_uint2(w0[0], w0[1]);
+                    }
+                    if (py0 + 1 < a.PH) {
+                        if constexpr (NCH == 16) *reinterpret_cast<uint32_t *>(dst + rowb) = w1[0];
+                        else *reinterpret_cast<uint2 *>(dst + rowb) = make_uint2(w1[0], w1[1]);
+                    }
+                }
+            }
+        } else {
+            uint32_t se0[4], se1[4], so0[4], so1[4];
+            tmem_ldq_sums(tq + NCH, tq + L::NB + NCH, se0, se1, so0, so1);
+            // window 0: conv rows (4w, 4w+1) = lanes (qi, qi+8) of half 0; window 1: rows (4w+2, 4w+3) = half 1
+            const int n0[4] = {-(int)se0[0], -(int)se0[2], -(int)so0[0], -(int)so0[2]};
+            const int n1[4] = {-(int)se1[0], -(int)se1[2], -(int)so1[0], -(int)so1[2]};
+            uint32_t w0[NCH / 16], w1[NCH / 16];
+#pragma unroll
+            for (int j = 0; j < NCH / 16; ++j) {
+                uint32_t e0[8], e1[8], o0[8], o1[8];
+                tmem_ldq_eo(tq + 16 * j, tq + L::NB + 16 * j, e0, e1, o0, o1);
+                int r0[4], r1w[4];
+                uint32_t orx = 0, orr = 0, xq;
+#pragma unroll
+                for (int cc = 0; cc < 4; ++cc) {
+                    const int k = 4 * j + cc, ri = 4 * (cc >> 1) + (cc & 1);
+                    r0[cc] = pool_requant(ch.zw[k], ch.bias[k], ch.m2[k], ch.sh[k], zo, (int)e0[ri], (int)e0[ri + 2], (int)o0[ri], (int)o0[ri + 2], n0[0],
+                                          n0[1], n0[2], n0[3], &xq);
+                    orx |= xq; orr |= (uint32_t)r0[cc];
+                    r1w[cc] = pool_requant(ch.zw[k], ch.bias[k], ch.m2[k], ch.sh[k], zo, (int)e1[ri], (int)e1[ri + 2], (int)o1[ri], (int)o1[ri + 2], n1[0],
+                                           n1[1], n1[2], n1[3], &xq);
+                    orx |= xq; orr |= (uint32_t)r1w[cc];
+                }
+                if (orx >= (1u << 22) || orr > 255u) {
+#pragma unroll
+                    for (int cc = 0; cc < 4; ++cc) {
+                        const int k = 4 * j + cc, ri = 4 * (cc >> 1) + (cc & 1);
+                        const double mcd = a.mc[qq * NPQ + k];
+                        r0[cc] = pool_requant_slow(ch.zw[k], ch.bias[k], mcd, zo, (int)e0[ri], (int)e0[ri + 2], (int)o0[ri], (int)o0[ri + 2], n0[0], n0[1],
+                                                   n0[2], n0[3]);
+                        r1w[cc] = pool_requant_slow(ch.zw[k], ch.bias[k], mcd, zo, (int)e1[ri], (int)e1[ri + 2], (int)o1[ri], (int)o1[ri + 2], n1[0], n1[1],
+                                                    n1[2], n1[3]);
+                    }
+                }
+                w0[j] = pack4(r0);
+                w1[j] = pack4(r1w);
+            }
+            const int px = tx * (G::TWPX / 2) + qi;
+            if (px < a.PW) {
+                uint8_t *dst = a.out_pool + ((size_t)(n * a.OHP + py0 + a.opad) * a.OWP + px + a.opad) * NCH + qq * NPQ;
+                const size_t rowb = (size_t)a.OWP * NCH;
+                if (py0 < a.PH) {
+                    if constexpr (NCH == 16) *reinterpret_cast<uint32_t *>(dst) = w0[0];
+                    else if constexpr (NCH == 32) *reinterpret_cast<uint2 *>(dst) = make_uint2(w0[0], w0[1]);
+                    else *reinterpret_cast<uint4 *>(dst) = make_uint4(w0[0], w0[1], w0[2], w0[3]);
+                }
+                if (py0 + 1 < a.PH) {
+                    if constexpr (NCH == 16) *reinterpret_cast<uint32_t *>(dst + rowb) = w1[0];
+                    else if constexpr (NCH == 32) *reinterpret_cast<uint2 *>(dst + rowb) = make_uint2(w1[0], w1[1]);
+                    else *reinterpret_cast<uint4 *>(dst + rowb) = make_uint4(w1[0], w1[1], w1[2], w1[3]);
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+        tc_fence_after();
+        tmem_dealloc<L::TMEM_COLS>(tmem_base);
+    }
+}
+
+struct RowsState {
+    int CS, NCH;
+    uint8_t *wimg = nullptr;
+};
+
+// byte position of element (row n, k) inside one [NB][32] filter tile: 8-row x 16-byte core matrices, the two K chunks of
+// a group side by side (LBO = 128), groups 256 bytes apart (SBO = 256)
+inline size_t bpos(int n, int k) { return (size_t)(n / 8) * 256 + (size_t)(k / 16) * 128 + (size_t)(n % 8) * 16 + (size_t)(k % 16); }
+
+template <int CS, int NCH>
+int launch_rows(const RowsArgs &a, cudaStream_t stream)
+{
+    using L = RowsCfg<CS, NCH>;
+    static int ctas_per_sm = 0, n_sm = 0;
+    const int smem = L::TOTAL + 128;
+    if (!ctas_per_sm) {
+        YQ_CUDA(cudaFuncSetAttribute(conv_u8_tc_rows_kernel<CS, NCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        int dev = 0, smem_sm = 0;
+        cudaFuncAttributes fa;
+        YQ_CUDA(cudaFuncGetAttributes(&fa, conv_u8_tc_rows_kernel<CS, NCH>));
+        YQ_CUDA(cudaGetDevice(&dev));
+        YQ_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
+        YQ_CUDA(cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev));
+        // counted by hand: the occupancy API answers 1 for kernels that allocate tensor memory (see yq_conv_tc_small.cu)
+        const int by_smem = smem_sm / (smem + 1024 + (int)fa.sharedSizeBytes);
+        const int by_regs = 65536 / (((fa.numRegs + 7) / 8 * 8) * RW_THREADS);
+        const int by_tmem = 512 / L::TMEM_COLS;
+        int occ = by_smem < by_regs ? by_smem : by_regs;
+        if (by_tmem < occ) occ = by_tmem;
+        if (getenv("YQ_DEBUG")) fprintf(stderr, "yq: rows<%d,%d> regs=%d by_smem=%d by_regs=%d by_tmem=%d smem=%d\n", CS, NCH, fa.numRegs, by_smem, by_regs, by_tmem, smem);
+        if (occ < 1) return yq::fail("conv_u8_tc_rows_kernel<%d,%d> does not fit on an SM", CS, NCH);
+        ctas_per_sm = occ;
+    }
+    int grid = n_sm * ctas_per_sm;
+    if (grid > a.num_tiles) grid = a.num_tiles;
+    conv_u8_tc_rows_kernel<CS, NCH><<<grid, RW_THREADS, smem, stream>>>(a);
+    YQ_CHECK_LAUNCH();
+    return 0;
+}
+
+}  // namespace
+
+int yq_tc_rows_supported(const yq_conv_layer *l)
+{
+    if (!l->int_form || !l->fused_mult || l->saturate || l->quant_stop_flag) return 0;
+    if (l->size != 3 || l->pad != 1 || l->stride != 1) return 0;
+    if (yq::act_mode(l->activation) != 0) return 0;                 // RELU6 only (pool-first needs a monotone, non-negative map)
+    if ((l->h & 1) || (l->w & 1)) return 0;                         // whole 2x2 windows only
+    if (l->n != l->cs_out) return 0;
+    const int ci = l->cs_in, co = l->cs_out;
+    return (ci == 4 && (co == 16 || co == 32)) || (ci == 16 && (co == 16 || co == 32 || co == 64)) || (ci == 32 && (co == 32 || co == 64));
+}
+
+void yq_tc_rows_input_geom(const yq_conv_layer *l, yq_act_geom *g)
+{
+    const int twpx = l->cs_in == 4 ? 32 : 16;
+    g->pad = 1;
+    g->pitch_w = yq::round_up(yq::round_up(l->w, twpx) + 4, 4);   // tile overhang + halo; rows start 16-byte aligned for c = 4
+    g->rows_h = yq::round_up(l->h, TILE_ROWS) + 2;
+}
+
+int yq_tc_rows_prepare(yq_conv_layer *l, void **state)
+{
+    RowsState *st = new RowsState();
+    st->CS = l->cs_in;
+    st->NCH = l->cs_out;
+    const int CS = st->CS, NCH = st->NCH, NPQ = NCH / 4;
+    const int NB = CS == 4 ? 4 * NCH + 16 : NCH + 16;
+    const int nblk = CS == 32 ? 2 : 1;
+    const int nmma = CS == 4 ? 3 : 12 * nblk;
+    std::vector<uint8_t> img((size_t)nmma * NB * 32, 0);
+    auto W = [&](int oc, int ci, int ky, int kx) -> uint8_t { return ci < l->c ? l->host_w[(((size_t)oc * l->c + ci) * 3 + ky) * 3 + kx] : 0; };
+    if (CS == 4) {
+        // TMEM column c = 8g + 2q + e: channel q*NPQ + g % NPQ, output pixel 2*(g / NPQ) + e of the 4-pixel segment;
+        // K byte k = 4*ip + ci: input pixel ip (0..7, the segment's window starts one pixel to the left), channel ci
+        for (int ky = 0; ky < 3; ++ky) {
+            uint8_t *tile = img.data() + (size_t)ky * NB * 32;
+            for (int c = 0; c < 4 * NCH; ++c) {
+                const int g = c / 8, q = (c % 8) / 2, e = c % 2;
+                const int oc = q * NPQ + g % NPQ, px = 2 * (g / NPQ) + e;
+                for (int kx = 0; kx < 3; ++kx)
+                    for (int ci = 0; ci < 4; ++ci) tile[bpos(c, 4 * (px + kx) + ci)] = W(oc, ci, ky, kx);
+            }
+            for (int c = 0; c < 16; ++c) {   // activation sums: column group c/8 = pixel pair, c % 2 = pixel of the pair
+                const int px = 2 * (c / 8) + c % 2;
+                for (int kx = 0; kx < 3; ++kx)
+                    for (int ci = 0; ci < l->c; ++ci) tile[bpos(4 * NCH + c, 4 * (px + kx) + ci)] = 1;
+            }
+        }
+    } else {
+        // TMEM column c = 8g + 2q + e of a group: channel q*NPQ + 2g + e.  K chunk order per MMA (see issue_mma)
+        int m = 0;
+        for (int par = 0; par < 2; ++par)
+            for (int blk = 0; blk < nblk; ++blk)
+                for (int ky = 0; ky < 3; ++ky)
+                    for (int step = 0; step < 2; ++step, ++m) {
+                        uint8_t *tile = img.data() + (size_t)m * NB * 32;
+                        // filter column kx read by chunk 0 / chunk 1 of this MMA (-1: nothing)
+                        const int kx0 = step == 0 ? (par == 0 ? 1 : 0) : 2;
+                        const int kx1 = step == 0 ? (par == 0 ? 0 : 1) : -1;
+                        for (int chunk = 0; chunk < 2; ++chunk) {
+                            const int kx = chunk ? kx1 : kx0;
+                            if (kx < 0) continue;
+                            for (int b = 0; b < 16; ++b) {
+                                const int ci = blk * 16 + b;
+                                for (int c = 0; c < NCH; ++c) {
+                                    const int g = c / 8, q = (c % 8) / 2, e = c % 2;
+                                    tile[bpos(c, chunk * 16 + b)] = W(q * NPQ + 2 * g + e, ci, ky, kx);
+                                }
+                                if (ci < l->c)
+                                    for (int c = 0; c < 16; ++c) tile[bpos(NCH + c, chunk * 16 + b)] = 1;
+                            }
+                        }
+                    }
+    }
+    if (cudaMalloc((void **)&st->wimg, img.size()) != cudaSuccess || cudaMemcpy(st->wimg, img.data(), img.size(), cudaMemcpyHostToDevice) != cudaSuccess) {
+        cudaFree(st->wimg);
+        delete st;
+        return yq::fail("tcgen05 rows flavour: weight upload failed");
+    }
+    *state = st;
+    return 0;
+}
+
+void yq_tc_rows_free(void *state)
+{
+    RowsState *st = (RowsState *)state;
+    if (!st) return;
+    cudaFree(st->wimg);
+    delete st;
+}
+
+int yq_tc_rows_forward(yq_conv_layer *l, void *state, const uint8_t *in_padded, uint8_t *out_pool, const yq_act_geom *og, int batch, cudaStream_t stream)
+{
+    RowsState *st = (RowsState *)state;
+    if (!st || !in_padded || !out_pool || !og) return yq::fail("tcgen05 rows flavour: bad argument");
+    RowsArgs a;
+    memset(&a, 0, sizeof a);
+    yq_act_geom ig;
+    yq_tc_rows_input_geom(l, &ig);
+    a.in = in_padded; a.out_pool = out_pool; a.wimg = st->wimg;
+    a.HP = ig.rows_h; a.WP = ig.pitch_w; a.OH = l->out_h; a.OW = l->out_w; a.PH = l->out_h / 2; a.PW = l->out_w / 2;
+    a.OHP = og->rows_h; a.OWP = og->pitch_w; a.opad = og->pad;
+    const int twpx = st->CS == 4 ? 32 : 16;
+    a.tiles_x = (l->out_w + twpx - 1) / twpx;
+    a.tiles_y = (l->out_h + TILE_ROWS - 1) / TILE_ROWS;
+    a.num_tiles = a.tiles_x * a.tiles_y * batch;
+    a.zp_out = l->zp_out;
+    memcpy(a.cq, l->host_chanq.data(), (size_t)l->n * 16);
+    memcpy(a.mc, l->host_mcomb.data(), (size_t)l->n * 8);
+#define YQ_RW(CS_, N_) if (st->CS == CS_ && st->NCH == N_) return launch_rows<CS_, N_>(a, stream)
+    YQ_RW(4, 16); YQ_RW(4, 32);
+    YQ_RW(16, 16); YQ_RW(16, 32); YQ_RW(16, 64);
+    YQ_RW(32, 32); YQ_RW(32, 64);
+#undef YQ_RW
+    return yq::fail("tcgen05 rows flavour: no instantiation for cs_in=%d cs_out=%d", st->CS, st->NCH);
+}

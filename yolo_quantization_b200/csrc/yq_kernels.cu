@@ -414,6 +414,10 @@ extern "C" yq_conv_layer *yq_make_convolutional_layer_quant(const yq_conv_desc *
     if (yq_tc_supported(l)) {
         if (yq_tc_prepare(l) == 0) l->kernel = 1;
     }
+    if (yq_tc_rows_supported(l) && yq_tc_rows_prepare(l, &l->tc_rows) != 0) {
+        yq_free_convolutional_layer_quant(l);
+        return nullptr;
+    }
     return l;
 }
 
@@ -421,6 +425,7 @@ extern "C" void yq_free_convolutional_layer_quant(yq_conv_layer *l)
 {
     if (!l) return;
     yq_tc_free(l);
+    yq_tc_rows_free(l->tc_rows);
     cudaFree(l->w_simt); cudaFree(l->bias); cudaFree(l->zw); cudaFree(l->mcomb); cudaFree(l->mval); cudaFree(l->rsh); cudaFree(l->chanq);
     delete l;
 }
@@ -456,6 +461,27 @@ extern "C" int yq_forward_convolutional_layer_quant_gpu(yq_conv_layer *l, const 
 }
 
 extern "C" int yq_conv_can_fuse_maxpool(const yq_conv_layer *l) { return l ? yq_tc_can_fuse_pool(l) : 0; }
+
+extern "C" int yq_conv_rows_supported(const yq_conv_layer *l) { return l && l->tc_rows ? 1 : 0; }
+extern "C" int yq_conv_rows_input_geom(const yq_conv_layer *l, yq_act_geom *g)
+{
+    if (!l || !g || !l->tc_rows) return yq::fail("yq_conv_rows_input_geom: the layer has no rows flavour");
+    yq_tc_rows_input_geom(l, g);
+    return 0;
+}
+extern "C" size_t yq_act_geom_bytes(const yq_act_geom *g, int batch, int c)
+{
+    return g ? (size_t)batch * g->rows_h * g->pitch_w * yq::channel_stride(c) : 0;
+}
+extern "C" int yq_forward_convolutional_layer_quant_rows_pool_gpu(yq_conv_layer *l, const uint8_t *in_padded, uint8_t *out_pool,
+                                                                  const yq_act_geom *out_geom, int batch, void *stream)
+{
+    if (!l || !in_padded || !out_pool || !out_geom || batch <= 0) return yq::fail("yq_forward_convolutional_layer_quant_rows_pool_gpu: bad argument");
+    if (!l->tc_rows) return yq::fail("this layer has no rows flavour (see yq_conv_rows_supported)");
+    if (out_geom->pitch_w < l->out_w / 2 + 2 * out_geom->pad || out_geom->rows_h < l->out_h / 2 + 2 * out_geom->pad)
+        return yq::fail("yq_forward_convolutional_layer_quant_rows_pool_gpu: output geometry smaller than the pooled tensor");
+    return yq_tc_rows_forward(l, l->tc_rows, in_padded, out_pool, out_geom, batch, (cudaStream_t)stream);
+}
 
 // ------------------------------------------------------------------------------------------------
 // maxpool (src/maxpool_layer.c:109-153): out = max(0, in-bounds taps); window origin i*stride - pad/2
@@ -700,6 +726,96 @@ __global__ void nhwc_to_nchw_kernel(const T *__restrict__ in, T *__restrict__ ou
         long long n = g / C;
         out[i] = in[((size_t)n * HW + p) * CS + ch];
     }
+}
+
+// ---- halo-padded variants: pixel (n, y, x) at ((n*rows_h + y + pad)*pitch_w + x + pad)*CS
+__global__ void nchw_to_nhwc_u8_geom_kernel(const uint8_t *__restrict__ in, uint8_t *__restrict__ out, int C, int H, int W, int CS, int pad,
+                                            int pitch_w, int rows_h, long long total /* B*HW*(CS/4) */)
+{
+    const int wpp = CS / 4, HW = H * W;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        long long g = i / HW;
+        int p = (int)(i - g * HW);
+        int wd = (int)(g % wpp);
+        long long n = g / wpp;
+        uint32_t v = 0;
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            int ch = wd * 4 + b;
+            if (ch < C) v |= (uint32_t)in[((size_t)n * C + ch) * HW + p] << (8 * b);
+        }
+        const int y = p / W, x = p - y * W;
+        *reinterpret_cast<uint32_t *>(out + (((size_t)n * rows_h + y + pad) * pitch_w + x + pad) * CS + wd * 4) = v;
+    }
+}
+
+// c <= 4, W % 4 == 0: one thread = 4 consecutive pixels of one row (the padded row start shifts them off 16-byte alignment:
+// four 4-byte stores, still fully coalesced across the warp)
+__global__ void nchw_to_nhwc4_u8_geom_kernel(const uint8_t *__restrict__ in, uint8_t *__restrict__ out, int C, int H, int W, int pad, int pitch_w,
+                                             int rows_h, long long total /* B*HW/4 */)
+{
+    const int HW = H * W, q = HW / 4, wq = W / 4;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long n = i / q;
+        const int p4 = (int)(i - n * q);
+        uint32_t pl[4] = {0, 0, 0, 0};
+#pragma unroll
+        for (int ch = 0; ch < 4; ++ch)
+            if (ch < C) pl[ch] = __ldg(reinterpret_cast<const uint32_t *>(in + ((size_t)n * C + ch) * HW) + p4);
+        const int y = p4 / wq, x = (p4 - y * wq) * 4;
+        uint32_t *o = reinterpret_cast<uint32_t *>(out) + ((size_t)n * rows_h + y + pad) * pitch_w + x + pad;
+        o[0] = __byte_perm(__byte_perm(pl[0], pl[1], 0x0040), __byte_perm(pl[2], pl[3], 0x0040), 0x5410);
+        o[1] = __byte_perm(__byte_perm(pl[0], pl[1], 0x0051), __byte_perm(pl[2], pl[3], 0x0051), 0x5410);
+        o[2] = __byte_perm(__byte_perm(pl[0], pl[1], 0x0062), __byte_perm(pl[2], pl[3], 0x0062), 0x5410);
+        o[3] = __byte_perm(__byte_perm(pl[0], pl[1], 0x0073), __byte_perm(pl[2], pl[3], 0x0073), 0x5410);
+    }
+}
+
+__global__ void nhwc_to_nchw_u8_geom_kernel(const uint8_t *__restrict__ in, uint8_t *__restrict__ out, int C, int H, int W, int CS, int pad,
+                                            int pitch_w, int rows_h, long long total)
+{
+    const int HW = H * W;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        int p = (int)(i % HW);
+        long long g = i / HW;
+        int ch = (int)(g % C);
+        long long n = g / C;
+        const int y = p / W, x = p - y * W;
+        out[i] = in[(((size_t)n * rows_h + y + pad) * pitch_w + x + pad) * CS + ch];
+    }
+}
+
+static int check_geom(const yq_act_geom *g, int h, int w)
+{
+    if (!g || g->pad < 0 || g->pitch_w < w + 2 * g->pad || g->rows_h < h + 2 * g->pad) return yq::fail("activation geometry does not hold a %dx%d tensor", h, w);
+    return 0;
+}
+
+extern "C" int yq_nchw_to_nhwc_u8_geom(const uint8_t *in, uint8_t *out, int batch, int c, int h, int w, const yq_act_geom *g, void *stream)
+{
+    if (!in || !out) return yq::fail("nchw_to_nhwc: null pointer");
+    if (check_geom(g, h, w)) return -1;
+    const int cs = yq::channel_stride(c);
+    if (cs == 4 && w % 4 == 0 && ((uintptr_t)in % 4) == 0) {
+        long long total4 = (long long)batch * h * w / 4;
+        nchw_to_nhwc4_u8_geom_kernel<<<grid_for(total4, 256), 256, 0, (cudaStream_t)stream>>>(in, out, c, h, w, g->pad, g->pitch_w, g->rows_h, total4);
+        YQ_CHECK_LAUNCH();
+        return 0;
+    }
+    long long total = (long long)batch * h * w * (cs / 4);
+    nchw_to_nhwc_u8_geom_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(in, out, c, h, w, cs, g->pad, g->pitch_w, g->rows_h, total);
+    YQ_CHECK_LAUNCH();
+    return 0;
+}
+extern "C" int yq_nhwc_to_nchw_u8_geom(const uint8_t *in, uint8_t *out, int batch, int c, int h, int w, const yq_act_geom *g, void *stream)
+{
+    if (!in || !out) return yq::fail("nhwc_to_nchw: null pointer");
+    if (check_geom(g, h, w)) return -1;
+    long long total = (long long)batch * c * h * w;
+    nhwc_to_nchw_u8_geom_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(in, out, c, h, w, yq::channel_stride(c), g->pad, g->pitch_w,
+                                                                                        g->rows_h, total);
+    YQ_CHECK_LAUNCH();
+    return 0;
 }
 
 extern "C" int yq_nchw_to_nhwc_u8(const uint8_t *in, uint8_t *out, int batch, int c, int h, int w, void *stream)

@@ -116,6 +116,8 @@ struct Layer {
     size_t u8_bytes = 0, f32_count = 0;
     bool fuse_pool = false;        // conv: the next layer (maxpool 2/2) is produced by this layer's epilogue
     bool fused_away = false;       // maxpool: produced by the previous conv, no launch
+    bool use_rows = false;         // conv: halo-input conv + pool flavour (yq_conv_tc_rows.cu); its input tensor is halo-padded
+    yq_act_geom geom = {0, 0, 0};  // geometry of out_u8 (plain unless the only consumer is a rows-flavour conv)
 };
 
 }  // namespace
@@ -127,6 +129,8 @@ struct yq_network {
     cudaStream_t stream = nullptr;
     uint8_t *in_stage_nchw = nullptr;   // staging for host-input predict
     uint8_t *in_nhwc = nullptr;
+    size_t in_nhwc_bytes = 0;
+    yq_act_geom in_geom = {0, 0, 0};    // geometry of in_nhwc (halo-padded when layer 0 runs the rows flavour)
     uint8_t *scratch = nullptr;         // pull_layer conversions
     size_t scratch_bytes = 0;
     int keep_acc = 0;
@@ -243,18 +247,44 @@ void drop_graph(yq_network *net)
 // Decide which conv -> maxpool(2,2) pairs run as one launch, and count launches.  A pair fuses when the conv's
 // flavour can pool in its epilogue and the pool is the 2x2 / stride-2 / default-padding kind.  The conv's own
 // (unpooled) tensor is still written when another layer routes from it or when debug pulls are enabled.
+bool conv_output_needed(const yq_network *net, int i);
+
+bool routed_from(const yq_network *net, int i)
+{
+    for (const auto &l : net->layers)
+        if (l.type == L_ROUTE)
+            for (int idx : l.inputs)
+                if (idx == i) return true;
+    return false;
+}
+
 void plan(yq_network *net)
 {
     const int n = (int)net->layers.size();
-    for (auto &l : net->layers) l.fuse_pool = l.fused_away = false;
+    for (auto &l : net->layers) {
+        l.fuse_pool = l.fused_away = l.use_rows = false;
+        l.geom = yq_act_geom{0, l.out_w, l.out_h};
+    }
+    net->in_geom = yq_act_geom{0, net->w, net->h};
     int launches = 1;
     for (int i = 0; i < n; ++i) {
         Layer &l = net->layers[i];
-        if (l.type == L_CONV && net->fusion && i + 1 < n && l.conv && yq_conv_can_fuse_maxpool(l.conv)) {
+        if (l.type == L_CONV && net->fusion && i + 1 < n && l.conv) {
             Layer &p = net->layers[i + 1];
-            if (p.type == L_MAXPOOL && p.size == 2 && p.stride == 2 && p.pad == 1) {
-                l.fuse_pool = true;
-                p.fused_away = true;
+            const bool pool22 = p.type == L_MAXPOOL && p.size == 2 && p.stride == 2 && p.pad == 1;
+            // rows flavour: needs a halo-padded input, i.e. a producer that can write one and no other reader of that tensor
+            const bool producer_ok = i == 0 || (i >= 2 && net->layers[i - 1].fused_away && net->layers[i - 2].use_rows && !routed_from(net, i - 1));
+            if (pool22 && net->conv_kernel != 0 && yq_conv_rows_supported(l.conv) && producer_ok && !conv_output_needed(net, i)) {
+                l.use_rows = l.fuse_pool = p.fused_away = true;
+                yq_act_geom g;
+                yq_conv_rows_input_geom(l.conv, &g);
+                uint8_t *buf = i == 0 ? net->in_nhwc : net->layers[i - 1].out_u8;
+                (i == 0 ? net->in_geom : net->layers[i - 1].geom) = g;
+                // the halo (and the slack around the image) is the conv's input zero point (im2col.c:5-14); producers
+                // only ever write the interior
+                cudaMemsetAsync(buf, l.zp_in, yq_act_geom_bytes(&g, net->batch, l.c), net->stream);
+            } else if (pool22 && yq_conv_can_fuse_maxpool(l.conv)) {
+                l.fuse_pool = p.fused_away = true;
             }
         }
         if (l.fused_away || (l.type == L_ROUTE && l.inputs.size() == 1)) continue;
@@ -266,11 +296,7 @@ void plan(yq_network *net)
 bool conv_output_needed(const yq_network *net, int i)
 {
     if (net->keep_acc) return true;   // debug: every layer stays pullable
-    for (const auto &l : net->layers)
-        if (l.type == L_ROUTE)
-            for (int idx : l.inputs)
-                if (idx == i) return true;
-    return false;
+    return routed_from(net, i);
 }
 
 // the kernel sequence of one forward_network pass (network.c:229-261)
@@ -279,7 +305,11 @@ int forward_body(yq_network *net, const uint8_t *in_u8_nchw, int *launches, bool
     cudaStream_t st = net->stream;
     int nl = 0;
     if (profile) cudaEventRecord(net->prof_events[0], st);
-    if (yq_nchw_to_nhwc_u8(in_u8_nchw, net->in_nhwc, net->batch, net->c, net->h, net->w, st)) return -1;
+    if (net->in_geom.pad) {
+        if (yq_nchw_to_nhwc_u8_geom(in_u8_nchw, net->in_nhwc, net->batch, net->c, net->h, net->w, &net->in_geom, st)) return -1;
+    } else if (yq_nchw_to_nhwc_u8(in_u8_nchw, net->in_nhwc, net->batch, net->c, net->h, net->w, st)) {
+        return -1;
+    }
     if (profile) cudaEventRecord(net->prof_events[1], st);
     ++nl;
     const uint8_t *cur = net->in_nhwc;
@@ -288,7 +318,10 @@ int forward_body(yq_network *net, const uint8_t *in_u8_nchw, int *launches, bool
         Layer &l = net->layers[i];
         switch (l.type) {
         case L_CONV:
-            if (l.fuse_pool) {
+            if (l.use_rows) {
+                if (yq_forward_convolutional_layer_quant_rows_pool_gpu(l.conv, cur, net->layers[i + 1].out_u8, &net->layers[i + 1].geom, net->batch, st))
+                    return -1;
+            } else if (l.fuse_pool) {
                 uint8_t *conv_out = conv_output_needed(net, (int)i) ? l.out_u8 : nullptr;
                 if (yq_forward_convolutional_layer_quant_pool_gpu(l.conv, cur, conv_out, net->layers[i + 1].out_u8, l.out_f32,
                                                                   net->keep_acc ? l.out_acc : nullptr, net->batch, st))
@@ -600,6 +633,7 @@ extern "C" yq_network *yq_load_network(const char *cfg, const char *weights, int
         }
         const int cs = yq::channel_stride(l.out_c);
         l.u8_bytes = (size_t)raw->batch * l.out_h * l.out_w * cs;
+        l.geom = yq_act_geom{0, l.out_w, l.out_h};
         if (l.type == L_ROUTE && l.inputs.size() == 1) {
             l.out_u8 = raw->layers[l.inputs[0]].out_u8;   // alias
         } else if (l.type != L_YOLO) {
@@ -619,9 +653,35 @@ extern "C" yq_network *yq_load_network(const char *cfg, const char *weights, int
             if (l.type == L_YOLO) raw->out_floats += l.f32_count;
         }
     }
+    // tensors that feed a rows-flavour conv may be switched to its halo-padded geometry by plan(): size them for it
+    for (size_t i = 0; i < raw->layers.size(); ++i) {
+        Layer &l = raw->layers[i];
+        if (l.type != L_CONV || !l.conv || !yq_conv_rows_supported(l.conv)) continue;
+        yq_act_geom g;
+        yq_conv_rows_input_geom(l.conv, &g);
+        const size_t need = yq_act_geom_bytes(&g, raw->batch, l.c);
+        if (i == 0) {
+            raw->in_nhwc_bytes = need;
+        } else {
+            Layer &p = raw->layers[i - 1];
+            if (p.owns_u8 && need > p.u8_bytes) {
+                cudaFree(p.out_u8);
+                p.out_u8 = nullptr;
+                p.u8_bytes = need;
+                if (cudaMalloc((void **)&p.out_u8, need) != cudaSuccess) {
+                    yq::fail("cudaMalloc of layer %zu output (%zu bytes) failed", i - 1, need);
+                    return bail();
+                }
+                cudaMemset(p.out_u8, 0, need);
+                for (auto &r : raw->layers)   // single-input routes alias their input's buffer
+                    if (r.type == L_ROUTE && r.inputs.size() == 1 && r.inputs[0] == (int)i - 1) r.out_u8 = p.out_u8;
+            }
+        }
+    }
     const size_t in_bytes = (size_t)raw->batch * raw->c * raw->h * raw->w;
-    if (cudaMalloc((void **)&raw->in_stage_nchw, in_bytes) != cudaSuccess ||
-        cudaMalloc((void **)&raw->in_nhwc, (size_t)raw->batch * raw->h * raw->w * yq::channel_stride(raw->c)) != cudaSuccess) {
+    const size_t plain_in = (size_t)raw->batch * raw->h * raw->w * yq::channel_stride(raw->c);
+    if (raw->in_nhwc_bytes < plain_in) raw->in_nhwc_bytes = plain_in;
+    if (cudaMalloc((void **)&raw->in_stage_nchw, in_bytes) != cudaSuccess || cudaMalloc((void **)&raw->in_nhwc, raw->in_nhwc_bytes) != cudaSuccess) {
         yq::fail("cudaMalloc of network input failed");
         return bail();
     }
@@ -710,6 +770,7 @@ extern "C" int yq_network_set_debug(yq_network *net, int keep_acc)
                 size_t bytes = (size_t)net->batch * l.out_h * l.out_w * yq::channel_stride(l.out_c) * sizeof(int32_t);
                 YQ_CUDA(cudaMalloc((void **)&l.out_acc, bytes));
             }
+    plan(net);
     return 0;
 }
 
@@ -948,7 +1009,7 @@ extern "C" int yq_network_pull_layer(yq_network *net, int layer, int what, void 
     }
     if (what == 0) {
         if (!l.out_u8) return yq::fail("layer %d has no uint8 output", layer);
-        if (yq_nhwc_to_nchw_u8(l.out_u8, net->scratch, net->batch, l.out_c, l.out_h, l.out_w, net->stream)) return -1;
+        if (yq_nhwc_to_nchw_u8_geom(l.out_u8, net->scratch, net->batch, l.out_c, l.out_h, l.out_w, &l.geom, net->stream)) return -1;
     } else if (what == 1) {
         if (!l.out_acc) return yq::fail("layer %d has no int32 accumulator (conv layers only, after yq_network_set_debug(net,1))", layer);
         if (yq_nhwc_to_nchw_i32(l.out_acc, (int32_t *)net->scratch, net->batch, l.out_c, l.out_h, l.out_w, net->stream)) return -1;

@@ -14,7 +14,7 @@ from typing import Dict, List, Optional, Sequence
 import numpy as np
 
 from . import _lib
-from ._lib import ConvDesc, LayerInfo, YqError, check
+from ._lib import ActGeom, ConvDesc, LayerInfo, YqError, check
 
 LAYER_TYPES = {0: "conv", 1: "maxpool", 2: "route", 3: "upsample", 4: "yolo"}
 ACTIVATIONS = {"logistic": 0, "relu": 1, "linear": 3, "relu6": 8, "leaky": 9}
@@ -127,6 +127,7 @@ class ConvolutionalLayerQuant:
         if not self.handle:
             raise YqError(_lib.last_error())
         self.h, self.w, self.c, self.n = h, w, c, n
+        self.zp_in = int(zp_in) & 255
         self.out_h, self.out_w = lib.yq_conv_out_h(self.handle), lib.yq_conv_out_w(self.handle)
         self.quant_stop_flag = quant_stop_flag
         if kernel >= 0:
@@ -184,6 +185,39 @@ class ConvolutionalLayerQuant:
             if d:
                 d.free()
         return res
+
+    @property
+    def rows_supported(self) -> bool:
+        return bool(_lib.load().yq_conv_rows_supported(self.handle))
+
+    def forward_rows_pooled(self, x_nchw: np.ndarray, out_pad: int = 0) -> np.ndarray:
+        """conv + RELU6 + maxpool(2,2) through the halo-input "rows" flavour: the input is staged in the padded
+        geometry the layer asks for (halo = zp_in); the pooled tensor is written into a tensor with an
+        ``out_pad``-pixel halo (as the next rows layer would want) and returned as [b,n,h/2,w/2]."""
+        lib = _lib.load()
+        b = x_nchw.shape[0]
+        x = np.ascontiguousarray(x_nchw, np.uint8)
+        g = ActGeom()
+        check(lib.yq_conv_rows_input_geom(self.handle, C.byref(g)), "yq_conv_rows_input_geom")
+        din = DeviceBuffer(lib.yq_act_geom_bytes(C.byref(g), b, self.c), zero=False)
+        check(lib.yq_cuda_memset(din.ptr, self.zp_in, din.nbytes, None))
+        src = DeviceBuffer.from_numpy(x)
+        check(lib.yq_nchw_to_nhwc_u8_geom(src.ptr, din.ptr, b, self.c, self.h, self.w, C.byref(g), None))
+        ph, pw = self.out_h // 2, self.out_w // 2
+        og = ActGeom(out_pad, pw + 2 * out_pad + (3 if out_pad else 0), ph + 2 * out_pad + (1 if out_pad else 0))
+        dout = DeviceBuffer(lib.yq_act_geom_bytes(C.byref(og), b, self.n), zero=False)
+        check(lib.yq_cuda_memset(dout.ptr, 0xEE, dout.nbytes, None))
+        check(lib.yq_forward_convolutional_layer_quant_rows_pool_gpu(self.handle, din.ptr, dout.ptr, C.byref(og), b, None),
+              "yq_forward_convolutional_layer_quant_rows_pool_gpu")
+        tmp = DeviceBuffer(b * self.n * ph * pw)
+        check(lib.yq_nhwc_to_nchw_u8_geom(dout.ptr, tmp.ptr, b, self.n, ph, pw, C.byref(og), None))
+        check(lib.yq_stream_synchronize(None))
+        out = tmp.pull((b, self.n, ph, pw), np.uint8)
+        raw = dout.pull((dout.nbytes,), np.uint8)
+        for d in (din, src, dout, tmp):
+            d.free()
+        self.last_rows_raw = (raw, og.pad, og.pitch_w, og.rows_h)
+        return out
 
     def free(self) -> None:
         if self.handle:
