@@ -99,12 +99,17 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
-def layer_work(li, batch):
-    """Algorithmic ops / bytes of one layer launch (SURVEY Appendix B2 accounting: activations in + out, weights once)."""
+def layer_work(li, batch, conv_written=True):
+    """Algorithmic ops / bytes of one layer launch (SURVEY Appendix B2 accounting: activations in + out, weights once).
+    A conv launch that fuses the following 2x2 max-pool is charged its input plus what it WRITES: the pooled tensor,
+    and the conv tensor only when that is materialised too (SURVEY 8(d) 'fully fused' figure)."""
     t = li.type
     if t == 0:
         macs = li.out_h * li.out_w * li.n * li.c * li.size * li.size
-        byts = batch * (li.h * li.w * li.c + li.out_h * li.out_w * li.n * (5 if li.quant_stop_flag else 1)) + li.c * li.n * li.size ** 2
+        out = li.out_h * li.out_w * li.n * (5 if li.quant_stop_flag else 1)
+        if li.fused:
+            out = (li.out_h // 2) * (li.out_w // 2) * li.n + (out if conv_written else 0)
+        byts = batch * (li.h * li.w * li.c + out) + li.c * li.n * li.size ** 2
         return 2 * macs * batch, byts
     if t == 4:
         return 0, 2 * 4 * batch * li.out_c * li.out_h * li.out_w
@@ -297,16 +302,22 @@ def main():
         infos = net.layers()
         rows = []
         for i, li in enumerate(infos):
-            ops, byts = layer_work(li, B)
+            ops, byts = layer_work(li, B, conv_written=False)   # production plan: fused convs write the pooled tensor only
             t_ms = float(lm[i + 1])
-            if t_ms <= 0:
+            if t_ms <= 0 or (li.type == 1 and li.fused):    # a fused-away max-pool has no launch of its own
                 continue
             t_tc = ops / (p_int8 * 1e12) * 1e3
             t_mem = byts / (pk["hbm_gbs"] * 1e9) * 1e3
             bound = "tensor" if t_tc > t_mem else "hbm"
             rows.append({"layer": i, "type": darknet.LAYER_TYPES[li.type], "ms": round(t_ms, 4), "bound": bound,
                          "frac": round(max(t_tc, t_mem) / t_ms, 4), "kernel": int(li.kernel) if li.type == 0 else None,
+                         "fused": int(li.fused),
                          "ops": ops, "bytes": byts})
+        # the NCHW -> NHWC(4) layout transform in front of layer 0 (lm[0]): in + out bytes
+        c0 = infos[0]
+        tb = B * c0.h * c0.w * (c0.c + darknet.channel_stride(c0.c))
+        rows.insert(0, {"layer": -1, "type": "nchw_to_nhwc", "ms": round(float(lm[0]), 4), "bound": "hbm",
+                        "frac": round(tb / (pk["hbm_gbs"] * 1e9) * 1e3 / float(lm[0]), 4), "kernel": None, "fused": 0, "ops": 0, "bytes": tb})
         top = max(rows, key=lambda r: r["ms"])
         if top["bound"] == "tensor":
             ach = top["ops"] / (top["ms"] * 1e-3) / 1e12
@@ -344,7 +355,7 @@ def main():
             "roofline": roof,
             "int8_tops_whole_net": ips / world * total_ops / 1e12,
             "frac_int8_peak_whole_net": ips / world * total_ops / 1e12 / p_int8,
-            "layers": [{k: r[k] for k in ("layer", "type", "ms", "bound", "frac", "kernel")} for r in rows],
+            "layers": [{k: r[k] for k in ("layer", "type", "ms", "bound", "frac", "kernel", "fused")} for r in rows],
         }
         if world == 1 and not args.no_cpu_baseline:
             im = synth.synthetic_image(1)

@@ -190,6 +190,8 @@ typedef struct yq_layer_info {
     int zp_in, zp_out;
     int kernel;               /* conv only: 0 SIMT, 1 tcgen05 */
     int classes, n_anchors;   /* yolo only */
+    int fused;                /* conv: 0 own launch writing the conv tensor, 1 following maxpool fused into the epilogue,
+                                 2 rows flavour (halo input, pooled tensor only); maxpool: 1 = produced by the previous conv */
 } yq_layer_info;
 
 /* batch <= 0 keeps the cfg's [net] batch.  Returns NULL on failure (see yq_last_error). */

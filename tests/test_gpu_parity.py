@@ -446,6 +446,32 @@ def test_layout_transform_roundtrip(built):
         d.free()
 
 
+def test_layout_transform_padded_geometry(built):
+    """NCHW -> halo-padded NHWC and back: the interior round-trips, the halo keeps what the runtime put there."""
+    import ctypes as C
+    from yolo_quantization_b200 import _lib
+    lib = _lib.load()
+    rng = np.random.default_rng(5)
+    for c, h, w, pad, pitch, rows in ((3, 8, 12, 1, 16, 10), (3, 6, 20, 1, 24, 9), (3, 5, 7, 1, 12, 8), (16, 6, 6, 1, 9, 8), (3, 4, 8, 2, 13, 9)):
+        x = rng.integers(0, 256, size=(2, c, h, w), dtype=np.uint8)
+        g = _lib.ActGeom(pad, pitch, rows)
+        cs = darknet.channel_stride(c)
+        src = darknet.DeviceBuffer.from_numpy(x)
+        dst = darknet.DeviceBuffer(lib.yq_act_geom_bytes(C.byref(g), 2, c), zero=False)
+        _lib.check(lib.yq_cuda_memset(dst.ptr, 0xA5, dst.nbytes, None))
+        _lib.check(lib.yq_nchw_to_nhwc_u8_geom(src.ptr, dst.ptr, 2, c, h, w, C.byref(g), None))
+        raw = dst.pull((2, rows, pitch, cs), np.uint8)
+        assert np.array_equal(raw[:, pad:pad + h, pad:pad + w, :c], x.transpose(0, 2, 3, 1))
+        halo = raw.copy()
+        halo[:, pad:pad + h, pad:pad + w, :] = 0xA5
+        assert (halo == 0xA5).all(), "the transform wrote outside the interior"
+        back = darknet.DeviceBuffer(x.nbytes)
+        _lib.check(lib.yq_nhwc_to_nchw_u8_geom(dst.ptr, back.ptr, 2, c, h, w, C.byref(g), None))
+        assert np.array_equal(back.pull(x.shape, np.uint8), x)
+        for d in (src, dst, back):
+            d.free()
+
+
 def test_full_size_batch128_properties(built, tiny_net_files):
     """BASELINE configs[2] size (batch 128 @ 416x416) through size-independent properties:
     batch-independence (image i of the batch == the same image alone), permutation equivariance and

@@ -37,9 +37,10 @@ def test_library_has_sm100a_code_only(built):
 
 
 def test_struct_layouts_match_header(built):
-    # yq_conv_desc: 12 ints/float (48 B) + 5 pointers + int (+pad) ; yq_layer_info: 21 4-byte fields
+    # yq_conv_desc: 12 ints/float (48 B) + 5 pointers + int (+pad) ; yq_layer_info: 22 4-byte fields; yq_act_geom: 3 ints
     assert ctypes.sizeof(_lib.ConvDesc) == 48 + 5 * 8 + 8
-    assert ctypes.sizeof(_lib.LayerInfo) == 21 * 4
+    assert ctypes.sizeof(_lib.LayerInfo) == 22 * 4
+    assert ctypes.sizeof(_lib.ActGeom) == 12
 
 
 def test_channel_stride(built):

@@ -40,7 +40,7 @@ class LayerInfo(C.Structure):
         ("n", C.c_int), ("size", C.c_int), ("stride", C.c_int), ("pad", C.c_int), ("activation", C.c_int),
         ("batch_normalize", C.c_int), ("quant_stop_flag", C.c_int),
         ("s_in", C.c_float), ("s_out", C.c_float), ("zp_in", C.c_int), ("zp_out", C.c_int),
-        ("kernel", C.c_int), ("classes", C.c_int), ("n_anchors", C.c_int),
+        ("kernel", C.c_int), ("classes", C.c_int), ("n_anchors", C.c_int), ("fused", C.c_int),
     ]
 
 

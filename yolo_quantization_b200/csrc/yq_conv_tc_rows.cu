@@ -77,6 +77,7 @@ struct RowsArgs {
     const uint8_t *wimg;    // shared-memory image of the filter tiles, one per MMA in issue order
     int HP, WP, OH, OW, PH, PW, OHP, OWP, opad;
     int tiles_x, tiles_y, num_tiles, zp_out;
+    uint32_t magic_x, magic_y;   // ceil(2^32 / tiles_x), ceil(2^32 / tiles_y): exact quotients by __umulhi for tile < 2^32 / tiles
     int4 cq[64];            // {bias, zw, 2*M0, shift} per channel
     double mc[64];          // M_value * 2^-s (FP64 fallback)
 };
@@ -138,17 +139,18 @@ struct ThreadChan {
 
 // One pooled output: the window's four raw accumulators v0..v3 with their activation sums -> exact zero-point
 // correction, max, bias, RELU6 requantize of the winner.  Returns q + zp_out; *xq is the requantizer's input.
-__device__ __forceinline__ int pool_requant(int zw, int bias, uint32_t m2, int sh, int zo, int v0, int v1, int v2, int v3, int n0, int n1, int n2,
+// nzw = -zp_w, n0..n3 = the four pixels' activation sums (as read from TMEM)
+__device__ __forceinline__ int pool_requant(int nzw, int bias, uint32_t m2, int sh, int zo, int v0, int v1, int v2, int v3, int n0, int n1, int n2,
                                             int n3, uint32_t *xq)
 {
-    const int m = max(max(zw * n0 + v0, zw * n1 + v1), max(zw * n2 + v2, zw * n3 + v3));
+    const int m = max(max(nzw * n0 + v0, nzw * n1 + v1), max(nzw * n2 + v2, nzw * n3 + v3));
     *xq = (uint32_t)max(m + bias, 0);
     return (int)(__umulhi(*xq, m2) >> sh) + zo;
 }
 // the reference's per-pixel arithmetic for one window (FP64 multiply, uint8 wrap, then the pool)
-__device__ __forceinline__ int pool_requant_slow(int zw, int bias, double mcd, int zo, int v0, int v1, int v2, int v3, int n0, int n1, int n2, int n3)
+__device__ __forceinline__ int pool_requant_slow(int nzw, int bias, double mcd, int zo, int v0, int v1, int v2, int v3, int n0, int n1, int n2, int n3)
 {
-    const int xs[4] = {zw * n0 + v0 + bias, zw * n1 + v1 + bias, zw * n2 + v2 + bias, zw * n3 + v3 + bias};
+    const int xs[4] = {nzw * n0 + v0 + bias, nzw * n1 + v1 + bias, nzw * n2 + v2 + bias, nzw * n3 + v3 + bias};
     int best = 0;
 #pragma unroll
     for (int p = 0; p < 4; ++p) {
@@ -215,10 +217,15 @@ __global__ void __launch_bounds__(RW_THREADS, (CS == 32 ? 2 : 4)) conv_u8_tc_row
         dst_off[k] = (uint32_t)d;
     }
     const uint32_t sA = smem_u32(smem + L::A_OFF);
-    auto issue_tile = [&](int tile, int buf) {
-        const int tx = tile % a.tiles_x, r1 = tile / a.tiles_x;
-        const int ty = r1 % a.tiles_y, n = r1 / a.tiles_y;
-        const uint8_t *src = a.in + ((size_t)(n * a.HP + ty * TILE_ROWS) * a.WP + tx * G::TWPX) * CS;
+    struct TileXY { int tx, ty, n; };
+    auto split_tile = [&](int tile) -> TileXY {
+        // (a divisor of 1 has no 32-bit magic: 2^32)
+        const int r1 = a.tiles_x == 1 ? tile : (int)__umulhi((uint32_t)tile, a.magic_x);
+        const int n = a.tiles_y == 1 ? r1 : (int)__umulhi((uint32_t)r1, a.magic_y);
+        return TileXY{tile - r1 * a.tiles_x, r1 - n * a.tiles_y, n};
+    };
+    auto issue_tile = [&](const TileXY &p, int buf) {
+        const uint8_t *src = a.in + (size_t)((uint32_t)((p.n * a.HP + p.ty * TILE_ROWS) * a.WP + p.tx * G::TWPX) * (uint32_t)CS);
         const uint32_t dst = sA + buf * L::A_STRIDE;
 #pragma unroll
         for (int k = 0; k < G::CPT; ++k)
@@ -256,45 +263,53 @@ __global__ void __launch_bounds__(RW_THREADS, (CS == 32 ? 2 : 4)) conv_u8_tc_row
 #pragma unroll
     for (int k = 0; k < NPQ; ++k) {
         const int4 c = a.cq[qq * NPQ + k];
-        ch.bias[k] = c.x; ch.zw[k] = c.y; ch.m2[k] = (uint32_t)c.z; ch.sh[k] = c.w;
+        ch.bias[k] = c.x; ch.zw[k] = -c.y; ch.m2[k] = (uint32_t)c.z; ch.sh[k] = c.w;   // zw holds MINUS the zero point
     }
     const int zo = a.zp_out;
 
+    // per-thread part of the pooled-output address (window 0 of this thread; window 1 is one pooled row further)
+    const uint32_t out_thr = (uint32_t)(((2 * warp + a.opad) * a.OWP + (CS == 4 ? 2 * qi : qi) + a.opad) * NCH + qq * NPQ);
+    const uint32_t out_row = (uint32_t)(a.OWP * NCH);
+
     const int first = blockIdx.x, step = gridDim.x;
     uint32_t phase = 0;
-    if (first < a.num_tiles) issue_tile(first, 0);
+    TileXY cur = split_tile(first), nxt = cur;
+    if (first < a.num_tiles) issue_tile(cur, 0);
+    cp_async_wait_all();
+    fence_proxy_async();          // generic-proxy smem writes -> visible to the tensor core (async proxy)
     int buf = 0;
-    for (int tile = first; tile < a.num_tiles; tile += step, buf ^= 1) {
-        // tile's copy has been in flight since the previous iteration
-        cp_async_wait_all();
-        fence_proxy_async();          // generic-proxy smem writes -> visible to the tensor core (async proxy)
-        tc_fence_before();            // (also orders the previous epilogue's TMEM reads before the next MMA)
+    for (int tile = first; tile < a.num_tiles; tile += step, buf ^= 1, cur = nxt) {
+        // tile's copy landed and was fenced by every thread before it got here
+        tc_fence_before();            // (orders the previous epilogue's TMEM reads before the next MMA)
         __syncthreads();
         if (t == 0) {
             tc_fence_after();
             issue_mma(buf);
         }
-        if (tile + step < a.num_tiles) issue_tile(tile + step, buf ^ 1);   // overlaps this tile's MMA + epilogue
+        if (tile + step < a.num_tiles) {   // overlaps this tile's MMA + epilogue
+            nxt = split_tile(tile + step);
+            issue_tile(nxt, buf ^ 1);
+        }
         mbar_wait(mma_done, phase);
         phase ^= 1u;
         tc_fence_after();
 
         // ---- epilogue: warp = TMEM lane quarter = 4 conv rows = 2 pooled rows; thread (qi, qq) = pooled column(s) qi, channels qq*NPQ ..
-        const int tx = tile % a.tiles_x, r1 = tile / a.tiles_x;
-        const int ty = r1 % a.tiles_y, n = r1 / a.tiles_y;
+        const int tx = cur.tx, ty = cur.ty, n = cur.n;
         const int py0 = ty * (TILE_ROWS / 2) + 2 * warp;
+        uint8_t *const out_tile = a.out_pool + (size_t)((uint32_t)((n * a.OHP + ty * (TILE_ROWS / 2)) * a.OWP + tx * (G::TWPX / 2)) * (uint32_t)NCH + out_thr);
         if (CS == 4) {
             uint32_t s0[8], s1[8];
             tmem_ldq(tq + 4 * NCH, s0, s1);
             int nsa0[8], nsa1[8];
 #pragma unroll
             for (int k = 0; k < 8; ++k) {
-                nsa0[k] = -(int)s0[k];
-                nsa1[k] = -(int)s1[k];
+                nsa0[k] = (int)s0[k];
+                nsa1[k] = (int)s1[k];
             }
+            uint32_t w0[2][NCH / 16], w1[2][NCH / 16];
 #pragma unroll
             for (int pair = 0; pair < 2; ++pair) {
-                uint32_t w0[NCH / 16], w1[NCH / 16];
 #pragma unroll
                 for (int jj = 0; jj < NCH / 16; ++jj) {
                     uint32_t v0[16], v1[16];
@@ -322,20 +337,24 @@ __global__ void __launch_bounds__(RW_THREADS, (CS == 32 ? 2 : 4)) conv_u8_tc_row
                                                         (int)v1[4 * gg + 3], nsa1[4 * pair], nsa1[4 * pair + 1], nsa1[4 * pair + 2], nsa1[4 * pair + 3]);
                         }
                     }
-                    w0[jj] = pack4(r0);
-                    w1[jj] = pack4(r1w);
+                    w0[pair][jj] = pack4(r0);
+                    w1[pair][jj] = pack4(r1w);
                 }
+            }
+            cp_async_wait_all();          // the next tile's copy has long landed: fence it before this tile's global stores queue up
+            fence_proxy_async();
+#pragma unroll
+            for (int pair = 0; pair < 2; ++pair) {
                 const int px = tx * (G::TWPX / 2) + 2 * qi + pair;
                 if (px < a.PW) {
-                    uint8_t *dst = a.out_pool + ((size_t)(n * a.OHP + py0 + a.opad) * a.OWP + px + a.opad) * NCH + qq * NPQ;
-                    const size_t rowb = (size_t)a.OWP * NCH;
+                    uint8_t *dst = out_tile + pair * NCH;
                     if (py0 < a.PH) {
-                        if constexpr (NCH == 16) *reinterpret_cast<uint32_t *>(dst) = w0[0];
-                        else *reinterpret_cast<uint2 *>(dst) = make_uint2(w0[0], w0[1]);
+                        if constexpr (NCH == 16) *reinterpret_cast<uint32_t *>(dst) = w0[pair][0];
+                        else *reinterpret_cast<uint2 *>(dst) = make_uint2(w0[pair][0], w0[pair][1]);
                     }
                     if (py0 + 1 < a.PH) {
-                        if constexpr (NCH == 16) *reinterpret_cast<uint32_t *>(dst + rowb) = w1[0];
-                        else *reinterpret_cast<uint2 *>(dst + rowb) = make_uint2(w1[0], w1[1]);
+                        if constexpr (NCH == 16) *reinterpret_cast<uint32_t *>(dst + out_row) = w1[pair][0];
+                        else *reinterpret_cast<uint2 *>(dst + out_row) = make_uint2(w1[pair][0], w1[pair][1]);
                     }
                 }
             }
@@ -343,8 +362,8 @@ __global__ void __launch_bounds__(RW_THREADS, (CS == 32 ? 2 : 4)) conv_u8_tc_row
             uint32_t se0[4], se1[4], so0[4], so1[4];
             tmem_ldq_sums(tq + NCH, tq + L::NB + NCH, se0, se1, so0, so1);
             // window 0: conv rows (4w, 4w+1) = lanes (qi, qi+8) of half 0; window 1: rows (4w+2, 4w+3) = half 1
-            const int n0[4] = {-(int)se0[0], -(int)se0[2], -(int)so0[0], -(int)so0[2]};
-            const int n1[4] = {-(int)se1[0], -(int)se1[2], -(int)so1[0], -(int)so1[2]};
+            const int n0[4] = {(int)se0[0], (int)se0[2], (int)so0[0], (int)so0[2]};
+            const int n1[4] = {(int)se1[0], (int)se1[2], (int)so1[0], (int)so1[2]};
             uint32_t w0[NCH / 16], w1[NCH / 16];
 #pragma unroll
             for (int j = 0; j < NCH / 16; ++j) {
@@ -376,10 +395,12 @@ __global__ void __launch_bounds__(RW_THREADS, (CS == 32 ? 2 : 4)) conv_u8_tc_row
                 w0[j] = pack4(r0);
                 w1[j] = pack4(r1w);
             }
+            cp_async_wait_all();          // the next tile's copy has long landed: fence it before this tile's global stores queue up
+            fence_proxy_async();
             const int px = tx * (G::TWPX / 2) + qi;
             if (px < a.PW) {
-                uint8_t *dst = a.out_pool + ((size_t)(n * a.OHP + py0 + a.opad) * a.OWP + px + a.opad) * NCH + qq * NPQ;
-                const size_t rowb = (size_t)a.OWP * NCH;
+                uint8_t *dst = out_tile;
+                const uint32_t rowb = out_row;
                 if (py0 < a.PH) {
                     if constexpr (NCH == 16) *reinterpret_cast<uint32_t *>(dst) = w0[0];
                     else if constexpr (NCH == 32) *reinterpret_cast<uint2 *>(dst) = make_uint2(w0[0], w0[1]);
@@ -549,6 +570,10 @@ int yq_tc_rows_forward(yq_conv_layer *l, void *state, const uint8_t *in_padded, 
     a.tiles_y = (l->out_h + TILE_ROWS - 1) / TILE_ROWS;
     a.num_tiles = a.tiles_x * a.tiles_y * batch;
     a.zp_out = l->zp_out;
+    a.magic_x = (uint32_t)((0x100000000ull + a.tiles_x - 1) / a.tiles_x);
+    a.magic_y = (uint32_t)((0x100000000ull + a.tiles_y - 1) / a.tiles_y);
+    if ((unsigned long long)a.num_tiles * (a.tiles_x > a.tiles_y ? a.tiles_x : a.tiles_y) >= 0x100000000ull || yq_act_geom_bytes(og, batch, l->n) >= 0x100000000ull)
+        return yq::fail("tcgen05 rows flavour: tensor too large for 32-bit tile arithmetic");
     memcpy(a.cq, l->host_chanq.data(), (size_t)l->n * 16);
     memcpy(a.mc, l->host_mcomb.data(), (size_t)l->n * 8);
 #define YQ_RW(CS_, N_) if (st->CS == CS_ && st->NCH == N_) return launch_rows<CS_, N_>(a, stream)

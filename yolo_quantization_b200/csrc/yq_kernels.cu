@@ -749,25 +749,58 @@ __global__ void nchw_to_nhwc_u8_geom_kernel(const uint8_t *__restrict__ in, uint
     }
 }
 
-// c <= 4, W % 4 == 0: one thread = 4 consecutive pixels of one row (the padded row start shifts them off 16-byte alignment:
-// four 4-byte stores, still fully coalesced across the warp)
-__global__ void nchw_to_nhwc4_u8_geom_kernel(const uint8_t *__restrict__ in, uint8_t *__restrict__ out, int C, int H, int W, int pad, int pitch_w,
-                                             int rows_h, long long total /* B*HW/4 */)
+// c <= 4, W % 4 == 0, pad == 1, pitch_w % 4 == 0: one thread = the 16-byte-aligned output chunk holding pixels 4j-1 .. 4j+2
+// of one row (two aligned 4-byte loads per channel plane, funnel-shifted by one pixel; one 16-byte store).  The two chunks
+// at the row ends store only their in-image pixels, so the halo is never touched.
+template <int RY>
+__global__ void nchw_to_nhwc4_u8_geom_kernel(const uint8_t *__restrict__ in, uint8_t *__restrict__ out, int C, int H, int W, int pitch_w,
+                                             int rows_h, int total_rows /* B*H */)
 {
-    const int HW = H * W, q = HW / 4, wq = W / 4;
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        const long long n = i / q;
-        const int p4 = (int)(i - n * q);
-        uint32_t pl[4] = {0, 0, 0, 0};
+    // one block = RY consecutive image rows, one thread = one 16-byte output chunk of each of them; every load of the RY
+    // rows is issued before the first use (the kernel is a pure latency / bandwidth problem)
+    const int HW = H * W, wq = W / 4;
+    const int row0 = blockIdx.x * RY;
+    for (int j = blockIdx.y * blockDim.x + threadIdx.x; j <= wq; j += gridDim.y * blockDim.x) {
+        uint32_t lo[RY][3], hi[RY][3];
 #pragma unroll
-        for (int ch = 0; ch < 4; ++ch)
-            if (ch < C) pl[ch] = __ldg(reinterpret_cast<const uint32_t *>(in + ((size_t)n * C + ch) * HW) + p4);
-        const int y = p4 / wq, x = (p4 - y * wq) * 4;
-        uint32_t *o = reinterpret_cast<uint32_t *>(out) + ((size_t)n * rows_h + y + pad) * pitch_w + x + pad;
-        o[0] = __byte_perm(__byte_perm(pl[0], pl[1], 0x0040), __byte_perm(pl[2], pl[3], 0x0040), 0x5410);
-        o[1] = __byte_perm(__byte_perm(pl[0], pl[1], 0x0051), __byte_perm(pl[2], pl[3], 0x0051), 0x5410);
-        o[2] = __byte_perm(__byte_perm(pl[0], pl[1], 0x0062), __byte_perm(pl[2], pl[3], 0x0062), 0x5410);
-        o[3] = __byte_perm(__byte_perm(pl[0], pl[1], 0x0073), __byte_perm(pl[2], pl[3], 0x0073), 0x5410);
+        for (int r = 0; r < RY; ++r) {
+            const int row = row0 + r, n = row / H, y = row - n * H;
+#pragma unroll
+            for (int ch = 0; ch < 3; ++ch) {
+                lo[r][ch] = hi[r][ch] = 0u;
+                if (ch < C && row < total_rows) {
+                    const uint32_t *src = reinterpret_cast<const uint32_t *>(in + ((size_t)n * C + ch) * HW + (size_t)y * W);
+                    if (j > 0) lo[r][ch] = __ldg(src + j - 1);
+                    if (j < wq) hi[r][ch] = __ldg(src + j);
+                }
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < RY; ++r) {
+            const int row = row0 + r, n = row / H, y = row - n * H;
+            if (row >= total_rows) break;
+            uint32_t pl[4] = {0, 0, 0, 0};
+#pragma unroll
+            for (int ch = 0; ch < 3; ++ch) pl[ch] = __byte_perm(lo[r][ch], hi[r][ch], 0x6543);   // pixels 4j-1, 4j, 4j+1, 4j+2 of this plane
+            if (C == 4) {
+                const uint32_t *src = reinterpret_cast<const uint32_t *>(in + ((size_t)n * C + 3) * HW + (size_t)y * W);
+                pl[3] = __byte_perm(j > 0 ? __ldg(src + j - 1) : 0u, j < wq ? __ldg(src + j) : 0u, 0x6543);
+            }
+            uint4 o;   // pixel k = byte k of every plane word
+            o.x = __byte_perm(__byte_perm(pl[0], pl[1], 0x0040), __byte_perm(pl[2], pl[3], 0x0040), 0x5410);
+            o.y = __byte_perm(__byte_perm(pl[0], pl[1], 0x0051), __byte_perm(pl[2], pl[3], 0x0051), 0x5410);
+            o.z = __byte_perm(__byte_perm(pl[0], pl[1], 0x0062), __byte_perm(pl[2], pl[3], 0x0062), 0x5410);
+            o.w = __byte_perm(__byte_perm(pl[0], pl[1], 0x0073), __byte_perm(pl[2], pl[3], 0x0073), 0x5410);
+            uint32_t *dst = reinterpret_cast<uint32_t *>(out) + ((size_t)n * rows_h + y + 1) * pitch_w + 4 * j;   // pixel 4j-1 sits at column 4j
+            if (j == 0) {
+                dst[1] = o.y;
+                *reinterpret_cast<uint2 *>(dst + 2) = make_uint2(o.z, o.w);
+            } else if (j == wq) {
+                dst[0] = o.x;
+            } else {
+                *reinterpret_cast<uint4 *>(dst) = o;
+            }
+        }
     }
 }
 
@@ -796,9 +829,12 @@ extern "C" int yq_nchw_to_nhwc_u8_geom(const uint8_t *in, uint8_t *out, int batc
     if (!in || !out) return yq::fail("nchw_to_nhwc: null pointer");
     if (check_geom(g, h, w)) return -1;
     const int cs = yq::channel_stride(c);
-    if (cs == 4 && w % 4 == 0 && ((uintptr_t)in % 4) == 0) {
-        long long total4 = (long long)batch * h * w / 4;
-        nchw_to_nhwc4_u8_geom_kernel<<<grid_for(total4, 256), 256, 0, (cudaStream_t)stream>>>(in, out, c, h, w, g->pad, g->pitch_w, g->rows_h, total4);
+    if (cs == 4 && w % 4 == 0 && ((uintptr_t)in % 4) == 0 && g->pad == 1 && g->pitch_w % 4 == 0 && ((uintptr_t)out % 16) == 0) {
+        constexpr int RY = 4;
+        const int cpr = w / 4 + 1, threads = cpr >= 128 ? 128 : (cpr + 31) / 32 * 32;
+        const int by = (cpr + threads - 1) / threads;
+        dim3 grid((unsigned)((batch * h + RY - 1) / RY), (unsigned)(by < 8 ? by : 8));
+        nchw_to_nhwc4_u8_geom_kernel<RY><<<grid, threads, 0, (cudaStream_t)stream>>>(in, out, c, h, w, g->pitch_w, g->rows_h, batch * h);
         YQ_CHECK_LAUNCH();
         return 0;
     }

@@ -742,6 +742,7 @@ extern "C" int yq_network_layer_info(const yq_network *net, int i, yq_layer_info
     o->batch_normalize = l.bn; o->quant_stop_flag = l.quant_stop; o->s_in = l.s_in; o->s_out = l.s_out;
     o->zp_in = l.zp_in; o->zp_out = l.zp_out; o->kernel = l.conv ? yq_conv_get_kernel(l.conv) : 0;
     o->classes = l.classes; o->n_anchors = l.n_anchors;
+    o->fused = l.type == L_CONV ? (l.use_rows ? 2 : (l.fuse_pool ? 1 : 0)) : (l.fused_away ? 1 : 0);
     return 0;
 }
 
