@@ -140,6 +140,18 @@ YQ_API size_t yq_act_geom_bytes(const yq_act_geom *geom, int batch, int c);
 YQ_API int yq_forward_convolutional_layer_quant_rows_pool_gpu(yq_conv_layer *l, const uint8_t *in_padded, uint8_t *out_pool,
                                                               const yq_act_geom *out_geom, int batch, void *stream);
 
+/* The "flat" flavour (stride 1, size 1 or 3, pad = size/2, c % 64 == 0): input and output are FLAT halo-padded
+ * tensors of identical geometry {pad 1, pitch_w w+1, rows_h h+1} (yq_act_geom_flat): one shared halo pixel after
+ * every image row, one shared halo row after every image, one trailing halo row (yq_act_geom_bytes counts it).
+ * Every filter tap reads the same shared-memory patch (no per-tap activation loads, no border fix-ups: the halo
+ * holds zp_in, src/im2col.c:5-14).  The kernel writes `halo_fill` (the CONSUMER's input zero point) at the halo
+ * positions of its output, so a chain of flat convolutions keeps its halos by itself.
+ * out_f32 / out_acc as in yq_forward_convolutional_layer_quant_gpu (dense, un-padded). */
+YQ_API int yq_conv_flat_supported(const yq_conv_layer *l);
+YQ_API int yq_act_geom_flat(int h, int w, yq_act_geom *geom);
+YQ_API int yq_forward_convolutional_layer_quant_flat_gpu(yq_conv_layer *l, const uint8_t *in_flat, uint8_t *out_flat, int halo_fill,
+                                                         float *out_f32, int32_t *out_acc, int batch, void *stream);
+
 /* ------------------------------------------------------------------------------------------------
  * memory-bound layers (all device pointers, uint8 NHWC, channel stride yq_channel_stride(c))
  * ---------------------------------------------------------------------------------------------- */
@@ -153,6 +165,16 @@ YQ_API int yq_forward_upsample_layer_quant_gpu(const uint8_t *in, uint8_t *out, 
  * channel concat of n_inputs tensors of identical h, w; in_c[i] real channels each. */
 YQ_API int yq_forward_route_layer_quant_gpu(const uint8_t *const *inputs, const int *in_c, int n_inputs,
                                             uint8_t *out, int batch, int h, int w, void *stream);
+/* the same three layers between halo-padded tensors (NULL geometry = plain); only interiors are read / written */
+YQ_API int yq_forward_maxpool_layer_quant_geom_gpu(const uint8_t *in, const yq_act_geom *in_geom, uint8_t *out,
+                                                   const yq_act_geom *out_geom, int batch, int h, int w, int c, int size,
+                                                   int stride, int pad, void *stream);
+YQ_API int yq_forward_upsample_layer_quant_geom_gpu(const uint8_t *in, const yq_act_geom *in_geom, uint8_t *out,
+                                                    const yq_act_geom *out_geom, int batch, int h, int w, int c, int stride,
+                                                    void *stream);
+YQ_API int yq_forward_route_layer_quant_geom_gpu(const uint8_t *const *inputs, const yq_act_geom *in_geoms, const int *in_c,
+                                                 int n_inputs, uint8_t *out, const yq_act_geom *out_geom, int batch, int h,
+                                                 int w, void *stream);
 /* replaces forward_yolo_layer's inference part (src/yolo_layer.c:132-146): float NCHW in/out,
  * logistic on channels {0,1} and {4..4+classes} of each anchor. */
 YQ_API int yq_forward_yolo_layer_gpu(const float *in, float *out, int batch, int n_anchors, int classes, int h,
@@ -188,7 +210,7 @@ typedef struct yq_layer_info {
     int n, size, stride, pad, activation, batch_normalize, quant_stop_flag;
     float s_in, s_out;
     int zp_in, zp_out;
-    int kernel;               /* conv only: 0 SIMT, 1 tcgen05 */
+    int kernel;               /* conv only: 0 SIMT, 1 tcgen05 (per-tap TMA / small-c), 2 tcgen05 flat strip, 3 tcgen05 rows */
     int classes, n_anchors;   /* yolo only */
     int fused;                /* conv: 0 own launch writing the conv tensor, 1 following maxpool fused into the epilogue,
                                  2 rows flavour (halo input, pooled tensor only); maxpool: 1 = produced by the previous conv */

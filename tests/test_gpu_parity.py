@@ -159,6 +159,50 @@ def test_conv_fused_maxpool_vs_oracle(built, case, s_out):
     layer.free()
 
 
+FLAT_CASES = [
+    # c, h, w, n, k, act, zp_in, zp_out, batch
+    (64, 13, 13, 128, 3, "relu6", 0, 0, 3),
+    (64, 52, 52, 128, 3, "leaky", 40, 40, 1),      # widest supported row (patch = 236 positions), KC = 64
+    (128, 7, 5, 256, 3, "relu", 5, 9, 2),
+    (128, 26, 26, 64, 3, "relu6", 11, 0, 2),
+    (256, 13, 13, 30, 1, "linear", 0, 128, 2),     # head: n = 30 -> stride 32, quant_stop float output
+    (1024, 5, 5, 256, 1, "relu6", 0, 0, 1),
+    (384, 6, 6, 80, 3, "relu6", 3, 0, 1),          # K = 3456, n not a multiple of 64
+    (512, 4, 4, 48, 3, "leaky", 200, 77, 1),       # K = 4608
+    (64, 20, 33, 64, 3, "linear", 77, 20, 2),
+    (192, 1, 1, 32, 3, "relu6", 7, 0, 4),          # 1x1 image: every tap but the centre is halo
+]
+
+
+@pytest.mark.parametrize("case", FLAT_CASES, ids=lambda c: "c%d_%dx%d_n%d_k%d_%s" % c[:6])
+def test_conv_flat_flavour_vs_oracle(built, case):
+    """flat-strip tcgen05 flavour (one shared-memory patch per channel chunk, row-shifted descriptors per tap): int32
+    accumulators, bytes and floats equal the oracle; the output strip's halo holds exactly halo_fill afterwards."""
+    c, h, w, n, k, act, zp_in, zp_out, batch = case
+    rng = np.random.default_rng(zlib.crc32(repr(case).encode()) + 9)
+    wq, zp_w, s_w, bias = make_params(rng, n, c * k * k, zp_in)
+    spec = synth.LayerSpec("conv", n, k, 1, 1, 0, act)
+    sl = synth.SynthLayer("conv", c, h, w, n, 0, 0, spec, s_out=0.05, biases=bias, s_w=s_w, zp_w=zp_w, w_u8=wq.reshape(n, c, k, k))
+    p = O.prepare_conv(sl, 0.02, zp_in)
+    x = rng.integers(0, 256, size=(batch, c, h, w), dtype=np.uint8)
+    qs = 1 if act == "linear" and n == 30 else 0
+    layer = darknet.ConvolutionalLayerQuant(h, w, c, n, k, 1, k // 2, synth.ACT_CODES[act], wq, zp_w, p["biases_int32"], p["M_value"],
+                                            p["M0_right_shift_value"], zp_in, zp_out, 0.05, quant_stop_flag=qs)
+    assert layer.flat_supported
+    for want_acc in (True, False):   # the side-output variant and the production variant
+        got = layer.forward_flat(x, halo_fill=zp_out ^ 0x5A, want_acc=want_acc)
+        assert got["halo_ok"], "halo / pad lanes of the output strip"
+        for b in range(batch):
+            acc = O.conv_acc(x[b], wq.reshape(n, c, k, k), zp_w, 1, k // 2, zp_in)
+            if want_acc:
+                assert np.array_equal(got["acc"][b], acc), f"int32 accumulator mismatch, image {b}"
+            u8 = O.requant(acc, p["biases_int32"], p["M_value"], p["M0_right_shift_value"], synth.ACT_CODES[act], zp_out)
+            assert np.array_equal(got["u8"][b], u8), f"uint8 mismatch, image {b}"
+            if qs:
+                assert np.array_equal(got["f32"][b], O.dequant(u8, zp_out, 0.05))
+    layer.free()
+
+
 ROWS_CASES = [
     # c, h, w, n, zp_in, zp_out, batch
     (3, 48, 64, 16, 0, 0, 2),
@@ -200,7 +244,7 @@ def test_conv_rows_flavour_vs_oracle(built, case, s_out, out_pad):
     if out_pad:
         raw, pad, pitch, rows = layer.last_rows_raw
         cs = darknet.channel_stride(n)
-        t = raw.reshape(batch, rows, pitch, cs).copy()
+        t = raw[:batch * rows * pitch * cs].reshape(batch, rows, pitch, cs).copy()
         t[:, pad:pad + h // 2, pad:pad + w // 2, :] = 0xEE
         assert (t == 0xEE).all(), "the rows kernel wrote outside the pooled interior"
     layer.free()

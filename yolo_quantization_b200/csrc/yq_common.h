@@ -55,6 +55,7 @@ struct yq_conv_layer {
     void *tc = nullptr;
     void *tc_small = nullptr;   // small-c tcgen05 flavour state (yq_conv_tc_small.cu)
     void *tc_rows = nullptr;    // halo-input conv + pool flavour state (yq_conv_tc_rows.cu), or nullptr
+    void *tc_flat = nullptr;    // flat-strip patch flavour state (yq_conv_tc_flat.cu), or nullptr
     std::vector<uint8_t> host_w;  // OIHW copy kept for repacking
     std::vector<uint8_t> host_zw;
     std::vector<int32_t> host_chanq;   // 4 ints per channel {bias, zw, 2*M0, shift} (copy of chanq)
@@ -80,6 +81,14 @@ int yq_tc_rows_prepare(yq_conv_layer *l, void **state);
 void yq_tc_rows_free(void *state);
 int yq_tc_rows_forward(yq_conv_layer *l, void *state, const uint8_t *in_padded, uint8_t *out_pool, const yq_act_geom *out_geom, int batch,
                        cudaStream_t stream);
+
+// implemented in yq_conv_tc_flat.cu (flat halo-padded strip, one patch per channel chunk shared by all taps; c % 64 == 0)
+int yq_tc_flat_supported(const yq_conv_layer *l);
+void yq_tc_flat_geom(int h, int w, yq_act_geom *g);
+int yq_tc_flat_prepare(yq_conv_layer *l, void **state);
+void yq_tc_flat_free(void *state);
+int yq_tc_flat_forward(yq_conv_layer *l, void *state, const uint8_t *in_flat, uint8_t *out_flat, int halo_fill, float *out_f32, int32_t *out_acc,
+                       int batch, cudaStream_t stream);
 
 // implemented in yq_conv_tc.cu (TMA-fed; c % 64 == 0)
 int yq_tc_supported(const yq_conv_layer *l);

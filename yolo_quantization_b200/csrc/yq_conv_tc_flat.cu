@@ -1,0 +1,429 @@
+// yq_conv_tc_flat.cu -- tcgen05 (kind::i8) implicit-GEMM convolution over a FLAT halo-padded activation tensor:
+// every filter tap reads the SAME shared-memory patch through a row-shifted descriptor (no per-tap activation loads).
+//
+// Flat geometry (yq_act_geom{pad 1, pitch_w W+1, rows_h H+1}): the batch is one long strip of "positions"
+//     P(n, y, x) = (n*(H+1) + y + 1)*(W+1) + x + 1
+// in which every image row is followed by ONE halo pixel (shared by the row's right edge and the next row's left edge)
+// and every image by ONE halo row (shared likewise), plus a trailing halo row.  Halo positions hold the consumer's
+// input zero point -- exactly what im2col_cpu_uint8 pads with (src/im2col.c:5-14) -- so tap (ky,kx) of output position
+// p is simply position p + (ky-pad)*(W+1) + (kx-pad): a stride-1 convolution is a 1-D correlation over the strip.
+//
+// GEMM view:  D[M = 128 consecutive positions][N = BN output channels] += A[M][K] * B[N][K]^T,  K = (ky, kx, ci)
+//   A  per KC-byte channel chunk ONE 2-D TMA load brings the patch [p0 - pad*(W+2), p0 + 128 + pad*(W+2)) x KC into
+//      shared memory (SWIZZLE_128B / 64B, one position per row).  The MMA of tap (ky,kx) uses the descriptor start
+//      patch + (ky*(W+1) + kx) * KC: the tensor core applies the swizzle to ABSOLUTE shared-memory address bits, so a
+//      start shifted by whole rows reads the shifted rows correctly with base_offset = 0 (measured on B200:
+//      tools/probes/probe_shift.cu).  Activation ingest per tile drops from 9 x 128 rows to 128 + 2W + 4 rows.
+//   B  weights [oc][ky][kx][ci], one 2-D TMA load of BN x KC per (tap, chunk) through its own ring; 16 all-ones rows
+//      appended to every stage give sum(a) per position in TMEM columns [BN, BN+16) (uint8 weights with a uint8 zero
+//      point: acc = sum w*a - zp_w * sum a, convolutional_layer.c:718-721).
+//   epilogue  thread = TMEM lane = position: integer-form requantize (yq_epilogue.cuh) -> swizzled smem tile -> TMA
+//      store.  Halo positions of the OUTPUT strip are written with the consumer's zero point, so the kernel keeps its
+//      output's halo intact by itself and garbage computed there never escapes.
+//
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer, warps 2-5 = epilogue.
+// One tile per CTA, two CTAs per SM (one CTA's epilogue overlaps the other's main loop).
+// Restates convolutional_layer.c:694-761 for stride 1, pad = size/2, size in {1, 3}, c % 64 == 0.
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <string.h>
+
+#include <map>
+#include <vector>
+
+#include "yq_common.h"
+#include "yq_epilogue.cuh"
+#include "yq_tc_ptx.cuh"
+
+using namespace yqtc;
+
+namespace {
+
+constexpr int FL_THREADS = 192;
+constexpr int FL_BSTAGES = 3;
+constexpr int FL_ONES = 16;
+
+struct FlatArgs {
+    yq::EpiParams ep;
+    float *out_f32;        // dense NCHW [B][N][H][W] (quant_stop) or nullptr
+    int32_t *out_acc;      // dense NHWC [B][H][W][CSO] (parity checks) or nullptr
+    int N, CSO, n_pad;
+    int B, H, W, NP;       // NP = B*(H+1)*(W+1): positions that belong to images (their halo included)
+    int size, taps, cpt /* KC-chunks per tap */, CS;
+    int q_off;             // first patch position relative to the tile's first position: -(pad*(W+1) + pad)
+    int patch_rows, a_stage_bytes;
+    uint32_t halo_word;    // byte the consumer pads with, replicated
+    uint32_t magic_w, magic_h;   // ceil(2^32 / (W+1)), ceil(2^32 / (H+1))
+};
+
+template <int BN>
+__host__ __device__ constexpr int fl_tmem_cols()
+{
+    return BN + FL_ONES <= 32 ? 32 : BN + FL_ONES <= 64 ? 64 : BN + FL_ONES <= 128 ? 128 : 256;
+}
+
+template <int BN, int KC>
+struct FlatSmem {
+    static constexpr int B_BYTES = BN * KC;
+    static constexpr int B_STAGE = (BN + FL_ONES) * KC;          // multiple of 1024 for every instantiated (BN, KC)
+    static constexpr int PARAM_BYTES = BN * 24;
+    static_assert(B_STAGE % 1024 == 0, "stage buffers must keep the 1024-byte swizzle alignment");
+    static_assert(128 * BN <= FL_BSTAGES * B_STAGE, "output staging aliases the weight ring");
+};
+
+template <bool HAS_EXTRA>
+__device__ __forceinline__ void fl_epi_chunk(int actm, int sat, const uint32_t (&v)[16], int nsa, const int4 *cq, const double *mc, int zo,
+                                             uint32_t (&packed)[4])
+{
+    int extra[16];
+    if (sat) {
+        if (actm == 0) yq::requant_chunk<0, true, 16, false>(v, nsa, extra, cq, mc, zo, packed);
+        else if (actm == 1) yq::requant_chunk<1, true, 16, false>(v, nsa, extra, cq, mc, zo, packed);
+        else yq::requant_chunk<2, true, 16, false>(v, nsa, extra, cq, mc, zo, packed);
+    } else {
+        if (actm == 0) yq::requant_chunk<0, false, 16, false>(v, nsa, extra, cq, mc, zo, packed);
+        else if (actm == 1) yq::requant_chunk<1, false, 16, false>(v, nsa, extra, cq, mc, zo, packed);
+        else yq::requant_chunk<2, false, 16, false>(v, nsa, extra, cq, mc, zo, packed);
+    }
+}
+
+// SLOW = the variant that also serves the int32 / float side outputs and the saturate switch.
+template <int BN, int KC, bool SLOW>
+__global__ void __launch_bounds__(FL_THREADS, 2) conv_u8_tc_flat_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                                                                    const __grid_constant__ CUtensorMap tmO, const FlatArgs a)
+{
+    using L = FlatSmem<BN, KC>;
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint8_t *sA = smem;                                     // 2 patch stages of a.a_stage_bytes
+    uint8_t *sB = smem + 2 * a.a_stage_bytes;               // FL_BSTAGES weight stages (+ constant ones rows)
+    int4 *s_q = (int4 *)(sB + FL_BSTAGES * L::B_STAGE);     // {bias, zw, 2*M0, shift}
+    double *s_mc = (double *)(s_q + BN);
+    uint64_t *a_full = (uint64_t *)(s_mc + BN);
+    uint64_t *a_empty = a_full + 2;
+    uint64_t *b_full = a_empty + 2;
+    uint64_t *b_empty = b_full + FL_BSTAGES;
+    uint64_t *accum_full = b_empty + FL_BSTAGES;
+    uint32_t *tmem_slot = (uint32_t *)(accum_full + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int oc0 = blockIdx.y * BN;
+    const int p0 = blockIdx.x * 128;
+    const int chunks = a.cpt;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(&a_full[s], 1);
+            mbar_init(&a_empty[s], 1);
+        }
+        for (int s = 0; s < FL_BSTAGES; ++s) {
+            mbar_init(&b_full[s], 1);
+            mbar_init(&b_empty[s], 1);
+        }
+        mbar_init(accum_full, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) tmem_alloc<fl_tmem_cols<BN>()>(tmem_slot);
+    if (warp >= 2) {
+        const int t = threadIdx.x - 64;
+        for (int i = t; i < BN; i += 128) {
+            s_q[i] = __ldg(a.ep.chanq + oc0 + i);
+            s_mc[i] = __ldg(a.ep.mcomb + oc0 + i);
+        }
+        for (int s = 0; s < FL_BSTAGES; ++s) {   // the 16 all-ones filter rows behind the TMA-written BN rows of every stage
+            uint32_t *ones = (uint32_t *)(sB + s * L::B_STAGE + L::B_BYTES);
+            for (int i = t; i < FL_ONES * KC / 4; i += 128) ones[i] = 0x01010101u;
+        }
+        fence_proxy_async();
+    }
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmO) : "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            int it = 0;
+            for (int c = 0; c < chunks; ++c) {
+                const int sa = c & 1;
+                mbar_wait(&a_empty[sa], ((c >> 1) & 1) ^ 1);
+                mbar_expect_tx(&a_full[sa], (uint32_t)(a.patch_rows * KC));
+                tma_load_2d(sA + sa * a.a_stage_bytes, &tmA, &a_full[sa], c * KC, p0 + a.q_off);
+                for (int tap = 0; tap < a.taps; ++tap, ++it) {
+                    const int s = it % FL_BSTAGES;
+                    mbar_wait(&b_empty[s], ((it / FL_BSTAGES) & 1) ^ 1);
+                    mbar_expect_tx(&b_full[s], (uint32_t)(BN * KC));
+                    tma_load_2d(sB + s * L::B_STAGE, &tmB, &b_full[s], tap * a.CS + c * KC, oc0);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc(BN + FL_ONES);
+            const int pitch = a.W + 1;
+            int it = 0;
+            for (int c = 0; c < chunks; ++c) {
+                const int sa = c & 1;
+                mbar_wait(&a_full[sa], (c >> 1) & 1);
+                const uint32_t patch = smem_u32(sA + sa * a.a_stage_bytes);
+                int ky = 0, kx = 0;
+                for (int tap = 0; tap < a.taps; ++tap, ++it) {
+                    const int s = it % FL_BSTAGES;
+                    mbar_wait(&b_full[s], (it / FL_BSTAGES) & 1);
+                    tc_fence_after();
+                    const uint64_t da = make_desc<KC>(patch + (uint32_t)((ky * pitch + kx) * KC));   // row-shifted start, base_offset 0
+                    const uint64_t db = make_desc<KC>(smem_u32(sB + s * L::B_STAGE));
+#pragma unroll
+                    for (int k = 0; k < KC / 32; ++k) umma_i8(tmem_base, da + 2 * k, db + 2 * k, idesc, (it | k) ? 1u : 0u);
+                    umma_commit(&b_empty[s]);
+                    if (++kx == a.size) { kx = 0; ++ky; }
+                }
+                umma_commit(&a_empty[sa]);
+            }
+            umma_commit(accum_full);
+        }
+    } else {
+        // ===================== epilogue =====================
+        const int q = warp & 3;                 // TMEM lane quarter this warp may access
+        const int r = q * 32 + lane;            // tile row = TMEM lane = position p0 + r
+        const int p = p0 + r;
+        // position -> (image, y, x); halo positions (and positions past the last image) are not pixels
+        const int row = (int)__umulhi((uint32_t)p, a.magic_w);
+        const int col = p - row * (a.W + 1);
+        const int n = (int)__umulhi((uint32_t)row, a.magic_h);
+        const int y1 = row - n * (a.H + 1);
+        const bool valid = p < a.NP && col >= 1 && y1 >= 1;
+        mbar_wait(accum_full, 0);
+        tc_fence_after();
+        const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
+        const int nsa = -(int)tmem_ld1(trow + BN);   // minus the position's activation sum (ones-row columns)
+        uint8_t *stage_out = sB;                // aliases the weight ring (all MMAs have completed)
+        const int actm = yq::act_mode(a.ep.act);
+        const bool side = SLOW && ((a.out_acc != nullptr) || (a.out_f32 != nullptr));
+        const int sat = SLOW ? a.ep.saturate : 0;
+        const size_t pix = ((size_t)n * a.H + (y1 - 1)) * a.W + (col - 1);
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 16) {
+            uint32_t v[16];
+            tmem_ld16(trow + c0, v);
+            uint32_t packed[4];
+            fl_epi_chunk<false>(actm, sat, v, nsa, s_q + c0, s_mc + c0, a.ep.zp_out, packed);
+            if (!valid) packed[0] = packed[1] = packed[2] = packed[3] = a.halo_word;
+            yq::mask_pad_channels<16>(packed, a.N - (oc0 + c0));
+            if (SLOW && side && valid) {   // parity / quant_stop side outputs (not on the throughput path)
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const int oc = oc0 + c0 + j;
+                    if (oc < a.N) {
+                        if (a.out_acc) a.out_acc[pix * a.CSO + oc] = (int)v[j] + s_q[c0 + j].y * nsa;
+                        if (a.out_f32) {
+                            const uint8_t u = (uint8_t)(packed[j / 4] >> (8 * (j % 4)));
+                            a.out_f32[((size_t)n * a.N + oc) * a.H * a.W + (size_t)(y1 - 1) * a.W + (col - 1)] = yq::dequant_f32(a.ep, u);
+                        }
+                    }
+                }
+            }
+            {   // swizzled staging (matches the TMA-store tensor map): 16-byte chunk index XOR row bits
+                const int chunk = c0 / 16;
+                int sw;
+                if (BN >= 128) sw = chunk ^ (r & 7);
+                else if (BN == 64) sw = chunk ^ ((r >> 1) & 3);
+                else sw = chunk ^ ((r >> 2) & 1);
+                *reinterpret_cast<uint4 *>(stage_out + (size_t)r * BN + sw * 16) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+            }
+        }
+        tc_fence_before();
+        fence_proxy_async();
+        asm volatile("bar.sync 1, 128;" ::: "memory");   // the four epilogue warps only
+        if (threadIdx.x == 64) {
+            tma_store_2d(&tmO, stage_out, oc0, p0);
+            tma_store_commit_wait();
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc<fl_tmem_cols<BN>()>(tmem_base);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn fl_get_encode()
+{
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)p;
+    }
+    return fn;
+}
+
+CUtensorMapSwizzle fl_swizzle_for(int inner_bytes)
+{
+    return inner_bytes >= 128 ? CU_TENSOR_MAP_SWIZZLE_128B : inner_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B;
+}
+
+int fl_encode_2d(CUtensorMap *m, const void *ptr, uint64_t rows, int row_bytes, int box_c, int box_rows, CUtensorMapL2promotion prom)
+{
+    EncodeTiledFn enc = fl_get_encode();
+    if (!enc) return yq::fail("cuTensorMapEncodeTiled is not available from this driver");
+    cuuint64_t dims[2] = {(cuuint64_t)row_bytes, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)row_bytes};
+    cuuint32_t box[2] = {(cuuint32_t)box_c, (cuuint32_t)box_rows};
+    cuuint32_t es[2] = {1, 1};
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void *>(ptr), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     fl_swizzle_for(box_c), prom, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return yq::fail("cuTensorMapEncodeTiled(%llu x %d, box %d x %d) failed: %d", (unsigned long long)rows, row_bytes, box_c, box_rows, (int)r);
+    return 0;
+}
+
+struct FlatState {
+    int BN, KC, n_pad;
+    uint8_t *w = nullptr;       // [n_pad][size*size*cs_in]
+    CUtensorMap tmB;
+    struct Key {
+        const void *in;
+        void *out;
+        int batch;
+        bool operator<(const Key &o) const { return in != o.in ? in < o.in : out != o.out ? out < o.out : batch < o.batch; }
+    };
+    std::map<Key, std::pair<CUtensorMap, CUtensorMap>> maps;
+};
+
+template <int BN, int KC, bool SLOW>
+int fl_launch_v(FlatState *st, const CUtensorMap &tmA, const CUtensorMap &tmO, const FlatArgs &a, dim3 grid, cudaStream_t stream)
+{
+    using L = FlatSmem<BN, KC>;
+    static int attr_smem = 0;
+    const int smem = 2 * a.a_stage_bytes + FL_BSTAGES * L::B_STAGE + L::PARAM_BYTES + 128 + 1024;
+    auto kern = conv_u8_tc_flat_kernel<BN, KC, SLOW>;
+    if (smem > attr_smem) {
+        YQ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        attr_smem = smem;
+    }
+    kern<<<grid, FL_THREADS, smem, stream>>>(tmA, st->tmB, tmO, a);
+    YQ_CHECK_LAUNCH();
+    return 0;
+}
+
+template <int BN, int KC>
+int fl_launch(FlatState *st, const CUtensorMap &tmA, const CUtensorMap &tmO, const FlatArgs &a, dim3 grid, cudaStream_t stream)
+{
+    if (a.out_acc || a.out_f32 || a.ep.saturate) return fl_launch_v<BN, KC, true>(st, tmA, tmO, a, grid, stream);
+    return fl_launch_v<BN, KC, false>(st, tmA, tmO, a, grid, stream);
+}
+
+}  // namespace
+
+int yq_tc_flat_supported(const yq_conv_layer *l)
+{
+    if (!l->int_form || !l->fused_mult) return 0;
+    if (l->stride != 1 || !(l->size == 1 || l->size == 3) || l->pad != l->size / 2) return 0;
+    if (l->c != l->cs_in || l->cs_in % 64) return 0;            // no pad lanes: the halo fill would count in sum(a)
+    if (l->cs_out < 32) return 0;
+    if (128 + (l->size - 1) * (l->w + 2) > 256) return 0;       // the patch is one TMA box (<= 256 rows)
+    return fl_get_encode() != nullptr;
+}
+
+void yq_tc_flat_geom(int h, int w, yq_act_geom *g)
+{
+    g->pad = 1;
+    g->pitch_w = w + 1;
+    g->rows_h = h + 1;
+}
+
+int yq_tc_flat_prepare(yq_conv_layer *l, void **state)
+{
+    FlatState *st = new FlatState();
+    st->BN = l->cs_out >= 128 ? 128 : (l->cs_out >= 64 ? 64 : 32);
+    st->KC = (l->cs_in % 128) ? 64 : 128;
+    st->n_pad = yq::round_up(l->n, st->BN);
+    const int taps = l->size * l->size;
+    const size_t ktot = (size_t)taps * l->cs_in;
+    std::vector<uint8_t> wp((size_t)st->n_pad * ktot, 0);
+    for (int oc = 0; oc < l->n; ++oc)
+        for (int t = 0; t < taps; ++t)
+            for (int ci = 0; ci < l->c; ++ci) wp[(size_t)oc * ktot + (size_t)t * l->cs_in + ci] = l->host_w[((size_t)oc * l->c + ci) * taps + t];
+    auto cleanup = [&]() {
+        cudaFree(st->w);
+        delete st;
+        return -1;
+    };
+    if (cudaMalloc((void **)&st->w, wp.size()) != cudaSuccess) return cleanup();
+    if (cudaMemcpy(st->w, wp.data(), wp.size(), cudaMemcpyHostToDevice) != cudaSuccess) return cleanup();
+    if (fl_encode_2d(&st->tmB, st->w, (uint64_t)st->n_pad, (int)ktot, st->KC, st->BN, CU_TENSOR_MAP_L2_PROMOTION_L2_256B)) return cleanup();
+    *state = st;
+    return 0;
+}
+
+void yq_tc_flat_free(void *state)
+{
+    FlatState *st = (FlatState *)state;
+    if (!st) return;
+    cudaFree(st->w);
+    delete st;
+}
+
+int yq_tc_flat_forward(yq_conv_layer *l, void *state, const uint8_t *in_flat, uint8_t *out_flat, int halo_fill, float *out_f32, int32_t *out_acc,
+                       int batch, cudaStream_t stream)
+{
+    FlatState *st = (FlatState *)state;
+    if (!st || !in_flat || !out_flat) return yq::fail("tcgen05 flat flavour: bad argument");
+    const int W1 = l->w + 1, H1 = l->h + 1;
+    const long long NP = (long long)batch * H1 * W1;
+    const long long rows_alloc = NP + W1 + 2;     // + the trailing halo row (yq_act_geom_bytes)
+    if (rows_alloc * W1 >= 0x100000000ll) return yq::fail("tcgen05 flat flavour: tensor too large for 32-bit position arithmetic");
+    FlatState::Key key{in_flat, out_flat, batch};
+    FlatArgs a;
+    memset(&a, 0, sizeof a);
+    const int pad = l->size / 2;
+    a.patch_rows = 128 + (l->size - 1) * (W1 + 1);
+    a.a_stage_bytes = yq::round_up(a.patch_rows * st->KC, 1024);
+    auto it = st->maps.find(key);
+    if (it == st->maps.end()) {
+        if (st->maps.size() > 64) st->maps.clear();
+        CUtensorMap tmA, tmO;
+        if (fl_encode_2d(&tmA, in_flat, (uint64_t)rows_alloc, l->cs_in, st->KC, a.patch_rows, CU_TENSOR_MAP_L2_PROMOTION_L2_128B)) return -1;
+        if (fl_encode_2d(&tmO, out_flat, (uint64_t)rows_alloc, l->cs_out, st->BN, 128, CU_TENSOR_MAP_L2_PROMOTION_L2_128B)) return -1;
+        it = st->maps.emplace(key, std::make_pair(tmA, tmO)).first;
+    }
+    a.ep = yq::make_epi(l);
+    a.out_f32 = l->quant_stop_flag ? out_f32 : nullptr;
+    a.out_acc = out_acc;
+    a.N = l->n; a.CSO = l->cs_out; a.n_pad = st->n_pad;
+    a.B = batch; a.H = l->h; a.W = l->w; a.NP = (int)NP;
+    a.size = l->size; a.taps = l->size * l->size; a.cpt = l->cs_in / st->KC; a.CS = l->cs_in;
+    a.q_off = -(pad * W1 + pad);
+    a.halo_word = 0x01010101u * (uint32_t)(halo_fill & 0xff);
+    a.magic_w = (uint32_t)((0x100000000ull + W1 - 1) / W1);
+    a.magic_h = (uint32_t)((0x100000000ull + H1 - 1) / H1);
+    dim3 grid((unsigned)((rows_alloc + 127) / 128), st->n_pad / st->BN);
+    const CUtensorMap &tmA = it->second.first, &tmO = it->second.second;
+#define YQ_FL(BN_, KC_) return fl_launch<BN_, KC_>(st, tmA, tmO, a, grid, stream)
+    if (st->KC == 128) {
+        if (st->BN == 128) YQ_FL(128, 128);
+        if (st->BN == 64) YQ_FL(64, 128);
+        YQ_FL(32, 128);
+    } else {
+        if (st->BN == 128) YQ_FL(128, 64);
+        if (st->BN == 64) YQ_FL(64, 64);
+        YQ_FL(32, 64);
+    }
+#undef YQ_FL
+}

@@ -414,7 +414,7 @@ extern "C" yq_conv_layer *yq_make_convolutional_layer_quant(const yq_conv_desc *
     if (yq_tc_supported(l)) {
         if (yq_tc_prepare(l) == 0) l->kernel = 1;
     }
-    if (yq_tc_rows_supported(l) && yq_tc_rows_prepare(l, &l->tc_rows) != 0) {
+    if ((yq_tc_rows_supported(l) && yq_tc_rows_prepare(l, &l->tc_rows) != 0) || (yq_tc_flat_supported(l) && yq_tc_flat_prepare(l, &l->tc_flat) != 0)) {
         yq_free_convolutional_layer_quant(l);
         return nullptr;
     }
@@ -426,6 +426,7 @@ extern "C" void yq_free_convolutional_layer_quant(yq_conv_layer *l)
     if (!l) return;
     yq_tc_free(l);
     yq_tc_rows_free(l->tc_rows);
+    yq_tc_flat_free(l->tc_flat);
     cudaFree(l->w_simt); cudaFree(l->bias); cudaFree(l->zw); cudaFree(l->mcomb); cudaFree(l->mval); cudaFree(l->rsh); cudaFree(l->chanq);
     delete l;
 }
@@ -462,6 +463,23 @@ extern "C" int yq_forward_convolutional_layer_quant_gpu(yq_conv_layer *l, const 
 
 extern "C" int yq_conv_can_fuse_maxpool(const yq_conv_layer *l) { return l ? yq_tc_can_fuse_pool(l) : 0; }
 
+static int check_geom(const yq_act_geom *g, int h, int w);
+extern "C" int yq_conv_flat_supported(const yq_conv_layer *l) { return l && l->tc_flat ? 1 : 0; }
+extern "C" int yq_act_geom_flat(int h, int w, yq_act_geom *g)
+{
+    if (!g || h <= 0 || w <= 0) return yq::fail("yq_act_geom_flat: bad argument");
+    yq_tc_flat_geom(h, w, g);
+    return 0;
+}
+extern "C" int yq_forward_convolutional_layer_quant_flat_gpu(yq_conv_layer *l, const uint8_t *in_flat, uint8_t *out_flat, int halo_fill, float *out_f32,
+                                                             int32_t *out_acc, int batch, void *stream)
+{
+    if (!l || !in_flat || !out_flat || batch <= 0) return yq::fail("yq_forward_convolutional_layer_quant_flat_gpu: bad argument");
+    if (!l->tc_flat) return yq::fail("this layer has no flat flavour (see yq_conv_flat_supported)");
+    if (l->quant_stop_flag && !out_f32) return yq::fail("quant_stop layer needs out_f32");
+    return yq_tc_flat_forward(l, l->tc_flat, in_flat, out_flat, halo_fill, out_f32, out_acc, batch, (cudaStream_t)stream);
+}
+
 extern "C" int yq_conv_rows_supported(const yq_conv_layer *l) { return l && l->tc_rows ? 1 : 0; }
 extern "C" int yq_conv_rows_input_geom(const yq_conv_layer *l, yq_act_geom *g)
 {
@@ -471,15 +489,15 @@ extern "C" int yq_conv_rows_input_geom(const yq_conv_layer *l, yq_act_geom *g)
 }
 extern "C" size_t yq_act_geom_bytes(const yq_act_geom *g, int batch, int c)
 {
-    return g ? (size_t)batch * g->rows_h * g->pitch_w * yq::channel_stride(c) : 0;
+    // + one trailing halo row and corner (the halo below the last image when halos are shared)
+    return g ? ((size_t)batch * g->rows_h * g->pitch_w + g->pitch_w + 2) * yq::channel_stride(c) : 0;
 }
 extern "C" int yq_forward_convolutional_layer_quant_rows_pool_gpu(yq_conv_layer *l, const uint8_t *in_padded, uint8_t *out_pool,
                                                                   const yq_act_geom *out_geom, int batch, void *stream)
 {
     if (!l || !in_padded || !out_pool || !out_geom || batch <= 0) return yq::fail("yq_forward_convolutional_layer_quant_rows_pool_gpu: bad argument");
     if (!l->tc_rows) return yq::fail("this layer has no rows flavour (see yq_conv_rows_supported)");
-    if (out_geom->pitch_w < l->out_w / 2 + 2 * out_geom->pad || out_geom->rows_h < l->out_h / 2 + 2 * out_geom->pad)
-        return yq::fail("yq_forward_convolutional_layer_quant_rows_pool_gpu: output geometry smaller than the pooled tensor");
+    if (check_geom(out_geom, l->out_h / 2, l->out_w / 2)) return -1;
     return yq_tc_rows_forward(l, l->tc_rows, in_padded, out_pool, out_geom, batch, (cudaStream_t)stream);
 }
 
@@ -491,9 +509,26 @@ __device__ __forceinline__ uint4 vmax16(uint4 a, uint4 b)
     return make_uint4(__vmaxu4(a.x, b.x), __vmaxu4(a.y, b.y), __vmaxu4(a.z, b.z), __vmaxu4(a.w, b.w));
 }
 
+// halo-padded tensor geometry on the device: pixel (n, y, x) -> pixel index
+struct Geo {
+    int pad, pitch, rows;
+    __device__ __forceinline__ size_t pix(int n, int y, int x) const { return ((size_t)(n * rows + y + pad)) * pitch + x + pad; }
+};
+static inline Geo geo_of(const yq_act_geom *g, int h, int w)
+{
+    if (!g) return Geo{0, w, h};
+    return Geo{g->pad, g->pitch_w, g->rows_h};
+}
+static int check_geom(const yq_act_geom *g, int h, int w)
+{
+    // (a halo may be shared between neighbouring rows / images: pitch_w = w + pad, rows_h = h + pad is the tightest form)
+    if (g && (g->pad < 0 || g->pitch_w < w + g->pad || g->rows_h < h + g->pad)) return yq::fail("activation geometry does not hold a %dx%d tensor", h, w);
+    return 0;
+}
+
 template <typename V>
 __global__ void maxpool_u8_kernel(const V *__restrict__ in, V *__restrict__ out, int B, int H, int W, int OH, int OW,
-                                  int vpp /* vectors per pixel */, int size, int stride, int off, long long total)
+                                  int vpp /* vectors per pixel */, int size, int stride, int off, long long total, Geo gi, Geo go)
 {
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
         int v = (int)(i % vpp);
@@ -510,12 +545,12 @@ __global__ void maxpool_u8_kernel(const V *__restrict__ in, V *__restrict__ out,
             for (int b = 0; b < size; ++b) {
                 int x = off + ox * stride + b;
                 if (x < 0 || x >= W) continue;
-                V t = __ldg(in + ((size_t)(n * H + y) * W + x) * vpp + v);
+                V t = __ldg(in + gi.pix(n, y, x) * vpp + v);
                 if constexpr (sizeof(V) == 16) m = vmax16(m, t);
                 else m = __vmaxu4(m, t);
             }
         }
-        out[i] = m;
+        out[go.pix(n, oy, ox) * vpp + v] = m;
     }
 }
 
@@ -526,24 +561,31 @@ static inline int grid_for(long long total, int threads)
     return (int)(b < cap ? (b > 0 ? b : 1) : cap);
 }
 
-extern "C" int yq_forward_maxpool_layer_quant_gpu(const uint8_t *in, uint8_t *out, int batch, int h, int w, int c,
-                                                  int size, int stride, int pad, void *stream)
+extern "C" int yq_forward_maxpool_layer_quant_geom_gpu(const uint8_t *in, const yq_act_geom *in_geom, uint8_t *out, const yq_act_geom *out_geom,
+                                                       int batch, int h, int w, int c, int size, int stride, int pad, void *stream)
 {
     if (!in || !out || batch <= 0) return yq::fail("maxpool: bad argument");
     const int cs = yq::channel_stride(c);
     const int oh = (h + pad - size) / stride + 1, ow = (w + pad - size) / stride + 1;   // maxpool_layer.c:31-32
+    if (check_geom(in_geom, h, w) || check_geom(out_geom, oh, ow)) return -1;
+    const Geo gi = geo_of(in_geom, h, w), go = geo_of(out_geom, oh, ow);
     const int off = -pad / 2;
     if (cs % 16 == 0) {
         long long total = (long long)batch * oh * ow * (cs / 16);
         maxpool_u8_kernel<uint4><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
-            (const uint4 *)in, (uint4 *)out, batch, h, w, oh, ow, cs / 16, size, stride, off, total);
+            (const uint4 *)in, (uint4 *)out, batch, h, w, oh, ow, cs / 16, size, stride, off, total, gi, go);
     } else {
         long long total = (long long)batch * oh * ow * (cs / 4);
         maxpool_u8_kernel<uint32_t><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
-            (const uint32_t *)in, (uint32_t *)out, batch, h, w, oh, ow, cs / 4, size, stride, off, total);
+            (const uint32_t *)in, (uint32_t *)out, batch, h, w, oh, ow, cs / 4, size, stride, off, total, gi, go);
     }
     YQ_CHECK_LAUNCH();
     return 0;
+}
+extern "C" int yq_forward_maxpool_layer_quant_gpu(const uint8_t *in, uint8_t *out, int batch, int h, int w, int c,
+                                                  int size, int stride, int pad, void *stream)
+{
+    return yq_forward_maxpool_layer_quant_geom_gpu(in, nullptr, out, nullptr, batch, h, w, c, size, stride, pad, stream);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -551,7 +593,7 @@ extern "C" int yq_forward_maxpool_layer_quant_gpu(const uint8_t *in, uint8_t *ou
 // ------------------------------------------------------------------------------------------------
 template <typename V>
 __global__ void upsample_u8_kernel(const V *__restrict__ in, V *__restrict__ out, int H, int W, int vpp, int stride,
-                                   long long total)
+                                   long long total, Geo gi, Geo go)
 {
     const int OW = W * stride, OH = H * stride;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -561,24 +603,31 @@ __global__ void upsample_u8_kernel(const V *__restrict__ in, V *__restrict__ out
         p /= OW;
         int oy = (int)(p % OH);
         int n = (int)(p / OH);
-        out[i] = __ldg(in + ((size_t)(n * H + oy / stride) * W + ox / stride) * vpp + v);
+        out[go.pix(n, oy, ox) * vpp + v] = __ldg(in + gi.pix(n, oy / stride, ox / stride) * vpp + v);
     }
 }
 
-extern "C" int yq_forward_upsample_layer_quant_gpu(const uint8_t *in, uint8_t *out, int batch, int h, int w, int c,
-                                                   int stride, void *stream)
+extern "C" int yq_forward_upsample_layer_quant_geom_gpu(const uint8_t *in, const yq_act_geom *in_geom, uint8_t *out, const yq_act_geom *out_geom,
+                                                        int batch, int h, int w, int c, int stride, void *stream)
 {
     if (!in || !out || batch <= 0 || stride <= 0) return yq::fail("upsample: bad argument");
+    if (check_geom(in_geom, h, w) || check_geom(out_geom, h * stride, w * stride)) return -1;
+    const Geo gi = geo_of(in_geom, h, w), go = geo_of(out_geom, h * stride, w * stride);
     const int cs = yq::channel_stride(c);
     if (cs % 16 == 0) {
         long long total = (long long)batch * h * stride * w * stride * (cs / 16);
-        upsample_u8_kernel<uint4><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>((const uint4 *)in, (uint4 *)out, h, w, cs / 16, stride, total);
+        upsample_u8_kernel<uint4><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>((const uint4 *)in, (uint4 *)out, h, w, cs / 16, stride, total, gi, go);
     } else {
         long long total = (long long)batch * h * stride * w * stride * (cs / 4);
-        upsample_u8_kernel<uint32_t><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>((const uint32_t *)in, (uint32_t *)out, h, w, cs / 4, stride, total);
+        upsample_u8_kernel<uint32_t><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>((const uint32_t *)in, (uint32_t *)out, h, w, cs / 4, stride, total, gi, go);
     }
     YQ_CHECK_LAUNCH();
     return 0;
+}
+extern "C" int yq_forward_upsample_layer_quant_gpu(const uint8_t *in, uint8_t *out, int batch, int h, int w, int c,
+                                                   int stride, void *stream)
+{
+    return yq_forward_upsample_layer_quant_geom_gpu(in, nullptr, out, nullptr, batch, h, w, c, stride, stream);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -590,62 +639,77 @@ struct RouteArgs {
     int c[ROUTE_MAX_INPUTS];     // real channels
     int cs[ROUTE_MAX_INPUTS];    // channel strides
     int off[ROUTE_MAX_INPUTS];   // channel offset in the output
-    int n, cs_out, c_out;
+    Geo g[ROUTE_MAX_INPUTS];     // input geometries
+    Geo go;
+    int n, cs_out, c_out, H, W;
     long long pixels;
 };
 
 __global__ void route_u8_kernel(const RouteArgs a, uint8_t *__restrict__ out, int vec)
 {
+    const int HW = a.H * a.W;
     if (vec) {
         const int vpp = a.cs_out / 16;
         const long long total = a.pixels * vpp;
         for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
             int v = (int)(i % vpp);
             long long p = i / vpp;
+            const int n = (int)(p / HW), rem = (int)(p - (long long)n * HW), y = rem / a.W, x = rem - y * a.W;
             int ch = v * 16;
             uint4 val = make_uint4(0, 0, 0, 0);
             for (int k = 0; k < a.n; ++k)
                 if (ch >= a.off[k] && ch < a.off[k] + a.c[k])
-                    val = __ldg(reinterpret_cast<const uint4 *>(a.in[k] + (size_t)p * a.cs[k] + (ch - a.off[k])));
-            *reinterpret_cast<uint4 *>(out + (size_t)p * a.cs_out + ch) = val;
+                    val = __ldg(reinterpret_cast<const uint4 *>(a.in[k] + a.g[k].pix(n, y, x) * a.cs[k] + (ch - a.off[k])));
+            *reinterpret_cast<uint4 *>(out + a.go.pix(n, y, x) * a.cs_out + ch) = val;
         }
     } else {
         const long long total = a.pixels * a.cs_out;
         for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
             int ch = (int)(i % a.cs_out);
             long long p = i / a.cs_out;
+            const int n = (int)(p / HW), rem = (int)(p - (long long)n * HW), y = rem / a.W, x = rem - y * a.W;
             uint8_t val = 0;
             for (int k = 0; k < a.n; ++k)
-                if (ch >= a.off[k] && ch < a.off[k] + a.c[k]) val = a.in[k][(size_t)p * a.cs[k] + (ch - a.off[k])];
-            out[i] = val;
+                if (ch >= a.off[k] && ch < a.off[k] + a.c[k]) val = a.in[k][a.g[k].pix(n, y, x) * a.cs[k] + (ch - a.off[k])];
+            out[a.go.pix(n, y, x) * a.cs_out + ch] = val;
         }
     }
 }
 
-extern "C" int yq_forward_route_layer_quant_gpu(const uint8_t *const *inputs, const int *in_c, int n_inputs,
-                                                uint8_t *out, int batch, int h, int w, void *stream)
+extern "C" int yq_forward_route_layer_quant_geom_gpu(const uint8_t *const *inputs, const yq_act_geom *in_geoms, const int *in_c, int n_inputs,
+                                                     uint8_t *out, const yq_act_geom *out_geom, int batch, int h, int w, void *stream)
 {
     if (!inputs || !in_c || !out || n_inputs <= 0 || n_inputs > ROUTE_MAX_INPUTS) return yq::fail("route: bad argument");
     RouteArgs a;
     memset(&a, 0, sizeof a);
     int off = 0, vec = 1;
     for (int i = 0; i < n_inputs; ++i) {
+        if (check_geom(in_geoms ? &in_geoms[i] : nullptr, h, w)) return -1;
         a.in[i] = inputs[i];
         a.c[i] = in_c[i];
         a.cs[i] = yq::channel_stride(in_c[i]);
         a.off[i] = off;
+        a.g[i] = geo_of(in_geoms ? &in_geoms[i] : nullptr, h, w);
         off += in_c[i];
         if (in_c[i] % 16) vec = 0;
     }
+    if (check_geom(out_geom, h, w)) return -1;
+    a.go = geo_of(out_geom, h, w);
     a.n = n_inputs;
     a.c_out = off;
     a.cs_out = yq::channel_stride(off);
+    a.H = h; a.W = w;
     a.pixels = (long long)batch * h * w;
     if (a.cs_out % 16) vec = 0;
     long long total = vec ? a.pixels * (a.cs_out / 16) : a.pixels * a.cs_out;
     route_u8_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(a, out, vec);
     YQ_CHECK_LAUNCH();
     return 0;
+}
+extern "C" int yq_forward_route_layer_quant_gpu(const uint8_t *const *inputs, const int *in_c, int n_inputs,
+                                                uint8_t *out, int batch, int h, int w, void *stream)
+{
+    return yq_forward_route_layer_quant_geom_gpu(inputs, nullptr, in_c, n_inputs, out, nullptr, batch, h, w, stream);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -818,16 +882,11 @@ __global__ void nhwc_to_nchw_u8_geom_kernel(const uint8_t *__restrict__ in, uint
     }
 }
 
-static int check_geom(const yq_act_geom *g, int h, int w)
-{
-    if (!g || g->pad < 0 || g->pitch_w < w + 2 * g->pad || g->rows_h < h + 2 * g->pad) return yq::fail("activation geometry does not hold a %dx%d tensor", h, w);
-    return 0;
-}
 
 extern "C" int yq_nchw_to_nhwc_u8_geom(const uint8_t *in, uint8_t *out, int batch, int c, int h, int w, const yq_act_geom *g, void *stream)
 {
     if (!in || !out) return yq::fail("nchw_to_nhwc: null pointer");
-    if (check_geom(g, h, w)) return -1;
+    if (!g || check_geom(g, h, w)) return -1;
     const int cs = yq::channel_stride(c);
     if (cs == 4 && w % 4 == 0 && ((uintptr_t)in % 4) == 0 && g->pad == 1 && g->pitch_w % 4 == 0 && ((uintptr_t)out % 16) == 0) {
         constexpr int RY = 4;
@@ -846,7 +905,7 @@ extern "C" int yq_nchw_to_nhwc_u8_geom(const uint8_t *in, uint8_t *out, int batc
 extern "C" int yq_nhwc_to_nchw_u8_geom(const uint8_t *in, uint8_t *out, int batch, int c, int h, int w, const yq_act_geom *g, void *stream)
 {
     if (!in || !out) return yq::fail("nhwc_to_nchw: null pointer");
-    if (check_geom(g, h, w)) return -1;
+    if (!g || check_geom(g, h, w)) return -1;
     long long total = (long long)batch * c * h * w;
     nhwc_to_nchw_u8_geom_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(in, out, c, h, w, yq::channel_stride(c), g->pad, g->pitch_w,
                                                                                         g->rows_h, total);

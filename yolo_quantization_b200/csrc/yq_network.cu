@@ -117,6 +117,9 @@ struct Layer {
     bool fuse_pool = false;        // conv: the next layer (maxpool 2/2) is produced by this layer's epilogue
     bool fused_away = false;       // maxpool: produced by the previous conv, no launch
     bool use_rows = false;         // conv: halo-input conv + pool flavour (yq_conv_tc_rows.cu); its input tensor is halo-padded
+    bool use_flat = false;         // conv: flat-strip flavour (yq_conv_tc_flat.cu); input and output tensors are flat
+    int halo_fill = 0;             // byte kept in the halo of out_u8: the zero point its consumer convolutions pad with
+    int src = -2;                  // layer whose out_u8 this layer reads (-1: the network input); routes use `inputs`
     yq_act_geom geom = {0, 0, 0};  // geometry of out_u8 (plain unless the only consumer is a rows-flavour conv)
 };
 
@@ -130,7 +133,8 @@ struct yq_network {
     uint8_t *in_stage_nchw = nullptr;   // staging for host-input predict
     uint8_t *in_nhwc = nullptr;
     size_t in_nhwc_bytes = 0;
-    yq_act_geom in_geom = {0, 0, 0};    // geometry of in_nhwc (halo-padded when layer 0 runs the rows flavour)
+    yq_act_geom in_geom = {0, 0, 0};    // geometry of in_nhwc (halo-padded when layer 0 runs a halo-input flavour)
+    int in_halo_fill = 0;
     uint8_t *scratch = nullptr;         // pull_layer conversions
     size_t scratch_bytes = 0;
     int keep_acc = 0;
@@ -258,33 +262,124 @@ bool routed_from(const yq_network *net, int i)
     return false;
 }
 
+bool same_geom(const yq_act_geom &a, const yq_act_geom &b) { return a.pad == b.pad && a.pitch_w == b.pitch_w && a.rows_h == b.rows_h; }
+
+// the layer whose buffer really holds layer i's output (single-input routes are aliases, route_layer.c:107-117 with n = 1)
+int tensor_of(const yq_network *net, int i)
+{
+    while (i >= 0 && net->layers[i].type == L_ROUTE && net->layers[i].inputs.size() == 1) i = net->layers[i].inputs[0];
+    return i;
+}
+
+// Decide the kernel flavour of every convolution, which conv -> maxpool(2,2) pairs run as one launch, and the geometry
+// of every activation tensor.  Halo-input flavours constrain the tensors next to them:
+//   rows conv  : input = its own padded geometry (any producer that can write one); writes the POOLED tensor, any geometry
+//   flat conv  : input and output = the flat strip of its image size
+//   other conv flavours (SIMT, small-c, per-tap TMA): plain tensors only
+//   maxpool / upsample / route / the input transform: any geometry on either side
+// A tensor touched by conflicting requirements makes the halo-input convs next to it fall back to a plain flavour.
 void plan(yq_network *net)
 {
     const int n = (int)net->layers.size();
-    for (auto &l : net->layers) {
-        l.fuse_pool = l.fused_away = l.use_rows = false;
+    std::vector<char> rows_ok(n, 0), flat_ok(n, 0);
+    int prev = -1;
+    for (int i = 0; i < n; ++i) {
+        Layer &l = net->layers[i];
+        l.src = prev;
+        if (l.type != L_YOLO) prev = i;
+        if (l.type != L_CONV || !l.conv || net->conv_kernel == 0) continue;
+        const bool pool22 = i + 1 < n && net->layers[i + 1].type == L_MAXPOOL && net->layers[i + 1].size == 2 && net->layers[i + 1].stride == 2 &&
+                            net->layers[i + 1].pad == 1;
+        // YQ_NO_ROWS / YQ_NO_FLAT = 1 keep the older flavours for A/B measurements
+        static const bool no_rows = getenv("YQ_NO_ROWS") && atoi(getenv("YQ_NO_ROWS")), no_flat = getenv("YQ_NO_FLAT") && atoi(getenv("YQ_NO_FLAT"));
+        rows_ok[i] = !no_rows && net->fusion && pool22 && yq_conv_rows_supported(l.conv) && !conv_output_needed(net, i);
+        flat_ok[i] = !no_flat && yq_conv_flat_supported(l.conv) != 0;
+    }
+    // requirement on tensor t (index t + 1; t = -1 is the network input): 0 none, 1 plain, 2 a specific padded geometry
+    struct Req { int kind = 0; yq_act_geom g = {0, 0, 0}; int fill = -1; bool conflict = false; };
+    std::vector<Req> req;
+    auto need = [&](int t, int kind, const yq_act_geom *g, int fill) {
+        Req &r = req[tensor_of(net, t) + 1];
+        if (kind == 2 && r.kind == 2 && !same_geom(r.g, *g)) r.conflict = true;
+        if ((kind == 1 && r.kind == 2) || (kind == 2 && r.kind == 1)) r.conflict = true;
+        if (kind == 2 && fill >= 0) {
+            if (r.fill >= 0 && r.fill != fill) r.conflict = true;
+            r.fill = fill;
+        }
+        if (kind > r.kind) r.kind = kind;
+        if (kind == 2) r.g = *g;
+    };
+    for (int pass = 0; pass < n + 2; ++pass) {
+        req.assign(n + 1, Req());
+        for (int i = 0; i < n; ++i) {
+            Layer &l = net->layers[i];
+            if (l.type != L_CONV) continue;
+            yq_act_geom g;
+            if (rows_ok[i]) {
+                yq_conv_rows_input_geom(l.conv, &g);
+                need(l.src, 2, &g, l.zp_in);            // (the pooled tensor it writes may have any geometry)
+            } else if (flat_ok[i]) {
+                yq_act_geom_flat(l.h, l.w, &g);
+                need(l.src, 2, &g, l.zp_in);
+                need(i, 2, &g, -1);
+            } else {
+                need(l.src, 1, nullptr, -1);
+                const bool fuses = net->fusion && i + 1 < n && net->layers[i + 1].type == L_MAXPOOL && net->layers[i + 1].size == 2 &&
+                                   net->layers[i + 1].stride == 2 && net->layers[i + 1].pad == 1 && yq_conv_can_fuse_maxpool(l.conv);
+                need(i, 1, nullptr, -1);
+                if (fuses) need(i + 1, 1, nullptr, -1);
+            }
+        }
+        bool changed = false;
+        for (int i = 0; i < n; ++i) {
+            Layer &l = net->layers[i];
+            if (l.type != L_CONV || !(rows_ok[i] || flat_ok[i])) continue;
+            const bool bad = req[tensor_of(net, l.src) + 1].conflict || (!rows_ok[i] && req[tensor_of(net, i) + 1].conflict);
+            if (bad) {
+                if (rows_ok[i]) rows_ok[i] = 0;     // (a rows conv that loses its input geometry may still run flat or plain)
+                else flat_ok[i] = 0;
+                changed = true;
+            }
+        }
+        if (!changed) break;
+    }
+    // ---- apply
+    for (int i = 0; i < n; ++i) {
+        Layer &l = net->layers[i];
+        l.fuse_pool = l.fused_away = l.use_rows = l.use_flat = false;
         l.geom = yq_act_geom{0, l.out_w, l.out_h};
+        l.halo_fill = 0;
     }
     net->in_geom = yq_act_geom{0, net->w, net->h};
+    net->in_halo_fill = 0;
+    for (int t = -1; t < n; ++t) {
+        const Req &r = req[t + 1];
+        if (r.kind != 2 || (t >= 0 && tensor_of(net, t) != t)) continue;
+        const int fill = r.fill >= 0 ? r.fill : 0;
+        uint8_t *buf = t < 0 ? net->in_nhwc : net->layers[t].out_u8;
+        const int c = t < 0 ? net->c : net->layers[t].out_c;
+        (t < 0 ? net->in_geom : net->layers[t].geom) = r.g;
+        (t < 0 ? net->in_halo_fill : net->layers[t].halo_fill) = fill;
+        // the halo (and any slack around the images) holds the consumers' input zero point (im2col.c:5-14); producers
+        // only ever write the interior (flat convs also rewrite the halo of their output with the same value)
+        cudaMemsetAsync(buf, fill, yq_act_geom_bytes(&r.g, net->batch, c), net->stream);
+    }
+    for (int i = 0; i < n; ++i)   // aliases share their tensor's geometry
+        if (tensor_of(net, i) != i && tensor_of(net, i) >= 0) {
+            net->layers[i].geom = net->layers[tensor_of(net, i)].geom;
+            net->layers[i].halo_fill = net->layers[tensor_of(net, i)].halo_fill;
+        }
     int launches = 1;
     for (int i = 0; i < n; ++i) {
         Layer &l = net->layers[i];
-        if (l.type == L_CONV && net->fusion && i + 1 < n && l.conv) {
-            Layer &p = net->layers[i + 1];
-            const bool pool22 = p.type == L_MAXPOOL && p.size == 2 && p.stride == 2 && p.pad == 1;
-            // rows flavour: needs a halo-padded input, i.e. a producer that can write one and no other reader of that tensor
-            const bool producer_ok = i == 0 || (i >= 2 && net->layers[i - 1].fused_away && net->layers[i - 2].use_rows && !routed_from(net, i - 1));
-            if (pool22 && net->conv_kernel != 0 && yq_conv_rows_supported(l.conv) && producer_ok && !conv_output_needed(net, i)) {
-                l.use_rows = l.fuse_pool = p.fused_away = true;
-                yq_act_geom g;
-                yq_conv_rows_input_geom(l.conv, &g);
-                uint8_t *buf = i == 0 ? net->in_nhwc : net->layers[i - 1].out_u8;
-                (i == 0 ? net->in_geom : net->layers[i - 1].geom) = g;
-                // the halo (and the slack around the image) is the conv's input zero point (im2col.c:5-14); producers
-                // only ever write the interior
-                cudaMemsetAsync(buf, l.zp_in, yq_act_geom_bytes(&g, net->batch, l.c), net->stream);
-            } else if (pool22 && yq_conv_can_fuse_maxpool(l.conv)) {
-                l.fuse_pool = p.fused_away = true;
+        if (l.type == L_CONV && l.conv) {
+            if (rows_ok[i]) {
+                l.use_rows = l.fuse_pool = net->layers[i + 1].fused_away = true;
+            } else if (flat_ok[i]) {
+                l.use_flat = true;
+            } else if (net->fusion && i + 1 < n && yq_conv_can_fuse_maxpool(l.conv)) {
+                Layer &p = net->layers[i + 1];
+                if (p.type == L_MAXPOOL && p.size == 2 && p.stride == 2 && p.pad == 1) l.fuse_pool = p.fused_away = true;
             }
         }
         if (l.fused_away || (l.type == L_ROUTE && l.inputs.size() == 1)) continue;
@@ -313,6 +408,7 @@ int forward_body(yq_network *net, const uint8_t *in_u8_nchw, int *launches, bool
     if (profile) cudaEventRecord(net->prof_events[1], st);
     ++nl;
     const uint8_t *cur = net->in_nhwc;
+    const yq_act_geom *cur_geom = &net->in_geom;
     const float *cur_f32 = nullptr;
     for (size_t i = 0; i < net->layers.size(); ++i) {
         Layer &l = net->layers[i];
@@ -320,6 +416,10 @@ int forward_body(yq_network *net, const uint8_t *in_u8_nchw, int *launches, bool
         case L_CONV:
             if (l.use_rows) {
                 if (yq_forward_convolutional_layer_quant_rows_pool_gpu(l.conv, cur, net->layers[i + 1].out_u8, &net->layers[i + 1].geom, net->batch, st))
+                    return -1;
+            } else if (l.use_flat) {
+                if (yq_forward_convolutional_layer_quant_flat_gpu(l.conv, cur, l.out_u8, l.halo_fill, l.out_f32, net->keep_acc ? l.out_acc : nullptr,
+                                                                  net->batch, st))
                     return -1;
             } else if (l.fuse_pool) {
                 uint8_t *conv_out = conv_output_needed(net, (int)i) ? l.out_u8 : nullptr;
@@ -332,32 +432,40 @@ int forward_body(yq_network *net, const uint8_t *in_u8_nchw, int *launches, bool
             }
             ++nl;
             cur = l.out_u8;
+            cur_geom = &l.geom;
             cur_f32 = l.out_f32;
             break;
         case L_MAXPOOL:
             if (!l.fused_away) {
-                if (yq_forward_maxpool_layer_quant_gpu(cur, l.out_u8, net->batch, l.h, l.w, l.c, l.size, l.stride, l.pad, st)) return -1;
+                if (yq_forward_maxpool_layer_quant_geom_gpu(cur, cur_geom, l.out_u8, &l.geom, net->batch, l.h, l.w, l.c, l.size, l.stride, l.pad, st))
+                    return -1;
                 ++nl;
             }
             cur = l.out_u8;
+            cur_geom = &l.geom;
             break;
         case L_UPSAMPLE:
-            if (yq_forward_upsample_layer_quant_gpu(cur, l.out_u8, net->batch, l.h, l.w, l.c, l.stride, st)) return -1;
+            if (yq_forward_upsample_layer_quant_geom_gpu(cur, cur_geom, l.out_u8, &l.geom, net->batch, l.h, l.w, l.c, l.stride, st)) return -1;
             ++nl;
             cur = l.out_u8;
+            cur_geom = &l.geom;
             break;
         case L_ROUTE:
             if (l.inputs.size() > 1) {
                 const uint8_t *ins[8];
+                yq_act_geom gs[8];
                 int cs[8];
                 for (size_t k = 0; k < l.inputs.size(); ++k) {
                     ins[k] = net->layers[l.inputs[k]].out_u8;
+                    gs[k] = net->layers[l.inputs[k]].geom;
                     cs[k] = net->layers[l.inputs[k]].out_c;
                 }
-                if (yq_forward_route_layer_quant_gpu(ins, cs, (int)l.inputs.size(), l.out_u8, net->batch, l.out_h, l.out_w, st)) return -1;
+                if (yq_forward_route_layer_quant_geom_gpu(ins, gs, cs, (int)l.inputs.size(), l.out_u8, &l.geom, net->batch, l.out_h, l.out_w, st))
+                    return -1;
                 ++nl;
             }   // a single-input route is an alias of its input (no copy)
             cur = l.out_u8;
+            cur_geom = &l.geom;
             break;
         case L_YOLO:
             if (!cur_f32) return yq::fail("layer %zu: yolo layer needs a float input (previous layer must be a quant_stop conv)", i);
@@ -631,19 +739,7 @@ extern "C" yq_network *yq_load_network(const char *cfg, const char *weights, int
             }
             if (prepare_conv(l, (int)i) || build_conv_device(raw, l)) return bail();
         }
-        const int cs = yq::channel_stride(l.out_c);
-        l.u8_bytes = (size_t)raw->batch * l.out_h * l.out_w * cs;
         l.geom = yq_act_geom{0, l.out_w, l.out_h};
-        if (l.type == L_ROUTE && l.inputs.size() == 1) {
-            l.out_u8 = raw->layers[l.inputs[0]].out_u8;   // alias
-        } else if (l.type != L_YOLO) {
-            if (cudaMalloc((void **)&l.out_u8, l.u8_bytes) != cudaSuccess) {
-                yq::fail("cudaMalloc of layer %zu output (%zu bytes) failed", i, l.u8_bytes);
-                return bail();
-            }
-            l.owns_u8 = true;
-            cudaMemset(l.out_u8, 0, l.u8_bytes);
-        }
         if ((l.type == L_CONV && l.quant_stop) || l.type == L_YOLO) {
             l.f32_count = (size_t)raw->batch * l.out_c * l.out_h * l.out_w;
             if (cudaMalloc((void **)&l.out_f32, l.f32_count * sizeof(float)) != cudaSuccess) {
@@ -653,34 +749,41 @@ extern "C" yq_network *yq_load_network(const char *cfg, const char *weights, int
             if (l.type == L_YOLO) raw->out_floats += l.f32_count;
         }
     }
-    // tensors that feed a rows-flavour conv may be switched to its halo-padded geometry by plan(): size them for it
+    // activation buffers: plan() may switch a tensor between its plain form, the flat strip and the padded geometry a
+    // rows-flavour consumer asks for -- size every buffer for the largest of them
+    auto tensor_bytes = [&](int c, int h, int w) -> size_t {
+        const int cs = yq::channel_stride(c);
+        size_t need = (size_t)raw->batch * h * w * cs;
+        yq_act_geom g;
+        yq_act_geom_flat(h, w, &g);
+        const size_t flat = yq_act_geom_bytes(&g, raw->batch, c);
+        if (flat > need) need = flat;
+        for (const Layer &k : raw->layers)   // any rows-flavour conv that could read a tensor of this shape
+            if (k.type == L_CONV && k.conv && k.c == c && k.h == h && k.w == w && yq_conv_rows_supported(k.conv)) {
+                yq_conv_rows_input_geom(k.conv, &g);
+                const size_t rows = yq_act_geom_bytes(&g, raw->batch, c);
+                if (rows > need) need = rows;
+            }
+        return need;
+    };
     for (size_t i = 0; i < raw->layers.size(); ++i) {
         Layer &l = raw->layers[i];
-        if (l.type != L_CONV || !l.conv || !yq_conv_rows_supported(l.conv)) continue;
-        yq_act_geom g;
-        yq_conv_rows_input_geom(l.conv, &g);
-        const size_t need = yq_act_geom_bytes(&g, raw->batch, l.c);
-        if (i == 0) {
-            raw->in_nhwc_bytes = need;
-        } else {
-            Layer &p = raw->layers[i - 1];
-            if (p.owns_u8 && need > p.u8_bytes) {
-                cudaFree(p.out_u8);
-                p.out_u8 = nullptr;
-                p.u8_bytes = need;
-                if (cudaMalloc((void **)&p.out_u8, need) != cudaSuccess) {
-                    yq::fail("cudaMalloc of layer %zu output (%zu bytes) failed", i - 1, need);
-                    return bail();
-                }
-                cudaMemset(p.out_u8, 0, need);
-                for (auto &r : raw->layers)   // single-input routes alias their input's buffer
-                    if (r.type == L_ROUTE && r.inputs.size() == 1 && r.inputs[0] == (int)i - 1) r.out_u8 = p.out_u8;
-            }
+        if (l.type == L_YOLO) continue;
+        if (l.type == L_ROUTE && l.inputs.size() == 1) {
+            l.out_u8 = raw->layers[l.inputs[0]].out_u8;   // alias (its input precedes it: already allocated)
+            l.u8_bytes = raw->layers[l.inputs[0]].u8_bytes;
+            continue;
         }
+        l.u8_bytes = tensor_bytes(l.out_c, l.out_h, l.out_w);
+        if (cudaMalloc((void **)&l.out_u8, l.u8_bytes) != cudaSuccess) {
+            yq::fail("cudaMalloc of layer %zu output (%zu bytes) failed", i, l.u8_bytes);
+            return bail();
+        }
+        l.owns_u8 = true;
+        cudaMemset(l.out_u8, 0, l.u8_bytes);
     }
+    raw->in_nhwc_bytes = tensor_bytes(raw->c, raw->h, raw->w);
     const size_t in_bytes = (size_t)raw->batch * raw->c * raw->h * raw->w;
-    const size_t plain_in = (size_t)raw->batch * raw->h * raw->w * yq::channel_stride(raw->c);
-    if (raw->in_nhwc_bytes < plain_in) raw->in_nhwc_bytes = plain_in;
     if (cudaMalloc((void **)&raw->in_stage_nchw, in_bytes) != cudaSuccess || cudaMalloc((void **)&raw->in_nhwc, raw->in_nhwc_bytes) != cudaSuccess) {
         yq::fail("cudaMalloc of network input failed");
         return bail();
@@ -740,7 +843,7 @@ extern "C" int yq_network_layer_info(const yq_network *net, int i, yq_layer_info
     o->type = l.type; o->c = l.c; o->h = l.h; o->w = l.w; o->out_c = l.out_c; o->out_h = l.out_h; o->out_w = l.out_w;
     o->n = l.n; o->size = l.size; o->stride = l.stride; o->pad = l.pad; o->activation = l.activation;
     o->batch_normalize = l.bn; o->quant_stop_flag = l.quant_stop; o->s_in = l.s_in; o->s_out = l.s_out;
-    o->zp_in = l.zp_in; o->zp_out = l.zp_out; o->kernel = l.conv ? yq_conv_get_kernel(l.conv) : 0;
+    o->zp_in = l.zp_in; o->zp_out = l.zp_out; o->kernel = l.conv ? (l.use_rows ? 3 : (l.use_flat ? 2 : yq_conv_get_kernel(l.conv))) : 0;
     o->classes = l.classes; o->n_anchors = l.n_anchors;
     o->fused = l.type == L_CONV ? (l.use_rows ? 2 : (l.fuse_pool ? 1 : 0)) : (l.fused_away ? 1 : 0);
     return 0;

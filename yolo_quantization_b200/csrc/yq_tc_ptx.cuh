@@ -96,6 +96,11 @@ __device__ __forceinline__ void tma_store_4d(const CUtensorMap *map, const void 
                  "r"(c0), "r"(c1), "r"(c2), "r"(c3)
                  : "memory");
 }
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap *map, const void *smem, int c0, int c1)
+{
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map), "r"(smem_u32(smem)), "r"(c0), "r"(c1)
+                 : "memory");
+}
 __device__ __forceinline__ void tma_store_commit_wait()
 {
     asm volatile("cp.async.bulk.commit_group;" ::: "memory");

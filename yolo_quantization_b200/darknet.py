@@ -219,6 +219,50 @@ class ConvolutionalLayerQuant:
         self.last_rows_raw = (raw, og.pad, og.pitch_w, og.rows_h)
         return out
 
+    @property
+    def flat_supported(self) -> bool:
+        return bool(_lib.load().yq_conv_flat_supported(self.handle))
+
+    def forward_flat(self, x_nchw: np.ndarray, halo_fill: int = 0, want_acc: bool = True) -> Dict[str, np.ndarray]:
+        """The flat-strip flavour: input staged as a flat halo-padded tensor (halo = zp_in), output read back from one.
+        Returns dict(u8, acc, f32 as in forward(), halo_ok=True when every halo byte of the output equals halo_fill)."""
+        lib = _lib.load()
+        b = x_nchw.shape[0]
+        x = np.ascontiguousarray(x_nchw, np.uint8)
+        g = ActGeom()
+        check(lib.yq_act_geom_flat(self.h, self.w, C.byref(g)), "yq_act_geom_flat")
+        cs_in, cs_out = channel_stride(self.c), channel_stride(self.n)
+        din = DeviceBuffer(lib.yq_act_geom_bytes(C.byref(g), b, self.c), zero=False)
+        check(lib.yq_cuda_memset(din.ptr, self.zp_in, din.nbytes, None))
+        src = DeviceBuffer.from_numpy(x)
+        check(lib.yq_nchw_to_nhwc_u8_geom(src.ptr, din.ptr, b, self.c, self.h, self.w, C.byref(g), None))
+        dout = DeviceBuffer(lib.yq_act_geom_bytes(C.byref(g), b, self.n), zero=False)
+        check(lib.yq_cuda_memset(dout.ptr, 0xEE, dout.nbytes, None))
+        dacc = DeviceBuffer(b * self.out_h * self.out_w * cs_out * 4) if want_acc else None
+        df32 = DeviceBuffer(b * self.n * self.out_h * self.out_w * 4) if self.quant_stop_flag else None
+        check(lib.yq_forward_convolutional_layer_quant_flat_gpu(self.handle, din.ptr, dout.ptr, int(halo_fill), df32.ptr if df32 else None,
+                                                                dacc.ptr if dacc else None, b, None),
+              "yq_forward_convolutional_layer_quant_flat_gpu")
+        tmp = DeviceBuffer(b * self.n * self.out_h * self.out_w)
+        check(lib.yq_nhwc_to_nchw_u8_geom(dout.ptr, tmp.ptr, b, self.n, self.out_h, self.out_w, C.byref(g), None))
+        check(lib.yq_stream_synchronize(None))
+        res = {"u8": tmp.pull((b, self.n, self.out_h, self.out_w), np.uint8)}
+        if dacc:
+            res["acc"] = pull_nhwc_i32(dacc, b, self.n, self.out_h, self.out_w)
+        if df32:
+            res["f32"] = df32.pull((b, self.n, self.out_h, self.out_w), np.float32)
+        raw = dout.pull((dout.nbytes // cs_out, cs_out), np.uint8)
+        rows = raw[: b * g.rows_h * g.pitch_w].reshape(b, g.rows_h, g.pitch_w, cs_out).copy()
+        interior = rows[:, 1:1 + self.out_h, 1:1 + self.out_w, :].copy()
+        rows[:, 1:1 + self.out_h, 1:1 + self.out_w, :self.n] = halo_fill
+        tail = raw[b * g.rows_h * g.pitch_w:]
+        res["halo_ok"] = bool((rows[..., :self.n] == halo_fill).all() and (tail[:, :self.n] == halo_fill).all()
+                              and not rows[..., self.n:].any() and not tail[:, self.n:].any() and not interior[..., self.n:].any())
+        for d in (din, src, dout, dacc, df32, tmp):
+            if d:
+                d.free()
+        return res
+
     def free(self) -> None:
         if self.handle:
             _lib.load().yq_free_convolutional_layer_quant(self.handle)
