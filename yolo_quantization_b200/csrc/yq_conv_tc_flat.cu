@@ -21,7 +21,8 @@
 //      store.  Halo positions of the OUTPUT strip are written with the consumer's zero point, so the kernel keeps its
 //      output's halo intact by itself and garbage computed there never escapes.
 //
-// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer, warps 2-5 = epilogue.
+// Warp roles (320 threads): warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer, warps 2-9 = epilogue (two per
+// TMEM lane quarter, half of the channels each: the epilogue of a short-K layer is its critical path).
 // One tile per CTA, two CTAs per SM (one CTA's epilogue overlaps the other's main loop).
 // Restates convolutional_layer.c:694-761 for stride 1, pad = size/2, size in {1, 3}, c % 64 == 0.
 #include <cuda.h>
@@ -29,6 +30,7 @@
 #include <string.h>
 
 #include <map>
+#include <type_traits>
 #include <vector>
 
 #include "yq_common.h"
@@ -39,7 +41,25 @@ using namespace yqtc;
 
 namespace {
 
-constexpr int FL_THREADS = 192;
+// -DYQ_TIMELINE: every CTA records globaltimer (ns) at a few events into yq_flat_timeline[blockIdx.x * 8 + event]
+#ifdef YQ_TIMELINE
+__device__ unsigned long long yq_flat_timeline[8 * 16384];
+__device__ __forceinline__ void tl_mark(int ev)
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    const int b = blockIdx.y * gridDim.x + blockIdx.x;
+    if (b < 16384) yq_flat_timeline[b * 8 + ev] = t;
+}
+#define TL_MARK(ev) tl_mark(ev)
+#else
+#define TL_MARK(ev)
+#endif
+
+__device__ unsigned int yq_flat_arrivals[256];
+
+constexpr int FL_EPI_WARPS = 8;          // two warps per TMEM lane quarter, each takes half of the tile's channels
+constexpr int FL_THREADS = 64 + 32 * FL_EPI_WARPS;
 constexpr int FL_BSTAGES = 3;
 constexpr int FL_ONES = 16;
 
@@ -54,6 +74,7 @@ struct FlatArgs {
     int patch_rows, a_stage_bytes;
     uint32_t halo_word;    // byte the consumer pads with, replicated
     uint32_t magic_w, magic_h;   // ceil(2^32 / (W+1)), ceil(2^32 / (H+1))
+    int n_sm, stagger_ns;        // first-wave stagger (see the kernel)
 };
 
 template <int BN>
@@ -70,22 +91,6 @@ struct FlatSmem {
     static_assert(B_STAGE % 1024 == 0, "stage buffers must keep the 1024-byte swizzle alignment");
     static_assert(128 * BN <= FL_BSTAGES * B_STAGE, "output staging aliases the weight ring");
 };
-
-template <bool HAS_EXTRA>
-__device__ __forceinline__ void fl_epi_chunk(int actm, int sat, const uint32_t (&v)[16], int nsa, const int4 *cq, const double *mc, int zo,
-                                             uint32_t (&packed)[4])
-{
-    int extra[16];
-    if (sat) {
-        if (actm == 0) yq::requant_chunk<0, true, 16, false>(v, nsa, extra, cq, mc, zo, packed);
-        else if (actm == 1) yq::requant_chunk<1, true, 16, false>(v, nsa, extra, cq, mc, zo, packed);
-        else yq::requant_chunk<2, true, 16, false>(v, nsa, extra, cq, mc, zo, packed);
-    } else {
-        if (actm == 0) yq::requant_chunk<0, false, 16, false>(v, nsa, extra, cq, mc, zo, packed);
-        else if (actm == 1) yq::requant_chunk<1, false, 16, false>(v, nsa, extra, cq, mc, zo, packed);
-        else yq::requant_chunk<2, false, 16, false>(v, nsa, extra, cq, mc, zo, packed);
-    }
-}
 
 // SLOW = the variant that also serves the int32 / float side outputs and the saturate switch.
 template <int BN, int KC, bool SLOW>
@@ -110,6 +115,25 @@ __global__ void __launch_bounds__(FL_THREADS, 2) conv_u8_tc_flat_kernel(const __
     const int oc0 = blockIdx.y * BN;
     const int p0 = blockIdx.x * 128;
     const int chunks = a.cpt;
+    if (threadIdx.x == 0) TL_MARK(0);                       // CTA start
+    // Two CTAs share an SM.  Launched together they run in lockstep -- both in the main loop (sharing the tensor pipe), then
+    // both in the epilogue (pipe idle): measured 55 % pipe utilisation on layer 12.  The CTAs that take the SECOND slot of
+    // every SM in the first wave therefore start half a tile period late; later waves inherit the offset because a new CTA
+    // starts when an old one retires.
+    if (threadIdx.x == 0 && a.stagger_ns > 0 && blockIdx.y * gridDim.x + blockIdx.x < 2 * a.n_sm) {
+        // which of the SM's two first-wave CTAs am I?  (a never-reset arrival counter per SM: two CTAs that arrive together get
+        // one even and one odd ticket whatever the count was)
+        uint32_t smid;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        if (atomicAdd(&yq_flat_arrivals[smid & 255], 1u) & 1u) {
+            unsigned long long t0, t1;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+            do {
+                __nanosleep(200);
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+            } while (t1 - t0 < (unsigned long long)a.stagger_ns);
+        }
+    }
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < 2; ++s) {
@@ -126,13 +150,13 @@ __global__ void __launch_bounds__(FL_THREADS, 2) conv_u8_tc_flat_kernel(const __
     if (warp == 1) tmem_alloc<fl_tmem_cols<BN>()>(tmem_slot);
     if (warp >= 2) {
         const int t = threadIdx.x - 64;
-        for (int i = t; i < BN; i += 128) {
+        for (int i = t; i < BN; i += 32 * FL_EPI_WARPS) {
             s_q[i] = __ldg(a.ep.chanq + oc0 + i);
             s_mc[i] = __ldg(a.ep.mcomb + oc0 + i);
         }
         for (int s = 0; s < FL_BSTAGES; ++s) {   // the 16 all-ones filter rows behind the TMA-written BN rows of every stage
             uint32_t *ones = (uint32_t *)(sB + s * L::B_STAGE + L::B_BYTES);
-            for (int i = t; i < FL_ONES * KC / 4; i += 128) ones[i] = 0x01010101u;
+            for (int i = t; i < FL_ONES * KC / 4; i += 32 * FL_EPI_WARPS) ones[i] = 0x01010101u;
         }
         fence_proxy_async();
     }
@@ -145,53 +169,66 @@ __global__ void __launch_bounds__(FL_THREADS, 2) conv_u8_tc_flat_kernel(const __
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    if (threadIdx.x == 0) TL_MARK(1);                       // setup done
 
     if (warp == 0) {
-        // ===================== TMA producer =====================
-        if (lane == 0) {
-            int it = 0;
-            for (int c = 0; c < chunks; ++c) {
-                const int sa = c & 1;
-                mbar_wait(&a_empty[sa], ((c >> 1) & 1) ^ 1);
+        // ===================== TMA producer (whole warp in uniform control flow, one elected lane issues) =====================
+        int it = 0;
+        for (int c = 0; c < chunks; ++c) {
+            const int sa = c & 1;
+            mbar_wait(&a_empty[sa], ((c >> 1) & 1) ^ 1);
+            if (elect_one()) {
                 mbar_expect_tx(&a_full[sa], (uint32_t)(a.patch_rows * KC));
                 tma_load_2d(sA + sa * a.a_stage_bytes, &tmA, &a_full[sa], c * KC, p0 + a.q_off);
-                for (int tap = 0; tap < a.taps; ++tap, ++it) {
-                    const int s = it % FL_BSTAGES;
-                    mbar_wait(&b_empty[s], ((it / FL_BSTAGES) & 1) ^ 1);
+            }
+            for (int tap = 0; tap < a.taps; ++tap, ++it) {
+                const int s = it % FL_BSTAGES;
+                mbar_wait(&b_empty[s], ((it / FL_BSTAGES) & 1) ^ 1);
+                if (elect_one()) {
+#ifdef YQ_TIMELINE
+                    if (a.stagger_ns == -1 && tap > 0) {     // experiment: skip the weight loads of taps 1.. (results are garbage)
+                        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&b_full[s])) : "memory");
+                        continue;
+                    }
+#endif
                     mbar_expect_tx(&b_full[s], (uint32_t)(BN * KC));
                     tma_load_2d(sB + s * L::B_STAGE, &tmB, &b_full[s], tap * a.CS + c * KC, oc0);
                 }
             }
         }
     } else if (warp == 1) {
-        // ===================== MMA issuer =====================
-        if (lane == 0) {
-            constexpr uint32_t idesc = make_idesc(BN + FL_ONES);
-            const int pitch = a.W + 1;
-            int it = 0;
-            for (int c = 0; c < chunks; ++c) {
-                const int sa = c & 1;
-                mbar_wait(&a_full[sa], (c >> 1) & 1);
-                const uint32_t patch = smem_u32(sA + sa * a.a_stage_bytes);
-                int ky = 0, kx = 0;
-                for (int tap = 0; tap < a.taps; ++tap, ++it) {
-                    const int s = it % FL_BSTAGES;
-                    mbar_wait(&b_full[s], (it / FL_BSTAGES) & 1);
-                    tc_fence_after();
-                    const uint64_t da = make_desc<KC>(patch + (uint32_t)((ky * pitch + kx) * KC));   // row-shifted start, base_offset 0
+        // ===================== MMA issuer (same form) =====================
+        constexpr uint32_t idesc = make_idesc(BN + FL_ONES);
+        const uint32_t row_step = (uint32_t)((a.W + 1 - a.size) * KC);   // from the last tap of a filter row to the first of the next
+        int it = 0;
+        for (int c = 0; c < chunks; ++c) {
+            const int sa = c & 1;
+            mbar_wait(&a_full[sa], (c >> 1) & 1);
+            uint32_t tap_addr = smem_u32(sA + sa * a.a_stage_bytes);    // row-shifted descriptor start of the current tap, base_offset 0
+            int kx = 0;
+            for (int tap = 0; tap < a.taps; ++tap, ++it) {
+                const int s = it % FL_BSTAGES;
+                mbar_wait(&b_full[s], (it / FL_BSTAGES) & 1);
+                tc_fence_after();
+                if (it == 0 && lane == 0) TL_MARK(2);       // first operands landed
+                if (elect_one()) {
+                    const uint64_t da = make_desc<KC>(tap_addr);
                     const uint64_t db = make_desc<KC>(smem_u32(sB + s * L::B_STAGE));
 #pragma unroll
                     for (int k = 0; k < KC / 32; ++k) umma_i8(tmem_base, da + 2 * k, db + 2 * k, idesc, (it | k) ? 1u : 0u);
                     umma_commit(&b_empty[s]);
-                    if (++kx == a.size) { kx = 0; ++ky; }
                 }
-                umma_commit(&a_empty[sa]);
+                tap_addr += KC;
+                if (++kx == a.size) { kx = 0; tap_addr += row_step; }
             }
-            umma_commit(accum_full);
+            if (elect_one()) umma_commit(&a_empty[sa]);
         }
+        if (elect_one()) umma_commit(accum_full);
+        if (lane == 0) TL_MARK(3);                          // last MMA issued
     } else {
         // ===================== epilogue =====================
         const int q = warp & 3;                 // TMEM lane quarter this warp may access
+        const int half = (warp - 2) >> 2;       // which half of the tile's channels this warp requantizes
         const int r = q * 32 + lane;            // tile row = TMEM lane = position p0 + r
         const int p = p0 + r;
         // position -> (image, y, x); halo positions (and positions past the last image) are not pixels
@@ -200,51 +237,73 @@ __global__ void __launch_bounds__(FL_THREADS, 2) conv_u8_tc_flat_kernel(const __
         const int n = (int)__umulhi((uint32_t)row, a.magic_h);
         const int y1 = row - n * (a.H + 1);
         const bool valid = p < a.NP && col >= 1 && y1 >= 1;
+        uint8_t *stage_out = sB;                // aliases the weight ring (all MMAs have completed)
+        const bool side = SLOW && ((a.out_acc != nullptr) || (a.out_f32 != nullptr));
+        const size_t pix = ((size_t)n * a.H + (y1 - 1)) * a.W + (col - 1);
+        constexpr int HALF = BN / 2, NCHUNK = HALF / 16;
+        const int cbeg = half * HALF;
         mbar_wait(accum_full, 0);
         tc_fence_after();
+        if (threadIdx.x == 64) TL_MARK(4);                  // accumulator complete
         const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
-        const int nsa = -(int)tmem_ld1(trow + BN);   // minus the position's activation sum (ones-row columns)
-        uint8_t *stage_out = sB;                // aliases the weight ring (all MMAs have completed)
-        const int actm = yq::act_mode(a.ep.act);
-        const bool side = SLOW && ((a.out_acc != nullptr) || (a.out_f32 != nullptr));
-        const int sat = SLOW ? a.ep.saturate : 0;
-        const size_t pix = ((size_t)n * a.H + (y1 - 1)) * a.W + (col - 1);
-#pragma unroll 1
-        for (int c0 = 0; c0 < BN; c0 += 16) {
-            uint32_t v[16];
-            tmem_ld16(trow + c0, v);
-            uint32_t packed[4];
-            fl_epi_chunk<false>(actm, sat, v, nsa, s_q + c0, s_mc + c0, a.ep.zp_out, packed);
-            if (!valid) packed[0] = packed[1] = packed[2] = packed[3] = a.halo_word;
-            yq::mask_pad_channels<16>(packed, a.N - (oc0 + c0));
-            if (SLOW && side && valid) {   // parity / quant_stop side outputs (not on the throughput path)
+        uint32_t vbuf[2][16];
+        tmem_ld16_issue(trow + cbeg, vbuf[0]);
+        const int nsa = -(int)tmem_ld1(trow + BN);   // minus the position's activation sum (ones-row columns); also completes the load above
+        auto run = [&](auto actm_tag, auto sat_tag) {
+            constexpr int ACTM = decltype(actm_tag)::value;
+            constexpr bool SAT = decltype(sat_tag)::value;
 #pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    const int oc = oc0 + c0 + j;
-                    if (oc < a.N) {
-                        if (a.out_acc) a.out_acc[pix * a.CSO + oc] = (int)v[j] + s_q[c0 + j].y * nsa;
-                        if (a.out_f32) {
-                            const uint8_t u = (uint8_t)(packed[j / 4] >> (8 * (j % 4)));
-                            a.out_f32[((size_t)n * a.N + oc) * a.H * a.W + (size_t)(y1 - 1) * a.W + (col - 1)] = yq::dequant_f32(a.ep, u);
+            for (int ch = 0; ch < NCHUNK; ++ch) {
+                const int c0 = cbeg + 16 * ch;
+                uint32_t(&v)[16] = vbuf[ch & 1];
+                if (ch + 1 < NCHUNK) tmem_ld16_issue(trow + c0 + 16, vbuf[(ch + 1) & 1]);   // in flight while this chunk is requantized
+                uint32_t packed[4];
+                int extra[16];
+                yq::requant_chunk<ACTM, SAT, 16, false>(v, nsa, extra, s_q + c0, s_mc + c0, a.ep.zp_out, packed);
+                if (!valid) packed[0] = packed[1] = packed[2] = packed[3] = a.halo_word;
+                yq::mask_pad_channels<16>(packed, a.N - (oc0 + c0));
+                if (SLOW && side && valid) {   // parity / quant_stop side outputs (not on the throughput path)
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        const int oc = oc0 + c0 + j;
+                        if (oc < a.N) {
+                            if (a.out_acc) a.out_acc[pix * a.CSO + oc] = (int)v[j] + s_q[c0 + j].y * nsa;
+                            if (a.out_f32) {
+                                const uint8_t u = (uint8_t)(packed[j / 4] >> (8 * (j % 4)));
+                                a.out_f32[((size_t)n * a.N + oc) * a.H * a.W + (size_t)(y1 - 1) * a.W + (col - 1)] = yq::dequant_f32(a.ep, u);
+                            }
                         }
                     }
                 }
+                {   // swizzled staging (matches the TMA-store tensor map): 16-byte chunk index XOR row bits
+                    const int chunk = c0 / 16;
+                    int sw;
+                    if (BN >= 128) sw = chunk ^ (r & 7);
+                    else if (BN == 64) sw = chunk ^ ((r >> 1) & 3);
+                    else sw = chunk ^ ((r >> 2) & 1);
+                    *reinterpret_cast<uint4 *>(stage_out + (size_t)r * BN + sw * 16) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+                }
+                if (ch + 1 < NCHUNK) tmem_ld_wait16(vbuf[(ch + 1) & 1]);
             }
-            {   // swizzled staging (matches the TMA-store tensor map): 16-byte chunk index XOR row bits
-                const int chunk = c0 / 16;
-                int sw;
-                if (BN >= 128) sw = chunk ^ (r & 7);
-                else if (BN == 64) sw = chunk ^ ((r >> 1) & 3);
-                else sw = chunk ^ ((r >> 2) & 1);
-                *reinterpret_cast<uint4 *>(stage_out + (size_t)r * BN + sw * 16) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
-            }
+        };
+        const int actm = yq::act_mode(a.ep.act);
+        if (SLOW && a.ep.saturate) {
+            if (actm == 0) run(std::integral_constant<int, 0>{}, std::true_type{});
+            else if (actm == 1) run(std::integral_constant<int, 1>{}, std::true_type{});
+            else run(std::integral_constant<int, 2>{}, std::true_type{});
+        } else {
+            if (actm == 0) run(std::integral_constant<int, 0>{}, std::false_type{});
+            else if (actm == 1) run(std::integral_constant<int, 1>{}, std::false_type{});
+            else run(std::integral_constant<int, 2>{}, std::false_type{});
         }
         tc_fence_before();
         fence_proxy_async();
-        asm volatile("bar.sync 1, 128;" ::: "memory");   // the four epilogue warps only
+        asm volatile("bar.sync 1, %0;" ::"n"(32 * FL_EPI_WARPS) : "memory");   // the epilogue warps only
         if (threadIdx.x == 64) {
+            TL_MARK(5);                                     // epilogue math done
             tma_store_2d(&tmO, stage_out, oc0, p0);
             tma_store_commit_wait();
+            TL_MARK(6);                                     // store drained
         }
     }
     tc_fence_before();
@@ -414,6 +473,21 @@ int yq_tc_flat_forward(yq_conv_layer *l, void *state, const uint8_t *in_flat, ui
     a.magic_w = (uint32_t)((0x100000000ull + W1 - 1) / W1);
     a.magic_h = (uint32_t)((0x100000000ull + H1 - 1) / H1);
     dim3 grid((unsigned)((rows_alloc + 127) / 128), st->n_pad / st->BN);
+    {
+        static int n_sm = 0, want = -1;
+        if (!n_sm) {
+            int dev = 0;
+            YQ_CUDA(cudaGetDevice(&dev));
+            YQ_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
+            const char *e = getenv("YQ_FLAT_STAGGER");      // 0 disables the first-wave stagger (A/B measurements)
+            want = e ? atoi(e) : 1;
+        }
+        a.n_sm = n_sm;
+        // half of one CTA's period: main loop alone on the pipe (N/2 clocks per MMA at ~1.9 GHz) + epilogue + prologue
+        const double main_ns = (double)a.taps * a.cpt * (st->KC / 32) * ((st->BN + FL_ONES) / 2) / 1.9;
+        a.stagger_ns = want && (long long)grid.x * grid.y > 2LL * n_sm ? (int)((main_ns + 3500.0) / 2.0) : 0;
+        if (want < 0) a.stagger_ns = -1;
+    }
     const CUtensorMap &tmA = it->second.first, &tmO = it->second.second;
 #define YQ_FL(BN_, KC_) return fl_launch<BN_, KC_>(st, tmA, tmO, a, grid, stream)
     if (st->KC == 128) {
@@ -427,3 +501,10 @@ int yq_tc_flat_forward(yq_conv_layer *l, void *state, const uint8_t *in_flat, ui
     }
 #undef YQ_FL
 }
+
+#ifdef YQ_TIMELINE
+extern "C" __attribute__((visibility("default"))) int yq_debug_flat_timeline(void *host, size_t bytes)
+{
+    return cudaMemcpyFromSymbol(host, yq_flat_timeline, bytes < sizeof(yq_flat_timeline) ? bytes : sizeof(yq_flat_timeline)) == cudaSuccess ? 0 : -1;
+}
+#endif
