@@ -23,7 +23,7 @@
 //
 // Warp roles (320 threads): warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer, warps 2-9 = epilogue (two per
 // TMEM lane quarter, half of the channels each: the epilogue of a short-K layer is its critical path).
-// Persistent, one CTA per SM, two TMEM accumulators (see the kernel).
+// One tile per CTA, two CTAs per SM (one CTA's epilogue overlaps the other's main loop).
 // Restates convolutional_layer.c:694-761 for stride 1, pad = size/2, size in {1, 3}, c % 64 == 0.
 #include <cuda.h>
 #include <cuda_runtime.h>
@@ -41,10 +41,26 @@ using namespace yqtc;
 
 namespace {
 
+// -DYQ_TIMELINE: every CTA records globaltimer (ns) at a few events into yq_flat_timeline[blockIdx.x * 8 + event]
+#ifdef YQ_TIMELINE
+__device__ unsigned long long yq_flat_timeline[8 * 16384];
+__device__ __forceinline__ void tl_mark(int ev)
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    const int b = blockIdx.y * gridDim.x + blockIdx.x;
+    if (b < 16384) yq_flat_timeline[b * 8 + ev] = t;
+}
+#define TL_MARK(ev) tl_mark(ev)
+#else
+#define TL_MARK(ev)
+#endif
+
+__device__ unsigned int yq_flat_arrivals[256];
+
 constexpr int FL_EPI_WARPS = 8;          // two warps per TMEM lane quarter, each takes half of the tile's channels
 constexpr int FL_THREADS = 64 + 32 * FL_EPI_WARPS;
-constexpr int FL_ASTAGES = 2;
-constexpr int FL_MAX_BSTAGES = 8;
+constexpr int FL_BSTAGES = 3;
 constexpr int FL_ONES = 16;
 
 struct FlatArgs {
@@ -56,84 +72,89 @@ struct FlatArgs {
     int size, taps, cpt /* KC-chunks per tap */, CS;
     int q_off;             // first patch position relative to the tile's first position: -(pad*(W+1) + pad)
     int patch_rows, a_stage_bytes;
-    int b_stages, b_group; // weight ring: b_stages stages, released in groups of b_group (one tcgen05.commit per group)
-    int m_tiles, num_tiles;   // tile t -> (n-tile t / m_tiles, m-tile t % m_tiles): concurrent CTAs share the weight slab in L2
     uint32_t halo_word;    // byte the consumer pads with, replicated
-    uint32_t magic_w, magic_h, magic_m;   // ceil(2^32 / (W+1)), ceil(2^32 / (H+1)), ceil(2^32 / m_tiles)
+    uint32_t magic_w, magic_h;   // ceil(2^32 / (W+1)), ceil(2^32 / (H+1))
+    int n_sm, stagger_ns;        // first-wave stagger (see the kernel)
 };
 
 template <int BN>
 __host__ __device__ constexpr int fl_tmem_cols()
 {
-    return 2 * (BN + FL_ONES) <= 128 ? 128 : 2 * (BN + FL_ONES) <= 256 ? 256 : 512;   // two accumulators
+    return BN + FL_ONES <= 32 ? 32 : BN + FL_ONES <= 64 ? 64 : BN + FL_ONES <= 128 ? 128 : 256;
 }
 
 template <int BN, int KC>
 struct FlatSmem {
     static constexpr int B_BYTES = BN * KC;
     static constexpr int B_STAGE = (BN + FL_ONES) * KC;          // multiple of 1024 for every instantiated (BN, KC)
-    static constexpr int OUT_BYTES = 128 * BN;
     static constexpr int PARAM_BYTES = BN * 24;
-    static_assert(B_STAGE % 1024 == 0 && OUT_BYTES % 1024 == 0, "stage buffers must keep the 1024-byte swizzle alignment");
+    static_assert(B_STAGE % 1024 == 0, "stage buffers must keep the 1024-byte swizzle alignment");
+    static_assert(128 * BN <= FL_BSTAGES * B_STAGE, "output staging aliases the weight ring");
 };
 
-__device__ __forceinline__ void mbar_arrive_plain(uint64_t *bar)
-{
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-
-// PERSISTENT: one CTA per SM walks tiles blockIdx.x, blockIdx.x + gridDim.x, ...  Two TMEM accumulators: the MMA warp
-// starts tile i+1 while the eight epilogue warps drain tile i, and the producer warp runs ahead across tile borders.
-// What was measured on B200 to get here (tools/probes/, -DYQ_TIMELINE history in git):
-//   * kind::i8 M=128 K=32 SS MMAs run at N/2 clocks each, dependent accumulation included -- one stream can fill the pipe;
-//   * every tcgen05.commit costs a 70-100 clock pipe bubble, so weight stages are released in GROUPS (one commit per group);
-//   * under `if (lane == 0)` the compiler wraps each UTCIMMA in an ELECT / R2UR loop and a single issuing warp becomes the
-//     limit: all issue loops are warp-uniform with elect.sync;
-//   * two co-resident one-tile CTAs run in lockstep (both in the main loop, then both in the epilogue: 55 % pipe use).
 // SLOW = the variant that also serves the int32 / float side outputs and the saturate switch.
 template <int BN, int KC, bool SLOW>
-__global__ void __launch_bounds__(FL_THREADS, 1) conv_u8_tc_flat_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+__global__ void __launch_bounds__(FL_THREADS, 2) conv_u8_tc_flat_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                                                                     const __grid_constant__ CUtensorMap tmO, const FlatArgs a)
 {
     using L = FlatSmem<BN, KC>;
-    constexpr int NACC = BN + FL_ONES;
     extern __shared__ __align__(16) uint8_t smem_raw[];
     uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-    uint8_t *sA = smem;                                              // FL_ASTAGES patch stages of a.a_stage_bytes
-    uint8_t *sB = sA + FL_ASTAGES * a.a_stage_bytes;                 // a.b_stages weight stages (+ constant ones rows)
-    uint8_t *sOut = sB + a.b_stages * L::B_STAGE;                    // output staging tile
-    int4 *s_q = (int4 *)(sOut + L::OUT_BYTES);                       // {bias, zw, 2*M0, shift} of the current n-tile
+    uint8_t *sA = smem;                                     // 2 patch stages of a.a_stage_bytes
+    uint8_t *sB = smem + 2 * a.a_stage_bytes;               // FL_BSTAGES weight stages (+ constant ones rows)
+    int4 *s_q = (int4 *)(sB + FL_BSTAGES * L::B_STAGE);     // {bias, zw, 2*M0, shift}
     double *s_mc = (double *)(s_q + BN);
     uint64_t *a_full = (uint64_t *)(s_mc + BN);
-    uint64_t *a_empty = a_full + FL_ASTAGES;
-    uint64_t *b_full = a_empty + FL_ASTAGES;
-    uint64_t *b_empty = b_full + FL_MAX_BSTAGES;                     // one per GROUP of stages
-    uint64_t *acc_full = b_empty + FL_MAX_BSTAGES;
-    uint64_t *acc_empty = acc_full + 2;
-    uint32_t *tmem_slot = (uint32_t *)(acc_empty + 2);
+    uint64_t *a_empty = a_full + 2;
+    uint64_t *b_full = a_empty + 2;
+    uint64_t *b_empty = b_full + FL_BSTAGES;
+    uint64_t *accum_full = b_empty + FL_BSTAGES;
+    uint32_t *tmem_slot = (uint32_t *)(accum_full + 1);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int chunks = a.cpt, nbs = a.b_stages, grp = a.b_group;
+    const int oc0 = blockIdx.y * BN;
+    const int p0 = blockIdx.x * 128;
+    const int chunks = a.cpt;
+    if (threadIdx.x == 0) TL_MARK(0);                       // CTA start
+    // Two CTAs share an SM.  Launched together they run in lockstep -- both in the main loop (sharing the tensor pipe), then
+    // both in the epilogue (pipe idle): measured 55 % pipe utilisation on layer 12.  The CTAs that take the SECOND slot of
+    // every SM in the first wave therefore start half a tile period late; later waves inherit the offset because a new CTA
+    // starts when an old one retires.
+    if (threadIdx.x == 0 && a.stagger_ns > 0 && blockIdx.y * gridDim.x + blockIdx.x < 2 * a.n_sm) {
+        // which of the SM's two first-wave CTAs am I?  (a never-reset arrival counter per SM: two CTAs that arrive together get
+        // one even and one odd ticket whatever the count was)
+        uint32_t smid;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        if (atomicAdd(&yq_flat_arrivals[smid & 255], 1u) & 1u) {
+            unsigned long long t0, t1;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+            do {
+                __nanosleep(200);
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+            } while (t1 - t0 < (unsigned long long)a.stagger_ns);
+        }
+    }
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < FL_ASTAGES; ++s) {
+        for (int s = 0; s < 2; ++s) {
             mbar_init(&a_full[s], 1);
             mbar_init(&a_empty[s], 1);
         }
-        for (int s = 0; s < FL_MAX_BSTAGES; ++s) {
+        for (int s = 0; s < FL_BSTAGES; ++s) {
             mbar_init(&b_full[s], 1);
             mbar_init(&b_empty[s], 1);
         }
-        for (int s = 0; s < 2; ++s) {
-            mbar_init(&acc_full[s], 1);
-            mbar_init(&acc_empty[s], FL_EPI_WARPS);
-        }
+        mbar_init(accum_full, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) tmem_alloc<fl_tmem_cols<BN>()>(tmem_slot);
     if (warp >= 2) {
         const int t = threadIdx.x - 64;
-        for (int s = 0; s < nbs; ++s) {   // the 16 all-ones filter rows behind the TMA-written BN rows of every stage
+        for (int i = t; i < BN; i += 32 * FL_EPI_WARPS) {
+            s_q[i] = __ldg(a.ep.chanq + oc0 + i);
+            s_mc[i] = __ldg(a.ep.mcomb + oc0 + i);
+        }
+        for (int s = 0; s < FL_BSTAGES; ++s) {   // the 16 all-ones filter rows behind the TMA-written BN rows of every stage
             uint32_t *ones = (uint32_t *)(sB + s * L::B_STAGE + L::B_BYTES);
             for (int i = t; i < FL_ONES * KC / 4; i += 32 * FL_EPI_WARPS) ones[i] = 0x01010101u;
         }
@@ -148,165 +169,142 @@ __global__ void __launch_bounds__(FL_THREADS, 1) conv_u8_tc_flat_kernel(const __
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    if (threadIdx.x == 0) TL_MARK(1);                       // setup done
 
     if (warp == 0) {
         // ===================== TMA producer (whole warp in uniform control flow, one elected lane issues) =====================
-        int sa = 0, s = 0;
-        uint32_t pha = 0, phb = 0;          // ring phases; they carry across tiles
-        for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
-            const int nt = a.m_tiles == 1 ? tile : (int)__umulhi((uint32_t)tile, a.magic_m), mt = tile - nt * a.m_tiles;
-            const int p0 = mt * 128, oc0 = nt * BN;
-            for (int c = 0; c < chunks; ++c) {
-                mbar_wait(&a_empty[sa], pha ^ 1);
+        int it = 0;
+        for (int c = 0; c < chunks; ++c) {
+            const int sa = c & 1;
+            mbar_wait(&a_empty[sa], ((c >> 1) & 1) ^ 1);
+            if (elect_one()) {
+                mbar_expect_tx(&a_full[sa], (uint32_t)(a.patch_rows * KC));
+                tma_load_2d(sA + sa * a.a_stage_bytes, &tmA, &a_full[sa], c * KC, p0 + a.q_off);
+            }
+            for (int tap = 0; tap < a.taps; ++tap, ++it) {
+                const int s = it % FL_BSTAGES;
+                mbar_wait(&b_empty[s], ((it / FL_BSTAGES) & 1) ^ 1);
                 if (elect_one()) {
-                    mbar_expect_tx(&a_full[sa], (uint32_t)(a.patch_rows * KC));
-                    tma_load_2d(sA + sa * a.a_stage_bytes, &tmA, &a_full[sa], c * KC, p0 + a.q_off);
-                }
-                if (++sa == FL_ASTAGES) { sa = 0; pha ^= 1; }
-                for (int tap = 0; tap < a.taps; ++tap) {
-                    if (s % grp == 0) mbar_wait(&b_empty[s / grp], phb ^ 1);    // the whole group s .. s+grp-1 is free
-                    if (elect_one()) {
-                        mbar_expect_tx(&b_full[s], (uint32_t)(BN * KC));
-                        tma_load_2d(sB + s * L::B_STAGE, &tmB, &b_full[s], tap * a.CS + c * KC, oc0);
+#ifdef YQ_TIMELINE
+                    if (a.stagger_ns == -1 && tap > 0) {     // experiment: skip the weight loads of taps 1.. (results are garbage)
+                        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&b_full[s])) : "memory");
+                        continue;
                     }
-                    if (++s == nbs) { s = 0; phb ^= 1; }
+#endif
+                    mbar_expect_tx(&b_full[s], (uint32_t)(BN * KC));
+                    tma_load_2d(sB + s * L::B_STAGE, &tmB, &b_full[s], tap * a.CS + c * KC, oc0);
                 }
             }
         }
     } else if (warp == 1) {
         // ===================== MMA issuer (same form) =====================
-        constexpr uint32_t idesc = make_idesc(NACC);
+        constexpr uint32_t idesc = make_idesc(BN + FL_ONES);
         const uint32_t row_step = (uint32_t)((a.W + 1 - a.size) * KC);   // from the last tap of a filter row to the first of the next
-        int sa = 0, s = 0;
-        uint32_t pha = 0, phb = 0, it = 0;
-        for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x, ++it) {
-            const int buf = it & 1;
-            mbar_wait(&acc_empty[buf], ((it >> 1) & 1) ^ 1);      // the epilogue has drained this accumulator
-            tc_fence_after();
-            const uint32_t acc = tmem_base + buf * NACC;
-            uint32_t accumulate = 0;
-            for (int c = 0; c < chunks; ++c) {
-                mbar_wait(&a_full[sa], pha);
-                uint32_t tap_addr = smem_u32(sA + sa * a.a_stage_bytes);    // row-shifted descriptor start of the current tap, base_offset 0
-                int kx = 0;
-                for (int tap = 0; tap < a.taps; ++tap) {
-                    mbar_wait(&b_full[s], phb);
-                    tc_fence_after();
-                    if (elect_one()) {
-                        const uint64_t da = make_desc<KC>(tap_addr);
-                        const uint64_t db = make_desc<KC>(smem_u32(sB + s * L::B_STAGE));
+        int it = 0;
+        for (int c = 0; c < chunks; ++c) {
+            const int sa = c & 1;
+            mbar_wait(&a_full[sa], (c >> 1) & 1);
+            uint32_t tap_addr = smem_u32(sA + sa * a.a_stage_bytes);    // row-shifted descriptor start of the current tap, base_offset 0
+            int kx = 0;
+            for (int tap = 0; tap < a.taps; ++tap, ++it) {
+                const int s = it % FL_BSTAGES;
+                mbar_wait(&b_full[s], (it / FL_BSTAGES) & 1);
+                tc_fence_after();
+                if (it == 0 && lane == 0) TL_MARK(2);       // first operands landed
+                if (elect_one()) {
+                    const uint64_t da = make_desc<KC>(tap_addr);
+                    const uint64_t db = make_desc<KC>(smem_u32(sB + s * L::B_STAGE));
 #pragma unroll
-                        for (int k = 0; k < KC / 32; ++k) umma_i8(acc, da + 2 * k, db + 2 * k, idesc, (k == 0) ? accumulate : 1u);
-                        if (s % grp == grp - 1) umma_commit(&b_empty[s / grp]);
-                    }
-                    accumulate = 1;
-                    tap_addr += KC;
-                    if (++kx == a.size) { kx = 0; tap_addr += row_step; }
-                    if (++s == nbs) { s = 0; phb ^= 1; }
+                    for (int k = 0; k < KC / 32; ++k) umma_i8(tmem_base, da + 2 * k, db + 2 * k, idesc, (it | k) ? 1u : 0u);
+                    umma_commit(&b_empty[s]);
                 }
-                if (elect_one()) umma_commit(&a_empty[sa]);
-                if (++sa == FL_ASTAGES) { sa = 0; pha ^= 1; }
+                tap_addr += KC;
+                if (++kx == a.size) { kx = 0; tap_addr += row_step; }
             }
-            if (elect_one()) umma_commit(&acc_full[buf]);
+            if (elect_one()) umma_commit(&a_empty[sa]);
         }
+        if (elect_one()) umma_commit(accum_full);
+        if (lane == 0) TL_MARK(3);                          // last MMA issued
     } else {
         // ===================== epilogue =====================
         const int q = warp & 3;                 // TMEM lane quarter this warp may access
         const int half = (warp - 2) >> 2;       // which half of the tile's channels this warp requantizes
         const int r = q * 32 + lane;            // tile row = TMEM lane = position p0 + r
-        const int et = threadIdx.x - 64;
+        const int p = p0 + r;
+        // position -> (image, y, x); halo positions (and positions past the last image) are not pixels
+        const int row = (int)__umulhi((uint32_t)p, a.magic_w);
+        const int col = p - row * (a.W + 1);
+        const int n = (int)__umulhi((uint32_t)row, a.magic_h);
+        const int y1 = row - n * (a.H + 1);
+        const bool valid = p < a.NP && col >= 1 && y1 >= 1;
+        uint8_t *stage_out = sB;                // aliases the weight ring (all MMAs have completed)
         const bool side = SLOW && ((a.out_acc != nullptr) || (a.out_f32 != nullptr));
+        const size_t pix = ((size_t)n * a.H + (y1 - 1)) * a.W + (col - 1);
         constexpr int HALF = BN / 2, NCHUNK = HALF / 16;
         const int cbeg = half * HALF;
-        const int actm = yq::act_mode(a.ep.act);
-        int cur_nt = -1;
-        uint32_t it = 0;
-        for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x, ++it) {
-            const int nt = a.m_tiles == 1 ? tile : (int)__umulhi((uint32_t)tile, a.magic_m), mt = tile - nt * a.m_tiles;
-            const int p0 = mt * 128, oc0 = nt * BN;
-            const int buf = it & 1;
-            // the previous tile's TMA store must have finished reading the staging tile; parameters follow the n-tile
-            if (et == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-            if (nt != cur_nt) {
-                for (int i = et; i < BN; i += 32 * FL_EPI_WARPS) {
-                    s_q[i] = __ldg(a.ep.chanq + oc0 + i);
-                    s_mc[i] = __ldg(a.ep.mcomb + oc0 + i);
-                }
-                cur_nt = nt;
-            }
-            asm volatile("bar.sync 1, %0;" ::"n"(32 * FL_EPI_WARPS) : "memory");
-            // position -> (image, y, x); halo positions (and positions past the last image) are not pixels
-            const int p = p0 + r;
-            const int row = (int)__umulhi((uint32_t)p, a.magic_w);
-            const int col = p - row * (a.W + 1);
-            const int n = (int)__umulhi((uint32_t)row, a.magic_h);
-            const int y1 = row - n * (a.H + 1);
-            const bool valid = p < a.NP && col >= 1 && y1 >= 1;
-            const size_t pix = ((size_t)n * a.H + (y1 - 1)) * a.W + (col - 1);
-            mbar_wait(&acc_full[buf], (it >> 1) & 1);
-            tc_fence_after();
-            const uint32_t trow = tmem_base + buf * NACC + ((uint32_t)(q * 32) << 16);
-            uint32_t vbuf[2][16];
-            tmem_ld16_issue(trow + cbeg, vbuf[0]);
-            const int nsa = -(int)tmem_ld1(trow + BN);   // minus the position's activation sum (ones-row columns); also completes the load above
-            auto run = [&](auto actm_tag, auto sat_tag) {
-                constexpr int ACTM = decltype(actm_tag)::value;
-                constexpr bool SAT = decltype(sat_tag)::value;
+        mbar_wait(accum_full, 0);
+        tc_fence_after();
+        if (threadIdx.x == 64) TL_MARK(4);                  // accumulator complete
+        const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
+        uint32_t vbuf[2][16];
+        tmem_ld16_issue(trow + cbeg, vbuf[0]);
+        const int nsa = -(int)tmem_ld1(trow + BN);   // minus the position's activation sum (ones-row columns); also completes the load above
+        auto run = [&](auto actm_tag, auto sat_tag) {
+            constexpr int ACTM = decltype(actm_tag)::value;
+            constexpr bool SAT = decltype(sat_tag)::value;
 #pragma unroll
-                for (int ch = 0; ch < NCHUNK; ++ch) {
-                    const int c0 = cbeg + 16 * ch;
-                    uint32_t(&v)[16] = vbuf[ch & 1];
-                    if (ch + 1 < NCHUNK) tmem_ld16_issue(trow + c0 + 16, vbuf[(ch + 1) & 1]);   // in flight while this chunk is requantized
-                    uint32_t packed[4];
-                    int extra[16];
-                    yq::requant_chunk<ACTM, SAT, 16, false>(v, nsa, extra, s_q + c0, s_mc + c0, a.ep.zp_out, packed);
-                    if (!valid) packed[0] = packed[1] = packed[2] = packed[3] = a.halo_word;
-                    yq::mask_pad_channels<16>(packed, a.N - (oc0 + c0));
-                    if (SLOW && side && valid) {   // parity / quant_stop side outputs (not on the throughput path)
+            for (int ch = 0; ch < NCHUNK; ++ch) {
+                const int c0 = cbeg + 16 * ch;
+                uint32_t(&v)[16] = vbuf[ch & 1];
+                if (ch + 1 < NCHUNK) tmem_ld16_issue(trow + c0 + 16, vbuf[(ch + 1) & 1]);   // in flight while this chunk is requantized
+                uint32_t packed[4];
+                int extra[16];
+                yq::requant_chunk<ACTM, SAT, 16, false>(v, nsa, extra, s_q + c0, s_mc + c0, a.ep.zp_out, packed);
+                if (!valid) packed[0] = packed[1] = packed[2] = packed[3] = a.halo_word;
+                yq::mask_pad_channels<16>(packed, a.N - (oc0 + c0));
+                if (SLOW && side && valid) {   // parity / quant_stop side outputs (not on the throughput path)
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) {
-                            const int oc = oc0 + c0 + j;
-                            if (oc < a.N) {
-                                if (a.out_acc) a.out_acc[pix * a.CSO + oc] = (int)v[j] + s_q[c0 + j].y * nsa;
-                                if (a.out_f32) {
-                                    const uint8_t u = (uint8_t)(packed[j / 4] >> (8 * (j % 4)));
-                                    a.out_f32[((size_t)n * a.N + oc) * a.H * a.W + (size_t)(y1 - 1) * a.W + (col - 1)] = yq::dequant_f32(a.ep, u);
-                                }
+                    for (int j = 0; j < 16; ++j) {
+                        const int oc = oc0 + c0 + j;
+                        if (oc < a.N) {
+                            if (a.out_acc) a.out_acc[pix * a.CSO + oc] = (int)v[j] + s_q[c0 + j].y * nsa;
+                            if (a.out_f32) {
+                                const uint8_t u = (uint8_t)(packed[j / 4] >> (8 * (j % 4)));
+                                a.out_f32[((size_t)n * a.N + oc) * a.H * a.W + (size_t)(y1 - 1) * a.W + (col - 1)] = yq::dequant_f32(a.ep, u);
                             }
                         }
                     }
-                    {   // swizzled staging (matches the TMA-store tensor map): 16-byte chunk index XOR row bits
-                        const int chunk = c0 / 16;
-                        int sw;
-                        if (BN >= 128) sw = chunk ^ (r & 7);
-                        else if (BN == 64) sw = chunk ^ ((r >> 1) & 3);
-                        else sw = chunk ^ ((r >> 2) & 1);
-                        *reinterpret_cast<uint4 *>(sOut + (size_t)r * BN + sw * 16) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
-                    }
-                    if (ch + 1 < NCHUNK) tmem_ld_wait16(vbuf[(ch + 1) & 1]);
                 }
-            };
-            if (SLOW && a.ep.saturate) {
-                if (actm == 0) run(std::integral_constant<int, 0>{}, std::true_type{});
-                else if (actm == 1) run(std::integral_constant<int, 1>{}, std::true_type{});
-                else run(std::integral_constant<int, 2>{}, std::true_type{});
-            } else {
-                if (actm == 0) run(std::integral_constant<int, 0>{}, std::false_type{});
-                else if (actm == 1) run(std::integral_constant<int, 1>{}, std::false_type{});
-                else run(std::integral_constant<int, 2>{}, std::false_type{});
+                {   // swizzled staging (matches the TMA-store tensor map): 16-byte chunk index XOR row bits
+                    const int chunk = c0 / 16;
+                    int sw;
+                    if (BN >= 128) sw = chunk ^ (r & 7);
+                    else if (BN == 64) sw = chunk ^ ((r >> 1) & 3);
+                    else sw = chunk ^ ((r >> 2) & 1);
+                    *reinterpret_cast<uint4 *>(stage_out + (size_t)r * BN + sw * 16) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+                }
+                if (ch + 1 < NCHUNK) tmem_ld_wait16(vbuf[(ch + 1) & 1]);
             }
-            // this warp's TMEM reads are done: hand the accumulator back to the MMA warp
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive_plain(&acc_empty[buf]);
-            fence_proxy_async();
-            asm volatile("bar.sync 1, %0;" ::"n"(32 * FL_EPI_WARPS) : "memory");
-            if (et == 0) {
-                tma_store_2d(&tmO, sOut, oc0, p0);
-                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-            }
+        };
+        const int actm = yq::act_mode(a.ep.act);
+        if (SLOW && a.ep.saturate) {
+            if (actm == 0) run(std::integral_constant<int, 0>{}, std::true_type{});
+            else if (actm == 1) run(std::integral_constant<int, 1>{}, std::true_type{});
+            else run(std::integral_constant<int, 2>{}, std::true_type{});
+        } else {
+            if (actm == 0) run(std::integral_constant<int, 0>{}, std::false_type{});
+            else if (actm == 1) run(std::integral_constant<int, 1>{}, std::false_type{});
+            else run(std::integral_constant<int, 2>{}, std::false_type{});
         }
-        if (et == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // global writes complete before the CTA retires
+        tc_fence_before();
+        fence_proxy_async();
+        asm volatile("bar.sync 1, %0;" ::"n"(32 * FL_EPI_WARPS) : "memory");   // the epilogue warps only
+        if (threadIdx.x == 64) {
+            TL_MARK(5);                                     // epilogue math done
+            tma_store_2d(&tmO, stage_out, oc0, p0);
+            tma_store_commit_wait();
+            TL_MARK(6);                                     // store drained
+        }
     }
     tc_fence_before();
     __syncthreads();
@@ -368,45 +366,26 @@ struct FlatState {
 };
 
 template <int BN, int KC, bool SLOW>
-int fl_launch_v(FlatState *st, const CUtensorMap &tmA, const CUtensorMap &tmO, FlatArgs a, cudaStream_t stream)
+int fl_launch_v(FlatState *st, const CUtensorMap &tmA, const CUtensorMap &tmO, const FlatArgs &a, dim3 grid, cudaStream_t stream)
 {
     using L = FlatSmem<BN, KC>;
-    static int attr_smem = 0, n_sm = 0, smem_max = 0, group = 0;
-    if (!n_sm) {
-        int dev = 0;
-        YQ_CUDA(cudaGetDevice(&dev));
-        YQ_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
-        YQ_CUDA(cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
-        const char *e = getenv("YQ_FLAT_GROUP");     // weight stages released per tcgen05.commit (A/B measurements)
-        group = e ? atoi(e) : 2;
-        if (group != 1 && group != 2 && group != 4) group = 2;
-    }
-    // as many weight stages as fit next to the patch stages, the staging tile and the parameters (at most 8)
-    const int fixed = FL_ASTAGES * a.a_stage_bytes + L::OUT_BYTES + L::PARAM_BYTES + 512 + 1024;
-    int nbs = (smem_max - fixed) / L::B_STAGE;
-    if (nbs > FL_MAX_BSTAGES) nbs = FL_MAX_BSTAGES;
-    a.b_group = group;
-    while (a.b_group > 1 && nbs / a.b_group < 2) a.b_group /= 2;
-    nbs = nbs / a.b_group * a.b_group;
-    if (nbs < 2) return yq::fail("conv_u8_tc_flat_kernel<%d,%d>: shared memory does not hold two weight stages", BN, KC);
-    a.b_stages = nbs;
-    const int smem = fixed + nbs * L::B_STAGE;
+    static int attr_smem = 0;
+    const int smem = 2 * a.a_stage_bytes + FL_BSTAGES * L::B_STAGE + L::PARAM_BYTES + 128 + 1024;
     auto kern = conv_u8_tc_flat_kernel<BN, KC, SLOW>;
     if (smem > attr_smem) {
         YQ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         attr_smem = smem;
     }
-    const int grid = a.num_tiles < n_sm ? a.num_tiles : n_sm;
     kern<<<grid, FL_THREADS, smem, stream>>>(tmA, st->tmB, tmO, a);
     YQ_CHECK_LAUNCH();
     return 0;
 }
 
 template <int BN, int KC>
-int fl_launch(FlatState *st, const CUtensorMap &tmA, const CUtensorMap &tmO, const FlatArgs &a, cudaStream_t stream)
+int fl_launch(FlatState *st, const CUtensorMap &tmA, const CUtensorMap &tmO, const FlatArgs &a, dim3 grid, cudaStream_t stream)
 {
-    if (a.out_acc || a.out_f32 || a.ep.saturate) return fl_launch_v<BN, KC, true>(st, tmA, tmO, a, stream);
-    return fl_launch_v<BN, KC, false>(st, tmA, tmO, a, stream);
+    if (a.out_acc || a.out_f32 || a.ep.saturate) return fl_launch_v<BN, KC, true>(st, tmA, tmO, a, grid, stream);
+    return fl_launch_v<BN, KC, false>(st, tmA, tmO, a, grid, stream);
 }
 
 }  // namespace
@@ -493,12 +472,24 @@ int yq_tc_flat_forward(yq_conv_layer *l, void *state, const uint8_t *in_flat, ui
     a.halo_word = 0x01010101u * (uint32_t)(halo_fill & 0xff);
     a.magic_w = (uint32_t)((0x100000000ull + W1 - 1) / W1);
     a.magic_h = (uint32_t)((0x100000000ull + H1 - 1) / H1);
-    a.m_tiles = (int)((rows_alloc + 127) / 128);
-    a.num_tiles = a.m_tiles * (st->n_pad / st->BN);
-    a.magic_m = a.m_tiles == 1 ? 0u : (uint32_t)((0x100000000ull + a.m_tiles - 1) / a.m_tiles);
-    if ((long long)a.num_tiles * a.m_tiles >= 0x100000000ll) return yq::fail("tcgen05 flat flavour: too many tiles for 32-bit tile arithmetic");
+    dim3 grid((unsigned)((rows_alloc + 127) / 128), st->n_pad / st->BN);
+    {
+        static int n_sm = 0, want = -1;
+        if (!n_sm) {
+            int dev = 0;
+            YQ_CUDA(cudaGetDevice(&dev));
+            YQ_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
+            const char *e = getenv("YQ_FLAT_STAGGER");      // 0 disables the first-wave stagger (A/B measurements)
+            want = e ? atoi(e) : 1;
+        }
+        a.n_sm = n_sm;
+        // half of one CTA's period: main loop alone on the pipe (N/2 clocks per MMA at ~1.9 GHz) + epilogue + prologue
+        const double main_ns = (double)a.taps * a.cpt * (st->KC / 32) * ((st->BN + FL_ONES) / 2) / 1.9;
+        a.stagger_ns = want && (long long)grid.x * grid.y > 2LL * n_sm ? (int)((main_ns + 3500.0) / 2.0) : 0;
+        if (want < 0) a.stagger_ns = -1;
+    }
     const CUtensorMap &tmA = it->second.first, &tmO = it->second.second;
-#define YQ_FL(BN_, KC_) return fl_launch<BN_, KC_>(st, tmA, tmO, a, stream)
+#define YQ_FL(BN_, KC_) return fl_launch<BN_, KC_>(st, tmA, tmO, a, grid, stream)
     if (st->KC == 128) {
         if (st->BN == 128) YQ_FL(128, 128);
         if (st->BN == 64) YQ_FL(64, 128);
@@ -511,3 +502,9 @@ int yq_tc_flat_forward(yq_conv_layer *l, void *state, const uint8_t *in_flat, ui
 #undef YQ_FL
 }
 
+#ifdef YQ_TIMELINE
+extern "C" __attribute__((visibility("default"))) int yq_debug_flat_timeline(void *host, size_t bytes)
+{
+    return cudaMemcpyFromSymbol(host, yq_flat_timeline, bytes < sizeof(yq_flat_timeline) ? bytes : sizeof(yq_flat_timeline)) == cudaSuccess ? 0 : -1;
+}
+#endif
