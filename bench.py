@@ -107,7 +107,7 @@ def layer_work(li, batch, conv_written=True):
     if t == 0:
         macs = li.out_h * li.out_w * li.n * li.c * li.size * li.size
         out = li.out_h * li.out_w * li.n * (5 if li.quant_stop_flag else 1)
-        if li.fused:
+        if li.fused in (1, 2):
             out = (li.out_h // 2) * (li.out_w // 2) * li.n + (out if conv_written else 0)
         byts = batch * (li.h * li.w * li.c + out) + li.c * li.n * li.size ** 2
         return 2 * macs * batch, byts
@@ -304,7 +304,7 @@ def main():
         for i, li in enumerate(infos):
             ops, byts = layer_work(li, B, conv_written=False)   # production plan: fused convs write the pooled tensor only
             t_ms = float(lm[i + 1])
-            if t_ms <= 0 or (li.type == 1 and li.fused):    # a fused-away max-pool has no launch of its own
+            if t_ms <= 0 or (li.type in (1, 4) and li.fused):    # a fused-away max-pool / yolo layer has no launch of its own
                 continue
             t_tc = ops / (p_int8 * 1e12) * 1e3
             t_mem = byts / (pk["hbm_gbs"] * 1e9) * 1e3

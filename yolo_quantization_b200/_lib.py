@@ -72,6 +72,7 @@ SIGNATURES = {
     "yq_conv_flat_supported": (_i, [_vp]),
     "yq_act_geom_flat": (_i, [_i, _i, C.POINTER(ActGeom)]),
     "yq_forward_convolutional_layer_quant_flat_gpu": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _i, _vp]),
+    "yq_forward_convolutional_layer_quant_flat_yolo_gpu": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _i, _vp, _i, _vp]),
     "yq_forward_maxpool_layer_quant_geom_gpu": (_i, [_vp, C.POINTER(ActGeom), _vp, C.POINTER(ActGeom), _i, _i, _i, _i, _i, _i, _i, _vp]),
     "yq_forward_upsample_layer_quant_geom_gpu": (_i, [_vp, C.POINTER(ActGeom), _vp, C.POINTER(ActGeom), _i, _i, _i, _i, _i, _vp]),
     "yq_forward_route_layer_quant_geom_gpu": (_i, [C.POINTER(_vp), C.POINTER(ActGeom), C.POINTER(_i), _i, _vp, C.POINTER(ActGeom), _i, _i, _i, _vp]),

@@ -87,8 +87,8 @@ int yq_tc_flat_supported(const yq_conv_layer *l);
 void yq_tc_flat_geom(int h, int w, yq_act_geom *g);
 int yq_tc_flat_prepare(yq_conv_layer *l, void **state);
 void yq_tc_flat_free(void *state);
-int yq_tc_flat_forward(yq_conv_layer *l, void *state, const uint8_t *in_flat, uint8_t *out_flat, int halo_fill, float *out_f32, int32_t *out_acc,
-                       int batch, cudaStream_t stream);
+int yq_tc_flat_forward(yq_conv_layer *l, void *state, const uint8_t *in_flat, uint8_t *out_flat, int halo_fill, float *out_f32, float *out_yolo,
+                       int yolo_classes, int32_t *out_acc, int batch, cudaStream_t stream);
 
 // implemented in yq_conv_tc.cu (TMA-fed; c % 64 == 0)
 int yq_tc_supported(const yq_conv_layer *l);

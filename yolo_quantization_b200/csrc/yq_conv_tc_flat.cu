@@ -27,6 +27,7 @@
 // Restates convolutional_layer.c:694-761 for stride 1, pad = size/2, size in {1, 3}, c % 64 == 0.
 #include <cuda.h>
 #include <cuda_runtime.h>
+#include <math.h>
 #include <string.h>
 
 #include <map>
@@ -66,6 +67,9 @@ constexpr int FL_ONES = 16;
 struct FlatArgs {
     yq::EpiParams ep;
     float *out_f32;        // dense NCHW [B][N][H][W] (quant_stop) or nullptr
+    float *out_yolo;       // same shape: the following yolo layer's output (logistic on x, y, objectness, classes), or nullptr
+    const float *lut;      // [0,256): (u8 - zp_out) * s_out   [256,512): its logistic -- the head's float values are a 256-entry table
+    int yolo_per;          // 4 + classes + 1 channels per anchor
     int32_t *out_acc;      // dense NHWC [B][H][W][CSO] (parity checks) or nullptr
     int N, CSO, n_pad;
     int B, H, W, NP;       // NP = B*(H+1)*(W+1): positions that belong to images (their halo included)
@@ -238,7 +242,7 @@ __global__ void __launch_bounds__(FL_THREADS, 2) conv_u8_tc_flat_kernel(const __
         const int y1 = row - n * (a.H + 1);
         const bool valid = p < a.NP && col >= 1 && y1 >= 1;
         uint8_t *stage_out = sB;                // aliases the weight ring (all MMAs have completed)
-        const bool side = SLOW && ((a.out_acc != nullptr) || (a.out_f32 != nullptr));
+        const bool side = SLOW && ((a.out_acc != nullptr) || (a.out_f32 != nullptr) || (a.out_yolo != nullptr));
         const size_t pix = ((size_t)n * a.H + (y1 - 1)) * a.W + (col - 1);
         constexpr int HALF = BN / 2, NCHUNK = HALF / 16;
         const int cbeg = half * HALF;
@@ -268,9 +272,12 @@ __global__ void __launch_bounds__(FL_THREADS, 2) conv_u8_tc_flat_kernel(const __
                         const int oc = oc0 + c0 + j;
                         if (oc < a.N) {
                             if (a.out_acc) a.out_acc[pix * a.CSO + oc] = (int)v[j] + s_q[c0 + j].y * nsa;
-                            if (a.out_f32) {
-                                const uint8_t u = (uint8_t)(packed[j / 4] >> (8 * (j % 4)));
-                                a.out_f32[((size_t)n * a.N + oc) * a.H * a.W + (size_t)(y1 - 1) * a.W + (col - 1)] = yq::dequant_f32(a.ep, u);
+                            const uint8_t u = (uint8_t)(packed[j / 4] >> (8 * (j % 4)));
+                            const size_t fidx = ((size_t)n * a.N + oc) * a.H * a.W + (size_t)(y1 - 1) * a.W + (col - 1);
+                            if (a.out_f32) a.out_f32[fidx] = yq::dequant_f32(a.ep, u);
+                            if (a.out_yolo) {   // yolo_layer.c:137-146: channels 2, 3 (w, h) of every anchor stay linear
+                                const int e = oc % a.yolo_per;
+                                a.out_yolo[fidx] = __ldg(a.lut + ((e == 2 || e == 3) ? 0 : 256) + u);
                             }
                         }
                     }
@@ -355,6 +362,7 @@ int fl_encode_2d(CUtensorMap *m, const void *ptr, uint64_t rows, int row_bytes, 
 struct FlatState {
     int BN, KC, n_pad;
     uint8_t *w = nullptr;       // [n_pad][size*size*cs_in]
+    float *lut = nullptr;       // quant_stop layers: dequantized value and its logistic for each of the 256 output bytes
     CUtensorMap tmB;
     struct Key {
         const void *in;
@@ -384,7 +392,7 @@ int fl_launch_v(FlatState *st, const CUtensorMap &tmA, const CUtensorMap &tmO, c
 template <int BN, int KC>
 int fl_launch(FlatState *st, const CUtensorMap &tmA, const CUtensorMap &tmO, const FlatArgs &a, dim3 grid, cudaStream_t stream)
 {
-    if (a.out_acc || a.out_f32 || a.ep.saturate) return fl_launch_v<BN, KC, true>(st, tmA, tmO, a, grid, stream);
+    if (a.out_acc || a.out_f32 || a.out_yolo || a.ep.saturate) return fl_launch_v<BN, KC, true>(st, tmA, tmO, a, grid, stream);
     return fl_launch_v<BN, KC, false>(st, tmA, tmO, a, grid, stream);
 }
 
@@ -421,12 +429,26 @@ int yq_tc_flat_prepare(yq_conv_layer *l, void **state)
             for (int ci = 0; ci < l->c; ++ci) wp[(size_t)oc * ktot + (size_t)t * l->cs_in + ci] = l->host_w[((size_t)oc * l->c + ci) * taps + t];
     auto cleanup = [&]() {
         cudaFree(st->w);
+        cudaFree(st->lut);
         delete st;
         return -1;
     };
     if (cudaMalloc((void **)&st->w, wp.size()) != cudaSuccess) return cleanup();
     if (cudaMemcpy(st->w, wp.data(), wp.size(), cudaMemcpyHostToDevice) != cudaSuccess) return cleanup();
     if (fl_encode_2d(&st->tmB, st->w, (uint64_t)st->n_pad, (int)ktot, st->KC, st->BN, CU_TENSOR_MAP_L2_PROMOTION_L2_256B)) return cleanup();
+    if (l->quant_stop_flag) {
+        // l.output = (u8 - zp_out) * s_out (convolutional_layer.c:752-760) takes 256 values; logistic_activate
+        // (activations.h:32: 1./(1. + exp(-x)) in double, stored as float) of each is tabulated with the host's libm,
+        // i.e. with the very arithmetic the reference runs
+        float lut[512];
+        for (int u = 0; u < 256; ++u) {
+            const float x = (float)(u - l->zp_out) * l->s_out;
+            lut[u] = x;
+            lut[256 + u] = (float)(1. / (1. + exp(-(double)x)));
+        }
+        if (cudaMalloc((void **)&st->lut, sizeof lut) != cudaSuccess) return cleanup();
+        if (cudaMemcpy(st->lut, lut, sizeof lut, cudaMemcpyHostToDevice) != cudaSuccess) return cleanup();
+    }
     *state = st;
     return 0;
 }
@@ -436,11 +458,12 @@ void yq_tc_flat_free(void *state)
     FlatState *st = (FlatState *)state;
     if (!st) return;
     cudaFree(st->w);
+    cudaFree(st->lut);
     delete st;
 }
 
-int yq_tc_flat_forward(yq_conv_layer *l, void *state, const uint8_t *in_flat, uint8_t *out_flat, int halo_fill, float *out_f32, int32_t *out_acc,
-                       int batch, cudaStream_t stream)
+int yq_tc_flat_forward(yq_conv_layer *l, void *state, const uint8_t *in_flat, uint8_t *out_flat, int halo_fill, float *out_f32, float *out_yolo,
+                       int yolo_classes, int32_t *out_acc, int batch, cudaStream_t stream)
 {
     FlatState *st = (FlatState *)state;
     if (!st || !in_flat || !out_flat) return yq::fail("tcgen05 flat flavour: bad argument");
@@ -464,6 +487,10 @@ int yq_tc_flat_forward(yq_conv_layer *l, void *state, const uint8_t *in_flat, ui
     }
     a.ep = yq::make_epi(l);
     a.out_f32 = l->quant_stop_flag ? out_f32 : nullptr;
+    a.out_yolo = l->quant_stop_flag ? out_yolo : nullptr;
+    a.lut = st->lut;
+    a.yolo_per = 4 + yolo_classes + 1;
+    if (a.out_yolo && (!st->lut || l->n % a.yolo_per)) return yq::fail("tcgen05 flat flavour: layer is not a yolo head for %d classes", yolo_classes);
     a.out_acc = out_acc;
     a.N = l->n; a.CSO = l->cs_out; a.n_pad = st->n_pad;
     a.B = batch; a.H = l->h; a.W = l->w; a.NP = (int)NP;

@@ -477,7 +477,14 @@ extern "C" int yq_forward_convolutional_layer_quant_flat_gpu(yq_conv_layer *l, c
     if (!l || !in_flat || !out_flat || batch <= 0) return yq::fail("yq_forward_convolutional_layer_quant_flat_gpu: bad argument");
     if (!l->tc_flat) return yq::fail("this layer has no flat flavour (see yq_conv_flat_supported)");
     if (l->quant_stop_flag && !out_f32) return yq::fail("quant_stop layer needs out_f32");
-    return yq_tc_flat_forward(l, l->tc_flat, in_flat, out_flat, halo_fill, out_f32, out_acc, batch, (cudaStream_t)stream);
+    return yq_tc_flat_forward(l, l->tc_flat, in_flat, out_flat, halo_fill, out_f32, nullptr, 0, out_acc, batch, (cudaStream_t)stream);
+}
+extern "C" int yq_forward_convolutional_layer_quant_flat_yolo_gpu(yq_conv_layer *l, const uint8_t *in_flat, uint8_t *out_flat, int halo_fill,
+                                                                  float *out_f32, float *out_yolo, int classes, int32_t *out_acc, int batch, void *stream)
+{
+    if (!l || !in_flat || !out_flat || !out_yolo || batch <= 0 || classes < 0) return yq::fail("yq_forward_convolutional_layer_quant_flat_yolo_gpu: bad argument");
+    if (!l->tc_flat || !l->quant_stop_flag) return yq::fail("the fused yolo head needs a quant_stop layer with the flat flavour");
+    return yq_tc_flat_forward(l, l->tc_flat, in_flat, out_flat, halo_fill, out_f32, out_yolo, classes, out_acc, batch, (cudaStream_t)stream);
 }
 
 extern "C" int yq_conv_rows_supported(const yq_conv_layer *l) { return l && l->tc_rows ? 1 : 0; }
@@ -526,24 +533,22 @@ static int check_geom(const yq_act_geom *g, int h, int w)
     return 0;
 }
 
+// One block row (blockIdx.x) = one output row (n, oy); threads walk (ox, vector) of that row: 32-bit index arithmetic only.
 template <typename V>
-__global__ void maxpool_u8_kernel(const V *__restrict__ in, V *__restrict__ out, int B, int H, int W, int OH, int OW,
-                                  int vpp /* vectors per pixel */, int size, int stride, int off, long long total, Geo gi, Geo go)
+__global__ void maxpool_u8_kernel(const V *__restrict__ in, V *__restrict__ out, int H, int W, int OH, int OW, int vpp /* vectors per pixel */,
+                                  int size, int stride, int off, Geo gi, Geo go)
 {
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        int v = (int)(i % vpp);
-        long long p = i / vpp;
-        int ox = (int)(p % OW);
-        p /= OW;
-        int oy = (int)(p % OH);
-        int n = (int)(p / OH);
+    const int n = blockIdx.x / OH, oy = blockIdx.x - n * OH;
+    const int per_row = OW * vpp;
+    for (int j = blockIdx.y * blockDim.x + threadIdx.x; j < per_row; j += gridDim.y * blockDim.x) {
+        const int ox = j / vpp, v = j - ox * vpp;
         V m;
         memset(&m, 0, sizeof(V));
         for (int a = 0; a < size; ++a) {
-            int y = off + oy * stride + a;
+            const int y = off + oy * stride + a;
             if (y < 0 || y >= H) continue;
             for (int b = 0; b < size; ++b) {
-                int x = off + ox * stride + b;
+                const int x = off + ox * stride + b;
                 if (x < 0 || x >= W) continue;
                 V t = __ldg(in + gi.pix(n, y, x) * vpp + v);
                 if constexpr (sizeof(V) == 16) m = vmax16(m, t);
@@ -552,6 +557,15 @@ __global__ void maxpool_u8_kernel(const V *__restrict__ in, V *__restrict__ out,
         }
         out[go.pix(n, oy, ox) * vpp + v] = m;
     }
+}
+
+// launch shape for the row-per-block kernels: rows x ceil(per_row / threads) blocks
+static inline void row_launch_shape(int rows, int per_row, dim3 *grid, int *threads)
+{
+    *threads = per_row >= 256 ? 256 : (per_row + 31) / 32 * 32;
+    int by = (per_row + *threads - 1) / *threads;
+    if (by > 64) by = 64;
+    *grid = dim3((unsigned)rows, (unsigned)by);
 }
 
 static inline int grid_for(long long total, int threads)
@@ -570,14 +584,15 @@ extern "C" int yq_forward_maxpool_layer_quant_geom_gpu(const uint8_t *in, const 
     if (check_geom(in_geom, h, w) || check_geom(out_geom, oh, ow)) return -1;
     const Geo gi = geo_of(in_geom, h, w), go = geo_of(out_geom, oh, ow);
     const int off = -pad / 2;
+    dim3 grid;
+    int threads;
     if (cs % 16 == 0) {
-        long long total = (long long)batch * oh * ow * (cs / 16);
-        maxpool_u8_kernel<uint4><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
-            (const uint4 *)in, (uint4 *)out, batch, h, w, oh, ow, cs / 16, size, stride, off, total, gi, go);
+        row_launch_shape(batch * oh, ow * (cs / 16), &grid, &threads);
+        maxpool_u8_kernel<uint4><<<grid, threads, 0, (cudaStream_t)stream>>>((const uint4 *)in, (uint4 *)out, h, w, oh, ow, cs / 16, size, stride, off, gi, go);
     } else {
-        long long total = (long long)batch * oh * ow * (cs / 4);
-        maxpool_u8_kernel<uint32_t><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
-            (const uint32_t *)in, (uint32_t *)out, batch, h, w, oh, ow, cs / 4, size, stride, off, total, gi, go);
+        row_launch_shape(batch * oh, ow * (cs / 4), &grid, &threads);
+        maxpool_u8_kernel<uint32_t><<<grid, threads, 0, (cudaStream_t)stream>>>((const uint32_t *)in, (uint32_t *)out, h, w, oh, ow, cs / 4, size, stride, off,
+                                                                                 gi, go);
     }
     YQ_CHECK_LAUNCH();
     return 0;
@@ -592,17 +607,13 @@ extern "C" int yq_forward_maxpool_layer_quant_gpu(const uint8_t *in, uint8_t *ou
 // upsample (src/blas.c:781-803): out[y][x] = in[y/stride][x/stride]
 // ------------------------------------------------------------------------------------------------
 template <typename V>
-__global__ void upsample_u8_kernel(const V *__restrict__ in, V *__restrict__ out, int H, int W, int vpp, int stride,
-                                   long long total, Geo gi, Geo go)
+__global__ void upsample_u8_kernel(const V *__restrict__ in, V *__restrict__ out, int H, int W, int vpp, int stride, Geo gi, Geo go)
 {
     const int OW = W * stride, OH = H * stride;
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        int v = (int)(i % vpp);
-        long long p = i / vpp;
-        int ox = (int)(p % OW);
-        p /= OW;
-        int oy = (int)(p % OH);
-        int n = (int)(p / OH);
+    const int n = blockIdx.x / OH, oy = blockIdx.x - n * OH;
+    const int per_row = OW * vpp;
+    for (int j = blockIdx.y * blockDim.x + threadIdx.x; j < per_row; j += gridDim.y * blockDim.x) {
+        const int ox = j / vpp, v = j - ox * vpp;
         out[go.pix(n, oy, ox) * vpp + v] = __ldg(in + gi.pix(n, oy / stride, ox / stride) * vpp + v);
     }
 }
@@ -614,12 +625,14 @@ extern "C" int yq_forward_upsample_layer_quant_geom_gpu(const uint8_t *in, const
     if (check_geom(in_geom, h, w) || check_geom(out_geom, h * stride, w * stride)) return -1;
     const Geo gi = geo_of(in_geom, h, w), go = geo_of(out_geom, h * stride, w * stride);
     const int cs = yq::channel_stride(c);
+    dim3 grid;
+    int threads;
     if (cs % 16 == 0) {
-        long long total = (long long)batch * h * stride * w * stride * (cs / 16);
-        upsample_u8_kernel<uint4><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>((const uint4 *)in, (uint4 *)out, h, w, cs / 16, stride, total, gi, go);
+        row_launch_shape(batch * h * stride, w * stride * (cs / 16), &grid, &threads);
+        upsample_u8_kernel<uint4><<<grid, threads, 0, (cudaStream_t)stream>>>((const uint4 *)in, (uint4 *)out, h, w, cs / 16, stride, gi, go);
     } else {
-        long long total = (long long)batch * h * stride * w * stride * (cs / 4);
-        upsample_u8_kernel<uint32_t><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>((const uint32_t *)in, (uint32_t *)out, h, w, cs / 4, stride, total, gi, go);
+        row_launch_shape(batch * h * stride, w * stride * (cs / 4), &grid, &threads);
+        upsample_u8_kernel<uint32_t><<<grid, threads, 0, (cudaStream_t)stream>>>((const uint32_t *)in, (uint32_t *)out, h, w, cs / 4, stride, gi, go);
     }
     YQ_CHECK_LAUNCH();
     return 0;
@@ -647,15 +660,11 @@ struct RouteArgs {
 
 __global__ void route_u8_kernel(const RouteArgs a, uint8_t *__restrict__ out, int vec)
 {
-    const int HW = a.H * a.W;
+    const int n = blockIdx.x / a.H, y = blockIdx.x - n * a.H;
     if (vec) {
-        const int vpp = a.cs_out / 16;
-        const long long total = a.pixels * vpp;
-        for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-            int v = (int)(i % vpp);
-            long long p = i / vpp;
-            const int n = (int)(p / HW), rem = (int)(p - (long long)n * HW), y = rem / a.W, x = rem - y * a.W;
-            int ch = v * 16;
+        const int vpp = a.cs_out / 16, per_row = a.W * vpp;
+        for (int j = blockIdx.y * blockDim.x + threadIdx.x; j < per_row; j += gridDim.y * blockDim.x) {
+            const int x = j / vpp, ch = (j - x * vpp) * 16;
             uint4 val = make_uint4(0, 0, 0, 0);
             for (int k = 0; k < a.n; ++k)
                 if (ch >= a.off[k] && ch < a.off[k] + a.c[k])
@@ -663,11 +672,9 @@ __global__ void route_u8_kernel(const RouteArgs a, uint8_t *__restrict__ out, in
             *reinterpret_cast<uint4 *>(out + a.go.pix(n, y, x) * a.cs_out + ch) = val;
         }
     } else {
-        const long long total = a.pixels * a.cs_out;
-        for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-            int ch = (int)(i % a.cs_out);
-            long long p = i / a.cs_out;
-            const int n = (int)(p / HW), rem = (int)(p - (long long)n * HW), y = rem / a.W, x = rem - y * a.W;
+        const int per_row = a.W * a.cs_out;
+        for (int j = blockIdx.y * blockDim.x + threadIdx.x; j < per_row; j += gridDim.y * blockDim.x) {
+            const int x = j / a.cs_out, ch = j - x * a.cs_out;
             uint8_t val = 0;
             for (int k = 0; k < a.n; ++k)
                 if (ch >= a.off[k] && ch < a.off[k] + a.c[k]) val = a.in[k][a.g[k].pix(n, y, x) * a.cs[k] + (ch - a.off[k])];
@@ -701,8 +708,10 @@ extern "C" int yq_forward_route_layer_quant_geom_gpu(const uint8_t *const *input
     a.H = h; a.W = w;
     a.pixels = (long long)batch * h * w;
     if (a.cs_out % 16) vec = 0;
-    long long total = vec ? a.pixels * (a.cs_out / 16) : a.pixels * a.cs_out;
-    route_u8_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(a, out, vec);
+    dim3 grid;
+    int threads;
+    row_launch_shape(batch * h, vec ? w * (a.cs_out / 16) : w * a.cs_out, &grid, &threads);
+    route_u8_kernel<<<grid, threads, 0, (cudaStream_t)stream>>>(a, out, vec);
     YQ_CHECK_LAUNCH();
     return 0;
 }

@@ -118,6 +118,7 @@ struct Layer {
     bool fused_away = false;       // maxpool: produced by the previous conv, no launch
     bool use_rows = false;         // conv: halo-input conv + pool flavour (yq_conv_tc_rows.cu); its input tensor is halo-padded
     bool use_flat = false;         // conv: flat-strip flavour (yq_conv_tc_flat.cu); input and output tensors are flat
+    bool fuse_yolo = false;        // quant_stop conv: the following yolo layer is produced by this layer's epilogue (yolo: fused_away)
     int halo_fill = 0;             // byte kept in the halo of out_u8: the zero point its consumer convolutions pad with
     int src = -2;                  // layer whose out_u8 this layer reads (-1: the network input); routes use `inputs`
     yq_act_geom geom = {0, 0, 0};  // geometry of out_u8 (plain unless the only consumer is a rows-flavour conv)
@@ -346,7 +347,7 @@ void plan(yq_network *net)
     // ---- apply
     for (int i = 0; i < n; ++i) {
         Layer &l = net->layers[i];
-        l.fuse_pool = l.fused_away = l.use_rows = l.use_flat = false;
+        l.fuse_pool = l.fused_away = l.use_rows = l.use_flat = l.fuse_yolo = false;
         l.geom = yq_act_geom{0, l.out_w, l.out_h};
         l.halo_fill = 0;
     }
@@ -377,6 +378,8 @@ void plan(yq_network *net)
                 l.use_rows = l.fuse_pool = net->layers[i + 1].fused_away = true;
             } else if (flat_ok[i]) {
                 l.use_flat = true;
+                if (net->fusion && l.quant_stop && i + 1 < n && net->layers[i + 1].type == L_YOLO && l.n % (net->layers[i + 1].classes + 5) == 0)
+                    l.fuse_yolo = net->layers[i + 1].fused_away = true;
             } else if (net->fusion && i + 1 < n && yq_conv_can_fuse_maxpool(l.conv)) {
                 Layer &p = net->layers[i + 1];
                 if (p.type == L_MAXPOOL && p.size == 2 && p.stride == 2 && p.pad == 1) l.fuse_pool = p.fused_away = true;
@@ -416,6 +419,12 @@ int forward_body(yq_network *net, const uint8_t *in_u8_nchw, int *launches, bool
         case L_CONV:
             if (l.use_rows) {
                 if (yq_forward_convolutional_layer_quant_rows_pool_gpu(l.conv, cur, net->layers[i + 1].out_u8, &net->layers[i + 1].geom, net->batch, st))
+                    return -1;
+            } else if (l.use_flat && l.fuse_yolo) {
+                // the head's own float tensor (l.output) is only materialised for debug pulls
+                if (yq_forward_convolutional_layer_quant_flat_yolo_gpu(l.conv, cur, l.out_u8, l.halo_fill, net->keep_acc ? l.out_f32 : nullptr,
+                                                                       net->layers[i + 1].out_f32, net->layers[i + 1].classes,
+                                                                       net->keep_acc ? l.out_acc : nullptr, net->batch, st))
                     return -1;
             } else if (l.use_flat) {
                 if (yq_forward_convolutional_layer_quant_flat_gpu(l.conv, cur, l.out_u8, l.halo_fill, l.out_f32, net->keep_acc ? l.out_acc : nullptr,
@@ -468,6 +477,7 @@ int forward_body(yq_network *net, const uint8_t *in_u8_nchw, int *launches, bool
             cur_geom = &l.geom;
             break;
         case L_YOLO:
+            if (l.fused_away) break;
             if (!cur_f32) return yq::fail("layer %zu: yolo layer needs a float input (previous layer must be a quant_stop conv)", i);
             if (yq_forward_yolo_layer_gpu(cur_f32, l.out_f32, net->batch, l.n_anchors, l.classes, l.h, l.w, st)) return -1;
             ++nl;
@@ -845,7 +855,7 @@ extern "C" int yq_network_layer_info(const yq_network *net, int i, yq_layer_info
     o->batch_normalize = l.bn; o->quant_stop_flag = l.quant_stop; o->s_in = l.s_in; o->s_out = l.s_out;
     o->zp_in = l.zp_in; o->zp_out = l.zp_out; o->kernel = l.conv ? (l.use_rows ? 3 : (l.use_flat ? 2 : yq_conv_get_kernel(l.conv))) : 0;
     o->classes = l.classes; o->n_anchors = l.n_anchors;
-    o->fused = l.type == L_CONV ? (l.use_rows ? 2 : (l.fuse_pool ? 1 : 0)) : (l.fused_away ? 1 : 0);
+    o->fused = l.type == L_CONV ? (l.use_rows ? 2 : (l.fuse_pool ? 1 : (l.fuse_yolo ? 3 : 0))) : (l.fused_away ? 1 : 0);
     return 0;
 }
 
