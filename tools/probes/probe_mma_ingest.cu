@@ -84,16 +84,13 @@ int main()
     uint8_t *src; const size_t src_bytes = 64u << 20; cudaMalloc(&src, src_bytes); cudaMemset(src, 1, src_bytes);
     cudaFuncSetAttribute(probe, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024);
     const int iters = 4000;
-    for (int N : {128, 144})
-        for (int accmask : {0, 1})
-            for (int tilemask : {0, 1})
-                for (int ce : {0, 1}) {
-                    cudaMemset(d, 0, 16);
-                    probe<<<148, 128, 225 * 1024>>>(N, iters, 0, 16384, accmask, tilemask, ce, src, src_bytes, d);
-                    long long h[2] = {0, 0};
-                    cudaError_t e = cudaMemcpy(h, d, 16, cudaMemcpyDeviceToHost);
-                    printf("N %3d alternate acc %d, alternate operand tiles %d, commit per 4 MMAs %d: %s  %.1f clk per MMA\n", N, accmask, tilemask, ce,
-                           cudaGetErrorString(e), (double)h[0] / (iters * 4.0));
-                }
+    for (int N : {16, 48, 64, 80, 96, 112, 128, 144, 160, 192, 256})
+        for (int ce : {0, 1}) {
+            cudaMemset(d, 0, 16);
+            probe<<<148, 128, 225 * 1024>>>(N, iters, 0, 16384, 1, 1, ce, src, src_bytes, d);
+            long long h[2] = {0, 0};
+            cudaError_t e = cudaMemcpy(h, d, 16, cudaMemcpyDeviceToHost);
+            printf("N %3d, commit per 4 MMAs %d: %s  %.1f clk per MMA (N/2 = %d)\n", N, ce, cudaGetErrorString(e), (double)h[0] / (iters * 4.0), N / 2);
+        }
     return 0;
 }

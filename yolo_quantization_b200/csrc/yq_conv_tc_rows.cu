@@ -52,7 +52,7 @@ struct RowsGeom {
     static constexpr int A_BYTES = A_ROWS * ROWP;
     static constexpr int CHUNKS = A_BYTES / 16;                     // 162 / 324 / 648
     static constexpr int CPT = (CHUNKS + RW_THREADS - 1) / RW_THREADS;
-    static constexpr int NMMA = CS == 4 ? 3 : 12 * NBLK;
+    static constexpr int NMMA = CS == 4 ? 3 : 6 * NBLK;
 };
 
 template <int CS, int NCH>
@@ -61,14 +61,15 @@ struct RowsCfg {
     static constexpr int NB = CS == 4 ? 4 * NCH + 16 : NCH + 16;    // filter rows (TMEM columns) per MMA group
     static constexpr int NACC = CS == 4 ? NB : 2 * NB;              // TMEM columns of one accumulator
     static constexpr int TMEM_COLS = NACC <= 32 ? 32 : NACC <= 64 ? 64 : NACC <= 128 ? 128 : NACC <= 256 ? 256 : 512;
-    static constexpr int BSUB = NB * 32;                            // one MMA's filter tile
+    static constexpr int NMMA_N = CS == 4 ? NB : 2 * NB;            // N of one MMA: for c >= 16 the even and the odd group share it
+    static constexpr int BSUB = NMMA_N * 32;                        // one MMA's filter tile
     static constexpr int B_BYTES = G::NMMA * BSUB;
     static constexpr int A_STRIDE = (G::A_BYTES + 32 + 127) / 128 * 128;   // +32: the last window's (zero-weight) overhang
     static constexpr int A_OFF = 0;
     static constexpr int B_OFF = 2 * A_STRIDE;
     static constexpr int BAR_OFF = B_OFF + B_BYTES;
     static constexpr int TOTAL = BAR_OFF + 64;
-    static_assert(NB % 16 == 0 && NB <= 256, "kind::i8 N");
+    static_assert(NMMA_N % 16 == 0 && NMMA_N <= 256, "kind::i8 N");
 };
 
 struct RowsArgs {
@@ -232,29 +233,25 @@ __global__ void __launch_bounds__(RW_THREADS, (CS == 32 ? 2 : 4)) conv_u8_tc_row
             if ((k + 1) * RW_THREADS <= G::CHUNKS || t + k * RW_THREADS < G::CHUNKS) cp_async16(dst + dst_off[k], src + src_off[k]);
     };
     auto issue_mma = [&](int buf) {   // one thread issues the MMAs of a whole tile
-        constexpr uint32_t idesc = make_idesc(L::NB);
+        constexpr uint32_t idesc = make_idesc(L::NMMA_N);
         const uint32_t a0 = sA + buf * L::A_STRIDE, b0 = smem_u32(smem + L::B_OFF);
         if (CS == 4) {
 #pragma unroll
             for (int ky = 0; ky < 3; ++ky)
                 umma_i8(tmem_base, make_desc_ns(a0 + ky * G::ROWP, 16, G::ROWP), make_desc_ns(b0 + ky * L::BSUB, 128, 256), idesc, ky ? 1u : 0u);
         } else {
+            // one MMA = K chunks (E[i + step], O[i + step]) of one image row and 16-channel block, N = even group | odd group:
+            //   even pixel 2i   : kx 1 = E[i], kx 0 = O[i]   (step 0);                 kx 2 = O[i+1] (step 1)
+            //   odd  pixel 2i+1 : kx 0 = E[i]                (step 0);  kx 2 = E[i+1], kx 1 = O[i+1] (step 1)       [O[] is the shifted plane]
             int m = 0;
 #pragma unroll
-            for (int par = 0; par < 2; ++par)
+            for (int blk = 0; blk < G::NBLK; ++blk)
 #pragma unroll
-                for (int blk = 0; blk < G::NBLK; ++blk)
+                for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
-                    for (int ky = 0; ky < 3; ++ky)
-#pragma unroll
-                        for (int step = 0; step < 2; ++step, ++m) {
-                            const uint32_t row = a0 + blk * 2 * PLANE + ky * G::ROWP;
-                            // even: (E[i], O[i]) then (O[i+1], -);   odd: (E[i], O[i+1]) then (E[i+1], -)    [O[] is the shifted plane]
-                            const uint32_t start = step == 0 ? row : (par == 0 ? row + PLANE + 16 : row + 16);
-                            const uint32_t lbo = step == 0 ? (par == 0 ? PLANE : PLANE + 16) : 16;
-                            umma_i8(tmem_base + par * L::NB, make_desc_ns(start, lbo, G::ROWP), make_desc_ns(b0 + m * L::BSUB, 128, 256), idesc,
-                                    (blk | ky | step) ? 1u : 0u);
-                        }
+                    for (int step = 0; step < 2; ++step, ++m)
+                        umma_i8(tmem_base, make_desc_ns(a0 + blk * 2 * PLANE + ky * G::ROWP + step * 16, PLANE, G::ROWP),
+                                make_desc_ns(b0 + m * L::BSUB, 128, 256), idesc, m ? 1u : 0u);
         }
         umma_commit(mma_done);
     };
@@ -491,8 +488,8 @@ int yq_tc_rows_prepare(yq_conv_layer *l, void **state)
     const int CS = st->CS, NCH = st->NCH, NPQ = NCH / 4;
     const int NB = CS == 4 ? 4 * NCH + 16 : NCH + 16;
     const int nblk = CS == 32 ? 2 : 1;
-    const int nmma = CS == 4 ? 3 : 12 * nblk;
-    std::vector<uint8_t> img((size_t)nmma * NB * 32, 0);
+    const int nmma = CS == 4 ? 3 : 6 * nblk;
+    std::vector<uint8_t> img((size_t)nmma * (CS == 4 ? NB : 2 * NB) * 32, 0);
     auto W = [&](int oc, int ci, int ky, int kx) -> uint8_t { return ci < l->c ? l->host_w[(((size_t)oc * l->c + ci) * 3 + ky) * 3 + kx] : 0; };
     if (CS == 4) {
         // TMEM column c = 8g + 2q + e: channel q*NPQ + g % NPQ, output pixel 2*(g / NPQ) + e of the 4-pixel segment;
@@ -512,30 +509,30 @@ int yq_tc_rows_prepare(yq_conv_layer *l, void **state)
             }
         }
     } else {
-        // TMEM column c = 8g + 2q + e of a group: channel q*NPQ + 2g + e.  K chunk order per MMA (see issue_mma)
+        // TMEM column c = 8g + 2q + e of a group: channel q*NPQ + 2g + e.  Filter rows [0, NB) = even-pixel group, [NB, 2NB) =
+        // odd-pixel group; K chunk 0 = plane E, chunk 1 = plane O of the MMA's step (see issue_mma)
         int m = 0;
-        for (int par = 0; par < 2; ++par)
-            for (int blk = 0; blk < nblk; ++blk)
-                for (int ky = 0; ky < 3; ++ky)
-                    for (int step = 0; step < 2; ++step, ++m) {
-                        uint8_t *tile = img.data() + (size_t)m * NB * 32;
-                        // filter column kx read by chunk 0 / chunk 1 of this MMA (-1: nothing)
-                        const int kx0 = step == 0 ? (par == 0 ? 1 : 0) : 2;
-                        const int kx1 = step == 0 ? (par == 0 ? 0 : 1) : -1;
+        for (int blk = 0; blk < nblk; ++blk)
+            for (int ky = 0; ky < 3; ++ky)
+                for (int step = 0; step < 2; ++step, ++m) {
+                    uint8_t *tile = img.data() + (size_t)m * 2 * NB * 32;
+                    // filter column kx read by [group][chunk] of this MMA (-1: nothing)
+                    const int kxmap[2][2][2] = {{{1, 0}, {-1, 2}}, {{0, -1}, {2, 1}}};   // [group even/odd][step][chunk]
+                    for (int grp = 0; grp < 2; ++grp)
                         for (int chunk = 0; chunk < 2; ++chunk) {
-                            const int kx = chunk ? kx1 : kx0;
+                            const int kx = kxmap[grp][step][chunk];
                             if (kx < 0) continue;
                             for (int b = 0; b < 16; ++b) {
                                 const int ci = blk * 16 + b;
                                 for (int c = 0; c < NCH; ++c) {
                                     const int g = c / 8, q = (c % 8) / 2, e = c % 2;
-                                    tile[bpos(c, chunk * 16 + b)] = W(q * NPQ + 2 * g + e, ci, ky, kx);
+                                    tile[bpos(grp * NB + c, chunk * 16 + b)] = W(q * NPQ + 2 * g + e, ci, ky, kx);
                                 }
                                 if (ci < l->c)
-                                    for (int c = 0; c < 16; ++c) tile[bpos(NCH + c, chunk * 16 + b)] = 1;
+                                    for (int c = 0; c < 16; ++c) tile[bpos(grp * NB + NCH + c, chunk * 16 + b)] = 1;
                             }
                         }
-                    }
+                }
     }
     if (cudaMalloc((void **)&st->wimg, img.size()) != cudaSuccess || cudaMemcpy(st->wimg, img.data(), img.size(), cudaMemcpyHostToDevice) != cudaSuccess) {
         cudaFree(st->wimg);
