@@ -56,6 +56,7 @@ struct yq_conv_layer {
     void *tc_small = nullptr;   // small-c tcgen05 flavour state (yq_conv_tc_small.cu)
     void *tc_rows = nullptr;    // halo-input conv + pool flavour state (yq_conv_tc_rows.cu), or nullptr
     void *tc_flat = nullptr;    // flat-strip patch flavour state (yq_conv_tc_flat.cu), or nullptr
+    void *tc_flat2 = nullptr;   // its persistent two-tiles-per-weight-stage form (yq_conv_tc_flat2.cu), or nullptr
     std::vector<uint8_t> host_w;  // OIHW copy kept for repacking
     std::vector<uint8_t> host_zw;
     std::vector<int32_t> host_chanq;   // 4 ints per channel {bias, zw, 2*M0, shift} (copy of chanq)
@@ -89,6 +90,13 @@ int yq_tc_flat_prepare(yq_conv_layer *l, void **state);
 void yq_tc_flat_free(void *state);
 int yq_tc_flat_forward(yq_conv_layer *l, void *state, const uint8_t *in_flat, uint8_t *out_flat, int halo_fill, float *out_f32, float *out_yolo,
                        int yolo_classes, int32_t *out_acc, int batch, cudaStream_t stream);
+
+// implemented in yq_conv_tc_flat2.cu (same tensors as the flat flavour; persistent, 256 positions per weight stage; n % 128 == 0)
+int yq_tc_flat2_supported(const yq_conv_layer *l);
+int yq_tc_flat2_prepare(yq_conv_layer *l, void **state);
+void yq_tc_flat2_free(void *state);
+int yq_tc_flat2_forward(yq_conv_layer *l, void *state, const uint8_t *in_flat, uint8_t *out_flat, int halo_fill, int32_t *out_acc, int batch,
+                        cudaStream_t stream);
 
 // implemented in yq_conv_tc.cu (TMA-fed; c % 64 == 0)
 int yq_tc_supported(const yq_conv_layer *l);

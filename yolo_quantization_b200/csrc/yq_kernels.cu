@@ -414,7 +414,8 @@ extern "C" yq_conv_layer *yq_make_convolutional_layer_quant(const yq_conv_desc *
     if (yq_tc_supported(l)) {
         if (yq_tc_prepare(l) == 0) l->kernel = 1;
     }
-    if ((yq_tc_rows_supported(l) && yq_tc_rows_prepare(l, &l->tc_rows) != 0) || (yq_tc_flat_supported(l) && yq_tc_flat_prepare(l, &l->tc_flat) != 0)) {
+    if ((yq_tc_rows_supported(l) && yq_tc_rows_prepare(l, &l->tc_rows) != 0) || (yq_tc_flat_supported(l) && yq_tc_flat_prepare(l, &l->tc_flat) != 0) ||
+        (yq_tc_flat2_supported(l) && yq_tc_flat2_prepare(l, &l->tc_flat2) != 0)) {
         yq_free_convolutional_layer_quant(l);
         return nullptr;
     }
@@ -427,6 +428,7 @@ extern "C" void yq_free_convolutional_layer_quant(yq_conv_layer *l)
     yq_tc_free(l);
     yq_tc_rows_free(l->tc_rows);
     yq_tc_flat_free(l->tc_flat);
+    yq_tc_flat2_free(l->tc_flat2);
     cudaFree(l->w_simt); cudaFree(l->bias); cudaFree(l->zw); cudaFree(l->mcomb); cudaFree(l->mval); cudaFree(l->rsh); cudaFree(l->chanq);
     delete l;
 }
@@ -477,6 +479,8 @@ extern "C" int yq_forward_convolutional_layer_quant_flat_gpu(yq_conv_layer *l, c
     if (!l || !in_flat || !out_flat || batch <= 0) return yq::fail("yq_forward_convolutional_layer_quant_flat_gpu: bad argument");
     if (!l->tc_flat) return yq::fail("this layer has no flat flavour (see yq_conv_flat_supported)");
     if (l->quant_stop_flag && !out_f32) return yq::fail("quant_stop layer needs out_f32");
+    static const bool no_flat2 = getenv("YQ_NO_FLAT2") && atoi(getenv("YQ_NO_FLAT2"));   // A/B measurements
+    if (l->tc_flat2 && !no_flat2) return yq_tc_flat2_forward(l, l->tc_flat2, in_flat, out_flat, halo_fill, out_acc, batch, (cudaStream_t)stream);
     return yq_tc_flat_forward(l, l->tc_flat, in_flat, out_flat, halo_fill, out_f32, nullptr, 0, out_acc, batch, (cudaStream_t)stream);
 }
 extern "C" int yq_forward_convolutional_layer_quant_flat_yolo_gpu(yq_conv_layer *l, const uint8_t *in_flat, uint8_t *out_flat, int halo_fill,
