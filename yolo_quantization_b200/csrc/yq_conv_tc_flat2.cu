@@ -51,6 +51,7 @@ struct Flat2Args {
     int m_pairs, num_tiles;   // tile t -> (n-tile t / m_pairs, position pair t % m_pairs)
     uint32_t halo_word;
     uint32_t magic_w, magic_h, magic_m;
+    int debug;             // YQ_FLAT2_DEBUG experiments (results are garbage): 1 = skip weight loads of taps > 0, 2 = skip the epilogue math
 };
 
 template <int KC>
@@ -133,8 +134,12 @@ __global__ void __launch_bounds__(F2_THREADS, 1) conv_u8_tc_flat2_kernel(const _
                 for (int tap = 0; tap < a.taps; ++tap) {
                     mbar_wait(&b_empty[s], phb ^ 1);
                     if (elect_one()) {
-                        mbar_expect_tx(&b_full[s], (uint32_t)(F2_BN * KC));
-                        tma_load_2d(sB + s * L::B_STAGE, &tmB, &b_full[s], tap * a.CS + c * KC, oc0);
+                        if (a.debug == 1 && tap > 0) {
+                            f2_arrive(&b_full[s]);
+                        } else {
+                            mbar_expect_tx(&b_full[s], (uint32_t)(F2_BN * KC));
+                            tma_load_2d(sB + s * L::B_STAGE, &tmB, &b_full[s], tap * a.CS + c * KC, oc0);
+                        }
                     }
                     if (++s == nbs) { s = 0; phb ^= 1; }
                 }
@@ -301,7 +306,8 @@ __global__ void __launch_bounds__(F2_THREADS, 1) conv_u8_tc_flat2_kernel(const _
                         if (ch == 0) tmem_ld_wait16(vbuf[1]);
                     }
                 };
-                if (SLOW && a.ep.saturate) {
+                if (a.debug == 2) {
+                } else if (SLOW && a.ep.saturate) {
                     if (actm == 0) run(std::integral_constant<int, 0>{}, std::true_type{});
                     else if (actm == 1) run(std::integral_constant<int, 1>{}, std::true_type{});
                     else run(std::integral_constant<int, 2>{}, std::true_type{});
@@ -420,6 +426,7 @@ int yq_tc_flat2_supported(const yq_conv_layer *l)
 {
     if (!yq_tc_flat_supported(l)) return 0;
     if (l->quant_stop_flag || l->cs_out % F2_BN) return 0;
+    if (l->size != 3) return 0;      // 1x1: one weight stage per patch -- the one-tile form is faster (measured: layer 13 0.0215 vs 0.0245 ms)
     if (256 + (l->size - 1) * (l->w + 2) > F2_MAX_ROWS) return 0;
     return 1;
 }
@@ -486,6 +493,11 @@ int yq_tc_flat2_forward(yq_conv_layer *l, void *state, const uint8_t *in_flat, u
     a.size = l->size; a.taps = l->size * l->size; a.cpt = l->cs_in / st->KC; a.CS = l->cs_in;
     a.q_off = -(pad * W1 + pad);
     a.halo_word = 0x01010101u * (uint32_t)(halo_fill & 0xff);
+    {
+        static int dbg = -1;
+        if (dbg < 0) dbg = getenv("YQ_FLAT2_DEBUG") ? atoi(getenv("YQ_FLAT2_DEBUG")) : 0;
+        a.debug = dbg;
+    }
     a.magic_w = (uint32_t)((0x100000000ull + W1 - 1) / W1);
     a.magic_h = (uint32_t)((0x100000000ull + H1 - 1) / H1);
     a.m_pairs = (int)((rows_alloc + 255) / 256);
