@@ -188,6 +188,14 @@ YQ_API int yq_forward_route_layer_quant_geom_gpu(const uint8_t *const *inputs, c
 YQ_API int yq_forward_yolo_layer_gpu(const float *in, float *out, int batch, int n_anchors, int classes, int h,
                                      int w, void *stream);
 
+/* replaces the layer-0 input quantiser quant_weights_with_min_max_channel(1, net->input, net->input_uint8, ...)
+ * (src/blas.c:108-168, called at :279) for a batch of float CHW images already on the device: per image
+ * s = (max(0,max x) - min(0,min x)) / 255, zp = clamp(round(-min/s)), u8 = clamp(round(x/s) + zp).
+ * scales [batch] and zero_points [batch] receive (s, zp) (zp = -1 flags the all-zero image the reference asserts on);
+ * scratch: 2*batch ints of device memory.  n = c*h*w elements per image. */
+YQ_API int yq_quantize_input_gpu(const float *in_f32_chw, uint8_t *out_u8_chw, float *scales, int *zero_points, int *scratch,
+                                 int batch, int n, void *stream);
+
 /* layout conversion at the boundary (reference tensors are CHW per image) */
 YQ_API int yq_nchw_to_nhwc_u8(const uint8_t *in_nchw, uint8_t *out_nhwc, int batch, int c, int h, int w,
                               void *stream);
@@ -249,6 +257,11 @@ YQ_API int yq_forward_network_device(yq_network *net, const uint8_t *in_u8_nchw)
 /* network_predict with HOST buffers: H2D of the uint8 input, forward, D2H of every yolo head into
  * out_f32 (heads concatenated in layer order, each [batch][out_c][out_h][out_w]); synchronous. */
 YQ_API int yq_network_predict_u8(yq_network *net, const uint8_t *in_u8_nchw_host, float *out_f32_host);
+/* network_predict with HOST FLOAT images (the reference's net->input): H2D, device input quantiser
+ * (yq_quantize_input_gpu), layer-0 re-prep when (s_in, zp_in) changed -- exactly what test_detector does per image
+ * (examples/detector.c:915-922) -- forward, D2H.  Layer 0's multipliers depend on (s_in, zp_in), so every image of the
+ * batch must quantize to the same pair (always true at batch 1); otherwise the call fails. */
+YQ_API int yq_network_predict_f32(yq_network *net, const float *in_f32_nchw_host, float *out_f32_host);
 /* the same, pipelined two deep so H2D / forward / D2H of neighbouring batches overlap (serving loop):
  * submit enqueues the H2D of one batch and its forward and returns a slot (>= 0; < 0 on error);
  * collect waits for that slot and copies the yolo heads to out_f32.  Use pinned host memory. */

@@ -490,6 +490,38 @@ def test_layout_transform_roundtrip(built):
         d.free()
 
 
+def test_input_quantiser_vs_oracle(built):
+    """the layer-0 dynamic input quantiser on the device == the oracle restatement of blas.c:108-168
+    (which tests/test_oracle_vs_reference_live.py pins against the compiled reference), per image, bit for bit."""
+    rng = np.random.default_rng(12)
+    imgs = [rng.random((3, 40, 56), dtype=np.float32),                                   # [0, 1): zp = 0
+            (rng.standard_normal((3, 40, 56)) * 0.7).astype(np.float32),                 # negative values: zp != 0
+            synth.image_to_float(synth.synthetic_image(5, 3, 40, 56)),                   # the benchmark's image class (u8 / 255)
+            np.full((3, 40, 56), 0.25, np.float32)]                                      # constant image
+    imgs[3][0, 0, 0] = -0.5
+    x = np.stack(imgs)
+    u8, scales, zps = darknet.quantize_input(x)
+    for b in range(len(imgs)):
+        ru8, rs, rz = O.quantize_input(x[b])
+        assert scales[b] == np.float32(rs) and int(zps[b]) == int(rz), (b, scales[b], rs, zps[b], rz)
+        assert np.array_equal(u8[b], ru8), f"image {b}: {np.count_nonzero(u8[b] != ru8)} bytes differ"
+
+
+def test_network_predict_f32_equals_predict_u8(built, tiny_net_files):
+    """float images through the device quantiser + layer-0 re-prep == the uint8 path fed with the oracle-quantized image
+    and the same (s_in, zp_in)."""
+    cfg, wts, info, _ = tiny_net_files
+    im = synth.synthetic_image(77)
+    xf = synth.image_to_float(im)[None]
+    ru8, rs, rz = O.quantize_input(xf[0])
+    net = darknet.load_network(cfg, wts, batch=1)
+    got = net.predict_f32(xf).copy()
+    net.set_input_quant(float(rs), int(rz))
+    want = net.predict_u8(ru8[None])
+    assert np.array_equal(got, want)
+    net.free()
+
+
 def test_layout_transform_padded_geometry(built):
     """NCHW -> halo-padded NHWC and back: the interior round-trips, the halo keeps what the runtime put there."""
     import ctypes as C

@@ -86,6 +86,8 @@ SIGNATURES = {
     "yq_forward_upsample_layer_quant_gpu": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "yq_forward_route_layer_quant_gpu": (_i, [C.POINTER(_vp), C.POINTER(_i), _i, _vp, _i, _i, _i, _vp]),
     "yq_forward_yolo_layer_gpu": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp]),
+    "yq_quantize_input_gpu": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _vp]),
+    "yq_network_predict_f32": (_i, [_vp, _vp, _vp]),
     "yq_nchw_to_nhwc_u8": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
     "yq_nhwc_to_nchw_u8": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
     "yq_nhwc_to_nchw_i32": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),

@@ -133,6 +133,8 @@ struct yq_network {
     cudaStream_t stream = nullptr;
     uint8_t *in_stage_nchw = nullptr;   // staging for host-input predict
     uint8_t *in_nhwc = nullptr;
+    float *in_f32 = nullptr;            // yq_network_predict_f32: float staging and per-image (scale, zero point, scratch)
+    void *in_quant = nullptr;
     size_t in_nhwc_bytes = 0;
     yq_act_geom in_geom = {0, 0, 0};    // geometry of in_nhwc (halo-padded when layer 0 runs a halo-input flavour)
     int in_halo_fill = 0;
@@ -826,6 +828,8 @@ extern "C" void yq_free_network(yq_network *net)
     cudaFree(net->counts_dev);
     cudaFree(net->in_stage_nchw);
     cudaFree(net->in_nhwc);
+    cudaFree(net->in_f32);
+    cudaFree(net->in_quant);
     cudaFree(net->scratch);
     if (net->out_host_pinned) cudaFreeHost(net->out_host_pinned);
     if (net->stream) cudaStreamDestroy(net->stream);
@@ -978,6 +982,44 @@ extern "C" int yq_network_predict_u8(yq_network *net, const uint8_t *in_host, fl
                 off += l.f32_count;
             }
     }
+    YQ_CUDA(cudaStreamSynchronize(net->stream));
+    return 0;
+}
+
+extern "C" int yq_network_predict_f32(yq_network *net, const float *in_host, float *out_host)
+{
+    if (!net || !in_host || !out_host) return yq::fail("yq_network_predict_f32: null argument");
+    if (net->layers.empty() || net->layers[0].type != L_CONV) return yq::fail("yq_network_predict_f32: layer 0 is not a convolution");
+    YQ_CUDA(cudaSetDevice(net->device));
+    const int n = net->c * net->h * net->w, B = net->batch;
+    if (!net->in_f32) {
+        YQ_CUDA(cudaMalloc((void **)&net->in_f32, sizeof(float) * (size_t)B * n));
+        YQ_CUDA(cudaMalloc((void **)&net->in_quant, (sizeof(float) + 3 * sizeof(int)) * (size_t)B));
+    }
+    float *scales = (float *)net->in_quant;
+    int *zps = (int *)(scales + B), *scratch = zps + B;
+    YQ_CUDA(cudaMemcpyAsync(net->in_f32, in_host, sizeof(float) * (size_t)B * n, cudaMemcpyHostToDevice, net->stream));
+    if (yq_quantize_input_gpu(net->in_f32, net->in_stage_nchw, scales, zps, scratch, B, n, net->stream)) return -1;
+    std::vector<float> hs(B);
+    std::vector<int> hz(B);
+    YQ_CUDA(cudaMemcpyAsync(hs.data(), scales, sizeof(float) * B, cudaMemcpyDeviceToHost, net->stream));
+    YQ_CUDA(cudaMemcpyAsync(hz.data(), zps, sizeof(int) * B, cudaMemcpyDeviceToHost, net->stream));
+    YQ_CUDA(cudaStreamSynchronize(net->stream));
+    for (int b = 0; b < B; ++b) {
+        if (hz[b] < 0) return yq::fail("yq_network_predict_f32: image %d is all zero (blas.c:124-127 asserts)", b);
+        if (hs[b] != hs[0] || hz[b] != hz[0])
+            return yq::fail("yq_network_predict_f32: images 0 and %d quantize differently (s %g/%g, zp %d/%d); layer 0 has one (s_in, zp_in) per forward", b,
+                            (double)hs[0], (double)hs[b], hz[0], hz[b]);
+    }
+    if (hs[0] != net->layers[0].s_in || hz[0] != net->layers[0].zp_in)
+        if (yq_network_set_input_quant(net, hs[0], hz[0])) return -1;      // blas.c:279 overwrites layer 0's file values per image
+    if (yq_forward_network_device(net, net->in_stage_nchw)) return -1;
+    size_t off = 0;
+    for (auto &l : net->layers)
+        if (l.type == L_YOLO) {
+            YQ_CUDA(cudaMemcpyAsync(out_host + off, l.out_f32, l.f32_count * sizeof(float), cudaMemcpyDeviceToHost, net->stream));
+            off += l.f32_count;
+        }
     YQ_CUDA(cudaStreamSynchronize(net->stream));
     return 0;
 }

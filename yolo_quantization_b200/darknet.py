@@ -100,6 +100,25 @@ def pull_nhwc_i32(buf: DeviceBuffer, b: int, c: int, h: int, w: int) -> np.ndarr
     return out
 
 
+def quantize_input(x: np.ndarray):
+    """quant_weights_with_min_max_channel(1, net->input, ...) (src/blas.c:108-168) on the device, per image.
+    x: float32 [b, ...]; returns (uint8 array of x's shape, scales [b], zero points [b])."""
+    lib = _lib.load()
+    x = np.ascontiguousarray(x, np.float32)
+    b, n = x.shape[0], int(np.prod(x.shape[1:]))
+    din = DeviceBuffer.from_numpy(x)
+    dout = DeviceBuffer(b * n)
+    meta = DeviceBuffer(16 * b)
+    check(lib.yq_quantize_input_gpu(din.ptr, dout.ptr, meta.ptr, meta.ptr + 4 * b, meta.ptr + 8 * b, b, n, None), "yq_quantize_input_gpu")
+    check(lib.yq_stream_synchronize(None))
+    u8 = dout.pull(x.shape, np.uint8)
+    raw = meta.pull((4 * b,), np.int32)
+    scales, zps = raw[:b].view(np.float32).copy(), raw[b:2 * b].copy()
+    for d in (din, dout, meta):
+        d.free()
+    return u8, scales, zps
+
+
 # ----------------------------------------------------------------------------------------------
 # layer level
 # ----------------------------------------------------------------------------------------------
@@ -396,6 +415,16 @@ class Network:
         if out is None:
             out = np.empty(self.output_floats, np.float32)
         check(_lib.load().yq_network_predict_u8(self._h, x.ctypes.data, out.ctypes.data), "yq_network_predict_u8")
+        return out
+
+    def predict_f32(self, x: np.ndarray, out: Optional[np.ndarray] = None) -> np.ndarray:
+        """network_predict with host FLOAT images [batch,c,h,w] (the reference's net->input): the layer-0 input
+        quantiser (src/blas.c:108-168 via :279) runs on the device, layer 0 is re-prepared when (s_in, zp_in) changed."""
+        x = np.ascontiguousarray(x, np.float32)
+        assert x.shape == (self.batch, self.c, self.h, self.w), x.shape
+        if out is None:
+            out = np.empty(self.output_floats, np.float32)
+        check(_lib.load().yq_network_predict_f32(self._h, x.ctypes.data, out.ctypes.data), "yq_network_predict_f32")
         return out
 
     def predict_raw(self, in_ptr: int, out_ptr: int) -> None:
