@@ -159,6 +159,47 @@ def test_conv_fused_maxpool_vs_oracle(built, case, s_out):
     layer.free()
 
 
+# every distinct convolution shape of the full yolov3 (BASELINE configs[4]: 75 conv layers, leaky, stride-2 down-samplers,
+# linear 1x1 heads with 255 filters): (c, n, size, stride, activation).  The reference pins each conv layer on its own
+# (SURVEY Appendix F); the quantized shortcut between them does not exist in the reference.
+YOLOV3_SHAPES = [
+    (3, 32, 3, 1, "leaky"), (32, 64, 3, 2, "leaky"), (64, 32, 1, 1, "leaky"), (32, 64, 3, 1, "leaky"),
+    (64, 128, 3, 2, "leaky"), (128, 64, 1, 1, "leaky"), (64, 128, 3, 1, "leaky"),
+    (128, 256, 3, 2, "leaky"), (256, 128, 1, 1, "leaky"), (128, 256, 3, 1, "leaky"),
+    (256, 512, 3, 2, "leaky"), (512, 256, 1, 1, "leaky"), (256, 512, 3, 1, "leaky"),
+    (512, 1024, 3, 2, "leaky"), (1024, 512, 1, 1, "leaky"), (512, 1024, 3, 1, "leaky"),
+    (1024, 255, 1, 1, "linear"), (768, 256, 1, 1, "leaky"), (512, 255, 1, 1, "linear"),
+    (384, 128, 1, 1, "leaky"), (256, 255, 1, 1, "linear"),
+]
+
+
+@pytest.mark.parametrize("shape", YOLOV3_SHAPES, ids=lambda s: "c%d_n%d_k%d_s%d_%s" % s)
+def test_full_yolov3_conv_shapes_vs_oracle(built, shape):
+    """BASELINE configs[4]: each conv shape of the full yolov3 through the default flavour selection (flat / flat2 for the
+    stride-1 layers with c % 64 == 0, SIMT for the stride-2 down-samplers, small-c for c <= 32) == oracle, bit for bit;
+    zp_in = 40 like a leaky net (padding value != 0)."""
+    c, n, k, stride, act = shape
+    h = w = 12
+    rng = np.random.default_rng(zlib.crc32(repr(shape).encode()) + 3)
+    wq, zp_w, s_w, bias = make_params(rng, n, c * k * k, 40)
+    spec = synth.LayerSpec("conv", n, k, stride, 1, 0, act)
+    sl = synth.SynthLayer("conv", c, h, w, n, 0, 0, spec, s_out=0.05, biases=bias, s_w=s_w, zp_w=zp_w, w_u8=wq.reshape(n, c, k, k))
+    p = O.prepare_conv(sl, 0.02, 40)
+    x = rng.integers(0, 256, size=(2, c, h, w), dtype=np.uint8)
+    qs = 1 if act == "linear" else 0
+    layer = darknet.ConvolutionalLayerQuant(h, w, c, n, k, stride, k // 2, synth.ACT_CODES[act], wq, zp_w, p["biases_int32"], p["M_value"],
+                                            p["M0_right_shift_value"], 40, 33, 0.05, quant_stop_flag=qs)
+    got = layer.forward_flat(x, halo_fill=40) if layer.flat_supported else layer.forward(x)
+    for b in range(2):
+        acc = O.conv_acc(x[b], wq.reshape(n, c, k, k), zp_w, stride, k // 2, 40)
+        assert np.array_equal(got["acc"][b], acc), f"int32 accumulator mismatch, image {b}"
+        u8 = O.requant(acc, p["biases_int32"], p["M_value"], p["M0_right_shift_value"], synth.ACT_CODES[act], 33)
+        assert np.array_equal(got["u8"][b], u8), f"uint8 mismatch, image {b}"
+        if qs:
+            assert np.array_equal(got["f32"][b], O.dequant(u8, 33, 0.05))
+    layer.free()
+
+
 FLAT_CASES = [
     # c, h, w, n, k, act, zp_in, zp_out, batch
     (64, 13, 13, 128, 3, "relu6", 0, 0, 3),
