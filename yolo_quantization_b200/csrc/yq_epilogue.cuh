@@ -107,34 +107,35 @@ __device__ __forceinline__ float dequant_f32(const EpiParams &e, uint8_t u8)
 // ---------------------------------------------------------------------------------------------
 // form (B): chunked integer epilogue for the tcgen05 flavours
 // ---------------------------------------------------------------------------------------------
-// ACTM: 0 = RELU6, 1 = LINEAR / RELU, 2 = LEAKY.  SAT: clamp instead of wrap.
-template <int ACTM, bool SAT>
-__device__ __forceinline__ uint32_t act_store_byte(int q, int zo)
-{
-    int r;
-    if (ACTM == 0) {
-        r = q + zo;                                    // callers pass q >= 0 with q == 0 for every x <= 0
-    } else if (ACTM == 2) {
-        if (q < 0) r = zo - (int)(__umulhi((uint32_t)(-q) + 5u, 0xCCCCCCCDu) >> 3);
-        else r = q + zo;
-    } else {
-        r = q + zo;
-    }
-    if (SAT) r = max(0, min(255, r));
-    return (uint32_t)r & 0xffu;
-}
-
 // One chunk of NV consecutive output channels of ONE pixel.
 //   v[j]   raw tensor-core accumulator  sum_k w*a   (uint8 x uint8, zero-filled padding)
 //   nsa    minus the pixel's activation sum          (so  acc = v + zw * nsa)
 //   extra  per-output additive correction (border taps) or nullptr
 //   cq     shared-memory {bias, zw, 2*M0, shift} of the chunk's first channel; mc = matching M_value*2^-s doubles
 // Writes NV/4 packed little-endian words.  Returns nothing; bit-exact for all inputs (see header).
+// four low bytes -> one little-endian word (PRMT takes the LOW byte of each value: the uint8 wrap comes for free)
+__device__ __forceinline__ uint32_t pack_low_bytes(int r0, int r1, int r2, int r3)
+{
+    return __byte_perm(__byte_perm((uint32_t)r0, (uint32_t)r1, 0x0040), __byte_perm((uint32_t)r2, (uint32_t)r3, 0x0040), 0x5410);
+}
+
+// ACTM: 0 = RELU6, 1 = LINEAR / RELU, 2 = LEAKY.  SAT: clamp instead of wrap.  Value before the uint8 store.
+template <int ACTM, bool SAT>
+__device__ __forceinline__ int act_value(int q, int zo)
+{
+    int r;
+    if (ACTM == 2 && q < 0) r = zo - (int)(__umulhi((uint32_t)(-q) + 5u, 0xCCCCCCCDu) >> 3);
+    else r = q + zo;                                   // (RELU6 callers pass q >= 0 with q == 0 for every x <= 0)
+    if (SAT) r = max(0, min(255, r));
+    return r;
+}
+
 template <int ACTM, bool SAT, int NV, bool HAS_EXTRA>
 __device__ __forceinline__ void requant_chunk(const uint32_t (&v)[NV], int nsa, const int (&extra)[NV], const int4 *cq, const double *mc,
                                               int zo, uint32_t (&packed)[NV / 4])
 {
     uint32_t mx = 0;
+    int r[NV];
 #pragma unroll
     for (int j = 0; j < NV; ++j) {
         const int4 c = cq[j];
@@ -152,9 +153,7 @@ __device__ __forceinline__ void requant_chunk(const uint32_t (&v)[NV], int nsa, 
             const int h = (int)(__umulhi(ax, (uint32_t)c.z) >> c.w);
             q = x < 0 ? -h : h;
         }
-        const uint32_t b = act_store_byte<ACTM, SAT>(q, zo);
-        if (j % 4 == 0) packed[j / 4] = b;
-        else packed[j / 4] |= b << (8 * (j % 4));
+        r[j] = act_value<ACTM, SAT>(q, zo);
     }
     if (mx >= (1u << 22)) {
         // |x*M0| may reach 2^53: the reference's double multiply rounds -> redo this chunk in FP64 form (A)
@@ -166,11 +165,11 @@ __device__ __forceinline__ void requant_chunk(const uint32_t (&v)[NV], int nsa, 
             x += c.x;
             int q = __double2int_rz(__dmul_rn((double)x, mc[j]));
             if (ACTM == 0) q = max(q, 0);
-            const uint32_t b = act_store_byte<ACTM, SAT>(q, zo);
-            if (j % 4 == 0) packed[j / 4] = b;
-            else packed[j / 4] |= b << (8 * (j % 4));
+            r[j] = act_value<ACTM, SAT>(q, zo);
         }
     }
+#pragma unroll
+    for (int k = 0; k < NV / 4; ++k) packed[k] = pack_low_bytes(r[4 * k], r[4 * k + 1], r[4 * k + 2], r[4 * k + 3]);
 }
 
 // zero the bytes of pad channels (channel index >= n_real within this chunk): pad lanes of an activation
