@@ -4,6 +4,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <stdlib.h>
+#include <string.h>
 #include <string>
 #include <vector>
 
@@ -30,6 +31,48 @@ static inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
 static inline int channel_stride(int c) { return c <= 4 ? 4 : round_up(c, 16); }
 
 }  // namespace yq
+
+// ------------------------------------------------------------------------------------------------
+// Programmatic dependent launch (PDL): every kernel of the forward is launched with the programmatic-stream-serialization
+// attribute, runs its own prologue (barrier init, TMEM allocation, constant filter tiles into shared memory) while the
+// previous kernel drains, and only then executes griddepcontrol.wait -- which returns once the previous grid has completed
+// and its writes are visible -- before it touches any activation tensor.  No global memory is written before the wait.
+// YQ_PDL=0 launches plainly.
+// ------------------------------------------------------------------------------------------------
+#ifdef __CUDACC__
+__device__ __forceinline__ void yq_pdl_wait_then_release()
+{
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // my own dependents may start their prologues
+}
+namespace yq {
+inline bool pdl_enabled()
+{
+    static int v = -1;
+    if (v < 0) {
+        const char *e = getenv("YQ_PDL");
+        v = e ? (atoi(e) != 0) : 1;
+    }
+    return v != 0;
+}
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args &&...args)
+{
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof cfg);
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+}
+}  // namespace yq
+#endif
 
 // One prepared quantized conv layer on the device.
 struct yq_conv_layer {

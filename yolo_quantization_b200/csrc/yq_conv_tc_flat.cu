@@ -174,6 +174,7 @@ __global__ void __launch_bounds__(FL_THREADS, 2) conv_u8_tc_flat_kernel(const __
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     if (threadIdx.x == 0) TL_MARK(1);                       // setup done
+    yq_pdl_wait_then_release();                             // no activation tensor was touched so far
 
     if (warp == 0) {
         // ===================== TMA producer (whole warp in uniform control flow, one elected lane issues) =====================
@@ -384,8 +385,7 @@ int fl_launch_v(FlatState *st, const CUtensorMap &tmA, const CUtensorMap &tmO, c
         YQ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         attr_smem = smem;
     }
-    kern<<<grid, FL_THREADS, smem, stream>>>(tmA, st->tmB, tmO, a);
-    YQ_CHECK_LAUNCH();
+    YQ_CUDA(yq::launch_pdl(kern, grid, dim3(FL_THREADS), smem, stream, tmA, st->tmB, tmO, a));
     return 0;
 }
 

@@ -115,6 +115,7 @@ __global__ void __launch_bounds__(F2_THREADS, 1) conv_u8_tc_flat2_kernel(const _
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    yq_pdl_wait_then_release();                             // no activation tensor was touched so far
 
     if (warp == 0) {
         // ===================== TMA producer (warp-uniform control flow, one elected lane issues) =====================
@@ -408,8 +409,7 @@ int f2_launch_v(Flat2State *st, const CUtensorMap &tmA, const CUtensorMap &tmO, 
         attr_smem = smem;
     }
     const int grid = a.num_tiles < n_sm ? a.num_tiles : n_sm;
-    kern<<<grid, F2_THREADS, smem, stream>>>(tmA, st->tmB, tmO, a);
-    YQ_CHECK_LAUNCH();
+    YQ_CUDA(yq::launch_pdl(kern, dim3(grid), dim3(F2_THREADS), smem, stream, tmA, st->tmB, tmO, a));
     return 0;
 }
 

@@ -268,6 +268,8 @@ __global__ void __launch_bounds__(RW_THREADS, (CS == 32 ? 2 : 4)) conv_u8_tc_row
     const uint32_t out_thr = (uint32_t)(((2 * warp + a.opad) * a.OWP + (CS == 4 ? 2 * qi : qi) + a.opad) * NCH + qq * NPQ);
     const uint32_t out_row = (uint32_t)(a.OWP * NCH);
 
+    yq_pdl_wait_then_release();      // everything above touched only constants and on-chip state
+
     const int first = blockIdx.x, step = gridDim.x;
     uint32_t phase = 0;
     TileXY cur = split_tile(first), nxt = cur;
@@ -454,8 +456,7 @@ int launch_rows(const RowsArgs &a, cudaStream_t stream)
     }
     int grid = n_sm * ctas_per_sm;
     if (grid > a.num_tiles) grid = a.num_tiles;
-    conv_u8_tc_rows_kernel<CS, NCH><<<grid, RW_THREADS, smem, stream>>>(a);
-    YQ_CHECK_LAUNCH();
+    YQ_CUDA(yq::launch_pdl(conv_u8_tc_rows_kernel<CS, NCH>, dim3(grid), dim3(RW_THREADS), smem, stream, a));
     return 0;
 }
 

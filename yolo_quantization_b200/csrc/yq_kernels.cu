@@ -542,6 +542,7 @@ template <typename V>
 __global__ void maxpool_u8_kernel(const V *__restrict__ in, V *__restrict__ out, int H, int W, int OH, int OW, int vpp /* vectors per pixel */,
                                   int size, int stride, int off, Geo gi, Geo go)
 {
+    yq_pdl_wait_then_release();
     const int n = blockIdx.x / OH, oy = blockIdx.x - n * OH;
     const int per_row = OW * vpp;
     for (int j = blockIdx.y * blockDim.x + threadIdx.x; j < per_row; j += gridDim.y * blockDim.x) {
@@ -592,11 +593,12 @@ extern "C" int yq_forward_maxpool_layer_quant_geom_gpu(const uint8_t *in, const 
     int threads;
     if (cs % 16 == 0) {
         row_launch_shape(batch * oh, ow * (cs / 16), &grid, &threads);
-        maxpool_u8_kernel<uint4><<<grid, threads, 0, (cudaStream_t)stream>>>((const uint4 *)in, (uint4 *)out, h, w, oh, ow, cs / 16, size, stride, off, gi, go);
+        YQ_CUDA(yq::launch_pdl(maxpool_u8_kernel<uint4>, grid, dim3(threads), 0, (cudaStream_t)stream, (const uint4 *)in, (uint4 *)out, h, w, oh, ow, cs / 16, size,
+                               stride, off, gi, go));
     } else {
         row_launch_shape(batch * oh, ow * (cs / 4), &grid, &threads);
-        maxpool_u8_kernel<uint32_t><<<grid, threads, 0, (cudaStream_t)stream>>>((const uint32_t *)in, (uint32_t *)out, h, w, oh, ow, cs / 4, size, stride, off,
-                                                                                 gi, go);
+        YQ_CUDA(yq::launch_pdl(maxpool_u8_kernel<uint32_t>, grid, dim3(threads), 0, (cudaStream_t)stream, (const uint32_t *)in, (uint32_t *)out, h, w, oh, ow,
+                               cs / 4, size, stride, off, gi, go));
     }
     YQ_CHECK_LAUNCH();
     return 0;
@@ -613,6 +615,7 @@ extern "C" int yq_forward_maxpool_layer_quant_gpu(const uint8_t *in, uint8_t *ou
 template <typename V>
 __global__ void upsample_u8_kernel(const V *__restrict__ in, V *__restrict__ out, int H, int W, int vpp, int stride, Geo gi, Geo go)
 {
+    yq_pdl_wait_then_release();
     const int OW = W * stride, OH = H * stride;
     const int n = blockIdx.x / OH, oy = blockIdx.x - n * OH;
     const int per_row = OW * vpp;
@@ -633,10 +636,11 @@ extern "C" int yq_forward_upsample_layer_quant_geom_gpu(const uint8_t *in, const
     int threads;
     if (cs % 16 == 0) {
         row_launch_shape(batch * h * stride, w * stride * (cs / 16), &grid, &threads);
-        upsample_u8_kernel<uint4><<<grid, threads, 0, (cudaStream_t)stream>>>((const uint4 *)in, (uint4 *)out, h, w, cs / 16, stride, gi, go);
+        YQ_CUDA(yq::launch_pdl(upsample_u8_kernel<uint4>, grid, dim3(threads), 0, (cudaStream_t)stream, (const uint4 *)in, (uint4 *)out, h, w, cs / 16, stride, gi, go));
     } else {
         row_launch_shape(batch * h * stride, w * stride * (cs / 4), &grid, &threads);
-        upsample_u8_kernel<uint32_t><<<grid, threads, 0, (cudaStream_t)stream>>>((const uint32_t *)in, (uint32_t *)out, h, w, cs / 4, stride, gi, go);
+        YQ_CUDA(yq::launch_pdl(upsample_u8_kernel<uint32_t>, grid, dim3(threads), 0, (cudaStream_t)stream, (const uint32_t *)in, (uint32_t *)out, h, w, cs / 4, stride,
+                               gi, go));
     }
     YQ_CHECK_LAUNCH();
     return 0;
@@ -664,6 +668,7 @@ struct RouteArgs {
 
 __global__ void route_u8_kernel(const RouteArgs a, uint8_t *__restrict__ out, int vec)
 {
+    yq_pdl_wait_then_release();
     const int n = blockIdx.x / a.H, y = blockIdx.x - n * a.H;
     if (vec) {
         const int vpp = a.cs_out / 16, per_row = a.W * vpp;
@@ -715,7 +720,7 @@ extern "C" int yq_forward_route_layer_quant_geom_gpu(const uint8_t *const *input
     dim3 grid;
     int threads;
     row_launch_shape(batch * h, vec ? w * (a.cs_out / 16) : w * a.cs_out, &grid, &threads);
-    route_u8_kernel<<<grid, threads, 0, (cudaStream_t)stream>>>(a, out, vec);
+    YQ_CUDA(yq::launch_pdl(route_u8_kernel, grid, dim3(threads), 0, (cudaStream_t)stream, a, out, vec));
     YQ_CHECK_LAUNCH();
     return 0;
 }
@@ -835,6 +840,7 @@ __global__ void nchw_to_nhwc4_u8_geom_kernel(const uint8_t *__restrict__ in, uin
 {
     // one block = RY consecutive image rows, one thread = one 16-byte output chunk of each of them; every load of the RY
     // rows is issued before the first use (the kernel is a pure latency / bandwidth problem)
+    yq_pdl_wait_then_release();
     const int HW = H * W, wq = W / 4;
     const int row0 = blockIdx.x * RY;
     for (int j = blockIdx.y * blockDim.x + threadIdx.x; j <= wq; j += gridDim.y * blockDim.x) {
@@ -906,7 +912,7 @@ extern "C" int yq_nchw_to_nhwc_u8_geom(const uint8_t *in, uint8_t *out, int batc
         const int cpr = w / 4 + 1, threads = cpr >= 128 ? 128 : (cpr + 31) / 32 * 32;
         const int by = (cpr + threads - 1) / threads;
         dim3 grid((unsigned)((batch * h + RY - 1) / RY), (unsigned)(by < 8 ? by : 8));
-        nchw_to_nhwc4_u8_geom_kernel<RY><<<grid, threads, 0, (cudaStream_t)stream>>>(in, out, c, h, w, g->pitch_w, g->rows_h, batch * h);
+        YQ_CUDA(yq::launch_pdl(nchw_to_nhwc4_u8_geom_kernel<RY>, grid, dim3(threads), 0, (cudaStream_t)stream, in, out, c, h, w, g->pitch_w, g->rows_h, batch * h));
         YQ_CHECK_LAUNCH();
         return 0;
     }
