@@ -14,8 +14,9 @@ c, h, w, n, k, batch = (int(x) for x in (sys.argv[1:7] + ["512", "13", "13", "10
 rng = np.random.default_rng(0)
 wq = rng.integers(0, 256, size=(n, c * k * k), dtype=np.uint8)
 zp_w = rng.integers(0, 256, size=n, dtype=np.uint8)
-layer = darknet.ConvolutionalLayerQuant(h, w, c, n, k, 1, k // 2, synth.ACT_CODES["relu6"], wq, zp_w, np.zeros(n, np.int32), np.full(n, 0.25 * 2.0 ** -8),
-                                        np.ones(n), 0, 0, 0.05)
+head = n % 128 != 0
+layer = darknet.ConvolutionalLayerQuant(h, w, c, n, k, 1, k // 2, synth.ACT_CODES["linear" if head else "relu6"], wq, zp_w, np.zeros(n, np.int32),
+                                        np.full(n, 0.25 * 2.0 ** -8), np.ones(n), 0, 128 if head else 0, 0.05, quant_stop_flag=1 if head else 0)
 x = rng.integers(0, 256, size=(batch, c, h, w), dtype=np.uint8)
 for _ in range(3):
     layer.forward_flat(x, want_acc=False)

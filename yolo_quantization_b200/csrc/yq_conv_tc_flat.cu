@@ -91,7 +91,7 @@ template <int BN, int KC>
 struct FlatSmem {
     static constexpr int B_BYTES = BN * KC;
     static constexpr int B_STAGE = (BN + FL_ONES) * KC;          // multiple of 1024 for every instantiated (BN, KC)
-    static constexpr int PARAM_BYTES = BN * 24;
+    static constexpr int PARAM_BYTES = BN * 24 + 2048 + 4 * BN;     // per-channel parameters, the head's 512-entry float table, its per-channel table offsets
     static_assert(B_STAGE % 1024 == 0, "stage buffers must keep the 1024-byte swizzle alignment");
     static_assert(128 * BN <= FL_BSTAGES * B_STAGE, "output staging aliases the weight ring");
 };
@@ -108,7 +108,9 @@ __global__ void __launch_bounds__(FL_THREADS, 2) conv_u8_tc_flat_kernel(const __
     uint8_t *sB = smem + 2 * a.a_stage_bytes;               // FL_BSTAGES weight stages (+ constant ones rows)
     int4 *s_q = (int4 *)(sB + FL_BSTAGES * L::B_STAGE);     // {bias, zw, 2*M0, shift}
     double *s_mc = (double *)(s_q + BN);
-    uint64_t *a_full = (uint64_t *)(s_mc + BN);
+    float *s_lut = (float *)(s_mc + BN);                    // yolo heads: (u8 - zp_out) * s_out, then its logistic
+    int *s_sel = (int *)(s_lut + 512);                      // 0 / 256: which half of the table channel oc0 + i reads
+    uint64_t *a_full = (uint64_t *)(s_sel + BN);
     uint64_t *a_empty = a_full + 2;
     uint64_t *b_full = a_empty + 2;
     uint64_t *b_empty = b_full + FL_BSTAGES;
@@ -157,6 +159,13 @@ __global__ void __launch_bounds__(FL_THREADS, 2) conv_u8_tc_flat_kernel(const __
         for (int i = t; i < BN; i += 32 * FL_EPI_WARPS) {
             s_q[i] = __ldg(a.ep.chanq + oc0 + i);
             s_mc[i] = __ldg(a.ep.mcomb + oc0 + i);
+        }
+        if (SLOW && a.out_yolo) {   // yolo_layer.c:137-146: channels 2, 3 (w, h) of every anchor stay linear, the rest go through the logistic
+            for (int i = t; i < 512; i += 32 * FL_EPI_WARPS) s_lut[i] = __ldg(a.lut + i);
+            for (int i = t; i < BN; i += 32 * FL_EPI_WARPS) {
+                const int e = (oc0 + i) % a.yolo_per;
+                s_sel[i] = (e == 2 || e == 3) ? 0 : 256;
+            }
         }
         for (int s = 0; s < FL_BSTAGES; ++s) {   // the 16 all-ones filter rows behind the TMA-written BN rows of every stage
             uint32_t *ones = (uint32_t *)(sB + s * L::B_STAGE + L::B_BYTES);
@@ -276,10 +285,7 @@ __global__ void __launch_bounds__(FL_THREADS, 2) conv_u8_tc_flat_kernel(const __
                             const uint8_t u = (uint8_t)(packed[j / 4] >> (8 * (j % 4)));
                             const size_t fidx = ((size_t)n * a.N + oc) * a.H * a.W + (size_t)(y1 - 1) * a.W + (col - 1);
                             if (a.out_f32) a.out_f32[fidx] = yq::dequant_f32(a.ep, u);
-                            if (a.out_yolo) {   // yolo_layer.c:137-146: channels 2, 3 (w, h) of every anchor stay linear
-                                const int e = oc % a.yolo_per;
-                                a.out_yolo[fidx] = __ldg(a.lut + ((e == 2 || e == 3) ? 0 : 256) + u);
-                            }
+                            if (a.out_yolo) a.out_yolo[fidx] = s_lut[s_sel[c0 + j] + u];
                         }
                     }
                 }
