@@ -569,7 +569,8 @@ def test_layout_transform_padded_geometry(built):
     from yolo_quantization_b200 import _lib
     lib = _lib.load()
     rng = np.random.default_rng(5)
-    for c, h, w, pad, pitch, rows in ((3, 8, 12, 1, 16, 10), (3, 6, 20, 1, 24, 9), (3, 5, 7, 1, 12, 8), (16, 6, 6, 1, 9, 8), (3, 4, 8, 2, 13, 9)):
+    for c, h, w, pad, pitch, rows in ((3, 8, 12, 1, 16, 10), (3, 6, 20, 1, 24, 9), (3, 5, 7, 1, 12, 8), (16, 6, 6, 1, 9, 8), (3, 4, 8, 2, 13, 9),
+                                      (3, 6, 32, 1, 40, 9), (4, 5, 48, 1, 52, 8), (1, 7, 16, 1, 20, 9), (3, 9, 64, 1, 68, 11)):   # 16-pixel fast path
         x = rng.integers(0, 256, size=(2, c, h, w), dtype=np.uint8)
         g = _lib.ActGeom(pad, pitch, rows)
         cs = darknet.channel_stride(c)
