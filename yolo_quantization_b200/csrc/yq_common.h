@@ -100,6 +100,7 @@ struct yq_conv_layer {
     void *tc_rows = nullptr;    // halo-input conv + pool flavour state (yq_conv_tc_rows.cu), or nullptr
     void *tc_flat = nullptr;    // flat-strip patch flavour state (yq_conv_tc_flat.cu), or nullptr
     void *tc_flat2 = nullptr;   // its persistent two-tiles-per-weight-stage form (yq_conv_tc_flat2.cu), or nullptr
+    void *tc_flat2x = nullptr;  // the same on CTA pairs, tcgen05 cta_group::2 (yq_conv_tc_flat2x.cu), or nullptr
     std::vector<uint8_t> host_w;  // OIHW copy kept for repacking
     std::vector<uint8_t> host_zw;
     std::vector<int32_t> host_chanq;   // 4 ints per channel {bias, zw, 2*M0, shift} (copy of chanq)
@@ -140,6 +141,13 @@ int yq_tc_flat2_prepare(yq_conv_layer *l, void **state);
 void yq_tc_flat2_free(void *state);
 int yq_tc_flat2_forward(yq_conv_layer *l, void *state, const uint8_t *in_flat, uint8_t *out_flat, int halo_fill, int32_t *out_acc, int batch,
                         cudaStream_t stream);
+
+// implemented in yq_conv_tc_flat2x.cu (flat2 on CTA pairs: cta_group::2 MMAs, each SM holds half of every weight stage)
+int yq_tc_flat2x_supported(const yq_conv_layer *l);
+int yq_tc_flat2x_prepare(yq_conv_layer *l, void **state);
+void yq_tc_flat2x_free(void *state);
+int yq_tc_flat2x_forward(yq_conv_layer *l, void *state, const uint8_t *in_flat, uint8_t *out_flat, int halo_fill, int32_t *out_acc, int batch,
+                         cudaStream_t stream);
 
 // implemented in yq_conv_tc.cu (TMA-fed; c % 64 == 0)
 int yq_tc_supported(const yq_conv_layer *l);

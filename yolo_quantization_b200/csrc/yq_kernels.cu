@@ -415,7 +415,8 @@ extern "C" yq_conv_layer *yq_make_convolutional_layer_quant(const yq_conv_desc *
         if (yq_tc_prepare(l) == 0) l->kernel = 1;
     }
     if ((yq_tc_rows_supported(l) && yq_tc_rows_prepare(l, &l->tc_rows) != 0) || (yq_tc_flat_supported(l) && yq_tc_flat_prepare(l, &l->tc_flat) != 0) ||
-        (yq_tc_flat2_supported(l) && yq_tc_flat2_prepare(l, &l->tc_flat2) != 0)) {
+        (yq_tc_flat2_supported(l) && yq_tc_flat2_prepare(l, &l->tc_flat2) != 0) ||
+        (yq_tc_flat2x_supported(l) && yq_tc_flat2x_prepare(l, &l->tc_flat2x) != 0)) {
         yq_free_convolutional_layer_quant(l);
         return nullptr;
     }
@@ -429,6 +430,7 @@ extern "C" void yq_free_convolutional_layer_quant(yq_conv_layer *l)
     yq_tc_rows_free(l->tc_rows);
     yq_tc_flat_free(l->tc_flat);
     yq_tc_flat2_free(l->tc_flat2);
+    yq_tc_flat2x_free(l->tc_flat2x);
     cudaFree(l->w_simt); cudaFree(l->bias); cudaFree(l->zw); cudaFree(l->mcomb); cudaFree(l->mval); cudaFree(l->rsh); cudaFree(l->chanq);
     delete l;
 }
@@ -480,6 +482,10 @@ extern "C" int yq_forward_convolutional_layer_quant_flat_gpu(yq_conv_layer *l, c
     if (!l->tc_flat) return yq::fail("this layer has no flat flavour (see yq_conv_flat_supported)");
     if (l->quant_stop_flag && !out_f32) return yq::fail("quant_stop layer needs out_f32");
     static const bool no_flat2 = getenv("YQ_NO_FLAT2") && atoi(getenv("YQ_NO_FLAT2"));   // A/B measurements
+    // CTA-pair form for the long-K layers (measured: layers 10/12/14/21 1.07-1.24x faster, the short-K layers 6/8 slower);
+    // YQ_FLAT2X=0 disables it, =2 forces it wherever it exists (A/B measurements)
+    static const int use_2x = getenv("YQ_FLAT2X") ? atoi(getenv("YQ_FLAT2X")) : 1;
+    if (l->tc_flat2x && !no_flat2 && (use_2x == 2 || (use_2x == 1 && l->c >= 256))) return yq_tc_flat2x_forward(l, l->tc_flat2x, in_flat, out_flat, halo_fill, out_acc, batch, (cudaStream_t)stream);
     if (l->tc_flat2 && !no_flat2) return yq_tc_flat2_forward(l, l->tc_flat2, in_flat, out_flat, halo_fill, out_acc, batch, (cudaStream_t)stream);
     return yq_tc_flat_forward(l, l->tc_flat, in_flat, out_flat, halo_fill, out_f32, nullptr, 0, out_acc, batch, (cudaStream_t)stream);
 }

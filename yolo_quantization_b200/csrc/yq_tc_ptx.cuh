@@ -240,6 +240,57 @@ __device__ __forceinline__ void tmem_ldq_first(uint32_t tsum, uint32_t taddr, ui
         : "r"(tsum), "r"(tsum + (16u << 16)), "r"(taddr), "r"(taddr + (16u << 16)));
 }
 
+// ---------------------------------------------------------------------------------------------
+// cta_group::2 (CTA pair of a cluster; forms follow cute/arch/{mma_sm100_umma,copy_sm100_tma,tmem_allocator_sm100}.hpp)
+// ---------------------------------------------------------------------------------------------
+template <int COLS>
+__device__ __forceinline__ void tmem_alloc_2cta(uint32_t *slot)   // one warp of EACH CTA of the pair, same slot offset
+{
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "n"(COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+template <int COLS>
+__device__ __forceinline__ void tmem_dealloc_2cta(uint32_t addr)
+{
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(addr), "n"(COLS) : "memory");
+}
+// M = 256 (128 rows from each CTA's A tile), B rows split between the two CTAs' tiles; issued by the leader CTA only
+__device__ __forceinline__ void umma_i8_2cta(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::i8 [%0], %1, %2, %3, {%5, %5, %5, %5, %5, %5, %5, %5}, p;\n\t}" ::"r"(tmem_d),
+        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate), "r"(0u)
+        : "memory");
+}
+// arrives (once the pair's prior MMAs have completed) on the same-offset mbarrier of every CTA in `mask`
+__device__ __forceinline__ void umma_commit_2cta(uint64_t *bar, uint16_t mask)
+{
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)), "h"(mask)
+                 : "memory");
+}
+// shared::cluster address of `p` (an address of MY shared memory) in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t map_to_cta(const void *p, uint32_t rank)
+{
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_u32(p)), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr)
+{
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// 2-D TMA load into MY shared memory whose completion is signalled on an mbarrier that may live in the peer CTA
+__device__ __forceinline__ void tma_load_2d_2cta(void *smem, const CUtensorMap *map, uint32_t bar_cluster_addr, int c0, int c1)
+{
+    asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+                     smem_u32(smem)),
+                 "l"(map), "r"(bar_cluster_addr), "r"(c0), "r"(c1)
+                 : "memory");
+}
+__host__ __device__ constexpr uint32_t make_idesc_m(int m, int n) { return (2u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24); }
+
 // kind::i8 instruction descriptor (cute::UMMA::InstrDescriptor): c_format S32 (2) [4,6), a/b format 0 = UINT8
 // [7,10)/[10,13), a/b K-major (0) [15]/[16], N>>3 [17,23), M>>4 [24,29); M is always 128 here.
 __host__ __device__ constexpr uint32_t make_idesc(int n) { return (2u << 4) | ((uint32_t)(n >> 3) << 17) | ((128u >> 4) << 24); }
