@@ -31,7 +31,7 @@ using namespace yqtc;
 
 namespace {
 
-constexpr int F2X_BN = 128;
+constexpr int F2X_BN = 128;            // channels per tile of the two-tile form; the WIDE form has one tile of 256 channels
 constexpr int F2X_EPI_WARPS = 16;
 constexpr int F2X_SUM_WARPS = 2;
 constexpr int F2X_THREADS = 32 * (2 + F2X_SUM_WARPS + F2X_EPI_WARPS);
@@ -53,29 +53,35 @@ struct Flat2xArgs {
     int debug;             // YQ_FLAT2_DEBUG experiments (results are garbage): 1 = skip weight loads of taps > 0, 2 = skip the epilogue math
 };
 
-template <int KC>
+// WIDE = false: two 128-position tiles x 128 channels per CTA and accumulator pair;  WIDE = true: one tile x 256 channels
+// (N = 256 MMAs: the patch is read once per 256 channels -> ~105 instead of ~126 B/clk of shared-memory traffic per SM)
+template <int KC, bool WIDE>
 struct Flat2xSmem {
-    static constexpr int B_STAGE = (F2X_BN / 2) * KC;            // each CTA of the pair holds 64 of the stage's 128 filter rows
-    static constexpr int OUT_BYTES = 128 * F2X_BN;                 // one staging tile; there are two
-    static constexpr int PARAM_BYTES = F2X_BN * 24;
+    static constexpr int BNT = WIDE ? 256 : 128;                  // channels per tile = N of the pair MMA
+    static constexpr int TPC = WIDE ? 1 : 2;                      // tiles per CTA
+    static constexpr int PPC = 128 * TPC;                         // positions per CTA; a cluster tile has 2 * PPC
+    static constexpr int B_STAGE = (BNT / 2) * KC;                // each CTA of the pair holds half of the stage's filter rows
+    static constexpr int OUT_BYTES = 128 * 128;                   // one staging tile [128 positions][128 channels]; there are two
+    static constexpr int PARAM_BYTES = BNT * 24;
     static constexpr int SUM_BYTES = 2 * F2X_MAX_ROWS * 4;         // S[pair buffer][patch row]
 };
 
 __device__ __forceinline__ void f2x_arrive(uint64_t *bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory"); }
 
-template <int KC, bool SLOW>
+template <int KC, bool SLOW, bool WIDE>
 __global__ void __launch_bounds__(F2X_THREADS, 1) conv_u8_tc_flat2x_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                                                                      const __grid_constant__ CUtensorMap tmO, const Flat2xArgs a)
 {
-    using L = Flat2xSmem<KC>;
+    using L = Flat2xSmem<KC, WIDE>;
+    constexpr int BNT = L::BNT, TPC = L::TPC, PPC = L::PPC;
     extern __shared__ __align__(16) uint8_t smem_raw[];
     uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     uint8_t *sA = smem;                                              // F2X_ASTAGES patch stages
     uint8_t *sB = sA + F2X_ASTAGES * a.a_stage_bytes;                 // a.b_stages weight stages
     uint8_t *sOut = sB + a.b_stages * L::B_STAGE;                    // two output staging tiles
     int4 *s_q = (int4 *)(sOut + 2 * L::OUT_BYTES);                   // {bias, zw, 2*M0, shift} of the current n-tile
-    double *s_mc = (double *)(s_q + F2X_BN);
-    int *s_sum = (int *)(s_mc + F2X_BN);                              // [2][F2X_MAX_ROWS]
+    double *s_mc = (double *)(s_q + BNT);
+    int *s_sum = (int *)(s_mc + BNT);                              // [2][F2X_MAX_ROWS]
     uint64_t *a_full = (uint64_t *)(s_sum + 2 * F2X_MAX_ROWS);
     uint64_t *a_empty = a_full + F2X_ASTAGES;
     uint64_t *b_full = a_empty + F2X_ASTAGES;
@@ -128,7 +134,7 @@ __global__ void __launch_bounds__(F2X_THREADS, 1) conv_u8_tc_flat2x_kernel(const
         uint32_t pha = 0, phb = 0;
         for (int tile = cid; tile < a.num_tiles; tile += ncl) {
             const int nt = a.m_pairs == 1 ? tile : (int)__umulhi((uint32_t)tile, a.magic_m), mp = tile - nt * a.m_pairs;
-            const int p0 = mp * 512 + (int)rank * 256, oc0 = nt * F2X_BN + (int)rank * (F2X_BN / 2);
+            const int p0 = mp * 2 * PPC + (int)rank * PPC, oc0 = nt * BNT + (int)rank * (BNT / 2);
             for (int c = 0; c < chunks; ++c) {
                 mbar_wait(&a_empty[sa], pha ^ 1);
                 if (elect_one()) {
@@ -141,7 +147,7 @@ __global__ void __launch_bounds__(F2X_THREADS, 1) conv_u8_tc_flat2x_kernel(const
                     mbar_wait(&b_empty[s], phb ^ 1);           // (released by the leader's multicast commit)
                     if (elect_one()) {
                         // my 64 filter rows of the stage; both halves complete on the LEADER's barrier
-                        if (rank == 0) mbar_expect_tx(&b_full[s], (uint32_t)(F2X_BN * KC));
+                        if (rank == 0) mbar_expect_tx(&b_full[s], (uint32_t)(BNT * KC));
                         tma_load_2d_2cta(sB + s * L::B_STAGE, &tmB, map_to_cta(&b_full[s], 0), tap * a.CS + c * KC, oc0);
                     }
                     if (++s == nbs) { s = 0; phb ^= 1; }
@@ -151,7 +157,7 @@ __global__ void __launch_bounds__(F2X_THREADS, 1) conv_u8_tc_flat2x_kernel(const
     } else if (warp == 1) {
         if (rank == 0) {
             // ===================== MMA issuer (leader CTA): M = 256 across the pair =====================
-            constexpr uint32_t idesc = make_idesc_m(256, F2X_BN);
+            constexpr uint32_t idesc = make_idesc_m(256, BNT);
             const uint32_t row_step = (uint32_t)((a.W + 1 - a.size) * KC);
             int sa = 0, s = 0;
             uint32_t pha = 0, phb = 0, it = 0;
@@ -160,7 +166,7 @@ __global__ void __launch_bounds__(F2X_THREADS, 1) conv_u8_tc_flat2x_kernel(const
                 mbar_wait(&acc_empty[pb], ((it >> 1) & 1) ^ 1);          // my epilogue has drained this pair of accumulators
                 mbar_wait(&acc_peer_empty[pb], ((it >> 1) & 1) ^ 1);     // ... and so has the peer's
                 tc_fence_after();
-                const uint32_t acc0 = tmem_base + pb * 2 * F2X_BN, acc1 = acc0 + F2X_BN;
+                const uint32_t acc0 = tmem_base + pb * 256, acc1 = acc0 + 128;     // (WIDE: one accumulator of 256 columns)
                 uint32_t accumulate = 0;
                 for (int c = 0; c < chunks; ++c) {
                     mbar_wait(&a_full[sa], pha);                         // my patch
@@ -176,7 +182,7 @@ __global__ void __launch_bounds__(F2X_THREADS, 1) conv_u8_tc_flat2x_kernel(const
 #pragma unroll
                             for (int k = 0; k < KC / 32; ++k) {
                                 umma_i8_2cta(acc0, da0 + 2 * k, db + 2 * k, idesc, (k == 0) ? accumulate : 1u);
-                                umma_i8_2cta(acc1, da1 + 2 * k, db + 2 * k, idesc, (k == 0) ? accumulate : 1u);
+                                if (!WIDE) umma_i8_2cta(acc1, da1 + 2 * k, db + 2 * k, idesc, (k == 0) ? accumulate : 1u);
                             }
                             umma_commit_2cta(&b_empty[s], 3);
                         }
@@ -262,12 +268,12 @@ __global__ void __launch_bounds__(F2X_THREADS, 1) conv_u8_tc_flat2x_kernel(const
         uint32_t it = 0;
         for (int tile = cid; tile < a.num_tiles; tile += ncl, ++it) {
             const int nt = a.m_pairs == 1 ? tile : (int)__umulhi((uint32_t)tile, a.magic_m), mp = tile - nt * a.m_pairs;
-            const int oc0 = nt * F2X_BN;
+            const int oc0 = nt * BNT;
             const int pb = it & 1;
             // both staging tiles must be free (the stores of the previous pair have finished reading them)
             if (et == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
             if (nt != cur_nt) {
-                for (int i = et; i < F2X_BN; i += EPI_THREADS) {
+                for (int i = et; i < BNT; i += EPI_THREADS) {
                     s_q[i] = __ldg(a.ep.chanq + oc0 + i);
                     s_mc[i] = __ldg(a.ep.mcomb + oc0 + i);
                 }
@@ -278,8 +284,8 @@ __global__ void __launch_bounds__(F2X_THREADS, 1) conv_u8_tc_flat2x_kernel(const
             mbar_wait(&acc_full[pb], (it >> 1) & 1);
             tc_fence_after();
 #pragma unroll 1
-            for (int j = 0; j < 2; ++j) {
-                const int p0 = mp * 512 + (int)rank * 256 + j * 128;
+            for (int j = 0; j < TPC; ++j) {
+                const int p0 = mp * 2 * PPC + (int)rank * PPC + j * 128;
                 const int p = p0 + r;
                 const int row = (int)__umulhi((uint32_t)p, a.magic_w);
                 const int col = p - row * pitch;
@@ -295,9 +301,11 @@ __global__ void __launch_bounds__(F2X_THREADS, 1) conv_u8_tc_flat2x_kernel(const
                         for (int kx = 0; kx < a.size; ++kx) sa_sum += sp[ky * pitch + kx];
                 }
                 const int nsa = -sa_sum;
-                uint8_t *stage = sOut + j * L::OUT_BYTES;
-                const uint32_t trow = tmem_base + (pb * 2 + j) * F2X_BN + ((uint32_t)(q * 32) << 16);
-                const int cbeg = part * 32;
+                constexpr int CPW = BNT / 4, NCH = CPW / 16;          // columns / 16-column chunks per epilogue warp
+                const int cbeg = part * CPW;
+                // staging tile: the tile's index (two-tile form) or the 128-channel half this warp works on (WIDE)
+                uint8_t *stage = sOut + (WIDE ? (cbeg >> 7) : j) * L::OUT_BYTES;
+                const uint32_t trow = tmem_base + pb * 256 + j * 128 + ((uint32_t)(q * 32) << 16);
                 uint32_t vbuf[2][16];
                 tmem_ld16_issue(trow + cbeg, vbuf[0]);
                 tmem_ld_wait16(vbuf[0]);
@@ -305,10 +313,10 @@ __global__ void __launch_bounds__(F2X_THREADS, 1) conv_u8_tc_flat2x_kernel(const
                     constexpr int ACTM = decltype(actm_tag)::value;
                     constexpr bool SAT = decltype(sat_tag)::value;
 #pragma unroll
-                    for (int ch = 0; ch < 2; ++ch) {
+                    for (int ch = 0; ch < NCH; ++ch) {
                         const int c0 = cbeg + 16 * ch;
                         uint32_t(&v)[16] = vbuf[ch & 1];
-                        if (ch == 0) tmem_ld16_issue(trow + c0 + 16, vbuf[1]);   // in flight while this chunk is requantized
+                        if (ch + 1 < NCH) tmem_ld16_issue(trow + c0 + 16, vbuf[(ch + 1) & 1]);   // in flight while this chunk is requantized
                         uint32_t packed[4];
                         int extra[16];
                         yq::requant_chunk<ACTM, SAT, 16, false>(v, nsa, extra, s_q + c0, s_mc + c0, a.ep.zp_out, packed);
@@ -321,8 +329,8 @@ __global__ void __launch_bounds__(F2X_THREADS, 1) conv_u8_tc_flat2x_kernel(const
                                 if (oc < a.N) a.out_acc[pix * a.CSO + oc] = (int)v[jj] + s_q[c0 + jj].y * nsa;
                             }
                         }
-                        *reinterpret_cast<uint4 *>(stage + (size_t)r * F2X_BN + (((c0 / 16) ^ (r & 7)) * 16)) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
-                        if (ch == 0) tmem_ld_wait16(vbuf[1]);
+                        *reinterpret_cast<uint4 *>(stage + (size_t)r * 128 + ((((c0 & 127) / 16) ^ (r & 7)) * 16)) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+                        if (ch + 1 < NCH) tmem_ld_wait16(vbuf[(ch + 1) & 1]);
                     }
                 };
                 if (a.debug == 2) {
@@ -335,7 +343,7 @@ __global__ void __launch_bounds__(F2X_THREADS, 1) conv_u8_tc_flat2x_kernel(const
                     else if (actm == 1) run(std::integral_constant<int, 1>{}, std::false_type{});
                     else run(std::integral_constant<int, 2>{}, std::false_type{});
                 }
-                if (j == 1) {   // this warp's TMEM and S reads of the pair are done: hand both accumulators back
+                if (j == TPC - 1) {   // this warp's TMEM and S reads of the pair are done: hand the accumulators back
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) {
@@ -347,7 +355,12 @@ __global__ void __launch_bounds__(F2X_THREADS, 1) conv_u8_tc_flat2x_kernel(const
                 fence_proxy_async();
                 asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");
                 if (et == 0) {
-                    tma_store_2d(&tmO, stage, oc0, p0);
+                    if (WIDE) {
+                        tma_store_2d(&tmO, sOut, oc0, p0);
+                        tma_store_2d(&tmO, sOut + L::OUT_BYTES, oc0 + 128, p0);
+                    } else {
+                        tma_store_2d(&tmO, sOut + j * L::OUT_BYTES, oc0, p0);
+                    }
                     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                 }
             }
@@ -398,7 +411,8 @@ int f2x_encode_2d(CUtensorMap *m, const void *ptr, uint64_t rows, int row_bytes,
 struct Flat2xState {
     int KC, n_pad;
     uint8_t *w = nullptr;       // [n_pad][size*size*cs_in]
-    CUtensorMap tmB;
+    CUtensorMap tmB, tmBw;      // weight boxes of 64 rows (two-tile form) / 128 rows (WIDE form)
+    bool wide = false;
     struct Key {
         const void *in;
         void *out;
@@ -408,10 +422,10 @@ struct Flat2xState {
     std::map<Key, std::pair<CUtensorMap, CUtensorMap>> maps;
 };
 
-template <int KC, bool SLOW>
+template <int KC, bool SLOW, bool WIDE>
 int f2x_launch_v(Flat2xState *st, const CUtensorMap &tmA, const CUtensorMap &tmO, Flat2xArgs a, cudaStream_t stream)
 {
-    using L = Flat2xSmem<KC>;
+    using L = Flat2xSmem<KC, WIDE>;
     static int attr_smem = 0, n_sm = 0, smem_max = 0;
     if (!n_sm) {
         int dev = 0;
@@ -425,7 +439,7 @@ int f2x_launch_v(Flat2xState *st, const CUtensorMap &tmA, const CUtensorMap &tmO
     if (nbs < 2) return yq::fail("conv_u8_tc_flat2x_kernel<%d>: shared memory does not hold two weight stages", KC);
     a.b_stages = nbs;
     const int smem = fixed + nbs * L::B_STAGE;
-    auto kern = conv_u8_tc_flat2x_kernel<KC, SLOW>;
+    auto kern = conv_u8_tc_flat2x_kernel<KC, SLOW, WIDE>;
     if (smem > attr_smem) {
         YQ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         attr_smem = smem;
@@ -446,15 +460,19 @@ int f2x_launch_v(Flat2xState *st, const CUtensorMap &tmA, const CUtensorMap &tmO
     at[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = at;
     cfg.numAttrs = yq::pdl_enabled() ? 2 : 1;
-    YQ_CUDA(cudaLaunchKernelEx(&cfg, kern, tmA, st->tmB, tmO, a));
+    YQ_CUDA(cudaLaunchKernelEx(&cfg, kern, tmA, WIDE ? st->tmBw : st->tmB, tmO, a));
     return 0;
 }
 
 template <int KC>
 int f2x_launch(Flat2xState *st, const CUtensorMap &tmA, const CUtensorMap &tmO, const Flat2xArgs &a, cudaStream_t stream)
 {
-    if (a.out_acc || a.ep.saturate) return f2x_launch_v<KC, true>(st, tmA, tmO, a, stream);
-    return f2x_launch_v<KC, false>(st, tmA, tmO, a, stream);
+    if (st->wide) {
+        if (a.out_acc || a.ep.saturate) return f2x_launch_v<KC, true, true>(st, tmA, tmO, a, stream);
+        return f2x_launch_v<KC, false, true>(st, tmA, tmO, a, stream);
+    }
+    if (a.out_acc || a.ep.saturate) return f2x_launch_v<KC, true, false>(st, tmA, tmO, a, stream);
+    return f2x_launch_v<KC, false, false>(st, tmA, tmO, a, stream);
 }
 
 }  // namespace
@@ -472,7 +490,11 @@ int yq_tc_flat2x_prepare(yq_conv_layer *l, void **state)
 {
     Flat2xState *st = new Flat2xState();
     st->KC = (l->cs_in % 128) ? 64 : 128;
-    st->n_pad = yq::round_up(l->n, F2X_BN);
+    {
+        const char *e = getenv("YQ_FLAT2X_WIDE");      // 0 keeps the two-tile N = 128 form everywhere (A/B measurements)
+        st->wide = l->cs_out % 256 == 0 && !(e && atoi(e) == 0);
+    }
+    st->n_pad = yq::round_up(l->n, st->wide ? 256 : F2X_BN);
     const int taps = l->size * l->size;
     const size_t ktot = (size_t)taps * l->cs_in;
     std::vector<uint8_t> wp((size_t)st->n_pad * ktot, 0);
@@ -486,7 +508,8 @@ int yq_tc_flat2x_prepare(yq_conv_layer *l, void **state)
     };
     if (cudaMalloc((void **)&st->w, wp.size()) != cudaSuccess) return cleanup();
     if (cudaMemcpy(st->w, wp.data(), wp.size(), cudaMemcpyHostToDevice) != cudaSuccess) return cleanup();
-    if (f2x_encode_2d(&st->tmB, st->w, (uint64_t)st->n_pad, (int)ktot, st->KC, F2X_BN / 2, CU_TENSOR_MAP_L2_PROMOTION_L2_256B)) return cleanup();
+    if (f2x_encode_2d(&st->tmB, st->w, (uint64_t)st->n_pad, (int)ktot, st->KC, 64, CU_TENSOR_MAP_L2_PROMOTION_L2_256B)) return cleanup();
+    if (f2x_encode_2d(&st->tmBw, st->w, (uint64_t)st->n_pad, (int)ktot, st->KC, 128, CU_TENSOR_MAP_L2_PROMOTION_L2_256B)) return cleanup();
     *state = st;
     return 0;
 }
@@ -511,7 +534,8 @@ int yq_tc_flat2x_forward(yq_conv_layer *l, void *state, const uint8_t *in_flat, 
     Flat2xArgs a;
     memset(&a, 0, sizeof a);
     const int pad = l->size / 2;
-    a.patch_rows = 256 + (l->size - 1) * (W1 + 1);
+    const int ppc = st->wide ? 128 : 256, bnt = st->wide ? 256 : F2X_BN;      // positions per CTA, channels per tile
+    a.patch_rows = ppc + (l->size - 1) * (W1 + 1);
     a.box_rows = yq::round_up((a.patch_rows + 1) / 2, 8);
     a.a_stage_bytes = yq::round_up(2 * a.box_rows * st->KC, 1024);
     Flat2xState::Key key{in_flat, out_flat, batch};
@@ -520,7 +544,7 @@ int yq_tc_flat2x_forward(yq_conv_layer *l, void *state, const uint8_t *in_flat, 
         if (st->maps.size() > 64) st->maps.clear();
         CUtensorMap tmA, tmO;
         if (f2x_encode_2d(&tmA, in_flat, (uint64_t)rows_alloc, l->cs_in, st->KC, a.box_rows, CU_TENSOR_MAP_L2_PROMOTION_L2_128B)) return -1;
-        if (f2x_encode_2d(&tmO, out_flat, (uint64_t)rows_alloc, l->cs_out, F2X_BN, 128, CU_TENSOR_MAP_L2_PROMOTION_L2_128B)) return -1;
+        if (f2x_encode_2d(&tmO, out_flat, (uint64_t)rows_alloc, l->cs_out, 128, 128, CU_TENSOR_MAP_L2_PROMOTION_L2_128B)) return -1;
         it = st->maps.emplace(key, std::make_pair(tmA, tmO)).first;
     }
     a.ep = yq::make_epi(l);
@@ -537,8 +561,8 @@ int yq_tc_flat2x_forward(yq_conv_layer *l, void *state, const uint8_t *in_flat, 
     }
     a.magic_w = (uint32_t)((0x100000000ull + W1 - 1) / W1);
     a.magic_h = (uint32_t)((0x100000000ull + H1 - 1) / H1);
-    a.m_pairs = (int)((rows_alloc + 511) / 512);      // 512-position cluster tiles (256 per CTA of the pair)
-    a.num_tiles = a.m_pairs * (st->n_pad / F2X_BN);
+    a.m_pairs = (int)((rows_alloc + 2 * ppc - 1) / (2 * ppc));      // cluster tiles of 2 * ppc positions
+    a.num_tiles = a.m_pairs * (st->n_pad / bnt);
     a.magic_m = a.m_pairs == 1 ? 0u : (uint32_t)((0x100000000ull + a.m_pairs - 1) / a.m_pairs);
     if ((long long)a.num_tiles * a.m_pairs >= 0x100000000ll) return yq::fail("tcgen05 flat2 flavour: too many tiles for 32-bit tile arithmetic");
     const CUtensorMap &tmA = it->second.first, &tmO = it->second.second;
