@@ -42,6 +42,23 @@ namespace {
 constexpr int RW_THREADS = 128;
 constexpr int TILE_ROWS = 16;           // conv output rows per tile
 constexpr int PLANE = 144;              // bytes of one shared-memory plane row: 9 x 16
+#ifndef YQ_ROWS_NBUF
+#define YQ_ROWS_NBUF 3
+#endif
+constexpr int NBUF = YQ_ROWS_NBUF;      // input-tile ring: the copy of tile i + NBUF - 1 is in flight while tile i is computed
+
+// -DYQ_TIMELINE: thread 0 of every CTA adds up the clocks it spends in each phase of a tile (yq_rows_timeline[cta * 8 + phase],
+// [cta * 8 + 7] = tiles); read back with yq_debug_rows_timeline (tools/probes/rows_timeline.py)
+#ifdef YQ_TIMELINE
+__device__ unsigned long long yq_rows_timeline[8 * 1024];
+#define TL_DECL long long tl_prev = clock64(); unsigned long long tl_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0}
+#define TL_MARK(ev) do { const long long tl_now = clock64(); tl_acc[ev] += (unsigned long long)(tl_now - tl_prev); tl_prev = tl_now; } while (0)
+#define TL_FLUSH() do { if (threadIdx.x == 0 && blockIdx.x < 1024) for (int e = 0; e < 8; ++e) yq_rows_timeline[blockIdx.x * 8 + e] = tl_acc[e]; } while (0)
+#else
+#define TL_DECL
+#define TL_MARK(ev)
+#define TL_FLUSH()
+#endif
 
 template <int CS>
 struct RowsGeom {
@@ -51,7 +68,6 @@ struct RowsGeom {
     static constexpr int A_ROWS = TILE_ROWS + 2;
     static constexpr int A_BYTES = A_ROWS * ROWP;
     static constexpr int CHUNKS = A_BYTES / 16;                     // 162 / 324 / 648
-    static constexpr int CPT = (CHUNKS + RW_THREADS - 1) / RW_THREADS;
     static constexpr int NMMA = CS == 4 ? 3 : 6 * NBLK;
 };
 
@@ -66,7 +82,7 @@ struct RowsCfg {
     static constexpr int B_BYTES = G::NMMA * BSUB;
     static constexpr int A_STRIDE = (G::A_BYTES + 32 + 127) / 128 * 128;   // +32: the last window's (zero-weight) overhang
     static constexpr int A_OFF = 0;
-    static constexpr int B_OFF = 2 * A_STRIDE;
+    static constexpr int B_OFF = NBUF * A_STRIDE;
     static constexpr int BAR_OFF = B_OFF + B_BYTES;
     static constexpr int TOTAL = BAR_OFF + 64;
     static_assert(NMMA_N % 16 == 0 && NMMA_N <= 256, "kind::i8 N");
@@ -131,6 +147,49 @@ __device__ __forceinline__ void tmem_ldq_sums(uint32_t te, uint32_t to, uint32_t
         : "r"(te), "r"(te + (16u << 16)), "r"(to), "r"(to + (16u << 16)));
 }
 
+// The same loads split into issue and wait, so that a chunk's TMEM round trip runs under the previous chunk's arithmetic
+// (the wait names the registers as in/out operands: their consumers are ordered after it)
+__device__ __forceinline__ void tmem_ldq4_issue(uint32_t taddr, uint32_t (&v0)[16], uint32_t (&v1)[16])
+{
+    asm volatile(
+        "tcgen05.ld.sync.aligned.16x256b.x4.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%32];\n\t"
+        "tcgen05.ld.sync.aligned.16x256b.x4.b32 {%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%33];"
+        : "=r"(v0[0]), "=r"(v0[1]), "=r"(v0[2]), "=r"(v0[3]), "=r"(v0[4]), "=r"(v0[5]), "=r"(v0[6]), "=r"(v0[7]), "=r"(v0[8]), "=r"(v0[9]),
+          "=r"(v0[10]), "=r"(v0[11]), "=r"(v0[12]), "=r"(v0[13]), "=r"(v0[14]), "=r"(v0[15]), "=r"(v1[0]), "=r"(v1[1]), "=r"(v1[2]),
+          "=r"(v1[3]), "=r"(v1[4]), "=r"(v1[5]), "=r"(v1[6]), "=r"(v1[7]), "=r"(v1[8]), "=r"(v1[9]), "=r"(v1[10]), "=r"(v1[11]),
+          "=r"(v1[12]), "=r"(v1[13]), "=r"(v1[14]), "=r"(v1[15])
+        : "r"(taddr), "r"(taddr + (16u << 16)));
+}
+__device__ __forceinline__ void tmem_wait32(uint32_t (&v0)[16], uint32_t (&v1)[16])
+{
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(v0[0]), "+r"(v0[1]), "+r"(v0[2]), "+r"(v0[3]), "+r"(v0[4]), "+r"(v0[5]), "+r"(v0[6]), "+r"(v0[7]), "+r"(v0[8]), "+r"(v0[9]),
+                   "+r"(v0[10]), "+r"(v0[11]), "+r"(v0[12]), "+r"(v0[13]), "+r"(v0[14]), "+r"(v0[15]), "+r"(v1[0]), "+r"(v1[1]), "+r"(v1[2]),
+                   "+r"(v1[3]), "+r"(v1[4]), "+r"(v1[5]), "+r"(v1[6]), "+r"(v1[7]), "+r"(v1[8]), "+r"(v1[9]), "+r"(v1[10]), "+r"(v1[11]),
+                   "+r"(v1[12]), "+r"(v1[13]), "+r"(v1[14]), "+r"(v1[15])::"memory");
+}
+__device__ __forceinline__ void tmem_ldq_eo_issue(uint32_t te, uint32_t to, uint32_t (&e0)[8], uint32_t (&e1)[8], uint32_t (&o0)[8], uint32_t (&o1)[8])
+{
+    asm volatile(
+        "tcgen05.ld.sync.aligned.16x256b.x2.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%32];\n\t"
+        "tcgen05.ld.sync.aligned.16x256b.x2.b32 {%8, %9, %10, %11, %12, %13, %14, %15}, [%33];\n\t"
+        "tcgen05.ld.sync.aligned.16x256b.x2.b32 {%16, %17, %18, %19, %20, %21, %22, %23}, [%34];\n\t"
+        "tcgen05.ld.sync.aligned.16x256b.x2.b32 {%24, %25, %26, %27, %28, %29, %30, %31}, [%35];"
+        : "=r"(e0[0]), "=r"(e0[1]), "=r"(e0[2]), "=r"(e0[3]), "=r"(e0[4]), "=r"(e0[5]), "=r"(e0[6]), "=r"(e0[7]), "=r"(e1[0]), "=r"(e1[1]),
+          "=r"(e1[2]), "=r"(e1[3]), "=r"(e1[4]), "=r"(e1[5]), "=r"(e1[6]), "=r"(e1[7]), "=r"(o0[0]), "=r"(o0[1]), "=r"(o0[2]), "=r"(o0[3]),
+          "=r"(o0[4]), "=r"(o0[5]), "=r"(o0[6]), "=r"(o0[7]), "=r"(o1[0]), "=r"(o1[1]), "=r"(o1[2]), "=r"(o1[3]), "=r"(o1[4]), "=r"(o1[5]),
+          "=r"(o1[6]), "=r"(o1[7])
+        : "r"(te), "r"(te + (16u << 16)), "r"(to), "r"(to + (16u << 16)));
+}
+__device__ __forceinline__ void tmem_wait_eo(uint32_t (&e0)[8], uint32_t (&e1)[8], uint32_t (&o0)[8], uint32_t (&o1)[8])
+{
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(e0[0]), "+r"(e0[1]), "+r"(e0[2]), "+r"(e0[3]), "+r"(e0[4]), "+r"(e0[5]), "+r"(e0[6]), "+r"(e0[7]), "+r"(e1[0]), "+r"(e1[1]),
+                   "+r"(e1[2]), "+r"(e1[3]), "+r"(e1[4]), "+r"(e1[5]), "+r"(e1[6]), "+r"(e1[7]), "+r"(o0[0]), "+r"(o0[1]), "+r"(o0[2]), "+r"(o0[3]),
+                   "+r"(o0[4]), "+r"(o0[5]), "+r"(o0[6]), "+r"(o0[7]), "+r"(o1[0]), "+r"(o1[1]), "+r"(o1[2]), "+r"(o1[3]), "+r"(o1[4]), "+r"(o1[5]),
+                   "+r"(o1[6]), "+r"(o1[7])::"memory");
+}
+
 // Per-launch channel parameters of ONE thread (its NCH/4 channels), kept in registers.
 template <int NPQ>
 struct ThreadChan {
@@ -165,29 +224,38 @@ __device__ __forceinline__ uint32_t pack4(const int (&r)[4])
     return __byte_perm(__byte_perm((uint32_t)r[0], (uint32_t)r[1], 0x0040), __byte_perm((uint32_t)r[2], (uint32_t)r[3], 0x0040), 0x5410);
 }
 
-template <int CS, int NCH>
-__global__ void __launch_bounds__(RW_THREADS, (CS == 32 ? 2 : 4)) conv_u8_tc_rows_kernel(const __grid_constant__ RowsArgs a)
+// SPLIT = 2: two warps per TMEM lane quarter share a tile's epilogue (c = 4: one pixel pair each; c >= 16: half of the
+// thread's channels each), which halves the time the accumulator is held between two tiles' MMAs
+template <int CS, int NCH, int SPLIT>
+__global__ void __launch_bounds__(RW_THREADS * SPLIT, (CS == 32 ? 2 : SPLIT == 2 ? 3 : 4)) conv_u8_tc_rows_kernel(const __grid_constant__ RowsArgs a)
 {
     using G = RowsGeom<CS>;
     using L = RowsCfg<CS, NCH>;
     constexpr int NPQ = NCH / 4;
+    constexpr int NT = RW_THREADS * SPLIT;
+    constexpr int CPT = (G::CHUNKS + NT - 1) / NT;
+    constexpr int NPT = CS == 4 ? NPQ : NPQ / SPLIT;      // channels whose parameters this thread keeps
+    // double-buffered TMEM loads (a chunk's round trip under the previous chunk's arithmetic) where the registers are there:
+    // c = 32 runs 2 CTAs per SM; measured slower for the 4-CTA kernels (layers 0, 2), faster for layer 4
+    constexpr bool PIPE = CS == 32;
+    static_assert(SPLIT == 1 || CS == 4 || NCH >= 32, "a thread needs at least one 4-channel chunk");
     extern __shared__ __align__(16) uint8_t smem_raw[];
     uint8_t *smem = smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u);
     uint64_t *mma_done = (uint64_t *)(smem + L::BAR_OFF);
     uint32_t *tmem_slot = (uint32_t *)(mma_done + 1);
 
-    const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+    const int t = threadIdx.x, warp = (t >> 5) & 3, half = SPLIT == 2 ? t >> 7 : 0, lane = t & 31;
     const int qi = lane >> 2, qq = lane & 3;
 
     // ---- one-time setup: resident filter tiles, barrier, TMEM
-    for (int i = t; i < L::B_BYTES / 16; i += RW_THREADS)
+    for (int i = t; i < L::B_BYTES / 16; i += NT)
         reinterpret_cast<uint4 *>(smem + L::B_OFF)[i] = __ldg(reinterpret_cast<const uint4 *>(a.wimg) + i);
-    for (int i = t; i < 2 * L::A_STRIDE / 16; i += RW_THREADS) reinterpret_cast<uint4 *>(smem + L::A_OFF)[i] = make_uint4(0, 0, 0, 0);
+    for (int i = t; i < NBUF * L::A_STRIDE / 16; i += NT) reinterpret_cast<uint4 *>(smem + L::A_OFF)[i] = make_uint4(0, 0, 0, 0);
     if (t == 0) {
         mbar_init(mma_done, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 0) tmem_alloc<L::TMEM_COLS>(tmem_slot);
+    if (t < 32) tmem_alloc<L::TMEM_COLS>(tmem_slot);
     fence_proxy_async();
     tc_fence_before();
     __syncthreads();
@@ -196,11 +264,11 @@ __global__ void __launch_bounds__(RW_THREADS, (CS == 32 ? 2 : 4)) conv_u8_tc_row
     const uint32_t tq = tmem_base + ((uint32_t)(warp * 32) << 16);
 
     // ---- this thread's share of a tile copy: CPT 16-byte chunks, (source offset, destination offset) fixed for the launch
-    int src_off[G::CPT];
-    uint32_t dst_off[G::CPT];
+    int src_off[CPT];
+    uint32_t dst_off[CPT];
 #pragma unroll
-    for (int k = 0; k < G::CPT; ++k) {
-        const int c = t + k * RW_THREADS;
+    for (int k = 0; k < CPT; ++k) {
+        const int c = t + k * NT;
         int so = 0, d = 0;
         if (CS == 4) {
             const int yy = c / 9, cx = c - yy * 9;
@@ -229,8 +297,8 @@ __global__ void __launch_bounds__(RW_THREADS, (CS == 32 ? 2 : 4)) conv_u8_tc_row
         const uint8_t *src = a.in + (size_t)((uint32_t)((p.n * a.HP + p.ty * TILE_ROWS) * a.WP + p.tx * G::TWPX) * (uint32_t)CS);
         const uint32_t dst = sA + buf * L::A_STRIDE;
 #pragma unroll
-        for (int k = 0; k < G::CPT; ++k)
-            if ((k + 1) * RW_THREADS <= G::CHUNKS || t + k * RW_THREADS < G::CHUNKS) cp_async16(dst + dst_off[k], src + src_off[k]);
+        for (int k = 0; k < CPT; ++k)
+            if ((k + 1) * NT <= G::CHUNKS || t + k * NT < G::CHUNKS) cp_async16(dst + dst_off[k], src + src_off[k]);
     };
     auto issue_mma = [&](int buf) {   // one thread issues the MMAs of a whole tile
         constexpr uint32_t idesc = make_idesc(L::NMMA_N);
@@ -256,118 +324,167 @@ __global__ void __launch_bounds__(RW_THREADS, (CS == 32 ? 2 : 4)) conv_u8_tc_row
         umma_commit(mma_done);
     };
 
-    ThreadChan<NPQ> ch;
+    const int ch0 = qq * NPQ + (CS == 4 ? 0 : half * NPT);       // first channel of this thread
+    ThreadChan<NPT> ch;
 #pragma unroll
-    for (int k = 0; k < NPQ; ++k) {
-        const int4 c = a.cq[qq * NPQ + k];
+    for (int k = 0; k < NPT; ++k) {
+        const int4 c = a.cq[ch0 + k];
         ch.bias[k] = c.x; ch.zw[k] = -c.y; ch.m2[k] = (uint32_t)c.z; ch.sh[k] = c.w;   // zw holds MINUS the zero point
     }
     const int zo = a.zp_out;
 
     // per-thread part of the pooled-output address (window 0 of this thread; window 1 is one pooled row further)
-    const uint32_t out_thr = (uint32_t)(((2 * warp + a.opad) * a.OWP + (CS == 4 ? 2 * qi : qi) + a.opad) * NCH + qq * NPQ);
+    const uint32_t out_thr = (uint32_t)(((2 * warp + a.opad) * a.OWP + (CS == 4 ? 2 * qi : qi) + a.opad) * NCH + ch0);
     const uint32_t out_row = (uint32_t)(a.OWP * NCH);
 
     yq_pdl_wait_then_release();      // everything above touched only constants and on-chip state
 
     const int first = blockIdx.x, step = gridDim.x;
     uint32_t phase = 0;
-    TileXY cur = split_tile(first), nxt = cur;
-    if (first < a.num_tiles) issue_tile(cur, 0);
-    cp_async_wait_all();
+    // ring of NBUF input tiles, one cp.async group per tile (empty groups past the end keep the counting uniform):
+    // q[0] = the tile being computed, q[d] = the tile d steps ahead, whose copy is already in flight
+    TileXY q[NBUF];
+#pragma unroll
+    for (int d = 0; d < NBUF - 1; ++d) {
+        q[d] = split_tile(first + d * step);
+        if (first + d * step < a.num_tiles) issue_tile(q[d], d);
+        cp_async_commit();
+    }
+    q[NBUF - 1] = q[0];
+    cp_async_wait_group<NBUF - 2>();
     fence_proxy_async();          // generic-proxy smem writes -> visible to the tensor core (async proxy)
     int buf = 0;
-    for (int tile = first; tile < a.num_tiles; tile += step, buf ^= 1, cur = nxt) {
+    TL_DECL;
+    for (int tile = first; tile < a.num_tiles; tile += step, buf = buf + 1 == NBUF ? 0 : buf + 1) {
         // tile's copy landed and was fenced by every thread before it got here
         tc_fence_before();            // (orders the previous epilogue's TMEM reads before the next MMA)
         __syncthreads();
+        TL_MARK(0);
         if (t == 0) {
             tc_fence_after();
             issue_mma(buf);
         }
-        if (tile + step < a.num_tiles) {   // overlaps this tile's MMA + epilogue
-            nxt = split_tile(tile + step);
-            issue_tile(nxt, buf ^ 1);
+        TL_MARK(1);
+        if (tile + (NBUF - 1) * step < a.num_tiles) {   // into the buffer the PREVIOUS tile's MMAs have finished with
+            q[NBUF - 1] = split_tile(tile + (NBUF - 1) * step);
+            issue_tile(q[NBUF - 1], buf == 0 ? NBUF - 1 : buf - 1);
         }
+        cp_async_commit();
+        const TileXY cur = q[0];
+#pragma unroll
+        for (int d = 0; d < NBUF - 1; ++d) q[d] = q[d + 1];
+        TL_MARK(2);
         mbar_wait(mma_done, phase);
         phase ^= 1u;
         tc_fence_after();
+        TL_MARK(3);
 
         // ---- epilogue: warp = TMEM lane quarter = 4 conv rows = 2 pooled rows; thread (qi, qq) = pooled column(s) qi, channels qq*NPQ ..
         const int tx = cur.tx, ty = cur.ty, n = cur.n;
         const int py0 = ty * (TILE_ROWS / 2) + 2 * warp;
         uint8_t *const out_tile = a.out_pool + (size_t)((uint32_t)((n * a.OHP + ty * (TILE_ROWS / 2)) * a.OWP + tx * (G::TWPX / 2)) * (uint32_t)NCH + out_thr);
         if (CS == 4) {
+            constexpr int NPAIR = 2 / SPLIT, NJ = NCH / 16, NCK = NPAIR * NJ;    // NCK chunks of 2 x 16 accumulators, double-buffered
+            uint32_t V[2][2][16];
+            auto chunk_addr = [&](int ck) { return tq + ((SPLIT == 2 ? half : ck / NJ) * NPQ + 4 * (ck % NJ)) * 8; };
+            if (PIPE) tmem_ldq4_issue(chunk_addr(0), V[0][0], V[0][1]);
             uint32_t s0[8], s1[8];
-            tmem_ldq(tq + 4 * NCH, s0, s1);
-            int nsa0[8], nsa1[8];
+            tmem_ldq(tq + 4 * NCH, s0, s1);        // its wait covers chunk 0 as well
+            if (PIPE) tmem_wait32(V[0][0], V[0][1]);
+            uint32_t w0[NPAIR][NCH / 16], w1[NPAIR][NCH / 16];
 #pragma unroll
-            for (int k = 0; k < 8; ++k) {
-                nsa0[k] = (int)s0[k];
-                nsa1[k] = (int)s1[k];
-            }
-            uint32_t w0[2][NCH / 16], w1[2][NCH / 16];
+            for (int pp = 0; pp < NPAIR; ++pp) {
+                const int pair = SPLIT == 2 ? half : pp;
+                int nsa0[4], nsa1[4];       // the pair's four activation sums
 #pragma unroll
-            for (int pair = 0; pair < 2; ++pair) {
+                for (int k = 0; k < 4; ++k) {
+                    nsa0[k] = (int)(SPLIT == 2 ? (half ? s0[4 + k] : s0[k]) : s0[4 * pp + k]);
+                    nsa1[k] = (int)(SPLIT == 2 ? (half ? s1[4 + k] : s1[k]) : s1[4 * pp + k]);
+                }
 #pragma unroll
                 for (int jj = 0; jj < NCH / 16; ++jj) {
-                    uint32_t v0[16], v1[16];
-                    tmem_ldq4(tq + (pair * NPQ + 4 * jj) * 8, v0, v1);
+                    const int ck = pp * NJ + jj;
+                    if (PIPE) {
+                        if (ck + 1 < NCK) tmem_ldq4_issue(chunk_addr(ck + 1), V[(ck + 1) & 1][0], V[(ck + 1) & 1][1]);
+                    } else {
+                        tmem_ldq4(chunk_addr(ck), V[0][0], V[0][1]);
+                    }
+                    uint32_t(&v0)[16] = V[PIPE ? ck & 1 : 0][0];
+                    uint32_t(&v1)[16] = V[PIPE ? ck & 1 : 0][1];
                     int r0[4], r1w[4];
                     uint32_t orx = 0, orr = 0, xq;
 #pragma unroll
                     for (int gg = 0; gg < 4; ++gg) {
                         const int k = 4 * jj + gg;
                         r0[gg] = pool_requant(ch.zw[k], ch.bias[k], ch.m2[k], ch.sh[k], zo, (int)v0[4 * gg], (int)v0[4 * gg + 1], (int)v0[4 * gg + 2],
-                                              (int)v0[4 * gg + 3], nsa0[4 * pair], nsa0[4 * pair + 1], nsa0[4 * pair + 2], nsa0[4 * pair + 3], &xq);
+                                              (int)v0[4 * gg + 3], nsa0[0], nsa0[1], nsa0[2], nsa0[3], &xq);
                         orx |= xq; orr |= (uint32_t)r0[gg];
                         r1w[gg] = pool_requant(ch.zw[k], ch.bias[k], ch.m2[k], ch.sh[k], zo, (int)v1[4 * gg], (int)v1[4 * gg + 1], (int)v1[4 * gg + 2],
-                                               (int)v1[4 * gg + 3], nsa1[4 * pair], nsa1[4 * pair + 1], nsa1[4 * pair + 2], nsa1[4 * pair + 3], &xq);
+                                               (int)v1[4 * gg + 3], nsa1[0], nsa1[1], nsa1[2], nsa1[3], &xq);
                         orx |= xq; orr |= (uint32_t)r1w[gg];
                     }
                     if (orx >= (1u << 22) || orr > 255u) {
 #pragma unroll
                         for (int gg = 0; gg < 4; ++gg) {
                             const int k = 4 * jj + gg;
-                            const double mcd = a.mc[qq * NPQ + k];
+                            const double mcd = a.mc[ch0 + k];
                             r0[gg] = pool_requant_slow(ch.zw[k], ch.bias[k], mcd, zo, (int)v0[4 * gg], (int)v0[4 * gg + 1], (int)v0[4 * gg + 2],
-                                                       (int)v0[4 * gg + 3], nsa0[4 * pair], nsa0[4 * pair + 1], nsa0[4 * pair + 2], nsa0[4 * pair + 3]);
+                                                       (int)v0[4 * gg + 3], nsa0[0], nsa0[1], nsa0[2], nsa0[3]);
                             r1w[gg] = pool_requant_slow(ch.zw[k], ch.bias[k], mcd, zo, (int)v1[4 * gg], (int)v1[4 * gg + 1], (int)v1[4 * gg + 2],
-                                                        (int)v1[4 * gg + 3], nsa1[4 * pair], nsa1[4 * pair + 1], nsa1[4 * pair + 2], nsa1[4 * pair + 3]);
+                                                        (int)v1[4 * gg + 3], nsa1[0], nsa1[1], nsa1[2], nsa1[3]);
                         }
                     }
-                    w0[pair][jj] = pack4(r0);
-                    w1[pair][jj] = pack4(r1w);
+                    w0[pp][jj] = pack4(r0);
+                    w1[pp][jj] = pack4(r1w);
+                    if (PIPE && ck + 1 < NCK) tmem_wait32(V[(ck + 1) & 1][0], V[(ck + 1) & 1][1]);
                 }
             }
-            cp_async_wait_all();          // the next tile's copy has long landed: fence it before this tile's global stores queue up
+            TL_MARK(4);
+            cp_async_wait_group<NBUF - 2>();   // the next tile's copy has long landed: fence it before this tile's global stores queue up
             fence_proxy_async();
+            TL_MARK(5);
 #pragma unroll
-            for (int pair = 0; pair < 2; ++pair) {
+            for (int pp = 0; pp < NPAIR; ++pp) {
+                const int pair = SPLIT == 2 ? half : pp;
                 const int px = tx * (G::TWPX / 2) + 2 * qi + pair;
                 if (px < a.PW) {
                     uint8_t *dst = out_tile + pair * NCH;
                     if (py0 < a.PH) {
-                        if constexpr (NCH == 16) *reinterpret_cast<uint32_t *>(dst) = w0[pair][0];
-                        else *reinterpret_cast<uint2 *>(dst) = make_uint2(w0[pair][0], w0[pair][1]);
+                        if constexpr (NCH == 16) *reinterpret_cast<uint32_t *>(dst) = w0[pp][0];
+                        else *reinterpret_cast<uint2 *>(dst) = make_uint2(w0[pp][0], w0[pp][1]);
                     }
                     if (py0 + 1 < a.PH) {
-                        if constexpr (NCH == 16) *reinterpret_cast<uint32_t *>(dst + out_row) = w1[pair][0];
-                        else *reinterpret_cast<uint2 *>(dst + out_row) = make_uint2(w1[pair][0], w1[pair][1]);
+                        if constexpr (NCH == 16) *reinterpret_cast<uint32_t *>(dst + out_row) = w1[pp][0];
+                        else *reinterpret_cast<uint2 *>(dst + out_row) = make_uint2(w1[pp][0], w1[pp][1]);
                     }
                 }
             }
         } else {
+            constexpr int JN = NCH / 16 / SPLIT > 0 ? NCH / 16 / SPLIT : 1;      // 4-channel chunks of this thread, double-buffered
+            uint32_t E[2][4][8];
+            auto chunk_addr = [&](int j) { return tq + 16 * (half * JN + j); };
+            if (PIPE) tmem_ldq_eo_issue(chunk_addr(0), chunk_addr(0) + L::NB, E[0][0], E[0][1], E[0][2], E[0][3]);
             uint32_t se0[4], se1[4], so0[4], so1[4];
-            tmem_ldq_sums(tq + NCH, tq + L::NB + NCH, se0, se1, so0, so1);
+            tmem_ldq_sums(tq + NCH, tq + L::NB + NCH, se0, se1, so0, so1);      // its wait covers chunk 0 as well
+            if (PIPE) tmem_wait_eo(E[0][0], E[0][1], E[0][2], E[0][3]);
             // window 0: conv rows (4w, 4w+1) = lanes (qi, qi+8) of half 0; window 1: rows (4w+2, 4w+3) = half 1
             const int n0[4] = {(int)se0[0], (int)se0[2], (int)so0[0], (int)so0[2]};
             const int n1[4] = {(int)se1[0], (int)se1[2], (int)so1[0], (int)so1[2]};
-            uint32_t w0[NCH / 16], w1[NCH / 16];
+            uint32_t w0[JN], w1[JN];
 #pragma unroll
-            for (int j = 0; j < NCH / 16; ++j) {
-                uint32_t e0[8], e1[8], o0[8], o1[8];
-                tmem_ldq_eo(tq + 16 * j, tq + L::NB + 16 * j, e0, e1, o0, o1);
+            for (int j = 0; j < JN; ++j) {
+                constexpr int NOW = 0;
+                const int set = PIPE ? j & 1 : NOW;
+                if (PIPE) {
+                    if (j + 1 < JN)
+                        tmem_ldq_eo_issue(chunk_addr(j + 1), chunk_addr(j + 1) + L::NB, E[(j + 1) & 1][0], E[(j + 1) & 1][1], E[(j + 1) & 1][2], E[(j + 1) & 1][3]);
+                } else {
+                    tmem_ldq_eo(chunk_addr(j), chunk_addr(j) + L::NB, E[NOW][0], E[NOW][1], E[NOW][2], E[NOW][3]);
+                }
+                uint32_t(&e0)[8] = E[set][0];
+                uint32_t(&e1)[8] = E[set][1];
+                uint32_t(&o0)[8] = E[set][2];
+                uint32_t(&o1)[8] = E[set][3];
                 int r0[4], r1w[4];
                 uint32_t orx = 0, orr = 0, xq;
 #pragma unroll
@@ -384,7 +501,7 @@ __global__ void __launch_bounds__(RW_THREADS, (CS == 32 ? 2 : 4)) conv_u8_tc_row
 #pragma unroll
                     for (int cc = 0; cc < 4; ++cc) {
                         const int k = 4 * j + cc, ri = 4 * (cc >> 1) + (cc & 1);
-                        const double mcd = a.mc[qq * NPQ + k];
+                        const double mcd = a.mc[ch0 + k];
                         r0[cc] = pool_requant_slow(ch.zw[k], ch.bias[k], mcd, zo, (int)e0[ri], (int)e0[ri + 2], (int)o0[ri], (int)o0[ri + 2], n0[0], n0[1],
                                                    n0[2], n0[3]);
                         r1w[cc] = pool_requant_slow(ch.zw[k], ch.bias[k], mcd, zo, (int)e1[ri], (int)e1[ri + 2], (int)o1[ri], (int)o1[ri + 2], n1[0], n1[1],
@@ -393,29 +510,37 @@ __global__ void __launch_bounds__(RW_THREADS, (CS == 32 ? 2 : 4)) conv_u8_tc_row
                 }
                 w0[j] = pack4(r0);
                 w1[j] = pack4(r1w);
+                if (PIPE && j + 1 < JN) tmem_wait_eo(E[(j + 1) & 1][0], E[(j + 1) & 1][1], E[(j + 1) & 1][2], E[(j + 1) & 1][3]);
             }
-            cp_async_wait_all();          // the next tile's copy has long landed: fence it before this tile's global stores queue up
+            TL_MARK(4);
+            cp_async_wait_group<NBUF - 2>();   // the next tile's copy has long landed: fence it before this tile's global stores queue up
             fence_proxy_async();
+            TL_MARK(5);
             const int px = tx * (G::TWPX / 2) + qi;
             if (px < a.PW) {
                 uint8_t *dst = out_tile;
                 const uint32_t rowb = out_row;
                 if (py0 < a.PH) {
-                    if constexpr (NCH == 16) *reinterpret_cast<uint32_t *>(dst) = w0[0];
-                    else if constexpr (NCH == 32) *reinterpret_cast<uint2 *>(dst) = make_uint2(w0[0], w0[1]);
+                    if constexpr (JN == 1) *reinterpret_cast<uint32_t *>(dst) = w0[0];
+                    else if constexpr (JN == 2) *reinterpret_cast<uint2 *>(dst) = make_uint2(w0[0], w0[1]);
                     else *reinterpret_cast<uint4 *>(dst) = make_uint4(w0[0], w0[1], w0[2], w0[3]);
                 }
                 if (py0 + 1 < a.PH) {
-                    if constexpr (NCH == 16) *reinterpret_cast<uint32_t *>(dst + rowb) = w1[0];
-                    else if constexpr (NCH == 32) *reinterpret_cast<uint2 *>(dst + rowb) = make_uint2(w1[0], w1[1]);
+                    if constexpr (JN == 1) *reinterpret_cast<uint32_t *>(dst + rowb) = w1[0];
+                    else if constexpr (JN == 2) *reinterpret_cast<uint2 *>(dst + rowb) = make_uint2(w1[0], w1[1]);
                     else *reinterpret_cast<uint4 *>(dst + rowb) = make_uint4(w1[0], w1[1], w1[2], w1[3]);
                 }
             }
         }
+        TL_MARK(6);
+#ifdef YQ_TIMELINE
+        tl_acc[7] += 1;
+#endif
     }
+    TL_FLUSH();
     tc_fence_before();
     __syncthreads();
-    if (warp == 0) {
+    if (t < 32) {
         tc_fence_after();
         tmem_dealloc<L::TMEM_COLS>(tmem_base);
     }
@@ -430,33 +555,34 @@ struct RowsState {
 // a group side by side (LBO = 128), groups 256 bytes apart (SBO = 256)
 inline size_t bpos(int n, int k) { return (size_t)(n / 8) * 256 + (size_t)(k / 16) * 128 + (size_t)(n % 8) * 16 + (size_t)(k % 16); }
 
-template <int CS, int NCH>
+template <int CS, int NCH, int SPLIT>
 int launch_rows(const RowsArgs &a, cudaStream_t stream)
 {
     using L = RowsCfg<CS, NCH>;
+    constexpr int NT = RW_THREADS * SPLIT;
     static int ctas_per_sm = 0, n_sm = 0;
     const int smem = L::TOTAL + 128;
     if (!ctas_per_sm) {
-        YQ_CUDA(cudaFuncSetAttribute(conv_u8_tc_rows_kernel<CS, NCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        YQ_CUDA(cudaFuncSetAttribute(conv_u8_tc_rows_kernel<CS, NCH, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         int dev = 0, smem_sm = 0;
         cudaFuncAttributes fa;
-        YQ_CUDA(cudaFuncGetAttributes(&fa, conv_u8_tc_rows_kernel<CS, NCH>));
+        YQ_CUDA(cudaFuncGetAttributes(&fa, conv_u8_tc_rows_kernel<CS, NCH, SPLIT>));
         YQ_CUDA(cudaGetDevice(&dev));
         YQ_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
         YQ_CUDA(cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev));
         // counted by hand: the occupancy API answers 1 for kernels that allocate tensor memory (see yq_conv_tc_small.cu)
         const int by_smem = smem_sm / (smem + 1024 + (int)fa.sharedSizeBytes);
-        const int by_regs = 65536 / (((fa.numRegs + 7) / 8 * 8) * RW_THREADS);
+        const int by_regs = 65536 / (((fa.numRegs + 7) / 8 * 8) * NT);
         const int by_tmem = 512 / L::TMEM_COLS;
         int occ = by_smem < by_regs ? by_smem : by_regs;
         if (by_tmem < occ) occ = by_tmem;
-        if (getenv("YQ_DEBUG")) fprintf(stderr, "yq: rows<%d,%d> regs=%d by_smem=%d by_regs=%d by_tmem=%d smem=%d\n", CS, NCH, fa.numRegs, by_smem, by_regs, by_tmem, smem);
+        if (getenv("YQ_DEBUG")) fprintf(stderr, "yq: rows<%d,%d,%d> regs=%d by_smem=%d by_regs=%d by_tmem=%d smem=%d\n", CS, NCH, SPLIT, fa.numRegs, by_smem, by_regs, by_tmem, smem);
         if (occ < 1) return yq::fail("conv_u8_tc_rows_kernel<%d,%d> does not fit on an SM", CS, NCH);
         ctas_per_sm = occ;
     }
     int grid = n_sm * ctas_per_sm;
     if (grid > a.num_tiles) grid = a.num_tiles;
-    YQ_CUDA(yq::launch_pdl(conv_u8_tc_rows_kernel<CS, NCH>, dim3(grid), dim3(RW_THREADS), smem, stream, a));
+    YQ_CUDA(yq::launch_pdl(conv_u8_tc_rows_kernel<CS, NCH, SPLIT>, dim3(grid), dim3(NT), smem, stream, a));
     return 0;
 }
 
@@ -574,10 +700,24 @@ int yq_tc_rows_forward(yq_conv_layer *l, void *state, const uint8_t *in_padded, 
         return yq::fail("tcgen05 rows flavour: tensor too large for 32-bit tile arithmetic");
     memcpy(a.cq, l->host_chanq.data(), (size_t)l->n * 16);
     memcpy(a.mc, l->host_mcomb.data(), (size_t)l->n * 8);
-#define YQ_RW(CS_, N_) if (st->CS == CS_ && st->NCH == N_) return launch_rows<CS_, N_>(a, stream)
-    YQ_RW(4, 16); YQ_RW(4, 32);
-    YQ_RW(16, 16); YQ_RW(16, 32); YQ_RW(16, 64);
-    YQ_RW(32, 32); YQ_RW(32, 64);
+    static const int split_env = getenv("YQ_ROWS_SPLIT") ? atoi(getenv("YQ_ROWS_SPLIT")) : -1;    // experiments: 0 / 1 force
+#define YQ_RW(CS_, N_, DEF_)                                                                                     \
+    if (st->CS == CS_ && st->NCH == N_) {                                                                        \
+        if constexpr (CS_ == 4 || N_ >= 32) {                                                                    \
+            if (split_env < 0 ? DEF_ : split_env) return launch_rows<CS_, N_, 2>(a, stream);                     \
+        }                                                                                                        \
+        return launch_rows<CS_, N_, 1>(a, stream);                                                               \
+    }
+    YQ_RW(4, 16, 0); YQ_RW(4, 32, 0);
+    YQ_RW(16, 16, 0); YQ_RW(16, 32, 0); YQ_RW(16, 64, 0);
+    YQ_RW(32, 32, 0); YQ_RW(32, 64, 0);
 #undef YQ_RW
     return yq::fail("tcgen05 rows flavour: no instantiation for cs_in=%d cs_out=%d", st->CS, st->NCH);
 }
+
+#ifdef YQ_TIMELINE
+extern "C" __attribute__((visibility("default"))) int yq_debug_rows_timeline(void *host, size_t bytes)
+{
+    return cudaMemcpyFromSymbol(host, yq_rows_timeline, bytes < sizeof(yq_rows_timeline) ? bytes : sizeof(yq_rows_timeline)) == cudaSuccess ? 0 : -1;
+}
+#endif

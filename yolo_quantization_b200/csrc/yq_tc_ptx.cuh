@@ -116,6 +116,9 @@ __device__ __forceinline__ void cp_async16(uint32_t dst, const void *src)
     asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait_group() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 __device__ __forceinline__ void st_shared32(uint32_t dst, uint32_t v) { asm volatile("st.shared.b32 [%0], %1;" ::"r"(dst), "r"(v) : "memory"); }
 __device__ __forceinline__ void st_shared128(uint32_t dst, uint4 v)
 {
