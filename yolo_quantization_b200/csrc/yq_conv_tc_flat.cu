@@ -276,16 +276,27 @@ __global__ void __launch_bounds__(FL_THREADS, 2) conv_u8_tc_flat_kernel(const __
                 yq::requant_chunk<ACTM, SAT, 16, false>(v, nsa, extra, s_q + c0, s_mc + c0, a.ep.zp_out, packed);
                 if (!valid) packed[0] = packed[1] = packed[2] = packed[3] = a.halo_word;
                 yq::mask_pad_channels<16>(packed, a.N - (oc0 + c0));
-                if (SLOW && side && valid) {   // parity / quant_stop side outputs (not on the throughput path)
+                if (SLOW && side && valid) {
+                    const int hw = a.H * a.W;
+                    const size_t f0 = ((size_t)n * a.N + oc0 + c0) * hw + (size_t)(y1 - 1) * a.W + (col - 1);
+                    const int nreal = a.N - (oc0 + c0);
+                    if (a.out_yolo && !a.out_acc && !a.out_f32) {
+                        // the detection heads on the throughput path: one table lookup and one 4-byte store per output
+                        float *dst = a.out_yolo + f0;
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        const int oc = oc0 + c0 + j;
-                        if (oc < a.N) {
-                            if (a.out_acc) a.out_acc[pix * a.CSO + oc] = (int)v[j] + s_q[c0 + j].y * nsa;
-                            const uint8_t u = (uint8_t)(packed[j / 4] >> (8 * (j % 4)));
-                            const size_t fidx = ((size_t)n * a.N + oc) * a.H * a.W + (size_t)(y1 - 1) * a.W + (col - 1);
-                            if (a.out_f32) a.out_f32[fidx] = yq::dequant_f32(a.ep, u);
-                            if (a.out_yolo) a.out_yolo[fidx] = s_lut[s_sel[c0 + j] + u];
+                        for (int j = 0; j < 16; ++j)
+                            if (j < nreal) dst[j * hw] = s_lut[s_sel[c0 + j] + ((packed[j / 4] >> (8 * (j % 4))) & 255u)];
+                    } else {   // parity / quant_stop side outputs (not on the throughput path)
+#pragma unroll 1
+                        for (int j = 0; j < 16; ++j) {
+                            if (j < nreal) {
+                                const int oc = oc0 + c0 + j;
+                                if (a.out_acc) a.out_acc[pix * a.CSO + oc] = (int)v[j] + s_q[c0 + j].y * nsa;
+                                const uint8_t u = (uint8_t)(packed[j / 4] >> (8 * (j % 4)));
+                                const size_t fidx = f0 + (size_t)j * hw;
+                                if (a.out_f32) a.out_f32[fidx] = yq::dequant_f32(a.ep, u);
+                                if (a.out_yolo) a.out_yolo[fidx] = s_lut[s_sel[c0 + j] + u];
+                            }
                         }
                     }
                 }
