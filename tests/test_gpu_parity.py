@@ -263,20 +263,30 @@ ROWS_CASES = [
 @pytest.mark.parametrize("case", ROWS_CASES, ids=lambda c: "c%d_%dx%d_n%d" % c[:4])
 @pytest.mark.parametrize("s_out", [0.05, 6.0], ids=["wrapping", "in_range"])
 @pytest.mark.parametrize("out_pad", [0, 1])
-def test_conv_rows_flavour_vs_oracle(built, case, s_out, out_pad):
+@pytest.mark.parametrize("variant", [2, 1], ids=["two_signed_blocks", "ones_rows"])
+def test_conv_rows_flavour_vs_oracle(built, case, s_out, out_pad, variant, monkeypatch):
     """halo-input conv + RELU6 + maxpool(2,2) (no im2col; Toeplitz / even-odd MMA groups) == oracle conv + oracle maxpool;
-    with out_pad = 1 the halo of the output tensor must stay untouched."""
+    with out_pad = 1 the halo of the output tensor must stay untouched.  Both weight forms: two signed blocks
+    h + l = w - zp_w (every difference <= 254) and, when some w - zp_w = 255, all-ones rows + zero-point correction."""
     c, h, w, n, zp_in, zp_out, batch = case
     k = 3
     rng = np.random.default_rng(zlib.crc32(repr(case).encode()) + 5)
     wq, zp_w, s_w, bias = make_params(rng, n, c * k * k, zp_in)
+    if variant == 2:
+        monkeypatch.setenv("YQ_ROWS_TWO", "1")          # (the default takes this form only where it pays: c <= 16, n <= 32)
+        zp_w = np.maximum(zp_w, 1).astype(zp_w.dtype)
+        zp_w[n // 2] = 255                              # w - zp_w down to -255
+        wq[n // 2, 0] = 0
+    else:
+        zp_w[n - 1] = 0
+        wq[n - 1, -1] = 255                             # the one difference the signed blocks cannot hold
     spec = synth.LayerSpec("conv", n, k, 1, 1, 0, "relu6")
     sl = synth.SynthLayer("conv", c, h, w, n, 0, 0, spec, s_out=s_out, biases=bias, s_w=s_w, zp_w=zp_w, w_u8=wq.reshape(n, c, k, k))
     p = O.prepare_conv(sl, 0.02, zp_in)
     x = rng.integers(0, 256, size=(batch, c, h, w), dtype=np.uint8)
     layer = darknet.ConvolutionalLayerQuant(h, w, c, n, k, 1, 1, synth.ACT_CODES["relu6"], wq, zp_w, p["biases_int32"], p["M_value"],
                                             p["M0_right_shift_value"], zp_in, zp_out, s_out)
-    assert layer.rows_supported
+    assert layer.rows_supported and layer.rows_variant == variant
     got = layer.forward_rows_pooled(x, out_pad=out_pad)
     for b in range(batch):
         acc = O.conv_acc(x[b], wq.reshape(n, c, k, k), zp_w, 1, 1, zp_in)

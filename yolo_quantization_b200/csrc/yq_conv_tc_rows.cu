@@ -28,7 +28,9 @@
 #include <limits.h>
 #include <string.h>
 
+#include <map>
 #include <type_traits>
+#include <utility>
 #include <vector>
 
 #include "yq_common.h"
@@ -45,19 +47,11 @@ constexpr int PLANE = 144;              // bytes of one shared-memory plane row:
 #ifndef YQ_ROWS_NBUF
 #define YQ_ROWS_NBUF 3
 #endif
-constexpr int NBUF = YQ_ROWS_NBUF;      // input-tile ring: the copy of tile i + NBUF - 1 is in flight while tile i is computed
 
-// -DYQ_TIMELINE: thread 0 of every CTA adds up the clocks it spends in each phase of a tile (yq_rows_timeline[cta * 8 + phase],
-// [cta * 8 + 7] = tiles); read back with yq_debug_rows_timeline (tools/probes/rows_timeline.py)
-#ifdef YQ_TIMELINE
-__device__ unsigned long long yq_rows_timeline[8 * 1024];
-#define TL_DECL long long tl_prev = clock64(); unsigned long long tl_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0}
-#define TL_MARK(ev) do { const long long tl_now = clock64(); tl_acc[ev] += (unsigned long long)(tl_now - tl_prev); tl_prev = tl_now; } while (0)
-#define TL_FLUSH() do { if (threadIdx.x == 0 && blockIdx.x < 1024) for (int e = 0; e < 8; ++e) yq_rows_timeline[blockIdx.x * 8 + e] = tl_acc[e]; } while (0)
+#ifdef YQ_ROWS_KNOBS
+#define KNOB(bit) (a.knobs & (bit))
 #else
-#define TL_DECL
-#define TL_MARK(ev)
-#define TL_FLUSH()
+#define KNOB(bit) 0
 #endif
 
 template <int CS>
@@ -66,25 +60,39 @@ struct RowsGeom {
     static constexpr int NBLK = CS == 32 ? 2 : 1;                   // 16-channel blocks
     static constexpr int ROWP = CS == 4 ? PLANE : 2 * PLANE * NBLK; // shared-memory bytes per tile row
     static constexpr int A_ROWS = TILE_ROWS + 2;
-    static constexpr int A_BYTES = A_ROWS * ROWP;
-    static constexpr int CHUNKS = A_BYTES / 16;                     // 162 / 324 / 648
+    static constexpr int NPLANES = CS == 4 ? 1 : 2 * NBLK;          // [18 rows][9 x 16 B] arrays of a tile: one per 16-channel block and pixel parity
+    static constexpr int TX_BYTES = NPLANES * A_ROWS * PLANE;       // what TMA delivers per tile
+    static constexpr int PLANE_BYTES = (A_ROWS * PLANE + 127) / 128 * 128;   // plane stride: TMA destinations are 128-byte aligned (2592 -> 2688)
+    static constexpr int A_BYTES = NPLANES * PLANE_BYTES;
     static constexpr int NMMA = CS == 4 ? 3 : 6 * NBLK;
 };
 
-template <int CS, int NCH>
+// TWO: the weights enter as two SIGNED blocks h + l = w - zp_w (each in [-128, 127]) multiplied with the same activation
+// tile, so the accumulator is the zero-point-corrected one and neither the all-ones rows nor the per-output correction
+// exist; twice the MMAs, 4 multiply-adds and one TMEM load less per pooled output (prepare falls back when some w - zp_w = 255)
+template <int CS, int NCH, bool TWO>
 struct RowsCfg {
     using G = RowsGeom<CS>;
-    static constexpr int NB = CS == 4 ? 4 * NCH + 16 : NCH + 16;    // filter rows (TMEM columns) per MMA group
+    static constexpr int NSUM = TWO ? 0 : 16;
+    static constexpr int NB = CS == 4 ? 4 * NCH + NSUM : NCH + NSUM;    // filter rows (TMEM columns) per MMA group
     static constexpr int NACC = CS == 4 ? NB : 2 * NB;              // TMEM columns of one accumulator
-    static constexpr int TMEM_COLS = NACC <= 32 ? 32 : NACC <= 64 ? 64 : NACC <= 128 ? 128 : NACC <= 256 ? 256 : 512;
+    // DB: two accumulators, the next tile's MMAs run under this tile's epilogue -- where two of them still leave
+    // room for 4 CTAs per SM (128 columns each), i.e. the TWO forms with <= 64 accumulator columns
+    static constexpr bool DB = TWO && CS != 32 && 2 * NACC <= 128;
+    static constexpr int NTM = NACC * (DB ? 2 : 1);
+    static constexpr int TMEM_COLS = NTM <= 32 ? 32 : NTM <= 64 ? 64 : NTM <= 128 ? 128 : NTM <= 256 ? 256 : 512;
+    // input-tile ring: the copy of tile i + NBUF - 1 is in flight while tile i is computed (DB consumes a tile one step earlier)
+    static constexpr int NBUF = DB ? YQ_ROWS_NBUF + 1 : YQ_ROWS_NBUF;
+    static_assert(NBUF <= 4, "barrier block");
     static constexpr int NMMA_N = CS == 4 ? NB : 2 * NB;            // N of one MMA: for c >= 16 the even and the odd group share it
     static constexpr int BSUB = NMMA_N * 32;                        // one MMA's filter tile
-    static constexpr int B_BYTES = G::NMMA * BSUB;
+    static constexpr int NMMA = G::NMMA * (TWO ? 2 : 1);
+    static constexpr int B_BYTES = NMMA * BSUB;
     static constexpr int A_STRIDE = (G::A_BYTES + 32 + 127) / 128 * 128;   // +32: the last window's (zero-weight) overhang
     static constexpr int A_OFF = 0;
     static constexpr int B_OFF = NBUF * A_STRIDE;
     static constexpr int BAR_OFF = B_OFF + B_BYTES;
-    static constexpr int TOTAL = BAR_OFF + 64;
+    static constexpr int TOTAL = BAR_OFF + 128;
     static_assert(NMMA_N % 16 == 0 && NMMA_N <= 256, "kind::i8 N");
 };
 
@@ -94,6 +102,7 @@ struct RowsArgs {
     const uint8_t *wimg;    // shared-memory image of the filter tiles, one per MMA in issue order
     int HP, WP, OH, OW, PH, PW, OHP, OWP, opad;
     int tiles_x, tiles_y, num_tiles, zp_out;
+    int knobs;              // -DYQ_ROWS_KNOBS experiments (results are garbage): 1 no MMAs, 2 no epilogue arithmetic, 4 no tile copies, 8 no stores
     uint32_t magic_x, magic_y;   // ceil(2^32 / tiles_x), ceil(2^32 / tiles_y): exact quotients by __umulhi for tile < 2^32 / tiles
     int4 cq[64];            // {bias, zw, 2*M0, shift} per channel
     double mc[64];          // M_value * 2^-s (FP64 fallback)
@@ -224,68 +233,56 @@ __device__ __forceinline__ uint32_t pack4(const int (&r)[4])
     return __byte_perm(__byte_perm((uint32_t)r[0], (uint32_t)r[1], 0x0040), __byte_perm((uint32_t)r[2], (uint32_t)r[3], 0x0040), 0x5410);
 }
 
-// SPLIT = 2: two warps per TMEM lane quarter share a tile's epilogue (c = 4: one pixel pair each; c >= 16: half of the
-// thread's channels each), which halves the time the accumulator is held between two tiles' MMAs
-template <int CS, int NCH, int SPLIT>
-__global__ void __launch_bounds__(RW_THREADS * SPLIT, (CS == 32 ? 2 : SPLIT == 2 ? 3 : 4)) conv_u8_tc_rows_kernel(const __grid_constant__ RowsArgs a)
+// Warp-specialised, persistent: one producer warp (a single elected lane) streams input tiles with TMA into a ring of
+// NBUF buffers and issues each tile's MMAs; 4 * SPLIT epilogue warps (warp % 4 = TMEM lane quarter) requantize + pool +
+// store.  No CTA-wide barrier and no proxy fence per tile: full[] (TMA bytes landed) -> MMAs -> acc_full[] (tcgen05.commit)
+// -> epilogue -> acc_empty[] (one arrival per epilogue warp, right after its last TMEM load).
+// SPLIT = 2: two warps per lane quarter share a tile's epilogue (c = 4: one pixel pair each; c >= 16: half of the thread's
+// channels each).  DBL: two accumulators, so the next tile's MMAs run under this tile's epilogue.
+template <int CS, int NCH, int SPLIT, bool TWO>
+__global__ void __launch_bounds__(RW_THREADS * SPLIT + 32, (CS == 32 ? 2 : SPLIT == 2 ? 3 : 4))
+conv_u8_tc_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ RowsArgs a)
 {
     using G = RowsGeom<CS>;
-    using L = RowsCfg<CS, NCH>;
+    using L = RowsCfg<CS, NCH, TWO>;
     constexpr int NPQ = NCH / 4;
-    constexpr int NT = RW_THREADS * SPLIT;
-    constexpr int CPT = (G::CHUNKS + NT - 1) / NT;
+    constexpr int NT = RW_THREADS * SPLIT;                 // epilogue threads; the producer warp comes after them
     constexpr int NPT = CS == 4 ? NPQ : NPQ / SPLIT;      // channels whose parameters this thread keeps
     // double-buffered TMEM loads (a chunk's round trip under the previous chunk's arithmetic) where the registers are there:
     // c = 32 runs 2 CTAs per SM; measured slower for the 4-CTA kernels (layers 0, 2), faster for layer 4
     constexpr bool PIPE = CS == 32;
+    constexpr int NACCS = L::DB ? 2 : 1;
+    constexpr int NBUF = L::NBUF;
     static_assert(SPLIT == 1 || CS == 4 || NCH >= 32, "a thread needs at least one 4-channel chunk");
     extern __shared__ __align__(16) uint8_t smem_raw[];
     uint8_t *smem = smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u);
-    uint64_t *mma_done = (uint64_t *)(smem + L::BAR_OFF);
-    uint32_t *tmem_slot = (uint32_t *)(mma_done + 1);
+    uint64_t *full = (uint64_t *)(smem + L::BAR_OFF);          // [NBUF] input tile landed
+    uint64_t *acc_full = full + NBUF;                          // [2] accumulator complete
+    uint64_t *acc_empty = acc_full + 2;                        // [2] accumulator read out
+    uint32_t *tmem_slot = (uint32_t *)(acc_empty + 2);
 
-    const int t = threadIdx.x, warp = (t >> 5) & 3, half = SPLIT == 2 ? t >> 7 : 0, lane = t & 31;
+    const int t = threadIdx.x, warp = (t >> 5) & 3, half = SPLIT == 2 ? (t >> 7) & 1 : 0, lane = t & 31;
+    const bool producer = t >= NT;
     const int qi = lane >> 2, qq = lane & 3;
 
-    // ---- one-time setup: resident filter tiles, barrier, TMEM
-    for (int i = t; i < L::B_BYTES / 16; i += NT)
+    // ---- one-time setup: resident filter tiles, barriers, TMEM
+    for (int i = t; i < L::B_BYTES / 16; i += NT + 32)
         reinterpret_cast<uint4 *>(smem + L::B_OFF)[i] = __ldg(reinterpret_cast<const uint4 *>(a.wimg) + i);
-    for (int i = t; i < NBUF * L::A_STRIDE / 16; i += NT) reinterpret_cast<uint4 *>(smem + L::A_OFF)[i] = make_uint4(0, 0, 0, 0);
     if (t == 0) {
-        mbar_init(mma_done, 1);
+        for (int b = 0; b < NBUF; ++b) mbar_init(&full[b], 1);
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(&acc_full[b], 1);
+            mbar_init(&acc_empty[b], NT / 32);
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (t < 32) tmem_alloc<L::TMEM_COLS>(tmem_slot);
-    fence_proxy_async();
+    fence_proxy_async();          // the filter tiles (generic-proxy stores) -> visible to the tensor core
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    const uint32_t tq = tmem_base + ((uint32_t)(warp * 32) << 16);
 
-    // ---- this thread's share of a tile copy: CPT 16-byte chunks, (source offset, destination offset) fixed for the launch
-    int src_off[CPT];
-    uint32_t dst_off[CPT];
-#pragma unroll
-    for (int k = 0; k < CPT; ++k) {
-        const int c = t + k * NT;
-        int so = 0, d = 0;
-        if (CS == 4) {
-            const int yy = c / 9, cx = c - yy * 9;
-            so = yy * a.WP * 4 + cx * 16;
-            d = yy * G::ROWP + cx * 16;
-        } else {
-            constexpr int PER_ROW = 18 * G::NBLK;
-            const int yy = c / PER_ROW, rem = c - yy * PER_ROW;
-            const int j = rem / G::NBLK, blk = rem - j * G::NBLK;      // j: pixel of the 18-pixel window x0-1 .. x0+16
-            so = (yy * a.WP + j) * CS + blk * 16;
-            // odd j = even output-pixel column x0 + (j-1): plane E; even j: plane O (shifted by one: O[m] = pixel x0-1+2m)
-            d = yy * G::ROWP + blk * 2 * PLANE + ((j & 1) ? ((j - 1) >> 1) * 16 : PLANE + (j >> 1) * 16);
-        }
-        src_off[k] = so;
-        dst_off[k] = (uint32_t)d;
-    }
-    const uint32_t sA = smem_u32(smem + L::A_OFF);
     struct TileXY { int tx, ty, n; };
     auto split_tile = [&](int tile) -> TileXY {
         // (a divisor of 1 has no 32-bit magic: 2^32)
@@ -293,251 +290,277 @@ __global__ void __launch_bounds__(RW_THREADS * SPLIT, (CS == 32 ? 2 : SPLIT == 2
         const int n = a.tiles_y == 1 ? r1 : (int)__umulhi((uint32_t)r1, a.magic_y);
         return TileXY{tile - r1 * a.tiles_x, r1 - n * a.tiles_y, n};
     };
-    auto issue_tile = [&](const TileXY &p, int buf) {
-        const uint8_t *src = a.in + (size_t)((uint32_t)((p.n * a.HP + p.ty * TILE_ROWS) * a.WP + p.tx * G::TWPX) * (uint32_t)CS);
-        const uint32_t dst = sA + buf * L::A_STRIDE;
-#pragma unroll
-        for (int k = 0; k < CPT; ++k)
-            if ((k + 1) * NT <= G::CHUNKS || t + k * NT < G::CHUNKS) cp_async16(dst + dst_off[k], src + src_off[k]);
-    };
-    auto issue_mma = [&](int buf) {   // one thread issues the MMAs of a whole tile
-        constexpr uint32_t idesc = make_idesc(L::NMMA_N);
-        const uint32_t a0 = sA + buf * L::A_STRIDE, b0 = smem_u32(smem + L::B_OFF);
-        if (CS == 4) {
-#pragma unroll
-            for (int ky = 0; ky < 3; ++ky)
-                umma_i8(tmem_base, make_desc_ns(a0 + ky * G::ROWP, 16, G::ROWP), make_desc_ns(b0 + ky * L::BSUB, 128, 256), idesc, ky ? 1u : 0u);
-        } else {
-            // one MMA = K chunks (E[i + step], O[i + step]) of one image row and 16-channel block, N = even group | odd group:
-            //   even pixel 2i   : kx 1 = E[i], kx 0 = O[i]   (step 0);                 kx 2 = O[i+1] (step 1)
-            //   odd  pixel 2i+1 : kx 0 = E[i]                (step 0);  kx 2 = E[i+1], kx 1 = O[i+1] (step 1)       [O[] is the shifted plane]
-            int m = 0;
-#pragma unroll
-            for (int blk = 0; blk < G::NBLK; ++blk)
-#pragma unroll
-                for (int ky = 0; ky < 3; ++ky)
-#pragma unroll
-                    for (int step = 0; step < 2; ++step, ++m)
-                        umma_i8(tmem_base, make_desc_ns(a0 + blk * 2 * PLANE + ky * G::ROWP + step * 16, PLANE, G::ROWP),
-                                make_desc_ns(b0 + m * L::BSUB, 128, 256), idesc, m ? 1u : 0u);
-        }
-        umma_commit(mma_done);
-    };
-
-    const int ch0 = qq * NPQ + (CS == 4 ? 0 : half * NPT);       // first channel of this thread
-    ThreadChan<NPT> ch;
-#pragma unroll
-    for (int k = 0; k < NPT; ++k) {
-        const int4 c = a.cq[ch0 + k];
-        ch.bias[k] = c.x; ch.zw[k] = -c.y; ch.m2[k] = (uint32_t)c.z; ch.sh[k] = c.w;   // zw holds MINUS the zero point
-    }
-    const int zo = a.zp_out;
-
-    // per-thread part of the pooled-output address (window 0 of this thread; window 1 is one pooled row further)
-    const uint32_t out_thr = (uint32_t)(((2 * warp + a.opad) * a.OWP + (CS == 4 ? 2 * qi : qi) + a.opad) * NCH + ch0);
-    const uint32_t out_row = (uint32_t)(a.OWP * NCH);
+    const int first = blockIdx.x, step = gridDim.x;
 
     yq_pdl_wait_then_release();      // everything above touched only constants and on-chip state
 
-    const int first = blockIdx.x, step = gridDim.x;
-    uint32_t phase = 0;
-    // ring of NBUF input tiles, one cp.async group per tile (empty groups past the end keep the counting uniform):
-    // q[0] = the tile being computed, q[d] = the tile d steps ahead, whose copy is already in flight
-    TileXY q[NBUF];
+    if (producer) {
+        if (elect_one()) {
+            asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+            const uint32_t sA = smem_u32(smem + L::A_OFF), b0 = smem_u32(smem + L::B_OFF);
+            auto load_tile = [&](int tile, int buf) {     // 18 halo rows of the tile: one box (c = 4) or one box per 16-channel block and pixel parity
+                const TileXY p = split_tile(tile);
+                uint8_t *dst = smem + L::A_OFF + buf * L::A_STRIDE;
+                const int row = p.n * a.HP + p.ty * TILE_ROWS;
+                if (KNOB(4)) {
+                    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&full[buf])) : "memory");
+                    return;
+                }
+                mbar_expect_tx(&full[buf], (uint32_t)G::TX_BYTES);
+                if (CS == 4) {
+                    tma_load_2d(dst, &tmA, &full[buf], p.tx * G::TWPX * 4, row);
+                } else {
 #pragma unroll
-    for (int d = 0; d < NBUF - 1; ++d) {
-        q[d] = split_tile(first + d * step);
-        if (first + d * step < a.num_tiles) issue_tile(q[d], d);
-        cp_async_commit();
-    }
-    q[NBUF - 1] = q[0];
-    cp_async_wait_group<NBUF - 2>();
-    fence_proxy_async();          // generic-proxy smem writes -> visible to the tensor core (async proxy)
-    int buf = 0;
-    TL_DECL;
-    for (int tile = first; tile < a.num_tiles; tile += step, buf = buf + 1 == NBUF ? 0 : buf + 1) {
-        // tile's copy landed and was fenced by every thread before it got here
-        tc_fence_before();            // (orders the previous epilogue's TMEM reads before the next MMA)
-        __syncthreads();
-        TL_MARK(0);
-        if (t == 0) {
+                    for (int blk = 0; blk < G::NBLK; ++blk)
+#pragma unroll
+                        for (int par = 0; par < 2; ++par)      // plane E = odd padded columns (parity 1), plane O = even ones
+                            tma_load_4d(dst + (blk * 2 + (par ^ 1)) * G::PLANE_BYTES, &tmA, &full[buf], blk * 16, par, p.tx * (G::TWPX / 2), row);
+                }
+            };
+            auto issue_mma = [&](int buf, int acc) {
+                constexpr uint32_t idesc = make_idesc(L::NMMA_N) | (TWO ? 1u << 10 : 0u);      // TWO: B (the filters) is SINT8
+                const uint32_t a0 = sA + buf * L::A_STRIDE;
+                const uint32_t tacc = tmem_base + (uint32_t)(acc * L::NACC);
+                if (CS == 4) {
+#pragma unroll
+                    for (int part = 0; part < (TWO ? 2 : 1); ++part)
+#pragma unroll
+                        for (int ky = 0; ky < 3; ++ky)
+                            umma_i8(tacc, make_desc_ns(a0 + ky * PLANE, 16, PLANE), make_desc_ns(b0 + (part * 3 + ky) * L::BSUB, 128, 256), idesc,
+                                    (part | ky) ? 1u : 0u);
+                } else {
+                    // one MMA = K chunks (E[i + step], O[i + step]) of one image row and 16-channel block, N = even group | odd group:
+                    //   even pixel 2i   : kx 1 = E[i], kx 0 = O[i]   (step 0);                 kx 2 = O[i+1] (step 1)
+                    //   odd  pixel 2i+1 : kx 0 = E[i]                (step 0);  kx 2 = E[i+1], kx 1 = O[i+1] (step 1)       [O[] is the shifted plane]
+                    // planes are separate [18 rows][9 x 16 B] arrays: LBO = E -> O plane, SBO = next image row
+                    int m = 0;
+#pragma unroll
+                    for (int part = 0; part < (TWO ? 2 : 1); ++part)
+#pragma unroll
+                        for (int blk = 0; blk < G::NBLK; ++blk)
+#pragma unroll
+                            for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+                                for (int st = 0; st < 2; ++st, ++m)
+                                    umma_i8(tacc, make_desc_ns(a0 + blk * 2 * G::PLANE_BYTES + ky * PLANE + st * 16, G::PLANE_BYTES, PLANE),
+                                            make_desc_ns(b0 + m * L::BSUB, 128, 256), idesc, m ? 1u : 0u);
+                }
+                umma_commit(&acc_full[acc]);
+            };
+#pragma unroll 1
+            for (int d = 0; d < NBUF; ++d)
+                if (first + d * step < a.num_tiles) load_tile(first + d * step, d);
+            int buf = 0, it = 0;
+#pragma unroll 1
+            for (int tile = first; tile < a.num_tiles; tile += step, buf = buf + 1 == NBUF ? 0 : buf + 1, ++it) {
+                const int acc = NACCS == 2 ? it & 1 : 0;
+                const uint32_t use = (uint32_t)(it / NACCS);            // how many times this accumulator has been used before
+                if (it >= NACCS) mbar_wait(&acc_empty[acc], (use & 1u) ^ 1u);      // its previous tile has been read out
+                mbar_wait(&full[buf], (uint32_t)((it / NBUF) & 1));
+                tc_fence_after();
+                if (KNOB(1)) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&acc_full[acc])) : "memory");
+                else issue_mma(buf, acc);
+                // refill the previous tile's buffer once its MMAs have finished reading it
+                // (one accumulator: the acc_empty wait above already implies it -- and by now acc_full may be a phase further)
+                if (it >= 1 && tile + (NBUF - 1) * step < a.num_tiles) {
+                    if (NACCS == 2) mbar_wait(&acc_full[(it - 1) & 1], (uint32_t)(((it - 1) >> 1) & 1));
+                    load_tile(tile + (NBUF - 1) * step, buf == 0 ? NBUF - 1 : buf - 1);
+                }
+            }
+        }
+        __syncwarp();
+    } else {
+        const int ch0 = qq * NPQ + (CS == 4 ? 0 : half * NPT);       // first channel of this thread
+        ThreadChan<NPT> ch;
+#pragma unroll
+        for (int k = 0; k < NPT; ++k) {
+            const int4 c = a.cq[ch0 + k];
+            ch.bias[k] = c.x; ch.zw[k] = TWO ? 0 : -c.y; ch.m2[k] = (uint32_t)c.z; ch.sh[k] = c.w;   // zw holds MINUS the zero point
+        }
+        const int zo = a.zp_out;
+        const uint32_t tq = tmem_base + ((uint32_t)(warp * 32) << 16);
+        // per-thread part of the pooled-output address (window 0 of this thread; window 1 is one pooled row further)
+        const uint32_t out_thr = (uint32_t)(((2 * warp + a.opad) * a.OWP + (CS == 4 ? 2 * qi : qi) + a.opad) * NCH + ch0);
+        const uint32_t out_row = (uint32_t)(a.OWP * NCH);
+        int it = 0;
+#pragma unroll 1
+        for (int tile = first; tile < a.num_tiles; tile += step, ++it) {
+            const TileXY cur = split_tile(tile);
+            const int acc = NACCS == 2 ? it & 1 : 0;
+            mbar_wait(&acc_full[acc], (uint32_t)((it / NACCS) & 1));
             tc_fence_after();
-            issue_mma(buf);
-        }
-        TL_MARK(1);
-        if (tile + (NBUF - 1) * step < a.num_tiles) {   // into the buffer the PREVIOUS tile's MMAs have finished with
-            q[NBUF - 1] = split_tile(tile + (NBUF - 1) * step);
-            issue_tile(q[NBUF - 1], buf == 0 ? NBUF - 1 : buf - 1);
-        }
-        cp_async_commit();
-        const TileXY cur = q[0];
-#pragma unroll
-        for (int d = 0; d < NBUF - 1; ++d) q[d] = q[d + 1];
-        TL_MARK(2);
-        mbar_wait(mma_done, phase);
-        phase ^= 1u;
-        tc_fence_after();
-        TL_MARK(3);
+            const uint32_t tqa = tq + (uint32_t)(acc * L::NACC);      // this tile's accumulator, this warp's lane quarter
+            auto release_acc = [&]() {       // this warp's TMEM reads of the tile are complete
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&acc_empty[acc])) : "memory");
+            };
+            if (KNOB(2)) {
+                release_acc();
+                continue;
+            }
 
         // ---- epilogue: warp = TMEM lane quarter = 4 conv rows = 2 pooled rows; thread (qi, qq) = pooled column(s) qi, channels qq*NPQ ..
-        const int tx = cur.tx, ty = cur.ty, n = cur.n;
-        const int py0 = ty * (TILE_ROWS / 2) + 2 * warp;
-        uint8_t *const out_tile = a.out_pool + (size_t)((uint32_t)((n * a.OHP + ty * (TILE_ROWS / 2)) * a.OWP + tx * (G::TWPX / 2)) * (uint32_t)NCH + out_thr);
-        if (CS == 4) {
-            constexpr int NPAIR = 2 / SPLIT, NJ = NCH / 16, NCK = NPAIR * NJ;    // NCK chunks of 2 x 16 accumulators, double-buffered
-            uint32_t V[2][2][16];
-            auto chunk_addr = [&](int ck) { return tq + ((SPLIT == 2 ? half : ck / NJ) * NPQ + 4 * (ck % NJ)) * 8; };
-            if (PIPE) tmem_ldq4_issue(chunk_addr(0), V[0][0], V[0][1]);
-            uint32_t s0[8], s1[8];
-            tmem_ldq(tq + 4 * NCH, s0, s1);        // its wait covers chunk 0 as well
-            if (PIPE) tmem_wait32(V[0][0], V[0][1]);
-            uint32_t w0[NPAIR][NCH / 16], w1[NPAIR][NCH / 16];
-#pragma unroll
-            for (int pp = 0; pp < NPAIR; ++pp) {
-                const int pair = SPLIT == 2 ? half : pp;
-                int nsa0[4], nsa1[4];       // the pair's four activation sums
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    nsa0[k] = (int)(SPLIT == 2 ? (half ? s0[4 + k] : s0[k]) : s0[4 * pp + k]);
-                    nsa1[k] = (int)(SPLIT == 2 ? (half ? s1[4 + k] : s1[k]) : s1[4 * pp + k]);
+            const int tx = cur.tx, ty = cur.ty, n = cur.n;
+            const int py0 = ty * (TILE_ROWS / 2) + 2 * warp;
+            uint8_t *const out_tile = a.out_pool + (size_t)((uint32_t)((n * a.OHP + ty * (TILE_ROWS / 2)) * a.OWP + tx * (G::TWPX / 2)) * (uint32_t)NCH + out_thr);
+            if (CS == 4) {
+                constexpr int NPAIR = 2 / SPLIT, NJ = NCH / 16, NCK = NPAIR * NJ;    // NCK chunks of 2 x 16 accumulators, double-buffered
+                uint32_t V[2][2][16];
+                auto chunk_addr = [&](int ck) { return tqa + ((SPLIT == 2 ? half : ck / NJ) * NPQ + 4 * (ck % NJ)) * 8; };
+                if (PIPE) tmem_ldq4_issue(chunk_addr(0), V[0][0], V[0][1]);
+                uint32_t s0[8] = {0, 0, 0, 0, 0, 0, 0, 0}, s1[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+                if (!TWO) tmem_ldq(tqa + 4 * NCH, s0, s1);        // its wait covers chunk 0 as well
+                if (PIPE) {
+                    tmem_wait32(V[0][0], V[0][1]);
+                    if (NCK == 1) release_acc();
                 }
+                uint32_t w0[NPAIR][NCH / 16], w1[NPAIR][NCH / 16];
 #pragma unroll
-                for (int jj = 0; jj < NCH / 16; ++jj) {
-                    const int ck = pp * NJ + jj;
-                    if (PIPE) {
-                        if (ck + 1 < NCK) tmem_ldq4_issue(chunk_addr(ck + 1), V[(ck + 1) & 1][0], V[(ck + 1) & 1][1]);
-                    } else {
-                        tmem_ldq4(chunk_addr(ck), V[0][0], V[0][1]);
-                    }
-                    uint32_t(&v0)[16] = V[PIPE ? ck & 1 : 0][0];
-                    uint32_t(&v1)[16] = V[PIPE ? ck & 1 : 0][1];
-                    int r0[4], r1w[4];
-                    uint32_t orx = 0, orr = 0, xq;
+                for (int pp = 0; pp < NPAIR; ++pp) {
+                    const int pair = SPLIT == 2 ? half : pp;
+                    int nsa0[4], nsa1[4];       // the pair's four activation sums
 #pragma unroll
-                    for (int gg = 0; gg < 4; ++gg) {
-                        const int k = 4 * jj + gg;
-                        r0[gg] = pool_requant(ch.zw[k], ch.bias[k], ch.m2[k], ch.sh[k], zo, (int)v0[4 * gg], (int)v0[4 * gg + 1], (int)v0[4 * gg + 2],
-                                              (int)v0[4 * gg + 3], nsa0[0], nsa0[1], nsa0[2], nsa0[3], &xq);
-                        orx |= xq; orr |= (uint32_t)r0[gg];
-                        r1w[gg] = pool_requant(ch.zw[k], ch.bias[k], ch.m2[k], ch.sh[k], zo, (int)v1[4 * gg], (int)v1[4 * gg + 1], (int)v1[4 * gg + 2],
-                                               (int)v1[4 * gg + 3], nsa1[0], nsa1[1], nsa1[2], nsa1[3], &xq);
-                        orx |= xq; orr |= (uint32_t)r1w[gg];
+                    for (int k = 0; k < 4; ++k) {
+                        nsa0[k] = (int)(SPLIT == 2 ? (half ? s0[4 + k] : s0[k]) : s0[4 * pp + k]);
+                        nsa1[k] = (int)(SPLIT == 2 ? (half ? s1[4 + k] : s1[k]) : s1[4 * pp + k]);
                     }
-                    if (orx >= (1u << 22) || orr > 255u) {
+#pragma unroll
+                    for (int jj = 0; jj < NCH / 16; ++jj) {
+                        const int ck = pp * NJ + jj;
+                        if (PIPE) {
+                            if (ck + 1 < NCK) tmem_ldq4_issue(chunk_addr(ck + 1), V[(ck + 1) & 1][0], V[(ck + 1) & 1][1]);
+                        } else {
+                            tmem_ldq4(chunk_addr(ck), V[0][0], V[0][1]);
+                            if (ck + 1 == NCK) release_acc();
+                        }
+                        uint32_t(&v0)[16] = V[PIPE ? ck & 1 : 0][0];
+                        uint32_t(&v1)[16] = V[PIPE ? ck & 1 : 0][1];
+                        int r0[4], r1w[4];
+                        uint32_t orx = 0, orr = 0, xq;
 #pragma unroll
                         for (int gg = 0; gg < 4; ++gg) {
                             const int k = 4 * jj + gg;
-                            const double mcd = a.mc[ch0 + k];
-                            r0[gg] = pool_requant_slow(ch.zw[k], ch.bias[k], mcd, zo, (int)v0[4 * gg], (int)v0[4 * gg + 1], (int)v0[4 * gg + 2],
-                                                       (int)v0[4 * gg + 3], nsa0[0], nsa0[1], nsa0[2], nsa0[3]);
-                            r1w[gg] = pool_requant_slow(ch.zw[k], ch.bias[k], mcd, zo, (int)v1[4 * gg], (int)v1[4 * gg + 1], (int)v1[4 * gg + 2],
-                                                        (int)v1[4 * gg + 3], nsa1[0], nsa1[1], nsa1[2], nsa1[3]);
+                            r0[gg] = pool_requant(ch.zw[k], ch.bias[k], ch.m2[k], ch.sh[k], zo, (int)v0[4 * gg], (int)v0[4 * gg + 1], (int)v0[4 * gg + 2],
+                                                  (int)v0[4 * gg + 3], nsa0[0], nsa0[1], nsa0[2], nsa0[3], &xq);
+                            orx |= xq; orr |= (uint32_t)r0[gg];
+                            r1w[gg] = pool_requant(ch.zw[k], ch.bias[k], ch.m2[k], ch.sh[k], zo, (int)v1[4 * gg], (int)v1[4 * gg + 1], (int)v1[4 * gg + 2],
+                                                   (int)v1[4 * gg + 3], nsa1[0], nsa1[1], nsa1[2], nsa1[3], &xq);
+                            orx |= xq; orr |= (uint32_t)r1w[gg];
+                        }
+                        if (orx >= (1u << 22) || orr > 255u) {
+#pragma unroll
+                            for (int gg = 0; gg < 4; ++gg) {
+                                const int k = 4 * jj + gg;
+                                const double mcd = a.mc[ch0 + k];
+                                r0[gg] = pool_requant_slow(ch.zw[k], ch.bias[k], mcd, zo, (int)v0[4 * gg], (int)v0[4 * gg + 1], (int)v0[4 * gg + 2],
+                                                           (int)v0[4 * gg + 3], nsa0[0], nsa0[1], nsa0[2], nsa0[3]);
+                                r1w[gg] = pool_requant_slow(ch.zw[k], ch.bias[k], mcd, zo, (int)v1[4 * gg], (int)v1[4 * gg + 1], (int)v1[4 * gg + 2],
+                                                            (int)v1[4 * gg + 3], nsa1[0], nsa1[1], nsa1[2], nsa1[3]);
+                            }
+                        }
+                        w0[pp][jj] = pack4(r0);
+                        w1[pp][jj] = pack4(r1w);
+                        if (PIPE && ck + 1 < NCK) {
+                            tmem_wait32(V[(ck + 1) & 1][0], V[(ck + 1) & 1][1]);
+                            if (ck + 2 == NCK) release_acc();
                         }
                     }
-                    w0[pp][jj] = pack4(r0);
-                    w1[pp][jj] = pack4(r1w);
-                    if (PIPE && ck + 1 < NCK) tmem_wait32(V[(ck + 1) & 1][0], V[(ck + 1) & 1][1]);
                 }
-            }
-            TL_MARK(4);
-            cp_async_wait_group<NBUF - 2>();   // the next tile's copy has long landed: fence it before this tile's global stores queue up
-            fence_proxy_async();
-            TL_MARK(5);
 #pragma unroll
-            for (int pp = 0; pp < NPAIR; ++pp) {
-                const int pair = SPLIT == 2 ? half : pp;
-                const int px = tx * (G::TWPX / 2) + 2 * qi + pair;
-                if (px < a.PW) {
-                    uint8_t *dst = out_tile + pair * NCH;
-                    if (py0 < a.PH) {
-                        if constexpr (NCH == 16) *reinterpret_cast<uint32_t *>(dst) = w0[pp][0];
-                        else *reinterpret_cast<uint2 *>(dst) = make_uint2(w0[pp][0], w0[pp][1]);
-                    }
-                    if (py0 + 1 < a.PH) {
-                        if constexpr (NCH == 16) *reinterpret_cast<uint32_t *>(dst + out_row) = w1[pp][0];
-                        else *reinterpret_cast<uint2 *>(dst + out_row) = make_uint2(w1[pp][0], w1[pp][1]);
+                for (int pp = 0; pp < NPAIR; ++pp) {
+                    const int pair = SPLIT == 2 ? half : pp;
+                    const int px = tx * (G::TWPX / 2) + 2 * qi + pair;
+                    if (px < a.PW && !KNOB(8)) {
+                        uint8_t *dst = out_tile + pair * NCH;
+                        if (py0 < a.PH) {
+                            if constexpr (NCH == 16) *reinterpret_cast<uint32_t *>(dst) = w0[pp][0];
+                            else *reinterpret_cast<uint2 *>(dst) = make_uint2(w0[pp][0], w0[pp][1]);
+                        }
+                        if (py0 + 1 < a.PH) {
+                            if constexpr (NCH == 16) *reinterpret_cast<uint32_t *>(dst + out_row) = w1[pp][0];
+                            else *reinterpret_cast<uint2 *>(dst + out_row) = make_uint2(w1[pp][0], w1[pp][1]);
+                        }
                     }
                 }
-            }
-        } else {
-            constexpr int JN = NCH / 16 / SPLIT > 0 ? NCH / 16 / SPLIT : 1;      // 4-channel chunks of this thread, double-buffered
-            uint32_t E[2][4][8];
-            auto chunk_addr = [&](int j) { return tq + 16 * (half * JN + j); };
-            if (PIPE) tmem_ldq_eo_issue(chunk_addr(0), chunk_addr(0) + L::NB, E[0][0], E[0][1], E[0][2], E[0][3]);
-            uint32_t se0[4], se1[4], so0[4], so1[4];
-            tmem_ldq_sums(tq + NCH, tq + L::NB + NCH, se0, se1, so0, so1);      // its wait covers chunk 0 as well
-            if (PIPE) tmem_wait_eo(E[0][0], E[0][1], E[0][2], E[0][3]);
-            // window 0: conv rows (4w, 4w+1) = lanes (qi, qi+8) of half 0; window 1: rows (4w+2, 4w+3) = half 1
-            const int n0[4] = {(int)se0[0], (int)se0[2], (int)so0[0], (int)so0[2]};
-            const int n1[4] = {(int)se1[0], (int)se1[2], (int)so1[0], (int)so1[2]};
-            uint32_t w0[JN], w1[JN];
-#pragma unroll
-            for (int j = 0; j < JN; ++j) {
-                constexpr int NOW = 0;
-                const int set = PIPE ? j & 1 : NOW;
+            } else {
+                constexpr int JN = NCH / 16 / SPLIT > 0 ? NCH / 16 / SPLIT : 1;      // 4-channel chunks of this thread, double-buffered
+                uint32_t E[2][4][8];
+                auto chunk_addr = [&](int j) { return tqa + 16 * (half * JN + j); };
+                if (PIPE) tmem_ldq_eo_issue(chunk_addr(0), chunk_addr(0) + L::NB, E[0][0], E[0][1], E[0][2], E[0][3]);
+                uint32_t se0[4] = {0, 0, 0, 0}, se1[4] = {0, 0, 0, 0}, so0[4] = {0, 0, 0, 0}, so1[4] = {0, 0, 0, 0};
+                if (!TWO) tmem_ldq_sums(tqa + NCH, tqa + L::NB + NCH, se0, se1, so0, so1);      // its wait covers chunk 0 as well
                 if (PIPE) {
-                    if (j + 1 < JN)
-                        tmem_ldq_eo_issue(chunk_addr(j + 1), chunk_addr(j + 1) + L::NB, E[(j + 1) & 1][0], E[(j + 1) & 1][1], E[(j + 1) & 1][2], E[(j + 1) & 1][3]);
-                } else {
-                    tmem_ldq_eo(chunk_addr(j), chunk_addr(j) + L::NB, E[NOW][0], E[NOW][1], E[NOW][2], E[NOW][3]);
+                    tmem_wait_eo(E[0][0], E[0][1], E[0][2], E[0][3]);
+                    if (JN == 1) release_acc();
                 }
-                uint32_t(&e0)[8] = E[set][0];
-                uint32_t(&e1)[8] = E[set][1];
-                uint32_t(&o0)[8] = E[set][2];
-                uint32_t(&o1)[8] = E[set][3];
-                int r0[4], r1w[4];
-                uint32_t orx = 0, orr = 0, xq;
+                // window 0: conv rows (4w, 4w+1) = lanes (qi, qi+8) of half 0; window 1: rows (4w+2, 4w+3) = half 1
+                const int n0[4] = {(int)se0[0], (int)se0[2], (int)so0[0], (int)so0[2]};
+                const int n1[4] = {(int)se1[0], (int)se1[2], (int)so1[0], (int)so1[2]};
+                uint32_t w0[JN], w1[JN];
 #pragma unroll
-                for (int cc = 0; cc < 4; ++cc) {
-                    const int k = 4 * j + cc, ri = 4 * (cc >> 1) + (cc & 1);
-                    r0[cc] = pool_requant(ch.zw[k], ch.bias[k], ch.m2[k], ch.sh[k], zo, (int)e0[ri], (int)e0[ri + 2], (int)o0[ri], (int)o0[ri + 2], n0[0],
-                                          n0[1], n0[2], n0[3], &xq);
-                    orx |= xq; orr |= (uint32_t)r0[cc];
-                    r1w[cc] = pool_requant(ch.zw[k], ch.bias[k], ch.m2[k], ch.sh[k], zo, (int)e1[ri], (int)e1[ri + 2], (int)o1[ri], (int)o1[ri + 2], n1[0],
-                                           n1[1], n1[2], n1[3], &xq);
-                    orx |= xq; orr |= (uint32_t)r1w[cc];
-                }
-                if (orx >= (1u << 22) || orr > 255u) {
+                for (int j = 0; j < JN; ++j) {
+                    constexpr int NOW = 0;
+                    const int set = PIPE ? j & 1 : NOW;
+                    if (PIPE) {
+                        if (j + 1 < JN)
+                            tmem_ldq_eo_issue(chunk_addr(j + 1), chunk_addr(j + 1) + L::NB, E[(j + 1) & 1][0], E[(j + 1) & 1][1], E[(j + 1) & 1][2], E[(j + 1) & 1][3]);
+                    } else {
+                        tmem_ldq_eo(chunk_addr(j), chunk_addr(j) + L::NB, E[NOW][0], E[NOW][1], E[NOW][2], E[NOW][3]);
+                        if (j + 1 == JN) release_acc();
+                    }
+                    uint32_t(&e0)[8] = E[set][0];
+                    uint32_t(&e1)[8] = E[set][1];
+                    uint32_t(&o0)[8] = E[set][2];
+                    uint32_t(&o1)[8] = E[set][3];
+                    int r0[4], r1w[4];
+                    uint32_t orx = 0, orr = 0, xq;
 #pragma unroll
                     for (int cc = 0; cc < 4; ++cc) {
                         const int k = 4 * j + cc, ri = 4 * (cc >> 1) + (cc & 1);
-                        const double mcd = a.mc[ch0 + k];
-                        r0[cc] = pool_requant_slow(ch.zw[k], ch.bias[k], mcd, zo, (int)e0[ri], (int)e0[ri + 2], (int)o0[ri], (int)o0[ri + 2], n0[0], n0[1],
-                                                   n0[2], n0[3]);
-                        r1w[cc] = pool_requant_slow(ch.zw[k], ch.bias[k], mcd, zo, (int)e1[ri], (int)e1[ri + 2], (int)o1[ri], (int)o1[ri + 2], n1[0], n1[1],
-                                                    n1[2], n1[3]);
+                        r0[cc] = pool_requant(ch.zw[k], ch.bias[k], ch.m2[k], ch.sh[k], zo, (int)e0[ri], (int)e0[ri + 2], (int)o0[ri], (int)o0[ri + 2], n0[0],
+                                              n0[1], n0[2], n0[3], &xq);
+                        orx |= xq; orr |= (uint32_t)r0[cc];
+                        r1w[cc] = pool_requant(ch.zw[k], ch.bias[k], ch.m2[k], ch.sh[k], zo, (int)e1[ri], (int)e1[ri + 2], (int)o1[ri], (int)o1[ri + 2], n1[0],
+                                               n1[1], n1[2], n1[3], &xq);
+                        orx |= xq; orr |= (uint32_t)r1w[cc];
+                    }
+                    if (orx >= (1u << 22) || orr > 255u) {
+#pragma unroll
+                        for (int cc = 0; cc < 4; ++cc) {
+                            const int k = 4 * j + cc, ri = 4 * (cc >> 1) + (cc & 1);
+                            const double mcd = a.mc[ch0 + k];
+                            r0[cc] = pool_requant_slow(ch.zw[k], ch.bias[k], mcd, zo, (int)e0[ri], (int)e0[ri + 2], (int)o0[ri], (int)o0[ri + 2], n0[0], n0[1],
+                                                       n0[2], n0[3]);
+                            r1w[cc] = pool_requant_slow(ch.zw[k], ch.bias[k], mcd, zo, (int)e1[ri], (int)e1[ri + 2], (int)o1[ri], (int)o1[ri + 2], n1[0], n1[1],
+                                                        n1[2], n1[3]);
+                        }
+                    }
+                    w0[j] = pack4(r0);
+                    w1[j] = pack4(r1w);
+                    if (PIPE && j + 1 < JN) {
+                        tmem_wait_eo(E[(j + 1) & 1][0], E[(j + 1) & 1][1], E[(j + 1) & 1][2], E[(j + 1) & 1][3]);
+                        if (j + 2 == JN) release_acc();
                     }
                 }
-                w0[j] = pack4(r0);
-                w1[j] = pack4(r1w);
-                if (PIPE && j + 1 < JN) tmem_wait_eo(E[(j + 1) & 1][0], E[(j + 1) & 1][1], E[(j + 1) & 1][2], E[(j + 1) & 1][3]);
-            }
-            TL_MARK(4);
-            cp_async_wait_group<NBUF - 2>();   // the next tile's copy has long landed: fence it before this tile's global stores queue up
-            fence_proxy_async();
-            TL_MARK(5);
-            const int px = tx * (G::TWPX / 2) + qi;
-            if (px < a.PW) {
-                uint8_t *dst = out_tile;
-                const uint32_t rowb = out_row;
-                if (py0 < a.PH) {
-                    if constexpr (JN == 1) *reinterpret_cast<uint32_t *>(dst) = w0[0];
-                    else if constexpr (JN == 2) *reinterpret_cast<uint2 *>(dst) = make_uint2(w0[0], w0[1]);
-                    else *reinterpret_cast<uint4 *>(dst) = make_uint4(w0[0], w0[1], w0[2], w0[3]);
-                }
-                if (py0 + 1 < a.PH) {
-                    if constexpr (JN == 1) *reinterpret_cast<uint32_t *>(dst + rowb) = w1[0];
-                    else if constexpr (JN == 2) *reinterpret_cast<uint2 *>(dst + rowb) = make_uint2(w1[0], w1[1]);
-                    else *reinterpret_cast<uint4 *>(dst + rowb) = make_uint4(w1[0], w1[1], w1[2], w1[3]);
+                const int px = tx * (G::TWPX / 2) + qi;
+                if (px < a.PW && !KNOB(8)) {
+                    uint8_t *dst = out_tile;
+                    const uint32_t rowb = out_row;
+                    if (py0 < a.PH) {
+                        if constexpr (JN == 1) *reinterpret_cast<uint32_t *>(dst) = w0[0];
+                        else if constexpr (JN == 2) *reinterpret_cast<uint2 *>(dst) = make_uint2(w0[0], w0[1]);
+                        else *reinterpret_cast<uint4 *>(dst) = make_uint4(w0[0], w0[1], w0[2], w0[3]);
+                    }
+                    if (py0 + 1 < a.PH) {
+                        if constexpr (JN == 1) *reinterpret_cast<uint32_t *>(dst + rowb) = w1[0];
+                        else if constexpr (JN == 2) *reinterpret_cast<uint2 *>(dst + rowb) = make_uint2(w1[0], w1[1]);
+                        else *reinterpret_cast<uint4 *>(dst + rowb) = make_uint4(w1[0], w1[1], w1[2], w1[3]);
+                    }
                 }
             }
         }
-        TL_MARK(6);
-#ifdef YQ_TIMELINE
-        tl_acc[7] += 1;
-#endif
     }
-    TL_FLUSH();
     tc_fence_before();
     __syncthreads();
     if (t < 32) {
@@ -548,41 +571,78 @@ __global__ void __launch_bounds__(RW_THREADS * SPLIT, (CS == 32 ? 2 : SPLIT == 2
 
 struct RowsState {
     int CS, NCH;
+    bool two = false;       // two signed weight blocks (see RowsCfg)
     uint8_t *wimg = nullptr;
+    std::map<std::pair<const void *, int>, CUtensorMap> maps;      // input tensor map per (input pointer, batch)
 };
+
+typedef CUresult (*RowsEncodeFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
+                                 const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+// The input tile as TMA boxes.  c = 4: the padded tensor as [rows][pitch * 4 bytes], box = 18 rows x 144 bytes.
+// c >= 16: [rows][pitch / 2][parity][c bytes], box = 18 rows x 9 pixels of ONE parity x 16 channels, so that the even and the
+// odd pixel columns land in separate planes (what the even/odd MMA groups read).
+int rows_encode(CUtensorMap *m, const void *in, int CS, int rows, int pitch)
+{
+    static RowsEncodeFn enc = nullptr;
+    if (!enc) {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess || !p)
+            return yq::fail("cuTensorMapEncodeTiled is not available from this driver");
+        enc = (RowsEncodeFn)p;
+    }
+    CUresult r;
+    const cuuint32_t es[4] = {1, 1, 1, 1};
+    if (CS == 4) {
+        const cuuint64_t dims[2] = {(cuuint64_t)pitch * 4, (cuuint64_t)rows};
+        const cuuint64_t strides[1] = {(cuuint64_t)pitch * 4};
+        const cuuint32_t box[2] = {(cuuint32_t)PLANE, (cuuint32_t)(TILE_ROWS + 2)};
+        r = enc(m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void *>(in), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    } else {
+        const cuuint64_t dims[4] = {(cuuint64_t)CS, 2, (cuuint64_t)pitch / 2, (cuuint64_t)rows};
+        const cuuint64_t strides[3] = {(cuuint64_t)CS, (cuuint64_t)2 * CS, (cuuint64_t)pitch * CS};
+        const cuuint32_t box[4] = {16, 1, PLANE / 16, (cuuint32_t)(TILE_ROWS + 2)};
+        r = enc(m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 4, const_cast<void *>(in), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    }
+    if (r != CUDA_SUCCESS) return yq::fail("tcgen05 rows flavour: cuTensorMapEncodeTiled(c %d, %d rows, pitch %d) failed: %d", CS, rows, pitch, (int)r);
+    return 0;
+}
 
 // byte position of element (row n, k) inside one [NB][32] filter tile: 8-row x 16-byte core matrices, the two K chunks of
 // a group side by side (LBO = 128), groups 256 bytes apart (SBO = 256)
 inline size_t bpos(int n, int k) { return (size_t)(n / 8) * 256 + (size_t)(k / 16) * 128 + (size_t)(n % 8) * 16 + (size_t)(k % 16); }
 
-template <int CS, int NCH, int SPLIT>
-int launch_rows(const RowsArgs &a, cudaStream_t stream)
+template <int CS, int NCH, int SPLIT, bool TWO>
+int launch_rows(const CUtensorMap &tmA, const RowsArgs &a, cudaStream_t stream)
 {
-    using L = RowsCfg<CS, NCH>;
+    using L = RowsCfg<CS, NCH, TWO>;
     constexpr int NT = RW_THREADS * SPLIT;
     static int ctas_per_sm = 0, n_sm = 0;
     const int smem = L::TOTAL + 128;
     if (!ctas_per_sm) {
-        YQ_CUDA(cudaFuncSetAttribute(conv_u8_tc_rows_kernel<CS, NCH, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        YQ_CUDA(cudaFuncSetAttribute(conv_u8_tc_rows_kernel<CS, NCH, SPLIT, TWO>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         int dev = 0, smem_sm = 0;
         cudaFuncAttributes fa;
-        YQ_CUDA(cudaFuncGetAttributes(&fa, conv_u8_tc_rows_kernel<CS, NCH, SPLIT>));
+        YQ_CUDA(cudaFuncGetAttributes(&fa, conv_u8_tc_rows_kernel<CS, NCH, SPLIT, TWO>));
         YQ_CUDA(cudaGetDevice(&dev));
         YQ_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
         YQ_CUDA(cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev));
         // counted by hand: the occupancy API answers 1 for kernels that allocate tensor memory (see yq_conv_tc_small.cu)
         const int by_smem = smem_sm / (smem + 1024 + (int)fa.sharedSizeBytes);
-        const int by_regs = 65536 / (((fa.numRegs + 7) / 8 * 8) * NT);
+        const int by_regs = 65536 / (((fa.numRegs + 7) / 8 * 8) * (NT + 32));
         const int by_tmem = 512 / L::TMEM_COLS;
         int occ = by_smem < by_regs ? by_smem : by_regs;
         if (by_tmem < occ) occ = by_tmem;
-        if (getenv("YQ_DEBUG")) fprintf(stderr, "yq: rows<%d,%d,%d> regs=%d by_smem=%d by_regs=%d by_tmem=%d smem=%d\n", CS, NCH, SPLIT, fa.numRegs, by_smem, by_regs, by_tmem, smem);
+        if (getenv("YQ_DEBUG")) fprintf(stderr, "yq: rows<%d,%d,%d,%d> regs=%d by_smem=%d by_regs=%d by_tmem=%d smem=%d\n", CS, NCH, SPLIT, (int)TWO, fa.numRegs, by_smem, by_regs, by_tmem, smem);
         if (occ < 1) return yq::fail("conv_u8_tc_rows_kernel<%d,%d> does not fit on an SM", CS, NCH);
         ctas_per_sm = occ;
     }
     int grid = n_sm * ctas_per_sm;
     if (grid > a.num_tiles) grid = a.num_tiles;
-    YQ_CUDA(yq::launch_pdl(conv_u8_tc_rows_kernel<CS, NCH, SPLIT>, dim3(grid), dim3(NT), smem, stream, a));
+    YQ_CUDA(yq::launch_pdl(conv_u8_tc_rows_kernel<CS, NCH, SPLIT, TWO>, dim3(grid), dim3(NT + 32), smem, stream, tmA, a));
     return 0;
 }
 
@@ -613,23 +673,45 @@ int yq_tc_rows_prepare(yq_conv_layer *l, void **state)
     st->CS = l->cs_in;
     st->NCH = l->cs_out;
     const int CS = st->CS, NCH = st->NCH, NPQ = NCH / 4;
-    const int NB = CS == 4 ? 4 * NCH + 16 : NCH + 16;
+    // two signed blocks h + l = w - zp_w unless some difference is 255 (h = 127 would leave l = 128).  By default only where the
+    // kernel can then double-buffer its accumulator (RowsCfg::DB): elsewhere twice the MMAs cost more than the epilogue saves
+    // (measured: layer 4 51 -> 76 us).  YQ_ROWS_TWO = 0 / 1 forces it off / on.
+    const int two_env = getenv("YQ_ROWS_TWO") ? atoi(getenv("YQ_ROWS_TWO")) : -1;
+    bool two = two_env >= 0 ? two_env != 0 : ((CS == 4 && NCH == 16) || (CS == 16 && NCH <= 32));
+    auto Wraw = [&](int oc, int ci, int ky, int kx) -> int { return l->host_w[(((size_t)oc * l->c + ci) * 3 + ky) * 3 + kx]; };
+    auto zpw = [&](int oc) -> int { return l->host_chanq[(size_t)oc * 4 + 1]; };
+    for (int oc = 0; oc < l->n && two; ++oc)
+        for (int i = 0; i < l->c * 9; ++i)
+            if ((int)l->host_w[(size_t)oc * l->c * 9 + i] - zpw(oc) == 255) { two = false; break; }
+    st->two = two;
+    const int nsum = two ? 0 : 16;
+    const int NB = CS == 4 ? 4 * NCH + nsum : NCH + nsum;
     const int nblk = CS == 32 ? 2 : 1;
     const int nmma = CS == 4 ? 3 : 6 * nblk;
-    std::vector<uint8_t> img((size_t)nmma * (CS == 4 ? NB : 2 * NB) * 32, 0);
-    auto W = [&](int oc, int ci, int ky, int kx) -> uint8_t { return ci < l->c ? l->host_w[(((size_t)oc * l->c + ci) * 3 + ky) * 3 + kx] : 0; };
+    const int parts = two ? 2 : 1;
+    std::vector<uint8_t> img((size_t)parts * nmma * (CS == 4 ? NB : 2 * NB) * 32, 0);
+    int part = 0;
+    // the filter byte of the block being laid out: the u8 weight, or (two) the signed block `part` of w - zp_w
+    auto W = [&](int oc, int ci, int ky, int kx) -> uint8_t {
+        if (ci >= l->c) return 0;
+        const int w = Wraw(oc, ci, ky, kx);
+        if (!two) return (uint8_t)w;
+        const int d = w - zpw(oc), h = d < -128 ? -128 : d > 127 ? 127 : d;
+        return (uint8_t)(int8_t)(part == 0 ? h : d - h);
+    };
+    for (part = 0; part < parts; ++part)
     if (CS == 4) {
         // TMEM column c = 8g + 2q + e: channel q*NPQ + g % NPQ, output pixel 2*(g / NPQ) + e of the 4-pixel segment;
         // K byte k = 4*ip + ci: input pixel ip (0..7, the segment's window starts one pixel to the left), channel ci
         for (int ky = 0; ky < 3; ++ky) {
-            uint8_t *tile = img.data() + (size_t)ky * NB * 32;
+            uint8_t *tile = img.data() + (size_t)(part * 3 + ky) * NB * 32;
             for (int c = 0; c < 4 * NCH; ++c) {
                 const int g = c / 8, q = (c % 8) / 2, e = c % 2;
                 const int oc = q * NPQ + g % NPQ, px = 2 * (g / NPQ) + e;
                 for (int kx = 0; kx < 3; ++kx)
                     for (int ci = 0; ci < 4; ++ci) tile[bpos(c, 4 * (px + kx) + ci)] = W(oc, ci, ky, kx);
             }
-            for (int c = 0; c < 16; ++c) {   // activation sums: column group c/8 = pixel pair, c % 2 = pixel of the pair
+            for (int c = 0; c < nsum; ++c) {   // activation sums: column group c/8 = pixel pair, c % 2 = pixel of the pair
                 const int px = 2 * (c / 8) + c % 2;
                 for (int kx = 0; kx < 3; ++kx)
                     for (int ci = 0; ci < l->c; ++ci) tile[bpos(4 * NCH + c, 4 * (px + kx) + ci)] = 1;
@@ -638,7 +720,7 @@ int yq_tc_rows_prepare(yq_conv_layer *l, void **state)
     } else {
         // TMEM column c = 8g + 2q + e of a group: channel q*NPQ + 2g + e.  Filter rows [0, NB) = even-pixel group, [NB, 2NB) =
         // odd-pixel group; K chunk 0 = plane E, chunk 1 = plane O of the MMA's step (see issue_mma)
-        int m = 0;
+        int m = part * nmma;
         for (int blk = 0; blk < nblk; ++blk)
             for (int ky = 0; ky < 3; ++ky)
                 for (int step = 0; step < 2; ++step, ++m) {
@@ -656,7 +738,7 @@ int yq_tc_rows_prepare(yq_conv_layer *l, void **state)
                                     tile[bpos(grp * NB + c, chunk * 16 + b)] = W(q * NPQ + 2 * g + e, ci, ky, kx);
                                 }
                                 if (ci < l->c)
-                                    for (int c = 0; c < 16; ++c) tile[bpos(grp * NB + NCH + c, chunk * 16 + b)] = 1;
+                                    for (int c = 0; c < nsum; ++c) tile[bpos(grp * NB + NCH + c, chunk * 16 + b)] = 1;
                             }
                         }
                 }
@@ -669,6 +751,8 @@ int yq_tc_rows_prepare(yq_conv_layer *l, void **state)
     *state = st;
     return 0;
 }
+
+int yq_tc_rows_two_blocks(const void *state) { return state && ((const RowsState *)state)->two ? 1 : 0; }
 
 void yq_tc_rows_free(void *state)
 {
@@ -694,19 +778,31 @@ int yq_tc_rows_forward(yq_conv_layer *l, void *state, const uint8_t *in_padded, 
     a.tiles_y = (l->out_h + TILE_ROWS - 1) / TILE_ROWS;
     a.num_tiles = a.tiles_x * a.tiles_y * batch;
     a.zp_out = l->zp_out;
+    a.knobs = getenv("YQ_ROWS_KNOBS") ? atoi(getenv("YQ_ROWS_KNOBS")) : 0;
     a.magic_x = (uint32_t)((0x100000000ull + a.tiles_x - 1) / a.tiles_x);
     a.magic_y = (uint32_t)((0x100000000ull + a.tiles_y - 1) / a.tiles_y);
     if ((unsigned long long)a.num_tiles * (a.tiles_x > a.tiles_y ? a.tiles_x : a.tiles_y) >= 0x100000000ull || yq_act_geom_bytes(og, batch, l->n) >= 0x100000000ull)
         return yq::fail("tcgen05 rows flavour: tensor too large for 32-bit tile arithmetic");
+    if (((uintptr_t)in_padded & 15) || (ig.pitch_w & 3)) return yq::fail("tcgen05 rows flavour: the input must be 16-byte aligned with a pitch that is a multiple of 4");
+    const auto key = std::make_pair((const void *)in_padded, batch);
+    auto it = st->maps.find(key);
+    if (it == st->maps.end()) {
+        CUtensorMap m;
+        if (rows_encode(&m, in_padded, st->CS, ig.rows_h * batch, ig.pitch_w)) return -1;
+        if (st->maps.size() > 64) st->maps.clear();
+        it = st->maps.emplace(key, m).first;
+    }
+    const CUtensorMap &tmA = it->second;
     memcpy(a.cq, l->host_chanq.data(), (size_t)l->n * 16);
     memcpy(a.mc, l->host_mcomb.data(), (size_t)l->n * 8);
     static const int split_env = getenv("YQ_ROWS_SPLIT") ? atoi(getenv("YQ_ROWS_SPLIT")) : -1;    // experiments: 0 / 1 force
 #define YQ_RW(CS_, N_, DEF_)                                                                                     \
     if (st->CS == CS_ && st->NCH == N_) {                                                                        \
         if constexpr (CS_ == 4 || N_ >= 32) {                                                                    \
-            if (split_env < 0 ? DEF_ : split_env) return launch_rows<CS_, N_, 2>(a, stream);                     \
+            if (split_env < 0 ? DEF_ : split_env)                                                                \
+                return st->two ? launch_rows<CS_, N_, 2, true>(tmA, a, stream) : launch_rows<CS_, N_, 2, false>(tmA, a, stream); \
         }                                                                                                        \
-        return launch_rows<CS_, N_, 1>(a, stream);                                                               \
+        return st->two ? launch_rows<CS_, N_, 1, true>(tmA, a, stream) : launch_rows<CS_, N_, 1, false>(tmA, a, stream);   \
     }
     YQ_RW(4, 16, 0); YQ_RW(4, 32, 0);
     YQ_RW(16, 16, 0); YQ_RW(16, 32, 0); YQ_RW(16, 64, 0);
@@ -715,9 +811,3 @@ int yq_tc_rows_forward(yq_conv_layer *l, void *state, const uint8_t *in_padded, 
     return yq::fail("tcgen05 rows flavour: no instantiation for cs_in=%d cs_out=%d", st->CS, st->NCH);
 }
 
-#ifdef YQ_TIMELINE
-extern "C" __attribute__((visibility("default"))) int yq_debug_rows_timeline(void *host, size_t bytes)
-{
-    return cudaMemcpyFromSymbol(host, yq_rows_timeline, bytes < sizeof(yq_rows_timeline) ? bytes : sizeof(yq_rows_timeline)) == cudaSuccess ? 0 : -1;
-}
-#endif

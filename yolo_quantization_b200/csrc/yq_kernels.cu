@@ -497,7 +497,7 @@ extern "C" int yq_forward_convolutional_layer_quant_flat_yolo_gpu(yq_conv_layer 
     return yq_tc_flat_forward(l, l->tc_flat, in_flat, out_flat, halo_fill, out_f32, out_yolo, classes, out_acc, batch, (cudaStream_t)stream);
 }
 
-extern "C" int yq_conv_rows_supported(const yq_conv_layer *l) { return l && l->tc_rows ? 1 : 0; }
+extern "C" int yq_conv_rows_supported(const yq_conv_layer *l) { return l && l->tc_rows ? 1 + yq_tc_rows_two_blocks(l->tc_rows) : 0; }
 extern "C" int yq_conv_rows_input_geom(const yq_conv_layer *l, yq_act_geom *g)
 {
     if (!l || !g || !l->tc_rows) return yq::fail("yq_conv_rows_input_geom: the layer has no rows flavour");

@@ -209,6 +209,11 @@ class ConvolutionalLayerQuant:
     def rows_supported(self) -> bool:
         return bool(_lib.load().yq_conv_rows_supported(self.handle))
 
+    @property
+    def rows_variant(self) -> int:
+        """0: no rows flavour; 1: all-ones filter rows + per-output zero-point correction; 2: two signed weight blocks."""
+        return int(_lib.load().yq_conv_rows_supported(self.handle))
+
     def forward_rows_pooled(self, x_nchw: np.ndarray, out_pad: int = 0) -> np.ndarray:
         """conv + RELU6 + maxpool(2,2) through the halo-input "rows" flavour: the input is staged in the padded
         geometry the layer asks for (halo = zp_in); the pooled tensor is written into a tensor with an
