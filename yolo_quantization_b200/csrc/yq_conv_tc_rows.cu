@@ -70,17 +70,18 @@ struct RowsGeom {
 // TWO: the weights enter as two SIGNED blocks h + l = w - zp_w (each in [-128, 127]) multiplied with the same activation
 // tile, so the accumulator is the zero-point-corrected one and neither the all-ones rows nor the per-output correction
 // exist; twice the MMAs, 4 multiply-adds and one TMEM load less per pooled output (prepare falls back when some w - zp_w = 255)
-template <int CS, int NCH, bool TWO>
+template <int CS, int NCH, bool TWO, bool DBL>
 struct RowsCfg {
     using G = RowsGeom<CS>;
     static constexpr int NSUM = TWO ? 0 : 16;
     static constexpr int NB = CS == 4 ? 4 * NCH + NSUM : NCH + NSUM;    // filter rows (TMEM columns) per MMA group
     static constexpr int NACC = CS == 4 ? NB : 2 * NB;              // TMEM columns of one accumulator
-    // DB: two accumulators, the next tile's MMAs run under this tile's epilogue -- where two of them still leave
-    // room for 4 CTAs per SM (128 columns each), i.e. the TWO forms with <= 64 accumulator columns
-    static constexpr bool DB = TWO && CS != 32 && 2 * NACC <= 128;
+    // DB: two accumulators, the next tile's MMAs run under this tile's epilogue (at the price of CTAs per SM once two of
+    // them need more than 128 columns)
+    static constexpr bool DB = DBL;
     static constexpr int NTM = NACC * (DB ? 2 : 1);
     static constexpr int TMEM_COLS = NTM <= 32 ? 32 : NTM <= 64 ? 64 : NTM <= 128 ? 128 : NTM <= 256 ? 256 : 512;
+    static constexpr int MAX_CTAS = 512 / TMEM_COLS;
     // input-tile ring: the copy of tile i + NBUF - 1 is in flight while tile i is computed (DB consumes a tile one step earlier)
     static constexpr int NBUF = DB ? YQ_ROWS_NBUF + 1 : YQ_ROWS_NBUF;
     static_assert(NBUF <= 4, "barrier block");
@@ -239,12 +240,18 @@ __device__ __forceinline__ uint32_t pack4(const int (&r)[4])
 // -> epilogue -> acc_empty[] (one arrival per epilogue warp, right after its last TMEM load).
 // SPLIT = 2: two warps per lane quarter share a tile's epilogue (c = 4: one pixel pair each; c >= 16: half of the thread's
 // channels each).  DBL: two accumulators, so the next tile's MMAs run under this tile's epilogue.
-template <int CS, int NCH, int SPLIT, bool TWO>
-__global__ void __launch_bounds__(RW_THREADS * SPLIT + 32, (CS == 32 ? 2 : SPLIT == 2 ? 3 : 4))
+constexpr int rows_min_ctas(int CS, int SPLIT, int by_tmem)
+{
+    const int want = CS == 32 ? 2 : SPLIT == 2 ? 3 : 4;
+    return want < by_tmem ? want : by_tmem;
+}
+
+template <int CS, int NCH, int SPLIT, bool TWO, bool DBL>
+__global__ void __launch_bounds__(RW_THREADS * SPLIT + 32, rows_min_ctas(CS, SPLIT, RowsCfg<CS, NCH, TWO, DBL>::MAX_CTAS))
 conv_u8_tc_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ RowsArgs a)
 {
     using G = RowsGeom<CS>;
-    using L = RowsCfg<CS, NCH, TWO>;
+    using L = RowsCfg<CS, NCH, TWO, DBL>;
     constexpr int NPQ = NCH / 4;
     constexpr int NT = RW_THREADS * SPLIT;                 // epilogue threads; the producer warp comes after them
     constexpr int NPT = CS == 4 ? NPQ : NPQ / SPLIT;      // channels whose parameters this thread keeps
@@ -615,18 +622,18 @@ int rows_encode(CUtensorMap *m, const void *in, int CS, int rows, int pitch)
 // a group side by side (LBO = 128), groups 256 bytes apart (SBO = 256)
 inline size_t bpos(int n, int k) { return (size_t)(n / 8) * 256 + (size_t)(k / 16) * 128 + (size_t)(n % 8) * 16 + (size_t)(k % 16); }
 
-template <int CS, int NCH, int SPLIT, bool TWO>
+template <int CS, int NCH, int SPLIT, bool TWO, bool DBL>
 int launch_rows(const CUtensorMap &tmA, const RowsArgs &a, cudaStream_t stream)
 {
-    using L = RowsCfg<CS, NCH, TWO>;
+    using L = RowsCfg<CS, NCH, TWO, DBL>;
     constexpr int NT = RW_THREADS * SPLIT;
     static int ctas_per_sm = 0, n_sm = 0;
     const int smem = L::TOTAL + 128;
     if (!ctas_per_sm) {
-        YQ_CUDA(cudaFuncSetAttribute(conv_u8_tc_rows_kernel<CS, NCH, SPLIT, TWO>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        YQ_CUDA(cudaFuncSetAttribute(conv_u8_tc_rows_kernel<CS, NCH, SPLIT, TWO, DBL>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         int dev = 0, smem_sm = 0;
         cudaFuncAttributes fa;
-        YQ_CUDA(cudaFuncGetAttributes(&fa, conv_u8_tc_rows_kernel<CS, NCH, SPLIT, TWO>));
+        YQ_CUDA(cudaFuncGetAttributes(&fa, conv_u8_tc_rows_kernel<CS, NCH, SPLIT, TWO, DBL>));
         YQ_CUDA(cudaGetDevice(&dev));
         YQ_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
         YQ_CUDA(cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev));
@@ -636,14 +643,29 @@ int launch_rows(const CUtensorMap &tmA, const RowsArgs &a, cudaStream_t stream)
         const int by_tmem = 512 / L::TMEM_COLS;
         int occ = by_smem < by_regs ? by_smem : by_regs;
         if (by_tmem < occ) occ = by_tmem;
-        if (getenv("YQ_DEBUG")) fprintf(stderr, "yq: rows<%d,%d,%d,%d> regs=%d by_smem=%d by_regs=%d by_tmem=%d smem=%d\n", CS, NCH, SPLIT, (int)TWO, fa.numRegs, by_smem, by_regs, by_tmem, smem);
+        if (getenv("YQ_DEBUG")) fprintf(stderr, "yq: rows<%d,%d,%d,%d,%d> regs=%d by_smem=%d by_regs=%d by_tmem=%d smem=%d\n", CS, NCH, SPLIT, (int)TWO, (int)DBL, fa.numRegs, by_smem, by_regs, by_tmem, smem);
         if (occ < 1) return yq::fail("conv_u8_tc_rows_kernel<%d,%d> does not fit on an SM", CS, NCH);
         ctas_per_sm = occ;
     }
     int grid = n_sm * ctas_per_sm;
     if (grid > a.num_tiles) grid = a.num_tiles;
-    YQ_CUDA(yq::launch_pdl(conv_u8_tc_rows_kernel<CS, NCH, SPLIT, TWO>, dim3(grid), dim3(NT + 32), smem, stream, tmA, a));
+    YQ_CUDA(yq::launch_pdl(conv_u8_tc_rows_kernel<CS, NCH, SPLIT, TWO, DBL>, dim3(grid), dim3(NT + 32), smem, stream, tmA, a));
     return 0;
+}
+
+// two signed blocks always come with two accumulators; SPLIT needs a 4-channel chunk per thread
+template <int CS, int NCH>
+int run_rows(bool two, bool split, bool dbl, const CUtensorMap &tmA, const RowsArgs &a, cudaStream_t stream)
+{
+    constexpr bool CAN_SPLIT = CS == 4 || NCH >= 32;
+    if constexpr (CAN_SPLIT) {
+        if (split) {
+            if (two) return launch_rows<CS, NCH, 2, true, true>(tmA, a, stream);
+            return dbl ? launch_rows<CS, NCH, 2, false, true>(tmA, a, stream) : launch_rows<CS, NCH, 2, false, false>(tmA, a, stream);
+        }
+    }
+    if (two) return launch_rows<CS, NCH, 1, true, true>(tmA, a, stream);
+    return dbl ? launch_rows<CS, NCH, 1, false, true>(tmA, a, stream) : launch_rows<CS, NCH, 1, false, false>(tmA, a, stream);
 }
 
 }  // namespace
@@ -795,18 +817,18 @@ int yq_tc_rows_forward(yq_conv_layer *l, void *state, const uint8_t *in_padded, 
     const CUtensorMap &tmA = it->second;
     memcpy(a.cq, l->host_chanq.data(), (size_t)l->n * 16);
     memcpy(a.mc, l->host_mcomb.data(), (size_t)l->n * 8);
-    static const int split_env = getenv("YQ_ROWS_SPLIT") ? atoi(getenv("YQ_ROWS_SPLIT")) : -1;    // experiments: 0 / 1 force
-#define YQ_RW(CS_, N_, DEF_)                                                                                     \
+    // form of the kernel: defaults from measurements on B200 (profiles/README.md), YQ_ROWS_SPLIT / YQ_ROWS_DB = 0 / 1 force
+    static const int split_env = getenv("YQ_ROWS_SPLIT") ? atoi(getenv("YQ_ROWS_SPLIT")) : -1;
+    static const int db_env = getenv("YQ_ROWS_DB") ? atoi(getenv("YQ_ROWS_DB")) : -1;
+#define YQ_RW(CS_, N_, SPLIT_DEF_, DB_DEF_)                                                                       \
     if (st->CS == CS_ && st->NCH == N_) {                                                                        \
-        if constexpr (CS_ == 4 || N_ >= 32) {                                                                    \
-            if (split_env < 0 ? DEF_ : split_env)                                                                \
-                return st->two ? launch_rows<CS_, N_, 2, true>(tmA, a, stream) : launch_rows<CS_, N_, 2, false>(tmA, a, stream); \
-        }                                                                                                        \
-        return st->two ? launch_rows<CS_, N_, 1, true>(tmA, a, stream) : launch_rows<CS_, N_, 1, false>(tmA, a, stream);   \
+        const bool split = (CS_ == 4 || N_ >= 32) && (split_env < 0 ? SPLIT_DEF_ : split_env);                   \
+        const bool dbl = st->two || (db_env < 0 ? DB_DEF_ : db_env);                                             \
+        return run_rows<CS_, N_>(st->two, split, dbl, tmA, a, stream);                                           \
     }
-    YQ_RW(4, 16, 0); YQ_RW(4, 32, 0);
-    YQ_RW(16, 16, 0); YQ_RW(16, 32, 0); YQ_RW(16, 64, 0);
-    YQ_RW(32, 32, 0); YQ_RW(32, 64, 0);
+    YQ_RW(4, 16, 0, 0); YQ_RW(4, 32, 0, 0);
+    YQ_RW(16, 16, 0, 0); YQ_RW(16, 32, 0, 0); YQ_RW(16, 64, 0, 0);
+    YQ_RW(32, 32, 0, 0); YQ_RW(32, 64, 0, 1);
 #undef YQ_RW
     return yq::fail("tcgen05 rows flavour: no instantiation for cs_in=%d cs_out=%d", st->CS, st->NCH);
 }
