@@ -140,6 +140,13 @@ YQ_API int yq_conv_rows_input_geom(const yq_conv_layer *l, yq_act_geom *geom);
 YQ_API size_t yq_act_geom_bytes(const yq_act_geom *geom, int batch, int c);
 YQ_API int yq_forward_convolutional_layer_quant_rows_pool_gpu(yq_conv_layer *l, const uint8_t *in_padded, uint8_t *out_pool,
                                                               const yq_act_geom *out_geom, int batch, void *stream);
+/* The same launch reading the network input where the reference keeps it -- net.input_uint8 as [batch][3][h][w] planes
+ * (network.c:248-250) -- with no layout transform before it: TMA fetches the three planes of a tile (zero outside the image,
+ * hence zp_in = 0) and the kernel's producer warp interleaves them.  Needs c = 3, zp_in = 0, w % 16 = 0, w >= 64 and a 16-byte
+ * aligned pointer; yq_conv_rows_nchw_supported() says whether the layer qualifies. */
+YQ_API int yq_conv_rows_nchw_supported(const yq_conv_layer *l);
+YQ_API int yq_forward_convolutional_layer_quant_rows_pool_nchw_gpu(yq_conv_layer *l, const uint8_t *in_nchw, uint8_t *out_pool,
+                                                                   const yq_act_geom *out_geom, int batch, void *stream);
 
 /* The "flat" flavour (stride 1, size 1 or 3, pad = size/2, c % 64 == 0): input and output are FLAT halo-padded
  * tensors of identical geometry {pad 1, pitch_w w+1, rows_h h+1} (yq_act_geom_flat): one shared halo pixel after

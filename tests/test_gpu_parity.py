@@ -301,6 +301,46 @@ def test_conv_rows_flavour_vs_oracle(built, case, s_out, out_pad, variant, monke
     layer.free()
 
 
+ROWS_NCHW_CASES = [
+    # h, w, n, batch   (c = 3, zp_in = 0, w % 16 == 0, w >= 64)
+    (48, 64, 16, 2),
+    (34, 80, 16, 3),       # partial tiles in x and y: the TMA box hangs over the right and bottom edges (zero fill)
+    (16, 64, 32, 1),
+    (50, 64, 16, 2),
+]
+
+
+@pytest.mark.parametrize("case", ROWS_NCHW_CASES, ids=lambda c: "%dx%d_n%d_b%d" % c)
+@pytest.mark.parametrize("variant", [2, 1], ids=["two_signed_blocks", "ones_rows"])
+def test_conv_rows_flavour_reads_nchw_planes(built, case, variant, monkeypatch):
+    """layer-0 class: the rows kernel fetches the [b,3,h,w] planes itself (TMA, zero fill outside the image) and interleaves
+    them on chip == oracle conv + maxpool; same result as through the padded NHWC4 copy."""
+    h, w, n, batch = case
+    c, k, zp_in, zp_out = 3, 3, 0, 0
+    rng = np.random.default_rng(zlib.crc32(repr(case).encode()) + 11)
+    wq, zp_w, s_w, bias = make_params(rng, n, c * k * k, zp_in)
+    if variant == 2:
+        monkeypatch.setenv("YQ_ROWS_TWO", "1")
+        zp_w = np.maximum(zp_w, 1).astype(zp_w.dtype)
+    else:
+        zp_w[n - 1] = 0
+        wq[n - 1, -1] = 255
+    spec = synth.LayerSpec("conv", n, k, 1, 1, 0, "relu6")
+    sl = synth.SynthLayer("conv", c, h, w, n, 0, 0, spec, s_out=0.05, biases=bias, s_w=s_w, zp_w=zp_w, w_u8=wq.reshape(n, c, k, k))
+    p = O.prepare_conv(sl, 0.02, zp_in)
+    x = rng.integers(0, 256, size=(batch, c, h, w), dtype=np.uint8)
+    layer = darknet.ConvolutionalLayerQuant(h, w, c, n, k, 1, 1, synth.ACT_CODES["relu6"], wq, zp_w, p["biases_int32"], p["M_value"],
+                                            p["M0_right_shift_value"], zp_in, zp_out, 0.05)
+    assert layer.rows_nchw_supported and layer.rows_variant == variant
+    got = layer.forward_rows_pooled(x, out_pad=1, nchw=True)
+    for b in range(batch):
+        acc = O.conv_acc(x[b], wq.reshape(n, c, k, k), zp_w, 1, 1, zp_in)
+        u8 = O.requant(acc, p["biases_int32"], p["M_value"], p["M0_right_shift_value"], synth.ACT_CODES["relu6"], zp_out)
+        assert np.array_equal(got[b], O.maxpool(u8, 2, 2)), f"pooled mismatch image {b}"
+    assert np.array_equal(got, layer.forward_rows_pooled(x, out_pad=1, nchw=False))
+    layer.free()
+
+
 def test_conv_fused_maxpool_large_accumulators(built):
     """accumulators beyond 2^22 with in-range bytes: the integer-form requantize is no longer guaranteed to equal
     the reference's double multiply, so the pool-first kernel must take its FP64 path and still match bit for bit."""

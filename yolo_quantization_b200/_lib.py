@@ -80,6 +80,8 @@ SIGNATURES = {
     "yq_conv_rows_input_geom": (_i, [_vp, C.POINTER(ActGeom)]),
     "yq_act_geom_bytes": (_sz, [C.POINTER(ActGeom), _i, _i]),
     "yq_forward_convolutional_layer_quant_rows_pool_gpu": (_i, [_vp, _vp, _vp, C.POINTER(ActGeom), _i, _vp]),
+    "yq_conv_rows_nchw_supported": (_i, [_vp]),
+    "yq_forward_convolutional_layer_quant_rows_pool_nchw_gpu": (_i, [_vp, _vp, _vp, C.POINTER(ActGeom), _i, _vp]),
     "yq_nchw_to_nhwc_u8_geom": (_i, [_vp, _vp, _i, _i, _i, _i, C.POINTER(ActGeom), _vp]),
     "yq_nhwc_to_nchw_u8_geom": (_i, [_vp, _vp, _i, _i, _i, _i, C.POINTER(ActGeom), _vp]),
     "yq_forward_maxpool_layer_quant_gpu": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),

@@ -125,8 +125,9 @@ void yq_tc_rows_input_geom(const yq_conv_layer *l, yq_act_geom *g);
 int yq_tc_rows_prepare(yq_conv_layer *l, void **state);
 void yq_tc_rows_free(void *state);
 int yq_tc_rows_two_blocks(const void *state);
-int yq_tc_rows_forward(yq_conv_layer *l, void *state, const uint8_t *in_padded, uint8_t *out_pool, const yq_act_geom *out_geom, int batch,
-                       cudaStream_t stream);
+int yq_tc_rows_forward(yq_conv_layer *l, void *state, const uint8_t *in, uint8_t *out_pool, const yq_act_geom *og, int batch, cudaStream_t stream,
+                       int planar = 0);
+int yq_tc_rows_planar_supported(const yq_conv_layer *l);
 
 // implemented in yq_conv_tc_flat.cu (flat halo-padded strip, one patch per channel chunk shared by all taps; c % 64 == 0)
 int yq_tc_flat_supported(const yq_conv_layer *l);

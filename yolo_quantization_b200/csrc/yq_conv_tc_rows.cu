@@ -70,8 +70,12 @@ struct RowsGeom {
 // TWO: the weights enter as two SIGNED blocks h + l = w - zp_w (each in [-128, 127]) multiplied with the same activation
 // tile, so the accumulator is the zero-point-corrected one and neither the all-ones rows nor the per-output correction
 // exist; twice the MMAs, 4 multiply-adds and one TMEM load less per pooled output (prepare falls back when some w - zp_w = 255)
-template <int CS, int NCH, bool TWO, bool DBL>
+// PLANAR (c = 3 only): the kernel reads the network input itself -- CHW planes, no halo (TMA zero-fills outside the image,
+// so zp_in must be 0) -- and its producer warp interleaves each tile into the pixel-major form the Toeplitz MMAs read,
+// instead of a separate layout-transform launch writing a padded NHWC4 copy.
+template <int CS, int NCH, bool TWO, bool DBL, bool PLANAR = false>
 struct RowsCfg {
+    static_assert(!PLANAR || CS == 4, "planar input: layer-0 class only");
     using G = RowsGeom<CS>;
     static constexpr int NSUM = TWO ? 0 : 16;
     static constexpr int NB = CS == 4 ? 4 * NCH + NSUM : NCH + NSUM;    // filter rows (TMEM columns) per MMA group
@@ -91,7 +95,14 @@ struct RowsCfg {
     static constexpr int B_BYTES = NMMA * BSUB;
     static constexpr int A_STRIDE = (G::A_BYTES + 32 + 127) / 128 * 128;   // +32: the last window's (zero-weight) overhang
     static constexpr int A_OFF = 0;
-    static constexpr int B_OFF = NBUF * A_STRIDE;
+    static constexpr int NA = PLANAR ? 3 : NBUF;                    // MMA operand tiles (PLANAR: written by the producer warp)
+    // PLANAR staging: [3 planes][18 rows][64 bytes] per tile.  A TMA box must start on a 16-byte boundary of a row, so it starts 16
+    // columns left of the tile (x0 - 16); the 36 columns the tile reads (x0 - 1 ...) sit at bytes 15 .. 50
+    static constexpr int S_COLS = 64;
+    static constexpr int S_BYTES = 3 * G::A_ROWS * S_COLS;
+    static constexpr int S_STRIDE = (S_BYTES + 127) / 128 * 128;
+    static constexpr int S_OFF = NA * A_STRIDE;
+    static constexpr int B_OFF = S_OFF + (PLANAR ? NBUF * S_STRIDE : 0);
     static constexpr int BAR_OFF = B_OFF + B_BYTES;
     static constexpr int TOTAL = BAR_OFF + 128;
     static_assert(NMMA_N % 16 == 0 && NMMA_N <= 256, "kind::i8 N");
@@ -246,12 +257,12 @@ constexpr int rows_min_ctas(int CS, int SPLIT, int by_tmem)
     return want < by_tmem ? want : by_tmem;
 }
 
-template <int CS, int NCH, int SPLIT, bool TWO, bool DBL>
-__global__ void __launch_bounds__(RW_THREADS * SPLIT + 32, rows_min_ctas(CS, SPLIT, RowsCfg<CS, NCH, TWO, DBL>::MAX_CTAS))
+template <int CS, int NCH, int SPLIT, bool TWO, bool DBL, bool PLANAR>
+__global__ void __launch_bounds__(RW_THREADS * SPLIT + 32, rows_min_ctas(CS, SPLIT, RowsCfg<CS, NCH, TWO, DBL, PLANAR>::MAX_CTAS))
 conv_u8_tc_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ RowsArgs a)
 {
     using G = RowsGeom<CS>;
-    using L = RowsCfg<CS, NCH, TWO, DBL>;
+    using L = RowsCfg<CS, NCH, TWO, DBL, PLANAR>;
     constexpr int NPQ = NCH / 4;
     constexpr int NT = RW_THREADS * SPLIT;                 // epilogue threads; the producer warp comes after them
     constexpr int NPT = CS == 4 ? NPQ : NPQ / SPLIT;      // channels whose parameters this thread keeps
@@ -302,9 +313,88 @@ conv_u8_tc_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
     yq_pdl_wait_then_release();      // everything above touched only constants and on-chip state
 
     if (producer) {
-        if (elect_one()) {
+        const uint32_t sA = smem_u32(smem + L::A_OFF), b0 = smem_u32(smem + L::B_OFF);
+        if constexpr (PLANAR) {
+            // the whole warp: wait for a tile's three planes, interleave them into an operand tile, then one lane refills the
+            // staging slot and issues the MMAs
+            auto load_planes = [&](int tile, int sbuf) {
+                const TileXY p = split_tile(tile);
+                mbar_expect_tx(&full[sbuf], (uint32_t)L::S_BYTES);
+                tma_load_3d(smem + L::S_OFF + sbuf * L::S_STRIDE, &tmA, &full[sbuf], p.tx * G::TWPX - 16, p.ty * TILE_ROWS - 1, p.n * 3);
+            };
+            auto issue_mma_planar = [&](int abuf, int acc) {
+                constexpr uint32_t idesc = make_idesc(L::NMMA_N) | (TWO ? 1u << 10 : 0u);
+                const uint32_t a0 = sA + abuf * L::A_STRIDE;
+                const uint32_t tacc = tmem_base + (uint32_t)(acc * L::NACC);
+#pragma unroll
+                for (int part = 0; part < (TWO ? 2 : 1); ++part)
+#pragma unroll
+                    for (int ky = 0; ky < 3; ++ky)
+                        umma_i8(tacc, make_desc_ns(a0 + ky * PLANE, 16, PLANE), make_desc_ns(b0 + (part * 3 + ky) * L::BSUB, 128, 256), idesc,
+                                (part | ky) ? 1u : 0u);
+                umma_commit(&acc_full[acc]);
+            };
+            if (lane == 0) {
+                asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+#pragma unroll 1
+                for (int d = 0; d < NBUF; ++d)
+                    if (first + d * step < a.num_tiles) load_planes(first + d * step, d);
+            }
+            __syncwarp();
+            constexpr int PL = G::A_ROWS * L::S_COLS;      // bytes of one staged plane
+            constexpr int NGROUPS = G::A_ROWS * 9, NG = (NGROUPS + 31) / 32;
+            int src_off[NG], dst_off[NG];                  // this lane's groups: (row r, pixels 4 q4 .. 4 q4 + 3), fixed for the launch
+#pragma unroll
+            for (int i = 0; i < NG; ++i) {
+                const int g = lane + 32 * i, r = g / 9, q4 = g - r * 9;
+                src_off[i] = r * L::S_COLS + 12 + 4 * q4;
+                dst_off[i] = r * PLANE + 16 * q4;
+            }
+            int sbuf = 0, abuf = 0, it = 0;
+#pragma unroll 1
+            for (int tile = first; tile < a.num_tiles;
+                 tile += step, sbuf = sbuf + 1 == NBUF ? 0 : sbuf + 1, abuf = abuf + 1 == L::NA ? 0 : abuf + 1, ++it) {
+                mbar_wait(&full[sbuf], (uint32_t)((it / NBUF) & 1));
+                const uint8_t *S = smem + L::S_OFF + sbuf * L::S_STRIDE;
+                uint8_t *A = smem + L::A_OFF + abuf * L::A_STRIDE;
+                // 18 rows x 9 groups of 4 pixels: (R, G, B) words of 4 pixels -> 4 pixel-major words (byte 3 of a pixel meets zero
+                // weights).  All loads of the lane's 6 groups first, so their latencies overlap.
+                uint32_t wr[NG][6];
+#pragma unroll
+                for (int i = 0; i < NG; ++i) {
+                    const uint32_t *w = reinterpret_cast<const uint32_t *>(S + src_off[i]);       // bytes 12 + 4 q4 .. 19 + 4 q4 of the row
+                    if (i + 1 < NG || lane + 32 * i < NGROUPS) {
+#pragma unroll
+                        for (int c = 0; c < 3; ++c) {
+                            wr[i][2 * c] = w[c * (PL / 4)];
+                            wr[i][2 * c + 1] = w[c * (PL / 4) + 1];
+                        }
+                    }
+                }
+#pragma unroll
+                for (int i = 0; i < NG; ++i) {
+                    if (i + 1 < NG || lane + 32 * i < NGROUPS) {
+                        const uint32_t R4 = __funnelshift_r(wr[i][0], wr[i][1], 24);              // bytes 15 + 4 q4 .. 18 + 4 q4
+                        const uint32_t G4 = __funnelshift_r(wr[i][2], wr[i][3], 24);
+                        const uint32_t B4 = __funnelshift_r(wr[i][4], wr[i][5], 24);
+                        const uint32_t t01 = __byte_perm(R4, G4, 0x5140), t23 = __byte_perm(R4, G4, 0x7362);
+                        *reinterpret_cast<uint4 *>(A + dst_off[i]) = make_uint4(__byte_perm(t01, B4, 0x4410), __byte_perm(t01, B4, 0x5532),
+                                                                                __byte_perm(t23, B4, 0x6610), __byte_perm(t23, B4, 0x7732));
+                    }
+                }
+                fence_proxy_async();      // the operand tile (generic-proxy stores) -> visible to the tensor core
+                __syncwarp();
+                if (lane == 0) {
+                    if (tile + NBUF * step < a.num_tiles) load_planes(tile + NBUF * step, sbuf);      // every lane has read the slot
+                    const int acc = NACCS == 2 ? it & 1 : 0;
+                    if (it >= NACCS) mbar_wait(&acc_empty[acc], ((uint32_t)(it / NACCS) & 1u) ^ 1u);
+                    tc_fence_after();
+                    issue_mma_planar(abuf, acc);
+                }
+                __syncwarp();             // (operand tile abuf + 1 is rewritten next: its MMAs, 2 tiles back, are known complete by now)
+            }
+        } else if (elect_one()) {
             asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
-            const uint32_t sA = smem_u32(smem + L::A_OFF), b0 = smem_u32(smem + L::B_OFF);
             auto load_tile = [&](int tile, int buf) {     // 18 halo rows of the tile: one box (c = 4) or one box per 16-channel block and pixel parity
                 const TileXY p = split_tile(tile);
                 uint8_t *dst = smem + L::A_OFF + buf * L::A_STRIDE;
@@ -589,16 +679,36 @@ typedef CUresult (*RowsEncodeFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t,
 // The input tile as TMA boxes.  c = 4: the padded tensor as [rows][pitch * 4 bytes], box = 18 rows x 144 bytes.
 // c >= 16: [rows][pitch / 2][parity][c bytes], box = 18 rows x 9 pixels of ONE parity x 16 channels, so that the even and the
 // odd pixel columns land in separate planes (what the even/odd MMA groups read).
-int rows_encode(CUtensorMap *m, const void *in, int CS, int rows, int pitch)
+RowsEncodeFn rows_encoder()
 {
     static RowsEncodeFn enc = nullptr;
     if (!enc) {
         void *p = nullptr;
         cudaDriverEntryPointQueryResult q;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess || !p)
-            return yq::fail("cuTensorMapEncodeTiled is not available from this driver");
-        enc = (RowsEncodeFn)p;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess) enc = (RowsEncodeFn)p;
     }
+    return enc;
+}
+
+// PLANAR: the network input as [planes][h][w bytes]; box = 3 planes x 18 rows x 64 bytes at (x0 - 16, y0 - 1, 3 n), zero outside the image
+int rows_encode_planar(CUtensorMap *m, const void *in, int w, int h, int planes)
+{
+    RowsEncodeFn enc = rows_encoder();
+    if (!enc) return yq::fail("cuTensorMapEncodeTiled is not available from this driver");
+    const cuuint32_t es[3] = {1, 1, 1};
+    const cuuint64_t dims[3] = {(cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)planes};
+    const cuuint64_t strides[2] = {(cuuint64_t)w, (cuuint64_t)w * h};
+    const cuuint32_t box[3] = {64, (cuuint32_t)(TILE_ROWS + 2), 3};
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<void *>(in), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return yq::fail("tcgen05 rows flavour: cuTensorMapEncodeTiled(planar %d x %d x %d) failed: %d", w, h, planes, (int)r);
+    return 0;
+}
+
+int rows_encode(CUtensorMap *m, const void *in, int CS, int rows, int pitch)
+{
+    RowsEncodeFn enc = rows_encoder();
+    if (!enc) return yq::fail("cuTensorMapEncodeTiled is not available from this driver");
     CUresult r;
     const cuuint32_t es[4] = {1, 1, 1, 1};
     if (CS == 4) {
@@ -622,18 +732,18 @@ int rows_encode(CUtensorMap *m, const void *in, int CS, int rows, int pitch)
 // a group side by side (LBO = 128), groups 256 bytes apart (SBO = 256)
 inline size_t bpos(int n, int k) { return (size_t)(n / 8) * 256 + (size_t)(k / 16) * 128 + (size_t)(n % 8) * 16 + (size_t)(k % 16); }
 
-template <int CS, int NCH, int SPLIT, bool TWO, bool DBL>
+template <int CS, int NCH, int SPLIT, bool TWO, bool DBL, bool PLANAR = false>
 int launch_rows(const CUtensorMap &tmA, const RowsArgs &a, cudaStream_t stream)
 {
-    using L = RowsCfg<CS, NCH, TWO, DBL>;
+    using L = RowsCfg<CS, NCH, TWO, DBL, PLANAR>;
     constexpr int NT = RW_THREADS * SPLIT;
     static int ctas_per_sm = 0, n_sm = 0;
     const int smem = L::TOTAL + 128;
     if (!ctas_per_sm) {
-        YQ_CUDA(cudaFuncSetAttribute(conv_u8_tc_rows_kernel<CS, NCH, SPLIT, TWO, DBL>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        YQ_CUDA(cudaFuncSetAttribute(conv_u8_tc_rows_kernel<CS, NCH, SPLIT, TWO, DBL, PLANAR>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         int dev = 0, smem_sm = 0;
         cudaFuncAttributes fa;
-        YQ_CUDA(cudaFuncGetAttributes(&fa, conv_u8_tc_rows_kernel<CS, NCH, SPLIT, TWO, DBL>));
+        YQ_CUDA(cudaFuncGetAttributes(&fa, conv_u8_tc_rows_kernel<CS, NCH, SPLIT, TWO, DBL, PLANAR>));
         YQ_CUDA(cudaGetDevice(&dev));
         YQ_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
         YQ_CUDA(cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev));
@@ -649,15 +759,25 @@ int launch_rows(const CUtensorMap &tmA, const RowsArgs &a, cudaStream_t stream)
     }
     int grid = n_sm * ctas_per_sm;
     if (grid > a.num_tiles) grid = a.num_tiles;
-    YQ_CUDA(yq::launch_pdl(conv_u8_tc_rows_kernel<CS, NCH, SPLIT, TWO, DBL>, dim3(grid), dim3(NT + 32), smem, stream, tmA, a));
+    YQ_CUDA(yq::launch_pdl(conv_u8_tc_rows_kernel<CS, NCH, SPLIT, TWO, DBL, PLANAR>, dim3(grid), dim3(NT + 32), smem, stream, tmA, a));
     return 0;
 }
 
 // two signed blocks always come with two accumulators; SPLIT needs a 4-channel chunk per thread
 template <int CS, int NCH>
-int run_rows(bool two, bool split, bool dbl, const CUtensorMap &tmA, const RowsArgs &a, cudaStream_t stream)
+int run_rows(bool two, bool split, bool dbl, bool planar, const CUtensorMap &tmA, const RowsArgs &a, cudaStream_t stream)
 {
     constexpr bool CAN_SPLIT = CS == 4 || NCH >= 32;
+    if constexpr (CS == 4) {
+        if (planar) {
+            if (split) {
+                if (two) return launch_rows<CS, NCH, 2, true, true, true>(tmA, a, stream);
+                return dbl ? launch_rows<CS, NCH, 2, false, true, true>(tmA, a, stream) : launch_rows<CS, NCH, 2, false, false, true>(tmA, a, stream);
+            }
+            if (two) return launch_rows<CS, NCH, 1, true, true, true>(tmA, a, stream);
+            return dbl ? launch_rows<CS, NCH, 1, false, true, true>(tmA, a, stream) : launch_rows<CS, NCH, 1, false, false, true>(tmA, a, stream);
+        }
+    }
     if constexpr (CAN_SPLIT) {
         if (split) {
             if (two) return launch_rows<CS, NCH, 2, true, true>(tmA, a, stream);
@@ -784,10 +904,19 @@ void yq_tc_rows_free(void *state)
     delete st;
 }
 
-int yq_tc_rows_forward(yq_conv_layer *l, void *state, const uint8_t *in_padded, uint8_t *out_pool, const yq_act_geom *og, int batch, cudaStream_t stream)
+int yq_tc_rows_planar_supported(const yq_conv_layer *l)
+{
+    // CHW planes read in place: three real channels, zero halo (TMA's out-of-bounds fill), rows a multiple of 16 bytes
+    return l->tc_rows && l->c == 3 && l->cs_in == 4 && l->zp_in == 0 && l->w % 16 == 0 && l->w >= 64;
+}
+
+// planar = 0: in = the halo-padded NHWC tensor of yq_tc_rows_input_geom; planar = 1: in = the plain [batch][3][h][w] planes
+int yq_tc_rows_forward(yq_conv_layer *l, void *state, const uint8_t *in_padded, uint8_t *out_pool, const yq_act_geom *og, int batch, cudaStream_t stream,
+                       int planar)
 {
     RowsState *st = (RowsState *)state;
     if (!st || !in_padded || !out_pool || !og) return yq::fail("tcgen05 rows flavour: bad argument");
+    if (planar && !yq_tc_rows_planar_supported(l)) return yq::fail("tcgen05 rows flavour: this layer cannot read CHW planes (c = 3, zp_in = 0, w %% 16 = 0)");
     RowsArgs a;
     memset(&a, 0, sizeof a);
     yq_act_geom ig;
@@ -806,11 +935,11 @@ int yq_tc_rows_forward(yq_conv_layer *l, void *state, const uint8_t *in_padded, 
     if ((unsigned long long)a.num_tiles * (a.tiles_x > a.tiles_y ? a.tiles_x : a.tiles_y) >= 0x100000000ull || yq_act_geom_bytes(og, batch, l->n) >= 0x100000000ull)
         return yq::fail("tcgen05 rows flavour: tensor too large for 32-bit tile arithmetic");
     if (((uintptr_t)in_padded & 15) || (ig.pitch_w & 3)) return yq::fail("tcgen05 rows flavour: the input must be 16-byte aligned with a pitch that is a multiple of 4");
-    const auto key = std::make_pair((const void *)in_padded, batch);
+    const auto key = std::make_pair((const void *)in_padded, planar ? -batch : batch);
     auto it = st->maps.find(key);
     if (it == st->maps.end()) {
         CUtensorMap m;
-        if (rows_encode(&m, in_padded, st->CS, ig.rows_h * batch, ig.pitch_w)) return -1;
+        if (planar ? rows_encode_planar(&m, in_padded, l->w, l->h, 3 * batch) : rows_encode(&m, in_padded, st->CS, ig.rows_h * batch, ig.pitch_w)) return -1;
         if (st->maps.size() > 64) st->maps.clear();
         it = st->maps.emplace(key, m).first;
     }
@@ -824,7 +953,7 @@ int yq_tc_rows_forward(yq_conv_layer *l, void *state, const uint8_t *in_padded, 
     if (st->CS == CS_ && st->NCH == N_) {                                                                        \
         const bool split = (CS_ == 4 || N_ >= 32) && (split_env < 0 ? SPLIT_DEF_ : split_env);                   \
         const bool dbl = st->two || (db_env < 0 ? DB_DEF_ : db_env);                                             \
-        return run_rows<CS_, N_>(st->two, split, dbl, tmA, a, stream);                                           \
+        return run_rows<CS_, N_>(st->two, split, dbl, planar != 0, tmA, a, stream);                              \
     }
     YQ_RW(4, 16, 0, 0); YQ_RW(4, 32, 0, 0);
     YQ_RW(16, 16, 0, 0); YQ_RW(16, 32, 0, 0); YQ_RW(16, 64, 0, 0);

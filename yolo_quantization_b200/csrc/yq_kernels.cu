@@ -517,6 +517,15 @@ extern "C" int yq_forward_convolutional_layer_quant_rows_pool_gpu(yq_conv_layer 
     if (check_geom(out_geom, l->out_h / 2, l->out_w / 2)) return -1;
     return yq_tc_rows_forward(l, l->tc_rows, in_padded, out_pool, out_geom, batch, (cudaStream_t)stream);
 }
+extern "C" int yq_conv_rows_nchw_supported(const yq_conv_layer *l) { return l && l->tc_rows && yq_tc_rows_planar_supported(l) ? 1 : 0; }
+extern "C" int yq_forward_convolutional_layer_quant_rows_pool_nchw_gpu(yq_conv_layer *l, const uint8_t *in_nchw, uint8_t *out_pool,
+                                                                       const yq_act_geom *out_geom, int batch, void *stream)
+{
+    if (!l || !in_nchw || !out_pool || !out_geom || batch <= 0) return yq::fail("yq_forward_convolutional_layer_quant_rows_pool_nchw_gpu: bad argument");
+    if (!l->tc_rows || !yq_tc_rows_planar_supported(l)) return yq::fail("this layer cannot read CHW planes (see yq_conv_rows_nchw_supported)");
+    if (check_geom(out_geom, l->out_h / 2, l->out_w / 2)) return -1;
+    return yq_tc_rows_forward(l, l->tc_rows, in_nchw, out_pool, out_geom, batch, (cudaStream_t)stream, 1);
+}
 
 // ------------------------------------------------------------------------------------------------
 // maxpool (src/maxpool_layer.c:109-153): out = max(0, in-bounds taps); window origin i*stride - pad/2

@@ -141,6 +141,7 @@ struct yq_network {
     uint8_t *scratch = nullptr;         // pull_layer conversions
     size_t scratch_bytes = 0;
     int keep_acc = 0;
+    bool no_planar_input = getenv("YQ_NO_PLANAR") && atoi(getenv("YQ_NO_PLANAR"));   // A/B: keep the layout-transform launch in front of layer 0
     int conv_kernel = -1;
     int fusion = 1;
     int use_graph = 0;
@@ -405,13 +406,20 @@ int forward_body(yq_network *net, const uint8_t *in_u8_nchw, int *launches, bool
     cudaStream_t st = net->stream;
     int nl = 0;
     if (profile) cudaEventRecord(net->prof_events[0], st);
-    if (net->in_geom.pad) {
+    // layer 0 in the rows flavour reads the planes itself when it can (no layout-transform launch, no padded copy)
+    const bool planar_in = !net->layers.empty() && net->layers[0].type == L_CONV && net->layers[0].use_rows && !net->no_planar_input &&
+                           yq_conv_rows_nchw_supported(net->layers[0].conv) && ((uintptr_t)in_u8_nchw & 15) == 0;
+    if (planar_in) {
+        // nothing to do
+    } else if (net->in_geom.pad) {
         if (yq_nchw_to_nhwc_u8_geom(in_u8_nchw, net->in_nhwc, net->batch, net->c, net->h, net->w, &net->in_geom, st)) return -1;
+        ++nl;
     } else if (yq_nchw_to_nhwc_u8(in_u8_nchw, net->in_nhwc, net->batch, net->c, net->h, net->w, st)) {
         return -1;
+    } else {
+        ++nl;
     }
     if (profile) cudaEventRecord(net->prof_events[1], st);
-    ++nl;
     const uint8_t *cur = net->in_nhwc;
     const yq_act_geom *cur_geom = &net->in_geom;
     const float *cur_f32 = nullptr;
@@ -419,7 +427,10 @@ int forward_body(yq_network *net, const uint8_t *in_u8_nchw, int *launches, bool
         Layer &l = net->layers[i];
         switch (l.type) {
         case L_CONV:
-            if (l.use_rows) {
+            if (l.use_rows && i == 0 && planar_in) {
+                if (yq_forward_convolutional_layer_quant_rows_pool_nchw_gpu(l.conv, in_u8_nchw, net->layers[1].out_u8, &net->layers[1].geom, net->batch, st))
+                    return -1;
+            } else if (l.use_rows) {
                 if (yq_forward_convolutional_layer_quant_rows_pool_gpu(l.conv, cur, net->layers[i + 1].out_u8, &net->layers[i + 1].geom, net->batch, st))
                     return -1;
             } else if (l.use_flat && l.fuse_yolo) {

@@ -214,10 +214,16 @@ class ConvolutionalLayerQuant:
         """0: no rows flavour; 1: all-ones filter rows + per-output zero-point correction; 2: two signed weight blocks."""
         return int(_lib.load().yq_conv_rows_supported(self.handle))
 
-    def forward_rows_pooled(self, x_nchw: np.ndarray, out_pad: int = 0) -> np.ndarray:
+    @property
+    def rows_nchw_supported(self) -> bool:
+        """the rows flavour can read the [b,3,h,w] planes directly (c = 3, zp_in = 0, w % 16 = 0, w >= 64)"""
+        return bool(_lib.load().yq_conv_rows_nchw_supported(self.handle))
+
+    def forward_rows_pooled(self, x_nchw: np.ndarray, out_pad: int = 0, nchw: bool = False) -> np.ndarray:
         """conv + RELU6 + maxpool(2,2) through the halo-input "rows" flavour: the input is staged in the padded
-        geometry the layer asks for (halo = zp_in); the pooled tensor is written into a tensor with an
-        ``out_pad``-pixel halo (as the next rows layer would want) and returned as [b,n,h/2,w/2]."""
+        geometry the layer asks for (halo = zp_in) -- or, with ``nchw``, handed over as the plain planes; the pooled
+        tensor is written into a tensor with an ``out_pad``-pixel halo (as the next rows layer would want) and
+        returned as [b,n,h/2,w/2]."""
         lib = _lib.load()
         b = x_nchw.shape[0]
         x = np.ascontiguousarray(x_nchw, np.uint8)
@@ -226,13 +232,18 @@ class ConvolutionalLayerQuant:
         din = DeviceBuffer(lib.yq_act_geom_bytes(C.byref(g), b, self.c), zero=False)
         check(lib.yq_cuda_memset(din.ptr, self.zp_in, din.nbytes, None))
         src = DeviceBuffer.from_numpy(x)
-        check(lib.yq_nchw_to_nhwc_u8_geom(src.ptr, din.ptr, b, self.c, self.h, self.w, C.byref(g), None))
+        if not nchw:
+            check(lib.yq_nchw_to_nhwc_u8_geom(src.ptr, din.ptr, b, self.c, self.h, self.w, C.byref(g), None))
         ph, pw = self.out_h // 2, self.out_w // 2
         og = ActGeom(out_pad, pw + 2 * out_pad + (3 if out_pad else 0), ph + 2 * out_pad + (1 if out_pad else 0))
         dout = DeviceBuffer(lib.yq_act_geom_bytes(C.byref(og), b, self.n), zero=False)
         check(lib.yq_cuda_memset(dout.ptr, 0xEE, dout.nbytes, None))
-        check(lib.yq_forward_convolutional_layer_quant_rows_pool_gpu(self.handle, din.ptr, dout.ptr, C.byref(og), b, None),
-              "yq_forward_convolutional_layer_quant_rows_pool_gpu")
+        if nchw:
+            check(lib.yq_forward_convolutional_layer_quant_rows_pool_nchw_gpu(self.handle, src.ptr, dout.ptr, C.byref(og), b, None),
+                  "yq_forward_convolutional_layer_quant_rows_pool_nchw_gpu")
+        else:
+            check(lib.yq_forward_convolutional_layer_quant_rows_pool_gpu(self.handle, din.ptr, dout.ptr, C.byref(og), b, None),
+                  "yq_forward_convolutional_layer_quant_rows_pool_gpu")
         tmp = DeviceBuffer(b * self.n * ph * pw)
         check(lib.yq_nhwc_to_nchw_u8_geom(dout.ptr, tmp.ptr, b, self.n, ph, pw, C.byref(og), None))
         check(lib.yq_stream_synchronize(None))
