@@ -95,7 +95,10 @@ struct RowsCfg {
     static constexpr int B_BYTES = NMMA * BSUB;
     static constexpr int A_STRIDE = (G::A_BYTES + 32 + 127) / 128 * 128;   // +32: the last window's (zero-weight) overhang
     static constexpr int A_OFF = 0;
-    static constexpr int NA = PLANAR ? 3 : NBUF;                    // MMA operand tiles (PLANAR: written by the producer warp)
+    // PLANAR with two accumulators: two producer warps, one per accumulator (tiles alternate between them), each with its own
+    // staging slots and operand tiles -- one warp's interleave + MMA issue per tile is otherwise the slowest stage
+    static constexpr int NPROD = PLANAR && DB ? 2 : 1;
+    static constexpr int NA = PLANAR ? (NPROD == 2 ? 4 : 3) : NBUF; // MMA operand tiles (PLANAR: written by the producer warps)
     // PLANAR staging: [3 planes][18 rows][64 bytes] per tile.  A TMA box must start on a 16-byte boundary of a row, so it starts 16
     // columns left of the tile (x0 - 16); the 36 columns the tile reads (x0 - 1 ...) sit at bytes 15 .. 50
     static constexpr int S_COLS = 64;
@@ -258,7 +261,8 @@ constexpr int rows_min_ctas(int CS, int SPLIT, int by_tmem)
 }
 
 template <int CS, int NCH, int SPLIT, bool TWO, bool DBL, bool PLANAR>
-__global__ void __launch_bounds__(RW_THREADS * SPLIT + 32, rows_min_ctas(CS, SPLIT, RowsCfg<CS, NCH, TWO, DBL, PLANAR>::MAX_CTAS))
+__global__ void __launch_bounds__(RW_THREADS * SPLIT + 32 * RowsCfg<CS, NCH, TWO, DBL, PLANAR>::NPROD,
+                                  rows_min_ctas(CS, SPLIT, RowsCfg<CS, NCH, TWO, DBL, PLANAR>::MAX_CTAS))
 conv_u8_tc_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ RowsArgs a)
 {
     using G = RowsGeom<CS>;
@@ -284,7 +288,7 @@ conv_u8_tc_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
     const int qi = lane >> 2, qq = lane & 3;
 
     // ---- one-time setup: resident filter tiles, barriers, TMEM
-    for (int i = t; i < L::B_BYTES / 16; i += NT + 32)
+    for (int i = t; i < L::B_BYTES / 16; i += NT + 32 * L::NPROD)
         reinterpret_cast<uint4 *>(smem + L::B_OFF)[i] = __ldg(reinterpret_cast<const uint4 *>(a.wimg) + i);
     if (t == 0) {
         for (int b = 0; b < NBUF; ++b) mbar_init(&full[b], 1);
@@ -334,11 +338,14 @@ conv_u8_tc_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
                                 (part | ky) ? 1u : 0u);
                 umma_commit(&acc_full[acc]);
             };
+            constexpr int NPROD = L::NPROD, SPP = NBUF / NPROD, APP = L::NA / NPROD;      // staging slots / operand tiles per producer warp
+            static_assert(NBUF % NPROD == 0 && L::NA % NPROD == 0 && (NPROD == 1 || NACCS == 2), "producer warps split the rings evenly");
+            const int pw = (t - NT) >> 5;                  // this producer warp handles tiles it = pw, pw + NPROD, ...
             if (lane == 0) {
                 asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
 #pragma unroll 1
-                for (int d = 0; d < NBUF; ++d)
-                    if (first + d * step < a.num_tiles) load_planes(first + d * step, d);
+                for (int d = 0; d < SPP; ++d)
+                    if (first + (pw + d * NPROD) * step < a.num_tiles) load_planes(first + (pw + d * NPROD) * step, pw * SPP + d);
             }
             __syncwarp();
             constexpr int PL = G::A_ROWS * L::S_COLS;      // bytes of one staged plane
@@ -350,11 +357,12 @@ conv_u8_tc_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
                 src_off[i] = r * L::S_COLS + 12 + 4 * q4;
                 dst_off[i] = r * PLANE + 16 * q4;
             }
-            int sbuf = 0, abuf = 0, it = 0;
+            int k = 0;
 #pragma unroll 1
-            for (int tile = first; tile < a.num_tiles;
-                 tile += step, sbuf = sbuf + 1 == NBUF ? 0 : sbuf + 1, abuf = abuf + 1 == L::NA ? 0 : abuf + 1, ++it) {
-                mbar_wait(&full[sbuf], (uint32_t)((it / NBUF) & 1));
+            for (int tile = first + pw * step; tile < a.num_tiles; tile += NPROD * step, ++k) {
+                const int it = pw + k * NPROD;
+                const int sbuf = pw * SPP + k % SPP, abuf = pw * APP + k % APP;
+                mbar_wait(&full[sbuf], (uint32_t)((k / SPP) & 1));
                 const uint8_t *S = smem + L::S_OFF + sbuf * L::S_STRIDE;
                 uint8_t *A = smem + L::A_OFF + abuf * L::A_STRIDE;
                 // 18 rows x 9 groups of 4 pixels: (R, G, B) words of 4 pixels -> 4 pixel-major words (byte 3 of a pixel meets zero
@@ -385,13 +393,13 @@ conv_u8_tc_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
                 fence_proxy_async();      // the operand tile (generic-proxy stores) -> visible to the tensor core
                 __syncwarp();
                 if (lane == 0) {
-                    if (tile + NBUF * step < a.num_tiles) load_planes(tile + NBUF * step, sbuf);      // every lane has read the slot
+                    if (tile + NBUF * step < a.num_tiles) load_planes(tile + NBUF * step, sbuf);      // every lane has read the slot (SPP * NPROD = NBUF tiles on)
                     const int acc = NACCS == 2 ? it & 1 : 0;
                     if (it >= NACCS) mbar_wait(&acc_empty[acc], ((uint32_t)(it / NACCS) & 1u) ^ 1u);
                     tc_fence_after();
                     issue_mma_planar(abuf, acc);
                 }
-                __syncwarp();             // (operand tile abuf + 1 is rewritten next: its MMAs, 2 tiles back, are known complete by now)
+                __syncwarp();             // (the operand tile rewritten next had its MMAs >= 2 of this warp's tiles back: known complete by now)
             }
         } else if (elect_one()) {
             asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
@@ -749,7 +757,7 @@ int launch_rows(const CUtensorMap &tmA, const RowsArgs &a, cudaStream_t stream)
         YQ_CUDA(cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev));
         // counted by hand: the occupancy API answers 1 for kernels that allocate tensor memory (see yq_conv_tc_small.cu)
         const int by_smem = smem_sm / (smem + 1024 + (int)fa.sharedSizeBytes);
-        const int by_regs = 65536 / (((fa.numRegs + 7) / 8 * 8) * (NT + 32));
+        const int by_regs = 65536 / (((fa.numRegs + 7) / 8 * 8) * (NT + 32 * L::NPROD));
         const int by_tmem = 512 / L::TMEM_COLS;
         int occ = by_smem < by_regs ? by_smem : by_regs;
         if (by_tmem < occ) occ = by_tmem;
@@ -759,7 +767,7 @@ int launch_rows(const CUtensorMap &tmA, const RowsArgs &a, cudaStream_t stream)
     }
     int grid = n_sm * ctas_per_sm;
     if (grid > a.num_tiles) grid = a.num_tiles;
-    YQ_CUDA(yq::launch_pdl(conv_u8_tc_rows_kernel<CS, NCH, SPLIT, TWO, DBL, PLANAR>, dim3(grid), dim3(NT + 32), smem, stream, tmA, a));
+    YQ_CUDA(yq::launch_pdl(conv_u8_tc_rows_kernel<CS, NCH, SPLIT, TWO, DBL, PLANAR>, dim3(grid), dim3(NT + 32 * L::NPROD), smem, stream, tmA, a));
     return 0;
 }
 
