@@ -316,8 +316,9 @@ def main():
         # the NCHW -> NHWC(4) layout transform in front of layer 0 (lm[0]): in + out bytes
         c0 = infos[0]
         tb = B * c0.h * c0.w * (c0.c + darknet.channel_stride(c0.c))
-        rows.insert(0, {"layer": -1, "type": "nchw_to_nhwc", "ms": round(float(lm[0]), 4), "bound": "hbm",
-                        "frac": round(tb / (pk["hbm_gbs"] * 1e9) * 1e3 / float(lm[0]), 4), "kernel": None, "fused": 0, "ops": 0, "bytes": tb})
+        if float(lm[0]) > 0.005:     # (not launched when layer 0 reads the CHW planes itself: the interval is two back-to-back events)
+            rows.insert(0, {"layer": -1, "type": "nchw_to_nhwc", "ms": round(float(lm[0]), 4), "bound": "hbm",
+                            "frac": round(tb / (pk["hbm_gbs"] * 1e9) * 1e3 / float(lm[0]), 4), "kernel": None, "fused": 0, "ops": 0, "bytes": tb})
         top = max(rows, key=lambda r: r["ms"])
         if top["bound"] == "tensor":
             ach = top["ops"] / (top["ms"] * 1e-3) / 1e12

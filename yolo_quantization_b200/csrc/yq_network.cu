@@ -391,6 +391,9 @@ void plan(yq_network *net)
         if (l.fused_away || (l.type == L_ROUTE && l.inputs.size() == 1)) continue;
         ++launches;
     }
+    // (layer 0 in the rows flavour reads the CHW planes itself when it can: no layout-transform launch, see forward_body)
+    if (n > 0 && net->layers[0].type == L_CONV && net->layers[0].use_rows && !net->no_planar_input && yq_conv_rows_nchw_supported(net->layers[0].conv))
+        --launches;
     net->launches = launches;
 }
 
