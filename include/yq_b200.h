@@ -286,6 +286,21 @@ YQ_API int yq_network_profile_forward(yq_network *net, const uint8_t *in_u8_nchw
 /* number of kernel launches one forward issues (for bench.py's gpu_launches) */
 YQ_API int yq_network_launches_per_forward(const yq_network *net);
 
+/* ---- "next" row 8f-4: packed-weight arena --------------------------------------------------------------------
+ * The reference repacks nothing because its GEMM reads `weights_uint8` as parsed (parser.c:1124-1159); the kernels here
+ * read kernel-layout filter images (OHWI rows padded to the channel stride, Toeplitz / even-odd tiles, ...) that the layer
+ * constructors build from the OIHW stream.  The arena keeps those images under a content key (layout version, layer shape,
+ * zero points, the u8 weights themselves), so a later load of the same `.weights` uploads them without repacking:
+ *   yq_pack_arena_load(path)  before yq_load_network / yq_make_convolutional_layer_quant: entries read (0 for a file of
+ *                             another layout version), -1 on error;
+ *   yq_pack_arena_save(path)  afterwards, when yq_pack_arena_stats reports dirty: entries written;
+ *   yq_pack_arena_clear()     drops the in-memory arena and its counters.
+ * A stale or foreign file can only miss, never alias: the weights are part of the key. */
+YQ_API int yq_pack_arena_load(const char *path);
+YQ_API int yq_pack_arena_save(const char *path);
+YQ_API int yq_pack_arena_clear(void);
+YQ_API int yq_pack_arena_stats(int *entries, int *hits, int *misses, int *dirty);
+
 /* ---- "next" row 8f-2: box decode + NMS on the device -------------------------------------------------------
  * get_network_boxes (src/network.c:635-640: get_yolo_detections + correct_yolo_boxes, src/yolo_layer.c:247-343) followed by
  * do_nms_sort (src/box.c:58-89) when nms_thresh > 0, for every image of the last forward.

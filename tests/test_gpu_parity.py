@@ -598,6 +598,37 @@ def test_input_quantiser_vs_oracle(built):
         assert np.array_equal(u8[b], ru8), f"image {b}: {np.count_nonzero(u8[b] != ru8)} bytes differ"
 
 
+def test_packed_weight_arena_round_trip(built, tiny_net_files, tmp_path):
+    """the first load builds the kernel-layout filter images and writes the arena; the second load of the same
+    weights fetches every image (no miss, nothing rewritten) and the network computes the same bytes; other weights
+    can only miss."""
+    cfg, wts, _, layers = tiny_net_files
+    arena = str(tmp_path / "tiny.yqpk")
+    x = np.random.default_rng(3).integers(0, 256, size=(2, 3, 416, 416), dtype=np.uint8)
+    net = darknet.load_network(cfg, wts, batch=2, packed=arena)
+    first = darknet.pack_arena_stats()
+    # (hits during the first load: the flat kernels of one layer share one image)
+    assert first["misses"] > 0 and first["entries"] == first["misses"] and os.path.getsize(arena) > 8_000_000
+    ref = net.predict_u8(x)
+    net.free()
+    mtime = os.stat(arena).st_mtime_ns
+    net = darknet.load_network(cfg, wts, batch=2, packed=arena)
+    second = darknet.pack_arena_stats()
+    assert second["misses"] == 0 and second["hits"] == first["hits"] + first["misses"] and second["dirty"] == 0
+    assert os.stat(arena).st_mtime_ns == mtime
+    assert np.array_equal(net.predict_u8(x), ref)
+    net.free()
+    other = str(tmp_path / "other.weights")
+    synth.write_weights(other, layers, seed=1)
+    net = darknet.load_network(cfg, other, batch=2, packed=arena)
+    third = darknet.pack_arena_stats()
+    assert third["hits"] == first["hits"] and third["misses"] == first["misses"]
+    plain = darknet.load_network(cfg, other, batch=2)
+    assert np.array_equal(net.predict_u8(x), plain.predict_u8(x))
+    net.free()
+    plain.free()
+
+
 def test_network_predict_f32_equals_predict_u8(built, tiny_net_files):
     """float images through the device quantiser + layer-0 re-prep == the uint8 path fed with the oracle-quantized image
     and the same (s_in, zp_in)."""

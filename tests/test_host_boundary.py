@@ -82,3 +82,17 @@ def test_synthetic_weights_stream_layout(tiny_net_files):
     assert macs == 2_724_074_496
     txt = open(cfg).read()
     assert txt.count("[convolutional]") == 13 and txt.count("[maxpool]") == 6 and txt.count("[yolo]") == 2
+
+
+def test_pack_arena_file_errors_and_empty_round_trip(built, tmp_path):
+    """yq_pack.cu host logic (no GPU): a missing or foreign file is an error with a message, an empty arena round-trips."""
+    from yolo_quantization_b200 import _lib
+    lib = _lib.load()
+    assert lib.yq_pack_arena_clear() == 0
+    assert lib.yq_pack_arena_load(str(tmp_path / "missing.yqpk").encode()) < 0 and "cannot open" in _lib.last_error()
+    junk = tmp_path / "junk.yqpk"
+    junk.write_bytes(b"not an arena at all")
+    assert lib.yq_pack_arena_load(str(junk).encode()) < 0 and "not a packed-weight arena" in _lib.last_error()
+    empty = tmp_path / "empty.yqpk"
+    assert lib.yq_pack_arena_save(str(empty).encode()) == 0
+    assert empty.read_bytes()[:4] == b"YQPK" and lib.yq_pack_arena_load(str(empty).encode()) == 0

@@ -112,6 +112,10 @@ SIGNATURES = {
     "yq_network_stream": (_vp, [_vp]),
     "yq_network_use_graph": (_i, [_vp, _i]),
     "yq_network_launches_per_forward": (_i, [_vp]),
+    "yq_pack_arena_load": (_i, [C.c_char_p]),
+    "yq_pack_arena_save": (_i, [C.c_char_p]),
+    "yq_pack_arena_clear": (_i, []),
+    "yq_pack_arena_stats": (_i, [C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "yq_network_profile_forward": (_i, [_vp, _vp, _vp]),
     "yq_network_box_capacity": (_i, [_vp]),
     "yq_network_classes": (_i, [_vp]),

@@ -102,6 +102,7 @@ struct yq_conv_layer {
     void *tc_flat2 = nullptr;   // its persistent two-tiles-per-weight-stage form (yq_conv_tc_flat2.cu), or nullptr
     void *tc_flat2x = nullptr;  // the same on CTA pairs, tcgen05 cta_group::2 (yq_conv_tc_flat2x.cu), or nullptr
     std::vector<uint8_t> host_w;  // OIHW copy kept for repacking
+    uint64_t pack_key = 0;        // content key of this layer's filter images in the packed-weight arena (yq_pack.cu)
     std::vector<uint8_t> host_zw;
     std::vector<int32_t> host_chanq;   // 4 ints per channel {bias, zw, 2*M0, shift} (copy of chanq)
     std::vector<double> host_mcomb;
@@ -114,6 +115,12 @@ int yq_detect_run(const float *const *head_pred, const int *lw, const int *lh, c
 
 // implemented in yq_conv_tc_small.cu (threads build the im2col rows; c <= 32)
 int yq_tc_small_supported(const yq_conv_layer *l);
+// packed-weight arena (yq_pack.cu): fetch a filter image built earlier for the same weights, or keep a freshly built one
+namespace yq {
+uint64_t pack_layer_key(const yq_conv_layer *l);
+bool pack_fetch(const yq_conv_layer *l, const char *tag, std::vector<uint8_t> &out);
+void pack_put(const yq_conv_layer *l, const char *tag, const std::vector<uint8_t> &img);
+}  // namespace yq
 int yq_tc_small_prepare(yq_conv_layer *l, void **state);
 void yq_tc_small_free(void *state);
 int yq_tc_small_forward(yq_conv_layer *l, void *state, const uint8_t *in_u8, uint8_t *out_u8, uint8_t *out_pool, float *out_f32,

@@ -497,10 +497,17 @@ int yq_tc_flat2x_prepare(yq_conv_layer *l, void **state)
     st->n_pad = yq::round_up(l->n, st->wide ? 256 : F2X_BN);
     const int taps = l->size * l->size;
     const size_t ktot = (size_t)taps * l->cs_in;
-    std::vector<uint8_t> wp((size_t)st->n_pad * ktot, 0);
-    for (int oc = 0; oc < l->n; ++oc)
-        for (int t = 0; t < taps; ++t)
-            for (int ci = 0; ci < l->c; ++ci) wp[(size_t)oc * ktot + (size_t)t * l->cs_in + ci] = l->host_w[((size_t)oc * l->c + ci) * taps + t];
+    // [n_pad][taps][cs_in] rows (shared by the flat kernels: same tag, same image)
+    std::vector<uint8_t> wp;
+    char tag[24];
+    snprintf(tag, sizeof tag, "ohwi.%d", st->n_pad);
+    if (!yq::pack_fetch(l, tag, wp) || wp.size() != (size_t)st->n_pad * ktot) {
+        wp.assign((size_t)st->n_pad * ktot, 0);
+        for (int oc = 0; oc < l->n; ++oc)
+            for (int t = 0; t < taps; ++t)
+                for (int ci = 0; ci < l->c; ++ci) wp[(size_t)oc * ktot + (size_t)t * l->cs_in + ci] = l->host_w[((size_t)oc * l->c + ci) * taps + t];
+        yq::pack_put(l, tag, wp);
+    }
     auto cleanup = [&]() {
         cudaFree(st->w);
         delete st;

@@ -839,7 +839,12 @@ int yq_tc_rows_prepare(yq_conv_layer *l, void **state)
     const int nblk = CS == 32 ? 2 : 1;
     const int nmma = CS == 4 ? 3 : 6 * nblk;
     const int parts = two ? 2 : 1;
-    std::vector<uint8_t> img((size_t)parts * nmma * (CS == 4 ? NB : 2 * NB) * 32, 0);
+    const size_t img_bytes = (size_t)parts * nmma * (CS == 4 ? NB : 2 * NB) * 32;
+    std::vector<uint8_t> img;
+    char tag[24];
+    snprintf(tag, sizeof tag, "rows.%d", two ? 2 : 1);
+    const bool cached = yq::pack_fetch(l, tag, img) && img.size() == img_bytes;
+    if (!cached) img.assign(img_bytes, 0);
     int part = 0;
     // the filter byte of the block being laid out: the u8 weight, or (two) the signed block `part` of w - zp_w
     auto W = [&](int oc, int ci, int ky, int kx) -> uint8_t {
@@ -849,7 +854,7 @@ int yq_tc_rows_prepare(yq_conv_layer *l, void **state)
         const int d = w - zpw(oc), h = d < -128 ? -128 : d > 127 ? 127 : d;
         return (uint8_t)(int8_t)(part == 0 ? h : d - h);
     };
-    for (part = 0; part < parts; ++part)
+    for (part = 0; part < (cached ? 0 : parts); ++part)
     if (CS == 4) {
         // TMEM column c = 8g + 2q + e: channel q*NPQ + g % NPQ, output pixel 2*(g / NPQ) + e of the 4-pixel segment;
         // K byte k = 4*ip + ci: input pixel ip (0..7, the segment's window starts one pixel to the left), channel ci
@@ -893,6 +898,7 @@ int yq_tc_rows_prepare(yq_conv_layer *l, void **state)
                         }
                 }
     }
+    if (!cached) yq::pack_put(l, tag, img);
     if (cudaMalloc((void **)&st->wimg, img.size()) != cudaSuccess || cudaMemcpy(st->wimg, img.data(), img.size(), cudaMemcpyHostToDevice) != cudaSuccess) {
         cudaFree(st->wimg);
         delete st;

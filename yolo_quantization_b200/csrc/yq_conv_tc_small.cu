@@ -527,14 +527,18 @@ int yq_tc_small_prepare(yq_conv_layer *l, void **state)
     st->BN = l->cs_out;
     const int K = TAPS * st->CS, KPAD = (K + 31) / 32 * 32, P = KPAD / 32;
     // shared-memory image: panel p = K bytes [32p, 32p+32) of every row; SWIZZLE_32B inside each 8-row atom
-    std::vector<uint8_t> img((size_t)P * st->BN * 32, 0);
-    for (int oc = 0; oc < l->n; ++oc)
-        for (int t = 0; t < TAPS; ++t)
-            for (int ci = 0; ci < l->c; ++ci) {
-                const int k = t * st->CS + ci;
-                const int p = k / 32, c = (k % 32) / 16, b = k % 16;
-                img[(size_t)p * st->BN * 32 + oc * 32 + ((c ^ ((oc >> 2) & 1)) << 4) + b] = l->host_w[((size_t)oc * l->c + ci) * TAPS + t];
-            }
+    std::vector<uint8_t> img;
+    if (!yq::pack_fetch(l, "small", img) || img.size() != (size_t)P * st->BN * 32) {
+        img.assign((size_t)P * st->BN * 32, 0);
+        for (int oc = 0; oc < l->n; ++oc)
+            for (int t = 0; t < TAPS; ++t)
+                for (int ci = 0; ci < l->c; ++ci) {
+                    const int k = t * st->CS + ci;
+                    const int p = k / 32, c = (k % 32) / 16, b = k % 16;
+                    img[(size_t)p * st->BN * 32 + oc * 32 + ((c ^ ((oc >> 2) & 1)) << 4) + b] = l->host_w[((size_t)oc * l->c + ci) * TAPS + t];
+                }
+        yq::pack_put(l, "small", img);
+    }
     if (cudaMalloc((void **)&st->wimg, img.size()) != cudaSuccess || cudaMemcpy(st->wimg, img.data(), img.size(), cudaMemcpyHostToDevice) != cudaSuccess) {
         cudaFree(st->wimg);
         delete st;

@@ -372,14 +372,20 @@ extern "C" yq_conv_layer *yq_make_convolutional_layer_quant(const yq_conv_desc *
     l->host_w.assign(d->weights_uint8, d->weights_uint8 + K * d->n);
     l->host_zw.assign(d->weight_zero_point, d->weight_zero_point + d->n);
 
+    l->pack_key = yq::pack_layer_key(l);
+
     // pack OIHW -> [oc][ky][kx][ci (stride cs_in)], zero padded (push_convolutional_layer's role)
-    std::vector<uint8_t> wp((size_t)l->n_pad * l->k_pad, 0);
-    for (int oc = 0; oc < l->n; ++oc)
-        for (int ci = 0; ci < l->c; ++ci)
-            for (int ky = 0; ky < l->size; ++ky)
-                for (int kx = 0; kx < l->size; ++kx)
-                    wp[(size_t)oc * l->k_pad + (size_t)(ky * l->size + kx) * l->cs_in + ci] =
-                        d->weights_uint8[((size_t)oc * l->c + ci) * l->size * l->size + ky * l->size + kx];
+    std::vector<uint8_t> wp;
+    if (!yq::pack_fetch(l, "simt", wp) || wp.size() != (size_t)l->n_pad * l->k_pad) {
+        wp.assign((size_t)l->n_pad * l->k_pad, 0);
+        for (int oc = 0; oc < l->n; ++oc)
+            for (int ci = 0; ci < l->c; ++ci)
+                for (int ky = 0; ky < l->size; ++ky)
+                    for (int kx = 0; kx < l->size; ++kx)
+                        wp[(size_t)oc * l->k_pad + (size_t)(ky * l->size + kx) * l->cs_in + ci] =
+                            d->weights_uint8[((size_t)oc * l->c + ci) * l->size * l->size + ky * l->size + kx];
+        yq::pack_put(l, "simt", wp);
+    }
     // per-channel parameter arrays are padded to a multiple of 128 so either flavour can read whole tiles
     const int p_pad = yq::round_up(l->n_pad, 128);
     std::vector<int32_t> bias(p_pad, 0), zw(p_pad, 0);

@@ -9,6 +9,7 @@ see ``load_network``), and per-layer ``forward_*_layer_quant_gpu`` forms.
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Dict, List, Optional, Sequence
 
 import numpy as np
@@ -503,14 +504,30 @@ class Network:
             pass
 
 
-def load_network(cfg: str, weights: str, batch: int = 0, device: int = 0) -> Network:
+def pack_arena_stats() -> Dict[str, int]:
+    """entries / hits / misses / dirty of the packed-weight arena (yq_pack.cu)"""
+    v = [C.c_int(0) for _ in range(4)]
+    check(_lib.load().yq_pack_arena_stats(*[C.byref(x) for x in v]))
+    return dict(zip(("entries", "hits", "misses", "dirty"), (int(x.value) for x in v)))
+
+
+def load_network(cfg: str, weights: str, batch: int = 0, device: int = 0, packed: Optional[str] = None) -> Network:
     """load_network(cfg, weights, clear) (src/network.c:49-57) + the one-time
     quantization_weights_and_activations host prep (src/blas.c:259-346).  ``batch`` overrides the
-    cfg's ``[net] batch`` (the reference sizes its buffers from the cfg at parse time)."""
+    cfg's ``[net] batch`` (the reference sizes its buffers from the cfg at parse time).
+    ``packed``: path of a packed-weight arena: read first if it exists, so that filter images built for the
+    same weights are uploaded as they are; (re)written afterwards when the load had to build any."""
     lib = _lib.load()
+    if packed is not None:
+        check(lib.yq_pack_arena_clear())
+        if os.path.exists(packed) and lib.yq_pack_arena_load(packed.encode()) < 0:
+            raise YqError(_lib.last_error())
     h = lib.yq_load_network(cfg.encode(), weights.encode(), int(batch), int(device))
     if not h:
         raise YqError(_lib.last_error())
+    if packed is not None:
+        if pack_arena_stats()["dirty"] and lib.yq_pack_arena_save(packed.encode()) < 0:
+            raise YqError(_lib.last_error())
     return Network(h)
 
 
