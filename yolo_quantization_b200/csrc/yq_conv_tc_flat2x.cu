@@ -477,11 +477,16 @@ int f2x_launch(Flat2xState *st, const CUtensorMap &tmA, const CUtensorMap &tmO, 
 
 }  // namespace
 
+#ifndef F2X_1X1_DEFAULT
+#define F2X_1X1_DEFAULT 0
+#endif
 int yq_tc_flat2x_supported(const yq_conv_layer *l)
 {
     if (!yq_tc_flat_supported(l)) return 0;
     if (l->quant_stop_flag || l->cs_out % F2X_BN) return 0;
-    if (l->size != 3) return 0;      // 1x1: one weight stage per patch -- the one-tile form is faster (measured: layer 13 0.0215 vs 0.0245 ms)
+    // 1x1 (one weight stage per patch chunk): YQ_FLAT2X_1X1 = 1 / 0 switches it on / off for A/B measurements
+    static const int one_env = getenv("YQ_FLAT2X_1X1") ? atoi(getenv("YQ_FLAT2X_1X1")) : -1;
+    if (l->size != 3 && !(l->size == 1 && (one_env < 0 ? F2X_1X1_DEFAULT : one_env))) return 0;
     if (256 + (l->size - 1) * (l->w + 2) > F2X_MAX_ROWS) return 0;
     return 1;
 }
