@@ -144,7 +144,7 @@ def run_reference(args):
                 t0 = time.perf_counter()
                 O.forward_network(info, im)
                 times.append(time.perf_counter() - t0)
-    timed = times[args.warmup:]
+    timed = times[args.warmup:] or times[-1:]
     total = sum(timed)
     val = len(timed) / total
     sample = (f"{len(timed)} steps of 1 image (batch 1, network_predict window, examples/detector.c:922-924), "
@@ -155,7 +155,7 @@ def run_reference(args):
             "config": {"workload": "yolov3-tiny INT8 per-channel 416x416, reference CPU QUANTIZATION=1 path, 1 image per step"},
             "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    emit(line)
     return 0
 
 
@@ -178,6 +178,24 @@ def cpu_baseline(cfg1, wts, img_f32, info, im):
                       f"{'oracle/_ref OpenMP build' if kind == 'reference' else 'oracle port'}, {cores} threads"}
 
 
+_REAL_STDOUT = None
+
+
+def _claim_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries print there too (NCCL's version banner at the first collective, the
+    oracle's make): from here on fd 1 points at stderr and emit() writes the line to the saved descriptor."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    sys.stdout.flush()
+    os.write(_REAL_STDOUT if _REAL_STDOUT is not None else 1, (json.dumps(line) + "\n").encode())
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -190,6 +208,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
+    _claim_stdout()
     if args.impl == "reference":
         return run_reference(args)
 
@@ -363,7 +382,7 @@ def main():
             img_f32 = os.path.join(tmp.name, "img.f32")
             synth.image_to_float(im).tofile(img_f32)
             line["cpu_baseline"] = cpu_baseline(cfg1, wts, img_f32, info, im)
-        print(json.dumps(line), flush=True)
+        emit(line)
     net.free()
     if world > 1:
         dist.barrier()

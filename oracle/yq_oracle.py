@@ -11,6 +11,7 @@ from __future__ import annotations
 
 import ctypes as C
 import os
+import re
 import subprocess
 from typing import Dict, List, Optional, Sequence
 
@@ -234,7 +235,8 @@ def run_reference(mode: str, cfg: str, weights: str, input_f32: str, out: str, o
 
 
 def ref_times(stderr: str) -> List[float]:
-    return [float(l.split()[2]) for l in stderr.splitlines() if l.startswith("REF_TIME")]
+    # (the reference writes its own progress text to stderr without a trailing newline: a REF_TIME record may not start a line)
+    return [float(t) for t in re.findall(r"REF_TIME\s+\d+\s+([0-9.eE+-]+)", stderr)]
 
 
 _DT = {"output_int32": np.int32, "output_uint8": np.uint8, "M0": np.int32, "M0_right_shift": np.int32,
