@@ -644,6 +644,20 @@ def test_network_predict_f32_equals_predict_u8(built, tiny_net_files):
     net.free()
 
 
+def test_network_input_paths_agree(built, tiny_net_files, monkeypatch):
+    """layer 0 fed by the in-kernel plane fetch (default) and by the layout-transform launch + padded NHWC4 copy
+    (YQ_NO_PLANAR=1, also the path of nets with zp_in != 0 or w % 16 != 0): same bytes out, one launch apart."""
+    cfg, wts, _, _ = tiny_net_files
+    x = np.random.default_rng(17).integers(0, 256, size=(3, 3, 416, 416), dtype=np.uint8)
+    net = darknet.load_network(cfg, wts, batch=3)
+    planar, n_planar = net.predict_u8(x).copy(), net.launches_per_forward
+    net.free()
+    monkeypatch.setenv("YQ_NO_PLANAR", "1")
+    net = darknet.load_network(cfg, wts, batch=3)
+    assert np.array_equal(net.predict_u8(x), planar) and net.launches_per_forward == n_planar + 1
+    net.free()
+
+
 def test_layout_transform_padded_geometry(built):
     """NCHW -> halo-padded NHWC and back: the interior round-trips, the halo keeps what the runtime put there."""
     import ctypes as C
