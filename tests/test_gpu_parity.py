@@ -488,6 +488,30 @@ def test_fused_network_equals_unfused_and_oracle(built, tiny_net_files):
     net.free()
 
 
+def test_full_size_batch_128_equals_per_image_runs_and_oracle(built, tiny_net_files):
+    """BASELINE's bench configuration (batch 128 at 416x416, production plan, CUDA graph): every image's heads equal the
+    heads of the same image in a batch-4 run bit for bit (tiles of the persistent kernels span image boundaries: no
+    cross-talk), whatever its slot in the batch, and two of them equal the oracle."""
+    cfg, wts, info, _ = tiny_net_files
+    four = np.stack([synth.synthetic_image(s) for s in (41, 42, 43, 44)])
+    slot = np.random.default_rng(9).integers(0, 4, size=128)
+    slot[:4] = (0, 1, 2, 3)
+    small = darknet.load_network(cfg, wts, batch=4)
+    heads4 = [h.copy() for h in small.split_heads(small.predict_u8(four))]
+    small.free()
+    net = darknet.load_network(cfg, wts, batch=128)
+    net.use_graph(True)
+    for _ in range(2):                                   # second pass = graph replay
+        heads128 = net.split_heads(net.predict_u8(four[slot]))
+        for h4, h128 in zip(heads4, heads128):
+            assert np.array_equal(h128, h4[slot])
+    net.free()
+    for img in (0, 3):
+        ref = O.forward_network(info, four[img])
+        for h4, i in zip(heads4, (16, 23)):
+            assert np.allclose(h4[img], ref[i]["f32"], atol=YOLO_ATOL, rtol=0)
+
+
 def test_tiny96_leaky_vs_oracle(built, tmp_path):
     """leaky net: zp_in = 40 padding in every conv after layer 0, leaky epilogue; GPU == exact-integer spec."""
     layers = synth.yolov3_tiny_quant("leaky")
