@@ -2,27 +2,29 @@
 // SMALL input-channel counts (c <= 32: layers 0, 2, 4 of yolov3-tiny) with NO im2col gather at all.
 //
 // These layers are HBM-bound on paper (45..384 op/B) but were issue-bound in practice: every thread built one im2col
-// row per pixel.  Here the activation tile is copied ONCE, row by row, from a halo-padded NHWC tensor into shared
-// memory (16-byte cp.async chunks, ~2..6 per thread per tile) and the tensor core reads overlapping windows of it
-// through a NO-SWIZZLE K-major descriptor whose leading-byte-offset makes consecutive K chunks overlap:
+// row per pixel.  Here a producer warp streams each activation tile ONCE into shared memory with TMA (from a halo-padded
+// NHWC tensor, or -- layer 0 -- straight from the network's CHW planes, interleaved on chip) and the tensor core reads
+// overlapping windows of it through a NO-SWIZZLE K-major descriptor whose leading-byte-offset makes consecutive K
+// chunks overlap:
 //
 //   c = 4  (layer 0): one MMA row = 4 output pixels.  Row i's K = 32 bytes = input pixels 4i-1 .. 4i+6 of one image
 //          row = two 16-byte chunks at 16i and 16i+16 (LBO = 16: chunk 1 of row i IS chunk 0 of row i+1).  The filter
 //          bank is a Toeplitz matrix [4 pixels x n channels][8 input pixels x 4 channels]; the tensor core multiplies
 //          by its zeros for free.  3 MMAs per tile (one per filter row ky, A start shifted by one tile row).
-//   c = 16, 32: pixels are de-interleaved into EVEN / ODD planes while they are copied, and two MMA groups compute
-//          the even and the odd output pixels of a row into different TMEM column ranges:
-//              even pixel 2i  : K chunks (E[i], O[i-1]) (O[i], -)       odd pixel 2i+1 : (E[i], O[i]) (E[i+1], -)
-//          (12 MMAs per tile and 16-channel block).
+//   c = 16, 32: TMA boxes over the input viewed as [rows][pitch / 2][parity][c] land the EVEN and the ODD pixel columns
+//          in separate planes, and one MMA computes the even and the odd output pixel of a row into different TMEM
+//          column ranges from K chunks (E[i + s], O[i + s]) (6 MMAs per tile and 16-channel block).
 //
 // Either way one TMEM lane then holds BOTH x-neighbours of a pooling window in its columns, tile rows are ordered so
 // that lanes {i, i+8} / {i+16, i+24} are y-neighbours, and the 16x256b tcgen05.ld shape hands one thread complete 2x2
 // windows: max in the accumulator domain, requantize the winner only (exact, see yq_conv_tc_small.cu), FP64 per-pixel
 // fallback when a byte would wrap or |x| >= 2^22.  Restates convolutional_layer.c:694-751 + maxpool_layer.c:109-153.
 //
-// Zero point of the weights: 16 extra all-ones filter rows per MMA group give sum(a) per output pixel
-// (acc = sum w*a - zp_w * sum a, convolutional_layer.c:718-721).  Padding: the input tensor carries a halo filled
-// with zp_in (im2col.c:5-14), written once by the host runtime; pad channels never count (their weights are 0).
+// Zero point of the weights: either 16 extra all-ones filter rows per MMA group give sum(a) per output pixel
+// (acc = sum w*a - zp_w * sum a, convolutional_layer.c:718-721), or the filters enter as two signed blocks
+// h + l = w - zp_w (RowsCfg, TWO).  Padding: the input tensor carries a halo filled with zp_in (im2col.c:5-14), written
+// once by the host runtime -- or TMA's zero fill outside the image for the planar layer-0 form (zp_in = 0); pad
+// channels never count (their weights are 0).  Pipeline, template forms and their measured trade-offs: DESIGN.md 4.1.
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <limits.h>
