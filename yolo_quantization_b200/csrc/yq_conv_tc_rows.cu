@@ -59,7 +59,7 @@ constexpr int PLANE = 144;              // bytes of one shared-memory plane row:
 template <int CS>
 struct RowsGeom {
     static constexpr int TWPX = CS == 4 ? 32 : 16;                  // conv output pixels per tile row
-    static constexpr int NBLK = CS == 32 ? 2 : 1;                   // 16-channel blocks
+    static constexpr int NBLK = CS == 4 ? 1 : CS / 16;              // 16-channel blocks (c = 16, 32, 64)
     static constexpr int ROWP = CS == 4 ? PLANE : 2 * PLANE * NBLK; // shared-memory bytes per tile row
     static constexpr int A_ROWS = TILE_ROWS + 2;
     static constexpr int NPLANES = CS == 4 ? 1 : 2 * NBLK;          // [18 rows][9 x 16 B] arrays of a tile: one per 16-channel block and pixel parity
@@ -119,6 +119,7 @@ struct RowsArgs {
     const uint8_t *wimg;    // shared-memory image of the filter tiles, one per MMA in issue order
     int HP, WP, OH, OW, PH, PW, OHP, OWP, opad;
     int tiles_x, tiles_y, num_tiles, zp_out;
+    int out_cs, ch_off;     // channel stride of the output tensor and first channel this launch writes (c = 64: n is done in slices of 64)
     int knobs;              // -DYQ_ROWS_KNOBS experiments (results are garbage): 1 no MMAs, 2 no epilogue arithmetic, 4 no tile copies, 8 no stores
     uint32_t magic_x, magic_y;   // ceil(2^32 / tiles_x), ceil(2^32 / tiles_y): exact quotients by __umulhi for tile < 2^32 / tiles
     int4 cq[64];            // {bias, zw, 2*M0, shift} per channel
@@ -258,7 +259,7 @@ __device__ __forceinline__ uint32_t pack4(const int (&r)[4])
 // channels each).  DBL: two accumulators, so the next tile's MMAs run under this tile's epilogue.
 constexpr int rows_min_ctas(int CS, int SPLIT, int by_tmem)
 {
-    const int want = CS == 32 ? 2 : SPLIT == 2 ? 3 : 4;
+    const int want = CS == 64 ? 1 : CS == 32 ? 2 : SPLIT == 2 ? 3 : 4;
     return want < by_tmem ? want : by_tmem;
 }
 
@@ -274,7 +275,7 @@ conv_u8_tc_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
     constexpr int NPT = CS == 4 ? NPQ : NPQ / SPLIT;      // channels whose parameters this thread keeps
     // double-buffered TMEM loads (a chunk's round trip under the previous chunk's arithmetic) where the registers are there:
     // c = 32 runs 2 CTAs per SM; measured slower for the 4-CTA kernels (layers 0, 2), faster for layer 4
-    constexpr bool PIPE = CS == 32;
+    constexpr bool PIPE = CS >= 32;
     constexpr int NACCS = L::DB ? 2 : 1;
     constexpr int NBUF = L::NBUF;
     static_assert(SPLIT == 1 || CS == 4 || NCH >= 32, "a thread needs at least one 4-channel chunk");
@@ -487,8 +488,8 @@ conv_u8_tc_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
         const int zo = a.zp_out;
         const uint32_t tq = tmem_base + ((uint32_t)(warp * 32) << 16);
         // per-thread part of the pooled-output address (window 0 of this thread; window 1 is one pooled row further)
-        const uint32_t out_thr = (uint32_t)(((2 * warp + a.opad) * a.OWP + (CS == 4 ? 2 * qi : qi) + a.opad) * NCH + ch0);
-        const uint32_t out_row = (uint32_t)(a.OWP * NCH);
+        const uint32_t out_thr = (uint32_t)(((2 * warp + a.opad) * a.OWP + (CS == 4 ? 2 * qi : qi) + a.opad) * a.out_cs + a.ch_off + ch0);
+        const uint32_t out_row = (uint32_t)(a.OWP * a.out_cs);
         int it = 0;
 #pragma unroll 1
         for (int tile = first; tile < a.num_tiles; tile += step, ++it) {
@@ -510,7 +511,7 @@ conv_u8_tc_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
         // ---- epilogue: warp = TMEM lane quarter = 4 conv rows = 2 pooled rows; thread (qi, qq) = pooled column(s) qi, channels qq*NPQ ..
             const int tx = cur.tx, ty = cur.ty, n = cur.n;
             const int py0 = ty * (TILE_ROWS / 2) + 2 * warp;
-            uint8_t *const out_tile = a.out_pool + (size_t)((uint32_t)((n * a.OHP + ty * (TILE_ROWS / 2)) * a.OWP + tx * (G::TWPX / 2)) * (uint32_t)NCH + out_thr);
+            uint8_t *const out_tile = a.out_pool + (size_t)((uint32_t)((n * a.OHP + ty * (TILE_ROWS / 2)) * a.OWP + tx * (G::TWPX / 2)) * (uint32_t)a.out_cs + out_thr);
             if (CS == 4) {
                 constexpr int NPAIR = 2 / SPLIT, NJ = NCH / 16, NCK = NPAIR * NJ;    // NCK chunks of 2 x 16 accumulators, double-buffered
                 uint32_t V[2][2][16];
@@ -579,7 +580,7 @@ conv_u8_tc_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
                     const int pair = SPLIT == 2 ? half : pp;
                     const int px = tx * (G::TWPX / 2) + 2 * qi + pair;
                     if (px < a.PW && !KNOB(8)) {
-                        uint8_t *dst = out_tile + pair * NCH;
+                        uint8_t *dst = out_tile + pair * a.out_cs;
                         if (py0 < a.PH) {
                             if constexpr (NCH == 16) *reinterpret_cast<uint32_t *>(dst) = w0[pp][0];
                             else *reinterpret_cast<uint2 *>(dst) = make_uint2(w0[pp][0], w0[pp][1]);
@@ -678,6 +679,8 @@ conv_u8_tc_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
 
 struct RowsState {
     int CS, NCH;
+    int slices = 1;         // launches per forward, NCH output channels each (c = 64 only)
+    size_t slice_bytes = 0; // filter image bytes of one slice
     bool two = false;       // two signed weight blocks (see RowsCfg)
     uint8_t *wimg = nullptr;
     std::map<std::pair<const void *, int>, CUtensorMap> maps;      // input tensor map per (input pointer, batch)
@@ -808,7 +811,9 @@ int yq_tc_rows_supported(const yq_conv_layer *l)
     if ((l->h & 1) || (l->w & 1)) return 0;                         // whole 2x2 windows only
     if (l->n != l->cs_out) return 0;
     const int ci = l->cs_in, co = l->cs_out;
-    return (ci == 4 && (co == 16 || co == 32)) || (ci == 16 && (co == 16 || co == 32 || co == 64)) || (ci == 32 && (co == 32 || co == 64));
+    // (c = 64: the filter tiles of 64 output channels fill shared memory -- n = 128 runs as two launches of 64 channels each)
+    return (ci == 4 && (co == 16 || co == 32)) || (ci == 16 && (co == 16 || co == 32 || co == 64)) || (ci == 32 && (co == 32 || co == 64)) ||
+           (ci == 64 && l->c == 64 && (co == 64 || co == 128));
 }
 
 void yq_tc_rows_input_geom(const yq_conv_layer *l, yq_act_geom *g)
@@ -823,13 +828,15 @@ int yq_tc_rows_prepare(yq_conv_layer *l, void **state)
 {
     RowsState *st = new RowsState();
     st->CS = l->cs_in;
-    st->NCH = l->cs_out;
+    st->slices = l->cs_in == 64 ? l->cs_out / 64 : 1;
+    st->NCH = l->cs_out / st->slices;       // output channels per launch
     const int CS = st->CS, NCH = st->NCH, NPQ = NCH / 4;
     // two signed blocks h + l = w - zp_w unless some difference is 255 (h = 127 would leave l = 128).  By default only where the
     // kernel can then double-buffer its accumulator (RowsCfg::DB): elsewhere twice the MMAs cost more than the epilogue saves
     // (measured: layer 4 51 -> 76 us).  YQ_ROWS_TWO = 0 / 1 forces it off / on.
     const int two_env = getenv("YQ_ROWS_TWO") ? atoi(getenv("YQ_ROWS_TWO")) : -1;
     bool two = two_env >= 0 ? two_env != 0 : ((CS == 4 && NCH == 16) || (CS == 16 && NCH <= 32));
+    if (CS == 64) two = false;              // (twice the filter tiles would not fit in shared memory)
     auto Wraw = [&](int oc, int ci, int ky, int kx) -> int { return l->host_w[(((size_t)oc * l->c + ci) * 3 + ky) * 3 + kx]; };
     auto zpw = [&](int oc) -> int { return l->host_chanq[(size_t)oc * 4 + 1]; };
     for (int oc = 0; oc < l->n && two; ++oc)
@@ -838,30 +845,35 @@ int yq_tc_rows_prepare(yq_conv_layer *l, void **state)
     st->two = two;
     const int nsum = two ? 0 : 16;
     const int NB = CS == 4 ? 4 * NCH + nsum : NCH + nsum;
-    const int nblk = CS == 32 ? 2 : 1;
+    const int nblk = CS == 4 ? 1 : CS / 16;
     const int nmma = CS == 4 ? 3 : 6 * nblk;
     const int parts = two ? 2 : 1;
-    const size_t img_bytes = (size_t)parts * nmma * (CS == 4 ? NB : 2 * NB) * 32;
+    const size_t slice_bytes = (size_t)parts * nmma * (CS == 4 ? NB : 2 * NB) * 32;
+    const size_t img_bytes = slice_bytes * st->slices;
+    st->slice_bytes = slice_bytes;
     std::vector<uint8_t> img;
     char tag[24];
     snprintf(tag, sizeof tag, "rows.%d", two ? 2 : 1);
     const bool cached = yq::pack_fetch(l, tag, img) && img.size() == img_bytes;
     if (!cached) img.assign(img_bytes, 0);
-    int part = 0;
-    // the filter byte of the block being laid out: the u8 weight, or (two) the signed block `part` of w - zp_w
+    int part = 0, slice = 0;
+    // the filter byte of the block being laid out (channel oc of the current slice): the u8 weight, or (two) the signed block
+    // `part` of w - zp_w
     auto W = [&](int oc, int ci, int ky, int kx) -> uint8_t {
         if (ci >= l->c) return 0;
+        oc += slice * NCH;
         const int w = Wraw(oc, ci, ky, kx);
         if (!two) return (uint8_t)w;
         const int d = w - zpw(oc), h = d < -128 ? -128 : d > 127 ? 127 : d;
         return (uint8_t)(int8_t)(part == 0 ? h : d - h);
     };
-    for (part = 0; part < (cached ? 0 : parts); ++part)
+    for (slice = 0; slice < (cached ? 0 : st->slices); ++slice)
+    for (part = 0; part < parts; ++part)
     if (CS == 4) {
         // TMEM column c = 8g + 2q + e: channel q*NPQ + g % NPQ, output pixel 2*(g / NPQ) + e of the 4-pixel segment;
         // K byte k = 4*ip + ci: input pixel ip (0..7, the segment's window starts one pixel to the left), channel ci
         for (int ky = 0; ky < 3; ++ky) {
-            uint8_t *tile = img.data() + (size_t)(part * 3 + ky) * NB * 32;
+            uint8_t *tile = img.data() + slice * slice_bytes + (size_t)(part * 3 + ky) * NB * 32;
             for (int c = 0; c < 4 * NCH; ++c) {
                 const int g = c / 8, q = (c % 8) / 2, e = c % 2;
                 const int oc = q * NPQ + g % NPQ, px = 2 * (g / NPQ) + e;
@@ -881,7 +893,7 @@ int yq_tc_rows_prepare(yq_conv_layer *l, void **state)
         for (int blk = 0; blk < nblk; ++blk)
             for (int ky = 0; ky < 3; ++ky)
                 for (int step = 0; step < 2; ++step, ++m) {
-                    uint8_t *tile = img.data() + (size_t)m * 2 * NB * 32;
+                    uint8_t *tile = img.data() + slice * slice_bytes + (size_t)m * 2 * NB * 32;
                     // filter column kx read by [group][chunk] of this MMA (-1: nothing)
                     const int kxmap[2][2][2] = {{{1, 0}, {-1, 2}}, {{0, -1}, {2, 1}}};   // [group even/odd][step][chunk]
                     for (int grp = 0; grp < 2; ++grp)
@@ -960,21 +972,31 @@ int yq_tc_rows_forward(yq_conv_layer *l, void *state, const uint8_t *in_padded, 
         it = st->maps.emplace(key, m).first;
     }
     const CUtensorMap &tmA = it->second;
-    memcpy(a.cq, l->host_chanq.data(), (size_t)l->n * 16);
-    memcpy(a.mc, l->host_mcomb.data(), (size_t)l->n * 8);
+    a.out_cs = l->cs_out;
     // form of the kernel: defaults from measurements on B200 (profiles/README.md), YQ_ROWS_SPLIT / YQ_ROWS_DB = 0 / 1 force
     static const int split_env = getenv("YQ_ROWS_SPLIT") ? atoi(getenv("YQ_ROWS_SPLIT")) : -1;
     static const int db_env = getenv("YQ_ROWS_DB") ? atoi(getenv("YQ_ROWS_DB")) : -1;
+    for (int slice = 0; slice < st->slices; ++slice) {
+        a.ch_off = slice * st->NCH;
+        a.wimg = st->wimg + slice * st->slice_bytes;
+        memcpy(a.cq, l->host_chanq.data() + (size_t)a.ch_off * 4, (size_t)st->NCH * 16);
+        memcpy(a.mc, l->host_mcomb.data() + a.ch_off, (size_t)st->NCH * 8);
+        int rc = -2;
 #define YQ_RW(CS_, N_, SPLIT_DEF_, DB_DEF_)                                                                       \
-    if (st->CS == CS_ && st->NCH == N_) {                                                                        \
-        const bool split = (CS_ == 4 || N_ >= 32) && (split_env < 0 ? SPLIT_DEF_ : split_env);                   \
-        const bool dbl = st->two || (db_env < 0 ? DB_DEF_ : db_env);                                             \
-        return run_rows<CS_, N_>(st->two, split, dbl, planar != 0, tmA, a, stream);                              \
-    }
-    YQ_RW(4, 16, 0, 0); YQ_RW(4, 32, 0, 0);
-    YQ_RW(16, 16, 0, 0); YQ_RW(16, 32, 0, 0); YQ_RW(16, 64, 0, 0);
-    YQ_RW(32, 32, 0, 0); YQ_RW(32, 64, 0, 1);
+        if (st->CS == CS_ && st->NCH == N_) {                                                                    \
+            const bool split = (CS_ == 4 || N_ >= 32) && (split_env < 0 ? SPLIT_DEF_ : split_env);               \
+            const bool dbl = st->two || (db_env < 0 ? DB_DEF_ : db_env);                                         \
+            rc = run_rows<CS_, N_>(st->two, split, dbl, planar != 0, tmA, a, stream);                            \
+        }
+        YQ_RW(4, 16, 0, 0); YQ_RW(4, 32, 0, 0);
+        YQ_RW(16, 16, 0, 0); YQ_RW(16, 32, 0, 0); YQ_RW(16, 64, 0, 0);
+        YQ_RW(32, 32, 0, 0); YQ_RW(32, 64, 0, 1);
+        YQ_RW(64, 64, 0, 1);
 #undef YQ_RW
+        if (rc == -2) break;
+        if (rc) return rc;
+        if (slice + 1 == st->slices) return 0;
+    }
     return yq::fail("tcgen05 rows flavour: no instantiation for cs_in=%d cs_out=%d", st->CS, st->NCH);
 }
 
