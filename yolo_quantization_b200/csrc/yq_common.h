@@ -132,6 +132,7 @@ void yq_tc_rows_input_geom(const yq_conv_layer *l, yq_act_geom *g);
 int yq_tc_rows_prepare(yq_conv_layer *l, void **state);
 void yq_tc_rows_free(void *state);
 int yq_tc_rows_two_blocks(const void *state);
+int yq_tc_rows_launches(const void *state);      // kernel launches of one forward (c = 64: one per 64 output channels)
 int yq_tc_rows_forward(yq_conv_layer *l, void *state, const uint8_t *in, uint8_t *out_pool, const yq_act_geom *og, int batch, cudaStream_t stream,
                        int planar = 0);
 int yq_tc_rows_planar_supported(const yq_conv_layer *l);

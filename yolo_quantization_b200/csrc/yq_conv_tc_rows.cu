@@ -923,6 +923,7 @@ int yq_tc_rows_prepare(yq_conv_layer *l, void **state)
 }
 
 int yq_tc_rows_two_blocks(const void *state) { return state && ((const RowsState *)state)->two ? 1 : 0; }
+int yq_tc_rows_launches(const void *state) { return state ? ((const RowsState *)state)->slices : 0; }
 
 void yq_tc_rows_free(void *state)
 {

@@ -379,6 +379,7 @@ void plan(yq_network *net)
         if (l.type == L_CONV && l.conv) {
             if (rows_ok[i]) {
                 l.use_rows = l.fuse_pool = net->layers[i + 1].fused_away = true;
+                launches += yq_tc_rows_launches(l.conv->tc_rows) - 1;
             } else if (flat_ok[i]) {
                 l.use_flat = true;
                 if (net->fusion && l.quant_stop && i + 1 < n && net->layers[i + 1].type == L_YOLO && l.n % (net->layers[i + 1].classes + 5) == 0)
@@ -436,6 +437,7 @@ int forward_body(yq_network *net, const uint8_t *in_u8_nchw, int *launches, bool
             } else if (l.use_rows) {
                 if (yq_forward_convolutional_layer_quant_rows_pool_gpu(l.conv, cur, net->layers[i + 1].out_u8, &net->layers[i + 1].geom, net->batch, st))
                     return -1;
+                nl += yq_tc_rows_launches(l.conv->tc_rows) - 1;
             } else if (l.use_flat && l.fuse_yolo) {
                 // the head's own float tensor (l.output) is only materialised for debug pulls
                 if (yq_forward_convolutional_layer_quant_flat_yolo_gpu(l.conv, cur, l.out_u8, l.halo_fill, net->keep_acc ? l.out_f32 : nullptr,
