@@ -79,7 +79,9 @@ template <int CS, int NCH, bool TWO, bool DBL, bool PLANAR = false>
 struct RowsCfg {
     static_assert(!PLANAR || CS == 4, "planar input: layer-0 class only");
     using G = RowsGeom<CS>;
-    static constexpr int NSUM = TWO ? 0 : 16;
+    // all-ones filter rows per MMA group: c = 4 needs one column pair per pixel pair of the segment (16); c >= 16 reads one
+    // 8-column TMEM atom of identical sums per group
+    static constexpr int NSUM = TWO ? 0 : (CS == 4 ? 16 : 8);
     static constexpr int NB = CS == 4 ? 4 * NCH + NSUM : NCH + NSUM;    // filter rows (TMEM columns) per MMA group
     static constexpr int NACC = CS == 4 ? NB : 2 * NB;              // TMEM columns of one accumulator
     // DB: two accumulators, the next tile's MMAs run under this tile's epilogue (at the price of CTAs per SM once two of
@@ -843,7 +845,7 @@ int yq_tc_rows_prepare(yq_conv_layer *l, void **state)
         for (int i = 0; i < l->c * 9; ++i)
             if ((int)l->host_w[(size_t)oc * l->c * 9 + i] - zpw(oc) == 255) { two = false; break; }
     st->two = two;
-    const int nsum = two ? 0 : 16;
+    const int nsum = two ? 0 : (CS == 4 ? 16 : 8);
     const int NB = CS == 4 ? 4 * NCH + nsum : NCH + nsum;
     const int nblk = CS == 4 ? 1 : CS / 16;
     const int nmma = CS == 4 ? 3 : 6 * nblk;

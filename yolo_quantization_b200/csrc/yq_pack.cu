@@ -20,7 +20,7 @@
 namespace {
 
 constexpr uint32_t PACK_MAGIC = 0x4B505159u;   // "YQPK"
-constexpr uint32_t PACK_VERSION = 3;           // bump when any kernel's filter image changes
+constexpr uint32_t PACK_VERSION = 4;           // bump when any kernel's filter image changes
 
 struct Arena {
     std::map<std::pair<uint64_t, std::string>, std::vector<uint8_t>> entries;
