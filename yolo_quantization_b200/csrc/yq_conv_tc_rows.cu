@@ -50,6 +50,19 @@ constexpr int PLANE = 144;              // bytes of one shared-memory plane row:
 #define YQ_ROWS_NBUF 3
 #endif
 
+// -DYQ_ROWS_TRACE: the producer lane of every CTA adds up the clocks of its phases (yq_rows_trace[cta * 8 + phase], [.. + 7] = tiles):
+// 0 wait acc_empty, 1 wait full, 2 MMA issue + commit, 3 wait acc_full of the previous tile, 4 refill (tile split + TMA issue)
+#ifdef YQ_ROWS_TRACE
+__device__ unsigned long long yq_rows_trace[5 * 8 * 1024];      // slot (0: c = 4, 1: c = 16, 2: c = 32, 3 / 4: c = 64 slices) x CTA x phase
+#define TR_DECL long long tr_prev = clock64(); unsigned long long tr_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0}
+#define TR_MARK(ev) do { const long long tr_now = clock64(); tr_acc[ev] += (unsigned long long)(tr_now - tr_prev); tr_prev = tr_now; } while (0)
+#define TR_FLUSH() do { if (blockIdx.x < 1024) for (int e = 0; e < 8; ++e) yq_rows_trace[(a.trace_slot * 1024 + blockIdx.x) * 8 + e] = tr_acc[e]; } while (0)
+#else
+#define TR_DECL
+#define TR_MARK(ev)
+#define TR_FLUSH()
+#endif
+
 #ifdef YQ_ROWS_KNOBS
 #define KNOB(bit) (a.knobs & (bit))
 #else
@@ -121,6 +134,7 @@ struct RowsArgs {
     const uint8_t *wimg;    // shared-memory image of the filter tiles, one per MMA in issue order
     int HP, WP, OH, OW, PH, PW, OHP, OWP, opad;
     int tiles_x, tiles_y, num_tiles, zp_out;
+    int trace_slot;         // -DYQ_ROWS_TRACE: which block of yq_rows_trace this launch fills
     int out_cs, ch_off;     // channel stride of the output tensor and first channel this launch writes (c = 64: n is done in slices of 64)
     int knobs;              // -DYQ_ROWS_KNOBS experiments (results are garbage): 1 no MMAs, 2 no epilogue arithmetic, 4 no tile copies, 8 no stores
     uint32_t magic_x, magic_y;   // ceil(2^32 / tiles_x), ceil(2^32 / tiles_y): exact quotients by __umulhi for tile < 2^32 / tiles
@@ -286,25 +300,31 @@ conv_u8_tc_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
     uint64_t *full = (uint64_t *)(smem + L::BAR_OFF);          // [NBUF] input tile landed
     uint64_t *acc_full = full + NBUF;                          // [2] accumulator complete
     uint64_t *acc_empty = acc_full + 2;                        // [2] accumulator read out
-    uint32_t *tmem_slot = (uint32_t *)(acc_empty + 2);
+    uint64_t *b_full = acc_empty + 2;                          // the resident filter tiles have landed
+    uint32_t *tmem_slot = (uint32_t *)(b_full + 1);
 
     const int t = threadIdx.x, warp = (t >> 5) & 3, half = SPLIT == 2 ? (t >> 7) & 1 : 0, lane = t & 31;
     const bool producer = t >= NT;
     const int qi = lane >> 2, qq = lane & 3;
 
-    // ---- one-time setup: resident filter tiles, barriers, TMEM
-    for (int i = t; i < L::B_BYTES / 16; i += NT + 32 * L::NPROD)
-        reinterpret_cast<uint4 *>(smem + L::B_OFF)[i] = __ldg(reinterpret_cast<const uint4 *>(a.wimg) + i);
+    // ---- one-time setup: barriers, TMEM, and the resident filter tiles as bulk copies (up to 123 KB per CTA: fetched by
+    // dependent 16-byte loads of 160 threads this took ~ 13 us of a 30 us layer-6 launch; they are constants, so they start
+    // before the wait on the previous kernel)
     if (t == 0) {
         for (int b = 0; b < NBUF; ++b) mbar_init(&full[b], 1);
         for (int b = 0; b < 2; ++b) {
             mbar_init(&acc_full[b], 1);
             mbar_init(&acc_empty[b], NT / 32);
         }
+        mbar_init(b_full, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        mbar_expect_tx(b_full, (uint32_t)L::B_BYTES);
+        constexpr int CHUNK = 32768;
+#pragma unroll 1
+        for (int off = 0; off < L::B_BYTES; off += CHUNK)
+            bulk_load(smem + L::B_OFF + off, a.wimg + off, (uint32_t)(L::B_BYTES - off < CHUNK ? L::B_BYTES - off : CHUNK), b_full);
     }
     if (t < 32) tmem_alloc<L::TMEM_COLS>(tmem_slot);
-    fence_proxy_async();          // the filter tiles (generic-proxy stores) -> visible to the tensor core
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -398,6 +418,7 @@ conv_u8_tc_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
                 fence_proxy_async();      // the operand tile (generic-proxy stores) -> visible to the tensor core
                 __syncwarp();
                 if (lane == 0) {
+                    if (k == 0) mbar_wait(b_full, 0);
                     if (tile + NBUF * step < a.num_tiles) load_planes(tile + NBUF * step, sbuf);      // every lane has read the slot (SPP * NPROD = NBUF tiles on)
                     const int acc = NACCS == 2 ? it & 1 : 0;
                     if (it >= NACCS) mbar_wait(&acc_empty[acc], ((uint32_t)(it / NACCS) & 1u) ^ 1u);
@@ -460,23 +481,34 @@ conv_u8_tc_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
 #pragma unroll 1
             for (int d = 0; d < NBUF; ++d)
                 if (first + d * step < a.num_tiles) load_tile(first + d * step, d);
+            mbar_wait(b_full, 0);
             int buf = 0, it = 0;
+            TR_DECL;
 #pragma unroll 1
             for (int tile = first; tile < a.num_tiles; tile += step, buf = buf + 1 == NBUF ? 0 : buf + 1, ++it) {
                 const int acc = NACCS == 2 ? it & 1 : 0;
                 const uint32_t use = (uint32_t)(it / NACCS);            // how many times this accumulator has been used before
                 if (it >= NACCS) mbar_wait(&acc_empty[acc], (use & 1u) ^ 1u);      // its previous tile has been read out
+                TR_MARK(0);
                 mbar_wait(&full[buf], (uint32_t)((it / NBUF) & 1));
+                TR_MARK(1);
                 tc_fence_after();
                 if (KNOB(1)) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&acc_full[acc])) : "memory");
                 else issue_mma(buf, acc);
+                TR_MARK(2);
                 // refill the previous tile's buffer once its MMAs have finished reading it
                 // (one accumulator: the acc_empty wait above already implies it -- and by now acc_full may be a phase further)
                 if (it >= 1 && tile + (NBUF - 1) * step < a.num_tiles) {
                     if (NACCS == 2) mbar_wait(&acc_full[(it - 1) & 1], (uint32_t)(((it - 1) >> 1) & 1));
+                    TR_MARK(3);
                     load_tile(tile + (NBUF - 1) * step, buf == 0 ? NBUF - 1 : buf - 1);
+                    TR_MARK(4);
                 }
+#ifdef YQ_ROWS_TRACE
+                tr_acc[7] += 1;
+#endif
             }
+            TR_FLUSH();
         }
         __syncwarp();
     } else {
@@ -981,6 +1013,7 @@ int yq_tc_rows_forward(yq_conv_layer *l, void *state, const uint8_t *in_padded, 
     static const int db_env = getenv("YQ_ROWS_DB") ? atoi(getenv("YQ_ROWS_DB")) : -1;
     for (int slice = 0; slice < st->slices; ++slice) {
         a.ch_off = slice * st->NCH;
+        a.trace_slot = st->CS == 4 ? 0 : st->CS == 16 ? 1 : st->CS == 32 ? 2 : 3 + (slice & 1);
         a.wimg = st->wimg + slice * st->slice_bytes;
         memcpy(a.cq, l->host_chanq.data() + (size_t)a.ch_off * 4, (size_t)st->NCH * 16);
         memcpy(a.mc, l->host_mcomb.data() + a.ch_off, (size_t)st->NCH * 8);
@@ -1003,3 +1036,10 @@ int yq_tc_rows_forward(yq_conv_layer *l, void *state, const uint8_t *in_padded, 
     return yq::fail("tcgen05 rows flavour: no instantiation for cs_in=%d cs_out=%d", st->CS, st->NCH);
 }
 
+
+#ifdef YQ_ROWS_TRACE
+extern "C" __attribute__((visibility("default"))) int yq_debug_rows_trace(void *host, size_t bytes)
+{
+    return cudaMemcpyFromSymbol(host, yq_rows_trace, bytes < sizeof(yq_rows_trace) ? bytes : sizeof(yq_rows_trace)) == cudaSuccess ? 0 : -1;
+}
+#endif
