@@ -51,13 +51,22 @@ constexpr int PLANE = 144;              // bytes of one shared-memory plane row:
 #endif
 
 // -DYQ_ROWS_TRACE: the producer lane of every CTA adds up the clocks of its phases (yq_rows_trace[cta * 8 + phase], [.. + 7] = tiles):
-// 0 wait acc_empty, 1 wait full, 2 MMA issue + commit, 3 wait acc_full of the previous tile, 4 refill (tile split + TMA issue)
+// 0 wait acc_empty, 1 wait full, 2 MMA issue + commit, 3 wait acc_full of the previous tile, 4 refill (tile split + TMA issue),
+// 5 / 6 = clocks / nanoseconds of the whole loop (their ratio is the SM clock the kernel really ran at)
 #ifdef YQ_ROWS_TRACE
 __device__ unsigned long long yq_rows_trace[5 * 8 * 1024];      // slot (0: c = 4, 1: c = 16, 2: c = 32, 3 / 4: c = 64 slices) x CTA x phase
-#define TR_DECL long long tr_prev = clock64(); unsigned long long tr_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0}
+__device__ __forceinline__ unsigned long long tr_ns() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+__device__ unsigned long long yq_rows_trace2[5 * 4 * 1024];     // ns: kernel entry, after the PDL wait, loop start, kernel exit -- minus loop start
+#define TR_ENTRY const unsigned long long tr_entry = tr_ns(); unsigned long long tr_pdl = 0, tr_loop = 0; bool tr_me = false
+#define TR_PDL() tr_pdl = tr_ns()
+#define TR_EXIT() do { if (tr_me && blockIdx.x < 1024) { unsigned long long *q = yq_rows_trace2 + (a.trace_slot * 1024 + blockIdx.x) * 4; q[0] = tr_loop - tr_entry; q[1] = tr_loop - tr_pdl; q[2] = tr_loop; q[3] = tr_ns() - tr_loop; } } while (0)
+#define TR_DECL tr_loop = tr_ns(); tr_me = true; long long tr_prev = clock64(); const long long tr_c0 = tr_prev; const unsigned long long tr_n0 = tr_ns(); unsigned long long tr_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0}
 #define TR_MARK(ev) do { const long long tr_now = clock64(); tr_acc[ev] += (unsigned long long)(tr_now - tr_prev); tr_prev = tr_now; } while (0)
-#define TR_FLUSH() do { if (blockIdx.x < 1024) for (int e = 0; e < 8; ++e) yq_rows_trace[(a.trace_slot * 1024 + blockIdx.x) * 8 + e] = tr_acc[e]; } while (0)
+#define TR_FLUSH() do { tr_acc[5] = (unsigned long long)(clock64() - tr_c0); tr_acc[6] = tr_ns() - tr_n0; if (blockIdx.x < 1024) for (int e = 0; e < 8; ++e) yq_rows_trace[(a.trace_slot * 1024 + blockIdx.x) * 8 + e] = tr_acc[e]; } while (0)
 #else
+#define TR_ENTRY
+#define TR_PDL()
+#define TR_EXIT()
 #define TR_DECL
 #define TR_MARK(ev)
 #define TR_FLUSH()
@@ -303,6 +312,7 @@ conv_u8_tc_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
     uint64_t *b_full = acc_empty + 2;                          // the resident filter tiles have landed
     uint32_t *tmem_slot = (uint32_t *)(b_full + 1);
 
+    TR_ENTRY;
     const int t = threadIdx.x, warp = (t >> 5) & 3, half = SPLIT == 2 ? (t >> 7) & 1 : 0, lane = t & 31;
     const bool producer = t >= NT;
     const int qi = lane >> 2, qq = lane & 3;
@@ -340,6 +350,7 @@ conv_u8_tc_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
     const int first = blockIdx.x, step = gridDim.x;
 
     yq_pdl_wait_then_release();      // everything above touched only constants and on-chip state
+    TR_PDL();
 
     if (producer) {
         const uint32_t sA = smem_u32(smem + L::A_OFF), b0 = smem_u32(smem + L::B_OFF);
@@ -705,6 +716,7 @@ conv_u8_tc_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
     }
     tc_fence_before();
     __syncthreads();
+    TR_EXIT();
     if (t < 32) {
         tc_fence_after();
         tmem_dealloc<L::TMEM_COLS>(tmem_base);
@@ -1038,6 +1050,10 @@ int yq_tc_rows_forward(yq_conv_layer *l, void *state, const uint8_t *in_padded, 
 
 
 #ifdef YQ_ROWS_TRACE
+extern "C" __attribute__((visibility("default"))) int yq_debug_rows_trace2(void *host, size_t bytes)
+{
+    return cudaMemcpyFromSymbol(host, yq_rows_trace2, bytes < sizeof(yq_rows_trace2) ? bytes : sizeof(yq_rows_trace2)) == cudaSuccess ? 0 : -1;
+}
 extern "C" __attribute__((visibility("default"))) int yq_debug_rows_trace(void *host, size_t bytes)
 {
     return cudaMemcpyFromSymbol(host, yq_rows_trace, bytes < sizeof(yq_rows_trace) ? bytes : sizeof(yq_rows_trace)) == cudaSuccess ? 0 : -1;
