@@ -131,7 +131,7 @@ typedef struct yq_act_geom {
 } yq_act_geom;
 
 /* The "rows" flavour: 3x3 / stride 1 / pad 1 convolution + RELU6 + the following 2x2/2 max-pool in ONE launch
- * (convolutional_layer.c:694-751 + maxpool_layer.c:109-153 fused), for c <= 32.  It reads a halo-padded input
+ * (convolutional_layer.c:694-751 + maxpool_layer.c:109-153 fused), for c <= 32 and c = 64 (n = 64 or 128).  It reads a halo-padded input
  * (geometry from yq_conv_rows_input_geom) with no im2col gather and writes only the pooled tensor, into any
  * geometry.  yq_conv_rows_supported() is nonzero when the layer has it: 2 when the filters went in as two signed blocks
  * h + l = w - zp_w (the accumulator needs no zero-point correction), 1 when some w - zp_w = 255 forced the all-ones-rows form. */

@@ -1,5 +1,5 @@
 // yq_conv_tc_rows.cu -- tcgen05 (kind::i8) 3x3 / stride 1 / pad 1 convolution + RELU6 + fused 2x2/2 max-pool for
-// SMALL input-channel counts (c <= 32: layers 0, 2, 4 of yolov3-tiny) with NO im2col gather at all.
+// SMALL input-channel counts (c <= 32 and c = 64: layers 0, 2, 4, 6 of yolov3-tiny) with NO im2col gather at all.
 //
 // These layers are HBM-bound on paper (45..384 op/B) but were issue-bound in practice: every thread built one im2col
 // row per pixel.  Here a producer warp streams each activation tile ONCE into shared memory with TMA (from a halo-padded
