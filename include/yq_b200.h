@@ -191,6 +191,12 @@ YQ_API int yq_forward_upsample_layer_quant_geom_gpu(const uint8_t *in, const yq_
 YQ_API int yq_forward_route_layer_quant_geom_gpu(const uint8_t *const *inputs, const yq_act_geom *in_geoms, const int *in_c,
                                                  int n_inputs, uint8_t *out, const yq_act_geom *out_geom, int batch, int h,
                                                  int w, void *stream);
+/* forward_upsample_layer_quant (src/upsample_layer.c:96-113, src/blas.c:781-803) folded into the forward_route_layer_quant
+ * (src/route_layer.c:107-130) that consumes it: input k holds (h / in_up[k]) x (w / in_up[k]) pixels and is read as
+ * in[y / up][x / up]; in_up = NULL or all ones is the plain route.  in_geoms[k] describes the stored (small) tensor. */
+YQ_API int yq_forward_route_layer_quant_up_gpu(const uint8_t *const *inputs, const yq_act_geom *in_geoms, const int *in_c,
+                                               const int *in_up, int n_inputs, uint8_t *out, const yq_act_geom *out_geom,
+                                               int batch, int h, int w, void *stream);
 /* replaces forward_yolo_layer's inference part (src/yolo_layer.c:132-146): float NCHW in/out,
  * logistic on channels {0,1} and {4..4+classes} of each anchor. */
 YQ_API int yq_forward_yolo_layer_gpu(const float *in, float *out, int batch, int n_anchors, int classes, int h,

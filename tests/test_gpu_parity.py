@@ -423,6 +423,16 @@ def test_route(built, cs):
     assert np.array_equal(got, np.concatenate(xs, axis=1))
 
 
+@pytest.mark.parametrize("cs,ups,hw", [((128, 256), (2, 1), (26, 26)), ((16, 16), (1, 2), (6, 10)), ((3, 5, 8), (2, 1, 2), (4, 6)), ((32,), (3,), (9, 6))])
+def test_route_reads_upsampled_inputs(built, cs, ups, hw):
+    # an upsample -> route pair as one launch: equals the oracle's upsample followed by the plain concat
+    rng = np.random.default_rng(sum(cs) + sum(ups))
+    xs = [rng.integers(0, 256, size=(2, c, hw[0] // u, hw[1] // u), dtype=np.uint8) for c, u in zip(cs, ups)]
+    got = darknet.forward_route_layer_quant_gpu(xs, ups)
+    want = np.concatenate([np.stack([O.upsample(x[b], u) for b in range(2)]) if u > 1 else x for x, u in zip(xs, ups)], axis=1)
+    assert got.shape == want.shape and np.array_equal(got, want)
+
+
 def test_yolo(built):
     x = (np.random.default_rng(0).standard_normal((3, 30, 13, 13)) * 3).astype(np.float32)
     got = darknet.forward_yolo_layer_gpu(x, 3, 5)
@@ -683,6 +693,31 @@ def test_network_input_paths_agree(built, tiny_net_files, monkeypatch):
     monkeypatch.setenv("YQ_NO_PLANAR", "1")
     net = darknet.load_network(cfg, wts, batch=3)
     assert np.array_equal(net.predict_u8(x), planar) and net.launches_per_forward == n_planar + 1
+    net.free()
+
+
+@pytest.mark.parametrize("uproute,branch", [(1, 0), (0, 1), (1, 1)])
+def test_network_schedule_switches_keep_every_byte(built, tiny_net_files, monkeypatch, uproute, branch):
+    """YQ_UPROUTE (upsample folded into the route behind it: one launch less) and YQ_BRANCH_STREAM (the first detection
+    head on a second stream beside the layers after it) change the schedule only: same bytes out, eager and replayed."""
+    cfg, wts, _, _ = tiny_net_files
+    x = np.random.default_rng(23).integers(0, 256, size=(4, 3, 416, 416), dtype=np.uint8)
+    monkeypatch.setenv("YQ_UPROUTE", "0")
+    monkeypatch.setenv("YQ_BRANCH_STREAM", "0")
+    net = darknet.load_network(cfg, wts, batch=4)
+    base, n_base = net.predict_u8(x).copy(), net.launches_per_forward
+    net.free()
+    monkeypatch.setenv("YQ_UPROUTE", str(uproute))
+    monkeypatch.setenv("YQ_BRANCH_STREAM", str(branch))
+    net = darknet.load_network(cfg, wts, batch=4)
+    assert net.launches_per_forward == n_base - uproute
+    for graph in (False, True):
+        net.use_graph(graph)
+        for _ in range(4):
+            assert np.array_equal(net.predict_u8(x), base)
+    y = np.random.default_rng(24).integers(0, 256, size=(4, 3, 416, 416), dtype=np.uint8)
+    other = net.predict_u8(y).copy()
+    assert not np.array_equal(other, base) and np.array_equal(net.predict_u8(x), base)
     net.free()
 
 

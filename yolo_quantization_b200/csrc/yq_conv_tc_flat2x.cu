@@ -438,7 +438,10 @@ int f2x_launch_v(Flat2xState *st, const CUtensorMap &tmA, const CUtensorMap &tmO
     if (nbs > F2X_MAX_BSTAGES) nbs = F2X_MAX_BSTAGES;
     if (nbs < 2) return yq::fail("conv_u8_tc_flat2x_kernel<%d>: shared memory does not hold two weight stages", KC);
     a.b_stages = nbs;
-    const int smem = fixed + nbs * L::B_STAGE;
+    int smem = fixed + nbs * L::B_STAGE;
+    // Never two of these CTAs on one SM: each takes all 512 TMEM columns, and two CTA pairs of concurrent launches (the
+    // side stream of yq_network.cu) that each hold one SM's columns while waiting for the other's would not finish.
+    if (smem <= smem_max / 2) smem = smem_max / 2 + 1024;
     auto kern = conv_u8_tc_flat2x_kernel<KC, SLOW, WIDE>;
     if (smem > attr_smem) {
         YQ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));

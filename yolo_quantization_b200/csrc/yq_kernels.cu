@@ -673,7 +673,9 @@ extern "C" int yq_forward_upsample_layer_quant_gpu(const uint8_t *in, uint8_t *o
 }
 
 // ------------------------------------------------------------------------------------------------
-// route (src/route_layer.c:107-117): channel concat, no rescale
+// route (src/route_layer.c:107-117): channel concat, no rescale.  An input may be stored at 1/up of the route's size
+// and read through the nearest-neighbour upsample (src/blas.c:781-803: out[y][x] = in[y/up][x/up]), so that an
+// upsample -> route pair needs no intermediate tensor.
 // ------------------------------------------------------------------------------------------------
 constexpr int ROUTE_MAX_INPUTS = 8;
 struct RouteArgs {
@@ -682,6 +684,7 @@ struct RouteArgs {
     int cs[ROUTE_MAX_INPUTS];    // channel strides
     int off[ROUTE_MAX_INPUTS];   // channel offset in the output
     Geo g[ROUTE_MAX_INPUTS];     // input geometries
+    int up[ROUTE_MAX_INPUTS];    // >= 1: the input holds (H/up) x (W/up) pixels
     Geo go;
     int n, cs_out, c_out, H, W;
     long long pixels;
@@ -698,7 +701,7 @@ __global__ void route_u8_kernel(const RouteArgs a, uint8_t *__restrict__ out, in
             uint4 val = make_uint4(0, 0, 0, 0);
             for (int k = 0; k < a.n; ++k)
                 if (ch >= a.off[k] && ch < a.off[k] + a.c[k])
-                    val = __ldg(reinterpret_cast<const uint4 *>(a.in[k] + a.g[k].pix(n, y, x) * a.cs[k] + (ch - a.off[k])));
+                    val = __ldg(reinterpret_cast<const uint4 *>(a.in[k] + a.g[k].pix(n, y / a.up[k], x / a.up[k]) * a.cs[k] + (ch - a.off[k])));
             *reinterpret_cast<uint4 *>(out + a.go.pix(n, y, x) * a.cs_out + ch) = val;
         }
     } else {
@@ -707,26 +710,29 @@ __global__ void route_u8_kernel(const RouteArgs a, uint8_t *__restrict__ out, in
             const int x = j / a.cs_out, ch = j - x * a.cs_out;
             uint8_t val = 0;
             for (int k = 0; k < a.n; ++k)
-                if (ch >= a.off[k] && ch < a.off[k] + a.c[k]) val = a.in[k][a.g[k].pix(n, y, x) * a.cs[k] + (ch - a.off[k])];
+                if (ch >= a.off[k] && ch < a.off[k] + a.c[k]) val = a.in[k][a.g[k].pix(n, y / a.up[k], x / a.up[k]) * a.cs[k] + (ch - a.off[k])];
             out[a.go.pix(n, y, x) * a.cs_out + ch] = val;
         }
     }
 }
 
-extern "C" int yq_forward_route_layer_quant_geom_gpu(const uint8_t *const *inputs, const yq_act_geom *in_geoms, const int *in_c, int n_inputs,
-                                                     uint8_t *out, const yq_act_geom *out_geom, int batch, int h, int w, void *stream)
+extern "C" int yq_forward_route_layer_quant_up_gpu(const uint8_t *const *inputs, const yq_act_geom *in_geoms, const int *in_c, const int *in_up,
+                                                   int n_inputs, uint8_t *out, const yq_act_geom *out_geom, int batch, int h, int w, void *stream)
 {
-    if (!inputs || !in_c || !out || n_inputs <= 0 || n_inputs > ROUTE_MAX_INPUTS) return yq::fail("route: bad argument");
+    if (!inputs || !in_c || !out || n_inputs <= 0 || n_inputs > ROUTE_MAX_INPUTS || batch <= 0) return yq::fail("route: bad argument");
     RouteArgs a;
     memset(&a, 0, sizeof a);
     int off = 0, vec = 1;
     for (int i = 0; i < n_inputs; ++i) {
-        if (check_geom(in_geoms ? &in_geoms[i] : nullptr, h, w)) return -1;
+        const int up = in_up ? in_up[i] : 1;
+        if (up < 1 || h % up || w % up) return yq::fail("route: input %d: upsample factor %d does not divide %dx%d", i, up, h, w);
+        if (check_geom(in_geoms ? &in_geoms[i] : nullptr, h / up, w / up)) return -1;
         a.in[i] = inputs[i];
+        a.up[i] = up;
         a.c[i] = in_c[i];
         a.cs[i] = yq::channel_stride(in_c[i]);
         a.off[i] = off;
-        a.g[i] = geo_of(in_geoms ? &in_geoms[i] : nullptr, h, w);
+        a.g[i] = geo_of(in_geoms ? &in_geoms[i] : nullptr, h / up, w / up);
         off += in_c[i];
         if (in_c[i] % 16) vec = 0;
     }
@@ -744,6 +750,11 @@ extern "C" int yq_forward_route_layer_quant_geom_gpu(const uint8_t *const *input
     YQ_CUDA(yq::launch_pdl(route_u8_kernel, grid, dim3(threads), 0, (cudaStream_t)stream, a, out, vec));
     YQ_CHECK_LAUNCH();
     return 0;
+}
+extern "C" int yq_forward_route_layer_quant_geom_gpu(const uint8_t *const *inputs, const yq_act_geom *in_geoms, const int *in_c, int n_inputs,
+                                                     uint8_t *out, const yq_act_geom *out_geom, int batch, int h, int w, void *stream)
+{
+    return yq_forward_route_layer_quant_up_gpu(inputs, in_geoms, in_c, nullptr, n_inputs, out, out_geom, batch, h, w, stream);
 }
 extern "C" int yq_forward_route_layer_quant_gpu(const uint8_t *const *inputs, const int *in_c, int n_inputs,
                                                 uint8_t *out, int batch, int h, int w, void *stream)

@@ -119,12 +119,21 @@ struct Layer {
     bool use_rows = false;         // conv: halo-input conv + pool flavour (yq_conv_tc_rows.cu); its input tensor is halo-padded
     bool use_flat = false;         // conv: flat-strip flavour (yq_conv_tc_flat.cu); input and output tensors are flat
     bool fuse_yolo = false;        // quant_stop conv: the following yolo layer is produced by this layer's epilogue (yolo: fused_away)
+    bool fuse_up = false;          // route: inputs that are upsample layers are read through the upsample (upsample: fused_away)
+    bool side = false;             // runs on the side stream: a detection branch nothing later reads (see plan())
     int halo_fill = 0;             // byte kept in the halo of out_u8: the zero point its consumer convolutions pad with
     int src = -2;                  // layer whose out_u8 this layer reads (-1: the network input); routes use `inputs`
     yq_act_geom geom = {0, 0, 0};  // geometry of out_u8 (plain unless the only consumer is a rows-flavour conv)
 };
 
 }  // namespace
+
+#ifndef YQ_DEFAULT_UPROUTE
+#define YQ_DEFAULT_UPROUTE 1
+#endif
+#ifndef YQ_DEFAULT_BRANCH_STREAM
+#define YQ_DEFAULT_BRANCH_STREAM 1
+#endif
 
 struct yq_network {
     int device = 0;
@@ -142,6 +151,12 @@ struct yq_network {
     size_t scratch_bytes = 0;
     int keep_acc = 0;
     bool no_planar_input = getenv("YQ_NO_PLANAR") && atoi(getenv("YQ_NO_PLANAR"));   // A/B: keep the layout-transform launch in front of layer 0
+    // YQ_UPROUTE: an upsample whose only reader is the route right behind it is folded into that route's launch;
+    // YQ_BRANCH_STREAM: a detection branch that nothing later reads runs on a second stream beside the layers after it
+    int fuse_uproute = getenv("YQ_UPROUTE") ? atoi(getenv("YQ_UPROUTE")) : YQ_DEFAULT_UPROUTE;
+    int branch_stream = getenv("YQ_BRANCH_STREAM") ? atoi(getenv("YQ_BRANCH_STREAM")) : YQ_DEFAULT_BRANCH_STREAM;
+    cudaStream_t side_stream = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     int conv_kernel = -1;
     int fusion = 1;
     int use_graph = 0;
@@ -275,6 +290,47 @@ int tensor_of(const yq_network *net, int i)
     return i;
 }
 
+// A route at layer i whose inputs all lie at or before layer m < i - 1 starts a new branch from old tensors: the layers
+// m+1 .. i-1 in front of it (a detection head: convs + yolo) are read by nothing later, so they run on the side stream
+// while the main stream goes on with layer i.  Every main-stream layer must read main-stream tensors only; if any
+// does not, no layer is marked.
+void plan_side_branches(yq_network *net)
+{
+    const int n = (int)net->layers.size();
+    if (!net->branch_stream) return;
+    // Two launches may now be in flight at once.  The flat-strip CTA pairs are sized so that two of them never share an SM
+    // (yq_conv_tc_flat2x.cu); the multicast clusters of the per-tap flavour (yq_conv_tc.cu) carry no such guarantee, so a
+    // network that runs any convolution on that flavour keeps the single stream.
+    for (const auto &l : net->layers)
+        if (l.type == L_CONV && l.conv && !l.use_rows && !l.use_flat && l.conv->kernel != 0) return;
+    for (int i = 1; i < n; ++i) {
+        const Layer &r = net->layers[i];
+        if (r.type != L_ROUTE) continue;
+        int m = -1;
+        for (int idx : r.inputs) m = idx > m ? idx : m;
+        if (m < 0 || m >= i - 1) continue;
+        bool ok = true;
+        for (int j = m + 1; j < i && ok; ++j) ok = !net->layers[j].side && net->layers[j].src >= m;
+        for (int j = i; j < n && ok; ++j)
+            if (net->layers[j].type == L_ROUTE)
+                for (int idx : net->layers[j].inputs) ok = ok && !(idx > m && idx < i);
+        if (ok)
+            for (int j = m + 1; j < i; ++j) net->layers[j].side = true;
+    }
+    bool ok = true;
+    for (int i = 0; i < n && ok; ++i) {
+        const Layer &l = net->layers[i];
+        if (l.side) continue;
+        if (l.type == L_ROUTE) {
+            for (int idx : l.inputs) ok = ok && !net->layers[idx].side;
+        } else if (l.src >= 0) {
+            ok = !net->layers[l.src].side;
+        }
+    }
+    if (!ok)
+        for (auto &l : net->layers) l.side = false;
+}
+
 // Decide the kernel flavour of every convolution, which conv -> maxpool(2,2) pairs run as one launch, and the geometry
 // of every activation tensor.  Halo-input flavours constrain the tensors next to them:
 //   rows conv  : input = its own padded geometry (any producer that can write one); writes the POOLED tensor, any geometry
@@ -350,7 +406,7 @@ void plan(yq_network *net)
     // ---- apply
     for (int i = 0; i < n; ++i) {
         Layer &l = net->layers[i];
-        l.fuse_pool = l.fused_away = l.use_rows = l.use_flat = l.fuse_yolo = false;
+        l.fuse_pool = l.fused_away = l.use_rows = l.use_flat = l.fuse_yolo = l.fuse_up = l.side = false;
         l.geom = yq_act_geom{0, l.out_w, l.out_h};
         l.halo_fill = 0;
     }
@@ -372,6 +428,18 @@ void plan(yq_network *net)
         if (tensor_of(net, i) != i && tensor_of(net, i) >= 0) {
             net->layers[i].geom = net->layers[tensor_of(net, i)].geom;
             net->layers[i].halo_fill = net->layers[tensor_of(net, i)].halo_fill;
+        }
+    // upsample -> route: the route reads the small tensor itself when nothing else needs the upsampled one
+    if (net->fusion && net->fuse_uproute && !net->keep_acc)
+        for (int i = 1; i < n; ++i) {
+            Layer &l = net->layers[i], &u = net->layers[i - 1];
+            if (l.type != L_ROUTE || l.inputs.size() < 2 || u.type != L_UPSAMPLE || u.src < 0) continue;
+            int reads = 0, others = 0;
+            for (int idx : l.inputs) reads += idx == i - 1;
+            for (int j = 0; j < n; ++j)
+                if (j != i && net->layers[j].type == L_ROUTE)
+                    for (int idx : net->layers[j].inputs) others += idx == i - 1;
+            if (reads == 1 && others == 0 && l.out_h % u.stride == 0 && l.out_w % u.stride == 0) l.fuse_up = u.fused_away = true;
         }
     int launches = 1;
     for (int i = 0; i < n; ++i) {
@@ -396,6 +464,7 @@ void plan(yq_network *net)
     if (n > 0 && net->layers[0].type == L_CONV && net->layers[0].use_rows && !net->no_planar_input && yq_conv_rows_nchw_supported(net->layers[0].conv))
         --launches;
     net->launches = launches;
+    plan_side_branches(net);
 }
 
 bool conv_output_needed(const yq_network *net, int i)
@@ -409,6 +478,7 @@ int forward_body(yq_network *net, const uint8_t *in_u8_nchw, int *launches, bool
 {
     cudaStream_t st = net->stream;
     int nl = 0;
+    bool on_side = false, forked = false;   // (per-layer profiling keeps everything on the one stream)
     if (profile) cudaEventRecord(net->prof_events[0], st);
     // layer 0 in the rows flavour reads the planes itself when it can (no layout-transform launch, no padded copy)
     const bool planar_in = !net->layers.empty() && net->layers[0].type == L_CONV && net->layers[0].use_rows && !net->no_planar_input &&
@@ -429,6 +499,14 @@ int forward_body(yq_network *net, const uint8_t *in_u8_nchw, int *launches, bool
     const float *cur_f32 = nullptr;
     for (size_t i = 0; i < net->layers.size(); ++i) {
         Layer &l = net->layers[i];
+        const bool side = l.side && !profile && net->side_stream;
+        if (side && !on_side) {   // fork: the side stream starts behind everything issued so far
+            YQ_CUDA(cudaEventRecord(net->ev_fork, net->stream));
+            YQ_CUDA(cudaStreamWaitEvent(net->side_stream, net->ev_fork, 0));
+            forked = true;
+        }
+        on_side = side;
+        st = side ? net->side_stream : net->stream;
         switch (l.type) {
         case L_CONV:
             if (l.use_rows && i == 0 && planar_in) {
@@ -472,6 +550,7 @@ int forward_body(yq_network *net, const uint8_t *in_u8_nchw, int *launches, bool
             cur_geom = &l.geom;
             break;
         case L_UPSAMPLE:
+            if (l.fused_away) break;   // the route behind it reads `cur` through the upsample
             if (yq_forward_upsample_layer_quant_geom_gpu(cur, cur_geom, l.out_u8, &l.geom, net->batch, l.h, l.w, l.c, l.stride, st)) return -1;
             ++nl;
             cur = l.out_u8;
@@ -481,13 +560,19 @@ int forward_body(yq_network *net, const uint8_t *in_u8_nchw, int *launches, bool
             if (l.inputs.size() > 1) {
                 const uint8_t *ins[8];
                 yq_act_geom gs[8];
-                int cs[8];
+                int cs[8], ups[8];
                 for (size_t k = 0; k < l.inputs.size(); ++k) {
-                    ins[k] = net->layers[l.inputs[k]].out_u8;
-                    gs[k] = net->layers[l.inputs[k]].geom;
-                    cs[k] = net->layers[l.inputs[k]].out_c;
+                    const Layer *p = &net->layers[l.inputs[k]];
+                    ups[k] = 1;
+                    if (l.fuse_up && p->type == L_UPSAMPLE && p->fused_away) {   // read the upsample's own input
+                        ups[k] = p->stride;
+                        p = &net->layers[p->src];
+                    }
+                    ins[k] = p->out_u8;
+                    gs[k] = p->geom;
+                    cs[k] = p->out_c;
                 }
-                if (yq_forward_route_layer_quant_geom_gpu(ins, gs, cs, (int)l.inputs.size(), l.out_u8, &l.geom, net->batch, l.out_h, l.out_w, st))
+                if (yq_forward_route_layer_quant_up_gpu(ins, gs, cs, ups, (int)l.inputs.size(), l.out_u8, &l.geom, net->batch, l.out_h, l.out_w, st))
                     return -1;
                 ++nl;
             }   // a single-input route is an alias of its input (no copy)
@@ -502,6 +587,10 @@ int forward_body(yq_network *net, const uint8_t *in_u8_nchw, int *launches, bool
             break;
         }
         if (profile) cudaEventRecord(net->prof_events[i + 2], st);
+    }
+    if (forked) {   // join: the forward is complete on net->stream
+        YQ_CUDA(cudaEventRecord(net->ev_join, net->side_stream));
+        YQ_CUDA(cudaStreamWaitEvent(net->stream, net->ev_join, 0));
     }
     if (launches) *launches = nl;
     return 0;
@@ -746,6 +835,12 @@ extern "C" yq_network *yq_load_network(const char *cfg, const char *weights, int
         yq::fail("cudaStreamCreate failed");
         return nullptr;
     }
+    if (net->branch_stream && (cudaStreamCreateWithFlags(&net->side_stream, cudaStreamNonBlocking) != cudaSuccess ||
+                               cudaEventCreateWithFlags(&net->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+                               cudaEventCreateWithFlags(&net->ev_join, cudaEventDisableTiming) != cudaSuccess)) {
+        yq::fail("cudaStreamCreate (side stream) failed");
+        return nullptr;
+    }
     yq_network *raw = net.release();
     auto bail = [&]() -> yq_network * {
         std::string keep = yq_last_error();
@@ -848,6 +943,9 @@ extern "C" void yq_free_network(yq_network *net)
     cudaFree(net->in_quant);
     cudaFree(net->scratch);
     if (net->out_host_pinned) cudaFreeHost(net->out_host_pinned);
+    if (net->ev_fork) cudaEventDestroy(net->ev_fork);
+    if (net->ev_join) cudaEventDestroy(net->ev_join);
+    if (net->side_stream) cudaStreamDestroy(net->side_stream);
     if (net->stream) cudaStreamDestroy(net->stream);
     delete net;
 }

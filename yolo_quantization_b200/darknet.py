@@ -333,15 +333,23 @@ def forward_upsample_layer_quant_gpu(x: np.ndarray, stride: int) -> np.ndarray:
     return out
 
 
-def forward_route_layer_quant_gpu(xs: Sequence[np.ndarray]) -> np.ndarray:
+def forward_route_layer_quant_gpu(xs: Sequence[np.ndarray], ups: Optional[Sequence[int]] = None) -> np.ndarray:
+    """Channel concat (route_layer.c:107-130).  ups[k] > 1: input k is stored at 1/ups[k] of the route's size and is
+    read through the nearest-neighbour upsample (upsample_layer.c:96-113 folded into the route)."""
+    ups = [1] * len(xs) if ups is None else [int(u) for u in ups]
     b, _, h, w = xs[0].shape
+    h, w = h * ups[0], w * ups[0]
     dins = [push_nchw_u8(x) for x in xs]
     cs = [int(x.shape[1]) for x in xs]
     ctot = sum(cs)
     dout = DeviceBuffer(b * h * w * channel_stride(ctot))
     ptrs = (C.c_void_p * len(xs))(*[d.ptr for d in dins])
     carr = (C.c_int * len(xs))(*cs)
-    check(_lib.load().yq_forward_route_layer_quant_gpu(ptrs, carr, len(xs), dout.ptr, b, h, w, None))
+    if any(u != 1 for u in ups):
+        uarr = (C.c_int * len(xs))(*ups)
+        check(_lib.load().yq_forward_route_layer_quant_up_gpu(ptrs, None, carr, uarr, len(xs), dout.ptr, None, b, h, w, None))
+    else:
+        check(_lib.load().yq_forward_route_layer_quant_gpu(ptrs, carr, len(xs), dout.ptr, b, h, w, None))
     out = pull_nhwc_u8(dout, b, ctot, h, w)
     for d in dins:
         d.free()
