@@ -1279,6 +1279,9 @@ extern "C" int yq_network_pull_layer(yq_network *net, int layer, int what, void 
     }
     if (what == 0) {
         if (!l.out_u8) return yq::fail("layer %d has no uint8 output", layer);
+        if (l.type == L_UPSAMPLE && l.fused_away)
+            return yq::fail("layer %d (upsample) is not materialised in this plan: the route behind it reads layer %d through the upsample "
+                            "(set_fusion(0), keep_acc or YQ_UPROUTE=0 keep the tensor)", layer, l.src);
         if (yq_nhwc_to_nchw_u8_geom(l.out_u8, net->scratch, net->batch, l.out_c, l.out_h, l.out_w, &l.geom, net->stream)) return -1;
     } else if (what == 1) {
         if (!l.out_acc) return yq::fail("layer %d has no int32 accumulator (conv layers only, after yq_network_set_debug(net,1))", layer);
