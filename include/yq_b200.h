@@ -197,6 +197,12 @@ YQ_API int yq_forward_route_layer_quant_geom_gpu(const uint8_t *const *inputs, c
 YQ_API int yq_forward_route_layer_quant_up_gpu(const uint8_t *const *inputs, const yq_act_geom *in_geoms, const int *in_c,
                                                const int *in_up, int n_inputs, uint8_t *out, const yq_act_geom *out_geom,
                                                int batch, int h, int w, void *stream);
+/* The same route with the inputs named by input_mask only (bit k = input k): the other inputs' channels of `out` are left
+ * untouched, so the copies of one route_layer (src/route_layer.c:107-117 loops over l.n inputs) may be issued as separate
+ * launches, each as soon as its input exists. */
+YQ_API int yq_forward_route_layer_quant_part_gpu(const uint8_t *const *inputs, const yq_act_geom *in_geoms, const int *in_c,
+                                                 const int *in_up, int n_inputs, unsigned input_mask, uint8_t *out,
+                                                 const yq_act_geom *out_geom, int batch, int h, int w, void *stream);
 /* replaces forward_yolo_layer's inference part (src/yolo_layer.c:132-146): float NCHW in/out,
  * logistic on channels {0,1} and {4..4+classes} of each anchor. */
 YQ_API int yq_forward_yolo_layer_gpu(const float *in, float *out, int batch, int n_anchors, int classes, int h,

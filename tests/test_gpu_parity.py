@@ -433,6 +433,24 @@ def test_route_reads_upsampled_inputs(built, cs, ups, hw):
     assert got.shape == want.shape and np.array_equal(got, want)
 
 
+@pytest.mark.parametrize("cs,ups,hw", [((128, 256), (2, 1), (26, 26)), ((3, 5, 8), (2, 1, 2), (4, 6)), ((16, 32, 16), (1, 1, 1), (5, 7))])
+def test_route_input_by_input(built, cs, ups, hw):
+    # the inputs of one route written by separate launches: each launch touches its own channels only
+    rng = np.random.default_rng(sum(cs) * 7 + sum(ups))
+    xs = [rng.integers(0, 256, size=(2, c, hw[0] // u, hw[1] // u), dtype=np.uint8) for c, u in zip(cs, ups)]
+    want = np.concatenate([np.stack([O.upsample(x[b], u) for b in range(2)]) if u > 1 else x for x, u in zip(xs, ups)], axis=1)
+    n = len(cs)
+    got = darknet.forward_route_layer_quant_gpu(xs, ups, parts=[1 << k for k in reversed(range(n))], fill=0xEE)
+    assert np.array_equal(got, want)
+    only_last = darknet.forward_route_layer_quant_gpu(xs, ups, parts=[1 << (n - 1)], fill=0xEE)
+    off = sum(cs[:-1])
+    assert np.array_equal(only_last[:, off:], want[:, off:]) and np.all(only_last[:, :off] == 0xEE)
+    if n > 2:
+        ends = darknet.forward_route_layer_quant_gpu(xs, ups, parts=[1 | 1 << (n - 1)], fill=0xEE)   # a mask with a gap
+        assert np.array_equal(ends[:, :cs[0]], want[:, :cs[0]]) and np.array_equal(ends[:, off:], want[:, off:])
+        assert np.all(ends[:, cs[0]:off] == 0xEE)
+
+
 def test_yolo(built):
     x = (np.random.default_rng(0).standard_normal((3, 30, 13, 13)) * 3).astype(np.float32)
     got = darknet.forward_yolo_layer_gpu(x, 3, 5)
@@ -700,21 +718,23 @@ def test_network_input_paths_agree(built, tiny_net_files, monkeypatch):
     net.free()
 
 
-@pytest.mark.parametrize("uproute,branch", [(1, 0), (0, 1), (1, 1)])
-def test_network_schedule_switches_keep_every_byte(built, tiny_net_files, monkeypatch, uproute, branch):
-    """YQ_UPROUTE (upsample folded into the route behind it: one launch less) and YQ_BRANCH_STREAM (the first detection
-    head on a second stream beside the layers after it) change the schedule only: same bytes out, eager and replayed."""
+@pytest.mark.parametrize("uproute,branch,early", [(1, 0, 0), (0, 1, 0), (1, 1, 0), (0, 1, 1), (1, 1, 1), (1, 0, 1)])
+def test_network_schedule_switches_keep_every_byte(built, tiny_net_files, monkeypatch, uproute, branch, early):
+    """YQ_UPROUTE (upsample folded into the route behind it: one launch less), YQ_BRANCH_STREAM (the first detection
+    head on a second stream beside the layers after it) and YQ_EARLY_ROUTE (layer 8 copied into route 20's tensor on
+    that stream right behind layer 8: one launch more) change the schedule only: same bytes out, eager and replayed."""
     cfg, wts, _, _ = tiny_net_files
     x = np.random.default_rng(23).integers(0, 256, size=(4, 3, 416, 416), dtype=np.uint8)
-    monkeypatch.setenv("YQ_UPROUTE", "0")
-    monkeypatch.setenv("YQ_BRANCH_STREAM", "0")
+    for k in ("YQ_UPROUTE", "YQ_BRANCH_STREAM", "YQ_EARLY_ROUTE"):
+        monkeypatch.setenv(k, "0")
     net = darknet.load_network(cfg, wts, batch=4)
     base, n_base = net.predict_u8(x).copy(), net.launches_per_forward
     net.free()
     monkeypatch.setenv("YQ_UPROUTE", str(uproute))
     monkeypatch.setenv("YQ_BRANCH_STREAM", str(branch))
+    monkeypatch.setenv("YQ_EARLY_ROUTE", str(early))
     net = darknet.load_network(cfg, wts, batch=4)
-    assert net.launches_per_forward == n_base - uproute
+    assert net.launches_per_forward == n_base - uproute + (1 if early and branch else 0)
     for graph in (False, True):
         net.use_graph(graph)
         for _ in range(4):

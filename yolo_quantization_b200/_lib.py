@@ -76,6 +76,7 @@ SIGNATURES = {
     "yq_forward_maxpool_layer_quant_geom_gpu": (_i, [_vp, C.POINTER(ActGeom), _vp, C.POINTER(ActGeom), _i, _i, _i, _i, _i, _i, _i, _vp]),
     "yq_forward_upsample_layer_quant_geom_gpu": (_i, [_vp, C.POINTER(ActGeom), _vp, C.POINTER(ActGeom), _i, _i, _i, _i, _i, _vp]),
     "yq_forward_route_layer_quant_geom_gpu": (_i, [C.POINTER(_vp), C.POINTER(ActGeom), C.POINTER(_i), _i, _vp, C.POINTER(ActGeom), _i, _i, _i, _vp]),
+    "yq_forward_route_layer_quant_part_gpu": (_i, [C.POINTER(_vp), C.POINTER(ActGeom), C.POINTER(_i), C.POINTER(_i), _i, C.c_uint, _vp, C.POINTER(ActGeom), _i, _i, _i, _vp]),
     "yq_forward_route_layer_quant_up_gpu": (_i, [C.POINTER(_vp), C.POINTER(ActGeom), C.POINTER(_i), C.POINTER(_i), _i, _vp, C.POINTER(ActGeom), _i, _i, _i, _vp]),
     "yq_conv_rows_supported": (_i, [_vp]),
     "yq_conv_rows_input_geom": (_i, [_vp, C.POINTER(ActGeom)]),

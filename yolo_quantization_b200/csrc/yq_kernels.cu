@@ -687,6 +687,8 @@ struct RouteArgs {
     int up[ROUTE_MAX_INPUTS];    // >= 1: the input holds (H/up) x (W/up) pixels
     Geo go;
     int n, cs_out, c_out, H, W;
+    int ch_lo, ch_hi;            // channels of `out` this launch covers
+    unsigned mask;               // inputs this launch copies
     long long pixels;
 };
 
@@ -695,61 +697,86 @@ __global__ void route_u8_kernel(const RouteArgs a, uint8_t *__restrict__ out, in
     yq_pdl_wait_then_release();
     const int n = blockIdx.x / a.H, y = blockIdx.x - n * a.H;
     if (vec) {
-        const int vpp = a.cs_out / 16, per_row = a.W * vpp;
+        const int vpp = (a.ch_hi - a.ch_lo) / 16, per_row = a.W * vpp;
         for (int j = blockIdx.y * blockDim.x + threadIdx.x; j < per_row; j += gridDim.y * blockDim.x) {
-            const int x = j / vpp, ch = (j - x * vpp) * 16;
+            const int x = j / vpp, ch = a.ch_lo + (j - x * vpp) * 16;
             uint4 val = make_uint4(0, 0, 0, 0);
+            bool mine = ch >= a.c_out;   // (channel-stride padding behind the last input: zeros, written with the last input)
             for (int k = 0; k < a.n; ++k)
-                if (ch >= a.off[k] && ch < a.off[k] + a.c[k])
+                if ((a.mask >> k & 1) && ch >= a.off[k] && ch < a.off[k] + a.c[k]) {
                     val = __ldg(reinterpret_cast<const uint4 *>(a.in[k] + a.g[k].pix(n, y / a.up[k], x / a.up[k]) * a.cs[k] + (ch - a.off[k])));
-            *reinterpret_cast<uint4 *>(out + a.go.pix(n, y, x) * a.cs_out + ch) = val;
+                    mine = true;
+                }
+            if (mine) *reinterpret_cast<uint4 *>(out + a.go.pix(n, y, x) * a.cs_out + ch) = val;
         }
     } else {
-        const int per_row = a.W * a.cs_out;
+        const int cpp = a.ch_hi - a.ch_lo, per_row = a.W * cpp;
         for (int j = blockIdx.y * blockDim.x + threadIdx.x; j < per_row; j += gridDim.y * blockDim.x) {
-            const int x = j / a.cs_out, ch = j - x * a.cs_out;
+            const int x = j / cpp, ch = a.ch_lo + (j - x * cpp);
             uint8_t val = 0;
+            bool mine = ch >= a.c_out;
             for (int k = 0; k < a.n; ++k)
-                if (ch >= a.off[k] && ch < a.off[k] + a.c[k]) val = a.in[k][a.g[k].pix(n, y / a.up[k], x / a.up[k]) * a.cs[k] + (ch - a.off[k])];
-            out[a.go.pix(n, y, x) * a.cs_out + ch] = val;
+                if ((a.mask >> k & 1) && ch >= a.off[k] && ch < a.off[k] + a.c[k]) {
+                    val = a.in[k][a.g[k].pix(n, y / a.up[k], x / a.up[k]) * a.cs[k] + (ch - a.off[k])];
+                    mine = true;
+                }
+            if (mine) out[a.go.pix(n, y, x) * a.cs_out + ch] = val;
         }
     }
 }
 
-extern "C" int yq_forward_route_layer_quant_up_gpu(const uint8_t *const *inputs, const yq_act_geom *in_geoms, const int *in_c, const int *in_up,
-                                                   int n_inputs, uint8_t *out, const yq_act_geom *out_geom, int batch, int h, int w, void *stream)
+// input_mask: bit k set = input k is copied by this call (the other inputs' channels of `out` are left alone), so that the
+// inputs of one route can be written by separate launches as they become ready.
+extern "C" int yq_forward_route_layer_quant_part_gpu(const uint8_t *const *inputs, const yq_act_geom *in_geoms, const int *in_c, const int *in_up,
+                                                     int n_inputs, unsigned input_mask, uint8_t *out, const yq_act_geom *out_geom, int batch, int h,
+                                                     int w, void *stream)
 {
     if (!inputs || !in_c || !out || n_inputs <= 0 || n_inputs > ROUTE_MAX_INPUTS || batch <= 0) return yq::fail("route: bad argument");
+    input_mask &= (1u << n_inputs) - 1u;
+    if (!input_mask) return yq::fail("route: empty input mask");
     RouteArgs a;
     memset(&a, 0, sizeof a);
-    int off = 0, vec = 1;
+    int off = 0, vec = 1, lo = -1, hi = 0;
     for (int i = 0; i < n_inputs; ++i) {
         const int up = in_up ? in_up[i] : 1;
         if (up < 1 || h % up || w % up) return yq::fail("route: input %d: upsample factor %d does not divide %dx%d", i, up, h, w);
         if (check_geom(in_geoms ? &in_geoms[i] : nullptr, h / up, w / up)) return -1;
+        if ((input_mask >> i & 1) && !inputs[i]) return yq::fail("route: input %d is NULL", i);
         a.in[i] = inputs[i];
         a.up[i] = up;
         a.c[i] = in_c[i];
         a.cs[i] = yq::channel_stride(in_c[i]);
         a.off[i] = off;
         a.g[i] = geo_of(in_geoms ? &in_geoms[i] : nullptr, h / up, w / up);
+        if (input_mask >> i & 1) {
+            if (lo < 0) lo = off;
+            hi = off + in_c[i];
+        }
         off += in_c[i];
         if (in_c[i] % 16) vec = 0;
     }
     if (check_geom(out_geom, h, w)) return -1;
     a.go = geo_of(out_geom, h, w);
     a.n = n_inputs;
+    a.mask = input_mask;
     a.c_out = off;
     a.cs_out = yq::channel_stride(off);
+    a.ch_lo = lo;
+    a.ch_hi = (input_mask >> (n_inputs - 1) & 1) ? a.cs_out : hi;
     a.H = h; a.W = w;
     a.pixels = (long long)batch * h * w;
     if (a.cs_out % 16) vec = 0;
     dim3 grid;
     int threads;
-    row_launch_shape(batch * h, vec ? w * (a.cs_out / 16) : w * a.cs_out, &grid, &threads);
+    row_launch_shape(batch * h, vec ? w * ((a.ch_hi - a.ch_lo) / 16) : w * (a.ch_hi - a.ch_lo), &grid, &threads);
     YQ_CUDA(yq::launch_pdl(route_u8_kernel, grid, dim3(threads), 0, (cudaStream_t)stream, a, out, vec));
     YQ_CHECK_LAUNCH();
     return 0;
+}
+extern "C" int yq_forward_route_layer_quant_up_gpu(const uint8_t *const *inputs, const yq_act_geom *in_geoms, const int *in_c, const int *in_up,
+                                                   int n_inputs, uint8_t *out, const yq_act_geom *out_geom, int batch, int h, int w, void *stream)
+{
+    return yq_forward_route_layer_quant_part_gpu(inputs, in_geoms, in_c, in_up, n_inputs, ~0u, out, out_geom, batch, h, w, stream);
 }
 extern "C" int yq_forward_route_layer_quant_geom_gpu(const uint8_t *const *inputs, const yq_act_geom *in_geoms, const int *in_c, int n_inputs,
                                                      uint8_t *out, const yq_act_geom *out_geom, int batch, int h, int w, void *stream)

@@ -120,6 +120,9 @@ struct Layer {
     bool use_flat = false;         // conv: flat-strip flavour (yq_conv_tc_flat.cu); input and output tensors are flat
     bool fuse_yolo = false;        // quant_stop conv: the following yolo layer is produced by this layer's epilogue (yolo: fused_away)
     bool fuse_up = false;          // route: inputs that are upsample layers are read through the upsample (upsample: fused_away)
+    unsigned early_mask = 0;       // route: inputs copied on the side stream as soon as they exist (see plan_early_copies())
+    cudaEvent_t ev_early = nullptr;
+    std::vector<std::pair<int, int>> early_copies;   // (route layer, input index) to issue behind this layer
     bool side = false;             // runs on the side stream: a detection branch nothing later reads (see plan())
     int halo_fill = 0;             // byte kept in the halo of out_u8: the zero point its consumer convolutions pad with
     int src = -2;                  // layer whose out_u8 this layer reads (-1: the network input); routes use `inputs`
@@ -130,6 +133,9 @@ struct Layer {
 
 #ifndef YQ_DEFAULT_UPROUTE
 #define YQ_DEFAULT_UPROUTE 1
+#endif
+#ifndef YQ_DEFAULT_EARLY_ROUTE
+#define YQ_DEFAULT_EARLY_ROUTE 0
 #endif
 #ifndef YQ_DEFAULT_BRANCH_STREAM
 #define YQ_DEFAULT_BRANCH_STREAM 1
@@ -155,6 +161,9 @@ struct yq_network {
     // YQ_BRANCH_STREAM: a detection branch that nothing later reads runs on a second stream beside the layers after it
     int fuse_uproute = getenv("YQ_UPROUTE") ? atoi(getenv("YQ_UPROUTE")) : YQ_DEFAULT_UPROUTE;
     int branch_stream = getenv("YQ_BRANCH_STREAM") ? atoi(getenv("YQ_BRANCH_STREAM")) : YQ_DEFAULT_BRANCH_STREAM;
+    // YQ_EARLY_ROUTE (needs the side stream): an old tensor a route concatenates is copied into the route's output on the
+    // side stream right behind its producer, under the convolutions in between, instead of in front of the route's consumer
+    int early_route = getenv("YQ_EARLY_ROUTE") ? atoi(getenv("YQ_EARLY_ROUTE")) : YQ_DEFAULT_EARLY_ROUTE;
     cudaStream_t side_stream = nullptr;
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     int conv_kernel = -1;
@@ -294,6 +303,40 @@ int tensor_of(const yq_network *net, int i)
 // m+1 .. i-1 in front of it (a detection head: convs + yolo) are read by nothing later, so they run on the side stream
 // while the main stream goes on with layer i.  Every main-stream layer must read main-stream tensors only; if any
 // does not, no layer is marked.
+bool side_stream_safe(const yq_network *net);
+
+// A route input that is at least three layers old (layer 8 under route 20 of yolov3-tiny) is copied behind its producer.
+void plan_early_copies(yq_network *net)
+{
+    const int n = (int)net->layers.size();
+    for (auto &l : net->layers) {
+        l.early_mask = 0;
+        l.early_copies.clear();
+    }
+    if (!net->branch_stream || !net->early_route || net->keep_acc || !side_stream_safe(net)) return;
+    for (int i = 0; i < n; ++i) {
+        Layer &r = net->layers[i];
+        if (r.type != L_ROUTE || r.inputs.size() < 2 || r.side) continue;
+        for (size_t k = 0; k < r.inputs.size(); ++k) {
+            const Layer &p = net->layers[r.inputs[k]];
+            if (p.type == L_UPSAMPLE && p.fused_away) continue;
+            const int t = tensor_of(net, r.inputs[k]);
+            if (t < 0 || t >= i - 3 || net->layers[t].side) continue;
+            if (!r.ev_early && cudaEventCreateWithFlags(&r.ev_early, cudaEventDisableTiming) != cudaSuccess) return;
+            r.early_mask |= 1u << k;
+            net->layers[t].early_copies.push_back({i, (int)k});
+            if (r.early_mask != (1u << r.inputs.size()) - 1u) ++net->launches;   // (one launch more unless the route's own launch vanished)
+        }
+    }
+}
+
+bool side_stream_safe(const yq_network *net)
+{
+    for (const auto &l : net->layers)
+        if (l.type == L_CONV && l.conv && !l.use_rows && !l.use_flat && l.conv->kernel != 0) return false;
+    return true;
+}
+
 void plan_side_branches(yq_network *net)
 {
     const int n = (int)net->layers.size();
@@ -301,8 +344,7 @@ void plan_side_branches(yq_network *net)
     // Two launches may now be in flight at once.  The flat-strip CTA pairs are sized so that two of them never share an SM
     // (yq_conv_tc_flat2x.cu); the multicast clusters of the per-tap flavour (yq_conv_tc.cu) carry no such guarantee, so a
     // network that runs any convolution on that flavour keeps the single stream.
-    for (const auto &l : net->layers)
-        if (l.type == L_CONV && l.conv && !l.use_rows && !l.use_flat && l.conv->kernel != 0) return;
+    if (!side_stream_safe(net)) return;
     for (int i = 1; i < n; ++i) {
         const Layer &r = net->layers[i];
         if (r.type != L_ROUTE) continue;
@@ -465,6 +507,7 @@ void plan(yq_network *net)
         --launches;
     net->launches = launches;
     plan_side_branches(net);
+    plan_early_copies(net);
 }
 
 bool conv_output_needed(const yq_network *net, int i)
@@ -497,6 +540,24 @@ int forward_body(yq_network *net, const uint8_t *in_u8_nchw, int *launches, bool
     const uint8_t *cur = net->in_nhwc;
     const yq_act_geom *cur_geom = &net->in_geom;
     const float *cur_f32 = nullptr;
+    const bool early_ok = !profile && net->side_stream;
+    auto issue_route = [&](Layer &r, unsigned mask, cudaStream_t s) -> int {
+        const uint8_t *ins[8];
+        yq_act_geom gs[8];
+        int cs[8], ups[8];
+        for (size_t k = 0; k < r.inputs.size(); ++k) {
+            const Layer *p = &net->layers[r.inputs[k]];
+            ups[k] = 1;
+            if (r.fuse_up && p->type == L_UPSAMPLE && p->fused_away) {   // read the upsample's own input
+                ups[k] = p->stride;
+                p = &net->layers[p->src];
+            }
+            ins[k] = p->out_u8;
+            gs[k] = p->geom;
+            cs[k] = p->out_c;
+        }
+        return yq_forward_route_layer_quant_part_gpu(ins, gs, cs, ups, (int)r.inputs.size(), mask, r.out_u8, &r.geom, net->batch, r.out_h, r.out_w, s);
+    };
     for (size_t i = 0; i < net->layers.size(); ++i) {
         Layer &l = net->layers[i];
         const bool side = l.side && !profile && net->side_stream;
@@ -558,23 +619,15 @@ int forward_body(yq_network *net, const uint8_t *in_u8_nchw, int *launches, bool
             break;
         case L_ROUTE:
             if (l.inputs.size() > 1) {
-                const uint8_t *ins[8];
-                yq_act_geom gs[8];
-                int cs[8], ups[8];
-                for (size_t k = 0; k < l.inputs.size(); ++k) {
-                    const Layer *p = &net->layers[l.inputs[k]];
-                    ups[k] = 1;
-                    if (l.fuse_up && p->type == L_UPSAMPLE && p->fused_away) {   // read the upsample's own input
-                        ups[k] = p->stride;
-                        p = &net->layers[p->src];
-                    }
-                    ins[k] = p->out_u8;
-                    gs[k] = p->geom;
-                    cs[k] = p->out_c;
+                unsigned mask = (1u << l.inputs.size()) - 1u;
+                if (early_ok && l.early_mask) {   // those inputs were copied on the side stream behind their producers
+                    YQ_CUDA(cudaStreamWaitEvent(st, l.ev_early, 0));
+                    mask &= ~l.early_mask;
                 }
-                if (yq_forward_route_layer_quant_up_gpu(ins, gs, cs, ups, (int)l.inputs.size(), l.out_u8, &l.geom, net->batch, l.out_h, l.out_w, st))
-                    return -1;
-                ++nl;
+                if (mask) {
+                    if (issue_route(l, mask, st)) return -1;
+                    ++nl;
+                }
             }   // a single-input route is an alias of its input (no copy)
             cur = l.out_u8;
             cur_geom = &l.geom;
@@ -586,6 +639,16 @@ int forward_body(yq_network *net, const uint8_t *in_u8_nchw, int *launches, bool
             ++nl;
             break;
         }
+        if (early_ok && !side)
+            for (const auto &ec : l.early_copies) {   // this layer's tensor into the routes that concatenate it much later
+                Layer &r = net->layers[ec.first];
+                YQ_CUDA(cudaEventRecord(net->ev_fork, net->stream));
+                YQ_CUDA(cudaStreamWaitEvent(net->side_stream, net->ev_fork, 0));
+                if (issue_route(r, 1u << ec.second, net->side_stream)) return -1;
+                ++nl;
+                YQ_CUDA(cudaEventRecord(r.ev_early, net->side_stream));
+                forked = true;
+            }
         if (profile) cudaEventRecord(net->prof_events[i + 2], st);
     }
     if (forked) {   // join: the forward is complete on net->stream
@@ -943,6 +1006,8 @@ extern "C" void yq_free_network(yq_network *net)
     cudaFree(net->in_quant);
     cudaFree(net->scratch);
     if (net->out_host_pinned) cudaFreeHost(net->out_host_pinned);
+    for (auto &l : net->layers)
+        if (l.ev_early) cudaEventDestroy(l.ev_early);
     if (net->ev_fork) cudaEventDestroy(net->ev_fork);
     if (net->ev_join) cudaEventDestroy(net->ev_join);
     if (net->side_stream) cudaStreamDestroy(net->side_stream);

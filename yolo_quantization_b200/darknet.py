@@ -333,9 +333,11 @@ def forward_upsample_layer_quant_gpu(x: np.ndarray, stride: int) -> np.ndarray:
     return out
 
 
-def forward_route_layer_quant_gpu(xs: Sequence[np.ndarray], ups: Optional[Sequence[int]] = None) -> np.ndarray:
+def forward_route_layer_quant_gpu(xs: Sequence[np.ndarray], ups: Optional[Sequence[int]] = None,
+                                 parts: Optional[Sequence[int]] = None, fill: int = 0) -> np.ndarray:
     """Channel concat (route_layer.c:107-130).  ups[k] > 1: input k is stored at 1/ups[k] of the route's size and is
-    read through the nearest-neighbour upsample (upsample_layer.c:96-113 folded into the route)."""
+    read through the nearest-neighbour upsample (upsample_layer.c:96-113 folded into the route).  parts: input masks,
+    one launch each, into an output pre-set to `fill` (the inputs of one route written as they become ready)."""
     ups = [1] * len(xs) if ups is None else [int(u) for u in ups]
     b, _, h, w = xs[0].shape
     h, w = h * ups[0], w * ups[0]
@@ -345,8 +347,12 @@ def forward_route_layer_quant_gpu(xs: Sequence[np.ndarray], ups: Optional[Sequen
     dout = DeviceBuffer(b * h * w * channel_stride(ctot))
     ptrs = (C.c_void_p * len(xs))(*[d.ptr for d in dins])
     carr = (C.c_int * len(xs))(*cs)
-    if any(u != 1 for u in ups):
-        uarr = (C.c_int * len(xs))(*ups)
+    uarr = (C.c_int * len(xs))(*ups)
+    if parts is not None:
+        check(_lib.load().yq_cuda_memset(dout.ptr, int(fill), dout.nbytes, None))
+        for m in parts:
+            check(_lib.load().yq_forward_route_layer_quant_part_gpu(ptrs, None, carr, uarr, len(xs), int(m), dout.ptr, None, b, h, w, None))
+    elif any(u != 1 for u in ups):
         check(_lib.load().yq_forward_route_layer_quant_up_gpu(ptrs, None, carr, uarr, len(xs), dout.ptr, None, b, h, w, None))
     else:
         check(_lib.load().yq_forward_route_layer_quant_gpu(ptrs, carr, len(xs), dout.ptr, b, h, w, None))
