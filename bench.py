@@ -8,7 +8,9 @@ layers, pools, upsample, routes, yolo heads) over one batch of B=128 synthetic i
 (BASELINE.json configs[2]; configs[3] is the same 128 images/GPU on 8 GPUs -> weak scaling).
 
   value  device-resident throughput: inputs already in HBM, CUDA-graph replay, CUDA events on the
-         network's stream, max over ranks.
+         networks' streams, max over ranks.  --streams S (default 2) keeps S forwards in flight per GPU, each on
+         its own network instance (own activation tensors and stream); K steps = K forwards in all, timed from
+         one start mark every stream waits for to the last stream's end mark.  --streams 1: one after the other.
   e2e    the same metric through the public host-buffer API (yq_network_submit_u8 / yq_network_collect, the
          2-deep pipelined form of network_predict): every step does the H2D of its uint8 batch from pinned
          memory, the forward and the D2H of both yolo heads inside the timed region.
