@@ -451,6 +451,18 @@ def test_route_input_by_input(built, cs, ups, hw):
         assert np.all(ends[:, cs[0]:off] == 0xEE)
 
 
+@pytest.mark.parametrize("cs,ups,hw", [((128, 256), (2, 1), (26, 26)), ((16, 16), (1, 2), (6, 10)), ((48, 16, 32), (2, 1, 2), (4, 6)), ((32,), (3,), (9, 6))])
+def test_route_rows_kernel(built, monkeypatch, cs, ups, hw):
+    # YQ_ROUTE_ROWS=1: one block per (output row, input); off by default until it has been timed
+    monkeypatch.setenv("YQ_ROUTE_ROWS", "1")
+    rng = np.random.default_rng(sum(cs) + 3 * sum(ups))
+    xs = [rng.integers(0, 256, size=(2, c, hw[0] // u, hw[1] // u), dtype=np.uint8) for c, u in zip(cs, ups)]
+    want = np.concatenate([np.stack([O.upsample(x[b], u) for b in range(2)]) if u > 1 else x for x, u in zip(xs, ups)], axis=1)
+    assert np.array_equal(darknet.forward_route_layer_quant_gpu(xs, ups), want)
+    n = len(cs)
+    assert np.array_equal(darknet.forward_route_layer_quant_gpu(xs, ups, parts=[1 << k for k in range(n)], fill=0xEE), want)
+
+
 def test_yolo(built):
     x = (np.random.default_rng(0).standard_normal((3, 30, 13, 13)) * 3).astype(np.float32)
     got = darknet.forward_yolo_layer_gpu(x, 3, 5)

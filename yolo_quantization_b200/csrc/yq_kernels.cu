@@ -689,6 +689,7 @@ struct RouteArgs {
     int n, cs_out, c_out, H, W;
     int ch_lo, ch_hi;            // channels of `out` this launch covers
     unsigned mask;               // inputs this launch copies
+    int sel[ROUTE_MAX_INPUTS];   // the same as a list (route_rows_u8_kernel: blockIdx.y picks one)
     long long pixels;
 };
 
@@ -722,6 +723,27 @@ __global__ void route_u8_kernel(const RouteArgs a, uint8_t *__restrict__ out, in
                 }
             if (mine) out[a.go.pix(n, y, x) * a.cs_out + ch] = val;
         }
+    }
+}
+
+// YQ_ROUTE_ROWS=1 (off by default: parity-tested on B200, not yet timed): the 16-byte-vector route with one block per
+// (output row, input) -- the per-vector loop over the inputs, the row decode and the pixel address arithmetic of
+// route_u8_kernel (239 warp instructions per vector, profiles/r1_route_full.csv) move out of the copy loop.
+__global__ void __launch_bounds__(256) route_rows_u8_kernel(const RouteArgs a, uint8_t *__restrict__ out)
+{
+    yq_pdl_wait_then_release();
+    const int k = a.sel[blockIdx.y];
+    const int n = blockIdx.x / a.H, y = blockIdx.x - n * a.H;
+    const int up = a.up[k], vk = a.c[k] >> 4;   // (vector path: c % 16 == 0, so the channel stride is c)
+    const int sh = (vk & (vk - 1)) == 0 ? __ffs(vk) - 1 : -1;
+    const uint4 *__restrict__ src = reinterpret_cast<const uint4 *>(a.in[k] + a.g[k].pix(n, y / up, 0) * a.cs[k]);
+    uint4 *__restrict__ dst = reinterpret_cast<uint4 *>(out + a.go.pix(n, y, 0) * a.cs_out + a.off[k]);
+    const int vo = a.cs_out >> 4, per_row = a.W * vk;
+#pragma unroll 2
+    for (int j = threadIdx.x; j < per_row; j += 256) {
+        const int x = sh >= 0 ? j >> sh : j / vk, v = j - x * vk;
+        const int xs = up == 1 ? x : (up == 2 ? x >> 1 : x / up);
+        dst[x * vo + v] = __ldg(src + xs * vk + v);
     }
 }
 
@@ -768,6 +790,15 @@ extern "C" int yq_forward_route_layer_quant_part_gpu(const uint8_t *const *input
     if (a.cs_out % 16) vec = 0;
     dim3 grid;
     int threads;
+    const char *rows_env = getenv("YQ_ROUTE_ROWS");
+    if (vec && rows_env && atoi(rows_env)) {
+        int nsel = 0;
+        for (int i = 0; i < n_inputs; ++i)
+            if (input_mask >> i & 1) a.sel[nsel++] = i;
+        YQ_CUDA(yq::launch_pdl(route_rows_u8_kernel, dim3((unsigned)(batch * h), (unsigned)nsel), dim3(256), 0, (cudaStream_t)stream, a, out));
+        YQ_CHECK_LAUNCH();
+        return 0;
+    }
     row_launch_shape(batch * h, vec ? w * ((a.ch_hi - a.ch_lo) / 16) : w * (a.ch_hi - a.ch_lo), &grid, &threads);
     YQ_CUDA(yq::launch_pdl(route_u8_kernel, grid, dim3(threads), 0, (cudaStream_t)stream, a, out, vec));
     YQ_CHECK_LAUNCH();
