@@ -252,7 +252,9 @@ def main():
     # --streams S > 1: S network instances (own activation tensors, own stream, same weights file) take the batches in turn,
     # so the thin tail layers of one forward share the SMs with the wide first layers of the next
     nets = [net]
-    for _ in range(1, max(1, args.streams)):
+    # (forced flavours run one forward at a time: the multicast-cluster per-tap kernel of --kernel 1 is not sized for sharing
+    # its SMs' TMEM columns with another launch's clusters)
+    for _ in range(1, max(1, args.streams if args.kernel < 0 else 1)):
         other = darknet.load_network(cfg, wts, batch=B, device=local)
         if args.kernel >= 0:
             other.set_conv_kernel(args.kernel)
