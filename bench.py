@@ -40,6 +40,14 @@ METRIC = "images/sec yolov3-tiny INT8 416x416"
 UNIT = "images/s"
 MACS_PER_IMAGE = 2_724_074_496
 NOMINAL_INT8_TOPS = 4500.0
+# --net yolov3: BASELINE configs[4] (full yolov3, 75 conv layers, INT8 per-channel, batch 64, HBM GB/s vs peak)
+NETS = {
+    "tiny": {"metric": METRIC, "macs": MACS_PER_IMAGE, "batch": 128,
+             "what": "yolov3-tiny INT8 per-channel (24 layers, relu6, 5 classes)", "configs": "BASELINE configs[2]; x{w} GPUs = configs[3] sharding"},
+    "yolov3": {"metric": "images/sec yolov3 INT8 416x416", "macs": 32_932_037_632, "batch": 64,
+               "what": "full yolov3 INT8 per-channel (107 layers: 75 conv, 23 quantized shortcut, leaky, 80 classes)",
+               "configs": "BASELINE configs[4]"},
+}
 
 
 def peaks():
@@ -115,6 +123,8 @@ def layer_work(li, batch, conv_written=True):
         return 2 * macs * batch, byts
     if t == 4:
         return 0, 2 * 4 * batch * li.out_c * li.out_h * li.out_w
+    if t == 5:      # quantized shortcut: two tensors read, one written
+        return 0, 3 * batch * li.out_h * li.out_w * li.out_c
     return 0, batch * (li.h * li.w * li.c + li.out_h * li.out_w * li.out_c)
 
 
@@ -161,10 +171,20 @@ def run_reference(args):
     return 0
 
 
-def cpu_baseline(cfg1, wts, img_f32, info, im):
+def cpu_baseline(cfg1, wts, img_f32, info, im, net="tiny"):
     from oracle import yq_oracle as O
     cores = os.cpu_count() or 1
     iters = 8
+    if net != "tiny":
+        # the reference has no quantized shortcut, so it cannot run this network: the oracle port (OpenMP over output channels) is timed
+        times = []
+        for _ in range(2):
+            t0 = time.perf_counter()
+            O.forward_network(info, im)
+            times.append(time.perf_counter() - t0)
+        return {"value": 1.0 / min(times), "unit": UNIT, "cores": cores, "kind": "port",
+                "sample": f"2 images at batch 1 (best), full yolov3 416x416, oracle port (exact-integer C restatement, OpenMP, {cores} threads); "
+                          "the reference itself cannot run a quantized shortcut"}
     if os.path.exists(O.REF_HARNESS_OMP):
         times = O.ref_times(O.run_reference("time", cfg1, wts, img_f32, str(iters), omp=True, threads=cores))
         kind = "reference"
@@ -203,7 +223,8 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--batch", type=int, default=128, help="images per GPU per step")
+    ap.add_argument("--batch", type=int, default=0, help="images per GPU per step (default: 128 for --net tiny, 64 for --net yolov3)")
+    ap.add_argument("--net", default="tiny", choices=sorted(NETS), help="tiny = the headline metric (BASELINE configs[2]); yolov3 = configs[4]")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--kernel", type=int, default=-1, help="-1 auto, 0 SIMT only, 1 tcgen05 where available")
     ap.add_argument("--no-graph", action="store_true")
@@ -212,8 +233,14 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
+    NET = NETS[args.net]
+    args.batch = args.batch or NET["batch"]
     _claim_stdout()
     if args.impl == "reference":
+        if args.net != "tiny":
+            # the reference has no quantized shortcut (src/shortcut_layer.c:62-67 is float only): it cannot run this network
+            emit({"impl": "reference", "unavailable": "the reference cannot run the full yolov3 in its QUANTIZATION=1 path (no quantized shortcut)"})
+            return 0
         return run_reference(args)
 
     import numpy as np
@@ -232,7 +259,7 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     B = args.batch
-    layers = synth.yolov3_tiny_quant()
+    layers = synth.yolov3_tiny_quant() if args.net == "tiny" else synth.yolov3_quant()
     tmp = tempfile.TemporaryDirectory()
     cfg = os.path.join(tmp.name, "tiny.cfg")
     cfg1 = os.path.join(tmp.name, "tiny_b1.cfg")
@@ -371,7 +398,7 @@ def main():
         traffic = None
         try:
             with open(os.path.join(ROOT, "profiles", "r1_traffic.json")) as f:
-                traffic = json.load(f).get(str(top["layer"])) if B == 128 else None
+                traffic = json.load(f).get(str(top["layer"])) if (B == 128 and args.net == "tiny") else None
         except Exception:
             pass
         roof.update(traffic=traffic, kernel=f"layer {top['layer']} ({top['type']}, flavour {top['kernel']})",
@@ -381,13 +408,13 @@ def main():
                                  f"HBM {pk['hbm_gbs']} GB/s; 'TFLOP/s' counts int8 ops") )
         ips = world * B * args.steps / (ms * 1e-3)
         ips_e2e = world * B * args.steps / (ms_e2e * 1e-3)
-        total_ops = 2 * MACS_PER_IMAGE
+        total_ops = 2 * NET["macs"]
+        step_bytes = sum(r["bytes"] for r in rows)
         line = {
-            "metric": METRIC, "value": ips, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "metric": NET["metric"], "value": ips, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u8", "data": "synthetic",
-            "config": {"workload": f"yolov3-tiny INT8 per-channel (24 layers, relu6, 5 classes), 416x416, batch {B} per GPU "
-                                   f"(BASELINE configs[2]; x{world} GPUs = configs[3] sharding)",
+            "config": {"workload": f"{NET['what']}, 416x416, batch {B} per GPU ({NET['configs'].format(w=world)})",
                        "global_batch": B * world, "parallelism": f"dp{world}", "cuda_graph": not args.no_graph, "streams": S,
                        "l2": f"{R} rotating input batches ({R * in_bytes >> 20} MiB) > 126 MB L2 and several hundred MiB of "
                              f"activations written per step; no explicit flush"},
@@ -396,6 +423,9 @@ def main():
             "gpu_launches": net.launches_per_forward * args.steps * world,
             "clocks": clocks,
             "roofline": roof,
+            # algorithmic activation + weight bytes of every launch of one step (unfused accounting per launch) over the step time
+            "hbm_gbs_algorithmic_whole_net": step_bytes / (ms / args.steps * 1e-3) / 1e9,
+            "hbm_frac_whole_net": step_bytes / (ms / args.steps * 1e-3) / 1e9 / pk["hbm_gbs"],
             "int8_tops_whole_net": ips / world * total_ops / 1e12,
             "frac_int8_peak_whole_net": ips / world * total_ops / 1e12 / p_int8,
             "layers": [{k: r[k] for k in ("layer", "type", "ms", "bound", "frac", "kernel", "fused")} for r in rows],
@@ -404,7 +434,7 @@ def main():
             im = synth.synthetic_image(1)
             img_f32 = os.path.join(tmp.name, "img.f32")
             synth.image_to_float(im).tofile(img_f32)
-            line["cpu_baseline"] = cpu_baseline(cfg1, wts, img_f32, info, im)
+            line["cpu_baseline"] = cpu_baseline(cfg1, wts, img_f32, info, im, args.net)
         emit(line)
     for n_ in nets:
         n_.free()

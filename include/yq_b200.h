@@ -122,6 +122,8 @@ YQ_API int yq_forward_convolutional_layer_quant_pool_gpu(yq_conv_layer *l, const
                                                          void *stream);
 YQ_API int yq_conv_can_fuse_maxpool(const yq_conv_layer *l);
 
+/* (declared below) the same convolution between halo-padded tensors: yq_forward_convolutional_layer_quant_geom_gpu */
+
 /* A halo-padded NHWC activation tensor: pixel (n, y, x) lives at
  *     base + (((size_t)n * rows_h + y + pad) * pitch_w + x + pad) * yq_channel_stride(c)
  * The halo (and any slack right / below the image) holds the CONSUMER's input zero point, which is what
@@ -129,6 +131,18 @@ YQ_API int yq_conv_can_fuse_maxpool(const yq_conv_layer *l);
 typedef struct yq_act_geom {
     int pad, pitch_w, rows_h;
 } yq_act_geom;
+
+/* forward_convolutional_layer_quant_inputi_outputi (src/convolutional_layer.c:694-761) between halo-padded tensors, any
+ * stride the reference's im2col takes (src/im2col.c:26-50; stride 1 and 2 have a tcgen05 flavour, the rest run SIMT):
+ * in_geom / out_geom describe the tensors (NULL = plain); only the interior of `out` is written.  in_halo_fill is the byte
+ * the input's halo is known to hold, or -1: when it equals the layer's zp_in (and the halo is at least l.pad wide) the
+ * kernel reads its padding from the halo (im2col.c:5-14 pads with zp_in), otherwise it treats everything outside the image
+ * as out of bounds and restores zp_in * sum(w - zp_w) per border tap in the epilogue.  Flavours that only take plain
+ * tensors (SIMT, c <= 32) fail on a padded geometry: yq_conv_geom_supported() says which kind the layer has. */
+YQ_API int yq_conv_geom_supported(const yq_conv_layer *l);
+YQ_API int yq_forward_convolutional_layer_quant_geom_gpu(yq_conv_layer *l, const uint8_t *in_u8, const yq_act_geom *in_geom, int in_halo_fill,
+                                                         uint8_t *out_u8, const yq_act_geom *out_geom, float *out_f32, int32_t *out_acc,
+                                                         int batch, void *stream);
 
 /* The "rows" flavour: 3x3 / stride 1 / pad 1 convolution + RELU6 + the following 2x2/2 max-pool in ONE launch
  * (convolutional_layer.c:694-751 + maxpool_layer.c:109-153 fused), for c <= 32 and c = 64 (n = 64 or 128).  It reads a halo-padded input
@@ -203,6 +217,18 @@ YQ_API int yq_forward_route_layer_quant_up_gpu(const uint8_t *const *inputs, con
 YQ_API int yq_forward_route_layer_quant_part_gpu(const uint8_t *const *inputs, const yq_act_geom *in_geoms, const int *in_c,
                                                  const int *in_up, int n_inputs, unsigned input_mask, uint8_t *out,
                                                  const yq_act_geom *out_geom, int batch, int h, int w, void *stream);
+/* Quantized shortcut -- an EXTENSION for the full yolov3 (BASELINE configs[4]): the reference's shortcut is float
+ * only (src/shortcut_layer.c:62-67, shortcut_cpu src/blas.c:456-477) and cannot feed a quantized convolution
+ * (src/network.c:248-255), so this layer's integer arithmetic is defined here and pinned by oracle/yq_oracle.c:yq_oracle_shortcut:
+ *     Ka = round(s_a / s_out * 2^16)   Kb = round(s_b / s_out * 2^16)                 (yq_shortcut_multiplier, in [1, 2^22))
+ *     out = clamp((((a - zp_a) * Ka + (b - zp_b) * Kb + 2^15) >> 16) + zp_out, 0, 255)       (activation = linear)
+ * a = the previous layer's output (net.input_uint8), b = the `from` layer's output_uint8_final, same h, w, c. */
+YQ_API int yq_shortcut_multiplier(float s_x, float s_out, int32_t *K);
+YQ_API int yq_forward_shortcut_layer_quant_gpu(const uint8_t *a, const uint8_t *b, uint8_t *out, int batch, int h, int w, int c,
+                                               int zp_a, int zp_b, int Ka, int Kb, int zp_out, void *stream);
+YQ_API int yq_forward_shortcut_layer_quant_geom_gpu(const uint8_t *a, const yq_act_geom *a_geom, const uint8_t *b,
+                                                    const yq_act_geom *b_geom, uint8_t *out, const yq_act_geom *out_geom, int batch,
+                                                    int h, int w, int c, int zp_a, int zp_b, int Ka, int Kb, int zp_out, void *stream);
 /* replaces forward_yolo_layer's inference part (src/yolo_layer.c:132-146): float NCHW in/out,
  * logistic on channels {0,1} and {4..4+classes} of each anchor. */
 YQ_API int yq_forward_yolo_layer_gpu(const float *in, float *out, int batch, int n_anchors, int classes, int h,
@@ -240,7 +266,7 @@ YQ_API int yq_nhwc_to_nchw_u8_geom(const uint8_t *in_nhwc, uint8_t *out_nchw, in
 typedef struct yq_network yq_network;
 
 typedef struct yq_layer_info {
-    int type;                 /* 0 conv, 1 maxpool, 2 route, 3 upsample, 4 yolo */
+    int type;                 /* 0 conv, 1 maxpool, 2 route, 3 upsample, 4 yolo, 5 shortcut (extension) */
     int c, h, w;              /* input  */
     int out_c, out_h, out_w;  /* output */
     int n, size, stride, pad, activation, batch_normalize, quant_stop_flag;

@@ -377,3 +377,38 @@ void yq_oracle_nms_sort(float *dets, int total, int classes, float thresh)
     }
     free(order);
 }
+
+/* ------------------------------------------------------------------------------------------------
+ * "next" row 8f-3: quantized shortcut -- an EXTENSION, NOT in the reference.
+ *
+ * The reference has only the float shortcut (src/shortcut_layer.c:62-67: copy the input, add the `from` layer's output
+ * through shortcut_cpu src/blas.c:456-477, then activate) and forward_network would hand the next quantized convolution a
+ * stale input_uint8 (src/network.c:248-255): SURVEY 0.10, Appendix F.  So nothing in the reference can pin this function;
+ * it IS the specification the CUDA path is held to ("parity unpinned by the reference" for this one layer type).
+ *
+ * Integer spec (dequant-add-requant with the layer's stored output scale, all integer):
+ *   a = previous layer's uint8 output (s_a, zp_a);  b = the `from` layer's uint8 output (s_b, zp_b), same shape
+ *   Ka = round(s_a / s_out * 2^16),  Kb = round(s_b / s_out * 2^16)          (double division of the float scales)
+ *   t  = (a - zp_a) * Ka + (b - zp_b) * Kb                                   (exact int32: Ka, Kb < 2^22)
+ *   q  = (t + 2^15) >> 16                                                    (arithmetic shift: round half up)
+ *   out = clamp(q + zp_out, 0, 255)                                          (saturates; activation = linear only)
+ * ---------------------------------------------------------------------------------------------- */
+int yq_oracle_shortcut_mult(float s_x, float s_out, int32_t *K)
+{
+    if (!(s_x > 0.f) || !(s_out > 0.f)) return -1;
+    double k = round((double)s_x / (double)s_out * 65536.0);
+    if (!(k >= 1.0) || k >= 4194304.0) return -1;
+    *K = (int32_t)k;
+    return 0;
+}
+
+void yq_oracle_shortcut(const uint8_t *a, const uint8_t *b, size_t n, int zp_a, int zp_b, int32_t Ka, int32_t Kb,
+                        int zp_out, uint8_t *out)
+{
+    for (size_t i = 0; i < n; ++i) {
+        int32_t t = ((int32_t)a[i] - zp_a) * Ka + ((int32_t)b[i] - zp_b) * Kb;
+        int32_t q = (t + 32768) >> 16;
+        int32_t r = q + zp_out;
+        out[i] = (uint8_t)(r < 0 ? 0 : r > 255 ? 255 : r);
+    }
+}

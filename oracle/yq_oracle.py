@@ -105,6 +105,25 @@ def upsample(x: np.ndarray, stride: int) -> np.ndarray:
     return out
 
 
+def shortcut_mult(s_x: float, s_out: float) -> int:
+    """K = round(s_x / s_out * 2^16) of the quantized-shortcut extension (oracle/yq_oracle.c: yq_oracle_shortcut_mult)."""
+    k = C.c_int32()
+    if lib().yq_oracle_shortcut_mult(C.c_float(s_x), C.c_float(s_out), C.byref(k)) != 0:
+        raise ValueError(f"shortcut multiplier {s_x}/{s_out} outside [2^-16, 64)")
+    return int(k.value)
+
+
+def shortcut(a: np.ndarray, b: np.ndarray, q_a, q_b, q_out) -> np.ndarray:
+    """Quantized shortcut (extension, not in the reference): a, b u8 of one shape; q_* = (scale, zero point)."""
+    a = np.ascontiguousarray(a, np.uint8)
+    b = np.ascontiguousarray(b, np.uint8)
+    assert a.shape == b.shape
+    out = np.empty(a.shape, np.uint8)
+    lib().yq_oracle_shortcut(_p(a, C.c_uint8), _p(b, C.c_uint8), C.c_size_t(a.size), int(q_a[1]), int(q_b[1]),
+                             shortcut_mult(q_a[0], q_out[0]), shortcut_mult(q_b[0], q_out[0]), int(q_out[1]), _p(out, C.c_uint8))
+    return out
+
+
 def yolo(x: np.ndarray, n_anchors: int, classes: int) -> np.ndarray:
     x = np.ascontiguousarray(x, np.float32)
     _, h, w = x.shape
@@ -204,6 +223,10 @@ def forward_network(info: Sequence, img_u8: np.ndarray, input_quant=(1.0 / 255.0
             o["u8"] = cur
         elif sl.kind == "route":
             cur = np.concatenate([outs[j]["u8"] for j in sl.inputs], axis=0)   # route_layer.c:107-117
+            o["u8"] = cur
+        elif sl.kind == "shortcut":
+            j = sl.inputs[0]                                                   # extension: see yq_oracle_shortcut
+            cur = shortcut(cur, outs[j]["u8"], prev_q, (info[j].s_out, info[j].zp_out), (sl.s_out, sl.zp_out))
             o["u8"] = cur
         elif sl.kind == "yolo":
             o["f32"] = yolo(cur_f32, len(sl.spec.mask), (sl.c // len(sl.spec.mask)) - 5)

@@ -1,0 +1,246 @@
+"""GPU (B200): BASELINE configs[4] -- the full yolov3 (75 conv, 23 shortcut, 4 route, 2 upsample, 3 yolo) as a network.
+
+* every distinct conv shape at its REAL spatial size (416 ... 13) against the oracle and, live, against the compiled
+  reference through the one-layer trick on a 2^24-safe input distribution;
+* the stride-2 down-samplers on the tcgen05 per-tap flavour (TMA box with elementStrides = 2), between plain, flat and
+  padded tensors, reading their padding from the halo or restoring it with the border-correction table;
+* the quantized shortcut (this repo's integer extension -- the reference has none, SURVEY 0.10: pinned by the oracle's
+  restatement of the spec only);
+* the 107-layer network against the oracle's layer walk, debug plan (every tensor + int32 accumulators) and production plan.
+Bit-exact for every integer / byte tensor; yolo floats within 1e-6 abs."""
+import zlib
+
+import numpy as np
+import pytest
+
+from oracle import yq_oracle as O
+from yolo_quantization_b200 import darknet, synth
+
+pytestmark = pytest.mark.gpu
+YOLO_ATOL = 1e-6
+
+
+def _rand_layer(rng, c, n, k, stride, act, zp_in, zp_out=33, s_out=0.05, h=12, w=12, quant_stop=None):
+    wq = rng.integers(0, 256, size=(n, c * k * k), dtype=np.uint8)
+    zp_w = rng.integers(0, 256, size=n, dtype=np.uint8)
+    s_w = (rng.random(n).astype(np.float32) * 0.01 + 0.001).astype(np.float32)
+    bias = (rng.standard_normal(n) * 0.5).astype(np.float32)
+    spec = synth.LayerSpec("conv", n, k, stride, 1, 0, act)
+    sl = synth.SynthLayer("conv", c, h, w, n, 0, 0, spec, s_out=s_out, biases=bias, s_w=s_w, zp_w=zp_w, w_u8=wq.reshape(n, c, k, k))
+    p = O.prepare_conv(sl, 0.02, zp_in)
+    qs = (1 if act == "linear" else 0) if quant_stop is None else quant_stop
+    layer = darknet.ConvolutionalLayerQuant(h, w, c, n, k, stride, k // 2, synth.ACT_CODES[act], wq, zp_w, p["biases_int32"], p["M_value"],
+                                            p["M0_right_shift_value"], zp_in, zp_out, s_out, quant_stop_flag=qs)
+    return layer, wq.reshape(n, c, k, k), zp_w, p
+
+
+def _check(got, x, wq, zp_w, p, stride, k, act, zp_in, zp_out, s_out=0.05, qs=0):
+    for b in range(x.shape[0]):
+        acc = O.conv_acc(x[b], wq, zp_w, stride, k // 2, zp_in)
+        if "acc" in got:
+            assert np.array_equal(got["acc"][b], acc), f"int32 accumulator mismatch, image {b}"
+        u8 = O.requant(acc, p["biases_int32"], p["M_value"], p["M0_right_shift_value"], synth.ACT_CODES[act], zp_out)
+        assert np.array_equal(got["u8"][b], u8), f"uint8 mismatch, image {b}"
+        if qs:
+            assert np.array_equal(got["f32"][b], O.dequant(u8, zp_out, s_out))
+
+
+STRIDE2_CASES = [
+    # c, h, w, n, zp_in, batch
+    (64, 16, 16, 128, 40, 2),
+    (128, 26, 26, 256, 17, 3),       # odd output rows per tile
+    (256, 12, 20, 512, 0, 2),        # zp_in = 0: no correction table at all
+    (512, 26, 26, 1024, 40, 1),      # yolov3's last down-sampler at its real size
+    (64, 9, 7, 48, 200, 2),          # odd sizes: (h + 2 - 3) / 2 + 1 rows, right / bottom taps stay inside
+    (192, 2, 2, 64, 9, 5),           # 1x1 outputs
+]
+
+
+@pytest.mark.parametrize("case", STRIDE2_CASES, ids=lambda c: "c%d_%dx%d_n%d_zi%d" % c[:5])
+def test_conv_stride2_tcgen05_vs_oracle(built, case):
+    """forward_convolutional_layer_quant_inputi_outputi is generic in stride (convolutional_layer.c:699-716, im2col.c:26-50);
+    3x3 / stride 2 with c % 64 == 0 runs the per-tap tcgen05 flavour.  Four tensor situations, all == oracle:
+    plain -> plain (zero fill + border correction), flat -> flat (padding read from the halo), padded with a foreign halo
+    byte -> plain (correction on a padded tensor), plain -> a wide padded tensor (only the interior may be written)."""
+    c, h, w, n, zp_in, batch = case
+    rng = np.random.default_rng(zlib.crc32(repr(case).encode()) + 11)
+    layer, wq, zp_w, p = _rand_layer(rng, c, n, 3, 2, "leaky", zp_in, h=h, w=w)
+    assert layer.kernel == 1 and layer.geom_supported
+    x = rng.integers(0, 256, size=(batch, c, h, w), dtype=np.uint8)
+    _check(layer.forward(x), x, wq, zp_w, p, 2, 3, "leaky", zp_in, 33)
+    oh, ow = layer.out_h, layer.out_w
+    for gi, go, fill in (("flat", "flat", None), ((2, w + 5, h + 3), None, (zp_in + 7) & 255), (None, (1, ow + 4, oh + 2), None),
+                         ((1, w + 2, h + 2), "flat", None)):
+        got = layer.forward_geom(x, gi, go, in_fill=fill)
+        assert got["halo_ok"], f"halo of the output was written ({gi} -> {go})"
+        _check(got, x, wq, zp_w, p, 2, 3, "leaky", zp_in, 33)
+    layer.free()
+
+
+@pytest.mark.parametrize("case", [(64, 13, 13, 128, 3, 40), (128, 9, 11, 64, 1, 5), (256, 6, 6, 255, 1, 0)], ids=lambda c: "c%d_%dx%d_n%d_k%d" % c[:5])
+def test_conv_stride1_per_tap_between_padded_tensors(built, case, monkeypatch):
+    """the per-tap flavour at stride 1 between tensors of any geometry (what a conv next to a conflicting tensor falls to)"""
+    c, h, w, n, k, zp_in = case
+    rng = np.random.default_rng(zlib.crc32(repr(case).encode()) + 12)
+    act = "linear" if n == 255 else "leaky"
+    layer, wq, zp_w, p = _rand_layer(rng, c, n, k, 1, act, zp_in, h=h, w=w)
+    x = rng.integers(0, 256, size=(2, c, h, w), dtype=np.uint8)
+    for gi, go, fill in (("flat", "flat", None), ("flat", None, zp_in ^ 0x55), (None, (2, w + 4, h + 4), None)):
+        got = layer.forward_geom(x, gi, go, in_fill=fill)
+        assert got["halo_ok"]
+        _check(got, x, wq, zp_w, p, 1, k, act, zp_in, 33, qs=1 if act == "linear" else 0)
+    layer.free()
+
+
+# (c, n, size, stride, activation, input h = w at 416x416)
+YOLOV3_REAL = [
+    (3, 32, 3, 1, "leaky", 416), (32, 64, 3, 2, "leaky", 416), (64, 32, 1, 1, "leaky", 208), (32, 64, 3, 1, "leaky", 208),
+    (64, 128, 3, 2, "leaky", 208), (128, 64, 1, 1, "leaky", 104), (64, 128, 3, 1, "leaky", 104),
+    (128, 256, 3, 2, "leaky", 104), (256, 128, 1, 1, "leaky", 52), (128, 256, 3, 1, "leaky", 52),
+    (256, 512, 3, 2, "leaky", 52), (512, 256, 1, 1, "leaky", 26), (256, 512, 3, 1, "leaky", 26),
+    (512, 1024, 3, 2, "leaky", 26), (1024, 512, 1, 1, "leaky", 13), (512, 1024, 3, 1, "leaky", 13),
+    (1024, 255, 1, 1, "linear", 13), (768, 256, 1, 1, "leaky", 26), (512, 255, 1, 1, "linear", 26),
+    (384, 128, 1, 1, "leaky", 52), (256, 255, 1, 1, "linear", 52),
+]
+
+
+@pytest.mark.parametrize("shape", YOLOV3_REAL, ids=lambda s: "c%d_n%d_k%d_s%d_%s_%d" % s)
+def test_full_yolov3_conv_shapes_at_real_sizes(built, shape, tmp_path):
+    """Every distinct convolution of the full yolov3 at the spatial size it has in the 416x416 network, through the flavour the
+    network's planner picks for it (flat / flat2 / flat2x, per-tap for the down-samplers, small-c), int32 accumulators and
+    uint8 outputs == oracle.  Where oracle/_ref is present the same layer also runs through the COMPILED REFERENCE (one-layer
+    cfg, l.forward called directly: SURVEY Appendix F) on the same bytes; the input stays below 25 so that the reference's
+    float-carried accumulator (gemm.c:279-296) remains exact -- asserted, not assumed."""
+    c, n, k, stride, act, hw = shape
+    s_in, zp_in = 0.03, 40 if c > 3 else 0
+    layers = synth.single_conv(n, k, stride, act, 1, 1 if act == "linear" else 0, act_scale=0.05, act_zp=33)
+    cfg, wts, img = (str(tmp_path / f) for f in ("l.cfg", "l.weights", "img.f32"))
+    synth.write_cfg(cfg, layers, width=hw, height=hw, channels=c)
+    info = synth.write_weights(wts, layers, width=hw, height=hw, channels=c, seed=hw + c, input_quant=(s_in, zp_in), identity_bn=False)
+    rng = np.random.default_rng(zlib.crc32(repr(shape).encode()) + 5)
+    x = rng.integers(0, 25, size=(c, hw, hw), dtype=np.uint8)
+    x.flat[0], x.flat[1] = 0, 255                  # the reference's dynamic input quantiser re-derives (s_in, zp_in) from these
+    sl = info[0]
+    p = O.prepare_conv(sl, s_in, zp_in)
+    qs = 1 if act == "linear" else 0
+    layer = darknet.ConvolutionalLayerQuant(hw, hw, c, n, k, stride, k // 2, synth.ACT_CODES[act], sl.w_u8, sl.zp_w, p["biases_int32"], p["M_value"],
+                                            p["M0_right_shift_value"], zp_in, 33, sl.s_out, quant_stop_flag=qs)
+    if layer.flat_supported and stride == 1:
+        got = layer.forward_flat(x[None], halo_fill=zp_in)
+    elif layer.geom_supported:
+        got = layer.forward_geom(x[None], "flat", "flat")
+    else:
+        got = layer.forward(x[None])
+    layer.free()
+    acc = O.conv_acc(x, sl.w_u8, sl.zp_w, stride, k // 2, zp_in)
+    assert np.array_equal(got["acc"][0], acc), "int32 accumulator vs oracle"
+    u8 = O.requant(acc, p["biases_int32"], p["M_value"], p["M0_right_shift_value"], synth.ACT_CODES[act], 33)
+    assert np.array_equal(got["u8"][0], u8), "uint8 vs oracle"
+    if O.have_reference():
+        synth.image_to_float(x, s_in, zp_in).tofile(img)
+        O.run_reference("layer", cfg, wts, img, str(tmp_path / "dump"), omp=True)
+        r = O.read_dump(str(tmp_path / "dump"))[0]
+        ref_in = np.fromfile(str(tmp_path / "dump" / "L00_input_uint8.bin"), dtype=np.uint8).reshape(c, hw, hw)
+        assert np.array_equal(ref_in, x) and r["zp_in"] == zp_in, "the reference's input quantiser did not reproduce the test tensor"
+        assert np.array_equal(r["biases_int32"], p["biases_int32"]) and np.array_equal(r["M0"], p["M0"])
+        assert np.array_equal(r["output_int32"], got["acc"][0]), "int32 accumulator vs the compiled reference"
+        assert np.array_equal(r["output_uint8"], got["u8"][0]), "uint8 vs the compiled reference"
+
+
+@pytest.mark.parametrize("c,h,w,batch", [(64, 16, 16, 2), (256, 13, 13, 3), (1024, 5, 7, 1), (24, 9, 4, 2), (3, 6, 5, 2)])
+def test_shortcut_vs_oracle(built, c, h, w, batch):
+    """the quantized shortcut (extension; spec in include/yq_b200.h) == its plain-C restatement, incl. saturation at both ends,
+    channel counts that leave pad lanes (24 -> stride 32, 3 -> stride 4: pad lanes stay zero) and halo-padded tensors."""
+    rng = np.random.default_rng(c * 31 + h)
+    a = rng.integers(0, 256, size=(batch, c, h, w), dtype=np.uint8)
+    b = rng.integers(0, 256, size=(batch, c, h, w), dtype=np.uint8)
+    for qa, qb, qo in (((0.02, 40), (0.03, 50), (0.03, 50)), ((0.05, 0), (0.05, 255), (0.011, 128)), ((0.001, 7), (0.5, 200), (0.02, 3))):
+        ref = np.stack([O.shortcut(a[i], b[i], qa, qb, qo) for i in range(batch)])
+        assert np.array_equal(darknet.forward_shortcut_layer_quant_gpu(a, b, qa, qb, qo), ref)
+        geoms = ((1, w + 1, h + 1), (0, w, h), (2, w + 7, h + 3))
+        assert np.array_equal(darknet.forward_shortcut_layer_quant_gpu(a, b, qa, qb, qo, geoms=geoms), ref)
+    assert ref.min() == 0 or ref.max() == 255       # the last case saturates
+    with pytest.raises(Exception, match="scale ratio"):
+        darknet.shortcut_multiplier(100.0, 0.01)
+
+
+def _yolov3_files(tmp_path, size, batch, seed=2):
+    layers = synth.yolov3_quant()
+    cfg, wts = str(tmp_path / "v3.cfg"), str(tmp_path / "v3.weights")
+    synth.write_cfg(cfg, layers, batch=batch, width=size, height=size)
+    info = synth.write_weights(wts, layers, width=size, height=size, seed=seed, identity_bn=False)
+    return cfg, wts, info
+
+
+def _walk(net, info, imgs, debug):
+    heads = net.split_heads(net.predict_u8(imgs))
+    for b in range(imgs.shape[0]):
+        ref = O.forward_network(info, imgs[b])
+        hi = 0
+        for i, (sl, r) in enumerate(zip(info, ref)):
+            li = net.layer_info(i)
+            if sl.kind == "yolo":
+                assert np.allclose(heads[hi][b], r["f32"], atol=YOLO_ATOL, rtol=0), f"yolo layer {i}"
+                hi += 1
+                continue
+            if sl.kind == "conv" and debug:
+                assert np.array_equal(net.pull_layer(i, "acc")[b], r["acc"]), f"layer {i} int32 mismatch (image {b})"
+            if not debug and (li.fused or (sl.kind == "conv" and sl.spec.quant_stop)):
+                continue                                  # not materialised in the production plan
+            assert np.array_equal(net.pull_layer(i, "u8")[b], r["u8"]), f"layer {i} ({sl.kind}) uint8 mismatch (image {b})"
+
+
+def test_yolov3_network_96_vs_oracle(built, tmp_path):
+    """BASELINE configs[4] as a NETWORK: all 107 layers at 96x96, batch 2 -- debug plan (every tensor, every int32
+    accumulator) and production plan (fused heads, flat strips, side streams) == the oracle's layer walk."""
+    cfg, wts, info = _yolov3_files(tmp_path, 96, 2)
+    assert sum(s.kind == "conv" for s in info) == 75 and sum(s.kind == "shortcut" for s in info) == 23
+    net = darknet.load_network(cfg, wts, batch=2)
+    assert net.n == 107
+    imgs = np.stack([synth.synthetic_image(s, 3, 96, 96) for s in (21, 22)])
+    net.set_debug(True)
+    _walk(net, info, imgs, debug=True)
+    dbg = net.predict_u8(imgs).copy()
+    net.set_debug(False)
+    _walk(net, info, imgs, debug=False)
+    assert np.array_equal(net.predict_u8(imgs), dbg)
+    kinds = [net.layer_info(i).kernel for i in range(net.n) if net.layer_info(i).type == 0]
+    assert 0 not in kinds, f"a convolution of the production plan runs the SIMT flavour: {kinds}"
+    net.use_graph(True)
+    for _ in range(2):
+        assert np.array_equal(net.predict_u8(imgs), dbg)
+    net.free()
+
+
+def test_yolov3_network_416_heads_vs_oracle(built, tmp_path):
+    """the real size: one 416x416 image in a batch of 3 (production plan, CUDA graph) -- the three yolo heads and the last
+    shortcut of every stage == oracle; every image equals its batch-1 run bit for bit."""
+    cfg, wts, info = _yolov3_files(tmp_path, 416, 3, seed=4)
+    imgs = np.stack([synth.synthetic_image(s) for s in (51, 52, 53)])
+    net = darknet.load_network(cfg, wts, batch=3)
+    net.use_graph(True)
+    flat = net.predict_u8(imgs).copy()
+    heads = net.split_heads(flat)
+    ref = O.forward_network(info, imgs[1])
+    for h, i in zip(heads, (82, 94, 106)):
+        assert np.allclose(h[1], ref[i]["f32"], atol=YOLO_ATOL, rtol=0), f"yolo layer {i}"
+    for i in (4, 11, 36, 61, 74):
+        assert np.array_equal(net.pull_layer(i, "u8")[1], ref[i]["u8"]), f"shortcut {i}"
+    net.free()
+    one = darknet.load_network(cfg, wts, batch=1)
+    for b in (0, 2):
+        h1 = one.split_heads(one.predict_u8(imgs[b:b + 1]))
+        for h3, h in zip(heads, h1):
+            assert np.array_equal(h3[b], h[0])
+    one.free()
+
+
+def test_shortcut_cfg_errors(built, tmp_path):
+    layers = [synth.LayerSpec("conv", 16, 3, activation="leaky"), synth.LayerSpec("conv", 32, 3, activation="leaky"),
+              synth.LayerSpec("shortcut", layers=(-2,))]
+    cfg, wts = str(tmp_path / "e.cfg"), str(tmp_path / "e.weights")
+    synth.write_cfg(cfg, layers, width=16, height=16)
+    with open(wts, "wb") as f:
+        f.write(b"\0" * 64)
+    with pytest.raises(Exception, match="differ in shape"):
+        darknet.load_network(cfg, wts)

@@ -163,7 +163,11 @@ int yq_tc_flat2x_forward(yq_conv_layer *l, void *state, const uint8_t *in_flat, 
 int yq_tc_supported(const yq_conv_layer *l);
 int yq_tc_prepare(yq_conv_layer *l);
 void yq_tc_free(yq_conv_layer *l);
+// in_geom / out_geom (null = plain) and in_halo_fill (-1 = unknown): only the per-tap TMA flavour takes halo-padded tensors
 int yq_tc_forward(yq_conv_layer *l, const uint8_t *in_u8, uint8_t *out_u8, uint8_t *out_pool, float *out_f32, int32_t *out_acc,
-                  int batch, cudaStream_t stream);
+                  int batch, cudaStream_t stream, const yq_act_geom *in_geom = nullptr, int in_halo_fill = -1,
+                  const yq_act_geom *out_geom = nullptr);
+int yq_tc_geom_supported(const yq_conv_layer *l);   // 1: the layer's current flavour is the per-tap TMA one (any tensor geometry)
+int yq_tc_cluster_enabled();                        // YQ_TC_CLUSTER: multicast clusters in the per-tap flavour (A/B switch, off)
 // 1 when this layer's current flavour can also emit the 2x2/stride-2 max-pooled tensor from its epilogue
 int yq_tc_can_fuse_pool(const yq_conv_layer *l);

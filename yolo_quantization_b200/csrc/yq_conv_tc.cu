@@ -47,6 +47,8 @@ struct TcArgs {
     int TW, TH, TN, tiles_x, tiles_y;
     int size, pad, cpt /* KC-chunks per tap */, CS;
     int H, W;
+    int stride;        // 1 or 2: the activation box steps through the input with elementStrides = stride
+    int cpad;          // coordinate offset of pixel (0, 0): l.pad when the map starts in the input's halo (which then holds zp_in), else 0
 };
 
 template <int BN>
@@ -164,13 +166,14 @@ __global__ void __launch_bounds__(TC_THREADS, 2) conv_u8_tc_kernel(const __grid_
                 const int tap = it / a.cpt, chunk = it - tap * a.cpt;
                 const int ky = tap / a.size, kx = tap - ky * a.size;
                 uint8_t *sa = smem + s * L::STAGE;
+                const int cx0 = x0 * a.stride + kx - a.pad + a.cpad, cy0 = y0 * a.stride + ky - a.pad + a.cpad;
                 if (!CLUSTER) {
-                    tma_load_4d(sa, &tmA, &full[s], chunk * KC, x0 + kx - a.pad, y0 + ky - a.pad, n0);
+                    tma_load_4d(sa, &tmA, &full[s], chunk * KC, cx0, cy0, n0);
                     tma_load_2d(sa + L::A_BYTES, &tmB, &full[s], tap * a.CS + chunk * KC, oc0);
                 } else {
                     // take turns: the CTA whose turn it is loads the stage for everyone sharing that operand
-                    if (CN == 1) tma_load_4d(sa, &tmA, &full[s], chunk * KC, x0 + kx - a.pad, y0 + ky - a.pad, n0);
-                    else if (it % CN == cy) tma_load_4d_mc(sa, &tmA, &full[s], chunk * KC, x0 + kx - a.pad, y0 + ky - a.pad, n0, mask_a);
+                    if (CN == 1) tma_load_4d(sa, &tmA, &full[s], chunk * KC, cx0, cy0, n0);
+                    else if (it % CN == cy) tma_load_4d_mc(sa, &tmA, &full[s], chunk * KC, cx0, cy0, n0, mask_a);
                     if (CM == 1) tma_load_2d(sa + L::A_BYTES, &tmB, &full[s], tap * a.CS + chunk * KC, oc0);
                     else if (it % CM == cx) tma_load_2d_mc(sa + L::A_BYTES, &tmB, &full[s], tap * a.CS + chunk * KC, oc0, mask_b);
                 }
@@ -211,7 +214,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) conv_u8_tc_kernel(const __grid_
         if (a.corr && valid) {
             for (int ky = 0; ky < a.size; ++ky)
                 for (int kx = 0; kx < a.size; ++kx) {
-                    const int iy = oy + ky - a.pad, ix = ox + kx - a.pad;
+                    const int iy = oy * a.stride + ky - a.pad, ix = ox * a.stride + kx - a.pad;
                     if (iy < 0 || iy >= a.H || ix < 0 || ix >= a.W) oob |= 1u << (ky * a.size + kx);
                 }
         }
@@ -317,22 +320,43 @@ struct TcState {
         const void *in;
         void *out;
         int batch;
-        bool operator<(const Key &o) const { return in != o.in ? in < o.in : out != o.out ? out < o.out : batch < o.batch; }
+        yq_act_geom gi, go;
+        int halo;
+        bool operator<(const Key &o) const
+        {
+            if (in != o.in) return in < o.in;
+            if (out != o.out) return out < o.out;
+            if (batch != o.batch) return batch < o.batch;
+            if (halo != o.halo) return halo < o.halo;
+            const int a[6] = {gi.pad, gi.pitch_w, gi.rows_h, go.pad, go.pitch_w, go.rows_h};
+            const int b[6] = {o.gi.pad, o.gi.pitch_w, o.gi.rows_h, o.go.pad, o.go.pitch_w, o.go.rows_h};
+            for (int i = 0; i < 6; ++i)
+                if (a[i] != b[i]) return a[i] < b[i];
+            return false;
+        }
     };
     std::map<Key, std::pair<CUtensorMap, CUtensorMap>> maps;
 };
 
-int encode_nhwc(CUtensorMap *m, const void *ptr, int B, int H, int W, int CS, int box_c, int TW, int TH, int TN)
+// 4-D map over an NHWC tensor stored in geometry g (plain when g is null).  halo > 0: coordinate (0, 0) is the halo pixel
+// (-halo, -halo) and the extents grow by 2 * halo (rows / images overlap their neighbours' shared halo: fine for a tensor map,
+// only the strides must be multiples of 16 bytes); halo = 0: the h x w interior, everything else out of bounds (zero fill on
+// loads, clipped on stores).  estride: the box picks every estride-th pixel in x and y (TW x TH pixels either way).
+int encode_nhwc(CUtensorMap *m, const void *ptr, const yq_act_geom *g, int halo, int B, int H, int W, int CS, int box_c, int TW, int TH, int TN, int estride)
 {
     EncodeTiledFn enc = get_encode();
     if (!enc) return yq::fail("cuTensorMapEncodeTiled is not available from this driver");
-    cuuint64_t dims[4] = {(cuuint64_t)CS, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
-    cuuint64_t strides[3] = {(cuuint64_t)CS, (cuuint64_t)W * CS, (cuuint64_t)H * W * CS};
-    cuuint32_t box[4] = {(cuuint32_t)box_c, (cuuint32_t)TW, (cuuint32_t)TH, (cuuint32_t)TN};
-    cuuint32_t es[4] = {1, 1, 1, 1};
-    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 4, const_cast<void *>(ptr), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+    const int gpad = g ? g->pad : 0, pitch = g ? g->pitch_w : W, rows = g ? g->rows_h : H;
+    const uint8_t *base = (const uint8_t *)ptr + ((size_t)(gpad - halo) * pitch + (gpad - halo)) * CS;
+    cuuint64_t dims[4] = {(cuuint64_t)CS, (cuuint64_t)(W + 2 * halo), (cuuint64_t)(H + 2 * halo), (cuuint64_t)B};
+    cuuint64_t strides[3] = {(cuuint64_t)CS, (cuuint64_t)pitch * CS, (cuuint64_t)rows * pitch * CS};
+    cuuint32_t box[4] = {(cuuint32_t)box_c, (cuuint32_t)(TW * estride), (cuuint32_t)(TH * estride), (cuuint32_t)TN};   // N pixels = box N * stride
+    cuuint32_t es[4] = {1, (cuuint32_t)estride, (cuuint32_t)estride, 1};
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 4, const_cast<uint8_t *>(base), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                      swizzle_for(box_c), CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) return yq::fail("cuTensorMapEncodeTiled(NHWC %dx%dx%dx%d box %d,%d,%d,%d) failed: %d", B, H, W, CS, box_c, TW, TH, TN, (int)r);
+    if (r != CUDA_SUCCESS)
+        return yq::fail("cuTensorMapEncodeTiled(NHWC %dx%dx%dx%d pitch %d rows %d box %d,%d,%d,%d stride %d) failed: %d", B, H, W, CS, pitch, rows, box_c, TW, TH,
+                        TN, estride, (int)r);
     return 0;
 }
 
@@ -340,7 +364,7 @@ int encode_nhwc(CUtensorMap *m, const void *ptr, int B, int H, int W, int CS, in
 void choose_tile(int B, int OH, int OW, int *tw, int *th, int *tn)
 {
     double best = -1;
-    for (int w = 1; w <= OW && w <= 128; ++w) {
+    for (int w = 1; w <= OW && w <= 128; ++w) {   // (box extent w * stride <= 256 holds for stride <= 2)
         const int txs = (OW + w - 1) / w;
         for (int h = 1; h <= OH && w * h <= 128; ++h) {
             const int tys = (OH + h - 1) / h;
@@ -430,7 +454,7 @@ int yq_tc_supported(const yq_conv_layer *l) { return tc_big_supported(l) || yq_t
 static int tc_big_supported(const yq_conv_layer *l)
 {
     if (!l->int_form || !l->fused_mult) return 0;   // the integer-form epilogue needs M0 * 2^-31 / 2^-s parameters
-    if (l->stride != 1) return 0;
+    if (l->stride != 1 && l->stride != 2) return 0;   // stride 2: the activation box walks the input with elementStrides = 2
     if (!(l->size == 1 || l->size == 3) || l->pad != l->size / 2) return 0;
     if (l->cs_in % 64) return 0;
     if (l->cs_out < 32) return 0;
@@ -508,22 +532,39 @@ void yq_tc_free(yq_conv_layer *l)
 
 int yq_tc_can_fuse_pool(const yq_conv_layer *l) { return l->kernel == 1 && l->tc_small != nullptr; }
 
-int yq_tc_forward(yq_conv_layer *l, const uint8_t *in_u8, uint8_t *out_u8, uint8_t *out_pool, float *out_f32, int32_t *out_acc, int batch,
-                  cudaStream_t stream)
+int yq_tc_geom_supported(const yq_conv_layer *l) { return l->kernel == 1 && l->tc && !l->tc_small; }
+
+int yq_tc_cluster_enabled()
 {
-    if (l->tc_small) return yq_tc_small_forward(l, l->tc_small, in_u8, out_u8, out_pool, out_f32, out_acc, batch, stream);
+    const char *e = getenv("YQ_TC_CLUSTER");
+    return e ? atoi(e) != 0 : 0;
+}
+
+int yq_tc_forward(yq_conv_layer *l, const uint8_t *in_u8, uint8_t *out_u8, uint8_t *out_pool, float *out_f32, int32_t *out_acc, int batch,
+                  cudaStream_t stream, const yq_act_geom *in_geom, int in_halo_fill, const yq_act_geom *out_geom)
+{
+    const bool plain_in = !in_geom || (in_geom->pad == 0 && in_geom->pitch_w == l->w && in_geom->rows_h == l->h);
+    const bool plain_out = !out_geom || (out_geom->pad == 0 && out_geom->pitch_w == l->out_w && out_geom->rows_h == l->out_h);
+    if (l->tc_small) {
+        if (!plain_in || !plain_out) return yq::fail("the small-c tcgen05 flavour reads and writes plain tensors only");
+        return yq_tc_small_forward(l, l->tc_small, in_u8, out_u8, out_pool, out_f32, out_acc, batch, stream);
+    }
     if (out_pool || !out_u8) return yq::fail("the TMA tcgen05 flavour has no fused max-pool output");
     TcState *st = (TcState *)l->tc;
     if (!st) return yq::fail("tcgen05 flavour was not prepared for this layer");
     int TW = 0, TH = 0, TN = 0;
     choose_tile(batch, l->out_h, l->out_w, &TW, &TH, &TN);
-    TcState::Key key{in_u8, out_u8, batch};
+    // padding comes out of the input's halo when that is wide enough and known to hold zp_in (im2col.c:5-14 pads with zp_in);
+    // otherwise the TMA unit zero-fills outside the image and the epilogue restores zp_in * sum(w - zp_w) per border tap
+    const int halo = (in_geom && in_geom->pad >= l->pad && in_halo_fill == l->zp_in) ? l->pad : 0;
+    const yq_act_geom gi = in_geom ? *in_geom : yq_act_geom{0, l->w, l->h}, go = out_geom ? *out_geom : yq_act_geom{0, l->out_w, l->out_h};
+    TcState::Key key{in_u8, out_u8, batch, gi, go, halo};
     auto it = st->maps.find(key);
     if (it == st->maps.end()) {
         if (st->maps.size() > 64) st->maps.clear();
         CUtensorMap tmA, tmO;
-        if (encode_nhwc(&tmA, in_u8, batch, l->h, l->w, l->cs_in, st->KC, TW, TH, TN)) return -1;
-        if (encode_nhwc(&tmO, out_u8, batch, l->out_h, l->out_w, l->cs_out, st->BN, TW, TH, TN)) return -1;
+        if (encode_nhwc(&tmA, in_u8, &gi, halo, batch, l->h, l->w, l->cs_in, st->KC, TW, TH, TN, l->stride)) return -1;
+        if (encode_nhwc(&tmO, out_u8, &go, 0, batch, l->out_h, l->out_w, l->cs_out, st->BN, TW, TH, TN, 1)) return -1;
         it = st->maps.emplace(key, std::make_pair(tmA, tmO)).first;
     }
     TcArgs a;
@@ -531,7 +572,9 @@ int yq_tc_forward(yq_conv_layer *l, const uint8_t *in_u8, uint8_t *out_u8, uint8
     a.ep = yq::make_epi(l);
     a.out_f32 = l->quant_stop_flag ? out_f32 : nullptr;
     a.out_acc = out_acc;
-    a.corr = st->corr;
+    a.corr = halo ? nullptr : st->corr;
+    a.stride = l->stride;
+    a.cpad = halo;
     a.B = batch; a.OH = l->out_h; a.OW = l->out_w; a.N = l->n; a.CSO = l->cs_out; a.n_pad = st->n_pad;
     a.TW = TW; a.TH = TH; a.TN = TN;
     a.tiles_x = (l->out_w + TW - 1) / TW;

@@ -473,6 +473,24 @@ extern "C" int yq_forward_convolutional_layer_quant_gpu(yq_conv_layer *l, const 
 
 extern "C" int yq_conv_can_fuse_maxpool(const yq_conv_layer *l) { return l ? yq_tc_can_fuse_pool(l) : 0; }
 
+extern "C" int yq_conv_geom_supported(const yq_conv_layer *l) { return l && yq_tc_geom_supported(l) ? 1 : 0; }
+extern "C" int yq_forward_convolutional_layer_quant_geom_gpu(yq_conv_layer *l, const uint8_t *in_u8, const yq_act_geom *in_geom, int in_halo_fill,
+                                                             uint8_t *out_u8, const yq_act_geom *out_geom, float *out_f32, int32_t *out_acc, int batch,
+                                                             void *stream)
+{
+    if (!l || !in_u8 || !out_u8 || batch <= 0) return yq::fail("yq_forward_convolutional_layer_quant_geom_gpu: bad argument");
+    if (l->quant_stop_flag && !out_f32) return yq::fail("quant_stop layer needs out_f32");
+    const bool plain_in = !in_geom || (in_geom->pad == 0 && in_geom->pitch_w == l->w && in_geom->rows_h == l->h);
+    const bool plain_out = !out_geom || (out_geom->pad == 0 && out_geom->pitch_w == l->out_w && out_geom->rows_h == l->out_h);
+    if (plain_in && plain_out) return yq_forward_convolutional_layer_quant_pool_gpu(l, in_u8, out_u8, nullptr, out_f32, out_acc, batch, stream);
+    if (!yq_tc_geom_supported(l)) return yq::fail("this layer's kernel flavour takes plain tensors only (see yq_conv_geom_supported)");
+    if (in_geom && (in_geom->pad < 0 || in_geom->pitch_w < l->w + in_geom->pad || in_geom->rows_h < l->h + in_geom->pad))
+        return yq::fail("input geometry does not hold a %dx%d tensor", l->h, l->w);
+    if (out_geom && (out_geom->pad < 0 || out_geom->pitch_w < l->out_w + out_geom->pad || out_geom->rows_h < l->out_h + out_geom->pad))
+        return yq::fail("output geometry does not hold a %dx%d tensor", l->out_h, l->out_w);
+    return yq_tc_forward(l, in_u8, out_u8, nullptr, out_f32, out_acc, batch, (cudaStream_t)stream, in_geom, in_halo_fill, out_geom);
+}
+
 static int check_geom(const yq_act_geom *g, int h, int w);
 extern "C" int yq_conv_flat_supported(const yq_conv_layer *l) { return l && l->tc_flat ? 1 : 0; }
 extern "C" int yq_act_geom_flat(int h, int w, yq_act_geom *g)
@@ -818,6 +836,99 @@ extern "C" int yq_forward_route_layer_quant_gpu(const uint8_t *const *inputs, co
                                                 uint8_t *out, int batch, int h, int w, void *stream)
 {
     return yq_forward_route_layer_quant_geom_gpu(inputs, nullptr, in_c, n_inputs, out, nullptr, batch, h, w, stream);
+}
+
+// ------------------------------------------------------------------------------------------------
+// quantized shortcut -- EXTENSION, not in the reference: its shortcut is float only (src/shortcut_layer.c:62-67 copies the
+// input and adds the `from` layer's output through shortcut_cpu, src/blas.c:456-477) and forward_network would hand the next
+// quantized convolution a stale input_uint8 (src/network.c:248-255).  Integer spec (include/yq_b200.h; the tests hold it to
+// a plain-C restatement of the same lines):
+//   Ka = round(s_a / s_out * 2^16), Kb = round(s_b / s_out * 2^16)
+//   out = clamp((((a - zp_a) * Ka + (b - zp_b) * Kb + 2^15) >> 16) + zp_out, 0, 255)
+// Device form: t = a * Ka + b * Kb + C0 with C0 = 2^15 + (zp_out << 16) - zp_a * Ka - zp_b * Kb, out = sat_u8(t >> 16): the same
+// integer (zp_out << 16 passes through the arithmetic shift unchanged).  HBM-bound: 2 bytes read + 1 written per element.
+// ------------------------------------------------------------------------------------------------
+extern "C" int yq_shortcut_multiplier(float s_x, float s_out, int32_t *K)
+{
+    if (!K) return yq::fail("yq_shortcut_multiplier: null argument");
+    if (!(s_x > 0.f) || !(s_out > 0.f)) return yq::fail("shortcut: scales must be positive (%g, %g)", (double)s_x, (double)s_out);
+    const double k = round((double)s_x / (double)s_out * 65536.0);
+    if (!(k >= 1.0) || k >= 4194304.0) return yq::fail("shortcut: scale ratio %g outside [2^-16, 64)", (double)s_x / (double)s_out);
+    *K = (int32_t)k;
+    return 0;
+}
+
+__device__ __forceinline__ uint32_t shortcut4(uint32_t a, uint32_t b, int Ka, int Kb, int C0)
+{
+    int t0 = (int)(a & 0xff) * Ka + (int)(b & 0xff) * Kb + C0;
+    int t1 = (int)((a >> 8) & 0xff) * Ka + (int)((b >> 8) & 0xff) * Kb + C0;
+    int t2 = (int)((a >> 16) & 0xff) * Ka + (int)((b >> 16) & 0xff) * Kb + C0;
+    int t3 = (int)(a >> 24) * Ka + (int)(b >> 24) * Kb + C0;
+    uint32_t lo, hi;
+    // cvt.pack.sat.u8.s32: d = {sat_u8(x), sat_u8(y)} in the low half, the upper half from c
+    asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, 0;" : "=r"(hi) : "r"(t3 >> 16), "r"(t2 >> 16));
+    asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(lo) : "r"(t1 >> 16), "r"(t0 >> 16), "r"(hi));
+    return lo;
+}
+
+// One block row = one image row (n, y); threads walk its 16-byte vectors.  VEC = 0: one byte per thread (c % 16 != 0 never
+// happens for channel strides > 4, kept for cs = 4).
+__device__ __forceinline__ uint32_t keep_bytes(uint32_t v, int n)   // keep the n low bytes (n <= 0: none, n >= 4: all)
+{
+    return n >= 4 ? v : (n <= 0 ? 0u : v & ((1u << (8 * n)) - 1u));
+}
+
+__global__ void __launch_bounds__(256) shortcut_u8_kernel(const uint8_t *__restrict__ a, const uint8_t *__restrict__ b, uint8_t *__restrict__ out, int H, int W,
+                                                          int c, int cs, int Ka, int Kb, int C0, Geo ga, Geo gb, Geo go)
+{
+    yq_pdl_wait_then_release();
+    const int n = blockIdx.x / H, y = blockIdx.x - n * H;
+    if (cs % 16 == 0) {
+        const int per_row = W * (cs / 16);   // a row's interior is contiguous in every geometry
+        const uint4 *pa = reinterpret_cast<const uint4 *>(a + ga.pix(n, y, 0) * cs);
+        const uint4 *pb = reinterpret_cast<const uint4 *>(b + gb.pix(n, y, 0) * cs);
+        uint4 *po = reinterpret_cast<uint4 *>(out + go.pix(n, y, 0) * cs);
+        for (int j = blockIdx.y * blockDim.x + threadIdx.x; j < per_row; j += gridDim.y * blockDim.x) {
+            const uint4 va = __ldg(pa + j), vb = __ldg(pb + j);
+            uint4 r = make_uint4(shortcut4(va.x, vb.x, Ka, Kb, C0), shortcut4(va.y, vb.y, Ka, Kb, C0), shortcut4(va.z, vb.z, Ka, Kb, C0),
+                                 shortcut4(va.w, vb.w, Ka, Kb, C0));
+            if (c != cs) {   // pad channels stay zero
+                const int left = c - (j % (cs / 16)) * 16;
+                r = make_uint4(keep_bytes(r.x, left), keep_bytes(r.y, left - 4), keep_bytes(r.z, left - 8), keep_bytes(r.w, left - 12));
+            }
+            po[j] = r;
+        }
+    } else {
+        const int per_row = W * (cs / 4);
+        const uint32_t *pa = reinterpret_cast<const uint32_t *>(a + ga.pix(n, y, 0) * cs);
+        const uint32_t *pb = reinterpret_cast<const uint32_t *>(b + gb.pix(n, y, 0) * cs);
+        uint32_t *po = reinterpret_cast<uint32_t *>(out + go.pix(n, y, 0) * cs);
+        for (int j = blockIdx.y * blockDim.x + threadIdx.x; j < per_row; j += gridDim.y * blockDim.x)
+            po[j] = keep_bytes(shortcut4(__ldg(pa + j), __ldg(pb + j), Ka, Kb, C0), c - (j % (cs / 4)) * 4);
+    }
+}
+
+extern "C" int yq_forward_shortcut_layer_quant_geom_gpu(const uint8_t *a, const yq_act_geom *a_geom, const uint8_t *b, const yq_act_geom *b_geom, uint8_t *out,
+                                                        const yq_act_geom *out_geom, int batch, int h, int w, int c, int zp_a, int zp_b, int Ka, int Kb,
+                                                        int zp_out, void *stream)
+{
+    if (!a || !b || !out || batch <= 0 || h <= 0 || w <= 0 || c <= 0) return yq::fail("shortcut: bad argument");
+    if (Ka < 1 || Kb < 1 || Ka >= (1 << 22) || Kb >= (1 << 22)) return yq::fail("shortcut: multipliers must lie in [1, 2^22) (see yq_shortcut_multiplier)");
+    if (check_geom(a_geom, h, w) || check_geom(b_geom, h, w) || check_geom(out_geom, h, w)) return -1;
+    const int cs = yq::channel_stride(c);
+    const int C0 = 32768 + ((zp_out & 0xff) << 16) - (zp_a & 0xff) * Ka - (zp_b & 0xff) * Kb;
+    dim3 grid;
+    int threads;
+    row_launch_shape(batch * h, w * (cs % 16 == 0 ? cs / 16 : cs / 4), &grid, &threads);
+    YQ_CUDA(yq::launch_pdl(shortcut_u8_kernel, grid, dim3(threads), 0, (cudaStream_t)stream, a, b, out, h, w, c, cs, Ka, Kb, C0, geo_of(a_geom, h, w),
+                           geo_of(b_geom, h, w), geo_of(out_geom, h, w)));
+    YQ_CHECK_LAUNCH();
+    return 0;
+}
+extern "C" int yq_forward_shortcut_layer_quant_gpu(const uint8_t *a, const uint8_t *b, uint8_t *out, int batch, int h, int w, int c, int zp_a, int zp_b,
+                                                   int Ka, int Kb, int zp_out, void *stream)
+{
+    return yq_forward_shortcut_layer_quant_geom_gpu(a, nullptr, b, nullptr, out, nullptr, batch, h, w, c, zp_a, zp_b, Ka, Kb, zp_out, stream);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -24,7 +24,8 @@
 
 namespace {
 
-enum LType { L_CONV = 0, L_MAXPOOL = 1, L_ROUTE = 2, L_UPSAMPLE = 3, L_YOLO = 4 };
+enum LType { L_CONV = 0, L_MAXPOOL = 1, L_ROUTE = 2, L_UPSAMPLE = 3, L_YOLO = 4, L_SHORTCUT = 5 };
+constexpr int MAX_ROUTE_INPUTS = 8;   // = ROUTE_MAX_INPUTS of the route kernel's by-value argument block (yq_kernels.cu)
 
 struct Section {
     std::string type;
@@ -96,7 +97,10 @@ struct Layer {
     int c = 0, h = 0, w = 0, out_c = 0, out_h = 0, out_w = 0;
     int n = 0, size = 0, stride = 1, pad = 0, activation = YQ_LINEAR, bn = 0;
     int quantized = 0, quant_stop = 0, first_time = 0;
-    std::vector<int> inputs;   // route
+    std::vector<int> inputs;   // route: the concatenated layers; shortcut: {from}
+    int Ka = 0, Kb = 0;        // shortcut (extension): round(s_prev / s_out * 2^16), round(s_from / s_out * 2^16)
+    int zp_a = 0, zp_b = 0;    // shortcut: zero points of the previous layer's and the `from` layer's outputs
+    bool use_geom = false;     // conv: per-tap TMA flavour between tensors of any geometry (yq_forward_convolutional_layer_quant_geom_gpu)
     int classes = 0, n_anchors = 0;
     std::vector<float> anchor_w, anchor_h;   // yolo: anchors selected by mask (l.biases[2*mask[n]], [2*mask[n]+1])
     // quantisation state as in `struct layer`
@@ -284,7 +288,7 @@ bool conv_output_needed(const yq_network *net, int i);
 bool routed_from(const yq_network *net, int i)
 {
     for (const auto &l : net->layers)
-        if (l.type == L_ROUTE)
+        if (l.type == L_ROUTE || l.type == L_SHORTCUT)
             for (int idx : l.inputs)
                 if (idx == i) return true;
     return false;
@@ -332,6 +336,8 @@ void plan_early_copies(yq_network *net)
 
 bool side_stream_safe(const yq_network *net)
 {
+    // (only the multicast-cluster form of the per-tap flavour has CTAs that wait for each other; it is an A/B switch, off by default)
+    if (!yq_tc_cluster_enabled()) return true;
     for (const auto &l : net->layers)
         if (l.type == L_CONV && l.conv && !l.use_rows && !l.use_flat && l.conv->kernel != 0) return false;
     return true;
@@ -354,7 +360,7 @@ void plan_side_branches(yq_network *net)
         bool ok = true;
         for (int j = m + 1; j < i && ok; ++j) ok = !net->layers[j].side && net->layers[j].src >= m;
         for (int j = i; j < n && ok; ++j)
-            if (net->layers[j].type == L_ROUTE)
+            if (net->layers[j].type == L_ROUTE || net->layers[j].type == L_SHORTCUT)
                 for (int idx : net->layers[j].inputs) ok = ok && !(idx > m && idx < i);
         if (ok)
             for (int j = m + 1; j < i; ++j) net->layers[j].side = true;
@@ -363,11 +369,9 @@ void plan_side_branches(yq_network *net)
     for (int i = 0; i < n && ok; ++i) {
         const Layer &l = net->layers[i];
         if (l.side) continue;
-        if (l.type == L_ROUTE) {
+        if (l.type == L_ROUTE || l.type == L_SHORTCUT)
             for (int idx : l.inputs) ok = ok && !net->layers[idx].side;
-        } else if (l.src >= 0) {
-            ok = !net->layers[l.src].side;
-        }
+        if (l.type != L_ROUTE && l.src >= 0) ok = ok && !net->layers[l.src].side;
     }
     if (!ok)
         for (auto &l : net->layers) l.side = false;
@@ -424,6 +428,8 @@ void plan(yq_network *net)
                 yq_act_geom_flat(l.h, l.w, &g);
                 need(l.src, 2, &g, l.zp_in);
                 need(i, 2, &g, -1);
+            } else if (yq_conv_geom_supported(l.conv)) {
+                // the per-tap TMA flavour reads and writes through tensor maps built for whatever geometry the tensors have
             } else {
                 need(l.src, 1, nullptr, -1);
                 const bool fuses = net->fusion && i + 1 < n && net->layers[i + 1].type == L_MAXPOOL && net->layers[i + 1].size == 2 &&
@@ -448,7 +454,7 @@ void plan(yq_network *net)
     // ---- apply
     for (int i = 0; i < n; ++i) {
         Layer &l = net->layers[i];
-        l.fuse_pool = l.fused_away = l.use_rows = l.use_flat = l.fuse_yolo = l.fuse_up = l.side = false;
+        l.fuse_pool = l.fused_away = l.use_rows = l.use_flat = l.use_geom = l.fuse_yolo = l.fuse_up = l.side = false;
         l.geom = yq_act_geom{0, l.out_w, l.out_h};
         l.halo_fill = 0;
     }
@@ -479,7 +485,7 @@ void plan(yq_network *net)
             int reads = 0, others = 0;
             for (int idx : l.inputs) reads += idx == i - 1;
             for (int j = 0; j < n; ++j)
-                if (j != i && net->layers[j].type == L_ROUTE)
+                if (j != i && (net->layers[j].type == L_ROUTE || net->layers[j].type == L_SHORTCUT))
                     for (int idx : net->layers[j].inputs) others += idx == i - 1;
             if (reads == 1 && others == 0 && l.out_h % u.stride == 0 && l.out_w % u.stride == 0) l.fuse_up = u.fused_away = true;
         }
@@ -494,6 +500,8 @@ void plan(yq_network *net)
                 l.use_flat = true;
                 if (net->fusion && l.quant_stop && i + 1 < n && net->layers[i + 1].type == L_YOLO && l.n % (net->layers[i + 1].classes + 5) == 0)
                     l.fuse_yolo = net->layers[i + 1].fused_away = true;
+            } else if (yq_conv_geom_supported(l.conv)) {
+                l.use_geom = true;
             } else if (net->fusion && i + 1 < n && yq_conv_can_fuse_maxpool(l.conv)) {
                 Layer &p = net->layers[i + 1];
                 if (p.type == L_MAXPOOL && p.size == 2 && p.stride == 2 && p.pad == 1) l.fuse_pool = p.fused_away = true;
@@ -539,6 +547,7 @@ int forward_body(yq_network *net, const uint8_t *in_u8_nchw, int *launches, bool
     if (profile) cudaEventRecord(net->prof_events[1], st);
     const uint8_t *cur = net->in_nhwc;
     const yq_act_geom *cur_geom = &net->in_geom;
+    int cur_fill = net->in_halo_fill;       // the byte the current tensor's halo holds (meaningful when cur_geom->pad > 0)
     const float *cur_f32 = nullptr;
     const bool early_ok = !profile && net->side_stream;
     auto issue_route = [&](Layer &r, unsigned mask, cudaStream_t s) -> int {
@@ -587,6 +596,10 @@ int forward_body(yq_network *net, const uint8_t *in_u8_nchw, int *launches, bool
                 if (yq_forward_convolutional_layer_quant_flat_gpu(l.conv, cur, l.out_u8, l.halo_fill, l.out_f32, net->keep_acc ? l.out_acc : nullptr,
                                                                   net->batch, st))
                     return -1;
+            } else if (l.use_geom) {
+                if (yq_forward_convolutional_layer_quant_geom_gpu(l.conv, cur, cur_geom, cur_geom->pad ? cur_fill : -1, l.out_u8, &l.geom, l.out_f32,
+                                                                  net->keep_acc ? l.out_acc : nullptr, net->batch, st))
+                    return -1;
             } else if (l.fuse_pool) {
                 uint8_t *conv_out = conv_output_needed(net, (int)i) ? l.out_u8 : nullptr;
                 if (yq_forward_convolutional_layer_quant_pool_gpu(l.conv, cur, conv_out, net->layers[i + 1].out_u8, l.out_f32,
@@ -599,8 +612,20 @@ int forward_body(yq_network *net, const uint8_t *in_u8_nchw, int *launches, bool
             ++nl;
             cur = l.out_u8;
             cur_geom = &l.geom;
+            cur_fill = l.halo_fill;
             cur_f32 = l.out_f32;
             break;
+        case L_SHORTCUT: {
+            const Layer &f = net->layers[l.inputs[0]];
+            if (yq_forward_shortcut_layer_quant_geom_gpu(cur, cur_geom, f.out_u8, &f.geom, l.out_u8, &l.geom, net->batch, l.h, l.w, l.c, l.zp_a, l.zp_b, l.Ka,
+                                                         l.Kb, l.zp_out, st))
+                return -1;
+            ++nl;
+            cur = l.out_u8;
+            cur_geom = &l.geom;
+            cur_fill = l.halo_fill;
+            break;
+        }
         case L_MAXPOOL:
             if (!l.fused_away) {
                 if (yq_forward_maxpool_layer_quant_geom_gpu(cur, cur_geom, l.out_u8, &l.geom, net->batch, l.h, l.w, l.c, l.size, l.stride, l.pad, st))
@@ -609,6 +634,7 @@ int forward_body(yq_network *net, const uint8_t *in_u8_nchw, int *launches, bool
             }
             cur = l.out_u8;
             cur_geom = &l.geom;
+            cur_fill = l.halo_fill;
             break;
         case L_UPSAMPLE:
             if (l.fused_away) break;   // the route behind it reads `cur` through the upsample
@@ -616,6 +642,7 @@ int forward_body(yq_network *net, const uint8_t *in_u8_nchw, int *launches, bool
             ++nl;
             cur = l.out_u8;
             cur_geom = &l.geom;
+            cur_fill = l.halo_fill;
             break;
         case L_ROUTE:
             if (l.inputs.size() > 1) {
@@ -631,6 +658,7 @@ int forward_body(yq_network *net, const uint8_t *in_u8_nchw, int *launches, bool
             }   // a single-input route is an alias of its input (no copy)
             cur = l.out_u8;
             cur_geom = &l.geom;
+            cur_fill = l.halo_fill;
             break;
         case L_YOLO:
             if (l.fused_away) break;
@@ -728,6 +756,10 @@ extern "C" yq_network *yq_load_network(const char *cfg, const char *weights, int
                          s.gets("activation", "logistic").c_str());
                 return nullptr;
             }
+            if (l.n <= 0 || l.size <= 0 || l.stride <= 0 || l.pad < 0) {
+                yq::fail("layer %d: convolution needs filters, size, stride > 0 (got %d, %d, %d)", index, l.n, l.size, l.stride);
+                return nullptr;
+            }
             l.c = c; l.h = h; l.w = w;
             l.out_c = l.n;
             l.out_h = (h + 2 * l.pad - l.size) / l.stride + 1;
@@ -737,6 +769,10 @@ extern "C" yq_network *yq_load_network(const char *cfg, const char *weights, int
             l.stride = s.geti("stride", 1);
             l.size = s.geti("size", l.stride);
             l.pad = s.geti("padding", l.size - 1);                          // parser.c:415
+            if (l.size <= 0 || l.stride <= 0) {
+                yq::fail("layer %d: maxpool needs size, stride > 0 (got %d, %d)", index, l.size, l.stride);
+                return nullptr;
+            }
             l.c = c; l.h = h; l.w = w;
             l.out_c = c;
             l.out_h = (h + l.pad - l.size) / l.stride + 1;                  // maxpool_layer.c:31-32
@@ -744,6 +780,10 @@ extern "C" yq_network *yq_load_network(const char *cfg, const char *weights, int
         } else if (s.type == "[upsample]") {
             l.type = L_UPSAMPLE;
             l.stride = s.geti("stride", 2);
+            if (l.stride <= 0) {
+                yq::fail("layer %d: upsample stride must be positive", index);
+                return nullptr;
+            }
             if (atof(s.gets("scale", "1").c_str()) != 1.0) {
                 yq::fail("layer %d: upsample scale must be 1 on the quantized path (blas.c:785 asserts)", index);
                 return nullptr;
@@ -768,6 +808,10 @@ extern "C" yq_network *yq_load_network(const char *cfg, const char *weights, int
                 }
                 l.inputs.push_back(idx);
             }
+            if ((int)l.inputs.size() > MAX_ROUTE_INPUTS) {
+                yq::fail("layer %d: route concatenates %zu layers, at most %d are supported", index, l.inputs.size(), MAX_ROUTE_INPUTS);
+                return nullptr;
+            }
             const Layer &first = net->layers[l.inputs[0]];
             l.out_h = first.out_h; l.out_w = first.out_w; l.out_c = 0;
             for (int idx : l.inputs) {
@@ -783,6 +827,33 @@ extern "C" yq_network *yq_load_network(const char *cfg, const char *weights, int
                 l.out_c += in.out_c;
             }
             l.c = l.out_c; l.h = l.out_h; l.w = l.out_w;
+        } else if (s.type == "[shortcut]") {
+            // EXTENSION: the reference's shortcut (parse_shortcut parser.c:484-503, src/shortcut_layer.c) is float only; this is
+            // the integer dequant-add-requant layer of include/yq_b200.h (yq_forward_shortcut_layer_quant_gpu)
+            l.type = L_SHORTCUT;
+            const std::string *from = s.find("from");
+            int idx = from ? atoi(from->c_str()) : index;                      // parser.c:487-489
+            if (idx < 0) idx = index + idx;
+            if (!from || idx < 0 || idx >= index || index == 0) {
+                yq::fail("layer %d: shortcut needs from= naming an earlier layer", index);
+                return nullptr;
+            }
+            if (activation_from_string(s.gets("activation", "linear")) != YQ_LINEAR) {
+                yq::fail("layer %d: the quantized shortcut has activation=linear only", index);
+                return nullptr;
+            }
+            const Layer &f = net->layers[idx];
+            if (f.type == L_YOLO || net->layers[index - 1].type == L_YOLO) {
+                yq::fail("layer %d: shortcut from / after a yolo layer has no uint8 tensor", index);
+                return nullptr;
+            }
+            if (f.out_c != c || f.out_h != h || f.out_w != w) {
+                yq::fail("layer %d: shortcut inputs differ in shape (%dx%dx%d from layer %d, %dx%dx%d before)", index, f.out_c, f.out_h, f.out_w, idx, c, h, w);
+                return nullptr;
+            }
+            l.inputs.push_back(idx);
+            l.activation = YQ_LINEAR;
+            l.c = c; l.h = h; l.w = w; l.out_c = c; l.out_h = h; l.out_w = w;
         } else if (s.type == "[yolo]") {
             l.type = L_YOLO;
             l.classes = s.geti("classes", 20);
@@ -878,6 +949,24 @@ extern "C" yq_network *yq_load_network(const char *cfg, const char *weights, int
         } else if (l.type == L_MAXPOOL || (l.type == L_UPSAMPLE && l.quantized && !l.first_time)) {
             ok = fread(&l.s_out, 4, 1, fp) == 1 && fread(&z, 1, 1, fp) == 1;
             l.zp_out = z;
+        } else if (l.type == L_SHORTCUT) {
+            // extension record: the layer's own output (scale, zero point), 5 bytes like load_maxpool_weights (parser.c:1161-1172)
+            ok = fread(&l.s_out, 4, 1, fp) == 1 && fread(&z, 1, 1, fp) == 1;
+            l.zp_out = z;
+            if (ok) {
+                const Layer &a = net->layers[i - 1], &b = net->layers[l.inputs[0]];
+                l.s_in = a.s_out;
+                l.zp_in = l.zp_a = a.zp_out;
+                l.zp_b = b.zp_out;
+                int32_t ka = 0, kb = 0;
+                if (yq_shortcut_multiplier(a.s_out, l.s_out, &ka) || yq_shortcut_multiplier(b.s_out, l.s_out, &kb)) {
+                    std::string why = yq_last_error();
+                    yq::fail("layer %zu: %s", i, why.c_str());
+                    return nullptr;
+                }
+                l.Ka = ka;
+                l.Kb = kb;
+            }
         } else if (l.type == L_ROUTE && l.quantized) {
             if (l.inputs.size() > 1 && !l.first_time) {                     // parser.c:1176-1182
                 ok = fread(&l.s_out, 4, 1, fp) == 1 && fread(&z, 1, 1, fp) == 1;

@@ -17,7 +17,7 @@ import numpy as np
 from . import _lib
 from ._lib import ActGeom, ConvDesc, LayerInfo, YqError, check
 
-LAYER_TYPES = {0: "conv", 1: "maxpool", 2: "route", 3: "upsample", 4: "yolo"}
+LAYER_TYPES = {0: "conv", 1: "maxpool", 2: "route", 3: "upsample", 4: "yolo", 5: "shortcut"}
 ACTIVATIONS = {"logistic": 0, "relu": 1, "linear": 3, "relu6": 8, "leaky": 9}
 
 
@@ -299,6 +299,60 @@ class ConvolutionalLayerQuant:
                 d.free()
         return res
 
+    @property
+    def geom_supported(self) -> bool:
+        """the layer's flavour reads / writes halo-padded tensors of any geometry (the per-tap TMA flavour)"""
+        return bool(_lib.load().yq_conv_geom_supported(self.handle))
+
+    def forward_geom(self, x_nchw: np.ndarray, in_geom=None, out_geom=None, in_fill: Optional[int] = None, want_acc: bool = True
+                     ) -> Dict[str, np.ndarray]:
+        """forward() between halo-padded tensors: in_geom / out_geom = (pad, pitch_w, rows_h) or "flat" or None (plain).
+        The input's halo is filled with ``in_fill`` (default zp_in) and announced as such; in_fill != zp_in exercises the
+        out-of-bounds + border-correction form on a padded tensor.  Returns dict(u8, acc, f32, halo_ok): halo_ok = the
+        output's halo still holds the 0xEE it was preset to (only the interior may be written)."""
+        lib = _lib.load()
+        b = x_nchw.shape[0]
+        x = np.ascontiguousarray(x_nchw, np.uint8)
+        cs_out = channel_stride(self.n)
+
+        def geom(g, h, w):
+            if g is None:
+                return ActGeom(0, w, h)
+            if g == "flat":
+                r = ActGeom()
+                check(lib.yq_act_geom_flat(h, w, C.byref(r)))
+                return r
+            return ActGeom(*g)
+        gi, go = geom(in_geom, self.h, self.w), geom(out_geom, self.out_h, self.out_w)
+        fill = self.zp_in if in_fill is None else int(in_fill)
+        din = DeviceBuffer(lib.yq_act_geom_bytes(C.byref(gi), b, self.c), zero=False)
+        check(lib.yq_cuda_memset(din.ptr, fill, din.nbytes, None))
+        src = DeviceBuffer.from_numpy(x)
+        check(lib.yq_nchw_to_nhwc_u8_geom(src.ptr, din.ptr, b, self.c, self.h, self.w, C.byref(gi), None))
+        dout = DeviceBuffer(lib.yq_act_geom_bytes(C.byref(go), b, self.n), zero=False)
+        check(lib.yq_cuda_memset(dout.ptr, 0xEE, dout.nbytes, None))
+        dacc = DeviceBuffer(b * self.out_h * self.out_w * cs_out * 4) if want_acc else None
+        df32 = DeviceBuffer(b * self.n * self.out_h * self.out_w * 4) if self.quant_stop_flag else None
+        check(lib.yq_forward_convolutional_layer_quant_geom_gpu(self.handle, din.ptr, C.byref(gi), fill if gi.pad else -1, dout.ptr, C.byref(go),
+                                                                df32.ptr if df32 else None, dacc.ptr if dacc else None, b, None),
+              "yq_forward_convolutional_layer_quant_geom_gpu")
+        tmp = DeviceBuffer(b * self.n * self.out_h * self.out_w)
+        check(lib.yq_nhwc_to_nchw_u8_geom(dout.ptr, tmp.ptr, b, self.n, self.out_h, self.out_w, C.byref(go), None))
+        check(lib.yq_stream_synchronize(None))
+        res = {"u8": tmp.pull((b, self.n, self.out_h, self.out_w), np.uint8)}
+        if dacc:
+            res["acc"] = pull_nhwc_i32(dacc, b, self.n, self.out_h, self.out_w)
+        if df32:
+            res["f32"] = df32.pull((b, self.n, self.out_h, self.out_w), np.float32)
+        raw = dout.pull((dout.nbytes // cs_out, cs_out), np.uint8)
+        rows = raw[: b * go.rows_h * go.pitch_w].reshape(b, go.rows_h, go.pitch_w, cs_out).copy()
+        rows[:, go.pad:go.pad + self.out_h, go.pad:go.pad + self.out_w, :] = 0xEE
+        res["halo_ok"] = bool((rows == 0xEE).all() and (raw[b * go.rows_h * go.pitch_w:] == 0xEE).all())
+        for d in (din, src, dout, dacc, df32, tmp):
+            if d:
+                d.free()
+        return res
+
     def free(self) -> None:
         if self.handle:
             _lib.load().yq_free_convolutional_layer_quant(self.handle)
@@ -360,6 +414,52 @@ def forward_route_layer_quant_gpu(xs: Sequence[np.ndarray], ups: Optional[Sequen
     for d in dins:
         d.free()
     dout.free()
+    return out
+
+
+def shortcut_multiplier(s_x: float, s_out: float) -> int:
+    k = C.c_int32()
+    check(_lib.load().yq_shortcut_multiplier(float(s_x), float(s_out), C.byref(k)), "yq_shortcut_multiplier")
+    return int(k.value)
+
+
+def forward_shortcut_layer_quant_gpu(a: np.ndarray, b: np.ndarray, q_a, q_b, q_out, geoms=None) -> np.ndarray:
+    """The quantized shortcut (extension: include/yq_b200.h).  a, b uint8 [n,c,h,w]; q_* = (scale, zero point).
+    geoms: optional ((pad, pitch_w, rows_h),) * 3 for a, b and the output (halo-padded tensors)."""
+    lib = _lib.load()
+    a = np.ascontiguousarray(a, np.uint8)
+    b = np.ascontiguousarray(b, np.uint8)
+    n, c, h, w = a.shape
+    ka, kb = shortcut_multiplier(q_a[0], q_out[0]), shortcut_multiplier(q_b[0], q_out[0])
+    if geoms is None:
+        da, db = push_nchw_u8(a), push_nchw_u8(b)
+        dout = DeviceBuffer(n * h * w * channel_stride(c))
+        check(lib.yq_forward_shortcut_layer_quant_gpu(da.ptr, db.ptr, dout.ptr, n, h, w, c, int(q_a[1]), int(q_b[1]), ka, kb, int(q_out[1]), None),
+              "yq_forward_shortcut_layer_quant_gpu")
+        out = pull_nhwc_u8(dout, n, c, h, w)
+        for d in (da, db, dout):
+            d.free()
+        return out
+    gs = [ActGeom(*g) for g in geoms]
+    bufs = []
+    for x, g in zip((a, b), gs[:2]):
+        d = DeviceBuffer(lib.yq_act_geom_bytes(C.byref(g), n, c), zero=False)
+        check(lib.yq_cuda_memset(d.ptr, 0x5A, d.nbytes, None))
+        src = DeviceBuffer.from_numpy(x)
+        check(lib.yq_nchw_to_nhwc_u8_geom(src.ptr, d.ptr, n, c, h, w, C.byref(g), None))
+        check(lib.yq_stream_synchronize(None))
+        src.free()
+        bufs.append(d)
+    dout = DeviceBuffer(lib.yq_act_geom_bytes(C.byref(gs[2]), n, c), zero=False)
+    check(lib.yq_cuda_memset(dout.ptr, 0xEE, dout.nbytes, None))
+    check(lib.yq_forward_shortcut_layer_quant_geom_gpu(bufs[0].ptr, C.byref(gs[0]), bufs[1].ptr, C.byref(gs[1]), dout.ptr, C.byref(gs[2]), n, h, w, c,
+                                                       int(q_a[1]), int(q_b[1]), ka, kb, int(q_out[1]), None), "yq_forward_shortcut_layer_quant_geom_gpu")
+    tmp = DeviceBuffer(n * c * h * w)
+    check(lib.yq_nhwc_to_nchw_u8_geom(dout.ptr, tmp.ptr, n, c, h, w, C.byref(gs[2]), None))
+    check(lib.yq_stream_synchronize(None))
+    out = tmp.pull((n, c, h, w), np.uint8)
+    for d in bufs + [dout, tmp]:
+        d.free()
     return out
 
 

@@ -28,7 +28,7 @@ ACT_CODES = {"logistic": 0, "relu": 1, "linear": 3, "relu6": 8, "leaky": 9}
 
 @dataclass
 class LayerSpec:
-    kind: str                       # conv | maxpool | route | upsample | yolo
+    kind: str                       # conv | maxpool | route | upsample | yolo | shortcut
     filters: int = 0
     size: int = 1
     stride: int = 1
@@ -36,8 +36,11 @@ class LayerSpec:
     bn: int = 1
     activation: str = "relu6"
     quant_stop: int = 0
-    layers: Tuple[int, ...] = ()    # route
+    layers: Tuple[int, ...] = ()    # route; shortcut: (from,)
     mask: Tuple[int, ...] = ()      # yolo
+    classes: Optional[int] = None   # yolo: None => module CLASSES / ANCHORS (the shipped 5-class, 6-anchor cfg)
+    anchors: Optional[str] = None
+    num: Optional[int] = None
     # activation quantisation of this layer's output (s_out, zp_out); None => defaults by activation
     act_scale: Optional[float] = None
     act_zp: Optional[int] = None
@@ -73,6 +76,44 @@ def yolov3_tiny_quant(activation: str = "relu6", head_filters: int = 3 * (5 + CL
     ]
 
 
+YOLOV3_ANCHORS = "10,13, 16,30, 33,23, 30,61, 62,45, 59,119, 116,90, 156,198, 373,326"
+
+
+def yolov3_quant(classes: int = 80, activation: str = "leaky") -> List[LayerSpec]:
+    """Full yolov3 (BASELINE configs[4]): 107 layers = 75 conv (3x3/1, 3x3/2 down-samplers, 1x1; BN + leaky except the three
+    linear heads), 23 shortcut, 4 route, 2 upsample, 3 yolo.  The reference ships no such cfg and has no quantized shortcut
+    (SURVEY 0.10, Appendix F); the layer table is the public darknet yolov3 topology re-derived here, every layer quantized=1,
+    the shortcut being this repo's integer extension (spec: include/yq_b200.h, yq_forward_shortcut_layer_quant_gpu)."""
+    a = activation
+    hf = 3 * (5 + classes)
+    L: List[LayerSpec] = []
+    conv = lambda f, k, s=1: L.append(LayerSpec("conv", f, k, s, activation=a))
+    def block(f: int, reps: int) -> None:
+        conv(f, 3, 2)                                  # down-sampler
+        for _ in range(reps):
+            conv(f // 2, 1)
+            conv(f, 3)
+            L.append(LayerSpec("shortcut", layers=(-3,)))
+    def head(mask) -> None:
+        L.append(LayerSpec("conv", hf, 1, bn=0, activation="linear", quant_stop=1))
+        L.append(LayerSpec("yolo", mask=mask, classes=classes, anchors=YOLOV3_ANCHORS, num=9))
+    conv(32, 3)
+    for f, reps in ((64, 1), (128, 2), (256, 8), (512, 8), (1024, 4)):
+        block(f, reps)
+    for f, mask, skip in ((512, (6, 7, 8), 61), (256, (3, 4, 5), 36), (128, (0, 1, 2), None)):
+        for _ in range(3):
+            conv(f, 1)
+            conv(f * 2, 3)
+        head(mask)
+        if skip is not None:
+            L.append(LayerSpec("route", layers=(-4,)))
+            conv(f // 2, 1)
+            L.append(LayerSpec("upsample", stride=2))
+            L.append(LayerSpec("route", layers=(-1, skip)))
+    assert len(L) == 107 and sum(l.kind == "conv" for l in L) == 75 and sum(l.kind == "shortcut" for l in L) == 23
+    return L
+
+
 def single_conv(filters: int, size: int, stride: int = 1, activation: str = "relu6", bn: int = 1,
                 quant_stop: int = 0, act_scale: Optional[float] = None, act_zp: Optional[int] = None
                 ) -> List[LayerSpec]:
@@ -99,9 +140,12 @@ def write_cfg(path: str, layers: Sequence[LayerSpec], batch: int = 1, width: int
         elif l.kind == "upsample":
             out += ["[upsample]", f"stride={l.stride}", "quantized=1", "quant_stop=0", ""]
         elif l.kind == "yolo":
-            out += ["[yolo]", "mask = " + ",".join(str(i) for i in l.mask), f"anchors = {ANCHORS}",
-                    f"classes={CLASSES}", "num=6", "jitter=.3", "ignore_thresh = .7", "truth_thresh = 1",
-                    "random=1", ""]
+            out += ["[yolo]", "mask = " + ",".join(str(i) for i in l.mask), f"anchors = {l.anchors or ANCHORS}",
+                    f"classes={CLASSES if l.classes is None else l.classes}", f"num={l.num or 6}", "jitter=.3",
+                    "ignore_thresh = .7", "truth_thresh = 1", "random=1", ""]
+        elif l.kind == "shortcut":
+            # the quantized shortcut is this repo's extension (the reference's shortcut is float only)
+            out += ["[shortcut]", f"from={l.layers[0]}", "activation=linear", "quantized=1", "quant_stop=0", ""]
         else:
             raise ValueError(l.kind)
     with open(path, "w") as f:
@@ -214,6 +258,15 @@ def write_weights(path: Optional[str], layers: Sequence[LayerSpec], width: int =
             sl = SynthLayer("route", oc, first.out_h, first.out_w, oc, first.out_h, first.out_w, l,
                             s_out=prev[0], zp_out=prev[1], inputs=idx)
             c, h, w = oc, first.out_h, first.out_w
+        elif l.kind == "shortcut":
+            j = l.layers[0] if l.layers[0] >= 0 else i + l.layers[0]
+            assert (res[j].out_c, res[j].out_h, res[j].out_w) == (c, h, w), "shortcut inputs must agree in shape"
+            # extension record: the layer's own output (scale, zero point), 5 bytes like a maxpool's (parser.c:1161-1172)
+            s_out = float(np.float32(l.act_scale if l.act_scale is not None else 0.03))
+            zp_out = int(l.act_zp if l.act_zp is not None else 50)
+            chunks.append(struct.pack("<f", s_out) + struct.pack("<B", zp_out))
+            sl = SynthLayer("shortcut", c, h, w, c, h, w, l, s_in=prev[0], zp_in=prev[1], s_out=s_out, zp_out=zp_out, inputs=(j,))
+            prev = (s_out, zp_out)
         elif l.kind == "yolo":
             sl = SynthLayer("yolo", c, h, w, c, h, w, l, s_out=prev[0], zp_out=prev[1])
         else:
