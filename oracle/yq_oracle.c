@@ -272,7 +272,12 @@ void yq_oracle_prepare_conv(int n, int K, const uint8_t *weights, const uint8_t 
 {
     for (int oc = 0; oc < n; ++oc) {
         float b = bias[oc];
-        if (bn) b = b - bn_scales[oc] * bn_mean[oc] / (sqrtf(bn_var[oc]) + .000001f);
+        /* batch_normalize_bias as ISO C evaluates it: the float product scales*mean, sqrt() in DOUBLE (its only prototype),
+           .000001f promoted, double division and subtraction, one rounding back to float.  The reference's -Ofast build is
+           free to narrow or reassociate this: measured here, its biases_int32 differs by +-1 from this form in ~1 of 3000
+           channels with non-identity batch-norm statistics (and by as much from an all-float form, on other channels), so no
+           single restatement reproduces that binary; tests against the compiled reference take ITS dumped parameters. */
+        if (bn) b = (float)((double)b - (double)(bn_scales[oc] * bn_mean[oc]) / (sqrt((double)bn_var[oc]) + (double).000001f));
         uint32_t mult_zero_point = (uint32_t)(K * zp_in * (int)zp_w[oc]);
         int32_t wsum = 0;
         for (int k = 0; k < K; ++k) wsum += weights[(size_t)oc * K + k];

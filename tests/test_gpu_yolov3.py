@@ -92,6 +92,36 @@ def test_conv_stride1_per_tap_between_padded_tensors(built, case, monkeypatch):
     layer.free()
 
 
+FLAT2_CASES = [
+    # c, h, w, n, k, act, zp_in, batch      (the persistent two-tile flat form beyond yolov3-tiny's shapes)
+    (256, 13, 13, 128, 1, "leaky", 40, 3),     # 1x1: one weight stage per patch chunk
+    (512, 9, 9, 256, 1, "leaky", 7, 2),        # 1x1, two n-tiles, four K chunks
+    (128, 20, 20, 64, 1, "leaky", 40, 2),      # 1x1, n = 64: half a tile of channels is stored (SWIZZLE_64B staging)
+    (64, 24, 24, 32, 1, "relu6", 0, 2),        # 1x1, n = 32 (SWIZZLE_32B staging), KC = 64
+    (64, 6, 104, 128, 3, "leaky", 40, 2),      # 3x3 on 104-wide rows: the patch arrives as two 240-row boxes
+    (64, 4, 208, 128, 3, "leaky", 33, 1),      # 3x3 on 208-wide rows: three boxes
+    (128, 5, 104, 64, 3, "leaky", 9, 2),       # wide rows, KC = 128, n = 64
+    (128, 3, 150, 120, 3, "linear", 200, 1),   # n = 120: pad lanes of the last 16 channels stay zero
+]
+
+
+@pytest.mark.parametrize("case", FLAT2_CASES, ids=lambda c: "c%d_%dx%d_n%d_k%d_%s" % c[:6])
+def test_conv_flat2_wide_rows_1x1_and_narrow_outputs(built, case, monkeypatch):
+    """conv_u8_tc_flat2_kernel on the shapes the full yolov3 adds: 1x1 layers (forced here: the dispatch takes it from a few waves
+    of tile pairs on), rows up to 222 pixels wide (patch in up to three TMA boxes) and layers with n < 128."""
+    c, h, w, n, k, act, zp_in, batch = case
+    monkeypatch.setenv("YQ_FLAT2_1X1", "1")
+    rng = np.random.default_rng(zlib.crc32(repr(case).encode()) + 13)
+    layer, wq, zp_w, p = _rand_layer(rng, c, n, k, 1, act, zp_in, h=h, w=w, quant_stop=0)
+    assert layer.flat_supported
+    x = rng.integers(0, 256, size=(batch, c, h, w), dtype=np.uint8)
+    for want_acc in (True, False):                 # SLOW (side outputs) and production variants
+        got = layer.forward_flat(x, halo_fill=zp_in ^ 0x33, want_acc=want_acc)
+        assert got["halo_ok"], "halo / pad lanes of the output"
+        _check(got, x, wq, zp_w, p, 1, k, act, zp_in, 33)
+    layer.free()
+
+
 # (c, n, size, stride, activation, input h = w at 416x416)
 YOLOV3_REAL = [
     (3, 32, 3, 1, "leaky", 416), (32, 64, 3, 2, "leaky", 416), (64, 32, 1, 1, "leaky", 208), (32, 64, 3, 1, "leaky", 208),
@@ -112,16 +142,31 @@ def test_full_yolov3_conv_shapes_at_real_sizes(built, shape, tmp_path):
     cfg, l.forward called directly: SURVEY Appendix F) on the same bytes; the input stays below 25 so that the reference's
     float-carried accumulator (gemm.c:279-296) remains exact -- asserted, not assumed."""
     c, n, k, stride, act, hw = shape
-    s_in, zp_in = 0.03, 40 if c > 3 else 0
+    # (small values AND a small zero point: the padding value counts in the reference's running sums too -- 13 x 13 corner
+    # outputs of a K = 4608 layer see 5 of 9 taps of padding)
+    s_in, zp_in = 0.03, 8 if c > 3 else 0
     layers = synth.single_conv(n, k, stride, act, 1, 1 if act == "linear" else 0, act_scale=0.05, act_zp=33)
     cfg, wts, img = (str(tmp_path / f) for f in ("l.cfg", "l.weights", "img.f32"))
     synth.write_cfg(cfg, layers, width=hw, height=hw, channels=c)
     info = synth.write_weights(wts, layers, width=hw, height=hw, channels=c, seed=hw + c, input_quant=(s_in, zp_in), identity_bn=False)
     rng = np.random.default_rng(zlib.crc32(repr(shape).encode()) + 5)
-    x = rng.integers(0, 25, size=(c, hw, hw), dtype=np.uint8)
+    x = rng.integers(0, max(6, min(25, int(1.0e7 / (c * k * k * 160)))), size=(c, hw, hw), dtype=np.uint8)
     x.flat[0], x.flat[1] = 0, 255                  # the reference's dynamic input quantiser re-derives (s_in, zp_in) from these
     sl = info[0]
-    p = O.prepare_conv(sl, s_in, zp_in)
+    r = None
+    if O.have_reference():
+        # the reference first: its own host prep (quantization_weights_and_activations, src/blas.c:259-346 -- "reused verbatim"
+        # in a drop-in) supplies the per-channel parameters, exactly as a binding would hand them over in yq_conv_desc
+        synth.image_to_float(x, s_in, zp_in).tofile(img)
+        O.run_reference("layer", cfg, wts, img, str(tmp_path / "dump"), omp=True)
+        r = O.read_dump(str(tmp_path / "dump"))[0]
+        ref_in = np.fromfile(str(tmp_path / "dump" / "L00_input_uint8.bin"), dtype=np.uint8).reshape(c, hw, hw)
+        assert np.array_equal(ref_in, x) and r["zp_in"] == zp_in, "the reference's input quantiser did not reproduce the test tensor"
+        p = {k_: r[k_] for k_ in ("biases_int32", "M_value", "M0_right_shift_value", "M0")}
+        mine = O.prepare_conv(sl, float(np.float32(r["s_in"])), zp_in)
+        assert np.array_equal(mine["M0"], p["M0"]) and np.abs(mine["biases_int32"] - p["biases_int32"]).max() <= 1   # (-Ofast: oracle header)
+    else:
+        p = O.prepare_conv(sl, s_in, zp_in)
     qs = 1 if act == "linear" else 0
     layer = darknet.ConvolutionalLayerQuant(hw, hw, c, n, k, stride, k // 2, synth.ACT_CODES[act], sl.w_u8, sl.zp_w, p["biases_int32"], p["M_value"],
                                             p["M0_right_shift_value"], zp_in, 33, sl.s_out, quant_stop_flag=qs)
@@ -136,15 +181,11 @@ def test_full_yolov3_conv_shapes_at_real_sizes(built, shape, tmp_path):
     assert np.array_equal(got["acc"][0], acc), "int32 accumulator vs oracle"
     u8 = O.requant(acc, p["biases_int32"], p["M_value"], p["M0_right_shift_value"], synth.ACT_CODES[act], 33)
     assert np.array_equal(got["u8"][0], u8), "uint8 vs oracle"
-    if O.have_reference():
-        synth.image_to_float(x, s_in, zp_in).tofile(img)
-        O.run_reference("layer", cfg, wts, img, str(tmp_path / "dump"), omp=True)
-        r = O.read_dump(str(tmp_path / "dump"))[0]
-        ref_in = np.fromfile(str(tmp_path / "dump" / "L00_input_uint8.bin"), dtype=np.uint8).reshape(c, hw, hw)
-        assert np.array_equal(ref_in, x) and r["zp_in"] == zp_in, "the reference's input quantiser did not reproduce the test tensor"
-        assert np.array_equal(r["biases_int32"], p["biases_int32"]) and np.array_equal(r["M0"], p["M0"])
+    if r is not None:
         assert np.array_equal(r["output_int32"], got["acc"][0]), "int32 accumulator vs the compiled reference"
         assert np.array_equal(r["output_uint8"], got["u8"][0]), "uint8 vs the compiled reference"
+        if qs:
+            assert np.array_equal(r["output_f32"].reshape(got["f32"][0].shape), got["f32"][0]), "dequantised head vs the compiled reference"
 
 
 @pytest.mark.parametrize("c,h,w,batch", [(64, 16, 16, 2), (256, 13, 13, 3), (1024, 5, 7, 1), (24, 9, 4, 2), (3, 6, 5, 2)])

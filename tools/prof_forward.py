@@ -1,4 +1,5 @@
-"""Profiling driver (run under ncu on the GPU box): N warm-up forwards + 1 forward of yolov3-tiny at batch B.
+"""Profiling driver (run under ncu on the GPU box): N warm-up forwards + 1 forward of yolov3-tiny at batch B
+(YQ_NET=yolov3: the full yolov3, default batch 64).
     ncu --set full --import-source on -k regex:conv_u8 -s 26 -c 13 -o gpurun_out/prof python tools/prof_forward.py
 """
 import os
@@ -10,10 +11,11 @@ import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from yolo_quantization_b200 import darknet, synth  # noqa: E402
 
-B = int(os.environ.get("YQ_BATCH", "128"))
+NET = os.environ.get("YQ_NET", "tiny")
+B = int(os.environ.get("YQ_BATCH", "128" if NET == "tiny" else "64"))
 WARM = int(os.environ.get("YQ_WARM", "2"))
 KERNEL = int(os.environ.get("YQ_KERNEL", "-1"))
-layers = synth.yolov3_tiny_quant()
+layers = synth.yolov3_tiny_quant() if NET == "tiny" else synth.yolov3_quant()
 with tempfile.TemporaryDirectory() as d:
     cfg, wts = os.path.join(d, "t.cfg"), os.path.join(d, "t.weights")
     synth.write_cfg(cfg, layers, batch=B)
@@ -26,5 +28,7 @@ with tempfile.TemporaryDirectory() as d:
     for _ in range(WARM + 1):
         net.forward_device(dev.ptr)
         net.synchronize()
-    print("done", net.profile_forward(dev.ptr).round(3).tolist())
+    print("launches per forward", net.launches_per_forward)
+    if not os.environ.get("YQ_NO_PROFILE_FORWARD"):
+        print("done", net.profile_forward(dev.ptr).round(3).tolist())
     net.free()

@@ -139,6 +139,7 @@ int yq_tc_rows_planar_supported(const yq_conv_layer *l);
 
 // implemented in yq_conv_tc_flat.cu (flat halo-padded strip, one patch per channel chunk shared by all taps; c % 64 == 0)
 int yq_tc_flat_supported(const yq_conv_layer *l);
+int yq_tc_flat_eligible(const yq_conv_layer *l);   // shape conditions shared by flat / flat2 / flat2x (no row-width limit)
 void yq_tc_flat_geom(int h, int w, yq_act_geom *g);
 int yq_tc_flat_prepare(yq_conv_layer *l, void **state);
 void yq_tc_flat_free(void *state);
@@ -149,8 +150,9 @@ int yq_tc_flat_forward(yq_conv_layer *l, void *state, const uint8_t *in_flat, ui
 int yq_tc_flat2_supported(const yq_conv_layer *l);
 int yq_tc_flat2_prepare(yq_conv_layer *l, void **state);
 void yq_tc_flat2_free(void *state);
+// plain = 1 (1x1 layers only): in / out are plain [B][H][W][C] tensors -- a 1x1 convolution needs no halo
 int yq_tc_flat2_forward(yq_conv_layer *l, void *state, const uint8_t *in_flat, uint8_t *out_flat, int halo_fill, int32_t *out_acc, int batch,
-                        cudaStream_t stream);
+                        cudaStream_t stream, int plain = 0);
 
 // implemented in yq_conv_tc_flat2x.cu (flat2 on CTA pairs: cta_group::2 MMAs, each SM holds half of every weight stage)
 int yq_tc_flat2x_supported(const yq_conv_layer *l);
@@ -167,6 +169,7 @@ void yq_tc_free(yq_conv_layer *l);
 int yq_tc_forward(yq_conv_layer *l, const uint8_t *in_u8, uint8_t *out_u8, uint8_t *out_pool, float *out_f32, int32_t *out_acc,
                   int batch, cudaStream_t stream, const yq_act_geom *in_geom = nullptr, int in_halo_fill = -1,
                   const yq_act_geom *out_geom = nullptr);
+int yq_conv_plain_1x1_fast(const yq_conv_layer *l);   // 1: the plain entry runs this 1x1 layer on conv_u8_tc_flat2_kernel (plain-strip mode)
 int yq_tc_geom_supported(const yq_conv_layer *l);   // 1: the layer's current flavour is the per-tap TMA one (any tensor geometry)
 int yq_tc_cluster_enabled();                        // YQ_TC_CLUSTER: multicast clusters in the per-tap flavour (A/B switch, off)
 // 1 when this layer's current flavour can also emit the 2x2/stride-2 max-pooled tensor from its epilogue

@@ -415,14 +415,21 @@ int fl_launch(FlatState *st, const CUtensorMap &tmA, const CUtensorMap &tmO, con
 
 }  // namespace
 
-int yq_tc_flat_supported(const yq_conv_layer *l)
+// what every flat-strip flavour needs of a layer (each adds its own limit on the row width)
+int yq_tc_flat_eligible(const yq_conv_layer *l)
 {
     if (!l->int_form || !l->fused_mult) return 0;
     if (l->stride != 1 || !(l->size == 1 || l->size == 3) || l->pad != l->size / 2) return 0;
     if (l->c != l->cs_in || l->cs_in % 64) return 0;            // no pad lanes: the halo fill would count in sum(a)
     if (l->cs_out < 32) return 0;
-    if (128 + (l->size - 1) * (l->w + 2) > 256) return 0;       // the patch is one TMA box (<= 256 rows)
     return fl_get_encode() != nullptr;
+}
+
+int yq_tc_flat_supported(const yq_conv_layer *l)
+{
+    if (!yq_tc_flat_eligible(l)) return 0;
+    if (128 + (l->size - 1) * (l->w + 2) > 256) return 0;       // the patch is one TMA box (<= 256 rows)
+    return 1;
 }
 
 void yq_tc_flat_geom(int h, int w, yq_act_geom *g)

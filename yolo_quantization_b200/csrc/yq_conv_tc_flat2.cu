@@ -38,7 +38,8 @@ constexpr int F2_SUM_WARPS = 2;
 constexpr int F2_THREADS = 32 * (2 + F2_SUM_WARPS + F2_EPI_WARPS);
 constexpr int F2_ASTAGES = 2;
 constexpr int F2_MAX_BSTAGES = 8;
-constexpr int F2_MAX_ROWS = 384;           // patch rows: 256 + 2W + 4 (W <= 61)
+constexpr int F2_MAX_ROWS = 704;           // patch rows: 256 + 2W + 4 (W <= 222: the 208 x 208 and 104 x 104 maps of the full yolov3)
+constexpr int F2_MAX_BOXES = 3;            // a patch arrives as up to three TMA boxes (a box holds at most 256 rows)
 
 struct Flat2Args {
     yq::EpiParams ep;
@@ -47,7 +48,9 @@ struct Flat2Args {
     int B, H, W, NP;       // NP = B*(H+1)*(W+1)
     int size, taps, cpt /* KC-chunks per tap */, CS;
     int q_off;             // first patch position relative to the pair's first position: -(pad*(W+1) + pad)
-    int patch_rows, box_rows, a_stage_bytes, b_stages;
+    int patch_rows, box_rows, n_boxes, a_stage_bytes, b_stages;
+    int plain;             // 1x1 only: the tensors are plain [B][H][W][C] strips (no halo positions: every p < NP is a pixel)
+    int out_cols;          // bytes per position the launch stores: min(128, channel stride of the output); 32 / 64: narrow layers
     int m_pairs, num_tiles;   // tile t -> (n-tile t / m_pairs, position pair t % m_pairs)
     uint32_t halo_word;
     uint32_t magic_w, magic_h, magic_m;
@@ -127,9 +130,9 @@ __global__ void __launch_bounds__(F2_THREADS, 1) conv_u8_tc_flat2_kernel(const _
             for (int c = 0; c < chunks; ++c) {
                 mbar_wait(&a_empty[sa], pha ^ 1);
                 if (elect_one()) {
-                    mbar_expect_tx(&a_full[sa], (uint32_t)(2 * a.box_rows * KC));
-                    tma_load_2d(sA + sa * a.a_stage_bytes, &tmA, &a_full[sa], c * KC, p0 + a.q_off);
-                    tma_load_2d(sA + sa * a.a_stage_bytes + a.box_rows * KC, &tmA, &a_full[sa], c * KC, p0 + a.q_off + a.box_rows);
+                    mbar_expect_tx(&a_full[sa], (uint32_t)(a.n_boxes * a.box_rows * KC));
+                    for (int b = 0; b < a.n_boxes; ++b)
+                        tma_load_2d(sA + sa * a.a_stage_bytes + b * a.box_rows * KC, &tmA, &a_full[sa], c * KC, p0 + a.q_off + b * a.box_rows);
                 }
                 if (++sa == F2_ASTAGES) { sa = 0; pha ^= 1; }
                 for (int tap = 0; tap < a.taps; ++tap) {
@@ -267,8 +270,8 @@ __global__ void __launch_bounds__(F2_THREADS, 1) conv_u8_tc_flat2_kernel(const _
                 const int col = p - row * pitch;
                 const int n = (int)__umulhi((uint32_t)row, a.magic_h);
                 const int y1 = row - n * (a.H + 1);
-                const bool valid = p < a.NP && col >= 1 && y1 >= 1;
-                const size_t pix = ((size_t)n * a.H + (y1 - 1)) * a.W + (col - 1);
+                const bool valid = p < a.NP && (a.plain || (col >= 1 && y1 >= 1));
+                const size_t pix = a.plain ? (size_t)p : ((size_t)n * a.H + (y1 - 1)) * a.W + (col - 1);
                 // sum of activations under this position's window, from the per-row sums of the patch
                 int sa_sum = 0;
                 {
@@ -280,9 +283,12 @@ __global__ void __launch_bounds__(F2_THREADS, 1) conv_u8_tc_flat2_kernel(const _
                 uint8_t *stage = sOut + j * L::OUT_BYTES;
                 const uint32_t trow = tmem_base + (pb * 2 + j) * F2_BN + ((uint32_t)(q * 32) << 16);
                 const int cbeg = part * 32;
+                const bool mine = cbeg < a.out_cols;      // narrow layers (n <= 64): the upper channel quarters are padding, never stored
                 uint32_t vbuf[2][16];
-                tmem_ld16_issue(trow + cbeg, vbuf[0]);
-                tmem_ld_wait16(vbuf[0]);
+                if (mine) {
+                    tmem_ld16_issue(trow + cbeg, vbuf[0]);
+                    tmem_ld_wait16(vbuf[0]);
+                }
                 auto run = [&](auto actm_tag, auto sat_tag) {
                     constexpr int ACTM = decltype(actm_tag)::value;
                     constexpr bool SAT = decltype(sat_tag)::value;
@@ -303,11 +309,14 @@ __global__ void __launch_bounds__(F2_THREADS, 1) conv_u8_tc_flat2_kernel(const _
                                 if (oc < a.N) a.out_acc[pix * a.CSO + oc] = (int)v[jj] + s_q[c0 + jj].y * nsa;
                             }
                         }
-                        *reinterpret_cast<uint4 *>(stage + (size_t)r * F2_BN + (((c0 / 16) ^ (r & 7)) * 16)) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+                        // staging rows of out_cols bytes in the swizzle of the store's tensor map (128B / 64B / 32B)
+                        const int chunk = c0 / 16;
+                        const int sw = a.out_cols >= 128 ? (chunk ^ (r & 7)) : (a.out_cols == 64 ? (chunk ^ ((r >> 1) & 3)) : (chunk ^ ((r >> 2) & 1)));
+                        *reinterpret_cast<uint4 *>(stage + (size_t)r * a.out_cols + sw * 16) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
                         if (ch == 0) tmem_ld_wait16(vbuf[1]);
                     }
                 };
-                if (a.debug == 2) {
+                if (a.debug == 2 || !mine) {
                 } else if (SLOW && a.ep.saturate) {
                     if (actm == 0) run(std::integral_constant<int, 0>{}, std::true_type{});
                     else if (actm == 1) run(std::integral_constant<int, 1>{}, std::true_type{});
@@ -368,7 +377,8 @@ int f2_encode_2d(CUtensorMap *m, const void *ptr, uint64_t rows, int row_bytes, 
     cuuint32_t box[2] = {(cuuint32_t)box_c, (cuuint32_t)box_rows};
     cuuint32_t es[2] = {1, 1};
     CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void *>(ptr), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                     box_c >= 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, prom, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                     box_c >= 128 ? CU_TENSOR_MAP_SWIZZLE_128B : (box_c == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B), prom,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return yq::fail("cuTensorMapEncodeTiled(%llu x %d, box %d x %d) failed: %d", (unsigned long long)rows, row_bytes, box_c, box_rows, (int)r);
     return 0;
 }
@@ -424,9 +434,11 @@ int f2_launch(Flat2State *st, const CUtensorMap &tmA, const CUtensorMap &tmO, co
 
 int yq_tc_flat2_supported(const yq_conv_layer *l)
 {
-    if (!yq_tc_flat_supported(l)) return 0;
-    if (l->quant_stop_flag || l->cs_out % F2_BN) return 0;
-    if (l->size != 3) return 0;      // 1x1: one weight stage per patch -- the one-tile form is faster (measured: layer 13 0.0215 vs 0.0245 ms)
+    if (!yq_tc_flat_eligible(l)) return 0;
+    if (l->quant_stop_flag) return 0;
+    if (l->cs_out % F2_BN && l->cs_out != 64 && l->cs_out != 32) return 0;   // narrow layers store 64 / 32 bytes per position of one 128-channel tile
+    // (1x1: with one wave of tiles or less the one-tile form is faster -- layer 13 of yolov3-tiny 0.0215 vs 0.0245 ms; the
+    // dispatch in yq_forward_convolutional_layer_quant_flat_gpu picks per launch from the tile count)
     if (256 + (l->size - 1) * (l->w + 2) > F2_MAX_ROWS) return 0;
     return 1;
 }
@@ -470,27 +482,32 @@ void yq_tc_flat2_free(void *state)
 }
 
 int yq_tc_flat2_forward(yq_conv_layer *l, void *state, const uint8_t *in_flat, uint8_t *out_flat, int halo_fill, int32_t *out_acc, int batch,
-                        cudaStream_t stream)
+                        cudaStream_t stream, int plain)
 {
     Flat2State *st = (Flat2State *)state;
     if (!st || !in_flat || !out_flat) return yq::fail("tcgen05 flat2 flavour: bad argument");
-    const int W1 = l->w + 1, H1 = l->h + 1;
+    if (plain && l->size != 1) return yq::fail("tcgen05 flat2 flavour: only 1x1 layers run on plain tensors");
+    // plain: a 1x1 convolution needs no halo, so a plain [B][H][W][C] tensor is a strip of B*H*W positions, all of them pixels
+    const int W1 = l->w + (plain ? 0 : 1), H1 = l->h + (plain ? 0 : 1);
     const long long NP = (long long)batch * H1 * W1;
-    const long long rows_alloc = NP + W1 + 2;     // + the trailing halo row (yq_act_geom_bytes)
+    const long long rows_alloc = plain ? NP : NP + W1 + 2;     // + the trailing halo row (yq_act_geom_bytes)
     if (rows_alloc * W1 >= 0x100000000ll) return yq::fail("tcgen05 flat2 flavour: tensor too large for 32-bit position arithmetic");
     Flat2Args a;
     memset(&a, 0, sizeof a);
     const int pad = l->size / 2;
     a.patch_rows = 256 + (l->size - 1) * (W1 + 1);
-    a.box_rows = yq::round_up((a.patch_rows + 1) / 2, 8);
-    a.a_stage_bytes = yq::round_up(2 * a.box_rows * st->KC, 1024);
-    Flat2State::Key key{in_flat, out_flat, batch};
+    a.n_boxes = a.patch_rows <= 256 ? 1 : (a.patch_rows <= 512 ? 2 : F2_MAX_BOXES);
+    a.box_rows = yq::round_up((a.patch_rows + a.n_boxes - 1) / a.n_boxes, 8);
+    a.a_stage_bytes = yq::round_up(a.n_boxes * a.box_rows * st->KC, 1024);
+    a.out_cols = l->cs_out < F2_BN ? l->cs_out : F2_BN;
+    a.plain = plain ? 1 : 0;
+    Flat2State::Key key{in_flat, out_flat, batch * 2 + (plain ? 1 : 0)};
     auto it = st->maps.find(key);
     if (it == st->maps.end()) {
         if (st->maps.size() > 64) st->maps.clear();
         CUtensorMap tmA, tmO;
         if (f2_encode_2d(&tmA, in_flat, (uint64_t)rows_alloc, l->cs_in, st->KC, a.box_rows, CU_TENSOR_MAP_L2_PROMOTION_L2_128B)) return -1;
-        if (f2_encode_2d(&tmO, out_flat, (uint64_t)rows_alloc, l->cs_out, F2_BN, 128, CU_TENSOR_MAP_L2_PROMOTION_L2_128B)) return -1;
+        if (f2_encode_2d(&tmO, out_flat, (uint64_t)rows_alloc, l->cs_out, a.out_cols, 128, CU_TENSOR_MAP_L2_PROMOTION_L2_128B)) return -1;
         it = st->maps.emplace(key, std::make_pair(tmA, tmO)).first;
     }
     a.ep = yq::make_epi(l);

@@ -517,7 +517,7 @@ int yq_tc_small_supported(const yq_conv_layer *l)
     if (!(l->cs_in == 4 || l->cs_in == 16 || l->cs_in == 32)) return 0;
     // instantiated (cs_in, cs_out) pairs -- see yq_tc_small_forward
     const int ci = l->cs_in, co = l->cs_out;
-    return (ci == 4 && (co == 16 || co == 64)) || (ci == 16 && (co == 16 || co == 32)) || (ci == 32 && co == 64);
+    return (ci == 4 && (co == 16 || co == 32 || co == 64)) || (ci == 16 && (co == 16 || co == 32)) || (ci == 32 && co == 64);
 }
 
 int yq_tc_small_prepare(yq_conv_layer *l, void **state)
@@ -596,7 +596,7 @@ int yq_tc_small_forward(yq_conv_layer *l, void *state, const uint8_t *in_u8, uin
     memcpy(a.mc, l->host_mcomb.data(), (size_t)p * 8);
     const int actm = yq::act_mode(l->activation);
 #define YQ_SM(CS_, BN_) if (st->CS == CS_ && st->BN == BN_) return launch_small_act<CS_, BN_>(st, a, actm, stream)
-    YQ_SM(4, 16); YQ_SM(4, 64);
+    YQ_SM(4, 16); YQ_SM(4, 32); YQ_SM(4, 64);   // (4, 32): layer 0 of the full yolov3
     YQ_SM(16, 16); YQ_SM(16, 32);
     YQ_SM(32, 64);
 #undef YQ_SM

@@ -460,6 +460,9 @@ extern "C" int yq_forward_convolutional_layer_quant_pool_gpu(yq_conv_layer *l, c
     if (!l || !in_u8 || (!out_u8 && !out_pool) || batch <= 0) return yq::fail("yq_forward_convolutional_layer_quant_gpu: bad argument");
     if (l->quant_stop_flag && !out_f32) return yq::fail("quant_stop layer needs out_f32");
     if (out_pool && !yq_tc_can_fuse_pool(l)) return yq::fail("this layer's kernel flavour cannot fuse the max-pool (see yq_conv_can_fuse_maxpool)");
+    // a 1x1 convolution between plain tensors is a flat strip without halo positions: the persistent two-tile kernel takes it
+    if (yq_conv_plain_1x1_fast(l) && !out_pool && out_u8)
+        return yq_tc_flat2_forward(l, l->tc_flat2, in_u8, out_u8, 0, out_acc, batch, (cudaStream_t)stream, 1);
     if (l->kernel == 1) return yq_tc_forward(l, in_u8, out_u8, out_pool, out_f32, out_acc, batch, (cudaStream_t)stream);
     return launch_simt(l, in_u8, out_u8, out_f32, out_acc, batch, (cudaStream_t)stream);
 }
@@ -474,6 +477,12 @@ extern "C" int yq_forward_convolutional_layer_quant_gpu(yq_conv_layer *l, const 
 extern "C" int yq_conv_can_fuse_maxpool(const yq_conv_layer *l) { return l ? yq_tc_can_fuse_pool(l) : 0; }
 
 extern "C" int yq_conv_geom_supported(const yq_conv_layer *l) { return l && yq_tc_geom_supported(l) ? 1 : 0; }
+// 1: yq_forward_convolutional_layer_quant_gpu runs this (1x1) layer on conv_u8_tc_flat2_kernel in its plain-tensor mode
+int yq_conv_plain_1x1_fast(const yq_conv_layer *l)
+{
+    static const bool off = getenv("YQ_NO_PLAIN_1X1") && atoi(getenv("YQ_NO_PLAIN_1X1"));   // A/B measurements
+    return l && !off && l->kernel == 1 && l->size == 1 && l->tc_flat2 && !l->quant_stop_flag ? 1 : 0;
+}
 extern "C" int yq_forward_convolutional_layer_quant_geom_gpu(yq_conv_layer *l, const uint8_t *in_u8, const yq_act_geom *in_geom, int in_halo_fill,
                                                              uint8_t *out_u8, const yq_act_geom *out_geom, float *out_f32, int32_t *out_acc, int batch,
                                                              void *stream)
@@ -492,7 +501,12 @@ extern "C" int yq_forward_convolutional_layer_quant_geom_gpu(yq_conv_layer *l, c
 }
 
 static int check_geom(const yq_act_geom *g, int h, int w);
-extern "C" int yq_conv_flat_supported(const yq_conv_layer *l) { return l && l->tc_flat ? 1 : 0; }
+extern "C" int yq_conv_flat_supported(const yq_conv_layer *l)
+{
+    if (!l) return 0;
+    if (l->quant_stop_flag) return l->tc_flat ? 1 : 0;   // only the one-tile form writes the float side output
+    return (l->tc_flat || l->tc_flat2 || l->tc_flat2x) ? 1 : 0;
+}
 extern "C" int yq_act_geom_flat(int h, int w, yq_act_geom *g)
 {
     if (!g || h <= 0 || w <= 0) return yq::fail("yq_act_geom_flat: bad argument");
@@ -503,15 +517,27 @@ extern "C" int yq_forward_convolutional_layer_quant_flat_gpu(yq_conv_layer *l, c
                                                              int32_t *out_acc, int batch, void *stream)
 {
     if (!l || !in_flat || !out_flat || batch <= 0) return yq::fail("yq_forward_convolutional_layer_quant_flat_gpu: bad argument");
-    if (!l->tc_flat) return yq::fail("this layer has no flat flavour (see yq_conv_flat_supported)");
+    if (!yq_conv_flat_supported(l)) return yq::fail("this layer has no flat flavour (see yq_conv_flat_supported)");
     if (l->quant_stop_flag && !out_f32) return yq::fail("quant_stop layer needs out_f32");
     static const bool no_flat2 = getenv("YQ_NO_FLAT2") && atoi(getenv("YQ_NO_FLAT2"));   // A/B measurements
     // CTA-pair form for the long-K layers (measured: layers 10/12/14/21 1.07-1.24x faster, the short-K layers 6/8 slower);
     // YQ_FLAT2X=0 disables it, =2 forces it wherever it exists (A/B measurements)
     static const int use_2x = getenv("YQ_FLAT2X") ? atoi(getenv("YQ_FLAT2X")) : 1;
-    if (l->tc_flat2x && !no_flat2 && (use_2x == 2 || (use_2x == 1 && l->c >= 256))) return yq_tc_flat2x_forward(l, l->tc_flat2x, in_flat, out_flat, halo_fill, out_acc, batch, (cudaStream_t)stream);
-    if (l->tc_flat2 && !no_flat2) return yq_tc_flat2_forward(l, l->tc_flat2, in_flat, out_flat, halo_fill, out_acc, batch, (cudaStream_t)stream);
-    return yq_tc_flat_forward(l, l->tc_flat, in_flat, out_flat, halo_fill, out_f32, nullptr, 0, out_acc, batch, (cudaStream_t)stream);
+    // 1x1 layers: the persistent two-tile form pays once there are a few waves of tile pairs (the 52 x 52 ... 208 x 208 maps of
+    // the full yolov3); with one wave or less the one-tile form wins (layer 13 of yolov3-tiny: 0.0215 vs 0.0245 ms).
+    // YQ_FLAT2_1X1 = 0 / 1 forces the choice (A/B measurements)
+    const int one_env = getenv("YQ_FLAT2_1X1") ? atoi(getenv("YQ_FLAT2_1X1")) : -1;   // (read per call: the tests flip it)
+    bool two = l->tc_flat2 != nullptr && !no_flat2 && !l->quant_stop_flag;
+    if (two && l->size == 1 && l->tc_flat) {
+        const long long pairs = ((long long)batch * (l->h + 1) * (l->w + 1) + 255) / 256 * ((l->n + 127) / 128);
+        two = one_env >= 0 ? one_env != 0 : pairs >= 2 * 148;
+    }
+    if (l->tc_flat2x && !no_flat2 && (use_2x == 2 || (use_2x == 1 && l->c >= 256)))
+        return yq_tc_flat2x_forward(l, l->tc_flat2x, in_flat, out_flat, halo_fill, out_acc, batch, (cudaStream_t)stream);
+    if (two) return yq_tc_flat2_forward(l, l->tc_flat2, in_flat, out_flat, halo_fill, out_acc, batch, (cudaStream_t)stream);
+    if (l->tc_flat) return yq_tc_flat_forward(l, l->tc_flat, in_flat, out_flat, halo_fill, out_f32, nullptr, 0, out_acc, batch, (cudaStream_t)stream);
+    if (l->tc_flat2) return yq_tc_flat2_forward(l, l->tc_flat2, in_flat, out_flat, halo_fill, out_acc, batch, (cudaStream_t)stream);
+    return yq_tc_flat2x_forward(l, l->tc_flat2x, in_flat, out_flat, halo_fill, out_acc, batch, (cudaStream_t)stream);
 }
 extern "C" int yq_forward_convolutional_layer_quant_flat_yolo_gpu(yq_conv_layer *l, const uint8_t *in_flat, uint8_t *out_flat, int halo_fill,
                                                                   float *out_f32, float *out_yolo, int classes, int32_t *out_acc, int batch, void *stream)

@@ -387,7 +387,7 @@ void plan_side_branches(yq_network *net)
 void plan(yq_network *net)
 {
     const int n = (int)net->layers.size();
-    std::vector<char> rows_ok(n, 0), flat_ok(n, 0);
+    std::vector<char> rows_ok(n, 0), flat_ok(n, 0), plain1_ok(n, 0);
     int prev = -1;
     for (int i = 0; i < n; ++i) {
         Layer &l = net->layers[i];
@@ -400,6 +400,8 @@ void plan(yq_network *net)
         static const bool no_rows = getenv("YQ_NO_ROWS") && atoi(getenv("YQ_NO_ROWS")), no_flat = getenv("YQ_NO_FLAT") && atoi(getenv("YQ_NO_FLAT"));
         rows_ok[i] = !no_rows && net->fusion && pool22 && yq_conv_rows_supported(l.conv) && !conv_output_needed(net, i);
         flat_ok[i] = !no_flat && yq_conv_flat_supported(l.conv) != 0;
+        // a 1x1 layer that cannot keep flat tensors still runs the persistent kernel between PLAIN ones (no halo needed at all)
+        plain1_ok[i] = yq_conv_plain_1x1_fast(l.conv) != 0;
     }
     // requirement on tensor t (index t + 1; t = -1 is the network input): 0 none, 1 plain, 2 a specific padded geometry
     struct Req { int kind = 0; yq_act_geom g = {0, 0, 0}; int fill = -1; bool conflict = false; };
@@ -428,6 +430,9 @@ void plan(yq_network *net)
                 yq_act_geom_flat(l.h, l.w, &g);
                 need(l.src, 2, &g, l.zp_in);
                 need(i, 2, &g, -1);
+            } else if (plain1_ok[i]) {
+                need(l.src, 1, nullptr, -1);
+                need(i, 1, nullptr, -1);
             } else if (yq_conv_geom_supported(l.conv)) {
                 // the per-tap TMA flavour reads and writes through tensor maps built for whatever geometry the tensors have
             } else {
@@ -439,6 +444,16 @@ void plan(yq_network *net)
             }
         }
         bool changed = false;
+        // a plain-strip 1x1 layer next to a conflicting tensor gives way first (it falls to the per-tap flavour, which takes any geometry)
+        for (int i = 0; i < n; ++i) {
+            Layer &l = net->layers[i];
+            if (l.type != L_CONV || rows_ok[i] || flat_ok[i] || !plain1_ok[i] || !yq_conv_geom_supported(l.conv)) continue;
+            if (req[tensor_of(net, l.src) + 1].conflict || req[tensor_of(net, i) + 1].conflict) {
+                plain1_ok[i] = 0;
+                changed = true;
+            }
+        }
+        if (changed) continue;
         for (int i = 0; i < n; ++i) {
             Layer &l = net->layers[i];
             if (l.type != L_CONV || !(rows_ok[i] || flat_ok[i])) continue;
@@ -500,7 +515,7 @@ void plan(yq_network *net)
                 l.use_flat = true;
                 if (net->fusion && l.quant_stop && i + 1 < n && net->layers[i + 1].type == L_YOLO && l.n % (net->layers[i + 1].classes + 5) == 0)
                     l.fuse_yolo = net->layers[i + 1].fused_away = true;
-            } else if (yq_conv_geom_supported(l.conv)) {
+            } else if (yq_conv_geom_supported(l.conv) && !plain1_ok[i]) {
                 l.use_geom = true;
             } else if (net->fusion && i + 1 < n && yq_conv_can_fuse_maxpool(l.conv)) {
                 Layer &p = net->layers[i + 1];
