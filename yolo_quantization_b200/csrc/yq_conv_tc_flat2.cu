@@ -233,91 +233,104 @@ __global__ void __launch_bounds__(F2_THREADS, 1) conv_u8_tc_flat2_kernel(const _
             if (lane == 0) f2_arrive(&sum_full[pb]);
         }
     } else {
-        // ===================== epilogue: 16 warps, 4 per TMEM lane quarter, 32 channels each =====================
+        // ===================== epilogue: 16 warps, each on its own =====================
+        // Warp (q, g): q = warp & 3 is the TMEM lane quarter the hardware lets it read (32 positions), g = 0..3 picks the tile of the
+        // pair (g >> 1) and the 64-channel half of it (g & 1).  A warp requantizes its 32 x 64 block into a PRIVATE 2 KB staging
+        // slice and issues its own TMA store: no barrier between epilogue warps on the tile path, so the warps drift apart and one
+        // warp's TMEM-load and store latencies hide behind the others' arithmetic (the CTA-wide barrier per tile of the first
+        // version kept all 16 in lockstep: issue slots 55 % used, profiles/r2_flat2_before.txt).
         const int ew = warp - (2 + F2_SUM_WARPS);
-        const int q = warp & 3;                 // TMEM lane quarter this warp may access
-        const int part = ew >> 2;               // which quarter of the tile's 128 channels
+        const int q = warp & 3;
+        const int g = ew >> 2;
+        const int j = g >> 1, half = g & 1;
         const int r = q * 32 + lane;            // tile row = TMEM lane
         const int et = threadIdx.x - 32 * (2 + F2_SUM_WARPS);
         constexpr int EPI_THREADS = 32 * F2_EPI_WARPS;
         const bool side = SLOW && a.out_acc != nullptr;
         const int actm = yq::act_mode(a.ep.act);
         const int pitch = a.W + 1;
+        const int cbeg = half * 64;
+        const int nch = a.out_cols - cbeg >= 64 ? 4 : (a.out_cols - cbeg > 0 ? (a.out_cols - cbeg) / 16 : 0);   // 16-channel chunks of mine
+        const int rowb = a.out_cols >= 64 ? 64 : 32;                      // bytes per staging row = inner box of the store
+        uint8_t *stage = sOut + ew * 2048;                               // [32 rows][rowb] in the store map's swizzle
+        const int lr = lane;                                             // row within my staging slice
         int cur_nt = -1;
         uint32_t it = 0;
         for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x, ++it) {
             const int nt = a.m_pairs == 1 ? tile : (int)__umulhi((uint32_t)tile, a.magic_m), mp = tile - nt * a.m_pairs;
             const int oc0 = nt * F2_BN;
             const int pb = it & 1;
-            // both staging tiles must be free (the stores of the previous pair have finished reading them)
-            if (et == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
             if (nt != cur_nt) {
+                // a new n-tile: every epilogue warp is done with the old parameters before they are overwritten (the only barrier
+                // among the epilogue warps; once per n-tile, i.e. once or twice per CTA on the big layers)
+                asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");
                 for (int i = et; i < F2_BN; i += EPI_THREADS) {
                     s_q[i] = __ldg(a.ep.chanq + oc0 + i);
                     s_mc[i] = __ldg(a.ep.mcomb + oc0 + i);
                 }
                 cur_nt = nt;
+                asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");
             }
-            asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");
+            const int p0 = mp * 256 + j * 128;
+            const int p = p0 + r;
+            const int row = (int)__umulhi((uint32_t)p, a.magic_w);
+            const int col = p - row * pitch;
+            const int n = (int)__umulhi((uint32_t)row, a.magic_h);
+            const int y1 = row - n * (a.H + 1);
+            const bool valid = p < a.NP && (a.plain || (col >= 1 && y1 >= 1));
+            const size_t pix = a.plain ? (size_t)p : ((size_t)n * a.H + (y1 - 1)) * a.W + (col - 1);
             mbar_wait(&sum_full[pb], (it >> 1) & 1);
+            // sum of activations under this position's window, from the per-row sums of the patch
+            int sa_sum;
+            {
+                const int *sp = s_sum + pb * F2_MAX_ROWS + j * 128 + r;
+                if (a.size == 3) {
+                    const int *s1 = sp + pitch, *s2 = s1 + pitch;
+                    sa_sum = (sp[0] + sp[1] + sp[2]) + (s1[0] + s1[1] + s1[2]) + (s2[0] + s2[1] + s2[2]);
+                } else {
+                    sa_sum = sp[0];
+                }
+            }
+            const int nsa = -sa_sum;
             mbar_wait(&acc_full[pb], (it >> 1) & 1);
             tc_fence_after();
-#pragma unroll 1
-            for (int j = 0; j < 2; ++j) {
-                const int p0 = mp * 256 + j * 128;
-                const int p = p0 + r;
-                const int row = (int)__umulhi((uint32_t)p, a.magic_w);
-                const int col = p - row * pitch;
-                const int n = (int)__umulhi((uint32_t)row, a.magic_h);
-                const int y1 = row - n * (a.H + 1);
-                const bool valid = p < a.NP && (a.plain || (col >= 1 && y1 >= 1));
-                const size_t pix = a.plain ? (size_t)p : ((size_t)n * a.H + (y1 - 1)) * a.W + (col - 1);
-                // sum of activations under this position's window, from the per-row sums of the patch
-                int sa_sum = 0;
-                {
-                    const int *sp = s_sum + pb * F2_MAX_ROWS + j * 128 + r;
-                    for (int ky = 0; ky < a.size; ++ky)
-                        for (int kx = 0; kx < a.size; ++kx) sa_sum += sp[ky * pitch + kx];
-                }
-                const int nsa = -sa_sum;
-                uint8_t *stage = sOut + j * L::OUT_BYTES;
-                const uint32_t trow = tmem_base + (pb * 2 + j) * F2_BN + ((uint32_t)(q * 32) << 16);
-                const int cbeg = part * 32;
-                const bool mine = cbeg < a.out_cols;      // narrow layers (n <= 64): the upper channel quarters are padding, never stored
-                uint32_t vbuf[2][16];
-                if (mine) {
-                    tmem_ld16_issue(trow + cbeg, vbuf[0]);
-                    tmem_ld_wait16(vbuf[0]);
-                }
+            const uint32_t trow = tmem_base + (pb * 2 + j) * F2_BN + ((uint32_t)(q * 32) << 16) + cbeg;
+            uint32_t vbuf[2][16];
+            if (nch > 0 && a.debug != 2) {
+                tmem_ld16_issue(trow, vbuf[0]);
+                // my staging slice is free once the store of the previous pair has read it
+                if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                tmem_ld_wait16(vbuf[0]);
+                __syncwarp();
                 auto run = [&](auto actm_tag, auto sat_tag) {
                     constexpr int ACTM = decltype(actm_tag)::value;
                     constexpr bool SAT = decltype(sat_tag)::value;
 #pragma unroll
-                    for (int ch = 0; ch < 2; ++ch) {
-                        const int c0 = cbeg + 16 * ch;
-                        uint32_t(&v)[16] = vbuf[ch & 1];
-                        if (ch == 0) tmem_ld16_issue(trow + c0 + 16, vbuf[1]);   // in flight while this chunk is requantized
-                        uint32_t packed[4];
-                        int extra[16];
-                        yq::requant_chunk<ACTM, SAT, 16, false>(v, nsa, extra, s_q + c0, s_mc + c0, a.ep.zp_out, packed);
-                        if (!valid) packed[0] = packed[1] = packed[2] = packed[3] = a.halo_word;
-                        yq::mask_pad_channels<16>(packed, a.N - (oc0 + c0));
-                        if (SLOW && side && valid) {
+                    for (int ch = 0; ch < 4; ++ch) {
+                        if (ch < nch) {
+                            const int c0 = cbeg + 16 * ch;
+                            uint32_t(&v)[16] = vbuf[ch & 1];
+                            if (ch + 1 < nch) tmem_ld16_issue(trow + 16 * (ch + 1), vbuf[(ch + 1) & 1]);   // in flight while this chunk is requantized
+                            uint32_t packed[4];
+                            int extra[16];
+                            yq::requant_chunk<ACTM, SAT, 16, false>(v, nsa, extra, s_q + c0, s_mc + c0, a.ep.zp_out, packed);
+                            if (!valid) packed[0] = packed[1] = packed[2] = packed[3] = a.halo_word;
+                            yq::mask_pad_channels<16>(packed, a.N - (oc0 + c0));
+                            if (SLOW && side && valid) {
 #pragma unroll
-                            for (int jj = 0; jj < 16; ++jj) {
-                                const int oc = oc0 + c0 + jj;
-                                if (oc < a.N) a.out_acc[pix * a.CSO + oc] = (int)v[jj] + s_q[c0 + jj].y * nsa;
+                                for (int jj = 0; jj < 16; ++jj) {
+                                    const int oc = oc0 + c0 + jj;
+                                    if (oc < a.N) a.out_acc[pix * a.CSO + oc] = (int)v[jj] + s_q[c0 + jj].y * nsa;
+                                }
                             }
+                            // 64-byte rows: SWIZZLE_64B (16-byte chunk ^ row bits 1-2); 32-byte rows: SWIZZLE_32B (chunk ^ row bit 2)
+                            const int sw = rowb == 64 ? (ch ^ ((lr >> 1) & 3)) : (ch ^ ((lr >> 2) & 1));
+                            *reinterpret_cast<uint4 *>(stage + lr * rowb + sw * 16) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+                            if (ch + 1 < nch) tmem_ld_wait16(vbuf[(ch + 1) & 1]);
                         }
-                        // staging rows of out_cols bytes in the swizzle of the store's tensor map (128B / 64B / 32B)
-                        const int chunk = c0 / 16;
-                        const int sw = a.out_cols >= 128 ? (chunk ^ (r & 7)) : (a.out_cols == 64 ? (chunk ^ ((r >> 1) & 3)) : (chunk ^ ((r >> 2) & 1)));
-                        *reinterpret_cast<uint4 *>(stage + (size_t)r * a.out_cols + sw * 16) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
-                        if (ch == 0) tmem_ld_wait16(vbuf[1]);
                     }
                 };
-                if (a.debug == 2 || !mine) {
-                } else if (SLOW && a.ep.saturate) {
+                if (SLOW && a.ep.saturate) {
                     if (actm == 0) run(std::integral_constant<int, 0>{}, std::true_type{});
                     else if (actm == 1) run(std::integral_constant<int, 1>{}, std::true_type{});
                     else run(std::integral_constant<int, 2>{}, std::true_type{});
@@ -326,20 +339,21 @@ __global__ void __launch_bounds__(F2_THREADS, 1) conv_u8_tc_flat2_kernel(const _
                     else if (actm == 1) run(std::integral_constant<int, 1>{}, std::false_type{});
                     else run(std::integral_constant<int, 2>{}, std::false_type{});
                 }
-                if (j == 1) {   // this warp's TMEM and S reads of the pair are done: hand both accumulators back
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) f2_arrive(&acc_empty[pb]);
-                }
-                fence_proxy_async();
-                asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");
-                if (et == 0) {
-                    tma_store_2d(&tmO, stage, oc0, p0);
+            }
+            // this warp's TMEM and S reads of the pair are done: hand the accumulators back
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) f2_arrive(&acc_empty[pb]);
+            if (nch > 0 && a.debug != 2) {
+                fence_proxy_async();          // my staging writes -> visible to the TMA unit
+                __syncwarp();
+                if (lane == 0) {
+                    tma_store_2d(&tmO, stage, oc0 + cbeg, p0 + q * 32);
                     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                 }
             }
         }
-        if (et == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // global writes complete before the CTA retires
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // global writes complete before the CTA retires
     }
     tc_fence_before();
     __syncthreads();
@@ -507,7 +521,8 @@ int yq_tc_flat2_forward(yq_conv_layer *l, void *state, const uint8_t *in_flat, u
         if (st->maps.size() > 64) st->maps.clear();
         CUtensorMap tmA, tmO;
         if (f2_encode_2d(&tmA, in_flat, (uint64_t)rows_alloc, l->cs_in, st->KC, a.box_rows, CU_TENSOR_MAP_L2_PROMOTION_L2_128B)) return -1;
-        if (f2_encode_2d(&tmO, out_flat, (uint64_t)rows_alloc, l->cs_out, a.out_cols, 128, CU_TENSOR_MAP_L2_PROMOTION_L2_128B)) return -1;
+        // the store box is one epilogue warp's block: 32 positions x 64 channels (32 when the layer has no more)
+        if (f2_encode_2d(&tmO, out_flat, (uint64_t)rows_alloc, l->cs_out, a.out_cols >= 64 ? 64 : 32, 32, CU_TENSOR_MAP_L2_PROMOTION_L2_128B)) return -1;
         it = st->maps.emplace(key, std::make_pair(tmA, tmO)).first;
     }
     a.ep = yq::make_epi(l);

@@ -254,69 +254,74 @@ __global__ void __launch_bounds__(F2X_THREADS, 1) conv_u8_tc_flat2x_kernel(const
             if (lane == 0) f2x_arrive(&sum_full[pb]);
         }
     } else {
-        // ===================== epilogue: 16 warps, 4 per TMEM lane quarter, 32 channels each =====================
+        // ===================== epilogue: 16 warps, each on its own (see yq_conv_tc_flat2.cu) =====================
+        // Warp (q, g): q = warp & 3 = its TMEM lane quarter (32 positions); g = 0..3 picks a 32 x 64 block of the CTA's part of the
+        // accumulator pair -- two-tile form: tile g >> 1, channel half g & 1; WIDE: channels [64 g, 64 g + 64) of the one tile.
+        // Private 2 KB staging slice, own TMA store, no barrier between epilogue warps on the tile path.
         const int ew = warp - (2 + F2X_SUM_WARPS);
-        const int q = warp & 3;                 // TMEM lane quarter this warp may access
-        const int part = ew >> 2;               // which quarter of the tile's 128 channels
+        const int q = warp & 3;
+        const int g = ew >> 2;
+        const int j = WIDE ? 0 : (g >> 1);
+        const int cbeg = WIDE ? 64 * g : 64 * (g & 1);
         const int r = q * 32 + lane;            // tile row = TMEM lane
         const int et = threadIdx.x - 32 * (2 + F2X_SUM_WARPS);
         constexpr int EPI_THREADS = 32 * F2X_EPI_WARPS;
         const bool side = SLOW && a.out_acc != nullptr;
         const int actm = yq::act_mode(a.ep.act);
         const int pitch = a.W + 1;
+        uint8_t *stage = sOut + ew * 2048;      // [32 rows][64 bytes], SWIZZLE_64B
         int cur_nt = -1;
         uint32_t it = 0;
         for (int tile = cid; tile < a.num_tiles; tile += ncl, ++it) {
             const int nt = a.m_pairs == 1 ? tile : (int)__umulhi((uint32_t)tile, a.magic_m), mp = tile - nt * a.m_pairs;
             const int oc0 = nt * BNT;
             const int pb = it & 1;
-            // both staging tiles must be free (the stores of the previous pair have finished reading them)
-            if (et == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-            if (nt != cur_nt) {
+            if (nt != cur_nt) {   // a new n-tile: everyone is done with the old parameters before they are overwritten
+                asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");
                 for (int i = et; i < BNT; i += EPI_THREADS) {
                     s_q[i] = __ldg(a.ep.chanq + oc0 + i);
                     s_mc[i] = __ldg(a.ep.mcomb + oc0 + i);
                 }
                 cur_nt = nt;
+                asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");
             }
-            asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");
+            const int p0 = mp * 2 * PPC + (int)rank * PPC + j * 128;
+            const int p = p0 + r;
+            const int row = (int)__umulhi((uint32_t)p, a.magic_w);
+            const int col = p - row * pitch;
+            const int n = (int)__umulhi((uint32_t)row, a.magic_h);
+            const int y1 = row - n * (a.H + 1);
+            const bool valid = p < a.NP && col >= 1 && y1 >= 1;
+            const size_t pix = ((size_t)n * a.H + (y1 - 1)) * a.W + (col - 1);
             mbar_wait(&sum_full[pb], (it >> 1) & 1);
+            int sa_sum;
+            {
+                const int *sp = s_sum + pb * F2X_MAX_ROWS + j * 128 + r;
+                if (a.size == 3) {
+                    const int *s1 = sp + pitch, *s2 = s1 + pitch;
+                    sa_sum = (sp[0] + sp[1] + sp[2]) + (s1[0] + s1[1] + s1[2]) + (s2[0] + s2[1] + s2[2]);
+                } else {
+                    sa_sum = sp[0];
+                }
+            }
+            const int nsa = -sa_sum;
             mbar_wait(&acc_full[pb], (it >> 1) & 1);
             tc_fence_after();
-#pragma unroll 1
-            for (int j = 0; j < TPC; ++j) {
-                const int p0 = mp * 2 * PPC + (int)rank * PPC + j * 128;
-                const int p = p0 + r;
-                const int row = (int)__umulhi((uint32_t)p, a.magic_w);
-                const int col = p - row * pitch;
-                const int n = (int)__umulhi((uint32_t)row, a.magic_h);
-                const int y1 = row - n * (a.H + 1);
-                const bool valid = p < a.NP && col >= 1 && y1 >= 1;
-                const size_t pix = ((size_t)n * a.H + (y1 - 1)) * a.W + (col - 1);
-                // sum of activations under this position's window, from the per-row sums of the patch
-                int sa_sum = 0;
-                {
-                    const int *sp = s_sum + pb * F2X_MAX_ROWS + j * 128 + r;
-                    for (int ky = 0; ky < a.size; ++ky)
-                        for (int kx = 0; kx < a.size; ++kx) sa_sum += sp[ky * pitch + kx];
-                }
-                const int nsa = -sa_sum;
-                constexpr int CPW = BNT / 4, NCH = CPW / 16;          // columns / 16-column chunks per epilogue warp
-                const int cbeg = part * CPW;
-                // staging tile: the tile's index (two-tile form) or the 128-channel half this warp works on (WIDE)
-                uint8_t *stage = sOut + (WIDE ? (cbeg >> 7) : j) * L::OUT_BYTES;
-                const uint32_t trow = tmem_base + pb * 256 + j * 128 + ((uint32_t)(q * 32) << 16);
-                uint32_t vbuf[2][16];
-                tmem_ld16_issue(trow + cbeg, vbuf[0]);
+            const uint32_t trow = tmem_base + pb * 256 + j * 128 + ((uint32_t)(q * 32) << 16) + cbeg;
+            uint32_t vbuf[2][16];
+            if (a.debug != 2) {
+                tmem_ld16_issue(trow, vbuf[0]);
+                if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // my staging slice is free again
                 tmem_ld_wait16(vbuf[0]);
+                __syncwarp();
                 auto run = [&](auto actm_tag, auto sat_tag) {
                     constexpr int ACTM = decltype(actm_tag)::value;
                     constexpr bool SAT = decltype(sat_tag)::value;
 #pragma unroll
-                    for (int ch = 0; ch < NCH; ++ch) {
+                    for (int ch = 0; ch < 4; ++ch) {
                         const int c0 = cbeg + 16 * ch;
                         uint32_t(&v)[16] = vbuf[ch & 1];
-                        if (ch + 1 < NCH) tmem_ld16_issue(trow + c0 + 16, vbuf[(ch + 1) & 1]);   // in flight while this chunk is requantized
+                        if (ch + 1 < 4) tmem_ld16_issue(trow + 16 * (ch + 1), vbuf[(ch + 1) & 1]);   // in flight while this chunk is requantized
                         uint32_t packed[4];
                         int extra[16];
                         yq::requant_chunk<ACTM, SAT, 16, false>(v, nsa, extra, s_q + c0, s_mc + c0, a.ep.zp_out, packed);
@@ -329,12 +334,11 @@ __global__ void __launch_bounds__(F2X_THREADS, 1) conv_u8_tc_flat2x_kernel(const
                                 if (oc < a.N) a.out_acc[pix * a.CSO + oc] = (int)v[jj] + s_q[c0 + jj].y * nsa;
                             }
                         }
-                        *reinterpret_cast<uint4 *>(stage + (size_t)r * 128 + ((((c0 & 127) / 16) ^ (r & 7)) * 16)) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
-                        if (ch + 1 < NCH) tmem_ld_wait16(vbuf[(ch + 1) & 1]);
+                        *reinterpret_cast<uint4 *>(stage + lane * 64 + ((ch ^ ((lane >> 1) & 3)) * 16)) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+                        if (ch + 1 < 4) tmem_ld_wait16(vbuf[(ch + 1) & 1]);
                     }
                 };
-                if (a.debug == 2) {
-                } else if (SLOW && a.ep.saturate) {
+                if (SLOW && a.ep.saturate) {
                     if (actm == 0) run(std::integral_constant<int, 0>{}, std::true_type{});
                     else if (actm == 1) run(std::integral_constant<int, 1>{}, std::true_type{});
                     else run(std::integral_constant<int, 2>{}, std::true_type{});
@@ -343,29 +347,24 @@ __global__ void __launch_bounds__(F2X_THREADS, 1) conv_u8_tc_flat2x_kernel(const
                     else if (actm == 1) run(std::integral_constant<int, 1>{}, std::false_type{});
                     else run(std::integral_constant<int, 2>{}, std::false_type{});
                 }
-                if (j == TPC - 1) {   // this warp's TMEM and S reads of the pair are done: hand the accumulators back
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) {
-                        f2x_arrive(&acc_empty[pb]);                                              // local: my sum warps / (leader) MMA warp
-                        if (rank == 1) mbar_arrive_cluster(map_to_cta(&acc_peer_empty[pb], 0));      // the leader's MMA warp
-                        else if (false) {}
-                    }
-                }
+            }
+            // this warp's TMEM and S reads of the pair are done: hand the accumulators back
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+                f2x_arrive(&acc_empty[pb]);                                              // local: my sum warps / (leader) MMA warp
+                if (rank == 1) mbar_arrive_cluster(map_to_cta(&acc_peer_empty[pb], 0));      // the leader's MMA warp
+            }
+            if (a.debug != 2) {
                 fence_proxy_async();
-                asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");
-                if (et == 0) {
-                    if (WIDE) {
-                        tma_store_2d(&tmO, sOut, oc0, p0);
-                        tma_store_2d(&tmO, sOut + L::OUT_BYTES, oc0 + 128, p0);
-                    } else {
-                        tma_store_2d(&tmO, sOut + j * L::OUT_BYTES, oc0, p0);
-                    }
+                __syncwarp();
+                if (lane == 0) {
+                    tma_store_2d(&tmO, stage, oc0 + cbeg, p0 + q * 32);
                     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                 }
             }
         }
-        if (et == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // global writes complete before the CTA retires
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // global writes complete before the CTA retires
     }
     tc_fence_before();
     cluster_sync_all();            // nobody leaves while the peer may still signal its barriers or use the pair's TMEM
@@ -559,7 +558,8 @@ int yq_tc_flat2x_forward(yq_conv_layer *l, void *state, const uint8_t *in_flat, 
         if (st->maps.size() > 64) st->maps.clear();
         CUtensorMap tmA, tmO;
         if (f2x_encode_2d(&tmA, in_flat, (uint64_t)rows_alloc, l->cs_in, st->KC, a.box_rows, CU_TENSOR_MAP_L2_PROMOTION_L2_128B)) return -1;
-        if (f2x_encode_2d(&tmO, out_flat, (uint64_t)rows_alloc, l->cs_out, 128, 128, CU_TENSOR_MAP_L2_PROMOTION_L2_128B)) return -1;
+        // the store box is one epilogue warp's block: 32 positions x 64 channels
+        if (f2x_encode_2d(&tmO, out_flat, (uint64_t)rows_alloc, l->cs_out, 64, 32, CU_TENSOR_MAP_L2_PROMOTION_L2_128B)) return -1;
         it = st->maps.emplace(key, std::make_pair(tmA, tmO)).first;
     }
     a.ep = yq::make_epi(l);

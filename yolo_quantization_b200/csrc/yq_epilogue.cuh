@@ -151,6 +151,14 @@ __device__ __forceinline__ void requant_chunk(const uint32_t (&v)[NV], int nsa, 
             const uint32_t ax = (uint32_t)abs(x);
             mx = max(mx, ax);
             const int h = (int)(__umulhi(ax, (uint32_t)c.z) >> c.w);
+            if (ACTM == 2) {
+                // LEAKY from the magnitude: x < 0 -> zo - round(h / 10) (half away from zero), else zo + h; one select, no second sign test
+                const int t = (int)(__umulhi((uint32_t)h + 5u, 0xCCCCCCCDu) >> 3);
+                int rr = x < 0 ? zo - t : zo + h;
+                if (SAT) rr = max(0, min(255, rr));
+                r[j] = rr;
+                continue;
+            }
             q = x < 0 ? -h : h;
         }
         r[j] = act_value<ACTM, SAT>(q, zo);
