@@ -242,6 +242,19 @@ YQ_API int yq_forward_yolo_layer_gpu(const float *in, float *out, int batch, int
 YQ_API int yq_quantize_input_gpu(const float *in_f32_chw, uint8_t *out_u8_chw, float *scales, int *zero_points, int *scratch,
                                  int batch, int n, void *stream);
 
+/* letterbox_image (src/image.c:812-831: resize_image :1199-1245 into a .5-filled w x h canvas, embed_image :428-439) for a
+ * batch of float CHW images of one size [batch][c][ih][iw] already on the device -> [batch][c][h][w].  Float operations in the
+ * reference's order, each rounded on its own (the test oracle's plain-C restatement matches the compiled reference bit for bit). */
+YQ_API int yq_letterbox_image_gpu(const float *in_chw, int batch, int c, int ih, int iw, float *out_chw, int h, int w, void *stream);
+
+/* Layer 0 behind the dynamic input quantiser when the images of a batch quantise DIFFERENTLY: the reference derives
+ * (s_in, zp_in) from its one image (src/blas.c:279) and M, biases_int32 (blas.c:301-334) and the im2col padding value
+ * (src/im2col.c:5-14) of layer 0 follow; here they are per-image device tables: biases_int32 [batch][table_pitch],
+ * multiplier = M_value * M0_right_shift_value [batch][table_pitch] (doubles), zp_in [batch].  Plain tensors, generic flavour. */
+YQ_API int yq_forward_convolutional_layer_quant_per_image_gpu(yq_conv_layer *l, const uint8_t *in_u8, uint8_t *out_u8, int32_t *out_acc,
+                                                              int batch, const int32_t *biases_int32_dev, const double *multiplier_dev,
+                                                              const uint8_t *zp_in_dev, int table_pitch, void *stream);
+
 /* layout conversion at the boundary (reference tensors are CHW per image) */
 YQ_API int yq_nchw_to_nhwc_u8(const uint8_t *in_nchw, uint8_t *out_nhwc, int batch, int c, int h, int w,
                               void *stream);
@@ -305,9 +318,14 @@ YQ_API int yq_forward_network_device(yq_network *net, const uint8_t *in_u8_nchw)
 YQ_API int yq_network_predict_u8(yq_network *net, const uint8_t *in_u8_nchw_host, float *out_f32_host);
 /* network_predict with HOST FLOAT images (the reference's net->input): H2D, device input quantiser
  * (yq_quantize_input_gpu), layer-0 re-prep when (s_in, zp_in) changed -- exactly what test_detector does per image
- * (examples/detector.c:915-922) -- forward, D2H.  Layer 0's multipliers depend on (s_in, zp_in), so every image of the
- * batch must quantize to the same pair (always true at batch 1); otherwise the call fails. */
+ * (examples/detector.c:915-922) -- forward, D2H.  Layer 0's multipliers, biases_int32 and padding value depend on
+ * (s_in, zp_in): when every image of the batch quantises to the same pair the planned (tensor-core) layer 0 runs, re-prepared
+ * if the pair changed; when they differ, layer 0 runs yq_forward_convolutional_layer_quant_per_image_gpu with per-image tables
+ * and the rest of the plan is unchanged. */
 YQ_API int yq_network_predict_f32(yq_network *net, const float *in_f32_nchw_host, float *out_f32_host);
+/* test_detector's whole input path (examples/detector.c:903-904, :915-922): host float CHW images of one size
+ * [batch][c][ih][iw] (what load_image_color returns) -> H2D, letterbox_image on the device, dynamic input quantiser, forward. */
+YQ_API int yq_network_predict_image_f32(yq_network *net, const float *images_host, int ih, int iw, float *out_f32_host);
 /* the same, pipelined two deep so H2D / forward / D2H of neighbouring batches overlap (serving loop):
  * submit enqueues the H2D of one batch and its forward and returns a slot (>= 0; < 0 on error);
  * collect waits for that slot and copies the yolo heads to out_f32.  Use pinned host memory. */
@@ -332,8 +350,11 @@ YQ_API int yq_network_launches_per_forward(const yq_network *net);
  *   yq_pack_arena_load(path)  before yq_load_network / yq_make_convolutional_layer_quant: entries read (0 for a file of
  *                             another layout version), -1 on error;
  *   yq_pack_arena_save(path)  afterwards, when yq_pack_arena_stats reports dirty: entries written;
- *   yq_pack_arena_clear()     drops the in-memory arena and its counters.
- * A stale or foreign file can only miss, never alias: the weights are part of the key. */
+ *   yq_pack_arena_clear()     drops the in-memory arena and its counters (and disables collecting);
+ *   yq_pack_arena_enable(1)   starts collecting freshly built images without a file to load (a successful load enables too).
+ * A stale or foreign file misses (the weights are part of the key); every entry carries a checksum of its data and a damaged
+ * entry is dropped at load (a miss).  It is a cache, not an authenticated container (see yq_pack.cu). */
+YQ_API int yq_pack_arena_enable(int enable);
 YQ_API int yq_pack_arena_load(const char *path);
 YQ_API int yq_pack_arena_save(const char *path);
 YQ_API int yq_pack_arena_clear(void);

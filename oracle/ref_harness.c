@@ -18,6 +18,7 @@
  *                                                            (forward_network reads layers[i+1] out of bounds on a
  *                                                             net that does not end in [yolo], network.c:247)
  *   ref_harness time  <cfg> <weights> <input.f32> <iters>    time network_predict, print seconds per call on stderr
+ *   ref_harness letterbox <in.f32> <c> <ih> <iw> <w> <h> <out.f32>   letterbox_image alone (src/image.c:812-831)
  *
  * <input.f32> is a raw little-endian float32 CHW image of net->c * net->h * net->w values.
  */
@@ -95,6 +96,18 @@ static void dump_layer(const char *dir, FILE *man, int i, layer *l)
 
 int main(int argc, char **argv)
 {
+ /* ref_harness letterbox <in.f32> <c> <ih> <iw> <w> <h> <out.f32> : the reference's letterbox_image (src/image.c:812-831) alone */
+    if (argc == 9 && !strcmp(argv[1], "letterbox")) {
+        int c = atoi(argv[3]), ih = atoi(argv[4]), iw = atoi(argv[5]), w = atoi(argv[6]), h = atoi(argv[7]);
+        image im = make_image(iw, ih, c);
+        float *src = read_f32(argv[2], (size_t)c * ih * iw);
+        memcpy(im.data, src, sizeof(float) * (size_t)c * ih * iw);
+        image boxed = letterbox_image(im, w, h);
+        FILE *fp = fopen(argv[8], "wb");
+        if (!fp || fwrite(boxed.data, sizeof(float), (size_t)c * h * w, fp) != (size_t)c * h * w) die("cannot write the letterboxed image");
+        fclose(fp);
+        return 0;
+    }
     if (argc < 6) die("usage: ref_harness net|layer|time <cfg> <weights> <input.f32> <outdir|iters>");
     const char *mode = argv[1];
     network *net = load_network(argv[2], argv[3], 0);

@@ -417,3 +417,57 @@ void yq_oracle_shortcut(const uint8_t *a, const uint8_t *b, size_t n, int zp_a, 
         out[i] = (uint8_t)(r < 0 ? 0 : r > 255 ? 255 : r);
     }
 }
+
+/*
+ * letterbox_image, src/image.c:812-831 = resize_image (:1199-1245: horizontal pass into `part`, vertical pass with set_pixel +
+ * add_pixel) into a w x h canvas filled with .5 (:695) at ((w - new_w)/2, (h - new_h)/2) (embed_image :428-439).  Plain float
+ * arithmetic in the reference's order.  (The reference's -Ofast build may fuse or reorder the multiply-adds: compared with the
+ * compiled reference the quantised bytes may differ by one LSB at rounding ties)
+ */
+void yq_oracle_letterbox(const float *im, int c, int ih, int iw, float *boxed, int h, int w)
+{
+    int new_w = iw, new_h = ih;
+    if (((float)w / iw) < ((float)h / ih)) { new_w = w; new_h = (ih * w) / iw; }
+    else { new_h = h; new_w = (iw * h) / ih; }
+    float *part = malloc(sizeof(float) * (size_t)c * ih * new_w);
+    float *res = malloc(sizeof(float) * (size_t)c * new_h * new_w);
+    float w_scale = (float)(iw - 1) / (new_w - 1);
+    float h_scale = (float)(ih - 1) / (new_h - 1);
+    for (int k = 0; k < c; ++k)
+        for (int r = 0; r < ih; ++r)
+            for (int x = 0; x < new_w; ++x) {
+                volatile float val;
+                if (x == new_w - 1 || iw == 1) {
+                    val = im[((size_t)k * ih + r) * iw + iw - 1];
+                } else {
+                    float sx = x * w_scale;
+                    int ix = (int)sx;
+                    float dx = sx - ix;
+                    volatile float a = (1 - dx) * im[((size_t)k * ih + r) * iw + ix];
+                    volatile float b = dx * im[((size_t)k * ih + r) * iw + ix + 1];
+                    val = a + b;
+                }
+                part[((size_t)k * ih + r) * new_w + x] = val;
+            }
+    for (int k = 0; k < c; ++k)
+        for (int r = 0; r < new_h; ++r) {
+            float sy = r * h_scale;
+            int iy = (int)sy;
+            float dy = sy - iy;
+            for (int x = 0; x < new_w; ++x) {
+                volatile float val = (1 - dy) * part[((size_t)k * ih + iy) * new_w + x];
+                if (!(r == new_h - 1 || ih == 1)) {
+                    volatile float t = dy * part[((size_t)k * ih + iy + 1) * new_w + x];
+                    val = val + t;
+                }
+                res[((size_t)k * new_h + r) * new_w + x] = val;
+            }
+        }
+    for (size_t i = 0; i < (size_t)c * h * w; ++i) boxed[i] = .5f;
+    int ox = (w - new_w) / 2, oy = (h - new_h) / 2;
+    for (int k = 0; k < c; ++k)
+        for (int y = 0; y < new_h; ++y)
+            for (int x = 0; x < new_w; ++x) boxed[((size_t)k * h + oy + y) * w + ox + x] = res[((size_t)k * new_h + y) * new_w + x];
+    free(part);
+    free(res);
+}

@@ -132,6 +132,15 @@ def yolo(x: np.ndarray, n_anchors: int, classes: int) -> np.ndarray:
     return out
 
 
+def letterbox(im: np.ndarray, h: int, w: int) -> np.ndarray:
+    """letterbox_image (src/image.c:812-831): float CHW image -> float [c, h, w] canvas (0.5 border)."""
+    im = np.ascontiguousarray(im, np.float32)
+    c, ih, iw = im.shape
+    out = np.empty((c, h, w), np.float32)
+    lib().yq_oracle_letterbox(_p(im, C.c_float), c, ih, iw, _p(out, C.c_float), h, w)
+    return out
+
+
 def quantize_input(x: np.ndarray):
     x = np.ascontiguousarray(x, np.float32)
     out = np.empty(x.shape, np.uint8)

@@ -96,3 +96,32 @@ def test_pack_arena_file_errors_and_empty_round_trip(built, tmp_path):
     empty = tmp_path / "empty.yqpk"
     assert lib.yq_pack_arena_save(str(empty).encode()) == 0
     assert empty.read_bytes()[:4] == b"YQPK" and lib.yq_pack_arena_load(str(empty).encode()) == 0
+
+
+def test_pack_arena_drops_damaged_entries(built, tmp_path):
+    """yq_pack.cu: every entry carries an FNV-1a checksum of its data; an entry whose data no longer matches is dropped at load
+    (a miss: the image is rebuilt), the others are kept; collecting is off until enabled."""
+    import struct
+    from yolo_quantization_b200 import _lib
+    lib = _lib.load()
+
+    def fnv(data, h=14695981039346656037):
+        for b in data:
+            h = ((h ^ b) * 1099511628211) & 0xFFFFFFFFFFFFFFFF
+        return h
+
+    good, bad = bytes(range(64)), bytes(range(64, 128))
+    blob = struct.pack("<III", 0x4B505159, 5, 2)
+    for key, tag, data, damage in ((1, b"ohwi.128", good, False), (2, b"rows", bad, True)):
+        blob += struct.pack("<Q", key) + tag.ljust(24, b"\0") + struct.pack("<QQ", len(data), fnv(data))
+        blob += (data[:-1] + bytes([data[-1] ^ 1])) if damage else data
+    path = tmp_path / "a.yqpk"
+    path.write_bytes(blob)
+    assert lib.yq_pack_arena_clear() == 0
+    assert lib.yq_pack_arena_load(str(path).encode()) == 1             # one of two entries survives
+    e, h, m, d = (ctypes.c_int() for _ in range(4))
+    assert lib.yq_pack_arena_stats(ctypes.byref(e), ctypes.byref(h), ctypes.byref(m), ctypes.byref(d)) == 0
+    assert e.value == 1 and d.value == 1                               # dirty: the file gets rewritten without the damaged entry
+    assert lib.yq_pack_arena_save(str(path).encode()) == 1
+    assert lib.yq_pack_arena_clear() == 0 and lib.yq_pack_arena_load(str(path).encode()) == 1
+    assert lib.yq_pack_arena_clear() == 0

@@ -105,3 +105,15 @@ def test_box_decode_and_nms_live(built, tmp_path):
     key = lambda a: sorted(map(tuple, a.tolist()))
     assert key(d) == key(post)
     assert (post[:, 5:] > 0).sum() < (pre[:, 5:] > 0).sum()        # NMS really suppressed something
+
+
+@pytest.mark.parametrize("c,ih,iw,h,w", [(3, 375, 500, 416, 416), (3, 500, 375, 416, 416), (3, 100, 100, 96, 96), (1, 7, 300, 64, 128), (3, 64, 64, 64, 64)])
+def test_letterbox_live(built, tmp_path, c, ih, iw, h, w):
+    """row 8f-1: letterbox_image (src/image.c:812-831) restated == the compiled reference, bit for bit (ref_harness letterbox)."""
+    import subprocess
+    im = np.random.default_rng(ih * 7 + iw).random((c, ih, iw), dtype=np.float32)
+    src, dst = str(tmp_path / "in.f32"), str(tmp_path / "out.f32")
+    im.tofile(src)
+    subprocess.check_call([O.REF_HARNESS, "letterbox", src, str(c), str(ih), str(iw), str(w), str(h), dst])
+    ref = np.fromfile(dst, np.float32).reshape(c, h, w)
+    assert np.array_equal(O.letterbox(im, h, w), ref)

@@ -98,6 +98,9 @@ SIGNATURES = {
     "yq_forward_yolo_layer_gpu": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "yq_quantize_input_gpu": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _vp]),
     "yq_network_predict_f32": (_i, [_vp, _vp, _vp]),
+    "yq_network_predict_image_f32": (_i, [_vp, _vp, _i, _i, _vp]),
+    "yq_letterbox_image_gpu": (_i, [_vp, _i, _i, _i, _i, _vp, _i, _i, _vp]),
+    "yq_forward_convolutional_layer_quant_per_image_gpu": (_i, [_vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _i, _vp]),
     "yq_nchw_to_nhwc_u8": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
     "yq_nhwc_to_nchw_u8": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
     "yq_nhwc_to_nchw_i32": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
@@ -123,6 +126,7 @@ SIGNATURES = {
     "yq_pack_arena_load": (_i, [C.c_char_p]),
     "yq_pack_arena_save": (_i, [C.c_char_p]),
     "yq_pack_arena_clear": (_i, []),
+    "yq_pack_arena_enable": (_i, [_i]),
     "yq_pack_arena_stats": (_i, [C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "yq_network_profile_forward": (_i, [_vp, _vp, _vp]),
     "yq_network_box_capacity": (_i, [_vp]),

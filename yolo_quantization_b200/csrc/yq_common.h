@@ -27,6 +27,20 @@ void clear_error();
 
 #define YQ_CHECK_LAUNCH() YQ_CUDA(cudaPeekAtLastError())
 
+// Per-DEVICE facts and settings.  Function attributes (cudaFuncAttributeMaxDynamicSharedMemorySize) belong to a device's
+// context and the ABI takes a device argument (yq_load_network(..., device), yq_set_device), so nothing of this kind may be
+// cached per process: these helpers key their caches by the CURRENT device and take a mutex (two host threads may drive two
+// network instances).
+int device_index();                 // cudaGetDevice, -1 on error
+int device_sm_count();              // multiprocessors of the current device (0 on error)
+int device_smem_optin();            // cudaDevAttrMaxSharedMemoryPerBlockOptin of the current device
+int device_smem_per_sm();           // cudaDevAttrMaxSharedMemoryPerMultiprocessor of the current device
+// make sure `kern` may be launched with `bytes` of dynamic shared memory on the current device (0 on success)
+int ensure_dynamic_smem(const void *kern, int bytes);
+// per-(kernel, device) integer memo for derived launch parameters (CTAs per SM, ...): returns false when not yet stored
+bool memo_get(const void *kern, int *value);
+void memo_put(const void *kern, int value);
+
 static inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
 static inline int channel_stride(int c) { return c <= 4 ? 4 : round_up(c, 16); }
 

@@ -387,13 +387,9 @@ template <int BN, int KC, bool SLOW, int CM, int CN>
 int launch_v(TcState *st, const CUtensorMap &tmA, const CUtensorMap &tmO, const TcArgs &a, dim3 grid, cudaStream_t stream)
 {
     using L = SmemLayout<BN, KC>;
-    static bool attr_done = false;
     const int smem = L::TOTAL + 1024;
     auto kern = conv_u8_tc_kernel<BN, KC, SLOW, CM, CN>;
-    if (!attr_done) {
-        YQ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        attr_done = true;
-    }
+    if (yq::ensure_dynamic_smem((const void *)kern, smem)) return -1;
     if (CM * CN == 1) {
         kern<<<grid, TC_THREADS, smem, stream>>>(tmA, st->tmB, tmO, a);
     } else {

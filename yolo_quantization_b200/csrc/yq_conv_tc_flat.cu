@@ -395,13 +395,9 @@ template <int BN, int KC, bool SLOW>
 int fl_launch_v(FlatState *st, const CUtensorMap &tmA, const CUtensorMap &tmO, const FlatArgs &a, dim3 grid, cudaStream_t stream)
 {
     using L = FlatSmem<BN, KC>;
-    static int attr_smem = 0;
     const int smem = 2 * a.a_stage_bytes + FL_BSTAGES * L::B_STAGE + L::PARAM_BYTES + 128 + 1024;
     auto kern = conv_u8_tc_flat_kernel<BN, KC, SLOW>;
-    if (smem > attr_smem) {
-        YQ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        attr_smem = smem;
-    }
+    if (yq::ensure_dynamic_smem((const void *)kern, smem)) return -1;
     YQ_CUDA(yq::launch_pdl(kern, grid, dim3(FL_THREADS), smem, stream, tmA, st->tmB, tmO, a));
     return 0;
 }
@@ -532,14 +528,9 @@ int yq_tc_flat_forward(yq_conv_layer *l, void *state, const uint8_t *in_flat, ui
     a.magic_h = (uint32_t)((0x100000000ull + H1 - 1) / H1);
     dim3 grid((unsigned)((rows_alloc + 127) / 128), st->n_pad / st->BN);
     {
-        static int n_sm = 0, want = -1;
-        if (!n_sm) {
-            int dev = 0;
-            YQ_CUDA(cudaGetDevice(&dev));
-            YQ_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
-            const char *e = getenv("YQ_FLAT_STAGGER");      // 0 disables the first-wave stagger (A/B measurements)
-            want = e ? atoi(e) : 1;
-        }
+        const int n_sm = yq::device_sm_count();
+        if (n_sm <= 0) return yq::fail("cannot query the device's multiprocessor count");
+        static const int want = getenv("YQ_FLAT_STAGGER") ? atoi(getenv("YQ_FLAT_STAGGER")) : 1;   // 0 disables the first-wave stagger (A/B measurements)
         a.n_sm = n_sm;
         // half of one CTA's period: main loop alone on the pipe (N/2 clocks per MMA at ~1.9 GHz) + epilogue + prologue
         const double main_ns = (double)a.taps * a.cpt * (st->KC / 32) * ((st->BN + FL_ONES) / 2) / 1.9;

@@ -414,13 +414,8 @@ template <int KC, bool SLOW>
 int f2_launch_v(Flat2State *st, const CUtensorMap &tmA, const CUtensorMap &tmO, Flat2Args a, cudaStream_t stream)
 {
     using L = Flat2Smem<KC>;
-    static int attr_smem = 0, n_sm = 0, smem_max = 0;
-    if (!n_sm) {
-        int dev = 0;
-        YQ_CUDA(cudaGetDevice(&dev));
-        YQ_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
-        YQ_CUDA(cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
-    }
+    const int n_sm = yq::device_sm_count(), smem_max = yq::device_smem_optin();   // (of the CURRENT device: nothing cached per process)
+    if (n_sm <= 0 || smem_max <= 0) return yq::fail("cannot query the device's multiprocessor count / shared memory size");
     const int fixed = F2_ASTAGES * a.a_stage_bytes + 2 * L::OUT_BYTES + L::PARAM_BYTES + L::SUM_BYTES + 512 + 1024;
     int nbs = (smem_max - fixed) / L::B_STAGE;
     if (nbs > F2_MAX_BSTAGES) nbs = F2_MAX_BSTAGES;
@@ -428,10 +423,7 @@ int f2_launch_v(Flat2State *st, const CUtensorMap &tmA, const CUtensorMap &tmO, 
     a.b_stages = nbs;
     const int smem = fixed + nbs * L::B_STAGE;
     auto kern = conv_u8_tc_flat2_kernel<KC, SLOW>;
-    if (smem > attr_smem) {
-        YQ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        attr_smem = smem;
-    }
+    if (yq::ensure_dynamic_smem((const void *)kern, smem)) return -1;
     const int grid = a.num_tiles < n_sm ? a.num_tiles : n_sm;
     YQ_CUDA(yq::launch_pdl(kern, dim3(grid), dim3(F2_THREADS), smem, stream, tmA, st->tmB, tmO, a));
     return 0;

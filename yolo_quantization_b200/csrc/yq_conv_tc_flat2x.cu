@@ -425,13 +425,8 @@ template <int KC, bool SLOW, bool WIDE>
 int f2x_launch_v(Flat2xState *st, const CUtensorMap &tmA, const CUtensorMap &tmO, Flat2xArgs a, cudaStream_t stream)
 {
     using L = Flat2xSmem<KC, WIDE>;
-    static int attr_smem = 0, n_sm = 0, smem_max = 0;
-    if (!n_sm) {
-        int dev = 0;
-        YQ_CUDA(cudaGetDevice(&dev));
-        YQ_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
-        YQ_CUDA(cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
-    }
+    const int n_sm = yq::device_sm_count(), smem_max = yq::device_smem_optin();   // (of the CURRENT device: nothing cached per process)
+    if (n_sm <= 0 || smem_max <= 0) return yq::fail("cannot query the device's multiprocessor count / shared memory size");
     const int fixed = F2X_ASTAGES * a.a_stage_bytes + 2 * L::OUT_BYTES + L::PARAM_BYTES + L::SUM_BYTES + 512 + 1024;
     int nbs = (smem_max - fixed) / L::B_STAGE;
     if (nbs > F2X_MAX_BSTAGES) nbs = F2X_MAX_BSTAGES;
@@ -442,10 +437,7 @@ int f2x_launch_v(Flat2xState *st, const CUtensorMap &tmA, const CUtensorMap &tmO
     // side stream of yq_network.cu) that each hold one SM's columns while waiting for the other's would not finish.
     if (smem <= smem_max / 2) smem = smem_max / 2 + 1024;
     auto kern = conv_u8_tc_flat2x_kernel<KC, SLOW, WIDE>;
-    if (smem > attr_smem) {
-        YQ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        attr_smem = smem;
-    }
+    if (yq::ensure_dynamic_smem((const void *)kern, smem)) return -1;
     int grid = 2 * a.num_tiles < n_sm ? 2 * a.num_tiles : n_sm / 2 * 2;      // whole CTA pairs
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof cfg);

@@ -796,16 +796,16 @@ int launch_rows(const CUtensorMap &tmA, const RowsArgs &a, cudaStream_t stream)
 {
     using L = RowsCfg<CS, NCH, TWO, DBL, PLANAR>;
     constexpr int NT = RW_THREADS * SPLIT;
-    static int ctas_per_sm = 0, n_sm = 0;
     const int smem = L::TOTAL + 128;
-    if (!ctas_per_sm) {
-        YQ_CUDA(cudaFuncSetAttribute(conv_u8_tc_rows_kernel<CS, NCH, SPLIT, TWO, DBL, PLANAR>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        int dev = 0, smem_sm = 0;
+    auto kern = conv_u8_tc_rows_kernel<CS, NCH, SPLIT, TWO, DBL, PLANAR>;
+    // per device: the shared-memory opt-in and the CTAs-per-SM count derived from this device's limits
+    if (yq::ensure_dynamic_smem((const void *)kern, smem)) return -1;
+    const int n_sm = yq::device_sm_count();
+    int ctas_per_sm = 0;
+    if (!yq::memo_get((const void *)kern, &ctas_per_sm)) {
+        const int smem_sm = yq::device_smem_per_sm();
         cudaFuncAttributes fa;
-        YQ_CUDA(cudaFuncGetAttributes(&fa, conv_u8_tc_rows_kernel<CS, NCH, SPLIT, TWO, DBL, PLANAR>));
-        YQ_CUDA(cudaGetDevice(&dev));
-        YQ_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
-        YQ_CUDA(cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev));
+        YQ_CUDA(cudaFuncGetAttributes(&fa, kern));
         // counted by hand: the occupancy API answers 1 for kernels that allocate tensor memory (see yq_conv_tc_small.cu)
         const int by_smem = smem_sm / (smem + 1024 + (int)fa.sharedSizeBytes);
         const int by_regs = 65536 / (((fa.numRegs + 7) / 8 * 8) * (NT + 32 * L::NPROD));
@@ -813,8 +813,9 @@ int launch_rows(const CUtensorMap &tmA, const RowsArgs &a, cudaStream_t stream)
         int occ = by_smem < by_regs ? by_smem : by_regs;
         if (by_tmem < occ) occ = by_tmem;
         if (getenv("YQ_DEBUG")) fprintf(stderr, "yq: rows<%d,%d,%d,%d,%d> regs=%d by_smem=%d by_regs=%d by_tmem=%d smem=%d\n", CS, NCH, SPLIT, (int)TWO, (int)DBL, fa.numRegs, by_smem, by_regs, by_tmem, smem);
-        if (occ < 1) return yq::fail("conv_u8_tc_rows_kernel<%d,%d> does not fit on an SM", CS, NCH);
+        if (occ < 1 || n_sm <= 0) return yq::fail("conv_u8_tc_rows_kernel<%d,%d> does not fit on an SM", CS, NCH);
         ctas_per_sm = occ;
+        yq::memo_put((const void *)kern, occ);
     }
     int grid = n_sm * ctas_per_sm;
     if (grid > a.num_tiles) grid = a.num_tiles;

@@ -459,18 +459,18 @@ template <int CS, int BN, int ACTM, bool SLOW, bool PQ = false>
 int launch_small(SmallState *st, const SmallArgs &a, cudaStream_t stream)
 {
     using L = SmallSmem<CS, BN>;
-    static int ctas_per_sm = 0, n_sm = 0;
     const int smem = L::TOTAL + 1024;
-    if (!ctas_per_sm) {
-        YQ_CUDA(cudaFuncSetAttribute(conv_u8_tc_small_kernel<CS, BN, ACTM, SLOW, PQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    auto kern = conv_u8_tc_small_kernel<CS, BN, ACTM, SLOW, PQ>;
+    // per device: the shared-memory opt-in and the CTAs-per-SM count derived from this device's limits
+    if (yq::ensure_dynamic_smem((const void *)kern, smem)) return -1;
+    const int n_sm = yq::device_sm_count();
+    int ctas_per_sm = 0;
+    if (!yq::memo_get((const void *)kern, &ctas_per_sm)) {
         // cudaOccupancyMaxActiveBlocksPerMultiprocessor answers 1 for kernels that allocate tensor memory (measured on
         // B200), although the hardware co-schedules as many CTAs as smem / registers / TMEM columns allow: count by hand.
-        int dev = 0, smem_sm = 0;
+        const int smem_sm = yq::device_smem_per_sm();
         cudaFuncAttributes fa;
-        YQ_CUDA(cudaFuncGetAttributes(&fa, conv_u8_tc_small_kernel<CS, BN, ACTM, SLOW, PQ>));
-        YQ_CUDA(cudaGetDevice(&dev));
-        YQ_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
-        YQ_CUDA(cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev));
+        YQ_CUDA(cudaFuncGetAttributes(&fa, kern));
         const int by_smem = smem_sm / (smem + 1024 + (int)fa.sharedSizeBytes);
         const int regs_per_cta = ((fa.numRegs + 7) / 8 * 8) * SM_THREADS;
         const int by_regs = 65536 / (regs_per_cta > 0 ? regs_per_cta : 1);
@@ -480,7 +480,8 @@ int launch_small(SmallState *st, const SmallArgs &a, cudaStream_t stream)
         const int tmem_limit = 512 / small_tmem_cols<BN>();   // every resident CTA must own its TMEM columns
         ctas_per_sm = occ < tmem_limit ? occ : tmem_limit;
         if (getenv("YQ_DEBUG")) fprintf(stderr, "yq: small<%d,%d,%d,%d> regs=%d occ=%d tmem_limit=%d n_sm=%d smem=%d\n", CS, BN, ACTM, (int)SLOW, fa.numRegs, occ, tmem_limit, n_sm, smem);
-        if (ctas_per_sm < 1) return yq::fail("conv_u8_tc_small_kernel<%d,%d> does not fit on an SM", CS, BN);
+        if (ctas_per_sm < 1 || n_sm <= 0) return yq::fail("conv_u8_tc_small_kernel<%d,%d> does not fit on an SM", CS, BN);
+        yq::memo_put((const void *)kern, ctas_per_sm);
     }
     int grid = n_sm * ctas_per_sm;
     if (grid > a.num_tiles) grid = a.num_tiles;

@@ -207,11 +207,7 @@ int yq_detect_run(const float *const *head_pred, const int *lw, const int *lh, c
         while (npow2 < cap) npow2 <<= 1;
         const size_t smem = (size_t)npow2 * (sizeof(unsigned long long) + 2 * sizeof(int));
         if (smem > 200 * 1024) return yq::fail("detect: %d candidate slots per image exceed the NMS sort capacity", cap);
-        static size_t attr_set = 0;
-        if (smem > attr_set) {
-            YQ_CUDA(cudaFuncSetAttribute(yolo_nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            attr_set = smem;
-        }
+        if (yq::ensure_dynamic_smem((const void *)yolo_nms_kernel, (int)smem)) return -1;
         yolo_nms_kernel<<<batch, 256, smem, stream>>>(dets_dev, counts_dev, cap, classes, nms_thresh, npow2);
         YQ_CHECK_LAUNCH();
     }

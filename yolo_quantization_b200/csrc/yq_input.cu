@@ -55,7 +55,65 @@ __global__ void input_quant_kernel(const float *__restrict__ x, uint8_t *__restr
     }
 }
 
+// letterbox_image (src/image.c:812-831) = resize_image (:1199-1245, two separable passes of linear interpolation) into a
+// w x h canvas filled with .5 (fill_image :695), embedded at ((w - new_w) / 2, (h - new_h) / 2) (embed_image :428-439).
+// One thread per canvas pixel; the float operations are the reference's, in its order, each rounded separately
+// (no fused multiply-add: the reference's horizontal pass stores `part` before the vertical pass reads it):
+//     part(c, r)  = c == new_w - 1 || iw == 1 ? im(iw - 1, r) : (1 - dx) * im(ix, r) + dx * im(ix + 1, r),  sx = c * w_scale
+//     res(c, r)   = (1 - dy) * part(c, iy)  [+ dy * part(c, iy + 1) unless r == new_h - 1 || ih == 1],        sy = r * h_scale
+__device__ __forceinline__ float lb_part(const float *__restrict__ plane, int iw, int new_w, float w_scale, int c, int r)
+{
+    if (c == new_w - 1 || iw == 1) return __ldg(plane + (size_t)r * iw + iw - 1);
+    const float sx = __fmul_rn((float)c, w_scale);
+    const int ix = (int)sx;
+    const float dx = __fsub_rn(sx, (float)ix);
+    return __fadd_rn(__fmul_rn(__fsub_rn(1.f, dx), __ldg(plane + (size_t)r * iw + ix)), __fmul_rn(dx, __ldg(plane + (size_t)r * iw + ix + 1)));
+}
+
+__global__ void letterbox_kernel(const float *__restrict__ in, float *__restrict__ out, int ch, int ih, int iw, int h, int w, int new_h, int new_w, int off_y,
+                                 int off_x, float w_scale, float h_scale)
+{
+    const size_t total = (size_t)ch * h * w;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int x = (int)(i % w), y = (int)((i / w) % h), k = (int)(i / ((size_t)w * h));
+        const float *src = in + (size_t)blockIdx.y * ch * ih * iw + (size_t)k * ih * iw;
+        const int c = x - off_x, r = y - off_y;
+        float val = .5f;
+        if (c >= 0 && c < new_w && r >= 0 && r < new_h) {
+            const float sy = __fmul_rn((float)r, h_scale);
+            const int iy = (int)sy;
+            const float dy = __fsub_rn(sy, (float)iy);
+            val = __fmul_rn(__fsub_rn(1.f, dy), lb_part(src, iw, new_w, w_scale, c, iy));
+            if (!(r == new_h - 1 || ih == 1)) val = __fadd_rn(val, __fmul_rn(dy, lb_part(src, iw, new_w, w_scale, c, iy + 1)));
+        }
+        out[(size_t)blockIdx.y * total + i] = val;
+    }
+}
+
 }  // namespace
+
+// letterbox_image (src/image.c:812-831) for a batch of float CHW images of one size, on the device
+extern "C" int yq_letterbox_image_gpu(const float *in_chw, int batch, int c, int ih, int iw, float *out_chw, int h, int w, void *stream)
+{
+    if (!in_chw || !out_chw || batch <= 0 || c <= 0 || ih <= 0 || iw <= 0 || h <= 0 || w <= 0) return yq::fail("yq_letterbox_image_gpu: bad argument");
+    int new_w = iw, new_h = ih;
+    if (((float)w / iw) < ((float)h / ih)) {          // image.c:816-822
+        new_w = w;
+        new_h = (ih * w) / iw;
+    } else {
+        new_h = h;
+        new_w = (iw * h) / ih;
+    }
+    if (new_w < 1 || new_h < 1) return yq::fail("yq_letterbox_image_gpu: %dx%d does not fit a %dx%d canvas", iw, ih, w, h);
+    const float w_scale = (float)(iw - 1) / (new_w - 1), h_scale = (float)(ih - 1) / (new_h - 1);   // image.c:1204-1205 (inf / nan when new == 1: unused then)
+    const size_t total = (size_t)c * h * w;
+    unsigned bx = (unsigned)((total + 255) / 256);
+    if (bx > 148 * 8) bx = 148 * 8;
+    letterbox_kernel<<<dim3(bx, (unsigned)batch), 256, 0, (cudaStream_t)stream>>>(in_chw, out_chw, c, ih, iw, h, w, new_h, new_w, (h - new_h) / 2, (w - new_w) / 2, w_scale,
+                                                                                   h_scale);
+    YQ_CHECK_LAUNCH();
+    return 0;
+}
 
 extern "C" int yq_quantize_input_gpu(const float *in_f32, uint8_t *out_u8, float *scales, int *zero_points, int *scratch, int batch, int n, void *stream)
 {

@@ -16,6 +16,10 @@
 
 #include <cmath>
 
+#include <map>
+#include <mutex>
+#include <utility>
+
 #include "yq_common.h"
 #include "yq_epilogue.cuh"
 
@@ -39,6 +43,77 @@ int fail(const char *fmt, ...)
     return -1;
 }
 void clear_error() { g_err[0] = 0; }
+
+namespace {
+std::mutex g_dev_mu;
+struct DevFacts { int n_sm = 0, smem_optin = 0, smem_sm = 0; };
+std::map<int, DevFacts> g_dev_facts;
+std::map<std::pair<const void *, int>, int> g_smem_optin, g_memo;
+const DevFacts *dev_facts()
+{
+    int dev = -1;
+    if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
+    auto it = g_dev_facts.find(dev);
+    if (it == g_dev_facts.end()) {
+        DevFacts f;
+        if (cudaDeviceGetAttribute(&f.n_sm, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess ||
+            cudaDeviceGetAttribute(&f.smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) != cudaSuccess ||
+            cudaDeviceGetAttribute(&f.smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev) != cudaSuccess)
+            return nullptr;
+        it = g_dev_facts.emplace(dev, f).first;
+    }
+    return &it->second;
+}
+}  // namespace
+int device_index()
+{
+    int dev = -1;
+    return cudaGetDevice(&dev) == cudaSuccess ? dev : -1;
+}
+int device_sm_count()
+{
+    std::lock_guard<std::mutex> lk(g_dev_mu);
+    const DevFacts *f = dev_facts();
+    return f ? f->n_sm : 0;
+}
+int device_smem_optin()
+{
+    std::lock_guard<std::mutex> lk(g_dev_mu);
+    const DevFacts *f = dev_facts();
+    return f ? f->smem_optin : 0;
+}
+int device_smem_per_sm()
+{
+    std::lock_guard<std::mutex> lk(g_dev_mu);
+    const DevFacts *f = dev_facts();
+    return f ? f->smem_sm : 0;
+}
+int ensure_dynamic_smem(const void *kern, int bytes)
+{
+    std::lock_guard<std::mutex> lk(g_dev_mu);
+    const int dev = device_index();
+    if (dev < 0) return fail("cudaGetDevice failed");
+    int &have = g_smem_optin[{kern, dev}];
+    if (bytes > have) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+        if (e != cudaSuccess) return fail("cudaFuncSetAttribute(MaxDynamicSharedMemorySize = %d) on device %d: %s", bytes, dev, cudaGetErrorString(e));
+        have = bytes;
+    }
+    return 0;
+}
+bool memo_get(const void *kern, int *value)
+{
+    std::lock_guard<std::mutex> lk(g_dev_mu);
+    auto it = g_memo.find({kern, device_index()});
+    if (it == g_memo.end()) return false;
+    *value = it->second;
+    return true;
+}
+void memo_put(const void *kern, int value)
+{
+    std::lock_guard<std::mutex> lk(g_dev_mu);
+    g_memo[{kern, device_index()}] = value;
+}
 }  // namespace yq
 
 extern "C" {
@@ -109,6 +184,11 @@ struct ConvArgs {
     const uint8_t *wpk;
     yq::EpiParams ep;
     int B, H, W, C, CS, OH, OW, N, CSO, size, stride, pad, k_pad, k_bytes, zp_in, M_total;
+    // per-IMAGE input quantisation (layer 0 behind the dynamic input quantiser, src/blas.c:279): device tables or nullptr
+    const int32_t *img_bias;     // [B][img_pitch]  biases_int32 of image b
+    const double *img_mcomb;     // [B][img_pitch]  M_value * M0_right_shift_value of image b
+    const uint8_t *img_zp;       // [B]             input zero point of image b (the im2col pad value, src/im2col.c:5-14)
+    int img_pitch;
 };
 
 constexpr int SIMT_BM = 64;        // output pixels per block
@@ -143,13 +223,14 @@ __global__ void __launch_bounds__(SIMT_THREADS) conv_u8_simt_kernel(const ConvAr
     }
     const int units_per_tap = a.CS / VEC;
     const int total_units = a.size * a.size * units_per_tap;
-    const uint32_t zp4 = (uint32_t)a.zp_in * 0x01010101u;
+    const int zp_in = a.img_zp && lvalid ? (int)__ldg(a.img_zp + ln) : a.zp_in;   // (per image when layer 0 follows the dynamic input quantiser)
+    const uint32_t zp4 = (uint32_t)zp_in * 0x01010101u;
 
     auto fill_word = [&](int ch0) -> uint32_t {   // zp_in in real channels, 0 in pad channels
         if (ch0 + 4 <= a.C) return zp4;
         uint32_t v = 0;
         for (int b = 0; b < 4; ++b)
-            if (ch0 + b < a.C) v |= (uint32_t)a.zp_in << (8 * b);
+            if (ch0 + b < a.C) v |= (uint32_t)zp_in << (8 * b);
         return v;
     };
 
@@ -247,11 +328,16 @@ __global__ void __launch_bounds__(SIMT_THREADS) conv_u8_simt_kernel(const ConvAr
 #pragma unroll
     for (int jj = 0; jj < OCT; ++jj) {
         const int oc = oc0 + tx + 16 * jj;
-        const yq::ChanParams cp = yq::load_chan(a.ep, oc);
+        yq::ChanParams cp = yq::load_chan(a.ep, oc);
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const int p = ty * 4 + j;
             const int m = m0 + p;
+            if (a.img_bias && m < a.M_total && oc < a.N) {      // this pixel's image has its own (bias, multiplier)
+                const int nimg = m / (a.OH * a.OW);
+                cp.bias = __ldg(a.img_bias + (size_t)nimg * a.img_pitch + oc);
+                cp.m0 = __ldg(a.img_mcomb + (size_t)nimg * a.img_pitch + oc);
+            }
             int accv = (int)acc[j][jj] - cp.zw * (int)sa[j];
             uint8_t r = 0;
             if (oc < a.N) r = yq::requant_u8(a.ep, cp, accv);
@@ -278,10 +364,12 @@ __global__ void __launch_bounds__(SIMT_THREADS) conv_u8_simt_kernel(const ConvAr
 }
 
 static int launch_simt(yq_conv_layer *l, const uint8_t *in, uint8_t *out, float *out_f32, int32_t *out_acc, int batch,
-                       cudaStream_t stream)
+                       cudaStream_t stream, const int32_t *img_bias = nullptr, const double *img_mcomb = nullptr, const uint8_t *img_zp = nullptr,
+                       int img_pitch = 0)
 {
     ConvArgs a;
     memset(&a, 0, sizeof a);
+    a.img_bias = img_bias; a.img_mcomb = img_mcomb; a.img_zp = img_zp; a.img_pitch = img_pitch;
     a.in = in;
     a.out = out;
     a.out_f32 = l->quant_stop_flag ? out_f32 : nullptr;
@@ -475,6 +563,20 @@ extern "C" int yq_forward_convolutional_layer_quant_gpu(yq_conv_layer *l, const 
 }
 
 extern "C" int yq_conv_can_fuse_maxpool(const yq_conv_layer *l) { return l ? yq_tc_can_fuse_pool(l) : 0; }
+
+// Layer 0 behind the reference's DYNAMIC input quantiser: quantization_weights_and_activations derives (s_in, zp_in) from the
+// image itself (quant_weights_with_min_max_channel, src/blas.c:108-168 via :279) and then M, biases_int32 and the padding value
+// of layer 0 follow (blas.c:301-334, im2col.c:5-14).  The reference does that for its one image; a batch needs it PER IMAGE.
+extern "C" int yq_forward_convolutional_layer_quant_per_image_gpu(yq_conv_layer *l, const uint8_t *in_u8, uint8_t *out_u8, int32_t *out_acc, int batch,
+                                                                  const int32_t *biases_int32_dev, const double *multiplier_dev,
+                                                                  const uint8_t *zp_in_dev, int table_pitch, void *stream)
+{
+    if (!l || !in_u8 || !out_u8 || batch <= 0 || !biases_int32_dev || !multiplier_dev || !zp_in_dev) return yq::fail("yq_forward_convolutional_layer_quant_per_image_gpu: bad argument");
+    if (table_pitch < l->n) return yq::fail("per-image tables need a pitch of at least %d entries", l->n);
+    if (!l->fused_mult) return yq::fail("per-image input quantisation needs power-of-two M0_right_shift values (blas.c:315)");
+    if (l->quant_stop_flag) return yq::fail("per-image input quantisation: quant_stop layers are not supported");
+    return launch_simt(l, in_u8, out_u8, nullptr, out_acc, batch, (cudaStream_t)stream, biases_int32_dev, multiplier_dev, zp_in_dev, table_pitch);
+}
 
 extern "C" int yq_conv_geom_supported(const yq_conv_layer *l) { return l && yq_tc_geom_supported(l) ? 1 : 0; }
 // 1: yq_forward_convolutional_layer_quant_gpu runs this (1x1) layer on conv_u8_tc_flat2_kernel in its plain-tensor mode

@@ -154,6 +154,14 @@ struct yq_network {
     uint8_t *in_nhwc = nullptr;
     float *in_f32 = nullptr;            // yq_network_predict_f32: float staging and per-image (scale, zero point, scratch)
     void *in_quant = nullptr;
+    float *in_raw = nullptr;            // yq_network_predict_image_f32: the images before letterbox_image
+    size_t in_raw_floats = 0;
+    // layer 0 with PER-IMAGE input quantisation (images of one batch quantise differently): plain NHWC input, per-image tables
+    uint8_t *in_plain = nullptr;
+    int32_t *img_bias = nullptr;
+    double *img_mcomb = nullptr;
+    uint8_t *img_zp = nullptr;
+    int img_pitch = 0;
     size_t in_nhwc_bytes = 0;
     yq_act_geom in_geom = {0, 0, 0};    // geometry of in_nhwc (halo-padded when layer 0 runs a halo-input flavour)
     int in_halo_fill = 0;
@@ -171,6 +179,7 @@ struct yq_network {
     cudaStream_t side_stream = nullptr;
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     int conv_kernel = -1;
+    bool plan_error = false;            // a CUDA call inside plan() failed (halo fills): every later forward refuses to run
     int fusion = 1;
     int use_graph = 0;
     std::vector<std::pair<const uint8_t *, cudaGraphExec_t>> graphs;   // one captured forward per input pointer
@@ -485,7 +494,7 @@ void plan(yq_network *net)
         (t < 0 ? net->in_halo_fill : net->layers[t].halo_fill) = fill;
         // the halo (and any slack around the images) holds the consumers' input zero point (im2col.c:5-14); producers
         // only ever write the interior (flat convs also rewrite the halo of their output with the same value)
-        cudaMemsetAsync(buf, fill, yq_act_geom_bytes(&r.g, net->batch, c), net->stream);
+        if (cudaMemsetAsync(buf, fill, yq_act_geom_bytes(&r.g, net->batch, c), net->stream) != cudaSuccess) net->plan_error = true;
     }
     for (int i = 0; i < n; ++i)   // aliases share their tensor's geometry
         if (tensor_of(net, i) != i && tensor_of(net, i) >= 0) {
@@ -540,16 +549,38 @@ bool conv_output_needed(const yq_network *net, int i)
 }
 
 // the kernel sequence of one forward_network pass (network.c:229-261)
-int forward_body(yq_network *net, const uint8_t *in_u8_nchw, int *launches, bool profile = false)
+int forward_body(yq_network *net, const uint8_t *in_u8_nchw, int *launches, bool profile = false, bool per_image = false)
 {
     cudaStream_t st = net->stream;
     int nl = 0;
     bool on_side = false, forked = false;   // (per-layer profiling keeps everything on the one stream)
+    size_t first = 0;
     if (profile) cudaEventRecord(net->prof_events[0], st);
+    if (per_image) {
+        // Layer 0 behind the dynamic input quantiser with a different (s_in, zp_in) per image (src/blas.c:279 does it for the
+        // reference's one image): the generic flavour with per-image (biases_int32, multiplier, padding value) tables writes
+        // layer 0's own tensor; a max-pool the plan had fused into layer 0 runs as its own launch; the rest of the plan is unchanged.
+        Layer &l0 = net->layers[0];
+        if (l0.type != L_CONV) return yq::fail("per-image input quantisation: layer 0 is not a convolution");
+        if (!l0.fuse_pool && !(l0.geom.pad == 0 && l0.geom.pitch_w == l0.out_w && l0.geom.rows_h == l0.out_h))
+            return yq::fail("per-image input quantisation: layer 0's output tensor is halo-padded in this plan (yq_network_set_fusion(net, 0) keeps it plain)");
+        if (yq_nchw_to_nhwc_u8(in_u8_nchw, net->in_plain, net->batch, net->c, net->h, net->w, st)) return -1;
+        if (yq_forward_convolutional_layer_quant_per_image_gpu(l0.conv, net->in_plain, l0.out_u8, net->keep_acc ? l0.out_acc : nullptr, net->batch, net->img_bias,
+                                                               net->img_mcomb, net->img_zp, net->img_pitch, st))
+            return -1;
+        nl += 2;
+        first = 1;
+        if (l0.fuse_pool) {
+            Layer &p = net->layers[1];
+            if (yq_forward_maxpool_layer_quant_geom_gpu(l0.out_u8, nullptr, p.out_u8, &p.geom, net->batch, p.h, p.w, p.c, p.size, p.stride, p.pad, st)) return -1;
+            ++nl;
+            first = 2;
+        }
+    }
     // layer 0 in the rows flavour reads the planes itself when it can (no layout-transform launch, no padded copy)
     const bool planar_in = !net->layers.empty() && net->layers[0].type == L_CONV && net->layers[0].use_rows && !net->no_planar_input &&
                            yq_conv_rows_nchw_supported(net->layers[0].conv) && ((uintptr_t)in_u8_nchw & 15) == 0;
-    if (planar_in) {
+    if (planar_in || per_image) {
         // nothing to do
     } else if (net->in_geom.pad) {
         if (yq_nchw_to_nhwc_u8_geom(in_u8_nchw, net->in_nhwc, net->batch, net->c, net->h, net->w, &net->in_geom, st)) return -1;
@@ -564,6 +595,12 @@ int forward_body(yq_network *net, const uint8_t *in_u8_nchw, int *launches, bool
     const yq_act_geom *cur_geom = &net->in_geom;
     int cur_fill = net->in_halo_fill;       // the byte the current tensor's halo holds (meaningful when cur_geom->pad > 0)
     const float *cur_f32 = nullptr;
+    if (first) {                            // (per-image layer 0 already ran: pick up behind it)
+        const Layer &done = net->layers[first - 1];
+        cur = done.out_u8;
+        cur_geom = &done.geom;
+        cur_fill = done.halo_fill;
+    }
     const bool early_ok = !profile && net->side_stream;
     auto issue_route = [&](Layer &r, unsigned mask, cudaStream_t s) -> int {
         const uint8_t *ins[8];
@@ -582,7 +619,7 @@ int forward_body(yq_network *net, const uint8_t *in_u8_nchw, int *launches, bool
         }
         return yq_forward_route_layer_quant_part_gpu(ins, gs, cs, ups, (int)r.inputs.size(), mask, r.out_u8, &r.geom, net->batch, r.out_h, r.out_w, s);
     };
-    for (size_t i = 0; i < net->layers.size(); ++i) {
+    for (size_t i = first; i < net->layers.size(); ++i) {
         Layer &l = net->layers[i];
         const bool side = l.side && !profile && net->side_stream;
         if (side && !on_side) {   // fork: the side stream starts behind everything issued so far
@@ -1070,7 +1107,10 @@ extern "C" yq_network *yq_load_network(const char *cfg, const char *weights, int
             return bail();
         }
         l.owns_u8 = true;
-        cudaMemset(l.out_u8, 0, l.u8_bytes);
+        if (cudaMemset(l.out_u8, 0, l.u8_bytes) != cudaSuccess) {
+            yq::fail("cudaMemset of layer %zu output failed", i);
+            return bail();
+        }
     }
     raw->in_nhwc_bytes = tensor_bytes(raw->c, raw->h, raw->w);
     const size_t in_bytes = (size_t)raw->batch * raw->c * raw->h * raw->w;
@@ -1079,6 +1119,10 @@ extern "C" yq_network *yq_load_network(const char *cfg, const char *weights, int
         return bail();
     }
     plan(raw);
+    if (raw->plan_error) {
+        yq::fail("yq_load_network: filling the tensor halos failed: %s", cudaGetErrorString(cudaGetLastError()));
+        return bail();
+    }
     return raw;
 }
 
@@ -1108,6 +1152,11 @@ extern "C" void yq_free_network(yq_network *net)
     cudaFree(net->in_nhwc);
     cudaFree(net->in_f32);
     cudaFree(net->in_quant);
+    cudaFree(net->in_raw);
+    cudaFree(net->in_plain);
+    cudaFree(net->img_bias);
+    cudaFree(net->img_mcomb);
+    cudaFree(net->img_zp);
     cudaFree(net->scratch);
     if (net->out_host_pinned) cudaFreeHost(net->out_host_pinned);
     for (auto &l : net->layers)
@@ -1203,6 +1252,7 @@ extern "C" int yq_network_use_graph(yq_network *net, int enable)
 extern "C" int yq_forward_network_device(yq_network *net, const uint8_t *in_u8_nchw)
 {
     if (!net || !in_u8_nchw) return yq::fail("yq_forward_network_device: null argument");
+    if (net->plan_error) return yq::fail("yq_forward_network_device: the last re-plan failed to fill the tensor halos");
     YQ_CUDA(cudaSetDevice(net->device));
     if (!net->use_graph) return forward_body(net, in_u8_nchw, nullptr);
     cudaGraphExec_t exec = nullptr;
@@ -1269,6 +1319,7 @@ extern "C" int yq_network_predict_u8(yq_network *net, const uint8_t *in_host, fl
     return 0;
 }
 
+static int predict_f32_device(yq_network *net, float *out_host);
 extern "C" int yq_network_predict_f32(yq_network *net, const float *in_host, float *out_host)
 {
     if (!net || !in_host || !out_host) return yq::fail("yq_network_predict_f32: null argument");
@@ -1279,24 +1330,72 @@ extern "C" int yq_network_predict_f32(yq_network *net, const float *in_host, flo
         YQ_CUDA(cudaMalloc((void **)&net->in_f32, sizeof(float) * (size_t)B * n));
         YQ_CUDA(cudaMalloc((void **)&net->in_quant, (sizeof(float) + 3 * sizeof(int)) * (size_t)B));
     }
+    YQ_CUDA(cudaMemcpyAsync(net->in_f32, in_host, sizeof(float) * (size_t)B * n, cudaMemcpyHostToDevice, net->stream));
+    return predict_f32_device(net, out_host);
+}
+
+// the float images are in net->in_f32: quantise per image, forward, copy the yolo heads out
+static int predict_f32_device(yq_network *net, float *out_host)
+{
+    const int n = net->c * net->h * net->w, B = net->batch;
     float *scales = (float *)net->in_quant;
     int *zps = (int *)(scales + B), *scratch = zps + B;
-    YQ_CUDA(cudaMemcpyAsync(net->in_f32, in_host, sizeof(float) * (size_t)B * n, cudaMemcpyHostToDevice, net->stream));
     if (yq_quantize_input_gpu(net->in_f32, net->in_stage_nchw, scales, zps, scratch, B, n, net->stream)) return -1;
     std::vector<float> hs(B);
     std::vector<int> hz(B);
     YQ_CUDA(cudaMemcpyAsync(hs.data(), scales, sizeof(float) * B, cudaMemcpyDeviceToHost, net->stream));
     YQ_CUDA(cudaMemcpyAsync(hz.data(), zps, sizeof(int) * B, cudaMemcpyDeviceToHost, net->stream));
     YQ_CUDA(cudaStreamSynchronize(net->stream));
+    bool uniform = true;
     for (int b = 0; b < B; ++b) {
         if (hz[b] < 0) return yq::fail("yq_network_predict_f32: image %d is all zero (blas.c:124-127 asserts)", b);
-        if (hs[b] != hs[0] || hz[b] != hz[0])
-            return yq::fail("yq_network_predict_f32: images 0 and %d quantize differently (s %g/%g, zp %d/%d); layer 0 has one (s_in, zp_in) per forward", b,
-                            (double)hs[0], (double)hs[b], hz[0], hz[b]);
+        uniform = uniform && hs[b] == hs[0] && hz[b] == hz[0];
     }
-    if (hs[0] != net->layers[0].s_in || hz[0] != net->layers[0].zp_in)
-        if (yq_network_set_input_quant(net, hs[0], hz[0])) return -1;      // blas.c:279 overwrites layer 0's file values per image
-    if (yq_forward_network_device(net, net->in_stage_nchw)) return -1;
+    if (uniform) {
+        if (hs[0] != net->layers[0].s_in || hz[0] != net->layers[0].zp_in)
+            if (yq_network_set_input_quant(net, hs[0], hz[0])) return -1;      // blas.c:279 overwrites layer 0's file values per image
+        if (yq_forward_network_device(net, net->in_stage_nchw)) return -1;
+    } else {
+        // the images of this batch quantise differently: layer 0's multipliers, biases_int32 and padding value per image
+        // (blas.c:301-334 with each image's own (s_in, zp_in)); everything behind layer 0 is the same for all of them
+        const Layer &l0 = net->layers[0];
+        const int pitch = yq::round_up(l0.n, 16);
+        if (!net->img_bias) {
+            net->img_pitch = pitch;
+            YQ_CUDA(cudaMalloc((void **)&net->in_plain, (size_t)B * net->h * net->w * yq::channel_stride(net->c)));
+            YQ_CUDA(cudaMalloc((void **)&net->img_bias, sizeof(int32_t) * (size_t)B * pitch));
+            YQ_CUDA(cudaMalloc((void **)&net->img_mcomb, sizeof(double) * (size_t)B * pitch));
+            YQ_CUDA(cudaMalloc((void **)&net->img_zp, (size_t)B));
+        }
+        std::vector<int32_t> hb((size_t)B * pitch, 0);
+        std::vector<double> hm((size_t)B * pitch, 0.0);
+        std::vector<uint8_t> hzp(B);
+        Layer tmp = l0;               // host copy: prepare_conv per distinct (s_in, zp_in)
+        tmp.conv = nullptr;
+        for (int b = 0; b < B; ++b) {
+            int same = -1;
+            for (int k = 0; k < b && same < 0; ++k)
+                if (hs[k] == hs[b] && hz[k] == hz[b]) same = k;
+            if (same >= 0) {
+                memcpy(&hb[(size_t)b * pitch], &hb[(size_t)same * pitch], sizeof(int32_t) * pitch);
+                memcpy(&hm[(size_t)b * pitch], &hm[(size_t)same * pitch], sizeof(double) * pitch);
+            } else {
+                tmp.s_in = hs[b];
+                tmp.zp_in = hz[b];
+                if (prepare_conv(tmp, 0)) return -1;
+                for (int oc = 0; oc < l0.n; ++oc) {
+                    hb[(size_t)b * pitch + oc] = tmp.biases_int32[oc];
+                    hm[(size_t)b * pitch + oc] = tmp.M_value[oc] * tmp.rshift_value[oc];   // exact: the shift is a power of two
+                }
+            }
+            hzp[b] = (uint8_t)hz[b];
+        }
+        YQ_CUDA(cudaMemcpyAsync(net->img_bias, hb.data(), hb.size() * sizeof(int32_t), cudaMemcpyHostToDevice, net->stream));
+        YQ_CUDA(cudaMemcpyAsync(net->img_mcomb, hm.data(), hm.size() * sizeof(double), cudaMemcpyHostToDevice, net->stream));
+        YQ_CUDA(cudaMemcpyAsync(net->img_zp, hzp.data(), hzp.size(), cudaMemcpyHostToDevice, net->stream));
+        if (forward_body(net, net->in_stage_nchw, nullptr, false, true)) return -1;
+        YQ_CUDA(cudaStreamSynchronize(net->stream));      // (the host tables above live on this stack frame)
+    }
     size_t off = 0;
     for (auto &l : net->layers)
         if (l.type == L_YOLO) {
@@ -1305,6 +1404,29 @@ extern "C" int yq_network_predict_f32(yq_network *net, const float *in_host, flo
         }
     YQ_CUDA(cudaStreamSynchronize(net->stream));
     return 0;
+}
+
+// test_detector's input path (examples/detector.c:903-904: load_image_color, letterbox_image) for a batch of float CHW images
+// of one size already decoded on the host: H2D, letterbox_image on the device, then yq_network_predict_f32's quantiser + forward.
+extern "C" int yq_network_predict_image_f32(yq_network *net, const float *images_host, int ih, int iw, float *out_host)
+{
+    if (!net || !images_host || !out_host || ih <= 0 || iw <= 0) return yq::fail("yq_network_predict_image_f32: bad argument");
+    YQ_CUDA(cudaSetDevice(net->device));
+    const size_t raw = (size_t)net->batch * net->c * ih * iw, boxed = (size_t)net->batch * net->c * net->h * net->w;
+    if (net->in_raw_floats < raw) {
+        cudaFree(net->in_raw);
+        net->in_raw = nullptr;
+        net->in_raw_floats = 0;
+        YQ_CUDA(cudaMalloc((void **)&net->in_raw, raw * sizeof(float)));
+        net->in_raw_floats = raw;
+    }
+    if (!net->in_f32) {
+        YQ_CUDA(cudaMalloc((void **)&net->in_f32, sizeof(float) * boxed));
+        YQ_CUDA(cudaMalloc((void **)&net->in_quant, (sizeof(float) + 3 * sizeof(int)) * (size_t)net->batch));
+    }
+    YQ_CUDA(cudaMemcpyAsync(net->in_raw, images_host, raw * sizeof(float), cudaMemcpyHostToDevice, net->stream));
+    if (yq_letterbox_image_gpu(net->in_raw, net->batch, net->c, ih, iw, net->in_f32, net->h, net->w, net->stream)) return -1;
+    return predict_f32_device(net, out_host);
 }
 
 static int pipe_init(yq_network *net)
@@ -1419,9 +1541,23 @@ extern "C" int yq_network_get_boxes(yq_network *net, int w, int h, float thresh,
     return 0;
 }
 
+// a tensor the current plan never writes (its launch is fused into a neighbour's): pulls of it must fail, not return stale bytes
+static const char *not_materialised(const yq_network *net, int layer, int what)
+{
+    const Layer &l = net->layers[layer];
+    if (what == 0) {
+        if (l.type == L_UPSAMPLE && l.fused_away) return "the route behind it reads its input through the upsample";
+        if (l.type == L_CONV && l.fuse_pool && (l.use_rows || !conv_output_needed(net, layer))) return "its launch writes the max-pooled tensor of the next layer only";
+    } else if (what == 2) {
+        if (l.type == L_CONV && l.fuse_yolo && !net->keep_acc) return "its launch writes the yolo layer's output only (pull that layer, or enable yq_network_set_debug)";
+    }
+    return nullptr;
+}
+
 extern "C" const float *yq_network_layer_output_f32_device(const yq_network *net, int layer)
 {
     if (!net || layer < 0 || layer >= (int)net->layers.size()) return nullptr;
+    if (not_materialised(net, layer, 2)) return nullptr;
     return net->layers[layer].out_f32;
 }
 
@@ -1433,6 +1569,8 @@ extern "C" int yq_network_pull_layer(yq_network *net, int layer, int what, void 
     const size_t elems = (size_t)net->batch * l.out_c * l.out_h * l.out_w;
     const size_t esz = what == 0 ? 1 : 4;
     if (bytes != elems * esz) return yq::fail("yq_network_pull_layer: expected %zu bytes, got %zu", elems * esz, bytes);
+    if (const char *why = not_materialised(net, layer, what))
+        return yq::fail("layer %d is not materialised in this plan: %s (yq_network_set_fusion(net, 0) or yq_network_set_debug(net, 1) keep every tensor)", layer, why);
     if (what == 2) {
         if (!l.out_f32) return yq::fail("layer %d has no float output", layer);
         YQ_CUDA(cudaMemcpyAsync(host_out, l.out_f32, bytes, cudaMemcpyDeviceToHost, net->stream));
@@ -1448,9 +1586,6 @@ extern "C" int yq_network_pull_layer(yq_network *net, int layer, int what, void 
     }
     if (what == 0) {
         if (!l.out_u8) return yq::fail("layer %d has no uint8 output", layer);
-        if (l.type == L_UPSAMPLE && l.fused_away)
-            return yq::fail("layer %d (upsample) is not materialised in this plan: the route behind it reads layer %d through the upsample "
-                            "(set_fusion(0), keep_acc or YQ_UPROUTE=0 keep the tensor)", layer, l.src);
         if (yq_nhwc_to_nchw_u8_geom(l.out_u8, net->scratch, net->batch, l.out_c, l.out_h, l.out_w, &l.geom, net->stream)) return -1;
     } else if (what == 1) {
         if (!l.out_acc) return yq::fail("layer %d has no int32 accumulator (conv layers only, after yq_network_set_debug(net,1))", layer);

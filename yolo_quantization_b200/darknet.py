@@ -101,6 +101,20 @@ def pull_nhwc_i32(buf: DeviceBuffer, b: int, c: int, h: int, w: int) -> np.ndarr
     return out
 
 
+def letterbox_image(images: np.ndarray, h: int, w: int) -> np.ndarray:
+    """letterbox_image (src/image.c:812-831) on the device: float [b,c,ih,iw] -> float [b,c,h,w]."""
+    lib = _lib.load()
+    x = np.ascontiguousarray(images, np.float32)
+    b, c, ih, iw = x.shape
+    din = DeviceBuffer.from_numpy(x)
+    dout = DeviceBuffer(b * c * h * w * 4)
+    check(lib.yq_letterbox_image_gpu(din.ptr, b, c, ih, iw, dout.ptr, h, w, None), "yq_letterbox_image_gpu")
+    check(lib.yq_stream_synchronize(None))
+    out = dout.pull((b, c, h, w), np.float32)
+    din.free(); dout.free()
+    return out
+
+
 def quantize_input(x: np.ndarray):
     """quant_weights_with_min_max_channel(1, net->input, ...) (src/blas.c:108-168) on the device, per image.
     x: float32 [b, ...]; returns (uint8 array of x's shape, scales [b], zero points [b])."""
@@ -558,6 +572,17 @@ class Network:
         check(_lib.load().yq_network_predict_f32(self._h, x.ctypes.data, out.ctypes.data), "yq_network_predict_f32")
         return out
 
+    def predict_image(self, images: np.ndarray, out: Optional[np.ndarray] = None) -> np.ndarray:
+        """test_detector's input path: host float images [batch,c,ih,iw] (load_image_color's layout, any size) ->
+        letterbox_image (src/image.c:812-831) + dynamic input quantiser (src/blas.c:108-168) on the device -> forward."""
+        x = np.ascontiguousarray(images, np.float32)
+        assert x.ndim == 4 and x.shape[:2] == (self.batch, self.c), x.shape
+        if out is None:
+            out = np.empty(self.output_floats, np.float32)
+        check(_lib.load().yq_network_predict_image_f32(self._h, x.ctypes.data, int(x.shape[2]), int(x.shape[3]), out.ctypes.data),
+              "yq_network_predict_image_f32")
+        return out
+
     def predict_raw(self, in_ptr: int, out_ptr: int) -> None:
         """Same as predict_u8 on raw host addresses (e.g. pinned torch tensors)."""
         check(_lib.load().yq_network_predict_u8(self._h, in_ptr, out_ptr), "yq_network_predict_u8")
@@ -634,6 +659,7 @@ def load_network(cfg: str, weights: str, batch: int = 0, device: int = 0, packed
     lib = _lib.load()
     if packed is not None:
         check(lib.yq_pack_arena_clear())
+        check(lib.yq_pack_arena_enable(1))
         if os.path.exists(packed) and lib.yq_pack_arena_load(packed.encode()) < 0:
             raise YqError(_lib.last_error())
     h = lib.yq_load_network(cfg.encode(), weights.encode(), int(batch), int(device))
@@ -642,6 +668,7 @@ def load_network(cfg: str, weights: str, batch: int = 0, device: int = 0, packed
     if packed is not None:
         if pack_arena_stats()["dirty"] and lib.yq_pack_arena_save(packed.encode()) < 0:
             raise YqError(_lib.last_error())
+        check(lib.yq_pack_arena_enable(0))       # later loads / re-preps keep no second copy of their filter images
     return Network(h)
 
 
