@@ -62,6 +62,46 @@ def peaks():
     return p
 
 
+def source_hash():
+    """sha256 over the kernel sources: profiles/*_traffic.json is only trusted for the build it was captured on"""
+    import glob
+    import hashlib
+    h = hashlib.sha256()
+    for f in sorted(glob.glob(os.path.join(ROOT, "yolo_quantization_b200", "csrc", "*.cu")) + glob.glob(os.path.join(ROOT, "yolo_quantization_b200", "csrc", "*.cuh")) +
+                    glob.glob(os.path.join(ROOT, "yolo_quantization_b200", "csrc", "*.h"))):
+        h.update(os.path.basename(f).encode())
+        h.update(open(f, "rb").read())
+    return h.hexdigest()[:16]
+
+
+def int8_peak(pk):
+    """the chip's tcgen05 kind::i8 rate: measured live by tools/probes/probe_i8_peak (all SMs, N = 256 MMAs back to back, CUDA events),
+    else the figure committed under profiles/, else 2 x the measured bf16 rate"""
+    probe = os.path.join(ROOT, "tools", "probes", "probe_i8_peak")
+    try:
+        out = subprocess.run([probe], capture_output=True, text=True, timeout=60).stdout
+        d = json.loads(out.strip().splitlines()[-1])
+        return float(d["int8_tops_cta1"]), "measured live: tools/probes/probe_i8_peak (tcgen05.mma kind::i8, M=128 N=256 K=32, all SMs)", d
+    except Exception:
+        pass
+    try:
+        with open(os.path.join(ROOT, "profiles", "r2_i8_peak.json")) as f:
+            d = json.load(f)
+        return float(d["int8_tops_cta1"]), "profiles/r2_i8_peak.json (tools/probes/probe_i8_peak on this pool's B200)", d
+    except Exception:
+        return 2.0 * pk["bf16_tflops_sustained"], "2 x sustained bf16 of MEASURED_PEAKS.json (probe unavailable)", None
+
+
+def cpu_model():
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name"):
+                return line.split(":", 1)[1].strip()
+    except Exception:
+        pass
+    return "unknown"
+
+
 class ClockSampler:
     """nvidia-smi clocks/throttle reasons sampled every 50 ms while the timed regions run."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
@@ -165,7 +205,7 @@ def run_reference(args):
             "warmup": args.warmup, "ms_per_step": 1e3 * total / len(timed), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u8", "data": "synthetic",
             "config": {"workload": "yolov3-tiny INT8 per-channel 416x416, reference CPU QUANTIZATION=1 path, 1 image per step"},
-            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample, "cpu_model": cpu_model()},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     emit(line)
     return 0
@@ -195,9 +235,15 @@ def cpu_baseline(cfg1, wts, img_f32, info, im, net="tiny"):
             O.forward_network(info, im)
             times.append(time.perf_counter() - t0)
     times = times[1:]
-    return {"value": 1.0 / statistics.median(times), "unit": UNIT, "cores": cores, "kind": kind,
-            "sample": f"{len(times)} images at batch 1 (median network_predict time, 1 warm-up), yolov3-tiny 416x416, "
-                      f"{'oracle/_ref OpenMP build' if kind == 'reference' else 'oracle port'}, {cores} threads"}
+    res = {"value": 1.0 / statistics.median(times), "unit": UNIT, "cores": cores, "kind": kind, "cpu_model": cpu_model(),
+           "sample": f"{len(times)} images at batch 1 (median network_predict time, 1 warm-up), yolov3-tiny 416x416, "
+                     f"{'oracle/_ref OpenMP build' if kind == 'reference' else 'oracle port'}, {cores} threads"}
+    if kind == "reference" and os.path.exists(O.REF_HARNESS):
+        # the reference's default build (MULTI_CORE=0), one thread
+        t1 = O.ref_times(O.run_reference("time", cfg1, wts, img_f32, "3"))[1:]
+        res["single_thread"] = {"value": 1.0 / statistics.median(t1), "unit": UNIT, "cores": 1,
+                                "sample": f"{len(t1)} images, MULTI_CORE=0 build (the reference's default), 1 warm-up"}
+    return res
 
 
 _REAL_STDOUT = None
@@ -231,6 +277,9 @@ def main():
     ap.add_argument("--streams", type=int, default=2,
                     help="device-resident arm: forwards in flight per GPU (each on its own network instance and stream)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--host-mem", default="pinned", choices=["pinned", "wc"],
+                    help="e2e arm: input batches in plain page-locked memory or write-combined page-locked memory (yq_host_alloc)")
+    ap.add_argument("--no-extras", action="store_true", help="skip the batch-1 latency, H2D ceiling and int8 peak probe legs")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     NET = NETS[args.net]
@@ -296,6 +345,16 @@ def main():
     host = torch.empty((R, B, 3, 416, 416), dtype=torch.uint8).pin_memory()
     host.numpy()[...] = rng.integers(0, 256, size=host.shape, dtype=np.uint8)
     dev = host.cuda(non_blocking=False)
+    host_ptrs = [host[i].data_ptr() for i in range(R)]
+    wc_block = None
+    if args.host_mem == "wc":      # the e2e arm's input batches in write-combined page-locked memory (DMA reads skip the CPU caches)
+        import ctypes as C
+        from yolo_quantization_b200 import _lib
+        wc_block = _lib.load().yq_host_alloc(host.numel(), 1)
+        if not wc_block:
+            raise SystemExit("yq_host_alloc failed: " + _lib.last_error())
+        C.memmove(wc_block, host.data_ptr(), host.numel())
+        host_ptrs = [wc_block + i * B * 3 * 416 * 416 for i in range(R)]
     out_host = torch.empty(net.output_floats, dtype=torch.float32).pin_memory()
     in_bytes = B * 3 * 416 * 416
     torch.cuda.synchronize()
@@ -332,7 +391,7 @@ def main():
     def e2e_loop(n):
         slots = []
         for i in range(n):
-            slots.append((net.submit_raw(host[i % R].data_ptr()), i))
+            slots.append((net.submit_raw(host_ptrs[i % R]), i))
             if len(slots) == 2:
                 sl, j = slots.pop(0)
                 net.collect_raw(sl, out_hosts[j % 2].data_ptr())
@@ -352,6 +411,41 @@ def main():
     # the last D2H completes on the host after the compute stream's last event: take the longer of the two clocks
     ms_e2e = max(e2.elapsed_time(e3), 1e3 * (t_e2e1 - t_e2e0))
     t_end = time.time()
+    # ---- extras: the box's H2D ceiling for this batch, batch-1 latency -------------------------------------------------
+    h2d_gbs = None
+    batch1 = None
+    if not args.no_extras:
+        ce0, ce1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        cstream = torch.cuda.Stream(device=local)
+        from yolo_quantization_b200 import _lib as _l
+        lib_ = _l.load()
+        with torch.cuda.stream(cstream):
+            lib_.yq_cuda_push(dev[0].data_ptr(), host_ptrs[0], in_bytes, cstream.cuda_stream)
+            ce0.record(cstream)
+            for i in range(10):
+                lib_.yq_cuda_push(dev[i % R].data_ptr(), host_ptrs[i % R], in_bytes, cstream.cuda_stream)
+            ce1.record(cstream)
+        cstream.synchronize()
+        h2d_gbs = 10 * in_bytes / (ce0.elapsed_time(ce1) * 1e-3) / 1e9
+        if world == 1 and args.net == "tiny":
+            cfgb1 = os.path.join(tmp.name, "b1.cfg")
+            synth.write_cfg(cfgb1, layers, batch=1)
+            n1 = darknet.load_network(cfgb1, wts, batch=1, device=local)
+            n1.use_graph(True)
+            s1 = torch.cuda.ExternalStream(n1.stream, device=local)
+            for i in range(20):
+                n1.forward_device(dev[i % R].data_ptr())
+            n1.synchronize()
+            b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            b0.record(s1)
+            for i in range(200):
+                n1.forward_device(dev[i % R][i % B].data_ptr())
+            b1.record(s1)
+            n1.synchronize()
+            lat = b0.elapsed_time(b1) / 200
+            batch1 = {"latency_ms": lat, "images_per_s": 1e3 / lat,
+                      "what": "BASELINE configs[1]: batch 1, device-resident input, CUDA-graph replay, 200 forwards back to back on one stream"}
+            n1.free()
     # ---- per-layer CUDA events (un-graphed forwards on the same stream) -------------------------
     prof_iters = max(3, min(20, args.steps))
     lm = np.zeros(net.n + 1, np.float64)
@@ -367,7 +461,10 @@ def main():
 
     if rank == 0:
         pk = peaks()
-        p_int8 = 2.0 * pk["bf16_tflops_sustained"]
+        if args.no_extras:
+            p_int8, p_src, p_raw = 2.0 * pk["bf16_tflops_sustained"], "2 x sustained bf16 of MEASURED_PEAKS.json (--no-extras)", None
+        else:
+            p_int8, p_src, p_raw = int8_peak(pk)
         infos = net.layers()
         rows = []
         for i, li in enumerate(infos):
@@ -395,17 +492,24 @@ def main():
         else:
             ach = top["bytes"] / (top["ms"] * 1e-3) / 1e9
             roof = {"bound": "hbm", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ach / pk["hbm_gbs"]}
-        traffic = None
+        # dram__bytes_read + dram__bytes_write of the same launch from the ncu capture tools/round_check.sh made -- trusted only for
+        # the build it was captured on (hash of the kernel sources) and for this net / batch
+        traffic, traffic_note = None, "no capture for this build"
         try:
-            with open(os.path.join(ROOT, "profiles", "r1_traffic.json")) as f:
-                traffic = json.load(f).get(str(top["layer"])) if (B == 128 and args.net == "tiny") else None
+            with open(os.path.join(ROOT, "profiles", f"r2_traffic_{args.net}.json")) as f:
+                tj = json.load(f)
+            if tj.get("source_hash") == source_hash() and tj.get("batch") == B:
+                traffic = tj["layers"].get(str(top["layer"]))
+                traffic_note = f"profiles/r2_traffic_{args.net}.json (ncu --set full, same kernel sources {tj['source_hash']})"
+            else:
+                traffic_note = f"profiles/r2_traffic_{args.net}.json is from other kernel sources ({tj.get('source_hash')} != {source_hash()}) or another batch: not used"
         except Exception:
             pass
-        roof.update(traffic=traffic, kernel=f"layer {top['layer']} ({top['type']}, flavour {top['kernel']})",
+        roof.update(traffic=traffic, traffic_source=traffic_note, kernel=f"layer {top['layer']} ({top['type']}, flavour {top['kernel']})",
                     share_of_step=top["ms"] / float(lm.sum()),
-                    peak_source=(f"{pk['source']} MEASURED_PEAKS.json: int8 tensor peak taken as 2 x sustained bf16 "
-                                 f"({pk['bf16_tflops_sustained']} TF/s; nominal dense int8 {NOMINAL_INT8_TOPS} TOP/s), "
-                                 f"HBM {pk['hbm_gbs']} GB/s; 'TFLOP/s' counts int8 ops") )
+                    peak_source=(f"HBM {pk['hbm_gbs']} GB/s ({pk['source']} MEASURED_PEAKS.json); int8 tensor peak {p_int8:.0f} TOP/s = {p_src} "
+                                 f"(2 x sustained bf16 would be {2 * pk['bf16_tflops_sustained']:.0f}, nominal dense int8 {NOMINAL_INT8_TOPS:.0f}); "
+                                 f"'TFLOP/s' counts int8 ops"))
         ips = world * B * args.steps / (ms * 1e-3)
         ips_e2e = world * B * args.steps / (ms_e2e * 1e-3)
         total_ops = 2 * NET["macs"]
@@ -419,13 +523,19 @@ def main():
                        "l2": f"{R} rotating input batches ({R * in_bytes >> 20} MiB) > 126 MB L2 and several hundred MiB of "
                              f"activations written per step; no explicit flush"},
             "e2e": {"value": ips_e2e, "unit": UNIT, "h2d_bytes_per_step": in_bytes * world,
-                    "d2h_bytes_per_step": int(net.output_floats) * 4 * world, "ms_per_step": ms_e2e / args.steps},
+                    "d2h_bytes_per_step": int(net.output_floats) * 4 * world, "ms_per_step": ms_e2e / args.steps, "host_memory": args.host_mem,
+                    # what this rank's link delivers for one batch-sized pinned copy on its own (10 back to back): the ceiling of e2e
+                    "h2d_ceiling_gbs_rank0": h2d_gbs,
+                    "h2d_achieved_gbs_per_gpu": in_bytes / (ms_e2e / args.steps * 1e-3) / 1e9,
+                    "frac_of_h2d_ceiling": (in_bytes / (ms_e2e / args.steps * 1e-3) / 1e9 / h2d_gbs) if h2d_gbs else None},
             "gpu_launches": net.launches_per_forward * args.steps * world,
             "clocks": clocks,
             "roofline": roof,
             # algorithmic activation + weight bytes of every launch of one step (unfused accounting per launch) over the step time
             "hbm_gbs_algorithmic_whole_net": step_bytes / (ms / args.steps * 1e-3) / 1e9,
             "hbm_frac_whole_net": step_bytes / (ms / args.steps * 1e-3) / 1e9 / pk["hbm_gbs"],
+            "int8_tops_measured_peak": p_int8, "int8_peak_probe": p_raw,
+            "batch1": batch1,
             "int8_tops_whole_net": ips / world * total_ops / 1e12,
             "frac_int8_peak_whole_net": ips / world * total_ops / 1e12 / p_int8,
             "layers": [{k: r[k] for k in ("layer", "type", "ms", "bound", "frac", "kernel", "fused")} for r in rows],
@@ -438,6 +548,9 @@ def main():
         emit(line)
     for n_ in nets:
         n_.free()
+    if wc_block:
+        from yolo_quantization_b200 import _lib
+        _lib.load().yq_host_free(wc_block)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

@@ -62,6 +62,11 @@ YQ_API int yq_cuda_pull(void *host, const void *dev, size_t bytes, void *stream)
 YQ_API int yq_cuda_memset(void *dev, int value, size_t bytes, void *stream);
 YQ_API int yq_stream_synchronize(void *stream);
 
+/* page-locked host memory for the host-buffer entry points (yq_network_submit_u8 / predict_*): cudaHostAlloc; write_combined = 1
+ * asks for write-combined pages (host writes stream, host READS are very slow): for input buffers the CPU only fills. */
+YQ_API void *yq_host_alloc(size_t bytes, int write_combined);
+YQ_API int yq_host_free(void *host);
+
 /* channel stride used for a c-channel NHWC activation tensor: 4 for c <= 4, else c rounded up to 16 */
 YQ_API int yq_channel_stride(int c);
 
@@ -341,6 +346,29 @@ YQ_API int yq_network_use_graph(yq_network *net, int enable);
 YQ_API int yq_network_profile_forward(yq_network *net, const uint8_t *in_u8_nchw, float *layer_ms);
 /* number of kernel launches one forward issues (for bench.py's gpu_launches) */
 YQ_API int yq_network_launches_per_forward(const yq_network *net);
+/* ... and how many of them belong to layer i in the current plan (0: fused into a neighbour's launch, or an aliased route);
+ * the input layout transform, when the plan has one, is the launch in front of layer 0's */
+YQ_API int yq_network_layer_launches(const yq_network *net, int i);
+
+/* ---- data-parallel inference over the GPUs of one box, C level ----------------------------------------------
+ * The path shards by image: a full replica per GPU, no per-step collective.  The reference's multi-GPU code is one host thread
+ * per device that calls cuda_set_device first (src/network.c:930-937, :1164-1194) and averages weights through the host; here
+ * replica 0 parses, prepares and packs, the packed filter images travel to the other devices in ONE ncclBroadcast (libnccl is
+ * bound at run time with dlopen; without it this entry fails with a message, everything else works), and one host thread per
+ * remaining device builds its replica from device-to-device copies out of that blob.
+ * yq_dp_network_predict_u8: in_host [n_devices][batch_per_device][c][h][w] uint8, out_host [n_devices][yq_network_output_floats];
+ * image block i runs on devices[i]; all devices' copies and forwards are enqueued before the first result is awaited. */
+typedef struct yq_dp_network yq_dp_network;
+YQ_API yq_dp_network *yq_dp_load_network(const char *cfg, const char *weights, int batch_per_device, const int *devices, int n_devices);
+YQ_API void yq_dp_free_network(yq_dp_network *dp);
+YQ_API int yq_dp_num_devices(const yq_dp_network *dp);
+YQ_API yq_network *yq_dp_replica(yq_dp_network *dp, int i);
+YQ_API size_t yq_dp_arena_bytes(const yq_dp_network *dp);          /* bytes the one broadcast carried */
+YQ_API int yq_dp_images_from_arena(const yq_dp_network *dp);      /* filter images replicas 1.. took from it (device-to-device) */
+YQ_API int yq_dp_network_predict_u8(yq_dp_network *dp, const uint8_t *in_u8_nchw_host, float *out_f32_host);
+/* the same, pipelined two deep like yq_network_submit_u8 / yq_network_collect (use pinned host memory: yq_host_alloc) */
+YQ_API int yq_dp_network_submit_u8(yq_dp_network *dp, const uint8_t *in_u8_nchw_host);
+YQ_API int yq_dp_network_collect(yq_dp_network *dp, int slot, float *out_f32_host);
 
 /* ---- "next" row 8f-4: packed-weight arena --------------------------------------------------------------------
  * The reference repacks nothing because its GEMM reads `weights_uint8` as parsed (parser.c:1124-1159); the kernels here

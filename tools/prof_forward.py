@@ -29,6 +29,9 @@ with tempfile.TemporaryDirectory() as d:
         net.forward_device(dev.ptr)
         net.synchronize()
     print("launches per forward", net.launches_per_forward)
+    # the layer behind every launch of one forward, in issue order (tools/make_traffic.py maps ncu's launch list with it)
+    import json
+    print("LAUNCH_ORDER", json.dumps(net.launch_order()))
     if not os.environ.get("YQ_NO_PROFILE_FORWARD"):
         print("done", net.profile_forward(dev.ptr).round(3).tolist())
     net.free()

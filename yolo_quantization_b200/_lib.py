@@ -59,6 +59,8 @@ SIGNATURES = {
     "yq_cuda_pull": (_i, [_vp, _vp, _sz, _vp]),
     "yq_cuda_memset": (_i, [_vp, _i, _sz, _vp]),
     "yq_stream_synchronize": (_i, [_vp]),
+    "yq_host_alloc": (_vp, [_sz, _i]),
+    "yq_host_free": (_i, [_vp]),
     "yq_channel_stride": (_i, [_i]),
     "yq_make_convolutional_layer_quant": (_vp, [C.POINTER(ConvDesc)]),
     "yq_free_convolutional_layer_quant": (None, [_vp]),
@@ -123,6 +125,16 @@ SIGNATURES = {
     "yq_network_stream": (_vp, [_vp]),
     "yq_network_use_graph": (_i, [_vp, _i]),
     "yq_network_launches_per_forward": (_i, [_vp]),
+    "yq_network_layer_launches": (_i, [_vp, _i]),
+    "yq_dp_load_network": (_vp, [C.c_char_p, C.c_char_p, _i, C.POINTER(_i), _i]),
+    "yq_dp_free_network": (None, [_vp]),
+    "yq_dp_num_devices": (_i, [_vp]),
+    "yq_dp_replica": (_vp, [_vp, _i]),
+    "yq_dp_arena_bytes": (_sz, [_vp]),
+    "yq_dp_images_from_arena": (_i, [_vp]),
+    "yq_dp_network_predict_u8": (_i, [_vp, _vp, _vp]),
+    "yq_dp_network_submit_u8": (_i, [_vp, _vp]),
+    "yq_dp_network_collect": (_i, [_vp, _i, _vp]),
     "yq_pack_arena_load": (_i, [C.c_char_p]),
     "yq_pack_arena_save": (_i, [C.c_char_p]),
     "yq_pack_arena_clear": (_i, []),

@@ -134,6 +134,17 @@ namespace yq {
 uint64_t pack_layer_key(const yq_conv_layer *l);
 bool pack_fetch(const yq_conv_layer *l, const char *tag, std::vector<uint8_t> &out);
 void pack_put(const yq_conv_layer *l, const char *tag, const std::vector<uint8_t> &img);
+// data-parallel replicas (yq_dp.cu): the arena as one blob + index; a replica thread that was handed the blob on ITS device
+// (one ncclBroadcast) takes its filter images from there by device-to-device copy -- no host packing, no host-to-device upload
+struct PackIndexEntry {
+    uint64_t key;
+    std::string tag;
+    size_t offset, bytes;
+};
+void pack_serialize(std::vector<uint8_t> &blob, std::vector<PackIndexEntry> &index);
+void pack_set_device_arena(const uint8_t *blob_dev, const std::vector<PackIndexEntry> *index);   // per host thread; nullptr switches it off
+int pack_device_arena_hits();
+bool pack_fetch_device(const yq_conv_layer *l, const char *tag, size_t bytes, void **dev_out);
 }  // namespace yq
 int yq_tc_small_prepare(yq_conv_layer *l, void **state);
 void yq_tc_small_free(void *state);

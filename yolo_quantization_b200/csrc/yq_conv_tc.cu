@@ -470,26 +470,35 @@ int yq_tc_prepare(yq_conv_layer *l)
     st->n_pad = yq::round_up(l->n, st->BN);
     const int taps = l->size * l->size;
     const size_t ktot = (size_t)taps * l->cs_in;
-    std::vector<uint8_t> wp((size_t)st->n_pad * ktot, 0);
+    // [n_pad][taps][cs_in] rows: the same image (and arena tag) as the flat kernels'
+    std::vector<uint8_t> wp;
     std::vector<int32_t> corr((size_t)taps * st->n_pad, 0);
+    char tag[24];
+    snprintf(tag, sizeof tag, "ohwi.%d", st->n_pad);
+    const bool on_dev = yq::pack_fetch_device(l, tag, (size_t)st->n_pad * ktot, (void **)&st->w);
+    const bool cached = on_dev || (yq::pack_fetch(l, tag, wp) && wp.size() == (size_t)st->n_pad * ktot);
+    if (!cached) wp.assign((size_t)st->n_pad * ktot, 0);
     for (int oc = 0; oc < l->n; ++oc)
         for (int t = 0; t < taps; ++t) {
             int tsum = 0;
             for (int ci = 0; ci < l->c; ++ci) {
                 const uint8_t w = l->host_w[((size_t)oc * l->c + ci) * taps + t];
-                wp[(size_t)oc * ktot + (size_t)t * l->cs_in + ci] = w;
+                if (!cached) wp[(size_t)oc * ktot + (size_t)t * l->cs_in + ci] = w;
                 tsum += w;
             }
             corr[(size_t)t * st->n_pad + oc] = l->zp_in * (tsum - (int)l->host_zw[oc] * l->c);
         }
+    if (!cached) yq::pack_put(l, tag, wp);
     auto cleanup = [&]() {
         cudaFree(st->w);
         cudaFree(st->corr);
         delete st;
         return -1;
     };
-    if (cudaMalloc((void **)&st->w, wp.size()) != cudaSuccess) return cleanup();
-    if (cudaMemcpy(st->w, wp.data(), wp.size(), cudaMemcpyHostToDevice) != cudaSuccess) return cleanup();
+    if (!on_dev) {
+        if (cudaMalloc((void **)&st->w, wp.size()) != cudaSuccess) return cleanup();
+        if (cudaMemcpy(st->w, wp.data(), wp.size(), cudaMemcpyHostToDevice) != cudaSuccess) return cleanup();
+    }
     if (l->zp_in != 0 && l->size > 1) {
         if (cudaMalloc((void **)&st->corr, corr.size() * 4) != cudaSuccess) return cleanup();
         if (cudaMemcpy(st->corr, corr.data(), corr.size() * 4, cudaMemcpyHostToDevice) != cudaSuccess) return cleanup();

@@ -460,7 +460,9 @@ int yq_tc_flat2_prepare(yq_conv_layer *l, void **state)
     std::vector<uint8_t> wp;
     char tag[24];
     snprintf(tag, sizeof tag, "ohwi.%d", st->n_pad);
-    if (!yq::pack_fetch(l, tag, wp) || wp.size() != (size_t)st->n_pad * ktot) {
+    // (a data-parallel replica takes the image from the arena blob broadcast to its device: no host packing, no upload)
+    const bool on_dev = yq::pack_fetch_device(l, tag, (size_t)st->n_pad * ktot, (void **)&st->w);
+    if (!on_dev && (!yq::pack_fetch(l, tag, wp) || wp.size() != (size_t)st->n_pad * ktot)) {
         wp.assign((size_t)st->n_pad * ktot, 0);
         for (int oc = 0; oc < l->n; ++oc)
             for (int t = 0; t < taps; ++t)
@@ -472,8 +474,10 @@ int yq_tc_flat2_prepare(yq_conv_layer *l, void **state)
         delete st;
         return -1;
     };
-    if (cudaMalloc((void **)&st->w, wp.size()) != cudaSuccess) return cleanup();
-    if (cudaMemcpy(st->w, wp.data(), wp.size(), cudaMemcpyHostToDevice) != cudaSuccess) return cleanup();
+    if (!on_dev) {
+        if (cudaMalloc((void **)&st->w, wp.size()) != cudaSuccess) return cleanup();
+        if (cudaMemcpy(st->w, wp.data(), wp.size(), cudaMemcpyHostToDevice) != cudaSuccess) return cleanup();
+    }
     if (f2_encode_2d(&st->tmB, st->w, (uint64_t)st->n_pad, (int)ktot, st->KC, F2_BN, CU_TENSOR_MAP_L2_PROMOTION_L2_256B)) return cleanup();
     *state = st;
     return 0;

@@ -960,7 +960,9 @@ int yq_tc_rows_prepare(yq_conv_layer *l, void **state)
                 }
     }
     if (!cached) yq::pack_put(l, tag, img);
-    if (cudaMalloc((void **)&st->wimg, img.size()) != cudaSuccess || cudaMemcpy(st->wimg, img.data(), img.size(), cudaMemcpyHostToDevice) != cudaSuccess) {
+    if (yq::pack_fetch_device(l, tag, img.size(), (void **)&st->wimg)) {
+        // (data-parallel replica: the image came from the arena blob on this device)
+    } else if (cudaMalloc((void **)&st->wimg, img.size()) != cudaSuccess || cudaMemcpy(st->wimg, img.data(), img.size(), cudaMemcpyHostToDevice) != cudaSuccess) {
         cudaFree(st->wimg);
         delete st;
         return yq::fail("tcgen05 rows flavour: weight upload failed");

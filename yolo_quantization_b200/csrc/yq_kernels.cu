@@ -165,6 +165,21 @@ int yq_cuda_memset(void *dev, int value, size_t bytes, void *stream)
     YQ_CUDA(cudaMemsetAsync(dev, value, bytes, (cudaStream_t)stream));
     return 0;
 }
+void *yq_host_alloc(size_t bytes, int write_combined)
+{
+    void *p = nullptr;
+    cudaError_t e = cudaHostAlloc(&p, bytes ? bytes : 1, write_combined ? cudaHostAllocWriteCombined : cudaHostAllocDefault);
+    if (e != cudaSuccess) {
+        yq::fail("cudaHostAlloc(%zu bytes) failed: %s", bytes, cudaGetErrorString(e));
+        return nullptr;
+    }
+    return p;
+}
+int yq_host_free(void *host)
+{
+    YQ_CUDA(cudaFreeHost(host));
+    return 0;
+}
 int yq_stream_synchronize(void *stream)
 {
     YQ_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
@@ -464,7 +479,8 @@ extern "C" yq_conv_layer *yq_make_convolutional_layer_quant(const yq_conv_desc *
 
     // pack OIHW -> [oc][ky][kx][ci (stride cs_in)], zero padded (push_convolutional_layer's role)
     std::vector<uint8_t> wp;
-    if (!yq::pack_fetch(l, "simt", wp) || wp.size() != (size_t)l->n_pad * l->k_pad) {
+    const bool simt_on_dev = yq::pack_fetch_device(l, "simt", (size_t)l->n_pad * l->k_pad, (void **)&l->w_simt);
+    if (!simt_on_dev && (!yq::pack_fetch(l, "simt", wp) || wp.size() != (size_t)l->n_pad * l->k_pad)) {
         wp.assign((size_t)l->n_pad * l->k_pad, 0);
         for (int oc = 0; oc < l->n; ++oc)
             for (int ci = 0; ci < l->c; ++ci)
@@ -499,7 +515,7 @@ extern "C" yq_conv_layer *yq_make_convolutional_layer_quant(const yq_conv_desc *
     l->host_chanq.resize((size_t)p_pad * 4);
     memcpy(l->host_chanq.data(), chanq.data(), (size_t)p_pad * 16);
     l->host_mcomb = mcomb;
-    if (upload(&l->w_simt, wp) || upload(&l->bias, bias) || upload(&l->zw, zw) || upload(&l->mcomb, mcomb) ||
+    if ((!simt_on_dev && upload(&l->w_simt, wp)) || upload(&l->bias, bias) || upload(&l->zw, zw) || upload(&l->mcomb, mcomb) ||
         upload(&l->mval, mval) || upload(&l->rsh, rsh) || upload((int4 **)&l->chanq, chanq)) {
         yq_free_convolutional_layer_quant(l);
         return nullptr;
@@ -872,7 +888,7 @@ __global__ void route_u8_kernel(const RouteArgs a, uint8_t *__restrict__ out, in
     }
 }
 
-// YQ_ROUTE_ROWS=1 (off by default: parity-tested on B200, not yet timed): the 16-byte-vector route with one block per
+// The 16-byte-vector route (default since r2; YQ_ROUTE_ROWS=0 selects route_u8_kernel) with one block per
 // (output row, input) -- the per-vector loop over the inputs, the row decode and the pixel address arithmetic of
 // route_u8_kernel (239 warp instructions per vector, profiles/r1_route_full.csv) move out of the copy loop.
 __global__ void __launch_bounds__(256) route_rows_u8_kernel(const RouteArgs a, uint8_t *__restrict__ out)
@@ -936,8 +952,10 @@ extern "C" int yq_forward_route_layer_quant_part_gpu(const uint8_t *const *input
     if (a.cs_out % 16) vec = 0;
     dim3 grid;
     int threads;
+    // one block per (output row, input) with the index arithmetic hoisted out of the copy loop: measured on B200 (r2) 264.9 k vs
+    // 261.2 k img/s for the whole yolov3-tiny step against route_u8_kernel; YQ_ROUTE_ROWS=0 keeps the old kernel for A/B runs
     const char *rows_env = getenv("YQ_ROUTE_ROWS");
-    if (vec && rows_env && atoi(rows_env)) {
+    if (vec && !(rows_env && !atoi(rows_env))) {
         int nsel = 0;
         for (int i = 0; i < n_inputs; ++i)
             if (input_mask >> i & 1) a.sel[nsel++] = i;

@@ -1180,6 +1180,15 @@ extern "C" int yq_network_input_dims(const yq_network *net, int *c, int *h, int 
 extern "C" size_t yq_network_output_floats(const yq_network *net) { return net->out_floats; }
 extern "C" void *yq_network_stream(yq_network *net) { return (void *)net->stream; }
 extern "C" int yq_network_launches_per_forward(const yq_network *net) { return net->launches; }
+extern "C" int yq_network_layer_launches(const yq_network *net, int i)
+{
+    if (!net || i < 0 || i >= (int)net->layers.size()) return -1;
+    const Layer &l = net->layers[i];
+    if (l.fused_away) return 0;
+    if (l.type == L_CONV) return l.use_rows ? yq_tc_rows_launches(l.conv->tc_rows) : 1;
+    if (l.type == L_ROUTE) return l.inputs.size() > 1 ? 1 : 0;      // (a single-input route is an alias; early copies aside)
+    return 1;
+}
 
 extern "C" int yq_network_layer_info(const yq_network *net, int i, yq_layer_info *o)
 {

@@ -78,6 +78,65 @@ void pack_put(const yq_conv_layer *l, const char *tag, const std::vector<uint8_t
     g_arena.dirty = true;
 }
 
+
+// ---- the arena as one blob (the file format, in memory) and its device-resident form for data-parallel replicas (yq_dp.cu) ----
+void pack_serialize(std::vector<uint8_t> &blob, std::vector<PackIndexEntry> &index)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    blob.clear();
+    index.clear();
+    auto put = [&](const void *p, size_t n) { blob.insert(blob.end(), (const uint8_t *)p, (const uint8_t *)p + n); };
+    const uint32_t hdr[3] = {PACK_MAGIC, PACK_VERSION, (uint32_t)g_arena.entries.size()};
+    put(hdr, sizeof hdr);
+    for (const auto &e : g_arena.entries) {
+        char tag[24] = {0};
+        strncpy(tag, e.first.second.c_str(), sizeof tag - 1);
+        const uint64_t key = e.first.first, bytes = e.second.size(), sum = fnv(14695981039346656037ull, e.second.data(), e.second.size());
+        put(&key, 8);
+        put(tag, sizeof tag);
+        put(&bytes, 8);
+        put(&sum, 8);
+        while (blob.size() % 256) blob.push_back(0);          // images start 256-byte aligned inside the blob (device copies)
+        index.push_back(PackIndexEntry{key, std::string(tag), blob.size(), (size_t)bytes});
+        put(e.second.data(), e.second.size());
+    }
+}
+
+namespace {
+struct DeviceArena {
+    const uint8_t *blob = nullptr;                 // on the thread's current device
+    const std::vector<PackIndexEntry> *index = nullptr;
+    int hits = 0;
+};
+thread_local DeviceArena tls_dev_arena;
+}  // namespace
+
+void pack_set_device_arena(const uint8_t *blob_dev, const std::vector<PackIndexEntry> *index)
+{
+    tls_dev_arena.blob = blob_dev;
+    tls_dev_arena.index = index;
+    tls_dev_arena.hits = 0;
+}
+int pack_device_arena_hits() { return tls_dev_arena.hits; }
+
+bool pack_fetch_device(const yq_conv_layer *l, const char *tag, size_t bytes, void **dev_out)
+{
+    if (!tls_dev_arena.blob || !tls_dev_arena.index) return false;
+    for (const auto &e : *tls_dev_arena.index)
+        if (e.key == l->pack_key && e.bytes == bytes && e.tag == tag) {
+            void *p = nullptr;
+            if (cudaMalloc(&p, bytes ? bytes : 1) != cudaSuccess) return false;
+            if (cudaMemcpy(p, tls_dev_arena.blob + e.offset, bytes, cudaMemcpyDeviceToDevice) != cudaSuccess) {
+                cudaFree(p);
+                return false;
+            }
+            *dev_out = p;
+            ++tls_dev_arena.hits;
+            return true;
+        }
+    return false;
+}
+
 }  // namespace yq
 
 extern "C" int yq_pack_arena_clear(void)

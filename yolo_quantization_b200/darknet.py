@@ -517,6 +517,12 @@ class Network:
     def launches_per_forward(self) -> int:
         return _lib.load().yq_network_launches_per_forward(self._h)
 
+    def launch_order(self) -> List[int]:
+        """the layer behind every launch of one forward, in issue order (-1 = the input layout transform)"""
+        lib = _lib.load()
+        per = [lib.yq_network_layer_launches(self._h, i) for i in range(self.n)]
+        return [-1] * (self.launches_per_forward - sum(per)) + [i for i, k in enumerate(per) for _ in range(k)]
+
     def layer_info(self, i: int) -> LayerInfo:
         info = LayerInfo()
         check(_lib.load().yq_network_layer_info(self._h, i, C.byref(info)))
