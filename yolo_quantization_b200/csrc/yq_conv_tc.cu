@@ -17,7 +17,8 @@
 //      FP64 requantize -> activation -> +zp_out -> uint8 wrap -> swizzled smem tile -> TMA store (clips
 //      partial tiles).  Optional int32 / float (quant_stop) side outputs go straight to global memory.
 //
-// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer, warps 2-5 = epilogue.
+// Warp roles (320 threads): warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer, warps 2-9 = epilogue (two per TMEM lane
+// quarter, each on half of the tile's channels: the epilogue is the longest phase of a tile, r2 profile).
 // One output tile per CTA, up to two CTAs per SM so one CTA's epilogue overlaps the other's main loop.
 #include <cuda.h>
 #include <cuda_runtime.h>
@@ -34,7 +35,8 @@ using namespace yqtc;
 
 namespace {
 
-constexpr int TC_THREADS = 192;
+constexpr int TC_EPI_WARPS = 8;
+constexpr int TC_THREADS = 32 * (2 + TC_EPI_WARPS);
 constexpr int TC_STAGES = 3;
 constexpr int ONES_ROWS = 16;
 
@@ -131,7 +133,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) conv_u8_tc_kernel(const __grid_
     if (warp == 1) tmem_alloc<tmem_cols<BN>()>(tmem_slot);
     if (warp >= 2) {
         const int t = threadIdx.x - 64;
-        for (int i = t; i < BN; i += 128) {
+        for (int i = t; i < BN; i += 32 * TC_EPI_WARPS) {
             const bool in = oc0 + i < a.n_pad;       // cluster padding may add CTAs past the last n-tile
             s_q[i] = in ? __ldg(a.ep.chanq + oc0 + i) : make_int4(0, 0, 0, 0);
             s_mc[i] = in ? __ldg(a.ep.mcomb + oc0 + i) : 0.0;
@@ -139,7 +141,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) conv_u8_tc_kernel(const __grid_
         // the 16 all-ones filter rows that follow the TMA-written BN rows of every stage's B tile (never overwritten)
         for (int s = 0; s < TC_STAGES; ++s) {
             uint32_t *ones = (uint32_t *)(smem + s * L::STAGE + L::A_BYTES + L::B_BYTES);
-            for (int i = t; i < L::ONES_BYTES / 4; i += 128) ones[i] = 0x01010101u;
+            for (int i = t; i < L::ONES_BYTES / 4; i += 32 * TC_EPI_WARPS) ones[i] = 0x01010101u;
         }
         fence_proxy_async();   // generic-proxy writes of the ones rows must be visible to the tensor core (async proxy)
     }
@@ -205,6 +207,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) conv_u8_tc_kernel(const __grid_
     } else {
         // ===================== epilogue =====================
         const int q = warp & 3;                 // TMEM lane quarter this warp may access
+        const int half = (warp - 2) >> 2;       // which half of the tile's channels (BN >= 32: at least one 16-channel chunk each)
         const int r = q * 32 + lane;            // tile row = TMEM lane = output pixel of the patch
         const int wi = r % a.TW, hi = (r / a.TW) % a.TH, ni = r / (a.TW * a.TH);
         const int ox = x0 + wi, oy = y0 + hi, n = n0 + ni;
@@ -228,7 +231,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) conv_u8_tc_kernel(const __grid_
         const bool side = SLOW && ((a.out_acc != nullptr) || (a.out_f32 != nullptr));
         const int sat = SLOW ? a.ep.saturate : 0;
 #pragma unroll 1
-        for (int c0 = 0; c0 < BN; c0 += 16) {
+        for (int c0 = half * (BN / 2); c0 < (half + 1) * (BN / 2); c0 += 16) {
             uint32_t v[16];
             tmem_ld16(trow + c0, v);
             uint32_t packed[4];
@@ -271,7 +274,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) conv_u8_tc_kernel(const __grid_
         }
         tc_fence_before();
         fence_proxy_async();
-        asm volatile("bar.sync 1, 128;" ::: "memory");   // the four epilogue warps only
+        asm volatile("bar.sync 1, %0;" ::"n"(32 * TC_EPI_WARPS) : "memory");   // the epilogue warps only
         if (threadIdx.x == 64) {
             tma_store_4d(&tmO, stage_out, oc0, x0, y0, n0);
             tma_store_commit_wait();
