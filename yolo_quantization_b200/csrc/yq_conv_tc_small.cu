@@ -28,12 +28,7 @@ using namespace yqtc;
 
 namespace {
 
-constexpr int SM_THREADS = 128;            // pool-first (PQ) variant: thread = im2col row = TMEM lane = output pixel of the tile
-// The general variant runs TWO threads per pixel (256 threads): both build half of the pixel's im2col row and requantize half of
-// its channels -- the epilogue is the long phase of a tile (16-20 instructions per output), and with 4 warps per CTA and 2 CTAs
-// per SM (c = 32) the issue slots were 37 % used (r2 profile of the full yolov3's layers 1 and 3).
-__host__ __device__ constexpr int small_threads(bool pq) { return pq ? 128 : 256; }
-__host__ __device__ constexpr int small_min_ctas(int cs, bool pq) { return pq ? (cs == 32 ? 2 : (cs == 16 ? 4 : 6)) : (cs == 32 ? 2 : 3); }
+constexpr int SM_THREADS = 128;            // thread = im2col row = TMEM lane = output pixel of the tile
 constexpr int TAPS = 9;
 constexpr int TILE_W = 16, TILE_H = 8;     // 128 output pixels per tile; power-of-two so row -> (x,y) is shifts/masks
 
@@ -126,7 +121,7 @@ struct TileWalker {
 // permuted on the host so that thread q = lane & 3 owns channels [q*BN/4, (q+1)*BN/4): its packed bytes are one
 // contiguous BN/4-byte store and a warp writes 8 pooled pixels = 8*BN contiguous bytes.
 template <int CS, int BN, int ACTM, bool SLOW, bool PQ>
-__global__ void __launch_bounds__(small_threads(PQ), small_min_ctas(CS, PQ)) conv_u8_tc_small_kernel(const __grid_constant__ SmallArgs a)
+__global__ void __launch_bounds__(SM_THREADS, (CS == 32 ? 2 : (CS == 16 ? 4 : 6))) conv_u8_tc_small_kernel(const __grid_constant__ SmallArgs a)
 {
     static_assert(!PQ || (ACTM == 0 && !SLOW), "the pool-first variant exists for RELU6 production launches only");
     using G = SmallGeom<CS>;
@@ -137,24 +132,22 @@ __global__ void __launch_bounds__(small_threads(PQ), small_min_ctas(CS, PQ)) con
     uint64_t *mma_done = (uint64_t *)(smem + L::BAR_OFF);   // [2]
     uint32_t *tmem_slot = (uint32_t *)(mma_done + 2);
 
-    constexpr int NT = small_threads(PQ);
-    const int r = threadIdx.x & 127;      // A-tile row == TMEM lane == pixel within the tile
-    const int part = threadIdx.x >> 7;    // general variant: which half of the row's chunks / the pixel's channels this thread takes
-    const int warp = r >> 5, lane = r & 31;   // warp & 3 of the hardware warp id: the TMEM lane quarter it may read
+    const int r = threadIdx.x;            // A-tile row == TMEM lane == pixel within the tile
+    const int warp = r >> 5, lane = r & 31;
     // pixel of the 16x8 tile this thread's im2col row / TMEM lane stands for
     const int wi = PQ ? 2 * (lane & 7) + ((lane >> 3) & 1) : (r & (TILE_W - 1));
     const int hi = PQ ? 2 * warp + (lane >> 4) : (r >> 4);
 
     // ---- one-time setup: resident filter bank, ones tile, barriers, TMEM
-    for (int i = threadIdx.x; i < L::B_BYTES / 16; i += NT)
+    for (int i = r; i < L::B_BYTES / 16; i += SM_THREADS)
         reinterpret_cast<uint4 *>(sB)[i] = __ldg(reinterpret_cast<const uint4 *>(a.wimg) + i);
-    for (int i = threadIdx.x; i < 512 / 4; i += NT) reinterpret_cast<uint32_t *>(smem + L::ONES_OFF)[i] = 0x01010101u;
-    if (threadIdx.x == 0) {
+    for (int i = r; i < 512 / 4; i += SM_THREADS) reinterpret_cast<uint32_t *>(smem + L::ONES_OFF)[i] = 0x01010101u;
+    if (r == 0) {
         mbar_init(&mma_done[0], 1);
         mbar_init(&mma_done[1], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (threadIdx.x < 32) tmem_alloc<small_tmem_cols<BN>()>(tmem_slot);
+    if (warp == 0) tmem_alloc<small_tmem_cols<BN>()>(tmem_slot);
     fence_proxy_async();
     tc_fence_before();
     __syncthreads();
@@ -199,18 +192,16 @@ __global__ void __launch_bounds__(small_threads(PQ), small_min_ctas(CS, PQ)) con
         // interior tile: every tap of every pixel is inside the image and every pixel inside the output
         const bool interior = y0 >= 0 && x0 >= 0 && y0 + (TILE_H - 1) * a.stride + 2 < a.H && x0 + (TILE_W - 1) * a.stride + 2 < a.W &&
                               t.ty * TILE_H + TILE_H <= a.OH && t.tx * TILE_W + TILE_W <= a.OW;
-        // (two threads per pixel: even / odd taps -- or chunks -- each)
         if (interior) {
             if (CS == 4) {
 #pragma unroll
-                for (int tap = 0; tap < TAPS; ++tap)
-                    if (NT == 128 || (tap & 1) == part) cp_async4(chunk_addr(buf, tap / 4) + (tap % 4) * 4, rows[tap / 3] + (tap % 3) * 4);
+                for (int tap = 0; tap < TAPS; ++tap) cp_async4(chunk_addr(buf, tap / 4) + (tap % 4) * 4, rows[tap / 3] + (tap % 3) * 4);
             } else {
                 constexpr int CPT = CS / 16;
 #pragma unroll
                 for (int g = 0; g < G::NREAL; ++g) {
                     const int tap = g / CPT;
-                    if (NT == 128 || (g & 1) == part) cp_async16(chunk_addr(buf, g), rows[tap / 3] + (tap % 3) * CS + (g % CPT) * 16);
+                    cp_async16(chunk_addr(buf, g), rows[tap / 3] + (tap % 3) * CS + (g % CPT) * 16);
                 }
             }
             return;
@@ -228,7 +219,6 @@ __global__ void __launch_bounds__(small_threads(PQ), small_min_ctas(CS, PQ)) con
             const uint32_t fw = valid ? fill_word(0) : 0u;
 #pragma unroll
             for (int tap = 0; tap < TAPS; ++tap) {
-                if (NT != 128 && (tap & 1) != part) continue;
                 const uint32_t dst = chunk_addr(buf, tap / 4) + (tap % 4) * 4;
                 if (vy[tap / 3] && vx[tap % 3]) cp_async4(dst, rows[tap / 3] + (tap % 3) * 4);
                 else st_shared32(dst, fw);
@@ -237,7 +227,6 @@ __global__ void __launch_bounds__(small_threads(PQ), small_min_ctas(CS, PQ)) con
             constexpr int CPT = CS / 16;   // 16-byte chunks per tap
 #pragma unroll
             for (int g = 0; g < G::NREAL; ++g) {
-                if (NT != 128 && (g & 1) != part) continue;
                 const int tap = g / CPT, sub = g % CPT;
                 const uint32_t dst = chunk_addr(buf, g);
                 if (vy[tap / 3] && vx[tap % 3]) cp_async16(dst, rows[tap / 3] + (tap % 3) * CS + sub * 16);
@@ -282,7 +271,7 @@ __global__ void __launch_bounds__(small_threads(PQ), small_min_ctas(CS, PQ)) con
         fence_proxy_async();     // generic-proxy smem writes -> visible to the tensor core (async proxy)
         tc_fence_before();
         __syncthreads();
-        if (threadIdx.x == 0) {
+        if (r == 0) {
             tc_fence_after();
             issue_mma(0);
         }
@@ -316,7 +305,7 @@ __global__ void __launch_bounds__(small_threads(PQ), small_min_ctas(CS, PQ)) con
             fence_proxy_async();
             tc_fence_before();
             __syncthreads();
-            if (threadIdx.x == 0) {
+            if (r == 0) {
                 tc_fence_after();
                 issue_mma(b ^ 1);
             }
@@ -414,16 +403,8 @@ __global__ void __launch_bounds__(small_threads(PQ), small_min_ctas(CS, PQ)) con
         // fused 2x2 stride-2 max-pool: partners are lane^1 (x neighbour) and lane^16 (next row); out-of-image pixels count as 0
         uint8_t *const prow = a.out_pool + ((size_t)(tn * a.PH + tty * (TILE_H / 2)) * a.PW + ttx * (TILE_W / 2)) * a.CSO + thr_pool_off;
         const bool pool_writer = a.out_pool && ((lane & 17) == 0) && (ox >> 1) < a.PW && (oy >> 1) < a.PH;
-        // two threads per pixel: channels [0, BN/2) and [BN/2, BN) (BN = 16: the second thread has none).  The half is a
-        // compile-time constant of each branch so that a.cq[...] stays an immediate constant-bank operand.
-        constexpr int CH_PER = (NT == 128 || BN < 32) ? BN : BN / 2;
-        auto run_half = [&](auto part_tag) {
-        constexpr int PART = decltype(part_tag)::value;
 #pragma unroll
-        for (int cc = 0; cc < CH_PER; cc += 16) {
-            constexpr int CBASE = PART * CH_PER;
-            const int c0 = CBASE + cc;
-            if (CBASE + cc >= BN) break;
+        for (int c0 = 0; c0 < BN; c0 += 16) {
             uint32_t v[16];
             tmem_ld16(tacc + c0, v);
             uint32_t packed[4];
@@ -456,13 +437,10 @@ __global__ void __launch_bounds__(small_threads(PQ), small_min_ctas(CS, PQ)) con
                 if (pool_writer) *reinterpret_cast<uint4 *>(prow + c0) = make_uint4(pm[0], pm[1], pm[2], pm[3]);
             }
         }
-        };
-        if (NT == 128 || part == 0) run_half(std::integral_constant<int, 0>{});
-        else run_half(std::integral_constant<int, 1>{});
         tc_fence_before();
     }
     __syncthreads();
-    if (threadIdx.x < 32) {
+    if (warp == 0) {
         tc_fence_after();
         tmem_dealloc<small_tmem_cols<BN>()>(tmem_base);
     }
@@ -494,9 +472,9 @@ int launch_small(SmallState *st, const SmallArgs &a, cudaStream_t stream)
         cudaFuncAttributes fa;
         YQ_CUDA(cudaFuncGetAttributes(&fa, kern));
         const int by_smem = smem_sm / (smem + 1024 + (int)fa.sharedSizeBytes);
-        const int regs_per_cta = ((fa.numRegs + 7) / 8 * 8) * small_threads(PQ);
+        const int regs_per_cta = ((fa.numRegs + 7) / 8 * 8) * SM_THREADS;
         const int by_regs = 65536 / (regs_per_cta > 0 ? regs_per_cta : 1);
-        const int by_threads = 2048 / small_threads(PQ);
+        const int by_threads = 2048 / SM_THREADS;
         int occ = by_smem < by_regs ? by_smem : by_regs;
         if (by_threads < occ) occ = by_threads;
         const int tmem_limit = 512 / small_tmem_cols<BN>();   // every resident CTA must own its TMEM columns
@@ -507,7 +485,7 @@ int launch_small(SmallState *st, const SmallArgs &a, cudaStream_t stream)
     }
     int grid = n_sm * ctas_per_sm;
     if (grid > a.num_tiles) grid = a.num_tiles;
-    conv_u8_tc_small_kernel<CS, BN, ACTM, SLOW, PQ><<<grid, small_threads(PQ), smem, stream>>>(a);
+    conv_u8_tc_small_kernel<CS, BN, ACTM, SLOW, PQ><<<grid, SM_THREADS, smem, stream>>>(a);
     YQ_CHECK_LAUNCH();
     return 0;
 }
