@@ -179,6 +179,15 @@ YQ_API int yq_act_geom_flat(int h, int w, yq_act_geom *geom);
 YQ_API int yq_forward_convolutional_layer_quant_flat_gpu(yq_conv_layer *l, const uint8_t *in_flat, uint8_t *out_flat, int halo_fill,
                                                          float *out_f32, int32_t *out_acc, int batch, void *stream);
 
+/* A flat convolution with the FOLLOWING quantized shortcut (the extension layer below) fused into its epilogue: out_flat receives
+ * the SHORTCUT's output  clamp((((a - zp_a) * Ka + (b - zp_b) * Kb + 2^15) >> 16) + zp_out, 0, 255)  where a = this convolution's
+ * uint8 result (never stored) and b = from_flat at the same position / channel (same flat geometry, same channel count);
+ * halo_fill = the byte the shortcut's consumers pad with.  Saves the shortcut's launch: 2 bytes read + 1 written per element. */
+YQ_API int yq_conv_flat_shortcut_supported(const yq_conv_layer *l);
+YQ_API int yq_forward_convolutional_layer_quant_flat_shortcut_gpu(yq_conv_layer *l, const uint8_t *in_flat, const uint8_t *from_flat,
+                                                                  uint8_t *out_flat, int halo_fill, int zp_from, int Ka, int Kb,
+                                                                  int zp_out_shortcut, int batch, void *stream);
+
 /* A quant_stop head with the FOLLOWING yolo layer fused (forward_yolo_layer's inference part, src/yolo_layer.c:132-146):
  * out_yolo [batch][n][h][w] receives the yolo layer's output.  The head's float values (u8 - zp_out) * s_out
  * (convolutional_layer.c:752-760) take only 256 values, so logistic_activate (src/activations.h:32) is a 256-entry
@@ -293,8 +302,9 @@ typedef struct yq_layer_info {
     int kernel;               /* conv only: 0 SIMT, 1 tcgen05 (per-tap TMA / small-c), 2 tcgen05 flat strip, 3 tcgen05 rows */
     int classes, n_anchors;   /* yolo only */
     int fused;                /* conv: 0 own launch writing the conv tensor, 1 following maxpool fused into the epilogue,
-                                 2 rows flavour (halo input, pooled tensor only), 3 following yolo layer fused;
-                                 maxpool / yolo: 1 = produced by the previous conv */
+                                 2 rows flavour (halo input, pooled tensor only), 3 following yolo layer fused,
+                                 4 following quantized shortcut fused (the launch writes the shortcut's tensor only);
+                                 maxpool / yolo / shortcut: 1 = produced by the previous conv */
 } yq_layer_info;
 
 /* batch <= 0 keeps the cfg's [net] batch.  Returns NULL on failure (see yq_last_error). */

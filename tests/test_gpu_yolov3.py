@@ -205,6 +205,57 @@ def test_shortcut_vs_oracle(built, c, h, w, batch):
         darknet.shortcut_multiplier(100.0, 0.01)
 
 
+@pytest.mark.parametrize("case", [(128, 13, 13, 256, 3, 3), (64, 20, 20, 128, 3, 2), (256, 9, 9, 512, 3, 2), (256, 13, 13, 128, 1, 2), (512, 7, 7, 1024, 3, 1)],
+                         ids=lambda c: "c%d_%dx%d_n%d_k%d" % c[:5])
+def test_conv_with_fused_shortcut_vs_oracle(built, case):
+    """a flat convolution (flat2 for c < 256, the CTA-pair flat2x from c = 256 on) with the FOLLOWING quantized shortcut fused into
+    its epilogue == oracle conv -> oracle shortcut, incl. halo bytes and saturation at both ends"""
+    import ctypes as C
+    from yolo_quantization_b200 import _lib
+    from yolo_quantization_b200._lib import ActGeom, check
+    c, h, w, n, k, batch = case
+    lib = _lib.load()
+    rng = np.random.default_rng(zlib.crc32(repr(case).encode()) + 21)
+    layer, wq, zp_w, p = _rand_layer(rng, c, n, k, 1, "leaky", 40, zp_out=33, h=h, w=w, quant_stop=0)
+    assert lib.yq_conv_flat_shortcut_supported(layer.handle)
+    x = rng.integers(0, 256, size=(batch, c, h, w), dtype=np.uint8)
+    b = rng.integers(0, 256, size=(batch, n, h, w), dtype=np.uint8)
+    qa, qb, qo = (0.05, 33), (0.03, 50), (0.021, 60)
+    ka, kb = darknet.shortcut_multiplier(qa[0], qo[0]), darknet.shortcut_multiplier(qb[0], qo[0])
+    g = ActGeom()
+    check(lib.yq_act_geom_flat(h, w, C.byref(g)))
+
+    def stage(t, ch, fill):
+        d = darknet.DeviceBuffer(lib.yq_act_geom_bytes(C.byref(g), batch, ch), zero=False)
+        check(lib.yq_cuda_memset(d.ptr, fill, d.nbytes, None))
+        src = darknet.DeviceBuffer.from_numpy(np.ascontiguousarray(t))
+        check(lib.yq_nchw_to_nhwc_u8_geom(src.ptr, d.ptr, batch, ch, h, w, C.byref(g), None))
+        check(lib.yq_stream_synchronize(None))
+        src.free()
+        return d
+    din, dres = stage(x, c, 40), stage(b, n, 0x77)
+    dout = darknet.DeviceBuffer(lib.yq_act_geom_bytes(C.byref(g), batch, n), zero=False)
+    check(lib.yq_cuda_memset(dout.ptr, 0xEE, dout.nbytes, None))
+    check(lib.yq_forward_convolutional_layer_quant_flat_shortcut_gpu(layer.handle, din.ptr, dres.ptr, dout.ptr, 0x5C, qb[1], ka, kb, qo[1], batch, None),
+          "yq_forward_convolutional_layer_quant_flat_shortcut_gpu")
+    tmp = darknet.DeviceBuffer(batch * n * h * w)
+    check(lib.yq_nhwc_to_nchw_u8_geom(dout.ptr, tmp.ptr, batch, n, h, w, C.byref(g), None))
+    check(lib.yq_stream_synchronize(None))
+    got = tmp.pull((batch, n, h, w), np.uint8)
+    raw = dout.pull((dout.nbytes // n, n), np.uint8)
+    rows = raw[: batch * g.rows_h * g.pitch_w].reshape(batch, g.rows_h, g.pitch_w, n).copy()
+    rows[:, 1:1 + h, 1:1 + w, :] = 0x5C
+    assert (rows == 0x5C).all() and (raw[batch * g.rows_h * g.pitch_w:] == 0x5C).all(), "halo of the fused launch's output"
+    for i in range(batch):
+        acc = O.conv_acc(x[i], wq, zp_w, 1, k // 2, 40)
+        a = O.requant(acc, p["biases_int32"], p["M_value"], p["M0_right_shift_value"], synth.ACT_CODES["leaky"], 33)
+        assert np.array_equal(got[i], O.shortcut(a, b[i], qa, qb, qo)), f"image {i}"
+    assert got.min() == 0 and got.max() == 255
+    for d in (din, dres, dout, tmp):
+        d.free()
+    layer.free()
+
+
 def _yolov3_files(tmp_path, size, batch, seed=2):
     layers = synth.yolov3_quant()
     cfg, wts = str(tmp_path / "v3.cfg"), str(tmp_path / "v3.weights")
@@ -226,8 +277,8 @@ def _walk(net, info, imgs, debug):
                 continue
             if sl.kind == "conv" and debug:
                 assert np.array_equal(net.pull_layer(i, "acc")[b], r["acc"]), f"layer {i} int32 mismatch (image {b})"
-            if not debug and (li.fused or (sl.kind == "conv" and sl.spec.quant_stop)):
-                continue                                  # not materialised in the production plan
+            if not debug and ((li.fused and sl.kind != "shortcut") or (sl.kind == "conv" and sl.spec.quant_stop)):
+                continue                                  # not materialised in the production plan (a fused shortcut's tensor is: its conv wrote it)
             assert np.array_equal(net.pull_layer(i, "u8")[b], r["u8"]), f"layer {i} ({sl.kind}) uint8 mismatch (image {b})"
 
 

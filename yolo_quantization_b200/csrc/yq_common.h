@@ -175,16 +175,22 @@ int yq_tc_flat_forward(yq_conv_layer *l, void *state, const uint8_t *in_flat, ui
 int yq_tc_flat2_supported(const yq_conv_layer *l);
 int yq_tc_flat2_prepare(yq_conv_layer *l, void **state);
 void yq_tc_flat2_free(void *state);
+// the FOLLOWING quantized shortcut fused into a flat2 / flat2x launch: `resid` = the shortcut's `from` tensor in the convolution's own
+// (flat) output geometry and channel stride; C0 = 2^15 + (zp_out << 16) - zp_a * Ka - zp_b * Kb.  The launch stores the shortcut's output.
+struct yq_fused_shortcut {
+    const uint8_t *resid;
+    int Ka, Kb, C0;
+};
 // plain = 1 (1x1 layers only): in / out are plain [B][H][W][C] tensors -- a 1x1 convolution needs no halo
 int yq_tc_flat2_forward(yq_conv_layer *l, void *state, const uint8_t *in_flat, uint8_t *out_flat, int halo_fill, int32_t *out_acc, int batch,
-                        cudaStream_t stream, int plain = 0);
+                        cudaStream_t stream, int plain = 0, const yq_fused_shortcut *sc = nullptr);
 
 // implemented in yq_conv_tc_flat2x.cu (flat2 on CTA pairs: cta_group::2 MMAs, each SM holds half of every weight stage)
 int yq_tc_flat2x_supported(const yq_conv_layer *l);
 int yq_tc_flat2x_prepare(yq_conv_layer *l, void **state);
 void yq_tc_flat2x_free(void *state);
 int yq_tc_flat2x_forward(yq_conv_layer *l, void *state, const uint8_t *in_flat, uint8_t *out_flat, int halo_fill, int32_t *out_acc, int batch,
-                         cudaStream_t stream);
+                         cudaStream_t stream, const yq_fused_shortcut *sc = nullptr);
 
 // implemented in yq_conv_tc.cu (TMA-fed; c % 64 == 0)
 int yq_tc_supported(const yq_conv_layer *l);

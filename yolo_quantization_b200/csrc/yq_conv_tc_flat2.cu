@@ -36,7 +36,9 @@ constexpr int F2_BN = 128;
 constexpr int F2_EPI_WARPS = 16;
 constexpr int F2_SUM_WARPS = 2;
 constexpr int F2_THREADS = 32 * (2 + F2_SUM_WARPS + F2_EPI_WARPS);
-constexpr int F2_ASTAGES = 2;
+constexpr int F2_ASTAGES = 4;              // barrier slots; a launch uses a.a_stages of them: 2 for 3x3 layers (nine taps of MMAs per
+                                           // patch chunk cover the next chunk's load), up to 4 for 1x1 layers (one tap per chunk: the
+                                           // loads have to run several chunks ahead of the tensor pipe)
 constexpr int F2_MAX_BSTAGES = 8;
 constexpr int F2_MAX_ROWS = 704;           // patch rows: 256 + 2W + 4 (W <= 222: the 208 x 208 and 104 x 104 maps of the full yolov3)
 constexpr int F2_MAX_BOXES = 3;            // a patch arrives as up to three TMA boxes (a box holds at most 256 rows)
@@ -48,12 +50,16 @@ struct Flat2Args {
     int B, H, W, NP;       // NP = B*(H+1)*(W+1)
     int size, taps, cpt /* KC-chunks per tap */, CS;
     int q_off;             // first patch position relative to the pair's first position: -(pad*(W+1) + pad)
-    int patch_rows, box_rows, n_boxes, a_stage_bytes, b_stages;
+    int patch_rows, box_rows, n_boxes, a_stage_bytes, a_stages, b_stages;
     int plain;             // 1x1 only: the tensors are plain [B][H][W][C] strips (no halo positions: every p < NP is a pixel)
     int out_cols;          // bytes per position the launch stores: min(128, channel stride of the output); 32 / 64: narrow layers
     int m_pairs, num_tiles;   // tile t -> (n-tile t / m_pairs, position pair t % m_pairs)
     uint32_t halo_word;
     uint32_t magic_w, magic_h, magic_m;
+    // the FOLLOWING quantized shortcut fused into the epilogue (extension layer, include/yq_b200.h): the `from` tensor in this
+    // layer's own flat geometry and channel stride; the launch then stores the SHORTCUT's output
+    const uint8_t *resid;
+    yq::ShortcutParams sc;
     int debug;             // YQ_FLAT2_DEBUG experiments (results are garbage): 1 = skip weight loads of taps > 0, 2 = skip the epilogue math
 };
 
@@ -75,7 +81,7 @@ __global__ void __launch_bounds__(F2_THREADS, 1) conv_u8_tc_flat2_kernel(const _
     extern __shared__ __align__(16) uint8_t smem_raw[];
     uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     uint8_t *sA = smem;                                              // F2_ASTAGES patch stages
-    uint8_t *sB = sA + F2_ASTAGES * a.a_stage_bytes;                 // a.b_stages weight stages
+    uint8_t *sB = sA + a.a_stages * a.a_stage_bytes;                 // a.b_stages weight stages
     uint8_t *sOut = sB + a.b_stages * L::B_STAGE;                    // two output staging tiles
     int4 *s_q = (int4 *)(sOut + 2 * L::OUT_BYTES);                   // {bias, zw, 2*M0, shift} of the current n-tile
     double *s_mc = (double *)(s_q + F2_BN);
@@ -134,7 +140,7 @@ __global__ void __launch_bounds__(F2_THREADS, 1) conv_u8_tc_flat2_kernel(const _
                     for (int b = 0; b < a.n_boxes; ++b)
                         tma_load_2d(sA + sa * a.a_stage_bytes + b * a.box_rows * KC, &tmA, &a_full[sa], c * KC, p0 + a.q_off + b * a.box_rows);
                 }
-                if (++sa == F2_ASTAGES) { sa = 0; pha ^= 1; }
+                if (++sa == a.a_stages) { sa = 0; pha ^= 1; }
                 for (int tap = 0; tap < a.taps; ++tap) {
                     mbar_wait(&b_empty[s], phb ^ 1);
                     if (elect_one()) {
@@ -184,7 +190,7 @@ __global__ void __launch_bounds__(F2_THREADS, 1) conv_u8_tc_flat2_kernel(const _
                     if (++s == nbs) { s = 0; phb ^= 1; }
                 }
                 if (elect_one()) umma_commit(&a_empty[sa]);
-                if (++sa == F2_ASTAGES) { sa = 0; pha ^= 1; }
+                if (++sa == a.a_stages) { sa = 0; pha ^= 1; }
             }
             if (elect_one()) umma_commit(&acc_full[pb]);
         }
@@ -221,7 +227,7 @@ __global__ void __launch_bounds__(F2_THREADS, 1) conv_u8_tc_flat2_kernel(const _
                 }
                 __syncwarp();
                 if (lane == 0) f2_arrive(&a_empty[sa]);
-                if (++sa == F2_ASTAGES) { sa = 0; pha ^= 1; }
+                if (++sa == a.a_stages) { sa = 0; pha ^= 1; }
             }
             mbar_wait(&acc_empty[pb], ((it >> 1) & 1) ^ 1);           // S[pb] was consumed by the epilogue of pair it-2
 #pragma unroll
@@ -313,7 +319,16 @@ __global__ void __launch_bounds__(F2_THREADS, 1) conv_u8_tc_flat2_kernel(const _
                             if (ch + 1 < nch) tmem_ld16_issue(trow + 16 * (ch + 1), vbuf[(ch + 1) & 1]);   // in flight while this chunk is requantized
                             uint32_t packed[4];
                             int extra[16];
-                            yq::requant_chunk<ACTM, SAT, 16, false>(v, nsa, extra, s_q + c0, s_mc + c0, a.ep.zp_out, packed);
+                            if (a.resid) {
+                                // conv -> shortcut in one launch: the residual bytes of this position / chunk travel while the chunk is requantized
+                                uint4 rb = make_uint4(0, 0, 0, 0);
+                                if (valid) rb = __ldg(reinterpret_cast<const uint4 *>(a.resid + (size_t)p * a.CSO + oc0 + c0));
+                                int rv[16];
+                                yq::requant_chunk_vals<ACTM, SAT, 16, false>(v, nsa, extra, s_q + c0, s_mc + c0, a.ep.zp_out, rv);
+                                yq::shortcut_pack16(rv, rb, a.sc, packed);
+                            } else {
+                                yq::requant_chunk<ACTM, SAT, 16, false>(v, nsa, extra, s_q + c0, s_mc + c0, a.ep.zp_out, packed);
+                            }
                             if (!valid) packed[0] = packed[1] = packed[2] = packed[3] = a.halo_word;
                             yq::mask_pad_channels<16>(packed, a.N - (oc0 + c0));
                             if (SLOW && side && valid) {
@@ -416,7 +431,13 @@ int f2_launch_v(Flat2State *st, const CUtensorMap &tmA, const CUtensorMap &tmO, 
     using L = Flat2Smem<KC>;
     const int n_sm = yq::device_sm_count(), smem_max = yq::device_smem_optin();   // (of the CURRENT device: nothing cached per process)
     if (n_sm <= 0 || smem_max <= 0) return yq::fail("cannot query the device's multiprocessor count / shared memory size");
-    const int fixed = F2_ASTAGES * a.a_stage_bytes + 2 * L::OUT_BYTES + L::PARAM_BYTES + L::SUM_BYTES + 512 + 1024;
+    // 1x1 layers: as many patch stages as fit beside the staging tiles and three weight stages (at most F2_ASTAGES)
+    a.a_stages = 2;
+    if (a.size == 1)
+        while (a.a_stages < F2_ASTAGES &&
+               (a.a_stages + 1) * a.a_stage_bytes + 2 * L::OUT_BYTES + L::PARAM_BYTES + L::SUM_BYTES + 512 + 1024 + 3 * L::B_STAGE <= smem_max)
+            ++a.a_stages;
+    const int fixed = a.a_stages * a.a_stage_bytes + 2 * L::OUT_BYTES + L::PARAM_BYTES + L::SUM_BYTES + 512 + 1024;
     int nbs = (smem_max - fixed) / L::B_STAGE;
     if (nbs > F2_MAX_BSTAGES) nbs = F2_MAX_BSTAGES;
     if (nbs < 2) return yq::fail("conv_u8_tc_flat2_kernel<%d>: shared memory does not hold two weight stages", KC);
@@ -492,7 +513,7 @@ void yq_tc_flat2_free(void *state)
 }
 
 int yq_tc_flat2_forward(yq_conv_layer *l, void *state, const uint8_t *in_flat, uint8_t *out_flat, int halo_fill, int32_t *out_acc, int batch,
-                        cudaStream_t stream, int plain)
+                        cudaStream_t stream, int plain, const yq_fused_shortcut *sc)
 {
     Flat2State *st = (Flat2State *)state;
     if (!st || !in_flat || !out_flat) return yq::fail("tcgen05 flat2 flavour: bad argument");
@@ -511,6 +532,11 @@ int yq_tc_flat2_forward(yq_conv_layer *l, void *state, const uint8_t *in_flat, u
     a.a_stage_bytes = yq::round_up(a.n_boxes * a.box_rows * st->KC, 1024);
     a.out_cols = l->cs_out < F2_BN ? l->cs_out : F2_BN;
     a.plain = plain ? 1 : 0;
+    if (sc && sc->resid) {
+        if (plain) return yq::fail("tcgen05 flat2 flavour: the fused shortcut needs flat tensors");
+        a.resid = sc->resid;
+        a.sc = yq::ShortcutParams{sc->Ka, sc->Kb, sc->C0};
+    }
     Flat2State::Key key{in_flat, out_flat, batch * 2 + (plain ? 1 : 0)};
     auto it = st->maps.find(key);
     if (it == st->maps.end()) {

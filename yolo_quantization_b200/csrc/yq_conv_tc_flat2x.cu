@@ -50,6 +50,10 @@ struct Flat2xArgs {
     int m_pairs, num_tiles;   // tile t -> (n-tile t / m_pairs, position pair t % m_pairs)
     uint32_t halo_word;
     uint32_t magic_w, magic_h, magic_m;
+    // the FOLLOWING quantized shortcut fused into the epilogue (extension layer, include/yq_b200.h): the `from` tensor in this
+    // layer's own flat geometry and channel stride; the launch then stores the SHORTCUT's output
+    const uint8_t *resid;
+    yq::ShortcutParams sc;
     int debug;             // YQ_FLAT2_DEBUG experiments (results are garbage): 1 = skip weight loads of taps > 0, 2 = skip the epilogue math
 };
 
@@ -324,7 +328,16 @@ __global__ void __launch_bounds__(F2X_THREADS, 1) conv_u8_tc_flat2x_kernel(const
                         if (ch + 1 < 4) tmem_ld16_issue(trow + 16 * (ch + 1), vbuf[(ch + 1) & 1]);   // in flight while this chunk is requantized
                         uint32_t packed[4];
                         int extra[16];
-                        yq::requant_chunk<ACTM, SAT, 16, false>(v, nsa, extra, s_q + c0, s_mc + c0, a.ep.zp_out, packed);
+                        if (a.resid) {
+                            // conv -> shortcut in one launch: the residual bytes of this position / chunk travel while the chunk is requantized
+                            uint4 rb = make_uint4(0, 0, 0, 0);
+                            if (valid) rb = __ldg(reinterpret_cast<const uint4 *>(a.resid + (size_t)p * a.CSO + oc0 + c0));
+                            int rv[16];
+                            yq::requant_chunk_vals<ACTM, SAT, 16, false>(v, nsa, extra, s_q + c0, s_mc + c0, a.ep.zp_out, rv);
+                            yq::shortcut_pack16(rv, rb, a.sc, packed);
+                        } else {
+                            yq::requant_chunk<ACTM, SAT, 16, false>(v, nsa, extra, s_q + c0, s_mc + c0, a.ep.zp_out, packed);
+                        }
                         if (!valid) packed[0] = packed[1] = packed[2] = packed[3] = a.halo_word;
                         yq::mask_pad_channels<16>(packed, a.N - (oc0 + c0));
                         if (SLOW && side && valid) {
@@ -533,7 +546,7 @@ void yq_tc_flat2x_free(void *state)
 }
 
 int yq_tc_flat2x_forward(yq_conv_layer *l, void *state, const uint8_t *in_flat, uint8_t *out_flat, int halo_fill, int32_t *out_acc, int batch,
-                        cudaStream_t stream)
+                        cudaStream_t stream, const yq_fused_shortcut *sc)
 {
     Flat2xState *st = (Flat2xState *)state;
     if (!st || !in_flat || !out_flat) return yq::fail("tcgen05 flat2 flavour: bad argument");
@@ -561,6 +574,10 @@ int yq_tc_flat2x_forward(yq_conv_layer *l, void *state, const uint8_t *in_flat, 
     a.ep = yq::make_epi(l);
     a.out_acc = out_acc;
     a.N = l->n; a.CSO = l->cs_out;
+    if (sc && sc->resid) {
+        a.resid = sc->resid;
+        a.sc = yq::ShortcutParams{sc->Ka, sc->Kb, sc->C0};
+    }
     a.B = batch; a.H = l->h; a.W = l->w; a.NP = (int)NP;
     a.size = l->size; a.taps = l->size * l->size; a.cpt = l->cs_in / st->KC; a.CS = l->cs_in;
     a.q_off = -(pad * W1 + pad);

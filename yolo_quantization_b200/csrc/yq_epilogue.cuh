@@ -130,12 +130,12 @@ __device__ __forceinline__ int act_value(int q, int zo)
     return r;
 }
 
+// the chunk's values BEFORE the uint8 store (the caller packs their low bytes, or feeds them to a fused quantized shortcut)
 template <int ACTM, bool SAT, int NV, bool HAS_EXTRA>
-__device__ __forceinline__ void requant_chunk(const uint32_t (&v)[NV], int nsa, const int (&extra)[NV], const int4 *cq, const double *mc,
-                                              int zo, uint32_t (&packed)[NV / 4])
+__device__ __forceinline__ void requant_chunk_vals(const uint32_t (&v)[NV], int nsa, const int (&extra)[NV], const int4 *cq, const double *mc,
+                                                   int zo, int (&r)[NV])
 {
     uint32_t mx = 0;
-    int r[NV];
 #pragma unroll
     for (int j = 0; j < NV; ++j) {
         const int4 c = cq[j];
@@ -176,9 +176,44 @@ __device__ __forceinline__ void requant_chunk(const uint32_t (&v)[NV], int nsa, 
             r[j] = act_value<ACTM, SAT>(q, zo);
         }
     }
+}
+
+template <int ACTM, bool SAT, int NV, bool HAS_EXTRA>
+__device__ __forceinline__ void requant_chunk(const uint32_t (&v)[NV], int nsa, const int (&extra)[NV], const int4 *cq, const double *mc,
+                                              int zo, uint32_t (&packed)[NV / 4])
+{
+    int r[NV];
+    requant_chunk_vals<ACTM, SAT, NV, HAS_EXTRA>(v, nsa, extra, cq, mc, zo, r);
 #pragma unroll
     for (int k = 0; k < NV / 4; ++k) packed[k] = pack_low_bytes(r[4 * k], r[4 * k + 1], r[4 * k + 2], r[4 * k + 3]);
 }
+
+// The quantized shortcut (extension, include/yq_b200.h) fused behind a convolution's requantisation: a = the convolution's uint8
+// result (the low byte of r: the reference's store wraps), b = the byte of the `from` tensor at the same position / channel:
+//     out = sat_u8((a * Ka + b * Kb + C0) >> 16),   C0 = 2^15 + (zp_out << 16) - zp_a * Ka - zp_b * Kb
+// 16 channels: r[16] and the 16 residual bytes (one 16-byte load) -> 4 packed words.
+struct ShortcutParams {
+    int Ka, Kb, C0;
+};
+__device__ __forceinline__ uint32_t shortcut_word(int r0, int r1, int r2, int r3, uint32_t b, const ShortcutParams &sp)
+{
+    const int t0 = (r0 & 0xff) * sp.Ka + (int)(b & 0xff) * sp.Kb + sp.C0;
+    const int t1 = (r1 & 0xff) * sp.Ka + (int)((b >> 8) & 0xff) * sp.Kb + sp.C0;
+    const int t2 = (r2 & 0xff) * sp.Ka + (int)((b >> 16) & 0xff) * sp.Kb + sp.C0;
+    const int t3 = (r3 & 0xff) * sp.Ka + (int)(b >> 24) * sp.Kb + sp.C0;
+    uint32_t lo, hi;
+    asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, 0;" : "=r"(hi) : "r"(t3 >> 16), "r"(t2 >> 16));
+    asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(lo) : "r"(t1 >> 16), "r"(t0 >> 16), "r"(hi));
+    return lo;
+}
+__device__ __forceinline__ void shortcut_pack16(const int (&r)[16], const uint4 &b, const ShortcutParams &sp, uint32_t (&packed)[4])
+{
+    packed[0] = shortcut_word(r[0], r[1], r[2], r[3], b.x, sp);
+    packed[1] = shortcut_word(r[4], r[5], r[6], r[7], b.y, sp);
+    packed[2] = shortcut_word(r[8], r[9], r[10], r[11], b.z, sp);
+    packed[3] = shortcut_word(r[12], r[13], r[14], r[15], b.w, sp);
+}
+
 
 // zero the bytes of pad channels (channel index >= n_real within this chunk): pad lanes of an activation
 // tensor must be 0 because consumers sum every byte of a pixel

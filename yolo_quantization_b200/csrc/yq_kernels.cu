@@ -631,8 +631,8 @@ extern "C" int yq_act_geom_flat(int h, int w, yq_act_geom *g)
     yq_tc_flat_geom(h, w, g);
     return 0;
 }
-extern "C" int yq_forward_convolutional_layer_quant_flat_gpu(yq_conv_layer *l, const uint8_t *in_flat, uint8_t *out_flat, int halo_fill, float *out_f32,
-                                                             int32_t *out_acc, int batch, void *stream)
+static int flat_dispatch(yq_conv_layer *l, const uint8_t *in_flat, uint8_t *out_flat, int halo_fill, float *out_f32, int32_t *out_acc, int batch, void *stream,
+                         const yq_fused_shortcut *sc)
 {
     if (!l || !in_flat || !out_flat || batch <= 0) return yq::fail("yq_forward_convolutional_layer_quant_flat_gpu: bad argument");
     if (!yq_conv_flat_supported(l)) return yq::fail("this layer has no flat flavour (see yq_conv_flat_supported)");
@@ -650,12 +650,40 @@ extern "C" int yq_forward_convolutional_layer_quant_flat_gpu(yq_conv_layer *l, c
         const long long pairs = ((long long)batch * (l->h + 1) * (l->w + 1) + 255) / 256 * ((l->n + 127) / 128);
         two = one_env >= 0 ? one_env != 0 : pairs >= 2 * 148;
     }
+    if (sc && !l->tc_flat2 && !l->tc_flat2x) return yq::fail("the fused shortcut needs the persistent flat flavours (see yq_conv_flat_shortcut_supported)");
+    if (sc) two = l->tc_flat2 != nullptr;          // (the one-tile form has no shortcut epilogue)
     if (l->tc_flat2x && !no_flat2 && (use_2x == 2 || (use_2x == 1 && l->c >= 256)))
-        return yq_tc_flat2x_forward(l, l->tc_flat2x, in_flat, out_flat, halo_fill, out_acc, batch, (cudaStream_t)stream);
-    if (two) return yq_tc_flat2_forward(l, l->tc_flat2, in_flat, out_flat, halo_fill, out_acc, batch, (cudaStream_t)stream);
+        return yq_tc_flat2x_forward(l, l->tc_flat2x, in_flat, out_flat, halo_fill, out_acc, batch, (cudaStream_t)stream, sc);
+    if (two) return yq_tc_flat2_forward(l, l->tc_flat2, in_flat, out_flat, halo_fill, out_acc, batch, (cudaStream_t)stream, 0, sc);
     if (l->tc_flat) return yq_tc_flat_forward(l, l->tc_flat, in_flat, out_flat, halo_fill, out_f32, nullptr, 0, out_acc, batch, (cudaStream_t)stream);
-    if (l->tc_flat2) return yq_tc_flat2_forward(l, l->tc_flat2, in_flat, out_flat, halo_fill, out_acc, batch, (cudaStream_t)stream);
-    return yq_tc_flat2x_forward(l, l->tc_flat2x, in_flat, out_flat, halo_fill, out_acc, batch, (cudaStream_t)stream);
+    if (l->tc_flat2) return yq_tc_flat2_forward(l, l->tc_flat2, in_flat, out_flat, halo_fill, out_acc, batch, (cudaStream_t)stream, 0, sc);
+    return yq_tc_flat2x_forward(l, l->tc_flat2x, in_flat, out_flat, halo_fill, out_acc, batch, (cudaStream_t)stream, sc);
+}
+extern "C" int yq_forward_convolutional_layer_quant_flat_gpu(yq_conv_layer *l, const uint8_t *in_flat, uint8_t *out_flat, int halo_fill, float *out_f32,
+                                                             int32_t *out_acc, int batch, void *stream)
+{
+    return flat_dispatch(l, in_flat, out_flat, halo_fill, out_f32, out_acc, batch, stream, nullptr);
+}
+extern "C" int yq_conv_flat_shortcut_supported(const yq_conv_layer *l)
+{
+    static const bool off = getenv("YQ_NO_FUSE_SHORTCUT") && atoi(getenv("YQ_NO_FUSE_SHORTCUT"));   // A/B measurements
+    return l && !off && !l->quant_stop_flag && (l->tc_flat2 || l->tc_flat2x) ? 1 : 0;
+}
+// A flat convolution with the FOLLOWING quantized shortcut (extension layer) fused into its epilogue: out_flat receives the
+// SHORTCUT's output, the convolution's own tensor is never written.  from_flat = the shortcut's `from` tensor in the same flat
+// geometry and channel count as the convolution's output; halo_fill = the byte the shortcut's consumers pad with.
+extern "C" int yq_forward_convolutional_layer_quant_flat_shortcut_gpu(yq_conv_layer *l, const uint8_t *in_flat, const uint8_t *from_flat, uint8_t *out_flat,
+                                                                      int halo_fill, int zp_from, int Ka, int Kb, int zp_out_shortcut, int batch, void *stream)
+{
+    if (!l || !in_flat || !from_flat || !out_flat || batch <= 0) return yq::fail("yq_forward_convolutional_layer_quant_flat_shortcut_gpu: bad argument");
+    if (!yq_conv_flat_shortcut_supported(l)) return yq::fail("this layer cannot fuse the shortcut (see yq_conv_flat_shortcut_supported)");
+    if (Ka < 1 || Kb < 1 || Ka >= (1 << 22) || Kb >= (1 << 22)) return yq::fail("shortcut: multipliers must lie in [1, 2^22) (see yq_shortcut_multiplier)");
+    yq_fused_shortcut sc;
+    sc.resid = from_flat;
+    sc.Ka = Ka;
+    sc.Kb = Kb;
+    sc.C0 = 32768 + ((zp_out_shortcut & 0xff) << 16) - l->zp_out * Ka - (zp_from & 0xff) * Kb;
+    return flat_dispatch(l, in_flat, out_flat, halo_fill, nullptr, nullptr, batch, stream, &sc);
 }
 extern "C" int yq_forward_convolutional_layer_quant_flat_yolo_gpu(yq_conv_layer *l, const uint8_t *in_flat, uint8_t *out_flat, int halo_fill,
                                                                   float *out_f32, float *out_yolo, int classes, int32_t *out_acc, int batch, void *stream)

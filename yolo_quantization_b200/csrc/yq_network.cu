@@ -123,6 +123,7 @@ struct Layer {
     bool use_rows = false;         // conv: halo-input conv + pool flavour (yq_conv_tc_rows.cu); its input tensor is halo-padded
     bool use_flat = false;         // conv: flat-strip flavour (yq_conv_tc_flat.cu); input and output tensors are flat
     bool fuse_yolo = false;        // quant_stop conv: the following yolo layer is produced by this layer's epilogue (yolo: fused_away)
+    bool fuse_shortcut = false;    // conv: the following quantized shortcut is produced by this layer's epilogue (shortcut: fused_away)
     bool fuse_up = false;          // route: inputs that are upsample layers are read through the upsample (upsample: fused_away)
     unsigned early_mask = 0;       // route: inputs copied on the side stream as soon as they exist (see plan_early_copies())
     cudaEvent_t ev_early = nullptr;
@@ -413,7 +414,7 @@ void plan(yq_network *net)
         plain1_ok[i] = yq_conv_plain_1x1_fast(l.conv) != 0;
     }
     // requirement on tensor t (index t + 1; t = -1 is the network input): 0 none, 1 plain, 2 a specific padded geometry
-    struct Req { int kind = 0; yq_act_geom g = {0, 0, 0}; int fill = -1; bool conflict = false; };
+    struct Req { int kind = 0; yq_act_geom g = {0, 0, 0}; int fill = -1, wish = -1; bool conflict = false; };
     std::vector<Req> req;
     auto need = [&](int t, int kind, const yq_act_geom *g, int fill) {
         Req &r = req[tensor_of(net, t) + 1];
@@ -422,9 +423,29 @@ void plan(yq_network *net)
         if (kind == 2 && fill >= 0) {
             if (r.fill >= 0 && r.fill != fill) r.conflict = true;
             r.fill = fill;
+        } else if (kind == 0 && fill >= 0) {
+            r.wish = fill;      // a geometry-agnostic consumer's wish: used when somebody else makes the tensor halo-padded
         }
         if (kind > r.kind) r.kind = kind;
         if (kind == 2) r.g = *g;
+    };
+    // conv i (flat) + the quantized shortcut right behind it in one launch: nobody else may read conv i's tensor, the shortcut's
+    // `from` tensor must be a flat strip of the same shape (it is whenever a flat conv of the same size reads it), and every
+    // convolution that reads the shortcut's tensor must accept a flat strip (flat convs of this size, or geometry-agnostic ones)
+    auto can_fuse_shortcut = [&](int i) -> bool {
+        if (!net->fusion || net->keep_acc || i + 1 >= n) return false;
+        const Layer &c = net->layers[i], &sc = net->layers[i + 1];
+        if (sc.type != L_SHORTCUT || !flat_ok[i] || !yq_conv_flat_shortcut_supported(c.conv) || routed_from(net, i)) return false;
+        const int from = tensor_of(net, sc.inputs[0]);
+        if (from < 0 || net->layers[from].out_c != c.out_c) return false;
+        bool from_flat = false;
+        for (int j = 0; j < n; ++j) {
+            const Layer &k = net->layers[j];
+            if (k.type != L_CONV || !k.conv) continue;
+            if (tensor_of(net, k.src) == from && flat_ok[j] && k.h == c.out_h && k.w == c.out_w) from_flat = true;
+            if (tensor_of(net, k.src) == i + 1 && !(flat_ok[j] && k.h == c.out_h && k.w == c.out_w) && !yq_conv_geom_supported(k.conv)) return false;
+        }
+        return from_flat;
     };
     for (int pass = 0; pass < n + 2; ++pass) {
         req.assign(n + 1, Req());
@@ -439,11 +460,14 @@ void plan(yq_network *net)
                 yq_act_geom_flat(l.h, l.w, &g);
                 need(l.src, 2, &g, l.zp_in);
                 need(i, 2, &g, -1);
+                if (can_fuse_shortcut(i)) need(i + 1, 2, &g, -1);      // the launch stores the shortcut's tensor, as a flat strip
             } else if (plain1_ok[i]) {
                 need(l.src, 1, nullptr, -1);
                 need(i, 1, nullptr, -1);
             } else if (yq_conv_geom_supported(l.conv)) {
-                // the per-tap TMA flavour reads and writes through tensor maps built for whatever geometry the tensors have
+                // the per-tap TMA flavour reads and writes through tensor maps built for whatever geometry the tensors have;
+                // if its input turns out halo-padded it would like the halo to hold its zp_in (no border correction then)
+                need(l.src, 0, nullptr, l.zp_in);
             } else {
                 need(l.src, 1, nullptr, -1);
                 const bool fuses = net->fusion && i + 1 < n && net->layers[i + 1].type == L_MAXPOOL && net->layers[i + 1].size == 2 &&
@@ -478,7 +502,7 @@ void plan(yq_network *net)
     // ---- apply
     for (int i = 0; i < n; ++i) {
         Layer &l = net->layers[i];
-        l.fuse_pool = l.fused_away = l.use_rows = l.use_flat = l.use_geom = l.fuse_yolo = l.fuse_up = l.side = false;
+        l.fuse_pool = l.fused_away = l.use_rows = l.use_flat = l.use_geom = l.fuse_yolo = l.fuse_shortcut = l.fuse_up = l.side = false;
         l.geom = yq_act_geom{0, l.out_w, l.out_h};
         l.halo_fill = 0;
     }
@@ -487,7 +511,7 @@ void plan(yq_network *net)
     for (int t = -1; t < n; ++t) {
         const Req &r = req[t + 1];
         if (r.kind != 2 || (t >= 0 && tensor_of(net, t) != t)) continue;
-        const int fill = r.fill >= 0 ? r.fill : 0;
+        const int fill = r.fill >= 0 ? r.fill : (r.wish >= 0 ? r.wish : 0);
         uint8_t *buf = t < 0 ? net->in_nhwc : net->layers[t].out_u8;
         const int c = t < 0 ? net->c : net->layers[t].out_c;
         (t < 0 ? net->in_geom : net->layers[t].geom) = r.g;
@@ -524,6 +548,12 @@ void plan(yq_network *net)
                 l.use_flat = true;
                 if (net->fusion && l.quant_stop && i + 1 < n && net->layers[i + 1].type == L_YOLO && l.n % (net->layers[i + 1].classes + 5) == 0)
                     l.fuse_yolo = net->layers[i + 1].fused_away = true;
+                if (can_fuse_shortcut(i)) {
+                    const Layer &sc = net->layers[i + 1], &from = net->layers[tensor_of(net, sc.inputs[0])];
+                    yq_act_geom g;
+                    yq_act_geom_flat(l.out_h, l.out_w, &g);
+                    if (same_geom(sc.geom, g) && same_geom(from.geom, g)) l.fuse_shortcut = net->layers[i + 1].fused_away = true;
+                }
             } else if (yq_conv_geom_supported(l.conv) && !plain1_ok[i]) {
                 l.use_geom = true;
             } else if (net->fusion && i + 1 < n && yq_conv_can_fuse_maxpool(l.conv)) {
@@ -644,6 +674,13 @@ int forward_body(yq_network *net, const uint8_t *in_u8_nchw, int *launches, bool
                                                                        net->layers[i + 1].out_f32, net->layers[i + 1].classes,
                                                                        net->keep_acc ? l.out_acc : nullptr, net->batch, st))
                     return -1;
+            } else if (l.use_flat && l.fuse_shortcut) {
+                // conv + the quantized shortcut behind it: the launch stores the shortcut's tensor (the conv's own is never written)
+                Layer &sc = net->layers[i + 1];
+                const Layer &from = net->layers[sc.inputs[0]];
+                if (yq_forward_convolutional_layer_quant_flat_shortcut_gpu(l.conv, cur, from.out_u8, sc.out_u8, sc.halo_fill, sc.zp_b, sc.Ka, sc.Kb, sc.zp_out,
+                                                                           net->batch, st))
+                    return -1;
             } else if (l.use_flat) {
                 if (yq_forward_convolutional_layer_quant_flat_gpu(l.conv, cur, l.out_u8, l.halo_fill, l.out_f32, net->keep_acc ? l.out_acc : nullptr,
                                                                   net->batch, st))
@@ -668,6 +705,12 @@ int forward_body(yq_network *net, const uint8_t *in_u8_nchw, int *launches, bool
             cur_f32 = l.out_f32;
             break;
         case L_SHORTCUT: {
+            if (l.fused_away) {          // produced by the convolution in front of it
+                cur = l.out_u8;
+                cur_geom = &l.geom;
+                cur_fill = l.halo_fill;
+                break;
+            }
             const Layer &f = net->layers[l.inputs[0]];
             if (yq_forward_shortcut_layer_quant_geom_gpu(cur, cur_geom, f.out_u8, &f.geom, l.out_u8, &l.geom, net->batch, l.h, l.w, l.c, l.zp_a, l.zp_b, l.Ka,
                                                          l.Kb, l.zp_out, st))
@@ -1200,7 +1243,7 @@ extern "C" int yq_network_layer_info(const yq_network *net, int i, yq_layer_info
     o->batch_normalize = l.bn; o->quant_stop_flag = l.quant_stop; o->s_in = l.s_in; o->s_out = l.s_out;
     o->zp_in = l.zp_in; o->zp_out = l.zp_out; o->kernel = l.conv ? (l.use_rows ? 3 : (l.use_flat ? 2 : yq_conv_get_kernel(l.conv))) : 0;
     o->classes = l.classes; o->n_anchors = l.n_anchors;
-    o->fused = l.type == L_CONV ? (l.use_rows ? 2 : (l.fuse_pool ? 1 : (l.fuse_yolo ? 3 : 0))) : (l.fused_away ? 1 : 0);
+    o->fused = l.type == L_CONV ? (l.use_rows ? 2 : (l.fuse_pool ? 1 : (l.fuse_yolo ? 3 : (l.fuse_shortcut ? 4 : 0)))) : (l.fused_away ? 1 : 0);
     return 0;
 }
 
@@ -1557,6 +1600,7 @@ static const char *not_materialised(const yq_network *net, int layer, int what)
     if (what == 0) {
         if (l.type == L_UPSAMPLE && l.fused_away) return "the route behind it reads its input through the upsample";
         if (l.type == L_CONV && l.fuse_pool && (l.use_rows || !conv_output_needed(net, layer))) return "its launch writes the max-pooled tensor of the next layer only";
+        if (l.type == L_CONV && l.fuse_shortcut) return "its launch writes the shortcut layer's tensor only";
     } else if (what == 2) {
         if (l.type == L_CONV && l.fuse_yolo && !net->keep_acc) return "its launch writes the yolo layer's output only (pull that layer, or enable yq_network_set_debug)";
     }
