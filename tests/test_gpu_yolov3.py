@@ -256,6 +256,39 @@ def test_conv_with_fused_shortcut_vs_oracle(built, case):
     layer.free()
 
 
+@pytest.mark.parametrize("full_m0", [True, False], ids=["M0_31_bits", "M0_from_float"])
+@pytest.mark.parametrize("act", ["leaky", "relu6"])
+def test_requant_beyond_2_22(built, full_m0, act):
+    """|acc + bias| far beyond 2^22.  The integer epilogue equals the reference's double arithmetic (convolutional_layer.c:732-733)
+    as long as |x| * M0 fits 53 bits: with the reference's own host prep M0 = round(M * 2^31) of a FLOAT M has >= 7 trailing zeros
+    and the integer form serves |x| < 2^29; a binding that hands in a full 31-bit (odd) M0 must get the FP64 re-do from 2^22 on,
+    where the double product really rounds.  Both against the oracle's literal double arithmetic, flat2x + flat2 + per-tap."""
+    c, h, w, n, k = 512, 6, 6, 128, 3
+    rng = np.random.default_rng(77 + full_m0)
+    wq = rng.integers(200, 256, size=(n, c * k * k), dtype=np.uint8)          # far above the zero points: huge accumulators
+    zp_w = rng.integers(0, 40, size=n, dtype=np.uint8)
+    x = rng.integers(180, 256, size=(2, c, h, w), dtype=np.uint8)
+    s_w = (rng.random(n).astype(np.float32) * 1e-5 + 1e-6).astype(np.float32)
+    spec = synth.LayerSpec("conv", n, k, 1, 1, 0, act)
+    sl = synth.SynthLayer("conv", c, h, w, n, 0, 0, spec, s_out=0.05, biases=np.zeros(n, np.float32), s_w=s_w, zp_w=zp_w, w_u8=wq.reshape(n, c, k, k))
+    p = O.prepare_conv(sl, 0.02, 3)
+    if full_m0:
+        m0 = (rng.integers(1 << 30, 1 << 31, size=n, dtype=np.int64) | 1)       # odd: all 31 bits significant
+        p["M_value"] = m0.astype(np.float64) * 2.0 ** -31
+        p["M0_right_shift_value"] = np.full(n, 2.0 ** -24)
+    for stride in (1, 2):
+        layer = darknet.ConvolutionalLayerQuant(h, w, c, n, k, stride, 1, synth.ACT_CODES[act], wq, zp_w, p["biases_int32"], p["M_value"],
+                                                p["M0_right_shift_value"], 3, 33, 0.05)
+        got = layer.forward_flat(x, halo_fill=3) if stride == 1 else layer.forward(x)
+        layer.free()
+        for b in range(2):
+            acc = O.conv_acc(x[b], wq.reshape(n, c, k, k), zp_w, stride, 1, 3)
+            assert np.abs(acc + p["biases_int32"][:, None, None]).max() > (1 << 24)
+            assert np.array_equal(got["acc"][b], acc)
+            u8 = O.requant(acc, p["biases_int32"], p["M_value"], p["M0_right_shift_value"], synth.ACT_CODES[act], 33)
+            assert np.array_equal(got["u8"][b], u8), f"stride {stride} image {b}"
+
+
 def _yolov3_files(tmp_path, size, batch, seed=2):
     layers = synth.yolov3_quant()
     cfg, wts = str(tmp_path / "v3.cfg"), str(tmp_path / "v3.weights")

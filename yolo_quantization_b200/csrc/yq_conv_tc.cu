@@ -76,16 +76,16 @@ struct SmemLayout {
 // activation / saturation are uniform per launch: dispatch once per 32-output chunk, not per output
 template <bool HAS_EXTRA>
 __device__ __forceinline__ void epi_chunk(int actm, int sat, const uint32_t (&v)[16], int nsa, const int (&extra)[16], const int4 *cq,
-                                          const double *mc, int zo, uint32_t (&packed)[4])
+                                          const double *mc, int zo, uint32_t (&packed)[4], uint32_t xlim)
 {
     if (sat) {
-        if (actm == 0) yq::requant_chunk<0, true, 16, HAS_EXTRA>(v, nsa, extra, cq, mc, zo, packed);
-        else if (actm == 1) yq::requant_chunk<1, true, 16, HAS_EXTRA>(v, nsa, extra, cq, mc, zo, packed);
-        else yq::requant_chunk<2, true, 16, HAS_EXTRA>(v, nsa, extra, cq, mc, zo, packed);
+        if (actm == 0) yq::requant_chunk<0, true, 16, HAS_EXTRA>(v, nsa, extra, cq, mc, zo, packed, xlim);
+        else if (actm == 1) yq::requant_chunk<1, true, 16, HAS_EXTRA>(v, nsa, extra, cq, mc, zo, packed, xlim);
+        else yq::requant_chunk<2, true, 16, HAS_EXTRA>(v, nsa, extra, cq, mc, zo, packed, xlim);
     } else {
-        if (actm == 0) yq::requant_chunk<0, false, 16, HAS_EXTRA>(v, nsa, extra, cq, mc, zo, packed);
-        else if (actm == 1) yq::requant_chunk<1, false, 16, HAS_EXTRA>(v, nsa, extra, cq, mc, zo, packed);
-        else yq::requant_chunk<2, false, 16, HAS_EXTRA>(v, nsa, extra, cq, mc, zo, packed);
+        if (actm == 0) yq::requant_chunk<0, false, 16, HAS_EXTRA>(v, nsa, extra, cq, mc, zo, packed, xlim);
+        else if (actm == 1) yq::requant_chunk<1, false, 16, HAS_EXTRA>(v, nsa, extra, cq, mc, zo, packed, xlim);
+        else yq::requant_chunk<2, false, 16, HAS_EXTRA>(v, nsa, extra, cq, mc, zo, packed, xlim);
     }
 }
 
@@ -244,9 +244,9 @@ __global__ void __launch_bounds__(TC_THREADS, 2) conv_u8_tc_kernel(const __grid_
 #pragma unroll
                     for (int j = 0; j < 16; ++j) extra[j] += __ldg(cr + j);
                 }
-                epi_chunk<true>(actm, sat, v, nsa, extra, s_q + c0, s_mc + c0, a.ep.zp_out, packed);
+                epi_chunk<true>(actm, sat, v, nsa, extra, s_q + c0, s_mc + c0, a.ep.zp_out, packed, a.ep.xlim);
             } else {
-                epi_chunk<false>(actm, sat, v, nsa, extra, s_q + c0, s_mc + c0, a.ep.zp_out, packed);
+                epi_chunk<false>(actm, sat, v, nsa, extra, s_q + c0, s_mc + c0, a.ep.zp_out, packed, a.ep.xlim);
             }
             yq::mask_pad_channels<16>(packed, a.N - (oc0 + c0));
             if (SLOW && side && valid) {   // parity / quant_stop side outputs (not on the throughput path)

@@ -273,7 +273,7 @@ __global__ void __launch_bounds__(FL_THREADS, 2) conv_u8_tc_flat_kernel(const __
                 if (ch + 1 < NCHUNK) tmem_ld16_issue(trow + c0 + 16, vbuf[(ch + 1) & 1]);   // in flight while this chunk is requantized
                 uint32_t packed[4];
                 int extra[16];
-                yq::requant_chunk<ACTM, SAT, 16, false>(v, nsa, extra, s_q + c0, s_mc + c0, a.ep.zp_out, packed);
+                yq::requant_chunk<ACTM, SAT, 16, false>(v, nsa, extra, s_q + c0, s_mc + c0, a.ep.zp_out, packed, a.ep.xlim);
                 if (!valid) packed[0] = packed[1] = packed[2] = packed[3] = a.halo_word;
                 yq::mask_pad_channels<16>(packed, a.N - (oc0 + c0));
                 if (SLOW && side && valid) {

@@ -73,7 +73,10 @@ struct Flat2Smem {
 
 __device__ __forceinline__ void f2_arrive(uint64_t *bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory"); }
 
-template <int KC, bool SLOW>
+// RESID: the following quantized shortcut is fused into the epilogue (a launch-uniform choice: a template parameter keeps the
+// other form's code out of the instruction cache -- the 16 epilogue warps run apart from each other and `no instruction` stalls
+// were 15 % of the samples with both forms and four unrolled chunks in one loop body, r2 profile)
+template <int KC, bool SLOW, bool RESID>
 __global__ void __launch_bounds__(F2_THREADS, 1) conv_u8_tc_flat2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                                                                      const __grid_constant__ CUtensorMap tmO, const Flat2Args a)
 {
@@ -311,23 +314,26 @@ __global__ void __launch_bounds__(F2_THREADS, 1) conv_u8_tc_flat2_kernel(const _
                 auto run = [&](auto actm_tag, auto sat_tag) {
                     constexpr int ACTM = decltype(actm_tag)::value;
                     constexpr bool SAT = decltype(sat_tag)::value;
+#pragma unroll 1
+                    for (int cp = 0; cp < 2; ++cp) {
 #pragma unroll
-                    for (int ch = 0; ch < 4; ++ch) {
+                    for (int h2 = 0; h2 < 2; ++h2) {
+                        const int ch = 2 * cp + h2;
                         if (ch < nch) {
                             const int c0 = cbeg + 16 * ch;
-                            uint32_t(&v)[16] = vbuf[ch & 1];
-                            if (ch + 1 < nch) tmem_ld16_issue(trow + 16 * (ch + 1), vbuf[(ch + 1) & 1]);   // in flight while this chunk is requantized
+                            uint32_t(&v)[16] = vbuf[h2];
+                            if (ch + 1 < nch) tmem_ld16_issue(trow + 16 * (ch + 1), vbuf[h2 ^ 1]);   // in flight while this chunk is requantized
                             uint32_t packed[4];
                             int extra[16];
-                            if (a.resid) {
+                            if (RESID) {
                                 // conv -> shortcut in one launch: the residual bytes of this position / chunk travel while the chunk is requantized
                                 uint4 rb = make_uint4(0, 0, 0, 0);
                                 if (valid) rb = __ldg(reinterpret_cast<const uint4 *>(a.resid + (size_t)p * a.CSO + oc0 + c0));
                                 int rv[16];
-                                yq::requant_chunk_vals<ACTM, SAT, 16, false>(v, nsa, extra, s_q + c0, s_mc + c0, a.ep.zp_out, rv);
+                                yq::requant_chunk_vals<ACTM, SAT, 16, false>(v, nsa, extra, s_q + c0, s_mc + c0, a.ep.zp_out, rv, a.ep.xlim);
                                 yq::shortcut_pack16(rv, rb, a.sc, packed);
                             } else {
-                                yq::requant_chunk<ACTM, SAT, 16, false>(v, nsa, extra, s_q + c0, s_mc + c0, a.ep.zp_out, packed);
+                                yq::requant_chunk<ACTM, SAT, 16, false>(v, nsa, extra, s_q + c0, s_mc + c0, a.ep.zp_out, packed, a.ep.xlim);
                             }
                             if (!valid) packed[0] = packed[1] = packed[2] = packed[3] = a.halo_word;
                             yq::mask_pad_channels<16>(packed, a.N - (oc0 + c0));
@@ -341,8 +347,9 @@ __global__ void __launch_bounds__(F2_THREADS, 1) conv_u8_tc_flat2_kernel(const _
                             // 64-byte rows: SWIZZLE_64B (16-byte chunk ^ row bits 1-2); 32-byte rows: SWIZZLE_32B (chunk ^ row bit 2)
                             const int sw = rowb == 64 ? (ch ^ ((lr >> 1) & 3)) : (ch ^ ((lr >> 2) & 1));
                             *reinterpret_cast<uint4 *>(stage + lr * rowb + sw * 16) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
-                            if (ch + 1 < nch) tmem_ld_wait16(vbuf[(ch + 1) & 1]);
+                            if (ch + 1 < nch) tmem_ld_wait16(vbuf[h2 ^ 1]);
                         }
+                    }
                     }
                 };
                 if (SLOW && a.ep.saturate) {
@@ -425,7 +432,7 @@ struct Flat2State {
     std::map<Key, std::pair<CUtensorMap, CUtensorMap>> maps;
 };
 
-template <int KC, bool SLOW>
+template <int KC, bool SLOW, bool RESID>
 int f2_launch_v(Flat2State *st, const CUtensorMap &tmA, const CUtensorMap &tmO, Flat2Args a, cudaStream_t stream)
 {
     using L = Flat2Smem<KC>;
@@ -443,7 +450,7 @@ int f2_launch_v(Flat2State *st, const CUtensorMap &tmA, const CUtensorMap &tmO, 
     if (nbs < 2) return yq::fail("conv_u8_tc_flat2_kernel<%d>: shared memory does not hold two weight stages", KC);
     a.b_stages = nbs;
     const int smem = fixed + nbs * L::B_STAGE;
-    auto kern = conv_u8_tc_flat2_kernel<KC, SLOW>;
+    auto kern = conv_u8_tc_flat2_kernel<KC, SLOW, RESID>;
     if (yq::ensure_dynamic_smem((const void *)kern, smem)) return -1;
     const int grid = a.num_tiles < n_sm ? a.num_tiles : n_sm;
     YQ_CUDA(yq::launch_pdl(kern, dim3(grid), dim3(F2_THREADS), smem, stream, tmA, st->tmB, tmO, a));
@@ -453,8 +460,9 @@ int f2_launch_v(Flat2State *st, const CUtensorMap &tmA, const CUtensorMap &tmO, 
 template <int KC>
 int f2_launch(Flat2State *st, const CUtensorMap &tmA, const CUtensorMap &tmO, const Flat2Args &a, cudaStream_t stream)
 {
-    if (a.out_acc || a.ep.saturate) return f2_launch_v<KC, true>(st, tmA, tmO, a, stream);
-    return f2_launch_v<KC, false>(st, tmA, tmO, a, stream);
+    if (a.resid) return f2_launch_v<KC, false, true>(st, tmA, tmO, a, stream);      // (the fused shortcut has no side outputs: production plan only)
+    if (a.out_acc || a.ep.saturate) return f2_launch_v<KC, true, false>(st, tmA, tmO, a, stream);
+    return f2_launch_v<KC, false, false>(st, tmA, tmO, a, stream);
 }
 
 }  // namespace

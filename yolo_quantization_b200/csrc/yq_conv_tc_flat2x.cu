@@ -72,7 +72,8 @@ struct Flat2xSmem {
 
 __device__ __forceinline__ void f2x_arrive(uint64_t *bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory"); }
 
-template <int KC, bool SLOW, bool WIDE>
+// RESID: the following quantized shortcut fused into the epilogue (launch-uniform: a template parameter, see yq_conv_tc_flat2.cu)
+template <int KC, bool SLOW, bool WIDE, bool RESID>
 __global__ void __launch_bounds__(F2X_THREADS, 1) conv_u8_tc_flat2x_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                                                                      const __grid_constant__ CUtensorMap tmO, const Flat2xArgs a)
 {
@@ -321,22 +322,25 @@ __global__ void __launch_bounds__(F2X_THREADS, 1) conv_u8_tc_flat2x_kernel(const
                 auto run = [&](auto actm_tag, auto sat_tag) {
                     constexpr int ACTM = decltype(actm_tag)::value;
                     constexpr bool SAT = decltype(sat_tag)::value;
+#pragma unroll 1
+                    for (int cp = 0; cp < 2; ++cp) {
 #pragma unroll
-                    for (int ch = 0; ch < 4; ++ch) {
+                    for (int h2 = 0; h2 < 2; ++h2) {
+                        const int ch = 2 * cp + h2;
                         const int c0 = cbeg + 16 * ch;
-                        uint32_t(&v)[16] = vbuf[ch & 1];
-                        if (ch + 1 < 4) tmem_ld16_issue(trow + 16 * (ch + 1), vbuf[(ch + 1) & 1]);   // in flight while this chunk is requantized
+                        uint32_t(&v)[16] = vbuf[h2];
+                        if (ch + 1 < 4) tmem_ld16_issue(trow + 16 * (ch + 1), vbuf[h2 ^ 1]);   // in flight while this chunk is requantized
                         uint32_t packed[4];
                         int extra[16];
-                        if (a.resid) {
+                        if (RESID) {
                             // conv -> shortcut in one launch: the residual bytes of this position / chunk travel while the chunk is requantized
                             uint4 rb = make_uint4(0, 0, 0, 0);
                             if (valid) rb = __ldg(reinterpret_cast<const uint4 *>(a.resid + (size_t)p * a.CSO + oc0 + c0));
                             int rv[16];
-                            yq::requant_chunk_vals<ACTM, SAT, 16, false>(v, nsa, extra, s_q + c0, s_mc + c0, a.ep.zp_out, rv);
+                            yq::requant_chunk_vals<ACTM, SAT, 16, false>(v, nsa, extra, s_q + c0, s_mc + c0, a.ep.zp_out, rv, a.ep.xlim);
                             yq::shortcut_pack16(rv, rb, a.sc, packed);
                         } else {
-                            yq::requant_chunk<ACTM, SAT, 16, false>(v, nsa, extra, s_q + c0, s_mc + c0, a.ep.zp_out, packed);
+                            yq::requant_chunk<ACTM, SAT, 16, false>(v, nsa, extra, s_q + c0, s_mc + c0, a.ep.zp_out, packed, a.ep.xlim);
                         }
                         if (!valid) packed[0] = packed[1] = packed[2] = packed[3] = a.halo_word;
                         yq::mask_pad_channels<16>(packed, a.N - (oc0 + c0));
@@ -348,7 +352,8 @@ __global__ void __launch_bounds__(F2X_THREADS, 1) conv_u8_tc_flat2x_kernel(const
                             }
                         }
                         *reinterpret_cast<uint4 *>(stage + lane * 64 + ((ch ^ ((lane >> 1) & 3)) * 16)) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
-                        if (ch + 1 < 4) tmem_ld_wait16(vbuf[(ch + 1) & 1]);
+                        if (ch + 1 < 4) tmem_ld_wait16(vbuf[h2 ^ 1]);
+                    }
                     }
                 };
                 if (SLOW && a.ep.saturate) {
@@ -434,7 +439,7 @@ struct Flat2xState {
     std::map<Key, std::pair<CUtensorMap, CUtensorMap>> maps;
 };
 
-template <int KC, bool SLOW, bool WIDE>
+template <int KC, bool SLOW, bool WIDE, bool RESID>
 int f2x_launch_v(Flat2xState *st, const CUtensorMap &tmA, const CUtensorMap &tmO, Flat2xArgs a, cudaStream_t stream)
 {
     using L = Flat2xSmem<KC, WIDE>;
@@ -449,7 +454,7 @@ int f2x_launch_v(Flat2xState *st, const CUtensorMap &tmA, const CUtensorMap &tmO
     // Never two of these CTAs on one SM: each takes all 512 TMEM columns, and two CTA pairs of concurrent launches (the
     // side stream of yq_network.cu) that each hold one SM's columns while waiting for the other's would not finish.
     if (smem <= smem_max / 2) smem = smem_max / 2 + 1024;
-    auto kern = conv_u8_tc_flat2x_kernel<KC, SLOW, WIDE>;
+    auto kern = conv_u8_tc_flat2x_kernel<KC, SLOW, WIDE, RESID>;
     if (yq::ensure_dynamic_smem((const void *)kern, smem)) return -1;
     int grid = 2 * a.num_tiles < n_sm ? 2 * a.num_tiles : n_sm / 2 * 2;      // whole CTA pairs
     cudaLaunchConfig_t cfg;
@@ -475,11 +480,13 @@ template <int KC>
 int f2x_launch(Flat2xState *st, const CUtensorMap &tmA, const CUtensorMap &tmO, const Flat2xArgs &a, cudaStream_t stream)
 {
     if (st->wide) {
-        if (a.out_acc || a.ep.saturate) return f2x_launch_v<KC, true, true>(st, tmA, tmO, a, stream);
-        return f2x_launch_v<KC, false, true>(st, tmA, tmO, a, stream);
+        if (a.resid) return f2x_launch_v<KC, false, true, true>(st, tmA, tmO, a, stream);
+        if (a.out_acc || a.ep.saturate) return f2x_launch_v<KC, true, true, false>(st, tmA, tmO, a, stream);
+        return f2x_launch_v<KC, false, true, false>(st, tmA, tmO, a, stream);
     }
-    if (a.out_acc || a.ep.saturate) return f2x_launch_v<KC, true, false>(st, tmA, tmO, a, stream);
-    return f2x_launch_v<KC, false, false>(st, tmA, tmO, a, stream);
+    if (a.resid) return f2x_launch_v<KC, false, false, true>(st, tmA, tmO, a, stream);
+    if (a.out_acc || a.ep.saturate) return f2x_launch_v<KC, true, false, false>(st, tmA, tmO, a, stream);
+    return f2x_launch_v<KC, false, false, false>(st, tmA, tmO, a, stream);
 }
 
 }  // namespace

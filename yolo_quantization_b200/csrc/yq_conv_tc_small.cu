@@ -75,11 +75,11 @@ __host__ __device__ constexpr int small_tmem_cols() { return 2 * (BN + 16) <= 64
 
 template <int ACTM, int NV>
 __device__ __forceinline__ void epi_chunk_small(int sat, const uint32_t (&v)[NV], int nsa, const int4 *cq, const double *mc, int zo,
-                                                uint32_t (&packed)[NV / 4])
+                                                uint32_t (&packed)[NV / 4], uint32_t xlim)
 {
     int extra[NV];   // unused (HAS_EXTRA = false): padded taps already carry zp_in
-    if (sat) yq::requant_chunk<ACTM, true, NV, false>(v, nsa, extra, cq, mc, zo, packed);
-    else yq::requant_chunk<ACTM, false, NV, false>(v, nsa, extra, cq, mc, zo, packed);
+    if (sat) yq::requant_chunk<ACTM, true, NV, false>(v, nsa, extra, cq, mc, zo, packed, xlim);
+    else yq::requant_chunk<ACTM, false, NV, false>(v, nsa, extra, cq, mc, zo, packed, xlim);
 }
 
 __device__ __forceinline__ void mbar_arrive(uint64_t *bar)
@@ -408,7 +408,7 @@ __global__ void __launch_bounds__(SM_THREADS, (CS == 32 ? 2 : (CS == 16 ? 4 : 6)
             uint32_t v[16];
             tmem_ld16(tacc + c0, v);
             uint32_t packed[4];
-            epi_chunk_small<ACTM, 16>(SLOW ? a.ep.saturate : 0, v, nsa, a.cq + c0, a.mc + c0, a.ep.zp_out, packed);
+            epi_chunk_small<ACTM, 16>(SLOW ? a.ep.saturate : 0, v, nsa, a.cq + c0, a.mc + c0, a.ep.zp_out, packed, a.ep.xlim);
             yq::mask_pad_channels<16>(packed, a.N - c0);
             if (SLOW && side && valid) {   // parity / quant_stop side outputs (not on the throughput path)
                 const size_t pix = ((size_t)tn * a.OH + oy) * a.OW + ox;

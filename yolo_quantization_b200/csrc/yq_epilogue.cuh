@@ -42,6 +42,7 @@ struct EpiParams {
     const int4 *chanq;       // {bias, zw, 2*M0, shift} per channel (integer form), or nullptr
     int fused, act, zp_out, saturate;
     float s_out;
+    uint32_t xlim;           // the integer form is the reference's double arithmetic for every |x| < xlim (see requant_exact_limit)
 };
 
 struct ChanParams {
@@ -49,9 +50,27 @@ struct ChanParams {
     double m0, m1;
 };
 
+// Largest power of two P such that for every channel the reference's double product x * M_value (convolutional_layer.c:732) is
+// EXACT for all |x| < P, i.e. |x| * M0 has at most 53 significant bits.  M0 = round(M * 2^31) of a FLOAT M (blas.c:313-316,
+// :387-418) carries at most 24 significant bits -- at least 7 trailing zeros -- so for the reference's own host prep P = 2^29 and
+// the FP64 re-do below never runs (|acc| <= K * 255 * 255 < 2^29 for K <= 8256); a binding that hands in a full 31-bit M0 gets the
+// 2^22 of the worst case.  A power of two so that kernels may test an OR of magnitudes instead of their maximum.
+static inline uint32_t requant_exact_limit(const yq_conv_layer *l)
+{
+    uint32_t lim = 1u << 31;
+    for (int oc = 0; oc < l->n; ++oc) {
+        uint32_t m = (uint32_t)l->host_chanq[(size_t)oc * 4 + 2] >> 1;      // chanq.z = 2 * M0
+        if (!m) continue;
+        while (!(m & 1u)) m >>= 1;                                           // significant bits of M0
+        while (lim > 1 && (unsigned long long)(lim - 1) * m >= (1ull << 53)) lim >>= 1;
+    }
+    return lim;
+}
+
 static inline EpiParams make_epi(const yq_conv_layer *l)
 {
     EpiParams e;
+    e.xlim = l->int_form ? requant_exact_limit(l) : (1u << 22);
     e.bias = l->bias; e.zw = l->zw; e.mcomb = l->mcomb; e.mval = l->mval; e.rsh = l->rsh; e.chanq = (const int4 *)l->chanq;
     e.fused = l->fused_mult; e.act = l->activation; e.zp_out = l->zp_out; e.saturate = l->saturate; e.s_out = l->s_out;
     return e;
@@ -133,7 +152,7 @@ __device__ __forceinline__ int act_value(int q, int zo)
 // the chunk's values BEFORE the uint8 store (the caller packs their low bytes, or feeds them to a fused quantized shortcut)
 template <int ACTM, bool SAT, int NV, bool HAS_EXTRA>
 __device__ __forceinline__ void requant_chunk_vals(const uint32_t (&v)[NV], int nsa, const int (&extra)[NV], const int4 *cq, const double *mc,
-                                                   int zo, int (&r)[NV])
+                                                   int zo, int (&r)[NV], uint32_t xlim = 1u << 22)
 {
     uint32_t mx = 0;
 #pragma unroll
@@ -163,8 +182,8 @@ __device__ __forceinline__ void requant_chunk_vals(const uint32_t (&v)[NV], int 
         }
         r[j] = act_value<ACTM, SAT>(q, zo);
     }
-    if (mx >= (1u << 22)) {
-        // |x*M0| may reach 2^53: the reference's double multiply rounds -> redo this chunk in FP64 form (A)
+    if (mx >= xlim) {
+        // |x*M0| may need more than 53 bits: the reference's double multiply rounds -> redo this chunk in FP64 form (A)
 #pragma unroll
         for (int j = 0; j < NV; ++j) {
             const int4 c = cq[j];
@@ -180,10 +199,10 @@ __device__ __forceinline__ void requant_chunk_vals(const uint32_t (&v)[NV], int 
 
 template <int ACTM, bool SAT, int NV, bool HAS_EXTRA>
 __device__ __forceinline__ void requant_chunk(const uint32_t (&v)[NV], int nsa, const int (&extra)[NV], const int4 *cq, const double *mc,
-                                              int zo, uint32_t (&packed)[NV / 4])
+                                              int zo, uint32_t (&packed)[NV / 4], uint32_t xlim = 1u << 22)
 {
     int r[NV];
-    requant_chunk_vals<ACTM, SAT, NV, HAS_EXTRA>(v, nsa, extra, cq, mc, zo, r);
+    requant_chunk_vals<ACTM, SAT, NV, HAS_EXTRA>(v, nsa, extra, cq, mc, zo, r, xlim);
 #pragma unroll
     for (int k = 0; k < NV / 4; ++k) packed[k] = pack_low_bytes(r[4 * k], r[4 * k + 1], r[4 * k + 2], r[4 * k + 3]);
 }

@@ -667,7 +667,7 @@ extern "C" int yq_forward_convolutional_layer_quant_flat_gpu(yq_conv_layer *l, c
 extern "C" int yq_conv_flat_shortcut_supported(const yq_conv_layer *l)
 {
     static const bool off = getenv("YQ_NO_FUSE_SHORTCUT") && atoi(getenv("YQ_NO_FUSE_SHORTCUT"));   // A/B measurements
-    return l && !off && !l->quant_stop_flag && (l->tc_flat2 || l->tc_flat2x) ? 1 : 0;
+    return l && !off && !l->quant_stop_flag && !l->saturate && (l->tc_flat2 || l->tc_flat2x) ? 1 : 0;
 }
 // A flat convolution with the FOLLOWING quantized shortcut (extension layer) fused into its epilogue: out_flat receives the
 // SHORTCUT's output, the convolution's own tensor is never written.  from_flat = the shortcut's `from` tensor in the same flat
