@@ -310,15 +310,24 @@ ROWS_NCHW_CASES = [
     (34, 80, 16, 3),       # partial tiles in x and y: the TMA box hangs over the right and bottom edges (zero fill)
     (16, 64, 32, 1),
     (50, 64, 16, 2),
+    (64, 416, 16, 1),      # the real row width: 6.5 tiles of 64 pixels (dense layer-0 flavour), 13 of 32 (rows flavour)
+    (22, 208, 16, 2),
+    (130, 96, 16, 3),      # more tiles than one wave of a small grid: both accumulators and every staging slot get reused
 ]
 
 
 @pytest.mark.parametrize("case", ROWS_NCHW_CASES, ids=lambda c: "%dx%d_n%d_b%d" % c)
-@pytest.mark.parametrize("variant", [2, 1], ids=["two_signed_blocks", "ones_rows"])
-def test_conv_rows_flavour_reads_nchw_planes(built, case, variant, monkeypatch):
-    """layer-0 class: the rows kernel fetches the [b,3,h,w] planes itself (TMA, zero fill outside the image) and interleaves
-    them on chip == oracle conv + maxpool; same result as through the padded NHWC4 copy."""
+@pytest.mark.parametrize("variant", [2, 1, 3], ids=["two_signed_blocks", "ones_rows", "rows_kernel_two_blocks"])
+@pytest.mark.parametrize("s_out", [0.05, 6.0], ids=["wrapping", "in_range"])
+def test_conv_rows_flavour_reads_nchw_planes(built, case, variant, s_out, monkeypatch):
+    """layer-0 class: the kernel fetches the [b,3,h,w] planes itself (TMA, zero fill outside the image) and rearranges
+    them on chip == oracle conv + maxpool; same result as through the padded NHWC4 copy.  n = 16 with two signed weight blocks
+    runs the dense layer-0 flavour (yq_conv_tc_l0.cu: 8 pixels per MMA row), everything else -- and variant 3, which switches
+    the dense flavour off -- the rows flavour's planar form."""
     h, w, n, batch = case
+    if variant == 3:
+        monkeypatch.setenv("YQ_NO_L0", "1")
+        variant = 2
     c, k, zp_in, zp_out = 3, 3, 0, 0
     rng = np.random.default_rng(zlib.crc32(repr(case).encode()) + 11)
     wq, zp_w, s_w, bias = make_params(rng, n, c * k * k, zp_in)
@@ -329,11 +338,12 @@ def test_conv_rows_flavour_reads_nchw_planes(built, case, variant, monkeypatch):
         zp_w[n - 1] = 0
         wq[n - 1, -1] = 255
     spec = synth.LayerSpec("conv", n, k, 1, 1, 0, "relu6")
-    sl = synth.SynthLayer("conv", c, h, w, n, 0, 0, spec, s_out=0.05, biases=bias, s_w=s_w, zp_w=zp_w, w_u8=wq.reshape(n, c, k, k))
+    sl = synth.SynthLayer("conv", c, h, w, n, 0, 0, spec, s_out=s_out, biases=bias, s_w=s_w, zp_w=zp_w, w_u8=wq.reshape(n, c, k, k))
     p = O.prepare_conv(sl, 0.02, zp_in)
     x = rng.integers(0, 256, size=(batch, c, h, w), dtype=np.uint8)
+    zp_out = 3 if s_out > 1 else 0
     layer = darknet.ConvolutionalLayerQuant(h, w, c, n, k, 1, 1, synth.ACT_CODES["relu6"], wq, zp_w, p["biases_int32"], p["M_value"],
-                                            p["M0_right_shift_value"], zp_in, zp_out, 0.05)
+                                            p["M0_right_shift_value"], zp_in, zp_out, s_out)
     assert layer.rows_nchw_supported and layer.rows_variant == variant
     got = layer.forward_rows_pooled(x, out_pad=1, nchw=True)
     for b in range(batch):

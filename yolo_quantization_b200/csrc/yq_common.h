@@ -162,6 +162,13 @@ int yq_tc_rows_forward(yq_conv_layer *l, void *state, const uint8_t *in, uint8_t
                        int planar = 0);
 int yq_tc_rows_planar_supported(const yq_conv_layer *l);
 
+// implemented in yq_conv_tc_l0.cu (the network's first layer from its CHW planes: c = 3, n = 16, RELU6 + 2x2 pool, dense Toeplitz MMAs;
+// owned by the rows state, which hands it the planar launches)
+int yq_tc_l0_supported(const yq_conv_layer *l);
+int yq_tc_l0_prepare(yq_conv_layer *l, void **state);      // *state stays null when the weights do not fit the two-signed-block form
+void yq_tc_l0_free(void *state);
+int yq_tc_l0_forward(yq_conv_layer *l, void *state, const uint8_t *in_planes, uint8_t *out_pool, const yq_act_geom *og, int batch, cudaStream_t stream);
+
 // implemented in yq_conv_tc_flat.cu (flat halo-padded strip, one patch per channel chunk shared by all taps; c % 64 == 0)
 int yq_tc_flat_supported(const yq_conv_layer *l);
 int yq_tc_flat_eligible(const yq_conv_layer *l);   // shape conditions shared by flat / flat2 / flat2x (no row-width limit)

@@ -729,6 +729,7 @@ struct RowsState {
     size_t slice_bytes = 0; // filter image bytes of one slice
     bool two = false;       // two signed weight blocks (see RowsCfg)
     uint8_t *wimg = nullptr;
+    void *l0 = nullptr;     // the dense layer-0 flavour (yq_conv_tc_l0.cu) when this layer qualifies: takes the planar launches
     std::map<std::pair<const void *, int>, CUtensorMap> maps;      // input tensor map per (input pointer, batch)
 };
 
@@ -967,6 +968,11 @@ int yq_tc_rows_prepare(yq_conv_layer *l, void **state)
         delete st;
         return yq::fail("tcgen05 rows flavour: weight upload failed");
     }
+    if (yq_tc_l0_supported(l) && yq_tc_l0_prepare(l, &st->l0) != 0) {
+        cudaFree(st->wimg);
+        delete st;
+        return -1;
+    }
     *state = st;
     return 0;
 }
@@ -978,6 +984,7 @@ void yq_tc_rows_free(void *state)
 {
     RowsState *st = (RowsState *)state;
     if (!st) return;
+    yq_tc_l0_free(st->l0);
     cudaFree(st->wimg);
     delete st;
 }
@@ -995,6 +1002,7 @@ int yq_tc_rows_forward(yq_conv_layer *l, void *state, const uint8_t *in_padded, 
     RowsState *st = (RowsState *)state;
     if (!st || !in_padded || !out_pool || !og) return yq::fail("tcgen05 rows flavour: bad argument");
     if (planar && !yq_tc_rows_planar_supported(l)) return yq::fail("tcgen05 rows flavour: this layer cannot read CHW planes (c = 3, zp_in = 0, w %% 16 = 0)");
+    if (planar && st->l0) return yq_tc_l0_forward(l, st->l0, in_padded, out_pool, og, batch, stream);      // the dense layer-0 form
     RowsArgs a;
     memset(&a, 0, sizeof a);
     yq_act_geom ig;

@@ -27,8 +27,8 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity)
     uint32_t ok;
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"      // (no suspend-time hint: measured on B200, a 10 ms hint as the CuTe
+        "selp.u32 %0, 1, 0, p;\n\t}"                                         // pipelines pass makes the waiters wake late -- layer 0 0.087 -> 0.110 ms)
         : "=r"(ok)
         : "r"(smem_u32(bar)), "r"(parity)
         : "memory");
@@ -39,7 +39,13 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
 {
     if (mbar_try_wait(bar, parity)) return;
     const long long t0 = clock64();
-    while (!mbar_try_wait(bar, parity)) {
+    for (;;) {
+        // four polls per look at the clock: the retry loop's compare / add / branch instructions compete with the working warps
+        // for the alu pipe (a quarter of the producer warps' instructions in the layer-0 kernel were this loop)
+        if (mbar_try_wait(bar, parity)) return;
+        if (mbar_try_wait(bar, parity)) return;
+        if (mbar_try_wait(bar, parity)) return;
+        if (mbar_try_wait(bar, parity)) return;
         if (clock64() - t0 > 4000000000LL) __trap();
     }
 }
