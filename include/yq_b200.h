@@ -145,6 +145,9 @@ typedef struct yq_act_geom {
  * as out of bounds and restores zp_in * sum(w - zp_w) per border tap in the epilogue.  Flavours that only take plain
  * tensors (SIMT, c <= 32) fail on a padded geometry: yq_conv_geom_supported() says which kind the layer has. */
 YQ_API int yq_conv_geom_supported(const yq_conv_layer *l);
+/* 1 when the layer's flavour can at least WRITE a halo-padded output tensor (plain input): the per-tap flavour, and the small-c
+ * flavour (c <= 32), whose threads store their pixels themselves. */
+YQ_API int yq_conv_out_geom_supported(const yq_conv_layer *l);
 YQ_API int yq_forward_convolutional_layer_quant_geom_gpu(yq_conv_layer *l, const uint8_t *in_u8, const yq_act_geom *in_geom, int in_halo_fill,
                                                          uint8_t *out_u8, const yq_act_geom *out_geom, float *out_f32, int32_t *out_acc,
                                                          int batch, void *stream);

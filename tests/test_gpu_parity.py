@@ -212,6 +212,9 @@ FLAT_CASES = [
     (512, 4, 4, 48, 3, "leaky", 200, 77, 1),       # K = 4608
     (64, 20, 33, 64, 3, "linear", 77, 20, 2),
     (192, 1, 1, 32, 3, "relu6", 7, 0, 4),          # 1x1 image: every tap but the centre is halo
+    (32, 20, 33, 64, 3, "leaky", 13, 40, 2),       # c = 32: 32-byte patch rows (SWIZZLE_32B, KC = 32), the persistent two-tile form only
+    (32, 208, 208, 64, 3, "leaky", 0, 3, 1),       # layer 3 of the full yolov3 at its real size (three TMA boxes per patch)
+    (32, 9, 7, 128, 1, "relu6", 5, 0, 3),
 ]
 
 

@@ -72,6 +72,7 @@ SIGNATURES = {
     "yq_forward_convolutional_layer_quant_pool_gpu": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _vp]),
     "yq_conv_can_fuse_maxpool": (_i, [_vp]),
     "yq_conv_geom_supported": (_i, [_vp]),
+    "yq_conv_out_geom_supported": (_i, [_vp]),
     "yq_forward_convolutional_layer_quant_geom_gpu": (_i, [_vp, _vp, C.POINTER(ActGeom), _i, _vp, C.POINTER(ActGeom), _vp, _vp, _i, _vp]),
     "yq_shortcut_multiplier": (_i, [C.c_float, C.c_float, C.POINTER(C.c_int32)]),
     "yq_forward_shortcut_layer_quant_gpu": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),

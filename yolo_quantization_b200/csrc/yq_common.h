@@ -148,8 +148,9 @@ bool pack_fetch_device(const yq_conv_layer *l, const char *tag, size_t bytes, vo
 }  // namespace yq
 int yq_tc_small_prepare(yq_conv_layer *l, void **state);
 void yq_tc_small_free(void *state);
+// out_geom (null = plain): geometry of the conv output tensor; the input and the pooled output are always plain
 int yq_tc_small_forward(yq_conv_layer *l, void *state, const uint8_t *in_u8, uint8_t *out_u8, uint8_t *out_pool, float *out_f32,
-                        int32_t *out_acc, int batch, cudaStream_t stream);
+                        int32_t *out_acc, int batch, cudaStream_t stream, const yq_act_geom *out_geom = nullptr);
 
 // implemented in yq_conv_tc_rows.cu (3x3/1/1 + RELU6 + 2x2 pool from a halo-padded input, no im2col; c <= 32)
 int yq_tc_rows_supported(const yq_conv_layer *l);
@@ -208,6 +209,7 @@ int yq_tc_forward(yq_conv_layer *l, const uint8_t *in_u8, uint8_t *out_u8, uint8
                   int batch, cudaStream_t stream, const yq_act_geom *in_geom = nullptr, int in_halo_fill = -1,
                   const yq_act_geom *out_geom = nullptr);
 int yq_conv_plain_1x1_fast(const yq_conv_layer *l);   // 1: the plain entry runs this 1x1 layer on conv_u8_tc_flat2_kernel (plain-strip mode)
+int yq_tc_out_geom_supported(const yq_conv_layer *l);   // 1: plain input, but the output may have any geometry (the small-c flavour)
 int yq_tc_geom_supported(const yq_conv_layer *l);   // 1: the layer's current flavour is the per-tap TMA one (any tensor geometry)
 int yq_tc_cluster_enabled();                        // YQ_TC_CLUSTER: multicast clusters in the per-tap flavour (A/B switch, off)
 // 1 when this layer's current flavour can also emit the 2x2/stride-2 max-pooled tensor from its epilogue

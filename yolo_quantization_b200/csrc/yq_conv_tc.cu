@@ -541,6 +541,7 @@ void yq_tc_free(yq_conv_layer *l)
 int yq_tc_can_fuse_pool(const yq_conv_layer *l) { return l->kernel == 1 && l->tc_small != nullptr; }
 
 int yq_tc_geom_supported(const yq_conv_layer *l) { return l->kernel == 1 && l->tc && !l->tc_small; }
+int yq_tc_out_geom_supported(const yq_conv_layer *l) { return l->kernel == 1 && l->tc_small != nullptr && !l->quant_stop_flag; }
 
 int yq_tc_cluster_enabled()
 {
@@ -554,8 +555,9 @@ int yq_tc_forward(yq_conv_layer *l, const uint8_t *in_u8, uint8_t *out_u8, uint8
     const bool plain_in = !in_geom || (in_geom->pad == 0 && in_geom->pitch_w == l->w && in_geom->rows_h == l->h);
     const bool plain_out = !out_geom || (out_geom->pad == 0 && out_geom->pitch_w == l->out_w && out_geom->rows_h == l->out_h);
     if (l->tc_small) {
-        if (!plain_in || !plain_out) return yq::fail("the small-c tcgen05 flavour reads and writes plain tensors only");
-        return yq_tc_small_forward(l, l->tc_small, in_u8, out_u8, out_pool, out_f32, out_acc, batch, stream);
+        if (!plain_in) return yq::fail("the small-c tcgen05 flavour reads plain tensors only");
+        if (!plain_out && (out_pool || out_acc || l->quant_stop_flag)) return yq::fail("the small-c tcgen05 flavour: a halo-padded output comes without side outputs");
+        return yq_tc_small_forward(l, l->tc_small, in_u8, out_u8, out_pool, out_f32, out_acc, batch, stream, plain_out ? nullptr : out_geom);
     }
     if (out_pool || !out_u8) return yq::fail("the TMA tcgen05 flavour has no fused max-pool output");
     TcState *st = (TcState *)l->tc;

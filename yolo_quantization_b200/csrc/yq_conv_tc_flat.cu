@@ -416,14 +416,15 @@ int yq_tc_flat_eligible(const yq_conv_layer *l)
 {
     if (!l->int_form || !l->fused_mult) return 0;
     if (l->stride != 1 || !(l->size == 1 || l->size == 3) || l->pad != l->size / 2) return 0;
-    if (l->c != l->cs_in || l->cs_in % 64) return 0;            // no pad lanes: the halo fill would count in sum(a)
+    // no pad lanes: the halo fill would count in sum(a).  c = 32 (32-byte rows, SWIZZLE_32B, one K step per tap): flat2 only
+    if (l->c != l->cs_in || (l->cs_in % 64 && l->cs_in != 32)) return 0;
     if (l->cs_out < 32) return 0;
     return fl_get_encode() != nullptr;
 }
 
 int yq_tc_flat_supported(const yq_conv_layer *l)
 {
-    if (!yq_tc_flat_eligible(l)) return 0;
+    if (!yq_tc_flat_eligible(l) || l->cs_in % 64) return 0;
     if (128 + (l->size - 1) * (l->w + 2) > 256) return 0;       // the patch is one TMA box (<= 256 rows)
     return 1;
 }

@@ -15,7 +15,8 @@
 // Same tensors, geometry, arithmetic and epilogue as yq_conv_tc_flat.cu (flat halo-padded strips, row-shifted swizzled
 // descriptors per tap, integer-form requantize, halo positions rewritten with the consumer's zero point).
 // Warp roles (20 warps): 0 = TMA producer, 1 = MMA issuer, 2-3 = activation sums, 4-19 = epilogue (4 per TMEM lane quarter).
-// Restates convolutional_layer.c:694-751 for stride 1, pad = size/2, size in {1, 3}, c % 64 == 0, n % 128 == 0.
+// Restates convolutional_layer.c:694-751 for stride 1, pad = size/2, size in {1, 3}, c % 64 == 0 or c = 32 (KC = 32: 32-byte patch
+// rows, SWIZZLE_32B, one K = 32 MMA per tile and tap), n % 128 == 0 or n in {32, 64}.
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <string.h>
@@ -49,10 +50,12 @@ struct Flat2Args {
     int N, CSO;
     int B, H, W, NP;       // NP = B*(H+1)*(W+1)
     int size, taps, cpt /* KC-chunks per tap */, CS;
+    int tps;               // taps per weight stage (Flat2Smem)
     int q_off;             // first patch position relative to the pair's first position: -(pad*(W+1) + pad)
     int patch_rows, box_rows, n_boxes, a_stage_bytes, a_stages, b_stages;
     int plain;             // 1x1 only: the tensors are plain [B][H][W][C] strips (no halo positions: every p < NP is a pixel)
     int out_cols;          // bytes per position the launch stores: min(128, channel stride of the output); 32 / 64: narrow layers
+    int warp_cols;         // channels of a tile one epilogue warp requantises and stores: 64, or out_cols / 2 in narrow layers (all 16 warps work)
     int m_pairs, num_tiles;   // tile t -> (n-tile t / m_pairs, position pair t % m_pairs)
     uint32_t halo_word;
     uint32_t magic_w, magic_h, magic_m;
@@ -65,7 +68,10 @@ struct Flat2Args {
 
 template <int KC>
 struct Flat2Smem {
-    static constexpr int B_STAGE = F2_BN * KC;
+    // a weight stage holds `tps` taps: 1, or -- KC = 32, 3x3 -- one filter row of three (a tap is then a single K = 32 MMA per tile: with
+    // one tap per stage the tensor pipe would wait on the commits, which cannot follow each other faster than every ~358 clocks)
+    static constexpr int TAP_BYTES = F2_BN * KC;
+    static constexpr int B_STAGE = TAP_BYTES * (KC == 32 ? 3 : 1);
     static constexpr int OUT_BYTES = 128 * F2_BN;                 // one staging tile; there are two
     static constexpr int PARAM_BYTES = F2_BN * 24;
     static constexpr int SUM_BYTES = 2 * F2_MAX_ROWS * 4;         // S[pair buffer][patch row]
@@ -144,14 +150,15 @@ __global__ void __launch_bounds__(F2_THREADS, 1) conv_u8_tc_flat2_kernel(const _
                         tma_load_2d(sA + sa * a.a_stage_bytes + b * a.box_rows * KC, &tmA, &a_full[sa], c * KC, p0 + a.q_off + b * a.box_rows);
                 }
                 if (++sa == a.a_stages) { sa = 0; pha ^= 1; }
-                for (int tap = 0; tap < a.taps; ++tap) {
+                for (int tap = 0; tap < a.taps; tap += a.tps) {
                     mbar_wait(&b_empty[s], phb ^ 1);
                     if (elect_one()) {
                         if (a.debug == 1 && tap > 0) {
                             f2_arrive(&b_full[s]);
                         } else {
-                            mbar_expect_tx(&b_full[s], (uint32_t)(F2_BN * KC));
-                            tma_load_2d(sB + s * L::B_STAGE, &tmB, &b_full[s], tap * a.CS + c * KC, oc0);
+                            mbar_expect_tx(&b_full[s], (uint32_t)(a.tps * L::TAP_BYTES));
+                            for (int t = 0; t < a.tps; ++t)
+                                tma_load_2d(sB + s * L::B_STAGE + t * L::TAP_BYTES, &tmB, &b_full[s], (tap + t) * a.CS + c * KC, oc0);
                         }
                     }
                     if (++s == nbs) { s = 0; phb ^= 1; }
@@ -174,22 +181,24 @@ __global__ void __launch_bounds__(F2_THREADS, 1) conv_u8_tc_flat2_kernel(const _
                 mbar_wait(&a_full[sa], pha);
                 uint32_t tap_addr = smem_u32(sA + sa * a.a_stage_bytes);    // row-shifted descriptor start of the current tap
                 int kx = 0;
-                for (int tap = 0; tap < a.taps; ++tap) {
+                for (int tap = 0; tap < a.taps; tap += a.tps) {
                     mbar_wait(&b_full[s], phb);
                     tc_fence_after();
-                    if (elect_one()) {
-                        const uint64_t da0 = make_desc<KC>(tap_addr), da1 = make_desc<KC>(tap_addr + 128 * KC);
-                        const uint64_t db = make_desc<KC>(smem_u32(sB + s * L::B_STAGE));
+                    for (int t = 0; t < a.tps; ++t) {
+                        if (elect_one()) {
+                            const uint64_t da0 = make_desc<KC>(tap_addr), da1 = make_desc<KC>(tap_addr + 128 * KC);
+                            const uint64_t db = make_desc<KC>(smem_u32(sB + s * L::B_STAGE + t * L::TAP_BYTES));
 #pragma unroll
-                        for (int k = 0; k < KC / 32; ++k) {
-                            umma_i8(acc0, da0 + 2 * k, db + 2 * k, idesc, (k == 0) ? accumulate : 1u);
-                            umma_i8(acc1, da1 + 2 * k, db + 2 * k, idesc, (k == 0) ? accumulate : 1u);
+                            for (int k = 0; k < KC / 32; ++k) {
+                                umma_i8(acc0, da0 + 2 * k, db + 2 * k, idesc, (k == 0) ? accumulate : 1u);
+                                umma_i8(acc1, da1 + 2 * k, db + 2 * k, idesc, (k == 0) ? accumulate : 1u);
+                            }
+                            if (t + 1 == a.tps) umma_commit(&b_empty[s]);
                         }
-                        umma_commit(&b_empty[s]);
+                        accumulate = 1;
+                        tap_addr += KC;
+                        if (++kx == a.size) { kx = 0; tap_addr += row_step; }
                     }
-                    accumulate = 1;
-                    tap_addr += KC;
-                    if (++kx == a.size) { kx = 0; tap_addr += row_step; }
                     if (++s == nbs) { s = 0; phb ^= 1; }
                 }
                 if (elect_one()) umma_commit(&a_empty[sa]);
@@ -258,9 +267,9 @@ __global__ void __launch_bounds__(F2_THREADS, 1) conv_u8_tc_flat2_kernel(const _
         const bool side = SLOW && a.out_acc != nullptr;
         const int actm = yq::act_mode(a.ep.act);
         const int pitch = a.W + 1;
-        const int cbeg = half * 64;
-        const int nch = a.out_cols - cbeg >= 64 ? 4 : (a.out_cols - cbeg > 0 ? (a.out_cols - cbeg) / 16 : 0);   // 16-channel chunks of mine
-        const int rowb = a.out_cols >= 64 ? 64 : 32;                      // bytes per staging row = inner box of the store
+        const int cbeg = half * a.warp_cols;
+        const int nch = a.warp_cols / 16;                                // 16-channel chunks of mine
+        const int rowb = a.warp_cols;                                    // bytes per staging row = inner box of the store: 64, 32 or 16
         uint8_t *stage = sOut + ew * 2048;                               // [32 rows][rowb] in the store map's swizzle
         const int lr = lane;                                             // row within my staging slice
         int cur_nt = -1;
@@ -344,8 +353,8 @@ __global__ void __launch_bounds__(F2_THREADS, 1) conv_u8_tc_flat2_kernel(const _
                                     if (oc < a.N) a.out_acc[pix * a.CSO + oc] = (int)v[jj] + s_q[c0 + jj].y * nsa;
                                 }
                             }
-                            // 64-byte rows: SWIZZLE_64B (16-byte chunk ^ row bits 1-2); 32-byte rows: SWIZZLE_32B (chunk ^ row bit 2)
-                            const int sw = rowb == 64 ? (ch ^ ((lr >> 1) & 3)) : (ch ^ ((lr >> 2) & 1));
+                            // 64-byte rows: SWIZZLE_64B (16-byte chunk ^ row bits 1-2); 32-byte rows: SWIZZLE_32B (chunk ^ row bit 2); 16-byte rows: plain
+                            const int sw = rowb == 64 ? (ch ^ ((lr >> 1) & 3)) : (rowb == 32 ? (ch ^ ((lr >> 2) & 1)) : 0);     // (16-byte rows: no swizzle)
                             *reinterpret_cast<uint4 *>(stage + lr * rowb + sw * 16) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
                             if (ch + 1 < nch) tmem_ld_wait16(vbuf[h2 ^ 1]);
                         }
@@ -413,7 +422,9 @@ int f2_encode_2d(CUtensorMap *m, const void *ptr, uint64_t rows, int row_bytes, 
     cuuint32_t box[2] = {(cuuint32_t)box_c, (cuuint32_t)box_rows};
     cuuint32_t es[2] = {1, 1};
     CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void *>(ptr), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                     box_c >= 128 ? CU_TENSOR_MAP_SWIZZLE_128B : (box_c == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B), prom,
+                     box_c >= 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                  : (box_c == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : (box_c == 32 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_NONE)),
+                     prom,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return yq::fail("cuTensorMapEncodeTiled(%llu x %d, box %d x %d) failed: %d", (unsigned long long)rows, row_bytes, box_c, box_rows, (int)r);
     return 0;
@@ -481,7 +492,7 @@ int yq_tc_flat2_supported(const yq_conv_layer *l)
 int yq_tc_flat2_prepare(yq_conv_layer *l, void **state)
 {
     Flat2State *st = new Flat2State();
-    st->KC = (l->cs_in % 128) ? 64 : 128;
+    st->KC = (l->cs_in % 128) ? ((l->cs_in % 64) ? 32 : 64) : 128;
     st->n_pad = yq::round_up(l->n, F2_BN);
     const int taps = l->size * l->size;
     const size_t ktot = (size_t)taps * l->cs_in;
@@ -539,6 +550,9 @@ int yq_tc_flat2_forward(yq_conv_layer *l, void *state, const uint8_t *in_flat, u
     a.box_rows = yq::round_up((a.patch_rows + a.n_boxes - 1) / a.n_boxes, 8);
     a.a_stage_bytes = yq::round_up(a.n_boxes * a.box_rows * st->KC, 1024);
     a.out_cols = l->cs_out < F2_BN ? l->cs_out : F2_BN;
+    // narrow layers (n = 64 / 32): the two warps of a lane quarter and tile split the channels that exist, instead of one of them idling
+    static const bool split_narrow = !(getenv("YQ_FLAT2_NARROW_SPLIT") && !atoi(getenv("YQ_FLAT2_NARROW_SPLIT")));     // A/B measurements
+    a.warp_cols = a.out_cols >= F2_BN ? 64 : (split_narrow ? a.out_cols / 2 : (a.out_cols >= 64 ? 64 : 32));
     a.plain = plain ? 1 : 0;
     if (sc && sc->resid) {
         if (plain) return yq::fail("tcgen05 flat2 flavour: the fused shortcut needs flat tensors");
@@ -551,8 +565,8 @@ int yq_tc_flat2_forward(yq_conv_layer *l, void *state, const uint8_t *in_flat, u
         if (st->maps.size() > 64) st->maps.clear();
         CUtensorMap tmA, tmO;
         if (f2_encode_2d(&tmA, in_flat, (uint64_t)rows_alloc, l->cs_in, st->KC, a.box_rows, CU_TENSOR_MAP_L2_PROMOTION_L2_128B)) return -1;
-        // the store box is one epilogue warp's block: 32 positions x 64 channels (32 when the layer has no more)
-        if (f2_encode_2d(&tmO, out_flat, (uint64_t)rows_alloc, l->cs_out, a.out_cols >= 64 ? 64 : 32, 32, CU_TENSOR_MAP_L2_PROMOTION_L2_128B)) return -1;
+        // the store box is one epilogue warp's block: 32 positions x 64 channels (narrow layers: half of their channels, 32 or 16)
+        if (f2_encode_2d(&tmO, out_flat, (uint64_t)rows_alloc, l->cs_out, a.warp_cols, 32, CU_TENSOR_MAP_L2_PROMOTION_L2_128B)) return -1;
         it = st->maps.emplace(key, std::make_pair(tmA, tmO)).first;
     }
     a.ep = yq::make_epi(l);
@@ -560,6 +574,7 @@ int yq_tc_flat2_forward(yq_conv_layer *l, void *state, const uint8_t *in_flat, u
     a.N = l->n; a.CSO = l->cs_out;
     a.B = batch; a.H = l->h; a.W = l->w; a.NP = (int)NP;
     a.size = l->size; a.taps = l->size * l->size; a.cpt = l->cs_in / st->KC; a.CS = l->cs_in;
+    a.tps = (st->KC == 32 && l->size == 3) ? 3 : 1;
     a.q_off = -(pad * W1 + pad);
     a.halo_word = 0x01010101u * (uint32_t)(halo_fill & 0xff);
     {
@@ -575,5 +590,6 @@ int yq_tc_flat2_forward(yq_conv_layer *l, void *state, const uint8_t *in_flat, u
     if ((long long)a.num_tiles * a.m_pairs >= 0x100000000ll) return yq::fail("tcgen05 flat2 flavour: too many tiles for 32-bit tile arithmetic");
     const CUtensorMap &tmA = it->second.first, &tmO = it->second.second;
     if (st->KC == 128) return f2_launch<128>(st, tmA, tmO, a, stream);
+    if (st->KC == 32) return f2_launch<32>(st, tmA, tmO, a, stream);
     return f2_launch<64>(st, tmA, tmO, a, stream);
 }

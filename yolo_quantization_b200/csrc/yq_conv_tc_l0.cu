@@ -127,6 +127,21 @@ __device__ __forceinline__ void l0_ld_wait(uint32_t (&v0)[16], uint32_t (&v1)[16
                    "+r"(v1[12]), "+r"(v1[13]), "+r"(v1[14]), "+r"(v1[15])::"memory");
 }
 
+// one 16-lane half only (GROUPS = 4: a warp requantises ONE pooled row of its lane quarter)
+__device__ __forceinline__ void l0_ld1_issue(uint32_t taddr, uint32_t (&v)[16])
+{
+    asm volatile("tcgen05.ld.sync.aligned.16x256b.x4.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]),
+                   "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+                 : "r"(taddr));
+}
+__device__ __forceinline__ void l0_ld1_wait(uint32_t (&v)[16])
+{
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]), "+r"(v[8]), "+r"(v[9]), "+r"(v[10]),
+                   "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15])::"memory");
+}
+
 // four bytes -> one little-endian word on the multiplier pipe (the alu pipe is this kernel's bottleneck: PRMT lives there)
 __device__ __forceinline__ uint32_t l0_pack(const int (&r)[4])
 {
@@ -156,11 +171,11 @@ __device__ __forceinline__ int l0_window_slow(int bias, double mcd, int zo, int 
 // BULK: a warp stages its two pooled rows (2 x 512 B) in shared memory and one lane writes them with two bulk copies
 // (cp.async.bulk shared -> global) -- whole 512-byte runs instead of 16 predicated 4-byte stores per thread
 template <int NCH, int GROUPS, bool CHECKX, bool BULK, bool BIASF>
-__global__ void __launch_bounds__(128 * GROUPS + 64, 2) conv_u8_tc_l0_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ L0Args a)
+__global__ void __launch_bounds__((GROUPS == 1 ? 128 : 256) + 64, 2) conv_u8_tc_l0_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ L0Args a)
 {
     using L = L0Cfg<NCH>;
     static_assert(NCH == 16, "one 32-column chunk per pixel pair");
-    constexpr int NT = 128 * GROUPS;                    // epilogue threads; the two producer warps come after them
+    constexpr int NT = GROUPS == 1 ? 128 : 256;         // epilogue threads; the two producer warps come after them
     constexpr int NBUF = L::NBUF;
     extern __shared__ __align__(16) uint8_t smem_raw[];
     uint8_t *smem = smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u);
@@ -173,7 +188,7 @@ __global__ void __launch_bounds__(128 * GROUPS + 64, 2) conv_u8_tc_l0_kernel(con
 #ifdef YQ_L0_TRACE
     const unsigned long long tr_entry = l0_ns();
 #endif
-    const int t = threadIdx.x, warp = (t >> 5) & 3, grp = GROUPS == 2 ? (t >> 7) & 1 : 0, lane = t & 31;
+    const int t = threadIdx.x, warp = (t >> 5) & 3, grp = GROUPS >= 2 ? (t >> 7) & 1 : 0, lane = t & 31;
     const bool producer = t >= NT;
     const int qi = lane >> 2, qq = lane & 3;
 
@@ -181,7 +196,7 @@ __global__ void __launch_bounds__(128 * GROUPS + 64, 2) conv_u8_tc_l0_kernel(con
         for (int b = 0; b < NBUF; ++b) mbar_init(&full[b], 1);
         for (int b = 0; b < 2; ++b) {
             mbar_init(&acc_full[b], 1);
-            mbar_init(&acc_empty[b], 4);                // the four warps that read an accumulator
+            mbar_init(&acc_empty[b], GROUPS == 4 ? 8 : 4);      // the warps that read an accumulator
         }
         mbar_init(b_full, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -307,6 +322,93 @@ __global__ void __launch_bounds__(128 * GROUPS + 64, 2) conv_u8_tc_l0_kernel(con
             bias[g] = BIASF ? 0 : c.x; m2[g] = (uint32_t)c.z; sh[g] = c.w; zsh[g] = (uint32_t)a.zp_out << c.w;
         }
         const int zo = a.zp_out;
+        if constexpr (GROUPS == 4) {
+            // ---- window halves: warp (w, hv) requantises pooled row 2w + hv of EVERY tile (lanes 16 hv .. 16 hv + 15 of quarter w): both
+            // accumulators alternate, each drained by all eight warps in half the time, so one fills while the other drains
+            static_assert(BULK, "window halves store by bulk copy");
+            const int hv = grp;
+            const uint32_t tq = tmem_base + ((uint32_t)(warp * 32 + hv * 16) << 16);
+            uint8_t *const stage = smem + L::ST_OFF + (t >> 5) * 1024;      // two buffers of [32 pixels][16 channels]
+            const uint32_t st_thr = (uint32_t)(4 * qi * 16 + 4 * qq);
+            const uint32_t zo4 = (uint32_t)zo * 0x01010101u, qlim = 255u - (uint32_t)zo;
+            const uint32_t out_row = (uint32_t)(a.OWP * a.out_cs);
+#ifdef YQ_L0_TRACE
+            unsigned long long tr_acc[2] = {0, 0};
+            long long tr_prev = clock64();
+            const long long tr_c0 = tr_prev;
+#endif
+            int j = 0;
+#pragma unroll 1
+            for (int tile = first; tile < a.num_tiles; tile += step, ++j) {
+                const int acc = j & 1;
+                mbar_wait(&acc_full[acc], (uint32_t)((j >> 1) & 1));
+                L0TR_MARK(0);
+                tc_fence_after();
+                const uint32_t tqa = tq + (uint32_t)(acc * L::N);
+                uint8_t *const st = stage + (j & 1) * 512;
+                if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");      // the copy that read this buffer two tiles ago
+                __syncwarp();
+                uint32_t V[2][16];
+                l0_ld1_issue(tqa, V[0]);
+                l0_ld1_wait(V[0]);
+#pragma unroll
+                for (int pp = 0; pp < 4; ++pp) {
+                    if (pp + 1 < 4) l0_ld1_issue(tqa + 32 * (pp + 1), V[(pp + 1) & 1]);
+                    uint32_t(&v)[16] = V[pp & 1];
+                    int r[4];
+                    uint32_t orx = 0, orr = 0;
+#pragma unroll
+                    for (int g = 0; g < 4; ++g) {
+                        uint32_t x;
+                        if (BIASF) x = (uint32_t)max(max(max((int)v[4 * g], (int)v[4 * g + 1]), (int)v[4 * g + 2]), max((int)v[4 * g + 3], 0));
+                        else x = (uint32_t)max(max(max((int)v[4 * g], (int)v[4 * g + 1]), max((int)v[4 * g + 2], (int)v[4 * g + 3])) + bias[g], 0);
+                        r[g] = (int)(__umulhi(x, m2[g]) >> sh[g]);
+                        if (CHECKX) orx |= x;
+                        orr |= (uint32_t)r[g];
+                    }
+                    uint32_t w;
+                    // (the OR of the values bounds each of them: a conservative test, exact for zp_out = 0)
+                    if (orr > qlim || (CHECKX && orx >= a.xlim)) {
+#pragma unroll
+                        for (int g = 0; g < 4; ++g)
+                            r[g] = l0_window_slow(bias[g], a.mc[4 * qq + g], zo, (int)v[4 * g], (int)v[4 * g + 1], (int)v[4 * g + 2], (int)v[4 * g + 3]);
+                        w = l0_pack(r);
+                    } else {
+                        w = l0_pack(r) + zo4;      // no byte carries: every value is <= 255 - zp_out
+                    }
+                    *reinterpret_cast<uint32_t *>(st + st_thr + pp * 16) = w;
+                    if (pp + 1 < 4) {
+                        l0_ld1_wait(V[(pp + 1) & 1]);
+                        if (pp + 2 == 4) {       // this warp's TMEM reads of the tile are complete
+                            tc_fence_before();
+                            __syncwarp();
+                            if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&acc_empty[acc])) : "memory");
+                        }
+                    }
+                }
+                fence_proxy_async();      // the staged row (generic-proxy stores) -> visible to the bulk copy engine
+                __syncwarp();
+                if (lane == 0) {
+                    const TileXY cur = split_tile(tile);
+                    const int py = cur.ty * (L0_ROWS / 2) + 2 * warp + hv;
+                    const int npx = min(L0_TWPX / 2, a.PW - cur.tx * (L0_TWPX / 2));      // pooled pixels of this tile inside the image
+                    if (py < a.PH && !L0KNOB(8)) {
+                        uint8_t *g0 = a.out_pool + (size_t)((uint32_t)((cur.n * a.OHP + py + a.opad) * a.OWP + cur.tx * (L0_TWPX / 2) + a.opad) * (uint32_t)a.out_cs);
+                        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(g0), "r"(smem_u32(st)), "r"((uint32_t)(npx * 16)) : "memory");
+                    }
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                }
+                L0TR_MARK(1);
+            }
+            (void)out_row;
+#ifdef YQ_L0_TRACE
+            if (t == 0 && blockIdx.x < 1024) {
+                unsigned long long *q = yq_l0_trace + blockIdx.x * 16;
+                q[8] = tr_acc[0]; q[9] = tr_acc[1]; q[10] = (unsigned long long)j; q[11] = (unsigned long long)(clock64() - tr_c0);
+            }
+#endif
+            if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+        } else {
         const uint32_t tq = tmem_base + ((uint32_t)(warp * 32) << 16);
         const uint32_t out_thr = (uint32_t)(((2 * warp + a.opad) * a.OWP + 4 * qi + a.opad) * a.out_cs + 4 * qq);
         const uint32_t out_row = (uint32_t)(a.OWP * a.out_cs);
@@ -425,6 +527,7 @@ __global__ void __launch_bounds__(128 * GROUPS + 64, 2) conv_u8_tc_l0_kernel(con
         }
 #endif
         if (BULK && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");      // the rows are in global memory before the grid may count as complete
+        }
     }
     tc_fence_before();
     __syncthreads();
@@ -487,7 +590,7 @@ int l0_launch(const CUtensorMap &tmA, const L0Args &a, cudaStream_t stream)
         YQ_CUDA(cudaFuncGetAttributes(&fa, kern));
         // counted by hand: the occupancy API answers 1 for kernels that allocate tensor memory
         const int by_smem = yq::device_smem_per_sm() / (smem + 1024 + (int)fa.sharedSizeBytes);
-        const int by_regs = 65536 / (((fa.numRegs + 7) / 8 * 8) * (128 * SPLIT + 64));
+        const int by_regs = 65536 / (((fa.numRegs + 7) / 8 * 8) * ((SPLIT == 1 ? 128 : 256) + 64));
         const int by_tmem = 512 / L::TMEM_COLS;
         int occ = by_smem < by_regs ? by_smem : by_regs;
         if (by_tmem < occ) occ = by_tmem;
@@ -498,7 +601,7 @@ int l0_launch(const CUtensorMap &tmA, const L0Args &a, cudaStream_t stream)
     }
     int grid = n_sm * ctas_per_sm;
     if (grid > a.num_tiles) grid = a.num_tiles;
-    YQ_CUDA(yq::launch_pdl(kern, dim3(grid), dim3(128 * SPLIT + 64), smem, stream, tmA, a));
+    YQ_CUDA(yq::launch_pdl(kern, dim3(grid), dim3((SPLIT == 1 ? 128 : 256) + 64), smem, stream, tmA, a));
     return 0;
 }
 
@@ -629,12 +732,13 @@ int yq_tc_l0_forward(yq_conv_layer *l, void *state, const uint8_t *in_planes, ui
     // form of the kernel: defaults from measurements on B200 (profiles/README.md); YQ_L0_GROUPS = 1 / 2 and YQ_L0_BULK = 0 / 1 force
     static const int groups_env = getenv("YQ_L0_GROUPS") ? atoi(getenv("YQ_L0_GROUPS")) : -1;
     static const int bulk_env = getenv("YQ_L0_BULK") ? atoi(getenv("YQ_L0_BULK")) : -1;
-    const int groups = groups_env < 0 ? 2 : (groups_env == 1 ? 1 : 2);
+    const int groups = groups_env < 0 ? 2 : (groups_env == 1 ? 1 : groups_env == 2 ? 2 : 4);
     const bool bulk = bulk_env < 0 ? true : bulk_env != 0;
     const CUtensorMap &tm = it->second;
 #define YQ_L0(G_, B_)                                                                                                                   \
     (st->biasf ? (st->checkx ? l0_launch<16, G_, true, B_, true>(tm, a, stream) : l0_launch<16, G_, false, B_, true>(tm, a, stream))    \
                : (st->checkx ? l0_launch<16, G_, true, B_, false>(tm, a, stream) : l0_launch<16, G_, false, B_, false>(tm, a, stream)))
+    if (groups == 4) return YQ_L0(4, true);
     if (groups == 2) return bulk ? YQ_L0(2, true) : YQ_L0(2, false);
     return bulk ? YQ_L0(1, true) : YQ_L0(1, false);
 #undef YQ_L0

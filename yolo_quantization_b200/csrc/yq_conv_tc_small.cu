@@ -42,6 +42,7 @@ struct SmallArgs {
     yq::EpiParams ep;
     int B, H, W, C, OH, OW, N, CSO, stride, pad, zp_in;
     int tiles_x, tiles_y, num_tiles, PH, PW;
+    int OHP, OWP, opad;    // geometry of the conv output tensor (rows per image, pixels per row, halo width): OH, OW, 0 when plain
     // per-channel parameters live in kernel-parameter (constant-bank) space: with the channel loop fully unrolled
     // they become immediate constant operands of the epilogue's IMAD / SHF instructions (no loads, no registers)
     int4 cq[64];       // {bias, zw, 2*M0, shift}
@@ -168,7 +169,7 @@ __global__ void __launch_bounds__(SM_THREADS, (CS == 32 ? 2 : (CS == 16 ? 4 : 6)
     // index arithmetic = per-thread constant part (computed once) + per-tile uniform part
     const int thr_in_off = (hi * a.stride * a.W + wi * a.stride) * CS;
     const int row_pitch = a.W * CS;
-    const int thr_out_off = (hi * a.OW + wi) * a.CSO;
+    const int thr_out_off = (hi * a.OWP + wi) * a.CSO;
     const int thr_pool_off = ((hi >> 1) * a.PW + (wi >> 1)) * a.CSO;
     uint8_t *const sA_thr = smem + L::A_OFF + r * 32;
 
@@ -399,7 +400,7 @@ __global__ void __launch_bounds__(SM_THREADS, (CS == 32 ? 2 : (CS == 16 ? 4 : 6)
         const bool valid = ox < a.OW && oy < a.OH;
         const uint32_t tacc = trow + b * (BN + 16);
         const int nsa = -(int)tmem_ld1(tacc + BN);   // minus the pixel's activation sum (ones-tile columns)
-        uint8_t *const orow = a.out + ((size_t)(tn * a.OH + tty * TILE_H) * a.OW + ttx * TILE_W) * a.CSO + thr_out_off;
+        uint8_t *const orow = a.out + ((size_t)(tn * a.OHP + tty * TILE_H + a.opad) * a.OWP + ttx * TILE_W + a.opad) * a.CSO + thr_out_off;
         // fused 2x2 stride-2 max-pool: partners are lane^1 (x neighbour) and lane^16 (next row); out-of-image pixels count as 0
         uint8_t *const prow = a.out_pool + ((size_t)(tn * a.PH + tty * (TILE_H / 2)) * a.PW + ttx * (TILE_W / 2)) * a.CSO + thr_pool_off;
         const bool pool_writer = a.out_pool && ((lane & 17) == 0) && (ox >> 1) < a.PW && (oy >> 1) < a.PH;
@@ -577,7 +578,7 @@ void yq_tc_small_free(void *state)
 }
 
 int yq_tc_small_forward(yq_conv_layer *l, void *state, const uint8_t *in_u8, uint8_t *out_u8, uint8_t *out_pool, float *out_f32,
-                        int32_t *out_acc, int batch, cudaStream_t stream)
+                        int32_t *out_acc, int batch, cudaStream_t stream, const yq_act_geom *out_geom)
 {
     SmallState *st = (SmallState *)state;
     SmallArgs a;
@@ -586,6 +587,8 @@ int yq_tc_small_forward(yq_conv_layer *l, void *state, const uint8_t *in_u8, uin
     a.ep = yq::make_epi(l);
     a.B = batch; a.H = l->h; a.W = l->w; a.C = l->c; a.OH = l->out_h; a.OW = l->out_w; a.N = l->n; a.CSO = l->cs_out;
     a.stride = l->stride; a.pad = l->pad; a.zp_in = l->zp_in;
+    // the conv output may be a halo-padded tensor (only its interior is written); the pooled output stays plain
+    a.OHP = out_geom ? out_geom->rows_h : l->out_h; a.OWP = out_geom ? out_geom->pitch_w : l->out_w; a.opad = out_geom ? out_geom->pad : 0;
     a.tiles_x = (l->out_w + TILE_W - 1) / TILE_W;
     a.tiles_y = (l->out_h + TILE_H - 1) / TILE_H;
     a.num_tiles = a.tiles_x * a.tiles_y * batch;

@@ -595,6 +595,7 @@ extern "C" int yq_forward_convolutional_layer_quant_per_image_gpu(yq_conv_layer 
 }
 
 extern "C" int yq_conv_geom_supported(const yq_conv_layer *l) { return l && yq_tc_geom_supported(l) ? 1 : 0; }
+extern "C" int yq_conv_out_geom_supported(const yq_conv_layer *l) { return l && (yq_tc_geom_supported(l) || yq_tc_out_geom_supported(l)) ? 1 : 0; }
 // 1: yq_forward_convolutional_layer_quant_gpu runs this (1x1) layer on conv_u8_tc_flat2_kernel in its plain-tensor mode
 int yq_conv_plain_1x1_fast(const yq_conv_layer *l)
 {
@@ -610,6 +611,12 @@ extern "C" int yq_forward_convolutional_layer_quant_geom_gpu(yq_conv_layer *l, c
     const bool plain_in = !in_geom || (in_geom->pad == 0 && in_geom->pitch_w == l->w && in_geom->rows_h == l->h);
     const bool plain_out = !out_geom || (out_geom->pad == 0 && out_geom->pitch_w == l->out_w && out_geom->rows_h == l->out_h);
     if (plain_in && plain_out) return yq_forward_convolutional_layer_quant_pool_gpu(l, in_u8, out_u8, nullptr, out_f32, out_acc, batch, stream);
+    if (plain_in && yq_tc_out_geom_supported(l) && !out_acc) {
+        // the small-c flavour's threads store their pixels themselves: any output geometry
+        if (out_geom->pad < 0 || out_geom->pitch_w < l->out_w + out_geom->pad || out_geom->rows_h < l->out_h + out_geom->pad)
+            return yq::fail("output geometry does not hold a %dx%d tensor", l->out_h, l->out_w);
+        return yq_tc_forward(l, in_u8, out_u8, nullptr, out_f32, out_acc, batch, (cudaStream_t)stream, nullptr, -1, out_geom);
+    }
     if (!yq_tc_geom_supported(l)) return yq::fail("this layer's kernel flavour takes plain tensors only (see yq_conv_geom_supported)");
     if (in_geom && (in_geom->pad < 0 || in_geom->pitch_w < l->w + in_geom->pad || in_geom->rows_h < l->h + in_geom->pad))
         return yq::fail("input geometry does not hold a %dx%d tensor", l->h, l->w);
@@ -775,6 +782,32 @@ __global__ void maxpool_u8_kernel(const V *__restrict__ in, V *__restrict__ out,
     }
 }
 
+// The two pools of the reference's cfgs (size 2, stride 2 or 1) over 16-channel vectors with a power-of-two number of vectors per
+// pixel: grid (x blocks, output row, image) -- no division anywhere, the four taps' row bases are block-uniform, every thread does
+// four loads, twelve byte-wise maxima and one store.  (The generic kernel above spent ~380 instructions per thread on index
+// arithmetic and its runtime-sized tap loops: with the tensors resident in L2 it was instruction-bound at 10 % of the L2's
+// throughput -- ncu, warm caches: 10.3 / 12.3 us for layers 9 / 11 of yolov3-tiny.)
+template <int STRIDE>
+__global__ void __launch_bounds__(256) maxpool2_u8_kernel(const uint4 *__restrict__ in, uint4 *__restrict__ out, int H, int W, int OW, int vshift, int off,
+                                                          Geo gi, Geo go)
+{
+    yq_pdl_wait_then_release();
+    const int n = blockIdx.z, oy = blockIdx.y;
+    const int j = blockIdx.x * 256 + threadIdx.x;
+    if (j >= (OW << vshift)) return;
+    const int ox = j >> vshift, v = j & ((1 << vshift) - 1);
+    const int y0 = off + oy * STRIDE, x0 = off + ox * STRIDE;
+    const uint4 *r0 = in + ((((size_t)n * gi.rows + y0 + gi.pad) * gi.pitch + gi.pad) << vshift);
+    const uint4 *r1 = r0 + ((size_t)gi.pitch << vshift);
+    const bool ya = y0 >= 0 && y0 < H, yb = y0 + 1 >= 0 && y0 + 1 < H;
+    const bool xa = x0 >= 0 && x0 < W, xb = x0 + 1 >= 0 && x0 + 1 < W;
+    const int o0 = x0 * (1 << vshift) + v, o1 = o0 + (1 << vshift);
+    const uint4 z = make_uint4(0, 0, 0, 0);
+    const uint4 t00 = ya && xa ? __ldg(r0 + o0) : z, t01 = ya && xb ? __ldg(r0 + o1) : z;
+    const uint4 t10 = yb && xa ? __ldg(r1 + o0) : z, t11 = yb && xb ? __ldg(r1 + o1) : z;
+    out[((((size_t)n * go.rows + oy + go.pad) * go.pitch + ox + go.pad) << vshift) + v] = vmax16(vmax16(t00, t01), vmax16(t10, t11));
+}
+
 // launch shape for the row-per-block kernels: rows x ceil(per_row / threads) blocks
 static inline void row_launch_shape(int rows, int per_row, dim3 *grid, int *threads)
 {
@@ -802,7 +835,17 @@ extern "C" int yq_forward_maxpool_layer_quant_geom_gpu(const uint8_t *in, const 
     const int off = -pad / 2;
     dim3 grid;
     int threads;
-    if (cs % 16 == 0) {
+    const int vpp16 = cs / 16;
+    static const bool lean_off = getenv("YQ_POOL_LEAN") && !atoi(getenv("YQ_POOL_LEAN"));     // A/B measurements
+    if (!lean_off && cs % 16 == 0 && (vpp16 & (vpp16 - 1)) == 0 && size == 2 && (stride == 1 || stride == 2) && oh <= 65535 && batch <= 65535) {
+        int vshift = 0;
+        while ((1 << vshift) < vpp16) ++vshift;
+        const dim3 g2((unsigned)((ow * vpp16 + 255) / 256), (unsigned)oh, (unsigned)batch);
+        if (stride == 2)
+            YQ_CUDA(yq::launch_pdl(maxpool2_u8_kernel<2>, g2, dim3(256), 0, (cudaStream_t)stream, (const uint4 *)in, (uint4 *)out, h, w, ow, vshift, off, gi, go));
+        else
+            YQ_CUDA(yq::launch_pdl(maxpool2_u8_kernel<1>, g2, dim3(256), 0, (cudaStream_t)stream, (const uint4 *)in, (uint4 *)out, h, w, ow, vshift, off, gi, go));
+    } else if (cs % 16 == 0) {
         row_launch_shape(batch * oh, ow * (cs / 16), &grid, &threads);
         YQ_CUDA(yq::launch_pdl(maxpool_u8_kernel<uint4>, grid, dim3(threads), 0, (cudaStream_t)stream, (const uint4 *)in, (uint4 *)out, h, w, oh, ow, cs / 16, size,
                                stride, off, gi, go));

@@ -101,6 +101,7 @@ struct Layer {
     int Ka = 0, Kb = 0;        // shortcut (extension): round(s_prev / s_out * 2^16), round(s_from / s_out * 2^16)
     int zp_a = 0, zp_b = 0;    // shortcut: zero points of the previous layer's and the `from` layer's outputs
     bool use_geom = false;     // conv: per-tap TMA flavour between tensors of any geometry (yq_forward_convolutional_layer_quant_geom_gpu)
+    bool use_outgeom = false;  // conv: plain input, halo-padded output (the small-c flavour through the same entry point)
     int classes = 0, n_anchors = 0;
     std::vector<float> anchor_w, anchor_h;   // yolo: anchors selected by mask (l.biases[2*mask[n]], [2*mask[n]+1])
     // quantisation state as in `struct layer`
@@ -472,7 +473,9 @@ void plan(yq_network *net)
                 need(l.src, 1, nullptr, -1);
                 const bool fuses = net->fusion && i + 1 < n && net->layers[i + 1].type == L_MAXPOOL && net->layers[i + 1].size == 2 &&
                                    net->layers[i + 1].stride == 2 && net->layers[i + 1].pad == 1 && yq_conv_can_fuse_maxpool(l.conv);
-                need(i, 1, nullptr, -1);
+                // (the small-c flavour's threads store their pixels themselves: its conv output may take whatever geometry the
+                // consumers ask for -- a stride-2 c = 32 layer in front of flat convolutions writes the flat strip directly)
+                if (fuses || net->keep_acc || !yq_conv_out_geom_supported(l.conv)) need(i, 1, nullptr, -1);
                 if (fuses) need(i + 1, 1, nullptr, -1);
             }
         }
@@ -497,12 +500,19 @@ void plan(yq_network *net)
                 changed = true;
             }
         }
+        if (getenv("YQ_DEBUG_PLAN"))
+            for (int i = 0; i < n && i < 12; ++i)
+                if (net->layers[i].type == L_CONV)
+                    fprintf(stderr, "yq plan pass %d layer %d: rows %d flat %d plain1 %d | src tensor %d kind %d conflict %d fill %d | own kind %d conflict %d\n", pass, i, rows_ok[i],
+                            flat_ok[i], plain1_ok[i], tensor_of(net, net->layers[i].src), req[tensor_of(net, net->layers[i].src) + 1].kind,
+                            (int)req[tensor_of(net, net->layers[i].src) + 1].conflict, req[tensor_of(net, net->layers[i].src) + 1].fill, req[tensor_of(net, i) + 1].kind,
+                            (int)req[tensor_of(net, i) + 1].conflict);
         if (!changed) break;
     }
     // ---- apply
     for (int i = 0; i < n; ++i) {
         Layer &l = net->layers[i];
-        l.fuse_pool = l.fused_away = l.use_rows = l.use_flat = l.use_geom = l.fuse_yolo = l.fuse_shortcut = l.fuse_up = l.side = false;
+        l.fuse_pool = l.fused_away = l.use_rows = l.use_flat = l.use_geom = l.use_outgeom = l.fuse_yolo = l.fuse_shortcut = l.fuse_up = l.side = false;
         l.geom = yq_act_geom{0, l.out_w, l.out_h};
         l.halo_fill = 0;
     }
@@ -560,6 +570,7 @@ void plan(yq_network *net)
                 Layer &p = net->layers[i + 1];
                 if (p.type == L_MAXPOOL && p.size == 2 && p.stride == 2 && p.pad == 1) l.fuse_pool = p.fused_away = true;
             }
+            if (!l.use_geom && !l.fuse_pool && !plain1_ok[i] && !(l.geom.pad == 0 && l.geom.pitch_w == l.out_w && l.geom.rows_h == l.out_h)) l.use_outgeom = true;
         }
         if (l.fused_away || (l.type == L_ROUTE && l.inputs.size() == 1)) continue;
         ++launches;
@@ -689,6 +700,8 @@ int forward_body(yq_network *net, const uint8_t *in_u8_nchw, int *launches, bool
                 if (yq_forward_convolutional_layer_quant_geom_gpu(l.conv, cur, cur_geom, cur_geom->pad ? cur_fill : -1, l.out_u8, &l.geom, l.out_f32,
                                                                   net->keep_acc ? l.out_acc : nullptr, net->batch, st))
                     return -1;
+            } else if (l.use_outgeom) {
+                if (yq_forward_convolutional_layer_quant_geom_gpu(l.conv, cur, nullptr, -1, l.out_u8, &l.geom, l.out_f32, nullptr, net->batch, st)) return -1;
             } else if (l.fuse_pool) {
                 uint8_t *conv_out = conv_output_needed(net, (int)i) ? l.out_u8 : nullptr;
                 if (yq_forward_convolutional_layer_quant_pool_gpu(l.conv, cur, conv_out, net->layers[i + 1].out_u8, l.out_f32,
