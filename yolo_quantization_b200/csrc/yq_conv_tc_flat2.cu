@@ -106,6 +106,7 @@ __global__ void __launch_bounds__(F2_THREADS, 1) conv_u8_tc_flat2_kernel(const _
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int chunks = a.cpt, nbs = a.b_stages;
+    const int tps = KC == 32 ? a.tps : 1;      // (a compile-time 1 for the wide layers: their tap loops stay as tight as they were)
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < F2_ASTAGES; ++s) {
@@ -150,14 +151,14 @@ __global__ void __launch_bounds__(F2_THREADS, 1) conv_u8_tc_flat2_kernel(const _
                         tma_load_2d(sA + sa * a.a_stage_bytes + b * a.box_rows * KC, &tmA, &a_full[sa], c * KC, p0 + a.q_off + b * a.box_rows);
                 }
                 if (++sa == a.a_stages) { sa = 0; pha ^= 1; }
-                for (int tap = 0; tap < a.taps; tap += a.tps) {
+                for (int tap = 0; tap < a.taps; tap += tps) {
                     mbar_wait(&b_empty[s], phb ^ 1);
                     if (elect_one()) {
                         if (a.debug == 1 && tap > 0) {
                             f2_arrive(&b_full[s]);
                         } else {
-                            mbar_expect_tx(&b_full[s], (uint32_t)(a.tps * L::TAP_BYTES));
-                            for (int t = 0; t < a.tps; ++t)
+                            mbar_expect_tx(&b_full[s], (uint32_t)(tps * L::TAP_BYTES));
+                            for (int t = 0; t < tps; ++t)
                                 tma_load_2d(sB + s * L::B_STAGE + t * L::TAP_BYTES, &tmB, &b_full[s], (tap + t) * a.CS + c * KC, oc0);
                         }
                     }
@@ -181,10 +182,10 @@ __global__ void __launch_bounds__(F2_THREADS, 1) conv_u8_tc_flat2_kernel(const _
                 mbar_wait(&a_full[sa], pha);
                 uint32_t tap_addr = smem_u32(sA + sa * a.a_stage_bytes);    // row-shifted descriptor start of the current tap
                 int kx = 0;
-                for (int tap = 0; tap < a.taps; tap += a.tps) {
+                for (int tap = 0; tap < a.taps; tap += tps) {
                     mbar_wait(&b_full[s], phb);
                     tc_fence_after();
-                    for (int t = 0; t < a.tps; ++t) {
+                    for (int t = 0; t < tps; ++t) {
                         if (elect_one()) {
                             const uint64_t da0 = make_desc<KC>(tap_addr), da1 = make_desc<KC>(tap_addr + 128 * KC);
                             const uint64_t db = make_desc<KC>(smem_u32(sB + s * L::B_STAGE + t * L::TAP_BYTES));
@@ -193,7 +194,7 @@ __global__ void __launch_bounds__(F2_THREADS, 1) conv_u8_tc_flat2_kernel(const _
                                 umma_i8(acc0, da0 + 2 * k, db + 2 * k, idesc, (k == 0) ? accumulate : 1u);
                                 umma_i8(acc1, da1 + 2 * k, db + 2 * k, idesc, (k == 0) ? accumulate : 1u);
                             }
-                            if (t + 1 == a.tps) umma_commit(&b_empty[s]);
+                            if (t + 1 == tps) umma_commit(&b_empty[s]);
                         }
                         accumulate = 1;
                         tap_addr += KC;

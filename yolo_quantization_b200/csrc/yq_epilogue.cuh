@@ -25,7 +25,9 @@
 //      max|x| over a chunk of outputs and re-does the chunk with form (A) in the (rare) case the bound is
 //      exceeded, so the result is bit-identical for every input.
 //      LEAKY's round(q*0.1) for q < 0 equals -((|q|+5)/10) exactly (the double product is q/10 + O(2^-22)
-//      and ties round away from zero either way), i.e. umulhi(|q|+5, 0xCCCCCCCD) >> 3.
+//      and ties round away from zero either way), i.e. umulhi(|q|+5, 0xCCCCCCCD) >> 3 -- or, while |q| + 5 < 81920,
+//      (|q| * 52429 + 262145) >> 19: one multiply-add on the light multiplier pipe instead of an add and a 64-bit-product multiply.
+//      make_epi() lowers xlim for LEAKY layers so that |x| < xlim implies that range; beyond it the chunk is redone in form (A).
 #pragma once
 #include <stdint.h>
 
@@ -67,10 +69,25 @@ static inline uint32_t requant_exact_limit(const yq_conv_layer *l)
     return lim;
 }
 
+// LEAKY: the epilogue divides h = trunc(|x| * M) by ten as (h * 52429 + 262145) >> 19, which is floor((h + 5) / 10) while h + 5 < 81920.
+// Largest power of two P <= lim such that |x| < P keeps every channel's h = (|x| * 2 M0) >> (32 + s) at or below 81914.
+static inline uint32_t leaky_div10_limit(const yq_conv_layer *l, uint32_t lim)
+{
+    for (int oc = 0; oc < l->n; ++oc) {
+        const unsigned __int128 z = (uint32_t)l->host_chanq[(size_t)oc * 4 + 2];
+        const int w = l->host_chanq[(size_t)oc * 4 + 3];
+        if (!z) continue;
+        const unsigned __int128 top = ((unsigned __int128)81915 << (32 + w)) - 1;      // (|x| * z) >> (32 + w) <= 81914  <=>  |x| * z <= top
+        while (lim > 1 && (unsigned __int128)(lim - 1) * z > top) lim >>= 1;
+    }
+    return lim;
+}
+
 static inline EpiParams make_epi(const yq_conv_layer *l)
 {
     EpiParams e;
     e.xlim = l->int_form ? requant_exact_limit(l) : (1u << 22);
+    if (l->int_form && l->activation == YQ_LEAKY) e.xlim = leaky_div10_limit(l, e.xlim);
     e.bias = l->bias; e.zw = l->zw; e.mcomb = l->mcomb; e.mval = l->mval; e.rsh = l->rsh; e.chanq = (const int4 *)l->chanq;
     e.fused = l->fused_mult; e.act = l->activation; e.zp_out = l->zp_out; e.saturate = l->saturate; e.s_out = l->s_out;
     return e;
@@ -152,8 +169,9 @@ __device__ __forceinline__ int act_value(int q, int zo)
 // the chunk's values BEFORE the uint8 store (the caller packs their low bytes, or feeds them to a fused quantized shortcut)
 template <int ACTM, bool SAT, int NV, bool HAS_EXTRA>
 __device__ __forceinline__ void requant_chunk_vals(const uint32_t (&v)[NV], int nsa, const int (&extra)[NV], const int4 *cq, const double *mc,
-                                                   int zo, int (&r)[NV], uint32_t xlim = 1u << 22)
+                                                   int zo, int (&r)[NV], uint32_t xlim)
 {
+    // xlim is a power of two: the OR of the magnitudes reaches it exactly when one of them does (two per LOP3 instead of one VIMNMX each)
     uint32_t mx = 0;
 #pragma unroll
     for (int j = 0; j < NV; ++j) {
@@ -164,15 +182,15 @@ __device__ __forceinline__ void requant_chunk_vals(const uint32_t (&v)[NV], int 
         int q;
         if (ACTM == 0) {
             const uint32_t xp = (uint32_t)max(x, 0);
-            mx = max(mx, xp);
+            mx |= xp;
             q = (int)(__umulhi(xp, (uint32_t)c.z) >> c.w);
         } else {
             const uint32_t ax = (uint32_t)abs(x);
-            mx = max(mx, ax);
+            mx |= ax;
             const int h = (int)(__umulhi(ax, (uint32_t)c.z) >> c.w);
             if (ACTM == 2) {
                 // LEAKY from the magnitude: x < 0 -> zo - round(h / 10) (half away from zero), else zo + h; one select, no second sign test
-                const int t = (int)(__umulhi((uint32_t)h + 5u, 0xCCCCCCCDu) >> 3);
+                const int t = (int)(((uint32_t)h * 52429u + 262145u) >> 19);      // floor((h + 5) / 10): h <= 81914 whenever |x| < xlim (make_epi)
                 int rr = x < 0 ? zo - t : zo + h;
                 if (SAT) rr = max(0, min(255, rr));
                 r[j] = rr;
@@ -199,7 +217,7 @@ __device__ __forceinline__ void requant_chunk_vals(const uint32_t (&v)[NV], int 
 
 template <int ACTM, bool SAT, int NV, bool HAS_EXTRA>
 __device__ __forceinline__ void requant_chunk(const uint32_t (&v)[NV], int nsa, const int (&extra)[NV], const int4 *cq, const double *mc,
-                                              int zo, uint32_t (&packed)[NV / 4], uint32_t xlim = 1u << 22)
+                                              int zo, uint32_t (&packed)[NV / 4], uint32_t xlim)
 {
     int r[NV];
     requant_chunk_vals<ACTM, SAT, NV, HAS_EXTRA>(v, nsa, extra, cq, mc, zo, r, xlim);
