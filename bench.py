@@ -470,7 +470,7 @@ def main():
         for i, li in enumerate(infos):
             ops, byts = layer_work(li, B, conv_written=False)   # production plan: fused convs write the pooled tensor only
             t_ms = float(lm[i + 1])
-            if t_ms <= 0 or (li.type in (1, 3, 4) and li.fused):    # a fused-away max-pool / upsample / yolo layer has no launch of its own
+            if t_ms <= 0 or (li.type in (1, 3, 4, 5) and li.fused):    # a fused-away max-pool / upsample / yolo / shortcut layer has no launch of its own
                 continue
             t_tc = ops / (p_int8 * 1e12) * 1e3
             t_mem = byts / (pk["hbm_gbs"] * 1e9) * 1e3
