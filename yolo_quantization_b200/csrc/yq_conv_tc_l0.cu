@@ -48,26 +48,42 @@ constexpr int L0_AROWS = L0_ROWS + 2;   // input rows of a tile
 constexpr int L0_SCOLS = 96;            // staged bytes per plane row: x0 - 16 .. x0 + 79 (the tile reads x0 - 1 .. x0 + 64 = bytes 15 .. 80)
 constexpr int L0_AROWB = 256;           // operand bytes per input row: [chunk 0: 8 segments x 16 B][chunk 1: 8 segments x 16 B]
 
-template <int NCH>
+// Forms of the kernel (GROUPS): 1 = one epilogue group (4 warps), 2 = two groups, group g owns accumulator g, 4 = two warp sets splitting
+// every tile by pooled row ("window halves"); all three: two producer warps, two accumulators (256 TMEM columns), two CTAs per SM.
+// 3 = THREE groups over FOUR accumulators with four producer warps, one CTA per SM: tile `it` goes to accumulator it % 4 and group
+// it % 3, so a group that finishes a tile finds its next accumulator already filled (with as many groups as accumulators -- form 2 --
+// group and producer wait for each other a quarter of their time)
+template <int GROUPS>
+struct L0Mode {
+    static constexpr int NGRP = GROUPS == 3 ? 3 : (GROUPS == 1 ? 1 : 2);      // epilogue warp sets of four warps
+    static constexpr int NPROD = GROUPS == 3 ? 4 : 2;                          // producer warps = accumulators
+    static constexpr int NACC = NPROD;
+    static constexpr int MINB = GROUPS == 3 ? 1 : 2;                           // CTAs per SM
+    static constexpr int NT = 128 * NGRP;                                      // epilogue threads; the producer warps come after them
+    static constexpr int THREADS = NT + 32 * NPROD;
+};
+
+template <int NCH, int GROUPS>
 struct L0Cfg {
+    using M = L0Mode<GROUPS>;
     static constexpr int N = 8 * NCH;                         // MMA N = TMEM columns of one accumulator
     static_assert(N % 16 == 0 && N <= 256, "kind::i8 N");
-    static constexpr int TMEM_COLS = 2 * N;                   // two accumulators
+    static constexpr int TMEM_COLS = M::NACC * N;
     static_assert(TMEM_COLS == 256 || TMEM_COLS == 512, "power of two");
     static constexpr int NMMA = 6;                            // 2 signed blocks x 3 filter rows
     static constexpr int BSUB = N * 32;
     static constexpr int B_BYTES = NMMA * BSUB;
     static constexpr int A_STRIDE = L0_AROWS * L0_AROWB;      // 4608
-    static constexpr int NA = 4;                              // operand tiles (two per producer warp)
-    static constexpr int NBUF = 4;                            // staging slots (two per producer warp)
+    static constexpr int NA = 2 * M::NPROD;                   // operand tiles (two per producer warp)
+    static constexpr int NBUF = 2 * M::NPROD;                 // staging slots (two per producer warp)
     static constexpr int S_BYTES = 3 * L0_AROWS * L0_SCOLS;   // 5184: what TMA delivers per tile
     static constexpr int S_STRIDE = (S_BYTES + 127) / 128 * 128;
     static constexpr int A_OFF = 0;
     static constexpr int S_OFF = NA * A_STRIDE;
     static constexpr int B_OFF = S_OFF + NBUF * S_STRIDE;
-    static constexpr int ST_OFF = B_OFF + B_BYTES;            // BULK: 8 epilogue warps x 2 buffers x [2 pooled rows][32 pixels][16 channels]
-    static constexpr int BAR_OFF = ST_OFF + 8 * 2 * 1024;
-    static constexpr int TOTAL = BAR_OFF + 128;
+    static constexpr int ST_OFF = B_OFF + B_BYTES;            // BULK: epilogue warps x 2 buffers x [2 pooled rows][32 pixels][16 channels]
+    static constexpr int BAR_OFF = ST_OFF + 4 * M::NGRP * 2 * 1024;
+    static constexpr int TOTAL = BAR_OFF + 256;
     static_assert(S_OFF % 128 == 0 && B_OFF % 128 == 0 && BAR_OFF % 8 == 0, "alignment");
 };
 
@@ -171,34 +187,37 @@ __device__ __forceinline__ int l0_window_slow(int bias, double mcd, int zo, int 
 // BULK: a warp stages its two pooled rows (2 x 512 B) in shared memory and one lane writes them with two bulk copies
 // (cp.async.bulk shared -> global) -- whole 512-byte runs instead of 16 predicated 4-byte stores per thread
 template <int NCH, int GROUPS, bool CHECKX, bool BULK, bool BIASF>
-__global__ void __launch_bounds__((GROUPS == 1 ? 128 : 256) + 64, 2) conv_u8_tc_l0_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ L0Args a)
+__global__ void __launch_bounds__(L0Mode<GROUPS>::THREADS, L0Mode<GROUPS>::MINB) conv_u8_tc_l0_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ L0Args a)
 {
-    using L = L0Cfg<NCH>;
+    using L = L0Cfg<NCH, GROUPS>;
+    using MD = L0Mode<GROUPS>;
     static_assert(NCH == 16, "one 32-column chunk per pixel pair");
-    constexpr int NT = GROUPS == 1 ? 128 : 256;         // epilogue threads; the two producer warps come after them
+    constexpr int NT = MD::NT, NPROD = MD::NPROD, NACC = MD::NACC, NGRP = MD::NGRP;
     constexpr int NBUF = L::NBUF;
     extern __shared__ __align__(16) uint8_t smem_raw[];
     uint8_t *smem = smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u);
     uint64_t *full = (uint64_t *)(smem + L::BAR_OFF);   // [NBUF] staged planes landed
-    uint64_t *acc_full = full + NBUF;                   // [2] accumulator complete
-    uint64_t *acc_empty = acc_full + 2;                 // [2] accumulator read out
-    uint64_t *b_full = acc_empty + 2;                   // the resident filter tiles have landed
+    uint64_t *acc_full = full + NBUF;                   // [NACC] accumulator complete
+    uint64_t *acc_empty = acc_full + NACC;              // [NACC] accumulator read out
+    uint64_t *b_full = acc_empty + NACC;                // the resident filter tiles have landed
     uint32_t *tmem_slot = (uint32_t *)(b_full + 1);
+    volatile int *epi_seq = (volatile int *)(tmem_slot + 1);     // GROUPS = 3: how many tiles have entered their epilogue (see below)
 
 #ifdef YQ_L0_TRACE
     const unsigned long long tr_entry = l0_ns();
 #endif
-    const int t = threadIdx.x, warp = (t >> 5) & 3, grp = GROUPS >= 2 ? (t >> 7) & 1 : 0, lane = t & 31;
+    const int t = threadIdx.x, warp = (t >> 5) & 3, grp = t >> 7, lane = t & 31;      // (grp: meaningful for epilogue threads)
     const bool producer = t >= NT;
     const int qi = lane >> 2, qq = lane & 3;
 
     if (t == 0) {
         for (int b = 0; b < NBUF; ++b) mbar_init(&full[b], 1);
-        for (int b = 0; b < 2; ++b) {
+        for (int b = 0; b < NACC; ++b) {
             mbar_init(&acc_full[b], 1);
             mbar_init(&acc_empty[b], GROUPS == 4 ? 8 : 4);      // the warps that read an accumulator
         }
         mbar_init(b_full, 1);
+        *epi_seq = 0;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         mbar_expect_tx(b_full, (uint32_t)L::B_BYTES);
         bulk_load(smem + L::B_OFF, a.wimg, (uint32_t)L::B_BYTES, b_full);      // constants: before the wait on the previous kernel
@@ -221,8 +240,8 @@ __global__ void __launch_bounds__((GROUPS == 1 ? 128 : 256) + 64, 2) conv_u8_tc_
 
     if (producer) {
         const uint32_t sA = smem_u32(smem + L::A_OFF), b0 = smem_u32(smem + L::B_OFF);
-        const int pw = (t - NT) >> 5;                   // producer warp pw: tiles it = pw, pw + 2, ... into accumulator pw
-        constexpr int SPP = NBUF / 2, APP = L::NA / 2;  // staging slots / operand tiles per producer warp
+        const int pw = (t - NT) >> 5;                   // producer warp pw: tiles it = pw, pw + NPROD, ... into accumulator pw
+        constexpr int SPP = NBUF / NPROD, APP = L::NA / NPROD;  // staging slots / operand tiles per producer warp
         auto load_planes = [&](int tile, int sbuf) {
             const TileXY p = split_tile(tile);
             mbar_expect_tx(&full[sbuf], (uint32_t)L::S_BYTES);
@@ -232,7 +251,7 @@ __global__ void __launch_bounds__((GROUPS == 1 ? 128 : 256) + 64, 2) conv_u8_tc_
             asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
 #pragma unroll 1
             for (int d = 0; d < SPP; ++d)
-                if (first + (pw + 2 * d) * step < a.num_tiles) load_planes(first + (pw + 2 * d) * step, pw * SPP + d);
+                if (first + (pw + NPROD * d) * step < a.num_tiles) load_planes(first + (pw + NPROD * d) * step, pw * SPP + d);
         }
         __syncwarp();
         constexpr int PLW = L0_AROWS * L0_SCOLS / 4;    // words of one staged plane
@@ -252,7 +271,7 @@ __global__ void __launch_bounds__((GROUPS == 1 ? 128 : 256) + 64, 2) conv_u8_tc_
 #endif
         int k = 0;
 #pragma unroll 1
-        for (int tile = first + pw * step; tile < a.num_tiles; tile += 2 * step, ++k) {
+        for (int tile = first + pw * step; tile < a.num_tiles; tile += NPROD * step, ++k) {
             const int sbuf = pw * SPP + k % SPP, abuf = pw * APP + k % APP;
             mbar_wait(&full[sbuf], (uint32_t)((k / SPP) & 1));
             L0TR_MARK(0);
@@ -283,7 +302,7 @@ __global__ void __launch_bounds__((GROUPS == 1 ? 128 : 256) + 64, 2) conv_u8_tc_
             L0TR_MARK(1);
             if (lane == 0) {
                 if (k == 0) mbar_wait(b_full, 0);
-                if (tile + NBUF * step < a.num_tiles) load_planes(tile + NBUF * step, sbuf);      // every lane has read the slot
+                if (tile + NBUF * step < a.num_tiles) load_planes(tile + NBUF * step, sbuf);      // every lane has read the slot (SPP * NPROD = NBUF tiles on)
                 if (k >= 1) mbar_wait(&acc_empty[pw], ((uint32_t)k & 1u) ^ 1u);                    // the accumulator's previous tile has been read out
                 tc_fence_after();
                 L0TR_MARK(2);
@@ -422,10 +441,25 @@ __global__ void __launch_bounds__((GROUPS == 1 ? 128 : 256) + 64, 2) conv_u8_tc_
 #endif
         int j = 0;
 #pragma unroll 1
-        for (int tile = first + (GROUPS == 2 ? grp * step : 0); tile < a.num_tiles; tile += GROUPS * step, ++j) {
+        for (int tile = first + grp * step; tile < a.num_tiles; tile += NGRP * step, ++j) {
             const TileXY cur = split_tile(tile);
-            const int acc = GROUPS == 2 ? grp : j & 1;
-            mbar_wait(&acc_full[acc], (uint32_t)((GROUPS == 2 ? j : j >> 1) & 1));
+            const int it = grp + NGRP * j;               // this CTA's it-th tile: accumulator it % NACC, its (it / NACC)-th use
+            const int acc = it % NACC;
+            if constexpr (NGRP != NACC && NGRP > 1) {
+                // A parity wait tells "this use" from "the use before" only.  With fewer groups than accumulators a group may come to wait
+                // for use u of an accumulator before its use u - 1 (drained by ANOTHER group) has even been filled -- and the phase of equal
+                // parity two uses back would let it through.  So tiles enter their epilogues in order: tile it waits until tile it - 1
+                // has seen its accumulator complete, which (by induction) puts every earlier use of this accumulator behind us.
+                const long long t0 = clock64();
+                while (*epi_seq < it) {
+                    __nanosleep(20);
+                    if (clock64() - t0 > 4000000000LL) __trap();
+                }
+            }
+            mbar_wait(&acc_full[acc], (uint32_t)((it / NACC) & 1));
+            if constexpr (NGRP != NACC && NGRP > 1) {
+                if (warp == 0 && lane == 0) *epi_seq = it + 1;
+            }
             L0TR_MARK(0);
             tc_fence_after();
             const uint32_t tqa = tq + (uint32_t)(acc * L::N);
@@ -450,24 +484,29 @@ __global__ void __launch_bounds__((GROUPS == 1 ? 128 : 256) + 64, 2) conv_u8_tc_
                 __syncwarp();
             }
             // GROUPS = 1 (registers for it): the whole accumulator first, then the release -- the next tile's MMAs run under ALL of this
-            // tile's arithmetic; GROUPS = 2: chunk by chunk
-            uint32_t V[GROUPS == 1 ? 4 : 1][2][16];
+            // tile's arithmetic; GROUPS = 2: chunk by chunk; GROUPS = 3 (128 registers): chunk by chunk, the next chunk's load in flight
+            constexpr int NV = GROUPS == 1 ? 4 : (GROUPS == 3 ? 2 : 1);
+            uint32_t V[NV][2][16];
             if (GROUPS == 1) {
 #pragma unroll
                 for (int pp = 0; pp < 4; ++pp) l0_ld_issue(tqa + 32 * pp, V[pp][0], V[pp][1]);
 #pragma unroll
                 for (int pp = 0; pp < 4; ++pp) l0_ld_wait(V[pp][0], V[pp][1]);
                 release_acc();
+            } else if (GROUPS == 3) {
+                l0_ld_issue(tqa, V[0][0], V[0][1]);
+                l0_ld_wait(V[0][0], V[0][1]);
             }
 #pragma unroll
             for (int pp = 0; pp < 4; ++pp) {
-                uint32_t(&v0)[16] = V[GROUPS == 1 ? pp : 0][0];
-                uint32_t(&v1)[16] = V[GROUPS == 1 ? pp : 0][1];
-                if (GROUPS != 1) {
+                uint32_t(&v0)[16] = V[GROUPS == 1 ? pp : (GROUPS == 3 ? pp & 1 : 0)][0];
+                uint32_t(&v1)[16] = V[GROUPS == 1 ? pp : (GROUPS == 3 ? pp & 1 : 0)][1];
+                if (GROUPS == 2) {
                     l0_ld_issue(tqa + 32 * pp, v0, v1);
                     l0_ld_wait(v0, v1);
                     if (pp == 3) release_acc();
                 }
+                if (GROUPS == 3 && pp + 1 < 4) l0_ld_issue(tqa + 32 * (pp + 1), V[NV == 2 ? (pp + 1) & 1 : 0][0], V[NV == 2 ? (pp + 1) & 1 : 0][1]);
                 int r0[4], r1[4];
                 uint32_t orx = 0, orr = 0;
 #pragma unroll
@@ -503,6 +542,10 @@ __global__ void __launch_bounds__((GROUPS == 1 ? 128 : 256) + 64, 2) conv_u8_tc_
                     uint8_t *dst = out_tile + pp * a.out_cs;
                     if (row0) *reinterpret_cast<uint32_t *>(dst) = w0;
                     if (row1) *reinterpret_cast<uint32_t *>(dst + out_row) = w1;
+                }
+                if (GROUPS == 3 && pp + 1 < 4) {
+                    l0_ld_wait(V[NV == 2 ? (pp + 1) & 1 : 0][0], V[NV == 2 ? (pp + 1) & 1 : 0][1]);
+                    if (pp + 2 == 4) release_acc();
                 }
             }
             if (BULK) {
@@ -579,7 +622,8 @@ inline size_t l0_bpos(int n, int k) { return (size_t)(n / 8) * 256 + (size_t)(k 
 template <int NCH, int SPLIT, bool CHECKX, bool BULK, bool BIASF>
 int l0_launch(const CUtensorMap &tmA, const L0Args &a, cudaStream_t stream)
 {
-    using L = L0Cfg<NCH>;
+    using L = L0Cfg<NCH, SPLIT>;
+    using MD = L0Mode<SPLIT>;
     const int smem = L::TOTAL + 128;
     auto kern = conv_u8_tc_l0_kernel<NCH, SPLIT, CHECKX, BULK, BIASF>;
     if (yq::ensure_dynamic_smem((const void *)kern, smem)) return -1;
@@ -590,10 +634,11 @@ int l0_launch(const CUtensorMap &tmA, const L0Args &a, cudaStream_t stream)
         YQ_CUDA(cudaFuncGetAttributes(&fa, kern));
         // counted by hand: the occupancy API answers 1 for kernels that allocate tensor memory
         const int by_smem = yq::device_smem_per_sm() / (smem + 1024 + (int)fa.sharedSizeBytes);
-        const int by_regs = 65536 / (((fa.numRegs + 7) / 8 * 8) * ((SPLIT == 1 ? 128 : 256) + 64));
+        const int by_regs = 65536 / (((fa.numRegs + 7) / 8 * 8) * MD::THREADS);
         const int by_tmem = 512 / L::TMEM_COLS;
         int occ = by_smem < by_regs ? by_smem : by_regs;
         if (by_tmem < occ) occ = by_tmem;
+        if (MD::MINB < occ) occ = MD::MINB;
         if (getenv("YQ_DEBUG")) fprintf(stderr, "yq: l0<%d,%d,%d,%d,%d> regs=%d by_smem=%d by_regs=%d by_tmem=%d smem=%d\n", NCH, SPLIT, (int)CHECKX, (int)BULK, (int)BIASF, fa.numRegs, by_smem, by_regs, by_tmem, smem);
         if (occ < 1 || n_sm <= 0) return yq::fail("conv_u8_tc_l0_kernel<%d> does not fit on an SM", NCH);
         ctas_per_sm = occ;
@@ -601,7 +646,7 @@ int l0_launch(const CUtensorMap &tmA, const L0Args &a, cudaStream_t stream)
     }
     int grid = n_sm * ctas_per_sm;
     if (grid > a.num_tiles) grid = a.num_tiles;
-    YQ_CUDA(yq::launch_pdl(kern, dim3(grid), dim3((SPLIT == 1 ? 128 : 256) + 64), smem, stream, tmA, a));
+    YQ_CUDA(yq::launch_pdl(kern, dim3(grid), dim3(MD::THREADS), smem, stream, tmA, a));
     return 0;
 }
 
@@ -732,13 +777,14 @@ int yq_tc_l0_forward(yq_conv_layer *l, void *state, const uint8_t *in_planes, ui
     // form of the kernel: defaults from measurements on B200 (profiles/README.md); YQ_L0_GROUPS = 1 / 2 and YQ_L0_BULK = 0 / 1 force
     static const int groups_env = getenv("YQ_L0_GROUPS") ? atoi(getenv("YQ_L0_GROUPS")) : -1;
     static const int bulk_env = getenv("YQ_L0_BULK") ? atoi(getenv("YQ_L0_BULK")) : -1;
-    const int groups = groups_env < 0 ? 2 : (groups_env == 1 ? 1 : groups_env == 2 ? 2 : 4);
+    const int groups = groups_env < 0 ? 2 : (groups_env >= 1 && groups_env <= 4 ? groups_env : 2);
     const bool bulk = bulk_env < 0 ? true : bulk_env != 0;
     const CUtensorMap &tm = it->second;
 #define YQ_L0(G_, B_)                                                                                                                   \
     (st->biasf ? (st->checkx ? l0_launch<16, G_, true, B_, true>(tm, a, stream) : l0_launch<16, G_, false, B_, true>(tm, a, stream))    \
                : (st->checkx ? l0_launch<16, G_, true, B_, false>(tm, a, stream) : l0_launch<16, G_, false, B_, false>(tm, a, stream)))
     if (groups == 4) return YQ_L0(4, true);
+    if (groups == 3) return bulk ? YQ_L0(3, true) : YQ_L0(3, false);
     if (groups == 2) return bulk ? YQ_L0(2, true) : YQ_L0(2, false);
     return bulk ? YQ_L0(1, true) : YQ_L0(1, false);
 #undef YQ_L0
