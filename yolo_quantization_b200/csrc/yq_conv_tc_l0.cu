@@ -94,6 +94,7 @@ struct L0Args {
     int tiles_x, tiles_y, num_tiles, zp_out;
     uint32_t magic_x, magic_y;   // ceil(2^32 / tiles_x), ceil(2^32 / tiles_y)
     uint32_t xlim;
+    int tstore;             // BULK: 1 = the staged rows leave through a 4-D tensor store (see the kernel), 0 = linear bulk copies
     int knobs;              // -DYQ_L0_KNOBS experiments (results are garbage): 1 no MMAs, 2 no epilogue arithmetic, 4 no rearrangement, 8 no stores
     int4 cq[32];            // {bias, zw, 2*M0, shift} per channel
     double mc[32];          // M_value * 2^-s (FP64 redo)
@@ -184,10 +185,14 @@ __device__ __forceinline__ int l0_window_slow(int bias, double mcd, int zo, int 
 
 // GROUPS = 2: two epilogue groups of four warps, group g owns accumulator g and every second tile (all four pixel pairs of its
 // threads' segments: 32 pooled outputs per thread and tile, like GROUPS = 1, with twice the warps to hide latencies behind)
-// BULK: a warp stages its two pooled rows (2 x 512 B) in shared memory and one lane writes them with two bulk copies
+// BULK: a warp stages its two pooled rows (2 x 512 B) in shared memory and one lane writes them out.  In pixel order (two linear bulk
+// copies per warp) the eight segments' words of one pixel pair sit 64 bytes apart -- a 4-way bank conflict on every staging store, and
+// this kernel's shared-memory data pipe is its bottleneck (ncu r2: 41 % LSU + 40 % tensor-core operand wavefronts).  `tstore` stages
+// [row][pair][segment][16 channels] instead -- 32 lanes, 32 banks -- and a 4-D tensor map over the pooled tensor viewed as
+// [rows][4 pixels of a segment][segments][16 channels] (strides W*16, 16, 64 bytes) lets ONE TMA store per row put the pixels back in order
 // (cp.async.bulk shared -> global) -- whole 512-byte runs instead of 16 predicated 4-byte stores per thread
 template <int NCH, int GROUPS, bool CHECKX, bool BULK, bool BIASF>
-__global__ void __launch_bounds__(L0Mode<GROUPS>::THREADS, L0Mode<GROUPS>::MINB) conv_u8_tc_l0_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ L0Args a)
+__global__ void __launch_bounds__(L0Mode<GROUPS>::THREADS, L0Mode<GROUPS>::MINB) conv_u8_tc_l0_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmO, const __grid_constant__ L0Args a)
 {
     using L = L0Cfg<NCH, GROUPS>;
     using MD = L0Mode<GROUPS>;
@@ -433,7 +438,7 @@ __global__ void __launch_bounds__(L0Mode<GROUPS>::THREADS, L0Mode<GROUPS>::MINB)
         const uint32_t out_row = (uint32_t)(a.OWP * a.out_cs);
         // BULK: this warp's staging, two buffers of [2 pooled rows][32 pixels][16 channels]
         uint8_t *const stage = smem + L::ST_OFF + ((t >> 5) * 2) * 1024;
-        const uint32_t st_thr = (uint32_t)(4 * qi * 16 + 4 * qq);
+        const uint32_t st_thr = (uint32_t)((a.tstore ? qi * 16 : 4 * qi * 16) + 4 * qq), st_pp = a.tstore ? 128u : 16u;
 #ifdef YQ_L0_TRACE
         unsigned long long tr_acc[2] = {0, 0};
         long long tr_prev = clock64();
@@ -536,8 +541,8 @@ __global__ void __launch_bounds__(L0Mode<GROUPS>::THREADS, L0Mode<GROUPS>::MINB)
                 }
                 const uint32_t w0 = l0_pack(r0), w1 = l0_pack(r1);      // every value is a byte here (fast path: checked; redo: masked)
                 if (BULK) {
-                    *reinterpret_cast<uint32_t *>(st + pp * 16) = w0;
-                    *reinterpret_cast<uint32_t *>(st + pp * 16 + 512) = w1;
+                    *reinterpret_cast<uint32_t *>(st + pp * st_pp) = w0;
+                    *reinterpret_cast<uint32_t *>(st + pp * st_pp + 512) = w1;
                 } else if (px0 + pp < a.PW && !L0KNOB(8)) {
                     uint8_t *dst = out_tile + pp * a.out_cs;
                     if (row0) *reinterpret_cast<uint32_t *>(dst) = w0;
@@ -556,8 +561,15 @@ __global__ void __launch_bounds__(L0Mode<GROUPS>::THREADS, L0Mode<GROUPS>::MINB)
                     const uint32_t nbytes = (uint32_t)(npx * 16);
                     uint8_t *g0 = a.out_pool + (size_t)(tile_off + (uint32_t)(((2 * warp + a.opad) * a.OWP + a.opad) * a.out_cs));
                     const uint32_t s0 = smem_u32(stage + (j & 1) * 1024);
-                    if (row0 && !L0KNOB(8)) asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(g0), "r"(s0), "r"(nbytes) : "memory");
-                    if (row1 && !L0KNOB(8)) asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(g0 + out_row), "r"(s0 + 512), "r"(nbytes) : "memory");
+                    if (a.tstore) {
+                        // box {16 channels, 8 segments, 4 pixels, 1 row} at (0, first segment, 0, row); segments beyond the image are clipped
+                        const int row = cur.n * a.OHP + py0;
+                        if (row0 && !L0KNOB(8)) tma_store_4d(&tmO, stage + (j & 1) * 1024, 0, cur.tx * L0_SEGS, 0, row);
+                        if (row1 && !L0KNOB(8)) tma_store_4d(&tmO, stage + (j & 1) * 1024 + 512, 0, cur.tx * L0_SEGS, 0, row + 1);
+                    } else {
+                        if (row0 && !L0KNOB(8)) asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(g0), "r"(s0), "r"(nbytes) : "memory");
+                        if (row1 && !L0KNOB(8)) asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(g0 + out_row), "r"(s0 + 512), "r"(nbytes) : "memory");
+                    }
                     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                 }
             }
@@ -590,6 +602,7 @@ struct L0State {
     uint32_t xlim = 1u << 22;
     uint8_t *wimg = nullptr;
     std::map<std::pair<const void *, int>, CUtensorMap> maps;      // input tensor map per (input pointer, batch)
+    std::map<std::pair<const void *, int>, CUtensorMap> omaps;     // pooled-output tensor map per (output pointer, batch)
 };
 
 typedef CUresult (*L0EncodeFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
@@ -615,12 +628,33 @@ int l0_encode(CUtensorMap *m, const void *in, int w, int h, int planes)
     return 0;
 }
 
+// the pooled output [rows][pitch][16 ch] viewed as [rows][4 pixels of a segment][segments][16 ch]: box {16, 8 segments, 4 pixels, 1 row}
+// = one staged row in the kernel's bank-conflict-free order; `base` = pixel (0, 0) of image 0 (behind the halo)
+int l0_encode_out(CUtensorMap *m, void *base, int segs, int pitch_px, long long rows)
+{
+    static L0EncodeFn enc = nullptr;
+    if (!enc) {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess) enc = (L0EncodeFn)p;
+    }
+    if (!enc) return yq::fail("cuTensorMapEncodeTiled is not available from this driver");
+    const cuuint32_t es[4] = {1, 1, 1, 1};
+    const cuuint64_t dims[4] = {16, (cuuint64_t)segs, 4, (cuuint64_t)rows};
+    const cuuint64_t strides[3] = {64, 16, (cuuint64_t)pitch_px * 16};
+    const cuuint32_t box[4] = {16, (cuuint32_t)L0_SEGS, 4, 1};
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 4, base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                     CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return yq::fail("layer-0 flavour: cuTensorMapEncodeTiled(pooled output, %d segments x %lld rows) failed: %d", segs, rows, (int)r);
+    return 0;
+}
+
 // byte position of element (row n, k) inside one [N][32] filter tile: 8-row x 16-byte core matrices, the two K chunks of a
 // group side by side (LBO = 128), groups 256 bytes apart (SBO = 256)
 inline size_t l0_bpos(int n, int k) { return (size_t)(n / 8) * 256 + (size_t)(k / 16) * 128 + (size_t)(n % 8) * 16 + (size_t)(k % 16); }
 
 template <int NCH, int SPLIT, bool CHECKX, bool BULK, bool BIASF>
-int l0_launch(const CUtensorMap &tmA, const L0Args &a, cudaStream_t stream)
+int l0_launch(const CUtensorMap &tmA, const CUtensorMap &tmO, const L0Args &a, cudaStream_t stream)
 {
     using L = L0Cfg<NCH, SPLIT>;
     using MD = L0Mode<SPLIT>;
@@ -646,7 +680,7 @@ int l0_launch(const CUtensorMap &tmA, const L0Args &a, cudaStream_t stream)
     }
     int grid = n_sm * ctas_per_sm;
     if (grid > a.num_tiles) grid = a.num_tiles;
-    YQ_CUDA(yq::launch_pdl(kern, dim3(grid), dim3(MD::THREADS), smem, stream, tmA, a));
+    YQ_CUDA(yq::launch_pdl(kern, dim3(grid), dim3(MD::THREADS), smem, stream, tmA, tmO, a));
     return 0;
 }
 
@@ -780,9 +814,26 @@ int yq_tc_l0_forward(yq_conv_layer *l, void *state, const uint8_t *in_planes, ui
     const int groups = groups_env < 0 ? 2 : (groups_env >= 1 && groups_env <= 4 ? groups_env : 2);
     const bool bulk = bulk_env < 0 ? true : bulk_env != 0;
     const CUtensorMap &tm = it->second;
+    // YQ_L0_TSTORE = 1: pooled rows by tensor store (conflict-free staging) when the row is a whole number of segments.  Off by default:
+    // measured equal on B200 (0.0835 vs 0.0831 ms) -- the 16-byte boxes cost the TMA unit what the bank conflicts cost the LSU
+    static const int tstore_env = getenv("YQ_L0_TSTORE") ? atoi(getenv("YQ_L0_TSTORE")) : -1;
+    a.tstore = (tstore_env < 0 ? 0 : tstore_env != 0) && bulk && groups != 4 && a.PW % 4 == 0 && l->cs_out == 16;
+    CUtensorMap tmo;
+    memset(&tmo, 0, sizeof tmo);
+    if (a.tstore) {
+        const auto okey = std::make_pair((const void *)out_pool, batch);
+        auto ot = st->omaps.find(okey);
+        if (ot == st->omaps.end()) {
+            CUtensorMap m;
+            if (l0_encode_out(&m, out_pool + ((size_t)og->pad * og->pitch_w + og->pad) * 16, a.PW / 4, og->pitch_w, (long long)batch * og->rows_h - og->pad)) return -1;
+            if (st->omaps.size() > 64) st->omaps.clear();
+            ot = st->omaps.emplace(okey, m).first;
+        }
+        tmo = ot->second;
+    }
 #define YQ_L0(G_, B_)                                                                                                                   \
-    (st->biasf ? (st->checkx ? l0_launch<16, G_, true, B_, true>(tm, a, stream) : l0_launch<16, G_, false, B_, true>(tm, a, stream))    \
-               : (st->checkx ? l0_launch<16, G_, true, B_, false>(tm, a, stream) : l0_launch<16, G_, false, B_, false>(tm, a, stream)))
+    (st->biasf ? (st->checkx ? l0_launch<16, G_, true, B_, true>(tm, tmo, a, stream) : l0_launch<16, G_, false, B_, true>(tm, tmo, a, stream))    \
+               : (st->checkx ? l0_launch<16, G_, true, B_, false>(tm, tmo, a, stream) : l0_launch<16, G_, false, B_, false>(tm, tmo, a, stream)))
     if (groups == 4) return YQ_L0(4, true);
     if (groups == 3) return bulk ? YQ_L0(3, true) : YQ_L0(3, false);
     if (groups == 2) return bulk ? YQ_L0(2, true) : YQ_L0(2, false);
