@@ -256,7 +256,7 @@ def test_conv_with_fused_shortcut_vs_oracle(built, case):
     layer.free()
 
 
-@pytest.mark.parametrize("full_m0", [True, False], ids=["M0_31_bits", "M0_from_float"])
+@pytest.mark.parametrize("full_m0", [True, False, 2], ids=["M0_31_bits", "M0_from_float", "M0_from_float_shift_3"])
 @pytest.mark.parametrize("act", ["leaky", "relu6"])
 def test_requant_beyond_2_22(built, full_m0, act):
     """|acc + bias| far beyond 2^22.  The integer epilogue equals the reference's double arithmetic (convolutional_layer.c:732-733)
@@ -272,7 +272,14 @@ def test_requant_beyond_2_22(built, full_m0, act):
     spec = synth.LayerSpec("conv", n, k, 1, 1, 0, act)
     sl = synth.SynthLayer("conv", c, h, w, n, 0, 0, spec, s_out=0.05, biases=np.zeros(n, np.float32), s_w=s_w, zp_w=zp_w, w_u8=wq.reshape(n, c, k, k))
     p = O.prepare_conv(sl, 0.02, 3)
-    if full_m0:
+    if full_m0 == 2:
+        # a LARGE multiplier (M in [2^-4, 2^-3)): h = trunc(|x| M) runs into the millions, far beyond the 81 914 up to which the LEAKY
+        # epilogue's divide-by-ten multiply-add is exact -- make_epi() must have lowered xlim so that these chunks take the FP64 re-do
+        # (and the uint8 store wraps, as the reference's does)
+        p["M0_right_shift_value"] = np.full(n, 2.0 ** -3)
+        p["M_value"] = (rng.random(n).astype(np.float32) * 0.5 + 0.5).astype(np.float64)
+        p["M_value"] = np.round(p["M_value"] * 2.0 ** 31) * 2.0 ** -31
+    elif full_m0:
         m0 = (rng.integers(1 << 30, 1 << 31, size=n, dtype=np.int64) | 1)       # odd: all 31 bits significant
         p["M_value"] = m0.astype(np.float64) * 2.0 ** -31
         p["M0_right_shift_value"] = np.full(n, 2.0 ** -24)

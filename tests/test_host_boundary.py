@@ -125,3 +125,16 @@ def test_pack_arena_drops_damaged_entries(built, tmp_path):
     assert lib.yq_pack_arena_save(str(path).encode()) == 1
     assert lib.yq_pack_arena_clear() == 0 and lib.yq_pack_arena_load(str(path).encode()) == 1
     assert lib.yq_pack_arena_clear() == 0
+
+
+def test_leaky_divide_by_ten_constant():
+    """yq_epilogue.cuh: LEAKY's round(q / 10) for q < 0 is (h * 52429 + 262145) >> 19 with h = |q| -- floor((h + 5) / 10) -- exact for
+    every h the epilogue lets through (make_epi lowers xlim so that h <= 81914), and the product stays inside 32 bits."""
+    import numpy as np
+    h = np.arange(0, 81915, dtype=np.uint64)
+    assert np.array_equal((h * 52429 + 262145) >> 19, (h + 5) // 10)
+    assert 81914 * 52429 + 262145 < 2 ** 32
+    # ... and it is the reference's double arithmetic: round-half-away of -h * 0.1 (convolutional_layer.c:737)
+    q = -h.astype(np.int64)
+    ref = np.where(q * 0.1 - np.trunc(q * 0.1) <= -0.5, np.trunc(q * 0.1) - 1, np.trunc(q * 0.1)).astype(np.int64)
+    assert np.array_equal(-((h.astype(np.int64) + 5) // 10), ref)
