@@ -20,6 +20,12 @@ KEEP = [
     ("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "gpu_dram_pct"),
     ("l1tex__throughput.avg.pct_of_peak_sustained_elapsed", "l1tex_pct"),
     ("lts__throughput.avg.pct_of_peak_sustained_elapsed", "l2_pct"),
+    ("sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_elapsed", "alu_pipe_pct"),
+    ("sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_elapsed", "fma_pipe_pct"),
+    ("sm__pipe_fmaheavy_cycles_active.avg.pct_of_peak_sustained_elapsed", "fmaheavy_pipe_pct"),
+    ("smsp__issue_active.avg.pct_of_peak_sustained_active", "issue_active_pct"),
+    ("l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed", "smem_lsu_wavefronts_pct"),
+    ("l1tex__data_pipe_tc_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed", "smem_tc_wavefronts_pct"),
     ("smsp__inst_executed.sum", "warp_inst"),
     ("sm__inst_executed.avg.per_cycle_elapsed", "ipc"),
 ]
