@@ -247,6 +247,57 @@ def test_conv_flat_flavour_vs_oracle(built, case):
     layer.free()
 
 
+PW_CASES = [
+    # c, h, w, n, act, zp_in, zp_out, batch, yolo classes (None: a plain 1x1 layer)
+    (64, 20, 33, 32, "leaky", 13, 40, 2, None),      # one chunk of 64 channels per tile (one commit per tile), four accumulators, 32-byte rows
+    (128, 26, 26, 64, "leaky", 0, 3, 3, None),       # one chunk of 128, 64-byte rows
+    (128, 9, 7, 128, "relu6", 5, 0, 2, None),        # one chunk, two accumulators (N = 144 columns each), channel halves per group
+    (256, 13, 13, 128, "relu6", 0, 0, 5, None),      # layer 18 of yolov3-tiny: two chunks per tile
+    (384, 11, 6, 128, "leaky", 77, 9, 2, None),      # three chunks (layer 99 of the full yolov3)
+    (256, 6, 10, 100, "linear", 3, 128, 2, None),    # n = 100 -> stride 112: not a pointwise shape, the flat kernels keep it
+    (512, 5, 5, 64, "relu", 9, 20, 1, None),         # four chunks, four accumulators
+    (256, 13, 13, 30, "linear", 0, 128, 3, 5),       # head of yolov3-tiny (layer 22 class): 3 anchors x (5 + 5)
+    (512, 13, 13, 30, "linear", 0, 100, 2, 5),       # layer 15: four chunks
+    (256, 12, 9, 255, "linear", 0, 120, 2, 80),      # heads of the full yolov3: 255 channels, two accumulators of 256 columns, ones row = row 255
+    (512, 7, 7, 255, "linear", 4, 131, 1, 80),       # 128 KB filter bank, three ring stages
+    (128, 50, 41, 64, "leaky", 0, 0, 4, None),       # several tiles per CTA on a small grid is not reached here; many tiles, ragged last tile
+]
+
+
+@pytest.mark.parametrize("case", PW_CASES, ids=lambda c: "c%d_%dx%d_n%d_%s" % c[:5])
+def test_conv_pointwise_flavour_vs_oracle(built, case, monkeypatch):
+    """1x1 layers and detection heads on the streaming pointwise flavour (filter bank resident in shared memory, ones row for the
+    activation sums): the production launch (no side outputs) equals the oracle byte for byte, heads within the yolo tolerance, the
+    output strip's halo holds halo_fill; and equals the flat kernels' result (YQ_PW=0) bit for bit, floats included."""
+    c, h, w, n, act, zp_in, zp_out, batch, classes = case
+    rng = np.random.default_rng(zlib.crc32(repr(case).encode()) + 21)
+    wq, zp_w, s_w, bias = make_params(rng, n, c, zp_in)
+    spec = synth.LayerSpec("conv", n, 1, 1, 1, 0, act)
+    sl = synth.SynthLayer("conv", c, h, w, n, 0, 0, spec, s_out=0.05, biases=bias, s_w=s_w, zp_w=zp_w, w_u8=wq.reshape(n, c, 1, 1))
+    p = O.prepare_conv(sl, 0.02, zp_in)
+    x = rng.integers(0, 256, size=(batch, c, h, w), dtype=np.uint8)
+    qs = 1 if classes is not None else 0
+    layer = darknet.ConvolutionalLayerQuant(h, w, c, n, 1, 1, 0, synth.ACT_CODES[act], wq, zp_w, p["biases_int32"], p["M_value"],
+                                            p["M0_right_shift_value"], zp_in, zp_out, 0.05, quant_stop_flag=qs)
+    assert layer.flat_supported
+    fill = zp_out ^ 0x5A
+    got = layer.forward_flat(x, halo_fill=fill, want_acc=False, yolo_classes=classes)
+    monkeypatch.setenv("YQ_PW", "0")
+    old = layer.forward_flat(x, halo_fill=fill, want_acc=False, yolo_classes=classes)
+    monkeypatch.delenv("YQ_PW")
+    assert got["halo_ok"], "halo / pad lanes of the output strip"
+    assert np.array_equal(got["u8"], old["u8"])
+    for b in range(batch):
+        acc = O.conv_acc(x[b], wq.reshape(n, c, 1, 1), zp_w, 1, 0, zp_in)
+        u8 = O.requant(acc, p["biases_int32"], p["M_value"], p["M0_right_shift_value"], synth.ACT_CODES[act], zp_out)
+        assert np.array_equal(got["u8"][b], u8), f"uint8 mismatch, image {b}"
+        if classes is not None:
+            ref = O.yolo(O.dequant(u8, zp_out, 0.05), n // (classes + 5), classes)
+            assert np.allclose(got["yolo"][b], ref, atol=YOLO_ATOL, rtol=0), f"yolo mismatch, image {b}"
+            assert np.array_equal(got["yolo"][b], old["yolo"][b])
+    layer.free()
+
+
 ROWS_CASES = [
     # c, h, w, n, zp_in, zp_out, batch
     (3, 48, 64, 16, 0, 0, 2),

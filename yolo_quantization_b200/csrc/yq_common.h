@@ -115,6 +115,7 @@ struct yq_conv_layer {
     void *tc_flat = nullptr;    // flat-strip patch flavour state (yq_conv_tc_flat.cu), or nullptr
     void *tc_flat2 = nullptr;   // its persistent two-tiles-per-weight-stage form (yq_conv_tc_flat2.cu), or nullptr
     void *tc_flat2x = nullptr;  // the same on CTA pairs, tcgen05 cta_group::2 (yq_conv_tc_flat2x.cu), or nullptr
+    void *tc_pw = nullptr;      // pointwise streaming form: narrow 1x1 layers and detection heads (yq_conv_tc_pw.cu), or nullptr
     std::vector<uint8_t> host_w;  // OIHW copy kept for repacking
     uint64_t pack_key = 0;        // content key of this layer's filter images in the packed-weight arena (yq_pack.cu)
     std::vector<uint8_t> host_zw;
@@ -199,6 +200,14 @@ int yq_tc_flat2x_prepare(yq_conv_layer *l, void **state);
 void yq_tc_flat2x_free(void *state);
 int yq_tc_flat2x_forward(yq_conv_layer *l, void *state, const uint8_t *in_flat, uint8_t *out_flat, int halo_fill, int32_t *out_acc, int batch,
                          cudaStream_t stream, const yq_fused_shortcut *sc = nullptr);
+
+// implemented in yq_conv_tc_pw.cu (1x1 layers with n <= 255 whose filter bank fits shared memory: persistent streaming GEMM; flat or
+// plain strips; out_yolo != null: the layer is a detection head and the following yolo layer's tensor is written as well)
+int yq_tc_pw_supported(const yq_conv_layer *l);
+int yq_tc_pw_prepare(yq_conv_layer *l, void **state);
+void yq_tc_pw_free(void *state);
+int yq_tc_pw_forward(yq_conv_layer *l, void *state, const uint8_t *in, uint8_t *out_u8, int halo_fill, float *out_yolo, int yolo_classes, int batch,
+                     cudaStream_t stream, int plain);
 
 // implemented in yq_conv_tc.cu (TMA-fed; c % 64 == 0)
 int yq_tc_supported(const yq_conv_layer *l);

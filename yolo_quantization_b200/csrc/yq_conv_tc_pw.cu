@@ -1,0 +1,499 @@
+// yq_conv_tc_pw.cu -- tcgen05 (kind::i8) POINTWISE (1x1, stride 1) convolution as a persistent streaming GEMM with the
+// whole filter bank RESIDENT in shared memory: the flavour of the narrow 1x1 layers and of the detection heads.
+//
+// Why (measured on B200, profiles/r2_forward_full.csv): in conv_u8_tc_flat_kernel a 1x1 layer with few output channels
+// is one short dependent chain per CTA -- barrier init, TMEM allocation, a TMA round trip, a handful of MMAs, the
+// epilogue, the store -- and the launch is a few waves of such chains: the heads of yolov3-tiny ran at 0.15 - 0.23 of
+// the HBM roofline with every pipe below 25 %.  These layers have no arithmetic to speak of (K <= 512, N <= 255); they
+// are a stream of activation rows through a small matrix.  So:
+//   * B  the filter bank [NC = round_up(n + 1, 16)][K] is loaded ONCE per CTA (before griddepcontrol.wait: it overlaps the
+//        previous kernel's tail) and stays in shared memory; row n is all ones, so TMEM column n of every accumulator is the
+//        position's activation sum (uint8 weights with a uint8 zero point: acc = sum w*a - zp_w * sum a,
+//        convolutional_layer.c:718-721) -- no separate ones rows per stage, no sum warps;
+//   * A  tiles of 128 consecutive positions x KC channels stream through a deep TMA ring (up to 12 stages) that runs
+//        across tile boundaries: the loads never drain between tiles;
+//   * D  2 or 4 TMEM accumulators; 16 epilogue warps in 4 groups, group g works on accumulator g % nbuf (and, with two
+//        accumulators, on one half of its channels): the epilogue of tile i overlaps the loads and MMAs of tiles i+1 ...;
+//   * one tcgen05.commit per tile when K is a single chunk (the commit both frees the ring stage and publishes the
+//        accumulator: commits cannot follow each other faster than every ~358 clocks per SM, see yq_conv_tc_flat2.cu).
+// Tensors, position arithmetic, requantisation and halo handling are those of yq_conv_tc_flat.cu (flat halo-padded strips;
+// halo positions of the output are written with the consumer's zero point), or plain [B][H][W][C] strips (plain = 1).
+// Detection heads (quant_stop followed by [yolo]): the float values are a 256-entry table per channel class
+// (yq_conv_tc_flat.cu), written straight to the yolo layer's NCHW tensor, one coalesced 128-byte store per channel and warp.
+// Restates convolutional_layer.c:694-761 for size 1, stride 1, pad 0, c % 64 == 0, n <= 255.
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <math.h>
+#include <string.h>
+
+#include <map>
+#include <type_traits>
+#include <vector>
+
+#include "yq_common.h"
+#include "yq_epilogue.cuh"
+#include "yq_tc_ptx.cuh"
+
+using namespace yqtc;
+
+namespace {
+
+constexpr int PW_GROUPS = 4;                       // epilogue groups of four warps (one warp per TMEM lane quarter)
+constexpr int PW_EPI_WARPS = 4 * PW_GROUPS;
+constexpr int PW_THREADS = 64 + 32 * PW_EPI_WARPS;
+constexpr int PW_MAX_ASTAGES = 12;
+constexpr int PW_MAX_NC = 256;
+constexpr int PW_STAGE_SLICE = 2048;               // one epilogue warp's staging slice: 32 positions x up to 64 channels
+
+struct PwArgs {
+    yq::EpiParams ep;
+    float *out_yolo;       // the following yolo layer's NCHW tensor (detection heads) or nullptr
+    const float *lut;      // [0,256): (u8 - zp_out) * s_out   [256,512): its logistic
+    int yolo_per;          // 4 + classes + 1 channels per anchor
+    int N, CSO, NC;        // real channels, channel stride of the output, MMA N (row N of the bank = ones)
+    int B, H, W, NP;       // NP = positions that belong to images (flat: their halo included)
+    int plain;             // plain [B][H][W][C] strips: every p < NP is a pixel
+    int cpt;               // KC-chunks per tile (K / KC)
+    int a_stages, nbuf;    // ring stages, TMEM accumulators (2 or 4)
+    int tmem_cols;         // power of two >= nbuf * NC
+    int wc;                // channels one epilogue warp requantises per tile: CSO / (4 / nbuf)
+    int rowb;              // bytes per staging row = inner box of the store: min(wc, 64)
+    int store_u8;          // the uint8 tensor is stored (always, except heads on request)
+    int num_tiles;
+    uint32_t halo_word;
+    uint32_t magic_w, magic_h;
+};
+
+__device__ __forceinline__ void pw_arrive(uint64_t *bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory"); }
+__device__ __forceinline__ void pw_tmem_alloc(uint32_t *slot, uint32_t cols)
+{
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "r"(cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void pw_tmem_dealloc(uint32_t addr, uint32_t cols)
+{
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
+}
+
+// ONE = K is a single chunk: one commit per tile on done[stage], which the producer (stage free) and the epilogue (accumulator
+// complete) both wait on; a_stages % nbuf == 0 makes the stage name the accumulator.  Otherwise a commit per chunk frees its
+// stage and one more per tile publishes the accumulator.
+template <int KC, bool ONE, bool YOLO>
+__global__ void __launch_bounds__(PW_THREADS, 1) conv_u8_tc_pw_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                                                                  const __grid_constant__ CUtensorMap tmO, const PwArgs a)
+{
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    constexpr int A_STAGE = 128 * KC;
+    const int b_chunk = a.NC * KC;                                   // multiple of 1024 (NC % 16 == 0, KC >= 64)
+    uint8_t *sB = smem;                                              // [cpt][NC rows][KC] resident filter bank
+    uint8_t *sA = sB + a.cpt * b_chunk;                              // a.a_stages ring stages of 128 positions x KC
+    uint8_t *sOut = sA + a.a_stages * A_STAGE;                       // one staging slice per epilogue warp
+    int4 *s_q = (int4 *)(sOut + PW_EPI_WARPS * PW_STAGE_SLICE);      // {bias, zw, 2*M0, shift}
+    double *s_mc = (double *)(s_q + PW_MAX_NC);
+    float *s_lut = (float *)(s_mc + PW_MAX_NC);
+    int *s_sel = (int *)(s_lut + 512);
+    uint64_t *a_full = (uint64_t *)(s_sel + PW_MAX_NC);
+    uint64_t *a_empty = a_full + PW_MAX_ASTAGES;                     // ONE: "done" (MMAs of the tile in this stage have completed)
+    uint64_t *acc_full = a_empty + PW_MAX_ASTAGES;
+    uint64_t *acc_empty = acc_full + 4;
+    uint64_t *b_full = acc_empty + 4;
+    uint32_t *tmem_slot = (uint32_t *)(b_full + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nst = a.a_stages, nbuf = a.nbuf, chunks = a.cpt;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < PW_MAX_ASTAGES; ++s) {
+            mbar_init(&a_full[s], 1);
+            mbar_init(&a_empty[s], 1);
+        }
+        for (int s = 0; s < 4; ++s) {
+            mbar_init(&acc_full[s], 1);
+            mbar_init(&acc_empty[s], (uint32_t)(PW_EPI_WARPS / nbuf));
+        }
+        mbar_init(b_full, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) pw_tmem_alloc(tmem_slot, (uint32_t)a.tmem_cols);
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmO) : "memory");
+    }
+    if (warp >= 2) {
+        const int t = threadIdx.x - 64;
+        for (int i = t; i < a.CSO; i += 32 * PW_EPI_WARPS) {   // (CSO <= the parameter arrays' padded length; NC may exceed it)
+            s_q[i] = __ldg(a.ep.chanq + i);
+            s_mc[i] = __ldg(a.ep.mcomb + i);
+        }
+        if (YOLO) {   // yolo_layer.c:137-146: channels 2, 3 (w, h) of every anchor stay linear, the rest go through the logistic
+            for (int i = t; i < 512; i += 32 * PW_EPI_WARPS) s_lut[i] = __ldg(a.lut + i);
+            for (int i = t; i < a.CSO; i += 32 * PW_EPI_WARPS) {
+                const int e = i % a.yolo_per;
+                s_sel[i] = (e == 2 || e == 3) ? 0 : 256;
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    // the filter bank is a constant of the network: its load may overlap the previous kernel's tail
+    if (warp == 0 && elect_one()) {
+        mbar_expect_tx(b_full, (uint32_t)(chunks * b_chunk));
+        for (int c = 0; c < chunks; ++c) tma_load_2d(sB + c * b_chunk, &tmB, b_full, c * KC, 0);
+    }
+    yq_pdl_wait_then_release();                             // no activation tensor was touched so far
+
+    if (warp == 0) {
+        // ===================== TMA producer (warp-uniform control flow, one elected lane issues) =====================
+        int s = 0;
+        uint32_t ph = 0;
+        for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
+            const int p0 = tile * 128;
+            for (int c = 0; c < chunks; ++c) {
+                mbar_wait(&a_empty[s], ph ^ 1);
+                if (elect_one()) {
+                    mbar_expect_tx(&a_full[s], (uint32_t)A_STAGE);
+                    tma_load_2d(sA + s * A_STAGE, &tmA, &a_full[s], c * KC, p0);
+                }
+                if (++s == nst) { s = 0; ph ^= 1; }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        const uint32_t idesc = make_idesc(a.NC);
+        int s = 0, b = 0;
+        uint32_t ph = 0, phb = 0;
+        mbar_wait(b_full, 0);
+        for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
+            mbar_wait(&acc_empty[b], phb ^ 1);               // the epilogue has drained this accumulator
+            tc_fence_after();
+            const uint32_t acc = tmem_base + (uint32_t)(b * a.NC);
+            for (int c = 0; c < chunks; ++c) {
+                mbar_wait(&a_full[s], ph);
+                tc_fence_after();
+                if (elect_one()) {
+                    const uint64_t da = make_desc<KC>(smem_u32(sA + s * A_STAGE));
+                    const uint64_t db = make_desc<KC>(smem_u32(sB + c * b_chunk));
+#pragma unroll
+                    for (int k = 0; k < KC / 32; ++k) umma_i8(acc, da + 2 * k, db + 2 * k, idesc, (c | k) ? 1u : 0u);
+                    umma_commit(&a_empty[s]);
+                }
+                if (++s == nst) { s = 0; ph ^= 1; }
+            }
+            if (!ONE && elect_one()) umma_commit(&acc_full[b]);
+            if (++b == nbuf) { b = 0; phb ^= 1; }
+        }
+    } else {
+        // ===================== epilogue: 16 warps, each on its own =====================
+        const int ew = warp - 2;
+        const int q = warp & 3;                 // TMEM lane quarter the hardware lets this warp read
+        const int g = ew >> 2;                  // group
+        const int b = g % nbuf;                 // my accumulator
+        const int part = g / nbuf;              // my share of its channels
+        const int cbeg = part * a.wc;
+        const int nch = a.wc / 16;              // 16-channel chunks of mine (2, 4 or 8)
+        const int rowb = a.rowb;                // 32 or 64
+        const int cpp = rowb / 16;              // chunks per store pass
+        const int npass = a.wc / rowb;
+        uint8_t *stage = sOut + ew * PW_STAGE_SLICE;
+        const int pitch = a.W + (a.plain ? 0 : 1), rows_h = a.H + (a.plain ? 0 : 1);
+        const int hw = a.H * a.W;
+        const int actm = yq::act_mode(a.ep.act);
+        for (int it = b; blockIdx.x + (long long)it * gridDim.x < a.num_tiles; it += nbuf) {
+            const int tile = blockIdx.x + it * gridDim.x;
+            const int p0 = tile * 128;
+            const int p = p0 + q * 32 + lane;
+            const int row = (int)__umulhi((uint32_t)p, a.magic_w);
+            const int col = p - row * pitch;
+            const int n = (int)__umulhi((uint32_t)row, a.magic_h);
+            const int y1 = row - n * rows_h;
+            const bool valid = p < a.NP && (a.plain || (col >= 1 && y1 >= 1));
+            const int yy = a.plain ? y1 : y1 - 1, xx = a.plain ? col : col - 1;
+            if (ONE) {
+                const int s = it % nst;
+                mbar_wait(&a_empty[s], (uint32_t)((it / nst) & 1));
+            } else {
+                mbar_wait(&acc_full[b], (uint32_t)((it / nbuf) & 1));
+            }
+            tc_fence_after();
+            const uint32_t trow = tmem_base + (uint32_t)(b * a.NC) + ((uint32_t)(q * 32) << 16);
+            uint32_t vbuf[2][16];
+            tmem_ld16_issue(trow + cbeg, vbuf[0]);
+            const int nsa = -(int)tmem_ld1(trow + a.N);      // minus the position's activation sum (the ones row); also completes the load above
+            auto run = [&](auto actm_tag) {
+                constexpr int ACTM = decltype(actm_tag)::value;
+#pragma unroll 1
+                for (int pass = 0; pass < npass; ++pass) {
+                    if (a.store_u8) {
+                        // my staging slice is free once the previous store has read it
+                        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                        __syncwarp();
+                    }
+#pragma unroll 1
+                    for (int cp = 0; cp < cpp; cp += 2) {
+#pragma unroll
+                        for (int h2 = 0; h2 < 2; ++h2) {
+                            const int chl = cp + h2;                 // chunk within the pass
+                            const int ch = pass * cpp + chl;
+                            const int c0 = cbeg + 16 * ch;
+                            uint32_t(&v)[16] = vbuf[h2];
+                            if (ch + 1 < nch) tmem_ld16_issue(trow + c0 + 16, vbuf[h2 ^ 1]);   // in flight while this chunk is requantized
+                            uint32_t packed[4];
+                            int extra[16];
+                            yq::requant_chunk<ACTM, false, 16, false>(v, nsa, extra, s_q + c0, s_mc + c0, a.ep.zp_out, packed, a.ep.xlim);
+                            if (!valid) packed[0] = packed[1] = packed[2] = packed[3] = a.halo_word;
+                            yq::mask_pad_channels<16>(packed, a.N - c0);
+                            if (YOLO && valid) {
+                                // the detection heads: one table lookup and one 4-byte store per output (lanes = consecutive pixels)
+                                float *dst = a.out_yolo + ((size_t)n * a.N + c0) * hw + (size_t)yy * a.W + xx;
+                                const int nreal = a.N - c0;
+#pragma unroll
+                                for (int j = 0; j < 16; ++j)
+                                    if (j < nreal) dst[(size_t)j * hw] = s_lut[s_sel[c0 + j] + ((packed[j / 4] >> (8 * (j % 4))) & 255u)];
+                            }
+                            if (a.store_u8) {
+                                // 64-byte rows: SWIZZLE_64B (16-byte chunk ^ row bits 1-2); 32-byte rows: SWIZZLE_32B (chunk ^ row bit 2)
+                                const int sw = rowb == 64 ? (chl ^ ((lane >> 1) & 3)) : (chl ^ ((lane >> 2) & 1));
+                                *reinterpret_cast<uint4 *>(stage + lane * rowb + sw * 16) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+                            }
+                            if (ch + 1 < nch) tmem_ld_wait16(vbuf[h2 ^ 1]);
+                        }
+                    }
+                    if (pass + 1 == npass) {
+                        // this warp's TMEM reads of the tile are done: hand the accumulator back
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) pw_arrive(&acc_empty[b]);
+                    }
+                    if (a.store_u8) {
+                        fence_proxy_async();          // my staging writes -> visible to the TMA unit
+                        __syncwarp();
+                        if (lane == 0) {
+                            tma_store_2d(&tmO, stage, cbeg + pass * rowb, p0 + q * 32);
+                            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                        }
+                    }
+                }
+            };
+            if (actm == 0) run(std::integral_constant<int, 0>{});
+            else if (actm == 1) run(std::integral_constant<int, 1>{});
+            else run(std::integral_constant<int, 2>{});
+        }
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // global writes complete before the CTA retires
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        pw_tmem_dealloc(tmem_base, (uint32_t)a.tmem_cols);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn pw_get_encode()
+{
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)p;
+    }
+    return fn;
+}
+
+int pw_encode_2d(CUtensorMap *m, const void *ptr, uint64_t rows, int row_bytes, int box_c, int box_rows, CUtensorMapL2promotion prom)
+{
+    EncodeTiledFn enc = pw_get_encode();
+    if (!enc) return yq::fail("cuTensorMapEncodeTiled is not available from this driver");
+    cuuint64_t dims[2] = {(cuuint64_t)row_bytes, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)row_bytes};
+    cuuint32_t box[2] = {(cuuint32_t)box_c, (cuuint32_t)box_rows};
+    cuuint32_t es[2] = {1, 1};
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void *>(ptr), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     box_c >= 128 ? CU_TENSOR_MAP_SWIZZLE_128B : (box_c == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B), prom,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return yq::fail("cuTensorMapEncodeTiled(%llu x %d, box %d x %d) failed: %d", (unsigned long long)rows, row_bytes, box_c, box_rows, (int)r);
+    return 0;
+}
+
+struct PwState {
+    int KC, NC;
+    uint8_t *w = nullptr;       // [NC][cs_in]: rows < n the filters, row n all ones, the rest zero
+    float *lut = nullptr;       // quant_stop layers: dequantized value and its logistic for each of the 256 output bytes
+    CUtensorMap tmB;
+    struct Key {
+        const void *in;
+        void *out;
+        int batch;
+        bool operator<(const Key &o) const { return in != o.in ? in < o.in : out != o.out ? out < o.out : batch < o.batch; }
+    };
+    std::map<Key, std::pair<CUtensorMap, CUtensorMap>> maps;
+};
+
+// shared memory of a launch with `stages` ring stages
+int pw_smem_bytes(int NC, int K, int KC, int stages)
+{
+    return 1024 + NC * K + stages * 128 * KC + PW_EPI_WARPS * PW_STAGE_SLICE + PW_MAX_NC * (16 + 8 + 4) + 2048 + 512;
+}
+
+template <int KC, bool ONE, bool YOLO>
+int pw_launch_v(PwState *st, const CUtensorMap &tmA, const CUtensorMap &tmO, const PwArgs &a, int smem, int grid, cudaStream_t stream)
+{
+    auto kern = conv_u8_tc_pw_kernel<KC, ONE, YOLO>;
+    if (yq::ensure_dynamic_smem((const void *)kern, smem)) return -1;
+    YQ_CUDA(yq::launch_pdl(kern, dim3(grid), dim3(PW_THREADS), smem, stream, tmA, st->tmB, tmO, a));
+    return 0;
+}
+
+template <int KC>
+int pw_launch(PwState *st, const CUtensorMap &tmA, const CUtensorMap &tmO, const PwArgs &a, int smem, int grid, cudaStream_t stream)
+{
+    if (a.cpt == 1) {
+        if (a.out_yolo) return pw_launch_v<KC, true, true>(st, tmA, tmO, a, smem, grid, stream);
+        return pw_launch_v<KC, true, false>(st, tmA, tmO, a, smem, grid, stream);
+    }
+    if (a.out_yolo) return pw_launch_v<KC, false, true>(st, tmA, tmO, a, smem, grid, stream);
+    return pw_launch_v<KC, false, false>(st, tmA, tmO, a, smem, grid, stream);
+}
+
+}  // namespace
+
+int yq_tc_pw_supported(const yq_conv_layer *l)
+{
+    static const bool off = getenv("YQ_NO_PW") && atoi(getenv("YQ_NO_PW"));      // A/B measurements
+    if (off || !l->int_form || !l->fused_mult || l->saturate) return 0;
+    if (l->size != 1 || l->stride != 1 || l->pad != 0) return 0;
+    if (l->c != l->cs_in || l->cs_in % 64) return 0;                             // no pad lanes: they would count in sum(a)
+    const int NC = yq::round_up(l->n + 1, 16);
+    if (NC > PW_MAX_NC) return 0;
+    if (l->cs_out > NC) return 0;
+    const int wc = l->cs_out / (PW_GROUPS / (4 * NC <= 512 ? 4 : 2));            // channels per epilogue warp: 32, 64 or a multiple of 64
+    if (wc % 32 || (wc > 64 && wc % 64)) return 0;
+    const int KC = (l->cs_in % 128) ? 64 : 128;
+    if (pw_smem_bytes(NC, l->cs_in, KC, l->cs_in == KC ? 4 : 3) > 227 * 1024) return 0;   // the bank and a minimal ring
+    return pw_get_encode() != nullptr;
+}
+
+int yq_tc_pw_prepare(yq_conv_layer *l, void **state)
+{
+    PwState *st = new PwState();
+    st->KC = (l->cs_in % 128) ? 64 : 128;
+    st->NC = yq::round_up(l->n + 1, 16);
+    const size_t K = (size_t)l->cs_in;
+    std::vector<uint8_t> wp;
+    char tag[24];
+    snprintf(tag, sizeof tag, "pw1.%d", st->NC);
+    // (a data-parallel replica takes the image from the arena blob broadcast to its device: no host packing, no upload)
+    const bool on_dev = yq::pack_fetch_device(l, tag, (size_t)st->NC * K, (void **)&st->w);
+    if (!on_dev && (!yq::pack_fetch(l, tag, wp) || wp.size() != (size_t)st->NC * K)) {
+        wp.assign((size_t)st->NC * K, 0);
+        for (int oc = 0; oc < l->n; ++oc)
+            for (int ci = 0; ci < l->c; ++ci) wp[(size_t)oc * K + ci] = l->host_w[(size_t)oc * l->c + ci];
+        for (size_t ci = 0; ci < K; ++ci) wp[(size_t)l->n * K + ci] = 1;         // the ones row: TMEM column n = sum of the position's activations
+        yq::pack_put(l, tag, wp);
+    }
+    auto cleanup = [&]() {
+        cudaFree(st->w);
+        cudaFree(st->lut);
+        delete st;
+        return -1;
+    };
+    if (!on_dev) {
+        if (cudaMalloc((void **)&st->w, wp.size()) != cudaSuccess) return cleanup();
+        if (cudaMemcpy(st->w, wp.data(), wp.size(), cudaMemcpyHostToDevice) != cudaSuccess) return cleanup();
+    }
+    if (pw_encode_2d(&st->tmB, st->w, (uint64_t)st->NC, (int)K, st->KC, st->NC, CU_TENSOR_MAP_L2_PROMOTION_L2_256B)) return cleanup();
+    if (l->quant_stop_flag) {
+        // the head's float values are a table of the 256 output bytes, tabulated with the host's libm (yq_conv_tc_flat.cu)
+        float lut[512];
+        for (int u = 0; u < 256; ++u) {
+            const float x = (float)(u - l->zp_out) * l->s_out;
+            lut[u] = x;
+            lut[256 + u] = (float)(1. / (1. + exp(-(double)x)));
+        }
+        if (cudaMalloc((void **)&st->lut, sizeof lut) != cudaSuccess) return cleanup();
+        if (cudaMemcpy(st->lut, lut, sizeof lut, cudaMemcpyHostToDevice) != cudaSuccess) return cleanup();
+    }
+    *state = st;
+    return 0;
+}
+
+void yq_tc_pw_free(void *state)
+{
+    PwState *st = (PwState *)state;
+    if (!st) return;
+    cudaFree(st->w);
+    cudaFree(st->lut);
+    delete st;
+}
+
+int yq_tc_pw_forward(yq_conv_layer *l, void *state, const uint8_t *in, uint8_t *out_u8, int halo_fill, float *out_yolo, int yolo_classes, int batch,
+                     cudaStream_t stream, int plain)
+{
+    PwState *st = (PwState *)state;
+    if (!st || !in || !out_u8) return yq::fail("tcgen05 pointwise flavour: bad argument");
+    if (l->quant_stop_flag && !out_yolo) return yq::fail("tcgen05 pointwise flavour: a quant_stop layer runs here only as a fused yolo head");
+    const int W1 = l->w + (plain ? 0 : 1), H1 = l->h + (plain ? 0 : 1);
+    const long long NP = (long long)batch * H1 * W1;
+    const long long rows_alloc = plain ? NP : NP + W1 + 2;     // + the trailing halo row (yq_act_geom_bytes)
+    if (rows_alloc * W1 >= 0x100000000ll || rows_alloc + 128 >= 0x7fffffffll) return yq::fail("tcgen05 pointwise flavour: tensor too large for 32-bit position arithmetic");
+    const int n_sm = yq::device_sm_count(), smem_max = yq::device_smem_optin();   // (of the CURRENT device: nothing cached per process)
+    if (n_sm <= 0 || smem_max <= 0) return yq::fail("cannot query the device's multiprocessor count / shared memory size");
+    PwArgs a;
+    memset(&a, 0, sizeof a);
+    a.ep = yq::make_epi(l);
+    a.out_yolo = out_yolo;
+    a.lut = st->lut;
+    a.yolo_per = 4 + yolo_classes + 1;
+    if (out_yolo && (!st->lut || l->n % a.yolo_per)) return yq::fail("tcgen05 pointwise flavour: layer is not a yolo head for %d classes", yolo_classes);
+    a.N = l->n; a.CSO = l->cs_out; a.NC = st->NC;
+    a.B = batch; a.H = l->h; a.W = l->w; a.NP = (int)NP;
+    a.plain = plain ? 1 : 0;
+    a.cpt = l->cs_in / st->KC;
+    a.nbuf = 4 * st->NC <= 512 ? 4 : 2;
+    a.tmem_cols = 32;
+    while (a.tmem_cols < a.nbuf * st->NC) a.tmem_cols *= 2;
+    // the epilogue walks the output's channel stride (pad channels are stored as zeros)
+    a.wc = l->cs_out / (PW_GROUPS / a.nbuf);
+    a.rowb = a.wc < 64 ? a.wc : 64;
+    if (a.wc % 32 || (a.wc > 64 && a.wc % 64)) return yq::fail("tcgen05 pointwise flavour: %d channels per epilogue warp", a.wc);
+    {
+        static const int head_u8 = getenv("YQ_PW_HEAD_U8") ? atoi(getenv("YQ_PW_HEAD_U8")) : 1;     // 0: heads skip their uint8 tensor (A/B measurements)
+        a.store_u8 = l->quant_stop_flag ? head_u8 : 1;
+    }
+    // ring depth: what fits, a multiple of the accumulator count when a commit serves stage and accumulator alike
+    int stages = PW_MAX_ASTAGES;
+    while (stages > 3 && pw_smem_bytes(st->NC, l->cs_in, st->KC, stages) > smem_max) --stages;
+    if (a.cpt == 1) stages = stages / 4 * 4;
+    if (pw_smem_bytes(st->NC, l->cs_in, st->KC, stages) > smem_max) return yq::fail("tcgen05 pointwise flavour: the filter bank does not fit shared memory");
+    a.a_stages = stages;
+    const int smem = pw_smem_bytes(st->NC, l->cs_in, st->KC, stages);
+    a.num_tiles = (int)((rows_alloc + 127) / 128);
+    a.halo_word = 0x01010101u * (uint32_t)(halo_fill & 0xff);
+    a.magic_w = (uint32_t)((0x100000000ull + W1 - 1) / W1);
+    a.magic_h = (uint32_t)((0x100000000ull + H1 - 1) / H1);
+    PwState::Key key{in, out_u8, batch * 2 + (plain ? 1 : 0)};
+    auto it = st->maps.find(key);
+    if (it == st->maps.end()) {
+        if (st->maps.size() > 64) st->maps.clear();
+        CUtensorMap tmA, tmO;
+        if (pw_encode_2d(&tmA, in, (uint64_t)rows_alloc, l->cs_in, st->KC, 128, CU_TENSOR_MAP_L2_PROMOTION_L2_128B)) return -1;
+        // the store box is one epilogue warp's pass: 32 positions x rowb channels
+        if (pw_encode_2d(&tmO, out_u8, (uint64_t)rows_alloc, l->cs_out, a.rowb, 32, CU_TENSOR_MAP_L2_PROMOTION_L2_128B)) return -1;
+        it = st->maps.emplace(key, std::make_pair(tmA, tmO)).first;
+    }
+    const int grid = a.num_tiles < n_sm ? a.num_tiles : n_sm;
+    const CUtensorMap &tmA = it->second.first, &tmO = it->second.second;
+    if (st->KC == 128) return pw_launch<128>(st, tmA, tmO, a, smem, grid, stream);
+    return pw_launch<64>(st, tmA, tmO, a, smem, grid, stream);
+}

@@ -526,7 +526,8 @@ extern "C" yq_conv_layer *yq_make_convolutional_layer_quant(const yq_conv_desc *
     }
     if ((yq_tc_rows_supported(l) && yq_tc_rows_prepare(l, &l->tc_rows) != 0) || (yq_tc_flat_supported(l) && yq_tc_flat_prepare(l, &l->tc_flat) != 0) ||
         (yq_tc_flat2_supported(l) && yq_tc_flat2_prepare(l, &l->tc_flat2) != 0) ||
-        (yq_tc_flat2x_supported(l) && yq_tc_flat2x_prepare(l, &l->tc_flat2x) != 0)) {
+        (yq_tc_flat2x_supported(l) && yq_tc_flat2x_prepare(l, &l->tc_flat2x) != 0) ||
+        (yq_tc_flat_eligible(l) && yq_tc_pw_supported(l) && yq_tc_pw_prepare(l, &l->tc_pw) != 0)) {
         yq_free_convolutional_layer_quant(l);
         return nullptr;
     }
@@ -541,6 +542,7 @@ extern "C" void yq_free_convolutional_layer_quant(yq_conv_layer *l)
     yq_tc_flat_free(l->tc_flat);
     yq_tc_flat2_free(l->tc_flat2);
     yq_tc_flat2x_free(l->tc_flat2x);
+    yq_tc_pw_free(l->tc_pw);
     cudaFree(l->w_simt); cudaFree(l->bias); cudaFree(l->zw); cudaFree(l->mcomb); cudaFree(l->mval); cudaFree(l->rsh); cudaFree(l->chanq);
     delete l;
 }
@@ -565,6 +567,8 @@ extern "C" int yq_forward_convolutional_layer_quant_pool_gpu(yq_conv_layer *l, c
     if (l->quant_stop_flag && !out_f32) return yq::fail("quant_stop layer needs out_f32");
     if (out_pool && !yq_tc_can_fuse_pool(l)) return yq::fail("this layer's kernel flavour cannot fuse the max-pool (see yq_conv_can_fuse_maxpool)");
     // a 1x1 convolution between plain tensors is a flat strip without halo positions: the persistent two-tile kernel takes it
+    if (yq_conv_plain_1x1_fast(l) && !out_pool && out_u8 && l->tc_pw && !out_acc && !(getenv("YQ_PW") && !atoi(getenv("YQ_PW"))))
+        return yq_tc_pw_forward(l, l->tc_pw, in_u8, out_u8, 0, nullptr, 0, batch, (cudaStream_t)stream, 1);
     if (yq_conv_plain_1x1_fast(l) && !out_pool && out_u8)
         return yq_tc_flat2_forward(l, l->tc_flat2, in_u8, out_u8, 0, out_acc, batch, (cudaStream_t)stream, 1);
     if (l->kernel == 1) return yq_tc_forward(l, in_u8, out_u8, out_pool, out_f32, out_acc, batch, (cudaStream_t)stream);
@@ -659,6 +663,9 @@ static int flat_dispatch(yq_conv_layer *l, const uint8_t *in_flat, uint8_t *out_
     }
     if (sc && !l->tc_flat2 && !l->tc_flat2x) return yq::fail("the fused shortcut needs the persistent flat flavours (see yq_conv_flat_shortcut_supported)");
     if (sc) two = l->tc_flat2 != nullptr;          // (the one-tile form has no shortcut epilogue)
+    // narrow 1x1 layers: the streaming form with the filter bank resident in shared memory (no side outputs; YQ_PW=0 switches it off per call)
+    if (l->tc_pw && !sc && !out_acc && !l->quant_stop_flag && !(getenv("YQ_PW") && !atoi(getenv("YQ_PW"))))
+        return yq_tc_pw_forward(l, l->tc_pw, in_flat, out_flat, halo_fill, nullptr, 0, batch, (cudaStream_t)stream, 0);
     if (l->tc_flat2x && !no_flat2 && (use_2x == 2 || (use_2x == 1 && l->c >= 256)))
         return yq_tc_flat2x_forward(l, l->tc_flat2x, in_flat, out_flat, halo_fill, out_acc, batch, (cudaStream_t)stream, sc);
     if (two) return yq_tc_flat2_forward(l, l->tc_flat2, in_flat, out_flat, halo_fill, out_acc, batch, (cudaStream_t)stream, 0, sc);
@@ -697,6 +704,8 @@ extern "C" int yq_forward_convolutional_layer_quant_flat_yolo_gpu(yq_conv_layer 
 {
     if (!l || !in_flat || !out_flat || !out_yolo || batch <= 0 || classes < 0) return yq::fail("yq_forward_convolutional_layer_quant_flat_yolo_gpu: bad argument");
     if (!l->tc_flat || !l->quant_stop_flag) return yq::fail("the fused yolo head needs a quant_stop layer with the flat flavour");
+    if (l->tc_pw && !out_f32 && !out_acc && !(getenv("YQ_PW") && !atoi(getenv("YQ_PW"))))      // the throughput path: no side outputs
+        return yq_tc_pw_forward(l, l->tc_pw, in_flat, out_flat, halo_fill, out_yolo, classes, batch, (cudaStream_t)stream, 0);
     return yq_tc_flat_forward(l, l->tc_flat, in_flat, out_flat, halo_fill, out_f32, out_yolo, classes, out_acc, batch, (cudaStream_t)stream);
 }
 

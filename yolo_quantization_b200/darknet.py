@@ -273,9 +273,13 @@ class ConvolutionalLayerQuant:
     def flat_supported(self) -> bool:
         return bool(_lib.load().yq_conv_flat_supported(self.handle))
 
-    def forward_flat(self, x_nchw: np.ndarray, halo_fill: int = 0, want_acc: bool = True) -> Dict[str, np.ndarray]:
+    def forward_flat(self, x_nchw: np.ndarray, halo_fill: int = 0, want_acc: bool = True, yolo_classes: Optional[int] = None
+                     ) -> Dict[str, np.ndarray]:
         """The flat-strip flavour: input staged as a flat halo-padded tensor (halo = zp_in), output read back from one.
-        Returns dict(u8, acc, f32 as in forward(), halo_ok=True when every halo byte of the output equals halo_fill)."""
+        Returns dict(u8, acc, f32 as in forward(), halo_ok=True when every halo byte of the output equals halo_fill).
+        yolo_classes (quant_stop layers): run the layer as a detection head with the following [yolo] layer fused
+        (yq_forward_convolutional_layer_quant_flat_yolo_gpu); adds yolo=[b,n,h,w] float32.  Without side outputs
+        (want_acc=False) this is the production launch of the heads: f32 is then not materialised."""
         lib = _lib.load()
         b = x_nchw.shape[0]
         x = np.ascontiguousarray(x_nchw, np.uint8)
@@ -289,10 +293,17 @@ class ConvolutionalLayerQuant:
         dout = DeviceBuffer(lib.yq_act_geom_bytes(C.byref(g), b, self.n), zero=False)
         check(lib.yq_cuda_memset(dout.ptr, 0xEE, dout.nbytes, None))
         dacc = DeviceBuffer(b * self.out_h * self.out_w * cs_out * 4) if want_acc else None
-        df32 = DeviceBuffer(b * self.n * self.out_h * self.out_w * 4) if self.quant_stop_flag else None
-        check(lib.yq_forward_convolutional_layer_quant_flat_gpu(self.handle, din.ptr, dout.ptr, int(halo_fill), df32.ptr if df32 else None,
-                                                                dacc.ptr if dacc else None, b, None),
-              "yq_forward_convolutional_layer_quant_flat_gpu")
+        df32 = DeviceBuffer(b * self.n * self.out_h * self.out_w * 4) if self.quant_stop_flag and (yolo_classes is None or want_acc) else None
+        dyolo = None
+        if yolo_classes is not None:
+            dyolo = DeviceBuffer(b * self.n * self.out_h * self.out_w * 4)
+            check(lib.yq_forward_convolutional_layer_quant_flat_yolo_gpu(self.handle, din.ptr, dout.ptr, int(halo_fill), df32.ptr if df32 else None,
+                                                                         dyolo.ptr, int(yolo_classes), dacc.ptr if dacc else None, b, None),
+                  "yq_forward_convolutional_layer_quant_flat_yolo_gpu")
+        else:
+            check(lib.yq_forward_convolutional_layer_quant_flat_gpu(self.handle, din.ptr, dout.ptr, int(halo_fill), df32.ptr if df32 else None,
+                                                                    dacc.ptr if dacc else None, b, None),
+                  "yq_forward_convolutional_layer_quant_flat_gpu")
         tmp = DeviceBuffer(b * self.n * self.out_h * self.out_w)
         check(lib.yq_nhwc_to_nchw_u8_geom(dout.ptr, tmp.ptr, b, self.n, self.out_h, self.out_w, C.byref(g), None))
         check(lib.yq_stream_synchronize(None))
@@ -301,6 +312,8 @@ class ConvolutionalLayerQuant:
             res["acc"] = pull_nhwc_i32(dacc, b, self.n, self.out_h, self.out_w)
         if df32:
             res["f32"] = df32.pull((b, self.n, self.out_h, self.out_w), np.float32)
+        if dyolo:
+            res["yolo"] = dyolo.pull((b, self.n, self.out_h, self.out_w), np.float32)
         raw = dout.pull((dout.nbytes // cs_out, cs_out), np.uint8)
         rows = raw[: b * g.rows_h * g.pitch_w].reshape(b, g.rows_h, g.pitch_w, cs_out).copy()
         interior = rows[:, 1:1 + self.out_h, 1:1 + self.out_w, :].copy()
@@ -308,7 +321,7 @@ class ConvolutionalLayerQuant:
         tail = raw[b * g.rows_h * g.pitch_w:]
         res["halo_ok"] = bool((rows[..., :self.n] == halo_fill).all() and (tail[:, :self.n] == halo_fill).all()
                               and not rows[..., self.n:].any() and not tail[:, self.n:].any() and not interior[..., self.n:].any())
-        for d in (din, src, dout, dacc, df32, tmp):
+        for d in (din, src, dout, dacc, df32, dyolo, tmp):
             if d:
                 d.free()
         return res
@@ -358,6 +371,8 @@ class ConvolutionalLayerQuant:
             res["acc"] = pull_nhwc_i32(dacc, b, self.n, self.out_h, self.out_w)
         if df32:
             res["f32"] = df32.pull((b, self.n, self.out_h, self.out_w), np.float32)
+        if dyolo:
+            res["yolo"] = dyolo.pull((b, self.n, self.out_h, self.out_w), np.float32)
         raw = dout.pull((dout.nbytes // cs_out, cs_out), np.uint8)
         rows = raw[: b * go.rows_h * go.pitch_w].reshape(b, go.rows_h, go.pitch_w, cs_out).copy()
         rows[:, go.pad:go.pad + self.out_h, go.pad:go.pad + self.out_w, :] = 0xEE
