@@ -205,6 +205,7 @@ int yq_tc_flat2x_forward(yq_conv_layer *l, void *state, const uint8_t *in_flat, 
 // plain strips; out_yolo != null: the layer is a detection head and the following yolo layer's tensor is written as well)
 int yq_tc_pw_supported(const yq_conv_layer *l);
 int yq_tc_pw_prepare(yq_conv_layer *l, void **state);
+int yq_tc_pw_head_supported(const yq_conv_layer *l);
 void yq_tc_pw_free(void *state);
 int yq_tc_pw_forward(yq_conv_layer *l, void *state, const uint8_t *in, uint8_t *out_u8, int halo_fill, float *out_yolo, int yolo_classes, int batch,
                      cudaStream_t stream, int plain);

@@ -60,9 +60,21 @@ struct PwArgs {
     int rowb;              // bytes per staging row = inner box of the store: min(wc, 64)
     int store_u8;          // the uint8 tensor is stored (always, except heads on request)
     int num_tiles;
+    int trace;             // YQ_PW_TRACE
     uint32_t halo_word;
     uint32_t magic_w, magic_h;
 };
+
+// YQ_PW_TRACE=1: every CTA records globaltimer (ns) at a few events into yq_pw_trace[blockIdx.x * 64 + event] (tools/probes/pw_trace.py)
+__device__ unsigned long long yq_pw_trace[256 * 64];
+__device__ __forceinline__ void pw_mark(int on, int ev)
+{
+    if (on && blockIdx.x < 256 && ev < 64) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        yq_pw_trace[blockIdx.x * 64 + ev] = t;
+    }
+}
 
 __device__ __forceinline__ void pw_arrive(uint64_t *bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory"); }
 __device__ __forceinline__ void pw_tmem_alloc(uint32_t *slot, uint32_t cols)
@@ -78,7 +90,7 @@ __device__ __forceinline__ void pw_tmem_dealloc(uint32_t addr, uint32_t cols)
 // ONE = K is a single chunk: one commit per tile on done[stage], which the producer (stage free) and the epilogue (accumulator
 // complete) both wait on; a_stages % nbuf == 0 makes the stage name the accumulator.  Otherwise a commit per chunk frees its
 // stage and one more per tile publishes the accumulator.
-template <int KC, bool ONE, bool YOLO>
+template <int KC, bool ONE, bool YOLO, int ACTM>
 __global__ void __launch_bounds__(PW_THREADS, 1) conv_u8_tc_pw_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                                                                   const __grid_constant__ CUtensorMap tmO, const PwArgs a)
 {
@@ -102,6 +114,7 @@ __global__ void __launch_bounds__(PW_THREADS, 1) conv_u8_tc_pw_kernel(const __gr
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nst = a.a_stages, nbuf = a.nbuf, chunks = a.cpt;
+    if (threadIdx.x == 0) pw_mark(a.trace, 0);                       // CTA start
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < PW_MAX_ASTAGES; ++s) {
@@ -139,18 +152,20 @@ __global__ void __launch_bounds__(PW_THREADS, 1) conv_u8_tc_pw_kernel(const __gr
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    if (threadIdx.x == 0) pw_mark(a.trace, 1);                       // setup done
     // the filter bank is a constant of the network: its load may overlap the previous kernel's tail
     if (warp == 0 && elect_one()) {
         mbar_expect_tx(b_full, (uint32_t)(chunks * b_chunk));
         for (int c = 0; c < chunks; ++c) tma_load_2d(sB + c * b_chunk, &tmB, b_full, c * KC, 0);
     }
     yq_pdl_wait_then_release();                             // no activation tensor was touched so far
+    if (threadIdx.x == 0) pw_mark(a.trace, 2);                       // previous grid complete
 
     if (warp == 0) {
         // ===================== TMA producer (warp-uniform control flow, one elected lane issues) =====================
-        int s = 0;
+        int s = 0, tr = 0;
         uint32_t ph = 0;
-        for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
+        for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x, ++tr) {
             const int p0 = tile * 128;
             for (int c = 0; c < chunks; ++c) {
                 mbar_wait(&a_empty[s], ph ^ 1);
@@ -160,6 +175,7 @@ __global__ void __launch_bounds__(PW_THREADS, 1) conv_u8_tc_pw_kernel(const __gr
                 }
                 if (++s == nst) { s = 0; ph ^= 1; }
             }
+            if (lane == 0 && tr < 8) pw_mark(a.trace, 4 + 4 * tr + 3);                     // tile's loads issued
         }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
@@ -167,7 +183,9 @@ __global__ void __launch_bounds__(PW_THREADS, 1) conv_u8_tc_pw_kernel(const __gr
         int s = 0, b = 0;
         uint32_t ph = 0, phb = 0;
         mbar_wait(b_full, 0);
-        for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
+        if (lane == 0) pw_mark(a.trace, 3);                  // filter bank landed
+        int tr = 0;
+        for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x, ++tr) {
             mbar_wait(&acc_empty[b], phb ^ 1);               // the epilogue has drained this accumulator
             tc_fence_after();
             const uint32_t acc = tmem_base + (uint32_t)(b * a.NC);
@@ -184,6 +202,7 @@ __global__ void __launch_bounds__(PW_THREADS, 1) conv_u8_tc_pw_kernel(const __gr
                 if (++s == nst) { s = 0; ph ^= 1; }
             }
             if (!ONE && elect_one()) umma_commit(&acc_full[b]);
+            if (lane == 0 && tr < 8) pw_mark(a.trace, 4 + 4 * tr);                         // tile's operands landed, MMAs issued
             if (++b == nbuf) { b = 0; phb ^= 1; }
         }
     } else {
@@ -194,14 +213,12 @@ __global__ void __launch_bounds__(PW_THREADS, 1) conv_u8_tc_pw_kernel(const __gr
         const int b = g % nbuf;                 // my accumulator
         const int part = g / nbuf;              // my share of its channels
         const int cbeg = part * a.wc;
-        const int nch = a.wc / 16;              // 16-channel chunks of mine (2, 4 or 8)
         const int rowb = a.rowb;                // 32 or 64
         const int cpp = rowb / 16;              // chunks per store pass
         const int npass = a.wc / rowb;
         uint8_t *stage = sOut + ew * PW_STAGE_SLICE;
         const int pitch = a.W + (a.plain ? 0 : 1), rows_h = a.H + (a.plain ? 0 : 1);
         const int hw = a.H * a.W;
-        const int actm = yq::act_mode(a.ep.act);
         for (int it = b; blockIdx.x + (long long)it * gridDim.x < a.num_tiles; it += nbuf) {
             const int tile = blockIdx.x + it * gridDim.x;
             const int p0 = tile * 128;
@@ -219,70 +236,84 @@ __global__ void __launch_bounds__(PW_THREADS, 1) conv_u8_tc_pw_kernel(const __gr
                 mbar_wait(&acc_full[b], (uint32_t)((it / nbuf) & 1));
             }
             tc_fence_after();
+            if ((ew & 3) == 0 && lane == 0 && it < 8) pw_mark(a.trace, 4 + 4 * it + 1);    // tile's accumulator complete
             const uint32_t trow = tmem_base + (uint32_t)(b * a.NC) + ((uint32_t)(q * 32) << 16);
-            uint32_t vbuf[2][16];
-            tmem_ld16_issue(trow + cbeg, vbuf[0]);
-            const int nsa = -(int)tmem_ld1(trow + a.N);      // minus the position's activation sum (the ones row); also completes the load above
-            auto run = [&](auto actm_tag) {
-                constexpr int ACTM = decltype(actm_tag)::value;
+            const int nsa = -(int)tmem_ld1(trow + a.N);      // minus the position's activation sum (the ones row)
+            // the head's plane of this pixel in the yolo tensor: channel c of it is ybase[c * hw]
+            float *ybase = YOLO ? a.out_yolo + (size_t)n * a.N * hw + (size_t)yy * a.W + xx : nullptr;
+            // One 16-channel chunk per trip of a ROLLED loop, its TMEM load not overlapped with the previous chunk's arithmetic by this
+            // warp: the other fifteen epilogue warps hide it, and the loop body stays a few hundred instructions.  (The first version
+            // unrolled pairs of chunks with the load of one in flight under the other: 1 300 instructions per tile and warp that each
+            // warp walks a handful of times per launch -- half of the epilogue's stall samples were instruction-cache misses.)
 #pragma unroll 1
-                for (int pass = 0; pass < npass; ++pass) {
-                    if (a.store_u8) {
-                        // my staging slice is free once the previous store has read it
-                        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-                        __syncwarp();
-                    }
+            for (int pass = 0; pass < npass; ++pass) {
+                if (a.store_u8) {
+                    // my staging slice is free once the previous store has read it
+                    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                    __syncwarp();
+                }
 #pragma unroll 1
-                    for (int cp = 0; cp < cpp; cp += 2) {
+                for (int chl = 0; chl < cpp; ++chl) {
+                    const int c0 = cbeg + 16 * (pass * cpp + chl);
+                    uint32_t v[16];
+                    tmem_ld16(trow + c0, v);
+                    int r[16];
+                    int extra[16];
+                    yq::requant_chunk_vals<ACTM, false, 16, false>(v, nsa, extra, s_q + c0, s_mc + c0, a.ep.zp_out, r, a.ep.xlim);
+                    if (YOLO && valid) {
+                        // the detection heads: one table lookup and one 4-byte store per output (lanes = consecutive pixels)
+                        float *dst = ybase + (size_t)c0 * hw;
+                        const int4 *sel = reinterpret_cast<const int4 *>(s_sel + c0);
+                        const int nreal = a.N - c0;
+                        if (nreal >= 16) {
 #pragma unroll
-                        for (int h2 = 0; h2 < 2; ++h2) {
-                            const int chl = cp + h2;                 // chunk within the pass
-                            const int ch = pass * cpp + chl;
-                            const int c0 = cbeg + 16 * ch;
-                            uint32_t(&v)[16] = vbuf[h2];
-                            if (ch + 1 < nch) tmem_ld16_issue(trow + c0 + 16, vbuf[h2 ^ 1]);   // in flight while this chunk is requantized
-                            uint32_t packed[4];
-                            int extra[16];
-                            yq::requant_chunk<ACTM, false, 16, false>(v, nsa, extra, s_q + c0, s_mc + c0, a.ep.zp_out, packed, a.ep.xlim);
-                            if (!valid) packed[0] = packed[1] = packed[2] = packed[3] = a.halo_word;
-                            yq::mask_pad_channels<16>(packed, a.N - c0);
-                            if (YOLO && valid) {
-                                // the detection heads: one table lookup and one 4-byte store per output (lanes = consecutive pixels)
-                                float *dst = a.out_yolo + ((size_t)n * a.N + c0) * hw + (size_t)yy * a.W + xx;
-                                const int nreal = a.N - c0;
+                            for (int j4 = 0; j4 < 4; ++j4) {
+                                const int4 sl = sel[j4];
+                                dst[(4 * j4 + 0) * hw] = s_lut[sl.x + (r[4 * j4 + 0] & 255)];
+                                dst[(4 * j4 + 1) * hw] = s_lut[sl.y + (r[4 * j4 + 1] & 255)];
+                                dst[(4 * j4 + 2) * hw] = s_lut[sl.z + (r[4 * j4 + 2] & 255)];
+                                dst[(4 * j4 + 3) * hw] = s_lut[sl.w + (r[4 * j4 + 3] & 255)];
+                            }
+                        } else {
+#pragma unroll 1
+                            for (int j = 0; j < nreal; ++j) {
+                                int rj = r[0];
 #pragma unroll
-                                for (int j = 0; j < 16; ++j)
-                                    if (j < nreal) dst[(size_t)j * hw] = s_lut[s_sel[c0 + j] + ((packed[j / 4] >> (8 * (j % 4))) & 255u)];
+                                for (int k = 1; k < 16; ++k) rj = j == k ? r[k] : rj;
+                                dst[j * hw] = s_lut[s_sel[c0 + j] + (rj & 255)];
                             }
-                            if (a.store_u8) {
-                                // 64-byte rows: SWIZZLE_64B (16-byte chunk ^ row bits 1-2); 32-byte rows: SWIZZLE_32B (chunk ^ row bit 2)
-                                const int sw = rowb == 64 ? (chl ^ ((lane >> 1) & 3)) : (chl ^ ((lane >> 2) & 1));
-                                *reinterpret_cast<uint4 *>(stage + lane * rowb + sw * 16) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
-                            }
-                            if (ch + 1 < nch) tmem_ld_wait16(vbuf[h2 ^ 1]);
                         }
                     }
-                    if (pass + 1 == npass) {
-                        // this warp's TMEM reads of the tile are done: hand the accumulator back
-                        tc_fence_before();
-                        __syncwarp();
-                        if (lane == 0) pw_arrive(&acc_empty[b]);
-                    }
                     if (a.store_u8) {
-                        fence_proxy_async();          // my staging writes -> visible to the TMA unit
-                        __syncwarp();
-                        if (lane == 0) {
-                            tma_store_2d(&tmO, stage, cbeg + pass * rowb, p0 + q * 32);
-                            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-                        }
+                        uint32_t packed[4];
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) packed[k] = yq::pack_low_bytes(r[4 * k], r[4 * k + 1], r[4 * k + 2], r[4 * k + 3]);
+                        if (!valid) packed[0] = packed[1] = packed[2] = packed[3] = a.halo_word;
+                        yq::mask_pad_channels<16>(packed, a.N - c0);
+                        // 64-byte rows: SWIZZLE_64B (16-byte chunk ^ row bits 1-2); 32-byte rows: SWIZZLE_32B (chunk ^ row bit 2)
+                        const int sw = rowb == 64 ? (chl ^ ((lane >> 1) & 3)) : (chl ^ ((lane >> 2) & 1));
+                        *reinterpret_cast<uint4 *>(stage + lane * rowb + sw * 16) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
                     }
                 }
-            };
-            if (actm == 0) run(std::integral_constant<int, 0>{});
-            else if (actm == 1) run(std::integral_constant<int, 1>{});
-            else run(std::integral_constant<int, 2>{});
+                if (pass + 1 == npass) {
+                    // this warp's TMEM reads of the tile are done: hand the accumulator back
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) pw_arrive(&acc_empty[b]);
+                }
+                if (a.store_u8) {
+                    fence_proxy_async();          // my staging writes -> visible to the TMA unit
+                    __syncwarp();
+                    if (lane == 0) {
+                        tma_store_2d(&tmO, stage, cbeg + pass * rowb, p0 + q * 32);
+                        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                    }
+                }
+            }
+            if ((ew & 3) == 0 && lane == 0 && it < 8) pw_mark(a.trace, 4 + 4 * it + 2);    // tile's epilogue done (stores issued)
         }
         if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // global writes complete before the CTA retires
+        if (ew == 0 && lane == 0) pw_mark(a.trace, 40);
     }
     tc_fence_before();
     __syncthreads();
@@ -290,6 +321,7 @@ __global__ void __launch_bounds__(PW_THREADS, 1) conv_u8_tc_pw_kernel(const __gr
         tc_fence_after();
         pw_tmem_dealloc(tmem_base, (uint32_t)a.tmem_cols);
     }
+    if (threadIdx.x == 0) pw_mark(a.trace, 41);                      // CTA end
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -346,10 +378,10 @@ int pw_smem_bytes(int NC, int K, int KC, int stages)
     return 1024 + NC * K + stages * 128 * KC + PW_EPI_WARPS * PW_STAGE_SLICE + PW_MAX_NC * (16 + 8 + 4) + 2048 + 512;
 }
 
-template <int KC, bool ONE, bool YOLO>
+template <int KC, bool ONE, bool YOLO, int ACTM>
 int pw_launch_v(PwState *st, const CUtensorMap &tmA, const CUtensorMap &tmO, const PwArgs &a, int smem, int grid, cudaStream_t stream)
 {
-    auto kern = conv_u8_tc_pw_kernel<KC, ONE, YOLO>;
+    auto kern = conv_u8_tc_pw_kernel<KC, ONE, YOLO, ACTM>;
     if (yq::ensure_dynamic_smem((const void *)kern, smem)) return -1;
     YQ_CUDA(yq::launch_pdl(kern, dim3(grid), dim3(PW_THREADS), smem, stream, tmA, st->tmB, tmO, a));
     return 0;
@@ -358,12 +390,18 @@ int pw_launch_v(PwState *st, const CUtensorMap &tmA, const CUtensorMap &tmO, con
 template <int KC>
 int pw_launch(PwState *st, const CUtensorMap &tmA, const CUtensorMap &tmO, const PwArgs &a, int smem, int grid, cudaStream_t stream)
 {
+    // the activation is a launch constant: one epilogue form per kernel keeps the code each warp walks short (heads are LINEAR: checked by the caller)
+    const int actm = yq::act_mode(a.ep.act);
     if (a.cpt == 1) {
-        if (a.out_yolo) return pw_launch_v<KC, true, true>(st, tmA, tmO, a, smem, grid, stream);
-        return pw_launch_v<KC, true, false>(st, tmA, tmO, a, smem, grid, stream);
+        if (a.out_yolo) return pw_launch_v<KC, true, true, 1>(st, tmA, tmO, a, smem, grid, stream);
+        if (actm == 0) return pw_launch_v<KC, true, false, 0>(st, tmA, tmO, a, smem, grid, stream);
+        if (actm == 1) return pw_launch_v<KC, true, false, 1>(st, tmA, tmO, a, smem, grid, stream);
+        return pw_launch_v<KC, true, false, 2>(st, tmA, tmO, a, smem, grid, stream);
     }
-    if (a.out_yolo) return pw_launch_v<KC, false, true>(st, tmA, tmO, a, smem, grid, stream);
-    return pw_launch_v<KC, false, false>(st, tmA, tmO, a, smem, grid, stream);
+    if (a.out_yolo) return pw_launch_v<KC, false, true, 1>(st, tmA, tmO, a, smem, grid, stream);
+    if (actm == 0) return pw_launch_v<KC, false, false, 0>(st, tmA, tmO, a, smem, grid, stream);
+    if (actm == 1) return pw_launch_v<KC, false, false, 1>(st, tmA, tmO, a, smem, grid, stream);
+    return pw_launch_v<KC, false, false, 2>(st, tmA, tmO, a, smem, grid, stream);
 }
 
 }  // namespace
@@ -383,6 +421,9 @@ int yq_tc_pw_supported(const yq_conv_layer *l)
     if (pw_smem_bytes(NC, l->cs_in, KC, l->cs_in == KC ? 4 : 3) > 227 * 1024) return 0;   // the bank and a minimal ring
     return pw_get_encode() != nullptr;
 }
+
+// a detection head (quant_stop + fused yolo) runs here when its activation is LINEAR (every yolo cfg of the reference); others keep the flat kernel
+int yq_tc_pw_head_supported(const yq_conv_layer *l) { return l->tc_pw && l->quant_stop_flag && yq::act_mode(l->activation) == 1 ? 1 : 0; }
 
 int yq_tc_pw_prepare(yq_conv_layer *l, void **state)
 {
@@ -443,6 +484,7 @@ int yq_tc_pw_forward(yq_conv_layer *l, void *state, const uint8_t *in, uint8_t *
     PwState *st = (PwState *)state;
     if (!st || !in || !out_u8) return yq::fail("tcgen05 pointwise flavour: bad argument");
     if (l->quant_stop_flag && !out_yolo) return yq::fail("tcgen05 pointwise flavour: a quant_stop layer runs here only as a fused yolo head");
+    if (out_yolo && yq::act_mode(l->activation) != 1) return yq::fail("tcgen05 pointwise flavour: detection heads are LINEAR (see yq_tc_pw_head_supported)");
     const int W1 = l->w + (plain ? 0 : 1), H1 = l->h + (plain ? 0 : 1);
     const long long NP = (long long)batch * H1 * W1;
     const long long rows_alloc = plain ? NP : NP + W1 + 2;     // + the trailing halo row (yq_act_geom_bytes)
@@ -479,6 +521,7 @@ int yq_tc_pw_forward(yq_conv_layer *l, void *state, const uint8_t *in, uint8_t *
     a.a_stages = stages;
     const int smem = pw_smem_bytes(st->NC, l->cs_in, st->KC, stages);
     a.num_tiles = (int)((rows_alloc + 127) / 128);
+    a.trace = getenv("YQ_PW_TRACE") && atoi(getenv("YQ_PW_TRACE")) ? 1 : 0;
     a.halo_word = 0x01010101u * (uint32_t)(halo_fill & 0xff);
     a.magic_w = (uint32_t)((0x100000000ull + W1 - 1) / W1);
     a.magic_h = (uint32_t)((0x100000000ull + H1 - 1) / H1);
@@ -496,4 +539,10 @@ int yq_tc_pw_forward(yq_conv_layer *l, void *state, const uint8_t *in, uint8_t *
     const CUtensorMap &tmA = it->second.first, &tmO = it->second.second;
     if (st->KC == 128) return pw_launch<128>(st, tmA, tmO, a, smem, grid, stream);
     return pw_launch<64>(st, tmA, tmO, a, smem, grid, stream);
+}
+
+// YQ_PW_TRACE=1: the event times of the last traced launch (64 events x up to 256 CTAs, ns; tools/probes/pw_trace.py)
+extern "C" __attribute__((visibility("default"))) int yq_debug_pw_trace(void *host, size_t bytes)
+{
+    return cudaMemcpyFromSymbol(host, yq_pw_trace, bytes < sizeof(yq_pw_trace) ? bytes : sizeof(yq_pw_trace)) == cudaSuccess ? 0 : -1;
 }

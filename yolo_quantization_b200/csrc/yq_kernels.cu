@@ -704,7 +704,7 @@ extern "C" int yq_forward_convolutional_layer_quant_flat_yolo_gpu(yq_conv_layer 
 {
     if (!l || !in_flat || !out_flat || !out_yolo || batch <= 0 || classes < 0) return yq::fail("yq_forward_convolutional_layer_quant_flat_yolo_gpu: bad argument");
     if (!l->tc_flat || !l->quant_stop_flag) return yq::fail("the fused yolo head needs a quant_stop layer with the flat flavour");
-    if (l->tc_pw && !out_f32 && !out_acc && !(getenv("YQ_PW") && !atoi(getenv("YQ_PW"))))      // the throughput path: no side outputs
+    if (yq_tc_pw_head_supported(l) && !out_f32 && !out_acc && !(getenv("YQ_PW") && !atoi(getenv("YQ_PW"))))      // the throughput path: no side outputs
         return yq_tc_pw_forward(l, l->tc_pw, in_flat, out_flat, halo_fill, out_yolo, classes, batch, (cudaStream_t)stream, 0);
     return yq_tc_flat_forward(l, l->tc_flat, in_flat, out_flat, halo_fill, out_f32, out_yolo, classes, out_acc, batch, (cudaStream_t)stream);
 }
