@@ -469,6 +469,10 @@ def main():
         rows = []
         for i, li in enumerate(infos):
             ops, byts = layer_work(li, B, conv_written=False)   # production plan: fused convs write the pooled tensor only
+            if li.type == 2 and li.fused == 5:
+                # a route the next conv reads in two parts: its launch (if any) only brings the upsampled input into shape
+                up = infos[i - 1] if i > 0 and infos[i - 1].type == 3 and infos[i - 1].fused else None
+                byts = B * (up.h * up.w * up.c + up.out_h * up.out_w * up.out_c) if up else 0
             t_ms = float(lm[i + 1])
             if t_ms <= 0 or (li.type in (1, 3, 4, 5) and li.fused):    # a fused-away max-pool / upsample / yolo / shortcut layer has no launch of its own
                 continue

@@ -191,6 +191,15 @@ YQ_API int yq_forward_convolutional_layer_quant_flat_shortcut_gpu(yq_conv_layer 
                                                                   uint8_t *out_flat, int halo_fill, int zp_from, int Ka, int Kb,
                                                                   int zp_out_shortcut, int batch, void *stream);
 
+/* A flat convolution behind a [route] that is never materialised: the input is the channel concatenation
+ * [in_first (c_first channels) | in_second (c - c_first channels)] of two flat tensors of the layer's input geometry, as
+ * forward_route_layer (src/route_layer.c:77-95) would have copied them; the convolution's patch loads pick the tensor per
+ * channel chunk instead.  Both halos must hold the layer's input zero point.  yq_conv_flat_cat_supported: 1 when the layer's
+ * kernel can do this for a split at c_first (the CTA-pair flavour, c >= 256, c_first a multiple of its channel chunk). */
+YQ_API int yq_conv_flat_cat_supported(const yq_conv_layer *l, int c_first);
+YQ_API int yq_forward_convolutional_layer_quant_flat_cat_gpu(yq_conv_layer *l, const uint8_t *in_first, int c_first, const uint8_t *in_second,
+                                                             uint8_t *out_flat, int halo_fill, int batch, void *stream);
+
 /* A quant_stop head with the FOLLOWING yolo layer fused (forward_yolo_layer's inference part, src/yolo_layer.c:132-146):
  * out_yolo [batch][n][h][w] receives the yolo layer's output.  The head's float values (u8 - zp_out) * s_out
  * (convolutional_layer.c:752-760) take only 256 values, so logistic_activate (src/activations.h:32) is a 256-entry

@@ -298,6 +298,32 @@ def test_conv_pointwise_flavour_vs_oracle(built, case, monkeypatch):
     layer.free()
 
 
+@pytest.mark.parametrize("case", [(384, 26, 26, 256, 128, "relu6", 0, 0, 3), (384, 9, 12, 256, 256, "leaky", 11, 7, 2), (512, 13, 13, 512, 128, "relu6", 5, 0, 2),
+                                  (320, 7, 7, 128, 64, "leaky", 0, 9, 1)],
+                         ids=lambda c: "c%d_%dx%d_n%d_first%d" % c[:5])
+def test_conv_reads_two_tensors_as_their_concatenation(built, case):
+    """the convolution behind a route that is never materialised (layer 21 of yolov3-tiny reads [upsampled layer 18 | layer 8]):
+    two flat tensors in, bytes equal to the oracle's convolution over their concatenation and to the one-tensor launch"""
+    c, h, w, n, c_first, act, zp_in, zp_out, batch = case
+    rng = np.random.default_rng(zlib.crc32(repr(case).encode()) + 5)
+    wq, zp_w, s_w, bias = make_params(rng, n, c * 9, zp_in)
+    spec = synth.LayerSpec("conv", n, 3, 1, 1, 0, act)
+    sl = synth.SynthLayer("conv", c, h, w, n, 0, 0, spec, s_out=0.05, biases=bias, s_w=s_w, zp_w=zp_w, w_u8=wq.reshape(n, c, 3, 3))
+    p = O.prepare_conv(sl, 0.02, zp_in)
+    x = rng.integers(0, 256, size=(batch, c, h, w), dtype=np.uint8)
+    layer = darknet.ConvolutionalLayerQuant(h, w, c, n, 3, 1, 1, synth.ACT_CODES[act], wq, zp_w, p["biases_int32"], p["M_value"],
+                                            p["M0_right_shift_value"], zp_in, zp_out, 0.05)
+    assert layer.flat_cat_supported(c_first) and not layer.flat_cat_supported(c_first + 16)
+    got = layer.forward_flat_cat(x, c_first, halo_fill=zp_out)
+    one = layer.forward_flat(x, halo_fill=zp_out, want_acc=False)
+    assert np.array_equal(got["u8"], one["u8"])
+    for b in range(batch):
+        acc = O.conv_acc(x[b], wq.reshape(n, c, 3, 3), zp_w, 1, 1, zp_in)
+        u8 = O.requant(acc, p["biases_int32"], p["M_value"], p["M0_right_shift_value"], synth.ACT_CODES[act], zp_out)
+        assert np.array_equal(got["u8"][b], u8), f"uint8 mismatch, image {b}"
+    layer.free()
+
+
 ROWS_CASES = [
     # c, h, w, n, zp_in, zp_out, batch
     (3, 48, 64, 16, 0, 0, 2),
@@ -588,7 +614,8 @@ def test_fused_network_equals_unfused_and_oracle(built, tiny_net_files):
     for i, (sl, r) in enumerate(zip(info, ref)):
         # (the conv tensors of layers 0, 2, 4, 6 never exist: their launches write the pooled tensor only; nor does the
         # upsampled tensor of layer 19: route 20 reads layer 18 through the upsample, and pulling it fails loudly)
-        if sl.kind == "upsample" and net.layers()[i].fused:
+        if sl.kind in ("upsample", "route") and net.layers()[i].fused:
+            # (likewise route 20: layer 21 reads [layer 18 through the upsample | layer 8] itself)
             with pytest.raises(Exception, match="not materialised"):
                 net.pull_layer(i, "u8")
         elif sl.kind == "maxpool" or (sl.kind == "conv" and i >= 8) or sl.kind in ("route", "upsample"):
@@ -794,11 +821,13 @@ def test_network_input_paths_agree(built, tiny_net_files, monkeypatch):
     net.free()
 
 
-@pytest.mark.parametrize("uproute,branch,early", [(1, 0, 0), (0, 1, 0), (1, 1, 0), (0, 1, 1), (1, 1, 1), (1, 0, 1)])
-def test_network_schedule_switches_keep_every_byte(built, tiny_net_files, monkeypatch, uproute, branch, early):
+@pytest.mark.parametrize("uproute,branch,early,nocat", [(1, 0, 0, 0), (0, 1, 0, 0), (1, 1, 0, 0), (0, 1, 1, 0), (1, 1, 1, 0), (1, 0, 1, 0), (1, 1, 1, 1), (1, 1, 0, 1)])
+def test_network_schedule_switches_keep_every_byte(built, tiny_net_files, monkeypatch, uproute, branch, early, nocat):
     """YQ_UPROUTE (upsample folded into the route behind it: one launch less), YQ_BRANCH_STREAM (the first detection
     head on a second stream beside the layers after it) and YQ_EARLY_ROUTE (layer 8 copied into route 20's tensor on
-    that stream right behind layer 8: one launch more) change the schedule only: same bytes out, eager and replayed."""
+    that stream right behind layer 8: one launch more) change the schedule only: same bytes out, eager and replayed.
+    With the upsample folded in, layer 21 reads [layer 18 through the upsample | layer 8] itself (route 20 is never
+    written, there is nothing to copy early) unless YQ_NO_CAT=1 keeps the materialised route."""
     cfg, wts, _, _ = tiny_net_files
     x = np.random.default_rng(23).integers(0, 256, size=(4, 3, 416, 416), dtype=np.uint8)
     for k in ("YQ_UPROUTE", "YQ_BRANCH_STREAM", "YQ_EARLY_ROUTE"):
@@ -809,8 +838,11 @@ def test_network_schedule_switches_keep_every_byte(built, tiny_net_files, monkey
     monkeypatch.setenv("YQ_UPROUTE", str(uproute))
     monkeypatch.setenv("YQ_BRANCH_STREAM", str(branch))
     monkeypatch.setenv("YQ_EARLY_ROUTE", str(early))
+    monkeypatch.setenv("YQ_NO_CAT", str(nocat))
     net = darknet.load_network(cfg, wts, batch=4)
-    assert net.launches_per_forward == n_base - uproute + (1 if early and branch else 0)
+    cat = uproute and not nocat
+    assert bool(net.layers()[20].fused) == bool(cat)
+    assert net.launches_per_forward == n_base - uproute + (1 if early and branch and not cat else 0)
     for graph in (False, True):
         net.use_graph(graph)
         for _ in range(4):

@@ -83,6 +83,8 @@ SIGNATURES = {
     "yq_forward_convolutional_layer_quant_flat_gpu": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _i, _vp]),
     "yq_conv_flat_shortcut_supported": (_i, [_vp]),
     "yq_forward_convolutional_layer_quant_flat_shortcut_gpu": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
+    "yq_conv_flat_cat_supported": (_i, [_vp, _i]),
+    "yq_forward_convolutional_layer_quant_flat_cat_gpu": (_i, [_vp, _vp, _i, _vp, _vp, _i, _i, _vp]),
     "yq_forward_convolutional_layer_quant_flat_yolo_gpu": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _i, _vp, _i, _vp]),
     "yq_forward_maxpool_layer_quant_geom_gpu": (_i, [_vp, C.POINTER(ActGeom), _vp, C.POINTER(ActGeom), _i, _i, _i, _i, _i, _i, _i, _vp]),
     "yq_forward_upsample_layer_quant_geom_gpu": (_i, [_vp, C.POINTER(ActGeom), _vp, C.POINTER(ActGeom), _i, _i, _i, _i, _i, _vp]),

@@ -198,8 +198,11 @@ int yq_tc_flat2_forward(yq_conv_layer *l, void *state, const uint8_t *in_flat, u
 int yq_tc_flat2x_supported(const yq_conv_layer *l);
 int yq_tc_flat2x_prepare(yq_conv_layer *l, void **state);
 void yq_tc_flat2x_free(void *state);
+// in_first != null: the input is the channel concatenation [in_first (c_first channels) | in_flat] of two flat tensors of the same geometry
+// (a route that is never materialised); c_first a multiple of the layer's channel chunk
 int yq_tc_flat2x_forward(yq_conv_layer *l, void *state, const uint8_t *in_flat, uint8_t *out_flat, int halo_fill, int32_t *out_acc, int batch,
-                         cudaStream_t stream, const yq_fused_shortcut *sc = nullptr);
+                         cudaStream_t stream, const yq_fused_shortcut *sc = nullptr, const uint8_t *in_first = nullptr, int c_first = 0);
+int yq_tc_flat2x_chunk(const void *state);     // channels per patch chunk (64 or 128)
 
 // implemented in yq_conv_tc_pw.cu (1x1 layers with n <= 255 whose filter bank fits shared memory: persistent streaming GEMM; flat or
 // plain strips; out_yolo != null: the layer is a detection head and the following yolo layer's tensor is written as well)

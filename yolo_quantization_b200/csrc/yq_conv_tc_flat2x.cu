@@ -52,6 +52,7 @@ struct Flat2xArgs {
     uint32_t magic_w, magic_h, magic_m;
     // the FOLLOWING quantized shortcut fused into the epilogue (extension layer, include/yq_b200.h): the `from` tensor in this
     // layer's own flat geometry and channel stride; the launch then stores the SHORTCUT's output
+    int split;             // chunks [0, split) of the input channels come from the second tensor map (virtual route), the rest from the first
     const uint8_t *resid;
     yq::ShortcutParams sc;
     int debug;             // YQ_FLAT2_DEBUG experiments (results are garbage): 1 = skip weight loads of taps > 0, 2 = skip the epilogue math
@@ -75,7 +76,8 @@ __device__ __forceinline__ void f2x_arrive(uint64_t *bar) { asm volatile("mbarri
 // RESID: the following quantized shortcut fused into the epilogue (launch-uniform: a template parameter, see yq_conv_tc_flat2.cu)
 template <int KC, bool SLOW, bool WIDE, bool RESID>
 __global__ void __launch_bounds__(F2X_THREADS, 1) conv_u8_tc_flat2x_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                                                                     const __grid_constant__ CUtensorMap tmO, const Flat2xArgs a)
+                                                                     const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmA2,
+                                                                     const Flat2xArgs a)
 {
     using L = Flat2xSmem<KC, WIDE>;
     constexpr int BNT = L::BNT, TPC = L::TPC, PPC = L::PPC;
@@ -126,6 +128,7 @@ __global__ void __launch_bounds__(F2X_THREADS, 1) conv_u8_tc_flat2x_kernel(const
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmO) : "memory");
+        if (a.split) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA2) : "memory");
     }
     tc_fence_before();
     cluster_sync_all();            // both CTAs' barriers are initialised before anyone signals across the pair
@@ -143,9 +146,13 @@ __global__ void __launch_bounds__(F2X_THREADS, 1) conv_u8_tc_flat2x_kernel(const
             for (int c = 0; c < chunks; ++c) {
                 mbar_wait(&a_empty[sa], pha ^ 1);
                 if (elect_one()) {
+                    // the input is the channel concatenation [tmA2 | tmA] of two tensors of the same geometry (a route that is never
+                    // materialised): the first a.split chunks come from tmA2; a.split = 0: one tensor
+                    const CUtensorMap *src = c < a.split ? &tmA2 : &tmA;
+                    const int cc = (c < a.split ? c : c - a.split) * KC;
                     mbar_expect_tx(&a_full[sa], (uint32_t)(2 * a.box_rows * KC));
-                    tma_load_2d(sA + sa * a.a_stage_bytes, &tmA, &a_full[sa], c * KC, p0 + a.q_off);
-                    tma_load_2d(sA + sa * a.a_stage_bytes + a.box_rows * KC, &tmA, &a_full[sa], c * KC, p0 + a.q_off + a.box_rows);
+                    tma_load_2d(sA + sa * a.a_stage_bytes, src, &a_full[sa], cc, p0 + a.q_off);
+                    tma_load_2d(sA + sa * a.a_stage_bytes + a.box_rows * KC, src, &a_full[sa], cc, p0 + a.q_off + a.box_rows);
                 }
                 if (++sa == F2X_ASTAGES) { sa = 0; pha ^= 1; }
                 for (int tap = 0; tap < a.taps; ++tap) {
@@ -431,16 +438,19 @@ struct Flat2xState {
     CUtensorMap tmB, tmBw;      // weight boxes of 64 rows (two-tile form) / 128 rows (WIDE form)
     bool wide = false;
     struct Key {
-        const void *in;
+        const void *in, *in2;
         void *out;
         int batch;
-        bool operator<(const Key &o) const { return in != o.in ? in < o.in : out != o.out ? out < o.out : batch < o.batch; }
+        bool operator<(const Key &o) const { return in != o.in ? in < o.in : in2 != o.in2 ? in2 < o.in2 : out != o.out ? out < o.out : batch < o.batch; }
     };
-    std::map<Key, std::pair<CUtensorMap, CUtensorMap>> maps;
+    struct Maps {
+        CUtensorMap a, o, a2;
+    };
+    std::map<Key, Maps> maps;
 };
 
 template <int KC, bool SLOW, bool WIDE, bool RESID>
-int f2x_launch_v(Flat2xState *st, const CUtensorMap &tmA, const CUtensorMap &tmO, Flat2xArgs a, cudaStream_t stream)
+int f2x_launch_v(Flat2xState *st, const CUtensorMap &tmA, const CUtensorMap &tmO, const CUtensorMap &tmA2, Flat2xArgs a, cudaStream_t stream)
 {
     using L = Flat2xSmem<KC, WIDE>;
     const int n_sm = yq::device_sm_count(), smem_max = yq::device_smem_optin();   // (of the CURRENT device: nothing cached per process)
@@ -472,21 +482,21 @@ int f2x_launch_v(Flat2xState *st, const CUtensorMap &tmA, const CUtensorMap &tmO
     at[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = at;
     cfg.numAttrs = yq::pdl_enabled() ? 2 : 1;
-    YQ_CUDA(cudaLaunchKernelEx(&cfg, kern, tmA, WIDE ? st->tmBw : st->tmB, tmO, a));
+    YQ_CUDA(cudaLaunchKernelEx(&cfg, kern, tmA, WIDE ? st->tmBw : st->tmB, tmO, tmA2, a));
     return 0;
 }
 
 template <int KC>
-int f2x_launch(Flat2xState *st, const CUtensorMap &tmA, const CUtensorMap &tmO, const Flat2xArgs &a, cudaStream_t stream)
+int f2x_launch(Flat2xState *st, const CUtensorMap &tmA, const CUtensorMap &tmO, const CUtensorMap &tmA2, const Flat2xArgs &a, cudaStream_t stream)
 {
     if (st->wide) {
-        if (a.resid) return f2x_launch_v<KC, false, true, true>(st, tmA, tmO, a, stream);
-        if (a.out_acc || a.ep.saturate) return f2x_launch_v<KC, true, true, false>(st, tmA, tmO, a, stream);
-        return f2x_launch_v<KC, false, true, false>(st, tmA, tmO, a, stream);
+        if (a.resid) return f2x_launch_v<KC, false, true, true>(st, tmA, tmO, tmA2, a, stream);
+        if (a.out_acc || a.ep.saturate) return f2x_launch_v<KC, true, true, false>(st, tmA, tmO, tmA2, a, stream);
+        return f2x_launch_v<KC, false, true, false>(st, tmA, tmO, tmA2, a, stream);
     }
-    if (a.resid) return f2x_launch_v<KC, false, false, true>(st, tmA, tmO, a, stream);
-    if (a.out_acc || a.ep.saturate) return f2x_launch_v<KC, true, false, false>(st, tmA, tmO, a, stream);
-    return f2x_launch_v<KC, false, false, false>(st, tmA, tmO, a, stream);
+    if (a.resid) return f2x_launch_v<KC, false, false, true>(st, tmA, tmO, tmA2, a, stream);
+    if (a.out_acc || a.ep.saturate) return f2x_launch_v<KC, true, false, false>(st, tmA, tmO, tmA2, a, stream);
+    return f2x_launch_v<KC, false, false, false>(st, tmA, tmO, tmA2, a, stream);
 }
 
 }  // namespace
@@ -544,6 +554,8 @@ int yq_tc_flat2x_prepare(yq_conv_layer *l, void **state)
     return 0;
 }
 
+int yq_tc_flat2x_chunk(const void *state) { return state ? ((const Flat2xState *)state)->KC : 0; }
+
 void yq_tc_flat2x_free(void *state)
 {
     Flat2xState *st = (Flat2xState *)state;
@@ -553,10 +565,14 @@ void yq_tc_flat2x_free(void *state)
 }
 
 int yq_tc_flat2x_forward(yq_conv_layer *l, void *state, const uint8_t *in_flat, uint8_t *out_flat, int halo_fill, int32_t *out_acc, int batch,
-                        cudaStream_t stream, const yq_fused_shortcut *sc)
+                        cudaStream_t stream, const yq_fused_shortcut *sc, const uint8_t *in_first, int c_first)
 {
     Flat2xState *st = (Flat2xState *)state;
     if (!st || !in_flat || !out_flat) return yq::fail("tcgen05 flat2 flavour: bad argument");
+    // in_first != null: the input is the concatenation [in_first (c_first channels) | in_flat (the rest)] of two flat tensors
+    if (in_first && (c_first <= 0 || c_first >= l->cs_in || c_first % st->KC || (l->cs_in - c_first) % 16))
+        return yq::fail("tcgen05 flat2 flavour: a two-tensor input splits at a multiple of %d channels", st->KC);
+    const int c_second = in_first ? l->cs_in - c_first : l->cs_in;
     const int W1 = l->w + 1, H1 = l->h + 1;
     const long long NP = (long long)batch * H1 * W1;
     const long long rows_alloc = NP + W1 + 2;     // + the trailing halo row (yq_act_geom_bytes)
@@ -568,16 +584,19 @@ int yq_tc_flat2x_forward(yq_conv_layer *l, void *state, const uint8_t *in_flat, 
     a.patch_rows = ppc + (l->size - 1) * (W1 + 1);
     a.box_rows = yq::round_up((a.patch_rows + 1) / 2, 8);
     a.a_stage_bytes = yq::round_up(2 * a.box_rows * st->KC, 1024);
-    Flat2xState::Key key{in_flat, out_flat, batch};
+    Flat2xState::Key key{in_flat, in_first, out_flat, batch};
     auto it = st->maps.find(key);
     if (it == st->maps.end()) {
         if (st->maps.size() > 64) st->maps.clear();
-        CUtensorMap tmA, tmO;
-        if (f2x_encode_2d(&tmA, in_flat, (uint64_t)rows_alloc, l->cs_in, st->KC, a.box_rows, CU_TENSOR_MAP_L2_PROMOTION_L2_128B)) return -1;
+        Flat2xState::Maps m;
+        if (f2x_encode_2d(&m.a, in_flat, (uint64_t)rows_alloc, c_second, st->KC, a.box_rows, CU_TENSOR_MAP_L2_PROMOTION_L2_128B)) return -1;
         // the store box is one epilogue warp's block: 32 positions x 64 channels
-        if (f2x_encode_2d(&tmO, out_flat, (uint64_t)rows_alloc, l->cs_out, 64, 32, CU_TENSOR_MAP_L2_PROMOTION_L2_128B)) return -1;
-        it = st->maps.emplace(key, std::make_pair(tmA, tmO)).first;
+        if (f2x_encode_2d(&m.o, out_flat, (uint64_t)rows_alloc, l->cs_out, 64, 32, CU_TENSOR_MAP_L2_PROMOTION_L2_128B)) return -1;
+        m.a2 = m.a;
+        if (in_first && f2x_encode_2d(&m.a2, in_first, (uint64_t)rows_alloc, c_first, st->KC, a.box_rows, CU_TENSOR_MAP_L2_PROMOTION_L2_128B)) return -1;
+        it = st->maps.emplace(key, m).first;
     }
+    a.split = in_first ? c_first / st->KC : 0;
     a.ep = yq::make_epi(l);
     a.out_acc = out_acc;
     a.N = l->n; a.CSO = l->cs_out;
@@ -591,7 +610,7 @@ int yq_tc_flat2x_forward(yq_conv_layer *l, void *state, const uint8_t *in_flat, 
     a.halo_word = 0x01010101u * (uint32_t)(halo_fill & 0xff);
     {
         static int dbg = -1;
-        if (dbg < 0) dbg = getenv("YQ_FLAT2X_DEBUG") ? atoi(getenv("YQ_FLAT2_DEBUG")) : 0;
+        if (dbg < 0) dbg = getenv("YQ_FLAT2X_DEBUG") ? atoi(getenv("YQ_FLAT2X_DEBUG")) : 0;
         a.debug = dbg;
     }
     a.magic_w = (uint32_t)((0x100000000ull + W1 - 1) / W1);
@@ -600,7 +619,7 @@ int yq_tc_flat2x_forward(yq_conv_layer *l, void *state, const uint8_t *in_flat, 
     a.num_tiles = a.m_pairs * (st->n_pad / bnt);
     a.magic_m = a.m_pairs == 1 ? 0u : (uint32_t)((0x100000000ull + a.m_pairs - 1) / a.m_pairs);
     if ((long long)a.num_tiles * a.m_pairs >= 0x100000000ll) return yq::fail("tcgen05 flat2 flavour: too many tiles for 32-bit tile arithmetic");
-    const CUtensorMap &tmA = it->second.first, &tmO = it->second.second;
-    if (st->KC == 128) return f2x_launch<128>(st, tmA, tmO, a, stream);
-    return f2x_launch<64>(st, tmA, tmO, a, stream);
+    const CUtensorMap &tmA = it->second.a, &tmO = it->second.o, &tmA2 = it->second.a2;
+    if (st->KC == 128) return f2x_launch<128>(st, tmA, tmO, tmA2, a, stream);
+    return f2x_launch<64>(st, tmA, tmO, tmA2, a, stream);
 }

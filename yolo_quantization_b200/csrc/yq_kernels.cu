@@ -699,6 +699,25 @@ extern "C" int yq_forward_convolutional_layer_quant_flat_shortcut_gpu(yq_conv_la
     sc.C0 = 32768 + ((zp_out_shortcut & 0xff) << 16) - l->zp_out * Ka - (zp_from & 0xff) * Kb;
     return flat_dispatch(l, in_flat, out_flat, halo_fill, nullptr, nullptr, batch, stream, &sc);
 }
+// A flat convolution whose input is the channel concatenation [in_first (c_first channels) | in_second (the rest)] of two flat tensors of
+// the layer's input geometry: a [route] in front of it that is never materialised (route_layer.c:77-95 only copies bytes; here the
+// convolution's patch loads pick the tensor per channel chunk).  Both halos must hold the layer's input zero point.
+extern "C" int yq_conv_flat_cat_supported(const yq_conv_layer *l, int c_first)
+{
+    const bool off = getenv("YQ_NO_CAT") && atoi(getenv("YQ_NO_CAT"));   // A/B measurements (read per call: the tests flip it)
+    if (!l || off || !l->tc_flat2x || l->quant_stop_flag || l->c < 256) return 0;
+    if (getenv("YQ_NO_FLAT2") && atoi(getenv("YQ_NO_FLAT2"))) return 0;
+    if (getenv("YQ_FLAT2X") && atoi(getenv("YQ_FLAT2X")) == 0) return 0;
+    const int kc = yq_tc_flat2x_chunk(l->tc_flat2x);
+    return c_first > 0 && c_first < l->cs_in && c_first % kc == 0 && (l->cs_in - c_first) % 16 == 0 ? 1 : 0;
+}
+extern "C" int yq_forward_convolutional_layer_quant_flat_cat_gpu(yq_conv_layer *l, const uint8_t *in_first, int c_first, const uint8_t *in_second,
+                                                                 uint8_t *out_flat, int halo_fill, int batch, void *stream)
+{
+    if (!l || !in_first || !in_second || !out_flat || batch <= 0) return yq::fail("yq_forward_convolutional_layer_quant_flat_cat_gpu: bad argument");
+    if (!yq_conv_flat_cat_supported(l, c_first)) return yq::fail("this layer cannot read a two-tensor input split at channel %d (see yq_conv_flat_cat_supported)", c_first);
+    return yq_tc_flat2x_forward(l, l->tc_flat2x, in_second, out_flat, halo_fill, nullptr, batch, (cudaStream_t)stream, nullptr, in_first, c_first);
+}
 extern "C" int yq_forward_convolutional_layer_quant_flat_yolo_gpu(yq_conv_layer *l, const uint8_t *in_flat, uint8_t *out_flat, int halo_fill,
                                                                   float *out_f32, float *out_yolo, int classes, int32_t *out_acc, int batch, void *stream)
 {

@@ -126,6 +126,10 @@ struct Layer {
     bool fuse_yolo = false;        // quant_stop conv: the following yolo layer is produced by this layer's epilogue (yolo: fused_away)
     bool fuse_shortcut = false;    // conv: the following quantized shortcut is produced by this layer's epilogue (shortcut: fused_away)
     bool fuse_up = false;          // route: inputs that are upsample layers are read through the upsample (upsample: fused_away)
+    bool cat = false;              // route (two inputs): never materialised -- the flat conv behind it reads [input 0 | input 1] itself
+                                   // (yq_forward_convolutional_layer_quant_flat_cat_gpu); out_u8 then holds input 0 alone when that
+                                   // one has to be brought into shape first (the upsample folded into this route)
+    bool cat_copy = false;         //   ... input 0 is copied (upsampled) into out_u8; false: both inputs are read in place
     unsigned early_mask = 0;       // route: inputs copied on the side stream as soon as they exist (see plan_early_copies())
     cudaEvent_t ev_early = nullptr;
     std::vector<std::pair<int, int>> early_copies;   // (route layer, input index) to issue behind this layer
@@ -331,7 +335,7 @@ void plan_early_copies(yq_network *net)
     if (!net->branch_stream || !net->early_route || net->keep_acc || !side_stream_safe(net)) return;
     for (int i = 0; i < n; ++i) {
         Layer &r = net->layers[i];
-        if (r.type != L_ROUTE || r.inputs.size() < 2 || r.side) continue;
+        if (r.type != L_ROUTE || r.inputs.size() < 2 || r.side || r.cat) continue;
         for (size_t k = 0; k < r.inputs.size(); ++k) {
             const Layer &p = net->layers[r.inputs[k]];
             if (p.type == L_UPSAMPLE && p.fused_away) continue;
@@ -513,6 +517,7 @@ void plan(yq_network *net)
     for (int i = 0; i < n; ++i) {
         Layer &l = net->layers[i];
         l.fuse_pool = l.fused_away = l.use_rows = l.use_flat = l.use_geom = l.use_outgeom = l.fuse_yolo = l.fuse_shortcut = l.fuse_up = l.side = false;
+        l.cat = l.cat_copy = false;
         l.geom = yq_act_geom{0, l.out_w, l.out_h};
         l.halo_fill = 0;
     }
@@ -575,6 +580,28 @@ void plan(yq_network *net)
         if (l.fused_away || (l.type == L_ROUTE && l.inputs.size() == 1)) continue;
         ++launches;
     }
+    // route -> flat conv: the convolution reads the route's two inputs itself when its kernel can (the CTA-pair flavour) and nobody
+    // else wants the concatenated tensor; an input 0 that is an upsample folded into the route is still written, alone, into the
+    // route's buffer (a quarter of the bytes the full route moved: route 20 of yolov3-tiny copied 22 MB of layer 8 per step)
+    if (net->fusion && !net->keep_acc)
+        for (int i = 0; i + 1 < n; ++i) {
+            Layer &r = net->layers[i], &cv = net->layers[i + 1];
+            if (r.type != L_ROUTE || r.inputs.size() != 2 || cv.type != L_CONV || !cv.conv || !cv.use_flat || cv.fuse_yolo || routed_from(net, i)) continue;
+            const Layer &a0 = net->layers[r.inputs[0]], &a1 = net->layers[r.inputs[1]];
+            const bool up0 = r.fuse_up && a0.type == L_UPSAMPLE && a0.fused_away;
+            if (a1.type == L_UPSAMPLE && a1.fused_away) continue;
+            if (!yq_conv_flat_cat_supported(cv.conv, a0.out_c) || a0.out_c + a1.out_c != cv.c) continue;
+            yq_act_geom g;
+            yq_act_geom_flat(cv.h, cv.w, &g);
+            auto in_place = [&](const Layer &a) {
+                const int t = tensor_of(net, (int)(&a - &net->layers[0]));
+                return t >= 0 && same_geom(net->layers[t].geom, g) && net->layers[t].halo_fill == r.halo_fill;
+            };
+            if (!same_geom(r.geom, g) || !in_place(a1) || (!up0 && !in_place(a0))) continue;
+            r.cat = true;
+            r.cat_copy = up0;
+            if (!up0) --launches;        // nothing is copied at all
+        }
     // (layer 0 in the rows flavour reads the CHW planes itself when it can: no layout-transform launch, see forward_body)
     if (n > 0 && net->layers[0].type == L_CONV && net->layers[0].use_rows && !net->no_planar_input && yq_conv_rows_nchw_supported(net->layers[0].conv))
         --launches;
@@ -643,7 +670,7 @@ int forward_body(yq_network *net, const uint8_t *in_u8_nchw, int *launches, bool
         cur_fill = done.halo_fill;
     }
     const bool early_ok = !profile && net->side_stream;
-    auto issue_route = [&](Layer &r, unsigned mask, cudaStream_t s) -> int {
+    auto issue_route = [&](Layer &r, unsigned mask, cudaStream_t s, bool first_alone = false) -> int {
         const uint8_t *ins[8];
         yq_act_geom gs[8];
         int cs[8], ups[8];
@@ -658,7 +685,9 @@ int forward_body(yq_network *net, const uint8_t *in_u8_nchw, int *launches, bool
             gs[k] = p->geom;
             cs[k] = p->out_c;
         }
-        return yq_forward_route_layer_quant_part_gpu(ins, gs, cs, ups, (int)r.inputs.size(), mask, r.out_u8, &r.geom, net->batch, r.out_h, r.out_w, s);
+        // first_alone: the buffer receives input 0 only, as a tensor of that input's channel count (a route the next conv reads in two parts)
+        return yq_forward_route_layer_quant_part_gpu(ins, gs, cs, ups, first_alone ? 1 : (int)r.inputs.size(), first_alone ? 1u : mask, r.out_u8, &r.geom, net->batch,
+                                                     r.out_h, r.out_w, s);
     };
     for (size_t i = first; i < net->layers.size(); ++i) {
         Layer &l = net->layers[i];
@@ -685,6 +714,12 @@ int forward_body(yq_network *net, const uint8_t *in_u8_nchw, int *launches, bool
                                                                        net->layers[i + 1].out_f32, net->layers[i + 1].classes,
                                                                        net->keep_acc ? l.out_acc : nullptr, net->batch, st))
                     return -1;
+            } else if (l.use_flat && i > 0 && net->layers[i - 1].cat) {
+                // the route in front is not materialised: [its input 0 (brought into the route's buffer when it had to be upsampled) | its input 1]
+                const Layer &r = net->layers[i - 1];
+                const Layer &a0 = net->layers[r.inputs[0]], &a1 = net->layers[tensor_of(net, r.inputs[1])];
+                const uint8_t *first_in = r.cat_copy ? r.out_u8 : net->layers[tensor_of(net, r.inputs[0])].out_u8;
+                if (yq_forward_convolutional_layer_quant_flat_cat_gpu(l.conv, first_in, a0.out_c, a1.out_u8, l.out_u8, l.halo_fill, net->batch, st)) return -1;
             } else if (l.use_flat && l.fuse_shortcut) {
                 // conv + the quantized shortcut behind it: the launch stores the shortcut's tensor (the conv's own is never written)
                 Layer &sc = net->layers[i + 1];
@@ -753,7 +788,12 @@ int forward_body(yq_network *net, const uint8_t *in_u8_nchw, int *launches, bool
             cur_fill = l.halo_fill;
             break;
         case L_ROUTE:
-            if (l.inputs.size() > 1) {
+            if (l.cat) {
+                if (l.cat_copy) {
+                    if (issue_route(l, 1u, st, true)) return -1;
+                    ++nl;
+                }
+            } else if (l.inputs.size() > 1) {
                 unsigned mask = (1u << l.inputs.size()) - 1u;
                 if (early_ok && l.early_mask) {   // those inputs were copied on the side stream behind their producers
                     YQ_CUDA(cudaStreamWaitEvent(st, l.ev_early, 0));
@@ -1242,6 +1282,7 @@ extern "C" int yq_network_layer_launches(const yq_network *net, int i)
     const Layer &l = net->layers[i];
     if (l.fused_away) return 0;
     if (l.type == L_CONV) return l.use_rows ? yq_tc_rows_launches(l.conv->tc_rows) : 1;
+    if (l.type == L_ROUTE && l.cat) return l.cat_copy ? 1 : 0;      // (read in two parts by the conv behind it; only an upsampled part is written)
     if (l.type == L_ROUTE) return l.inputs.size() > 1 ? 1 : 0;      // (a single-input route is an alias; early copies aside)
     return 1;
 }
@@ -1256,7 +1297,7 @@ extern "C" int yq_network_layer_info(const yq_network *net, int i, yq_layer_info
     o->batch_normalize = l.bn; o->quant_stop_flag = l.quant_stop; o->s_in = l.s_in; o->s_out = l.s_out;
     o->zp_in = l.zp_in; o->zp_out = l.zp_out; o->kernel = l.conv ? (l.use_rows ? 3 : (l.use_flat ? 2 : yq_conv_get_kernel(l.conv))) : 0;
     o->classes = l.classes; o->n_anchors = l.n_anchors;
-    o->fused = l.type == L_CONV ? (l.use_rows ? 2 : (l.fuse_pool ? 1 : (l.fuse_yolo ? 3 : (l.fuse_shortcut ? 4 : 0)))) : (l.fused_away ? 1 : 0);
+    o->fused = l.type == L_CONV ? (l.use_rows ? 2 : (l.fuse_pool ? 1 : (l.fuse_yolo ? 3 : (l.fuse_shortcut ? 4 : 0)))) : (l.fused_away ? 1 : (l.type == L_ROUTE && l.cat ? 5 : 0));
     return 0;
 }
 
@@ -1614,6 +1655,7 @@ static const char *not_materialised(const yq_network *net, int layer, int what)
         if (l.type == L_UPSAMPLE && l.fused_away) return "the route behind it reads its input through the upsample";
         if (l.type == L_CONV && l.fuse_pool && (l.use_rows || !conv_output_needed(net, layer))) return "its launch writes the max-pooled tensor of the next layer only";
         if (l.type == L_CONV && l.fuse_shortcut) return "its launch writes the shortcut layer's tensor only";
+        if (l.type == L_ROUTE && l.cat) return "the convolution behind it reads the route's inputs itself";
     } else if (what == 2) {
         if (l.type == L_CONV && l.fuse_yolo && !net->keep_acc) return "its launch writes the yolo layer's output only (pull that layer, or enable yq_network_set_debug)";
     }

@@ -326,6 +326,36 @@ class ConvolutionalLayerQuant:
                 d.free()
         return res
 
+    def flat_cat_supported(self, c_first: int) -> bool:
+        return bool(_lib.load().yq_conv_flat_cat_supported(self.handle, int(c_first)))
+
+    def forward_flat_cat(self, x_nchw: np.ndarray, c_first: int, halo_fill: int = 0) -> Dict[str, np.ndarray]:
+        """forward_flat() with the input handed over as TWO flat tensors, channels [0, c_first) and [c_first, c): the convolution
+        behind a route that is never materialised (yq_forward_convolutional_layer_quant_flat_cat_gpu).  Returns dict(u8)."""
+        lib = _lib.load()
+        b = x_nchw.shape[0]
+        x = np.ascontiguousarray(x_nchw, np.uint8)
+        g = ActGeom()
+        check(lib.yq_act_geom_flat(self.h, self.w, C.byref(g)), "yq_act_geom_flat")
+        parts = []
+        for lo, hi in ((0, c_first), (c_first, self.c)):
+            d = DeviceBuffer(lib.yq_act_geom_bytes(C.byref(g), b, hi - lo), zero=False)
+            check(lib.yq_cuda_memset(d.ptr, self.zp_in, d.nbytes, None))
+            src = DeviceBuffer.from_numpy(np.ascontiguousarray(x[:, lo:hi]))
+            check(lib.yq_nchw_to_nhwc_u8_geom(src.ptr, d.ptr, b, hi - lo, self.h, self.w, C.byref(g), None))
+            parts += [d, src]
+        dout = DeviceBuffer(lib.yq_act_geom_bytes(C.byref(g), b, self.n), zero=False)
+        check(lib.yq_cuda_memset(dout.ptr, 0xEE, dout.nbytes, None))
+        check(lib.yq_forward_convolutional_layer_quant_flat_cat_gpu(self.handle, parts[0].ptr, int(c_first), parts[2].ptr, dout.ptr, int(halo_fill), b, None),
+              "yq_forward_convolutional_layer_quant_flat_cat_gpu")
+        tmp = DeviceBuffer(b * self.n * self.out_h * self.out_w)
+        check(lib.yq_nhwc_to_nchw_u8_geom(dout.ptr, tmp.ptr, b, self.n, self.out_h, self.out_w, C.byref(g), None))
+        check(lib.yq_stream_synchronize(None))
+        res = {"u8": tmp.pull((b, self.n, self.out_h, self.out_w), np.uint8)}
+        for d in parts + [dout, tmp]:
+            d.free()
+        return res
+
     @property
     def geom_supported(self) -> bool:
         """the layer's flavour reads / writes halo-padded tensors of any geometry (the per-tap TMA flavour)"""
@@ -371,8 +401,6 @@ class ConvolutionalLayerQuant:
             res["acc"] = pull_nhwc_i32(dacc, b, self.n, self.out_h, self.out_w)
         if df32:
             res["f32"] = df32.pull((b, self.n, self.out_h, self.out_w), np.float32)
-        if dyolo:
-            res["yolo"] = dyolo.pull((b, self.n, self.out_h, self.out_w), np.float32)
         raw = dout.pull((dout.nbytes // cs_out, cs_out), np.uint8)
         rows = raw[: b * go.rows_h * go.pitch_w].reshape(b, go.rows_h, go.pitch_w, cs_out).copy()
         rows[:, go.pad:go.pad + self.out_h, go.pad:go.pad + self.out_w, :] = 0xEE
