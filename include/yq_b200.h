@@ -191,6 +191,13 @@ YQ_API int yq_forward_convolutional_layer_quant_flat_shortcut_gpu(yq_conv_layer 
                                                                   uint8_t *out_flat, int halo_fill, int zp_from, int Ka, int Kb,
                                                                   int zp_out_shortcut, int batch, void *stream);
 
+/* A flat 1x1 convolution with the FOLLOWING stride-2 upsample layer fused (forward_upsample_layer, src/upsample_layer.c:92-101 ->
+ * upsample_cpu, src/blas.c:334-351: every pixel four times): out_up_flat = the flat tensor of (2h x 2w) pixels with the layer's output
+ * channel stride.  Only its interior is written (the halo keeps the caller's fill); the layer's own tensor is not written.
+ * Runs on the pointwise flavour (yq_conv_tc_pw.cu): 1x1, n <= 255, filter bank resident in shared memory. */
+YQ_API int yq_conv_flat_up2_supported(const yq_conv_layer *l);
+YQ_API int yq_forward_convolutional_layer_quant_flat_up2_gpu(yq_conv_layer *l, const uint8_t *in_flat, uint8_t *out_up_flat, int batch, void *stream);
+
 /* A flat convolution behind a [route] that is never materialised: the input is the channel concatenation
  * [in_first (c_first channels) | in_second (c - c_first channels)] of two flat tensors of the layer's input geometry, as
  * forward_route_layer (src/route_layer.c:77-95) would have copied them; the convolution's patch loads pick the tensor per
@@ -315,8 +322,10 @@ typedef struct yq_layer_info {
     int classes, n_anchors;   /* yolo only */
     int fused;                /* conv: 0 own launch writing the conv tensor, 1 following maxpool fused into the epilogue,
                                  2 rows flavour (halo input, pooled tensor only), 3 following yolo layer fused,
-                                 4 following quantized shortcut fused (the launch writes the shortcut's tensor only);
-                                 maxpool / yolo / shortcut: 1 = produced by the previous conv */
+                                 4 following quantized shortcut fused (the launch writes the shortcut's tensor only),
+                                 6 following upsample fused (the launch writes the upsampled tensor only);
+                                 maxpool / upsample / yolo / shortcut: 1 = produced by a neighbour's launch;
+                                 route: 5 = never written, the conv behind it reads its inputs itself */
 } yq_layer_info;
 
 /* batch <= 0 keeps the cfg's [net] batch.  Returns NULL on failure (see yq_last_error). */

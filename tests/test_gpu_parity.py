@@ -298,6 +298,35 @@ def test_conv_pointwise_flavour_vs_oracle(built, case, monkeypatch):
     layer.free()
 
 
+@pytest.mark.parametrize("case", [(256, 13, 13, 128, "relu6", 0, 0, 5), (128, 9, 7, 64, "leaky", 13, 40, 2), (64, 6, 11, 32, "leaky", 0, 3, 3),
+                                  (512, 5, 5, 100, "linear", 7, 128, 1)],
+                         ids=lambda c: "c%d_%dx%d_n%d_%s" % c[:5])
+def test_conv_pointwise_fused_upsample_vs_oracle(built, case):
+    """1x1 convolution + the stride-2 upsample behind it in one launch (layer 18 -> upsample 19 of yolov3-tiny): every pixel of the
+    oracle's convolution output four times (blas.c:334-351), the upsampled strip's halo untouched, pad lanes zero"""
+    c, h, w, n, act, zp_in, zp_out, batch = case
+    rng = np.random.default_rng(zlib.crc32(repr(case).encode()) + 77)
+    wq, zp_w, s_w, bias = make_params(rng, n, c, zp_in)
+    spec = synth.LayerSpec("conv", n, 1, 1, 1, 0, act)
+    sl = synth.SynthLayer("conv", c, h, w, n, 0, 0, spec, s_out=0.05, biases=bias, s_w=s_w, zp_w=zp_w, w_u8=wq.reshape(n, c, 1, 1))
+    p = O.prepare_conv(sl, 0.02, zp_in)
+    x = rng.integers(0, 256, size=(batch, c, h, w), dtype=np.uint8)
+    layer = darknet.ConvolutionalLayerQuant(h, w, c, n, 1, 1, 0, synth.ACT_CODES[act], wq, zp_w, p["biases_int32"], p["M_value"],
+                                            p["M0_right_shift_value"], zp_in, zp_out, 0.05)
+    if n == 100:
+        assert not layer.flat_up2_supported     # n = 100 -> stride 112: not a pointwise shape
+        layer.free()
+        return
+    assert layer.flat_up2_supported
+    got = layer.forward_flat_up2(x)
+    assert got["halo_ok"], "halo / pad lanes of the upsampled strip"
+    for b in range(batch):
+        acc = O.conv_acc(x[b], wq.reshape(n, c, 1, 1), zp_w, 1, 0, zp_in)
+        u8 = O.requant(acc, p["biases_int32"], p["M_value"], p["M0_right_shift_value"], synth.ACT_CODES[act], zp_out)
+        assert np.array_equal(got["u8"][b], O.upsample(u8, 2)), f"image {b}"
+    layer.free()
+
+
 @pytest.mark.parametrize("case", [(384, 26, 26, 256, 128, "relu6", 0, 0, 3), (384, 9, 12, 256, 256, "leaky", 11, 7, 2), (512, 13, 13, 512, 128, "relu6", 5, 0, 2),
                                   (320, 7, 7, 128, 64, "leaky", 0, 9, 1)],
                          ids=lambda c: "c%d_%dx%d_n%d_first%d" % c[:5])
@@ -618,6 +647,10 @@ def test_fused_network_equals_unfused_and_oracle(built, tiny_net_files):
             # (likewise route 20: layer 21 reads [layer 18 through the upsample | layer 8] itself)
             with pytest.raises(Exception, match="not materialised"):
                 net.pull_layer(i, "u8")
+        elif sl.kind == "conv" and net.layers()[i].fused == 6:
+            # (layer 18: its launch writes the upsampled tensor, the first part of what layer 21 reads)
+            with pytest.raises(Exception, match="not materialised"):
+                net.pull_layer(i, "u8")
         elif sl.kind == "maxpool" or (sl.kind == "conv" and i >= 8) or sl.kind in ("route", "upsample"):
             assert np.array_equal(net.pull_layer(i, "u8")[0], r["u8"]), f"layer {i}"
     for h, i in zip(net.split_heads(fused_flat), (16, 23)):
@@ -841,8 +874,9 @@ def test_network_schedule_switches_keep_every_byte(built, tiny_net_files, monkey
     monkeypatch.setenv("YQ_NO_CAT", str(nocat))
     net = darknet.load_network(cfg, wts, batch=4)
     cat = uproute and not nocat
-    assert bool(net.layers()[20].fused) == bool(cat)
-    assert net.launches_per_forward == n_base - uproute + (1 if early and branch and not cat else 0)
+    assert bool(net.layers()[20].fused) == bool(cat) and (net.layers()[18].fused == 6) == bool(cat)
+    # (with the route gone, layer 18 writes the upsampled tensor itself: the route's launch goes too)
+    assert net.launches_per_forward == n_base - uproute - (1 if cat else 0) + (1 if early and branch and not cat else 0)
     for graph in (False, True):
         net.use_graph(graph)
         for _ in range(4):

@@ -58,7 +58,9 @@ struct PwArgs {
     int tmem_cols;         // power of two >= nbuf * NC
     int wc;                // channels one epilogue warp requantises per tile: CSO / (4 / nbuf)
     int rowb;              // bytes per staging row = inner box of the store: min(wc, 64)
-    int store_u8;          // the uint8 tensor is stored (always, except heads on request)
+    int store_u8;          // the uint8 tensor is stored (always, except heads on request and layers that only write the upsampled tensor)
+    uint8_t *up_out;       // the FOLLOWING upsample layer (stride 2, upsample_layer.c:92-101 / blas.c:334-351) fused: the flat tensor of
+                           // (2H x 2W) pixels, same channel stride, that receives every output pixel four times; or nullptr
     int num_tiles;
     int trace;             // YQ_PW_TRACE
     uint32_t halo_word;
@@ -284,7 +286,24 @@ __global__ void __launch_bounds__(PW_THREADS, 1) conv_u8_tc_pw_kernel(const __gr
                             }
                         }
                     }
-                    if (a.store_u8) {
+                    if (!YOLO && a.up_out) {
+                        // conv -> upsample(2) in one launch: the pixel's 16 bytes go to its four copies in the (2H x 2W) flat strip
+                        // (that strip's halo is never written: it keeps the fill the plan gave it)
+                        if (valid) {
+                            uint32_t packed[4];
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) packed[k] = yq::pack_low_bytes(r[4 * k], r[4 * k + 1], r[4 * k + 2], r[4 * k + 3]);
+                            yq::mask_pad_channels<16>(packed, a.N - c0);
+                            const uint4 val = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+                            const int W2 = 2 * a.W + 1;
+                            const size_t P = ((size_t)n * (2 * a.H + 1) + 2 * yy + 1) * W2 + 2 * xx + 1;
+                            uint8_t *d = a.up_out + P * a.CSO + c0;
+                            *reinterpret_cast<uint4 *>(d) = val;
+                            *reinterpret_cast<uint4 *>(d + a.CSO) = val;
+                            *reinterpret_cast<uint4 *>(d + (size_t)W2 * a.CSO) = val;
+                            *reinterpret_cast<uint4 *>(d + (size_t)(W2 + 1) * a.CSO) = val;
+                        }
+                    } else if (a.store_u8) {
                         uint32_t packed[4];
 #pragma unroll
                         for (int k = 0; k < 4; ++k) packed[k] = yq::pack_low_bytes(r[4 * k], r[4 * k + 1], r[4 * k + 2], r[4 * k + 3]);
@@ -479,10 +498,11 @@ void yq_tc_pw_free(void *state)
 }
 
 int yq_tc_pw_forward(yq_conv_layer *l, void *state, const uint8_t *in, uint8_t *out_u8, int halo_fill, float *out_yolo, int yolo_classes, int batch,
-                     cudaStream_t stream, int plain)
+                     cudaStream_t stream, int plain, uint8_t *out_up2)
 {
     PwState *st = (PwState *)state;
     if (!st || !in || !out_u8) return yq::fail("tcgen05 pointwise flavour: bad argument");
+    if (out_up2 && (plain || l->quant_stop_flag)) return yq::fail("tcgen05 pointwise flavour: the fused upsample needs a flat, quantized layer");
     if (l->quant_stop_flag && !out_yolo) return yq::fail("tcgen05 pointwise flavour: a quant_stop layer runs here only as a fused yolo head");
     if (out_yolo && yq::act_mode(l->activation) != 1) return yq::fail("tcgen05 pointwise flavour: detection heads are LINEAR (see yq_tc_pw_head_supported)");
     const int W1 = l->w + (plain ? 0 : 1), H1 = l->h + (plain ? 0 : 1);
@@ -511,7 +531,8 @@ int yq_tc_pw_forward(yq_conv_layer *l, void *state, const uint8_t *in, uint8_t *
     if (a.wc % 32 || (a.wc > 64 && a.wc % 64)) return yq::fail("tcgen05 pointwise flavour: %d channels per epilogue warp", a.wc);
     {
         static const int head_u8 = getenv("YQ_PW_HEAD_U8") ? atoi(getenv("YQ_PW_HEAD_U8")) : 1;     // 0: heads skip their uint8 tensor (A/B measurements)
-        a.store_u8 = l->quant_stop_flag ? head_u8 : 1;
+        a.store_u8 = l->quant_stop_flag ? head_u8 : (out_up2 ? 0 : 1);
+        a.up_out = out_up2;
     }
     // ring depth: what fits, a multiple of the accumulator count when a commit serves stage and accumulator alike
     int stages = PW_MAX_ASTAGES;

@@ -699,6 +699,20 @@ extern "C" int yq_forward_convolutional_layer_quant_flat_shortcut_gpu(yq_conv_la
     sc.C0 = 32768 + ((zp_out_shortcut & 0xff) << 16) - l->zp_out * Ka - (zp_from & 0xff) * Kb;
     return flat_dispatch(l, in_flat, out_flat, halo_fill, nullptr, nullptr, batch, stream, &sc);
 }
+// A flat 1x1 convolution with the FOLLOWING stride-2 upsample fused (upsample_layer.c:92-101, blas.c:334-351: every pixel four times):
+// out_up_flat = the flat tensor of (2h x 2w) pixels with the layer's output channel stride; only its interior is written (its halo keeps
+// the caller's fill).  The layer's own tensor is not written.
+extern "C" int yq_conv_flat_up2_supported(const yq_conv_layer *l)
+{
+    const bool off = (getenv("YQ_NO_UP2") && atoi(getenv("YQ_NO_UP2"))) || (getenv("YQ_PW") && !atoi(getenv("YQ_PW")));   // A/B measurements
+    return l && !off && l->tc_pw && !l->quant_stop_flag ? 1 : 0;
+}
+extern "C" int yq_forward_convolutional_layer_quant_flat_up2_gpu(yq_conv_layer *l, const uint8_t *in_flat, uint8_t *out_up_flat, int batch, void *stream)
+{
+    if (!l || !in_flat || !out_up_flat || batch <= 0) return yq::fail("yq_forward_convolutional_layer_quant_flat_up2_gpu: bad argument");
+    if (!yq_conv_flat_up2_supported(l)) return yq::fail("this layer cannot fuse the upsample behind it (see yq_conv_flat_up2_supported)");
+    return yq_tc_pw_forward(l, l->tc_pw, in_flat, out_up_flat, 0, nullptr, 0, batch, (cudaStream_t)stream, 0, out_up_flat);
+}
 // A flat convolution whose input is the channel concatenation [in_first (c_first channels) | in_second (the rest)] of two flat tensors of
 // the layer's input geometry: a [route] in front of it that is never materialised (route_layer.c:77-95 only copies bytes; here the
 // convolution's patch loads pick the tensor per channel chunk).  Both halos must hold the layer's input zero point.

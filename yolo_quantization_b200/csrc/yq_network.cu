@@ -129,7 +129,9 @@ struct Layer {
     bool cat = false;              // route (two inputs): never materialised -- the flat conv behind it reads [input 0 | input 1] itself
                                    // (yq_forward_convolutional_layer_quant_flat_cat_gpu); out_u8 then holds input 0 alone when that
                                    // one has to be brought into shape first (the upsample folded into this route)
-    bool cat_copy = false;         //   ... input 0 is copied (upsampled) into out_u8; false: both inputs are read in place
+    bool cat_copy = false;         //   ... input 0 is copied (upsampled) into out_u8 by the route's own launch
+    bool cat_buf = false;          //   ... input 0 lives in out_u8 (copied there, or written there by the conv in front of the upsample)
+    int up2_route = -1;            // conv: the stride-2 upsample behind it is fused -- the launch writes the upsampled tensor into that route's buffer
     unsigned early_mask = 0;       // route: inputs copied on the side stream as soon as they exist (see plan_early_copies())
     cudaEvent_t ev_early = nullptr;
     std::vector<std::pair<int, int>> early_copies;   // (route layer, input index) to issue behind this layer
@@ -517,7 +519,8 @@ void plan(yq_network *net)
     for (int i = 0; i < n; ++i) {
         Layer &l = net->layers[i];
         l.fuse_pool = l.fused_away = l.use_rows = l.use_flat = l.use_geom = l.use_outgeom = l.fuse_yolo = l.fuse_shortcut = l.fuse_up = l.side = false;
-        l.cat = l.cat_copy = false;
+        l.cat = l.cat_copy = l.cat_buf = false;
+        l.up2_route = -1;
         l.geom = yq_act_geom{0, l.out_w, l.out_h};
         l.halo_fill = 0;
     }
@@ -599,8 +602,21 @@ void plan(yq_network *net)
             };
             if (!same_geom(r.geom, g) || !in_place(a1) || (!up0 && !in_place(a0))) continue;
             r.cat = true;
-            r.cat_copy = up0;
+            r.cat_copy = r.cat_buf = up0;
             if (!up0) --launches;        // nothing is copied at all
+            // ... and the upsampled part is written by the 1x1 convolution in front of the upsample when that one runs the pointwise
+            // flavour and nobody else reads its tensor (layer 18 -> upsample 19 -> route 20 -> layer 21 of yolov3-tiny: no launch in between)
+            if (up0) {
+                const int ui = r.inputs[0], pc = ui - 1;
+                Layer &u = net->layers[ui];
+                if (pc >= 0 && u.src == pc && u.stride == 2 && net->layers[pc].type == L_CONV && net->layers[pc].conv && net->layers[pc].use_flat &&
+                    !net->layers[pc].fuse_yolo && !net->layers[pc].fuse_shortcut && !routed_from(net, pc) && !net->layers[pc].side && !r.side &&
+                    yq_conv_flat_up2_supported(net->layers[pc].conv) && net->layers[pc].out_c == a0.out_c) {
+                    net->layers[pc].up2_route = i;
+                    r.cat_copy = false;
+                    --launches;
+                }
+            }
         }
     // (layer 0 in the rows flavour reads the CHW planes itself when it can: no layout-transform launch, see forward_body)
     if (n > 0 && net->layers[0].type == L_CONV && net->layers[0].use_rows && !net->no_planar_input && yq_conv_rows_nchw_supported(net->layers[0].conv))
@@ -714,11 +730,14 @@ int forward_body(yq_network *net, const uint8_t *in_u8_nchw, int *launches, bool
                                                                        net->layers[i + 1].out_f32, net->layers[i + 1].classes,
                                                                        net->keep_acc ? l.out_acc : nullptr, net->batch, st))
                     return -1;
+            } else if (l.use_flat && l.up2_route >= 0) {
+                // conv + the upsample behind it: the launch writes the upsampled tensor (the first part of what the conv behind the route reads)
+                if (yq_forward_convolutional_layer_quant_flat_up2_gpu(l.conv, cur, net->layers[l.up2_route].out_u8, net->batch, st)) return -1;
             } else if (l.use_flat && i > 0 && net->layers[i - 1].cat) {
                 // the route in front is not materialised: [its input 0 (brought into the route's buffer when it had to be upsampled) | its input 1]
                 const Layer &r = net->layers[i - 1];
                 const Layer &a0 = net->layers[r.inputs[0]], &a1 = net->layers[tensor_of(net, r.inputs[1])];
-                const uint8_t *first_in = r.cat_copy ? r.out_u8 : net->layers[tensor_of(net, r.inputs[0])].out_u8;
+                const uint8_t *first_in = r.cat_buf ? r.out_u8 : net->layers[tensor_of(net, r.inputs[0])].out_u8;
                 if (yq_forward_convolutional_layer_quant_flat_cat_gpu(l.conv, first_in, a0.out_c, a1.out_u8, l.out_u8, l.halo_fill, net->batch, st)) return -1;
             } else if (l.use_flat && l.fuse_shortcut) {
                 // conv + the quantized shortcut behind it: the launch stores the shortcut's tensor (the conv's own is never written)
@@ -1297,7 +1316,7 @@ extern "C" int yq_network_layer_info(const yq_network *net, int i, yq_layer_info
     o->batch_normalize = l.bn; o->quant_stop_flag = l.quant_stop; o->s_in = l.s_in; o->s_out = l.s_out;
     o->zp_in = l.zp_in; o->zp_out = l.zp_out; o->kernel = l.conv ? (l.use_rows ? 3 : (l.use_flat ? 2 : yq_conv_get_kernel(l.conv))) : 0;
     o->classes = l.classes; o->n_anchors = l.n_anchors;
-    o->fused = l.type == L_CONV ? (l.use_rows ? 2 : (l.fuse_pool ? 1 : (l.fuse_yolo ? 3 : (l.fuse_shortcut ? 4 : 0)))) : (l.fused_away ? 1 : (l.type == L_ROUTE && l.cat ? 5 : 0));
+    o->fused = l.type == L_CONV ? (l.use_rows ? 2 : (l.fuse_pool ? 1 : (l.fuse_yolo ? 3 : (l.fuse_shortcut ? 4 : (l.up2_route >= 0 ? 6 : 0))))) : (l.fused_away ? 1 : (l.type == L_ROUTE && l.cat ? 5 : 0));
     return 0;
 }
 
@@ -1656,6 +1675,7 @@ static const char *not_materialised(const yq_network *net, int layer, int what)
         if (l.type == L_CONV && l.fuse_pool && (l.use_rows || !conv_output_needed(net, layer))) return "its launch writes the max-pooled tensor of the next layer only";
         if (l.type == L_CONV && l.fuse_shortcut) return "its launch writes the shortcut layer's tensor only";
         if (l.type == L_ROUTE && l.cat) return "the convolution behind it reads the route's inputs itself";
+        if (l.type == L_CONV && l.up2_route >= 0) return "its launch writes the upsampled tensor the convolution behind the route reads";
     } else if (what == 2) {
         if (l.type == L_CONV && l.fuse_yolo && !net->keep_acc) return "its launch writes the yolo layer's output only (pull that layer, or enable yq_network_set_debug)";
     }

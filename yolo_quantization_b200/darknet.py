@@ -326,6 +326,41 @@ class ConvolutionalLayerQuant:
                 d.free()
         return res
 
+    @property
+    def flat_up2_supported(self) -> bool:
+        return bool(_lib.load().yq_conv_flat_up2_supported(self.handle))
+
+    def forward_flat_up2(self, x_nchw: np.ndarray) -> Dict[str, np.ndarray]:
+        """The flat 1x1 convolution with the following stride-2 upsample fused (yq_forward_convolutional_layer_quant_flat_up2_gpu).
+        Returns dict(u8=[b,n,2h,2w], halo_ok=True when the upsampled strip's halo and pad lanes still hold their preset)."""
+        lib = _lib.load()
+        b = x_nchw.shape[0]
+        x = np.ascontiguousarray(x_nchw, np.uint8)
+        g, g2 = ActGeom(), ActGeom()
+        check(lib.yq_act_geom_flat(self.h, self.w, C.byref(g)), "yq_act_geom_flat")
+        check(lib.yq_act_geom_flat(2 * self.out_h, 2 * self.out_w, C.byref(g2)), "yq_act_geom_flat")
+        cs_out = channel_stride(self.n)
+        din = DeviceBuffer(lib.yq_act_geom_bytes(C.byref(g), b, self.c), zero=False)
+        check(lib.yq_cuda_memset(din.ptr, self.zp_in, din.nbytes, None))
+        src = DeviceBuffer.from_numpy(x)
+        check(lib.yq_nchw_to_nhwc_u8_geom(src.ptr, din.ptr, b, self.c, self.h, self.w, C.byref(g), None))
+        dout = DeviceBuffer(lib.yq_act_geom_bytes(C.byref(g2), b, self.n), zero=False)
+        check(lib.yq_cuda_memset(dout.ptr, 0xEE, dout.nbytes, None))
+        check(lib.yq_forward_convolutional_layer_quant_flat_up2_gpu(self.handle, din.ptr, dout.ptr, b, None),
+              "yq_forward_convolutional_layer_quant_flat_up2_gpu")
+        tmp = DeviceBuffer(b * self.n * 4 * self.out_h * self.out_w)
+        check(lib.yq_nhwc_to_nchw_u8_geom(dout.ptr, tmp.ptr, b, self.n, 2 * self.out_h, 2 * self.out_w, C.byref(g2), None))
+        check(lib.yq_stream_synchronize(None))
+        res = {"u8": tmp.pull((b, self.n, 2 * self.out_h, 2 * self.out_w), np.uint8)}
+        raw = dout.pull((dout.nbytes // cs_out, cs_out), np.uint8)
+        rows = raw[: b * g2.rows_h * g2.pitch_w].reshape(b, g2.rows_h, g2.pitch_w, cs_out).copy()
+        pads = rows[:, 1:, 1:, self.n:].copy()
+        rows[:, 1:, 1:, :] = 0xEE
+        res["halo_ok"] = bool((rows == 0xEE).all() and (raw[b * g2.rows_h * g2.pitch_w:] == 0xEE).all() and not pads.any())
+        for d in (din, src, dout, tmp):
+            d.free()
+        return res
+
     def flat_cat_supported(self, c_first: int) -> bool:
         return bool(_lib.load().yq_conv_flat_cat_supported(self.handle, int(c_first)))
 
