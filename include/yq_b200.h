@@ -202,7 +202,8 @@ YQ_API int yq_forward_convolutional_layer_quant_flat_up2_gpu(yq_conv_layer *l, c
  * [in_first (c_first channels) | in_second (c - c_first channels)] of two flat tensors of the layer's input geometry, as
  * forward_route_layer (src/route_layer.c:77-95) would have copied them; the convolution's patch loads pick the tensor per
  * channel chunk instead.  Both halos must hold the layer's input zero point.  yq_conv_flat_cat_supported: 1 when the layer's
- * kernel can do this for a split at c_first (the CTA-pair flavour, c >= 256, c_first a multiple of its channel chunk). */
+ * kernel can do this for a split at c_first (the CTA-pair flavour, c >= 256, or the pointwise flavour of narrow 1x1 layers; c_first a
+ * multiple of the kernel's channel chunk). */
 YQ_API int yq_conv_flat_cat_supported(const yq_conv_layer *l, int c_first);
 YQ_API int yq_forward_convolutional_layer_quant_flat_cat_gpu(yq_conv_layer *l, const uint8_t *in_first, int c_first, const uint8_t *in_second,
                                                              uint8_t *out_flat, int halo_fill, int batch, void *stream);

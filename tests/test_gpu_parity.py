@@ -327,27 +327,28 @@ def test_conv_pointwise_fused_upsample_vs_oracle(built, case):
     layer.free()
 
 
-@pytest.mark.parametrize("case", [(384, 26, 26, 256, 128, "relu6", 0, 0, 3), (384, 9, 12, 256, 256, "leaky", 11, 7, 2), (512, 13, 13, 512, 128, "relu6", 5, 0, 2),
-                                  (320, 7, 7, 128, 64, "leaky", 0, 9, 1)],
+@pytest.mark.parametrize("case", [(384, 26, 26, 256, 128, "relu6", 0, 0, 3, 3), (384, 9, 12, 256, 256, "leaky", 11, 7, 2, 3), (512, 13, 13, 512, 128, "relu6", 5, 0, 2, 3),
+                                  (320, 7, 7, 128, 64, "leaky", 0, 9, 1, 3), (384, 11, 6, 128, 128, "leaky", 77, 9, 2, 1), (192, 20, 9, 64, 64, "leaky", 0, 3, 3, 1)],
                          ids=lambda c: "c%d_%dx%d_n%d_first%d" % c[:5])
 def test_conv_reads_two_tensors_as_their_concatenation(built, case):
-    """the convolution behind a route that is never materialised (layer 21 of yolov3-tiny reads [upsampled layer 18 | layer 8]):
-    two flat tensors in, bytes equal to the oracle's convolution over their concatenation and to the one-tensor launch"""
-    c, h, w, n, c_first, act, zp_in, zp_out, batch = case
+    """the convolution behind a route that is never materialised (layer 21 of yolov3-tiny reads [upsampled layer 18 | layer 8]; layer 99
+    of the full yolov3, a 1x1 layer on the pointwise flavour, reads [upsampled layer 96 | layer 36]): two flat tensors in, bytes equal to
+    the oracle's convolution over their concatenation and to the one-tensor launch"""
+    c, h, w, n, c_first, act, zp_in, zp_out, batch, k = case
     rng = np.random.default_rng(zlib.crc32(repr(case).encode()) + 5)
-    wq, zp_w, s_w, bias = make_params(rng, n, c * 9, zp_in)
-    spec = synth.LayerSpec("conv", n, 3, 1, 1, 0, act)
-    sl = synth.SynthLayer("conv", c, h, w, n, 0, 0, spec, s_out=0.05, biases=bias, s_w=s_w, zp_w=zp_w, w_u8=wq.reshape(n, c, 3, 3))
+    wq, zp_w, s_w, bias = make_params(rng, n, c * k * k, zp_in)
+    spec = synth.LayerSpec("conv", n, k, 1, 1, 0, act)
+    sl = synth.SynthLayer("conv", c, h, w, n, 0, 0, spec, s_out=0.05, biases=bias, s_w=s_w, zp_w=zp_w, w_u8=wq.reshape(n, c, k, k))
     p = O.prepare_conv(sl, 0.02, zp_in)
     x = rng.integers(0, 256, size=(batch, c, h, w), dtype=np.uint8)
-    layer = darknet.ConvolutionalLayerQuant(h, w, c, n, 3, 1, 1, synth.ACT_CODES[act], wq, zp_w, p["biases_int32"], p["M_value"],
+    layer = darknet.ConvolutionalLayerQuant(h, w, c, n, k, 1, k // 2, synth.ACT_CODES[act], wq, zp_w, p["biases_int32"], p["M_value"],
                                             p["M0_right_shift_value"], zp_in, zp_out, 0.05)
     assert layer.flat_cat_supported(c_first) and not layer.flat_cat_supported(c_first + 16)
     got = layer.forward_flat_cat(x, c_first, halo_fill=zp_out)
     one = layer.forward_flat(x, halo_fill=zp_out, want_acc=False)
     assert np.array_equal(got["u8"], one["u8"])
     for b in range(batch):
-        acc = O.conv_acc(x[b], wq.reshape(n, c, 3, 3), zp_w, 1, 1, zp_in)
+        acc = O.conv_acc(x[b], wq.reshape(n, c, k, k), zp_w, 1, k // 2, zp_in)
         u8 = O.requant(acc, p["biases_int32"], p["M_value"], p["M0_right_shift_value"], synth.ACT_CODES[act], zp_out)
         assert np.array_equal(got["u8"][b], u8), f"uint8 mismatch, image {b}"
     layer.free()

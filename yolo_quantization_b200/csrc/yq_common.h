@@ -213,7 +213,8 @@ void yq_tc_pw_free(void *state);
 // out_up2 != null (flat tensors only): the FOLLOWING stride-2 upsample fused -- the launch writes the (2H x 2W) flat tensor out_up2 (same
 // channel stride, interior only) INSTEAD of the layer's own tensor (out_u8 only names the tensor-map cache entry then)
 int yq_tc_pw_forward(yq_conv_layer *l, void *state, const uint8_t *in, uint8_t *out_u8, int halo_fill, float *out_yolo, int yolo_classes, int batch,
-                     cudaStream_t stream, int plain, uint8_t *out_up2 = nullptr);
+                     cudaStream_t stream, int plain, uint8_t *out_up2 = nullptr, const uint8_t *in_first = nullptr, int c_first = 0);
+int yq_tc_pw_chunk(const void *state);         // channels per ring stage (64 or 128)
 
 // implemented in yq_conv_tc.cu (TMA-fed; c % 64 == 0)
 int yq_tc_supported(const yq_conv_layer *l);

@@ -62,6 +62,7 @@ struct PwArgs {
     uint8_t *up_out;       // the FOLLOWING upsample layer (stride 2, upsample_layer.c:92-101 / blas.c:334-351) fused: the flat tensor of
                            // (2H x 2W) pixels, same channel stride, that receives every output pixel four times; or nullptr
     int num_tiles;
+    int split;             // chunks [0, split) of the input channels come from the second tensor map (see yq_conv_tc_flat2x.cu)
     int trace;             // YQ_PW_TRACE
     uint32_t halo_word;
     uint32_t magic_w, magic_h;
@@ -94,7 +95,8 @@ __device__ __forceinline__ void pw_tmem_dealloc(uint32_t addr, uint32_t cols)
 // stage and one more per tile publishes the accumulator.
 template <int KC, bool ONE, bool YOLO, int ACTM>
 __global__ void __launch_bounds__(PW_THREADS, 1) conv_u8_tc_pw_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                                                                  const __grid_constant__ CUtensorMap tmO, const PwArgs a)
+                                                                  const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmA2,
+                                                                  const PwArgs a)
 {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -135,6 +137,7 @@ __global__ void __launch_bounds__(PW_THREADS, 1) conv_u8_tc_pw_kernel(const __gr
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmO) : "memory");
+        if (a.split) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA2) : "memory");
     }
     if (warp >= 2) {
         const int t = threadIdx.x - 64;
@@ -172,8 +175,9 @@ __global__ void __launch_bounds__(PW_THREADS, 1) conv_u8_tc_pw_kernel(const __gr
             for (int c = 0; c < chunks; ++c) {
                 mbar_wait(&a_empty[s], ph ^ 1);
                 if (elect_one()) {
+                    // a.split > 0: the input is the channel concatenation [tmA2 | tmA] of two tensors (a route that is never materialised)
                     mbar_expect_tx(&a_full[s], (uint32_t)A_STAGE);
-                    tma_load_2d(sA + s * A_STAGE, &tmA, &a_full[s], c * KC, p0);
+                    tma_load_2d(sA + s * A_STAGE, c < a.split ? &tmA2 : &tmA, &a_full[s], (c < a.split ? c : c - a.split) * KC, p0);
                 }
                 if (++s == nst) { s = 0; ph ^= 1; }
             }
@@ -383,12 +387,15 @@ struct PwState {
     float *lut = nullptr;       // quant_stop layers: dequantized value and its logistic for each of the 256 output bytes
     CUtensorMap tmB;
     struct Key {
-        const void *in;
+        const void *in, *in2;
         void *out;
         int batch;
-        bool operator<(const Key &o) const { return in != o.in ? in < o.in : out != o.out ? out < o.out : batch < o.batch; }
+        bool operator<(const Key &o) const { return in != o.in ? in < o.in : in2 != o.in2 ? in2 < o.in2 : out != o.out ? out < o.out : batch < o.batch; }
     };
-    std::map<Key, std::pair<CUtensorMap, CUtensorMap>> maps;
+    struct Maps {
+        CUtensorMap a, o, a2;
+    };
+    std::map<Key, Maps> maps;
 };
 
 // shared memory of a launch with `stages` ring stages
@@ -398,29 +405,29 @@ int pw_smem_bytes(int NC, int K, int KC, int stages)
 }
 
 template <int KC, bool ONE, bool YOLO, int ACTM>
-int pw_launch_v(PwState *st, const CUtensorMap &tmA, const CUtensorMap &tmO, const PwArgs &a, int smem, int grid, cudaStream_t stream)
+int pw_launch_v(PwState *st, const CUtensorMap &tmA, const CUtensorMap &tmO, const CUtensorMap &tmA2, const PwArgs &a, int smem, int grid, cudaStream_t stream)
 {
     auto kern = conv_u8_tc_pw_kernel<KC, ONE, YOLO, ACTM>;
     if (yq::ensure_dynamic_smem((const void *)kern, smem)) return -1;
-    YQ_CUDA(yq::launch_pdl(kern, dim3(grid), dim3(PW_THREADS), smem, stream, tmA, st->tmB, tmO, a));
+    YQ_CUDA(yq::launch_pdl(kern, dim3(grid), dim3(PW_THREADS), smem, stream, tmA, st->tmB, tmO, tmA2, a));
     return 0;
 }
 
 template <int KC>
-int pw_launch(PwState *st, const CUtensorMap &tmA, const CUtensorMap &tmO, const PwArgs &a, int smem, int grid, cudaStream_t stream)
+int pw_launch(PwState *st, const CUtensorMap &tmA, const CUtensorMap &tmO, const CUtensorMap &tmA2, const PwArgs &a, int smem, int grid, cudaStream_t stream)
 {
     // the activation is a launch constant: one epilogue form per kernel keeps the code each warp walks short (heads are LINEAR: checked by the caller)
     const int actm = yq::act_mode(a.ep.act);
     if (a.cpt == 1) {
-        if (a.out_yolo) return pw_launch_v<KC, true, true, 1>(st, tmA, tmO, a, smem, grid, stream);
-        if (actm == 0) return pw_launch_v<KC, true, false, 0>(st, tmA, tmO, a, smem, grid, stream);
-        if (actm == 1) return pw_launch_v<KC, true, false, 1>(st, tmA, tmO, a, smem, grid, stream);
-        return pw_launch_v<KC, true, false, 2>(st, tmA, tmO, a, smem, grid, stream);
+        if (a.out_yolo) return pw_launch_v<KC, true, true, 1>(st, tmA, tmO, tmA2, a, smem, grid, stream);
+        if (actm == 0) return pw_launch_v<KC, true, false, 0>(st, tmA, tmO, tmA2, a, smem, grid, stream);
+        if (actm == 1) return pw_launch_v<KC, true, false, 1>(st, tmA, tmO, tmA2, a, smem, grid, stream);
+        return pw_launch_v<KC, true, false, 2>(st, tmA, tmO, tmA2, a, smem, grid, stream);
     }
-    if (a.out_yolo) return pw_launch_v<KC, false, true, 1>(st, tmA, tmO, a, smem, grid, stream);
-    if (actm == 0) return pw_launch_v<KC, false, false, 0>(st, tmA, tmO, a, smem, grid, stream);
-    if (actm == 1) return pw_launch_v<KC, false, false, 1>(st, tmA, tmO, a, smem, grid, stream);
-    return pw_launch_v<KC, false, false, 2>(st, tmA, tmO, a, smem, grid, stream);
+    if (a.out_yolo) return pw_launch_v<KC, false, true, 1>(st, tmA, tmO, tmA2, a, smem, grid, stream);
+    if (actm == 0) return pw_launch_v<KC, false, false, 0>(st, tmA, tmO, tmA2, a, smem, grid, stream);
+    if (actm == 1) return pw_launch_v<KC, false, false, 1>(st, tmA, tmO, tmA2, a, smem, grid, stream);
+    return pw_launch_v<KC, false, false, 2>(st, tmA, tmO, tmA2, a, smem, grid, stream);
 }
 
 }  // namespace
@@ -442,6 +449,7 @@ int yq_tc_pw_supported(const yq_conv_layer *l)
 }
 
 // a detection head (quant_stop + fused yolo) runs here when its activation is LINEAR (every yolo cfg of the reference); others keep the flat kernel
+int yq_tc_pw_chunk(const void *state) { return state ? ((const PwState *)state)->KC : 0; }
 int yq_tc_pw_head_supported(const yq_conv_layer *l) { return l->tc_pw && l->quant_stop_flag && yq::act_mode(l->activation) == 1 ? 1 : 0; }
 
 int yq_tc_pw_prepare(yq_conv_layer *l, void **state)
@@ -498,10 +506,14 @@ void yq_tc_pw_free(void *state)
 }
 
 int yq_tc_pw_forward(yq_conv_layer *l, void *state, const uint8_t *in, uint8_t *out_u8, int halo_fill, float *out_yolo, int yolo_classes, int batch,
-                     cudaStream_t stream, int plain, uint8_t *out_up2)
+                     cudaStream_t stream, int plain, uint8_t *out_up2, const uint8_t *in_first, int c_first)
 {
     PwState *st = (PwState *)state;
     if (!st || !in || !out_u8) return yq::fail("tcgen05 pointwise flavour: bad argument");
+    // in_first != null: the input is the concatenation [in_first (c_first channels) | in (the rest)] of two tensors of the same geometry
+    if (in_first && (c_first <= 0 || c_first >= l->cs_in || c_first % st->KC || (l->cs_in - c_first) % 16))
+        return yq::fail("tcgen05 pointwise flavour: a two-tensor input splits at a multiple of %d channels", st->KC);
+    const int c_second = in_first ? l->cs_in - c_first : l->cs_in;
     if (out_up2 && (plain || l->quant_stop_flag)) return yq::fail("tcgen05 pointwise flavour: the fused upsample needs a flat, quantized layer");
     if (l->quant_stop_flag && !out_yolo) return yq::fail("tcgen05 pointwise flavour: a quant_stop layer runs here only as a fused yolo head");
     if (out_yolo && yq::act_mode(l->activation) != 1) return yq::fail("tcgen05 pointwise flavour: detection heads are LINEAR (see yq_tc_pw_head_supported)");
@@ -546,20 +558,23 @@ int yq_tc_pw_forward(yq_conv_layer *l, void *state, const uint8_t *in, uint8_t *
     a.halo_word = 0x01010101u * (uint32_t)(halo_fill & 0xff);
     a.magic_w = (uint32_t)((0x100000000ull + W1 - 1) / W1);
     a.magic_h = (uint32_t)((0x100000000ull + H1 - 1) / H1);
-    PwState::Key key{in, out_u8, batch * 2 + (plain ? 1 : 0)};
+    PwState::Key key{in, in_first, out_u8, batch * 2 + (plain ? 1 : 0)};
     auto it = st->maps.find(key);
     if (it == st->maps.end()) {
         if (st->maps.size() > 64) st->maps.clear();
-        CUtensorMap tmA, tmO;
-        if (pw_encode_2d(&tmA, in, (uint64_t)rows_alloc, l->cs_in, st->KC, 128, CU_TENSOR_MAP_L2_PROMOTION_L2_128B)) return -1;
+        PwState::Maps m;
+        if (pw_encode_2d(&m.a, in, (uint64_t)rows_alloc, c_second, st->KC, 128, CU_TENSOR_MAP_L2_PROMOTION_L2_128B)) return -1;
         // the store box is one epilogue warp's pass: 32 positions x rowb channels
-        if (pw_encode_2d(&tmO, out_u8, (uint64_t)rows_alloc, l->cs_out, a.rowb, 32, CU_TENSOR_MAP_L2_PROMOTION_L2_128B)) return -1;
-        it = st->maps.emplace(key, std::make_pair(tmA, tmO)).first;
+        if (pw_encode_2d(&m.o, out_u8, (uint64_t)rows_alloc, l->cs_out, a.rowb, 32, CU_TENSOR_MAP_L2_PROMOTION_L2_128B)) return -1;
+        m.a2 = m.a;
+        if (in_first && pw_encode_2d(&m.a2, in_first, (uint64_t)rows_alloc, c_first, st->KC, 128, CU_TENSOR_MAP_L2_PROMOTION_L2_128B)) return -1;
+        it = st->maps.emplace(key, m).first;
     }
+    a.split = in_first ? c_first / st->KC : 0;
     const int grid = a.num_tiles < n_sm ? a.num_tiles : n_sm;
-    const CUtensorMap &tmA = it->second.first, &tmO = it->second.second;
-    if (st->KC == 128) return pw_launch<128>(st, tmA, tmO, a, smem, grid, stream);
-    return pw_launch<64>(st, tmA, tmO, a, smem, grid, stream);
+    const CUtensorMap &tmA = it->second.a, &tmO = it->second.o, &tmA2 = it->second.a2;
+    if (st->KC == 128) return pw_launch<128>(st, tmA, tmO, tmA2, a, smem, grid, stream);
+    return pw_launch<64>(st, tmA, tmO, tmA2, a, smem, grid, stream);
 }
 
 // YQ_PW_TRACE=1: the event times of the last traced launch (64 events x up to 256 CTAs, ns; tools/probes/pw_trace.py)

@@ -719,7 +719,12 @@ extern "C" int yq_forward_convolutional_layer_quant_flat_up2_gpu(yq_conv_layer *
 extern "C" int yq_conv_flat_cat_supported(const yq_conv_layer *l, int c_first)
 {
     const bool off = getenv("YQ_NO_CAT") && atoi(getenv("YQ_NO_CAT"));   // A/B measurements (read per call: the tests flip it)
-    if (!l || off || !l->tc_flat2x || l->quant_stop_flag || l->c < 256) return 0;
+    if (!l || off || l->quant_stop_flag) return 0;
+    if (l->tc_pw && !(getenv("YQ_PW") && !atoi(getenv("YQ_PW")))) {     // a 1x1 layer on the pointwise flavour (its dispatch comes first)
+        const int kc = yq_tc_pw_chunk(l->tc_pw);
+        return c_first > 0 && c_first < l->cs_in && c_first % kc == 0 && (l->cs_in - c_first) % 16 == 0 ? 1 : 0;
+    }
+    if (!l->tc_flat2x || l->c < 256) return 0;
     if (getenv("YQ_NO_FLAT2") && atoi(getenv("YQ_NO_FLAT2"))) return 0;
     if (getenv("YQ_FLAT2X") && atoi(getenv("YQ_FLAT2X")) == 0) return 0;
     const int kc = yq_tc_flat2x_chunk(l->tc_flat2x);
@@ -730,6 +735,8 @@ extern "C" int yq_forward_convolutional_layer_quant_flat_cat_gpu(yq_conv_layer *
 {
     if (!l || !in_first || !in_second || !out_flat || batch <= 0) return yq::fail("yq_forward_convolutional_layer_quant_flat_cat_gpu: bad argument");
     if (!yq_conv_flat_cat_supported(l, c_first)) return yq::fail("this layer cannot read a two-tensor input split at channel %d (see yq_conv_flat_cat_supported)", c_first);
+    if (l->tc_pw && !(getenv("YQ_PW") && !atoi(getenv("YQ_PW"))))
+        return yq_tc_pw_forward(l, l->tc_pw, in_second, out_flat, halo_fill, nullptr, 0, batch, (cudaStream_t)stream, 0, nullptr, in_first, c_first);
     return yq_tc_flat2x_forward(l, l->tc_flat2x, in_second, out_flat, halo_fill, nullptr, batch, (cudaStream_t)stream, nullptr, in_first, c_first);
 }
 extern "C" int yq_forward_convolutional_layer_quant_flat_yolo_gpu(yq_conv_layer *l, const uint8_t *in_flat, uint8_t *out_flat, int halo_fill,

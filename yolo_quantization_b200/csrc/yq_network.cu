@@ -598,7 +598,8 @@ void plan(yq_network *net)
             yq_act_geom_flat(cv.h, cv.w, &g);
             auto in_place = [&](const Layer &a) {
                 const int t = tensor_of(net, (int)(&a - &net->layers[0]));
-                return t >= 0 && same_geom(net->layers[t].geom, g) && net->layers[t].halo_fill == r.halo_fill;
+                // (a 1x1 convolution never looks at a halo position: whatever the tensor's other consumers pad with is fine)
+                return t >= 0 && same_geom(net->layers[t].geom, g) && (cv.size == 1 || net->layers[t].halo_fill == r.halo_fill);
             };
             if (!same_geom(r.geom, g) || !in_place(a1) || (!up0 && !in_place(a0))) continue;
             r.cat = true;
