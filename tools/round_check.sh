@@ -13,6 +13,8 @@ for NET in tiny yolov3; do
   B=$( [ $NET = tiny ] && echo 128 || echo 64 )
   python tools/make_traffic.py gpurun_out/launches_$NET.csv gpurun_out/prof_$NET.log $NET $B gpurun_out/r2_traffic_$NET.json
 done
+# kernel timelines of the forward in steady state (graph replays, one stream; CUPTI records through torch.profiler)
+for NET in tiny yolov3; do YQ_NET=$NET timeout 300 python tools/timeline.py gpurun_out/r2_timeline_$NET.json > gpurun_out/r2_timeline_$NET.txt 2>&1; done
 cat gpurun_out/tests.log gpurun_out/smoke.log gpurun_out/i8_peak.json; cut -c1-300 gpurun_out/bench.json; cut -c1-200 gpurun_out/bench_s1.json; cut -c1-300 gpurun_out/bench_v3.json; tail -n 2 gpurun_out/bench.err; tail -n 2 gpurun_out/bench_v3.err
 # evidence for profiles/ (copy after the LAST kernel change: bench.py trusts r2_traffic_*.json only for the same kernel sources)
 python tools/ncu_summary.py gpurun_out/launches_tiny.csv /dev/null > /dev/null 2>&1 || true

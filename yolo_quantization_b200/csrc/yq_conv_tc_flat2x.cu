@@ -35,7 +35,8 @@ constexpr int F2X_BN = 128;            // channels per tile of the two-tile form
 constexpr int F2X_EPI_WARPS = 16;
 constexpr int F2X_SUM_WARPS = 2;
 constexpr int F2X_THREADS = 32 * (2 + F2X_SUM_WARPS + F2X_EPI_WARPS);
-constexpr int F2X_ASTAGES = 2;
+constexpr int F2X_ASTAGES = 6;              // barrier slots; a launch uses a.a_stages of them: 2 for 3x3 layers (nine taps of MMAs per patch chunk cover the next
+                                            // chunk's load), up to 6 for 1x1 layers (one tap per chunk: the loads run several chunks ahead of the tensor pipe)
 constexpr int F2X_MAX_BSTAGES = 8;
 constexpr int F2X_MAX_ROWS = 384;           // patch rows: 256 + 2W + 4 (W <= 61)
 
@@ -46,7 +47,7 @@ struct Flat2xArgs {
     int B, H, W, NP;       // NP = B*(H+1)*(W+1)
     int size, taps, cpt /* KC-chunks per tap */, CS;
     int q_off;             // first patch position relative to the pair's first position: -(pad*(W+1) + pad)
-    int patch_rows, box_rows, a_stage_bytes, b_stages;
+    int patch_rows, box_rows, a_stage_bytes, a_stages, b_stages;
     int m_pairs, num_tiles;   // tile t -> (n-tile t / m_pairs, position pair t % m_pairs)
     uint32_t halo_word;
     uint32_t magic_w, magic_h, magic_m;
@@ -84,7 +85,7 @@ __global__ void __launch_bounds__(F2X_THREADS, 1) conv_u8_tc_flat2x_kernel(const
     extern __shared__ __align__(16) uint8_t smem_raw[];
     uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     uint8_t *sA = smem;                                              // F2X_ASTAGES patch stages
-    uint8_t *sB = sA + F2X_ASTAGES * a.a_stage_bytes;                 // a.b_stages weight stages
+    uint8_t *sB = sA + a.a_stages * a.a_stage_bytes;                  // a.b_stages weight stages
     uint8_t *sOut = sB + a.b_stages * L::B_STAGE;                    // two output staging tiles
     int4 *s_q = (int4 *)(sOut + 2 * L::OUT_BYTES);                   // {bias, zw, 2*M0, shift} of the current n-tile
     double *s_mc = (double *)(s_q + BNT);
@@ -154,7 +155,7 @@ __global__ void __launch_bounds__(F2X_THREADS, 1) conv_u8_tc_flat2x_kernel(const
                     tma_load_2d(sA + sa * a.a_stage_bytes, src, &a_full[sa], cc, p0 + a.q_off);
                     tma_load_2d(sA + sa * a.a_stage_bytes + a.box_rows * KC, src, &a_full[sa], cc, p0 + a.q_off + a.box_rows);
                 }
-                if (++sa == F2X_ASTAGES) { sa = 0; pha ^= 1; }
+                if (++sa == a.a_stages) { sa = 0; pha ^= 1; }
                 for (int tap = 0; tap < a.taps; ++tap) {
                     mbar_wait(&b_empty[s], phb ^ 1);           // (released by the leader's multicast commit)
                     if (elect_one()) {
@@ -204,20 +205,20 @@ __global__ void __launch_bounds__(F2X_THREADS, 1) conv_u8_tc_flat2x_kernel(const
                         if (++s == nbs) { s = 0; phb ^= 1; }
                     }
                     if (elect_one()) umma_commit_2cta(&a_empty[sa], 3);
-                    if (++sa == F2X_ASTAGES) { sa = 0; pha ^= 1; }
+                    if (++sa == a.a_stages) { sa = 0; pha ^= 1; }
                 }
                 if (elect_one()) umma_commit_2cta(&acc_full[pb], 3);
             }
         } else {
             // ===================== peer CTA: tell the leader when my patch stages have landed =====================
-            const uint32_t remote0 = map_to_cta(&a_peer_full[0], 0), remote1 = map_to_cta(&a_peer_full[1], 0);
+            const uint32_t remote0 = map_to_cta(&a_peer_full[0], 0);       // (the barriers are consecutive 8-byte words)
             int sa = 0;
             uint32_t pha = 0;
             for (int tile = cid; tile < a.num_tiles; tile += ncl) {
                 for (int c = 0; c < chunks; ++c) {
                     mbar_wait(&a_full[sa], pha);
-                    if (elect_one()) mbar_arrive_cluster(sa ? remote1 : remote0);
-                    if (++sa == F2X_ASTAGES) { sa = 0; pha ^= 1; }
+                    if (elect_one()) mbar_arrive_cluster(remote0 + 8u * (uint32_t)sa);
+                    if (++sa == a.a_stages) { sa = 0; pha ^= 1; }
                 }
             }
         }
@@ -254,7 +255,7 @@ __global__ void __launch_bounds__(F2X_THREADS, 1) conv_u8_tc_flat2x_kernel(const
                 }
                 __syncwarp();
                 if (lane == 0) f2x_arrive(&a_empty[sa]);
-                if (++sa == F2X_ASTAGES) { sa = 0; pha ^= 1; }
+                if (++sa == a.a_stages) { sa = 0; pha ^= 1; }
             }
             mbar_wait(&acc_empty[pb], ((it >> 1) & 1) ^ 1);           // S[pb] was consumed by the epilogue of pair it-2
 #pragma unroll
@@ -455,7 +456,13 @@ int f2x_launch_v(Flat2xState *st, const CUtensorMap &tmA, const CUtensorMap &tmO
     using L = Flat2xSmem<KC, WIDE>;
     const int n_sm = yq::device_sm_count(), smem_max = yq::device_smem_optin();   // (of the CURRENT device: nothing cached per process)
     if (n_sm <= 0 || smem_max <= 0) return yq::fail("cannot query the device's multiprocessor count / shared memory size");
-    const int fixed = F2X_ASTAGES * a.a_stage_bytes + 2 * L::OUT_BYTES + L::PARAM_BYTES + L::SUM_BYTES + 512 + 1024;
+    // 1x1 layers: as many patch stages as fit beside the staging tiles and four weight stages (at most F2X_ASTAGES)
+    a.a_stages = 2;
+    if (a.size == 1)
+        while (a.a_stages < F2X_ASTAGES &&
+               (a.a_stages + 1) * a.a_stage_bytes + 2 * L::OUT_BYTES + L::PARAM_BYTES + L::SUM_BYTES + 512 + 1024 + 4 * L::B_STAGE <= smem_max)
+            ++a.a_stages;
+    const int fixed = a.a_stages * a.a_stage_bytes + 2 * L::OUT_BYTES + L::PARAM_BYTES + L::SUM_BYTES + 512 + 1024;
     int nbs = (smem_max - fixed) / L::B_STAGE;
     if (nbs > F2X_MAX_BSTAGES) nbs = F2X_MAX_BSTAGES;
     if (nbs < 2) return yq::fail("conv_u8_tc_flat2x_kernel<%d>: shared memory does not hold two weight stages", KC);
