@@ -52,6 +52,7 @@ rows = []
 for k in range(per):
     rows.append({"launch": k, "layer": order[k], "kernel": ev[k].name.replace("(anonymous namespace)::", "").replace("void ", "").split("(")[0][:70], "us": round(float(dur[1:, k].mean()), 2), "gap_us": round(float(gap[1:, k].mean()), 2)})
     print(f"{k:3d} layer {order[k]:3d}  {rows[-1]['us']:8.2f} us  gap {rows[-1]['gap_us']:7.2f}  {rows[-1]['kernel']}")
+print("(launches are listed in start order; the layer column follows the issue order: a side-stream launch may sit under its neighbour's layer)")
 print(f"forward period {span:.1f} us; sum of kernel durations {dur[1:].sum(1).mean():.1f} us; sum of positive gaps {np.clip(gap[1:], 0, None).sum(1).mean():.1f} us; "
       f"overlap (negative gaps) {-np.clip(gap[1:], None, 0).sum(1).mean():.1f} us")
 if len(sys.argv) > 1:
