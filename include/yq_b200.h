@@ -145,6 +145,10 @@ typedef struct yq_act_geom {
  * as out of bounds and restores zp_in * sum(w - zp_w) per border tap in the epilogue.  Flavours that only take plain
  * tensors (SIMT, c <= 32) fail on a padded geometry: yq_conv_geom_supported() says which kind the layer has. */
 YQ_API int yq_conv_geom_supported(const yq_conv_layer *l);
+/* 1: the layer also has the resident-bank kernel in patch mode (3x3, stride 2, n <= 255, filter bank resident in shared memory): handed a
+ * halo-padded input whose halo holds its zp_in (in_halo_fill == zp_in) and no side outputs, yq_forward_convolutional_layer_quant_geom_gpu
+ * runs it there (persistent, one tcgen05.commit per tile or filter row) instead of the one-tile-per-CTA per-tap / small-c flavours. */
+YQ_API int yq_conv_patch_supported(const yq_conv_layer *l);
 /* 1 when the layer's flavour can at least WRITE a halo-padded output tensor (plain input): the per-tap flavour, and the small-c
  * flavour (c <= 32), whose threads store their pixels themselves. */
 YQ_API int yq_conv_out_geom_supported(const yq_conv_layer *l);

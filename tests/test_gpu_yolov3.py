@@ -77,6 +77,54 @@ def test_conv_stride2_tcgen05_vs_oracle(built, case):
     layer.free()
 
 
+PATCH_CASES = [
+    # c, h, w, n, zp_in, batch
+    (32, 32, 32, 64, 40, 2),         # layer 1 of the full yolov3 in small: c = 32 (32-byte rows), whole filter per ring stage, one commit per tile
+    (64, 32, 48, 128, 17, 2),        # layer 5 in small: c = 64, a filter row per stage
+    (32, 37, 45, 64, 0, 3),          # odd sizes: partial tiles in x and y
+    (64, 26, 20, 32, 200, 1),        # narrow output (32-byte staging rows)
+    (32, 416, 416, 64, 3, 1),        # layer 1 at its real size
+    (64, 208, 208, 128, 9, 1),       # layer 5 at its real size
+    (96, 16, 24, 100, 5, 2),         # n = 100 -> stride 112: not a patch-mode shape
+]
+
+
+@pytest.mark.parametrize("case", PATCH_CASES, ids=lambda c: "c%d_%dx%d_n%d_zi%d" % c[:5])
+def test_conv_stride2_resident_bank_patch_mode_vs_oracle(built, case, monkeypatch):
+    monkeypatch.setenv("YQ_PWT_C32", "1")       # (c = 32 is kept as a tested switch: slower than the small-c flavour, off by default)
+    """narrow 3x3 / stride-2 layers (layers 1 and 5 of the full yolov3) on the resident-bank kernel in patch mode: flat input whose halo
+    holds zp_in, no side outputs -> bytes equal the oracle and the older flavours (YQ_PW=0), the output's halo is untouched; with side
+    outputs, a plain input or a foreign halo byte the older flavours still serve the call."""
+    c, h, w, n, zp_in, batch = case
+    rng = np.random.default_rng(zlib.crc32(repr(case).encode()) + 19)
+    layer, wq, zp_w, p = _rand_layer(rng, c, n, 3, 2, "leaky", zp_in, h=h, w=w)
+    x = rng.integers(0, 256, size=(batch, c, h, w), dtype=np.uint8)
+    assert layer.patch_supported == (n != 100)
+    if n == 100:
+        _check(layer.forward(x), x, wq, zp_w, p, 2, 3, "leaky", zp_in, 33)
+        layer.free()
+        return
+    if c % 64 == 0:      # (a c = 32 layer falls back to the small-c flavour, which reads plain tensors only)
+        oh, ow = layer.out_h, layer.out_w
+        for gi, go in (("flat", "flat"), ("flat", None), ((2, w + 5, h + 3), (1, ow + 4, oh + 2))):
+            got = layer.forward_geom(x, gi, go, want_acc=False)
+            assert got["halo_ok"], f"halo of the output was written ({gi} -> {go})"
+            _check(got, x, wq, zp_w, p, 2, 3, "leaky", zp_in, 33)
+        monkeypatch.setenv("YQ_PW", "0")
+        old = layer.forward_geom(x, "flat", "flat", want_acc=False)
+        monkeypatch.delenv("YQ_PW")
+        assert np.array_equal(old["u8"], layer.forward_geom(x, "flat", "flat", want_acc=False)["u8"])
+        _check(layer.forward_geom(x, "flat", "flat", want_acc=True), x, wq, zp_w, p, 2, 3, "leaky", zp_in, 33)          # side output: per-tap flavour
+        _check(layer.forward_geom(x, "flat", "flat", in_fill=(zp_in + 7) & 255, want_acc=False), x, wq, zp_w, p, 2, 3, "leaky", zp_in, 33)
+    else:
+        for go in ("flat", None):
+            got = layer.forward_geom(x, "flat", go, want_acc=False)
+            assert got["halo_ok"]
+            _check(got, x, wq, zp_w, p, 2, 3, "leaky", zp_in, 33)
+        _check(layer.forward(x), x, wq, zp_w, p, 2, 3, "leaky", zp_in, 33)                                                # plain: small-c flavour
+    layer.free()
+
+
 @pytest.mark.parametrize("case", [(64, 13, 13, 128, 3, 40), (128, 9, 11, 64, 1, 5), (256, 6, 6, 255, 1, 0)], ids=lambda c: "c%d_%dx%d_n%d_k%d" % c[:5])
 def test_conv_stride1_per_tap_between_padded_tensors(built, case, monkeypatch):
     """the per-tap flavour at stride 1 between tensors of any geometry (what a conv next to a conflicting tensor falls to)"""

@@ -83,6 +83,7 @@ SIGNATURES = {
     "yq_forward_convolutional_layer_quant_flat_gpu": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _i, _vp]),
     "yq_conv_flat_shortcut_supported": (_i, [_vp]),
     "yq_forward_convolutional_layer_quant_flat_shortcut_gpu": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
+    "yq_conv_patch_supported": (_i, [_vp]),
     "yq_conv_flat_up2_supported": (_i, [_vp]),
     "yq_forward_convolutional_layer_quant_flat_up2_gpu": (_i, [_vp, _vp, _vp, _i, _vp]),
     "yq_conv_flat_cat_supported": (_i, [_vp, _i]),

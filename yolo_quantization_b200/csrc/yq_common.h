@@ -116,6 +116,7 @@ struct yq_conv_layer {
     void *tc_flat2 = nullptr;   // its persistent two-tiles-per-weight-stage form (yq_conv_tc_flat2.cu), or nullptr
     void *tc_flat2x = nullptr;  // the same on CTA pairs, tcgen05 cta_group::2 (yq_conv_tc_flat2x.cu), or nullptr
     void *tc_pw = nullptr;      // pointwise streaming form: narrow 1x1 layers and detection heads (yq_conv_tc_pw.cu), or nullptr
+    void *tc_pwt = nullptr;     // the same kernel in patch mode: narrow 3x3 stride-2 layers between halo-padded tensors, or nullptr
     std::vector<uint8_t> host_w;  // OIHW copy kept for repacking
     uint64_t pack_key = 0;        // content key of this layer's filter images in the packed-weight arena (yq_pack.cu)
     std::vector<uint8_t> host_zw;
@@ -215,6 +216,12 @@ void yq_tc_pw_free(void *state);
 int yq_tc_pw_forward(yq_conv_layer *l, void *state, const uint8_t *in, uint8_t *out_u8, int halo_fill, float *out_yolo, int yolo_classes, int batch,
                      cudaStream_t stream, int plain, uint8_t *out_up2 = nullptr, const uint8_t *in_first = nullptr, int c_first = 0);
 int yq_tc_pw_chunk(const void *state);         // channels per ring stage (64 or 128)
+// patch mode of the same kernel: 3x3 stride-2 layers with n <= 255 whose filter bank [n + 1][9 c] fits shared memory; the input is
+// halo-padded (pad >= 1) with the halo holding zp_in, the output tensor may have any geometry (its interior is written)
+int yq_tc_pwt_supported(const yq_conv_layer *l);
+int yq_tc_pwt_prepare(yq_conv_layer *l, void **state);
+int yq_tc_pwt_forward(yq_conv_layer *l, void *state, const uint8_t *in, const yq_act_geom *in_geom, uint8_t *out_u8, const yq_act_geom *out_geom, int batch,
+                      cudaStream_t stream);
 
 // implemented in yq_conv_tc.cu (TMA-fed; c % 64 == 0)
 int yq_tc_supported(const yq_conv_layer *l);

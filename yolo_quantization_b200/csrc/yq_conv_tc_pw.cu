@@ -63,6 +63,14 @@ struct PwArgs {
                            // (2H x 2W) pixels, same channel stride, that receives every output pixel four times; or nullptr
     int num_tiles;
     int split;             // chunks [0, split) of the input channels come from the second tensor map (see yq_conv_tc_flat2x.cu)
+    int group;             // chunks per ring stage: loaded under one barrier, released by one commit (1: pointwise; 3 or 9: patch mode)
+    // patch mode (size x size filters, stride 1 or 2, bank [NC][taps][cs_in] resident): a tile is a TW x TH patch of output pixels of one
+    // image (TW * TH = 128, TW a power of two), chunk c = (tap, channel chunk) is ONE 4-D tiled TMA box whose start is shifted by the tap
+    // and which steps through the input with elementStrides = stride (yq_conv_tc.cu); the input's halo holds zp_in, the output map
+    // covers the interior of the output tensor (partial tiles are clipped by the TMA unit)
+    int patch;
+    int tw_shift, tiles_x, tiles_y, OH, OW;
+    int size, stride, cptap;   // filter size, stride, KC-chunks per tap
     int trace;             // YQ_PW_TRACE
     uint32_t halo_word;
     uint32_t magic_w, magic_h;
@@ -100,10 +108,11 @@ __global__ void __launch_bounds__(PW_THREADS, 1) conv_u8_tc_pw_kernel(const __gr
 {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-    constexpr int A_STAGE = 128 * KC;
-    const int b_chunk = a.NC * KC;                                   // multiple of 1024 (NC % 16 == 0, KC >= 64)
+    constexpr int A_CHUNK = 128 * KC;
+    const int A_STAGE = a.group * A_CHUNK;
+    const int b_chunk = a.NC * KC;                                   // whole swizzle atoms (NC % 16 == 0)
     uint8_t *sB = smem;                                              // [cpt][NC rows][KC] resident filter bank
-    uint8_t *sA = sB + a.cpt * b_chunk;                              // a.a_stages ring stages of 128 positions x KC
+    uint8_t *sA = sB + ((a.cpt * b_chunk + 1023) & ~1023);           // a.a_stages ring stages of a.group x (128 positions x KC)
     uint8_t *sOut = sA + a.a_stages * A_STAGE;                       // one staging slice per epilogue warp
     int4 *s_q = (int4 *)(sOut + PW_EPI_WARPS * PW_STAGE_SLICE);      // {bias, zw, 2*M0, shift}
     double *s_mc = (double *)(s_q + PW_MAX_NC);
@@ -117,7 +126,7 @@ __global__ void __launch_bounds__(PW_THREADS, 1) conv_u8_tc_pw_kernel(const __gr
     uint32_t *tmem_slot = (uint32_t *)(b_full + 1);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int nst = a.a_stages, nbuf = a.nbuf, chunks = a.cpt;
+    const int nst = a.a_stages, nbuf = a.nbuf, chunks = a.cpt, group = a.group, groups = a.cpt / a.group;
     if (threadIdx.x == 0) pw_mark(a.trace, 0);                       // CTA start
 
     if (threadIdx.x == 0) {
@@ -172,12 +181,24 @@ __global__ void __launch_bounds__(PW_THREADS, 1) conv_u8_tc_pw_kernel(const __gr
         uint32_t ph = 0;
         for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x, ++tr) {
             const int p0 = tile * 128;
-            for (int c = 0; c < chunks; ++c) {
+            const int tx = tile % a.tiles_x, t2 = tile / a.tiles_x, ty = t2 % a.tiles_y, n0 = t2 / a.tiles_y;     // (patch mode)
+            const int cx0 = (tx << a.tw_shift) * a.stride, cy0 = (ty << (7 - a.tw_shift)) * a.stride;            // tap (0, 0) of the patch: the map starts in the halo
+            for (int g = 0; g < groups; ++g) {
                 mbar_wait(&a_empty[s], ph ^ 1);
                 if (elect_one()) {
-                    // a.split > 0: the input is the channel concatenation [tmA2 | tmA] of two tensors (a route that is never materialised)
                     mbar_expect_tx(&a_full[s], (uint32_t)A_STAGE);
-                    tma_load_2d(sA + s * A_STAGE, c < a.split ? &tmA2 : &tmA, &a_full[s], (c < a.split ? c : c - a.split) * KC, p0);
+                    for (int j = 0; j < group; ++j) {
+                        const int c = g * group + j;
+                        uint8_t *dst = sA + s * A_STAGE + j * A_CHUNK;
+                        if (a.patch) {
+                            const int tap = c / a.cptap, chunk = c - tap * a.cptap;
+                            const int ky = tap / a.size, kx = tap - ky * a.size;
+                            tma_load_4d(dst, &tmA, &a_full[s], chunk * KC, cx0 + kx, cy0 + ky, n0);
+                        } else {
+                            // a.split > 0: the input is the channel concatenation [tmA2 | tmA] of two tensors (a route that is never materialised)
+                            tma_load_2d(dst, c < a.split ? &tmA2 : &tmA, &a_full[s], (c < a.split ? c : c - a.split) * KC, p0);
+                        }
+                    }
                 }
                 if (++s == nst) { s = 0; ph ^= 1; }
             }
@@ -195,14 +216,17 @@ __global__ void __launch_bounds__(PW_THREADS, 1) conv_u8_tc_pw_kernel(const __gr
             mbar_wait(&acc_empty[b], phb ^ 1);               // the epilogue has drained this accumulator
             tc_fence_after();
             const uint32_t acc = tmem_base + (uint32_t)(b * a.NC);
-            for (int c = 0; c < chunks; ++c) {
+            for (int g = 0; g < groups; ++g) {
                 mbar_wait(&a_full[s], ph);
                 tc_fence_after();
                 if (elect_one()) {
-                    const uint64_t da = make_desc<KC>(smem_u32(sA + s * A_STAGE));
-                    const uint64_t db = make_desc<KC>(smem_u32(sB + c * b_chunk));
+                    for (int j = 0; j < group; ++j) {
+                        const int c = g * group + j;
+                        const uint64_t da = make_desc<KC>(smem_u32(sA + s * A_STAGE + j * A_CHUNK));
+                        const uint64_t db = make_desc<KC>(smem_u32(sB + c * b_chunk));
 #pragma unroll
-                    for (int k = 0; k < KC / 32; ++k) umma_i8(acc, da + 2 * k, db + 2 * k, idesc, (c | k) ? 1u : 0u);
+                        for (int k = 0; k < KC / 32; ++k) umma_i8(acc, da + 2 * k, db + 2 * k, idesc, (c | k) ? 1u : 0u);
+                    }
                     umma_commit(&a_empty[s]);
                 }
                 if (++s == nst) { s = 0; ph ^= 1; }
@@ -228,13 +252,28 @@ __global__ void __launch_bounds__(PW_THREADS, 1) conv_u8_tc_pw_kernel(const __gr
         for (int it = b; blockIdx.x + (long long)it * gridDim.x < a.num_tiles; it += nbuf) {
             const int tile = blockIdx.x + it * gridDim.x;
             const int p0 = tile * 128;
-            const int p = p0 + q * 32 + lane;
-            const int row = (int)__umulhi((uint32_t)p, a.magic_w);
-            const int col = p - row * pitch;
-            const int n = (int)__umulhi((uint32_t)row, a.magic_h);
-            const int y1 = row - n * rows_h;
-            const bool valid = p < a.NP && (a.plain || (col >= 1 && y1 >= 1));
-            const int yy = a.plain ? y1 : y1 - 1, xx = a.plain ? col : col - 1;
+            int n, yy, xx, px0 = 0, py0 = 0;
+            bool valid;
+            if (a.patch) {
+                // tile row r = (hi, wi) of the TW x TH patch at (px0, py0) of image n; rows outside the image are clipped by the store
+                const int tx = tile % a.tiles_x, t2 = tile / a.tiles_x, ty = t2 % a.tiles_y;
+                const int r = q * 32 + lane;
+                n = t2 / a.tiles_y;
+                px0 = tx << a.tw_shift;
+                py0 = ty << (7 - a.tw_shift);
+                xx = px0 + (r & ((1 << a.tw_shift) - 1));
+                yy = py0 + (r >> a.tw_shift);
+                valid = xx < a.OW && yy < a.OH;
+            } else {
+                const int p = p0 + q * 32 + lane;
+                const int row = (int)__umulhi((uint32_t)p, a.magic_w);
+                const int col = p - row * pitch;
+                n = (int)__umulhi((uint32_t)row, a.magic_h);
+                const int y1 = row - n * rows_h;
+                valid = p < a.NP && (a.plain || (col >= 1 && y1 >= 1));
+                yy = a.plain ? y1 : y1 - 1;
+                xx = a.plain ? col : col - 1;
+            }
             if (ONE) {
                 const int s = it % nst;
                 mbar_wait(&a_empty[s], (uint32_t)((it / nst) & 1));
@@ -311,7 +350,7 @@ __global__ void __launch_bounds__(PW_THREADS, 1) conv_u8_tc_pw_kernel(const __gr
                         uint32_t packed[4];
 #pragma unroll
                         for (int k = 0; k < 4; ++k) packed[k] = yq::pack_low_bytes(r[4 * k], r[4 * k + 1], r[4 * k + 2], r[4 * k + 3]);
-                        if (!valid) packed[0] = packed[1] = packed[2] = packed[3] = a.halo_word;
+                        if (!valid && !a.patch) packed[0] = packed[1] = packed[2] = packed[3] = a.halo_word;
                         yq::mask_pad_channels<16>(packed, a.N - c0);
                         // 64-byte rows: SWIZZLE_64B (16-byte chunk ^ row bits 1-2); 32-byte rows: SWIZZLE_32B (chunk ^ row bit 2)
                         const int sw = rowb == 64 ? (chl ^ ((lane >> 1) & 3)) : (chl ^ ((lane >> 2) & 1));
@@ -328,7 +367,8 @@ __global__ void __launch_bounds__(PW_THREADS, 1) conv_u8_tc_pw_kernel(const __gr
                     fence_proxy_async();          // my staging writes -> visible to the TMA unit
                     __syncwarp();
                     if (lane == 0) {
-                        tma_store_2d(&tmO, stage, cbeg + pass * rowb, p0 + q * 32);
+                        if (a.patch) tma_store_4d(&tmO, stage, cbeg + pass * rowb, px0, py0 + q * (32 >> a.tw_shift), n);   // my 32 / TW rows of the patch
+                        else tma_store_2d(&tmO, stage, cbeg + pass * rowb, p0 + q * 32);
                         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                     }
                 }
@@ -398,10 +438,10 @@ struct PwState {
     std::map<Key, Maps> maps;
 };
 
-// shared memory of a launch with `stages` ring stages
-int pw_smem_bytes(int NC, int K, int KC, int stages)
+// shared memory of a launch with `stages` ring stages of `group` chunks each
+int pw_smem_bytes(int NC, int K, int KC, int stages, int group = 1)
 {
-    return 1024 + NC * K + stages * 128 * KC + PW_EPI_WARPS * PW_STAGE_SLICE + PW_MAX_NC * (16 + 8 + 4) + 2048 + 512;
+    return 1024 + ((NC * K + 1023) & ~1023) + stages * group * 128 * KC + PW_EPI_WARPS * PW_STAGE_SLICE + PW_MAX_NC * (16 + 8 + 4) + 2048 + 512;
 }
 
 template <int KC, bool ONE, bool YOLO, int ACTM>
@@ -418,7 +458,7 @@ int pw_launch(PwState *st, const CUtensorMap &tmA, const CUtensorMap &tmO, const
 {
     // the activation is a launch constant: one epilogue form per kernel keeps the code each warp walks short (heads are LINEAR: checked by the caller)
     const int actm = yq::act_mode(a.ep.act);
-    if (a.cpt == 1) {
+    if (a.cpt == a.group) {      // one ring stage per tile: a single commit frees the stage and publishes the accumulator
         if (a.out_yolo) return pw_launch_v<KC, true, true, 1>(st, tmA, tmO, tmA2, a, smem, grid, stream);
         if (actm == 0) return pw_launch_v<KC, true, false, 0>(st, tmA, tmO, tmA2, a, smem, grid, stream);
         if (actm == 1) return pw_launch_v<KC, true, false, 1>(st, tmA, tmO, tmA2, a, smem, grid, stream);
@@ -525,6 +565,8 @@ int yq_tc_pw_forward(yq_conv_layer *l, void *state, const uint8_t *in, uint8_t *
     if (n_sm <= 0 || smem_max <= 0) return yq::fail("cannot query the device's multiprocessor count / shared memory size");
     PwArgs a;
     memset(&a, 0, sizeof a);
+    a.group = 1;
+    a.tiles_x = a.tiles_y = 1;
     a.ep = yq::make_epi(l);
     a.out_yolo = out_yolo;
     a.lut = st->lut;
@@ -575,6 +617,149 @@ int yq_tc_pw_forward(yq_conv_layer *l, void *state, const uint8_t *in, uint8_t *
     const CUtensorMap &tmA = it->second.a, &tmO = it->second.o, &tmA2 = it->second.a2;
     if (st->KC == 128) return pw_launch<128>(st, tmA, tmO, tmA2, a, smem, grid, stream);
     return pw_launch<64>(st, tmA, tmO, tmA2, a, smem, grid, stream);
+}
+
+// ---------------------------------------------------------------------------------------------
+// patch mode: size x size filters (3x3), stride 1 or 2, between halo-padded tensors; bank [NC][taps][cs_in] resident
+// ---------------------------------------------------------------------------------------------
+namespace {
+// 4-D map over an NHWC tensor stored in geometry g (yq_conv_tc.cu: encode_nhwc).  halo > 0: coordinate (0, 0) is the halo pixel
+// (-halo, -halo); halo = 0: the h x w interior, everything else out of bounds (zero fill on loads, clipped on stores).
+int pw_encode_nhwc(CUtensorMap *m, const void *ptr, const yq_act_geom *g, int halo, int B, int H, int W, int CS, int box_c, int TW, int TH, int estride)
+{
+    EncodeTiledFn enc = pw_get_encode();
+    if (!enc) return yq::fail("cuTensorMapEncodeTiled is not available from this driver");
+    const uint8_t *base = (const uint8_t *)ptr + ((size_t)(g->pad - halo) * g->pitch_w + (g->pad - halo)) * CS;
+    cuuint64_t dims[4] = {(cuuint64_t)CS, (cuuint64_t)(W + 2 * halo), (cuuint64_t)(H + 2 * halo), (cuuint64_t)B};
+    cuuint64_t strides[3] = {(cuuint64_t)CS, (cuuint64_t)g->pitch_w * CS, (cuuint64_t)g->rows_h * g->pitch_w * CS};
+    cuuint32_t box[4] = {(cuuint32_t)box_c, (cuuint32_t)(TW * estride), (cuuint32_t)(TH * estride), 1};
+    cuuint32_t es[4] = {1, (cuuint32_t)estride, (cuuint32_t)estride, 1};
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 4, const_cast<uint8_t *>(base), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     box_c >= 128 ? CU_TENSOR_MAP_SWIZZLE_128B : (box_c == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B),
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS)
+        return yq::fail("cuTensorMapEncodeTiled(NHWC %dx%dx%dx%d pitch %d rows %d box %d,%d,%d stride %d) failed: %d", B, H, W, CS, g->pitch_w, g->rows_h, box_c, TW, TH,
+                        estride, (int)r);
+    return 0;
+}
+int pwt_kc(const yq_conv_layer *l) { return (l->cs_in % 128) ? ((l->cs_in % 64) ? 32 : 64) : 128; }
+// chunks per ring stage: the whole filter (one commit per tile) when four such stages fit beside the bank, else one filter row
+int pwt_group(const yq_conv_layer *l, int NC, int KC, int smem_max)
+{
+    const int taps = l->size * l->size, cpt = taps * (l->cs_in / KC);
+    if (pw_smem_bytes(NC, taps * l->cs_in, KC, 4, cpt) <= smem_max) return cpt;
+    return l->size * (l->cs_in / KC);
+}
+}  // namespace
+
+int yq_tc_pwt_supported(const yq_conv_layer *l)
+{
+    static const bool off = (getenv("YQ_NO_PW") && atoi(getenv("YQ_NO_PW"))) || (getenv("YQ_NO_PWT") && atoi(getenv("YQ_NO_PWT")));      // A/B measurements
+    if (off || !l->int_form || !l->fused_mult || l->saturate || l->quant_stop_flag) return 0;
+    if (l->size != 3 || l->pad != 1 || l->stride != 2) return 0;               // (stride-1 3x3 layers run the flat family: shared patches, fused shortcut)
+    if (l->c != l->cs_in || l->cs_in % 32) return 0;                             // no pad lanes: they would count in sum(a)
+    // c = 32 (32-byte rows: 128 strided 32-byte requests per tap box) is correct but slow: layer 1 of the full yolov3 0.339 ms against the
+    // 0.266 ms of the small-c flavour, whose taps share an L1-cached patch -- nine boxes per tile re-read the input through L2.  YQ_PWT_C32=1 keeps it.
+    {
+        const bool c32 = getenv("YQ_PWT_C32") && atoi(getenv("YQ_PWT_C32"));      // (read per call: the tests flip it)
+        if (l->cs_in % 64 && !c32) return 0;
+    }
+    if (l->out_w < 8 || l->out_h < 4) return 0;
+    const int NC = yq::round_up(l->n + 1, 16);
+    if (NC > PW_MAX_NC || l->cs_out > NC) return 0;
+    const int wc = l->cs_out / (PW_GROUPS / (4 * NC <= 512 ? 4 : 2));
+    if (wc % 32 || (wc > 64 && wc % 64)) return 0;
+    const int KC = pwt_kc(l);
+    if (pw_smem_bytes(NC, 9 * l->cs_in, KC, 3, 3 * (l->cs_in / KC)) > 227 * 1024) return 0;   // the bank and three stages of one filter row each
+    return pw_get_encode() != nullptr;
+}
+
+int yq_tc_pwt_prepare(yq_conv_layer *l, void **state)
+{
+    PwState *st = new PwState();
+    st->KC = pwt_kc(l);
+    st->NC = yq::round_up(l->n + 1, 16);
+    const int taps = l->size * l->size;
+    const size_t K = (size_t)taps * l->cs_in;
+    std::vector<uint8_t> wp;
+    char tag[24];
+    snprintf(tag, sizeof tag, "pwt.%d", st->NC);
+    const bool on_dev = yq::pack_fetch_device(l, tag, (size_t)st->NC * K, (void **)&st->w);
+    if (!on_dev && (!yq::pack_fetch(l, tag, wp) || wp.size() != (size_t)st->NC * K)) {
+        wp.assign((size_t)st->NC * K, 0);
+        for (int oc = 0; oc < l->n; ++oc)
+            for (int t = 0; t < taps; ++t)
+                for (int ci = 0; ci < l->c; ++ci) wp[(size_t)oc * K + (size_t)t * l->cs_in + ci] = l->host_w[((size_t)oc * l->c + ci) * taps + t];
+        for (size_t k = 0; k < K; ++k) wp[(size_t)l->n * K + k] = 1;             // the ones row: TMEM column n = sum of the activations under the window
+        yq::pack_put(l, tag, wp);
+    }
+    auto cleanup = [&]() {
+        cudaFree(st->w);
+        delete st;
+        return -1;
+    };
+    if (!on_dev) {
+        if (cudaMalloc((void **)&st->w, wp.size()) != cudaSuccess) return cleanup();
+        if (cudaMemcpy(st->w, wp.data(), wp.size(), cudaMemcpyHostToDevice) != cudaSuccess) return cleanup();
+    }
+    if (pw_encode_2d(&st->tmB, st->w, (uint64_t)st->NC, (int)K, st->KC, st->NC, CU_TENSOR_MAP_L2_PROMOTION_L2_256B)) return cleanup();
+    *state = st;
+    return 0;
+}
+
+// in_geom: halo-padded (pad >= 1) with the halo holding the layer's zp_in; out_geom: any geometry (only the interior is written)
+int yq_tc_pwt_forward(yq_conv_layer *l, void *state, const uint8_t *in, const yq_act_geom *in_geom, uint8_t *out_u8, const yq_act_geom *out_geom, int batch,
+                      cudaStream_t stream)
+{
+    PwState *st = (PwState *)state;
+    if (!st || !in || !out_u8 || !in_geom || in_geom->pad < l->pad) return yq::fail("tcgen05 pointwise flavour (patch mode): bad argument");
+    const int n_sm = yq::device_sm_count(), smem_max = yq::device_smem_optin();
+    if (n_sm <= 0 || smem_max <= 0) return yq::fail("cannot query the device's multiprocessor count / shared memory size");
+    const yq_act_geom go = out_geom ? *out_geom : yq_act_geom{0, l->out_w, l->out_h};
+    PwArgs a;
+    memset(&a, 0, sizeof a);
+    a.ep = yq::make_epi(l);
+    a.N = l->n; a.CSO = l->cs_out; a.NC = st->NC;
+    a.B = batch; a.H = l->h; a.W = l->w; a.OH = l->out_h; a.OW = l->out_w;
+    a.patch = 1;
+    a.size = l->size; a.stride = l->stride; a.cptap = l->cs_in / st->KC;
+    a.cpt = l->size * l->size * a.cptap;
+    a.group = pwt_group(l, st->NC, st->KC, smem_max);
+    a.tw_shift = l->out_w >= 16 ? 4 : 3;                        // TW = 16 (TH = 8) or 8 (TH = 16)
+    const int TW = 1 << a.tw_shift, TH = 128 >> a.tw_shift;
+    a.tiles_x = (l->out_w + TW - 1) / TW;
+    a.tiles_y = (l->out_h + TH - 1) / TH;
+    a.num_tiles = a.tiles_x * a.tiles_y * batch;
+    a.nbuf = 4 * st->NC <= 512 ? 4 : 2;
+    a.tmem_cols = 32;
+    while (a.tmem_cols < a.nbuf * st->NC) a.tmem_cols *= 2;
+    a.wc = l->cs_out / (PW_GROUPS / a.nbuf);
+    a.rowb = a.wc < 64 ? a.wc : 64;
+    a.store_u8 = 1;
+    const int K = l->size * l->size * l->cs_in;
+    int stages = PW_MAX_ASTAGES;
+    while (stages > 3 && pw_smem_bytes(st->NC, K, st->KC, stages, a.group) > smem_max) --stages;
+    if (a.cpt == a.group) stages = stages / 4 * 4;
+    if (stages < 3 || pw_smem_bytes(st->NC, K, st->KC, stages, a.group) > smem_max) return yq::fail("tcgen05 pointwise flavour (patch mode): the filter bank does not fit shared memory");
+    a.a_stages = stages;
+    const int smem = pw_smem_bytes(st->NC, K, st->KC, stages, a.group);
+    a.trace = getenv("YQ_PW_TRACE") && atoi(getenv("YQ_PW_TRACE")) ? 1 : 0;
+    PwState::Key key{in, (const void *)(uintptr_t)(in_geom->pitch_w * 65536 + go.pitch_w), out_u8, batch * 4 + 2 + (go.pad ? 1 : 0)};
+    auto it = st->maps.find(key);
+    if (it == st->maps.end()) {
+        if (st->maps.size() > 64) st->maps.clear();
+        PwState::Maps m;
+        if (pw_encode_nhwc(&m.a, in, in_geom, l->pad, batch, l->h, l->w, l->cs_in, st->KC, TW, TH, l->stride)) return -1;
+        // the store box is one epilogue warp's pass: its 32 / TW rows of the patch x rowb channels
+        if (pw_encode_nhwc(&m.o, out_u8, &go, 0, batch, l->out_h, l->out_w, l->cs_out, a.rowb, TW, 32 / TW, 1)) return -1;
+        m.a2 = m.a;
+        it = st->maps.emplace(key, m).first;
+    }
+    const int grid = a.num_tiles < n_sm ? a.num_tiles : n_sm;
+    const CUtensorMap &tmA = it->second.a, &tmO = it->second.o, &tmA2 = it->second.a2;
+    if (st->KC == 128) return pw_launch<128>(st, tmA, tmO, tmA2, a, smem, grid, stream);
+    if (st->KC == 64) return pw_launch<64>(st, tmA, tmO, tmA2, a, smem, grid, stream);
+    return pw_launch<32>(st, tmA, tmO, tmA2, a, smem, grid, stream);
 }
 
 // YQ_PW_TRACE=1: the event times of the last traced launch (64 events x up to 256 CTAs, ns; tools/probes/pw_trace.py)

@@ -527,7 +527,8 @@ extern "C" yq_conv_layer *yq_make_convolutional_layer_quant(const yq_conv_desc *
     if ((yq_tc_rows_supported(l) && yq_tc_rows_prepare(l, &l->tc_rows) != 0) || (yq_tc_flat_supported(l) && yq_tc_flat_prepare(l, &l->tc_flat) != 0) ||
         (yq_tc_flat2_supported(l) && yq_tc_flat2_prepare(l, &l->tc_flat2) != 0) ||
         (yq_tc_flat2x_supported(l) && yq_tc_flat2x_prepare(l, &l->tc_flat2x) != 0) ||
-        (yq_tc_flat_eligible(l) && yq_tc_pw_supported(l) && yq_tc_pw_prepare(l, &l->tc_pw) != 0)) {
+        (yq_tc_flat_eligible(l) && yq_tc_pw_supported(l) && yq_tc_pw_prepare(l, &l->tc_pw) != 0) ||
+        (yq_tc_pwt_supported(l) && yq_tc_pwt_prepare(l, &l->tc_pwt) != 0)) {
         yq_free_convolutional_layer_quant(l);
         return nullptr;
     }
@@ -543,6 +544,7 @@ extern "C" void yq_free_convolutional_layer_quant(yq_conv_layer *l)
     yq_tc_flat2_free(l->tc_flat2);
     yq_tc_flat2x_free(l->tc_flat2x);
     yq_tc_pw_free(l->tc_pw);
+    yq_tc_pw_free(l->tc_pwt);
     cudaFree(l->w_simt); cudaFree(l->bias); cudaFree(l->zw); cudaFree(l->mcomb); cudaFree(l->mval); cudaFree(l->rsh); cudaFree(l->chanq);
     delete l;
 }
@@ -599,6 +601,9 @@ extern "C" int yq_forward_convolutional_layer_quant_per_image_gpu(yq_conv_layer 
 }
 
 extern "C" int yq_conv_geom_supported(const yq_conv_layer *l) { return l && yq_tc_geom_supported(l) ? 1 : 0; }
+// 1: the layer has the resident-bank patch-mode kernel (3x3 stride 2, narrow): it wants a halo-padded input whose halo holds its zp_in
+// and then runs through yq_forward_convolutional_layer_quant_geom_gpu without side outputs
+extern "C" int yq_conv_patch_supported(const yq_conv_layer *l) { return l && l->tc_pwt && !(getenv("YQ_PW") && !atoi(getenv("YQ_PW"))) ? 1 : 0; }
 extern "C" int yq_conv_out_geom_supported(const yq_conv_layer *l) { return l && (yq_tc_geom_supported(l) || yq_tc_out_geom_supported(l)) ? 1 : 0; }
 // 1: yq_forward_convolutional_layer_quant_gpu runs this (1x1) layer on conv_u8_tc_flat2_kernel in its plain-tensor mode
 int yq_conv_plain_1x1_fast(const yq_conv_layer *l)
@@ -620,6 +625,13 @@ extern "C" int yq_forward_convolutional_layer_quant_geom_gpu(yq_conv_layer *l, c
         if (out_geom->pad < 0 || out_geom->pitch_w < l->out_w + out_geom->pad || out_geom->rows_h < l->out_h + out_geom->pad)
             return yq::fail("output geometry does not hold a %dx%d tensor", l->out_h, l->out_w);
         return yq_tc_forward(l, in_u8, out_u8, nullptr, out_f32, out_acc, batch, (cudaStream_t)stream, nullptr, -1, out_geom);
+    }
+    // a narrow 3x3 stride-2 layer whose input halo holds its zp_in: the resident-bank kernel in patch mode (no side outputs)
+    if (l->tc_pwt && !plain_in && !out_acc && !out_f32 && in_geom->pad >= l->pad && in_halo_fill == l->zp_in && in_geom->pitch_w >= l->w + in_geom->pad &&
+        in_geom->rows_h >= l->h + in_geom->pad && !(getenv("YQ_PW") && !atoi(getenv("YQ_PW")))) {
+        if (out_geom && (out_geom->pad < 0 || out_geom->pitch_w < l->out_w + out_geom->pad || out_geom->rows_h < l->out_h + out_geom->pad))
+            return yq::fail("output geometry does not hold a %dx%d tensor", l->out_h, l->out_w);
+        return yq_tc_pwt_forward(l, l->tc_pwt, in_u8, in_geom, out_u8, out_geom, batch, (cudaStream_t)stream);
     }
     if (!yq_tc_geom_supported(l)) return yq::fail("this layer's kernel flavour takes plain tensors only (see yq_conv_geom_supported)");
     if (in_geom && (in_geom->pad < 0 || in_geom->pitch_w < l->w + in_geom->pad || in_geom->rows_h < l->h + in_geom->pad))

@@ -404,7 +404,7 @@ void plan_side_branches(yq_network *net)
 void plan(yq_network *net)
 {
     const int n = (int)net->layers.size();
-    std::vector<char> rows_ok(n, 0), flat_ok(n, 0), plain1_ok(n, 0);
+    std::vector<char> rows_ok(n, 0), flat_ok(n, 0), plain1_ok(n, 0), patch_ok(n, 0);
     int prev = -1;
     for (int i = 0; i < n; ++i) {
         Layer &l = net->layers[i];
@@ -419,6 +419,8 @@ void plan(yq_network *net)
         flat_ok[i] = !no_flat && yq_conv_flat_supported(l.conv) != 0;
         // a 1x1 layer that cannot keep flat tensors still runs the persistent kernel between PLAIN ones (no halo needed at all)
         plain1_ok[i] = yq_conv_plain_1x1_fast(l.conv) != 0;
+        // a narrow 3x3 stride-2 layer on the resident-bank kernel (patch mode): wants its input as a flat strip whose halo holds its zp_in
+        patch_ok[i] = net->fusion && !net->keep_acc && !rows_ok[i] && !flat_ok[i] && yq_conv_patch_supported(l.conv) != 0;
     }
     // requirement on tensor t (index t + 1; t = -1 is the network input): 0 none, 1 plain, 2 a specific padded geometry
     struct Req { int kind = 0; yq_act_geom g = {0, 0, 0}; int fill = -1, wish = -1; bool conflict = false; };
@@ -468,6 +470,9 @@ void plan(yq_network *net)
                 need(l.src, 2, &g, l.zp_in);
                 need(i, 2, &g, -1);
                 if (can_fuse_shortcut(i)) need(i + 1, 2, &g, -1);      // the launch stores the shortcut's tensor, as a flat strip
+            } else if (patch_ok[i]) {
+                yq_act_geom_flat(l.h, l.w, &g);
+                need(l.src, 2, &g, l.zp_in);            // (the tensor it writes may have any geometry)
             } else if (plain1_ok[i]) {
                 need(l.src, 1, nullptr, -1);
                 need(i, 1, nullptr, -1);
@@ -492,6 +497,14 @@ void plan(yq_network *net)
             if (l.type != L_CONV || rows_ok[i] || flat_ok[i] || !plain1_ok[i] || !yq_conv_geom_supported(l.conv)) continue;
             if (req[tensor_of(net, l.src) + 1].conflict || req[tensor_of(net, i) + 1].conflict) {
                 plain1_ok[i] = 0;
+                changed = true;
+            }
+        }
+        for (int i = 0; i < n && !changed; ++i) {
+            Layer &l = net->layers[i];
+            if (l.type != L_CONV || !patch_ok[i]) continue;
+            if (req[tensor_of(net, l.src) + 1].conflict) {
+                patch_ok[i] = 0;
                 changed = true;
             }
         }
@@ -572,7 +585,7 @@ void plan(yq_network *net)
                     yq_act_geom_flat(l.out_h, l.out_w, &g);
                     if (same_geom(sc.geom, g) && same_geom(from.geom, g)) l.fuse_shortcut = net->layers[i + 1].fused_away = true;
                 }
-            } else if (yq_conv_geom_supported(l.conv) && !plain1_ok[i]) {
+            } else if (patch_ok[i] || (yq_conv_geom_supported(l.conv) && !plain1_ok[i])) {
                 l.use_geom = true;
             } else if (net->fusion && i + 1 < n && yq_conv_can_fuse_maxpool(l.conv)) {
                 Layer &p = net->layers[i + 1];

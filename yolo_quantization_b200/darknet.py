@@ -327,6 +327,11 @@ class ConvolutionalLayerQuant:
         return res
 
     @property
+    def patch_supported(self) -> bool:
+        """the layer has the resident-bank kernel in patch mode (narrow 3x3 stride-2 layers between halo-padded tensors)"""
+        return bool(_lib.load().yq_conv_patch_supported(self.handle))
+
+    @property
     def flat_up2_supported(self) -> bool:
         return bool(_lib.load().yq_conv_flat_up2_supported(self.handle))
 
