@@ -89,13 +89,19 @@ PATCH_CASES = [
 ]
 
 
+@pytest.mark.parametrize("form", ["default", "nine_boxes"])
 @pytest.mark.parametrize("case", PATCH_CASES, ids=lambda c: "c%d_%dx%d_n%d_zi%d" % c[:5])
-def test_conv_stride2_resident_bank_patch_mode_vs_oracle(built, case, monkeypatch):
-    monkeypatch.setenv("YQ_PWT_C32", "1")       # (c = 32 is kept as a tested switch: slower than the small-c flavour, off by default)
+def test_conv_stride2_resident_bank_patch_mode_vs_oracle(built, case, form, monkeypatch):
     """narrow 3x3 / stride-2 layers (layers 1 and 5 of the full yolov3) on the resident-bank kernel in patch mode: flat input whose halo
     holds zp_in, no side outputs -> bytes equal the oracle and the older flavours (YQ_PW=0), the output's halo is untouched; with side
-    outputs, a plain input or a foreign halo byte the older flavours still serve the call."""
+    outputs, a plain input or a foreign halo byte the older flavours still serve the call.  c = 32 runs the PAIR form by default (the
+    input as 64-byte pixel pairs, two boxes per filter row); its nine-box form is a tested switch (slower than the small-c flavour)."""
     c, h, w, n, zp_in, batch = case
+    if form == "nine_boxes":
+        if c != 32:
+            pytest.skip("only c = 32 has two forms")
+        monkeypatch.setenv("YQ_PWT_C32", "1")
+        monkeypatch.setenv("YQ_NO_PWT_PAIR", "1")
     rng = np.random.default_rng(zlib.crc32(repr(case).encode()) + 19)
     layer, wq, zp_w, p = _rand_layer(rng, c, n, 3, 2, "leaky", zp_in, h=h, w=w)
     x = rng.integers(0, 256, size=(batch, c, h, w), dtype=np.uint8)
@@ -117,9 +123,9 @@ def test_conv_stride2_resident_bank_patch_mode_vs_oracle(built, case, monkeypatc
         _check(layer.forward_geom(x, "flat", "flat", want_acc=True), x, wq, zp_w, p, 2, 3, "leaky", zp_in, 33)          # side output: per-tap flavour
         _check(layer.forward_geom(x, "flat", "flat", in_fill=(zp_in + 7) & 255, want_acc=False), x, wq, zp_w, p, 2, 3, "leaky", zp_in, 33)
     else:
-        for go in ("flat", None):
-            got = layer.forward_geom(x, "flat", go, want_acc=False)
-            assert got["halo_ok"]
+        for gi, go in (("flat", "flat"), ("flat", None), ((2, w + 5, h + 3), "flat")):
+            got = layer.forward_geom(x, gi, go, want_acc=False)
+            assert got["halo_ok"], f"halo of the output was written ({gi} -> {go})"
             _check(got, x, wq, zp_w, p, 2, 3, "leaky", zp_in, 33)
         _check(layer.forward(x), x, wq, zp_w, p, 2, 3, "leaky", zp_in, 33)                                                # plain: small-c flavour
     layer.free()

@@ -68,7 +68,8 @@ struct PwArgs {
     // image (TW * TH = 128, TW a power of two), chunk c = (tap, channel chunk) is ONE 4-D tiled TMA box whose start is shifted by the tap
     // and which steps through the input with elementStrides = stride (yq_conv_tc.cu); the input's halo holds zp_in, the output map
     // covers the interior of the output tensor (partial tiles are clipped by the TMA unit)
-    int patch;
+    int patch;             // 1: nine (tap) boxes per channel chunk; 2: PAIR form for c = 32, stride 2 -- the input seen as pixel pairs (64 contiguous bytes),
+                           //    a filter row is two boxes of consecutive pairs: [px 2x | px 2x+1] and [px 2x+2 | (zero weights)], K = 6 x 64 per tile
     int tw_shift, tiles_x, tiles_y, OH, OW;
     int size, stride, cptap;   // filter size, stride, KC-chunks per tap
     int trace;             // YQ_PW_TRACE
@@ -101,7 +102,9 @@ __device__ __forceinline__ void pw_tmem_dealloc(uint32_t addr, uint32_t cols)
 // ONE = K is a single chunk: one commit per tile on done[stage], which the producer (stage free) and the epilogue (accumulator
 // complete) both wait on; a_stages % nbuf == 0 makes the stage name the accumulator.  Otherwise a commit per chunk frees its
 // stage and one more per tile publishes the accumulator.
-template <int KC, bool ONE, bool YOLO, int ACTM>
+// PATCH: 0 = pointwise strips, 1 = patch mode with a box per tap, 2 = its PAIR form (a compile-time choice: the strip kernels carry none of
+// the patch arithmetic -- with it in one kernel the narrow 1x1 layers of the full yolov3 ran 5 - 28 % slower, twice the code per tile)
+template <int KC, bool ONE, bool YOLO, int ACTM, int PATCH>
 __global__ void __launch_bounds__(PW_THREADS, 1) conv_u8_tc_pw_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                                                                   const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmA2,
                                                                   const PwArgs a)
@@ -126,7 +129,7 @@ __global__ void __launch_bounds__(PW_THREADS, 1) conv_u8_tc_pw_kernel(const __gr
     uint32_t *tmem_slot = (uint32_t *)(b_full + 1);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int nst = a.a_stages, nbuf = a.nbuf, chunks = a.cpt, group = a.group, groups = a.cpt / a.group;
+    const int nst = a.a_stages, nbuf = a.nbuf, chunks = a.cpt, group = PATCH ? a.group : 1, groups = PATCH ? a.cpt / a.group : a.cpt;
     if (threadIdx.x == 0) pw_mark(a.trace, 0);                       // CTA start
 
     if (threadIdx.x == 0) {
@@ -181,7 +184,13 @@ __global__ void __launch_bounds__(PW_THREADS, 1) conv_u8_tc_pw_kernel(const __gr
         uint32_t ph = 0;
         for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x, ++tr) {
             const int p0 = tile * 128;
-            const int tx = tile % a.tiles_x, t2 = tile / a.tiles_x, ty = t2 % a.tiles_y, n0 = t2 / a.tiles_y;     // (patch mode)
+            int tx = 0, ty = 0, n0 = 0;
+            if (PATCH) {
+                const int t2 = tile / a.tiles_x;
+                tx = tile - t2 * a.tiles_x;
+                n0 = t2 / a.tiles_y;
+                ty = t2 - n0 * a.tiles_y;
+            }
             const int cx0 = (tx << a.tw_shift) * a.stride, cy0 = (ty << (7 - a.tw_shift)) * a.stride;            // tap (0, 0) of the patch: the map starts in the halo
             for (int g = 0; g < groups; ++g) {
                 mbar_wait(&a_empty[s], ph ^ 1);
@@ -190,7 +199,10 @@ __global__ void __launch_bounds__(PW_THREADS, 1) conv_u8_tc_pw_kernel(const __gr
                     for (int j = 0; j < group; ++j) {
                         const int c = g * group + j;
                         uint8_t *dst = sA + s * A_STAGE + j * A_CHUNK;
-                        if (a.patch) {
+                        if (PATCH == 2) {
+                            // chunk c = (filter row c / 2, pair x + c % 2): rows of 64 contiguous bytes, consecutive pairs, every second input row
+                            tma_load_4d(dst, &tmA, &a_full[s], 0, (tx << a.tw_shift) + (c & 1), cy0 + (c >> 1), n0);
+                        } else if (PATCH == 1) {
                             const int tap = c / a.cptap, chunk = c - tap * a.cptap;
                             const int ky = tap / a.size, kx = tap - ky * a.size;
                             tma_load_4d(dst, &tmA, &a_full[s], chunk * KC, cx0 + kx, cy0 + ky, n0);
@@ -254,7 +266,7 @@ __global__ void __launch_bounds__(PW_THREADS, 1) conv_u8_tc_pw_kernel(const __gr
             const int p0 = tile * 128;
             int n, yy, xx, px0 = 0, py0 = 0;
             bool valid;
-            if (a.patch) {
+            if (PATCH) {
                 // tile row r = (hi, wi) of the TW x TH patch at (px0, py0) of image n; rows outside the image are clipped by the store
                 const int tx = tile % a.tiles_x, t2 = tile / a.tiles_x, ty = t2 % a.tiles_y;
                 const int r = q * 32 + lane;
@@ -329,7 +341,7 @@ __global__ void __launch_bounds__(PW_THREADS, 1) conv_u8_tc_pw_kernel(const __gr
                             }
                         }
                     }
-                    if (!YOLO && a.up_out) {
+                    if (!YOLO && !PATCH && a.up_out) {
                         // conv -> upsample(2) in one launch: the pixel's 16 bytes go to its four copies in the (2H x 2W) flat strip
                         // (that strip's halo is never written: it keeps the fill the plan gave it)
                         if (valid) {
@@ -350,7 +362,7 @@ __global__ void __launch_bounds__(PW_THREADS, 1) conv_u8_tc_pw_kernel(const __gr
                         uint32_t packed[4];
 #pragma unroll
                         for (int k = 0; k < 4; ++k) packed[k] = yq::pack_low_bytes(r[4 * k], r[4 * k + 1], r[4 * k + 2], r[4 * k + 3]);
-                        if (!valid && !a.patch) packed[0] = packed[1] = packed[2] = packed[3] = a.halo_word;
+                        if (!valid && !PATCH) packed[0] = packed[1] = packed[2] = packed[3] = a.halo_word;
                         yq::mask_pad_channels<16>(packed, a.N - c0);
                         // 64-byte rows: SWIZZLE_64B (16-byte chunk ^ row bits 1-2); 32-byte rows: SWIZZLE_32B (chunk ^ row bit 2)
                         const int sw = rowb == 64 ? (chl ^ ((lane >> 1) & 3)) : (chl ^ ((lane >> 2) & 1));
@@ -367,7 +379,7 @@ __global__ void __launch_bounds__(PW_THREADS, 1) conv_u8_tc_pw_kernel(const __gr
                     fence_proxy_async();          // my staging writes -> visible to the TMA unit
                     __syncwarp();
                     if (lane == 0) {
-                        if (a.patch) tma_store_4d(&tmO, stage, cbeg + pass * rowb, px0, py0 + q * (32 >> a.tw_shift), n);   // my 32 / TW rows of the patch
+                        if (PATCH) tma_store_4d(&tmO, stage, cbeg + pass * rowb, px0, py0 + q * (32 >> a.tw_shift), n);   // my 32 / TW rows of the patch
                         else tma_store_2d(&tmO, stage, cbeg + pass * rowb, p0 + q * 32);
                         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                     }
@@ -423,6 +435,7 @@ int pw_encode_2d(CUtensorMap *m, const void *ptr, uint64_t rows, int row_bytes, 
 
 struct PwState {
     int KC, NC;
+    bool pair = false;          // patch mode, PAIR form (PwArgs::patch == 2)
     uint8_t *w = nullptr;       // [NC][cs_in]: rows < n the filters, row n all ones, the rest zero
     float *lut = nullptr;       // quant_stop layers: dequantized value and its logistic for each of the 256 output bytes
     CUtensorMap tmB;
@@ -444,30 +457,30 @@ int pw_smem_bytes(int NC, int K, int KC, int stages, int group = 1)
     return 1024 + ((NC * K + 1023) & ~1023) + stages * group * 128 * KC + PW_EPI_WARPS * PW_STAGE_SLICE + PW_MAX_NC * (16 + 8 + 4) + 2048 + 512;
 }
 
-template <int KC, bool ONE, bool YOLO, int ACTM>
+template <int KC, bool ONE, bool YOLO, int ACTM, int PATCH>
 int pw_launch_v(PwState *st, const CUtensorMap &tmA, const CUtensorMap &tmO, const CUtensorMap &tmA2, const PwArgs &a, int smem, int grid, cudaStream_t stream)
 {
-    auto kern = conv_u8_tc_pw_kernel<KC, ONE, YOLO, ACTM>;
+    auto kern = conv_u8_tc_pw_kernel<KC, ONE, YOLO, ACTM, PATCH>;
     if (yq::ensure_dynamic_smem((const void *)kern, smem)) return -1;
     YQ_CUDA(yq::launch_pdl(kern, dim3(grid), dim3(PW_THREADS), smem, stream, tmA, st->tmB, tmO, tmA2, a));
     return 0;
 }
 
-template <int KC>
+template <int KC, int PATCH>
 int pw_launch(PwState *st, const CUtensorMap &tmA, const CUtensorMap &tmO, const CUtensorMap &tmA2, const PwArgs &a, int smem, int grid, cudaStream_t stream)
 {
     // the activation is a launch constant: one epilogue form per kernel keeps the code each warp walks short (heads are LINEAR: checked by the caller)
     const int actm = yq::act_mode(a.ep.act);
     if (a.cpt == a.group) {      // one ring stage per tile: a single commit frees the stage and publishes the accumulator
-        if (a.out_yolo) return pw_launch_v<KC, true, true, 1>(st, tmA, tmO, tmA2, a, smem, grid, stream);
-        if (actm == 0) return pw_launch_v<KC, true, false, 0>(st, tmA, tmO, tmA2, a, smem, grid, stream);
-        if (actm == 1) return pw_launch_v<KC, true, false, 1>(st, tmA, tmO, tmA2, a, smem, grid, stream);
-        return pw_launch_v<KC, true, false, 2>(st, tmA, tmO, tmA2, a, smem, grid, stream);
+        if (!PATCH && a.out_yolo) return pw_launch_v<KC, true, !PATCH, 1, PATCH>(st, tmA, tmO, tmA2, a, smem, grid, stream);
+        if (actm == 0) return pw_launch_v<KC, true, false, 0, PATCH>(st, tmA, tmO, tmA2, a, smem, grid, stream);
+        if (actm == 1) return pw_launch_v<KC, true, false, 1, PATCH>(st, tmA, tmO, tmA2, a, smem, grid, stream);
+        return pw_launch_v<KC, true, false, 2, PATCH>(st, tmA, tmO, tmA2, a, smem, grid, stream);
     }
-    if (a.out_yolo) return pw_launch_v<KC, false, true, 1>(st, tmA, tmO, tmA2, a, smem, grid, stream);
-    if (actm == 0) return pw_launch_v<KC, false, false, 0>(st, tmA, tmO, tmA2, a, smem, grid, stream);
-    if (actm == 1) return pw_launch_v<KC, false, false, 1>(st, tmA, tmO, tmA2, a, smem, grid, stream);
-    return pw_launch_v<KC, false, false, 2>(st, tmA, tmO, tmA2, a, smem, grid, stream);
+    if (!PATCH && a.out_yolo) return pw_launch_v<KC, false, !PATCH, 1, PATCH>(st, tmA, tmO, tmA2, a, smem, grid, stream);
+    if (actm == 0) return pw_launch_v<KC, false, false, 0, PATCH>(st, tmA, tmO, tmA2, a, smem, grid, stream);
+    if (actm == 1) return pw_launch_v<KC, false, false, 1, PATCH>(st, tmA, tmO, tmA2, a, smem, grid, stream);
+    return pw_launch_v<KC, false, false, 2, PATCH>(st, tmA, tmO, tmA2, a, smem, grid, stream);
 }
 
 }  // namespace
@@ -615,8 +628,8 @@ int yq_tc_pw_forward(yq_conv_layer *l, void *state, const uint8_t *in, uint8_t *
     a.split = in_first ? c_first / st->KC : 0;
     const int grid = a.num_tiles < n_sm ? a.num_tiles : n_sm;
     const CUtensorMap &tmA = it->second.a, &tmO = it->second.o, &tmA2 = it->second.a2;
-    if (st->KC == 128) return pw_launch<128>(st, tmA, tmO, tmA2, a, smem, grid, stream);
-    return pw_launch<64>(st, tmA, tmO, tmA2, a, smem, grid, stream);
+    if (st->KC == 128) return pw_launch<128, 0>(st, tmA, tmO, tmA2, a, smem, grid, stream);
+    return pw_launch<64, 0>(st, tmA, tmO, tmA2, a, smem, grid, stream);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -652,6 +665,13 @@ int pwt_group(const yq_conv_layer *l, int NC, int KC, int smem_max)
 }
 }  // namespace
 
+// PAIR form (c = 32, stride 2): see PwArgs::patch
+static bool pwt_pair(const yq_conv_layer *l)
+{
+    const bool off = getenv("YQ_NO_PWT_PAIR") && atoi(getenv("YQ_NO_PWT_PAIR"));      // A/B measurements (read per call: the tests flip it)
+    return !off && l->cs_in == 32 && l->stride == 2 && l->size == 3;
+}
+
 int yq_tc_pwt_supported(const yq_conv_layer *l)
 {
     static const bool off = (getenv("YQ_NO_PW") && atoi(getenv("YQ_NO_PW"))) || (getenv("YQ_NO_PWT") && atoi(getenv("YQ_NO_PWT")));      // A/B measurements
@@ -662,7 +682,7 @@ int yq_tc_pwt_supported(const yq_conv_layer *l)
     // 0.266 ms of the small-c flavour, whose taps share an L1-cached patch -- nine boxes per tile re-read the input through L2.  YQ_PWT_C32=1 keeps it.
     {
         const bool c32 = getenv("YQ_PWT_C32") && atoi(getenv("YQ_PWT_C32"));      // (read per call: the tests flip it)
-        if (l->cs_in % 64 && !c32) return 0;
+        if (l->cs_in % 64 && !c32 && !pwt_pair(l)) return 0;
     }
     if (l->out_w < 8 || l->out_h < 4) return 0;
     const int NC = yq::round_up(l->n + 1, 16);
@@ -670,6 +690,7 @@ int yq_tc_pwt_supported(const yq_conv_layer *l)
     const int wc = l->cs_out / (PW_GROUPS / (4 * NC <= 512 ? 4 : 2));
     if (wc % 32 || (wc > 64 && wc % 64)) return 0;
     const int KC = pwt_kc(l);
+    if (pwt_pair(l)) return pw_smem_bytes(NC, 6 * 64, 64, 2, 6) <= 227 * 1024 && 2 * NC <= 512 && pw_get_encode() != nullptr;   // two stages of a whole tile
     if (pw_smem_bytes(NC, 9 * l->cs_in, KC, 3, 3 * (l->cs_in / KC)) > 227 * 1024) return 0;   // the bank and three stages of one filter row each
     return pw_get_encode() != nullptr;
 }
@@ -680,6 +701,26 @@ int yq_tc_pwt_prepare(yq_conv_layer *l, void **state)
     st->KC = pwt_kc(l);
     st->NC = yq::round_up(l->n + 1, 16);
     const int taps = l->size * l->size;
+    if (pwt_pair(l)) {
+        // [NC][filter row ky][j = 0: kx 0, kx 1 | j = 1: kx 2, zeros][32 channels]; the ones row counts every real input byte once
+        st->KC = 64;
+        st->pair = true;
+        const size_t K = 6 * 64;
+        std::vector<uint8_t> wp((size_t)st->NC * K, 0);
+        for (int oc = 0; oc <= l->n; ++oc)
+            for (int ky = 0; ky < 3; ++ky)
+                for (int kx = 0; kx < 3; ++kx)
+                    for (int ci = 0; ci < l->c; ++ci)
+                        wp[(size_t)oc * K + (size_t)(ky * 2 + kx / 2) * 64 + (kx & 1) * 32 + ci] = oc == l->n ? 1 : l->host_w[((size_t)oc * l->c + ci) * taps + ky * 3 + kx];
+        if (cudaMalloc((void **)&st->w, wp.size()) != cudaSuccess || cudaMemcpy(st->w, wp.data(), wp.size(), cudaMemcpyHostToDevice) != cudaSuccess ||
+            pw_encode_2d(&st->tmB, st->w, (uint64_t)st->NC, (int)K, 64, st->NC, CU_TENSOR_MAP_L2_PROMOTION_L2_256B)) {
+            cudaFree(st->w);
+            delete st;
+            return -1;
+        }
+        *state = st;
+        return 0;
+    }
     const size_t K = (size_t)taps * l->cs_in;
     std::vector<uint8_t> wp;
     char tag[24];
@@ -721,26 +762,28 @@ int yq_tc_pwt_forward(yq_conv_layer *l, void *state, const uint8_t *in, const yq
     a.ep = yq::make_epi(l);
     a.N = l->n; a.CSO = l->cs_out; a.NC = st->NC;
     a.B = batch; a.H = l->h; a.W = l->w; a.OH = l->out_h; a.OW = l->out_w;
-    a.patch = 1;
-    a.size = l->size; a.stride = l->stride; a.cptap = l->cs_in / st->KC;
-    a.cpt = l->size * l->size * a.cptap;
-    a.group = pwt_group(l, st->NC, st->KC, smem_max);
+    a.patch = st->pair ? 2 : 1;
+    a.size = l->size; a.stride = l->stride; a.cptap = st->pair ? 1 : l->cs_in / st->KC;
+    a.cpt = st->pair ? 6 : l->size * l->size * a.cptap;
+    a.group = st->pair ? 6 : pwt_group(l, st->NC, st->KC, smem_max);
     a.tw_shift = l->out_w >= 16 ? 4 : 3;                        // TW = 16 (TH = 8) or 8 (TH = 16)
     const int TW = 1 << a.tw_shift, TH = 128 >> a.tw_shift;
     a.tiles_x = (l->out_w + TW - 1) / TW;
     a.tiles_y = (l->out_h + TH - 1) / TH;
     a.num_tiles = a.tiles_x * a.tiles_y * batch;
-    a.nbuf = 4 * st->NC <= 512 ? 4 : 2;
+    const int K = st->pair ? 6 * 64 : l->size * l->size * l->cs_in;
+    int stages = PW_MAX_ASTAGES;
+    while (stages > 2 && pw_smem_bytes(st->NC, K, st->KC, stages, a.group) > smem_max) --stages;
+    if (a.cpt == a.group) stages = stages >= 4 ? stages / 4 * 4 : 2;     // one commit per tile: the stage names the accumulator (stages % nbuf == 0)
+    if ((a.cpt != a.group && stages < 3) || pw_smem_bytes(st->NC, K, st->KC, stages, a.group) > smem_max)
+        return yq::fail("tcgen05 pointwise flavour (patch mode): the filter bank does not fit shared memory");
+    a.nbuf = (4 * st->NC <= 512 && !(a.cpt == a.group && stages == 2)) ? 4 : 2;
     a.tmem_cols = 32;
     while (a.tmem_cols < a.nbuf * st->NC) a.tmem_cols *= 2;
     a.wc = l->cs_out / (PW_GROUPS / a.nbuf);
     a.rowb = a.wc < 64 ? a.wc : 64;
+    if (a.wc % 32 || (a.wc > 64 && a.wc % 64)) return yq::fail("tcgen05 pointwise flavour (patch mode): %d channels per epilogue warp", a.wc);
     a.store_u8 = 1;
-    const int K = l->size * l->size * l->cs_in;
-    int stages = PW_MAX_ASTAGES;
-    while (stages > 3 && pw_smem_bytes(st->NC, K, st->KC, stages, a.group) > smem_max) --stages;
-    if (a.cpt == a.group) stages = stages / 4 * 4;
-    if (stages < 3 || pw_smem_bytes(st->NC, K, st->KC, stages, a.group) > smem_max) return yq::fail("tcgen05 pointwise flavour (patch mode): the filter bank does not fit shared memory");
     a.a_stages = stages;
     const int smem = pw_smem_bytes(st->NC, K, st->KC, stages, a.group);
     a.trace = getenv("YQ_PW_TRACE") && atoi(getenv("YQ_PW_TRACE")) ? 1 : 0;
@@ -749,7 +792,18 @@ int yq_tc_pwt_forward(yq_conv_layer *l, void *state, const uint8_t *in, const yq
     if (it == st->maps.end()) {
         if (st->maps.size() > 64) st->maps.clear();
         PwState::Maps m;
-        if (pw_encode_nhwc(&m.a, in, in_geom, l->pad, batch, l->h, l->w, l->cs_in, st->KC, TW, TH, l->stride)) return -1;
+        if (st->pair) {
+            // pixel pairs from the halo pixel (-1, -1) on: 64 contiguous bytes each, consecutive in x, every second row in y
+            EncodeTiledFn enc = pw_get_encode();
+            const uint8_t *base = in + ((size_t)(in_geom->pad - 1) * in_geom->pitch_w + (in_geom->pad - 1)) * 32;
+            cuuint64_t dims[4] = {64, (cuuint64_t)((l->w + 3) / 2), (cuuint64_t)(l->h + 2), (cuuint64_t)batch};
+            cuuint64_t strides[3] = {64, (cuuint64_t)in_geom->pitch_w * 32, (cuuint64_t)in_geom->rows_h * in_geom->pitch_w * 32};
+            cuuint32_t box[4] = {64, (cuuint32_t)TW, (cuuint32_t)(TH * 2), 1};
+            cuuint32_t es[4] = {1, 1, 2, 1};
+            CUresult r = enc(&m.a, CU_TENSOR_MAP_DATA_TYPE_UINT8, 4, const_cast<uint8_t *>(base), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                             CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            if (r != CUDA_SUCCESS) return yq::fail("cuTensorMapEncodeTiled(pixel pairs %dx%d pitch %d) failed: %d", l->h, l->w, in_geom->pitch_w, (int)r);
+        } else if (pw_encode_nhwc(&m.a, in, in_geom, l->pad, batch, l->h, l->w, l->cs_in, st->KC, TW, TH, l->stride)) return -1;
         // the store box is one epilogue warp's pass: its 32 / TW rows of the patch x rowb channels
         if (pw_encode_nhwc(&m.o, out_u8, &go, 0, batch, l->out_h, l->out_w, l->cs_out, a.rowb, TW, 32 / TW, 1)) return -1;
         m.a2 = m.a;
@@ -757,9 +811,10 @@ int yq_tc_pwt_forward(yq_conv_layer *l, void *state, const uint8_t *in, const yq
     }
     const int grid = a.num_tiles < n_sm ? a.num_tiles : n_sm;
     const CUtensorMap &tmA = it->second.a, &tmO = it->second.o, &tmA2 = it->second.a2;
-    if (st->KC == 128) return pw_launch<128>(st, tmA, tmO, tmA2, a, smem, grid, stream);
-    if (st->KC == 64) return pw_launch<64>(st, tmA, tmO, tmA2, a, smem, grid, stream);
-    return pw_launch<32>(st, tmA, tmO, tmA2, a, smem, grid, stream);
+    if (st->pair) return pw_launch<64, 2>(st, tmA, tmO, tmA2, a, smem, grid, stream);
+    if (st->KC == 128) return pw_launch<128, 1>(st, tmA, tmO, tmA2, a, smem, grid, stream);
+    if (st->KC == 64) return pw_launch<64, 1>(st, tmA, tmO, tmA2, a, smem, grid, stream);
+    return pw_launch<32, 1>(st, tmA, tmO, tmA2, a, smem, grid, stream);
 }
 
 // YQ_PW_TRACE=1: the event times of the last traced launch (64 events x up to 256 CTAs, ns; tools/probes/pw_trace.py)
