@@ -79,3 +79,31 @@ def test_network_predict_image_letterbox_path(built, tmp_path):
         for h, r in zip(heads, want):
             assert np.allclose(h[b], r, atol=YOLO_ATOL, rtol=0), f"image {b}"
     net.free()
+
+
+def test_full_yolov3_predict_f32_per_image_quantisation_replans_layer1(built, tmp_path):
+    """the full yolov3 (96x96): its production plan hands layer 1 -- a narrow 3x3 stride-2 layer on the resident-bank kernel in patch mode -- a
+    flat, halo-padded layer-0 tensor; a batch whose images quantise differently runs layer 0 on the generic per-image flavour, which writes a
+    plain tensor: the first such forward re-plans once (layer 1 back on its plain-input flavour) and every image's heads equal the oracle's
+    batch-1 walk with that image's own (s_in, zp_in); a uniform u8 batch afterwards still equals the oracle."""
+    layers = synth.yolov3_quant()
+    cfg, wts = str(tmp_path / "v3.cfg"), str(tmp_path / "v3.weights")
+    synth.write_cfg(cfg, layers, batch=3, width=96, height=96)
+    info = synth.write_weights(wts, layers, width=96, height=96, seed=5, identity_bn=False)
+    net = darknet.load_network(cfg, wts, batch=3)
+    assert net.layer_info(1).kernel == 1 and net.layers()[0].type == 0
+    rng = np.random.default_rng(8)
+    x = rng.random((3, 3, 96, 96), dtype=np.float32)
+    x[1] *= 0.6
+    x[2] = x[2] * 1.1 - 0.2
+    heads = net.split_heads(net.predict_f32(x))
+    for b in range(3):
+        want, _ = _oracle_heads(info, x[b])
+        for h, r in zip(heads, want):
+            assert np.allclose(h[b], r, atol=YOLO_ATOL, rtol=0), f"image {b}"
+    imgs = np.stack([synth.synthetic_image(s, 3, 96, 96) for s in (1, 2, 3)])
+    heads = net.split_heads(net.predict_u8(imgs))
+    ref = [r["f32"] for r, sl in zip(O.forward_network(info, imgs[2]), info) if sl.kind == "yolo"]
+    for h, r in zip(heads, ref):
+        assert np.allclose(h[2], r, atol=YOLO_ATOL, rtol=0)
+    net.free()

@@ -176,6 +176,7 @@ struct yq_network {
     uint8_t *scratch = nullptr;         // pull_layer conversions
     size_t scratch_bytes = 0;
     int keep_acc = 0;
+    bool plain_l0_out = false;     // set by the first per-image-quantised forward whose plan had given layer 0 a halo-padded output (see yq_network_predict_f32)
     bool no_planar_input = getenv("YQ_NO_PLANAR") && atoi(getenv("YQ_NO_PLANAR"));   // A/B: keep the layout-transform launch in front of layer 0
     // YQ_UPROUTE: an upsample whose only reader is the route right behind it is folded into that route's launch;
     // YQ_BRANCH_STREAM: a detection branch that nothing later reads runs on a second stream beside the layers after it
@@ -421,6 +422,8 @@ void plan(yq_network *net)
         plain1_ok[i] = yq_conv_plain_1x1_fast(l.conv) != 0;
         // a narrow 3x3 stride-2 layer on the resident-bank kernel (patch mode): wants its input as a flat strip whose halo holds its zp_in
         patch_ok[i] = net->fusion && !net->keep_acc && !rows_ok[i] && !flat_ok[i] && yq_conv_patch_supported(l.conv) != 0;
+        // (layer 0 behind the per-image input quantiser writes a plain tensor: once such a forward has run, its reader gives the flat input up)
+        if (net->plain_l0_out && tensor_of(net, l.src) == 0) patch_ok[i] = 0;
     }
     // requirement on tensor t (index t + 1; t = -1 is the network input): 0 none, 1 plain, 2 a specific padded geometry
     struct Req { int kind = 0; yq_act_geom g = {0, 0, 0}; int fill = -1, wish = -1; bool conflict = false; };
@@ -1532,6 +1535,18 @@ static int predict_f32_device(yq_network *net, float *out_host)
         YQ_CUDA(cudaMemcpyAsync(net->img_bias, hb.data(), hb.size() * sizeof(int32_t), cudaMemcpyHostToDevice, net->stream));
         YQ_CUDA(cudaMemcpyAsync(net->img_mcomb, hm.data(), hm.size() * sizeof(double), cudaMemcpyHostToDevice, net->stream));
         YQ_CUDA(cudaMemcpyAsync(net->img_zp, hzp.data(), hzp.size(), cudaMemcpyHostToDevice, net->stream));
+        {
+            // the per-image layer 0 (generic flavour) writes a plain tensor: if this plan had made layer 0's output halo-padded for the
+            // patch-mode convolution behind it (full yolov3: layer 1), re-plan once with that reader on its plain-input flavour
+            const Layer &f0 = net->layers[0];
+            if (!f0.fuse_pool && !(f0.geom.pad == 0 && f0.geom.pitch_w == f0.out_w && f0.geom.rows_h == f0.out_h) && !net->plain_l0_out) {
+                YQ_CUDA(cudaStreamSynchronize(net->stream));
+                drop_graph(net);
+                net->plain_l0_out = true;
+                plan(net);
+                if (net->plan_error) return yq::fail("yq_network_predict_f32: re-plan for the per-image input quantiser failed");
+            }
+        }
         if (forward_body(net, net->in_stage_nchw, nullptr, false, true)) return -1;
         YQ_CUDA(cudaStreamSynchronize(net->stream));      // (the host tables above live on this stack frame)
     }
